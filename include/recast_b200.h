@@ -1,0 +1,185 @@
+/*
+ * recast_b200.h — C ABI of the B200-native tiled voxelization front end for recast-rs.
+ *
+ * This is the drop-in boundary: a Rust `-sys` crate, a C++ caller or Python
+ * ctypes binds exactly these symbols.  Plain pointers and sizes only; no C++/torch types.
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * recast-rs workspace, `crates/recast/src/...`).
+ *
+ * Conventions
+ *   - all functions return 0 (RCB_OK) or a negative rcb_status; a human-readable message for the
+ *     last failure on a context is available from rcb_last_error().  Nothing aborts or throws
+ *     across this boundary.  Error kinds mirror recast_common::Error (recast-common/src/lib.rs:19-43).
+ *   - one rcb_ctx per host thread and per device; calls on one context are serialised by the
+ *     caller (the reference types are !Send/!Sync: heightfield.rs:75 Rc<RefCell<Span>>).
+ *   - inputs are borrowed for the duration of the call; outputs are owned by an rcb_result and
+ *     stay valid until rcb_result_free().
+ *   - "NONE" for an Option<usize> in the reference is 0xFFFFFFFF here (RCB_NONE).
+ *   - span / connection indices inside a tile view are TILE-RELATIVE, exactly the values the
+ *     reference stores in a single CompactHeightfield.
+ *   - there is no CPU fallback: without a CUDA device rcb_create fails with RCB_ECUDA.
+ */
+#ifndef RECAST_B200_H
+#define RECAST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RCB_NONE 0xFFFFFFFFu
+#define RCB_NOT_CONNECTED 63u /* compact_heightfield.rs:61 — sentinel in con[4] (collides with a real offset 63, replicated) */
+
+typedef enum rcb_status {
+    RCB_OK = 0,
+    RCB_EINVALID_MESH = -1, /* Error::InvalidMesh      (config.rs:113-133, tile_cache_builder.rs:138-143) */
+    RCB_ENAVMESH_GEN = -2,  /* Error::NavMeshGeneration (lib.rs:199-233, heightfield.rs:103-115) */
+    RCB_ECUDA = -3,         /* CUDA runtime failure / no device */
+    RCB_EOVERFLOW = -4,     /* an internal pool overflowed (clip polygon > RCB_MAX_POLY_VERTS) */
+    RCB_EARG = -5           /* bad argument (null pointer, bad tile index, wrong stage order) */
+} rcb_status;
+
+/* Stage mask for rcb_build_tiles / rcb_build_from_spans. */
+enum {
+    RCB_STAGE_RASTER = 1u,  /* rasterization.rs:246-366 rasterize_tri + :51-168 add_span_internal */
+    RCB_STAGE_FILTER = 2u,  /* heightfield.rs:286-531 the three walkable filters (lib.rs:278-287) */
+    RCB_STAGE_COMPACT = 4u, /* compact_heightfield.rs:175-430 build_from_heightfield + build_connections */
+    RCB_STAGE_ERODE = 8u,   /* area.rs:73-234 erode_walkable_area (runs before DIST when both set) */
+    RCB_STAGE_DIST = 16u,   /* compact_heightfield.rs:514-727 build_distance_field */
+    RCB_STAGE_ALL_BUILD = 1u | 2u | 4u | 16u /* what RecastBuilder::build_mesh reaches (lib.rs:77-87 → watershed.rs:375) */
+};
+
+/* Field-for-field RecastConfig (config.rs:7-51). */
+typedef struct rcb_config {
+    int32_t width;  /* cells along x */
+    int32_t height; /* cells along z */
+    float cs;
+    float ch;
+    float bmin[3];
+    float bmax[3];
+    float walkable_slope_angle;
+    int32_t walkable_height;
+    int32_t walkable_climb;
+    int32_t walkable_radius;
+    int32_t max_edge_len;
+    float max_simplification_error;
+    int32_t min_region_area;
+    int32_t merge_region_area;
+    int32_t max_vertices_per_polygon;
+    float detail_sample_dist;
+    float detail_sample_max_error;
+    int32_t border_size;
+} rcb_config;
+
+typedef struct rcb_ctx rcb_ctx;
+typedef struct rcb_result rcb_result;
+
+/* Totals over a batch (the T,V,C,S,K of SURVEY.md §8(d)); filled by rcb_result_totals. */
+typedef struct rcb_totals {
+    uint64_t tiles;
+    uint64_t triangles;
+    uint64_t vertices;
+    uint64_t cells;
+    uint64_t fragments; /* (triangle,cell) fragments emitted by the clipper; 0 when RASTER did not run */
+    uint64_t spans;
+    uint64_t connections;
+    uint64_t walkable_spans;
+    uint64_t result_bytes; /* bytes of the result arena (what rcb_result_download copies D2H) */
+} rcb_totals;
+
+/*
+ * One tile's result, flat SoA.  Pointers are host pointers (after rcb_result_download) or
+ * device pointers (rcb_result_tile_device); arrays that a skipped stage would have produced
+ * are NULL.  Layouts replace, in order:
+ *   Heightfield  (heightfield.rs:58-76)           -> CSR: hf_cell_offset[C+1], span_min/max/area[S]
+ *   CompactCell  (compact_heightfield.rs:15-20)   -> cell_index[C] (RCB_NONE = None), cell_count[C]
+ *   CompactSpan  (compact_heightfield.rs:31-48)   -> span_min/max[S], span_area[S], con[4*S], first_conn[S]
+ *                                                    (y == min, h == (u8)(max-min), reg == 0: derivable)
+ *   CompactConnection (:68-75)                    -> conn_ref[K], conn_dir[K], conn_next[K]
+ *   CompactHeightfield.{areas,dist} (:152-154)    -> areas[S], dist[S]
+ */
+typedef struct rcb_tile_view {
+    int32_t width, height;
+    uint32_t cell_count;  /* C = width*height */
+    uint32_t span_count;  /* S */
+    uint32_t conn_count;  /* K */
+    uint32_t walkable_span_count;
+    uint16_t max_height;   /* compact_heightfield.rs:240 */
+    uint16_t max_distance; /* compact_heightfield.rs:540,672 — max BEFORE the blur */
+    uint32_t status;       /* 0 ok; bit0: clip polygon overflow */
+    const uint32_t* hf_cell_offset; /* [C+1], tile-relative, ascending */
+    const int16_t* span_min;        /* [S] */
+    const int16_t* span_max;        /* [S] */
+    const uint8_t* span_area;       /* [S]  Span.area / CompactSpan.area (post-filter when FILTER ran) */
+    const uint32_t* cell_index;     /* [C]  Some(first span) or RCB_NONE */
+    const uint32_t* cell_count_arr; /* [C] */
+    const uint8_t* areas;           /* [S]  CompactHeightfield.areas (post-erosion when ERODE ran) */
+    const uint16_t* con;            /* [4*S] span-major: con[4*s + d4], d4: 0 W,1 S,2 E,3 N; 63 = none */
+    const uint32_t* first_conn;     /* [S]  RCB_NONE = None */
+    const uint32_t* conn_ref;       /* [K]  tile-relative span index */
+    const uint8_t* conn_dir;        /* [K]  0..7 = NW,N,NE,E,SE,S,SW,W */
+    const uint32_t* conn_next;      /* [K]  RCB_NONE = None */
+    const uint16_t* dist;           /* [S]  zeros unless DIST ran (compact_heightfield.rs:253) */
+} rcb_tile_view;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int rcb_create(int device, rcb_ctx** out);
+void rcb_destroy(rcb_ctx* ctx);
+const char* rcb_last_error(const rcb_ctx* ctx);
+/* Launch every kernel and copy of this context on `cuda_stream` (a cudaStream_t; NULL = the
+ * context's own stream).  Lets a caller time with its own events (bench.py passes torch's stream). */
+int rcb_set_stream(rcb_ctx* ctx, void* cuda_stream);
+/* Number of kernel launches issued by this context since creation (bench `gpu_launches`). */
+uint64_t rcb_launch_count(const rcb_ctx* ctx);
+
+/* ---- config (config.rs) ------------------------------------------------------------------ */
+void rcb_config_default(rcb_config* cfg);                                        /* config.rs:53-76 */
+void rcb_config_calculate_grid_size(rcb_config* cfg, const float bmin[3], const float bmax[3]); /* config.rs:85-107 */
+int rcb_config_validate(const rcb_config* cfg);                                  /* config.rs:110-136; RCB_EINVALID_MESH */
+
+/* ---- mesh ---------------------------------------------------------------------------------
+ * The (&[f32] vertices, &[i32] indices) pair every RecastBuilder entry point takes (lib.rs:68,116,186).
+ * rcb_upload_mesh copies host -> device; rcb_set_mesh_device borrows device memory (zero-copy). */
+int rcb_upload_mesh(rcb_ctx* ctx, const float* verts, size_t nfloats, const int32_t* tris, size_t nidx);
+int rcb_set_mesh_device(rcb_ctx* ctx, const void* d_verts, size_t nfloats, const void* d_tris, size_t nidx);
+
+/* ---- batched tile build ---------------------------------------------------------------------
+ * rcb_build_tiles: for every tile config runs RecastBuilder::build_heightfield (lib.rs:116-135 ->
+ * rasterize_triangles lib.rs:186-290: slope classification, rasterize_triangle with merge
+ * threshold 1, then the three filters when FILTER is set), then the stages named by stage_mask.
+ * Errors follow lib.rs:195-233: empty verts/indices => Ok with empty heightfields; len%3 != 0 or an
+ * index >= nverts => RCB_ENAVMESH_GEN (validated up front; the reference drops its partial
+ * heightfield on Err so the observable result is the same).
+ * This is the multi-tile entry the reference lacks: each tile is an independent
+ * Heightfield, as in DynamicTile::build (detour-dynamic/src/dynamic_tile.rs:444-483). */
+int rcb_build_tiles(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stage_mask,
+                    int erode_radius, rcb_result** out);
+
+/* rcb_rasterize: the free function rasterize_triangles(verts, tris, tri_area_ids, n, hf, thr)
+ * (rasterization.rs:405-428) per tile, with caller-provided per-triangle areas and merge
+ * threshold; no slope classification, no degenerate-triangle skip.  Later stages per stage_mask. */
+int rcb_rasterize(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const uint8_t* tri_areas,
+                  int32_t flag_merge_threshold, uint32_t stage_mask, int erode_radius, rcb_result** out);
+
+/* rcb_build_from_spans: start from existing heightfields (host CSR, one per tile, concatenated):
+ * Heightfield::filter_* (heightfield.rs:286,332,492), CompactHeightfield::build_from_heightfield
+ * (compact_heightfield.rs:175), build_distance_field (:514), erode_walkable_area (area.rs:73).
+ * cell_offset holds, tile after tile, width*height+1 tile-relative offsets; span arrays are
+ * concatenated in tile order.  RCB_STAGE_RASTER must not be set. */
+int rcb_build_from_spans(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const uint32_t* cell_offset,
+                         const int16_t* span_min, const int16_t* span_max, const uint8_t* span_area,
+                         uint32_t stage_mask, int erode_radius, rcb_result** out);
+
+/* ---- results ------------------------------------------------------------------------------- */
+int rcb_result_totals(const rcb_result* res, rcb_totals* out);
+int rcb_result_download(rcb_result* res);                       /* one D2H of the result arena into pinned memory */
+int rcb_result_tile(const rcb_result* res, int tile, rcb_tile_view* out);        /* host pointers; needs download */
+int rcb_result_tile_device(const rcb_result* res, int tile, rcb_tile_view* out); /* device pointers; scalars need download */
+void rcb_result_free(rcb_result* res);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECAST_B200_H */

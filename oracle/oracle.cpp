@@ -1,0 +1,992 @@
+// oracle.cpp — CPU restatement of the recast-rs voxelization front end.
+//
+// TEST INFRASTRUCTURE ONLY.  This file is the parity checker and the CPU baseline: only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.  The
+// product (recast_rs_b200/csrc) never links, calls or falls back to anything in oracle/.
+//
+// What it is: a C++17 restatement ("port") of the Rust reference's algorithm for the hot path,
+// written from the cited lines with flat arrays and index-linked span lists instead of
+// HashMap<(i32,i32),Option<Rc<RefCell<Span>>>>.  The Rust reference cannot be compiled in this
+// image (no cargo/rustc), so this is NOT the reference binary.
+//
+// Parity pinning: every expectation the reference's own unit tests hold for this path
+// (rasterization.rs:484-559, heightfield.rs:1206-1250,1417-1452, compact_heightfield.rs:1028-1117)
+// is asserted against this oracle in tests/test_oracle_reference_kats.py.  Functions the reference
+// never tests (RecastBuilder, filter_ledge_spans, filter_walkable_low_height_spans,
+// build_distance_field, box_blur, erode_walkable_area, the clipper's numerics) are pinned only by
+// the source text => for those rows "parity unpinned" (see DESIGN.md).
+//
+// Third-party arithmetic: glam 0.29.3 (Cargo.lock) Vec3 sub/cross/length/normalize used at
+// lib.rs:253-262 is restated from the published glam source (scalar Vec3):
+//   cross = (a.y*b.z - b.y*a.z, a.z*b.x - b.z*a.x, a.x*b.y - b.x*a.y); dot = (x*x + y*y) + z*z;
+//   length = sqrt(dot); normalize = v * (1.0/length).
+//
+// Build: g++ -O2 -std=c++17 -ffp-contract=off -fno-fast-math -fPIC -shared (oracle/Makefile).
+// All paths cited are relative to /root/reference/crates/recast/src/ unless stated.
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <thread>
+#include <vector>
+
+#include "../include/recast_b200.h"
+
+namespace {
+
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+
+// ---- Rust `as` cast semantics (saturating float->int, NaN -> 0) -----------------------------
+inline int32_t f32_as_i32(float v) {
+    if (std::isnan(v)) return 0;
+    if (v >= 2147483648.0f) return std::numeric_limits<int32_t>::max();
+    if (v <= -2147483648.0f) return std::numeric_limits<int32_t>::min();
+    return (int32_t)v;  // truncates toward zero
+}
+inline int16_t f32_as_i16(float v) {
+    if (std::isnan(v)) return 0;
+    if (v >= 32767.0f) return 32767;
+    if (v <= -32768.0f) return -32768;
+    return (int16_t)v;
+}
+
+// ---- Heightfield (heightfield.rs:23-32, 58-99) ------------------------------------------------
+struct Span {
+    int16_t smin, smax;
+    uint8_t area;
+    uint32_t next;
+};
+
+struct Heightfield {
+    int32_t width = 0, height = 0;
+    float bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0};
+    float cs = 0, ch = 0;
+    std::vector<uint32_t> first;  // per cell z*width+x, NONE = empty column (heightfield.rs:86)
+    std::vector<Span> pool;
+    bool poly_overflow = false;
+
+    uint32_t alloc(int16_t mn, int16_t mx, uint8_t a, uint32_t nx) {
+        pool.push_back(Span{mn, mx, a, nx});
+        return (uint32_t)pool.size() - 1;
+    }
+};
+
+// rasterization.rs:51-168 add_span_internal — the rasterizer's ordered insert + merge.
+void add_span_internal(Heightfield& hf, int32_t x, int32_t z, int16_t smin, int16_t smax, uint8_t area,
+                       int32_t thr) {
+    uint32_t& head = hf.first[(size_t)z * hf.width + x];
+    if (head == NONE) {  // :65-74
+        head = hf.alloc(smin, smax, area, NONE);
+        return;
+    }
+    uint32_t prev = NONE;
+    uint32_t cur = head;
+    while (cur != NONE) {
+        // NB: take copies, alloc() may grow the pool
+        const int16_t cmin = hf.pool[cur].smin, cmax = hf.pool[cur].smax;
+        if (smax < cmin) {  // :84-100 insert before current
+            uint32_t n = hf.alloc(smin, smax, area, cur);
+            if (prev != NONE)
+                hf.pool[prev].next = n;
+            else
+                hf.first[(size_t)z * hf.width + x] = n;
+            return;
+        }
+        if (smin > cmax) {  // :102-109
+            prev = cur;
+            cur = hf.pool[cur].next;
+            continue;
+        }
+        // :111-153 overlap (closed intervals): merge into `cur`
+        int16_t mmin = std::min(smin, cmin);
+        int16_t mmax = std::max(smax, cmax);
+        uint8_t marea = area;
+        if (std::abs((int32_t)mmax - (int32_t)cmax) <= thr) marea = std::max(marea, hf.pool[cur].area);  // :125-128
+        uint32_t nx = hf.pool[cur].next;
+        while (nx != NONE) {  // :131-145 absorb followers, their areas are dropped
+            if (hf.pool[nx].smin > mmax) break;
+            mmax = std::max(mmax, hf.pool[nx].smax);
+            nx = hf.pool[nx].next;
+        }
+        Span& c = hf.pool[cur];
+        c.smin = mmin;
+        c.smax = mmax;
+        c.area = marea;
+        c.next = nx;
+        return;
+    }
+    // :156-165 append
+    if (prev != NONE) {
+        uint32_t n = hf.alloc(smin, smax, area, NONE);
+        hf.pool[prev].next = n;
+    }
+}
+
+// heightfield.rs:102-222 Heightfield::add_span + insert_span — the second, different merge rule.
+int hf_add_span2(Heightfield& hf, int32_t x, int32_t z, int16_t mn, int16_t mx, uint8_t area) {
+    if (x < 0 || x >= hf.width || z < 0 || z >= hf.height) return RCB_ENAVMESH_GEN;  // :103-108
+    if (mn > mx) return RCB_ENAVMESH_GEN;                                             // :110-115
+    const size_t cell = (size_t)z * hf.width + x;
+    if (hf.first[cell] == NONE) {  // :122-125
+        hf.first[cell] = hf.alloc(mn, mx, area, NONE);
+        return 0;
+    }
+    uint32_t prev = NONE, cur = hf.first[cell];
+    for (;;) {
+        Span c = hf.pool[cur];
+        if (c.area == area && c.smax >= mn && mx >= c.smin) {  // :160-192 same-area overlap
+            int16_t mmin = std::min(c.smin, mn), mmax = std::max(c.smax, mx);
+            hf.pool[cur].smin = mmin;
+            hf.pool[cur].smax = mmax;
+            uint32_t nx = c.next;
+            if (nx != NONE) {  // :173-189 absorb at most ONE following span
+                Span n = hf.pool[nx];
+                if (n.area == area && mmax >= n.smin) {
+                    hf.pool[cur].smax = std::max(mmax, n.smax);
+                    hf.pool[cur].next = n.next;
+                }
+            }
+            return 0;
+        }
+        if (mx < c.smin) {  // :195-207 insert before current
+            uint32_t n = hf.alloc(mn, mx, area, cur);
+            if (prev != NONE)
+                hf.pool[prev].next = n;
+            else
+                hf.first[cell] = n;
+            return 0;
+        }
+        if (c.next == NONE) {  // :210-214 append
+            uint32_t n = hf.alloc(mn, mx, area, NONE);
+            hf.pool[cur].next = n;
+            return 0;
+        }
+        prev = cur;  // :217-218
+        cur = c.next;
+    }
+}
+
+// ---- clipper ------------------------------------------------------------------------------------
+constexpr int MAXV = 16;  // reference uses growable Vec; geometric bound is 7, overflow is flagged
+struct Poly {
+    int n = 0;
+    float v[MAXV * 3];
+};
+
+// rasterization.rs:172-242 divide_poly.  out1 = side < offset, out2 = side > offset.
+bool divide_poly(const Poly& in, Poly& out1, Poly& out2, float offset, int axis) {
+    out1.n = 0;
+    out2.n = 0;
+    const int n = in.n;
+    if (n == 0) return true;  // :185-187
+    int side[MAXV];
+    for (int i = 0; i < n; ++i) {  // :190-200
+        float c = in.v[i * 3 + axis];
+        side[i] = c < offset ? -1 : (c > offset ? 1 : 0);
+    }
+    bool ok = true;
+    auto push = [&ok](Poly& p, const float* q) {
+        if (p.n >= MAXV) {
+            ok = false;
+            return;
+        }
+        p.v[p.n * 3 + 0] = q[0];
+        p.v[p.n * 3 + 1] = q[1];
+        p.v[p.n * 3 + 2] = q[2];
+        p.n++;
+    };
+    for (int i = 0; i < n; ++i) {  // :203-241
+        const int j = (i + 1) % n;
+        const float* vi = &in.v[i * 3];
+        const float* vj = &in.v[j * 3];
+        const int si = side[i], sj = side[j];
+        if (si == 0) {
+            push(out1, vi);
+            push(out2, vi);
+        } else if (si < 0) {
+            push(out1, vi);
+            if (sj > 0) {
+                float t = (offset - vi[axis]) / (vj[axis] - vi[axis]);
+                float p[3];
+                for (int k = 0; k < 3; ++k) p[k] = vi[k] + t * (vj[k] - vi[k]);
+                push(out1, p);
+                push(out2, p);
+            }
+        } else {
+            push(out2, vi);
+            if (sj < 0) {
+                float t = (offset - vi[axis]) / (vj[axis] - vi[axis]);
+                float p[3];
+                for (int k = 0; k < 3; ++k) p[k] = vi[k] + t * (vj[k] - vi[k]);
+                push(out1, p);
+                push(out2, p);
+            }
+        }
+    }
+    return ok;
+}
+
+// rasterization.rs:246-366 rasterize_tri (+ :370-377 overlap_bounds).
+// `sink(x,z,smin,smax)` receives every fragment in emission order.
+template <class Sink>
+void rasterize_tri(const float* v0, const float* v1, const float* v2, const Heightfield& hf, bool& overflow,
+                   Sink&& sink) {
+    const float ics = 1.0f / hf.cs;  // :254-255
+    const float ich = 1.0f / hf.ch;
+    float tmin[3], tmax[3];
+    for (int i = 0; i < 3; ++i) {  // :258-264
+        tmin[i] = std::fmin(std::fmin(v0[i], v1[i]), v2[i]);
+        tmax[i] = std::fmax(std::fmax(v0[i], v1[i]), v2[i]);
+    }
+    // :270 overlap_bounds, inclusive on all three axes
+    if (!(tmin[0] <= hf.bmax[0] && tmax[0] >= hf.bmin[0] && tmin[1] <= hf.bmax[1] && tmax[1] >= hf.bmin[1] &&
+          tmin[2] <= hf.bmax[2] && tmax[2] >= hf.bmin[2]))
+        return;
+    int32_t x0 = f32_as_i32((tmin[0] - hf.bmin[0]) * ics);  // :275-278
+    int32_t x1 = f32_as_i32((tmax[0] - hf.bmin[0]) * ics);
+    int32_t z0 = f32_as_i32((tmin[2] - hf.bmin[2]) * ics);
+    int32_t z1 = f32_as_i32((tmax[2] - hf.bmin[2]) * ics);
+    x0 = std::max(x0, 0);  // :281-285
+    x1 = std::min(x1, hf.width - 1);
+    z0 = std::max(z0, -1);
+    z1 = std::min(z1, hf.height - 1);
+
+    Poly p1, in_row, rest, p2, cell;
+    p1.n = 3;
+    for (int k = 0; k < 3; ++k) {
+        p1.v[k] = v0[k];
+        p1.v[3 + k] = v1[k];
+        p1.v[6 + k] = v2[k];
+    }
+    for (int32_t z = z0; z <= z1; ++z) {  // :300-363
+        const float cz_max = hf.bmin[2] + (float)(z + 1) * hf.cs;
+        if (!divide_poly(p1, in_row, rest, cz_max, 2)) overflow = true;
+        p1 = rest;
+        if (in_row.n < 3 || z < 0) continue;
+        p2 = in_row;
+        for (int32_t x = x0; x <= x1; ++x) {
+            const float cx_max = hf.bmin[0] + (float)(x + 1) * hf.cs;
+            if (!divide_poly(p2, cell, rest, cx_max, 0)) overflow = true;
+            p2 = rest;
+            if (cell.n < 3) continue;
+            float min_y = cell.v[1], max_y = cell.v[1];
+            for (int i = 1; i < cell.n; ++i) {
+                min_y = std::fmin(min_y, cell.v[i * 3 + 1]);
+                max_y = std::fmax(max_y, cell.v[i * 3 + 1]);
+            }
+            int16_t smin = f32_as_i16(std::floor((min_y - hf.bmin[1]) * ich));  // :346-347
+            int16_t smax = f32_as_i16(std::ceil((max_y - hf.bmin[1]) * ich));
+            smin = std::max<int16_t>(smin, 0);  // :350
+            sink(x, z, smin, smax);
+        }
+    }
+}
+
+void rasterize_triangle(Heightfield& hf, const float* v0, const float* v1, const float* v2, uint8_t area,
+                        int32_t thr) {
+    bool ovf = false;
+    rasterize_tri(v0, v1, v2, hf, ovf,
+                  [&](int32_t x, int32_t z, int16_t a, int16_t b) { add_span_internal(hf, x, z, a, b, area, thr); });
+    if (ovf) hf.poly_overflow = true;
+}
+
+// lib.rs:212-213 — threshold computed once per call in f32 (libm cosf).
+inline float slope_threshold(float angle) { return std::cos(angle * 3.14159265358979323846f / 180.0f); }
+
+// lib.rs:252-270 — returns false when the triangle is skipped (degenerate).
+inline bool classify(const float* v0, const float* v1, const float* v2, float thr, uint8_t& area) {
+    const float e1x = v1[0] - v0[0], e1y = v1[1] - v0[1], e1z = v1[2] - v0[2];
+    const float e2x = v2[0] - v0[0], e2y = v2[1] - v0[1], e2z = v2[2] - v0[2];
+    const float cx = e1y * e2z - e2y * e1z;
+    const float cy = e1z * e2x - e2z * e1x;
+    const float cz = e1x * e2y - e2x * e1y;
+    const float len = std::sqrt((cx * cx + cy * cy) + cz * cz);
+    if (len < std::numeric_limits<float>::epsilon()) return false;  // :258
+    const float ny = cy * (1.0f / len);
+    area = (std::fabs(ny) >= thr) ? 1 : 0;  // :266-270
+    return true;
+}
+
+// heightfield.rs:286-328
+void filter_low_hanging(Heightfield& hf, int16_t climb) {
+    for (size_t c = 0; c < hf.first.size(); ++c) {
+        bool prev_walkable = false;
+        uint8_t prev_area = 0;
+        uint32_t prev = NONE;
+        for (uint32_t s = hf.first[c]; s != NONE; s = hf.pool[s].next) {
+            const bool walkable = hf.pool[s].area != 0;
+            if (!walkable && prev_walkable && prev != NONE) {
+                if ((int32_t)hf.pool[s].smax - (int32_t)hf.pool[prev].smax <= (int32_t)climb) hf.pool[s].area = prev_area;
+            }
+            prev_walkable = walkable;
+            prev_area = hf.pool[s].area;
+            prev = s;
+        }
+    }
+}
+
+// heightfield.rs:332-488
+void filter_ledge(Heightfield& hf, int16_t height, int16_t climb) {
+    constexpr int32_t MAXH = 0xffff;
+    const int32_t neg_climb = (int32_t)(int16_t)(-climb);  // `-walkable_climb as i32` = (-climb) as i32
+    static const int dx[4] = {0, 1, 0, -1}, dz[4] = {-1, 0, 1, 0};
+    for (int32_t z = 0; z < hf.height; ++z)
+        for (int32_t x = 0; x < hf.width; ++x)
+            for (uint32_t s = hf.first[(size_t)z * hf.width + x]; s != NONE; s = hf.pool[s].next) {
+                if (hf.pool[s].area == 0) continue;
+                const int32_t floor = hf.pool[s].smax;
+                const int32_t ceiling = hf.pool[s].next != NONE ? (int32_t)hf.pool[hf.pool[s].next].smin : MAXH;
+                int32_t lowest_diff = MAXH;
+                int32_t lo = floor, hi = floor;
+                bool ledge = false;
+                for (int d = 0; d < 4; ++d) {
+                    const int32_t nx = x + dx[d], nz = z + dz[d];
+                    if (nx < 0 || nz < 0 || nx >= hf.width || nz >= hf.height) {  // :377-385
+                        lowest_diff = neg_climb - 1;
+                        ledge = true;
+                        break;
+                    }
+                    uint32_t ns = hf.first[(size_t)nz * hf.width + nx];
+                    if (ns == NONE) {  // :448-453 empty neighbour column => ledge
+                        lowest_diff = neg_climb - 1;
+                        ledge = true;
+                        break;
+                    }
+                    int32_t nceil = hf.pool[ns].smin;  // :393-398
+                    if (std::min(ceiling, nceil) - floor >= (int32_t)height) {  // :401-406
+                        lowest_diff = neg_climb - 1;
+                        ledge = true;
+                        break;
+                    }
+                    for (; ns != NONE; ns = hf.pool[ns].next) {  // :409-447
+                        const int32_t nfloor = hf.pool[ns].smax;
+                        nceil = hf.pool[ns].next != NONE ? (int32_t)hf.pool[hf.pool[ns].next].smin : MAXH;
+                        if (std::min(ceiling, nceil) - std::max(floor, nfloor) < (int32_t)height) continue;
+                        const int32_t diff = nfloor - floor;
+                        lowest_diff = std::min(lowest_diff, diff);
+                        if (std::abs(diff) <= (int32_t)climb) {
+                            lo = std::min(lo, nfloor);
+                            hi = std::max(hi, nfloor);
+                        } else if (diff < neg_climb) {
+                            break;
+                        }
+                    }
+                }
+                if (ledge)
+                    hf.pool[s].area = 0;
+                else if (lowest_diff < neg_climb)
+                    hf.pool[s].area = 0;
+                else if (hi - lo > (int32_t)climb)
+                    hf.pool[s].area = 0;
+            }
+}
+
+// heightfield.rs:492-531
+void filter_low_height(Heightfield& hf, int16_t height) {
+    constexpr int32_t MAXH = 0xffff;
+    for (size_t c = 0; c < hf.first.size(); ++c)
+        for (uint32_t s = hf.first[c]; s != NONE; s = hf.pool[s].next) {
+            const int32_t floor = hf.pool[s].smax;
+            const int32_t ceiling = hf.pool[s].next != NONE ? (int32_t)hf.pool[hf.pool[s].next].smin : MAXH;
+            if (ceiling - floor < (int32_t)height) hf.pool[s].area = 0;
+        }
+}
+
+// lib.rs:186-290 RecastBuilder::rasterize_triangles.  Returns rcb_status.
+int builder_rasterize(Heightfield& hf, const rcb_config& cfg, const float* verts, size_t nfloats,
+                      const int32_t* idx, size_t nidx, bool run_filters) {
+    if (nfloats == 0 || nidx == 0) return 0;           // :195-197
+    if (nfloats % 3 != 0) return RCB_ENAVMESH_GEN;     // :199-203
+    if (nidx % 3 != 0) return RCB_ENAVMESH_GEN;        // :205-209
+    const float thr = slope_threshold(cfg.walkable_slope_angle);
+    const size_t ntri = nidx / 3, max_idx = nfloats / 3;
+    for (size_t i = 0; i < ntri; ++i) {
+        // `as usize` of a negative i32 is huge => out of bounds (:219-233)
+        const uint64_t i0 = (uint64_t)(int64_t)idx[i * 3], i1 = (uint64_t)(int64_t)idx[i * 3 + 1],
+                       i2 = (uint64_t)(int64_t)idx[i * 3 + 2];
+        if (i0 >= max_idx || i1 >= max_idx || i2 >= max_idx) return RCB_ENAVMESH_GEN;
+        const float *v0 = verts + i0 * 3, *v1 = verts + i1 * 3, *v2 = verts + i2 * 3;
+        uint8_t area;
+        if (!classify(v0, v1, v2, thr, area)) continue;
+        rasterize_triangle(hf, v0, v1, v2, area, 1);  // :273
+    }
+    if (run_filters) {
+        filter_low_hanging(hf, (int16_t)cfg.walkable_climb);                              // :278
+        filter_ledge(hf, (int16_t)cfg.walkable_height, (int16_t)cfg.walkable_climb);      // :281-284
+        filter_low_height(hf, (int16_t)cfg.walkable_height);                              // :287
+    }
+    return 0;
+}
+
+// ---- CompactHeightfield (compact_heightfield.rs:129-170) ----------------------------------------
+struct Compact {
+    int32_t width = 0, height = 0;
+    std::vector<uint32_t> cell_index, cell_count;
+    std::vector<int16_t> smin, smax;
+    std::vector<uint8_t> span_area, areas;
+    std::vector<uint16_t> con;  // 4 per span
+    std::vector<uint32_t> first_conn;
+    std::vector<uint32_t> conn_ref, conn_next;
+    std::vector<uint8_t> conn_dir;
+    std::vector<uint16_t> dist;
+    uint32_t walkable_span_count = 0;
+    uint16_t max_height = 0, max_distance = 0;
+
+    // compact_heightfield.rs:495-510 get_neighbor — literal list walk
+    uint32_t get_neighbor(uint32_t s, uint8_t dir) const {
+        uint32_t c = first_conn[s];
+        while (c != NONE) {
+            if (conn_dir[c] == dir) return conn_ref[c];
+            c = conn_next[c];
+        }
+        return NONE;
+    }
+};
+
+const int DIRX[8] = {-1, 0, 1, 1, 1, 0, -1, -1};  // compact_heightfield.rs:109-111
+const int DIRZ[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
+
+// compact_heightfield.rs:175-281 build_from_heightfield + :284-430 build_connections
+void compact_build(const Heightfield& hf, Compact& c) {
+    const int32_t w = hf.width, h = hf.height;
+    c.width = w;
+    c.height = h;
+    const size_t ncell = (size_t)w * h;
+    c.cell_index.assign(ncell, NONE);
+    c.cell_count.assign(ncell, 0);
+    c.walkable_span_count = 0;
+    c.max_height = 0;
+    for (size_t i = 0; i < ncell; ++i) {  // :203-250, row-major
+        if (hf.first[i] == NONE) continue;
+        c.cell_index[i] = (uint32_t)c.smin.size();
+        uint32_t n = 0;
+        for (uint32_t s = hf.first[i]; s != NONE; s = hf.pool[s].next) {
+            const Span& sp = hf.pool[s];
+            c.smin.push_back(sp.smin);
+            c.smax.push_back(sp.smax);
+            c.span_area.push_back(sp.area);
+            c.areas.push_back(sp.area);
+            c.max_height = std::max(c.max_height, (uint16_t)sp.smax);  // :240 `as u16` wraps
+            if (sp.area != 0) c.walkable_span_count++;
+            ++n;
+        }
+        c.cell_count[i] = n;
+    }
+    const size_t S = c.smin.size();
+    c.dist.assign(S, 0);  // :253
+    c.con.assign(S * 4, 63);
+    c.first_conn.assign(S, NONE);
+
+    // :297-372 per walkable span, 8 directions, best overlapping walkable neighbour
+    std::vector<uint32_t> nei(S * 8, NONE);
+    for (size_t i = 0; i < ncell; ++i) {
+        if (c.cell_index[i] == NONE) continue;
+        const int32_t x = (int32_t)(i % w), z = (int32_t)(i / w);
+        for (uint32_t k = 0; k < c.cell_count[i]; ++k) {
+            const uint32_t s = c.cell_index[i] + k;
+            if (c.areas[s] == 0) continue;
+            for (int dir = 0; dir < 8; ++dir) {
+                const int32_t nx = x + DIRX[dir], nz = z + DIRZ[dir];
+                if (nx < 0 || nz < 0 || nx >= w || nz >= h) continue;
+                const size_t nc = (size_t)nz * w + nx;
+                if (c.cell_index[nc] == NONE) continue;
+                uint32_t best = NONE;
+                int32_t best_diff = std::numeric_limits<int32_t>::max();
+                for (uint32_t nk = 0; nk < c.cell_count[nc]; ++nk) {
+                    const uint32_t ns = c.cell_index[nc] + nk;
+                    if (c.areas[ns] == 0) continue;
+                    const int16_t bot = std::max(c.smin[ns], c.smin[s]);
+                    const int16_t top = std::min(c.smax[ns], c.smax[s]);
+                    if (bot > top) continue;
+                    // abs_diff on i16 -> u16; the u16 sum wraps in release builds (:352-354)
+                    const uint16_t d0 = (uint16_t)std::abs((int32_t)c.smin[ns] - (int32_t)c.smin[s]);
+                    const uint16_t d1 = (uint16_t)std::abs((int32_t)c.smax[ns] - (int32_t)c.smax[s]);
+                    const int32_t diff = (int32_t)(uint16_t)(d0 + d1);
+                    if (diff < best_diff) {
+                        best_diff = diff;
+                        best = ns;
+                    }
+                }
+                nei[(size_t)s * 8 + dir] = best;
+            }
+        }
+    }
+    // :375-389 connection array: spans in index order, each span's connections pushed in REVERSE
+    // direction order, `next` -> previously pushed, first_connection = last pushed (lowest dir)
+    for (size_t s = 0; s < S; ++s) {
+        uint32_t first = NONE;
+        for (int dir = 7; dir >= 0; --dir) {
+            const uint32_t n = nei[s * 8 + dir];
+            if (n == NONE) continue;
+            c.conn_ref.push_back(n);
+            c.conn_dir.push_back((uint8_t)dir);
+            c.conn_next.push_back(first);
+            first = (uint32_t)c.conn_ref.size() - 1;
+        }
+        c.first_conn[s] = first;
+    }
+    // :392-427 con[4]: 8-dir 7->0 (W), 5->1 (S), 3->2 (E), 1->3 (N); value = offset inside the
+    // neighbour's cell.  (The reference finds that cell with an O(cells) scan, :433-442; the
+    // neighbour cell is known here.)
+    static const int d8of4[4] = {7, 5, 3, 1};
+    for (size_t i = 0; i < ncell; ++i) {
+        if (c.cell_index[i] == NONE) continue;
+        const int32_t x = (int32_t)(i % w), z = (int32_t)(i / w);
+        for (uint32_t k = 0; k < c.cell_count[i]; ++k) {
+            const uint32_t s = c.cell_index[i] + k;
+            for (int d4 = 0; d4 < 4; ++d4) {
+                const int dir = d8of4[d4];
+                const uint32_t n = nei[(size_t)s * 8 + dir];
+                if (n == NONE) continue;
+                const size_t nc = (size_t)(z + DIRZ[dir]) * w + (x + DIRX[dir]);
+                c.con[(size_t)s * 4 + d4] = (uint16_t)(n - c.cell_index[nc]);
+            }
+        }
+    }
+}
+
+inline uint16_t sat_add16(uint16_t a, uint16_t b) {
+    uint32_t r = (uint32_t)a + b;
+    return r > 0xffff ? 0xffff : (uint16_t)r;
+}
+inline uint8_t sat_add8(uint8_t a, uint8_t b) {
+    uint32_t r = (uint32_t)a + b;
+    return r > 0xff ? 0xff : (uint8_t)r;
+}
+
+// compact_heightfield.rs:514-543 build_distance_field, :546-675 calculate_distance_field, :679-727 box_blur
+void build_distance_field(Compact& c) {
+    const size_t S = c.smin.size();
+    const int32_t w = c.width, h = c.height;
+    std::vector<uint16_t> src(S, 0xffff), dst(S, 0);
+    auto for_spans = [&](bool reverse, auto&& fn) {
+        if (!reverse) {
+            for (int32_t y = 0; y < h; ++y)
+                for (int32_t x = 0; x < w; ++x) {
+                    const size_t ci = (size_t)y * w + x;
+                    if (c.cell_index[ci] == NONE) continue;
+                    for (uint32_t k = 0; k < c.cell_count[ci]; ++k) fn(c.cell_index[ci] + k);
+                }
+        } else {
+            for (int32_t y = h - 1; y >= 0; --y)
+                for (int32_t x = w - 1; x >= 0; --x) {
+                    const size_t ci = (size_t)y * w + x;
+                    if (c.cell_index[ci] == NONE) continue;
+                    for (uint32_t k = 0; k < c.cell_count[ci]; ++k) fn(c.cell_index[ci] + k);
+                }
+        }
+    };
+    // :556-585 boundary
+    for_spans(false, [&](uint32_t s) {
+        int cnt = 0;
+        for (uint8_t dir : {1, 3, 5, 7}) {
+            uint32_t n = c.get_neighbor(s, dir);
+            if (n != NONE && c.areas[n] == c.areas[s]) cnt++;
+        }
+        if (cnt != 4) src[s] = 0;
+    });
+    // :588-627 forward.  The dir numbers are 4-direction numbers applied to the 8-direction table.
+    for_spans(false, [&](uint32_t s) {
+        uint32_t a = c.get_neighbor(s, 0);
+        if (a != NONE) {
+            if (sat_add16(src[a], 2) < src[s]) src[s] = sat_add16(src[a], 2);
+            uint32_t aa = c.get_neighbor(a, 3);
+            if (aa != NONE && sat_add16(src[aa], 3) < src[s]) src[s] = sat_add16(src[aa], 3);
+        }
+        uint32_t b = c.get_neighbor(s, 3);
+        if (b != NONE) {
+            if (sat_add16(src[b], 2) < src[s]) src[s] = sat_add16(src[b], 2);
+            uint32_t bb = c.get_neighbor(b, 2);
+            if (bb != NONE && sat_add16(src[bb], 3) < src[s]) src[s] = sat_add16(src[bb], 3);
+        }
+    });
+    // :630-669 backward
+    for_spans(true, [&](uint32_t s) {
+        uint32_t a = c.get_neighbor(s, 2);
+        if (a != NONE) {
+            if (sat_add16(src[a], 2) < src[s]) src[s] = sat_add16(src[a], 2);
+            uint32_t aa = c.get_neighbor(a, 1);
+            if (aa != NONE && sat_add16(src[aa], 3) < src[s]) src[s] = sat_add16(src[aa], 3);
+        }
+        uint32_t b = c.get_neighbor(s, 1);
+        if (b != NONE) {
+            if (sat_add16(src[b], 2) < src[s]) src[s] = sat_add16(src[b], 2);
+            uint32_t bb = c.get_neighbor(b, 0);
+            if (bb != NONE && sat_add16(src[bb], 3) < src[s]) src[s] = sat_add16(src[bb], 3);
+        }
+    });
+    uint16_t max_dist = 0;  // :672
+    for (size_t i = 0; i < S; ++i) max_dist = std::max(max_dist, src[i]);
+    // :679-727 box_blur(threshold 1) -> thr = 2
+    const uint16_t thr = 2;
+    for_spans(false, [&](uint32_t s) {
+        const uint16_t cd = src[s];
+        if (cd <= thr) {
+            dst[s] = cd;
+            return;
+        }
+        int32_t d = cd, n = 1;
+        for (uint8_t dir : {1, 3, 5, 7}) {
+            uint32_t nb = c.get_neighbor(s, dir);
+            if (nb == NONE) continue;
+            d += src[nb];
+            n++;
+            uint32_t dg = c.get_neighbor(nb, (uint8_t)((dir + 1) % 8));
+            if (dg != NONE) {
+                d += src[dg];
+                n++;
+            }
+        }
+        dst[s] = (uint16_t)(d / n);
+    });
+    c.dist = dst;  // :531-534
+    c.max_distance = max_dist;
+}
+
+// area.rs:73-234 erode_walkable_area
+void erode_walkable_area(Compact& c, int32_t radius) {
+    const size_t S = c.smin.size();
+    const int32_t w = c.width, h = c.height;
+    std::vector<uint8_t> dist(S, 0xff);
+    static const uint8_t d8of4[4] = {7, 5, 3, 1};  // compact_heightfield.rs:732-745
+    for (int32_t z = 0; z < h; ++z)
+        for (int32_t x = 0; x < w; ++x) {
+            const size_t ci = (size_t)z * w + x;
+            if (c.cell_index[ci] == NONE) continue;
+            for (uint32_t k = 0; k < c.cell_count[ci]; ++k) {
+                const uint32_t s = c.cell_index[ci] + k;
+                if (c.areas[s] == 0) {  // :91-94
+                    dist[s] = 0;
+                    continue;
+                }
+                int cnt = 0;
+                for (int d = 0; d < 4; ++d) {  // :100-120
+                    uint32_t n = c.get_neighbor(s, d8of4[d]);
+                    if (n == NONE) break;
+                    if (c.areas[n] == 0) break;
+                    cnt++;
+                }
+                if (cnt != 4) dist[s] = 0;
+            }
+        }
+    auto relax = [&](uint32_t s, uint8_t d1, uint8_t d2) {
+        uint32_t a = c.get_neighbor(s, d1);
+        if (a == NONE) return;
+        uint8_t nd = sat_add8(dist[a], 2);
+        if (nd < dist[s]) dist[s] = nd;
+        uint32_t b = c.get_neighbor(a, d2);
+        if (b != NONE) {
+            nd = sat_add8(dist[b], 3);
+            if (nd < dist[s]) dist[s] = nd;
+        }
+    };
+    for (int32_t z = 0; z < h; ++z)  // :132-176
+        for (int32_t x = 0; x < w; ++x) {
+            const size_t ci = (size_t)z * w + x;
+            if (c.cell_index[ci] == NONE) continue;
+            for (uint32_t k = 0; k < c.cell_count[ci]; ++k) {
+                relax(c.cell_index[ci] + k, 0, 3);
+                relax(c.cell_index[ci] + k, 3, 2);
+            }
+        }
+    for (int32_t z = h - 1; z >= 0; --z)  // :179-223
+        for (int32_t x = w - 1; x >= 0; --x) {
+            const size_t ci = (size_t)z * w + x;
+            if (c.cell_index[ci] == NONE) continue;
+            for (uint32_t k = 0; k < c.cell_count[ci]; ++k) {
+                relax(c.cell_index[ci] + k, 2, 1);
+                relax(c.cell_index[ci] + k, 1, 0);
+            }
+        }
+    const uint8_t thr = (uint8_t)(uint32_t)(radius * 2);  // :226 `(radius*2) as u8`
+    for (size_t s = 0; s < S; ++s)
+        if (dist[s] < thr) c.areas[s] = 0;  // :227-231: spans[].area untouched
+}
+
+Heightfield* hf_new(int32_t w, int32_t h, const float* bmin, const float* bmax, float cs, float ch) {
+    auto* hf = new Heightfield();
+    hf->width = w;
+    hf->height = h;
+    for (int i = 0; i < 3; ++i) {
+        hf->bmin[i] = bmin[i];
+        hf->bmax[i] = bmax[i];
+    }
+    hf->cs = cs;
+    hf->ch = ch;
+    hf->first.assign((size_t)std::max(w, 0) * (size_t)std::max(h, 0), NONE);
+    return hf;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C API for ctypes (tests/, bench.py cpu_baseline, smoke)
+// =================================================================================================
+extern "C" {
+
+typedef struct orc_hf orc_hf;
+typedef struct orc_chf orc_chf;
+
+// config.rs:53-76
+void orc_config_default(rcb_config* c) {
+    std::memset(c, 0, sizeof(*c));
+    c->cs = 0.3f;
+    c->ch = 0.2f;
+    c->walkable_slope_angle = 45.0f;
+    c->walkable_height = 2;
+    c->walkable_climb = 1;
+    c->walkable_radius = 1;
+    c->max_edge_len = 12;
+    c->max_simplification_error = 1.3f;
+    c->min_region_area = 8;
+    c->merge_region_area = 20;
+    c->max_vertices_per_polygon = 6;
+    c->detail_sample_dist = 6.0f;
+    c->detail_sample_max_error = 1.0f;
+    c->border_size = 0;
+}
+
+// config.rs:85-107
+void orc_config_calculate_grid_size(rcb_config* c, const float* bmin, const float* bmax) {
+    for (int i = 0; i < 3; ++i) {
+        c->bmin[i] = bmin[i];
+        c->bmax[i] = bmax[i];
+    }
+    const float wf = (bmax[0] - bmin[0]) / c->cs;
+    const float hf = (bmax[2] - bmin[2]) / c->cs;
+    // f32::fract() = self - self.trunc()
+    c->width = (wf - std::trunc(wf)) == 0.0f ? f32_as_i32(wf) + 1 : f32_as_i32(std::ceil(wf));
+    c->height = (hf - std::trunc(hf)) == 0.0f ? f32_as_i32(hf) + 1 : f32_as_i32(std::ceil(hf));
+}
+
+// config.rs:110-136
+int orc_config_validate(const rcb_config* c) {
+    if (c->width <= 0 || c->height <= 0) return RCB_EINVALID_MESH;
+    if (c->cs <= 0.0f || c->ch <= 0.0f) return RCB_EINVALID_MESH;
+    if (c->walkable_slope_angle < 0.0f || c->walkable_slope_angle > 90.0f) return RCB_EINVALID_MESH;
+    if (c->max_vertices_per_polygon < 3) return RCB_EINVALID_MESH;
+    return 0;
+}
+
+orc_hf* orc_hf_new(int32_t w, int32_t h, const float* bmin, const float* bmax, float cs, float ch) {
+    return (orc_hf*)hf_new(w, h, bmin, bmax, cs, ch);
+}
+void orc_hf_free(orc_hf* p) { delete (Heightfield*)p; }
+
+// rasterization.rs:23-47 add_span (out of bounds silently ignored)
+int orc_add_span(orc_hf* p, int32_t x, int32_t z, int16_t smin, int16_t smax, uint8_t area, int32_t thr) {
+    Heightfield& hf = *(Heightfield*)p;
+    if (x < 0 || z < 0 || x >= hf.width || z >= hf.height) return 0;
+    add_span_internal(hf, x, z, smin, smax, area, thr);
+    return 0;
+}
+// heightfield.rs:102 Heightfield::add_span
+int orc_hf_add_span(orc_hf* p, int32_t x, int32_t z, int16_t mn, int16_t mx, uint8_t area) {
+    return hf_add_span2(*(Heightfield*)p, x, z, mn, mx, area);
+}
+// rasterization.rs:381-401
+int orc_rasterize_triangle(orc_hf* p, const float* v0, const float* v1, const float* v2, uint8_t area, int32_t thr) {
+    rasterize_triangle(*(Heightfield*)p, v0, v1, v2, area, thr);
+    return 0;
+}
+// rasterization.rs:405-428 (indices are trusted there; bounds-checked here to stay memory-safe)
+int orc_rasterize_triangles(orc_hf* p, const float* verts, size_t nfloats, const int32_t* tris,
+                            const uint8_t* areas, size_t ntris, int32_t thr) {
+    Heightfield& hf = *(Heightfield*)p;
+    const size_t nv = nfloats / 3;
+    for (size_t i = 0; i < ntris; ++i) {
+        const uint64_t a = (uint64_t)(int64_t)tris[i * 3], b = (uint64_t)(int64_t)tris[i * 3 + 1],
+                       c = (uint64_t)(int64_t)tris[i * 3 + 2];
+        if (a >= nv || b >= nv || c >= nv) return RCB_ENAVMESH_GEN;
+        rasterize_triangle(hf, verts + a * 3, verts + b * 3, verts + c * 3, areas[i], thr);
+    }
+    return 0;
+}
+// lib.rs:186-290
+int orc_builder_rasterize(orc_hf* p, const rcb_config* cfg, const float* verts, size_t nfloats,
+                          const int32_t* idx, size_t nidx, int run_filters) {
+    return builder_rasterize(*(Heightfield*)p, *cfg, verts, nfloats, idx, nidx, run_filters != 0);
+}
+void orc_filter_low_hanging_walkable_obstacles(orc_hf* p, int16_t climb) { filter_low_hanging(*(Heightfield*)p, climb); }
+void orc_filter_ledge_spans(orc_hf* p, int16_t height, int16_t climb) { filter_ledge(*(Heightfield*)p, height, climb); }
+void orc_filter_walkable_low_height_spans(orc_hf* p, int16_t height) { filter_low_height(*(Heightfield*)p, height); }
+int orc_hf_poly_overflow(const orc_hf* p) { return ((const Heightfield*)p)->poly_overflow ? 1 : 0; }
+
+uint64_t orc_hf_span_count(const orc_hf* p) {
+    const Heightfield& hf = *(const Heightfield*)p;
+    uint64_t n = 0;
+    for (uint32_t f : hf.first)
+        for (uint32_t s = f; s != NONE; s = hf.pool[s].next) ++n;
+    return n;
+}
+// CSR export: cell_offset[C+1], smin/smax/area[S]
+void orc_hf_export(const orc_hf* p, uint32_t* cell_offset, int16_t* smin, int16_t* smax, uint8_t* area) {
+    const Heightfield& hf = *(const Heightfield*)p;
+    uint32_t n = 0;
+    for (size_t c = 0; c < hf.first.size(); ++c) {
+        cell_offset[c] = n;
+        for (uint32_t s = hf.first[c]; s != NONE; s = hf.pool[s].next) {
+            smin[n] = hf.pool[s].smin;
+            smax[n] = hf.pool[s].smax;
+            area[n] = hf.pool[s].area;
+            ++n;
+        }
+    }
+    cell_offset[hf.first.size()] = n;
+}
+// Build a heightfield directly from CSR columns (no merge logic: test fixtures / round trips).
+orc_hf* orc_hf_from_csr(int32_t w, int32_t h, const float* bmin, const float* bmax, float cs, float ch,
+                        const uint32_t* cell_offset, const int16_t* smin, const int16_t* smax, const uint8_t* area) {
+    Heightfield* hf = hf_new(w, h, bmin, bmax, cs, ch);
+    const size_t C = hf->first.size();
+    for (size_t c = 0; c < C; ++c) {
+        uint32_t prev = NONE;
+        for (uint32_t i = cell_offset[c]; i < cell_offset[c + 1]; ++i) {
+            uint32_t n = hf->alloc(smin[i], smax[i], area[i], NONE);
+            if (prev == NONE)
+                hf->first[c] = n;
+            else
+                hf->pool[prev].next = n;
+            prev = n;
+        }
+    }
+    return (orc_hf*)hf;
+}
+
+orc_chf* orc_chf_build(const orc_hf* p) {
+    auto* c = new Compact();
+    compact_build(*(const Heightfield*)p, *c);
+    return (orc_chf*)c;
+}
+void orc_chf_free(orc_chf* p) { delete (Compact*)p; }
+void orc_chf_build_distance_field(orc_chf* p) { build_distance_field(*(Compact*)p); }
+void orc_chf_erode_walkable_area(orc_chf* p, int32_t radius) { erode_walkable_area(*(Compact*)p, radius); }
+uint32_t orc_chf_get_neighbor(const orc_chf* p, uint32_t span, uint8_t dir) {
+    return ((const Compact*)p)->get_neighbor(span, dir);
+}
+// sizes: out[0]=C out[1]=S out[2]=K out[3]=walkable_span_count out[4]=max_height out[5]=max_distance
+void orc_chf_sizes(const orc_chf* p, uint64_t* out) {
+    const Compact& c = *(const Compact*)p;
+    out[0] = c.cell_index.size();
+    out[1] = c.smin.size();
+    out[2] = c.conn_ref.size();
+    out[3] = c.walkable_span_count;
+    out[4] = c.max_height;
+    out[5] = c.max_distance;
+}
+void orc_chf_export(const orc_chf* p, uint32_t* cell_index, uint32_t* cell_count, int16_t* smin, int16_t* smax,
+                    uint8_t* span_area, uint8_t* areas, uint16_t* con, uint32_t* first_conn, uint32_t* conn_ref,
+                    uint8_t* conn_dir, uint32_t* conn_next, uint16_t* dist) {
+    const Compact& c = *(const Compact*)p;
+    auto cp = [](auto* dst, const auto& v) {
+        if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(v[0]));
+    };
+    cp(cell_index, c.cell_index);
+    cp(cell_count, c.cell_count);
+    cp(smin, c.smin);
+    cp(smax, c.smax);
+    cp(span_area, c.span_area);
+    cp(areas, c.areas);
+    cp(con, c.con);
+    cp(first_conn, c.first_conn);
+    cp(conn_ref, c.conn_ref);
+    cp(conn_dir, c.conn_dir);
+    cp(conn_next, c.conn_next);
+    cp(dist, c.dist);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Batched build for the CPU baseline: for every tile runs what the reference runs,
+//   Heightfield::new -> RecastBuilder::rasterize_triangles (whole mesh scanned per tile, lib.rs:217)
+//   -> CompactHeightfield::build_from_heightfield -> [erode] -> build_distance_field,
+// tiles distributed over `nthreads` std::threads (the reference itself is single-threaded; its
+// `parallel` cargo feature is dead).  `prebinned` != 0 scans only the triangles whose
+// AABB touches the tile (a courtesy the reference does not have; results are identical because
+// rasterize_tri rejects the others at rasterization.rs:270).
+// totals: [0]=spans [1]=connections [2]=walkable [3]=xor-fold checksum of all outputs
+// Returns elapsed seconds (wall) or a negative rcb_status.
+// -------------------------------------------------------------------------------------------------
+double orc_build_tiles(const float* verts, size_t nfloats, const int32_t* idx, size_t nidx, const rcb_config* cfgs,
+                       int ntiles, uint32_t stage_mask, int erode_radius, int nthreads, int prebinned,
+                       uint64_t* totals) {
+    if (nfloats % 3 != 0 || nidx % 3 != 0) return RCB_ENAVMESH_GEN;
+    const size_t ntri = nidx / 3, nv = nfloats / 3;
+    for (size_t i = 0; i < nidx; ++i)
+        if ((uint64_t)(int64_t)idx[i] >= nv) return RCB_ENAVMESH_GEN;
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<int> next{0};
+    std::vector<uint64_t> acc((size_t)nthreads * 4, 0);
+    auto t0 = std::chrono::steady_clock::now();
+    auto work = [&](int tid) {
+        std::vector<int32_t> local_idx;
+        for (;;) {
+            const int t = next.fetch_add(1);
+            if (t >= ntiles) break;
+            const rcb_config& cfg = cfgs[t];
+            Heightfield* hf = hf_new(cfg.width, cfg.height, cfg.bmin, cfg.bmax, cfg.cs, cfg.ch);
+            const int32_t* use_idx = idx;
+            size_t use_n = nidx;
+            if (prebinned) {
+                local_idx.clear();
+                for (size_t i = 0; i < ntri; ++i) {
+                    const float *a = verts + (size_t)idx[i * 3] * 3, *b = verts + (size_t)idx[i * 3 + 1] * 3,
+                                *c = verts + (size_t)idx[i * 3 + 2] * 3;
+                    const float x0 = std::fmin(std::fmin(a[0], b[0]), c[0]), x1 = std::fmax(std::fmax(a[0], b[0]), c[0]);
+                    const float z0 = std::fmin(std::fmin(a[2], b[2]), c[2]), z1 = std::fmax(std::fmax(a[2], b[2]), c[2]);
+                    if (x0 <= cfg.bmax[0] && x1 >= cfg.bmin[0] && z0 <= cfg.bmax[2] && z1 >= cfg.bmin[2]) {
+                        local_idx.push_back(idx[i * 3]);
+                        local_idx.push_back(idx[i * 3 + 1]);
+                        local_idx.push_back(idx[i * 3 + 2]);
+                    }
+                }
+                use_idx = local_idx.data();
+                use_n = local_idx.size();
+            }
+            if (stage_mask & RCB_STAGE_RASTER)
+                builder_rasterize(*hf, cfg, verts, nfloats, use_idx, use_n, (stage_mask & RCB_STAGE_FILTER) != 0);
+            uint64_t* a = &acc[(size_t)tid * 4];
+            if (stage_mask & RCB_STAGE_COMPACT) {
+                Compact c;
+                compact_build(*hf, c);
+                if (stage_mask & RCB_STAGE_ERODE) erode_walkable_area(c, erode_radius);
+                if (stage_mask & RCB_STAGE_DIST) build_distance_field(c);
+                a[0] += c.smin.size();
+                a[1] += c.conn_ref.size();
+                a[2] += c.walkable_span_count;
+                uint64_t x = 0;
+                for (size_t i = 0; i < c.dist.size(); ++i) x = x * 1099511628211ull + c.dist[i] + c.areas[i];
+                a[3] ^= x;
+            } else {
+                a[0] += hf->pool.size();
+            }
+            delete hf;
+        }
+    };
+    if (nthreads == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < nthreads; ++i) th.emplace_back(work, i);
+        for (auto& t : th) t.join();
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (totals) {
+        totals[0] = totals[1] = totals[2] = totals[3] = 0;
+        for (int i = 0; i < nthreads; ++i) {
+            totals[0] += acc[(size_t)i * 4];
+            totals[1] += acc[(size_t)i * 4 + 1];
+            totals[2] += acc[(size_t)i * 4 + 2];
+            totals[3] ^= acc[(size_t)i * 4 + 3];
+        }
+    }
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+int orc_hardware_concurrency(void) { return (int)std::thread::hardware_concurrency(); }
+
+}  // extern "C"

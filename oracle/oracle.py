@@ -1,0 +1,292 @@
+"""ctypes wrapper of oracle/liboracle.so — the CPU restatement of the reference hot path.
+
+TEST INFRASTRUCTURE ONLY (see oracle.cpp header).  Imported by tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs — never by recast_rs_b200.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import sys
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+from recast_rs_b200.config import RcbConfig, RecastConfig, configs_to_array  # noqa: E402  (plain data only)
+
+NONE = 0xFFFFFFFF
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+    return so
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = ctypes.CDLL(build())
+        vp, i32, i16, u8, u32, f32 = (ctypes.c_void_p, ctypes.c_int32, ctypes.c_int16, ctypes.c_uint8,
+                                      ctypes.c_uint32, ctypes.c_float)
+        L.orc_hf_new.restype = vp
+        L.orc_hf_new.argtypes = [i32, i32, vp, vp, f32, f32]
+        L.orc_hf_free.argtypes = [vp]
+        L.orc_add_span.argtypes = [vp, i32, i32, i16, i16, u8, i32]
+        L.orc_hf_add_span.argtypes = [vp, i32, i32, i16, i16, u8]
+        L.orc_rasterize_triangle.argtypes = [vp, vp, vp, vp, u8, i32]
+        L.orc_rasterize_triangles.argtypes = [vp, vp, ctypes.c_size_t, vp, vp, ctypes.c_size_t, i32]
+        L.orc_builder_rasterize.argtypes = [vp, vp, vp, ctypes.c_size_t, vp, ctypes.c_size_t, ctypes.c_int]
+        L.orc_filter_low_hanging_walkable_obstacles.argtypes = [vp, i16]
+        L.orc_filter_ledge_spans.argtypes = [vp, i16, i16]
+        L.orc_filter_walkable_low_height_spans.argtypes = [vp, i16]
+        L.orc_hf_poly_overflow.argtypes = [vp]
+        L.orc_hf_span_count.restype = ctypes.c_uint64
+        L.orc_hf_span_count.argtypes = [vp]
+        L.orc_hf_export.argtypes = [vp, vp, vp, vp, vp]
+        L.orc_hf_from_csr.restype = vp
+        L.orc_hf_from_csr.argtypes = [i32, i32, vp, vp, f32, f32, vp, vp, vp, vp]
+        L.orc_chf_build.restype = vp
+        L.orc_chf_build.argtypes = [vp]
+        L.orc_chf_free.argtypes = [vp]
+        L.orc_chf_build_distance_field.argtypes = [vp]
+        L.orc_chf_erode_walkable_area.argtypes = [vp, i32]
+        L.orc_chf_get_neighbor.restype = u32
+        L.orc_chf_get_neighbor.argtypes = [vp, u32, u8]
+        L.orc_chf_sizes.argtypes = [vp, vp]
+        L.orc_chf_export.argtypes = [vp] * 13
+        L.orc_config_default.argtypes = [vp]
+        L.orc_config_calculate_grid_size.argtypes = [vp, vp, vp]
+        L.orc_config_validate.argtypes = [vp]
+        L.orc_build_tiles.restype = ctypes.c_double
+        L.orc_build_tiles.argtypes = [vp, ctypes.c_size_t, vp, ctypes.c_size_t, vp, ctypes.c_int, u32,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
+        L.orc_hardware_concurrency.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _f3(v):
+    return np.ascontiguousarray(np.asarray(v, dtype=np.float32).reshape(3))
+
+
+class OracleError(Exception):
+    def __init__(self, status):
+        super().__init__(f"oracle status {status}")
+        self.status = status
+
+
+@dataclass
+class HfArrays:
+    """Heightfield as CSR (same arrays as rcb_tile_view)."""
+    cell_offset: np.ndarray
+    span_min: np.ndarray
+    span_max: np.ndarray
+    span_area: np.ndarray
+
+    def column(self, x, z, width):
+        c = z * width + x
+        a, b = int(self.cell_offset[c]), int(self.cell_offset[c + 1])
+        return [(int(self.span_min[i]), int(self.span_max[i]), int(self.span_area[i])) for i in range(a, b)]
+
+
+class Heightfield:
+    """Restated `Heightfield` (heightfield.rs:58-99) + the free functions of rasterization.rs."""
+
+    def __init__(self, width, height, bmin, bmax, cs, ch, _handle=None):
+        self.width, self.height = int(width), int(height)
+        self.bmin, self.bmax = _f3(bmin), _f3(bmax)
+        self.cs, self.ch = float(cs), float(ch)
+        self._h = _handle or lib().orc_hf_new(self.width, self.height, _p(self.bmin), _p(self.bmax), self.cs, self.ch)
+
+    @classmethod
+    def from_config(cls, cfg: RecastConfig):
+        return cls(cfg.width, cfg.height, cfg.bmin, cfg.bmax, cfg.cs, cfg.ch)
+
+    @classmethod
+    def from_csr(cls, width, height, bmin, bmax, cs, ch, cell_offset, smin, smax, area):
+        bmin, bmax = _f3(bmin), _f3(bmax)
+        co = np.ascontiguousarray(cell_offset, dtype=np.uint32)
+        a = np.ascontiguousarray(smin, dtype=np.int16)
+        b = np.ascontiguousarray(smax, dtype=np.int16)
+        c = np.ascontiguousarray(area, dtype=np.uint8)
+        h = lib().orc_hf_from_csr(width, height, _p(bmin), _p(bmax), cs, ch, _p(co), _p(a), _p(b), _p(c))
+        return cls(width, height, bmin, bmax, cs, ch, _handle=h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_hf_free(self._h)
+            self._h = None
+
+    # rasterization.rs:23 add_span
+    def add_span_raster(self, x, z, smin, smax, area, flag_merge_threshold):
+        lib().orc_add_span(self._h, x, z, smin, smax, area, flag_merge_threshold)
+
+    # heightfield.rs:102 Heightfield::add_span
+    def add_span(self, x, z, smin, smax, area):
+        st = lib().orc_hf_add_span(self._h, x, z, smin, smax, area)
+        if st:
+            raise OracleError(st)
+
+    def rasterize_triangle(self, v0, v1, v2, area, flag_merge_threshold):
+        a, b, c = _f3(v0), _f3(v1), _f3(v2)
+        lib().orc_rasterize_triangle(self._h, _p(a), _p(b), _p(c), area, flag_merge_threshold)
+
+    def rasterize_triangles(self, verts, tris, areas, flag_merge_threshold):
+        v = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1)
+        t = np.ascontiguousarray(tris, dtype=np.int32).reshape(-1)
+        a = np.ascontiguousarray(areas, dtype=np.uint8)
+        st = lib().orc_rasterize_triangles(self._h, _p(v), v.size, _p(t), _p(a), t.size // 3, flag_merge_threshold)
+        if st:
+            raise OracleError(st)
+
+    # lib.rs:186 RecastBuilder::rasterize_triangles
+    def builder_rasterize(self, cfg: RecastConfig, verts, indices, run_filters=True):
+        v = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1)
+        t = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1)
+        c = cfg.to_c()
+        st = lib().orc_builder_rasterize(self._h, ctypes.byref(c), _p(v), v.size, _p(t), t.size, int(run_filters))
+        if st:
+            raise OracleError(st)
+
+    def filter_low_hanging_walkable_obstacles(self, climb):
+        lib().orc_filter_low_hanging_walkable_obstacles(self._h, climb)
+
+    def filter_ledge_spans(self, height, climb):
+        lib().orc_filter_ledge_spans(self._h, height, climb)
+
+    def filter_walkable_low_height_spans(self, height):
+        lib().orc_filter_walkable_low_height_spans(self._h, height)
+
+    @property
+    def poly_overflow(self):
+        return bool(lib().orc_hf_poly_overflow(self._h))
+
+    def span_count(self):
+        return int(lib().orc_hf_span_count(self._h))
+
+    def export(self) -> HfArrays:
+        n = self.span_count()
+        co = np.zeros(self.width * self.height + 1, dtype=np.uint32)
+        a = np.zeros(n, dtype=np.int16)
+        b = np.zeros(n, dtype=np.int16)
+        c = np.zeros(n, dtype=np.uint8)
+        lib().orc_hf_export(self._h, _p(co), _p(a), _p(b), _p(c))
+        return HfArrays(co, a, b, c)
+
+
+@dataclass
+class ChfArrays:
+    cell_index: np.ndarray
+    cell_count: np.ndarray
+    span_min: np.ndarray
+    span_max: np.ndarray
+    span_area: np.ndarray
+    areas: np.ndarray
+    con: np.ndarray
+    first_conn: np.ndarray
+    conn_ref: np.ndarray
+    conn_dir: np.ndarray
+    conn_next: np.ndarray
+    dist: np.ndarray
+    walkable_span_count: int
+    max_height: int
+    max_distance: int
+
+
+class CompactHeightfield:
+    """Restated `CompactHeightfield` (compact_heightfield.rs:129-170)."""
+
+    def __init__(self, handle, width, height):
+        self._h, self.width, self.height = handle, width, height
+
+    @classmethod
+    def build_from_heightfield(cls, hf: Heightfield):
+        return cls(lib().orc_chf_build(hf._h), hf.width, hf.height)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_chf_free(self._h)
+            self._h = None
+
+    def build_distance_field(self):
+        lib().orc_chf_build_distance_field(self._h)
+
+    def erode_walkable_area(self, radius):
+        lib().orc_chf_erode_walkable_area(self._h, radius)
+
+    def get_neighbor(self, span, dir8):
+        r = lib().orc_chf_get_neighbor(self._h, span, dir8)
+        return None if r == NONE else int(r)
+
+    def export(self) -> ChfArrays:
+        sz = np.zeros(6, dtype=np.uint64)
+        lib().orc_chf_sizes(self._h, _p(sz))
+        C, S, K = int(sz[0]), int(sz[1]), int(sz[2])
+        arrs = [np.zeros(C, np.uint32), np.zeros(C, np.uint32), np.zeros(S, np.int16), np.zeros(S, np.int16),
+                np.zeros(S, np.uint8), np.zeros(S, np.uint8), np.zeros(S * 4, np.uint16), np.zeros(S, np.uint32),
+                np.zeros(K, np.uint32), np.zeros(K, np.uint8), np.zeros(K, np.uint32), np.zeros(S, np.uint16)]
+        lib().orc_chf_export(self._h, *[_p(a) for a in arrs])
+        return ChfArrays(*arrs, walkable_span_count=int(sz[3]), max_height=int(sz[4]), max_distance=int(sz[5]))
+
+
+# ---- config.rs ---------------------------------------------------------------------------------
+def config_default() -> RecastConfig:
+    c = RcbConfig()
+    lib().orc_config_default(ctypes.byref(c))
+    return RecastConfig.from_c(c)
+
+
+def calculate_grid_size(cfg: RecastConfig, bmin, bmax) -> RecastConfig:
+    c = cfg.to_c()
+    a, b = _f3(bmin), _f3(bmax)
+    lib().orc_config_calculate_grid_size(ctypes.byref(c), _p(a), _p(b))
+    return RecastConfig.from_c(c)
+
+
+def config_validate(cfg: RecastConfig) -> int:
+    c = cfg.to_c()
+    return lib().orc_config_validate(ctypes.byref(c))
+
+
+# ---- per-tile pipeline, returns (HfArrays, ChfArrays|None) ----------------------------------------
+def build_tile(cfg: RecastConfig, verts, indices, stage_mask=1 | 2 | 4 | 16, erode_radius=0):
+    hf = Heightfield.from_config(cfg)
+    if stage_mask & 1:
+        hf.builder_rasterize(cfg, verts, indices, run_filters=bool(stage_mask & 2))
+    hfa = hf.export()
+    if not stage_mask & 4:
+        return hfa, None
+    chf = CompactHeightfield.build_from_heightfield(hf)
+    if stage_mask & 8:
+        chf.erode_walkable_area(erode_radius)
+    if stage_mask & 16:
+        chf.build_distance_field()
+    return hfa, chf.export()
+
+
+def build_tiles_timed(verts, indices, cfgs, stage_mask=1 | 2 | 4 | 16, erode_radius=0, nthreads=1, prebinned=False):
+    """CPU baseline: returns (seconds, totals dict)."""
+    v = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1)
+    t = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1)
+    arr = configs_to_array(cfgs)
+    tot = np.zeros(4, dtype=np.uint64)
+    s = lib().orc_build_tiles(_p(v), v.size, _p(t), t.size, ctypes.cast(arr, ctypes.c_void_p), len(cfgs),
+                              stage_mask, erode_radius, nthreads, int(prebinned), _p(tot))
+    if s < 0:
+        raise OracleError(int(s))
+    return s, {"spans": int(tot[0]), "connections": int(tot[1]), "walkable": int(tot[2]), "checksum": int(tot[3])}
+
+
+def hardware_concurrency() -> int:
+    return int(lib().orc_hardware_concurrency())

@@ -1,0 +1,502 @@
+"""Second, independent restatement of the reference hot path in plain Python (small cases only).
+
+TEST INFRASTRUCTURE ONLY.  Written separately from oracle.cpp, with the reference's own data
+structures (dict keyed by (x,z) of singly linked span objects; connection list walked by
+get_neighbor) so that a differential test oracle.cpp <-> pymodel.py catches transcription slips
+in either.  Float arithmetic uses numpy.float32 scalars so every operation rounds to f32 like
+the Rust code.  Citations relative to /root/reference/crates/recast/src/.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+f32 = np.float32
+NONE = None
+
+
+class Span:
+    __slots__ = ("min", "max", "area", "next")
+
+    def __init__(self, mn, mx, area, nxt=None):
+        self.min, self.max, self.area, self.next = mn, mx, area, nxt
+
+
+class Heightfield:
+    def __init__(self, width, height, bmin, bmax, cs, ch):  # heightfield.rs:80-99
+        self.width, self.height = width, height
+        self.bmin = [f32(v) for v in bmin]
+        self.bmax = [f32(v) for v in bmax]
+        self.cs, self.ch = f32(cs), f32(ch)
+        self.spans = {(x, z): None for z in range(height) for x in range(width)}
+
+    def column(self, x, z):
+        out, s = [], self.spans[(x, z)]
+        while s is not None:
+            out.append((s.min, s.max, s.area))
+            s = s.next
+        return out
+
+    def export(self):
+        off, mn, mx, ar = [0], [], [], []
+        for z in range(self.height):
+            for x in range(self.width):
+                for (a, b, c) in self.column(x, z):
+                    mn.append(a), mx.append(b), ar.append(c)
+                off.append(len(mn))
+        return (np.array(off, np.uint32), np.array(mn, np.int16), np.array(mx, np.int16), np.array(ar, np.uint8))
+
+    # heightfield.rs:102-222
+    def add_span(self, x, z, mn, mx, area):
+        if x < 0 or x >= self.width or z < 0 or z >= self.height:
+            raise ValueError("oob")
+        if mn > mx:
+            raise ValueError("min>max")
+        new = Span(mn, mx, area)
+        first = self.spans[(x, z)]
+        if first is None:
+            self.spans[(x, z)] = new
+            return
+        prev, cur = None, first
+        while True:
+            if cur.area == area and cur.max >= mn and mx >= cur.min:
+                cur.min, cur.max = min(cur.min, mn), max(cur.max, mx)
+                nx = cur.next
+                if nx is not None and nx.area == area and cur.max >= nx.min:
+                    cur.max = max(cur.max, nx.max)
+                    cur.next = nx.next
+                return
+            if mx < cur.min:
+                new.next = cur
+                if prev is not None:
+                    prev.next = new
+                else:
+                    self.spans[(x, z)] = new
+                return
+            if cur.next is None:
+                cur.next = new
+                return
+            prev, cur = cur, cur.next
+
+
+# rasterization.rs:51-168
+def add_span_internal(hf, x, z, smin, smax, area, thr):
+    col = hf.spans.get((x, z))
+    if col is None:
+        hf.spans[(x, z)] = Span(smin, smax, area)
+        return
+    prev, cur = None, col
+    while cur is not None:
+        if smax < cur.min:
+            new = Span(smin, smax, area, cur)
+            if prev is not None:
+                prev.next = new
+            else:
+                hf.spans[(x, z)] = new
+            return
+        if smin > cur.max:
+            prev, cur = cur, cur.next
+            continue
+        mmin, mmax = min(smin, cur.min), max(smax, cur.max)
+        marea = area
+        if abs(mmax - cur.max) <= thr:
+            marea = max(marea, cur.area)
+        nx = cur.next
+        while nx is not None:
+            if nx.min > mmax:
+                break
+            mmax = max(mmax, nx.max)
+            nx = nx.next
+        cur.min, cur.max, cur.area, cur.next = mmin, mmax, marea, nx
+        return
+    if prev is not None:
+        prev.next = Span(smin, smax, area)
+
+
+def add_span(hf, x, z, smin, smax, area, thr):  # rasterization.rs:23-47
+    if x < 0 or z < 0 or x >= hf.width or z >= hf.height:
+        return
+    add_span_internal(hf, x, z, smin, smax, area, thr)
+
+
+def _as_i32(v):
+    v = float(v)
+    if math.isnan(v):
+        return 0
+    return int(max(-2147483648.0, min(2147483647.0, math.trunc(v))))
+
+
+def _as_i16(v):
+    v = float(v)
+    if math.isnan(v):
+        return 0
+    return int(max(-32768.0, min(32767.0, math.trunc(v))))
+
+
+# rasterization.rs:172-242
+def divide_poly(inv, offset, axis):
+    out1, out2 = [], []
+    n = len(inv)
+    if n == 0:
+        return out1, out2
+    sides = [(-1 if v[axis] < offset else (1 if v[axis] > offset else 0)) for v in inv]
+    for i in range(n):
+        j = (i + 1) % n
+        vi, vj, si, sj = inv[i], inv[j], sides[i], sides[j]
+        if si == 0:
+            out1.append(vi), out2.append(vi)
+        elif si < 0:
+            out1.append(vi)
+            if sj > 0:
+                t = f32(f32(offset - vi[axis]) / f32(vj[axis] - vi[axis]))
+                p = tuple(f32(vi[k] + f32(t * f32(vj[k] - vi[k]))) for k in range(3))
+                out1.append(p), out2.append(p)
+        else:
+            out2.append(vi)
+            if sj < 0:
+                t = f32(f32(offset - vi[axis]) / f32(vj[axis] - vi[axis]))
+                p = tuple(f32(vi[k] + f32(t * f32(vj[k] - vi[k]))) for k in range(3))
+                out1.append(p), out2.append(p)
+    return out1, out2
+
+
+# rasterization.rs:246-366
+def rasterize_tri(v0, v1, v2, area, hf, thr):
+    with np.errstate(all="ignore"):
+        v0, v1, v2 = (tuple(f32(c) for c in v) for v in (v0, v1, v2))
+        ics, ich = f32(f32(1.0) / hf.cs), f32(f32(1.0) / hf.ch)
+        tmin = [min(min(v0[i], v1[i]), v2[i]) for i in range(3)]
+        tmax = [max(max(v0[i], v1[i]), v2[i]) for i in range(3)]
+        for i in range(3):
+            if not (tmin[i] <= hf.bmax[i] and tmax[i] >= hf.bmin[i]):
+                return
+        x0 = _as_i32(f32(f32(tmin[0] - hf.bmin[0]) * ics))
+        x1 = _as_i32(f32(f32(tmax[0] - hf.bmin[0]) * ics))
+        z0 = _as_i32(f32(f32(tmin[2] - hf.bmin[2]) * ics))
+        z1 = _as_i32(f32(f32(tmax[2] - hf.bmin[2]) * ics))
+        x0, x1 = max(x0, 0), min(x1, hf.width - 1)
+        z0, z1 = max(z0, -1), min(z1, hf.height - 1)
+        p1 = [v0, v1, v2]
+        for z in range(z0, z1 + 1):
+            cz = f32(hf.bmin[2] + f32(f32(z + 1) * hf.cs))
+            in_row, p1 = divide_poly(p1, cz, 2)
+            if len(in_row) < 3 or z < 0:
+                continue
+            p2 = in_row
+            for x in range(x0, x1 + 1):
+                cx = f32(hf.bmin[0] + f32(f32(x + 1) * hf.cs))
+                cell, p2 = divide_poly(p2, cx, 0)
+                if len(cell) < 3:
+                    continue
+                ys = [v[1] for v in cell]
+                mn, mx = ys[0], ys[0]
+                for y in ys[1:]:
+                    mn, mx = min(mn, y), max(mx, y)
+                smin = _as_i16(np.floor(f32(f32(mn - hf.bmin[1]) * ich)))
+                smax = _as_i16(np.ceil(f32(f32(mx - hf.bmin[1]) * ich)))
+                smin = max(smin, 0)
+                add_span_internal(hf, x, z, smin, smax, area, thr)
+
+
+# lib.rs:252-270 with glam 0.29.3 scalar Vec3
+def classify(v0, v1, v2, thr):
+    with np.errstate(all="ignore"):
+        v0, v1, v2 = (tuple(f32(c) for c in v) for v in (v0, v1, v2))
+        e1 = tuple(f32(v1[i] - v0[i]) for i in range(3))
+        e2 = tuple(f32(v2[i] - v0[i]) for i in range(3))
+        cx = f32(f32(e1[1] * e2[2]) - f32(e2[1] * e1[2]))
+        cy = f32(f32(e1[2] * e2[0]) - f32(e2[2] * e1[0]))
+        cz = f32(f32(e1[0] * e2[1]) - f32(e2[0] * e1[1]))
+        ln = f32(np.sqrt(f32(f32(f32(cx * cx) + f32(cy * cy)) + f32(cz * cz))))
+        if ln < np.finfo(np.float32).eps:
+            return None
+        ny = f32(cy * f32(f32(1.0) / ln))
+        return 1 if abs(ny) >= thr else 0
+
+
+def _i16(v):
+    v &= 0xFFFF
+    return v - 0x10000 if v >= 0x8000 else v
+
+
+# heightfield.rs:286-328
+def filter_low_hanging(hf, climb):
+    for z in range(hf.height):
+        for x in range(hf.width):
+            prev, prev_walk, prev_area = None, False, 0
+            s = hf.spans[(x, z)]
+            while s is not None:
+                walk = s.area != 0
+                if (not walk) and prev_walk and prev is not None:
+                    if s.max - prev.max <= climb:
+                        s.area = prev_area
+                prev_walk, prev_area, prev = walk, s.area, s
+                s = s.next
+
+
+# heightfield.rs:332-488
+def filter_ledge(hf, height, climb):
+    MAXH = 0xFFFF
+    negc = _i16(-climb)
+    for z in range(hf.height):
+        for x in range(hf.width):
+            s = hf.spans[(x, z)]
+            while s is not None:
+                if s.area == 0:
+                    s = s.next
+                    continue
+                floor = s.max
+                ceiling = s.next.min if s.next is not None else MAXH
+                lowest = MAXH
+                lo = hi = s.max
+                ledge = False
+                for dx, dz in ((0, -1), (1, 0), (0, 1), (-1, 0)):
+                    nx, nz = x + dx, z + dz
+                    if nx < 0 or nz < 0 or nx >= hf.width or nz >= hf.height:
+                        lowest, ledge = negc - 1, True
+                        break
+                    ns = hf.spans[(nx, nz)]
+                    if ns is None:
+                        lowest, ledge = negc - 1, True
+                        break
+                    nceil = ns.min
+                    if min(ceiling, nceil) - floor >= height:
+                        lowest, ledge = negc - 1, True
+                        break
+                    while ns is not None:
+                        nfloor = ns.max
+                        nceil = ns.next.min if ns.next is not None else MAXH
+                        if min(ceiling, nceil) - max(floor, nfloor) < height:
+                            ns = ns.next
+                            continue
+                        d = nfloor - floor
+                        lowest = min(lowest, d)
+                        if abs(d) <= climb:
+                            lo, hi = min(lo, nfloor), max(hi, nfloor)
+                        elif d < negc:
+                            break
+                        ns = ns.next
+                if ledge or lowest < negc or (hi - lo) > climb:
+                    s.area = 0
+                s = s.next
+
+
+# heightfield.rs:492-531
+def filter_low_height(hf, height):
+    for z in range(hf.height):
+        for x in range(hf.width):
+            s = hf.spans[(x, z)]
+            while s is not None:
+                ceiling = s.next.min if s.next is not None else 0xFFFF
+                if ceiling - s.max < height:
+                    s.area = 0
+                s = s.next
+
+
+# lib.rs:186-290
+def builder_rasterize(hf, cfg, verts, indices, run_filters=True):
+    verts = np.asarray(verts, np.float32).reshape(-1)
+    indices = np.asarray(indices, np.int64).reshape(-1)
+    if verts.size == 0 or indices.size == 0:
+        return
+    if verts.size % 3 or indices.size % 3:
+        raise ValueError("NavMeshGeneration")
+    with np.errstate(all="ignore"):
+        thr = f32(math.cos(float(f32(f32(f32(cfg.walkable_slope_angle) * f32(math.pi)) / f32(180.0)))))  # cosf, correctly rounded
+    nv = verts.size // 3
+    for t in range(indices.size // 3):
+        i0, i1, i2 = (int(indices[t * 3 + k]) for k in range(3))
+        if not (0 <= i0 < nv and 0 <= i1 < nv and 0 <= i2 < nv):
+            raise ValueError("NavMeshGeneration")
+        v0, v1, v2 = (verts[i * 3:i * 3 + 3] for i in (i0, i1, i2))
+        area = classify(v0, v1, v2, thr)
+        if area is None:
+            continue
+        rasterize_tri(v0, v1, v2, area, hf, 1)
+    if run_filters:
+        filter_low_hanging(hf, _i16(cfg.walkable_climb))
+        filter_ledge(hf, _i16(cfg.walkable_height), _i16(cfg.walkable_climb))
+        filter_low_height(hf, _i16(cfg.walkable_height))
+
+
+DIRX = [-1, 0, 1, 1, 1, 0, -1, -1]
+DIRZ = [-1, -1, -1, 0, 1, 1, 1, 0]
+
+
+class Compact:
+    """compact_heightfield.rs:175-430, 495-727; area.rs:73-234 — literal, list-walking."""
+
+    def __init__(self, hf):
+        w, h = hf.width, hf.height
+        self.width, self.height = w, h
+        self.cells, self.spans, self.areas = [], [], []
+        self.max_height, self.walkable_span_count = 0, 0
+        for z in range(h):
+            for x in range(w):
+                col = hf.column(x, z)
+                if not col:
+                    self.cells.append((None, 0))
+                    continue
+                self.cells.append((len(self.spans), len(col)))
+                for (mn, mx, ar) in col:
+                    self.spans.append({"min": mn, "max": mx, "area": ar, "first": None, "con": [63] * 4})
+                    self.areas.append(ar)
+                    self.max_height = max(self.max_height, mx & 0xFFFF)
+                    if ar != 0:
+                        self.walkable_span_count += 1
+        self.dist = [0] * len(self.spans)
+        self.max_distance = 0
+        self.connections = []
+        per_span = [[] for _ in self.spans]
+        for i, (idx, cnt) in enumerate(self.cells):
+            if idx is None:
+                continue
+            x, z = i % w, i // w
+            for s in range(idx, idx + cnt):
+                if self.areas[s] == 0:
+                    continue
+                sp = self.spans[s]
+                for d in range(8):
+                    nx, nz = x + DIRX[d], z + DIRZ[d]
+                    if nx < 0 or nz < 0 or nx >= w or nz >= h:
+                        continue
+                    nidx, ncnt = self.cells[nz * w + nx]
+                    if nidx is None:
+                        continue
+                    best, bestd = None, 2 ** 31 - 1
+                    for ns in range(nidx, nidx + ncnt):
+                        if self.areas[ns] == 0:
+                            continue
+                        nsp = self.spans[ns]
+                        if max(nsp["min"], sp["min"]) > min(nsp["max"], sp["max"]):
+                            continue
+                        hd = (abs(nsp["min"] - sp["min"]) + abs(nsp["max"] - sp["max"])) & 0xFFFF
+                        if hd < bestd:
+                            bestd, best = hd, ns
+                    if best is not None:
+                        per_span[s].append((best, d))
+        for s, lst in enumerate(per_span):
+            first = None
+            for (n, d) in reversed(lst):
+                self.connections.append((n, d, first))
+                first = len(self.connections) - 1
+            self.spans[s]["first"] = first
+            for (n, d) in lst:
+                d4 = {7: 0, 5: 1, 3: 2, 1: 3}.get(d)
+                if d4 is None:
+                    continue
+                for (cidx, ccnt) in self.cells:  # :433-442 O(cells) scan
+                    if cidx is not None and cidx <= n < cidx + ccnt:
+                        self.spans[s]["con"][d4] = n - cidx
+                        break
+
+    def get_neighbor(self, s, d):
+        c = self.spans[s]["first"]
+        while c is not None:
+            n, cd, nx = self.connections[c]
+            if cd == d:
+                return n
+            c = nx
+        return None
+
+    def _iter(self, reverse=False):
+        w, h = self.width, self.height
+        ys = range(h - 1, -1, -1) if reverse else range(h)
+        for y in ys:
+            xs = range(w - 1, -1, -1) if reverse else range(w)
+            for x in xs:
+                idx, cnt = self.cells[y * w + x]
+                if idx is None:
+                    continue
+                for s in range(idx, idx + cnt):
+                    yield s
+
+    def build_distance_field(self):
+        S = len(self.spans)
+        src = [0xFFFF] * S
+        sat = lambda a, b: min(a + b, 0xFFFF)
+        for s in self._iter():
+            cnt = 0
+            for d in (1, 3, 5, 7):
+                n = self.get_neighbor(s, d)
+                if n is not None and self.areas[n] == self.areas[s]:
+                    cnt += 1
+            if cnt != 4:
+                src[s] = 0
+
+        def relax(s, d1, d2):
+            a = self.get_neighbor(s, d1)
+            if a is None:
+                return
+            if sat(src[a], 2) < src[s]:
+                src[s] = sat(src[a], 2)
+            b = self.get_neighbor(a, d2)
+            if b is not None and sat(src[b], 3) < src[s]:
+                src[s] = sat(src[b], 3)
+
+        for s in self._iter():
+            relax(s, 0, 3)
+            relax(s, 3, 2)
+        for s in self._iter(True):
+            relax(s, 2, 1)
+            relax(s, 1, 0)
+        self.raw_dist = list(src)
+        self.max_distance = max(src) if src else 0
+        dst = [0] * S
+        for s in self._iter():
+            cd = src[s]
+            if cd <= 2:
+                dst[s] = cd
+                continue
+            d, n = cd, 1
+            for dr in (1, 3, 5, 7):
+                nb = self.get_neighbor(s, dr)
+                if nb is None:
+                    continue
+                d += src[nb]
+                n += 1
+                dg = self.get_neighbor(nb, (dr + 1) % 8)
+                if dg is not None:
+                    d += src[dg]
+                    n += 1
+            dst[s] = (d // n) & 0xFFFF
+        self.dist = dst
+
+    def erode_walkable_area(self, radius):
+        S = len(self.spans)
+        dist = [0xFF] * S
+        sat = lambda a, b: min(a + b, 0xFF)
+        for s in self._iter():
+            if self.areas[s] == 0:
+                dist[s] = 0
+                continue
+            cnt = 0
+            for d in (7, 5, 3, 1):
+                n = self.get_neighbor(s, d)
+                if n is None or self.areas[n] == 0:
+                    break
+                cnt += 1
+            if cnt != 4:
+                dist[s] = 0
+
+        def relax(s, d1, d2):
+            a = self.get_neighbor(s, d1)
+            if a is None:
+                return
+            if sat(dist[a], 2) < dist[s]:
+                dist[s] = sat(dist[a], 2)
+            b = self.get_neighbor(a, d2)
+            if b is not None and sat(dist[b], 3) < dist[s]:
+                dist[s] = sat(dist[b], 3)
+
+        for s in self._iter():
+            relax(s, 0, 3)
+            relax(s, 3, 2)
+        for s in self._iter(True):
+            relax(s, 2, 1)
+            relax(s, 1, 0)
+        thr = (radius * 2) & 0xFF
+        for s in range(S):
+            if dist[s] < thr:
+                self.areas[s] = 0

@@ -1,0 +1,52 @@
+"""Error mapping: recast_common::Error (crates/recast-common/src/lib.rs:19-43) <-> rcb_status."""
+from __future__ import annotations
+
+RCB_OK = 0
+RCB_EINVALID_MESH = -1
+RCB_ENAVMESH_GEN = -2
+RCB_ECUDA = -3
+RCB_EOVERFLOW = -4
+RCB_EARG = -5
+
+
+class RecastError(Exception):
+    """Base of every error raised by this package (reference: recast_common::Error)."""
+
+
+class InvalidMesh(RecastError):
+    """Error::InvalidMesh — config.rs:113-133."""
+
+
+class NavMeshGeneration(RecastError):
+    """Error::NavMeshGeneration — lib.rs:199-233, heightfield.rs:103-115."""
+
+
+class CudaError(RecastError):
+    """CUDA runtime failure or missing device/extension; there is no CPU fallback."""
+
+
+class PoolOverflow(RecastError):
+    """An internal device pool overflowed (clip polygon vertex capacity)."""
+
+
+_MAP = {
+    RCB_EINVALID_MESH: InvalidMesh,
+    RCB_ENAVMESH_GEN: NavMeshGeneration,
+    RCB_ECUDA: CudaError,
+    RCB_EOVERFLOW: PoolOverflow,
+    RCB_EARG: ValueError,
+}
+
+
+def check(status: int, ctx=None, what: str = "") -> None:
+    """Raise the exception matching a negative rcb_status."""
+    if status == RCB_OK:
+        return
+    msg = what
+    if ctx is not None:
+        from . import _ffi
+
+        raw = _ffi.lib().rcb_last_error(ctx)
+        if raw:
+            msg = raw.decode("utf-8", "replace")
+    raise _MAP.get(status, RecastError)(msg or f"rcb_status {status}")
