@@ -48,6 +48,10 @@ enum {
     RCB_STAGE_COMPACT = 4u, /* compact_heightfield.rs:175-430 build_from_heightfield + build_connections */
     RCB_STAGE_ERODE = 8u,   /* area.rs:73-234 erode_walkable_area (runs before DIST when both set) */
     RCB_STAGE_DIST = 16u,   /* compact_heightfield.rs:514-727 build_distance_field */
+    /* individual filters (Heightfield::filter_* called one at a time); RCB_STAGE_FILTER = all three */
+    RCB_FILTER_LOW_HANGING = 0x100u, /* heightfield.rs:286 */
+    RCB_FILTER_LEDGE = 0x200u,       /* heightfield.rs:332 */
+    RCB_FILTER_LOW_HEIGHT = 0x400u,  /* heightfield.rs:492 */
     RCB_STAGE_ALL_BUILD = 1u | 2u | 4u | 16u /* what RecastBuilder::build_mesh reaches (lib.rs:77-87 → watershed.rs:375) */
 };
 
@@ -167,10 +171,14 @@ int rcb_rasterize(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const uint8_
  * Heightfield::filter_* (heightfield.rs:286,332,492), CompactHeightfield::build_from_heightfield
  * (compact_heightfield.rs:175), build_distance_field (:514), erode_walkable_area (area.rs:73).
  * cell_offset holds, tile after tile, width*height+1 tile-relative offsets; span arrays are
- * concatenated in tile order.  RCB_STAGE_RASTER must not be set. */
+ * concatenated in tile order.  RCB_STAGE_RASTER must not be set.
+ * areas_override (nullable, [S]): CompactHeightfield.areas as the caller last left them (after an
+ * earlier erode / area marking); it replaces the areas copied from span_area AFTER the connections
+ * are built and BEFORE ERODE / DIST run, which is the state the reference's operators see when they
+ * are called one at a time on a live CompactHeightfield (connections are never rebuilt). */
 int rcb_build_from_spans(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const uint32_t* cell_offset,
                          const int16_t* span_min, const int16_t* span_max, const uint8_t* span_area,
-                         uint32_t stage_mask, int erode_radius, rcb_result** out);
+                         const uint8_t* areas_override, uint32_t stage_mask, int erode_radius, rcb_result** out);
 
 /* ---- results ------------------------------------------------------------------------------- */
 int rcb_result_totals(const rcb_result* res, rcb_totals* out);

@@ -1,0 +1,344 @@
+"""Host-side mirror of the reference's voxelization interface over the C ABI.
+
+Same names, argument meaning and error behaviour as crates/recast/src/lib.rs (RecastBuilder),
+heightfield.rs (Heightfield filters), compact_heightfield.rs (CompactHeightfield) and area.rs
+(erode_walkable_area); every method is one call into librecast_b200.so.  Nothing here computes on
+the CPU and nothing imports oracle/.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+from .config import RcbConfig, RecastConfig, configs_to_array
+from .errors import check
+
+STAGE_RASTER, STAGE_FILTER, STAGE_COMPACT, STAGE_ERODE, STAGE_DIST = 1, 2, 4, 8, 16
+FILTER_LOW_HANGING, FILTER_LEDGE, FILTER_LOW_HEIGHT = 0x100, 0x200, 0x400
+STAGE_ALL_BUILD = STAGE_RASTER | STAGE_FILTER | STAGE_COMPACT | STAGE_DIST
+NONE = 0xFFFFFFFF
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _np_from(ptr, count, dtype):
+    if not ptr or count == 0:
+        return np.zeros(0, dtype=dtype)
+    nbytes = count * np.dtype(dtype).itemsize
+    buf = (ctypes.c_char * nbytes).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=count).copy()
+
+
+@dataclass
+class TileVoxels:
+    """One tile's output: heightfield CSR + compact heightfield (flat SoA of rcb_tile_view)."""
+    width: int
+    height: int
+    span_count: int
+    conn_count: int
+    walkable_span_count: int
+    max_height: int
+    max_distance: int
+    status: int
+    hf_cell_offset: np.ndarray
+    span_min: np.ndarray
+    span_max: np.ndarray
+    span_area: np.ndarray
+    cell_index: Optional[np.ndarray] = None
+    cell_count: Optional[np.ndarray] = None
+    areas: Optional[np.ndarray] = None
+    con: Optional[np.ndarray] = None
+    first_conn: Optional[np.ndarray] = None
+    conn_ref: Optional[np.ndarray] = None
+    conn_dir: Optional[np.ndarray] = None
+    conn_next: Optional[np.ndarray] = None
+    dist: Optional[np.ndarray] = None
+
+
+class BatchResult:
+    """Owner of an rcb_result (device arena + optional pinned host copy)."""
+
+    def __init__(self, ctx: "Context", handle):
+        self._ctx, self._h = ctx, handle
+
+    def totals(self) -> dict:
+        t = _ffi.RcbTotals()
+        check(_ffi.lib().rcb_result_totals(self._h, ctypes.byref(t)), self._ctx._h)
+        return {n: int(getattr(t, n)) for n, _ in _ffi.RcbTotals._fields_}
+
+    def download(self) -> "BatchResult":
+        check(_ffi.lib().rcb_result_download(self._h), self._ctx._h)
+        return self
+
+    def tile(self, i: int) -> TileVoxels:
+        v = _ffi.RcbTileView()
+        check(_ffi.lib().rcb_result_tile(self._h, i, ctypes.byref(v)), self._ctx._h)
+        C, S, K = v.cell_count, v.span_count, v.conn_count
+        tv = TileVoxels(v.width, v.height, S, K, v.walkable_span_count, v.max_height, v.max_distance, v.status,
+                        _np_from(v.hf_cell_offset, C + 1, np.uint32), _np_from(v.span_min, S, np.int16),
+                        _np_from(v.span_max, S, np.int16), _np_from(v.span_area, S, np.uint8))
+        if v.cell_index:
+            tv.cell_index = _np_from(v.cell_index, C, np.uint32)
+            tv.cell_count = _np_from(v.cell_count_arr, C, np.uint32)
+            tv.areas = _np_from(v.areas, S, np.uint8)
+            tv.con = _np_from(v.con, 4 * S, np.uint16)
+            tv.first_conn = _np_from(v.first_conn, S, np.uint32)
+            tv.conn_ref = _np_from(v.conn_ref, K, np.uint32)
+            tv.conn_dir = _np_from(v.conn_dir, K, np.uint8)
+            tv.conn_next = _np_from(v.conn_next, K, np.uint32)
+            tv.dist = _np_from(v.dist, S, np.uint16)
+        return tv
+
+    def tile_device_view(self, i: int) -> _ffi.RcbTileView:
+        v = _ffi.RcbTileView()
+        check(_ffi.lib().rcb_result_tile_device(self._h, i, ctypes.byref(v)), self._ctx._h)
+        return v
+
+    def free(self):
+        if self._h:
+            _ffi.lib().rcb_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.free()
+
+
+class Context:
+    """One rcb_ctx: a device, a stream, scratch pools.  One per host thread (reference types are !Send)."""
+
+    def __init__(self, device: int = 0):
+        h = ctypes.c_void_p()
+        check(_ffi.lib().rcb_create(device, ctypes.byref(h)), None,
+              f"rcb_create(device={device}) failed: no CUDA device (recast_rs_b200 has no CPU fallback)")
+        self._h = h
+        self.device = device
+        self._mesh_keep = None
+
+    def close(self):
+        if self._h:
+            _ffi.lib().rcb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int | None):
+        check(_ffi.lib().rcb_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)), self._h)
+
+    def launch_count(self) -> int:
+        return int(_ffi.lib().rcb_launch_count(self._h))
+
+    def upload_mesh(self, vertices, indices):
+        v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1)
+        t = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1)
+        check(_ffi.lib().rcb_upload_mesh(self._h, _ptr(v), v.size, _ptr(t), t.size), self._h)
+
+    def set_mesh_device(self, d_verts_ptr: int, nfloats: int, d_tris_ptr: int, nidx: int, keep=None):
+        self._mesh_keep = keep  # keeps the owning tensors alive
+        check(_ffi.lib().rcb_set_mesh_device(self._h, ctypes.c_void_p(d_verts_ptr), nfloats,
+                                             ctypes.c_void_p(d_tris_ptr), nidx), self._h)
+
+    def build_tiles(self, cfgs, stage_mask=STAGE_ALL_BUILD, erode_radius=0) -> BatchResult:
+        arr = cfgs if isinstance(cfgs, ctypes.Array) else configs_to_array(cfgs)
+        out = ctypes.c_void_p()
+        check(_ffi.lib().rcb_build_tiles(self._h, ctypes.cast(arr, ctypes.c_void_p), len(arr), stage_mask, erode_radius,
+                                         ctypes.byref(out)), self._h)
+        return BatchResult(self, out)
+
+    def rasterize(self, cfgs, tri_areas, flag_merge_threshold, stage_mask=STAGE_RASTER, erode_radius=0) -> BatchResult:
+        arr = cfgs if isinstance(cfgs, ctypes.Array) else configs_to_array(cfgs)
+        a = np.ascontiguousarray(tri_areas, dtype=np.uint8)
+        out = ctypes.c_void_p()
+        check(_ffi.lib().rcb_rasterize(self._h, ctypes.cast(arr, ctypes.c_void_p), len(arr), _ptr(a), flag_merge_threshold,
+                                       stage_mask, erode_radius, ctypes.byref(out)), self._h)
+        return BatchResult(self, out)
+
+    def build_from_spans(self, cfgs, cell_offset, span_min, span_max, span_area, stage_mask, erode_radius=0,
+                         areas_override=None) -> BatchResult:
+        arr = cfgs if isinstance(cfgs, ctypes.Array) else configs_to_array(cfgs)
+        co = np.ascontiguousarray(cell_offset, dtype=np.uint32)
+        a = np.ascontiguousarray(span_min, dtype=np.int16)
+        b = np.ascontiguousarray(span_max, dtype=np.int16)
+        c = np.ascontiguousarray(span_area, dtype=np.uint8)
+        ov = None if areas_override is None else np.ascontiguousarray(areas_override, dtype=np.uint8)
+        out = ctypes.c_void_p()
+        check(_ffi.lib().rcb_build_from_spans(self._h, ctypes.cast(arr, ctypes.c_void_p), len(arr), _ptr(co), _ptr(a),
+                                              _ptr(b), _ptr(c), _ptr(ov), stage_mask, erode_radius, ctypes.byref(out)),
+              self._h)
+        return BatchResult(self, out)
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+# ---- reference-shaped objects ------------------------------------------------------------------------
+class Heightfield:
+    """`Heightfield` (heightfield.rs:58-76) as CSR arrays; the filters run on the GPU."""
+
+    def __init__(self, width, height, bmin, bmax, cs, ch, cell_offset=None, span_min=None, span_max=None,
+                 span_area=None, ctx: Optional[Context] = None):
+        self.width, self.height = int(width), int(height)
+        self.bmin, self.bmax = tuple(float(x) for x in bmin), tuple(float(x) for x in bmax)
+        self.cs, self.ch = float(cs), float(ch)
+        n = self.width * self.height
+        self.cell_offset = np.zeros(n + 1, np.uint32) if cell_offset is None else np.asarray(cell_offset, np.uint32)
+        self.span_min = np.zeros(0, np.int16) if span_min is None else np.asarray(span_min, np.int16)
+        self.span_max = np.zeros(0, np.int16) if span_max is None else np.asarray(span_max, np.int16)
+        self.span_area = np.zeros(0, np.uint8) if span_area is None else np.asarray(span_area, np.uint8).copy()
+        self._ctx = ctx
+
+    @classmethod
+    def new(cls, width, height, bmin, bmax, cs, ch, ctx=None):  # heightfield.rs:80
+        return cls(width, height, bmin, bmax, cs, ch, ctx=ctx)
+
+    def _cfg(self, **kw) -> RecastConfig:
+        return RecastConfig(width=self.width, height=self.height, cs=self.cs, ch=self.ch, bmin=self.bmin, bmax=self.bmax,
+                            **kw)
+
+    def column(self, x, z):
+        c = z * self.width + x
+        return [(int(self.span_min[i]), int(self.span_max[i]), int(self.span_area[i]))
+                for i in range(int(self.cell_offset[c]), int(self.cell_offset[c + 1]))]
+
+    def get_span_count(self) -> int:  # heightfield.rs:1178
+        return int(self.span_min.size)
+
+    def _run_filter(self, bits, height, climb):
+        ctx = self._ctx or default_context()
+        cfg = self._cfg(walkable_height=int(height), walkable_climb=int(climb))
+        with ctx.build_from_spans([cfg], self.cell_offset, self.span_min, self.span_max, self.span_area, bits) as r:
+            self.span_area = r.download().tile(0).span_area
+
+    def filter_low_hanging_walkable_obstacles(self, walkable_climb: int):  # heightfield.rs:286
+        self._run_filter(FILTER_LOW_HANGING, 0, walkable_climb)
+
+    def filter_ledge_spans(self, walkable_height: int, walkable_climb: int):  # heightfield.rs:332
+        self._run_filter(FILTER_LEDGE, walkable_height, walkable_climb)
+
+    def filter_walkable_low_height_spans(self, walkable_height: int):  # heightfield.rs:492
+        self._run_filter(FILTER_LOW_HEIGHT, walkable_height, 0)
+
+
+class CompactHeightfield:
+    """`CompactHeightfield` (compact_heightfield.rs:129-170)."""
+
+    def __init__(self, hf: Heightfield, tv: TileVoxels, ctx: Context):
+        self._hf, self._ctx = hf, ctx
+        self.width, self.height = hf.width, hf.height
+        self.bmin, self.bmax, self.cs, self.ch = hf.bmin, hf.bmax, hf.cs, hf.ch
+        self._take(tv)
+        self.max_distance = 0
+        self.dist = np.zeros(self.span_min.size, np.uint16)
+
+    def _take(self, tv: TileVoxels):
+        self.cell_index, self.cell_count = tv.cell_index, tv.cell_count
+        self.span_min, self.span_max, self.span_area = tv.span_min, tv.span_max, tv.span_area
+        self.areas, self.con, self.first_conn = tv.areas, tv.con, tv.first_conn
+        self.conn_ref, self.conn_dir, self.conn_next = tv.conn_ref, tv.conn_dir, tv.conn_next
+        self.walkable_span_count, self.max_height = tv.walkable_span_count, tv.max_height
+        self.span_count, self.cell_total = tv.span_count, self.width * self.height
+
+    @classmethod
+    def build_from_heightfield(cls, hf: Heightfield, ctx: Optional[Context] = None):  # compact_heightfield.rs:175
+        ctx = ctx or hf._ctx or default_context()
+        with ctx.build_from_spans([hf._cfg()], hf.cell_offset, hf.span_min, hf.span_max, hf.span_area, STAGE_COMPACT) as r:
+            return cls(hf, r.download().tile(0), ctx)
+
+    def get_neighbor(self, span_idx: int, dir8: int) -> Optional[int]:  # compact_heightfield.rs:495
+        c = int(self.first_conn[span_idx])
+        while c != NONE:
+            if int(self.conn_dir[c]) == dir8:
+                return int(self.conn_ref[c])
+            c = int(self.conn_next[c])
+        return None
+
+    def _rerun(self, stage, radius=0) -> TileVoxels:
+        hf = self._hf
+        with self._ctx.build_from_spans([hf._cfg()], hf.cell_offset, hf.span_min, hf.span_max, hf.span_area,
+                                        STAGE_COMPACT | stage, radius, areas_override=self.areas) as r:
+            return r.download().tile(0)
+
+    def build_distance_field(self):  # compact_heightfield.rs:514
+        tv = self._rerun(STAGE_DIST)
+        self.dist, self.max_distance = tv.dist, tv.max_distance
+
+    def erode_walkable_area(self, radius: int):  # area.rs:73
+        self.areas = self._rerun(STAGE_ERODE, radius).areas
+
+
+def erode_walkable_area(chf: CompactHeightfield, erosion_radius: int):  # area.rs:73 (free function)
+    chf.erode_walkable_area(erosion_radius)
+
+
+class RecastBuilder:
+    """`RecastBuilder` (lib.rs:51-359), voxelization half."""
+
+    def __init__(self, config: RecastConfig, ctx: Optional[Context] = None):
+        self._config = config
+        self._ctx = ctx
+
+    @classmethod
+    def new(cls, config: RecastConfig) -> "RecastBuilder":
+        return cls(config)
+
+    def config(self) -> RecastConfig:
+        return self._config
+
+    def _context(self) -> Context:
+        return self._ctx or default_context()
+
+    def build_heightfield(self, vertices, indices) -> Heightfield:  # lib.rs:116-135
+        c = self._config
+        hf = Heightfield.new(c.width, c.height, c.bmin, c.bmax, c.cs, c.ch, ctx=self._context())
+        self.rasterize_triangles(hf, vertices, indices)
+        return hf
+
+    def rasterize_triangles(self, heightfield: Heightfield, vertices, indices) -> None:  # lib.rs:186-290
+        ctx = self._context()
+        ctx.upload_mesh(vertices, indices)
+        c = self._config
+        cfg = RecastConfig(**{**vars(c), "width": heightfield.width, "height": heightfield.height, "bmin": heightfield.bmin,
+                              "bmax": heightfield.bmax, "cs": heightfield.cs, "ch": heightfield.ch})
+        if heightfield.get_span_count() != 0:
+            raise NotImplementedError("rasterizing onto a non-empty heightfield is a SURVEY §8(f) 'next' row")
+        with ctx.build_tiles([cfg], STAGE_RASTER | STAGE_FILTER) as r:
+            tv = r.download().tile(0)
+        heightfield.cell_offset, heightfield.span_min = tv.hf_cell_offset, tv.span_min
+        heightfield.span_max, heightfield.span_area = tv.span_max, tv.span_area
+
+    def build_compact_heightfield(self, heightfield: Heightfield) -> CompactHeightfield:
+        return CompactHeightfield.build_from_heightfield(heightfield, self._context())
+
+    # The batch entry the reference lacks: one launch sequence for many tiles.
+    def build_tiles(self, vertices, indices, tiles: Sequence[RecastConfig], stage_mask=STAGE_ALL_BUILD,
+                    erode_radius=0) -> List[TileVoxels]:
+        ctx = self._context()
+        ctx.upload_mesh(vertices, indices)
+        with ctx.build_tiles(tiles, stage_mask, erode_radius) as r:
+            r.download()
+            return [r.tile(i) for i in range(len(tiles))]

@@ -1,0 +1,209 @@
+// k_compact.cu — compact heightfield: cells, span attributes, 8-direction linking, connection list.
+//
+// Replaces (crates/recast/src/compact_heightfield.rs):
+//   :175-281 build_from_heightfield  (cells row-major, ALL spans kept, areas copy, max_height,
+//                                     walkable_span_count)
+//   :284-430 build_connections       (best-overlap walkable neighbour in 8 directions, connection
+//                                     array in reverse direction order per span, con[4])
+//   :433-442 get_cell_index_for_span (O(cells) scan in the reference; the neighbour cell is known here)
+// The heightfield CSR (hf_off) is already the compaction prefix sum, so "compaction" is a gather of
+// offsets; linking is a per-column stencil over the 8 neighbour columns.
+#include "rcb_common.cuh"
+
+namespace {
+
+__constant__ int c_dirx[8] = {-1, 0, 1, 1, 1, 0, -1, -1};  // compact_heightfield.rs:109-111
+__constant__ int c_dirz[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
+
+__global__ void k_tile_bases(const TileDesc* __restrict__ tiles, int ntiles, const uint32_t* __restrict__ hf_off,
+                             const uint32_t* __restrict__ conn_off, TileInfo* __restrict__ tinfo) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const uint32_t c0 = tiles[t].cell_base, c1 = c0 + (uint32_t)(tiles[t].width * tiles[t].height);
+    if (hf_off) {
+        tinfo[t].span_base = hf_off[c0];
+        tinfo[t].span_count = hf_off[c1] - hf_off[c0];
+    }
+    if (conn_off) {
+        tinfo[t].conn_base = conn_off[c0];
+        tinfo[t].conn_count = conn_off[c1] - conn_off[c0];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_cells(const TileDesc* __restrict__ tiles, TileMap tm,
+                                               const uint32_t* __restrict__ hf_off, uint32_t* __restrict__ hf_cell_offset,
+                                               uint32_t* __restrict__ cell_index, uint32_t* __restrict__ cell_count,
+                                               const TileInfo* __restrict__ tinfo) {
+    const uint32_t tile = RCB_TILE_OF_BLOCK();
+    if (tile >= tm.ntiles) return;
+    const TileDesc& td = tiles[tile];
+    const uint32_t C = (uint32_t)(td.width * td.height);
+    const uint32_t lc = RCB_CELL_OF_THREAD();
+    if (lc >= C) return;
+    const uint32_t g = td.cell_base + lc;
+    const uint32_t base = tinfo[tile].span_base;
+    const uint32_t b = hf_off[g], e = hf_off[g + 1];
+    uint32_t* off = hf_cell_offset + td.cell_base + tile;  // each tile owns C+1 entries
+    off[lc] = b - base;
+    if (lc == C - 1) off[C] = e - base;
+    if (cell_index) {
+        cell_index[g] = (e > b) ? (b - base) : RCB_NONE;  // compact_heightfield.rs:209-223
+        cell_count[g] = e - b;
+    }
+}
+
+// One thread per column: for every walkable span pick, per direction, the first neighbour span with
+// minimal |dmin|+|dmax| among the walkable overlapping ones (compact_heightfield.rs:316-368).
+__global__ void __launch_bounds__(256) k_link_spans(const TileDesc* __restrict__ tiles, TileMap tm,
+                                                    const uint32_t* __restrict__ hf_off,
+                                                    const int16_t* __restrict__ smin, const int16_t* __restrict__ smax,
+                                                    const uint8_t* __restrict__ sarea, uint8_t* __restrict__ areas,
+                                                    uint16_t* __restrict__ nei16, size_t S, uint16_t* __restrict__ con,
+                                                    uint32_t* __restrict__ cell_conn_cnt, TileInfo* __restrict__ tinfo) {
+    const uint32_t tile = RCB_TILE_OF_BLOCK();
+    if (tile >= tm.ntiles) return;
+    const TileDesc& td = tiles[tile];
+    const int W = td.width, H = td.height;
+    const uint32_t lc = RCB_CELL_OF_THREAD();
+    uint32_t walkable = 0, maxh = 0;
+    if (lc < (uint32_t)(W * H)) {
+        const int x = lc % W, z = lc / W;
+        const uint32_t g = td.cell_base + lc;
+        const uint32_t b = hf_off[g], e = hf_off[g + 1];
+        uint32_t nconn = 0;
+        if (e > b) {
+            uint32_t nb[8], ne[8];
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                const int nx = x + c_dirx[d], nz = z + c_dirz[d];
+                if (nx < 0 || nz < 0 || nx >= W || nz >= H) {
+                    nb[d] = ne[d] = 0;
+                } else {
+                    const uint32_t ng = td.cell_base + (uint32_t)nz * W + nx;
+                    nb[d] = hf_off[ng];
+                    ne[d] = hf_off[ng + 1];
+                }
+            }
+            for (uint32_t s = b; s < e; ++s) {
+                const int mn = smin[s], mx = smax[s];
+                const uint32_t a = sarea[s];
+                areas[s] = (uint8_t)a;                       // :237
+                maxh = max(maxh, (uint32_t)(uint16_t)mx);    // :240
+                uint16_t c4[4] = {63, 63, 63, 63};
+                if (a != 0) {
+                    walkable++;  // :243-245
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) {
+                        uint32_t best = RCB_NEI_NONE;
+                        int best_diff = 0x7fffffff;
+                        for (uint32_t ns = nb[d]; ns < ne[d]; ++ns) {
+                            if (sarea[ns] == 0) continue;
+                            const int nmn = smin[ns], nmx = smax[ns];
+                            if (max(nmn, mn) > min(nmx, mx)) continue;
+                            const int diff = (int)(uint16_t)(abs(nmn - mn) + abs(nmx - mx));
+                            if (diff < best_diff) {
+                                best_diff = diff;
+                                best = ns - nb[d];
+                            }
+                        }
+                        nei16[(size_t)d * S + s] = (uint16_t)best;
+                        if (best != RCB_NEI_NONE) {
+                            nconn++;
+                            if (d == 7) c4[0] = (uint16_t)best;  // :404-410
+                            if (d == 5) c4[1] = (uint16_t)best;
+                            if (d == 3) c4[2] = (uint16_t)best;
+                            if (d == 1) c4[3] = (uint16_t)best;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) nei16[(size_t)d * S + s] = RCB_NEI_NONE;
+                }
+                *reinterpret_cast<uint2*>(con + 4 * (size_t)s) =
+                    make_uint2((uint32_t)c4[0] | ((uint32_t)c4[1] << 16), (uint32_t)c4[2] | ((uint32_t)c4[3] << 16));
+            }
+        }
+        cell_conn_cnt[g] = nconn;
+    }
+    // per-tile reductions (every block belongs to exactly one tile)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        walkable += __shfl_down_sync(0xffffffffu, walkable, d);
+        maxh = max(maxh, __shfl_down_sync(0xffffffffu, maxh, d));
+    }
+    if (lane_id() == 0) {
+        if (walkable) atomicAdd(&tinfo[tile].walkable_span_count, walkable);
+        if (maxh) atomicMax(&tinfo[tile].max_height, maxh);
+    }
+}
+
+// Connection list layout (compact_heightfield.rs:375-389): spans in index order; each span pushes its
+// connections in REVERSE direction order, next -> previously pushed, first_connection = last pushed.
+__global__ void __launch_bounds__(256) k_write_connections(const TileDesc* __restrict__ tiles, TileMap tm,
+                                                           const uint32_t* __restrict__ hf_off,
+                                                           const uint16_t* __restrict__ nei16, size_t S,
+                                                           const uint32_t* __restrict__ conn_off,
+                                                           const TileInfo* __restrict__ tinfo,
+                                                           uint32_t* __restrict__ first_conn, uint32_t* __restrict__ conn_ref,
+                                                           uint8_t* __restrict__ conn_dir, uint32_t* __restrict__ conn_next) {
+    const uint32_t tile = RCB_TILE_OF_BLOCK();
+    if (tile >= tm.ntiles) return;
+    const TileDesc& td = tiles[tile];
+    const int W = td.width, H = td.height;
+    const uint32_t lc = RCB_CELL_OF_THREAD();
+    if (lc >= (uint32_t)(W * H)) return;
+    const int x = lc % W, z = lc / W;
+    const uint32_t g = td.cell_base + lc;
+    const uint32_t b = hf_off[g], e = hf_off[g + 1];
+    if (b == e) return;
+    const uint32_t span_base = tinfo[tile].span_base, conn_base = tinfo[tile].conn_base;
+    uint32_t k = conn_off[g];  // global connection cursor of this column
+    for (uint32_t s = b; s < e; ++s) {
+        uint32_t first = RCB_NONE;
+        for (int d = 7; d >= 0; --d) {
+            const uint32_t o = nei16[(size_t)d * S + s];
+            if (o == RCB_NEI_NONE) continue;
+            const uint32_t ng = td.cell_base + (uint32_t)(z + c_dirz[d]) * W + (x + c_dirx[d]);
+            conn_ref[k] = hf_off[ng] + o - span_base;
+            conn_dir[k] = (uint8_t)d;
+            conn_next[k] = first;
+            first = k - conn_base;
+            ++k;
+        }
+        first_conn[s] = first;
+    }
+}
+
+}  // namespace
+
+void launch_tile_bases(const TileDesc* tiles, int ntiles, const uint32_t* hf_off, const uint32_t* conn_off,
+                       TileInfo* tinfo, cudaStream_t s) {
+    if (ntiles == 0) return;
+    k_tile_bases<<<(ntiles + 127) / 128, 128, 0, s>>>(tiles, ntiles, hf_off, conn_off, tinfo);
+    g_rcb_launches++;
+}
+
+void launch_cells_and_offsets(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, uint32_t* hf_cell_offset,
+                              uint32_t* cell_index, uint32_t* cell_count, TileInfo* tinfo, int, cudaStream_t s) {
+    if (tm.nblocks == 0) return;
+    k_cells<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, hf_cell_offset, cell_index, cell_count, tinfo);
+    g_rcb_launches++;
+}
+
+void launch_link_spans(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smin,
+                       const int16_t* smax, const uint8_t* sarea, uint8_t* areas, uint16_t* nei16, size_t S,
+                       uint16_t* con, uint32_t* cell_conn_cnt, TileInfo* tinfo, cudaStream_t s) {
+    if (tm.nblocks == 0) return;
+    k_link_spans<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, smin, smax, sarea, areas, nei16, S, con, cell_conn_cnt,
+                                            tinfo);
+    g_rcb_launches++;
+}
+
+void launch_write_connections(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const uint16_t* nei16,
+                              size_t S, const uint32_t* conn_off, const TileInfo* tinfo, uint32_t* first_conn,
+                              uint32_t* conn_ref, uint8_t* conn_dir, uint32_t* conn_next, cudaStream_t s) {
+    if (tm.nblocks == 0) return;
+    k_write_connections<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, conn_off, tinfo, first_conn, conn_ref,
+                                                   conn_dir, conn_next);
+    g_rcb_launches++;
+}

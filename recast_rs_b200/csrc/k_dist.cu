@@ -1,0 +1,227 @@
+// k_dist.cu — distance field and walkable-area erosion on the compact heightfield.
+//
+// Replaces:
+//   compact_heightfield.rs:514-543 build_distance_field, :546-675 calculate_distance_field,
+//   :679-727 box_blur;  area.rs:73-234 erode_walkable_area.
+//
+// The reference's "two-pass chamfer" indexes the 8-direction connection table with 4-direction
+// numbers.  Reading the loops literally:
+//   forward  (z up,   x up)  : F[i] = min(init[i], F[NW]+2, F[NW.E]+3, init[E]+2, F[E.NE]+3)
+//       NW, NW.E and E.NE lie in row z-1 (already final), E lies in row z and has not been visited
+//       yet (still its init value)  =>  rows are sequential, spans inside a row are independent.
+//   backward (z down, x down): D[i] = min(F[i], F[NE]+2, F[NE.N]+3, F[N]+2, F[N.NW]+3)
+//       NE, N are in row z-1 and NE.N, N.NW in row z-2, all visited LATER by the descending sweep
+//       =>  they still hold forward values: the backward pass is a pure gather.
+// (x.y means "neighbour y of neighbour x"; all additions saturate in u16 / u8.)
+// tests/test_oracle_* pin this equivalence against the literal sequential sweeps of the oracle.
+//
+// Kernels: init (boundary marking) -> forward (one CTA per tile, H sequential row steps with
+// __syncthreads) -> backward gather [+ max | + erosion threshold] -> blur.
+#include "rcb_common.cuh"
+
+namespace {
+
+__constant__ int d_dirx[8] = {-1, 0, 1, 1, 1, 0, -1, -1};
+__constant__ int d_dirz[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
+
+struct Grid {
+    const uint32_t* hf_off;
+    const uint16_t* nei16;
+    size_t S;
+    uint32_t cell_base;
+    int W, H;
+};
+
+// neighbour `dir` of span `s` that lives in cell (x,z); returns global span index or RCB_NONE
+__device__ __forceinline__ uint32_t nei(const Grid& g, uint32_t s, int x, int z, int dir) {
+    const uint32_t o = g.nei16[(size_t)dir * g.S + s];
+    if (o == RCB_NEI_NONE) return RCB_NONE;
+    const int nx = x + d_dirx[dir], nz = z + d_dirz[dir];
+    return g.hf_off[g.cell_base + (uint32_t)nz * g.W + nx] + o;
+}
+
+template <typename T>
+__device__ __forceinline__ T sat_add(T a, unsigned b) {
+    const unsigned r = (unsigned)a + b;
+    const unsigned mx = (T)~(T)0;
+    return (T)(r > mx ? mx : r);
+}
+
+// ---- boundary marking -----------------------------------------------------------------------------
+// DIST : every span with fewer than 4 cardinal neighbours of EQUAL areas[] -> 0 (compact_heightfield.rs:556-585)
+// ERODE: areas==0 -> 0; else 0 unless all of W,S,E,N exist with areas != 0        (area.rs:91-125)
+template <typename T, bool ERODE>
+__global__ void __launch_bounds__(256) k_boundary(const TileDesc* __restrict__ tiles, TileMap tm,
+                                                  const uint32_t* __restrict__ hf_off,
+                                                  const uint16_t* __restrict__ nei16, size_t S,
+                                                  const uint8_t* __restrict__ areas, T* __restrict__ init) {
+    const uint32_t tile = RCB_TILE_OF_BLOCK();
+    if (tile >= tm.ntiles) return;
+    const TileDesc& td = tiles[tile];
+    const int W = td.width, H = td.height;
+    const uint32_t lc = RCB_CELL_OF_THREAD();
+    if (lc >= (uint32_t)(W * H)) return;
+    const int x = lc % W, z = lc / W;
+    const Grid g{hf_off, nei16, S, td.cell_base, W, H};
+    const uint32_t gc = td.cell_base + lc;
+    const uint32_t b = hf_off[gc], e = hf_off[gc + 1];
+    const T inf = (T)~(T)0;
+    for (uint32_t s = b; s < e; ++s) {
+        const uint8_t a = areas[s];
+        int cnt = 0;
+        if (!ERODE || a != 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int dir = 7 - 2 * k;  // 7,5,3,1
+                const uint32_t n = nei(g, s, x, z, dir);
+                if (n == RCB_NONE) continue;
+                if (ERODE ? (areas[n] != 0) : (areas[n] == a)) cnt++;
+            }
+        }
+        init[s] = (cnt == 4) ? inf : (T)0;
+    }
+}
+
+// ---- forward sweep: one CTA per tile, rows in sequence ----------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_forward(const TileDesc* __restrict__ tiles,
+                                                 const uint32_t* __restrict__ hf_off,
+                                                 const uint16_t* __restrict__ nei16, size_t S,
+                                                 const T* __restrict__ init, T* F) {
+    const TileDesc& td = tiles[blockIdx.x];
+    const int W = td.width, H = td.height;
+    const Grid g{hf_off, nei16, S, td.cell_base, W, H};
+    for (int z = 0; z < H; ++z) {
+        for (int x = threadIdx.x; x < W; x += blockDim.x) {
+            const uint32_t gc = td.cell_base + (uint32_t)z * W + x;
+            const uint32_t b = hf_off[gc], e = hf_off[gc + 1];
+            for (uint32_t s = b; s < e; ++s) {
+                T v = init[s];
+                const uint32_t a = nei(g, s, x, z, 0);  // NW  (row z-1)
+                if (a != RCB_NONE) {
+                    v = min(v, sat_add<T>(F[a], 2));
+                    const uint32_t aa = nei(g, a, x - 1, z - 1, 3);  // NW.E (row z-1)
+                    if (aa != RCB_NONE) v = min(v, sat_add<T>(F[aa], 3));
+                }
+                const uint32_t bn = nei(g, s, x, z, 3);  // E (row z, not yet visited: init value)
+                if (bn != RCB_NONE) {
+                    v = min(v, sat_add<T>(init[bn], 2));
+                    const uint32_t bb = nei(g, bn, x + 1, z, 2);  // E.NE (row z-1)
+                    if (bb != RCB_NONE) v = min(v, sat_add<T>(F[bb], 3));
+                }
+                F[s] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- backward gather ---------------------------------------------------------------------------------
+// DIST : D = gather, per-tile max (before blur) -> tinfo.max_distance
+// ERODE: D < thr  =>  areas = 0 (area.rs:226-231)
+template <typename T, bool ERODE>
+__global__ void __launch_bounds__(256) k_backward(const TileDesc* __restrict__ tiles, TileMap tm,
+                                                  const uint32_t* __restrict__ hf_off,
+                                                  const uint16_t* __restrict__ nei16, size_t S,
+                                                  const T* __restrict__ F, T* __restrict__ D, uint8_t* areas,
+                                                  unsigned thr, TileInfo* __restrict__ tinfo) {
+    const uint32_t tile = RCB_TILE_OF_BLOCK();
+    if (tile >= tm.ntiles) return;
+    const TileDesc& td = tiles[tile];
+    const int W = td.width, H = td.height;
+    const uint32_t lc = RCB_CELL_OF_THREAD();
+    uint32_t vmax = 0;
+    if (lc < (uint32_t)(W * H)) {
+        const int x = lc % W, z = lc / W;
+        const Grid g{hf_off, nei16, S, td.cell_base, W, H};
+        const uint32_t gc = td.cell_base + lc;
+        const uint32_t b = hf_off[gc], e = hf_off[gc + 1];
+        for (uint32_t s = b; s < e; ++s) {
+            T v = F[s];
+            const uint32_t a = nei(g, s, x, z, 2);  // NE
+            if (a != RCB_NONE) {
+                v = min(v, sat_add<T>(F[a], 2));
+                const uint32_t aa = nei(g, a, x + 1, z - 1, 1);  // NE.N
+                if (aa != RCB_NONE) v = min(v, sat_add<T>(F[aa], 3));
+            }
+            const uint32_t bn = nei(g, s, x, z, 1);  // N
+            if (bn != RCB_NONE) {
+                v = min(v, sat_add<T>(F[bn], 2));
+                const uint32_t bb = nei(g, bn, x, z - 1, 0);  // N.NW
+                if (bb != RCB_NONE) v = min(v, sat_add<T>(F[bb], 3));
+            }
+            if (ERODE) {
+                if ((unsigned)v < thr) areas[s] = 0;
+            } else {
+                D[s] = v;
+                vmax = max(vmax, (uint32_t)v);
+            }
+        }
+    }
+    if (!ERODE) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) vmax = max(vmax, __shfl_down_sync(0xffffffffu, vmax, d));
+        if (lane_id() == 0 && vmax) atomicMax(&tinfo[tile].max_distance, vmax);
+    }
+}
+
+// ---- box blur (compact_heightfield.rs:679-727, threshold 1 -> thr 2) ----------------------------------
+__global__ void __launch_bounds__(256) k_blur(const TileDesc* __restrict__ tiles, TileMap tm,
+                                              const uint32_t* __restrict__ hf_off, const uint16_t* __restrict__ nei16,
+                                              size_t S, const uint16_t* __restrict__ D, uint16_t* __restrict__ dist) {
+    const uint32_t tile = RCB_TILE_OF_BLOCK();
+    if (tile >= tm.ntiles) return;
+    const TileDesc& td = tiles[tile];
+    const int W = td.width, H = td.height;
+    const uint32_t lc = RCB_CELL_OF_THREAD();
+    if (lc >= (uint32_t)(W * H)) return;
+    const int x = lc % W, z = lc / W;
+    const Grid g{hf_off, nei16, S, td.cell_base, W, H};
+    const uint32_t gc = td.cell_base + lc;
+    const uint32_t b = hf_off[gc], e = hf_off[gc + 1];
+    for (uint32_t s = b; s < e; ++s) {
+        const uint32_t cd = D[s];
+        if (cd <= 2) {
+            dist[s] = (uint16_t)cd;
+            continue;
+        }
+        int d = (int)cd, n = 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int dir = 1 + 2 * k;  // 1,3,5,7
+            const uint32_t nb = nei(g, s, x, z, dir);
+            if (nb == RCB_NONE) continue;
+            d += D[nb];
+            n++;
+            const uint32_t dg = nei(g, nb, x + d_dirx[dir], z + d_dirz[dir], (dir + 1) & 7);
+            if (dg != RCB_NONE) {
+                d += D[dg];
+                n++;
+            }
+        }
+        dist[s] = (uint16_t)(d / n);
+    }
+}
+
+}  // namespace
+
+void launch_distance_field(const TileDesc* tiles, int ntiles, TileMap tm, const uint32_t* hf_off,
+                           const uint16_t* nei16, size_t S, const uint8_t* areas, uint16_t* tmp_init, uint16_t* tmp_f,
+                           uint16_t* tmp_d, uint16_t* dist, TileInfo* tinfo, cudaStream_t s) {
+    if (tm.nblocks == 0 || ntiles == 0) return;
+    k_boundary<uint16_t, false><<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, areas, tmp_init);
+    k_forward<uint16_t><<<ntiles, 256, 0, s>>>(tiles, hf_off, nei16, S, tmp_init, tmp_f);
+    k_backward<uint16_t, false><<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, tmp_f, tmp_d, nullptr, 0, tinfo);
+    k_blur<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, tmp_d, dist);
+    g_rcb_launches += 4;
+}
+
+void launch_erode(const TileDesc* tiles, int ntiles, TileMap tm, const uint32_t* hf_off, const uint16_t* nei16,
+                  size_t S, uint8_t* areas, uint8_t* tmp_init, uint8_t* tmp_f, int radius, cudaStream_t s) {
+    if (tm.nblocks == 0 || ntiles == 0) return;
+    const unsigned thr = (unsigned)(uint8_t)(uint32_t)(radius * 2);  // area.rs:226 `(radius*2) as u8`
+    k_boundary<uint8_t, true><<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, areas, tmp_init);
+    k_forward<uint8_t><<<ntiles, 256, 0, s>>>(tiles, hf_off, nei16, S, tmp_init, tmp_f);
+    k_backward<uint8_t, true><<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, tmp_f, nullptr, areas, thr, nullptr);
+    g_rcb_launches += 3;
+}

@@ -1,0 +1,422 @@
+// k_raster.cu — triangle -> span fragments -> per-column span lists.
+//
+// Replaces (paths under crates/recast/src/):
+//   lib.rs:217-274              per-triangle loop, index check, slope classification (glam 0.29.3)
+//   rasterization.rs:246-366    rasterize_tri  (+ :370-377 overlap_bounds)
+//   rasterization.rs:172-242    divide_poly
+//   rasterization.rs:51-168     add_span_internal (ordered insert + merge)
+//
+// Bit-exactness: every float expression keeps the reference's operand order and is written with
+// round-to-nearest intrinsics (__fadd_rn/__fsub_rn/__fmul_rn/__fdiv_rn/__fsqrt_rn), which ptxas
+// never contracts into FMA; the file is additionally compiled with --fmad=false --prec-div=true
+// --prec-sqrt=true --ftz=false.  `as i32` = __float2int_rz (saturating, NaN -> 0), like Rust.
+//
+// Order dependence: span AREA depends on the order triangles hit a column.  Fragments
+// are therefore keyed (cell, triangle index) and each column is replayed in ascending triangle
+// index by one thread, running the reference's merge rule verbatim.
+#include "rcb_common.cuh"
+
+namespace {
+
+struct Poly {
+    int n;
+    float v[RCB_MAX_POLY_VERTS * 3];
+};
+
+__device__ __forceinline__ void poly_push(Poly& p, float x, float y, float z, bool& ovf) {
+    if (p.n >= RCB_MAX_POLY_VERTS) {
+        ovf = true;
+        return;
+    }
+    p.v[p.n * 3 + 0] = x;
+    p.v[p.n * 3 + 1] = y;
+    p.v[p.n * 3 + 2] = z;
+    p.n++;
+}
+
+// rasterization.rs:172-242.  out1: side < offset, out2: side > offset.
+__device__ void divide_poly(const Poly& in, Poly& out1, Poly& out2, float offset, int axis, bool& ovf) {
+    out1.n = 0;
+    out2.n = 0;
+    const int n = in.n;
+    if (n == 0) return;
+    for (int i = 0; i < n; ++i) {
+        const int j = (i + 1 == n) ? 0 : i + 1;
+        const float vix = in.v[i * 3], viy = in.v[i * 3 + 1], viz = in.v[i * 3 + 2];
+        const float vjx = in.v[j * 3], vjy = in.v[j * 3 + 1], vjz = in.v[j * 3 + 2];
+        const float ci = axis == 0 ? vix : viz;
+        const float cj = axis == 0 ? vjx : vjz;
+        const int si = ci < offset ? -1 : (ci > offset ? 1 : 0);
+        const int sj = cj < offset ? -1 : (cj > offset ? 1 : 0);
+        if (si == 0) {
+            poly_push(out1, vix, viy, viz, ovf);
+            poly_push(out2, vix, viy, viz, ovf);
+        } else {
+            Poly& mine = si < 0 ? out1 : out2;
+            poly_push(mine, vix, viy, viz, ovf);
+            if ((si < 0 && sj > 0) || (si > 0 && sj < 0)) {
+                // t = (offset - vi[a]) / (vj[a] - vi[a]);  p[k] = vi[k] + t * (vj[k] - vi[k])
+                const float t = __fdiv_rn(__fsub_rn(offset, ci), __fsub_rn(cj, ci));
+                const float px = __fadd_rn(vix, __fmul_rn(t, __fsub_rn(vjx, vix)));
+                const float py = __fadd_rn(viy, __fmul_rn(t, __fsub_rn(vjy, viy)));
+                const float pz = __fadd_rn(viz, __fmul_rn(t, __fsub_rn(vjz, viz)));
+                poly_push(out1, px, py, pz, ovf);
+                poly_push(out2, px, py, pz, ovf);
+            }
+        }
+    }
+}
+
+struct Tri {
+    float v0[3], v1[3], v2[3];
+    float tmin[3], tmax[3];
+};
+
+__device__ __forceinline__ void tri_bounds(Tri& t) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {  // rasterization.rs:258-264
+        t.tmin[i] = fminf(fminf(t.v0[i], t.v1[i]), t.v2[i]);
+        t.tmax[i] = fmaxf(fmaxf(t.v0[i], t.v1[i]), t.v2[i]);
+    }
+}
+
+// rasterization.rs:270 + :275-285.  Returns false when the triangle misses the tile.
+__device__ __forceinline__ bool tile_footprint(const Tri& t, const TileDesc& td, int& x0, int& x1, int& z0, int& z1) {
+    if (!(t.tmin[0] <= td.bmax[0] && t.tmax[0] >= td.bmin[0] && t.tmin[1] <= td.bmax[1] && t.tmax[1] >= td.bmin[1] &&
+          t.tmin[2] <= td.bmax[2] && t.tmax[2] >= td.bmin[2]))
+        return false;
+    x0 = __float2int_rz(__fmul_rn(__fsub_rn(t.tmin[0], td.bmin[0]), td.ics));
+    x1 = __float2int_rz(__fmul_rn(__fsub_rn(t.tmax[0], td.bmin[0]), td.ics));
+    z0 = __float2int_rz(__fmul_rn(__fsub_rn(t.tmin[2], td.bmin[2]), td.ics));
+    z1 = __float2int_rz(__fmul_rn(__fsub_rn(t.tmax[2], td.bmin[2]), td.ics));
+    x0 = max(x0, 0);
+    x1 = min(x1, td.width - 1);
+    z0 = max(z0, -1);
+    z1 = min(z1, td.height - 1);
+    return true;
+}
+
+// lib.rs:252-270 (glam scalar Vec3).  Returns false for a skipped (degenerate) triangle.
+__device__ __forceinline__ bool classify(const Tri& t, float thr, uint8_t& area) {
+    const float e1x = __fsub_rn(t.v1[0], t.v0[0]), e1y = __fsub_rn(t.v1[1], t.v0[1]), e1z = __fsub_rn(t.v1[2], t.v0[2]);
+    const float e2x = __fsub_rn(t.v2[0], t.v0[0]), e2y = __fsub_rn(t.v2[1], t.v0[1]), e2z = __fsub_rn(t.v2[2], t.v0[2]);
+    const float cx = __fsub_rn(__fmul_rn(e1y, e2z), __fmul_rn(e2y, e1z));
+    const float cy = __fsub_rn(__fmul_rn(e1z, e2x), __fmul_rn(e2z, e1x));
+    const float cz = __fsub_rn(__fmul_rn(e1x, e2y), __fmul_rn(e2x, e1y));
+    const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz)));
+    if (len < 1.1920928955078125e-07f) return false;  // f32::EPSILON
+    const float ny = __fmul_rn(cy, __fdiv_rn(1.0f, len));
+    area = (fabsf(ny) >= thr) ? 1 : 0;
+    return true;
+}
+
+__device__ __forceinline__ bool load_triangle(const MeshView& m, uint32_t tri, Tri& t, bool& bad_index) {
+    const int32_t i0 = m.tris[tri * 3ull], i1 = m.tris[tri * 3ull + 1], i2 = m.tris[tri * 3ull + 2];
+    if ((uint32_t)i0 >= m.nverts || (uint32_t)i1 >= m.nverts || (uint32_t)i2 >= m.nverts) {  // lib.rs:224-233
+        bad_index = true;
+        return false;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        t.v0[k] = m.verts[i0 * 3ull + k];
+        t.v1[k] = m.verts[i1 * 3ull + k];
+        t.v2[k] = m.verts[i2 * 3ull + k];
+    }
+    tri_bounds(t);
+    return true;
+}
+
+// Enumerate the tiles whose AABB the triangle AABB touches (conservative via the locator grid, then
+// the reference's exact inclusive test inside tile_footprint).  A tile registered in several bins is
+// visited once: only in the bin (max(tri lower bin, tile lower bin)).
+template <class Fn>
+__device__ __forceinline__ void for_each_tile(const Tri& t, const Locator& loc, const TileDesc* tiles, Fn&& fn) {
+    // NaN coordinates fail every comparison of overlap_bounds => no tile
+    if (!(t.tmin[0] <= t.tmax[0]) || !(t.tmin[2] <= t.tmax[2])) return;
+    const int bx0 = rcb_bin_coord(t.tmin[0], loc.gx0, loc.inv_bx, loc.nbx);
+    const int bx1 = rcb_bin_coord(t.tmax[0], loc.gx0, loc.inv_bx, loc.nbx);
+    const int bz0 = rcb_bin_coord(t.tmin[2], loc.gz0, loc.inv_bz, loc.nbz);
+    const int bz1 = rcb_bin_coord(t.tmax[2], loc.gz0, loc.inv_bz, loc.nbz);
+    for (int bz = bz0; bz <= bz1; ++bz)
+        for (int bx = bx0; bx <= bx1; ++bx) {
+            const uint32_t b = (uint32_t)bz * loc.nbx + bx;
+            const uint32_t e = loc.bin_off[b + 1];
+            for (uint32_t k = loc.bin_off[b]; k < e; ++k) {
+                const uint32_t tile = loc.bin_tiles[k];
+                const TileDesc& td = tiles[tile];
+                if (bx != max(bx0, td.bin_x0) || bz != max(bz0, td.bin_z0)) continue;
+                int x0, x1, z0, z1;
+                if (!tile_footprint(t, td, x0, x1, z0, z1)) continue;
+                fn(tile, td, x0, x1, z0, z1);
+            }
+        }
+}
+
+// ---- pass 1: validate indices, upper bound of the fragment count --------------------------------
+__global__ void __launch_bounds__(256) k_count_fragments(RasterBuffers rb) {
+    const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long ub = 0;
+    bool bad = false;
+    if (tri < rb.mesh.ntris) {
+        Tri t;
+        if (load_triangle(rb.mesh, tri, t, bad)) {
+            for_each_tile(t, rb.loc, rb.tiles, [&](uint32_t, const TileDesc&, int x0, int x1, int z0, int z1) {
+                const int zz0 = max(z0, 0);
+                if (x1 >= x0 && z1 >= zz0) ub += (unsigned long long)(x1 - x0 + 1) * (unsigned long long)(z1 - zz0 + 1);
+            });
+        }
+    }
+    // block reduction -> one atomic per block
+    __shared__ unsigned long long sh[8];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ub += __shfl_down_sync(0xffffffffu, ub, d);
+    if (lane_id() == 0) sh[threadIdx.x >> 5] = ub;
+    const bool any_bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) {
+        unsigned long long s = 0;
+        for (int i = 0; i < 8; ++i) s += sh[i];
+        if (s) atomicAdd(&rb.counters[0], s);
+        if (any_bad) atomicOr(&rb.counters[3], 1ull);
+    }
+}
+
+// ---- pass 2: clip and emit fragments --------------------------------------------------------------
+__device__ __forceinline__ void emit_fragment(const RasterBuffers& rb, uint32_t gcell, uint32_t tri, int smin, int smax,
+                                              uint32_t area) {
+    const uint32_t rank = atomicAdd(&rb.cell_cnt[gcell], 1u);
+    // warp-aggregated append to the unsorted fragment list
+    const unsigned m = __activemask();
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if ((int)lane_id() == leader) base = atomicAdd(&rb.counters[1], (unsigned long long)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    const unsigned long long slot = base + __popc(m & ((1u << lane_id()) - 1u));
+    if (slot < rb.frag_cap)
+        rb.frag_tmp[slot] = make_uint4(gcell, tri, ((uint32_t)smin & 0xffffu) | ((uint32_t)smax << 16),
+                                       (rank & 0xffffffu) | (area << 24));
+    else
+        atomicOr(&rb.counters[2], 2ull);  // cannot happen: frag_cap >= upper bound
+}
+
+__global__ void __launch_bounds__(128) k_clip_emit(RasterBuffers rb, TileInfo* __restrict__ tinfo) {
+    const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tri >= rb.mesh.ntris) return;
+    Tri t;
+    bool bad = false;
+    if (!load_triangle(rb.mesh, tri, t, bad)) return;
+    const bool explicit_area = rb.mesh.tri_areas != nullptr;
+    const uint32_t given_area = explicit_area ? rb.mesh.tri_areas[tri] : 0;
+
+    for_each_tile(t, rb.loc, rb.tiles, [&](uint32_t tile, const TileDesc& td, int x0, int x1, int z0, int z1) {
+        uint32_t area = given_area;
+        if (!explicit_area) {
+            uint8_t a;
+            if (!classify(t, td.slope_thr, a)) return;  // lib.rs:258-260
+            area = a;
+        }
+        bool ovf = false;
+        Poly bufA, bufB, in_row, cell, rest2;
+        Poly* p1 = &bufA;
+        Poly* rest = &bufB;
+        p1->n = 3;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            p1->v[k] = t.v0[k];
+            p1->v[3 + k] = t.v1[k];
+            p1->v[6 + k] = t.v2[k];
+        }
+        for (int z = z0; z <= z1; ++z) {  // rasterization.rs:300-363
+            const float cz_max = __fadd_rn(td.bmin[2], __fmul_rn((float)(z + 1), td.cs));
+            divide_poly(*p1, in_row, *rest, cz_max, 2, ovf);
+            Poly* sw = p1;
+            p1 = rest;
+            rest = sw;
+            if (in_row.n < 3 || z < 0) continue;
+            Poly* p2 = &in_row;
+            Poly* r2 = &rest2;
+            // in_row is consumed by the column loop; p2/r2 ping-pong between in_row and rest2
+            for (int x = x0; x <= x1; ++x) {
+                const float cx_max = __fadd_rn(td.bmin[0], __fmul_rn((float)(x + 1), td.cs));
+                divide_poly(*p2, cell, *r2, cx_max, 0, ovf);
+                Poly* s2 = p2;
+                p2 = r2;
+                r2 = s2;
+                if (cell.n < 3) continue;
+                float min_y = cell.v[1], max_y = cell.v[1];
+                for (int i = 1; i < cell.n; ++i) {
+                    min_y = fminf(min_y, cell.v[i * 3 + 1]);
+                    max_y = fmaxf(max_y, cell.v[i * 3 + 1]);
+                }
+                // rasterization.rs:346-350: floor/ceil, saturating `as i16`, clamp smin to 0
+                int smin = __float2int_rz(floorf(__fmul_rn(__fsub_rn(min_y, td.bmin[1]), td.ich)));
+                int smax = __float2int_rz(ceilf(__fmul_rn(__fsub_rn(max_y, td.bmin[1]), td.ich)));
+                smin = min(max(smin, -32768), 32767);
+                smax = min(max(smax, -32768), 32767);
+                smin = max(smin, 0);
+                emit_fragment(rb, td.cell_base + (uint32_t)z * td.width + x, tri, smin, smax, area);
+            }
+        }
+        if (ovf) atomicOr(&tinfo[tile].status, 1u);
+    });
+}
+
+// ---- pass 3: scatter fragments to their column segment --------------------------------------------
+__global__ void __launch_bounds__(256) k_scatter_fragments(const uint4* __restrict__ frag_tmp,
+                                                           const unsigned long long* __restrict__ nfrag_dev,
+                                                           const uint32_t* __restrict__ frag_off,
+                                                           uint32_t* __restrict__ fs_tri, uint32_t* __restrict__ fs_mm,
+                                                           uint8_t* __restrict__ fs_area) {
+    const unsigned long long n = *nfrag_dev;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint4 r = frag_tmp[i];
+        const uint32_t pos = frag_off[r.x] + (r.w & 0xffffffu);
+        fs_tri[pos] = r.y;
+        fs_mm[pos] = r.z;
+        fs_area[pos] = (uint8_t)(r.w >> 24);
+    }
+}
+
+// ---- pass 4: per-column ordered replay of add_span_internal ----------------------------------------
+// One thread per column.  The column's fragments occupy [frag_off[c], frag_off[c+1]) in arbitrary
+// order; they are sorted by triangle index in place, then replayed.  The span list is built in place
+// over the consumed prefix of the same segment (#spans <= #fragments consumed).
+__global__ void __launch_bounds__(256) k_replay_columns(uint32_t ncells, const uint32_t* __restrict__ frag_off,
+                                                        uint32_t* __restrict__ fs_tri, uint32_t* __restrict__ fs_mm,
+                                                        uint8_t* __restrict__ fs_area, uint32_t* __restrict__ span_cnt,
+                                                        int32_t thr) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const uint32_t b = frag_off[c], e = frag_off[c + 1];
+    const uint32_t n = e - b;
+    if (n == 0) {
+        span_cnt[c] = 0;
+        return;
+    }
+    uint32_t* tri = fs_tri + b;
+    uint32_t* mm = fs_mm + b;
+    uint8_t* ar = fs_area + b;
+    // insertion sort by triangle index (typical n: 2-4 on terrain, ~40 in the 16-floor interior)
+    for (uint32_t i = 1; i < n; ++i) {
+        const uint32_t kt = tri[i], km = mm[i];
+        const uint8_t ka = ar[i];
+        uint32_t j = i;
+        while (j > 0 && tri[j - 1] > kt) {
+            tri[j] = tri[j - 1];
+            mm[j] = mm[j - 1];
+            ar[j] = ar[j - 1];
+            --j;
+        }
+        tri[j] = kt;
+        mm[j] = km;
+        ar[j] = ka;
+    }
+    // replay (rasterization.rs:51-168) on the array form of the list
+    uint32_t ns = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t w = mm[i];
+        const int smin = (int16_t)(w & 0xffffu), smax = (int16_t)(w >> 16);
+        const uint32_t area = ar[i];
+        uint32_t p = 0;
+        bool done = false;
+        while (p < ns) {
+            const uint32_t cw = mm[p];
+            const int cmin = (int16_t)(cw & 0xffffu), cmax = (int16_t)(cw >> 16);
+            if (smax < cmin) break;  // insert before p
+            if (smin > cmax) {
+                ++p;
+                continue;
+            }
+            // merge into p
+            const int mmin = min(smin, cmin);
+            int mmax = max(smax, cmax);
+            uint32_t marea = area;
+            if (abs(mmax - cmax) <= thr) marea = max(marea, (uint32_t)ar[p]);
+            uint32_t q = p + 1;
+            while (q < ns) {
+                const uint32_t nw = mm[q];
+                if ((int)(int16_t)(nw & 0xffffu) > mmax) break;
+                mmax = max(mmax, (int)(int16_t)(nw >> 16));
+                ++q;
+            }
+            mm[p] = ((uint32_t)mmin & 0xffffu) | ((uint32_t)mmax << 16);
+            ar[p] = (uint8_t)marea;
+            if (q > p + 1) {  // drop absorbed spans (p, q)
+                const uint32_t drop = q - (p + 1);
+                for (uint32_t k = q; k < ns; ++k) {
+                    mm[k - drop] = mm[k];
+                    ar[k - drop] = ar[k];
+                }
+                ns -= drop;
+            }
+            done = true;
+            break;
+        }
+        if (!done) {  // insert at p (p == ns: append)
+            for (uint32_t k = ns; k > p; --k) {
+                mm[k] = mm[k - 1];
+                ar[k] = ar[k - 1];
+            }
+            mm[p] = w;
+            ar[p] = (uint8_t)area;
+            ++ns;
+        }
+    }
+    span_cnt[c] = ns;
+}
+
+// ---- pass 5: compact the per-column span prefixes into the final heightfield CSR -------------------
+__global__ void __launch_bounds__(256) k_gather_spans(uint32_t ncells, const uint32_t* __restrict__ frag_off,
+                                                      const uint32_t* __restrict__ fs_mm,
+                                                      const uint8_t* __restrict__ fs_area,
+                                                      const uint32_t* __restrict__ hf_off, int16_t* __restrict__ smin,
+                                                      int16_t* __restrict__ smax, uint8_t* __restrict__ sarea) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const uint32_t src = frag_off[c];
+    const uint32_t dst = hf_off[c], n = hf_off[c + 1] - dst;
+    for (uint32_t k = 0; k < n; ++k) {
+        const uint32_t w = fs_mm[src + k];
+        smin[dst + k] = (int16_t)(w & 0xffffu);
+        smax[dst + k] = (int16_t)(w >> 16);
+        sarea[dst + k] = fs_area[src + k];
+    }
+}
+
+}  // namespace
+
+void launch_count_fragments(const RasterBuffers& rb, cudaStream_t s) {
+    if (rb.mesh.ntris == 0) return;
+    k_count_fragments<<<(rb.mesh.ntris + 255) / 256, 256, 0, s>>>(rb);
+    g_rcb_launches++;
+}
+
+void launch_clip_emit(const RasterBuffers& rb, TileInfo* tinfo, cudaStream_t s) {
+    if (rb.mesh.ntris == 0) return;
+    k_clip_emit<<<(rb.mesh.ntris + 127) / 128, 128, 0, s>>>(rb, tinfo);
+    g_rcb_launches++;
+}
+
+void launch_scatter_fragments(const uint4* frag_tmp, const unsigned long long* nfrag_dev, uint32_t nfrag_hint,
+                              const uint32_t* frag_off, uint32_t* fs_tri, uint32_t* fs_mm, uint8_t* fs_area,
+                              cudaStream_t s) {
+    if (nfrag_hint == 0) return;
+    unsigned blocks = (unsigned)((nfrag_hint + 255ull) / 256ull);
+    if (blocks > 148u * 64u) blocks = 148u * 64u;
+    k_scatter_fragments<<<blocks, 256, 0, s>>>(frag_tmp, nfrag_dev, frag_off, fs_tri, fs_mm, fs_area);
+    g_rcb_launches++;
+}
+
+void launch_replay_columns(uint32_t ncells, const uint32_t* frag_off, uint32_t* fs_tri, uint32_t* fs_mm,
+                           uint8_t* fs_area, uint32_t* span_cnt, int32_t merge_thr, cudaStream_t s) {
+    if (ncells == 0) return;
+    k_replay_columns<<<(ncells + 255) / 256, 256, 0, s>>>(ncells, frag_off, fs_tri, fs_mm, fs_area, span_cnt, merge_thr);
+    g_rcb_launches++;
+}
+
+void launch_gather_spans(uint32_t ncells, const uint32_t* frag_off, const uint32_t* fs_mm, const uint8_t* fs_area,
+                         const uint32_t* hf_off, int16_t* smin, int16_t* smax, uint8_t* sarea, cudaStream_t s) {
+    if (ncells == 0) return;
+    k_gather_spans<<<(ncells + 255) / 256, 256, 0, s>>>(ncells, frag_off, fs_mm, fs_area, hf_off, smin, smax, sarea);
+    g_rcb_launches++;
+}

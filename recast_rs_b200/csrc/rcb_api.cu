@@ -1,0 +1,813 @@
+// rcb_api.cu — C ABI (include/recast_b200.h), context, device memory pools and the stage pipeline.
+//
+// Host-side counterpart of the reference's RecastBuilder (crates/recast/src/lib.rs:56-359):
+//   rcb_build_tiles      = for each tile: build_heightfield (lib.rs:116) [+ filters] + build_from_heightfield
+//                          (compact_heightfield.rs:175) [+ erode (area.rs:73)] + build_distance_field (:514)
+//   rcb_rasterize        = rasterization.rs:405 rasterize_triangles with explicit areas
+//   rcb_build_from_spans = the same stages starting from existing Heightfields
+// No CPU fallback exists in this file: every stage is a CUDA kernel launch.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rcb_common.cuh"
+
+// ---------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const {
+        return (T*)p;
+    }
+};
+
+struct Arena {
+    char* p = nullptr;
+    size_t cap = 0;
+};
+
+struct ArenaLayout {  // byte offsets inside arena A (cells + spans) and arena B (connections)
+    size_t tinfo, hf_cell_offset, cell_index, cell_count, span_min, span_max, span_area, areas, con, first_conn, dist;
+    size_t bytesA;
+    size_t conn_ref, conn_dir, conn_next;
+    size_t bytesB;
+};
+
+struct rcb_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    unsigned long long launches0 = 0;
+    // mesh
+    DevBuf d_verts, d_tris, d_tri_areas;
+    const float* verts = nullptr;
+    const int32_t* tris = nullptr;
+    size_t nfloats = 0, nidx = 0;
+    // per batch
+    DevBuf d_tiles, d_bin_off, d_bin_tiles;
+    // scratch
+    DevBuf d_counters, d_cell_cnt, d_frag_off, d_frag_tmp, d_fs_tri, d_fs_mm, d_fs_area, d_scan_tmp, d_hf_off, d_conn_cnt,
+        d_conn_off, d_nei16, d_t16a, d_t16b, d_t16c, d_t8a, d_t8b;
+    // pinned staging
+    char* h_stage = nullptr;
+    size_t h_stage_cap = 0;
+    unsigned long long* h_counters = nullptr;  // pinned, 8 entries
+    // pools
+    std::vector<Arena> free_dev, free_host;
+};
+
+struct rcb_result {
+    rcb_ctx* ctx = nullptr;
+    int ntiles = 0;
+    uint32_t stage_mask = 0;
+    std::vector<TileDesc> tiles;
+    uint64_t Ctot = 0, S = 0, K = 0, F = 0, ntris = 0, nverts = 0;
+    bool have_K = false;
+    ArenaLayout lay{};
+    Arena devA, devB, hostA, hostB;
+    bool downloaded = false, have_tinfo = false;
+    std::vector<TileInfo> tinfo;
+};
+
+namespace {
+
+int fail(rcb_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess)                                                                             \
+            return fail(ctx, RCB_ECUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, __LINE__, #expr); \
+    } while (0)
+
+size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+cudaError_t pool_get(std::vector<Arena>& pool, size_t bytes, bool host, Arena& out) {
+    int best = -1;
+    for (size_t i = 0; i < pool.size(); ++i)
+        if (pool[i].cap >= bytes && pool[i].cap <= 2 * bytes + (1u << 20) && (best < 0 || pool[i].cap < pool[best].cap))
+            best = (int)i;
+    if (best >= 0) {
+        out = pool[best];
+        pool.erase(pool.begin() + best);
+        return cudaSuccess;
+    }
+    out.cap = align_up(bytes + bytes / 8 + 256);
+    cudaError_t e = host ? cudaMallocHost((void**)&out.p, out.cap) : cudaMalloc((void**)&out.p, out.cap);
+    if (e != cudaSuccess) {
+        // drop the pool and retry with the exact size
+        for (auto& a : pool) host ? cudaFreeHost(a.p) : cudaFree(a.p);
+        pool.clear();
+        out.cap = align_up(bytes + 256);
+        e = host ? cudaMallocHost((void**)&out.p, out.cap) : cudaMalloc((void**)&out.p, out.cap);
+    }
+    if (e != cudaSuccess) out = Arena{};
+    return e;
+}
+
+void pool_put(std::vector<Arena>& pool, Arena& a, bool host) {
+    if (!a.p) return;
+    if (pool.size() >= 8) {  // bound the pool: release the smallest
+        size_t m = 0;
+        for (size_t i = 1; i < pool.size(); ++i)
+            if (pool[i].cap < pool[m].cap) m = i;
+        host ? cudaFreeHost(pool[m].p) : cudaFree(pool[m].p);
+        pool.erase(pool.begin() + m);
+    }
+    pool.push_back(a);
+    a = Arena{};
+}
+
+int stage_upload(rcb_ctx* ctx, DevBuf& dst, const void* src, size_t bytes, size_t& stage_off) {
+    if (bytes == 0) return RCB_OK;
+    CU(dst.ensure(bytes));
+    memcpy(ctx->h_stage + stage_off, src, bytes);
+    CU(cudaMemcpyAsync(dst.p, ctx->h_stage + stage_off, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    stage_off += align_up(bytes);
+    return RCB_OK;
+}
+
+int ensure_stage(rcb_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->h_stage_cap) return RCB_OK;
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    ctx->h_stage = nullptr;
+    ctx->h_stage_cap = 0;
+    CU(cudaMallocHost((void**)&ctx->h_stage, bytes + bytes / 2));
+    ctx->h_stage_cap = bytes + bytes / 2;
+    return RCB_OK;
+}
+
+// `as i16` of an i32 config value (lib.rs:278-287): wraps
+inline int32_t as_i16(int32_t v) { return (int32_t)(int16_t)(uint16_t)(uint32_t)v; }
+
+struct HostLocator {
+    Locator loc{};
+    std::vector<uint32_t> bin_off, bin_tiles;
+};
+
+void build_locator(std::vector<TileDesc>& tiles, HostLocator& L) {
+    const int n = (int)tiles.size();
+    float gx0 = INFINITY, gz0 = INFINITY, gx1 = -INFINITY, gz1 = -INFINITY, bsx = 0, bsz = 0;
+    for (auto& t : tiles) {
+        gx0 = fminf(gx0, t.bmin[0]);
+        gz0 = fminf(gz0, t.bmin[2]);
+        gx1 = fmaxf(gx1, t.bmax[0]);
+        gz1 = fmaxf(gz1, t.bmax[2]);
+        bsx = fmaxf(bsx, t.bmax[0] - t.bmin[0]);
+        bsz = fmaxf(bsz, t.bmax[2] - t.bmin[2]);
+    }
+    if (!(bsx > 0) || !std::isfinite(bsx)) bsx = 1.0f;
+    if (!(bsz > 0) || !std::isfinite(bsz)) bsz = 1.0f;
+    if (!std::isfinite(gx0)) gx0 = 0;
+    if (!std::isfinite(gz0)) gz0 = 0;
+    double ex = (double)gx1 - gx0, ez = (double)gz1 - gz0;
+    if (!std::isfinite(ex) || ex < 0) ex = 0;
+    if (!std::isfinite(ez) || ez < 0) ez = 0;
+    int nbx = (int)fmin(1024.0, floor(ex / bsx) + 1.0), nbz = (int)fmin(1024.0, floor(ez / bsz) + 1.0);
+    if (nbx < 1) nbx = 1;
+    if (nbz < 1) nbz = 1;
+    // if the cap was hit, enlarge the bins so the grid still spans the extent
+    if ((double)nbx * bsx < ex) bsx = (float)(ex / nbx) * 1.0001f;
+    if ((double)nbz * bsz < ez) bsz = (float)(ez / nbz) * 1.0001f;
+    L.loc.gx0 = gx0;
+    L.loc.gz0 = gz0;
+    L.loc.inv_bx = 1.0f / bsx;
+    L.loc.inv_bz = 1.0f / bsz;
+    L.loc.nbx = nbx;
+    L.loc.nbz = nbz;
+    std::vector<uint32_t> cnt((size_t)nbx * nbz + 1, 0);
+    std::vector<int> r(4 * (size_t)n);
+    for (int i = 0; i < n; ++i) {
+        TileDesc& t = tiles[i];
+        int x0 = rcb_bin_coord(t.bmin[0], gx0, L.loc.inv_bx, nbx), x1 = rcb_bin_coord(t.bmax[0], gx0, L.loc.inv_bx, nbx);
+        int z0 = rcb_bin_coord(t.bmin[2], gz0, L.loc.inv_bz, nbz), z1 = rcb_bin_coord(t.bmax[2], gz0, L.loc.inv_bz, nbz);
+        t.bin_x0 = x0;
+        t.bin_z0 = z0;
+        r[4 * i] = x0, r[4 * i + 1] = x1, r[4 * i + 2] = z0, r[4 * i + 3] = z1;
+        for (int z = z0; z <= z1; ++z)
+            for (int x = x0; x <= x1; ++x) cnt[(size_t)z * nbx + x + 1]++;
+    }
+    for (size_t i = 1; i < cnt.size(); ++i) cnt[i] += cnt[i - 1];
+    L.bin_off = cnt;
+    L.bin_tiles.assign(cnt.back(), 0);
+    std::vector<uint32_t> cur(cnt.begin(), cnt.end() - 1);
+    for (int i = 0; i < n; ++i)
+        for (int z = r[4 * i + 2]; z <= r[4 * i + 3]; ++z)
+            for (int x = r[4 * i]; x <= r[4 * i + 1]; ++x) L.bin_tiles[cur[(size_t)z * nbx + x]++] = (uint32_t)i;
+}
+
+void make_layout(ArenaLayout& l, int ntiles, uint64_t C, uint64_t S, uint32_t stage_mask) {
+    size_t o = 0;
+    auto put = [&o](size_t bytes) {
+        size_t r = o;
+        o = align_up(o + bytes);
+        return r;
+    };
+    const bool compact = stage_mask & RCB_STAGE_COMPACT;
+    l.tinfo = put(sizeof(TileInfo) * (size_t)ntiles);
+    l.hf_cell_offset = put(4 * (C + ntiles));
+    l.span_min = put(2 * S);
+    l.span_max = put(2 * S);
+    l.span_area = put(S);
+    l.cell_index = put(compact ? 4 * C : 0);
+    l.cell_count = put(compact ? 4 * C : 0);
+    l.areas = put(compact ? S : 0);
+    l.con = put(compact ? 8 * S : 0);
+    l.first_conn = put(compact ? 4 * S : 0);
+    l.dist = put(compact ? 2 * S : 0);
+    l.bytesA = o;
+}
+void make_layout_conn(ArenaLayout& l, uint64_t K) {
+    size_t o = 0;
+    auto put = [&o](size_t bytes) {
+        size_t r = o;
+        o = align_up(o + bytes);
+        return r;
+    };
+    l.conn_ref = put(4 * K);
+    l.conn_next = put(4 * K);
+    l.conn_dir = put(K);
+    l.bytesB = o;
+}
+
+struct Source {  // where the heightfield comes from
+    bool raster = false;
+    const uint8_t* tri_areas = nullptr;  // host, explicit areas (rcb_rasterize)
+    int32_t merge_thr = 1;
+    const uint32_t* cell_offset = nullptr;  // host CSR (rcb_build_from_spans)
+    const int16_t* smin = nullptr;
+    const int16_t* smax = nullptr;
+    const uint8_t* sarea = nullptr;
+    const uint8_t* areas_override = nullptr;  // host, optional
+};
+
+int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stage_mask, int erode_radius,
+                 const Source& src, rcb_result** out) {
+    if (!ctx || !out || (ntiles > 0 && !cfgs) || ntiles < 0) return fail(ctx, RCB_EARG, "null argument");
+    *out = nullptr;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if ((stage_mask & (RCB_STAGE_ERODE | RCB_STAGE_DIST)) && !(stage_mask & RCB_STAGE_COMPACT))
+        return fail(ctx, RCB_EARG, "ERODE/DIST need RCB_STAGE_COMPACT");
+    uint32_t fmask = 0;
+    if (stage_mask & RCB_STAGE_FILTER) fmask = 7;
+    if (stage_mask & RCB_FILTER_LOW_HANGING) fmask |= 1;
+    if (stage_mask & RCB_FILTER_LEDGE) fmask |= 2;
+    if (stage_mask & RCB_FILTER_LOW_HEIGHT) fmask |= 4;
+
+    // ---- configs -> tile descriptors ---------------------------------------------------------------
+    auto* res = new rcb_result();
+    res->ctx = ctx;
+    res->ntiles = ntiles;
+    res->stage_mask = stage_mask;
+    res->tiles.resize(ntiles);
+    uint64_t Ctot = 0;
+    uint32_t max_cells = 0;
+    for (int i = 0; i < ntiles; ++i) {
+        const rcb_config& c = cfgs[i];
+        const int v = rcb_config_validate(&c);  // lib.rs:74 / config.rs:110-136
+        if (v != RCB_OK) {
+            delete res;
+            return fail(ctx, v, "tile %d: invalid configuration (width/height <= 0, cs/ch <= 0, slope outside [0,90] or max_verts < 3)", i);
+        }
+        TileDesc& t = res->tiles[i];
+        t.width = c.width;
+        t.height = c.height;
+        for (int k = 0; k < 3; ++k) t.bmin[k] = c.bmin[k], t.bmax[k] = c.bmax[k];
+        t.cs = c.cs;
+        t.ch = c.ch;
+        t.ics = 1.0f / c.cs;
+        t.ich = 1.0f / c.ch;
+        t.slope_thr = cosf(c.walkable_slope_angle * 3.14159265358979323846f / 180.0f);  // lib.rs:212-213
+        t.walkable_height = as_i16(c.walkable_height);
+        t.walkable_climb = as_i16(c.walkable_climb);
+        t.neg_climb = (int32_t)(int16_t)(-(int16_t)t.walkable_climb);
+        const uint64_t cells = (uint64_t)c.width * (uint64_t)c.height;
+        if (cells > 0x7fffffffull || Ctot + cells + ntiles >= 0xffffffffull) {
+            delete res;
+            return fail(ctx, RCB_EARG, "batch too large: more than 2^32 cells");
+        }
+        t.cell_base = (uint32_t)Ctot;
+        Ctot += cells;
+        if (cells > max_cells) max_cells = (uint32_t)cells;
+    }
+    res->Ctot = Ctot;
+    TileMap tm{(uint32_t)ntiles, (max_cells + 255) / 256, 0};
+    tm.nblocks = tm.blocks_per_tile * tm.ntiles;
+
+    auto bail = [&](int code) {
+        rcb_result_free(res);
+        return code;
+    };
+
+    // ---- mesh checks (lib.rs:195-209) ----------------------------------------------------------------
+    bool do_raster = src.raster;
+    size_t ntris = 0, nverts = 0;
+    if (src.raster) {
+        if (ctx->nfloats == 0 || ctx->nidx == 0) {
+            do_raster = false;  // Ok(()) with untouched heightfields
+        } else {
+            if (ctx->nfloats % 3 != 0) return bail(fail(ctx, RCB_ENAVMESH_GEN, "Vertex array length must be a multiple of 3"));
+            if (ctx->nidx % 3 != 0) return bail(fail(ctx, RCB_ENAVMESH_GEN, "Index array length must be a multiple of 3"));
+            ntris = ctx->nidx / 3;
+            nverts = ctx->nfloats / 3;
+            if (ntris > 0xffffffffull / 3 || nverts > 0x7fffffffull) return bail(fail(ctx, RCB_EARG, "mesh too large"));
+        }
+    }
+    res->ntris = ntris;
+    res->nverts = nverts;
+
+    // ---- upload per-batch tables --------------------------------------------------------------------
+    HostLocator L;
+    if (do_raster) build_locator(res->tiles, L);
+    {
+        const size_t need = align_up(sizeof(TileDesc) * (size_t)ntiles) + align_up(4 * L.bin_off.size()) +
+                            align_up(4 * L.bin_tiles.size()) + align_up(ntris) + 1024;
+        int r = ensure_stage(ctx, need);
+        if (r) return bail(r);
+        size_t so = 0;
+        if ((r = stage_upload(ctx, ctx->d_tiles, res->tiles.data(), sizeof(TileDesc) * (size_t)ntiles, so))) return bail(r);
+        if (do_raster) {
+            if ((r = stage_upload(ctx, ctx->d_bin_off, L.bin_off.data(), 4 * L.bin_off.size(), so))) return bail(r);
+            if ((r = stage_upload(ctx, ctx->d_bin_tiles, L.bin_tiles.data(), 4 * L.bin_tiles.size(), so))) return bail(r);
+            if (src.tri_areas && (r = stage_upload(ctx, ctx->d_tri_areas, src.tri_areas, ntris, so))) return bail(r);
+        }
+    }
+    const TileDesc* d_tiles = ctx->d_tiles.as<TileDesc>();
+
+#define CUB(expr)                                                                                            \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess)                                                                               \
+            return bail(fail(ctx, RCB_ECUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, __LINE__, #expr)); \
+    } while (0)
+
+    CUB(ctx->d_hf_off.ensure(4 * (Ctot + 1)));
+    CUB(ctx->d_scan_tmp.ensure(4 * scan_tmp_elems(Ctot + 1)));
+    uint32_t* d_hf_off = ctx->d_hf_off.as<uint32_t>();
+    uint64_t S = 0, F = 0;
+
+    if (src.raster) {
+        // ---- RASTER: count -> clip/emit -> scan -> scatter -> replay -> scan -------------------------
+        CUB(ctx->d_counters.ensure(8 * sizeof(unsigned long long)));
+        CUB(ctx->d_cell_cnt.ensure(4 * (Ctot + 1)));
+        CUB(ctx->d_frag_off.ensure(4 * (Ctot + 1)));
+        CUB(cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(unsigned long long), st));
+        CUB(cudaMemsetAsync(ctx->d_cell_cnt.p, 0, 4 * (Ctot + 1), st));
+        // tile info lives in the arena, which is sized after the span count is known: keep the clip
+        // status in scratch until then
+        CUB(ctx->d_t16a.ensure(sizeof(TileInfo) * (size_t)ntiles + 256));
+        TileInfo* d_tinfo_tmp = ctx->d_t16a.as<TileInfo>();
+        CUB(cudaMemsetAsync(d_tinfo_tmp, 0, sizeof(TileInfo) * (size_t)ntiles, st));
+
+        RasterBuffers rb{};
+        rb.tiles = d_tiles;
+        rb.ntiles = ntiles;
+        rb.loc = L.loc;
+        rb.loc.bin_off = ctx->d_bin_off.as<uint32_t>();
+        rb.loc.bin_tiles = ctx->d_bin_tiles.as<uint32_t>();
+        rb.mesh.verts = ctx->verts;
+        rb.mesh.tris = ctx->tris;
+        rb.mesh.ntris = (uint32_t)ntris;
+        rb.mesh.nverts = (uint32_t)nverts;
+        rb.mesh.tri_areas = src.tri_areas ? ctx->d_tri_areas.as<uint8_t>() : nullptr;
+        rb.mesh.merge_thr = src.merge_thr;
+        rb.counters = ctx->d_counters.as<unsigned long long>();
+        rb.cell_cnt = ctx->d_cell_cnt.as<uint32_t>();
+        uint64_t ub = 0;
+        if (do_raster && ntiles > 0) {
+            launch_count_fragments(rb, st);
+            CUB(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CUB(cudaStreamSynchronize(st));
+            if (ctx->h_counters[3]) return bail(fail(ctx, RCB_ENAVMESH_GEN, "Triangle index out of bounds (max: %zu)", nverts - 1));
+            ub = ctx->h_counters[0];
+            if (ub >= 0xfffffff0ull) return bail(fail(ctx, RCB_EARG, "batch too large: fragment bound %llu", (unsigned long long)ub));
+        }
+        if (ub > 0) {
+            CUB(ctx->d_frag_tmp.ensure(16 * ub));
+            CUB(ctx->d_fs_tri.ensure(4 * ub));
+            CUB(ctx->d_fs_mm.ensure(4 * ub));
+            CUB(ctx->d_fs_area.ensure(ub));
+            rb.frag_tmp = ctx->d_frag_tmp.as<uint4>();
+            rb.frag_cap = (uint32_t)ub;
+            launch_clip_emit(rb, d_tinfo_tmp, st);
+        }
+        uint32_t* d_frag_off = ctx->d_frag_off.as<uint32_t>();
+        launch_exclusive_scan(rb.cell_cnt, d_frag_off, Ctot, ctx->d_scan_tmp.as<uint32_t>(), st);
+        if (ub > 0) {
+            launch_scatter_fragments(rb.frag_tmp, rb.counters + 1, (uint32_t)ub, d_frag_off, ctx->d_fs_tri.as<uint32_t>(),
+                                     ctx->d_fs_mm.as<uint32_t>(), ctx->d_fs_area.as<uint8_t>(), st);
+            launch_replay_columns((uint32_t)Ctot, d_frag_off, ctx->d_fs_tri.as<uint32_t>(), ctx->d_fs_mm.as<uint32_t>(),
+                                  ctx->d_fs_area.as<uint8_t>(), rb.cell_cnt, src.merge_thr, st);
+        }
+        launch_exclusive_scan(rb.cell_cnt, d_hf_off, Ctot, ctx->d_scan_tmp.as<uint32_t>(), st);
+        CUB(cudaMemcpyAsync(&ctx->h_counters[4], d_hf_off + Ctot, 4, cudaMemcpyDeviceToHost, st));
+        CUB(cudaMemcpyAsync(&ctx->h_counters[5], ctx->d_counters.as<unsigned long long>() + 1, 8, cudaMemcpyDeviceToHost, st));
+        CUB(cudaMemcpyAsync(&ctx->h_counters[6], ctx->d_counters.as<unsigned long long>() + 2, 8, cudaMemcpyDeviceToHost, st));
+        CUB(cudaStreamSynchronize(st));
+        S = (uint32_t)ctx->h_counters[4];
+        F = ctx->h_counters[5];
+        if (ctx->h_counters[6] & 2ull) return bail(fail(ctx, RCB_EOVERFLOW, "fragment pool overflow"));
+        res->F = F;
+        res->S = S;
+        make_layout(res->lay, ntiles, Ctot, S, stage_mask);
+        CUB(pool_get(ctx->free_dev, res->lay.bytesA, false, res->devA));
+        char* A = res->devA.p;
+        CUB(cudaMemcpyAsync(A + res->lay.tinfo, d_tinfo_tmp, sizeof(TileInfo) * (size_t)ntiles, cudaMemcpyDeviceToDevice, st));
+        if (S > 0)
+            launch_gather_spans((uint32_t)Ctot, d_frag_off, ctx->d_fs_mm.as<uint32_t>(), ctx->d_fs_area.as<uint8_t>(), d_hf_off,
+                                (int16_t*)(A + res->lay.span_min), (int16_t*)(A + res->lay.span_max),
+                                (uint8_t*)(A + res->lay.span_area), st);
+    } else {
+        // ---- existing heightfields (host CSR) -------------------------------------------------------------
+        std::vector<uint32_t> goff(Ctot + 1);
+        uint64_t sbase = 0, pos = 0;
+        for (int i = 0; i < ntiles; ++i) {
+            const uint64_t C = (uint64_t)res->tiles[i].width * res->tiles[i].height;
+            const uint32_t* co = src.cell_offset + pos;
+            for (uint64_t c = 0; c < C; ++c) {
+                if (co[c + 1] < co[c]) return bail(fail(ctx, RCB_EARG, "tile %d: cell_offset not ascending", i));
+                goff[res->tiles[i].cell_base + c] = (uint32_t)(sbase + co[c]);
+            }
+            if (co[0] != 0) return bail(fail(ctx, RCB_EARG, "tile %d: cell_offset[0] != 0", i));
+            sbase += co[C];
+            pos += C + 1;
+            if (sbase >= 0xffffffffull) return bail(fail(ctx, RCB_EARG, "too many spans"));
+        }
+        goff[Ctot] = (uint32_t)sbase;
+        S = sbase;
+        res->S = S;
+        make_layout(res->lay, ntiles, Ctot, S, stage_mask);
+        CUB(pool_get(ctx->free_dev, res->lay.bytesA, false, res->devA));
+        char* A = res->devA.p;
+        CUB(cudaMemsetAsync(A + res->lay.tinfo, 0, sizeof(TileInfo) * (size_t)ntiles, st));
+        CUB(cudaMemcpyAsync(d_hf_off, goff.data(), 4 * (Ctot + 1), cudaMemcpyHostToDevice, st));
+        if (S > 0) {
+            CUB(cudaMemcpyAsync(A + res->lay.span_min, src.smin, 2 * S, cudaMemcpyHostToDevice, st));
+            CUB(cudaMemcpyAsync(A + res->lay.span_max, src.smax, 2 * S, cudaMemcpyHostToDevice, st));
+            CUB(cudaMemcpyAsync(A + res->lay.span_area, src.sarea, S, cudaMemcpyHostToDevice, st));
+        }
+        CUB(cudaStreamSynchronize(st));  // goff is a stack-owned pageable buffer
+    }
+
+    char* A = res->devA.p;
+    TileInfo* d_tinfo = (TileInfo*)(A + res->lay.tinfo);
+    int16_t* d_smin = (int16_t*)(A + res->lay.span_min);
+    int16_t* d_smax = (int16_t*)(A + res->lay.span_max);
+    uint8_t* d_sarea = (uint8_t*)(A + res->lay.span_area);
+
+    // ---- FILTER ------------------------------------------------------------------------------------------
+    if (fmask && S > 0) launch_filter_spans(d_tiles, tm, d_hf_off, d_smin, d_smax, d_sarea, fmask, st);
+
+    // ---- cells / offsets ---------------------------------------------------------------------------------
+    const bool compact = stage_mask & RCB_STAGE_COMPACT;
+    launch_tile_bases(d_tiles, ntiles, d_hf_off, nullptr, d_tinfo, st);
+    launch_cells_and_offsets(d_tiles, tm, d_hf_off, (uint32_t*)(A + res->lay.hf_cell_offset),
+                             compact ? (uint32_t*)(A + res->lay.cell_index) : nullptr,
+                             compact ? (uint32_t*)(A + res->lay.cell_count) : nullptr, d_tinfo, ntiles, st);
+
+    // ---- COMPACT: link, connection list ----------------------------------------------------------------------
+    if (compact) {
+        CUB(ctx->d_conn_cnt.ensure(4 * (Ctot + 1)));
+        CUB(ctx->d_conn_off.ensure(4 * (Ctot + 1)));
+        CUB(ctx->d_nei16.ensure(16 * S + 256));
+        uint32_t* d_conn_cnt = ctx->d_conn_cnt.as<uint32_t>();
+        uint32_t* d_conn_off = ctx->d_conn_off.as<uint32_t>();
+        uint16_t* d_nei16 = ctx->d_nei16.as<uint16_t>();
+        uint8_t* d_areas = (uint8_t*)(A + res->lay.areas);
+        launch_link_spans(d_tiles, tm, d_hf_off, d_smin, d_smax, d_sarea, d_areas, d_nei16, S, (uint16_t*)(A + res->lay.con),
+                          d_conn_cnt, d_tinfo, st);
+        launch_exclusive_scan(d_conn_cnt, d_conn_off, Ctot, ctx->d_scan_tmp.as<uint32_t>(), st);
+        CUB(cudaMemcpyAsync(&ctx->h_counters[4], d_conn_off + Ctot, 4, cudaMemcpyDeviceToHost, st));
+        CUB(cudaStreamSynchronize(st));
+        const uint64_t K = (uint32_t)ctx->h_counters[4];
+        res->K = K;
+        res->have_K = true;
+        make_layout_conn(res->lay, K);
+        CUB(pool_get(ctx->free_dev, res->lay.bytesB, false, res->devB));
+        char* B = res->devB.p;
+        launch_tile_bases(d_tiles, ntiles, nullptr, d_conn_off, d_tinfo, st);
+        if (S > 0)
+            launch_write_connections(d_tiles, tm, d_hf_off, d_nei16, S, d_conn_off, d_tinfo, (uint32_t*)(A + res->lay.first_conn),
+                                     (uint32_t*)(B + res->lay.conn_ref), (uint8_t*)(B + res->lay.conn_dir),
+                                     (uint32_t*)(B + res->lay.conn_next), st);
+        CUB(cudaMemsetAsync(A + res->lay.dist, 0, 2 * S, st));  // compact_heightfield.rs:253
+        if (src.areas_override && S > 0) {
+            CUB(cudaMemcpyAsync(d_areas, src.areas_override, S, cudaMemcpyHostToDevice, st));
+            CUB(cudaStreamSynchronize(st));
+        }
+        if ((stage_mask & RCB_STAGE_ERODE) && S > 0) {
+            CUB(ctx->d_t8a.ensure(S));
+            CUB(ctx->d_t8b.ensure(S));
+            launch_erode(d_tiles, ntiles, tm, d_hf_off, d_nei16, S, d_areas, ctx->d_t8a.as<uint8_t>(), ctx->d_t8b.as<uint8_t>(),
+                         erode_radius, st);
+        }
+        if ((stage_mask & RCB_STAGE_DIST) && S > 0) {
+            CUB(ctx->d_t16a.ensure(2 * S));
+            CUB(ctx->d_t16b.ensure(2 * S));
+            CUB(ctx->d_t16c.ensure(2 * S));
+            launch_distance_field(d_tiles, ntiles, tm, d_hf_off, d_nei16, S, d_areas, ctx->d_t16a.as<uint16_t>(),
+                                  ctx->d_t16b.as<uint16_t>(), ctx->d_t16c.as<uint16_t>(), (uint16_t*)(A + res->lay.dist), d_tinfo,
+                                  st);
+        }
+    }
+    CUB(cudaGetLastError());
+    *out = res;
+    return RCB_OK;
+#undef CUB
+}
+
+int fetch_tinfo(rcb_result* res) {
+    rcb_ctx* ctx = res->ctx;
+    if (res->have_tinfo) return RCB_OK;
+    res->tinfo.resize(res->ntiles);
+    if (res->ntiles > 0) {
+        CU(cudaMemcpyAsync(res->tinfo.data(), res->devA.p + res->lay.tinfo, sizeof(TileInfo) * (size_t)res->ntiles,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    res->have_tinfo = true;
+    return RCB_OK;
+}
+
+}  // namespace
+
+// ===================================================================================================
+extern "C" {
+
+int rcb_create(int device, rcb_ctx** out) {
+    if (!out) return RCB_EARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return RCB_ECUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return RCB_ECUDA;
+    auto* ctx = new rcb_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(unsigned long long)) != cudaSuccess) {
+        delete ctx;
+        return RCB_ECUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    ctx->launches0 = g_rcb_launches;
+    *out = ctx;
+    return RCB_OK;
+}
+
+void rcb_destroy(rcb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    DevBuf* bufs[] = {&ctx->d_verts, &ctx->d_tris, &ctx->d_tri_areas, &ctx->d_tiles, &ctx->d_bin_off, &ctx->d_bin_tiles,
+                      &ctx->d_counters, &ctx->d_cell_cnt, &ctx->d_frag_off, &ctx->d_frag_tmp, &ctx->d_fs_tri, &ctx->d_fs_mm,
+                      &ctx->d_fs_area, &ctx->d_scan_tmp, &ctx->d_hf_off, &ctx->d_conn_cnt, &ctx->d_conn_off, &ctx->d_nei16,
+                      &ctx->d_t16a, &ctx->d_t16b, &ctx->d_t16c, &ctx->d_t8a, &ctx->d_t8b};
+    for (auto* b : bufs) b->release();
+    for (auto& a : ctx->free_dev) cudaFree(a.p);
+    for (auto& a : ctx->free_host) cudaFreeHost(a.p);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* rcb_last_error(const rcb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int rcb_set_stream(rcb_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return RCB_EARG;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return RCB_OK;
+}
+
+uint64_t rcb_launch_count(const rcb_ctx* ctx) { return ctx ? g_rcb_launches - ctx->launches0 : 0; }
+
+// config.rs:53-76
+void rcb_config_default(rcb_config* c) {
+    memset(c, 0, sizeof *c);
+    c->cs = 0.3f;
+    c->ch = 0.2f;
+    c->walkable_slope_angle = 45.0f;
+    c->walkable_height = 2;
+    c->walkable_climb = 1;
+    c->walkable_radius = 1;
+    c->max_edge_len = 12;
+    c->max_simplification_error = 1.3f;
+    c->min_region_area = 8;
+    c->merge_region_area = 20;
+    c->max_vertices_per_polygon = 6;
+    c->detail_sample_dist = 6.0f;
+    c->detail_sample_max_error = 1.0f;
+    c->border_size = 0;
+}
+
+static int32_t rust_f32_as_i32(float v) {
+    if (v != v) return 0;
+    if (v >= 2147483648.0f) return INT32_MAX;
+    if (v <= -2147483648.0f) return INT32_MIN;
+    return (int32_t)v;
+}
+
+// config.rs:85-107: fract()==0 -> trunc+1 else ceil
+void rcb_config_calculate_grid_size(rcb_config* c, const float bmin[3], const float bmax[3]) {
+    for (int i = 0; i < 3; ++i) c->bmin[i] = bmin[i], c->bmax[i] = bmax[i];
+    const float wf = (bmax[0] - bmin[0]) / c->cs;
+    const float hf = (bmax[2] - bmin[2]) / c->cs;
+    c->width = (wf - truncf(wf) == 0.0f) ? rust_f32_as_i32(wf) + 1 : rust_f32_as_i32(ceilf(wf));
+    c->height = (hf - truncf(hf) == 0.0f) ? rust_f32_as_i32(hf) + 1 : rust_f32_as_i32(ceilf(hf));
+}
+
+// config.rs:110-136
+int rcb_config_validate(const rcb_config* c) {
+    if (!c) return RCB_EARG;
+    if (c->width <= 0 || c->height <= 0) return RCB_EINVALID_MESH;
+    if (c->cs <= 0.0f || c->ch <= 0.0f) return RCB_EINVALID_MESH;
+    if (c->walkable_slope_angle < 0.0f || c->walkable_slope_angle > 90.0f) return RCB_EINVALID_MESH;
+    if (c->max_vertices_per_polygon < 3) return RCB_EINVALID_MESH;
+    return RCB_OK;
+}
+
+int rcb_upload_mesh(rcb_ctx* ctx, const float* verts, size_t nfloats, const int32_t* tris, size_t nidx) {
+    if (!ctx || (nfloats && !verts) || (nidx && !tris)) return fail(ctx, RCB_EARG, "null mesh pointer");
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->d_verts.ensure(4 * nfloats + 16));
+    CU(ctx->d_tris.ensure(4 * nidx + 16));
+    if (nfloats) CU(cudaMemcpyAsync(ctx->d_verts.p, verts, 4 * nfloats, cudaMemcpyHostToDevice, ctx->stream));
+    if (nidx) CU(cudaMemcpyAsync(ctx->d_tris.p, tris, 4 * nidx, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // the caller's buffers are only borrowed for this call
+    ctx->verts = ctx->d_verts.as<float>();
+    ctx->tris = ctx->d_tris.as<int32_t>();
+    ctx->nfloats = nfloats;
+    ctx->nidx = nidx;
+    return RCB_OK;
+}
+
+int rcb_set_mesh_device(rcb_ctx* ctx, const void* d_verts, size_t nfloats, const void* d_tris, size_t nidx) {
+    if (!ctx || (nfloats && !d_verts) || (nidx && !d_tris)) return fail(ctx, RCB_EARG, "null mesh pointer");
+    ctx->verts = (const float*)d_verts;
+    ctx->tris = (const int32_t*)d_tris;
+    ctx->nfloats = nfloats;
+    ctx->nidx = nidx;
+    return RCB_OK;
+}
+
+int rcb_build_tiles(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stage_mask, int erode_radius,
+                    rcb_result** out) {
+    if (!(stage_mask & RCB_STAGE_RASTER)) return fail(ctx, RCB_EARG, "rcb_build_tiles needs RCB_STAGE_RASTER");
+    Source s;
+    s.raster = true;
+    s.merge_thr = 1;  // lib.rs:273
+    return run_pipeline(ctx, cfgs, ntiles, stage_mask, erode_radius, s, out);
+}
+
+int rcb_rasterize(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const uint8_t* tri_areas, int32_t flag_merge_threshold,
+                  uint32_t stage_mask, int erode_radius, rcb_result** out) {
+    if (!tri_areas && ctx && ctx->nidx) return fail(ctx, RCB_EARG, "tri_areas is null");
+    Source s;
+    s.raster = true;
+    s.tri_areas = tri_areas;
+    s.merge_thr = flag_merge_threshold;
+    return run_pipeline(ctx, cfgs, ntiles, stage_mask | RCB_STAGE_RASTER, erode_radius, s, out);
+}
+
+int rcb_build_from_spans(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const uint32_t* cell_offset, const int16_t* span_min,
+                         const int16_t* span_max, const uint8_t* span_area, const uint8_t* areas_override, uint32_t stage_mask,
+                         int erode_radius, rcb_result** out) {
+    if (stage_mask & RCB_STAGE_RASTER) return fail(ctx, RCB_EARG, "rcb_build_from_spans: RCB_STAGE_RASTER must not be set");
+    if (ntiles > 0 && !cell_offset) return fail(ctx, RCB_EARG, "cell_offset is null");
+    Source s;
+    s.cell_offset = cell_offset;
+    s.smin = span_min;
+    s.smax = span_max;
+    s.sarea = span_area;
+    s.areas_override = areas_override;
+    return run_pipeline(ctx, cfgs, ntiles, stage_mask, erode_radius, s, out);
+}
+
+int rcb_result_totals(const rcb_result* cres, rcb_totals* out) {
+    auto* res = const_cast<rcb_result*>(cres);
+    if (!res || !out) return RCB_EARG;
+    int r = fetch_tinfo(res);
+    if (r) return r;
+    memset(out, 0, sizeof *out);
+    out->tiles = res->ntiles;
+    out->triangles = res->ntris;
+    out->vertices = res->nverts;
+    out->cells = res->Ctot;
+    out->fragments = res->F;
+    out->spans = res->S;
+    out->connections = res->K;
+    for (auto& t : res->tinfo) out->walkable_spans += t.walkable_span_count;
+    out->result_bytes = res->lay.bytesA + res->lay.bytesB;
+    return RCB_OK;
+}
+
+int rcb_result_download(rcb_result* res) {
+    if (!res) return RCB_EARG;
+    rcb_ctx* ctx = res->ctx;
+    if (res->downloaded) return RCB_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(pool_get(ctx->free_host, res->lay.bytesA, true, res->hostA));
+    CU(cudaMemcpyAsync(res->hostA.p, res->devA.p, res->lay.bytesA, cudaMemcpyDeviceToHost, ctx->stream));
+    if (res->lay.bytesB) {
+        CU(pool_get(ctx->free_host, res->lay.bytesB, true, res->hostB));
+        CU(cudaMemcpyAsync(res->hostB.p, res->devB.p, res->lay.bytesB, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    res->tinfo.assign((TileInfo*)(res->hostA.p + res->lay.tinfo), (TileInfo*)(res->hostA.p + res->lay.tinfo) + res->ntiles);
+    res->have_tinfo = true;
+    res->downloaded = true;
+    return RCB_OK;
+}
+
+static int fill_view(const rcb_result* res, int tile, rcb_tile_view* v, const char* A, const char* B) {
+    const TileDesc& td = res->tiles[tile];
+    const TileInfo& ti = res->tinfo[tile];
+    const ArenaLayout& l = res->lay;
+    memset(v, 0, sizeof *v);
+    v->width = td.width;
+    v->height = td.height;
+    v->cell_count = (uint32_t)(td.width * td.height);
+    v->span_count = ti.span_count;
+    v->conn_count = ti.conn_count;
+    v->walkable_span_count = ti.walkable_span_count;
+    v->max_height = (uint16_t)ti.max_height;
+    v->max_distance = (uint16_t)ti.max_distance;
+    v->status = ti.status;
+    v->hf_cell_offset = (const uint32_t*)(A + l.hf_cell_offset) + td.cell_base + tile;
+    v->span_min = (const int16_t*)(A + l.span_min) + ti.span_base;
+    v->span_max = (const int16_t*)(A + l.span_max) + ti.span_base;
+    v->span_area = (const uint8_t*)(A + l.span_area) + ti.span_base;
+    if (res->stage_mask & RCB_STAGE_COMPACT) {
+        v->cell_index = (const uint32_t*)(A + l.cell_index) + td.cell_base;
+        v->cell_count_arr = (const uint32_t*)(A + l.cell_count) + td.cell_base;
+        v->areas = (const uint8_t*)(A + l.areas) + ti.span_base;
+        v->con = (const uint16_t*)(A + l.con) + 4 * (size_t)ti.span_base;
+        v->first_conn = (const uint32_t*)(A + l.first_conn) + ti.span_base;
+        v->dist = (const uint16_t*)(A + l.dist) + ti.span_base;
+        v->conn_ref = (const uint32_t*)(B + l.conn_ref) + ti.conn_base;
+        v->conn_dir = (const uint8_t*)(B + l.conn_dir) + ti.conn_base;
+        v->conn_next = (const uint32_t*)(B + l.conn_next) + ti.conn_base;
+    }
+    return RCB_OK;
+}
+
+int rcb_result_tile(const rcb_result* res, int tile, rcb_tile_view* out) {
+    if (!res || !out || tile < 0 || tile >= res->ntiles) return RCB_EARG;
+    if (!res->downloaded) return fail(res->ctx, RCB_EARG, "rcb_result_tile: call rcb_result_download first");
+    return fill_view(res, tile, out, res->hostA.p, res->hostB.p);
+}
+
+int rcb_result_tile_device(const rcb_result* cres, int tile, rcb_tile_view* out) {
+    auto* res = const_cast<rcb_result*>(cres);
+    if (!res || !out || tile < 0 || tile >= res->ntiles) return RCB_EARG;
+    int r = fetch_tinfo(res);
+    if (r) return r;
+    return fill_view(res, tile, out, res->devA.p, res->devB.p);
+}
+
+void rcb_result_free(rcb_result* res) {
+    if (!res) return;
+    rcb_ctx* ctx = res->ctx;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        // arenas go back to the pool; work that still reads them is ordered on the same stream
+        pool_put(ctx->free_dev, res->devA, false);
+        pool_put(ctx->free_dev, res->devB, false);
+        pool_put(ctx->free_host, res->hostA, true);
+        pool_put(ctx->free_host, res->hostB, true);
+    }
+    delete res;
+}
+
+}  // extern "C"

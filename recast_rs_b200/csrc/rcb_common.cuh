@@ -1,0 +1,139 @@
+// rcb_common.cuh — shared device/host declarations for the B200 voxelization kernels.
+//
+// Data layout in HBM for one batch of tiles (DESIGN.md "Data layout"):
+//   * cells of all tiles are concatenated in tile order; tile t owns global cells
+//     [cell_base[t], cell_base[t] + W_t*H_t), row-major z*W + x inside the tile;
+//   * spans of all tiles are concatenated in global cell order (so also tile order); every
+//     index handed back through the C ABI is made tile-relative by subtracting the tile's base;
+//   * connections likewise.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/recast_b200.h"
+
+#define RCB_MAX_POLY_VERTS 12  // clip polygon capacity (geometric bound is 7); overflow sets status bit0
+#define RCB_NEI_NONE 0xFFFFu
+
+// Per-tile constants, uploaded once per batch.
+struct TileDesc {
+    int32_t width, height;
+    float bmin[3], bmax[3];
+    float cs, ch;
+    float ics, ich;          // 1/cs, 1/ch (rasterization.rs:254-255)
+    float slope_thr;         // cos(angle*PI/180) computed on the host with cosf (lib.rs:212-213)
+    int32_t walkable_height; // already cast `as i16` then widened (lib.rs:278-287)
+    int32_t walkable_climb;
+    int32_t neg_climb;       // (-climb as i16) as i32, heightfield.rs:382
+    uint32_t cell_base;      // first global cell
+    int32_t bin_x0, bin_z0;  // lower corner of the tile's range in the locator grid (dedup rule)
+};
+
+// Per-tile results (device-written, downloaded with the arena).
+struct TileInfo {
+    uint32_t span_base, span_count;
+    uint32_t conn_base, conn_count;
+    uint32_t walkable_span_count;
+    uint32_t max_height;    // u16 value
+    uint32_t max_distance;  // u16 value
+    uint32_t status;
+};
+
+// Uniform locator grid over the tile AABBs: maps a triangle AABB to candidate tiles.
+struct Locator {
+    float gx0, gz0;      // origin
+    float inv_bx, inv_bz;  // 1 / bin size
+    int32_t nbx, nbz;
+    const uint32_t* bin_off;    // [nbx*nbz + 1]
+    const uint32_t* bin_tiles;  // tile ids
+};
+
+// Device-side bin coordinate; monotone in v, identical on host and device (sub, mul, floor, clamp).
+__host__ __device__ inline int32_t rcb_bin_coord(float v, float g0, float inv, int32_t nb) {
+    float f = floorf((v - g0) * inv);
+    if (!(f > 0.0f)) return 0;  // also NaN
+    if (f >= (float)(nb - 1)) return nb - 1;
+    return (int32_t)f;
+}
+
+struct MeshView {
+    const float* verts;
+    const int32_t* tris;
+    uint32_t ntris;
+    uint32_t nverts;
+    const uint8_t* tri_areas;  // explicit areas (rcb_rasterize) or nullptr (classify by slope)
+    int32_t merge_thr;         // flag_merge_threshold
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+#endif
+
+// ---- launchers (one per .cu file) ---------------------------------------------------------------
+struct RasterBuffers {
+    // inputs
+    const TileDesc* tiles;
+    int ntiles;
+    Locator loc;
+    MeshView mesh;
+    // scratch
+    unsigned long long* counters;  // [0] fragment upper bound, [1] fragment cursor, [2] overflow flags
+    uint32_t* cell_cnt;            // [Ctot] fragment count per cell, later span count per cell
+    uint4* frag_tmp;               // [frag capacity] unsorted fragment records
+    uint32_t frag_cap;
+};
+
+void launch_count_fragments(const RasterBuffers& rb, cudaStream_t s);
+void launch_clip_emit(const RasterBuffers& rb, TileInfo* tinfo, cudaStream_t s);
+void launch_scatter_fragments(const uint4* frag_tmp, const unsigned long long* nfrag_dev, uint32_t nfrag_hint,
+                              const uint32_t* frag_off, uint32_t* fs_tri, uint32_t* fs_mm, uint8_t* fs_area,
+                              cudaStream_t s);
+void launch_replay_columns(uint32_t ncells, const uint32_t* frag_off, uint32_t* fs_tri, uint32_t* fs_mm,
+                           uint8_t* fs_area, uint32_t* span_cnt, int32_t merge_thr, cudaStream_t s);
+void launch_gather_spans(uint32_t ncells, const uint32_t* frag_off, const uint32_t* fs_mm, const uint8_t* fs_area,
+                         const uint32_t* hf_off, int16_t* smin, int16_t* smax, uint8_t* sarea, cudaStream_t s);
+
+// exclusive scan of n u32 values, out has n+1 entries (out[n] = total).  tmp: >= scan_tmp_elems(n) u32.
+size_t scan_tmp_elems(size_t n);
+void launch_exclusive_scan(const uint32_t* in, uint32_t* out, size_t n, uint32_t* tmp, cudaStream_t s);
+
+// Per-column kernels run on a 3-D grid: blockIdx.x = 256-column block inside a tile,
+// tile = blockIdx.z * gridDim.y + blockIdx.y.  Blocks past a (partial) tile's last cell exit.
+struct TileMap {
+    uint32_t ntiles;
+    uint32_t blocks_per_tile;  // ceil(max cells per tile / 256)
+    uint32_t nblocks;          // 0 when there is nothing to launch
+#ifdef __CUDACC__
+    dim3 grid() const {
+        const uint32_t gy = ntiles < 65535u ? ntiles : 65535u;
+        return dim3(blocks_per_tile, gy, (ntiles + gy - 1) / gy);
+    }
+#endif
+};
+#ifdef __CUDACC__
+#define RCB_TILE_OF_BLOCK() (blockIdx.z * gridDim.y + blockIdx.y)
+#define RCB_CELL_OF_THREAD() (blockIdx.x * blockDim.x + threadIdx.x)
+#endif
+
+void launch_filter_spans(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smin,
+                         const int16_t* smax, uint8_t* sarea, uint32_t fmask /*1 F1, 2 F2, 4 F3*/, cudaStream_t s);
+void launch_cells_and_offsets(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, uint32_t* hf_cell_offset,
+                              uint32_t* cell_index, uint32_t* cell_count, TileInfo* tinfo, int ntiles,
+                              cudaStream_t s);
+void launch_link_spans(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smin,
+                       const int16_t* smax, const uint8_t* sarea, uint8_t* areas, uint16_t* nei16, size_t S,
+                       uint16_t* con, uint32_t* cell_conn_cnt, TileInfo* tinfo, cudaStream_t s);
+void launch_write_connections(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const uint16_t* nei16,
+                              size_t S, const uint32_t* conn_off, const TileInfo* tinfo, uint32_t* first_conn,
+                              uint32_t* conn_ref, uint8_t* conn_dir, uint32_t* conn_next, cudaStream_t s);
+void launch_tile_bases(const TileDesc* tiles, int ntiles, const uint32_t* hf_off, const uint32_t* conn_off,
+                       TileInfo* tinfo, cudaStream_t s);
+
+void launch_distance_field(const TileDesc* tiles, int ntiles, TileMap tm, const uint32_t* hf_off,
+                           const uint16_t* nei16, size_t S, const uint8_t* areas, uint16_t* tmp_init, uint16_t* tmp_f,
+                           uint16_t* tmp_d, uint16_t* dist, TileInfo* tinfo, cudaStream_t s);
+void launch_erode(const TileDesc* tiles, int ntiles, TileMap tm, const uint32_t* hf_off, const uint16_t* nei16,
+                  size_t S, uint8_t* areas, uint8_t* tmp_init, uint8_t* tmp_f, int radius, cudaStream_t s);
+
+// number of kernel launches issued through the launchers above since process start
+extern unsigned long long g_rcb_launches;

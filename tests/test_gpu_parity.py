@@ -1,0 +1,257 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle, bit-exact.
+Run on the B200 box with `pytest -m gpu`."""
+import numpy as np
+import pytest
+
+from tests.parity import assert_tile_equal, random_soup
+
+pytestmark = pytest.mark.gpu
+
+DIR_E = 3
+
+
+@pytest.fixture(scope="module")
+def rb():
+    import recast_rs_b200.builder as b
+
+    return b
+
+
+@pytest.fixture(scope="module")
+def ctx(rb):
+    c = rb.Context(0)
+    yield c
+    c.close()
+
+
+def _oracle_tiles(oracle, verts, idx, cfgs, stage_mask, erode_radius=0):
+    return [oracle.build_tile(c, verts, idx, stage_mask, erode_radius) for c in cfgs]
+
+
+def _check_batch(oracle, rb, ctx, verts, idx, cfgs, stage_mask, erode_radius=0):
+    ctx.upload_mesh(verts, idx)
+    with ctx.build_tiles(cfgs, stage_mask, erode_radius) as r:
+        r.download()
+        tot = r.totals()
+        ref = _oracle_tiles(oracle, verts, idx, cfgs, stage_mask, erode_radius)
+        S = K = 0
+        for i, (hfa, chfa) in enumerate(ref):
+            assert_tile_equal(r.tile(i), hfa, chfa, what=f"tile {i}")
+            S += hfa.span_min.size
+            K += 0 if chfa is None else chfa.conn_ref.size
+        assert tot["spans"] == S and tot["connections"] == K and tot["tiles"] == len(cfgs)
+    return tot
+
+
+# ---- the reference's own unit tests, through the product API -------------------------------------------
+def _fixture_hf(oracle, rb, ctx, w, h, bmax, spans):
+    """Build the fixture with the reference's Heightfield::add_span rule (oracle restatement of
+    heightfield.rs:102) and hand its columns to the product as a Heightfield."""
+    o = oracle.Heightfield(w, h, (0, 0, 0), bmax, 1.0, 1.0)
+    for s in spans:
+        o.add_span(*s)
+    e = o.export()
+    return o, rb.Heightfield(w, h, (0, 0, 0), bmax, 1.0, 1.0, e.cell_offset, e.span_min, e.span_max, e.span_area, ctx=ctx)
+
+
+def test_ref_filter_low_hanging_walkable_obstacles(oracle, rb, ctx):  # heightfield.rs:1417-1452
+    _, hf = _fixture_hf(oracle, rb, ctx, 5, 5, (5, 10, 5), [(2, 2, 0, 5, 1), (2, 2, 6, 8, 0), (2, 2, 9, 15, 1)])
+    hf.filter_low_hanging_walkable_obstacles(3)
+    assert hf.column(2, 2) == [(0, 5, 1), (6, 8, 1), (9, 15, 1)]
+
+
+def test_ref_compact_heightfield_creation(oracle, rb, ctx):  # compact_heightfield.rs:1028-1059 + KAT-1
+    o, hf = _fixture_hf(oracle, rb, ctx, 3, 3, (3, 3, 3), [(0, 0, 0, 2, 1), (0, 0, 3, 5, 1), (1, 0, 0, 2, 1), (0, 1, 0, 2, 1)])
+    chf = rb.CompactHeightfield.build_from_heightfield(hf)
+    assert (chf.width, chf.height) == (3, 3)
+    assert chf.cell_index.size == 9 and chf.span_min.size == 4 and chf.conn_ref.size > 0
+    conns = list(zip(chf.conn_ref.tolist(), chf.conn_dir.tolist(), chf.conn_next.tolist()))
+    N = 0xFFFFFFFF
+    assert conns == [(3, 5, N), (2, 3, 0), (0, 7, N), (3, 6, 2), (2, 2, N), (0, 1, 4)]
+    assert chf.con.reshape(-1, 4).tolist() == [[63, 0, 0, 63], [63, 63, 63, 63], [0, 63, 63, 63], [63, 63, 63, 0]]
+    assert chf.first_conn.tolist() == [1, N, 3, 5]
+
+
+def test_ref_get_neighbor(oracle, rb, ctx):  # compact_heightfield.rs:1093-1117
+    _, hf = _fixture_hf(oracle, rb, ctx, 2, 1, (2, 1, 1), [(0, 0, 0, 1, 1), (1, 0, 0, 1, 1)])
+    chf = rb.CompactHeightfield.build_from_heightfield(hf)
+    assert chf.get_neighbor(0, DIR_E) == 1
+
+
+def test_ref_add_span_merge_via_rasterize(oracle, rb, ctx):
+    """rasterization.rs:507-530: (10,20,a1) then (15,25,a2), thr 1 -> (10,25,a2) — reproduced through
+    the explicit-area rasterizer with two flat triangles covering one cell at those heights."""
+    import recast_rs_b200 as r
+
+    cfg = r.RecastConfig(width=1, height=1, cs=1.0, ch=1.0, bmin=(0, 0, 0), bmax=(1, 40, 1))
+    # triangle k spans y in [lo,hi] over the whole cell
+    def tri(lo, hi):
+        return [(-1, lo, -1), (3, lo, -1), (-1, hi, 3)]
+    v = np.array(tri(10, 20) + tri(15, 25), np.float32).reshape(-1)
+    idx = np.arange(6, dtype=np.int32)
+    ctx.upload_mesh(v, idx)
+    with ctx.rasterize([cfg], np.array([1, 2], np.uint8), 1) as res:
+        tv = res.download().tile(0)
+    o = oracle.Heightfield.from_config(cfg)
+    o.rasterize_triangles(v, idx, np.array([1, 2], np.uint8), 1)
+    assert_tile_equal(tv, o.export())
+    assert tv.span_area.tolist() == [2] and tv.span_count == 1
+
+
+# ---- KATs 2-4 --------------------------------------------------------------------------
+def _flat(oracle, rb, ctx, n):
+    return _fixture_hf(oracle, rb, ctx, n, n, (n, 10, n), [(x, z, 0, 5, 1) for z in range(n) for x in range(n)])
+
+
+def _rows(a, n):
+    return ["".join(str(int(v)) for v in a[z * n:(z + 1) * n]) for z in range(n)]
+
+
+def test_kat2_kat3_distance(oracle, rb, ctx):
+    _, hf = _flat(oracle, rb, ctx, 5)
+    chf = rb.CompactHeightfield.build_from_heightfield(hf)
+    chf.build_distance_field()
+    assert chf.conn_ref.size == 144 and chf.max_distance == 3
+    assert _rows(chf.dist, 5) == ["00000", "02220", "02120", "02120", "00000"]
+    _, hf = _flat(oracle, rb, ctx, 8)
+    chf = rb.CompactHeightfield.build_from_heightfield(hf)
+    chf.build_distance_field()
+    assert chf.max_distance == 6
+    assert _rows(chf.dist, 8) == ["00000000", "02222220", "02222220", "02333220", "02344320", "02343220", "02233220",
+                                  "00000000"]
+
+
+def test_kat4_erode(oracle, rb, ctx):
+    _, hf = _flat(oracle, rb, ctx, 8)
+    chf = rb.CompactHeightfield.build_from_heightfield(hf)
+    rb.erode_walkable_area(chf, 2)
+    keep = {(x, z) for z in range(8) for x in range(8) if chf.areas[z * 8 + x] == 1}
+    assert keep == {(x, z) for x in (2, 3, 4) for z in (3, 4, 5, 6)}
+    assert (chf.span_area == 1).all()
+    chf.build_distance_field()  # distance field on eroded areas with the ORIGINAL connections
+    o, _ = _flat(oracle, rb, ctx, 8)
+    oc = oracle.CompactHeightfield.build_from_heightfield(o)
+    oc.erode_walkable_area(2)
+    oc.build_distance_field()
+    e = oc.export()
+    np.testing.assert_array_equal(chf.dist, e.dist)
+    assert chf.max_distance == e.max_distance
+
+
+# ---- randomized differential tests ----------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(6))
+def test_random_soup_tiles(oracle, rb, ctx, seed):
+    import recast_rs_b200 as r
+    from recast_rs_b200 import synth
+
+    rng = np.random.default_rng(500 + seed)
+    cs, ch = [(0.3, 0.2), (0.5, 0.25), (1.0, 1.0)][seed % 3]
+    v, idx = random_soup(rng, 400, 0.0, 40 * cs, -1.0, 8.0, small=cs)
+    base = r.RecastConfig(cs=cs, ch=ch, walkable_height=int(rng.integers(1, 5)), walkable_climb=int(rng.integers(0, 3)),
+                          walkable_slope_angle=float(rng.choice([30.0, 45.0, 60.0])))
+    cfgs = synth.tile_grid(v, [8, 16, 13][seed % 3], base)
+    _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_RASTER)
+    _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_RASTER | rb.STAGE_FILTER)
+    _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_ALL_BUILD)
+    _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_ALL_BUILD | rb.STAGE_ERODE, erode_radius=1 + seed % 2)
+
+
+def test_permuted_triangle_order(oracle, rb, ctx):
+    """Span area is order dependent: the GPU must replay fragments in triangle order."""
+    import recast_rs_b200 as r
+    from recast_rs_b200 import synth
+
+    rng = np.random.default_rng(42)
+    v, idx = random_soup(rng, 300, 0.0, 6.0, 0.0, 5.0)
+    cfgs = synth.tile_grid(v, 12, r.RecastConfig(cs=0.5, ch=0.25))
+    for k in range(3):
+        perm = np.random.default_rng(k).permutation(idx.size // 3)
+        pidx = idx.reshape(-1, 3)[perm].reshape(-1).copy()
+        _check_batch(oracle, rb, ctx, v, pidx, cfgs, rb.STAGE_RASTER | rb.STAGE_FILTER)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_terrain_tiles(oracle, rb, ctx, seed):
+    from recast_rs_b200 import synth
+
+    v, t = synth.terrain(40, 1.2, 4.0, seed)
+    cfgs = synth.tile_grid(v, 64)
+    tot = _check_batch(oracle, rb, ctx, v, t, cfgs, rb.STAGE_ALL_BUILD)
+    assert tot["triangles"] == 3200 and tot["fragments"] > tot["spans"] > 0
+
+
+def test_terrain_single_tile_config1_shape(oracle, rb, ctx):
+    from recast_rs_b200 import synth
+
+    v, t, cfgs = synth.config1(seed=1, nq=48)  # config 1 scaled down: one tile over the whole mesh
+    assert len(cfgs) == 1
+    _check_batch(oracle, rb, ctx, v, t, cfgs, rb.STAGE_ALL_BUILD)
+
+
+def test_interior_multilevel(oracle, rb, ctx):
+    from recast_rs_b200 import synth
+
+    v, t, cfgs = synth.config4(seed=1, floors=6, nq=24, tile=32)
+    tot = _check_batch(oracle, rb, ctx, v, t, cfgs, rb.STAGE_ALL_BUILD | rb.STAGE_ERODE, erode_radius=1)
+    assert tot["spans"] > 3 * tot["cells"]  # many spans per column
+
+
+def test_open_world_boxes(oracle, rb, ctx):
+    from recast_rs_b200 import synth
+
+    v, t = synth.open_world(nq=60, lattice=5)
+    cfgs = synth.tile_grid(v, 128)
+    _check_batch(oracle, rb, ctx, v, t, cfgs, rb.STAGE_ALL_BUILD)
+
+
+# ---- edge cases and error behaviour (lib.rs:195-233, config.rs:110-136) -----------------------------------
+def test_empty_inputs_and_errors(rb, ctx):
+    import recast_rs_b200 as r
+
+    cfg = r.RecastConfig(width=4, height=4, cs=1.0, ch=1.0, bmin=(0, 0, 0), bmax=(4, 4, 4))
+    ctx.upload_mesh(np.zeros(0, np.float32), np.zeros(0, np.int32))  # lib.rs:195 -> Ok, empty heightfield
+    with ctx.build_tiles([cfg], rb.STAGE_ALL_BUILD) as res:
+        tv = res.download().tile(0)
+        assert tv.span_count == 0 and tv.hf_cell_offset.tolist() == [0] * 17 and (tv.cell_index == 0xFFFFFFFF).all()
+    v = np.array([0, 0, 0, 1, 0, 0, 0, 0, 1], np.float32)
+    ctx.upload_mesh(v, np.array([0, 1], np.int32))  # lib.rs:205
+    with pytest.raises(r.NavMeshGeneration):
+        ctx.build_tiles([cfg], rb.STAGE_RASTER)
+    ctx.upload_mesh(v[:8], np.array([0, 1, 2], np.int32))  # lib.rs:199
+    with pytest.raises(r.NavMeshGeneration):
+        ctx.build_tiles([cfg], rb.STAGE_RASTER)
+    ctx.upload_mesh(v, np.array([0, 1, 3], np.int32))  # lib.rs:224-233
+    with pytest.raises(r.NavMeshGeneration):
+        ctx.build_tiles([cfg], rb.STAGE_RASTER)
+    ctx.upload_mesh(v, np.array([0, -1, 2], np.int32))
+    with pytest.raises(r.NavMeshGeneration):
+        ctx.build_tiles([cfg], rb.STAGE_RASTER)
+    bad = r.RecastConfig(width=0, height=4, cs=1.0, ch=1.0)
+    ctx.upload_mesh(v, np.array([0, 1, 2], np.int32))
+    with pytest.raises(r.InvalidMesh):
+        ctx.build_tiles([bad], rb.STAGE_RASTER)
+    with ctx.build_tiles([], rb.STAGE_ALL_BUILD) as res:  # zero tiles
+        assert res.totals()["tiles"] == 0
+
+
+def test_recast_builder_facade(oracle, rb, ctx):
+    """RecastBuilder::build_heightfield (lib.rs:116) — the reference has no test for it; compare with the oracle."""
+    import recast_rs_b200 as r
+    from recast_rs_b200 import synth
+
+    v, t, cfgs = synth.config1(seed=3, nq=20)
+    builder = r.RecastBuilder(cfgs[0], ctx)
+    hf = builder.build_heightfield(v, t)
+    o = oracle.Heightfield.from_config(cfgs[0])
+    o.builder_rasterize(cfgs[0], v, t, run_filters=True)
+    e = o.export()
+    np.testing.assert_array_equal(hf.cell_offset, e.cell_offset)
+    np.testing.assert_array_equal(hf.span_area, e.span_area)
+    chf = builder.build_compact_heightfield(hf)
+    chf.build_distance_field()
+    oc = oracle.CompactHeightfield.build_from_heightfield(o)
+    oc.build_distance_field()
+    ea = oc.export()
+    np.testing.assert_array_equal(chf.dist, ea.dist)
+    np.testing.assert_array_equal(chf.conn_ref, ea.conn_ref)
+    assert chf.max_distance == ea.max_distance
