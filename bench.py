@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py — tiled voxelization throughput (BASELINE.json metric) on N B200s.
+
+A step = one pass of the hot path (rasterize -> filters -> compact heightfield + connections ->
+distance field) over every tile of the workload.  One process per GPU; tiles shard across ranks with
+no data-path collective (each rank owns a slab of the world: its tiles and the triangles over them),
+so scaling is "weak".
+
+  value : triangles voxelized per second, whole job, inputs resident in HBM, results left in HBM
+  e2e   : same metric through the C ABI with HOST buffers: per step H2D of the mesh from pinned
+          memory, the build, and D2H of every result array into pinned memory
+  roofline: algorithmic bytes / device time of the step vs the measured HBM peak
+  cpu_baseline: the C++ oracle (a port of the reference; the Rust reference cannot be built here)
+          on the host cores, bounded sample
+
+`--impl reference` times the oracle port with all host threads (the reference arm of the contract).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "input triangles voxelized/sec"
+UNIT = "triangles/s"
+
+
+def make_workload(config: int, seed: int):
+    from recast_rs_b200 import synth
+
+    if config == 1:
+        v, t, cfgs = synth.config1(seed)
+        name = "config1: 100k-triangle terrain(nq=224), single tile (cs=0.3, ch=0.2)"
+    elif config == 2:
+        v, t, cfgs = synth.config2(seed)
+        name = "config2: 1M-triangle terrain(nq=708), 64x64-cell tiles (2025 tiles), cs=0.3 ch=0.2"
+    elif config == 3:
+        v, t, cfgs = synth.config3(seed)
+        name = "config3: 10M-triangle open world (terrain nq=2200 + 26896 boxes), 128x128-cell tiles"
+    elif config == 4:
+        v, t, cfgs = synth.config4(seed)
+        name = "config4: 1M-triangle 16-floor interior, 64x64-cell tiles"
+    elif config == 0:  # tiny, for CPU-side tests of this script
+        v, t, cfgs = synth.config2(seed, nq=64, tile=64)
+        name = "tiny: 8k-triangle terrain, 64x64-cell tiles"
+    else:
+        raise SystemExit(f"unknown config {config}")
+    return v, t, cfgs, name
+
+
+def alg_bytes(tot):
+    """B_alg of SURVEY.md §8(d) / BASELINE.md §3."""
+    T, V, C, S, K = tot["triangles"], tot["vertices"], tot["cells"], tot["spans"], tot["connections"]
+    return 12 * T + 12 * V + 8 * C + 5 * S + 1 * S + 8 * S + 2 * S + 5 * K
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_leg(v, t, cfgs, threads, budget_s, prebinned=False):
+    """Oracle port on a bounded sample of tiles sized for ~budget_s; returns (triangles/s, sample text, secs)."""
+    from oracle import oracle as orc
+
+    ntiles, T = len(cfgs), t.size // 3
+    probe = min(ntiles, max(threads * 2, 8))
+    s0, _ = orc.build_tiles_timed(v, t, cfgs[:probe], nthreads=threads, prebinned=prebinned)
+    per_tile = max(s0 / probe, 1e-6)
+    m = int(min(ntiles, max(probe, budget_s / per_tile)))
+    secs, _ = orc.build_tiles_timed(v, t, cfgs[:m], nthreads=threads, prebinned=prebinned)
+    return T * (m / ntiles) / secs, f"first {m} of {ntiles} tiles (each scans the whole mesh as lib.rs:217 does)", secs
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the oracle port (kind 'port') with all host threads; rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+
+    v, t, cfgs, name = make_workload(args.config, args.seed)
+    threads = orc.hardware_concurrency()
+    vals, ms = [], []
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        val, sample, secs = cpu_leg(v, t, cfgs, threads, budget_s=max(2.0, 60.0 / (args.warmup + args.steps)))
+        if i >= args.warmup:
+            vals.append(val)
+            ms.append(secs * 1e3)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 clip + i16/u16 spans", "data": "synthetic",
+        "config": {"workload": name, "seed": args.seed},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "note": "C++ restatement of recast-rs (oracle/), not the Rust build: no cargo/rustc in the image"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_native(args, rank, world, local_rank):
+    import torch
+
+    import recast_rs_b200.builder as rb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; recast_rs_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # every rank owns one slab of the world: its own tiles and the triangles over them
+    v, t, cfgs, name = make_workload(args.config, args.seed + rank)
+    from recast_rs_b200.config import configs_to_array
+
+    cfg_arr = configs_to_array(cfgs)
+    ctx = rb.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    d_v = torch.from_numpy(v).to(dev)
+    d_t = torch.from_numpy(t).to(dev)
+    ctx.set_mesh_device(d_v.data_ptr(), d_v.numel(), d_t.data_ptr(), d_t.numel(), keep=(d_v, d_t))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stage = rb.STAGE_ALL_BUILD
+
+    def step():
+        r = ctx.build_tiles(cfg_arr, stage)
+        return r
+
+    tot = None
+    for _ in range(max(args.warmup, 3)):
+        r = step()
+        tot = r.totals()
+        r.free()
+    barrier()
+
+    # ---- timed region: K steps, device time by CUDA events on the launching stream ----------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = []
+    l0 = ctx.launch_count()
+    barrier()
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        r = step()
+        b.record(stream)
+        r.free()
+        evs.append((a, b))
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop()
+    dev_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(sum(dev_ms))
+
+    # ---- per-kernel device time (separate, untimed pass) ---------------------------------------------------
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    nprof = 3
+    for _ in range(nprof):
+        flush.zero_()
+        step().free()
+    kern = ctx.profile_read()
+    ctx.profile_enable(False)
+    kern_ms = {k: ms / nprof for k, (ms, _) in kern.items()}
+
+    # ---- e2e: host buffers in, host buffers out ------------------------------------------------------------
+    hv = torch.from_numpy(v).pin_memory()
+    ht = torch.from_numpy(t).pin_memory()
+    e2e_ms = []
+    d2h_bytes = 0
+    ctx2 = rb.Context(local_rank)  # a context that owns its mesh copy
+    ctx2.set_stream(stream.cuda_stream)
+    for i in range(2 + args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx2.upload_mesh(hv.numpy(), ht.numpy())
+        r = ctx2.build_tiles(cfg_arr, stage)
+        r.download()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) * 1e3
+        d2h_bytes = r.totals()["result_bytes"]
+        r.free()
+        if i >= 2:
+            e2e_ms.append(dt)
+    barrier()
+
+    # ---- aggregate over ranks ------------------------------------------------------------------------------
+    T = tot["triangles"]
+    agg = torch.tensor([total_ms, float(sum(e2e_ms))], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([T, len(cfgs), alg_bytes(tot)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    max_total_ms, max_e2e_ms = float(agg[0]), float(agg[1])
+    T_all, tiles_all, balg_all = float(cnt[0]), float(cnt[1]), float(cnt[2])
+
+    if rank == 0:
+        peak, peak_src = read_peaks()
+        ms_per_step = max_total_ms / args.steps
+        value = T_all * args.steps / (max_total_ms * 1e-3)
+        e2e_value = T_all * len(e2e_ms) / (max_e2e_ms * 1e-3)
+        achieved = balg_all / world / (ms_per_step * 1e-3) / 1e9  # per GPU
+        dom = max(kern_ms.items(), key=lambda kv: kv[1]) if kern_ms else ("", 0.0)
+        ksum = sum(kern_ms.values())
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 clip + i16/u16 spans", "data": "synthetic",
+            "config": {"workload": name + (f" x {world} slabs (one per rank, seeds {args.seed}..{args.seed + world - 1})" if world > 1 else ""),
+                       "seed": args.seed, "stages": "raster+filters+compact+connections+distance_field",
+                       "l2": "256 MiB flush between timed steps; per-step working set > L2",
+                       "totals_rank0": tot},
+            "tiles_per_s": tiles_all * args.steps / (max_total_ms * 1e-3),
+            "wall_ms_per_step": wall * 1e3 / args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(v.nbytes + t.nbytes),
+                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": max_e2e_ms / len(e2e_ms)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "whole step (all launches)",
+                         "alg_bytes_per_step_per_gpu": balg_all / world,
+                         "alg_bytes_per_triangle": balg_all / T_all,
+                         "dominant_kernel": {"name": dom[0], "ms": dom[1], "share_of_kernel_time": dom[1] / ksum if ksum else None},
+                         "kernel_ms": {k: round(ms, 4) for k, ms in sorted(kern_ms.items(), key=lambda kv: -kv[1])},
+                         "kernel_ms_sum": ksum},
+        }
+        if world == 1 and not args.no_cpu:
+            try:
+                val, sample, _ = cpu_leg(v, t, cfgs, 1, budget_s=args.cpu_budget)
+                cb = {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                      "note": "C++ restatement of recast-rs (oracle/), single thread like the reference (its `parallel` feature is dead code)"}
+                val2, _, _ = cpu_leg(v, t, cfgs, 1, budget_s=args.cpu_budget / 3, prebinned=True)
+                cb["prebinned_value"] = val2
+                line["cpu_baseline"] = cb
+            except Exception as e:  # the oracle is test infrastructure; its absence must not kill the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    ctx2.close()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_native(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -138,6 +138,20 @@ int rcb_set_stream(rcb_ctx* ctx, void* cuda_stream);
 /* Number of kernel launches issued by this context since creation (bench `gpu_launches`). */
 uint64_t rcb_launch_count(const rcb_ctx* ctx);
 
+/* Per-stage device timers (CUDA events around every kernel launch), the device-side counterpart of
+ * RecastContext::start_timer/stop_timer with TimerCategory::{Rasterization, Filtering,
+ * CompactHeightfield, ...} (context.rs:25-54,223-251).  Off by default.  rcb_profile_read
+ * synchronises the stream, writes up to `cap` entries accumulated since the last reset and
+ * returns the number of entries available. */
+typedef struct rcb_stage_time {
+    char name[40];
+    float ms;       /* summed device time of the stage's launches */
+    uint32_t calls; /* launches accumulated */
+} rcb_stage_time;
+int rcb_profile_enable(rcb_ctx* ctx, int on);
+int rcb_profile_read(rcb_ctx* ctx, rcb_stage_time* out, int cap);
+int rcb_profile_reset(rcb_ctx* ctx);
+
 /* ---- config (config.rs) ------------------------------------------------------------------ */
 void rcb_config_default(rcb_config* cfg);                                        /* config.rs:53-76 */
 void rcb_config_calculate_grid_size(rcb_config* cfg, const float bmin[3], const float bmax[3]); /* config.rs:85-107 */

@@ -34,7 +34,14 @@ class RcbTileView(ctypes.Structure):
     ]
 
 
+class RcbStageTime(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 40), ("ms", ctypes.c_float), ("calls", _u32)]
+
+
 SYMBOLS = {
+    "rcb_profile_enable": (_i, [_vp, _i]),
+    "rcb_profile_read": (_i, [_vp, ctypes.POINTER(RcbStageTime), _i]),
+    "rcb_profile_reset": (_i, [_vp]),
     "rcb_create": (_i, [_i, _pp]),
     "rcb_destroy": (None, [_vp]),
     "rcb_last_error": (ctypes.c_char_p, [_vp]),

@@ -143,6 +143,18 @@ class Context:
     def set_stream(self, cuda_stream: int | None):
         check(_ffi.lib().rcb_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)), self._h)
 
+    def profile_enable(self, on: bool = True):
+        check(_ffi.lib().rcb_profile_enable(self._h, int(on)), self._h)
+
+    def profile_reset(self):
+        check(_ffi.lib().rcb_profile_reset(self._h), self._h)
+
+    def profile_read(self) -> dict:
+        """{kernel name: (summed device ms, launches)} since the last reset."""
+        arr = (_ffi.RcbStageTime * 64)()
+        n = _ffi.lib().rcb_profile_read(self._h, arr, 64)
+        return {arr[i].name.decode(): (float(arr[i].ms), int(arr[i].calls)) for i in range(min(n, 64))}
+
     def launch_count(self) -> int:
         return int(_ffi.lib().rcb_launch_count(self._h))
 

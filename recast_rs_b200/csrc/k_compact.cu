@@ -179,31 +179,39 @@ __global__ void __launch_bounds__(256) k_write_connections(const TileDesc* __res
 void launch_tile_bases(const TileDesc* tiles, int ntiles, const uint32_t* hf_off, const uint32_t* conn_off,
                        TileInfo* tinfo, cudaStream_t s) {
     if (ntiles == 0) return;
-    k_tile_bases<<<(ntiles + 127) / 128, 128, 0, s>>>(tiles, ntiles, hf_off, conn_off, tinfo);
-    g_rcb_launches++;
+    {
+        KScope _k("k_tile_bases", s);
+        k_tile_bases<<<(ntiles + 127) / 128, 128, 0, s>>>(tiles, ntiles, hf_off, conn_off, tinfo);
+    }
 }
 
 void launch_cells_and_offsets(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, uint32_t* hf_cell_offset,
                               uint32_t* cell_index, uint32_t* cell_count, TileInfo* tinfo, int, cudaStream_t s) {
     if (tm.nblocks == 0) return;
-    k_cells<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, hf_cell_offset, cell_index, cell_count, tinfo);
-    g_rcb_launches++;
+    {
+        KScope _k("k_cells", s);
+        k_cells<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, hf_cell_offset, cell_index, cell_count, tinfo);
+    }
 }
 
 void launch_link_spans(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smin,
                        const int16_t* smax, const uint8_t* sarea, uint8_t* areas, uint16_t* nei16, size_t S,
                        uint16_t* con, uint32_t* cell_conn_cnt, TileInfo* tinfo, cudaStream_t s) {
     if (tm.nblocks == 0) return;
-    k_link_spans<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, smin, smax, sarea, areas, nei16, S, con, cell_conn_cnt,
+    {
+        KScope _k("k_link_spans", s);
+        k_link_spans<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, smin, smax, sarea, areas, nei16, S, con, cell_conn_cnt,
                                             tinfo);
-    g_rcb_launches++;
+    }
 }
 
 void launch_write_connections(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const uint16_t* nei16,
                               size_t S, const uint32_t* conn_off, const TileInfo* tinfo, uint32_t* first_conn,
                               uint32_t* conn_ref, uint8_t* conn_dir, uint32_t* conn_next, cudaStream_t s) {
     if (tm.nblocks == 0) return;
-    k_write_connections<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, conn_off, tinfo, first_conn, conn_ref,
+    {
+        KScope _k("k_write_connections", s);
+        k_write_connections<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, conn_off, tinfo, first_conn, conn_ref,
                                                    conn_dir, conn_next);
-    g_rcb_launches++;
+    }
 }

@@ -209,19 +209,38 @@ void launch_distance_field(const TileDesc* tiles, int ntiles, TileMap tm, const 
                            const uint16_t* nei16, size_t S, const uint8_t* areas, uint16_t* tmp_init, uint16_t* tmp_f,
                            uint16_t* tmp_d, uint16_t* dist, TileInfo* tinfo, cudaStream_t s) {
     if (tm.nblocks == 0 || ntiles == 0) return;
-    k_boundary<uint16_t, false><<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, areas, tmp_init);
-    k_forward<uint16_t><<<ntiles, 256, 0, s>>>(tiles, hf_off, nei16, S, tmp_init, tmp_f);
-    k_backward<uint16_t, false><<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, tmp_f, tmp_d, nullptr, 0, tinfo);
-    k_blur<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, tmp_d, dist);
-    g_rcb_launches += 4;
+    {
+        KScope _k("k_boundary", s);
+        k_boundary<uint16_t, false><<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, areas, tmp_init);
+    }
+    {
+        KScope _k("k_forward", s);
+        k_forward<uint16_t><<<ntiles, 256, 0, s>>>(tiles, hf_off, nei16, S, tmp_init, tmp_f);
+    }
+    {
+        KScope _k("k_backward", s);
+        k_backward<uint16_t, false><<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, tmp_f, tmp_d, nullptr, 0, tinfo);
+    }
+    {
+        KScope _k("k_blur", s);
+        k_blur<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, tmp_d, dist);
+    }
 }
 
 void launch_erode(const TileDesc* tiles, int ntiles, TileMap tm, const uint32_t* hf_off, const uint16_t* nei16,
                   size_t S, uint8_t* areas, uint8_t* tmp_init, uint8_t* tmp_f, int radius, cudaStream_t s) {
     if (tm.nblocks == 0 || ntiles == 0) return;
     const unsigned thr = (unsigned)(uint8_t)(uint32_t)(radius * 2);  // area.rs:226 `(radius*2) as u8`
-    k_boundary<uint8_t, true><<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, areas, tmp_init);
-    k_forward<uint8_t><<<ntiles, 256, 0, s>>>(tiles, hf_off, nei16, S, tmp_init, tmp_f);
-    k_backward<uint8_t, true><<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, tmp_f, nullptr, areas, thr, nullptr);
-    g_rcb_launches += 3;
+    {
+        KScope _k("k_boundary", s);
+        k_boundary<uint8_t, true><<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, areas, tmp_init);
+    }
+    {
+        KScope _k("k_forward", s);
+        k_forward<uint8_t><<<ntiles, 256, 0, s>>>(tiles, hf_off, nei16, S, tmp_init, tmp_f);
+    }
+    {
+        KScope _k("k_backward", s);
+        k_backward<uint8_t, true><<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, tmp_f, nullptr, areas, thr, nullptr);
+    }
 }

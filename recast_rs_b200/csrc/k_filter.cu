@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(256) k_filter_spans(const TileDesc* __restrict
 void launch_filter_spans(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smin,
                          const int16_t* smax, uint8_t* sarea, uint32_t fmask, cudaStream_t s) {
     if (tm.nblocks == 0) return;
-    k_filter_spans<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, smin, smax, sarea, fmask);
-    g_rcb_launches++;
+    {
+        KScope _k("k_filter_spans", s);
+        k_filter_spans<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, smin, smax, sarea, fmask);
+    }
 }

@@ -387,14 +387,18 @@ __global__ void __launch_bounds__(256) k_gather_spans(uint32_t ncells, const uin
 
 void launch_count_fragments(const RasterBuffers& rb, cudaStream_t s) {
     if (rb.mesh.ntris == 0) return;
-    k_count_fragments<<<(rb.mesh.ntris + 255) / 256, 256, 0, s>>>(rb);
-    g_rcb_launches++;
+    {
+        KScope _k("k_count_fragments", s);
+        k_count_fragments<<<(rb.mesh.ntris + 255) / 256, 256, 0, s>>>(rb);
+    }
 }
 
 void launch_clip_emit(const RasterBuffers& rb, TileInfo* tinfo, cudaStream_t s) {
     if (rb.mesh.ntris == 0) return;
-    k_clip_emit<<<(rb.mesh.ntris + 127) / 128, 128, 0, s>>>(rb, tinfo);
-    g_rcb_launches++;
+    {
+        KScope _k("k_clip_emit", s);
+        k_clip_emit<<<(rb.mesh.ntris + 127) / 128, 128, 0, s>>>(rb, tinfo);
+    }
 }
 
 void launch_scatter_fragments(const uint4* frag_tmp, const unsigned long long* nfrag_dev, uint32_t nfrag_hint,
@@ -403,20 +407,26 @@ void launch_scatter_fragments(const uint4* frag_tmp, const unsigned long long* n
     if (nfrag_hint == 0) return;
     unsigned blocks = (unsigned)((nfrag_hint + 255ull) / 256ull);
     if (blocks > 148u * 64u) blocks = 148u * 64u;
-    k_scatter_fragments<<<blocks, 256, 0, s>>>(frag_tmp, nfrag_dev, frag_off, fs_tri, fs_mm, fs_area);
-    g_rcb_launches++;
+    {
+        KScope _k("k_scatter_fragments", s);
+        k_scatter_fragments<<<blocks, 256, 0, s>>>(frag_tmp, nfrag_dev, frag_off, fs_tri, fs_mm, fs_area);
+    }
 }
 
 void launch_replay_columns(uint32_t ncells, const uint32_t* frag_off, uint32_t* fs_tri, uint32_t* fs_mm,
                            uint8_t* fs_area, uint32_t* span_cnt, int32_t merge_thr, cudaStream_t s) {
     if (ncells == 0) return;
-    k_replay_columns<<<(ncells + 255) / 256, 256, 0, s>>>(ncells, frag_off, fs_tri, fs_mm, fs_area, span_cnt, merge_thr);
-    g_rcb_launches++;
+    {
+        KScope _k("k_replay_columns", s);
+        k_replay_columns<<<(ncells + 255) / 256, 256, 0, s>>>(ncells, frag_off, fs_tri, fs_mm, fs_area, span_cnt, merge_thr);
+    }
 }
 
 void launch_gather_spans(uint32_t ncells, const uint32_t* frag_off, const uint32_t* fs_mm, const uint8_t* fs_area,
                          const uint32_t* hf_off, int16_t* smin, int16_t* smax, uint8_t* sarea, cudaStream_t s) {
     if (ncells == 0) return;
-    k_gather_spans<<<(ncells + 255) / 256, 256, 0, s>>>(ncells, frag_off, fs_mm, fs_area, hf_off, smin, smax, sarea);
-    g_rcb_launches++;
+    {
+        KScope _k("k_gather_spans", s);
+        k_gather_spans<<<(ncells + 255) / 256, 256, 0, s>>>(ncells, frag_off, fs_mm, fs_area, hf_off, smin, smax, sarea);
+    }
 }

@@ -5,6 +5,7 @@
 #include "rcb_common.cuh"
 
 unsigned long long g_rcb_launches = 0;
+RcbProfHook g_rcb_prof = {nullptr, nullptr};
 
 namespace {
 
@@ -100,8 +101,16 @@ void launch_exclusive_scan(const uint32_t* in, uint32_t* out, size_t n, uint32_t
         return;
     }
     const size_t nblocks = (n + SCAN_TILE - 1) / SCAN_TILE;
-    k_scan_reduce<<<(unsigned)nblocks, SCAN_THREADS, 0, s>>>(in, n, tmp);
-    k_scan_blocksums<<<1, SCAN_THREADS, 0, s>>>(tmp, nblocks, out + n);
-    k_scan_apply<<<(unsigned)nblocks, SCAN_THREADS, 0, s>>>(in, out, n, tmp);
-    g_rcb_launches += 3;
+    {
+        KScope _k("k_scan_reduce", s);
+        k_scan_reduce<<<(unsigned)nblocks, SCAN_THREADS, 0, s>>>(in, n, tmp);
+    }
+    {
+        KScope _k("k_scan_blocksums", s);
+        k_scan_blocksums<<<1, SCAN_THREADS, 0, s>>>(tmp, nblocks, out + n);
+    }
+    {
+        KScope _k("k_scan_apply", s);
+        k_scan_apply<<<(unsigned)nblocks, SCAN_THREADS, 0, s>>>(in, out, n, tmp);
+    }
 }

@@ -77,6 +77,15 @@ struct rcb_ctx {
     unsigned long long* h_counters = nullptr;  // pinned, 8 entries
     // pools
     std::vector<Arena> free_dev, free_host;
+    // per-stage timers
+    bool prof_on = false;
+    struct ProfEv {
+        const char* name;
+        cudaEvent_t a, b;
+    };
+    std::vector<ProfEv> prof_pending;
+    std::vector<cudaEvent_t> prof_free;
+    std::vector<rcb_stage_time> prof_acc;
 };
 
 struct rcb_result {
@@ -102,6 +111,60 @@ int fail(rcb_ctx* ctx, int code, const char* fmt, ...) {
     va_end(ap);
     if (ctx) ctx->err = buf;
     return code;
+}
+
+cudaEvent_t prof_event(rcb_ctx* ctx) {
+    cudaEvent_t e = nullptr;
+    if (!ctx->prof_free.empty()) {
+        e = ctx->prof_free.back();
+        ctx->prof_free.pop_back();
+    } else {
+        cudaEventCreate(&e);
+    }
+    return e;
+}
+// g_rcb_prof callback: event pair around every kernel launch
+void prof_mark(void* user, const char* name, int begin, cudaStream_t s) {
+    rcb_ctx* ctx = (rcb_ctx*)user;
+    cudaEvent_t e = prof_event(ctx);
+    cudaEventRecord(e, s);
+    if (begin)
+        ctx->prof_pending.push_back({name, e, nullptr});
+    else if (!ctx->prof_pending.empty())
+        ctx->prof_pending.back().b = e;
+}
+struct ProfInstall {  // installs the hook for the duration of one pipeline run
+    explicit ProfInstall(rcb_ctx* ctx) {
+        if (ctx->prof_on) g_rcb_prof = RcbProfHook{prof_mark, ctx};
+    }
+    ~ProfInstall() { g_rcb_prof = RcbProfHook{nullptr, nullptr}; }
+};
+
+void prof_collect(rcb_ctx* ctx) {
+    for (auto& p : ctx->prof_pending) {
+        float ms = 0;
+        if (!p.b) continue;
+        cudaEventSynchronize(p.b);
+        cudaEventElapsedTime(&ms, p.a, p.b);
+        bool found = false;
+        for (auto& acc : ctx->prof_acc)
+            if (!strcmp(acc.name, p.name)) {
+                acc.ms += ms;
+                acc.calls++;
+                found = true;
+                break;
+            }
+        if (!found) {
+            rcb_stage_time st{};
+            strncpy(st.name, p.name, sizeof(st.name) - 1);
+            st.ms = ms;
+            st.calls = 1;
+            ctx->prof_acc.push_back(st);
+        }
+        ctx->prof_free.push_back(p.a);
+        ctx->prof_free.push_back(p.b);
+    }
+    ctx->prof_pending.clear();
 }
 
 #define CU(expr)                                                                                           \
@@ -278,6 +341,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
     *out = nullptr;
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    ProfInstall prof_install(ctx);
     if ((stage_mask & (RCB_STAGE_ERODE | RCB_STAGE_DIST)) && !(stage_mask & RCB_STAGE_COMPACT))
         return fail(ctx, RCB_EARG, "ERODE/DIST need RCB_STAGE_COMPACT");
     uint32_t fmask = 0;
@@ -598,6 +662,8 @@ void rcb_destroy(rcb_ctx* ctx) {
     for (auto& a : ctx->free_host) cudaFreeHost(a.p);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    prof_collect(ctx);
+    for (auto e : ctx->prof_free) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -607,6 +673,28 @@ const char* rcb_last_error(const rcb_ctx* ctx) { return ctx ? ctx->err.c_str() :
 int rcb_set_stream(rcb_ctx* ctx, void* cuda_stream) {
     if (!ctx) return RCB_EARG;
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return RCB_OK;
+}
+
+int rcb_profile_enable(rcb_ctx* ctx, int on) {
+    if (!ctx) return RCB_EARG;
+    ctx->prof_on = on != 0;
+    return RCB_OK;
+}
+
+int rcb_profile_read(rcb_ctx* ctx, rcb_stage_time* out, int cap) {
+    if (!ctx) return RCB_EARG;
+    cudaSetDevice(ctx->device);
+    prof_collect(ctx);
+    const int n = (int)ctx->prof_acc.size();
+    for (int i = 0; i < n && i < cap && out; ++i) out[i] = ctx->prof_acc[i];
+    return n;
+}
+
+int rcb_profile_reset(rcb_ctx* ctx) {
+    if (!ctx) return RCB_EARG;
+    prof_collect(ctx);
+    ctx->prof_acc.clear();
     return RCB_OK;
 }
 

@@ -137,3 +137,22 @@ void launch_erode(const TileDesc* tiles, int ntiles, TileMap tm, const uint32_t*
 
 // number of kernel launches issued through the launchers above since process start
 extern unsigned long long g_rcb_launches;
+
+// Per-kernel timing hook (rcb_profile_*): the pipeline installs a callback; every launcher brackets
+// each kernel with a KScope so device time is attributed per kernel name.
+struct RcbProfHook {
+    void (*mark)(void* user, const char* name, int begin, cudaStream_t s);
+    void* user;
+};
+extern RcbProfHook g_rcb_prof;
+struct KScope {
+    const char* name;
+    cudaStream_t s;
+    KScope(const char* n, cudaStream_t st) : name(n), s(st) {
+        if (g_rcb_prof.mark) g_rcb_prof.mark(g_rcb_prof.user, name, 1, s);
+    }
+    ~KScope() {
+        g_rcb_launches++;
+        if (g_rcb_prof.mark) g_rcb_prof.mark(g_rcb_prof.user, name, 0, s);
+    }
+};

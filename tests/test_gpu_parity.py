@@ -84,10 +84,11 @@ def test_ref_add_span_merge_via_rasterize(oracle, rb, ctx):
     import recast_rs_b200 as r
 
     cfg = r.RecastConfig(width=1, height=1, cs=1.0, ch=1.0, bmin=(0, 0, 0), bmax=(1, 40, 1))
-    # triangle k spans y in [lo,hi] over the whole cell
-    def tri(lo, hi):
-        return [(-1, lo, -1), (3, lo, -1), (-1, hi, 3)]
-    v = np.array(tri(10, 20) + tri(15, 25), np.float32).reshape(-1)
+    # plane y = a + 9.5 z over the whole cell [0,1]^2: y-range [a, a+9.5] -> span (floor, ceil).
+    # (the slope is along z: column 0 keeps polygon parts left of the tile, rasterization.rs:281)
+    def tri(a, b=9.5):
+        return [(-2, a - 2 * b, -2), (6, a - 2 * b, -2), (-2, a + 6 * b, 6)]
+    v = np.array(tri(10.25) + tri(15.25), np.float32).reshape(-1)
     idx = np.arange(6, dtype=np.int32)
     ctx.upload_mesh(v, idx)
     with ctx.rasterize([cfg], np.array([1, 2], np.uint8), 1) as res:
@@ -95,7 +96,7 @@ def test_ref_add_span_merge_via_rasterize(oracle, rb, ctx):
     o = oracle.Heightfield.from_config(cfg)
     o.rasterize_triangles(v, idx, np.array([1, 2], np.uint8), 1)
     assert_tile_equal(tv, o.export())
-    assert tv.span_area.tolist() == [2] and tv.span_count == 1
+    assert (tv.span_min.tolist(), tv.span_max.tolist(), tv.span_area.tolist()) == ([10], [25], [2])
 
 
 # ---- KATs 2-4 --------------------------------------------------------------------------
