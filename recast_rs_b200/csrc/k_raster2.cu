@@ -1,0 +1,421 @@
+// k_raster2.cu — second-generation clipper: (triangle, tile, row-chunk) work items, polygons in
+// shared memory, row-granular load balance.
+//
+// Replaces the same reference code as k_raster.cu (lib.rs:217-274, rasterization.rs:172-366) and is
+// bit-identical to it; what changes is the mapping to the machine.  ncu on the v1 clipper
+// (profiles/r01_v1_*) showed 10.8 of 32 lanes active (threads walked whole triangles of very different
+// row/column counts), 610 M local-memory sectors and 716 MB of DRAM writes from polygon spills.
+//
+// Structure (one CTA = CLIP_THREADS work items):
+//   phase 1  thread = item (tri, tile, chunk of CLIP_ROWS rows): z-chain.  The chain of a triangle is
+//            sequential (each cut interpolates from the previous cut's rounded points), so a chunk that
+//            starts at row r first replays the r cuts before it (cheap: one divide per row), then stores
+//            the row polygons of its rows — x,y only, z is never read again — into shared-memory slots.
+//   phase 2  thread = row slot: x-chain over the columns of that row.  Only the count and the y-range of
+//            the cell piece are needed, so the cell polygon is never stored.  Columns whose cut lies
+//            strictly left of every vertex are skipped without a divide (the divide would return the
+//            polygon unchanged and an empty cell piece, so skipping is exact).
+// Fragments go either to one global list with a per-column rank (v1 back end) or to per-tile segments
+// (tile-resident back end, k_tile.cu).
+#include "rcb_common.cuh"
+
+namespace {
+
+constexpr int CLIP_THREADS = 128;
+constexpr int CLIP_ROWS = RCB_CLIP_ROWS;                  // rows per work item
+constexpr int ZCAP = 6;                                   // z-chain polygon capacity (geometric bound 4-5)
+constexpr int XCAP = 6;                                   // row / rest polygon capacity (geometric bound 5-6)
+constexpr int SLOT_WORDS = 4 + 2 * XCAP + 1;              // header + verts + pad (odd stride: no bank conflicts)
+static_assert(2 * XCAP * 2 <= 2 * ZCAP * 3, "phase-2 buffers alias the z-chain scratch");
+constexpr int NSLOTS = CLIP_THREADS * CLIP_ROWS;
+
+struct Tri {
+    float v0[3], v1[3], v2[3];
+    float tmin[3], tmax[3];
+};
+
+__device__ __forceinline__ bool load_triangle(const MeshView& m, uint32_t tri, Tri& t) {
+    const int32_t i0 = m.tris[tri * 3ull], i1 = m.tris[tri * 3ull + 1], i2 = m.tris[tri * 3ull + 2];
+    if ((uint32_t)i0 >= m.nverts || (uint32_t)i1 >= m.nverts || (uint32_t)i2 >= m.nverts) return false;  // lib.rs:224-233
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        t.v0[k] = m.verts[i0 * 3ull + k];
+        t.v1[k] = m.verts[i1 * 3ull + k];
+        t.v2[k] = m.verts[i2 * 3ull + k];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {  // rasterization.rs:258-264
+        t.tmin[i] = fminf(fminf(t.v0[i], t.v1[i]), t.v2[i]);
+        t.tmax[i] = fmaxf(fmaxf(t.v0[i], t.v1[i]), t.v2[i]);
+    }
+    return true;
+}
+
+// rasterization.rs:270 + :275-285
+__device__ __forceinline__ bool tile_footprint(const Tri& t, const TileDesc& td, int& x0, int& x1, int& z0, int& z1) {
+    if (!(t.tmin[0] <= td.bmax[0] && t.tmax[0] >= td.bmin[0] && t.tmin[1] <= td.bmax[1] && t.tmax[1] >= td.bmin[1] &&
+          t.tmin[2] <= td.bmax[2] && t.tmax[2] >= td.bmin[2]))
+        return false;
+    x0 = __float2int_rz(__fmul_rn(__fsub_rn(t.tmin[0], td.bmin[0]), td.ics));
+    x1 = __float2int_rz(__fmul_rn(__fsub_rn(t.tmax[0], td.bmin[0]), td.ics));
+    z0 = __float2int_rz(__fmul_rn(__fsub_rn(t.tmin[2], td.bmin[2]), td.ics));
+    z1 = __float2int_rz(__fmul_rn(__fsub_rn(t.tmax[2], td.bmin[2]), td.ics));
+    x0 = max(x0, 0);
+    x1 = min(x1, td.width - 1);
+    z0 = max(z0, -1);
+    z1 = min(z1, td.height - 1);
+    return true;
+}
+
+// lib.rs:252-270 (glam scalar Vec3)
+__device__ __forceinline__ bool classify(const Tri& t, float thr, uint32_t& area) {
+    const float e1x = __fsub_rn(t.v1[0], t.v0[0]), e1y = __fsub_rn(t.v1[1], t.v0[1]), e1z = __fsub_rn(t.v1[2], t.v0[2]);
+    const float e2x = __fsub_rn(t.v2[0], t.v0[0]), e2y = __fsub_rn(t.v2[1], t.v0[1]), e2z = __fsub_rn(t.v2[2], t.v0[2]);
+    const float cx = __fsub_rn(__fmul_rn(e1y, e2z), __fmul_rn(e2y, e1z));
+    const float cy = __fsub_rn(__fmul_rn(e1z, e2x), __fmul_rn(e2z, e1x));
+    const float cz = __fsub_rn(__fmul_rn(e1x, e2y), __fmul_rn(e2x, e1y));
+    const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz)));
+    if (len < 1.1920928955078125e-07f) return false;
+    const float ny = __fmul_rn(cy, __fdiv_rn(1.0f, len));
+    area = (fabsf(ny) >= thr) ? 1u : 0u;
+    return true;
+}
+
+template <class Fn>
+__device__ __forceinline__ void for_each_tile(const Tri& t, const Locator& loc, const TileDesc* __restrict__ tiles, Fn&& fn) {
+    if (!(t.tmin[0] <= t.tmax[0]) || !(t.tmin[2] <= t.tmax[2])) return;  // NaN: overlap_bounds is false everywhere
+    const int bx0 = rcb_bin_coord(t.tmin[0], loc.gx0, loc.inv_bx, loc.nbx);
+    const int bx1 = rcb_bin_coord(t.tmax[0], loc.gx0, loc.inv_bx, loc.nbx);
+    const int bz0 = rcb_bin_coord(t.tmin[2], loc.gz0, loc.inv_bz, loc.nbz);
+    const int bz1 = rcb_bin_coord(t.tmax[2], loc.gz0, loc.inv_bz, loc.nbz);
+    for (int bz = bz0; bz <= bz1; ++bz)
+        for (int bx = bx0; bx <= bx1; ++bx) {
+            const uint32_t b = (uint32_t)bz * loc.nbx + bx;
+            const uint32_t e = loc.bin_off[b + 1];
+            for (uint32_t k = loc.bin_off[b]; k < e; ++k) {
+                const uint32_t tile = loc.bin_tiles[k];
+                const TileDesc& td = tiles[tile];
+                if (bx != max(bx0, td.bin_x0) || bz != max(bz0, td.bin_z0)) continue;
+                int x0, x1, z0, z1;
+                if (!tile_footprint(t, td, x0, x1, z0, z1)) continue;
+                fn(tile, td, x0, x1, z0, z1);
+            }
+        }
+}
+
+// ---- pass 1: validate indices; per triangle: number of work items; per tile: fragment upper bound ----
+__global__ void __launch_bounds__(256) k_bin_count(Raster2 rb) {
+    const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long ub = 0;
+    uint32_t items = 0;
+    bool bad = false;
+    if (tri < rb.mesh.ntris) {
+        Tri t;
+        if (load_triangle(rb.mesh, tri, t)) {
+            for_each_tile(t, rb.loc, rb.tiles, [&](uint32_t tile, const TileDesc&, int x0, int x1, int z0, int z1) {
+                const int zz0 = max(z0, 0);
+                if (x1 < x0 || z1 < zz0) return;
+                const uint32_t nrows = (uint32_t)(z1 - zz0 + 1);
+                const uint32_t f = (uint32_t)(x1 - x0 + 1) * nrows;
+                items += (nrows + CLIP_ROWS - 1) / CLIP_ROWS;
+                ub += f;
+                if (rb.tile_ub) atomicAdd(&rb.tile_ub[tile], f);
+            });
+        } else {
+            bad = true;
+        }
+        rb.item_cnt[tri] = items;
+    }
+    __shared__ unsigned long long sh_ub[8];
+    __shared__ uint32_t sh_it[8];
+    unsigned long long it64 = items;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        ub += __shfl_down_sync(0xffffffffu, ub, d);
+        it64 += __shfl_down_sync(0xffffffffu, it64, d);
+    }
+    if (lane_id() == 0) {
+        sh_ub[threadIdx.x >> 5] = ub;
+        sh_it[threadIdx.x >> 5] = (uint32_t)it64;
+    }
+    const bool any_bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) {
+        unsigned long long s = 0, si = 0;
+        for (int i = 0; i < 8; ++i) {
+            s += sh_ub[i];
+            si += sh_it[i];
+        }
+        if (s) atomicAdd(&rb.counters[0], s);
+        if (si) atomicAdd(&rb.counters[4], si);
+        if (any_bad) atomicOr(&rb.counters[3], 1ull);
+    }
+}
+
+// ---- pass 2: write the work items (tri, tile, chunk) in triangle order -------------------------------
+__global__ void __launch_bounds__(256) k_fill_items(Raster2 rb, const uint32_t* __restrict__ item_off, uint2* __restrict__ items) {
+    const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tri >= rb.mesh.ntris) return;
+    uint32_t o = item_off[tri];
+    if (item_off[tri + 1] == o) return;
+    Tri t;
+    if (!load_triangle(rb.mesh, tri, t)) return;
+    for_each_tile(t, rb.loc, rb.tiles, [&](uint32_t tile, const TileDesc&, int x0, int x1, int z0, int z1) {
+        const int zz0 = max(z0, 0);
+        if (x1 < x0 || z1 < zz0) return;
+        const uint32_t nchunks = ((uint32_t)(z1 - zz0 + 1) + CLIP_ROWS - 1) / CLIP_ROWS;
+        for (uint32_t c = 0; c < nchunks; ++c) items[o++] = make_uint2(tri, (tile << 12) | c);
+    });
+}
+
+// ---- clip --------------------------------------------------------------------------------------------
+struct ClipSmem {
+    float zbuf[2 * ZCAP * 3 * CLIP_THREADS];  // phase 1: [(buf*ZCAP + v)*3 + k][tid]; phase 2: two x/y buffers per thread
+    uint32_t slots[NSLOTS * SLOT_WORDS];      // slot tid*CLIP_ROWS + r belongs to thread tid, row r of its chunk
+    uint16_t list[NSLOTS];                    // compacted ids of the slots that hold a row polygon
+    uint32_t nlist;
+};
+
+#define ZB(buf, v, k) sm.zbuf[(((buf) * ZCAP + (v)) * 3 + (k)) * CLIP_THREADS + threadIdx.x]
+#define XB(buf, v, k) sm.zbuf[(((buf) * XCAP + (v)) * 2 + (k)) * CLIP_THREADS + threadIdx.x]
+
+__device__ __forceinline__ void emit_fragment(const Raster2& rb, const TileDesc& td, uint32_t tile, uint32_t lcell,
+                                              uint32_t tri, int smin, int smax, uint32_t area) {
+    const uint32_t mm = ((uint32_t)smin & 0xffffu) | ((uint32_t)smax << 16);
+    if (rb.tile_cursor) {
+        // per-tile segment (tile-resident back end); lanes of a warp mostly hit the same tile
+        const unsigned act = __activemask();
+        const unsigned peers = __match_any_sync(act, tile);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if ((int)lane_id() == leader) base = atomicAdd(&rb.tile_cursor[tile], (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        const uint32_t pos = base + __popc(peers & ((1u << lane_id()) - 1u));
+        if (pos < rb.tile_cap[tile]) {
+            uint32_t* rec = rb.tile_frags + 3ull * (rb.tile_base[tile] + pos);
+            rec[0] = lcell | (area << 24);
+            rec[1] = mm;
+            rec[2] = tri;
+        } else {
+            atomicOr(&rb.counters[2], 2ull);
+        }
+    } else {
+        const uint32_t gcell = td.cell_base + lcell;
+        const uint32_t rank = atomicAdd(&rb.cell_cnt[gcell], 1u);
+        const unsigned m = __activemask();
+        const int leader = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if ((int)lane_id() == leader) base = atomicAdd(&rb.counters[1], (unsigned long long)__popc(m));
+        base = __shfl_sync(m, base, leader);
+        const unsigned long long slot = base + __popc(m & ((1u << lane_id()) - 1u));
+        if (slot < rb.frag_cap)
+            rb.frag_tmp[slot] = make_uint4(gcell, tri, mm, (rank & 0xffffffu) | (area << 24));
+        else
+            atomicOr(&rb.counters[2], 2ull);
+    }
+}
+
+__global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const uint2* __restrict__ items, uint32_t nitems,
+                                                             TileInfo* __restrict__ tinfo) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ClipSmem& sm = *reinterpret_cast<ClipSmem*>(smem_raw);
+    if (threadIdx.x == 0) sm.nlist = 0;
+    __syncthreads();
+
+    // ---------------- phase 1: z-chain of one work item ------------------------------------------------
+    const uint32_t it = blockIdx.x * CLIP_THREADS + threadIdx.x;
+    if (it < nitems) {
+        const uint2 item = items[it];
+        const uint32_t tri = item.x, tile = item.y >> 12, chunk = item.y & 0xfffu;
+        const TileDesc& td = rb.tiles[tile];
+        Tri t;
+        int x0 = 0, x1 = 0, z0 = 0, z1 = 0;
+        uint32_t area = rb.mesh.tri_areas ? (uint32_t)rb.mesh.tri_areas[tri] : 0u;
+        bool ok = load_triangle(rb.mesh, tri, t) && tile_footprint(t, td, x0, x1, z0, z1);
+        if (ok && !rb.mesh.tri_areas) ok = classify(t, td.slope_thr, area);  // lib.rs:258-260: degenerate => skipped
+        if (ok) {
+            const int zs = max(z0, 0) + (int)chunk * CLIP_ROWS;
+            const int ze = min(zs + CLIP_ROWS - 1, z1);
+            bool ovf = false;
+            int cur = 0, n = 3;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                ZB(0, 0, k) = t.v0[k];
+                ZB(0, 1, k) = t.v1[k];
+                ZB(0, 2, k) = t.v2[k];
+            }
+            for (int z = z0; z <= ze && n > 0; ++z) {  // rasterization.rs:300-311
+                const float cz = __fadd_rn(td.bmin[2], __fmul_rn((float)(z + 1), td.cs));
+                const bool keep = z >= zs;  // rows before the chunk only advance the chain
+                const uint32_t slot_id = threadIdx.x * CLIP_ROWS + (uint32_t)(keep ? z - zs : 0);
+                uint32_t* slot = sm.slots + slot_id * SLOT_WORDS;
+                int nrow = 0, nrest = 0;
+                const int nxt = cur ^ 1;
+                // divide_poly(p1 -> in_row (slot, x/y only), rest (zbuf[nxt]))  rasterization.rs:172-242
+                for (int i = 0; i < n; ++i) {
+                    const int j = (i + 1 == n) ? 0 : i + 1;
+                    const float vix = ZB(cur, i, 0), viy = ZB(cur, i, 1), viz = ZB(cur, i, 2);
+                    const float vjz = ZB(cur, j, 2);
+                    const int si = viz < cz ? -1 : (viz > cz ? 1 : 0);
+                    const int sj = vjz < cz ? -1 : (vjz > cz ? 1 : 0);
+                    if (si <= 0) {
+                        if (keep) {
+                            if (nrow < XCAP) {
+                                slot[4 + 2 * nrow] = __float_as_uint(vix);
+                                slot[5 + 2 * nrow] = __float_as_uint(viy);
+                            } else
+                                ovf = true;
+                        }
+                        nrow++;
+                    }
+                    if (si >= 0) {
+                        if (nrest < ZCAP) {
+                            ZB(nxt, nrest, 0) = vix;
+                            ZB(nxt, nrest, 1) = viy;
+                            ZB(nxt, nrest, 2) = viz;
+                        } else
+                            ovf = true;
+                        nrest++;
+                    }
+                    if ((si < 0 && sj > 0) || (si > 0 && sj < 0)) {
+                        const float vjx = ZB(cur, j, 0), vjy = ZB(cur, j, 1);
+                        const float tt = __fdiv_rn(__fsub_rn(cz, viz), __fsub_rn(vjz, viz));
+                        const float px = __fadd_rn(vix, __fmul_rn(tt, __fsub_rn(vjx, vix)));
+                        const float py = __fadd_rn(viy, __fmul_rn(tt, __fsub_rn(vjy, viy)));
+                        const float pz = __fadd_rn(viz, __fmul_rn(tt, __fsub_rn(vjz, viz)));
+                        if (keep) {
+                            if (nrow < XCAP) {
+                                slot[4 + 2 * nrow] = __float_as_uint(px);
+                                slot[5 + 2 * nrow] = __float_as_uint(py);
+                            } else
+                                ovf = true;
+                        }
+                        nrow++;
+                        if (nrest < ZCAP) {
+                            ZB(nxt, nrest, 0) = px;
+                            ZB(nxt, nrest, 1) = py;
+                            ZB(nxt, nrest, 2) = pz;
+                        } else
+                            ovf = true;
+                        nrest++;
+                    }
+                }
+                cur = nxt;
+                n = min(nrest, ZCAP);
+                if (keep && nrow >= 3 && z >= 0) {  // rasterization.rs:308-311
+                    slot[0] = tri;
+                    slot[1] = tile;
+                    slot[2] = (uint32_t)z | ((uint32_t)min(nrow, XCAP) << 16) | (area << 24);
+                    slot[3] = (uint32_t)x0 | ((uint32_t)x1 << 16);
+                    sm.list[atomicAdd(&sm.nlist, 1u)] = (uint16_t)slot_id;
+                }
+            }
+            if (ovf) {
+                atomicOr(&tinfo[tile].status, 1u);
+                atomicOr(&rb.counters[2], 1ull);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 2: x-chain, one row polygon per thread at a time ------------------------------
+    const uint32_t nlist = sm.nlist;
+    for (uint32_t li = threadIdx.x; li < nlist; li += CLIP_THREADS) {
+        const uint32_t* slot = sm.slots + (uint32_t)sm.list[li] * SLOT_WORDS;
+        const uint32_t tri = slot[0], tile = slot[1];
+        const uint32_t h2 = slot[2], h3 = slot[3];
+        const int z = (int)(h2 & 0xffffu);
+        int n = (int)((h2 >> 16) & 0xffu);
+        const uint32_t area = h2 >> 24;
+        const int x0 = (int)(h3 & 0xffffu), x1 = (int)(h3 >> 16);
+        const TileDesc& td = rb.tiles[tile];
+        for (int v = 0; v < n; ++v) {
+            XB(0, v, 0) = __uint_as_float(slot[4 + 2 * v]);
+            XB(0, v, 1) = __uint_as_float(slot[5 + 2 * v]);
+        }
+        bool ovf = false;
+        int cur = 0;
+        for (int x = x0; x <= x1 && n > 0; ++x) {  // rasterization.rs:317-362
+            const float cx = __fadd_rn(td.bmin[0], __fmul_rn((float)(x + 1), td.cs));
+            // exact skip: every vertex strictly right of the cut => cell piece empty, rest == polygon
+            bool all_right = true;
+            for (int i = 0; i < n; ++i) all_right = all_right && (XB(cur, i, 0) > cx);
+            if (all_right) continue;
+            const int nxt = cur ^ 1;
+            int ncell = 0, nrest = 0;
+            float miny = 0.f, maxy = 0.f;
+            for (int i = 0; i < n; ++i) {
+                const int j = (i + 1 == n) ? 0 : i + 1;
+                const float vix = XB(cur, i, 0), viy = XB(cur, i, 1), vjx = XB(cur, j, 0);
+                const int si = vix < cx ? -1 : (vix > cx ? 1 : 0);
+                const int sj = vjx < cx ? -1 : (vjx > cx ? 1 : 0);
+                if (si <= 0) {
+                    miny = ncell ? fminf(miny, viy) : viy;
+                    maxy = ncell ? fmaxf(maxy, viy) : viy;
+                    ncell++;
+                }
+                if (si >= 0) {
+                    if (nrest < XCAP) {
+                        XB(nxt, nrest, 0) = vix;
+                        XB(nxt, nrest, 1) = viy;
+                    } else
+                        ovf = true;
+                    nrest++;
+                }
+                if ((si < 0 && sj > 0) || (si > 0 && sj < 0)) {
+                    const float vjy = XB(cur, j, 1);
+                    const float tt = __fdiv_rn(__fsub_rn(cx, vix), __fsub_rn(vjx, vix));
+                    const float px = __fadd_rn(vix, __fmul_rn(tt, __fsub_rn(vjx, vix)));
+                    const float py = __fadd_rn(viy, __fmul_rn(tt, __fsub_rn(vjy, viy)));
+                    miny = ncell ? fminf(miny, py) : py;
+                    maxy = ncell ? fmaxf(maxy, py) : py;
+                    ncell++;
+                    if (nrest < XCAP) {
+                        XB(nxt, nrest, 0) = px;
+                        XB(nxt, nrest, 1) = py;
+                    } else
+                        ovf = true;
+                    nrest++;
+                }
+            }
+            cur = nxt;
+            n = min(nrest, XCAP);
+            if (ncell >= 3) {  // rasterization.rs:325-361
+                int smin = __float2int_rz(floorf(__fmul_rn(__fsub_rn(miny, td.bmin[1]), td.ich)));
+                int smax = __float2int_rz(ceilf(__fmul_rn(__fsub_rn(maxy, td.bmin[1]), td.ich)));
+                smin = min(max(smin, -32768), 32767);
+                smax = min(max(smax, -32768), 32767);
+                smin = max(smin, 0);
+                emit_fragment(rb, td, tile, (uint32_t)z * td.width + x, tri, smin, smax, area);
+            }
+        }
+        if (ovf) {
+            atomicOr(&tinfo[tile].status, 1u);
+            atomicOr(&rb.counters[2], 1ull);
+        }
+    }
+}
+
+}  // namespace
+
+void launch_bin_count(const Raster2& rb, cudaStream_t s) {
+    if (rb.mesh.ntris == 0) return;
+    KScope _k("k_bin_count", s);
+    k_bin_count<<<(rb.mesh.ntris + 255) / 256, 256, 0, s>>>(rb);
+}
+
+void launch_fill_items(const Raster2& rb, const uint32_t* item_off, uint2* items, cudaStream_t s) {
+    if (rb.mesh.ntris == 0) return;
+    KScope _k("k_fill_items", s);
+    k_fill_items<<<(rb.mesh.ntris + 255) / 256, 256, 0, s>>>(rb, item_off, items);
+}
+
+void launch_clip_items(const Raster2& rb, const uint2* items, uint32_t nitems, TileInfo* tinfo, cudaStream_t s) {
+    if (nitems == 0) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_clip_items, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClipSmem));
+        attr_set = true;
+    }
+    KScope _k("k_clip_items", s);
+    k_clip_items<<<(nitems + CLIP_THREADS - 1) / CLIP_THREADS, CLIP_THREADS, sizeof(ClipSmem), s>>>(rb, items, nitems, tinfo);
+}

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -70,7 +71,8 @@ struct rcb_ctx {
     DevBuf d_tiles, d_bin_off, d_bin_tiles;
     // scratch
     DevBuf d_counters, d_cell_cnt, d_frag_off, d_frag_tmp, d_fs_tri, d_fs_mm, d_fs_area, d_scan_tmp, d_hf_off, d_conn_cnt,
-        d_conn_off, d_nei16, d_t16a, d_t16b, d_t16c, d_t8a, d_t8b;
+        d_conn_off, d_nei16, d_t16a, d_t16b, d_t16c, d_t8a, d_t8b, d_item_cnt, d_item_off, d_items;
+    bool force_v1 = false;  // RCB_FORCE_V1=1: first-generation clipper (k_raster.cu), kept as the wide-tile fallback
     // pinned staging
     char* h_stage = nullptr;
     size_t h_stage_cap = 0;
@@ -455,6 +457,11 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         TileInfo* d_tinfo_tmp = ctx->d_t16a.as<TileInfo>();
         CUB(cudaMemsetAsync(d_tinfo_tmp, 0, sizeof(TileInfo) * (size_t)ntiles, st));
 
+        // v2 front end (k_raster2.cu) needs 16-bit cell coordinates and the (tile, chunk) item encoding
+        bool v2 = ntiles <= (1 << 20) && !ctx->force_v1;
+        for (int i = 0; i < ntiles && v2; ++i)
+            if (res->tiles[i].width > 65535 || res->tiles[i].height > 4096 * RCB_CLIP_ROWS) v2 = false;
+
         RasterBuffers rb{};
         rb.tiles = d_tiles;
         rb.ntiles = ntiles;
@@ -469,14 +476,31 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         rb.mesh.merge_thr = src.merge_thr;
         rb.counters = ctx->d_counters.as<unsigned long long>();
         rb.cell_cnt = ctx->d_cell_cnt.as<uint32_t>();
-        uint64_t ub = 0;
+        Raster2 r2{};
+        r2.tiles = rb.tiles;
+        r2.ntiles = ntiles;
+        r2.loc = rb.loc;
+        r2.mesh = rb.mesh;
+        r2.counters = rb.counters;
+        r2.cell_cnt = rb.cell_cnt;
+        uint64_t ub = 0, nitems = 0;
         if (do_raster && ntiles > 0) {
-            launch_count_fragments(rb, st);
-            CUB(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            if (v2) {
+                CUB(ctx->d_item_cnt.ensure(4 * (ntris + 2)));
+                CUB(ctx->d_item_off.ensure(4 * (ntris + 2)));
+                CUB(ctx->d_scan_tmp.ensure(4 * scan_tmp_elems(ntris + 1)));
+                r2.item_cnt = ctx->d_item_cnt.as<uint32_t>();
+                launch_bin_count(r2, st);
+            } else {
+                launch_count_fragments(rb, st);
+            }
+            CUB(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             CUB(cudaStreamSynchronize(st));
             if (ctx->h_counters[3]) return bail(fail(ctx, RCB_ENAVMESH_GEN, "Triangle index out of bounds (max: %zu)", nverts - 1));
             ub = ctx->h_counters[0];
-            if (ub >= 0xfffffff0ull) return bail(fail(ctx, RCB_EARG, "batch too large: fragment bound %llu", (unsigned long long)ub));
+            nitems = ctx->h_counters[4];
+            if (ub >= 0xfffffff0ull || nitems >= 0xfffffff0ull)
+                return bail(fail(ctx, RCB_EARG, "batch too large: fragment bound %llu", (unsigned long long)ub));
         }
         if (ub > 0) {
             CUB(ctx->d_frag_tmp.ensure(16 * ub));
@@ -485,7 +509,16 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             CUB(ctx->d_fs_area.ensure(ub));
             rb.frag_tmp = ctx->d_frag_tmp.as<uint4>();
             rb.frag_cap = (uint32_t)ub;
-            launch_clip_emit(rb, d_tinfo_tmp, st);
+            if (v2) {
+                r2.frag_tmp = rb.frag_tmp;
+                r2.frag_cap = rb.frag_cap;
+                CUB(ctx->d_items.ensure(8 * nitems + 64));
+                launch_exclusive_scan(r2.item_cnt, ctx->d_item_off.as<uint32_t>(), ntris, ctx->d_scan_tmp.as<uint32_t>(), st);
+                launch_fill_items(r2, ctx->d_item_off.as<uint32_t>(), ctx->d_items.as<uint2>(), st);
+                launch_clip_items(r2, ctx->d_items.as<uint2>(), (uint32_t)nitems, d_tinfo_tmp, st);
+            } else {
+                launch_clip_emit(rb, d_tinfo_tmp, st);
+            }
         }
         uint32_t* d_frag_off = ctx->d_frag_off.as<uint32_t>();
         launch_exclusive_scan(rb.cell_cnt, d_frag_off, Ctot, ctx->d_scan_tmp.as<uint32_t>(), st);
@@ -645,6 +678,7 @@ int rcb_create(int device, rcb_ctx** out) {
     }
     ctx->stream = ctx->own_stream;
     ctx->launches0 = g_rcb_launches;
+    if (const char* e = getenv("RCB_FORCE_V1")) ctx->force_v1 = e[0] == '1';
     *out = ctx;
     return RCB_OK;
 }
@@ -656,7 +690,7 @@ void rcb_destroy(rcb_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_verts, &ctx->d_tris, &ctx->d_tri_areas, &ctx->d_tiles, &ctx->d_bin_off, &ctx->d_bin_tiles,
                       &ctx->d_counters, &ctx->d_cell_cnt, &ctx->d_frag_off, &ctx->d_frag_tmp, &ctx->d_fs_tri, &ctx->d_fs_mm,
                       &ctx->d_fs_area, &ctx->d_scan_tmp, &ctx->d_hf_off, &ctx->d_conn_cnt, &ctx->d_conn_off, &ctx->d_nei16,
-                      &ctx->d_t16a, &ctx->d_t16b, &ctx->d_t16c, &ctx->d_t8a, &ctx->d_t8b};
+                      &ctx->d_t16a, &ctx->d_t16b, &ctx->d_t16c, &ctx->d_t8a, &ctx->d_t8b, &ctx->d_item_cnt, &ctx->d_item_off, &ctx->d_items};
     for (auto* b : bufs) b->release();
     for (auto& a : ctx->free_dev) cudaFree(a.p);
     for (auto& a : ctx->free_host) cudaFreeHost(a.p);

@@ -14,6 +14,7 @@
 
 #define RCB_MAX_POLY_VERTS 12  // clip polygon capacity (geometric bound is 7); overflow sets status bit0
 #define RCB_NEI_NONE 0xFFFFu
+#define RCB_CLIP_ROWS 4  // rows of one (triangle, tile) pair handled by one clip work item
 
 // Per-tile constants, uploaded once per batch.
 struct TileDesc {
@@ -92,6 +93,30 @@ void launch_replay_columns(uint32_t ncells, const uint32_t* frag_off, uint32_t* 
                            uint8_t* fs_area, uint32_t* span_cnt, int32_t merge_thr, cudaStream_t s);
 void launch_gather_spans(uint32_t ncells, const uint32_t* frag_off, const uint32_t* fs_mm, const uint8_t* fs_area,
                          const uint32_t* hf_off, int16_t* smin, int16_t* smax, uint8_t* sarea, cudaStream_t s);
+
+// second-generation front end (k_raster2.cu)
+struct Raster2 {
+    const TileDesc* tiles;
+    int ntiles;
+    Locator loc;
+    MeshView mesh;
+    unsigned long long* counters;  // [0] frag upper bound [1] frag cursor [2] flags (1 poly overflow, 2 pool overflow)
+                                   // [3] bad index [4] work items
+    uint32_t* item_cnt;            // [ntris + 1]
+    uint32_t* tile_ub;             // [ntiles] per-tile fragment upper bound (nullable)
+    // global-list mode (v1 back end)
+    uint32_t* cell_cnt;
+    uint4* frag_tmp;
+    uint32_t frag_cap;
+    // per-tile segment mode (tile-resident back end); enabled when tile_cursor != nullptr
+    uint32_t* tile_cursor;     // [ntiles]
+    const uint32_t* tile_base; // [ntiles] first record of the tile's segment
+    const uint32_t* tile_cap;  // [ntiles]
+    uint32_t* tile_frags;      // 3 words per record: cell | area<<24, smin | smax<<16, triangle
+};
+void launch_bin_count(const Raster2& rb, cudaStream_t s);
+void launch_fill_items(const Raster2& rb, const uint32_t* item_off, uint2* items, cudaStream_t s);
+void launch_clip_items(const Raster2& rb, const uint2* items, uint32_t nitems, TileInfo* tinfo, cudaStream_t s);
 
 // exclusive scan of n u32 values, out has n+1 entries (out[n] = total).  tmp: >= scan_tmp_elems(n) u32.
 size_t scan_tmp_elems(size_t n);
