@@ -71,7 +71,9 @@ struct rcb_ctx {
     DevBuf d_tiles, d_bin_off, d_bin_tiles;
     // scratch
     DevBuf d_counters, d_cell_cnt, d_frag_off, d_frag_tmp, d_fs_tri, d_fs_mm, d_fs_area, d_scan_tmp, d_hf_off, d_conn_cnt,
-        d_conn_off, d_nei16, d_t16a, d_t16b, d_t16c, d_t8a, d_t8b, d_item_cnt, d_item_off, d_items;
+        d_conn_off, d_nei16, d_t16a, d_t16b, d_t16c, d_t8a, d_t8b, d_item_cnt, d_item_off, d_items, d_tile_ub, d_tile_base, d_tile_cursor,
+        d_tile_frags, d_ts_mm, d_ts_area, d_celloff_tmp, d_lookback;
+    bool force_global = false;  // RCB_FORCE_GLOBAL=1: never use the tile-resident back end (k_tile.cu)
     bool force_v1 = false;  // RCB_FORCE_V1=1: first-generation clipper (k_raster.cu), kept as the wide-tile fallback
     // pinned staging
     char* h_stage = nullptr;
@@ -100,6 +102,8 @@ struct rcb_result {
     ArenaLayout lay{};
     Arena devA, devB, hostA, hostB;
     bool downloaded = false, have_tinfo = false;
+    bool tile_mode = false;  // connections arena sized by an upper bound (Kcap); exact K comes from tinfo
+    uint64_t Kcap = 0;
     std::vector<TileInfo> tinfo;
 };
 
@@ -175,6 +179,8 @@ void prof_collect(rcb_ctx* ctx) {
         if (_e != cudaSuccess)                                                                             \
             return fail(ctx, RCB_ECUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, __LINE__, #expr); \
     } while (0)
+
+constexpr uint64_t kTileSmem = 226 * 1024;  // dynamic shared memory budget of the tile-resident kernels
 
 size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
@@ -335,6 +341,7 @@ struct Source {  // where the heightfield comes from
     const int16_t* smax = nullptr;
     const uint8_t* sarea = nullptr;
     const uint8_t* areas_override = nullptr;  // host, optional
+    bool no_tile_mode = false;                // set when the tile-resident back end reported an overflow
 };
 
 int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stage_mask, int erode_radius,
@@ -446,10 +453,10 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
 
     if (src.raster) {
         // ---- RASTER: count -> clip/emit -> scan -> scatter -> replay -> scan -------------------------
-        CUB(ctx->d_counters.ensure(8 * sizeof(unsigned long long)));
+        CUB(ctx->d_counters.ensure(16 * sizeof(unsigned long long)));
         CUB(ctx->d_cell_cnt.ensure(4 * (Ctot + 1)));
         CUB(ctx->d_frag_off.ensure(4 * (Ctot + 1)));
-        CUB(cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(unsigned long long), st));
+        CUB(cudaMemsetAsync(ctx->d_counters.p, 0, 16 * sizeof(unsigned long long), st));
         CUB(cudaMemsetAsync(ctx->d_cell_cnt.p, 0, 4 * (Ctot + 1), st));
         // tile info lives in the arena, which is sized after the span count is known: keep the clip
         // status in scratch until then
@@ -484,23 +491,135 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         r2.counters = rb.counters;
         r2.cell_cnt = rb.cell_cnt;
         uint64_t ub = 0, nitems = 0;
+        bool want_tile = false;
         if (do_raster && ntiles > 0) {
             if (v2) {
                 CUB(ctx->d_item_cnt.ensure(4 * (ntris + 2)));
                 CUB(ctx->d_item_off.ensure(4 * (ntris + 2)));
                 CUB(ctx->d_scan_tmp.ensure(4 * scan_tmp_elems(ntris + 1)));
                 r2.item_cnt = ctx->d_item_cnt.as<uint32_t>();
+                // tile-resident back end candidates: moderate tiles (the CSR arrays of a tile must fit shared memory)
+                want_tile = !ctx->force_global && !src.no_tile_mode && 12ull * max_cells + 4096 <= kTileSmem;
+                if (want_tile) {
+                    CUB(ctx->d_tile_ub.ensure(4 * ((size_t)ntiles + 1)));
+                    CUB(ctx->d_tile_base.ensure(4 * ((size_t)ntiles + 2)));
+                    CUB(ctx->d_tile_cursor.ensure(4 * ((size_t)ntiles + 1)));
+                    CUB(cudaMemsetAsync(ctx->d_tile_ub.p, 0, 4 * ((size_t)ntiles + 1), st));
+                    CUB(cudaMemsetAsync(ctx->d_tile_cursor.p, 0, 4 * ((size_t)ntiles + 1), st));
+                    r2.tile_ub = ctx->d_tile_ub.as<uint32_t>();
+                }
                 launch_bin_count(r2, st);
+                if (want_tile) launch_tile_segments(r2.tile_ub, ctx->d_tile_base.as<uint32_t>(), ntiles, r2.counters, st);
             } else {
                 launch_count_fragments(rb, st);
             }
-            CUB(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CUB(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             CUB(cudaStreamSynchronize(st));
             if (ctx->h_counters[3]) return bail(fail(ctx, RCB_ENAVMESH_GEN, "Triangle index out of bounds (max: %zu)", nverts - 1));
             ub = ctx->h_counters[0];
             nitems = ctx->h_counters[4];
             if (ub >= 0xfffffff0ull || nitems >= 0xfffffff0ull)
                 return bail(fail(ctx, RCB_EARG, "batch too large: fragment bound %llu", (unsigned long long)ub));
+            // the bound counts whole footprints; real fragment counts are about half of it on triangle meshes
+            if (want_tile && 12ull * max_cells + 9ull * (ctx->h_counters[5] / 3) + 4096 > kTileSmem) want_tile = false;
+        }
+        if (want_tile && ub > 0) {
+            // ================= tile-resident back end (k_tile.cu) ==============================================
+            const uint64_t ub_max = ctx->h_counters[5];
+            CUB(ctx->d_tile_frags.ensure(12 * ub + 64));
+            CUB(ctx->d_ts_mm.ensure(4 * ub + 64));
+            CUB(ctx->d_ts_area.ensure(ub + 64));
+            CUB(ctx->d_celloff_tmp.ensure(4 * (Ctot + ntiles) + 64));
+            CUB(ctx->d_lookback.ensure(8 * ((size_t)ntiles + 2)));
+            CUB(ctx->d_items.ensure(8 * nitems + 64));
+            CUB(cudaMemsetAsync(ctx->d_lookback.p, 0, 8 * ((size_t)ntiles + 2), st));
+            r2.tile_cursor = ctx->d_tile_cursor.as<uint32_t>();
+            r2.tile_base = ctx->d_tile_base.as<uint32_t>();
+            r2.tile_cap = ctx->d_tile_ub.as<uint32_t>();
+            r2.tile_frags = ctx->d_tile_frags.as<uint32_t>();
+            launch_exclusive_scan(r2.item_cnt, ctx->d_item_off.as<uint32_t>(), ntris, ctx->d_scan_tmp.as<uint32_t>(), st);
+            launch_fill_items(r2, ctx->d_item_off.as<uint32_t>(), ctx->d_items.as<uint2>(), st);
+            launch_clip_items(r2, ctx->d_items.as<uint2>(), (uint32_t)nitems, d_tinfo_tmp, st);
+            TileSpansArgs ta{};
+            ta.tiles = d_tiles;
+            ta.tile_frags = r2.tile_frags;
+            ta.tile_base = r2.tile_base;
+            ta.tile_cap = r2.tile_cap;
+            ta.tile_cursor = r2.tile_cursor;
+            ta.hf_cell_offset = ctx->d_celloff_tmp.as<uint32_t>();
+            ta.ts_mm = ctx->d_ts_mm.as<uint32_t>();
+            ta.ts_area = ctx->d_ts_area.as<uint8_t>();
+            ta.tinfo = d_tinfo_tmp;
+            ta.counters = r2.counters;
+            ta.fmask = fmask;
+            ta.merge_thr = src.merge_thr;
+            {
+                const uint64_t exact = 12ull * max_cells + 9ull * ub_max + 64;  // never overflows when it fits
+                ta.smem_bytes = (uint32_t)(exact <= kTileSmem ? exact : kTileSmem);
+            }
+            launch_tile_spans(ta, ntiles, st);
+            launch_tile_scan(d_tinfo_tmp, ntiles, r2.counters, st);
+            CUB(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CUB(cudaStreamSynchronize(st));
+            bool overflow = (ctx->h_counters[2] & 6ull) != 0;
+            S = ctx->h_counters[6];
+            const uint64_t walk = ctx->h_counters[7], s_max = ctx->h_counters[8];
+            const bool compact = (stage_mask & RCB_STAGE_COMPACT) != 0;
+            const uint64_t needB = compact ? 8ull * max_cells + 18ull * s_max + 256 : 4ull * max_cells + 64;
+            if (needB > kTileSmem) overflow = true;
+            if (overflow) {  // a tile does not fit shared memory: redo the batch on the global-memory back end
+                Source s2 = src;
+                s2.no_tile_mode = true;
+                rcb_result_free(res);
+                return run_pipeline(ctx, cfgs, ntiles, stage_mask, erode_radius, s2, out);
+            }
+            res->S = S;
+            res->F = ctx->h_counters[1];
+            make_layout(res->lay, ntiles, Ctot, S, stage_mask);
+            CUB(pool_get(ctx->free_dev, res->lay.bytesA, false, res->devA));
+            char* A = res->devA.p;
+            TileInfo* d_tinfo = (TileInfo*)(A + res->lay.tinfo);
+            CUB(cudaMemcpyAsync(d_tinfo, d_tinfo_tmp, sizeof(TileInfo) * (size_t)ntiles, cudaMemcpyDeviceToDevice, st));
+            const uint64_t Kcap = compact ? 8ull * walk : 0;
+            make_layout_conn(res->lay, Kcap);
+            if (compact) CUB(pool_get(ctx->free_dev, res->lay.bytesB, false, res->devB));
+            char* B = res->devB.p;
+            TileCompactArgs tc{};
+            tc.tiles = d_tiles;
+            tc.tile_base = r2.tile_base;
+            tc.hf_cell_offset_in = ctx->d_celloff_tmp.as<uint32_t>();
+            tc.ts_mm = ctx->d_ts_mm.as<uint32_t>();
+            tc.ts_area = ctx->d_ts_area.as<uint8_t>();
+            tc.tinfo = d_tinfo;
+            tc.counters = r2.counters;
+            tc.lookback = ctx->d_lookback.as<unsigned long long>();
+            tc.tile_ticket = (uint32_t*)(ctx->d_lookback.as<unsigned long long>() + ntiles);
+            tc.hf_cell_offset = (uint32_t*)(A + res->lay.hf_cell_offset);
+            tc.smin = (int16_t*)(A + res->lay.span_min);
+            tc.smax = (int16_t*)(A + res->lay.span_max);
+            tc.sarea = (uint8_t*)(A + res->lay.span_area);
+            if (compact) {
+                tc.cell_index = (uint32_t*)(A + res->lay.cell_index);
+                tc.cell_count = (uint32_t*)(A + res->lay.cell_count);
+                tc.areas = (uint8_t*)(A + res->lay.areas);
+                tc.con = (uint16_t*)(A + res->lay.con);
+                tc.first_conn = (uint32_t*)(A + res->lay.first_conn);
+                tc.dist = (uint16_t*)(A + res->lay.dist);
+                tc.conn_ref = (uint32_t*)(B + res->lay.conn_ref);
+                tc.conn_dir = (uint8_t*)(B + res->lay.conn_dir);
+                tc.conn_next = (uint32_t*)(B + res->lay.conn_next);
+            }
+            tc.do_compact = compact;
+            tc.do_erode = (stage_mask & RCB_STAGE_ERODE) != 0;
+            tc.do_dist = (stage_mask & RCB_STAGE_DIST) != 0;
+            tc.erode_radius = erode_radius;
+            tc.smem_bytes = (uint32_t)needB;
+            launch_tile_compact(tc, ntiles, st);
+            res->tile_mode = true;
+            res->Kcap = Kcap;
+            CUB(cudaGetLastError());
+            *out = res;
+            return RCB_OK;
         }
         if (ub > 0) {
             CUB(ctx->d_frag_tmp.ensure(16 * ub));
@@ -655,6 +774,12 @@ int fetch_tinfo(rcb_result* res) {
         CU(cudaStreamSynchronize(ctx->stream));
     }
     res->have_tinfo = true;
+    if (res->tile_mode) {
+        uint64_t k = 0;
+        for (auto& t : res->tinfo) k += t.conn_count;
+        res->K = k;
+        res->have_K = true;
+    }
     return RCB_OK;
 }
 
@@ -672,13 +797,14 @@ int rcb_create(int device, rcb_ctx** out) {
     auto* ctx = new rcb_ctx();
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(unsigned long long)) != cudaSuccess) {
+        cudaMallocHost((void**)&ctx->h_counters, 32 * sizeof(unsigned long long)) != cudaSuccess) {
         delete ctx;
         return RCB_ECUDA;
     }
     ctx->stream = ctx->own_stream;
     ctx->launches0 = g_rcb_launches;
     if (const char* e = getenv("RCB_FORCE_V1")) ctx->force_v1 = e[0] == '1';
+    if (const char* e = getenv("RCB_FORCE_GLOBAL")) ctx->force_global = e[0] == '1';
     *out = ctx;
     return RCB_OK;
 }
@@ -690,7 +816,8 @@ void rcb_destroy(rcb_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_verts, &ctx->d_tris, &ctx->d_tri_areas, &ctx->d_tiles, &ctx->d_bin_off, &ctx->d_bin_tiles,
                       &ctx->d_counters, &ctx->d_cell_cnt, &ctx->d_frag_off, &ctx->d_frag_tmp, &ctx->d_fs_tri, &ctx->d_fs_mm,
                       &ctx->d_fs_area, &ctx->d_scan_tmp, &ctx->d_hf_off, &ctx->d_conn_cnt, &ctx->d_conn_off, &ctx->d_nei16,
-                      &ctx->d_t16a, &ctx->d_t16b, &ctx->d_t16c, &ctx->d_t8a, &ctx->d_t8b, &ctx->d_item_cnt, &ctx->d_item_off, &ctx->d_items};
+                      &ctx->d_t16a, &ctx->d_t16b, &ctx->d_t16c, &ctx->d_t8a, &ctx->d_t8b, &ctx->d_item_cnt, &ctx->d_item_off, &ctx->d_items, &ctx->d_tile_ub, &ctx->d_tile_base,
+                      &ctx->d_tile_cursor, &ctx->d_tile_frags, &ctx->d_ts_mm, &ctx->d_ts_area, &ctx->d_celloff_tmp, &ctx->d_lookback};
     for (auto* b : bufs) b->release();
     for (auto& a : ctx->free_dev) cudaFree(a.p);
     for (auto& a : ctx->free_host) cudaFreeHost(a.p);
@@ -850,7 +977,7 @@ int rcb_result_totals(const rcb_result* cres, rcb_totals* out) {
     out->spans = res->S;
     out->connections = res->K;
     for (auto& t : res->tinfo) out->walkable_spans += t.walkable_span_count;
-    out->result_bytes = res->lay.bytesA + res->lay.bytesB;
+    out->result_bytes = res->lay.bytesA + (res->tile_mode ? 9 * res->K : res->lay.bytesB);
     return RCB_OK;
 }
 
@@ -863,7 +990,18 @@ int rcb_result_download(rcb_result* res) {
     CU(cudaMemcpyAsync(res->hostA.p, res->devA.p, res->lay.bytesA, cudaMemcpyDeviceToHost, ctx->stream));
     if (res->lay.bytesB) {
         CU(pool_get(ctx->free_host, res->lay.bytesB, true, res->hostB));
-        CU(cudaMemcpyAsync(res->hostB.p, res->devB.p, res->lay.bytesB, cudaMemcpyDeviceToHost, ctx->stream));
+        if (res->tile_mode) {  // the arena is sized by a bound on K: copy the used prefix of each array
+            int r = fetch_tinfo(res);
+            if (r) return r;
+            const size_t K = res->K;
+            if (K) {
+                CU(cudaMemcpyAsync(res->hostB.p + res->lay.conn_ref, res->devB.p + res->lay.conn_ref, 4 * K, cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaMemcpyAsync(res->hostB.p + res->lay.conn_next, res->devB.p + res->lay.conn_next, 4 * K, cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaMemcpyAsync(res->hostB.p + res->lay.conn_dir, res->devB.p + res->lay.conn_dir, K, cudaMemcpyDeviceToHost, ctx->stream));
+            }
+        } else {
+            CU(cudaMemcpyAsync(res->hostB.p, res->devB.p, res->lay.bytesB, cudaMemcpyDeviceToHost, ctx->stream));
+        }
     }
     CU(cudaStreamSynchronize(ctx->stream));
     res->tinfo.assign((TileInfo*)(res->hostA.p + res->lay.tinfo), (TileInfo*)(res->hostA.p + res->lay.tinfo) + res->ntiles);

@@ -118,6 +118,55 @@ void launch_bin_count(const Raster2& rb, cudaStream_t s);
 void launch_fill_items(const Raster2& rb, const uint32_t* item_off, uint2* items, cudaStream_t s);
 void launch_clip_items(const Raster2& rb, const uint2* items, uint32_t nitems, TileInfo* tinfo, cudaStream_t s);
 
+// tile-resident back end (k_tile.cu)
+struct TileSpansArgs {
+    const TileDesc* tiles;
+    const uint32_t* tile_frags;   // 3 words per record, per-tile segments
+    const uint32_t* tile_base;    // [ntiles] first record of the segment (also the base of ts_* below)
+    const uint32_t* tile_cap;     // [ntiles]
+    const uint32_t* tile_cursor;  // [ntiles] records written
+    uint32_t* hf_cell_offset;     // [Ctot + ntiles] tile-relative CSR offsets (C+1 per tile)
+    uint32_t* ts_mm;              // tile-local compact spans: smin | smax << 16
+    uint8_t* ts_area;
+    TileInfo* tinfo;
+    unsigned long long* counters;
+    uint32_t fmask;
+    int32_t merge_thr;
+    uint32_t smem_bytes;
+};
+struct TileCompactArgs {
+    const TileDesc* tiles;
+    const uint32_t* tile_base;
+    const uint32_t* hf_cell_offset_in;  // from k_tile_spans
+    const uint32_t* ts_mm;
+    const uint8_t* ts_area;
+    TileInfo* tinfo;
+    unsigned long long* counters;
+    unsigned long long* lookback;  // [ntiles], zeroed
+    uint32_t* tile_ticket;         // zeroed
+    // outputs (final arrays)
+    uint32_t* hf_cell_offset;
+    int16_t* smin;
+    int16_t* smax;
+    uint8_t* sarea;
+    uint32_t* cell_index;
+    uint32_t* cell_count;
+    uint8_t* areas;
+    uint16_t* con;
+    uint32_t* first_conn;
+    uint16_t* dist;
+    uint32_t* conn_ref;
+    uint8_t* conn_dir;
+    uint32_t* conn_next;
+    int do_compact, do_erode, do_dist, erode_radius;
+    uint32_t smem_bytes;
+};
+void launch_tile_spans(const TileSpansArgs& a, int ntiles, cudaStream_t s);
+void launch_tile_segments(const uint32_t* tile_ub, uint32_t* tile_base, int ntiles, unsigned long long* counters, cudaStream_t s);
+void launch_tile_segments(const uint32_t* tile_ub, uint32_t* tile_base, int ntiles, unsigned long long* counters, cudaStream_t s);
+void launch_tile_scan(TileInfo* tinfo, int ntiles, unsigned long long* counters, cudaStream_t s);
+void launch_tile_compact(const TileCompactArgs& a, int ntiles, cudaStream_t s);
+
 // exclusive scan of n u32 values, out has n+1 entries (out[n] = total).  tmp: >= scan_tmp_elems(n) u32.
 size_t scan_tmp_elems(size_t n);
 void launch_exclusive_scan(const uint32_t* in, uint32_t* out, size_t n, uint32_t* tmp, cudaStream_t s);
