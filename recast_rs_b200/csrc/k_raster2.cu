@@ -119,7 +119,11 @@ __global__ void __launch_bounds__(256) k_bin_count(Raster2 rb) {
                 const uint32_t f = (uint32_t)(x1 - x0 + 1) * nrows;
                 items += (nrows + CLIP_ROWS - 1) / CLIP_ROWS;
                 ub += f;
-                if (rb.tile_ub) atomicAdd(&rb.tile_ub[tile], f);
+                if (rb.tile_ub) {  // neighbouring triangles mostly share the tile: one atomic per (warp, tile)
+                    const unsigned peers = __match_any_sync(__activemask(), tile);
+                    const uint32_t sum = __reduce_add_sync(peers, f);
+                    if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&rb.tile_ub[tile], sum);
+                }
             });
         } else {
             bad = true;
@@ -318,6 +322,7 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
     __syncthreads();
 
     // ---------------- phase 2: x-chain, one row polygon per thread at a time ------------------------------
+    const bool use_minx = (rb.flags & 1u) != 0;
     const uint32_t nlist = sm.nlist;
     for (uint32_t li = threadIdx.x; li < nlist; li += CLIP_THREADS) {
         const uint32_t* slot = sm.slots + (uint32_t)sm.list[li] * SLOT_WORDS;
@@ -328,21 +333,31 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
         const uint32_t area = h2 >> 24;
         const int x0 = (int)(h3 & 0xffffu), x1 = (int)(h3 >> 16);
         const TileDesc& td = rb.tiles[tile];
+        float minx = 0.f;
+        bool has_nan = false;
         for (int v = 0; v < n; ++v) {
-            XB(0, v, 0) = __uint_as_float(slot[4 + 2 * v]);
+            const float vx = __uint_as_float(slot[4 + 2 * v]);
+            XB(0, v, 0) = vx;
             XB(0, v, 1) = __uint_as_float(slot[5 + 2 * v]);
+            has_nan = has_nan || (vx != vx);
+            minx = v ? fminf(minx, vx) : vx;
         }
         bool ovf = false;
         int cur = 0;
         for (int x = x0; x <= x1 && n > 0; ++x) {  // rasterization.rs:317-362
             const float cx = __fadd_rn(td.bmin[0], __fmul_rn((float)(x + 1), td.cs));
             // exact skip: every vertex strictly right of the cut => cell piece empty, rest == polygon
-            bool all_right = true;
-            for (int i = 0; i < n; ++i) all_right = all_right && (XB(cur, i, 0) > cx);
-            if (all_right) continue;
+            if (use_minx) {
+                if (!has_nan && minx > cx) continue;
+            } else {
+                bool all_right = true;
+                for (int i = 0; i < n; ++i) all_right = all_right && (XB(cur, i, 0) > cx);
+                if (all_right) continue;
+            }
             const int nxt = cur ^ 1;
             int ncell = 0, nrest = 0;
-            float miny = 0.f, maxy = 0.f;
+            float miny = 0.f, maxy = 0.f, nminx = 0.f;
+            bool nnan = false;
             for (int i = 0; i < n; ++i) {
                 const int j = (i + 1 == n) ? 0 : i + 1;
                 const float vix = XB(cur, i, 0), viy = XB(cur, i, 1), vjx = XB(cur, j, 0);
@@ -359,6 +374,8 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
                         XB(nxt, nrest, 1) = viy;
                     } else
                         ovf = true;
+                    nminx = nrest ? fminf(nminx, vix) : vix;
+                    nnan = nnan || (vix != vix);
                     nrest++;
                 }
                 if ((si < 0 && sj > 0) || (si > 0 && sj < 0)) {
@@ -374,11 +391,15 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
                         XB(nxt, nrest, 1) = py;
                     } else
                         ovf = true;
+                    nminx = nrest ? fminf(nminx, px) : px;
+                    nnan = nnan || (px != px);
                     nrest++;
                 }
             }
             cur = nxt;
             n = min(nrest, XCAP);
+            minx = nminx;
+            has_nan = nnan;
             if (ncell >= 3) {  // rasterization.rs:325-361
                 int smin = __float2int_rz(floorf(__fmul_rn(__fsub_rn(miny, td.bmin[1]), td.ich)));
                 int smax = __float2int_rz(ceilf(__fmul_rn(__fsub_rn(maxy, td.bmin[1]), td.ich)));

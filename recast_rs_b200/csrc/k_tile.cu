@@ -32,33 +32,31 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
     return v;
 }
 
-// In-place exclusive scan of cnt[0..n) into out[0..n], out[n] = total (cnt and out may alias).
-// Every thread scans a contiguous chunk; uses sh_warp[TILE_THREADS/32 + 1].
+// Exclusive scan of cnt[0..n) into out[0..n], out[n] = total (cnt and out may alias).  Rounds of
+// TILE_THREADS consecutive elements (thread t takes element r*TILE_THREADS + t: conflict-free), each
+// round one block-wide scan with a running carry.  Uses sh_warp[TILE_THREADS/32 + 1].
 __device__ uint32_t block_scan_array(const uint32_t* cnt, uint32_t* out, uint32_t n, uint32_t* sh_warp) {
-    const uint32_t per = (n + TILE_THREADS - 1) / TILE_THREADS;
-    const uint32_t b = min(n, threadIdx.x * per), e = min(n, b + per);
-    uint32_t s = 0;
-    for (uint32_t i = b; i < e; ++i) s += cnt[i];
-    const uint32_t inc = warp_incl_scan(s);
-    if ((threadIdx.x & 31) == 31) sh_warp[threadIdx.x >> 5] = inc;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        const uint32_t w = threadIdx.x < TILE_THREADS / 32 ? sh_warp[threadIdx.x] : 0;
-        const uint32_t winc = warp_incl_scan(w);
-        if (threadIdx.x < TILE_THREADS / 32) sh_warp[threadIdx.x] = winc - w;
-        if (threadIdx.x == 31) sh_warp[TILE_THREADS / 32] = winc;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n; base += TILE_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n ? cnt[i] : 0;
+        const uint32_t inc = warp_incl_scan(v);
+        if ((threadIdx.x & 31) == 31) sh_warp[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const uint32_t w = threadIdx.x < TILE_THREADS / 32 ? sh_warp[threadIdx.x] : 0;
+            const uint32_t winc = warp_incl_scan(w);
+            if (threadIdx.x < TILE_THREADS / 32) sh_warp[threadIdx.x] = winc - w;
+            if (threadIdx.x == 31) sh_warp[TILE_THREADS / 32] = winc;
+        }
+        __syncthreads();
+        if (i < n) out[i] = carry + inc - v + sh_warp[threadIdx.x >> 5];
+        carry += sh_warp[TILE_THREADS / 32];
+        __syncthreads();
     }
+    if (threadIdx.x == 0) out[n] = carry;
     __syncthreads();
-    uint32_t run = inc - s + sh_warp[threadIdx.x >> 5];
-    const uint32_t total = sh_warp[TILE_THREADS / 32];
-    for (uint32_t i = b; i < e; ++i) {
-        const uint32_t c = cnt[i];
-        out[i] = run;
-        run += c;
-    }
-    if (threadIdx.x == 0) out[n] = total;
-    __syncthreads();
-    return total;
+    return carry;
 }
 
 // ======================================================================================================
@@ -72,6 +70,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_spans(TileSpansArgs a)
     const TileDesc& td = a.tiles[tile];
     const int W = td.width, H = td.height;
     const uint32_t C = (uint32_t)(W * H);
+    const unsigned long long wmagic = td.wmagic;
     const uint32_t F = min(a.tile_cursor[tile], a.tile_cap[tile]);
     // layout: off[C+1] | cnt[C] | soff[C+1] | tri[F] | mm[F] | area[F bytes]
     const size_t need = 4ull * (3ull * C + 2) + 9ull * F + 16;
@@ -194,7 +193,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_spans(TileSpansArgs a)
     for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
         const uint32_t b = off[c], e = b + cnt[c];
         if (b == e) continue;
-        const int x = c % W, z = c / W;
+        const int z = (int)rcb_div_w(c, wmagic), x = (int)c - z * W;
         const int dx[4] = {0, 1, 0, -1}, dz[4] = {-1, 0, 1, 0};
         uint32_t nb[4], ne[4];
         bool oob[4];
@@ -370,12 +369,13 @@ struct TileB {
     const uint8_t* area;   // [S] span area (post-filter)
     uint8_t* areas;        // [S] chf.areas (erosion writes it)
     const uint8_t* nei;    // [8][S] neighbour offset inside the neighbour cell, 0xff = none
-    uint32_t S;
+    uint32_t S, S4;  // S4: S rounded up to 4 (row pitch of nei)
     int W, H;
+    unsigned long long wmagic;
 };
 
 __device__ __forceinline__ uint32_t tnei(const TileB& g, uint32_t s, int x, int z, int dir) {
-    const uint32_t o = g.nei[(uint32_t)dir * g.S + s];
+    const uint32_t o = g.nei[(uint32_t)dir * g.S4 + s];
     if (o == 0xffu) return RCB_NONE;
     return g.soff[(z + t_dirz[dir]) * g.W + (x + t_dirx[dir])] + o;
 }
@@ -387,14 +387,33 @@ __device__ __forceinline__ T sat_add(T v, unsigned b) {
     return (T)(r > mx ? mx : r);
 }
 
+// Forward-sweep gather table: for every span the tile-local ids of NW, NW.E, E, E.NE (0xffff = none).
+// The chain nei -> cell offset -> nei -> cell offset does not depend on distances, so it is hoisted out
+// of the H sequential row steps (it was 27 % of k_tile_compact's stall samples, profiles/r01_v3_*).
+__device__ void build_forward_index(const TileB& g, uint2* fidx) {
+    const int W = g.W;
+    const uint32_t C = (uint32_t)(W * g.H);
+    for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
+        const int z = (int)rcb_div_w(c, g.wmagic), x = (int)c - z * W;
+        for (uint32_t s = g.soff[c]; s < g.soff[c + 1]; ++s) {
+            uint32_t a0 = tnei(g, s, x, z, 0), a1 = RCB_NONE, b0 = tnei(g, s, x, z, 3), b1 = RCB_NONE;
+            if (a0 != RCB_NONE) a1 = tnei(g, a0, x - 1, z - 1, 3);
+            if (b0 != RCB_NONE) b1 = tnei(g, b0, x + 1, z, 2);
+            fidx[s] = make_uint2((a0 & 0xffffu) | (a1 << 16), (b0 & 0xffffu) | (b1 << 16));
+        }
+    }
+}
+
 // boundary -> forward rows -> backward gather, on shared memory.  ERODE: thresholds areas; else D + max.
+// fidx: optional forward gather table (nullptr: walk the neighbour chain inside the row loop).
 template <typename T, bool ERODE>
-__device__ void tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_t* sh_max) {
+__device__ void tile_sweep(const TileB& g, T* init, T* Fw, const uint2* fidx, unsigned thr, uint32_t* sh_max) {
     const int W = g.W, H = g.H;
     const uint32_t C = (uint32_t)(W * H);
+    const unsigned long long wmagic = g.wmagic;
     const T inf = (T)~(T)0;
     for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
-        const int x = c % W, z = c / W;
+        const int z = (int)rcb_div_w(c, wmagic), x = (int)c - z * W;
         for (uint32_t s = g.soff[c]; s < g.soff[c + 1]; ++s) {
             const uint8_t ar = g.areas[s];
             int cnt = 0;
@@ -410,32 +429,48 @@ __device__ void tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_
         }
     }
     __syncthreads();
-    for (int z = 0; z < H; ++z) {  // forward: row z needs row z-1 final and row z init (see k_dist.cu)
-        for (int x = threadIdx.x; x < W; x += TILE_THREADS) {
-            const uint32_t c = (uint32_t)(z * W + x);
-            for (uint32_t s = g.soff[c]; s < g.soff[c + 1]; ++s) {
-                T v = init[s];
-                const uint32_t aa = tnei(g, s, x, z, 0);
-                if (aa != RCB_NONE) {
-                    v = min(v, sat_add<T>(Fw[aa], 2));
-                    const uint32_t ab = tnei(g, aa, x - 1, z - 1, 3);
-                    if (ab != RCB_NONE) v = min(v, sat_add<T>(Fw[ab], 3));
+    // forward: row z needs row z-1 final and row z init (see k_dist.cu).  Only the warps that own a
+    // column take part in the H row barriers (named barrier 1); the rest wait at the __syncthreads below.
+    const int sweep_threads = min(TILE_THREADS, ((W + 31) / 32) * 32);
+    if ((int)threadIdx.x < sweep_threads) {
+        for (int z = 0; z < H; ++z) {
+            for (int x = threadIdx.x; x < W; x += sweep_threads) {
+                const uint32_t c = (uint32_t)(z * W + x);
+                const uint32_t sb = g.soff[c], se = g.soff[c + 1];
+                for (uint32_t s = sb; s < se; ++s) {
+                    T v = init[s];
+                    if (fidx) {
+                        const uint2 ix = fidx[s];
+                        const uint32_t a0 = ix.x & 0xffffu, a1 = ix.x >> 16, b0 = ix.y & 0xffffu, b1 = ix.y >> 16;
+                        if (a0 != 0xffffu) v = min(v, sat_add<T>(Fw[a0], 2));
+                        if (a1 != 0xffffu) v = min(v, sat_add<T>(Fw[a1], 3));
+                        if (b0 != 0xffffu) v = min(v, sat_add<T>(init[b0], 2));
+                        if (b1 != 0xffffu) v = min(v, sat_add<T>(Fw[b1], 3));
+                    } else {
+                        const uint32_t aa = tnei(g, s, x, z, 0);
+                        if (aa != RCB_NONE) {
+                            v = min(v, sat_add<T>(Fw[aa], 2));
+                            const uint32_t ab = tnei(g, aa, x - 1, z - 1, 3);
+                            if (ab != RCB_NONE) v = min(v, sat_add<T>(Fw[ab], 3));
+                        }
+                        const uint32_t ba = tnei(g, s, x, z, 3);
+                        if (ba != RCB_NONE) {
+                            v = min(v, sat_add<T>(init[ba], 2));
+                            const uint32_t bb = tnei(g, ba, x + 1, z, 2);
+                            if (bb != RCB_NONE) v = min(v, sat_add<T>(Fw[bb], 3));
+                        }
+                    }
+                    Fw[s] = v;
                 }
-                const uint32_t ba = tnei(g, s, x, z, 3);
-                if (ba != RCB_NONE) {
-                    v = min(v, sat_add<T>(init[ba], 2));
-                    const uint32_t bb = tnei(g, ba, x + 1, z, 2);
-                    if (bb != RCB_NONE) v = min(v, sat_add<T>(Fw[bb], 3));
-                }
-                Fw[s] = v;
             }
+            asm volatile("bar.sync 1, %0;" ::"r"(sweep_threads) : "memory");
         }
-        __syncthreads();
     }
+    __syncthreads();
     // backward = gather from forward values; D overwrites init (init is dead)
     uint32_t vmax = 0;
     for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
-        const int x = c % W, z = c / W;
+        const int z = (int)rcb_div_w(c, wmagic), x = (int)c - z * W;
         for (uint32_t s = g.soff[c]; s < g.soff[c + 1]; ++s) {
             T v = Fw[s];
             const uint32_t aa = tnei(g, s, x, z, 2);
@@ -467,6 +502,34 @@ __device__ void tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_
     }
 }
 
+// Exclusive prefix of `mine` over tiles by decoupled look-back (warp 0 calls this with all 32 lanes).
+// look[t] = flag << 62 | value; flag 1 = tile aggregate, 2 = inclusive prefix.  Tiles obtain their ids
+// from a ticket counter, so every predecessor is already running or done.
+__device__ uint32_t lookback_exclusive(volatile unsigned long long* look, uint32_t tile, uint32_t mine) {
+    const uint32_t lane = threadIdx.x & 31;
+    if (lane == 0) look[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | mine;
+    uint32_t excl = 0;
+    for (int t0 = (int)tile - 1; t0 >= 0; t0 -= 32) {
+        const int t = t0 - (int)lane;
+        unsigned long long v = 2ull << 62;  // before tile 0: inclusive prefix 0
+        if (t >= 0) {
+            do {
+                v = look[t];
+            } while ((v >> 62) == 0);
+        }
+        const unsigned incl = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+        const uint32_t val = (uint32_t)(v & 0xffffffffull);
+        if (incl) {
+            const int first = __ffs(incl) - 1;  // nearest predecessor with an inclusive prefix
+            excl += __reduce_add_sync(0xffffffffu, (int)lane <= first ? val : 0u);
+            break;
+        }
+        excl += __reduce_add_sync(0xffffffffu, val);
+    }
+    if (lane == 0 && tile != 0) look[tile] = (2ull << 62) | (unsigned long long)(excl + mine);
+    return excl;
+}
+
 __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_compact(TileCompactArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t sh_warp[TILE_THREADS / 32 + 1];
@@ -482,37 +545,33 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_compact(TileCompactArg
     const TileDesc& td = a.tiles[tile];
     const int W = td.width, H = td.height;
     const uint32_t C = (uint32_t)(W * H);
+    const unsigned long long wmagic = td.wmagic;
     const uint32_t S = a.tinfo[tile].span_count;
     const uint32_t span_base = a.tinfo[tile].span_base;
-    // layout: soff[C+1] | coff[C+1] | mm[S] | d16a[S] u16 | d16b[S] u16 | area[S] | areas[S] | nei[8S]
+    // layout: soff[C+1] | d16a[S] u16 | d16b[S] u16 | areas[S] | nei[8S] | coff[C+1] | mm[S] | area[S]
+    // (coff, mm and area are dead once the connections are written; the forward gather table reuses them)
     const size_t need = 4ull * (2ull * C + 2) + 4ull * S + 4ull * S + 2ull * S + 8ull * S + 64;
     const bool fits = a.do_compact ? need <= a.smem_bytes : 4ull * (C + 1) <= a.smem_bytes;
+    const uint32_t S2 = (S + 1) & ~1u, S4 = (S + 3) & ~3u;
     uint32_t* soff = smem;
-    uint32_t* coff = soff + (C + 1);
+    uint16_t* d16a = reinterpret_cast<uint16_t*>(soff + (C + 1));
+    uint16_t* d16b = d16a + S2;
+    uint8_t* areas = reinterpret_cast<uint8_t*>(d16b + S2);
+    uint8_t* nei = areas + S4;
+    uint32_t* coff = reinterpret_cast<uint32_t*>(nei + 8ull * S4);
     uint32_t* mm = coff + (C + 1);
-    uint16_t* d16a = reinterpret_cast<uint16_t*>(mm + S);
-    uint16_t* d16b = d16a + ((S + 1) & ~1u);
-    uint8_t* area = reinterpret_cast<uint8_t*>(d16b + ((S + 1) & ~1u));
-    uint8_t* areas = area + ((S + 3) & ~3u);
-    uint8_t* nei = areas + ((S + 3) & ~3u);
+    uint8_t* area = reinterpret_cast<uint8_t*>(mm + S);
 
     volatile unsigned long long* look = a.lookback;
     if (!fits) {
         // still take part in the look-back chain so later tiles do not wait forever
-        if (threadIdx.x == 0) {
-            atomicOr(&a.counters[2], 4ull);
-            unsigned long long excl = 0;
-            for (int t = (int)tile - 1; t >= 0; --t) {
-                unsigned long long v;
-                do {
-                    v = look[t];
-                } while ((v >> 62) == 0);
-                excl += v & 0xffffffffull;
-                if ((v >> 62) == 2) break;
+        if (threadIdx.x < 32) {
+            const uint32_t excl = lookback_exclusive(look, tile, 0);
+            if (threadIdx.x == 0) {
+                atomicOr(&a.counters[2], 4ull);
+                a.tinfo[tile].conn_base = excl;
+                a.tinfo[tile].conn_count = 0;
             }
-            look[tile] = (2ull << 62) | excl;
-            a.tinfo[tile].conn_base = (uint32_t)excl;
-            a.tinfo[tile].conn_count = 0;
         }
         return;
     }
@@ -552,7 +611,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_compact(TileCompactArg
         const uint32_t b = soff[c], e = soff[c + 1];
         uint32_t nconn = 0;
         if (e > b) {
-            const int x = c % W, z = c / W;
+            const int z = (int)rcb_div_w(c, wmagic), x = (int)c - z * W;
             uint32_t nb[8], ne[8];
 #pragma unroll
             for (int d = 0; d < 8; ++d) {
@@ -584,7 +643,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_compact(TileCompactArg
                                 best = ns - nb[d];
                             }
                         }
-                        nei[(uint32_t)d * S + s] = (uint8_t)best;
+                        nei[(uint32_t)d * S4 + s] = (uint8_t)best;
                         if (best != 0xffu) {
                             nconn++;
                             if (d == 7) c4[0] = best;
@@ -595,7 +654,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_compact(TileCompactArg
                     }
                 } else {
 #pragma unroll
-                    for (int d = 0; d < 8; ++d) nei[(uint32_t)d * S + s] = 0xffu;
+                    for (int d = 0; d < 8; ++d) nei[(uint32_t)d * S4 + s] = 0xffu;
                 }
                 *reinterpret_cast<uint2*>(a.con + 4ull * (span_base + s)) = make_uint2(c4[0] | (c4[1] << 16), c4[2] | (c4[3] << 16));
             }
@@ -605,23 +664,14 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_compact(TileCompactArg
     __syncthreads();
     // 4. connection offsets inside the tile, then the tile's base by decoupled look-back over tiles
     const uint32_t K = block_scan_array(coff, coff, C, sh_warp);
-    if (threadIdx.x == 0) {
-        if (sh_misc[3]) atomicOr(&a.counters[2], 4ull);
-        look[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | K;
-        __threadfence();
-        unsigned long long excl = 0;
-        for (int t = (int)tile - 1; t >= 0; --t) {
-            unsigned long long v;
-            do {
-                v = look[t];
-            } while ((v >> 62) == 0);
-            excl += v & 0xffffffffull;
-            if ((v >> 62) == 2) break;
+    if (threadIdx.x < 32) {
+        const uint32_t excl = lookback_exclusive(look, tile, K);
+        if (threadIdx.x == 0) {
+            if (sh_misc[3]) atomicOr(&a.counters[2], 4ull);
+            sh_misc[1] = excl;
+            a.tinfo[tile].conn_base = excl;
+            a.tinfo[tile].conn_count = K;
         }
-        if (tile != 0) look[tile] = (2ull << 62) | (excl + K);
-        sh_misc[1] = (uint32_t)excl;
-        a.tinfo[tile].conn_base = (uint32_t)excl;
-        a.tinfo[tile].conn_count = K;
     }
     __syncthreads();
     const uint32_t conn_base = sh_misc[1];
@@ -629,12 +679,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_compact(TileCompactArg
     for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
         const uint32_t b = soff[c], e = soff[c + 1];
         if (b == e) continue;
-        const int x = c % W, z = c / W;
+        const int z = (int)rcb_div_w(c, wmagic), x = (int)c - z * W;
         uint32_t k = coff[c];
         for (uint32_t s = b; s < e; ++s) {
             uint32_t first = RCB_NONE;
             for (int d = 7; d >= 0; --d) {
-                const uint32_t o = nei[(uint32_t)d * S + s];
+                const uint32_t o = nei[(uint32_t)d * S4 + s];
                 if (o == 0xffu) continue;
                 a.conn_ref[conn_base + k] = soff[(z + t_dirz[d]) * W + (x + t_dirx[d])] + o;
                 a.conn_dir[conn_base + k] = (uint8_t)d;
@@ -645,19 +695,27 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_compact(TileCompactArg
             a.first_conn[span_base + s] = first;
         }
     }
-    const TileB g{soff, mm, area, areas, nei, S, W, H};
+    const TileB g{soff, mm, area, areas, nei, S, S4, W, H, wmagic};
+    // coff and mm are dead once the connections are written: reuse them for the forward gather table
+    uint2* fidx = nullptr;
+    if ((a.do_erode || a.do_dist) && S < 0xffffu && 8ull * S + 8 <= 4ull * (C + 1) + 5ull * S) {
+        __syncthreads();
+        fidx = reinterpret_cast<uint2*>(reinterpret_cast<uintptr_t>(coff + 1) & ~(uintptr_t)7);
+        build_forward_index(g, fidx);
+        __syncthreads();
+    }
     // 6. erosion (area.rs:73-234) — before the distance field when both are requested
     if (a.do_erode) {
         const unsigned thr = (unsigned)(uint8_t)(uint32_t)(a.erode_radius * 2);
-        tile_sweep<uint8_t, true>(g, reinterpret_cast<uint8_t*>(d16a), reinterpret_cast<uint8_t*>(d16b), thr, nullptr);
+        tile_sweep<uint8_t, true>(g, reinterpret_cast<uint8_t*>(d16a), reinterpret_cast<uint8_t*>(d16b), fidx, thr, nullptr);
     }
     for (uint32_t s = threadIdx.x; s < S; s += TILE_THREADS) a.areas[span_base + s] = areas[s];
     // 7. distance field (compact_heightfield.rs:514-727)
     if (a.do_dist) {
-        tile_sweep<uint16_t, false>(g, d16a, d16b, 0, &sh_misc[2]);
+        tile_sweep<uint16_t, false>(g, d16a, d16b, fidx, 0, &sh_misc[2]);
         // box blur: d16a holds D; result to global
         for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
-            const int x = c % W, z = c / W;
+            const int z = (int)rcb_div_w(c, wmagic), x = (int)c - z * W;
             for (uint32_t s = soff[c]; s < soff[c + 1]; ++s) {
                 const uint32_t cd = d16a[s];
                 uint32_t r = cd;

@@ -73,6 +73,7 @@ struct rcb_ctx {
     DevBuf d_counters, d_cell_cnt, d_frag_off, d_frag_tmp, d_fs_tri, d_fs_mm, d_fs_area, d_scan_tmp, d_hf_off, d_conn_cnt,
         d_conn_off, d_nei16, d_t16a, d_t16b, d_t16c, d_t8a, d_t8b, d_item_cnt, d_item_off, d_items, d_tile_ub, d_tile_base, d_tile_cursor,
         d_tile_frags, d_ts_mm, d_ts_area, d_celloff_tmp, d_lookback;
+    uint32_t clip_flags = 1;    // RCB_CLIP_FLAGS (A/B runs): bit0 min-x skip test in the clipper
     bool force_global = false;  // RCB_FORCE_GLOBAL=1: never use the tile-resident back end (k_tile.cu)
     bool force_v1 = false;  // RCB_FORCE_V1=1: first-generation clipper (k_raster.cu), kept as the wide-tile fallback
     // pinned staging
@@ -392,6 +393,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             return fail(ctx, RCB_EARG, "batch too large: more than 2^32 cells");
         }
         t.cell_base = (uint32_t)Ctot;
+        t.wmagic = ((1ull << 40) / (unsigned long long)c.width) + 1;
         Ctot += cells;
         if (cells > max_cells) max_cells = (uint32_t)cells;
     }
@@ -490,6 +492,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         r2.mesh = rb.mesh;
         r2.counters = rb.counters;
         r2.cell_cnt = rb.cell_cnt;
+        r2.flags = ctx->clip_flags;
         uint64_t ub = 0, nitems = 0;
         bool want_tile = false;
         if (do_raster && ntiles > 0) {
@@ -805,6 +808,7 @@ int rcb_create(int device, rcb_ctx** out) {
     ctx->launches0 = g_rcb_launches;
     if (const char* e = getenv("RCB_FORCE_V1")) ctx->force_v1 = e[0] == '1';
     if (const char* e = getenv("RCB_FORCE_GLOBAL")) ctx->force_global = e[0] == '1';
+    if (const char* e = getenv("RCB_CLIP_FLAGS")) ctx->clip_flags = (uint32_t)atoi(e);
     *out = ctx;
     return RCB_OK;
 }

@@ -28,7 +28,12 @@ struct TileDesc {
     int32_t neg_climb;       // (-climb as i16) as i32, heightfield.rs:382
     uint32_t cell_base;      // first global cell
     int32_t bin_x0, bin_z0;  // lower corner of the tile's range in the locator grid (dedup rule)
+    unsigned long long wmagic;  // ceil(2^40 / width): c / width == (c * wmagic) >> 40 for c < 2^24, width < 2^16
 };
+
+__host__ __device__ inline uint32_t rcb_div_w(uint32_t c, unsigned long long wmagic) {
+    return (uint32_t)(((unsigned long long)c * wmagic) >> 40);
+}
 
 // Per-tile results (device-written, downloaded with the arena).
 struct TileInfo {
@@ -113,6 +118,7 @@ struct Raster2 {
     const uint32_t* tile_base; // [ntiles] first record of the tile's segment
     const uint32_t* tile_cap;  // [ntiles]
     uint32_t* tile_frags;      // 3 words per record: cell | area<<24, smin | smax<<16, triangle
+    uint32_t flags;            // bit0: min-x skip test (0: explicit per-vertex test; kept for A/B runs)
 };
 void launch_bin_count(const Raster2& rb, cudaStream_t s);
 void launch_fill_items(const Raster2& rb, const uint32_t* item_off, uint2* items, cudaStream_t s);
