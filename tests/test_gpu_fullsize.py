@@ -25,7 +25,7 @@ def _context(force_global=False):
             os.environ["RCB_FORCE_GLOBAL"] = old
 
 
-def _invariants(tv, what):
+def _invariants(tv, what, eroded=False):
     """Properties every tile satisfies (SURVEY.md Appendix B invariants + layout rules of §8(a) row BC)."""
     C, S, K = tv.width * tv.height, tv.span_count, tv.conn_count
     off = tv.hf_cell_offset.astype(np.int64)
@@ -41,12 +41,13 @@ def _invariants(tv, what):
         k = np.flatnonzero(same_col[1:]) + 1
         assert (tv.span_min[k].astype(int) > tv.span_max[k - 1].astype(int)).all(), what
         assert (tv.span_min >= 0).all()
-        assert (tv.dist[tv.areas == 0] == 0).all()  # no connections => boundary => 0
+        if not eroded:  # after erosion connections survive, so this no longer holds
+            assert (tv.dist[tv.areas == 0] == 0).all()  # no connections => boundary => 0
         assert tv.walkable_span_count == int((tv.span_area != 0).sum())
         assert tv.max_height == int(tv.span_max.astype(np.uint16).max())
     if K:
         assert (tv.conn_ref < S).all() and (tv.conn_dir < 8).all()
-        assert (tv.areas[tv.conn_ref] != 0).all()  # connections only reach walkable spans
+        assert (tv.span_area[tv.conn_ref] != 0).all()  # connections only reach spans walkable at compaction
         nconn = np.zeros(S, np.int64)
         has = tv.first_conn != 0xFFFFFFFF
         # first_conn is the LAST entry of the span's block (blocks are laid out in span order)
@@ -95,6 +96,7 @@ def test_config2_full(oracle):
     with ct.build_tiles(cfgs, rb.STAGE_ALL_BUILD) as r1, cg.build_tiles(cfgs, rb.STAGE_ALL_BUILD) as r2:
         r1.download(), r2.download()
         t1, t2 = r1.totals(), r2.totals()
+        t1.pop("result_bytes"), t2.pop("result_bytes")  # arena padding differs between the back ends
         assert t1 == t2 and t1["tiles"] == 2025 and t1["cells"] == sum(c.width * c.height for c in cfgs)
         _compare_results(r1, r2, len(cfgs), NAMES)
         for i in range(0, len(cfgs), 7):
@@ -117,7 +119,7 @@ def test_config1_full_single_tile(oracle):
         tv = r.download().tile(0)
         hfa, chfa = oracle.build_tile(cfgs[0], v, t, rb.STAGE_ALL_BUILD | rb.STAGE_ERODE, 1)
         assert_tile_equal(tv, hfa, chfa, what="config1")
-        _invariants(tv, "config1")
+        _invariants(tv, "config1", eroded=True)
     ctx.close()
 
 
@@ -154,7 +156,9 @@ def test_config3_scaled_open_world(oracle):
         c.upload_mesh(v, t)
     with ct.build_tiles(cfgs, rb.STAGE_ALL_BUILD) as r1, cg.build_tiles(cfgs, rb.STAGE_ALL_BUILD) as r2:
         r1.download(), r2.download()
-        assert r1.totals() == r2.totals()
+        ta, tb = r1.totals(), r2.totals()
+        ta.pop("result_bytes"), tb.pop("result_bytes")
+        assert ta == tb
         _compare_results(r1, r2, len(cfgs), NAMES)
         for i in range(0, len(cfgs), 11):
             _invariants(r1.tile(i), f"config3 tile {i}")
