@@ -28,6 +28,18 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 METRIC = "input triangles voxelized/sec"
 UNIT = "triangles/s"
 
@@ -190,7 +202,7 @@ def run_reference(args, rank, world):
                          "note": "C++ restatement of recast-rs (oracle/), not the Rust build: no cargo/rustc in the image"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_native(args, rank, world, local_rank):
@@ -344,7 +356,7 @@ def run_native(args, rank, world, local_rank):
                 line["cpu_baseline"] = cb
             except Exception as e:  # the oracle is test infrastructure; its absence must not kill the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
-        print(json.dumps(line))
+        emit(line)
     ctx2.close()
     ctx.close()
     if dist is not None:
@@ -362,6 +374,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything else written to fd 1 (NCCL's version banner,
+    # library chatter) is rerouted to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -128,3 +128,25 @@ def test_oracle_batch_matches_per_tile(oracle):
     for nthreads, pre in ((1, False), (2, True)):
         secs, tot = oracle.build_tiles_timed(v, t, cfgs, nthreads=nthreads, prebinned=pre)
         assert tot["spans"] == S and tot["connections"] == K and secs > 0
+
+
+def test_cpp_wrapper_compiles_and_fails_loudly_without_gpu(tmp_path):
+    """cpp/recast_b200.hpp (C++ mirror of RecastBuilder) builds against the library; without a GPU the
+    example reports RCB_ECUDA instead of computing anything on the CPU."""
+    import subprocess
+
+    import torch
+
+    from recast_rs_b200 import build
+
+    build.build_native()
+    exe = tmp_path / "example"
+    libdir = os.path.join(ROOT, "recast_rs_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", os.path.join(ROOT, "cpp", "example.cpp"), "-L" + libdir, "-lrecast_b200",
+                           "-Wl,-rpath," + libdir, "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    if not torch.cuda.is_available():
+        assert "error -3" in out.stdout
+    else:
+        assert "cells 441 spans" in out.stdout
