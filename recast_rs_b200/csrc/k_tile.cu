@@ -23,6 +23,23 @@ constexpr int MAXH = 0xffff;
 __constant__ int t_dirx[8] = {-1, 0, 1, 1, 1, 0, -1, -1};  // compact_heightfield.rs:109-111
 __constant__ int t_dirz[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
 
+// Optional per-phase cycle accounting (rcb_profile_* with RCB_PHASE_TIMERS=1): thread 0 of every CTA adds the
+// cycles since the previous mark to phase slot `id`.  phase == nullptr (the default) costs one predicate.
+struct PhaseClock {
+    unsigned long long* acc;
+    long long t;
+    __device__ PhaseClock(unsigned long long* a) : acc(a), t(0) {
+        if (acc && threadIdx.x == 0) t = clock64();
+    }
+    __device__ void mark(int id) {
+        if (acc && threadIdx.x == 0) {
+            const long long n = clock64();
+            atomicAdd(&acc[id], (unsigned long long)(n - t));
+            t = n;
+        }
+    }
+};
+
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -62,7 +79,7 @@ __device__ uint32_t block_scan_array(const uint32_t* cnt, uint32_t* out, uint32_
 // ======================================================================================================
 // A: fragments -> spans
 // ======================================================================================================
-__global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_spans(TileSpansArgs a) {
+__global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_spans(TileSpansArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t sh_warp[TILE_THREADS / 32 + 1];
     __shared__ uint32_t sh_red[2];
@@ -72,75 +89,79 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_spans(TileSpansArgs a)
     const uint32_t C = (uint32_t)(W * H);
     const unsigned long long wmagic = td.wmagic;
     const uint32_t F = min(a.tile_cursor[tile], a.tile_cap[tile]);
-    // layout: off[C+1] | cnt[C] | soff[C+1] | tri[F] | mm[F] | area[F bytes]
-    const size_t need = 4ull * (3ull * C + 2) + 9ull * F + 16;
+    // Two launches share this kernel: pass 0 runs with a shared-memory size that lets two CTAs share an SM
+    // and defers the tiles that need more; pass 1 (large allocation) handles only the deferred tiles.
+    constexpr uint32_t DEFERRED = 0x80000000u;
+    if (a.pass == 1 && !(a.tinfo[tile].status & DEFERRED)) return;
+    // layout: off[C+1] | cnt[C] | soff[C+1] | rec[F] (uint2: area << 24 | triangle, smin | smax << 16)
+    const size_t need = 4ull * (3ull * C + 4) + 8ull * F + 16;
     if (need > a.smem_bytes) {
         if (threadIdx.x == 0) {
-            atomicOr(&a.counters[2], 4ull);  // does not fit: the host reruns the batch on the v1 back end
-            a.tinfo[tile].span_count = 0;
-            a.tinfo[tile].walkable_span_count = 0;
+            if (a.pass == 0 && a.defer) {
+                a.tinfo[tile].status |= DEFERRED;
+            } else {
+                atomicOr(&a.counters[2], 4ull);  // does not fit: the host reruns the batch on the v1 back end
+                a.tinfo[tile].span_count = 0;
+                a.tinfo[tile].walkable_span_count = 0;
+            }
         }
         return;
     }
     uint32_t* off = smem;
     uint32_t* cnt = off + (C + 1);
     uint32_t* soff = cnt + C;
-    uint32_t* f_tri = soff + (C + 1);
-    uint32_t* f_mm = f_tri + F;
-    uint8_t* f_area = reinterpret_cast<uint8_t*>(f_mm + F);
+    uint2* rec = reinterpret_cast<uint2*>(reinterpret_cast<uintptr_t>(soff + (C + 1) + 1) & ~(uintptr_t)7);
     const uint32_t* frags = a.tile_frags + 3ull * a.tile_base[tile];
 
+    PhaseClock pc(a.phase);
     for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) cnt[c] = 0;
     if (threadIdx.x < 2) sh_red[threadIdx.x] = 0;
     __syncthreads();
     // 1. histogram by column
     for (uint32_t i = threadIdx.x; i < F; i += TILE_THREADS) atomicAdd(&cnt[frags[3ull * i] & 0xffffffu], 1u);
     __syncthreads();
+    pc.mark(0);
     // 2. column offsets
     block_scan_array(cnt, off, C, sh_warp);
     for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) cnt[c] = 0;
     __syncthreads();
+    pc.mark(1);
     // 3. scatter into column order (order inside a column is arbitrary; the replay sorts by triangle)
     for (uint32_t i = threadIdx.x; i < F; i += TILE_THREADS) {
         const uint32_t r0 = frags[3ull * i], r1 = frags[3ull * i + 1], r2 = frags[3ull * i + 2];
         const uint32_t cell = r0 & 0xffffffu;
         const uint32_t pos = off[cell] + atomicAdd(&cnt[cell], 1u);
-        f_tri[pos] = r2;
-        f_mm[pos] = r1;
-        f_area[pos] = (uint8_t)(r0 >> 24);
+        rec[pos] = make_uint2((r0 & 0xff000000u) | (r2 & 0xffffffu), r1);
     }
     __syncthreads();
+    pc.mark(2);
     // 4. per-column replay (rasterization.rs:51-168), spans built in place over the consumed prefix
     const int thr = a.merge_thr;
     for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
-        const uint32_t b = off[c], n = cnt[c];
-        uint32_t* tri = f_tri + b;
-        uint32_t* mm = f_mm + b;
-        uint8_t* ar = f_area + b;
+        const uint32_t n = cnt[c];
+        if (n <= 1) continue;  // empty column, or a single fragment which is its own span
+        uint2* r = rec + off[c];
         for (uint32_t i = 1; i < n; ++i) {  // insertion sort by triangle index
-            const uint32_t kt = tri[i], km = mm[i];
-            const uint8_t ka = ar[i];
+            const uint2 key = r[i];
+            const uint32_t kt = key.x & 0xffffffu;
             uint32_t j = i;
-            while (j > 0 && tri[j - 1] > kt) {
-                tri[j] = tri[j - 1];
-                mm[j] = mm[j - 1];
-                ar[j] = ar[j - 1];
+            while (j > 0 && (r[j - 1].x & 0xffffffu) > kt) {
+                r[j] = r[j - 1];
                 --j;
             }
-            tri[j] = kt;
-            mm[j] = km;
-            ar[j] = ka;
+            if (j != i) r[j] = key;
         }
-        uint32_t ns = 0;
-        for (uint32_t i = 0; i < n; ++i) {
-            const uint32_t w = mm[i];
+        uint32_t ns = 1;  // the first fragment opens the column (:65-74)
+        for (uint32_t i = 1; i < n; ++i) {
+            const uint2 fr = r[i];
+            const uint32_t w = fr.y;
             const int smin = (int16_t)(w & 0xffffu), smax = (int16_t)(w >> 16);
-            const uint32_t area = ar[i];
+            const uint32_t area = fr.x >> 24;
             uint32_t p = 0;
             bool done = false;
             while (p < ns) {
-                const uint32_t cw = mm[p];
-                const int cmin = (int16_t)(cw & 0xffffu), cmax = (int16_t)(cw >> 16);
+                const uint2 cs = r[p];
+                const int cmin = (int16_t)(cs.y & 0xffffu), cmax = (int16_t)(cs.y >> 16);
                 if (smax < cmin) break;
                 if (smin > cmax) {
                     ++p;
@@ -149,42 +170,36 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_spans(TileSpansArgs a)
                 const int mmin = min(smin, cmin);
                 int mmax = max(smax, cmax);
                 uint32_t marea = area;
-                if (abs(mmax - cmax) <= thr) marea = max(marea, (uint32_t)ar[p]);
+                if (abs(mmax - cmax) <= thr) marea = max(marea, cs.x >> 24);
                 uint32_t q = p + 1;
                 while (q < ns) {
-                    const uint32_t nw = mm[q];
+                    const uint32_t nw = r[q].y;
                     if ((int)(int16_t)(nw & 0xffffu) > mmax) break;
                     mmax = max(mmax, (int)(int16_t)(nw >> 16));
                     ++q;
                 }
-                mm[p] = ((uint32_t)mmin & 0xffffu) | ((uint32_t)mmax << 16);
-                ar[p] = (uint8_t)marea;
+                r[p] = make_uint2(marea << 24, ((uint32_t)mmin & 0xffffu) | ((uint32_t)mmax << 16));
                 if (q > p + 1) {
                     const uint32_t drop = q - (p + 1);
-                    for (uint32_t k = q; k < ns; ++k) {
-                        mm[k - drop] = mm[k];
-                        ar[k - drop] = ar[k];
-                    }
+                    for (uint32_t k = q; k < ns; ++k) r[k - drop] = r[k];
                     ns -= drop;
                 }
                 done = true;
                 break;
             }
             if (!done) {
-                for (uint32_t k = ns; k > p; --k) {
-                    mm[k] = mm[k - 1];
-                    ar[k] = ar[k - 1];
-                }
-                mm[p] = w;
-                ar[p] = (uint8_t)area;
+                for (uint32_t k = ns; k > p; --k) r[k] = r[k - 1];
+                r[p] = fr;
                 ++ns;
             }
         }
         cnt[c] = ns;
     }
     __syncthreads();
+    pc.mark(3);
     // 5. span offsets (tile-local compact order)
     const uint32_t S = block_scan_array(cnt, soff, C, sh_warp);
+    pc.mark(4);
 
     // 6. filters, fused (see k_filter.cu for why one bottom-up walk per column is exact)
     uint32_t walkable = 0, maxh = 0;
@@ -209,10 +224,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_spans(TileSpansArgs a)
         uint32_t prev_area_f1 = 0;
         int prev_max = 0;
         for (uint32_t s = b; s < e; ++s) {
-            const uint32_t w = f_mm[s];
+            const uint2 sp = rec[s];
+            const uint32_t w = sp.y;
             const int floor = (int16_t)(w >> 16);
-            const int ceiling = (s + 1 < e) ? (int)(int16_t)(f_mm[s + 1] & 0xffffu) : MAXH;
-            const uint32_t orig = f_area[s];
+            const int ceiling = (s + 1 < e) ? (int)(int16_t)(rec[s + 1].y & 0xffffu) : MAXH;
+            const uint32_t orig = sp.x >> 24;
             const bool wk = orig != 0;
             uint32_t ar = orig;
             if ((fmask & 1u) && !wk && prev_walkable && have_prev && (floor - prev_max) <= climb) ar = prev_area_f1;
@@ -229,14 +245,14 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_spans(TileSpansArgs a)
                         ledge = true;
                         break;
                     }
-                    int nceil = (int16_t)(f_mm[nb[d]] & 0xffffu);
+                    int nceil = (int16_t)(rec[nb[d]].y & 0xffffu);
                     if (min(ceiling, nceil) - floor >= height) {
                         ledge = true;
                         break;
                     }
                     for (uint32_t ns = nb[d]; ns < ne[d]; ++ns) {
-                        const int nfloor = (int16_t)(f_mm[ns] >> 16);
-                        nceil = (ns + 1 < ne[d]) ? (int)(int16_t)(f_mm[ns + 1] & 0xffffu) : MAXH;
+                        const int nfloor = (int16_t)(rec[ns].y >> 16);
+                        nceil = (ns + 1 < ne[d]) ? (int)(int16_t)(rec[ns + 1].y & 0xffffu) : MAXH;
                         if (min(ceiling, nceil) - max(floor, nfloor) < height) continue;
                         const int diff = nfloor - floor;
                         lowest = min(lowest, diff);
@@ -251,12 +267,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_spans(TileSpansArgs a)
                 if (ledge || lowest < neg_climb || (hi - lo) > climb) ar = 0;
             }
             if ((fmask & 4u) && ceiling - floor < height) ar = 0;
-            if (ar != orig) f_area[s] = (uint8_t)ar;
+            if (ar != orig) rec[s].x = ar << 24;  // neighbours read .y only
             walkable += ar != 0;
             maxh = max(maxh, (uint32_t)(uint16_t)(w >> 16));
         }
     }
     __syncthreads();
+    pc.mark(5);
     // 7. outputs: final heightfield CSR offsets, spans in tile-local compact order
     uint32_t* out_off = a.hf_cell_offset + td.cell_base + tile;
     const uint32_t tb = a.tile_base[tile];
@@ -264,8 +281,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_spans(TileSpansArgs a)
         const uint32_t so = soff[c], n = cnt[c], b = off[c];
         out_off[c] = so;
         for (uint32_t k = 0; k < n; ++k) {
-            a.ts_mm[tb + so + k] = f_mm[b + k];
-            a.ts_area[tb + so + k] = f_area[b + k];
+            const uint2 sp = rec[b + k];
+            a.ts_mm[tb + so + k] = sp.y;
+            a.ts_area[tb + so + k] = (uint8_t)(sp.x >> 24);
         }
     }
 #pragma unroll
@@ -278,12 +296,14 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_spans(TileSpansArgs a)
         atomicMax(&sh_red[1], maxh);
     }
     __syncthreads();
+    pc.mark(6);
     if (threadIdx.x == 0) {
         out_off[C] = S;
         if (F) atomicAdd(&a.counters[1], (unsigned long long)F);
         a.tinfo[tile].span_count = S;
         a.tinfo[tile].walkable_span_count = sh_red[0];
         a.tinfo[tile].max_height = sh_red[1];
+        if (a.pass == 1) a.tinfo[tile].status &= ~DEFERRED;
     }
 }
 
@@ -530,7 +550,7 @@ __device__ uint32_t lookback_exclusive(volatile unsigned long long* look, uint32
     return excl;
 }
 
-__global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_compact(TileCompactArgs a) {
+__global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t sh_warp[TILE_THREADS / 32 + 1];
     __shared__ uint32_t sh_misc[4];  // [0] tile id, [1] conn base, [2] max distance, [3] overflow
@@ -575,6 +595,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_compact(TileCompactArg
         }
         return;
     }
+    PhaseClock pc(a.phase ? a.phase + 8 : nullptr);
     // 1. load the tile's spans
     const uint32_t* g_off = a.hf_cell_offset_in + td.cell_base + tile;
     uint32_t* g_off_out = a.hf_cell_offset + td.cell_base + tile;
@@ -599,6 +620,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_compact(TileCompactArg
     }
     if (!a.do_compact) return;  // heightfield-only result
     __syncthreads();
+    pc.mark(0);
     // 2. cells (compact_heightfield.rs:203-223)
     for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
         const uint32_t b = soff[c], n = soff[c + 1] - b;
@@ -662,6 +684,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_compact(TileCompactArg
         coff[c] = nconn;
     }
     __syncthreads();
+    pc.mark(1);
     // 4. connection offsets inside the tile, then the tile's base by decoupled look-back over tiles
     const uint32_t K = block_scan_array(coff, coff, C, sh_warp);
     if (threadIdx.x < 32) {
@@ -675,6 +698,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_compact(TileCompactArg
     }
     __syncthreads();
     const uint32_t conn_base = sh_misc[1];
+    pc.mark(2);
     // 5. connection list (compact_heightfield.rs:375-389): reverse direction order, next -> previous
     for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
         const uint32_t b = soff[c], e = soff[c + 1];
@@ -695,6 +719,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_compact(TileCompactArg
             a.first_conn[span_base + s] = first;
         }
     }
+    pc.mark(3);
     const TileB g{soff, mm, area, areas, nei, S, S4, W, H, wmagic};
     // coff and mm are dead once the connections are written: reuse them for the forward gather table
     uint2* fidx = nullptr;
@@ -704,15 +729,18 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_compact(TileCompactArg
         build_forward_index(g, fidx);
         __syncthreads();
     }
+    pc.mark(4);
     // 6. erosion (area.rs:73-234) — before the distance field when both are requested
     if (a.do_erode) {
         const unsigned thr = (unsigned)(uint8_t)(uint32_t)(a.erode_radius * 2);
         tile_sweep<uint8_t, true>(g, reinterpret_cast<uint8_t*>(d16a), reinterpret_cast<uint8_t*>(d16b), fidx, thr, nullptr);
     }
     for (uint32_t s = threadIdx.x; s < S; s += TILE_THREADS) a.areas[span_base + s] = areas[s];
+    pc.mark(5);
     // 7. distance field (compact_heightfield.rs:514-727)
     if (a.do_dist) {
         tile_sweep<uint16_t, false>(g, d16a, d16b, fidx, 0, &sh_misc[2]);
+        pc.mark(6);
         // box blur: d16a holds D; result to global
         for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
             const int z = (int)rcb_div_w(c, wmagic), x = (int)c - z * W;
@@ -740,6 +768,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_compact(TileCompactArg
             }
         }
         __syncthreads();
+        pc.mark(7);
         if (threadIdx.x == 0) a.tinfo[tile].max_distance = sh_misc[2];
     } else {
         for (uint32_t s = threadIdx.x; s < S; s += TILE_THREADS) a.dist[span_base + s] = 0;  // compact_heightfield.rs:253

@@ -74,6 +74,7 @@ struct rcb_ctx {
         d_conn_off, d_nei16, d_t16a, d_t16b, d_t16c, d_t8a, d_t8b, d_item_cnt, d_item_off, d_items, d_tile_ub, d_tile_base, d_tile_cursor,
         d_tile_frags, d_ts_mm, d_ts_area, d_celloff_tmp, d_lookback;
     uint32_t clip_flags = 1;    // RCB_CLIP_FLAGS (A/B runs): bit0 min-x skip test in the clipper
+    bool phase_timers = false;  // RCB_PHASE_TIMERS=1: per-phase cycle sums of the tile kernels on stderr
     bool force_global = false;  // RCB_FORCE_GLOBAL=1: never use the tile-resident back end (k_tile.cu)
     bool force_v1 = false;  // RCB_FORCE_V1=1: first-generation clipper (k_raster.cu), kept as the wide-tile fallback
     // pinned staging
@@ -455,10 +456,10 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
 
     if (src.raster) {
         // ---- RASTER: count -> clip/emit -> scan -> scatter -> replay -> scan -------------------------
-        CUB(ctx->d_counters.ensure(16 * sizeof(unsigned long long)));
+        CUB(ctx->d_counters.ensure(32 * sizeof(unsigned long long)));
         CUB(ctx->d_cell_cnt.ensure(4 * (Ctot + 1)));
         CUB(ctx->d_frag_off.ensure(4 * (Ctot + 1)));
-        CUB(cudaMemsetAsync(ctx->d_counters.p, 0, 16 * sizeof(unsigned long long), st));
+        CUB(cudaMemsetAsync(ctx->d_counters.p, 0, 32 * sizeof(unsigned long long), st));
         CUB(cudaMemsetAsync(ctx->d_cell_cnt.p, 0, 4 * (Ctot + 1), st));
         // tile info lives in the arena, which is sized after the span count is known: keep the clip
         // status in scratch until then
@@ -502,7 +503,8 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                 CUB(ctx->d_scan_tmp.ensure(4 * scan_tmp_elems(ntris + 1)));
                 r2.item_cnt = ctx->d_item_cnt.as<uint32_t>();
                 // tile-resident back end candidates: moderate tiles (the CSR arrays of a tile must fit shared memory)
-                want_tile = !ctx->force_global && !src.no_tile_mode && 12ull * max_cells + 4096 <= kTileSmem;
+                // (fragment records carry a 24-bit triangle index)
+                want_tile = !ctx->force_global && !src.no_tile_mode && 12ull * max_cells + 4096 <= kTileSmem && ntris < (1u << 24);
                 if (want_tile) {
                     CUB(ctx->d_tile_ub.ensure(4 * ((size_t)ntiles + 1)));
                     CUB(ctx->d_tile_base.ensure(4 * ((size_t)ntiles + 2)));
@@ -556,11 +558,23 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             ta.counters = r2.counters;
             ta.fmask = fmask;
             ta.merge_thr = src.merge_thr;
+            ta.phase = ctx->phase_timers ? r2.counters + 16 : nullptr;
             {
-                const uint64_t exact = 12ull * max_cells + 9ull * ub_max + 64;  // never overflows when it fits
-                ta.smem_bytes = (uint32_t)(exact <= kTileSmem ? exact : kTileSmem);
+                // exact bound: never overflows when it fits.  Above the two-CTAs-per-SM budget the first
+                // launch runs small and defers the few tiles that need more to a second, large launch.
+                const uint64_t exact = 12ull * max_cells + 8ull * ub_max + 64;
+                const uint64_t small = kTileSmem / 2 - 2048;
+                ta.pass = 0;
+                ta.defer = exact > small;
+                ta.smem_bytes = (uint32_t)(exact <= small ? exact : small);
+                launch_tile_spans(ta, ntiles, st);
+                if (ta.defer) {
+                    ta.pass = 1;
+                    ta.defer = 0;
+                    ta.smem_bytes = (uint32_t)(exact <= kTileSmem ? exact : kTileSmem);
+                    launch_tile_spans(ta, ntiles, st);
+                }
             }
-            launch_tile_spans(ta, ntiles, st);
             launch_tile_scan(d_tinfo_tmp, ntiles, r2.counters, st);
             CUB(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             CUB(cudaStreamSynchronize(st));
@@ -616,8 +630,19 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             tc.do_erode = (stage_mask & RCB_STAGE_ERODE) != 0;
             tc.do_dist = (stage_mask & RCB_STAGE_DIST) != 0;
             tc.erode_radius = erode_radius;
+            tc.phase = ctx->phase_timers ? r2.counters + 16 : nullptr;
             tc.smem_bytes = (uint32_t)needB;
             launch_tile_compact(tc, ntiles, st);
+            if (ctx->phase_timers) {
+                unsigned long long ph[16];
+                cudaMemcpyAsync(ph, r2.counters + 16, sizeof ph, cudaMemcpyDeviceToHost, st);
+                cudaStreamSynchronize(st);
+                fprintf(stderr, "[rcb phase cycles/tile] spans:");
+                for (int i = 0; i < 7; ++i) fprintf(stderr, " %llu", ph[i] / (unsigned long long)ntiles);
+                fprintf(stderr, " | compact:");
+                for (int i = 8; i < 16; ++i) fprintf(stderr, " %llu", ph[i] / (unsigned long long)ntiles);
+                fprintf(stderr, "\n");
+            }
             res->tile_mode = true;
             res->Kcap = Kcap;
             CUB(cudaGetLastError());
@@ -808,6 +833,7 @@ int rcb_create(int device, rcb_ctx** out) {
     ctx->launches0 = g_rcb_launches;
     if (const char* e = getenv("RCB_FORCE_V1")) ctx->force_v1 = e[0] == '1';
     if (const char* e = getenv("RCB_FORCE_GLOBAL")) ctx->force_global = e[0] == '1';
+    if (const char* e = getenv("RCB_PHASE_TIMERS")) ctx->phase_timers = e[0] == '1';
     if (const char* e = getenv("RCB_CLIP_FLAGS")) ctx->clip_flags = (uint32_t)atoi(e);
     *out = ctx;
     return RCB_OK;

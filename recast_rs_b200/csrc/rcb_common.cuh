@@ -139,6 +139,9 @@ struct TileSpansArgs {
     uint32_t fmask;
     int32_t merge_thr;
     uint32_t smem_bytes;
+    unsigned long long* phase;  // optional [16] per-phase cycle accumulators (nullptr = off)
+    int pass;                   // 0: first launch, 1: second launch for tiles deferred by pass 0
+    int defer;                  // pass 0 may defer tiles that need more shared memory (a pass 1 follows)
 };
 struct TileCompactArgs {
     const TileDesc* tiles;
@@ -166,6 +169,7 @@ struct TileCompactArgs {
     uint32_t* conn_next;
     int do_compact, do_erode, do_dist, erode_radius;
     uint32_t smem_bytes;
+    unsigned long long* phase;  // optional [16]: slots 8.. are this kernel's phases
 };
 void launch_tile_spans(const TileSpansArgs& a, int ntiles, cudaStream_t s);
 void launch_tile_segments(const uint32_t* tile_ub, uint32_t* tile_base, int ntiles, unsigned long long* counters, cudaStream_t s);
