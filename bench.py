@@ -232,7 +232,11 @@ def run_native(args, rank, world, local_rank):
 
     cfg_arr = configs_to_array(cfgs)
     ctx = rb.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: the library launches on exactly this stream, so the events
+    # recorded on it bracket every kernel of the step, including the ones after the last host sync
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     d_v = torch.from_numpy(v).to(dev)
     d_t = torch.from_numpy(t).to(dev)

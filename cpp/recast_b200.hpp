@@ -55,7 +55,7 @@ class Context {
     Context(const Context&) = delete;
     Context& operator=(const Context&) = delete;
     rcb_ctx* raw() const { return ctx_; }
-    void set_stream(void* cuda_stream) { check(rcb_set_stream(ctx_, cuda_stream), ctx_, "set_stream"); }
+    void set_stream(void* cuda_stream) { check(rcb_set_stream(ctx_, cuda_stream), ctx_, "set_stream"); }  // verbatim; nullptr = legacy default stream
 
    private:
     rcb_ctx* ctx_ = nullptr;

@@ -132,9 +132,11 @@ typedef struct rcb_tile_view {
 int rcb_create(int device, rcb_ctx** out);
 void rcb_destroy(rcb_ctx* ctx);
 const char* rcb_last_error(const rcb_ctx* ctx);
-/* Launch every kernel and copy of this context on `cuda_stream` (a cudaStream_t; NULL = the
- * context's own stream).  Lets a caller time with its own events (bench.py passes torch's stream). */
+/* Launch every kernel and copy of this context on `cuda_stream` (a cudaStream_t, used verbatim: NULL is
+ * the legacy default stream).  Lets a caller order and time the work with its own events (bench.py passes
+ * a torch stream).  A new context runs on a private non-blocking stream; rcb_use_own_stream returns to it. */
 int rcb_set_stream(rcb_ctx* ctx, void* cuda_stream);
+int rcb_use_own_stream(rcb_ctx* ctx);
 /* Number of kernel launches issued by this context since creation (bench `gpu_launches`). */
 uint64_t rcb_launch_count(const rcb_ctx* ctx);
 

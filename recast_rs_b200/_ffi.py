@@ -46,6 +46,7 @@ SYMBOLS = {
     "rcb_destroy": (None, [_vp]),
     "rcb_last_error": (ctypes.c_char_p, [_vp]),
     "rcb_set_stream": (_i, [_vp, _vp]),
+    "rcb_use_own_stream": (_i, [_vp]),
     "rcb_launch_count": (_u64, [_vp]),
     "rcb_config_default": (None, [ctypes.POINTER(RcbConfig)]),
     "rcb_config_calculate_grid_size": (None, [ctypes.POINTER(RcbConfig), _vp, _vp]),

@@ -141,7 +141,11 @@ class Context:
             pass
 
     def set_stream(self, cuda_stream: int | None):
+        """Run on the given cudaStream_t handle (0 / None = the legacy default stream)."""
         check(_ffi.lib().rcb_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)), self._h)
+
+    def use_own_stream(self):
+        check(_ffi.lib().rcb_use_own_stream(self._h), self._h)
 
     def profile_enable(self, on: bool = True):
         check(_ffi.lib().rcb_profile_enable(self._h, int(on)), self._h)

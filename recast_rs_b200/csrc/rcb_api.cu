@@ -863,7 +863,13 @@ const char* rcb_last_error(const rcb_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 int rcb_set_stream(rcb_ctx* ctx, void* cuda_stream) {
     if (!ctx) return RCB_EARG;
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)cuda_stream;  // verbatim: NULL is the legacy default stream
+    return RCB_OK;
+}
+
+int rcb_use_own_stream(rcb_ctx* ctx) {
+    if (!ctx) return RCB_EARG;
+    ctx->stream = ctx->own_stream;
     return RCB_OK;
 }
 

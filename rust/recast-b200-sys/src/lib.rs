@@ -105,6 +105,7 @@ extern "C" {
     pub fn rcb_destroy(ctx: *mut rcb_ctx);
     pub fn rcb_last_error(ctx: *const rcb_ctx) -> *const c_char;
     pub fn rcb_set_stream(ctx: *mut rcb_ctx, cuda_stream: *mut c_void) -> c_int;
+    pub fn rcb_use_own_stream(ctx: *mut rcb_ctx) -> c_int;
     pub fn rcb_launch_count(ctx: *const rcb_ctx) -> u64;
     pub fn rcb_profile_enable(ctx: *mut rcb_ctx, on: c_int) -> c_int;
     pub fn rcb_profile_read(ctx: *mut rcb_ctx, out: *mut rcb_stage_time, cap: c_int) -> c_int;

@@ -10,7 +10,7 @@ cfgno = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 v, t, cfgs = {1: synth.config1, 2: synth.config2, 3: synth.config3, 4: synth.config4}[cfgno]()
 arr = configs_to_array(cfgs)
 ctx = rb.Context(0)
-st = torch.cuda.current_stream(); ctx.set_stream(st.cuda_stream)
+st = torch.cuda.Stream(); torch.cuda.set_stream(st); assert st.cuda_stream != 0; ctx.set_stream(st.cuda_stream)
 dv, dt = torch.from_numpy(v).cuda(), torch.from_numpy(t).cuda()
 ctx.set_mesh_device(dv.data_ptr(), dv.numel(), dt.data_ptr(), dt.numel(), keep=(dv, dt))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
