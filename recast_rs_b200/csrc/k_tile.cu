@@ -336,8 +336,15 @@ __global__ void __launch_bounds__(1024) k_tile_scan(TileInfo* __restrict__ tinfo
         carry += sh[32];
         __syncthreads();
     }
-    atomicAdd(&sh_walk, walk);
-    atomicMax(&sh_maxs, maxs);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {  // one shared-memory atomic per warp, not per thread
+        walk += __shfl_down_sync(0xffffffffu, walk, d);
+        maxs = max(maxs, __shfl_down_sync(0xffffffffu, maxs, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sh_walk, walk);
+        atomicMax(&sh_maxs, maxs);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         counters[6] = carry;
@@ -372,7 +379,9 @@ __global__ void __launch_bounds__(1024) k_tile_segments(const uint32_t* __restri
         carry += sh[32];
         __syncthreads();
     }
-    atomicMax(&sh_max, mx);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, d));
+    if ((threadIdx.x & 31) == 0) atomicMax(&sh_max, mx);
     __syncthreads();
     if (threadIdx.x == 0) {
         tile_base[ntiles] = carry;
