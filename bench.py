@@ -205,6 +205,103 @@ def run_reference(args, rank, world):
     emit(line)
 
 
+def run_tilecache(args, rank, world, local_rank):
+    """BASELINE config 5: batched rebuild of 256 dirty tile-cache layers per frame; metric = tiles/s."""
+    import torch
+
+    import recast_rs_b200.builder as rb
+    from recast_rs_b200 import tilecache as tcm
+
+    layers, obstacles = tcm.config5(256, 48, seed=args.seed + rank)
+    name = "config5: 256 dirty tile-cache layers of 48x48 cells per frame, 1-3 cylinder/box/oriented-box obstacles each"
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import oracle as orc
+
+        threads = orc.hardware_concurrency()
+        ms = []
+        for i in range(args.warmup + args.steps):
+            secs, _ = orc.tilecache_build_timed(layers, obstacles, 0.3, 0.2, nthreads=threads)
+            if i >= args.warmup:
+                ms.append(secs * 1e3)
+        value = len(layers) / (np.mean(ms) * 1e-3)
+        emit({"impl": "reference", "metric": "tile-cache tiles rebuilt/sec", "value": value, "unit": "tiles/s", "n_gpus": args.gpus,
+              "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak",
+              "vs_baseline": None, "dtype": "u8/i16 cells + f32 obstacle tests", "data": "synthetic", "config": {"workload": name},
+              "cpu_baseline": {"value": value, "unit": "tiles/s", "cores": threads, "kind": "port", "sample": "all 256 layers"},
+              "e2e": {"value": value, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = rb.Context(local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    tot = None
+    for _ in range(max(args.warmup, 3)):
+        with ctx.build_tilecache_layers(layers, obstacles, 0.3, 0.2) as r:
+            tot = r.totals()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count()
+    dev_ms, e2e_ms = [], []
+    for _ in range(args.steps):  # the layers are HOST data in the reference too: every step is end to end
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        a.record(stream)
+        r = ctx.build_tilecache_layers(layers, obstacles, 0.3, 0.2)
+        b.record(stream)
+        r.download()
+        torch.cuda.synchronize()
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)
+        dev_ms.append(a.elapsed_time(b))
+        d2h = r.totals()["result_bytes"]
+        r.free()
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop()
+    agg = torch.tensor([float(sum(dev_ms)), float(sum(e2e_ms))], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        peak, peak_src = read_peaks()
+        ntl = len(layers) * world
+        C, S, K = tot["cells"], tot["spans"], tot["connections"]
+        balg = 2 * C + 8 * C + 5 * S + S + 8 * S + 5 * K  # regons+areas in; cells, spans, areas, con, connections out
+        ms_step = float(agg[0]) / args.steps
+        line = {"metric": "tile-cache tiles rebuilt/sec", "value": ntl * args.steps / (float(agg[0]) * 1e-3), "unit": "tiles/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8/i16 cells + f32 obstacle tests", "data": "synthetic",
+                "config": {"workload": name, "totals_rank0": tot, "note": "value includes the H2D of the layer bytes (host data by definition)"},
+                "e2e": {"value": ntl * args.steps / (float(agg[1]) * 1e-3), "unit": "tiles/s", "h2d_bytes_per_step": int(2 * C),
+                        "d2h_bytes_per_step": int(d2h), "ms_per_step": float(agg[1]) / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"bound": "hbm", "achieved": balg / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": balg / (ms_step * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "kernel": "whole step (launch-latency bound at this size)"}}
+        if world == 1 and not args.no_cpu:
+            from oracle import oracle as orc
+
+            secs, _ = orc.tilecache_build_timed(layers, obstacles, 0.3, 0.2, nthreads=1)
+            line["cpu_baseline"] = {"value": len(layers) / secs, "unit": "tiles/s", "cores": 1, "kind": "port", "sample": "all 256 layers"}
+        emit(line)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def run_native(args, rank, world, local_rank):
     import torch
 
@@ -387,7 +484,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
+    if args.config == 5:
+        run_tilecache(args, rank, world, local_rank)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_native(args, rank, world, local_rank)

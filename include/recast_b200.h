@@ -196,6 +196,46 @@ int rcb_build_from_spans(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const
                          const int16_t* span_min, const int16_t* span_max, const uint8_t* span_area,
                          const uint8_t* areas_override, uint32_t stage_mask, int erode_radius, rcb_result** out);
 
+/* ---- tile-cache layers (SURVEY §8(a) row TC, BASELINE config 5) ---------------------------------------
+ * rcb_build_tilecache_layers: TileCacheBuilder::layer_to_compact_heightfield
+ * (detour-tilecache/src/tile_cache_builder.rs:100-126: decode_layer_to_heightfield :129-172, then
+ * CompactHeightfield::build_from_heightfield) followed by rasterize_obstacles (:175-251 with
+ * rasterize_cylinder/box/oriented_box_obstacle :254-320, :422-467, :470-549) for a batch of layers.
+ * Every non-empty cell (regons != 0) becomes ONE span (hmin, hmin+1, areas[idx]); obstacles are applied
+ * AFTER the connections are built and clear CompactSpan.area only (never CompactHeightfield.areas), as
+ * the reference does.  Errors: regons_len/areas_len != width*height -> RCB_EINVALID_MESH (:138-143);
+ * hmin == 32767 with a non-empty cell -> RCB_ENAVMESH_GEN (Heightfield::add_span min > max,
+ * heightfield.rs:110-115).  stage_mask: RCB_STAGE_COMPACT is implied; RCB_STAGE_DIST / _ERODE optional. */
+typedef struct rcb_tc_layer {
+    float bmin[3], bmax[3]; /* TileCacheLayerHeader.bmin/bmax (tile_cache_data.rs:33-35) */
+    uint16_t hmin, hmax;    /* :37-39 */
+    uint8_t width, height;  /* :41-43 */
+    uint16_t _pad;
+    const uint8_t* regons;  /* [width*height], 0 = empty cell (TileCacheLayer.regons :242) */
+    const uint8_t* areas;   /* [width*height] (:244) */
+    uint32_t regons_len, areas_len;
+    uint32_t first_obstacle, obstacle_count; /* the obstacles passed to build_tile_from_layer for this layer */
+} rcb_tc_layer;
+
+enum { RCB_OBSTACLE_CYLINDER = 0, RCB_OBSTACLE_BOX = 1, RCB_OBSTACLE_ORIENTED_BOX = 2 };
+enum { RCB_OBSTACLE_EMPTY = 0, RCB_OBSTACLE_PROCESSING = 1, RCB_OBSTACLE_PROCESSED = 2, RCB_OBSTACLE_REMOVING = 3 };
+
+/* ObstacleData (tile_cache.rs:126-152) + ObstacleState (:109-118), flattened:
+ *   cylinder:     a = pos,    b[0] = radius, b[1] = height
+ *   box:          a = bmin,   b = bmax
+ *   oriented box: a = center, b = half_extents, rot_aux = [cos(a/2)sin(-a/2), cos(a/2)cos(a/2) - 0.5] */
+typedef struct rcb_tc_obstacle {
+    int32_t type;
+    int32_t state;
+    float a[3];
+    float b[3];
+    float rot_aux[2];
+} rcb_tc_obstacle;
+
+int rcb_build_tilecache_layers(rcb_ctx* ctx, const rcb_tc_layer* layers, int nlayers, const rcb_tc_obstacle* obstacles,
+                               int nobstacles, float cs, float ch, uint32_t stage_mask, int erode_radius,
+                               rcb_result** out);
+
 /* ---- results ------------------------------------------------------------------------------- */
 int rcb_result_totals(const rcb_result* res, rcb_totals* out);
 int rcb_result_download(rcb_result* res);                       /* one D2H of the result arena into pinned memory */

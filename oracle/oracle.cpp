@@ -990,3 +990,162 @@ double orc_build_tiles(const float* verts, size_t nfloats, const int32_t* idx, s
 int orc_hardware_concurrency(void) { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"
+
+// =================================================================================================
+// Tile-cache layers (detour-tilecache/src/tile_cache_builder.rs), SURVEY §8(a) row TC
+// =================================================================================================
+namespace {
+
+// rasterize_obstacles (:175-251) and the three shape rasterizers, on a Compact built from the layer.
+void tc_apply_obstacle(Compact& c, const float* hbmin, const float* hbmax, float cs, float ch, const rcb_tc_obstacle& o) {
+    if (o.state == RCB_OBSTACLE_EMPTY || o.state == RCB_OBSTACLE_REMOVING) return;  // :183-185
+    float omin[3], omax[3];
+    if (o.type == RCB_OBSTACLE_CYLINDER) {  // :192-200
+        omin[0] = o.a[0] - o.b[0], omin[1] = o.a[1], omin[2] = o.a[2] - o.b[0];
+        omax[0] = o.a[0] + o.b[0], omax[1] = o.a[1] + o.b[1], omax[2] = o.a[2] + o.b[0];
+    } else if (o.type == RCB_OBSTACLE_BOX) {  // :201-205
+        for (int i = 0; i < 3; ++i) omin[i] = o.a[i], omax[i] = o.b[i];
+    } else {  // :206-224
+        const float radius = std::sqrt(o.b[0] * o.b[0] + o.b[2] * o.b[2]);
+        omin[0] = o.a[0] - radius, omin[1] = o.a[1] - o.b[1], omin[2] = o.a[2] - radius;
+        omax[0] = o.a[0] + radius, omax[1] = o.a[1] + o.b[1], omax[2] = o.a[2] + radius;
+    }
+    if (omax[0] < hbmin[0] || omin[0] > hbmax[0] || omax[2] < hbmin[2] || omin[2] > hbmax[2]) return;  // :228-234
+    const int32_t W = c.width, H = c.height;
+    auto clampx = [&](int32_t& lo, int32_t& hi, int32_t n) {
+        lo = std::max(lo, 0);
+        hi = std::min(hi, n - 1);
+    };
+    if (o.type == RCB_OBSTACLE_CYLINDER) {  // :254-320
+        const float cx = o.a[0], cy = o.a[1], cz = o.a[2], radius = o.b[0], height = o.b[1];
+        int32_t min_x = f32_as_i32(std::floor((cx - radius - hbmin[0]) / cs)), max_x = f32_as_i32(std::ceil((cx + radius - hbmin[0]) / cs));
+        int32_t min_z = f32_as_i32(std::floor((cz - radius - hbmin[2]) / cs)), max_z = f32_as_i32(std::ceil((cz + radius - hbmin[2]) / cs));
+        clampx(min_x, max_x, W);
+        clampx(min_z, max_z, H);
+        for (int32_t z = min_z; z <= max_z; ++z)
+            for (int32_t x = min_x; x <= max_x; ++x) {
+                const float cell_x = hbmin[0] + ((float)x + 0.5f) * cs;
+                const float cell_z = hbmin[2] + ((float)z + 0.5f) * cs;
+                const float dx = cell_x - cx, dz = cell_z - cz;
+                if (dx * dx + dz * dz <= radius * radius) {
+                    const size_t ci = (size_t)z * W + x;
+                    if (c.cell_index[ci] == NONE) continue;
+                    for (uint32_t k = 0; k < c.cell_count[ci]; ++k) {
+                        const uint32_t s = c.cell_index[ci] + k;
+                        const float y0 = hbmin[1] + (float)(int32_t)c.smin[s] * ch;  // span.y == span.min
+                        const float y1 = y0 + ch;
+                        if (y0 < cy + height && y1 > cy) c.span_area[s] = 0;  // :307-310, CompactSpan.area only
+                    }
+                }
+            }
+    } else if (o.type == RCB_OBSTACLE_BOX) {  // :422-467
+        int32_t min_x = f32_as_i32(std::floor((o.a[0] - hbmin[0]) / cs)), max_x = f32_as_i32(std::ceil((o.b[0] - hbmin[0]) / cs));
+        int32_t min_z = f32_as_i32(std::floor((o.a[2] - hbmin[2]) / cs)), max_z = f32_as_i32(std::ceil((o.b[2] - hbmin[2]) / cs));
+        clampx(min_x, max_x, W);
+        clampx(min_z, max_z, H);
+        for (int32_t z = min_z; z <= max_z; ++z)
+            for (int32_t x = min_x; x <= max_x; ++x) {
+                const size_t ci = (size_t)x + (size_t)z * W;
+                if (c.cell_index[ci] == NONE) continue;
+                for (uint32_t s = c.cell_index[ci]; s < c.cell_index[ci] + c.cell_count[ci]; ++s) {
+                    const float y0 = (float)c.smin[s] * ch + hbmin[1], y1 = (float)c.smax[s] * ch + hbmin[1];
+                    if (y1 > o.a[1] && y0 < o.b[1]) c.span_area[s] = 0;
+                }
+            }
+    } else {  // :470-549
+        const float chc = o.rot_aux[1] + 0.5f, chs = o.rot_aux[0];
+        const float radius = std::sqrt(o.b[0] * o.b[0] + o.b[2] * o.b[2]);
+        int32_t min_x = f32_as_i32(std::floor((o.a[0] - radius - hbmin[0]) / cs)), max_x = f32_as_i32(std::ceil((o.a[0] + radius - hbmin[0]) / cs));
+        int32_t min_z = f32_as_i32(std::floor((o.a[2] - radius - hbmin[2]) / cs)), max_z = f32_as_i32(std::ceil((o.a[2] + radius - hbmin[2]) / cs));
+        clampx(min_x, max_x, W);
+        clampx(min_z, max_z, H);
+        for (int32_t z = min_z; z <= max_z; ++z)
+            for (int32_t x = min_x; x <= max_x; ++x) {
+                const float cell_x = (float)x * cs + hbmin[0] + cs * 0.5f;
+                const float cell_z = (float)z * cs + hbmin[2] + cs * 0.5f;
+                const float dx = cell_x - o.a[0], dz = cell_z - o.a[2];
+                const float cos_a = 2.0f * chc - 1.0f, sin_a = 2.0f * chs;
+                const float lx = cos_a * dx + sin_a * dz;
+                const float lz = -sin_a * dx + cos_a * dz;
+                if (std::fabs(lx) <= o.b[0] && std::fabs(lz) <= o.b[2]) {
+                    const size_t ci = (size_t)x + (size_t)z * W;
+                    if (c.cell_index[ci] == NONE) continue;
+                    for (uint32_t s = c.cell_index[ci]; s < c.cell_index[ci] + c.cell_count[ci]; ++s) {
+                        const float y0 = (float)c.smin[s] * ch + hbmin[1], y1 = (float)c.smax[s] * ch + hbmin[1];
+                        if (y1 > o.a[1] - o.b[1] && y0 < o.a[1] + o.b[1]) c.span_area[s] = 0;
+                    }
+                }
+            }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// layer_to_compact_heightfield (:100-126) + rasterize_obstacles (:175-251).  Returns an orc_chf (free with
+// orc_chf_free) or nullptr with *status set (RCB_EINVALID_MESH / RCB_ENAVMESH_GEN).
+orc_chf* orc_tilecache_build(const rcb_tc_layer* layer, const rcb_tc_obstacle* obstacles, float cs, float ch, int* status) {
+    *status = 0;
+    const size_t n = (size_t)layer->width * layer->height;
+    if (layer->regons_len != n || layer->areas_len != n) {  // :138-143
+        *status = RCB_EINVALID_MESH;
+        return nullptr;
+    }
+    Heightfield* hf = hf_new(layer->width, layer->height, layer->bmin, layer->bmax, cs, ch);
+    for (size_t y = 0; y < layer->height; ++y)
+        for (size_t x = 0; x < layer->width; ++x) {  // :146-169
+            const size_t idx = y * layer->width + x;
+            if (layer->regons[idx] == 0) continue;
+            const int32_t cell_height = (int32_t)layer->hmin;
+            const int st = hf_add_span2(*hf, (int32_t)x, (int32_t)y, (int16_t)cell_height, (int16_t)(cell_height + 1), layer->areas[idx]);
+            if (st) {
+                *status = st;
+                delete hf;
+                return nullptr;
+            }
+        }
+    auto* c = new Compact();
+    compact_build(*hf, *c);
+    delete hf;
+    for (uint32_t i = 0; i < layer->obstacle_count; ++i)
+        tc_apply_obstacle(*c, layer->bmin, layer->bmax, cs, ch, obstacles[layer->first_obstacle + i]);
+    return (orc_chf*)c;
+}
+
+// batched, timed (bench cpu_baseline for config 5); returns seconds
+double orc_tilecache_build_batch(const rcb_tc_layer* layers, int nlayers, const rcb_tc_obstacle* obstacles, float cs, float ch,
+                                 int nthreads, uint64_t* totals) {
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<int> next{0};
+    std::vector<uint64_t> acc((size_t)nthreads * 2, 0);
+    auto t0 = std::chrono::steady_clock::now();
+    auto work = [&](int tid) {
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= nlayers) break;
+            int st = 0;
+            orc_chf* c = orc_tilecache_build(&layers[i], obstacles, cs, ch, &st);
+            if (c) {
+                acc[(size_t)tid * 2] += ((Compact*)c)->smin.size();
+                acc[(size_t)tid * 2 + 1] += ((Compact*)c)->conn_ref.size();
+                orc_chf_free(c);
+            }
+        }
+    };
+    if (nthreads == 1)
+        work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < nthreads; ++i) th.emplace_back(work, i);
+        for (auto& t : th) t.join();
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (totals) {
+        totals[0] = totals[1] = 0;
+        for (int i = 0; i < nthreads; ++i) totals[0] += acc[(size_t)i * 2], totals[1] += acc[(size_t)i * 2 + 1];
+    }
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+}  // extern "C"

@@ -67,6 +67,10 @@ def lib():
         L.orc_build_tiles.restype = ctypes.c_double
         L.orc_build_tiles.argtypes = [vp, ctypes.c_size_t, vp, ctypes.c_size_t, vp, ctypes.c_int, u32,
                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
+        L.orc_tilecache_build.restype = vp
+        L.orc_tilecache_build.argtypes = [vp, vp, f32, f32, vp]
+        L.orc_tilecache_build_batch.restype = ctypes.c_double
+        L.orc_tilecache_build_batch.argtypes = [vp, ctypes.c_int, vp, f32, f32, ctypes.c_int, vp]
         L.orc_hardware_concurrency.restype = ctypes.c_int
         _lib = L
     return _lib
@@ -290,3 +294,32 @@ def build_tiles_timed(verts, indices, cfgs, stage_mask=1 | 2 | 4 | 16, erode_rad
 
 def hardware_concurrency() -> int:
     return int(lib().orc_hardware_concurrency())
+
+
+# ---- tile-cache layers (detour-tilecache/src/tile_cache_builder.rs:100-320, 422-549) -------------------------
+def tilecache_build(layers, obstacles, cs, ch):
+    """Per layer: ChfArrays, or the rcb_status (int) the reference's Err maps to."""
+    from recast_rs_b200 import tilecache as tcm
+
+    la, oa, keep = tcm.pack(layers, obstacles)
+    out = []
+    for i, l in enumerate(layers):
+        st = ctypes.c_int(0)
+        h = lib().orc_tilecache_build(ctypes.byref(la[i]), ctypes.cast(oa, ctypes.c_void_p), cs, ch, ctypes.byref(st))
+        if not h:
+            out.append(int(st.value))
+            continue
+        out.append(CompactHeightfield(h, l.width, l.height).export())
+    del keep
+    return out
+
+
+def tilecache_build_timed(layers, obstacles, cs, ch, nthreads=1):
+    from recast_rs_b200 import tilecache as tcm
+
+    la, oa, keep = tcm.pack(layers, obstacles)
+    tot = np.zeros(2, dtype=np.uint64)
+    s = lib().orc_tilecache_build_batch(ctypes.cast(la, ctypes.c_void_p), len(layers), ctypes.cast(oa, ctypes.c_void_p), cs, ch,
+                                        nthreads, _p(tot))
+    del keep
+    return s, {"spans": int(tot[0]), "connections": int(tot[1])}

@@ -500,3 +500,92 @@ class Compact:
         for s in range(S):
             if dist[s] < thr:
                 self.areas[s] = 0
+
+
+# ---- tile-cache layers (detour-tilecache/src/tile_cache_builder.rs) ------------------------------------------
+def _fl(v):
+    return _as_i32(np.floor(v))
+
+
+def _ce(v):
+    return _as_i32(np.ceil(v))
+
+
+def tilecache_build(layer, obstacles, cs, ch):
+    """layer_to_compact_heightfield (:100-126) + rasterize_obstacles (:175-251); returns a Compact whose
+    spans[i]["area"] carries the obstacle marks (chf.areas is left alone, as in the reference)."""
+    cs, ch = f32(cs), f32(ch)
+    w, h = layer.width, layer.height
+    if len(layer.regons) != w * h or len(layer.areas) != w * h:
+        raise ValueError("InvalidMesh")
+    hf = Heightfield(w, h, layer.bmin, layer.bmax, cs, ch)
+    for y in range(h):
+        for x in range(w):
+            idx = y * w + x
+            if layer.regons[idx] == 0:
+                continue
+            hf.add_span(x, y, _i16(int(layer.hmin)), _i16(int(layer.hmin) + 1), int(layer.areas[idx]))
+    c = Compact(hf)
+    bmin = [f32(v) for v in layer.bmin]
+    bmax = [f32(v) for v in layer.bmax]
+    with np.errstate(all="ignore"):
+        for o in obstacles[layer.first_obstacle:layer.first_obstacle + layer.obstacle_count]:
+            if o.state in (0, 3):
+                continue
+            a = [f32(v) for v in o.a]
+            b = [f32(v) for v in o.b]
+            if o.type == 0:
+                omin, omax = (f32(a[0] - b[0]), f32(a[2] - b[0])), (f32(a[0] + b[0]), f32(a[2] + b[0]))
+            elif o.type == 1:
+                omin, omax = (a[0], a[2]), (b[0], b[2])
+            else:
+                rad = f32(np.sqrt(f32(f32(b[0] * b[0]) + f32(b[2] * b[2]))))
+                omin, omax = (f32(a[0] - rad), f32(a[2] - rad)), (f32(a[0] + rad), f32(a[2] + rad))
+            if omax[0] < bmin[0] or omin[0] > bmax[0] or omax[1] < bmin[2] or omin[1] > bmax[2]:
+                continue
+            if o.type == 1:
+                x0, x1 = _fl(f32(f32(a[0] - bmin[0]) / cs)), _ce(f32(f32(b[0] - bmin[0]) / cs))
+                z0, z1 = _fl(f32(f32(a[2] - bmin[2]) / cs)), _ce(f32(f32(b[2] - bmin[2]) / cs))
+            else:
+                r = b[0] if o.type == 0 else rad
+                x0, x1 = _fl(f32(f32(f32(a[0] - r) - bmin[0]) / cs)), _ce(f32(f32(f32(a[0] + r) - bmin[0]) / cs))
+                z0, z1 = _fl(f32(f32(f32(a[2] - r) - bmin[2]) / cs)), _ce(f32(f32(f32(a[2] + r) - bmin[2]) / cs))
+            x0, x1, z0, z1 = max(x0, 0), min(x1, w - 1), max(z0, 0), min(z1, h - 1)
+            for z in range(z0, z1 + 1):
+                for x in range(x0, x1 + 1):
+                    if o.type == 0:
+                        cx_ = f32(bmin[0] + f32(f32(f32(x) + f32(0.5)) * cs))
+                        cz_ = f32(bmin[2] + f32(f32(f32(z) + f32(0.5)) * cs))
+                        dx, dz = f32(cx_ - a[0]), f32(cz_ - a[2])
+                        inside = f32(f32(dx * dx) + f32(dz * dz)) <= f32(b[0] * b[0])
+                        lo, hi = a[1], f32(a[1] + b[1])
+                    elif o.type == 1:
+                        inside, lo, hi = True, a[1], b[1]
+                    else:
+                        cx_ = f32(f32(f32(f32(x) * cs) + bmin[0]) + f32(cs * f32(0.5)))
+                        cz_ = f32(f32(f32(f32(z) * cs) + bmin[2]) + f32(cs * f32(0.5)))
+                        dx, dz = f32(cx_ - a[0]), f32(cz_ - a[2])
+                        cos_a = f32(f32(f32(2.0) * f32(f32(o.rot_aux[1]) + f32(0.5))) - f32(1.0))
+                        sin_a = f32(f32(2.0) * f32(o.rot_aux[0]))
+                        lx = f32(f32(cos_a * dx) + f32(sin_a * dz))
+                        lz = f32(f32(f32(-sin_a) * dx) + f32(cos_a * dz))
+                        inside = abs(lx) <= b[0] and abs(lz) <= b[2]
+                        lo, hi = f32(a[1] - b[1]), f32(a[1] + b[1])
+                    if not inside:
+                        continue
+                    idx, cnt = c.cells[z * w + x]
+                    if idx is None:
+                        continue
+                    for s in range(idx, idx + cnt):
+                        sp = c.spans[s]
+                        if o.type == 0:
+                            y0 = f32(bmin[1] + f32(f32(sp["min"]) * ch))
+                            y1 = f32(y0 + ch)
+                            hit = y0 < hi and y1 > lo
+                        else:
+                            y0 = f32(f32(f32(sp["min"]) * ch) + bmin[1])
+                            y1 = f32(f32(f32(sp["max"]) * ch) + bmin[1])
+                            hit = y1 > lo and y0 < hi
+                        if hit:
+                            sp["area"] = 0
+    return c

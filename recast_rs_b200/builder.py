@@ -202,6 +202,21 @@ class Context:
         return BatchResult(self, out)
 
 
+    def build_tilecache_layers(self, layers, obstacles, cs: float, ch: float, stage_mask=STAGE_COMPACT, erode_radius=0
+                               ) -> BatchResult:
+        """TileCacheBuilder::layer_to_compact_heightfield + rasterize_obstacles for a batch of layers
+        (detour-tilecache/src/tile_cache_builder.rs:100-126, 175-251)."""
+        from . import tilecache as tcm
+
+        la, oa, keep = tcm.pack(layers, obstacles)
+        out = ctypes.c_void_p()
+        check(_ffi.lib().rcb_build_tilecache_layers(self._h, ctypes.cast(la, ctypes.c_void_p), len(layers),
+                                                    ctypes.cast(oa, ctypes.c_void_p), len(obstacles), cs, ch, stage_mask,
+                                                    erode_radius, ctypes.byref(out)), self._h)
+        del keep
+        return BatchResult(self, out)
+
+
 _default_ctx: Optional[Context] = None
 
 

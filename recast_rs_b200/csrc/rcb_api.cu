@@ -72,7 +72,7 @@ struct rcb_ctx {
     // scratch
     DevBuf d_counters, d_cell_cnt, d_frag_off, d_frag_tmp, d_fs_tri, d_fs_mm, d_fs_area, d_scan_tmp, d_hf_off, d_conn_cnt,
         d_conn_off, d_nei16, d_t16a, d_t16b, d_t16c, d_t8a, d_t8b, d_item_cnt, d_item_off, d_items, d_tile_ub, d_tile_base, d_tile_cursor,
-        d_tile_frags, d_ts_mm, d_ts_area, d_celloff_tmp, d_lookback;
+        d_tile_frags, d_ts_mm, d_ts_area, d_celloff_tmp, d_lookback, d_tc_regons, d_tc_areas, d_tc_obs;
     uint32_t clip_flags = 1;    // RCB_CLIP_FLAGS (A/B runs): bit0 min-x skip test in the clipper
     bool phase_timers = false;  // RCB_PHASE_TIMERS=1: per-phase cycle sums of the tile kernels on stderr
     bool force_global = false;  // RCB_FORCE_GLOBAL=1: never use the tile-resident back end (k_tile.cu)
@@ -345,6 +345,76 @@ struct Source {  // where the heightfield comes from
     const uint8_t* areas_override = nullptr;  // host, optional
     bool no_tile_mode = false;                // set when the tile-resident back end reported an overflow
 };
+
+// Global-memory back end (v1 kernels) from a heightfield CSR that is already in the result arena:
+// filters -> cells/offsets -> link + connection list -> erosion -> distance field.
+int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, TileMap tm, int ntiles, uint64_t Ctot, uint64_t S,
+                    uint32_t fmask, uint32_t stage_mask, int erode_radius, const uint8_t* areas_override) {
+    cudaStream_t st = ctx->stream;
+    uint32_t* d_hf_off = ctx->d_hf_off.as<uint32_t>();
+    char* A = res->devA.p;
+    TileInfo* d_tinfo = (TileInfo*)(A + res->lay.tinfo);
+    int16_t* d_smin = (int16_t*)(A + res->lay.span_min);
+    int16_t* d_smax = (int16_t*)(A + res->lay.span_max);
+    uint8_t* d_sarea = (uint8_t*)(A + res->lay.span_area);
+
+    // ---- FILTER ------------------------------------------------------------------------------------------
+    if (fmask && S > 0) launch_filter_spans(d_tiles, tm, d_hf_off, d_smin, d_smax, d_sarea, fmask, st);
+
+    // ---- cells / offsets ---------------------------------------------------------------------------------
+    const bool compact = stage_mask & RCB_STAGE_COMPACT;
+    launch_tile_bases(d_tiles, ntiles, d_hf_off, nullptr, d_tinfo, st);
+    launch_cells_and_offsets(d_tiles, tm, d_hf_off, (uint32_t*)(A + res->lay.hf_cell_offset),
+                             compact ? (uint32_t*)(A + res->lay.cell_index) : nullptr,
+                             compact ? (uint32_t*)(A + res->lay.cell_count) : nullptr, d_tinfo, ntiles, st);
+
+    // ---- COMPACT: link, connection list ----------------------------------------------------------------------
+    if (compact) {
+        CU(ctx->d_conn_cnt.ensure(4 * (Ctot + 1)));
+        CU(ctx->d_conn_off.ensure(4 * (Ctot + 1)));
+        CU(ctx->d_nei16.ensure(16 * S + 256));
+        uint32_t* d_conn_cnt = ctx->d_conn_cnt.as<uint32_t>();
+        uint32_t* d_conn_off = ctx->d_conn_off.as<uint32_t>();
+        uint16_t* d_nei16 = ctx->d_nei16.as<uint16_t>();
+        uint8_t* d_areas = (uint8_t*)(A + res->lay.areas);
+        launch_link_spans(d_tiles, tm, d_hf_off, d_smin, d_smax, d_sarea, d_areas, d_nei16, S, (uint16_t*)(A + res->lay.con),
+                          d_conn_cnt, d_tinfo, st);
+        launch_exclusive_scan(d_conn_cnt, d_conn_off, Ctot, ctx->d_scan_tmp.as<uint32_t>(), st);
+        CU(cudaMemcpyAsync(&ctx->h_counters[4], d_conn_off + Ctot, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const uint64_t K = (uint32_t)ctx->h_counters[4];
+        res->K = K;
+        res->have_K = true;
+        make_layout_conn(res->lay, K);
+        CU(pool_get(ctx->free_dev, res->lay.bytesB, false, res->devB));
+        char* B = res->devB.p;
+        launch_tile_bases(d_tiles, ntiles, nullptr, d_conn_off, d_tinfo, st);
+        if (S > 0)
+            launch_write_connections(d_tiles, tm, d_hf_off, d_nei16, S, d_conn_off, d_tinfo, (uint32_t*)(A + res->lay.first_conn),
+                                     (uint32_t*)(B + res->lay.conn_ref), (uint8_t*)(B + res->lay.conn_dir),
+                                     (uint32_t*)(B + res->lay.conn_next), st);
+        CU(cudaMemsetAsync(A + res->lay.dist, 0, 2 * S, st));  // compact_heightfield.rs:253
+        if (areas_override && S > 0) {
+            CU(cudaMemcpyAsync(d_areas, areas_override, S, cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));
+        }
+        if ((stage_mask & RCB_STAGE_ERODE) && S > 0) {
+            CU(ctx->d_t8a.ensure(S));
+            CU(ctx->d_t8b.ensure(S));
+            launch_erode(d_tiles, ntiles, tm, d_hf_off, d_nei16, S, d_areas, ctx->d_t8a.as<uint8_t>(), ctx->d_t8b.as<uint8_t>(),
+                         erode_radius, st);
+        }
+        if ((stage_mask & RCB_STAGE_DIST) && S > 0) {
+            CU(ctx->d_t16a.ensure(2 * S));
+            CU(ctx->d_t16b.ensure(2 * S));
+            CU(ctx->d_t16c.ensure(2 * S));
+            launch_distance_field(d_tiles, ntiles, tm, d_hf_off, d_nei16, S, d_areas, ctx->d_t16a.as<uint16_t>(),
+                                  ctx->d_t16b.as<uint16_t>(), ctx->d_t16c.as<uint16_t>(), (uint16_t*)(A + res->lay.dist), d_tinfo,
+                                  st);
+        }
+    }
+    return RCB_OK;
+}
 
 int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stage_mask, int erode_radius,
                  const Source& src, rcb_result** out) {
@@ -725,66 +795,9 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         CUB(cudaStreamSynchronize(st));  // goff is a stack-owned pageable buffer
     }
 
-    char* A = res->devA.p;
-    TileInfo* d_tinfo = (TileInfo*)(A + res->lay.tinfo);
-    int16_t* d_smin = (int16_t*)(A + res->lay.span_min);
-    int16_t* d_smax = (int16_t*)(A + res->lay.span_max);
-    uint8_t* d_sarea = (uint8_t*)(A + res->lay.span_area);
-
-    // ---- FILTER ------------------------------------------------------------------------------------------
-    if (fmask && S > 0) launch_filter_spans(d_tiles, tm, d_hf_off, d_smin, d_smax, d_sarea, fmask, st);
-
-    // ---- cells / offsets ---------------------------------------------------------------------------------
-    const bool compact = stage_mask & RCB_STAGE_COMPACT;
-    launch_tile_bases(d_tiles, ntiles, d_hf_off, nullptr, d_tinfo, st);
-    launch_cells_and_offsets(d_tiles, tm, d_hf_off, (uint32_t*)(A + res->lay.hf_cell_offset),
-                             compact ? (uint32_t*)(A + res->lay.cell_index) : nullptr,
-                             compact ? (uint32_t*)(A + res->lay.cell_count) : nullptr, d_tinfo, ntiles, st);
-
-    // ---- COMPACT: link, connection list ----------------------------------------------------------------------
-    if (compact) {
-        CUB(ctx->d_conn_cnt.ensure(4 * (Ctot + 1)));
-        CUB(ctx->d_conn_off.ensure(4 * (Ctot + 1)));
-        CUB(ctx->d_nei16.ensure(16 * S + 256));
-        uint32_t* d_conn_cnt = ctx->d_conn_cnt.as<uint32_t>();
-        uint32_t* d_conn_off = ctx->d_conn_off.as<uint32_t>();
-        uint16_t* d_nei16 = ctx->d_nei16.as<uint16_t>();
-        uint8_t* d_areas = (uint8_t*)(A + res->lay.areas);
-        launch_link_spans(d_tiles, tm, d_hf_off, d_smin, d_smax, d_sarea, d_areas, d_nei16, S, (uint16_t*)(A + res->lay.con),
-                          d_conn_cnt, d_tinfo, st);
-        launch_exclusive_scan(d_conn_cnt, d_conn_off, Ctot, ctx->d_scan_tmp.as<uint32_t>(), st);
-        CUB(cudaMemcpyAsync(&ctx->h_counters[4], d_conn_off + Ctot, 4, cudaMemcpyDeviceToHost, st));
-        CUB(cudaStreamSynchronize(st));
-        const uint64_t K = (uint32_t)ctx->h_counters[4];
-        res->K = K;
-        res->have_K = true;
-        make_layout_conn(res->lay, K);
-        CUB(pool_get(ctx->free_dev, res->lay.bytesB, false, res->devB));
-        char* B = res->devB.p;
-        launch_tile_bases(d_tiles, ntiles, nullptr, d_conn_off, d_tinfo, st);
-        if (S > 0)
-            launch_write_connections(d_tiles, tm, d_hf_off, d_nei16, S, d_conn_off, d_tinfo, (uint32_t*)(A + res->lay.first_conn),
-                                     (uint32_t*)(B + res->lay.conn_ref), (uint8_t*)(B + res->lay.conn_dir),
-                                     (uint32_t*)(B + res->lay.conn_next), st);
-        CUB(cudaMemsetAsync(A + res->lay.dist, 0, 2 * S, st));  // compact_heightfield.rs:253
-        if (src.areas_override && S > 0) {
-            CUB(cudaMemcpyAsync(d_areas, src.areas_override, S, cudaMemcpyHostToDevice, st));
-            CUB(cudaStreamSynchronize(st));
-        }
-        if ((stage_mask & RCB_STAGE_ERODE) && S > 0) {
-            CUB(ctx->d_t8a.ensure(S));
-            CUB(ctx->d_t8b.ensure(S));
-            launch_erode(d_tiles, ntiles, tm, d_hf_off, d_nei16, S, d_areas, ctx->d_t8a.as<uint8_t>(), ctx->d_t8b.as<uint8_t>(),
-                         erode_radius, st);
-        }
-        if ((stage_mask & RCB_STAGE_DIST) && S > 0) {
-            CUB(ctx->d_t16a.ensure(2 * S));
-            CUB(ctx->d_t16b.ensure(2 * S));
-            CUB(ctx->d_t16c.ensure(2 * S));
-            launch_distance_field(d_tiles, ntiles, tm, d_hf_off, d_nei16, S, d_areas, ctx->d_t16a.as<uint16_t>(),
-                                  ctx->d_t16b.as<uint16_t>(), ctx->d_t16c.as<uint16_t>(), (uint16_t*)(A + res->lay.dist), d_tinfo,
-                                  st);
-        }
+    {
+        const int r = global_back_end(ctx, res, d_tiles, tm, ntiles, Ctot, S, fmask, stage_mask, erode_radius, src.areas_override);
+        if (r) return bail(r);
     }
     CUB(cudaGetLastError());
     *out = res;
@@ -847,7 +860,8 @@ void rcb_destroy(rcb_ctx* ctx) {
                       &ctx->d_counters, &ctx->d_cell_cnt, &ctx->d_frag_off, &ctx->d_frag_tmp, &ctx->d_fs_tri, &ctx->d_fs_mm,
                       &ctx->d_fs_area, &ctx->d_scan_tmp, &ctx->d_hf_off, &ctx->d_conn_cnt, &ctx->d_conn_off, &ctx->d_nei16,
                       &ctx->d_t16a, &ctx->d_t16b, &ctx->d_t16c, &ctx->d_t8a, &ctx->d_t8b, &ctx->d_item_cnt, &ctx->d_item_off, &ctx->d_items, &ctx->d_tile_ub, &ctx->d_tile_base,
-                      &ctx->d_tile_cursor, &ctx->d_tile_frags, &ctx->d_ts_mm, &ctx->d_ts_area, &ctx->d_celloff_tmp, &ctx->d_lookback};
+                      &ctx->d_tile_cursor, &ctx->d_tile_frags, &ctx->d_ts_mm, &ctx->d_ts_area, &ctx->d_celloff_tmp, &ctx->d_lookback, &ctx->d_tc_regons, &ctx->d_tc_areas,
+                      &ctx->d_tc_obs};
     for (auto* b : bufs) b->release();
     for (auto& a : ctx->free_dev) cudaFree(a.p);
     for (auto& a : ctx->free_host) cudaFreeHost(a.p);
@@ -997,6 +1011,132 @@ int rcb_build_from_spans(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const
     s.sarea = span_area;
     s.areas_override = areas_override;
     return run_pipeline(ctx, cfgs, ntiles, stage_mask, erode_radius, s, out);
+}
+
+int rcb_build_tilecache_layers(rcb_ctx* ctx, const rcb_tc_layer* layers, int nlayers, const rcb_tc_obstacle* obstacles, int nobstacles,
+                               float cs, float ch, uint32_t stage_mask, int erode_radius, rcb_result** out) {
+    if (!ctx || !out || nlayers < 0 || (nlayers > 0 && !layers) || nobstacles < 0 || (nobstacles > 0 && !obstacles))
+        return fail(ctx, RCB_EARG, "null argument");
+    *out = nullptr;
+    if (!(cs > 0.0f) || !(ch > 0.0f)) return fail(ctx, RCB_EINVALID_MESH, "Invalid cell size or height");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ProfInstall prof_install(ctx);
+    stage_mask = (stage_mask | RCB_STAGE_COMPACT) & ~(uint32_t)(RCB_STAGE_RASTER | RCB_STAGE_FILTER | 0x700u);
+    auto* res = new rcb_result();
+    res->ctx = ctx;
+    res->ntiles = nlayers;
+    res->stage_mask = stage_mask;
+    res->tiles.resize(nlayers);
+    uint64_t Ctot = 0;
+    uint32_t max_cells = 0;
+    auto bail = [&](int code) {
+        rcb_result_free(res);
+        return code;
+    };
+    for (int i = 0; i < nlayers; ++i) {
+        const rcb_tc_layer& l = layers[i];
+        const uint32_t cells = (uint32_t)l.width * l.height;
+        if (l.regons_len != cells) return bail(fail(ctx, RCB_EINVALID_MESH, "Invalid region data size"));  // :138-140
+        if (l.areas_len != cells) return bail(fail(ctx, RCB_EINVALID_MESH, "Invalid area data size"));     // :141-143
+        if (cells && (!l.regons || !l.areas)) return bail(fail(ctx, RCB_EARG, "layer %d: null data", i));
+        if ((uint64_t)l.first_obstacle + l.obstacle_count > (uint64_t)nobstacles) return bail(fail(ctx, RCB_EARG, "layer %d: obstacle range", i));
+        if (l.hmin == 32767) {  // (32767 as i16, 32768 as i16 = -32768): Heightfield::add_span rejects min > max
+            for (uint32_t c = 0; c < cells; ++c)
+                if (l.regons[c] != 0) return bail(fail(ctx, RCB_ENAVMESH_GEN, "Invalid span height: min (32767) > max (-32768)"));
+        }
+        TileDesc& t = res->tiles[i];
+        memset(&t, 0, sizeof t);
+        t.width = l.width;
+        t.height = l.height;
+        for (int k = 0; k < 3; ++k) t.bmin[k] = l.bmin[k], t.bmax[k] = l.bmax[k];
+        t.cs = cs;
+        t.ch = ch;
+        t.ics = 1.0f / cs;
+        t.ich = 1.0f / ch;
+        t.aux0 = (int32_t)l.hmin;
+        t.aux1 = (int32_t)l.first_obstacle;
+        t.aux2 = (int32_t)l.obstacle_count;
+        t.cell_base = (uint32_t)Ctot;
+        t.wmagic = l.width ? ((1ull << 40) / (unsigned long long)l.width) + 1 : 0;
+        Ctot += cells;
+        if (cells > max_cells) max_cells = cells;
+    }
+    res->Ctot = Ctot;
+    TileMap tm{(uint32_t)nlayers, (max_cells + 255) / 256, 0};
+    tm.nblocks = tm.blocks_per_tile * tm.ntiles;
+#define CUB(expr)                                                                                            \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess)                                                                               \
+            return bail(fail(ctx, RCB_ECUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, __LINE__, #expr)); \
+    } while (0)
+    // upload: tile descriptors, cell data (concatenated in layer order), obstacles
+    const size_t need = align_up(sizeof(TileDesc) * (size_t)nlayers) + 2 * align_up(Ctot) + align_up(sizeof(rcb_tc_obstacle) * (size_t)nobstacles) + 1024;
+    {
+        int r = ensure_stage(ctx, need);
+        if (r) return bail(r);
+    }
+    CUB(ctx->d_tiles.ensure(sizeof(TileDesc) * (size_t)nlayers + 16));
+    CUB(ctx->d_tc_regons.ensure(Ctot + 16));
+    CUB(ctx->d_tc_areas.ensure(Ctot + 16));
+    CUB(ctx->d_tc_obs.ensure(sizeof(rcb_tc_obstacle) * (size_t)nobstacles + 16));
+    {
+        char* h = ctx->h_stage;
+        size_t o = 0;
+        memcpy(h + o, res->tiles.data(), sizeof(TileDesc) * (size_t)nlayers);
+        if (nlayers) CUB(cudaMemcpyAsync(ctx->d_tiles.p, h + o, sizeof(TileDesc) * (size_t)nlayers, cudaMemcpyHostToDevice, st));
+        o += align_up(sizeof(TileDesc) * (size_t)nlayers);
+        char* hr = h + o;
+        o += align_up(Ctot);
+        char* ha = h + o;
+        o += align_up(Ctot);
+        for (int i = 0; i < nlayers; ++i) {
+            const uint32_t cells = (uint32_t)layers[i].width * layers[i].height;
+            if (!cells) continue;
+            memcpy(hr + res->tiles[i].cell_base, layers[i].regons, cells);
+            memcpy(ha + res->tiles[i].cell_base, layers[i].areas, cells);
+        }
+        if (Ctot) {
+            CUB(cudaMemcpyAsync(ctx->d_tc_regons.p, hr, Ctot, cudaMemcpyHostToDevice, st));
+            CUB(cudaMemcpyAsync(ctx->d_tc_areas.p, ha, Ctot, cudaMemcpyHostToDevice, st));
+        }
+        if (nobstacles) {
+            memcpy(h + o, obstacles, sizeof(rcb_tc_obstacle) * (size_t)nobstacles);
+            CUB(cudaMemcpyAsync(ctx->d_tc_obs.p, h + o, sizeof(rcb_tc_obstacle) * (size_t)nobstacles, cudaMemcpyHostToDevice, st));
+        }
+    }
+    const TileDesc* d_tiles = ctx->d_tiles.as<TileDesc>();
+    CUB(ctx->d_hf_off.ensure(4 * (Ctot + 1)));
+    CUB(ctx->d_cell_cnt.ensure(4 * (Ctot + 1)));
+    CUB(ctx->d_scan_tmp.ensure(4 * scan_tmp_elems(Ctot + 1)));
+    uint32_t* d_hf_off = ctx->d_hf_off.as<uint32_t>();
+    launch_tc_count(d_tiles, tm, ctx->d_tc_regons.as<uint8_t>(), ctx->d_cell_cnt.as<uint32_t>(), st);
+    launch_exclusive_scan(ctx->d_cell_cnt.as<uint32_t>(), d_hf_off, Ctot, ctx->d_scan_tmp.as<uint32_t>(), st);
+    CUB(cudaMemcpyAsync(&ctx->h_counters[4], d_hf_off + Ctot, 4, cudaMemcpyDeviceToHost, st));
+    CUB(cudaStreamSynchronize(st));
+    const uint64_t S = (uint32_t)ctx->h_counters[4];
+    res->S = S;
+    make_layout(res->lay, nlayers, Ctot, S, stage_mask);
+    CUB(pool_get(ctx->free_dev, res->lay.bytesA, false, res->devA));
+    char* A = res->devA.p;
+    CUB(cudaMemsetAsync(A + res->lay.tinfo, 0, sizeof(TileInfo) * (size_t)nlayers, st));
+    int16_t* d_smin = (int16_t*)(A + res->lay.span_min);
+    int16_t* d_smax = (int16_t*)(A + res->lay.span_max);
+    uint8_t* d_sarea = (uint8_t*)(A + res->lay.span_area);
+    if (S > 0)
+        launch_tc_spans(d_tiles, tm, ctx->d_tc_regons.as<uint8_t>(), ctx->d_tc_areas.as<uint8_t>(), d_hf_off, d_smin, d_smax, d_sarea, st);
+    {
+        const int r = global_back_end(ctx, res, d_tiles, tm, nlayers, Ctot, S, 0, stage_mask, erode_radius, nullptr);
+        if (r) return bail(r);
+    }
+    // obstacles come AFTER the connections exist and only clear CompactSpan.area (:65-68, :309)
+    if (nobstacles > 0 && S > 0)
+        launch_tc_obstacles(d_tiles, nlayers, ctx->d_tc_obs.as<rcb_tc_obstacle>(), d_hf_off, d_smin, d_smax, d_sarea, st);
+    CUB(cudaGetLastError());
+    *out = res;
+    return RCB_OK;
+#undef CUB
 }
 
 int rcb_result_totals(const rcb_result* cres, rcb_totals* out) {

@@ -28,6 +28,7 @@ struct TileDesc {
     int32_t neg_climb;       // (-climb as i16) as i32, heightfield.rs:382
     uint32_t cell_base;      // first global cell
     int32_t bin_x0, bin_z0;  // lower corner of the tile's range in the locator grid (dedup rule)
+    int32_t aux0, aux1, aux2;   // tile-cache layers: hmin, first obstacle, obstacle count
     unsigned long long wmagic;  // ceil(2^40 / width): c / width == (c * wmagic) >> 40 for c < 2^24, width < 2^16
 };
 
@@ -218,6 +219,13 @@ void launch_distance_field(const TileDesc* tiles, int ntiles, TileMap tm, const 
                            uint16_t* tmp_d, uint16_t* dist, TileInfo* tinfo, cudaStream_t s);
 void launch_erode(const TileDesc* tiles, int ntiles, TileMap tm, const uint32_t* hf_off, const uint16_t* nei16,
                   size_t S, uint8_t* areas, uint8_t* tmp_init, uint8_t* tmp_f, int radius, cudaStream_t s);
+
+// tile-cache layers (k_tilecache.cu)
+void launch_tc_count(const TileDesc* tiles, TileMap tm, const uint8_t* regons, uint32_t* cell_cnt, cudaStream_t s);
+void launch_tc_spans(const TileDesc* tiles, TileMap tm, const uint8_t* regons, const uint8_t* areas, const uint32_t* hf_off,
+                     int16_t* smin, int16_t* smax, uint8_t* sarea, cudaStream_t s);
+void launch_tc_obstacles(const TileDesc* tiles, int ntiles, const rcb_tc_obstacle* obs, const uint32_t* hf_off, const int16_t* smin,
+                         const int16_t* smax, uint8_t* sarea, cudaStream_t s);
 
 // number of kernel launches issued through the launchers above since process start
 extern unsigned long long g_rcb_launches;
