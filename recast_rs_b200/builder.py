@@ -208,12 +208,12 @@ class Context:
         (detour-tilecache/src/tile_cache_builder.rs:100-126, 175-251)."""
         from . import tilecache as tcm
 
-        la, oa, keep = tcm.pack(layers, obstacles)
+        # `layers` may be a tilecache.Packed (C structs built once, e.g. outside a timed loop)
+        pk = layers if isinstance(layers, tcm.Packed) else tcm.Packed(layers, obstacles)
         out = ctypes.c_void_p()
-        check(_ffi.lib().rcb_build_tilecache_layers(self._h, ctypes.cast(la, ctypes.c_void_p), len(layers),
-                                                    ctypes.cast(oa, ctypes.c_void_p), len(obstacles), cs, ch, stage_mask,
+        check(_ffi.lib().rcb_build_tilecache_layers(self._h, ctypes.cast(pk.layers, ctypes.c_void_p), pk.nlayers,
+                                                    ctypes.cast(pk.obstacles, ctypes.c_void_p), pk.nobstacles, cs, ch, stage_mask,
                                                     erode_radius, ctypes.byref(out)), self._h)
-        del keep
         return BatchResult(self, out)
 
 

@@ -88,6 +88,15 @@ def pack(layers: Sequence[TileCacheLayer], obstacles: Sequence[Obstacle]):
     return la, oa, keep
 
 
+class Packed:
+    """rcb_tc_layer[] / rcb_tc_obstacle[] built once from the Python-side descriptions (what a native caller
+    holds already); keeps the numpy buffers the structs point to alive."""
+
+    def __init__(self, layers: Sequence[TileCacheLayer], obstacles: Sequence[Obstacle]):
+        self.layers, self.obstacles, self._keep = pack(layers, obstacles)
+        self.nlayers, self.nobstacles = len(layers), len(obstacles)
+
+
 def config5(ntiles: int = 256, size: int = 48, cs: float = 0.3, ch: float = 0.2, seed: int = 1
             ) -> Tuple[List[TileCacheLayer], List[Obstacle]]:
     """BASELINE config 5: `ntiles` dirty tile-cache layers of size x size cells, regons = 1, areas = 63,
