@@ -196,6 +196,30 @@ int rcb_build_from_spans(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const
                          const int16_t* span_min, const int16_t* span_max, const uint8_t* span_area,
                          const uint8_t* areas_override, uint32_t stage_mask, int erode_radius, rcb_result** out);
 
+/* ---- area operators on the compact heightfield ----------------------------------------
+ * rcb_apply_area_ops: the reference's stand-alone CompactHeightfield.areas operators, applied IN ORDER to
+ * every tile of the batch (volumes are given in world coordinates):
+ *   RCB_AREA_OP_MEDIAN      median_filter_walkable_area (area.rs:238-294)
+ *   RCB_AREA_OP_BOX         mark_box_area               (area.rs:298-355)  a = bmin, b = bmax
+ *   RCB_AREA_OP_CYLINDER    mark_cylinder_area          (area.rs:544-618)  a = position, b[0] = radius, b[1] = height
+ *   RCB_AREA_OP_CONVEX_POLY mark_convex_poly_area       (area.rs:359-437)  a[1] = min_y, b[1] = max_y,
+ *                           vertices poly_verts[3*first_vert .. 3*(first_vert+num_verts))
+ * Input is an existing heightfield (CSR, as rcb_build_from_spans) plus the caller's current areas
+ * (areas_override, nullable); the connections are rebuilt from span_area exactly as
+ * CompactHeightfield::build_from_heightfield does, then the operators run, then ERODE / DIST when asked. */
+enum { RCB_AREA_OP_MEDIAN = 0, RCB_AREA_OP_BOX = 1, RCB_AREA_OP_CYLINDER = 2, RCB_AREA_OP_CONVEX_POLY = 3 };
+typedef struct rcb_area_op {
+    int32_t type;
+    uint32_t area_id;
+    float a[3];
+    float b[3];
+    uint32_t first_vert, num_verts;
+} rcb_area_op;
+int rcb_apply_area_ops(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const uint32_t* cell_offset, const int16_t* span_min,
+                       const int16_t* span_max, const uint8_t* span_area, const uint8_t* areas_override, const rcb_area_op* ops,
+                       int nops, const float* poly_verts, size_t npoly_floats, uint32_t stage_mask, int erode_radius,
+                       rcb_result** out);
+
 /* ---- tile-cache layers (SURVEY §8(a) row TC, BASELINE config 5) ---------------------------------------
  * rcb_build_tilecache_layers: TileCacheBuilder::layer_to_compact_heightfield
  * (detour-tilecache/src/tile_cache_builder.rs:100-126: decode_layer_to_heightfield :129-172, then

@@ -426,6 +426,7 @@ int builder_rasterize(Heightfield& hf, const rcb_config& cfg, const float* verts
 // ---- CompactHeightfield (compact_heightfield.rs:129-170) ----------------------------------------
 struct Compact {
     int32_t width = 0, height = 0;
+    float bmin[3] = {0, 0, 0}, cs = 0, ch = 0;
     std::vector<uint32_t> cell_index, cell_count;
     std::vector<int16_t> smin, smax;
     std::vector<uint8_t> span_area, areas;
@@ -456,6 +457,9 @@ void compact_build(const Heightfield& hf, Compact& c) {
     const int32_t w = hf.width, h = hf.height;
     c.width = w;
     c.height = h;
+    for (int i = 0; i < 3; ++i) c.bmin[i] = hf.bmin[i];
+    c.cs = hf.cs;
+    c.ch = hf.ch;
     const size_t ncell = (size_t)w * h;
     c.cell_index.assign(ncell, NONE);
     c.cell_count.assign(ncell, 0);
@@ -1146,6 +1150,134 @@ double orc_tilecache_build_batch(const rcb_tc_layer* layers, int nlayers, const 
         for (int i = 0; i < nthreads; ++i) totals[0] += acc[(size_t)i * 2], totals[1] += acc[(size_t)i * 2 + 1];
     }
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+}  // extern "C"
+
+
+// =================================================================================================
+// Area operators on CompactHeightfield.areas (area.rs), SURVEY §8(f) rank 1
+// =================================================================================================
+namespace {
+
+// area.rs:29-50
+bool point_in_poly(uint32_t nv, const float* verts, float px, float pz) {
+    bool in = false;
+    for (uint32_t i = 0, j = nv - 1; i < nv; j = i++) {
+        const float* vi = verts + i * 3;
+        const float* vj = verts + j * 3;
+        if ((vi[2] > pz) == (vj[2] > pz)) continue;
+        if (px < (vj[0] - vi[0]) * (pz - vi[2]) / (vj[2] - vi[2]) + vi[0]) in = !in;
+    }
+    return in;
+}
+
+template <class Fn>
+void for_footprint(Compact& c, int32_t minx, int32_t maxx, int32_t minz, int32_t maxz, Fn&& fn) {
+    const int32_t w = c.width, h = c.height;
+    if (maxx < 0 || minx >= w || maxz < 0 || minz >= h) return;
+    minx = std::max(minx, 0), maxx = std::min(maxx, w - 1), minz = std::max(minz, 0), maxz = std::min(maxz, h - 1);
+    for (int32_t z = minz; z <= maxz; ++z)
+        for (int32_t x = minx; x <= maxx; ++x) {
+            const size_t ci = (size_t)z * w + x;
+            if (c.cell_index[ci] == NONE) continue;
+            for (uint32_t k = 0; k < c.cell_count[ci]; ++k) fn(x, z, c.cell_index[ci] + k);
+        }
+}
+
+}  // namespace
+
+extern "C" {
+
+// area.rs:238-294
+void orc_chf_median_filter_walkable_area(orc_chf* p) {
+    Compact& c = *(Compact*)p;
+    const size_t S = c.smin.size();
+    std::vector<uint8_t> out(S, 0xff);
+    for (uint32_t s = 0; s < S; ++s) {
+        if (c.areas[s] == 0) {
+            out[s] = 0;
+            continue;
+        }
+        uint8_t nei[9];
+        for (int i = 0; i < 9; ++i) nei[i] = c.areas[s];
+        static const uint8_t dirs[4] = {1, 3, 5, 7};
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t a = c.get_neighbor(s, dirs[i]);
+            if (a == NONE) continue;
+            if (c.areas[a] != 0) nei[i * 2] = c.areas[a];
+            const uint32_t b = c.get_neighbor(a, (uint8_t)((dirs[i] + 1) % 8));
+            if (b != NONE && c.areas[b] != 0) nei[i * 2 + 1] = c.areas[b];
+        }
+        for (int i = 1; i < 9; ++i) {  // insert_sort area.rs:13-25
+            const uint8_t v = nei[i];
+            int j = i - 1;
+            while (j >= 0 && nei[j] > v) {
+                nei[j + 1] = nei[j];
+                --j;
+            }
+            nei[j + 1] = v;
+        }
+        out[s] = nei[4];
+    }
+    c.areas = out;
+}
+
+// area.rs:298-355
+void orc_chf_mark_box_area(orc_chf* p, const float* bmin, const float* bmax, uint8_t area_id) {
+    Compact& c = *(Compact*)p;
+    const int32_t minx = f32_as_i32((bmin[0] - c.bmin[0]) / c.cs), miny = f32_as_i32((bmin[1] - c.bmin[1]) / c.ch),
+                  minz = f32_as_i32((bmin[2] - c.bmin[2]) / c.cs), maxx = f32_as_i32((bmax[0] - c.bmin[0]) / c.cs),
+                  maxy = f32_as_i32((bmax[1] - c.bmin[1]) / c.ch), maxz = f32_as_i32((bmax[2] - c.bmin[2]) / c.cs);
+    for_footprint(c, minx, maxx, minz, maxz, [&](int32_t, int32_t, uint32_t s) {
+        const int32_t y = c.smin[s];
+        if (y < miny || y > maxy) return;
+        if (c.areas[s] == 0) return;
+        c.areas[s] = area_id;
+    });
+}
+
+// area.rs:544-618
+void orc_chf_mark_cylinder_area(orc_chf* p, const float* pos, float radius, float height, uint8_t area_id) {
+    Compact& c = *(Compact*)p;
+    const float bbmin[3] = {pos[0] - radius, pos[1], pos[2] - radius}, bbmax[3] = {pos[0] + radius, pos[1] + height, pos[2] + radius};
+    const int32_t minx = f32_as_i32((bbmin[0] - c.bmin[0]) / c.cs), miny = f32_as_i32((bbmin[1] - c.bmin[1]) / c.ch),
+                  minz = f32_as_i32((bbmin[2] - c.bmin[2]) / c.cs), maxx = f32_as_i32((bbmax[0] - c.bmin[0]) / c.cs),
+                  maxy = f32_as_i32((bbmax[1] - c.bmin[1]) / c.ch), maxz = f32_as_i32((bbmax[2] - c.bmin[2]) / c.cs);
+    const float r2 = radius * radius;
+    for_footprint(c, minx, maxx, minz, maxz, [&](int32_t x, int32_t z, uint32_t s) {
+        const float cx = c.bmin[0] + ((float)x + 0.5f) * c.cs, cz = c.bmin[2] + ((float)z + 0.5f) * c.cs;
+        const float dx = cx - pos[0], dz = cz - pos[2];
+        if (dx * dx + dz * dz >= r2) return;
+        if (c.areas[s] == 0) return;
+        const int32_t y = c.smin[s];
+        if (y >= miny && y <= maxy) c.areas[s] = area_id;
+    });
+}
+
+// area.rs:359-437
+void orc_chf_mark_convex_poly_area(orc_chf* p, const float* verts, uint32_t nv, float min_y, float max_y, uint8_t area_id) {
+    Compact& c = *(Compact*)p;
+    float bmin[3] = {verts[0], min_y, verts[2]}, bmax[3] = {verts[0], max_y, verts[2]};
+    for (uint32_t i = 1; i < nv; ++i) {
+        bmin[0] = std::fmin(bmin[0], verts[i * 3]), bmin[2] = std::fmin(bmin[2], verts[i * 3 + 2]);
+        bmax[0] = std::fmax(bmax[0], verts[i * 3]), bmax[2] = std::fmax(bmax[2], verts[i * 3 + 2]);
+    }
+    const int32_t minx = f32_as_i32((bmin[0] - c.bmin[0]) / c.cs), miny = f32_as_i32((bmin[1] - c.bmin[1]) / c.ch),
+                  minz = f32_as_i32((bmin[2] - c.bmin[2]) / c.cs), maxx = f32_as_i32((bmax[0] - c.bmin[0]) / c.cs),
+                  maxy = f32_as_i32((bmax[1] - c.bmin[1]) / c.ch), maxz = f32_as_i32((bmax[2] - c.bmin[2]) / c.cs);
+    for_footprint(c, minx, maxx, minz, maxz, [&](int32_t x, int32_t z, uint32_t s) {
+        if (c.areas[s] == 0) return;
+        const int32_t y = c.smin[s];
+        if (y < miny || y > maxy) return;
+        const float px = c.bmin[0] + ((float)x + 0.5f) * c.cs, pz = c.bmin[2] + ((float)z + 0.5f) * c.cs;
+        if (point_in_poly(nv, verts, px, pz)) c.areas[s] = area_id;
+    });
+}
+
+void orc_chf_set_areas(orc_chf* p, const uint8_t* areas) {
+    Compact& c = *(Compact*)p;
+    std::memcpy(c.areas.data(), areas, c.areas.size());
 }
 
 }  // extern "C"

@@ -71,6 +71,11 @@ def lib():
         L.orc_tilecache_build.argtypes = [vp, vp, f32, f32, vp]
         L.orc_tilecache_build_batch.restype = ctypes.c_double
         L.orc_tilecache_build_batch.argtypes = [vp, ctypes.c_int, vp, f32, f32, ctypes.c_int, vp]
+        L.orc_chf_median_filter_walkable_area.argtypes = [vp]
+        L.orc_chf_mark_box_area.argtypes = [vp, vp, vp, u8]
+        L.orc_chf_mark_cylinder_area.argtypes = [vp, vp, f32, f32, u8]
+        L.orc_chf_mark_convex_poly_area.argtypes = [vp, vp, u32, f32, f32, u8]
+        L.orc_chf_set_areas.argtypes = [vp, vp]
         L.orc_hardware_concurrency.restype = ctypes.c_int
         _lib = L
     return _lib
@@ -228,6 +233,26 @@ class CompactHeightfield:
 
     def erode_walkable_area(self, radius):
         lib().orc_chf_erode_walkable_area(self._h, radius)
+
+    # area.rs:238 / :298 / :544 / :359
+    def median_filter_walkable_area(self):
+        lib().orc_chf_median_filter_walkable_area(self._h)
+
+    def mark_box_area(self, bmin, bmax, area_id):
+        a, b = _f3(bmin), _f3(bmax)
+        lib().orc_chf_mark_box_area(self._h, _p(a), _p(b), area_id)
+
+    def mark_cylinder_area(self, position, radius, height, area_id):
+        a = _f3(position)
+        lib().orc_chf_mark_cylinder_area(self._h, _p(a), radius, height, area_id)
+
+    def mark_convex_poly_area(self, verts, min_y, max_y, area_id):
+        v = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1)
+        lib().orc_chf_mark_convex_poly_area(self._h, _p(v), v.size // 3, min_y, max_y, area_id)
+
+    def set_areas(self, areas):
+        a = np.ascontiguousarray(areas, dtype=np.uint8)
+        lib().orc_chf_set_areas(self._h, _p(a))
 
     def get_neighbor(self, span, dir8):
         r = lib().orc_chf_get_neighbor(self._h, span, dir8)

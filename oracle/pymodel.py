@@ -330,6 +330,7 @@ class Compact:
     def __init__(self, hf):
         w, h = hf.width, hf.height
         self.width, self.height = w, h
+        self.bmin, self.cs, self.ch = list(hf.bmin), hf.cs, hf.ch
         self.cells, self.spans, self.areas = [], [], []
         self.max_height, self.walkable_span_count = 0, 0
         for z in range(h):
@@ -589,3 +590,107 @@ def tilecache_build(layer, obstacles, cs, ch):
                         if hit:
                             sp["area"] = 0
     return c
+
+
+# ---- area operators (area.rs) -----------------------------------------------------------------------------------
+def _trunc_div(a, b, d):
+    with np.errstate(all="ignore"):
+        return _as_i32(f32(f32(f32(a) - f32(b)) / f32(d)))
+
+
+def _point_in_poly(verts, px, pz):  # area.rs:29-50
+    inside = False
+    n = len(verts)
+    j = n - 1
+    for i in range(n):
+        vi, vj = verts[i], verts[j]
+        if (vi[2] > pz) == (vj[2] > pz):
+            j = i
+            continue
+        with np.errstate(all="ignore"):
+            if px < f32(f32(f32(f32(vj[0] - vi[0]) * f32(pz - vi[2])) / f32(vj[2] - vi[2])) + vi[0]):
+                inside = not inside
+        j = i
+    return inside
+
+
+def _footprint(c, minx, maxx, minz, maxz):
+    w, h = c.width, c.height
+    if maxx < 0 or minx >= w or maxz < 0 or minz >= h:
+        return
+    for z in range(max(minz, 0), min(maxz, h - 1) + 1):
+        for x in range(max(minx, 0), min(maxx, w - 1) + 1):
+            idx, cnt = c.cells[z * w + x]
+            if idx is None:
+                continue
+            for s in range(idx, idx + cnt):
+                yield x, z, s
+
+
+def median_filter_walkable_area(c):  # area.rs:238-294
+    out = [0xFF] * len(c.spans)
+    for s in range(len(c.spans)):
+        if c.areas[s] == 0:
+            out[s] = 0
+            continue
+        nei = [c.areas[s]] * 9
+        for i, d in enumerate((1, 3, 5, 7)):
+            a = c.get_neighbor(s, d)
+            if a is None:
+                continue
+            if c.areas[a] != 0:
+                nei[i * 2] = c.areas[a]
+            b = c.get_neighbor(a, (d + 1) % 8)
+            if b is not None and c.areas[b] != 0:
+                nei[i * 2 + 1] = c.areas[b]
+        out[s] = sorted(nei)[4]
+    c.areas = out
+
+
+def mark_box_area(c, bmin, bmax, area_id):  # area.rs:298-355
+    minx, miny, minz = _trunc_div(bmin[0], c.bmin[0], c.cs), _trunc_div(bmin[1], c.bmin[1], c.ch), _trunc_div(bmin[2], c.bmin[2], c.cs)
+    maxx, maxy, maxz = _trunc_div(bmax[0], c.bmin[0], c.cs), _trunc_div(bmax[1], c.bmin[1], c.ch), _trunc_div(bmax[2], c.bmin[2], c.cs)
+    for _, _, s in _footprint(c, minx, maxx, minz, maxz):
+        y = c.spans[s]["min"]
+        if y < miny or y > maxy or c.areas[s] == 0:
+            continue
+        c.areas[s] = area_id
+
+
+def mark_cylinder_area(c, pos, radius, height, area_id):  # area.rs:544-618
+    pos = [f32(v) for v in pos]
+    radius, height = f32(radius), f32(height)
+    lo = [f32(pos[0] - radius), pos[1], f32(pos[2] - radius)]
+    hi = [f32(pos[0] + radius), f32(pos[1] + height), f32(pos[2] + radius)]
+    minx, miny, minz = _trunc_div(lo[0], c.bmin[0], c.cs), _trunc_div(lo[1], c.bmin[1], c.ch), _trunc_div(lo[2], c.bmin[2], c.cs)
+    maxx, maxy, maxz = _trunc_div(hi[0], c.bmin[0], c.cs), _trunc_div(hi[1], c.bmin[1], c.ch), _trunc_div(hi[2], c.bmin[2], c.cs)
+    r2 = f32(radius * radius)
+    for x, z, s in _footprint(c, minx, maxx, minz, maxz):
+        cx = f32(c.bmin[0] + f32(f32(f32(x) + f32(0.5)) * c.cs))
+        cz = f32(c.bmin[2] + f32(f32(f32(z) + f32(0.5)) * c.cs))
+        dx, dz = f32(cx - pos[0]), f32(cz - pos[2])
+        if f32(f32(dx * dx) + f32(dz * dz)) >= r2 or c.areas[s] == 0:
+            continue
+        y = c.spans[s]["min"]
+        if miny <= y <= maxy:
+            c.areas[s] = area_id
+
+
+def mark_convex_poly_area(c, verts, min_y, max_y, area_id):  # area.rs:359-437
+    verts = [tuple(f32(x) for x in v) for v in np.asarray(verts, np.float32).reshape(-1, 3)]
+    lo = [verts[0][0], f32(min_y), verts[0][2]]
+    hi = [verts[0][0], f32(max_y), verts[0][2]]
+    for v in verts[1:]:
+        lo[0], lo[2], hi[0], hi[2] = min(lo[0], v[0]), min(lo[2], v[2]), max(hi[0], v[0]), max(hi[2], v[2])
+    minx, miny, minz = _trunc_div(lo[0], c.bmin[0], c.cs), _trunc_div(lo[1], c.bmin[1], c.ch), _trunc_div(lo[2], c.bmin[2], c.cs)
+    maxx, maxy, maxz = _trunc_div(hi[0], c.bmin[0], c.cs), _trunc_div(hi[1], c.bmin[1], c.ch), _trunc_div(hi[2], c.bmin[2], c.cs)
+    for x, z, s in _footprint(c, minx, maxx, minz, maxz):
+        if c.areas[s] == 0:
+            continue
+        y = c.spans[s]["min"]
+        if y < miny or y > maxy:
+            continue
+        px = f32(c.bmin[0] + f32(f32(f32(x) + f32(0.5)) * c.cs))
+        pz = f32(c.bmin[2] + f32(f32(f32(z) + f32(0.5)) * c.cs))
+        if _point_in_poly(verts, px, pz):
+            c.areas[s] = area_id

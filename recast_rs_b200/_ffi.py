@@ -34,6 +34,11 @@ class RcbTileView(ctypes.Structure):
     ]
 
 
+class RcbAreaOp(ctypes.Structure):
+    _fields_ = [("type", ctypes.c_int32), ("area_id", _u32), ("a", ctypes.c_float * 3), ("b", ctypes.c_float * 3),
+                ("first_vert", _u32), ("num_verts", _u32)]
+
+
 class RcbStageTime(ctypes.Structure):
     _fields_ = [("name", ctypes.c_char * 40), ("ms", ctypes.c_float), ("calls", _u32)]
 
@@ -56,6 +61,7 @@ SYMBOLS = {
     "rcb_build_tiles": (_i, [_vp, _vp, _i, _u32, _i, _pp]),
     "rcb_rasterize": (_i, [_vp, _vp, _i, _vp, ctypes.c_int32, _u32, _i, _pp]),
     "rcb_build_from_spans": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _u32, _i, _pp]),
+    "rcb_apply_area_ops": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _u32, _i, _pp]),
     "rcb_build_tilecache_layers": (_i, [_vp, _vp, _i, _vp, _i, ctypes.c_float, ctypes.c_float, _u32, _i, _pp]),
     "rcb_result_totals": (_i, [_vp, ctypes.POINTER(RcbTotals)]),
     "rcb_result_download": (_i, [_vp]),

@@ -202,6 +202,41 @@ class Context:
         return BatchResult(self, out)
 
 
+    def apply_area_ops(self, cfgs, cell_offset, span_min, span_max, span_area, ops, areas_override=None, stage_mask=STAGE_COMPACT,
+                       erode_radius=0) -> BatchResult:
+        """ops: list of ("median",) | ("box", bmin, bmax, area) | ("cylinder", pos, radius, height, area) |
+        ("poly", verts[n,3], min_y, max_y, area), applied in order (area.rs:238, 298, 544, 359)."""
+        arr = cfgs if isinstance(cfgs, ctypes.Array) else configs_to_array(cfgs)
+        co = np.ascontiguousarray(cell_offset, dtype=np.uint32)
+        a = np.ascontiguousarray(span_min, dtype=np.int16)
+        b = np.ascontiguousarray(span_max, dtype=np.int16)
+        c = np.ascontiguousarray(span_area, dtype=np.uint8)
+        ov = None if areas_override is None else np.ascontiguousarray(areas_override, dtype=np.uint8)
+        oa = (_ffi.RcbAreaOp * max(len(ops), 1))()
+        poly = []
+        f3 = lambda v: (ctypes.c_float * 3)(*[float(x) for x in v])  # noqa: E731
+        for i, op in enumerate(ops):
+            kind = op[0]
+            if kind == "median":
+                oa[i].type = 0
+            elif kind == "box":
+                oa[i].type, oa[i].a, oa[i].b, oa[i].area_id = 1, f3(op[1]), f3(op[2]), int(op[3])
+            elif kind == "cylinder":
+                oa[i].type, oa[i].a, oa[i].b, oa[i].area_id = 2, f3(op[1]), f3((op[2], op[3], 0.0)), int(op[4])
+            elif kind == "poly":
+                v = np.asarray(op[1], dtype=np.float32).reshape(-1, 3)
+                oa[i].type, oa[i].a, oa[i].b, oa[i].area_id = 3, f3((0.0, op[2], 0.0)), f3((0.0, op[3], 0.0)), int(op[4])
+                oa[i].first_vert, oa[i].num_verts = sum(len(p) for p in poly), len(v)
+                poly.append(v)
+            else:
+                raise ValueError(kind)
+        pv = np.ascontiguousarray(np.concatenate(poly).reshape(-1) if poly else np.zeros(0, np.float32), dtype=np.float32)
+        out = ctypes.c_void_p()
+        check(_ffi.lib().rcb_apply_area_ops(self._h, ctypes.cast(arr, ctypes.c_void_p), len(arr), _ptr(co), _ptr(a), _ptr(b), _ptr(c),
+                                            _ptr(ov), ctypes.cast(oa, ctypes.c_void_p), len(ops), _ptr(pv), pv.size, stage_mask,
+                                            erode_radius, ctypes.byref(out)), self._h)
+        return BatchResult(self, out)
+
     def build_tilecache_layers(self, layers, obstacles, cs: float, ch: float, stage_mask=STAGE_COMPACT, erode_radius=0
                                ) -> BatchResult:
         """TileCacheBuilder::layer_to_compact_heightfield + rasterize_obstacles for a batch of layers
@@ -321,9 +356,43 @@ class CompactHeightfield:
     def erode_walkable_area(self, radius: int):  # area.rs:73
         self.areas = self._rerun(STAGE_ERODE, radius).areas
 
+    def _area_ops(self, ops):
+        hf = self._hf
+        with self._ctx.apply_area_ops([hf._cfg()], hf.cell_offset, hf.span_min, hf.span_max, hf.span_area, ops,
+                                      areas_override=self.areas) as r:
+            self.areas = r.download().tile(0).areas
+
+    def median_filter_walkable_area(self):  # area.rs:238
+        self._area_ops([("median",)])
+
+    def mark_box_area(self, bmin, bmax, area_id: int):  # area.rs:298
+        self._area_ops([("box", bmin, bmax, area_id)])
+
+    def mark_cylinder_area(self, position, radius: float, height: float, area_id: int):  # area.rs:544
+        self._area_ops([("cylinder", position, radius, height, area_id)])
+
+    def mark_convex_poly_area(self, verts, min_y: float, max_y: float, area_id: int):  # area.rs:359
+        self._area_ops([("poly", verts, min_y, max_y, area_id)])
+
 
 def erode_walkable_area(chf: CompactHeightfield, erosion_radius: int):  # area.rs:73 (free function)
     chf.erode_walkable_area(erosion_radius)
+
+
+def median_filter_walkable_area(chf: CompactHeightfield):  # area.rs:238
+    chf.median_filter_walkable_area()
+
+
+def mark_box_area(chf: CompactHeightfield, bmin, bmax, area_id: int):  # area.rs:298
+    chf.mark_box_area(bmin, bmax, area_id)
+
+
+def mark_cylinder_area(chf: CompactHeightfield, position, radius: float, height: float, area_id: int):  # area.rs:544
+    chf.mark_cylinder_area(position, radius, height, area_id)
+
+
+def mark_convex_poly_area(chf: CompactHeightfield, verts, num_verts: int, min_y: float, max_y: float, area_id: int):  # area.rs:359
+    chf.mark_convex_poly_area(np.asarray(verts, np.float32).reshape(-1, 3)[:num_verts], min_y, max_y, area_id)
 
 
 class RecastBuilder:

@@ -344,12 +344,17 @@ struct Source {  // where the heightfield comes from
     const uint8_t* sarea = nullptr;
     const uint8_t* areas_override = nullptr;  // host, optional
     bool no_tile_mode = false;                // set when the tile-resident back end reported an overflow
+    const rcb_area_op* ops = nullptr;         // host, area operators applied after linking (rcb_apply_area_ops)
+    int nops = 0;
+    const float* poly_verts = nullptr;
+    size_t npoly_floats = 0;
 };
 
 // Global-memory back end (v1 kernels) from a heightfield CSR that is already in the result arena:
 // filters -> cells/offsets -> link + connection list -> erosion -> distance field.
 int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, TileMap tm, int ntiles, uint64_t Ctot, uint64_t S,
-                    uint32_t fmask, uint32_t stage_mask, int erode_radius, const uint8_t* areas_override) {
+                    uint32_t fmask, uint32_t stage_mask, int erode_radius, const uint8_t* areas_override,
+                    const rcb_area_op* ops = nullptr, int nops = 0, const float* poly_verts = nullptr, size_t npoly_floats = 0) {
     cudaStream_t st = ctx->stream;
     uint32_t* d_hf_off = ctx->d_hf_off.as<uint32_t>();
     char* A = res->devA.p;
@@ -397,6 +402,29 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
         if (areas_override && S > 0) {
             CU(cudaMemcpyAsync(d_areas, areas_override, S, cudaMemcpyHostToDevice, st));
             CU(cudaStreamSynchronize(st));
+        }
+        if (nops > 0 && S > 0) {
+            // area operators in order: runs of marks are one pass each, a median is a gather into a second buffer
+            CU(ctx->d_tc_obs.ensure(sizeof(rcb_area_op) * (size_t)nops + 4 * npoly_floats + 64));
+            rcb_area_op* d_ops = ctx->d_tc_obs.as<rcb_area_op>();
+            float* d_poly = (float*)(d_ops + nops);
+            CU(cudaMemcpyAsync(d_ops, ops, sizeof(rcb_area_op) * (size_t)nops, cudaMemcpyHostToDevice, st));
+            if (npoly_floats) CU(cudaMemcpyAsync(d_poly, poly_verts, 4 * npoly_floats, cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));
+            CU(ctx->d_t8a.ensure(S));
+            int i = 0;
+            while (i < nops) {
+                if (ops[i].type == RCB_AREA_OP_MEDIAN) {
+                    launch_area_median(d_tiles, tm, d_hf_off, d_nei16, S, d_areas, ctx->d_t8a.as<uint8_t>(), st);
+                    CU(cudaMemcpyAsync(d_areas, ctx->d_t8a.p, S, cudaMemcpyDeviceToDevice, st));  // area.rs:291
+                    ++i;
+                } else {
+                    int j = i;
+                    while (j < nops && ops[j].type != RCB_AREA_OP_MEDIAN) ++j;
+                    launch_area_marks(d_tiles, tm, d_hf_off, d_smin, d_areas, d_ops, i, j, d_poly, st);
+                    i = j;
+                }
+            }
         }
         if ((stage_mask & RCB_STAGE_ERODE) && S > 0) {
             CU(ctx->d_t8a.ensure(S));
@@ -796,7 +824,8 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
     }
 
     {
-        const int r = global_back_end(ctx, res, d_tiles, tm, ntiles, Ctot, S, fmask, stage_mask, erode_radius, src.areas_override);
+        const int r = global_back_end(ctx, res, d_tiles, tm, ntiles, Ctot, S, fmask, stage_mask, erode_radius, src.areas_override, src.ops,
+                                      src.nops, src.poly_verts, src.npoly_floats);
         if (r) return bail(r);
     }
     CUB(cudaGetLastError());
@@ -1137,6 +1166,31 @@ int rcb_build_tilecache_layers(rcb_ctx* ctx, const rcb_tc_layer* layers, int nla
     *out = res;
     return RCB_OK;
 #undef CUB
+}
+
+int rcb_apply_area_ops(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const uint32_t* cell_offset, const int16_t* span_min,
+                       const int16_t* span_max, const uint8_t* span_area, const uint8_t* areas_override, const rcb_area_op* ops, int nops,
+                       const float* poly_verts, size_t npoly_floats, uint32_t stage_mask, int erode_radius, rcb_result** out) {
+    if (stage_mask & RCB_STAGE_RASTER) return fail(ctx, RCB_EARG, "rcb_apply_area_ops: RCB_STAGE_RASTER must not be set");
+    if (ntiles > 0 && !cell_offset) return fail(ctx, RCB_EARG, "cell_offset is null");
+    if (nops < 0 || (nops > 0 && !ops)) return fail(ctx, RCB_EARG, "ops is null");
+    for (int i = 0; i < nops; ++i) {
+        if (ops[i].type < RCB_AREA_OP_MEDIAN || ops[i].type > RCB_AREA_OP_CONVEX_POLY) return fail(ctx, RCB_EARG, "op %d: unknown type", i);
+        if (ops[i].type == RCB_AREA_OP_CONVEX_POLY &&
+            (ops[i].num_verts == 0 || !poly_verts || 3ull * ((uint64_t)ops[i].first_vert + ops[i].num_verts) > npoly_floats))
+            return fail(ctx, RCB_EARG, "op %d: polygon vertices out of range", i);
+    }
+    Source s;
+    s.cell_offset = cell_offset;
+    s.smin = span_min;
+    s.smax = span_max;
+    s.sarea = span_area;
+    s.areas_override = areas_override;
+    s.ops = ops;
+    s.nops = nops;
+    s.poly_verts = poly_verts;
+    s.npoly_floats = npoly_floats;
+    return run_pipeline(ctx, cfgs, ntiles, stage_mask | RCB_STAGE_COMPACT, erode_radius, s, out);
 }
 
 int rcb_result_totals(const rcb_result* cres, rcb_totals* out) {

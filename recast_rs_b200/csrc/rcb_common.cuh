@@ -220,6 +220,12 @@ void launch_distance_field(const TileDesc* tiles, int ntiles, TileMap tm, const 
 void launch_erode(const TileDesc* tiles, int ntiles, TileMap tm, const uint32_t* hf_off, const uint16_t* nei16,
                   size_t S, uint8_t* areas, uint8_t* tmp_init, uint8_t* tmp_f, int radius, cudaStream_t s);
 
+// area operators (k_area.cu)
+void launch_area_marks(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smin, uint8_t* areas,
+                       const rcb_area_op* ops, int op0, int op1, const float* poly_verts, cudaStream_t s);
+void launch_area_median(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const uint16_t* nei16, size_t S, const uint8_t* areas,
+                        uint8_t* out, cudaStream_t s);
+
 // tile-cache layers (k_tilecache.cu)
 void launch_tc_count(const TileDesc* tiles, TileMap tm, const uint8_t* regons, uint32_t* cell_cnt, cudaStream_t s);
 void launch_tc_spans(const TileDesc* tiles, TileMap tm, const uint8_t* regons, const uint8_t* areas, const uint32_t* hf_off,

@@ -92,6 +92,45 @@ pub struct rcb_stage_time {
 }
 
 #[repr(C)]
+#[derive(Clone, Copy)]
+pub struct rcb_area_op {
+    pub type_: i32,
+    pub area_id: u32,
+    pub a: [f32; 3],
+    pub b: [f32; 3],
+    pub first_vert: u32,
+    pub num_verts: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct rcb_tc_layer {
+    pub bmin: [f32; 3],
+    pub bmax: [f32; 3],
+    pub hmin: u16,
+    pub hmax: u16,
+    pub width: u8,
+    pub height: u8,
+    pub _pad: u16,
+    pub regons: *const u8,
+    pub areas: *const u8,
+    pub regons_len: u32,
+    pub areas_len: u32,
+    pub first_obstacle: u32,
+    pub obstacle_count: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct rcb_tc_obstacle {
+    pub type_: i32,
+    pub state: i32,
+    pub a: [f32; 3],
+    pub b: [f32; 3],
+    pub rot_aux: [f32; 2],
+}
+
+#[repr(C)]
 pub struct rcb_ctx {
     _private: [u8; 0],
 }
@@ -118,6 +157,8 @@ extern "C" {
     pub fn rcb_build_tiles(ctx: *mut rcb_ctx, cfgs: *const rcb_config, ntiles: c_int, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
     pub fn rcb_rasterize(ctx: *mut rcb_ctx, cfgs: *const rcb_config, ntiles: c_int, tri_areas: *const u8, flag_merge_threshold: i32, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
     pub fn rcb_build_from_spans(ctx: *mut rcb_ctx, cfgs: *const rcb_config, ntiles: c_int, cell_offset: *const u32, span_min: *const i16, span_max: *const i16, span_area: *const u8, areas_override: *const u8, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
+    pub fn rcb_apply_area_ops(ctx: *mut rcb_ctx, cfgs: *const rcb_config, ntiles: c_int, cell_offset: *const u32, span_min: *const i16, span_max: *const i16, span_area: *const u8, areas_override: *const u8, ops: *const rcb_area_op, nops: c_int, poly_verts: *const f32, npoly_floats: usize, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
+    pub fn rcb_build_tilecache_layers(ctx: *mut rcb_ctx, layers: *const rcb_tc_layer, nlayers: c_int, obstacles: *const rcb_tc_obstacle, nobstacles: c_int, cs: f32, ch: f32, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
     pub fn rcb_result_totals(res: *const rcb_result, out: *mut rcb_totals) -> c_int;
     pub fn rcb_result_download(res: *mut rcb_result) -> c_int;
     pub fn rcb_result_tile(res: *const rcb_result, tile: c_int, out: *mut rcb_tile_view) -> c_int;
