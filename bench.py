@@ -97,6 +97,15 @@ def alg_bytes(tot):
     return 12 * T + 12 * V + 8 * C + 5 * S + 1 * S + 8 * S + 2 * S + 5 * K
 
 
+def read_traffic():
+    """dram__bytes_read+write per launch of the main kernels, from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
 def read_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -441,7 +450,9 @@ def run_native(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "whole step (all launches)",
+                         "traffic": (read_traffic() or {}).get("main_kernels_sum") if args.config == 2 and world == 1 else None,
+                         "traffic_per_kernel": (read_traffic() or {}).get("per_launch_dram_bytes") if args.config == 2 and world == 1 else None,
+                         "peak_source": peak_src, "kernel": "whole step (all launches)",
                          "alg_bytes_per_step_per_gpu": balg_all / world,
                          "alg_bytes_per_triangle": balg_all / T_all,
                          "dominant_kernel": {"name": dom[0], "ms": dom[1], "share_of_kernel_time": dom[1] / ksum if ksum else None},
