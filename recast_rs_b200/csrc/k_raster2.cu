@@ -28,6 +28,7 @@ constexpr int XCAP = 6;                                   // row / rest polygon 
 constexpr int SLOT_WORDS = 4 + 2 * XCAP + 1;              // header + verts + pad (odd stride: no bank conflicts)
 static_assert(2 * XCAP * 2 <= 2 * ZCAP * 3, "phase-2 buffers alias the z-chain scratch");
 constexpr int NSLOTS = CLIP_THREADS * CLIP_ROWS;
+constexpr int NBUCK = 16;  // phase-2 rows are grouped by (vertex count 3..6+, columns spanned 1..4+): a scheduling hint only
 
 struct Tri {
     float v0[3], v1[3], v2[3];
@@ -176,6 +177,7 @@ struct ClipSmem {
     float zbuf[2 * ZCAP * 3 * CLIP_THREADS];  // phase 1: [(buf*ZCAP + v)*3 + k][tid]; phase 2: two x/y buffers per thread
     uint32_t slots[NSLOTS * SLOT_WORDS];      // slot tid*CLIP_ROWS + r belongs to thread tid, row r of its chunk
     uint16_t list[NSLOTS];                    // compacted ids of the slots that hold a row polygon
+    uint32_t nb[NBUCK], cur[NBUCK];           // rows per (vertex count, columns spanned) bucket and fill cursors
     uint32_t nlist;
 };
 
@@ -222,7 +224,10 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
                                                              TileInfo* __restrict__ tinfo) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ClipSmem& sm = *reinterpret_cast<ClipSmem*>(smem_raw);
+    if (threadIdx.x < NBUCK) sm.nb[threadIdx.x] = sm.cur[threadIdx.x] = 0;
     if (threadIdx.x == 0) sm.nlist = 0;
+#pragma unroll
+    for (int r = 0; r < CLIP_ROWS; ++r) sm.slots[(threadIdx.x * CLIP_ROWS + r) * SLOT_WORDS + 2] = 0;  // slot empty
     __syncthreads();
 
     // ---------------- phase 1: z-chain of one work item ------------------------------------------------
@@ -253,6 +258,7 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
                 const uint32_t slot_id = threadIdx.x * CLIP_ROWS + (uint32_t)(keep ? z - zs : 0);
                 uint32_t* slot = sm.slots + slot_id * SLOT_WORDS;
                 int nrow = 0, nrest = 0;
+                float rminx = 3.0e38f, rmaxx = -3.0e38f;  // x-extent of the row polygon (bucketing hint)
                 const int nxt = cur ^ 1;
                 // divide_poly(p1 -> in_row (slot, x/y only), rest (zbuf[nxt]))  rasterization.rs:172-242
                 for (int i = 0; i < n; ++i) {
@@ -268,6 +274,8 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
                                 slot[5 + 2 * nrow] = __float_as_uint(viy);
                             } else
                                 ovf = true;
+                            rminx = fminf(rminx, vix);
+                            rmaxx = fmaxf(rmaxx, vix);
                         }
                         nrow++;
                     }
@@ -292,6 +300,8 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
                                 slot[5 + 2 * nrow] = __float_as_uint(py);
                             } else
                                 ovf = true;
+                            rminx = fminf(rminx, px);
+                            rmaxx = fmaxf(rmaxx, px);
                         }
                         nrow++;
                         if (nrest < ZCAP) {
@@ -310,7 +320,11 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
                     slot[1] = tile;
                     slot[2] = (uint32_t)z | ((uint32_t)min(nrow, XCAP) << 16) | (area << 24);
                     slot[3] = (uint32_t)x0 | ((uint32_t)x1 << 16);
-                    sm.list[atomicAdd(&sm.nlist, 1u)] = (uint16_t)slot_id;
+                    const int ncols = min(max(__float2int_rz((rmaxx - rminx) * td.ics), 0), 3);
+                    const int bk = min(min(nrow, XCAP) - 3, 3) * 4 + ncols;
+                    slot[SLOT_WORDS - 1] = (uint32_t)bk;  // the pad word carries the bucket
+                    // bucket by vertex count so the lanes of a warp run vertex loops of equal length
+                    atomicAdd(&sm.nb[bk], 1u);
                 }
             }
             if (ovf) {
@@ -323,7 +337,26 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
 
     // ---------------- phase 2: x-chain, one row polygon per thread at a time ------------------------------
     const bool use_minx = (rb.flags & 1u) != 0;
-    const uint32_t nlist = sm.nlist;
+    // every thread files its own row slots into `list`, grouped by bucket
+    uint32_t boff[NBUCK], nlist = 0;
+#pragma unroll
+    for (int k = 0; k < NBUCK; ++k) {
+        boff[k] = nlist;
+        nlist += sm.nb[k];
+    }
+#pragma unroll
+    for (int r = 0; r < CLIP_ROWS; ++r) {
+        const uint32_t slot_id = threadIdx.x * CLIP_ROWS + r;
+        const uint32_t* sl = sm.slots + slot_id * SLOT_WORDS;
+        if (((sl[2] >> 16) & 0xffu) >= 3) {
+            const uint32_t bk = sl[SLOT_WORDS - 1];
+            uint32_t o = 0;
+#pragma unroll
+            for (int k = 0; k < NBUCK; ++k) o = (k == (int)bk) ? boff[k] : o;
+            sm.list[o + atomicAdd(&sm.cur[bk], 1u)] = (uint16_t)slot_id;
+        }
+    }
+    __syncthreads();
     for (uint32_t li = threadIdx.x; li < nlist; li += CLIP_THREADS) {
         const uint32_t* slot = sm.slots + (uint32_t)sm.list[li] * SLOT_WORDS;
         const uint32_t tri = slot[0], tile = slot[1];
