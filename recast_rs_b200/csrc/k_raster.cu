@@ -256,7 +256,10 @@ __global__ void __launch_bounds__(128) k_clip_emit(RasterBuffers rb, TileInfo* _
                 emit_fragment(rb, td.cell_base + (uint32_t)z * td.width + x, tri, smin, smax, area);
             }
         }
-        if (ovf) atomicOr(&tinfo[tile].status, 1u);
+        if (ovf) {
+            atomicOr(&tinfo[tile].status, 1u);
+            atomicOr(&rb.counters[2], 1ull);
+        }
     });
 }
 

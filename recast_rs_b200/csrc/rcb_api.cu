@@ -344,6 +344,7 @@ struct Source {  // where the heightfield comes from
     const uint8_t* sarea = nullptr;
     const uint8_t* areas_override = nullptr;  // host, optional
     bool no_tile_mode = false;                // set when the tile-resident back end reported an overflow
+    bool wide_clip = false;                   // set when the 6-vertex clipper overflowed: use the 12-vertex one
     const rcb_area_op* ops = nullptr;         // host, area operators applied after linking (rcb_apply_area_ops)
     int nops = 0;
     const float* poly_verts = nullptr;
@@ -566,7 +567,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         CUB(cudaMemsetAsync(d_tinfo_tmp, 0, sizeof(TileInfo) * (size_t)ntiles, st));
 
         // v2 front end (k_raster2.cu) needs 16-bit cell coordinates and the (tile, chunk) item encoding
-        bool v2 = ntiles <= (1 << 20) && !ctx->force_v1;
+        bool v2 = ntiles <= (1 << 20) && !ctx->force_v1 && !src.wide_clip;
         for (int i = 0; i < ntiles && v2; ++i)
             if (res->tiles[i].width > 65535 || res->tiles[i].height > 4096 * RCB_CLIP_ROWS) v2 = false;
 
@@ -677,14 +678,16 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             CUB(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             CUB(cudaStreamSynchronize(st));
             bool overflow = (ctx->h_counters[2] & 6ull) != 0;
+            const bool poly_overflow = (ctx->h_counters[2] & 1ull) != 0;  // a clip polygon outgrew the 6-vertex slots
             S = ctx->h_counters[6];
             const uint64_t walk = ctx->h_counters[7], s_max = ctx->h_counters[8];
             const bool compact = (stage_mask & RCB_STAGE_COMPACT) != 0;
             const uint64_t needB = compact ? 8ull * max_cells + 18ull * s_max + 256 : 4ull * max_cells + 64;
             if (needB > kTileSmem) overflow = true;
-            if (overflow) {  // a tile does not fit shared memory: redo the batch on the global-memory back end
+            if (overflow || poly_overflow) {  // redo the batch on the global-memory back end (and the wide clipper)
                 Source s2 = src;
                 s2.no_tile_mode = true;
+                s2.wide_clip = src.wide_clip || poly_overflow;
                 rcb_result_free(res);
                 return run_pipeline(ctx, cfgs, ntiles, stage_mask, erode_radius, s2, out);
             }
@@ -781,6 +784,15 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         S = (uint32_t)ctx->h_counters[4];
         F = ctx->h_counters[5];
         if (ctx->h_counters[6] & 2ull) return bail(fail(ctx, RCB_EOVERFLOW, "fragment pool overflow"));
+        if ((ctx->h_counters[6] & 1ull) && v2) {  // the fast clipper's 6-vertex polygons overflowed: 12-vertex clipper
+            Source s2 = src;
+            s2.no_tile_mode = true;
+            s2.wide_clip = true;
+            rcb_result_free(res);
+            return run_pipeline(ctx, cfgs, ntiles, stage_mask, erode_radius, s2, out);
+        }
+        if (ctx->h_counters[6] & 1ull)
+            return bail(fail(ctx, RCB_EOVERFLOW, "clip polygon exceeded %d vertices", RCB_MAX_POLY_VERTS));
         res->F = F;
         res->S = S;
         make_layout(res->lay, ntiles, Ctot, S, stage_mask);

@@ -256,3 +256,22 @@ def test_recast_builder_facade(oracle, rb, ctx):
     np.testing.assert_array_equal(chf.dist, ea.dist)
     np.testing.assert_array_equal(chf.conn_ref, ea.conn_ref)
     assert chf.max_distance == ea.max_distance
+
+
+def test_precision_collapse_far_from_origin(oracle, rb, ctx):
+    """Coordinates so large that consecutive cell boundaries round to the same float: clip polygons pick up
+    extra on-the-line vertices.  The fast clipper's 6-vertex slots may overflow; the library must then fall
+    back to the wide clipper and still match the oracle bit for bit."""
+    import recast_rs_b200 as r
+    from recast_rs_b200 import synth
+
+    rng = np.random.default_rng(77)
+    base = np.float32(4.0e6)  # ulp(4e6) = 0.5 > cs
+    v, idx = random_soup(rng, 200, 0.0, 12.0, 0.0, 5.0, small=0.5)
+    v = v.reshape(-1, 3).copy()
+    v[:, 0] += base
+    v[:, 2] += base
+    v = v.astype(np.float32).reshape(-1)
+    cfgs = synth.tile_grid(v, 16, r.RecastConfig(cs=0.3, ch=0.2))
+    cfgs = cfgs[:40]
+    _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_ALL_BUILD)
