@@ -393,21 +393,16 @@ __global__ void __launch_bounds__(1024) k_tile_segments(const uint32_t* __restri
 // B: spans -> compact heightfield, connections, erosion, distance field
 // ======================================================================================================
 struct TileB {
-    const uint32_t* soff;  // [C+1]
-    const uint32_t* mm;    // [S] smin | smax << 16
-    const uint8_t* area;   // [S] span area (post-filter)
+    const uint16_t* soff;  // [C+1] first span of every cell (tile-local)
     uint8_t* areas;        // [S] chf.areas (erosion writes it)
-    const uint8_t* nei;    // [8][S] neighbour offset inside the neighbour cell, 0xff = none
-    uint32_t S, S4;  // S4: S rounded up to 4 (row pitch of nei)
+    const uint16_t* nid;   // [8][S2] tile-local id of the neighbour span per direction; S = none.  Entry S of
+                           // every row is a dummy span whose neighbours are itself (branch-free sweeps)
+    uint32_t S, S2;        // S2 >= S + 1: row pitch of nid and of the sweep buffers
     int W, H;
     unsigned long long wmagic;
 };
 
-__device__ __forceinline__ uint32_t tnei(const TileB& g, uint32_t s, int x, int z, int dir) {
-    const uint32_t o = g.nei[(uint32_t)dir * g.S4 + s];
-    if (o == 0xffu) return RCB_NONE;
-    return g.soff[(z + t_dirz[dir]) * g.W + (x + t_dirx[dir])] + o;
-}
+__device__ __forceinline__ uint32_t tnei(const TileB& g, uint32_t s, int dir) { return g.nid[(uint32_t)dir * g.S2 + s]; }
 
 template <typename T>
 __device__ __forceinline__ T sat_add(T v, unsigned b) {
@@ -416,107 +411,74 @@ __device__ __forceinline__ T sat_add(T v, unsigned b) {
     return (T)(r > mx ? mx : r);
 }
 
-// Forward-sweep gather table: for every span the tile-local ids of NW, NW.E, E, E.NE (0xffff = none).
-// The chain nei -> cell offset -> nei -> cell offset does not depend on distances, so it is hoisted out
-// of the H sequential row steps (it was 27 % of k_tile_compact's stall samples, profiles/r01_v3_*).
-__device__ void build_forward_index(const TileB& g, uint2* fidx) {
-    const int W = g.W;
-    const uint32_t C = (uint32_t)(W * g.H);
-    for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
-        const int z = (int)rcb_div_w(c, g.wmagic), x = (int)c - z * W;
-        for (uint32_t s = g.soff[c]; s < g.soff[c + 1]; ++s) {
-            uint32_t a0 = tnei(g, s, x, z, 0), a1 = RCB_NONE, b0 = tnei(g, s, x, z, 3), b1 = RCB_NONE;
-            if (a0 != RCB_NONE) a1 = tnei(g, a0, x - 1, z - 1, 3);
-            if (b0 != RCB_NONE) b1 = tnei(g, b0, x + 1, z, 2);
-            fidx[s] = make_uint2((a0 & 0xffffu) | (a1 << 16), (b0 & 0xffffu) | (b1 << 16));
-        }
-    }
-}
-
 // boundary -> forward rows -> backward gather, on shared memory.  ERODE: thresholds areas; else D + max.
-// fidx: optional forward gather table (nullptr: walk the neighbour chain inside the row loop).
 template <typename T, bool ERODE>
-__device__ void tile_sweep(const TileB& g, T* init, T* Fw, const uint2* fidx, unsigned thr, uint32_t* sh_max) {
+__device__ void tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_t* sh_max, PhaseClock* pc = nullptr) {
     const int W = g.W, H = g.H;
-    const uint32_t C = (uint32_t)(W * H);
-    const unsigned long long wmagic = g.wmagic;
+    const uint32_t TN = g.S;  // "no neighbour" == the dummy span
     const T inf = (T)~(T)0;
-    for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
-        const int z = (int)rcb_div_w(c, wmagic), x = (int)c - z * W;
-        for (uint32_t s = g.soff[c]; s < g.soff[c + 1]; ++s) {
-            const uint8_t ar = g.areas[s];
-            int cnt = 0;
-            if (!ERODE || ar != 0) {
+    // boundary marking (compact_heightfield.rs:556-585 / area.rs:91-125)
+    for (uint32_t s = threadIdx.x; s < g.S; s += TILE_THREADS) {
+        const uint8_t ar = g.areas[s];
+        int cnt = 0;
+        if (!ERODE || ar != 0) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t n = tnei(g, s, x, z, 7 - 2 * k);
-                    if (n == RCB_NONE) continue;
-                    if (ERODE ? (g.areas[n] != 0) : (g.areas[n] == ar)) cnt++;
-                }
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t n = tnei(g, s, 7 - 2 * k);
+                if (n == TN) continue;
+                if (ERODE ? (g.areas[n] != 0) : (g.areas[n] == ar)) cnt++;
             }
-            init[s] = (cnt == 4) ? inf : (T)0;
         }
+        init[s] = (cnt == 4) ? inf : (T)0;
     }
+    if (threadIdx.x == 0) init[g.S] = Fw[g.S] = inf;  // the dummy span never lowers a minimum
     __syncthreads();
-    // forward: row z needs row z-1 final and row z init (see k_dist.cu).  Only the warps that own a
-    // column take part in the H row barriers (named barrier 1); the rest wait at the __syncthreads below.
+    if (pc) pc->mark(8);
+    // forward: row z needs row z-1 final and row z init (see k_dist.cu).  The chain is one warp-instruction
+    // stream deep (H dependent steps), so the body is branch-free: missing neighbours point at the dummy
+    // span (value inf), and a + 2 never needs clamping because the running minimum is already <= inf.
+    // Only the warps that own a column take part in the H row barriers (named barrier 1).
     const int sweep_threads = min(TILE_THREADS, ((W + 31) / 32) * 32);
     if ((int)threadIdx.x < sweep_threads) {
+        const uint16_t* __restrict__ soff = g.soff;
+        const uint16_t* __restrict__ nid0 = g.nid;             // NW
+        const uint16_t* __restrict__ nid2 = g.nid + 2 * g.S2;  // NE
+        const uint16_t* __restrict__ nid3 = g.nid + 3 * g.S2;  // E
         for (int z = 0; z < H; ++z) {
             for (int x = threadIdx.x; x < W; x += sweep_threads) {
                 const uint32_t c = (uint32_t)(z * W + x);
-                const uint32_t sb = g.soff[c], se = g.soff[c + 1];
+                const uint32_t sb = soff[c], se = soff[c + 1];
                 for (uint32_t s = sb; s < se; ++s) {
-                    T v = init[s];
-                    if (fidx) {
-                        const uint2 ix = fidx[s];
-                        const uint32_t a0 = ix.x & 0xffffu, a1 = ix.x >> 16, b0 = ix.y & 0xffffu, b1 = ix.y >> 16;
-                        if (a0 != 0xffffu) v = min(v, sat_add<T>(Fw[a0], 2));
-                        if (a1 != 0xffffu) v = min(v, sat_add<T>(Fw[a1], 3));
-                        if (b0 != 0xffffu) v = min(v, sat_add<T>(init[b0], 2));
-                        if (b1 != 0xffffu) v = min(v, sat_add<T>(Fw[b1], 3));
-                    } else {
-                        const uint32_t aa = tnei(g, s, x, z, 0);
-                        if (aa != RCB_NONE) {
-                            v = min(v, sat_add<T>(Fw[aa], 2));
-                            const uint32_t ab = tnei(g, aa, x - 1, z - 1, 3);
-                            if (ab != RCB_NONE) v = min(v, sat_add<T>(Fw[ab], 3));
-                        }
-                        const uint32_t ba = tnei(g, s, x, z, 3);
-                        if (ba != RCB_NONE) {
-                            v = min(v, sat_add<T>(init[ba], 2));
-                            const uint32_t bb = tnei(g, ba, x + 1, z, 2);
-                            if (bb != RCB_NONE) v = min(v, sat_add<T>(Fw[bb], 3));
-                        }
-                    }
-                    Fw[s] = v;
+                    const uint32_t a0 = nid0[s], b0 = nid3[s];      // NW (row z-1), E (row z: init value)
+                    const uint32_t a1 = nid3[a0], b1 = nid2[b0];    // NW.E, E.NE (row z-1)
+                    uint32_t v = init[s];
+                    v = min(v, (uint32_t)Fw[a0] + 2u);
+                    v = min(v, (uint32_t)Fw[a1] + 3u);
+                    v = min(v, (uint32_t)init[b0] + 2u);
+                    v = min(v, (uint32_t)Fw[b1] + 3u);
+                    Fw[s] = (T)v;
                 }
             }
-            asm volatile("bar.sync 1, %0;" ::"r"(sweep_threads) : "memory");
+            if (sweep_threads == 32)
+                __syncwarp();
+            else
+                asm volatile("bar.sync 1, %0;" ::"r"(sweep_threads) : "memory");
         }
     }
     __syncthreads();
+    if (pc) pc->mark(9);
     // backward = gather from forward values; D overwrites init (init is dead)
     uint32_t vmax = 0;
-    for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
-        const int z = (int)rcb_div_w(c, wmagic), x = (int)c - z * W;
-        for (uint32_t s = g.soff[c]; s < g.soff[c + 1]; ++s) {
-            T v = Fw[s];
-            const uint32_t aa = tnei(g, s, x, z, 2);
-            if (aa != RCB_NONE) {
-                v = min(v, sat_add<T>(Fw[aa], 2));
-                const uint32_t ab = tnei(g, aa, x + 1, z - 1, 1);
-                if (ab != RCB_NONE) v = min(v, sat_add<T>(Fw[ab], 3));
-            }
-            const uint32_t ba = tnei(g, s, x, z, 1);
-            if (ba != RCB_NONE) {
-                v = min(v, sat_add<T>(Fw[ba], 2));
-                const uint32_t bb = tnei(g, ba, x, z - 1, 0);
-                if (bb != RCB_NONE) v = min(v, sat_add<T>(Fw[bb], 3));
-            }
-            init[s] = v;
-            if (!ERODE) vmax = max(vmax, (uint32_t)v);
-        }
+    for (uint32_t s = threadIdx.x; s < g.S; s += TILE_THREADS) {
+        const uint32_t a0 = tnei(g, s, 2), b0 = tnei(g, s, 1);    // NE, N
+        const uint32_t a1 = tnei(g, a0, 1), b1 = tnei(g, b0, 0);  // NE.N, N.NW
+        uint32_t v = Fw[s];
+        v = min(v, (uint32_t)Fw[a0] + 2u);
+        v = min(v, (uint32_t)Fw[a1] + 3u);
+        v = min(v, (uint32_t)Fw[b0] + 2u);
+        v = min(v, (uint32_t)Fw[b1] + 3u);
+        init[s] = (T)v;
+        if (!ERODE) vmax = max(vmax, v);
     }
     if (!ERODE) {
 #pragma unroll
@@ -531,12 +493,15 @@ __device__ void tile_sweep(const TileB& g, T* init, T* Fw, const uint2* fidx, un
     }
 }
 
-// Exclusive prefix of `mine` over tiles by decoupled look-back (warp 0 calls this with all 32 lanes).
-// look[t] = flag << 62 | value; flag 1 = tile aggregate, 2 = inclusive prefix.  Tiles obtain their ids
-// from a ticket counter, so every predecessor is already running or done.
-__device__ uint32_t lookback_exclusive(volatile unsigned long long* look, uint32_t tile, uint32_t mine) {
+// Decoupled look-back over tiles, split in two so that nobody waits: a tile PUBLISHES its connection count
+// as soon as it is known and RESOLVES its exclusive prefix only when it needs it (after the distance field),
+// by which time every predecessor has published.  look[t] = flag << 62 | value; flag 1 = tile aggregate,
+// 2 = inclusive prefix.  Tile ids come from a ticket counter, so predecessors are running or done.
+__device__ __forceinline__ void lookback_publish(volatile unsigned long long* look, uint32_t tile, uint32_t mine) {
+    look[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | mine;
+}
+__device__ uint32_t lookback_resolve(volatile unsigned long long* look, uint32_t tile, uint32_t mine) {  // warp 0, all lanes
     const uint32_t lane = threadIdx.x & 31;
-    if (lane == 0) look[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | mine;
     uint32_t excl = 0;
     for (int t0 = (int)tile - 1; t0 >= 0; t0 -= 32) {
         const int t = t0 - (int)lane;
@@ -563,7 +528,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t sh_warp[TILE_THREADS / 32 + 1];
     __shared__ uint32_t sh_misc[4];  // [0] tile id, [1] conn base, [2] max distance, [3] overflow
-    // dynamic tile id: tiles start in order, which the look-back below relies on
+    // dynamic tile id: tiles start in order, which the look-back relies on
     if (threadIdx.x == 0) {
         sh_misc[0] = atomicAdd(a.tile_ticket, 1u);
         sh_misc[2] = 0;
@@ -577,27 +542,41 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
     const unsigned long long wmagic = td.wmagic;
     const uint32_t S = a.tinfo[tile].span_count;
     const uint32_t span_base = a.tinfo[tile].span_base;
-    // layout: soff[C+1] | d16a[S] u16 | d16b[S] u16 | areas[S] | nei[8S] | coff[C+1] | mm[S] | area[S]
-    // (coff, mm and area are dead once the connections are written; the forward gather table reuses them)
-    const size_t need = 4ull * (2ull * C + 2) + 4ull * S + 4ull * S + 2ull * S + 8ull * S + 64;
-    const bool fits = a.do_compact ? need <= a.smem_bytes : 4ull * (C + 1) <= a.smem_bytes;
-    const uint32_t S2 = (S + 1) & ~1u, S4 = (S + 3) & ~3u;
-    uint32_t* soff = smem;
-    uint16_t* d16a = reinterpret_cast<uint16_t*>(soff + (C + 1));
-    uint16_t* d16b = d16a + S2;
-    uint8_t* areas = reinterpret_cast<uint8_t*>(d16b + S2);
-    uint8_t* nei = areas + S4;
-    uint32_t* coff = reinterpret_cast<uint32_t*>(nei + 8ull * S4);
+    // layout: coff u32[C+1] | mm u32[S] (aliased later by d16a,d16b u16[S2]) | nid u16[8][S2] | soff u16[C+1] | areas u8[S]
+    const uint32_t S2 = (S + 2) & ~1u;  // >= S + 1: one dummy span behind the real ones
+    const uint32_t TN = S;              // "no neighbour" is the dummy span's id
+    const size_t need = 6ull * (C + 2) + 21ull * S + 160;
+    const bool fits = a.do_compact ? (need <= a.smem_bytes && S < 0xffffu) : true;
+    uint32_t* coff = smem;
     uint32_t* mm = coff + (C + 1);
-    uint8_t* area = reinterpret_cast<uint8_t*>(mm + S);
+    uint16_t* d16a = reinterpret_cast<uint16_t*>(mm);
+    uint16_t* d16b = d16a + S2;
+    uint16_t* nid = reinterpret_cast<uint16_t*>(mm + S2);
+    uint16_t* soff = nid + 8ull * S2;
+    uint8_t* areas = reinterpret_cast<uint8_t*>(soff + ((C + 2) & ~1u));
 
     volatile unsigned long long* look = a.lookback;
-    if (!fits) {
-        // still take part in the look-back chain so later tiles do not wait forever
-        if (threadIdx.x < 32) {
-            const uint32_t excl = lookback_exclusive(look, tile, 0);
+    const uint32_t* g_off = a.hf_cell_offset_in + td.cell_base + tile;
+    uint32_t* g_off_out = a.hf_cell_offset + td.cell_base + tile;
+    const uint32_t tb = a.tile_base[tile];
+    if (!a.do_compact || !fits) {
+        // heightfield-only result, or a tile too large for shared memory (the host then reruns the batch on
+        // the global back end): copy the spans through, keep the look-back chain alive
+        for (uint32_t c = threadIdx.x; c <= C; c += TILE_THREADS) g_off_out[c] = g_off[c];
+        for (uint32_t s = threadIdx.x; s < S; s += TILE_THREADS) {
+            const uint32_t w = a.ts_mm[tb + s];
+            a.smin[span_base + s] = (int16_t)(w & 0xffffu);
+            a.smax[span_base + s] = (int16_t)(w >> 16);
+            a.sarea[span_base + s] = a.ts_area[tb + s];
+        }
+        if (a.do_compact && threadIdx.x < 32) {
             if (threadIdx.x == 0) {
                 atomicOr(&a.counters[2], 4ull);
+                lookback_publish(look, tile, 0);
+            }
+            __syncwarp();
+            const uint32_t excl = lookback_resolve(look, tile, 0);
+            if (threadIdx.x == 0) {
                 a.tinfo[tile].conn_base = excl;
                 a.tinfo[tile].conn_count = 0;
             }
@@ -605,41 +584,28 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
         return;
     }
     PhaseClock pc(a.phase ? a.phase + 8 : nullptr);
-    // 1. load the tile's spans
-    const uint32_t* g_off = a.hf_cell_offset_in + td.cell_base + tile;
-    uint32_t* g_off_out = a.hf_cell_offset + td.cell_base + tile;
+    // 1. load the tile's spans; final span attributes (compact_heightfield.rs:231-237)
     for (uint32_t c = threadIdx.x; c <= C; c += TILE_THREADS) {
         const uint32_t o = g_off[c];
-        soff[c] = o;
+        soff[c] = (uint16_t)o;
         g_off_out[c] = o;
     }
-    const uint32_t tb = a.tile_base[tile];
     for (uint32_t s = threadIdx.x; s < S; s += TILE_THREADS) {
         const uint32_t w = a.ts_mm[tb + s];
         const uint8_t ar = a.ts_area[tb + s];
-        if (a.do_compact) {
-            mm[s] = w;
-            area[s] = ar;
-            areas[s] = ar;
-        }
-        // final span attributes (compact_heightfield.rs:231-237)
+        mm[s] = w;
+        areas[s] = ar;  // chf.areas == span area until erosion runs
         a.smin[span_base + s] = (int16_t)(w & 0xffffu);
         a.smax[span_base + s] = (int16_t)(w >> 16);
         a.sarea[span_base + s] = ar;
     }
-    if (!a.do_compact) return;  // heightfield-only result
     __syncthreads();
     pc.mark(0);
-    // 2. cells (compact_heightfield.rs:203-223)
-    for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
-        const uint32_t b = soff[c], n = soff[c + 1] - b;
-        a.cell_index[td.cell_base + c] = n ? b : RCB_NONE;
-        a.cell_count[td.cell_base + c] = n;
-        if (n > 254) sh_misc[3] = 1;  // neighbour offsets are stored in 8 bits here
-    }
-    // 3. link (compact_heightfield.rs:297-372) + con[4] (:392-427)
+    // 2. cells (compact_heightfield.rs:203-223) + 3. link (:297-372) + con[4] (:392-427)
     for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
         const uint32_t b = soff[c], e = soff[c + 1];
+        a.cell_index[td.cell_base + c] = e > b ? b : RCB_NONE;
+        a.cell_count[td.cell_base + c] = e - b;
         uint32_t nconn = 0;
         if (e > b) {
             const int z = (int)rcb_div_w(c, wmagic), x = (int)c - z * W;
@@ -658,68 +624,113 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
                 const uint32_t w = mm[s];
                 const int mn = (int16_t)(w & 0xffffu), mx = (int16_t)(w >> 16);
                 uint32_t c4[4] = {63, 63, 63, 63};
-                if (area[s] != 0) {
+                if (areas[s] != 0) {
 #pragma unroll
                     for (int d = 0; d < 8; ++d) {
-                        uint32_t best = 0xffu;
+                        uint32_t best = TN;
                         int best_diff = 0x7fffffff;
                         for (uint32_t ns = nb[d]; ns < ne[d]; ++ns) {
-                            if (area[ns] == 0) continue;
+                            if (areas[ns] == 0) continue;
                             const uint32_t nw = mm[ns];
                             const int nmn = (int16_t)(nw & 0xffffu), nmx = (int16_t)(nw >> 16);
                             if (max(nmn, mn) > min(nmx, mx)) continue;
                             const int diff = (int)(uint16_t)(abs(nmn - mn) + abs(nmx - mx));
                             if (diff < best_diff) {
                                 best_diff = diff;
-                                best = ns - nb[d];
+                                best = ns;
                             }
                         }
-                        nei[(uint32_t)d * S4 + s] = (uint8_t)best;
-                        if (best != 0xffu) {
+                        nid[(uint32_t)d * S2 + s] = (uint16_t)best;
+                        if (best != TN) {
                             nconn++;
-                            if (d == 7) c4[0] = best;
-                            if (d == 5) c4[1] = best;
-                            if (d == 3) c4[2] = best;
-                            if (d == 1) c4[3] = best;
+                            const uint32_t o = best - nb[d];  // offset inside the neighbour cell (:418-421)
+                            if (d == 7) c4[0] = o;
+                            if (d == 5) c4[1] = o;
+                            if (d == 3) c4[2] = o;
+                            if (d == 1) c4[3] = o;
                         }
                     }
                 } else {
 #pragma unroll
-                    for (int d = 0; d < 8; ++d) nei[(uint32_t)d * S4 + s] = 0xffu;
+                    for (int d = 0; d < 8; ++d) nid[(uint32_t)d * S2 + s] = (uint16_t)TN;
                 }
-                *reinterpret_cast<uint2*>(a.con + 4ull * (span_base + s)) = make_uint2(c4[0] | (c4[1] << 16), c4[2] | (c4[3] << 16));
+                *reinterpret_cast<uint2*>(a.con + 4ull * (span_base + s)) =
+                    make_uint2((c4[0] & 0xffffu) | (c4[1] << 16), (c4[2] & 0xffffu) | (c4[3] << 16));
             }
         }
         coff[c] = nconn;
     }
+    if (threadIdx.x < 8) nid[threadIdx.x * S2 + S] = (uint16_t)S;  // the dummy span's neighbours are itself
     __syncthreads();
     pc.mark(1);
-    // 4. connection offsets inside the tile, then the tile's base by decoupled look-back over tiles
+    // 4. connection offsets inside the tile; publish the tile's count (nobody waits here)
     const uint32_t K = block_scan_array(coff, coff, C, sh_warp);
+    if (threadIdx.x == 0) lookback_publish(look, tile, K);
+    pc.mark(2);
+    const TileB g{soff, areas, nid, S, S2, W, H, wmagic};
+    // 5. erosion (area.rs:73-234) — before the distance field when both are requested.  mm is dead: its
+    //    bytes are the sweep buffers d16a / d16b from here on.
+    if (a.do_erode) {
+        const unsigned thr = (unsigned)(uint8_t)(uint32_t)(a.erode_radius * 2);
+        tile_sweep<uint8_t, true>(g, reinterpret_cast<uint8_t*>(d16a), reinterpret_cast<uint8_t*>(d16b), thr, nullptr);
+    }
+    for (uint32_t s = threadIdx.x; s < S; s += TILE_THREADS) a.areas[span_base + s] = areas[s];
+    pc.mark(3);
+    // 6. distance field (compact_heightfield.rs:514-727)
+    if (a.do_dist) {
+        tile_sweep<uint16_t, false>(g, d16a, d16b, 0, &sh_misc[2], &pc);
+        pc.mark(4);
+        // box blur: d16a holds D; result to global
+        for (uint32_t s = threadIdx.x; s < S; s += TILE_THREADS) {
+            const uint32_t cd = d16a[s];
+            uint32_t r = cd;
+            if (cd > 2) {
+                int d = (int)cd, n = 1;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int dir = 1 + 2 * k;
+                    const uint32_t nbr = tnei(g, s, dir);
+                    if (nbr == TN) continue;
+                    d += d16a[nbr];
+                    n++;
+                    const uint32_t dg = tnei(g, nbr, (dir + 1) & 7);
+                    if (dg != TN) {
+                        d += d16a[dg];
+                        n++;
+                    }
+                }
+                r = (uint32_t)(d / n);
+            }
+            a.dist[span_base + s] = (uint16_t)r;
+        }
+        pc.mark(5);
+    } else {
+        for (uint32_t s = threadIdx.x; s < S; s += TILE_THREADS) a.dist[span_base + s] = 0;  // compact_heightfield.rs:253
+    }
+    // 7. resolve the tile's first connection index, then the connection list (compact_heightfield.rs:375-389):
+    //    reverse direction order, next -> previously pushed, first_connection = last pushed
     if (threadIdx.x < 32) {
-        const uint32_t excl = lookback_exclusive(look, tile, K);
+        const uint32_t excl = lookback_resolve(look, tile, K);
         if (threadIdx.x == 0) {
-            if (sh_misc[3]) atomicOr(&a.counters[2], 4ull);
             sh_misc[1] = excl;
             a.tinfo[tile].conn_base = excl;
             a.tinfo[tile].conn_count = K;
+            if (a.do_dist) a.tinfo[tile].max_distance = sh_misc[2];
         }
     }
     __syncthreads();
+    pc.mark(6);
     const uint32_t conn_base = sh_misc[1];
-    pc.mark(2);
-    // 5. connection list (compact_heightfield.rs:375-389): reverse direction order, next -> previous
     for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
         const uint32_t b = soff[c], e = soff[c + 1];
         if (b == e) continue;
-        const int z = (int)rcb_div_w(c, wmagic), x = (int)c - z * W;
         uint32_t k = coff[c];
         for (uint32_t s = b; s < e; ++s) {
             uint32_t first = RCB_NONE;
             for (int d = 7; d >= 0; --d) {
-                const uint32_t o = nei[(uint32_t)d * S4 + s];
-                if (o == 0xffu) continue;
-                a.conn_ref[conn_base + k] = soff[(z + t_dirz[d]) * W + (x + t_dirx[d])] + o;
+                const uint32_t n = nid[(uint32_t)d * S2 + s];
+                if (n == TN) continue;
+                a.conn_ref[conn_base + k] = n;
                 a.conn_dir[conn_base + k] = (uint8_t)d;
                 a.conn_next[conn_base + k] = first;
                 first = k;
@@ -728,60 +739,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
             a.first_conn[span_base + s] = first;
         }
     }
-    pc.mark(3);
-    const TileB g{soff, mm, area, areas, nei, S, S4, W, H, wmagic};
-    // coff and mm are dead once the connections are written: reuse them for the forward gather table
-    uint2* fidx = nullptr;
-    if ((a.do_erode || a.do_dist) && S < 0xffffu && 8ull * S + 8 <= 4ull * (C + 1) + 5ull * S) {
-        __syncthreads();
-        fidx = reinterpret_cast<uint2*>(reinterpret_cast<uintptr_t>(coff + 1) & ~(uintptr_t)7);
-        build_forward_index(g, fidx);
-        __syncthreads();
-    }
-    pc.mark(4);
-    // 6. erosion (area.rs:73-234) — before the distance field when both are requested
-    if (a.do_erode) {
-        const unsigned thr = (unsigned)(uint8_t)(uint32_t)(a.erode_radius * 2);
-        tile_sweep<uint8_t, true>(g, reinterpret_cast<uint8_t*>(d16a), reinterpret_cast<uint8_t*>(d16b), fidx, thr, nullptr);
-    }
-    for (uint32_t s = threadIdx.x; s < S; s += TILE_THREADS) a.areas[span_base + s] = areas[s];
-    pc.mark(5);
-    // 7. distance field (compact_heightfield.rs:514-727)
-    if (a.do_dist) {
-        tile_sweep<uint16_t, false>(g, d16a, d16b, fidx, 0, &sh_misc[2]);
-        pc.mark(6);
-        // box blur: d16a holds D; result to global
-        for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
-            const int z = (int)rcb_div_w(c, wmagic), x = (int)c - z * W;
-            for (uint32_t s = soff[c]; s < soff[c + 1]; ++s) {
-                const uint32_t cd = d16a[s];
-                uint32_t r = cd;
-                if (cd > 2) {
-                    int d = (int)cd, n = 1;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int dir = 1 + 2 * k;
-                        const uint32_t nbr = tnei(g, s, x, z, dir);
-                        if (nbr == RCB_NONE) continue;
-                        d += d16a[nbr];
-                        n++;
-                        const uint32_t dg = tnei(g, nbr, x + t_dirx[dir], z + t_dirz[dir], (dir + 1) & 7);
-                        if (dg != RCB_NONE) {
-                            d += d16a[dg];
-                            n++;
-                        }
-                    }
-                    r = (uint32_t)(d / n);
-                }
-                a.dist[span_base + s] = (uint16_t)r;
-            }
-        }
-        __syncthreads();
-        pc.mark(7);
-        if (threadIdx.x == 0) a.tinfo[tile].max_distance = sh_misc[2];
-    } else {
-        for (uint32_t s = threadIdx.x; s < S; s += TILE_THREADS) a.dist[span_base + s] = 0;  // compact_heightfield.rs:253
-    }
+    pc.mark(7);
 }
 
 }  // namespace

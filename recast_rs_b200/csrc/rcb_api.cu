@@ -555,10 +555,10 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
 
     if (src.raster) {
         // ---- RASTER: count -> clip/emit -> scan -> scatter -> replay -> scan -------------------------
-        CUB(ctx->d_counters.ensure(32 * sizeof(unsigned long long)));
+        CUB(ctx->d_counters.ensure(48 * sizeof(unsigned long long)));
         CUB(ctx->d_cell_cnt.ensure(4 * (Ctot + 1)));
         CUB(ctx->d_frag_off.ensure(4 * (Ctot + 1)));
-        CUB(cudaMemsetAsync(ctx->d_counters.p, 0, 32 * sizeof(unsigned long long), st));
+        CUB(cudaMemsetAsync(ctx->d_counters.p, 0, 48 * sizeof(unsigned long long), st));
         CUB(cudaMemsetAsync(ctx->d_cell_cnt.p, 0, 4 * (Ctot + 1), st));
         // tile info lives in the arena, which is sized after the span count is known: keep the clip
         // status in scratch until then
@@ -682,7 +682,8 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             S = ctx->h_counters[6];
             const uint64_t walk = ctx->h_counters[7], s_max = ctx->h_counters[8];
             const bool compact = (stage_mask & RCB_STAGE_COMPACT) != 0;
-            const uint64_t needB = compact ? 8ull * max_cells + 18ull * s_max + 256 : 4ull * max_cells + 64;
+            const uint64_t needB = compact ? 6ull * (max_cells + 2) + 21ull * s_max + 192 : 64;
+            if (compact && s_max >= 0xffffu) overflow = true;  // tile-local span ids are 16 bit
             if (needB > kTileSmem) overflow = true;
             if (overflow || poly_overflow) {  // redo the batch on the global-memory back end (and the wide clipper)
                 Source s2 = src;
@@ -735,13 +736,13 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             tc.smem_bytes = (uint32_t)needB;
             launch_tile_compact(tc, ntiles, st);
             if (ctx->phase_timers) {
-                unsigned long long ph[16];
+                unsigned long long ph[32];
                 cudaMemcpyAsync(ph, r2.counters + 16, sizeof ph, cudaMemcpyDeviceToHost, st);
                 cudaStreamSynchronize(st);
                 fprintf(stderr, "[rcb phase cycles/tile] spans:");
                 for (int i = 0; i < 7; ++i) fprintf(stderr, " %llu", ph[i] / (unsigned long long)ntiles);
                 fprintf(stderr, " | compact:");
-                for (int i = 8; i < 16; ++i) fprintf(stderr, " %llu", ph[i] / (unsigned long long)ntiles);
+                for (int i = 8; i < 20; ++i) fprintf(stderr, " %llu", ph[i] / (unsigned long long)ntiles);
                 fprintf(stderr, "\n");
             }
             res->tile_mode = true;
