@@ -444,25 +444,72 @@ __device__ void tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_
         const uint16_t* __restrict__ nid0 = g.nid;             // NW
         const uint16_t* __restrict__ nid2 = g.nid + 2 * g.S2;  // NE
         const uint16_t* __restrict__ nid3 = g.nid + 3 * g.S2;  // E
-        for (int z = 0; z < H; ++z) {
-            for (int x = threadIdx.x; x < W; x += sweep_threads) {
-                const uint32_t c = (uint32_t)(z * W + x);
-                const uint32_t sb = soff[c], se = soff[c + 1];
-                for (uint32_t s = sb; s < se; ++s) {
-                    const uint32_t a0 = nid0[s], b0 = nid3[s];      // NW (row z-1), E (row z: init value)
-                    const uint32_t a1 = nid3[a0], b1 = nid2[b0];    // NW.E, E.NE (row z-1)
-                    uint32_t v = init[s];
-                    v = min(v, (uint32_t)Fw[a0] + 2u);
-                    v = min(v, (uint32_t)Fw[a1] + 3u);
-                    v = min(v, (uint32_t)init[b0] + 2u);
-                    v = min(v, (uint32_t)Fw[b1] + 3u);
-                    Fw[s] = (T)v;
-                }
-            }
+        const uint32_t DUMMY = g.S;
+        auto relax = [&](uint32_t s, uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
+            uint32_t v = init[s];
+            v = min(v, (uint32_t)Fw[a0] + 2u);
+            v = min(v, (uint32_t)Fw[a1] + 3u);
+            v = min(v, (uint32_t)init[b0] + 2u);
+            v = min(v, (uint32_t)Fw[b1] + 3u);
+            return v;
+        };
+        auto row_barrier = [&]() {
             if (sweep_threads == 32)
                 __syncwarp();
             else
                 asm volatile("bar.sync 1, %0;" ::"r"(sweep_threads) : "memory");
+        };
+        if (W <= sweep_threads) {
+            // One column per thread, software-pipelined three rows deep: the neighbour ids of a span do not
+            // depend on distances, so while row z is relaxed the ids of row z+1 (second hop), row z+2 (first
+            // hop) and the cell offsets of row z+3 are already in flight.  The dependent chain per row
+            // shrinks from five shared-memory round trips to one.
+            const int x = threadIdx.x;
+            const bool col = x < W;
+            auto cell_span = [&](int z, uint32_t& sb, uint32_t& n) {  // first span + count of cell (x, z)
+                sb = DUMMY;
+                n = 0;
+                if (col && z < H) {
+                    const uint32_t b = soff[z * W + x], e = soff[z * W + x + 1];
+                    n = e - b;
+                    sb = n ? b : DUMMY;
+                }
+            };
+            uint32_t s0, n0, s1, n1, s2, n2, s3, n3;
+            cell_span(0, s0, n0);
+            cell_span(1, s1, n1);
+            cell_span(2, s2, n2);
+            uint32_t a0 = nid0[s0], b0 = nid3[s0];
+            uint32_t a1 = nid3[a0], b1 = nid2[b0];
+            uint32_t a0n = nid0[s1], b0n = nid3[s1];
+            for (int z = 0; z < H; ++z) {
+                // everything below is independent of this row's result
+                const uint32_t a1n = nid3[a0n], b1n = nid2[b0n];    // row z+1, second hop
+                const uint32_t a0nn = nid0[s2], b0nn = nid3[s2];    // row z+2, first hop
+                cell_span(z + 3, s3, n3);                           // row z+3, cell offsets
+                if (n0) {
+                    Fw[s0] = (T)relax(s0, a0, a1, b0, b1);
+                    for (uint32_t s = s0 + 1; s < s0 + n0; ++s) {  // further spans of the column: not pipelined
+                        const uint32_t c0 = nid0[s], d0 = nid3[s];
+                        Fw[s] = (T)relax(s, c0, nid3[c0], d0, nid2[d0]);
+                    }
+                }
+                row_barrier();
+                s0 = s1, n0 = n1, a0 = a0n, b0 = b0n, a1 = a1n, b1 = b1n;
+                s1 = s2, n1 = n2, a0n = a0nn, b0n = b0nn;
+                s2 = s3, n2 = n3;
+            }
+        } else {
+            for (int z = 0; z < H; ++z) {
+                for (int x = threadIdx.x; x < W; x += sweep_threads) {
+                    const uint32_t c = (uint32_t)(z * W + x);
+                    for (uint32_t s = soff[c]; s < soff[c + 1]; ++s) {
+                        const uint32_t c0 = nid0[s], d0 = nid3[s];  // NW (row z-1), E (row z: init value)
+                        Fw[s] = (T)relax(s, c0, nid3[c0], d0, nid2[d0]);  // NW.E, E.NE (row z-1)
+                    }
+                }
+                row_barrier();
+            }
         }
     }
     __syncthreads();
@@ -584,20 +631,47 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
         return;
     }
     PhaseClock pc(a.phase ? a.phase + 8 : nullptr);
-    // 1. load the tile's spans; final span attributes (compact_heightfield.rs:231-237)
-    for (uint32_t c = threadIdx.x; c <= C; c += TILE_THREADS) {
-        const uint32_t o = g_off[c];
-        soff[c] = (uint16_t)o;
-        g_off_out[c] = o;
-    }
-    for (uint32_t s = threadIdx.x; s < S; s += TILE_THREADS) {
-        const uint32_t w = a.ts_mm[tb + s];
-        const uint8_t ar = a.ts_area[tb + s];
-        mm[s] = w;
-        areas[s] = ar;  // chf.areas == span area until erosion runs
-        a.smin[span_base + s] = (int16_t)(w & 0xffffu);
-        a.smax[span_base + s] = (int16_t)(w >> 16);
-        a.sarea[span_base + s] = ar;
+    // 1. load the tile's spans; final span attributes (compact_heightfield.rs:231-237).  Loads are issued in
+    //    batches of four per thread so their latencies overlap.
+    {
+        const uint32_t* __restrict__ in_off = g_off;
+        const uint32_t* __restrict__ in_mm = a.ts_mm + tb;
+        const uint8_t* __restrict__ in_ar = a.ts_area + tb;
+        int16_t* __restrict__ o_min = a.smin + span_base;
+        int16_t* __restrict__ o_max = a.smax + span_base;
+        uint8_t* __restrict__ o_ar = a.sarea + span_base;
+        for (uint32_t c0 = threadIdx.x; c0 <= C; c0 += 4 * TILE_THREADS) {
+            uint32_t o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) o[u] = (c0 + u * TILE_THREADS <= C) ? in_off[c0 + u * TILE_THREADS] : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (c0 + u * TILE_THREADS <= C) {
+                    soff[c0 + u * TILE_THREADS] = (uint16_t)o[u];
+                    g_off_out[c0 + u * TILE_THREADS] = o[u];
+                }
+        }
+        for (uint32_t s0 = threadIdx.x; s0 < S; s0 += 4 * TILE_THREADS) {
+            uint32_t w[4];
+            uint8_t ar[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t i = s0 + u * TILE_THREADS;
+                w[u] = i < S ? in_mm[i] : 0u;
+                ar[u] = i < S ? in_ar[i] : (uint8_t)0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t i = s0 + u * TILE_THREADS;
+                if (i < S) {
+                    mm[i] = w[u];
+                    areas[i] = ar[u];  // chf.areas == span area until erosion runs
+                    o_min[i] = (int16_t)(w[u] & 0xffffu);
+                    o_max[i] = (int16_t)(w[u] >> 16);
+                    o_ar[i] = ar[u];
+                }
+            }
+        }
     }
     __syncthreads();
     pc.mark(0);
@@ -727,10 +801,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
         uint32_t k = coff[c];
         for (uint32_t s = b; s < e; ++s) {
             uint32_t first = RCB_NONE;
+            uint32_t nn[8];
+#pragma unroll
+            for (int d = 0; d < 8; ++d) nn[d] = nid[(uint32_t)d * S2 + s];  // eight independent loads
+#pragma unroll
             for (int d = 7; d >= 0; --d) {
-                const uint32_t n = nid[(uint32_t)d * S2 + s];
-                if (n == TN) continue;
-                a.conn_ref[conn_base + k] = n;
+                if (nn[d] == TN) continue;
+                a.conn_ref[conn_base + k] = nn[d];
                 a.conn_dir[conn_base + k] = (uint8_t)d;
                 a.conn_next[conn_base + k] = first;
                 first = k;
