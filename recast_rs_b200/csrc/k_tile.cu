@@ -52,7 +52,8 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
 // Exclusive scan of cnt[0..n) into out[0..n], out[n] = total (cnt and out may alias).  Rounds of
 // TILE_THREADS consecutive elements (thread t takes element r*TILE_THREADS + t: conflict-free), each
 // round one block-wide scan with a running carry.  Uses sh_warp[TILE_THREADS/32 + 1].
-__device__ uint32_t block_scan_array(const uint32_t* cnt, uint32_t* out, uint32_t n, uint32_t* sh_warp) {
+template <typename OutT>
+__device__ uint32_t block_scan_array(const uint32_t* cnt, OutT* out, uint32_t n, uint32_t* sh_warp) {
     uint32_t carry = 0;
     for (uint32_t base = 0; base < n; base += TILE_THREADS) {
         const uint32_t i = base + threadIdx.x;
@@ -67,11 +68,11 @@ __device__ uint32_t block_scan_array(const uint32_t* cnt, uint32_t* out, uint32_
             if (threadIdx.x == 31) sh_warp[TILE_THREADS / 32] = winc;
         }
         __syncthreads();
-        if (i < n) out[i] = carry + inc - v + sh_warp[threadIdx.x >> 5];
+        if (i < n) out[i] = (OutT)(carry + inc - v + sh_warp[threadIdx.x >> 5]);
         carry += sh_warp[TILE_THREADS / 32];
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[n] = carry;
+    if (threadIdx.x == 0) out[n] = (OutT)carry;
     __syncthreads();
     return carry;
 }
@@ -93,9 +94,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_spans(TileSpansArgs a)
     // and defers the tiles that need more; pass 1 (large allocation) handles only the deferred tiles.
     constexpr uint32_t DEFERRED = 0x80000000u;
     if (a.pass == 1 && !(a.tinfo[tile].status & DEFERRED)) return;
-    // layout: off[C+1] | cnt[C] | soff[C+1] | rec[F] (uint2: area << 24 | triangle, smin | smax << 16)
-    const size_t need = 4ull * (3ull * C + 4) + 8ull * F + 16;
-    if (need > a.smem_bytes) {
+    // layout: cnt u32[C] | off u16[C+1] | soff u16[C+1] | rec[F] (uint2: area << 24 | triangle, smin | smax << 16)
+    const size_t need = 8ull * (C + 4) + 8ull * F + 16;
+    if (need > a.smem_bytes || F >= 0xffffu) {
         if (threadIdx.x == 0) {
             if (a.pass == 0 && a.defer) {
                 a.tinfo[tile].status |= DEFERRED;
@@ -107,10 +108,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_spans(TileSpansArgs a)
         }
         return;
     }
-    uint32_t* off = smem;
-    uint32_t* cnt = off + (C + 1);
-    uint32_t* soff = cnt + C;
-    uint2* rec = reinterpret_cast<uint2*>(reinterpret_cast<uintptr_t>(soff + (C + 1) + 1) & ~(uintptr_t)7);
+    uint32_t* cnt = smem;
+    uint16_t* off = reinterpret_cast<uint16_t*>(cnt + C);
+    uint16_t* soff = off + ((C + 2) & ~1u);
+    uint2* rec = reinterpret_cast<uint2*>((reinterpret_cast<uintptr_t>(soff + ((C + 2) & ~1u)) + 7) & ~(uintptr_t)7);
     const uint32_t* frags = a.tile_frags + 3ull * a.tile_base[tile];
 
     PhaseClock pc(a.phase);

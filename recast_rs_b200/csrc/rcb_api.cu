@@ -603,7 +603,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                 r2.item_cnt = ctx->d_item_cnt.as<uint32_t>();
                 // tile-resident back end candidates: moderate tiles (the CSR arrays of a tile must fit shared memory)
                 // (fragment records carry a 24-bit triangle index)
-                want_tile = !ctx->force_global && !src.no_tile_mode && 12ull * max_cells + 4096 <= kTileSmem && ntris < (1u << 24);
+                want_tile = !ctx->force_global && !src.no_tile_mode && 8ull * max_cells + 4096 <= kTileSmem && ntris < (1u << 24);
                 if (want_tile) {
                     CUB(ctx->d_tile_ub.ensure(4 * ((size_t)ntiles + 1)));
                     CUB(ctx->d_tile_base.ensure(4 * ((size_t)ntiles + 2)));
@@ -625,7 +625,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             if (ub >= 0xfffffff0ull || nitems >= 0xfffffff0ull)
                 return bail(fail(ctx, RCB_EARG, "batch too large: fragment bound %llu", (unsigned long long)ub));
             // the bound counts whole footprints; real fragment counts are about half of it on triangle meshes
-            if (want_tile && 12ull * max_cells + 9ull * (ctx->h_counters[5] / 3) + 4096 > kTileSmem) want_tile = false;
+            if (want_tile && 8ull * max_cells + 8ull * (ctx->h_counters[5] / 3) + 4096 > kTileSmem) want_tile = false;
         }
         if (want_tile && ub > 0) {
             // ================= tile-resident back end (k_tile.cu) ==============================================
@@ -661,7 +661,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             {
                 // exact bound: never overflows when it fits.  Above the two-CTAs-per-SM budget the first
                 // launch runs small and defers the few tiles that need more to a second, large launch.
-                const uint64_t exact = 12ull * max_cells + 8ull * ub_max + 64;
+                const uint64_t exact = 8ull * (max_cells + 4) + 8ull * ub_max + 64;
                 const uint64_t small = kTileSmem / 2 - 2048;
                 ta.pass = 0;
                 ta.defer = exact > small;

@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""profiles/: launch-list summary, top-kernel metrics and DRAM traffic from the ncu artefacts of one version.
+usage: summarize_profiles.py <tag, e.g. r01_v5> <gpurun_out/xxx.ncu-rep>"""
+import collections, csv, io, json, subprocess, sys
+tag, rep = sys.argv[1], sys.argv[2]
+rows = list(csv.reader(l for l in open(f"profiles/{tag}_launches.csv") if l.startswith('"')))
+hdr = rows[0]; i_name = hdr.index("Kernel Name"); i_val = hdr.index("Metric Value")
+agg = collections.OrderedDict()
+for r in rows[1:]:
+    n = r[i_name].split("(")[0].replace("<unnamed>::", "").replace("void ", "")
+    agg.setdefault(n, [0, 0.0]); agg[n][0] += 1; agg[n][1] += float(r[i_val].replace(",", ""))
+tot = sum(v[1] for v in agg.values())
+out = [f"# {tag} — ncu launch list summary, config 2, `python bench.py --steps 2 --warmup 3 --no-cpu`",
+       "# per-launch times are cold-cache/serialised: compare SHARES", "kernel,launches,total_us,share"]
+for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    out.append(f"{k},{c},{t / 1000:.1f},{t / tot:.3f}")
+open(f"profiles/{tag}_launch_summary.csv", "w").write("\n".join(out) + "\n")
+print("\n".join(out[:9]))
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw))); hdr = rows[0]; idx = {h: i for i, h in enumerate(hdr)}
+keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]
+summ = {}
+for r in rows[2:]:
+    name = r[idx["Kernel Name"]].split("(")[0].replace("<unnamed>::", "")
+    summ.setdefault(name, {k: r[idx[k]] for k in keys if k in idx})
+json.dump(summ, open(f"profiles/{tag}_ncu_top_kernels.json", "w"), indent=1)
+t = {k: int((float(v["dram__bytes_read.sum"]) + float(v["dram__bytes_write.sum"])) * 1e6) for k, v in summ.items()}
+json.dump({"source": f"profiles/{tag}_ncu_top_kernels.json (ncu --set full, config 2, one launch each; units as ncu reports them: Mbyte)",
+           "per_launch_dram_bytes": t, "main_kernels_sum": sum(t.values())}, open("profiles/ncu_traffic.json", "w"), indent=1)
+print(json.dumps(summ, indent=1)); print(t)
