@@ -275,3 +275,48 @@ def test_precision_collapse_far_from_origin(oracle, rb, ctx):
     cfgs = synth.tile_grid(v, 16, r.RecastConfig(cs=0.3, ch=0.2))
     cfgs = cfgs[:40]
     _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_ALL_BUILD)
+
+
+def test_sparse_world_mostly_empty_tiles(oracle, rb, ctx):
+    """Few small triangles over many tiles: most tiles receive no fragment at all (tile-resident back end)."""
+    import recast_rs_b200 as r
+    from recast_rs_b200 import synth
+
+    rng = np.random.default_rng(5)
+    v, idx = random_soup(rng, 12, 0.0, 30.0, 0.0, 3.0, small=0.4)
+    v = np.concatenate([v, np.array([0, 0, 0, 0.1, 0, 0, 0, 0, 0.1, 30, 0, 30, 30.1, 0, 30, 30, 0, 30.1], np.float32)])  # pin the AABB
+    idx = np.concatenate([idx, np.arange(36, 42, dtype=np.int32)])
+    cfgs = synth.tile_grid(v, 8, r.RecastConfig(cs=0.5, ch=0.25))
+    tot = _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_ALL_BUILD)
+    assert tot["tiles"] > 30 and tot["spans"] < tot["cells"] / 4
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 37), (53, 1), (7, 5), (64, 3)])
+def test_odd_tile_shapes(oracle, rb, ctx, shape):
+    """Tiles that are one cell wide / tall or otherwise not warp-shaped."""
+    import recast_rs_b200 as r
+
+    w, h = shape
+    rng = np.random.default_rng(w * 100 + h)
+    cs, ch = 0.5, 0.25
+    v, idx = random_soup(rng, 60, 0.0, max(w, h) * cs, 0.0, 4.0, small=0.3)
+    cfgs = [r.RecastConfig(width=w, height=h, cs=cs, ch=ch, bmin=(0.0, -0.5, 0.0), bmax=(w * cs, 5.0, h * cs)),
+            r.RecastConfig(width=h, height=w, cs=cs, ch=ch, bmin=(0.25, -0.5, 0.1), bmax=(0.25 + h * cs, 5.0, 0.1 + w * cs))]
+    _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_ALL_BUILD | rb.STAGE_ERODE, erode_radius=1)
+
+
+def test_heterogeneous_tile_sizes_in_one_batch(oracle, rb, ctx):
+    """Arbitrary tile AABBs / sizes / agent parameters in one batch (overlapping tiles allowed)."""
+    import recast_rs_b200 as r
+
+    rng = np.random.default_rng(11)
+    v, idx = random_soup(rng, 300, 0.0, 20.0, -1.0, 6.0, small=0.4)
+    cfgs = []
+    for k in range(9):
+        w, h = int(rng.integers(3, 40)), int(rng.integers(3, 40))
+        cs = float(rng.choice([0.25, 0.5, 0.3]))
+        bx, bz = float(rng.uniform(-2, 12)), float(rng.uniform(-2, 12))
+        cfgs.append(r.RecastConfig(width=w, height=h, cs=cs, ch=float(rng.choice([0.2, 0.5])), bmin=(bx, float(rng.uniform(-1, 1)), bz),
+                                   bmax=(bx + w * cs, float(rng.uniform(4, 7)), bz + h * cs), walkable_height=int(rng.integers(1, 6)),
+                                   walkable_climb=int(rng.integers(0, 4)), walkable_slope_angle=float(rng.uniform(20, 70))))
+    _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_ALL_BUILD)
