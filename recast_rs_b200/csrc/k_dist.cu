@@ -82,37 +82,94 @@ __global__ void __launch_bounds__(256) k_boundary(const TileDesc* __restrict__ t
     }
 }
 
-// ---- forward sweep: one CTA per tile, rows in sequence ----------------------------------------------
+// ---- forward sweep ----------------------------------------------------------------------------------------
+// The neighbour ids a row needs (NW, NW.E, E, E.NE) do not depend on distances: k_fwd_index gathers them
+// once for every span, in parallel, as global span ids.  A missing neighbour becomes the dummy span S
+// (value inf), which makes the sweep body branch-free, and "+2 / +3" needs no clamp because the running
+// minimum never exceeds inf.  k_forward2 then walks the rows of a tile with one CTA: per row one 16-byte
+// index load (prefetched one row ahead) and the distance loads.
+__global__ void __launch_bounds__(256) k_fwd_index(const TileDesc* __restrict__ tiles, TileMap tm, const uint32_t* __restrict__ hf_off,
+                                                   const uint16_t* __restrict__ nei16, size_t S, uint4* __restrict__ fidx) {
+    const uint32_t tile = RCB_TILE_OF_BLOCK();
+    if (tile >= tm.ntiles) return;
+    const TileDesc& td = tiles[tile];
+    const int W = td.width, H = td.height;
+    const uint32_t lc = RCB_CELL_OF_THREAD();
+    if (lc >= (uint32_t)(W * H)) return;
+    const int x = lc % W, z = lc / W;
+    const Grid g{hf_off, nei16, S, td.cell_base, W, H};
+    const uint32_t gc = td.cell_base + lc;
+    const uint32_t dummy = (uint32_t)S;
+    for (uint32_t s = hf_off[gc]; s < hf_off[gc + 1]; ++s) {
+        uint32_t a0 = nei(g, s, x, z, 0), a1 = dummy, b0 = nei(g, s, x, z, 3), b1 = dummy;
+        if (a0 != RCB_NONE) {
+            const uint32_t t = nei(g, a0, x - 1, z - 1, 3);
+            if (t != RCB_NONE) a1 = t;
+        } else
+            a0 = dummy;
+        if (b0 != RCB_NONE) {
+            const uint32_t t = nei(g, b0, x + 1, z, 2);
+            if (t != RCB_NONE) b1 = t;
+        } else
+            b0 = dummy;
+        fidx[s] = make_uint4(a0, a1, b0, b1);
+    }
+}
+
 template <typename T>
-__global__ void __launch_bounds__(256) k_forward(const TileDesc* __restrict__ tiles,
-                                                 const uint32_t* __restrict__ hf_off,
-                                                 const uint16_t* __restrict__ nei16, size_t S,
-                                                 const T* __restrict__ init, T* F) {
+__global__ void __launch_bounds__(1024) k_forward2(const TileDesc* __restrict__ tiles, const uint32_t* __restrict__ hf_off,
+                                                   const uint4* __restrict__ fidx, size_t S, T* init, T* F) {
     const TileDesc& td = tiles[blockIdx.x];
     const int W = td.width, H = td.height;
-    const Grid g{hf_off, nei16, S, td.cell_base, W, H};
-    for (int z = 0; z < H; ++z) {
-        for (int x = threadIdx.x; x < W; x += blockDim.x) {
-            const uint32_t gc = td.cell_base + (uint32_t)z * W + x;
-            const uint32_t b = hf_off[gc], e = hf_off[gc + 1];
-            for (uint32_t s = b; s < e; ++s) {
-                T v = init[s];
-                const uint32_t a = nei(g, s, x, z, 0);  // NW  (row z-1)
-                if (a != RCB_NONE) {
-                    v = min(v, sat_add<T>(F[a], 2));
-                    const uint32_t aa = nei(g, a, x - 1, z - 1, 3);  // NW.E (row z-1)
-                    if (aa != RCB_NONE) v = min(v, sat_add<T>(F[aa], 3));
-                }
-                const uint32_t bn = nei(g, s, x, z, 3);  // E (row z, not yet visited: init value)
-                if (bn != RCB_NONE) {
-                    v = min(v, sat_add<T>(init[bn], 2));
-                    const uint32_t bb = nei(g, bn, x + 1, z, 2);  // E.NE (row z-1)
-                    if (bb != RCB_NONE) v = min(v, sat_add<T>(F[bb], 3));
-                }
-                F[s] = v;
+    const T inf = (T)~(T)0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) init[S] = inf;  // dummy span (every CTA only ever reads it)
+    if (threadIdx.x == 0) F[S] = inf;                       // same value from every CTA: benign
+    __syncthreads();
+    auto relax = [&](uint32_t s, const uint4 ix) {
+        uint32_t v = init[s];
+        v = min(v, (uint32_t)F[ix.x] + 2u);
+        v = min(v, (uint32_t)F[ix.y] + 3u);
+        v = min(v, (uint32_t)init[ix.z] + 2u);
+        v = min(v, (uint32_t)F[ix.w] + 3u);
+        return (T)v;
+    };
+    const uint32_t* __restrict__ off = hf_off + td.cell_base;
+    if (W <= (int)blockDim.x) {
+        // one column per thread; the next row's cell range and first index vector are fetched a row ahead
+        const int x = threadIdx.x;
+        const bool col = x < W;
+        uint32_t sb = 0, se = 0, nb = 0, ne = 0;
+        if (col) {
+            sb = off[x];
+            se = off[x + 1];
+            if (H > 1) {
+                nb = off[W + x];
+                ne = off[W + x + 1];
             }
         }
-        __syncthreads();
+        uint4 ix = make_uint4(0, 0, 0, 0);
+        if (sb < se) ix = fidx[sb];
+        for (int z = 0; z < H; ++z) {
+            uint4 nix = make_uint4(0, 0, 0, 0);
+            if (nb < ne) nix = fidx[nb];  // row z+1, independent of this row's result
+            uint32_t nnb = 0, nne = 0;
+            if (col && z + 2 < H) {
+                nnb = off[(z + 2) * W + x];
+                nne = off[(z + 2) * W + x + 1];
+            }
+            if (sb < se) {
+                F[sb] = relax(sb, ix);
+                for (uint32_t s = sb + 1; s < se; ++s) F[s] = relax(s, fidx[s]);
+            }
+            __syncthreads();
+            sb = nb, se = ne, ix = nix, nb = nnb, ne = nne;
+        }
+    } else {
+        for (int z = 0; z < H; ++z) {
+            for (int x = threadIdx.x; x < W; x += blockDim.x)
+                for (uint32_t s = off[z * W + x]; s < off[z * W + x + 1]; ++s) F[s] = relax(s, fidx[s]);
+            __syncthreads();
+        }
     }
 }
 
@@ -207,15 +264,19 @@ __global__ void __launch_bounds__(256) k_blur(const TileDesc* __restrict__ tiles
 
 void launch_distance_field(const TileDesc* tiles, int ntiles, TileMap tm, const uint32_t* hf_off,
                            const uint16_t* nei16, size_t S, const uint8_t* areas, uint16_t* tmp_init, uint16_t* tmp_f,
-                           uint16_t* tmp_d, uint16_t* dist, TileInfo* tinfo, cudaStream_t s) {
+                           uint16_t* tmp_d, uint16_t* dist, TileInfo* tinfo, uint4* fidx, cudaStream_t s) {
     if (tm.nblocks == 0 || ntiles == 0) return;
     {
         KScope _k("k_boundary", s);
         k_boundary<uint16_t, false><<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, areas, tmp_init);
     }
     {
-        KScope _k("k_forward", s);
-        k_forward<uint16_t><<<ntiles, 256, 0, s>>>(tiles, hf_off, nei16, S, tmp_init, tmp_f);
+        KScope _k("k_fwd_index", s);
+        k_fwd_index<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, fidx);
+    }
+    {
+        KScope _k("k_forward2", s);
+        k_forward2<uint16_t><<<ntiles, 1024, 0, s>>>(tiles, hf_off, fidx, S, tmp_init, tmp_f);
     }
     {
         KScope _k("k_backward", s);
@@ -228,7 +289,7 @@ void launch_distance_field(const TileDesc* tiles, int ntiles, TileMap tm, const 
 }
 
 void launch_erode(const TileDesc* tiles, int ntiles, TileMap tm, const uint32_t* hf_off, const uint16_t* nei16,
-                  size_t S, uint8_t* areas, uint8_t* tmp_init, uint8_t* tmp_f, int radius, cudaStream_t s) {
+                  size_t S, uint8_t* areas, uint8_t* tmp_init, uint8_t* tmp_f, int radius, uint4* fidx, cudaStream_t s) {
     if (tm.nblocks == 0 || ntiles == 0) return;
     const unsigned thr = (unsigned)(uint8_t)(uint32_t)(radius * 2);  // area.rs:226 `(radius*2) as u8`
     {
@@ -236,8 +297,12 @@ void launch_erode(const TileDesc* tiles, int ntiles, TileMap tm, const uint32_t*
         k_boundary<uint8_t, true><<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, areas, tmp_init);
     }
     {
-        KScope _k("k_forward", s);
-        k_forward<uint8_t><<<ntiles, 256, 0, s>>>(tiles, hf_off, nei16, S, tmp_init, tmp_f);
+        KScope _k("k_fwd_index", s);
+        k_fwd_index<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, fidx);
+    }
+    {
+        KScope _k("k_forward2", s);
+        k_forward2<uint8_t><<<ntiles, 1024, 0, s>>>(tiles, hf_off, fidx, S, tmp_init, tmp_f);
     }
     {
         KScope _k("k_backward", s);

@@ -72,7 +72,7 @@ struct rcb_ctx {
     // scratch
     DevBuf d_counters, d_cell_cnt, d_frag_off, d_frag_tmp, d_fs_tri, d_fs_mm, d_fs_area, d_scan_tmp, d_hf_off, d_conn_cnt,
         d_conn_off, d_nei16, d_t16a, d_t16b, d_t16c, d_t8a, d_t8b, d_item_cnt, d_item_off, d_items, d_tile_ub, d_tile_base, d_tile_cursor,
-        d_tile_frags, d_ts_mm, d_ts_area, d_celloff_tmp, d_lookback, d_tc_regons, d_tc_areas, d_tc_obs;
+        d_tile_frags, d_ts_mm, d_ts_area, d_celloff_tmp, d_lookback, d_tc_regons, d_tc_areas, d_tc_obs, d_fidx;
     uint32_t clip_flags = 1;    // RCB_CLIP_FLAGS (A/B runs): bit0 min-x skip test in the clipper
     bool phase_timers = false;  // RCB_PHASE_TIMERS=1: per-phase cycle sums of the tile kernels on stderr
     bool force_global = false;  // RCB_FORCE_GLOBAL=1: never use the tile-resident back end (k_tile.cu)
@@ -428,18 +428,20 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
             }
         }
         if ((stage_mask & RCB_STAGE_ERODE) && S > 0) {
-            CU(ctx->d_t8a.ensure(S));
-            CU(ctx->d_t8b.ensure(S));
+            CU(ctx->d_t8a.ensure(S + 16));
+            CU(ctx->d_t8b.ensure(S + 16));
+            CU(ctx->d_fidx.ensure(16 * (S + 1)));
             launch_erode(d_tiles, ntiles, tm, d_hf_off, d_nei16, S, d_areas, ctx->d_t8a.as<uint8_t>(), ctx->d_t8b.as<uint8_t>(),
-                         erode_radius, st);
+                         erode_radius, ctx->d_fidx.as<uint4>(), st);
         }
         if ((stage_mask & RCB_STAGE_DIST) && S > 0) {
-            CU(ctx->d_t16a.ensure(2 * S));
-            CU(ctx->d_t16b.ensure(2 * S));
-            CU(ctx->d_t16c.ensure(2 * S));
+            CU(ctx->d_t16a.ensure(2 * S + 16));
+            CU(ctx->d_t16b.ensure(2 * S + 16));
+            CU(ctx->d_t16c.ensure(2 * S + 16));
+            CU(ctx->d_fidx.ensure(16 * (S + 1)));
             launch_distance_field(d_tiles, ntiles, tm, d_hf_off, d_nei16, S, d_areas, ctx->d_t16a.as<uint16_t>(),
                                   ctx->d_t16b.as<uint16_t>(), ctx->d_t16c.as<uint16_t>(), (uint16_t*)(A + res->lay.dist), d_tinfo,
-                                  st);
+                                  ctx->d_fidx.as<uint4>(), st);
         }
     }
     return RCB_OK;
@@ -903,7 +905,7 @@ void rcb_destroy(rcb_ctx* ctx) {
                       &ctx->d_fs_area, &ctx->d_scan_tmp, &ctx->d_hf_off, &ctx->d_conn_cnt, &ctx->d_conn_off, &ctx->d_nei16,
                       &ctx->d_t16a, &ctx->d_t16b, &ctx->d_t16c, &ctx->d_t8a, &ctx->d_t8b, &ctx->d_item_cnt, &ctx->d_item_off, &ctx->d_items, &ctx->d_tile_ub, &ctx->d_tile_base,
                       &ctx->d_tile_cursor, &ctx->d_tile_frags, &ctx->d_ts_mm, &ctx->d_ts_area, &ctx->d_celloff_tmp, &ctx->d_lookback, &ctx->d_tc_regons, &ctx->d_tc_areas,
-                      &ctx->d_tc_obs};
+                      &ctx->d_tc_obs, &ctx->d_fidx};
     for (auto* b : bufs) b->release();
     for (auto& a : ctx->free_dev) cudaFree(a.p);
     for (auto& a : ctx->free_host) cudaFreeHost(a.p);

@@ -216,9 +216,9 @@ void launch_tile_bases(const TileDesc* tiles, int ntiles, const uint32_t* hf_off
 
 void launch_distance_field(const TileDesc* tiles, int ntiles, TileMap tm, const uint32_t* hf_off,
                            const uint16_t* nei16, size_t S, const uint8_t* areas, uint16_t* tmp_init, uint16_t* tmp_f,
-                           uint16_t* tmp_d, uint16_t* dist, TileInfo* tinfo, cudaStream_t s);
+                           uint16_t* tmp_d, uint16_t* dist, TileInfo* tinfo, uint4* fidx, cudaStream_t s);
 void launch_erode(const TileDesc* tiles, int ntiles, TileMap tm, const uint32_t* hf_off, const uint16_t* nei16,
-                  size_t S, uint8_t* areas, uint8_t* tmp_init, uint8_t* tmp_f, int radius, cudaStream_t s);
+                  size_t S, uint8_t* areas, uint8_t* tmp_init, uint8_t* tmp_f, int radius, uint4* fidx, cudaStream_t s);
 
 // area operators (k_area.cu)
 void launch_area_marks(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smin, uint8_t* areas,
