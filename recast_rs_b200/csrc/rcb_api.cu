@@ -606,16 +606,15 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                 // tile-resident back end candidates: moderate tiles (the CSR arrays of a tile must fit shared memory)
                 // (fragment records carry a 24-bit triangle index)
                 want_tile = !ctx->force_global && !src.no_tile_mode && 8ull * max_cells + 4096 <= kTileSmem && ntris < (1u << 24);
-                if (want_tile) {
-                    CUB(ctx->d_tile_ub.ensure(4 * ((size_t)ntiles + 1)));
-                    CUB(ctx->d_tile_base.ensure(4 * ((size_t)ntiles + 2)));
-                    CUB(ctx->d_tile_cursor.ensure(4 * ((size_t)ntiles + 1)));
-                    CUB(cudaMemsetAsync(ctx->d_tile_ub.p, 0, 4 * ((size_t)ntiles + 1), st));
-                    CUB(cudaMemsetAsync(ctx->d_tile_cursor.p, 0, 4 * ((size_t)ntiles + 1), st));
-                    r2.tile_ub = ctx->d_tile_ub.as<uint32_t>();
-                }
+                // per-tile fragment bounds -> per-tile segments (both back ends consume fragments tile by tile)
+                CUB(ctx->d_tile_ub.ensure(4 * ((size_t)ntiles + 1)));
+                CUB(ctx->d_tile_base.ensure(4 * ((size_t)ntiles + 2)));
+                CUB(ctx->d_tile_cursor.ensure(4 * ((size_t)ntiles + 1)));
+                CUB(cudaMemsetAsync(ctx->d_tile_ub.p, 0, 4 * ((size_t)ntiles + 1), st));
+                CUB(cudaMemsetAsync(ctx->d_tile_cursor.p, 0, 4 * ((size_t)ntiles + 1), st));
+                r2.tile_ub = ctx->d_tile_ub.as<uint32_t>();
                 launch_bin_count(r2, st);
-                if (want_tile) launch_tile_segments(r2.tile_ub, ctx->d_tile_base.as<uint32_t>(), ntiles, r2.counters, st);
+                launch_tile_segments(r2.tile_ub, ctx->d_tile_base.as<uint32_t>(), ntiles, r2.counters, st);
             } else {
                 launch_count_fragments(rb, st);
             }
@@ -753,29 +752,40 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             *out = res;
             return RCB_OK;
         }
+        uint32_t* d_frag_off = ctx->d_frag_off.as<uint32_t>();
         if (ub > 0) {
-            CUB(ctx->d_frag_tmp.ensure(16 * ub));
             CUB(ctx->d_fs_tri.ensure(4 * ub));
             CUB(ctx->d_fs_mm.ensure(4 * ub));
             CUB(ctx->d_fs_area.ensure(ub));
-            rb.frag_tmp = ctx->d_frag_tmp.as<uint4>();
-            rb.frag_cap = (uint32_t)ub;
             if (v2) {
-                r2.frag_tmp = rb.frag_tmp;
-                r2.frag_cap = rb.frag_cap;
+                // fragments go to per-tile segments; each tile then counts and scatters its own columns
+                CUB(ctx->d_tile_frags.ensure(12 * ub + 64));
                 CUB(ctx->d_items.ensure(8 * nitems + 64));
+                r2.tile_cursor = ctx->d_tile_cursor.as<uint32_t>();
+                r2.tile_base = ctx->d_tile_base.as<uint32_t>();
+                r2.tile_cap = ctx->d_tile_ub.as<uint32_t>();
+                r2.tile_frags = ctx->d_tile_frags.as<uint32_t>();
                 launch_exclusive_scan(r2.item_cnt, ctx->d_item_off.as<uint32_t>(), ntris, ctx->d_scan_tmp.as<uint32_t>(), st);
                 launch_fill_items(r2, ctx->d_item_off.as<uint32_t>(), ctx->d_items.as<uint2>(), st);
                 launch_clip_items(r2, ctx->d_items.as<uint2>(), (uint32_t)nitems, d_tinfo_tmp, st);
+                launch_seg_count(d_tiles, ntiles, r2.tile_frags, r2.tile_base, r2.tile_cap, r2.tile_cursor, rb.cell_cnt, rb.counters,
+                                 (uint32_t)ctx->h_counters[5], st);
             } else {
+                CUB(ctx->d_frag_tmp.ensure(16 * ub));
+                rb.frag_tmp = ctx->d_frag_tmp.as<uint4>();
+                rb.frag_cap = (uint32_t)ub;
                 launch_clip_emit(rb, d_tinfo_tmp, st);
             }
         }
-        uint32_t* d_frag_off = ctx->d_frag_off.as<uint32_t>();
         launch_exclusive_scan(rb.cell_cnt, d_frag_off, Ctot, ctx->d_scan_tmp.as<uint32_t>(), st);
         if (ub > 0) {
-            launch_scatter_fragments(rb.frag_tmp, rb.counters + 1, (uint32_t)ub, d_frag_off, ctx->d_fs_tri.as<uint32_t>(),
-                                     ctx->d_fs_mm.as<uint32_t>(), ctx->d_fs_area.as<uint8_t>(), st);
+            if (v2)
+                launch_seg_scatter(d_tiles, ntiles, r2.tile_frags, r2.tile_base, r2.tile_cap, r2.tile_cursor, d_frag_off, rb.cell_cnt,
+                                   ctx->d_fs_tri.as<uint32_t>(), ctx->d_fs_mm.as<uint32_t>(), ctx->d_fs_area.as<uint8_t>(),
+                                   (uint32_t)ctx->h_counters[5], st);
+            else
+                launch_scatter_fragments(rb.frag_tmp, rb.counters + 1, (uint32_t)ub, d_frag_off, ctx->d_fs_tri.as<uint32_t>(),
+                                         ctx->d_fs_mm.as<uint32_t>(), ctx->d_fs_area.as<uint8_t>(), st);
             launch_replay_columns((uint32_t)Ctot, d_frag_off, ctx->d_fs_tri.as<uint32_t>(), ctx->d_fs_mm.as<uint32_t>(),
                                   ctx->d_fs_area.as<uint8_t>(), rb.cell_cnt, src.merge_thr, st);
         }
