@@ -38,7 +38,8 @@ typedef enum rcb_status {
     RCB_ENAVMESH_GEN = -2,  /* Error::NavMeshGeneration (lib.rs:199-233, heightfield.rs:103-115) */
     RCB_ECUDA = -3,         /* CUDA runtime failure / no device */
     RCB_EOVERFLOW = -4,     /* an internal pool overflowed (clip polygon > RCB_MAX_POLY_VERTS) */
-    RCB_EARG = -5           /* bad argument (null pointer, bad tile index, wrong stage order) */
+    RCB_EARG = -5,          /* bad argument (null pointer, bad tile index, wrong stage order) */
+    RCB_ERECAST = -6        /* Error::Recast (detour-dynamic/src/dynamic_tile.rs:171-216: short span data) */
 } rcb_status;
 
 /* Stage mask for rcb_build_tiles / rcb_build_from_spans. */
@@ -219,6 +220,35 @@ int rcb_apply_area_ops(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const u
                        const int16_t* span_max, const uint8_t* span_area, const uint8_t* areas_override, const rcb_area_op* ops,
                        int nops, const float* poly_verts, size_t npoly_floats, uint32_t stage_mask, int erode_radius,
                        rcb_result** out);
+
+/* ---- heightfield wire formats of detour-dynamic ----------------------------------------
+ * A tile's span data is, per cell in z-major order, `u16 count` then count x (`u32 min, u32 max, u32 area`).
+ *   RCB_WIRE_VOXEL_TILE    big-endian.  Writer: VoxelTile::serialize_spans (io/voxel_tile.rs:70-118, `min as u32`
+ *                          sign-extends the i16).  Reader: VoxelTile::deserialize_spans (:120-176) — lenient: a
+ *                          short buffer ends the span loop of the cell it hits and the walk goes on from
+ *                          there; add_span errors (min > max) drop the span.
+ *   RCB_WIRE_DYNAMIC_TILE  little-endian.  Reader: DynamicTile::reconstruct_heightfield (dynamic_tile.rs:147-257)
+ *                          — strict: short buffer -> RCB_ERECAST, add_span error -> RCB_ENAVMESH_GEN.  The
+ *                          reference has no writer for this byte order (its own writer/reader pair disagree,
+ *                          SURVEY §8(f)); the writer here is the byte-swapped twin of serialize_spans.
+ * Both readers insert every span through Heightfield::add_span (heightfield.rs:102-222), whose merge rule
+ * (same-area overlap, at most one follower absorbed) is NOT the rasterizer's.
+ *
+ * rcb_result_span_data_size: bytes of all tiles' streams = 2 * cells + 12 * spans.
+ * rcb_result_serialize_spans: writes the streams of every tile of a result (heightfield as it stands after
+ *   the result's filters), tile after tile, into `out` (host, >= rcb_result_span_data_size bytes);
+ *   tile_offsets (nullable) receives ntiles + 1 byte offsets.
+ * rcb_build_from_span_data: parses ntiles streams (data + tile_offsets[i] .. tile_offsets[i+1]) into
+ *   heightfields on the device and runs the later stages of stage_mask on them (RCB_STAGE_RASTER must not be
+ *   set), exactly like rcb_build_from_spans.
+ * RCB_STAGE_READD (for rcb_build_from_spans): re-insert the given spans through Heightfield::add_span, in
+ *   column order, before anything else — DynamicTileCheckpoint::clone_heightfield (checkpoint.rs:29-60). */
+typedef enum rcb_wire_format { RCB_WIRE_VOXEL_TILE = 0, RCB_WIRE_DYNAMIC_TILE = 1 } rcb_wire_format;
+#define RCB_STAGE_READD 0x20u
+uint64_t rcb_result_span_data_size(const rcb_result* res);
+int rcb_result_serialize_spans(rcb_result* res, int format, uint8_t* out, uint64_t capacity, uint64_t* tile_offsets);
+int rcb_build_from_span_data(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const uint8_t* data, const uint64_t* tile_offsets,
+                             int format, uint32_t stage_mask, int erode_radius, rcb_result** out);
 
 /* ---- tile-cache layers (SURVEY §8(a) row TC, BASELINE config 5) ---------------------------------------
  * rcb_build_tilecache_layers: TileCacheBuilder::layer_to_compact_heightfield

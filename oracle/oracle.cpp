@@ -14,7 +14,8 @@
 // is asserted against this oracle in tests/test_oracle_reference_kats.py.  Functions the reference
 // never tests (RecastBuilder, filter_ledge_spans, filter_walkable_low_height_spans,
 // build_distance_field, box_blur, erode_walkable_area, the clipper's numerics) are pinned only by
-// the source text => for those rows "parity unpinned" (see DESIGN.md).
+// the source text => for those rows "parity unpinned" (see DESIGN.md).  The same holds for the
+// detour-dynamic wire formats at the end of this file (no reference test touches them).
 //
 // Third-party arithmetic: glam 0.29.3 (Cargo.lock) Vec3 sub/cross/length/normalize used at
 // lib.rs:253-262 is restated from the published glam source (scalar Vec3):
@@ -1278,6 +1279,101 @@ void orc_chf_mark_convex_poly_area(orc_chf* p, const float* verts, uint32_t nv, 
 void orc_chf_set_areas(orc_chf* p, const uint8_t* areas) {
     Compact& c = *(Compact*)p;
     std::memcpy(c.areas.data(), areas, c.areas.size());
+}
+
+}  // extern "C"
+
+// ======================================================================================================
+// Heightfield wire formats.  Paths relative to /root/reference/crates/detour-dynamic/src/.
+// The reference holds no test or golden vector for these functions: "parity unpinned" — the restatement is
+// cross-checked against oracle/pymodel.py and by serialize -> deserialize round trips.
+// ======================================================================================================
+extern "C" {
+
+// io/voxel_tile.rs:70-118 VoxelTile::serialize_spans.  Per cell (z-major): u16 count, then per span
+// `min as u32`, `max as u32` (i16 -> u32 sign-extends), `area as u32`, everything BIG-endian.
+// big_endian == 0 writes the byte-swapped twin (no writer of that form exists in the reference; it is
+// what DynamicTile::reconstruct_heightfield expects to read).  out holds 2*C + 12*S bytes.
+void orc_voxel_serialize_spans(const orc_hf* p, int big_endian, uint8_t* out) {
+    const Heightfield& hf = *(const Heightfield*)p;
+    size_t o = 0;
+    auto put16 = [&](uint16_t v) {
+        if (big_endian) out[o++] = (uint8_t)(v >> 8), out[o++] = (uint8_t)v;
+        else out[o++] = (uint8_t)v, out[o++] = (uint8_t)(v >> 8);
+    };
+    auto put32 = [&](uint32_t v) {
+        for (int k = 0; k < 4; ++k) out[o++] = (uint8_t)(v >> (big_endian ? 24 - 8 * k : 8 * k));
+    };
+    for (size_t c = 0; c < hf.first.size(); ++c) {
+        uint16_t n = 0;  // :72-87 counts[index] += 1 on a u16
+        for (uint32_t s = hf.first[c]; s != NONE; s = hf.pool[s].next) ++n;
+        put16(n);
+        for (uint32_t s = hf.first[c]; s != NONE; s = hf.pool[s].next) {
+            put32((uint32_t)(int32_t)hf.pool[s].smin);
+            put32((uint32_t)(int32_t)hf.pool[s].smax);
+            put32((uint32_t)hf.pool[s].area);
+        }
+    }
+}
+
+// io/voxel_tile.rs:120-176 VoxelTile::deserialize_spans: BIG-endian, lenient.  A short buffer `break`s the
+// innermost loop only (the walk then goes on from wherever it stands), add_span errors are dropped (`let _ =`).
+void orc_voxel_deserialize_spans(orc_hf* p, const uint8_t* d, uint64_t len) {
+    Heightfield& hf = *(Heightfield*)p;
+    uint64_t pos = 0;
+    auto be32 = [&](uint64_t q) { return ((uint32_t)d[q] << 24) | ((uint32_t)d[q + 1] << 16) | ((uint32_t)d[q + 2] << 8) | d[q + 3]; };
+    for (int32_t z = 0; z < hf.height; ++z) {
+        for (int32_t x = 0; x < hf.width; ++x) {
+            if (pos + 2 > len) break;  // :129-131
+            const uint32_t count = ((uint32_t)d[pos] << 8) | d[pos + 1];
+            pos += 2;
+            for (uint32_t i = 0; i < count; ++i) {
+                if (pos + 12 > len) break;  // :138-140
+                const int16_t mn = (int16_t)be32(pos), mx = (int16_t)be32(pos + 4);
+                const uint8_t ar = (uint8_t)be32(pos + 8);
+                pos += 12;
+                (void)hf_add_span2(hf, x, z, mn, mx, ar);  // :169
+            }
+        }
+    }
+}
+
+// dynamic_tile.rs:147-257 DynamicTile::reconstruct_heightfield: LITTLE-endian, strict.
+// Returns 0, RCB_ERECAST (-6, Error::Recast: short buffer) or RCB_ENAVMESH_GEN (add_span's error, `?`).
+int orc_dynamic_reconstruct_heightfield(orc_hf* p, const uint8_t* d, uint64_t len) {
+    Heightfield& hf = *(Heightfield*)p;
+    const uint64_t cells = (uint64_t)((int64_t)hf.width * hf.height);
+    if (len < cells * 2) return -6;  // :171-175
+    uint64_t pos = 0;
+    auto le32 = [&](uint64_t q) { return (uint32_t)d[q] | ((uint32_t)d[q + 1] << 8) | ((uint32_t)d[q + 2] << 16) | ((uint32_t)d[q + 3] << 24); };
+    for (int32_t z = 0; z < hf.height; ++z) {
+        for (int32_t x = 0; x < hf.width; ++x) {
+            if (pos + 2 > len) return -6;  // :181-189
+            const uint64_t count = (uint32_t)d[pos] | ((uint32_t)d[pos + 1] << 8);
+            pos += 2;
+            if (count == 0) continue;
+            if (pos + count * 12 > len) return -6;  // :207-216
+            for (uint64_t i = 0; i < count; ++i) {
+                const int32_t mn = (int32_t)le32(pos), mx = (int32_t)le32(pos + 4), ar = (int32_t)le32(pos + 8);
+                pos += 12;
+                const int st = hf_add_span2(hf, x, z, (int16_t)mn, (int16_t)mx, (uint8_t)ar);  // :253
+                if (st) return st;
+            }
+        }
+    }
+    return 0;
+}
+
+// checkpoint.rs:29-60 DynamicTileCheckpoint::clone_heightfield: every span re-added through
+// Heightfield::add_span in column order (errors dropped), which may merge touching same-area spans.
+orc_hf* orc_checkpoint_clone_heightfield(const orc_hf* p) {
+    const Heightfield& src = *(const Heightfield*)p;
+    Heightfield* dst = hf_new(src.width, src.height, src.bmin, src.bmax, src.cs, src.ch);
+    for (int32_t z = 0; z < src.height; ++z)
+        for (int32_t x = 0; x < src.width; ++x)
+            for (uint32_t s = src.first[(size_t)z * src.width + x]; s != NONE; s = src.pool[s].next)
+                (void)hf_add_span2(*dst, x, z, src.pool[s].smin, src.pool[s].smax, src.pool[s].area);
+    return (orc_hf*)dst;
 }
 
 }  // extern "C"

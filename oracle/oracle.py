@@ -77,6 +77,11 @@ def lib():
         L.orc_chf_mark_convex_poly_area.argtypes = [vp, vp, u32, f32, f32, u8]
         L.orc_chf_set_areas.argtypes = [vp, vp]
         L.orc_hardware_concurrency.restype = ctypes.c_int
+        L.orc_voxel_serialize_spans.argtypes = [vp, ctypes.c_int, vp]
+        L.orc_voxel_deserialize_spans.argtypes = [vp, vp, ctypes.c_uint64]
+        L.orc_dynamic_reconstruct_heightfield.argtypes = [vp, vp, ctypes.c_uint64]
+        L.orc_checkpoint_clone_heightfield.restype = vp
+        L.orc_checkpoint_clone_heightfield.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -133,7 +138,7 @@ class Heightfield:
         return cls(width, height, bmin, bmax, cs, ch, _handle=h)
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:  # module globals may be gone at interpreter exit
             lib().orc_hf_free(self._h)
             self._h = None
 
@@ -176,6 +181,30 @@ class Heightfield:
 
     def filter_walkable_low_height_spans(self, height):
         lib().orc_filter_walkable_low_height_spans(self._h, height)
+
+    # ---- wire formats (detour-dynamic) ----
+    def serialize_spans(self, big_endian=True) -> np.ndarray:
+        """VoxelTile::serialize_spans (io/voxel_tile.rs:70-118); big_endian=False is the byte-swapped twin."""
+        out = np.zeros(2 * self.width * self.height + 12 * self.span_count(), dtype=np.uint8)
+        lib().orc_voxel_serialize_spans(self._h, 1 if big_endian else 0, _p(out))
+        return out
+
+    def deserialize_spans(self, data):
+        """VoxelTile::deserialize_spans (io/voxel_tile.rs:120-176) into this (empty) heightfield."""
+        d = np.ascontiguousarray(data, dtype=np.uint8)
+        lib().orc_voxel_deserialize_spans(self._h, _p(d), d.size)
+
+    def reconstruct_heightfield(self, data):
+        """DynamicTile::reconstruct_heightfield (dynamic_tile.rs:147-257); raises OracleError on Err."""
+        d = np.ascontiguousarray(data, dtype=np.uint8)
+        st = lib().orc_dynamic_reconstruct_heightfield(self._h, _p(d), d.size)
+        if st:
+            raise OracleError(st)
+
+    def checkpoint_clone(self):
+        """DynamicTileCheckpoint::clone_heightfield (checkpoint.rs:29-60)."""
+        h = lib().orc_checkpoint_clone_heightfield(self._h)
+        return Heightfield(self.width, self.height, self.bmin, self.bmax, self.cs, self.ch, _handle=h)
 
     @property
     def poly_overflow(self):

@@ -694,3 +694,91 @@ def mark_convex_poly_area(c, verts, min_y, max_y, area_id):  # area.rs:359-437
         pz = f32(c.bmin[2] + f32(f32(f32(z) + f32(0.5)) * c.cs))
         if _point_in_poly(verts, px, pz):
             c.areas[s] = area_id
+
+
+# ---- heightfield wire formats (detour-dynamic/src) --------------------------------------------------
+class WireError(Exception):
+    """Err(..) of the strict reader: kind = 'recast' (short buffer) or 'navmesh' (add_span)."""
+
+    def __init__(self, kind):
+        super().__init__(kind)
+        self.kind = kind
+
+
+def voxel_serialize_spans(hf, big_endian=True):  # io/voxel_tile.rs:70-118
+    order = "big" if big_endian else "little"
+    out = bytearray()
+    for z in range(hf.height):
+        for x in range(hf.width):
+            col = hf.column(x, z)
+            out += (len(col) & 0xFFFF).to_bytes(2, order)
+            for (mn, mx, ar) in col:
+                out += (mn & 0xFFFFFFFF).to_bytes(4, order)  # i16 as u32: sign extension
+                out += (mx & 0xFFFFFFFF).to_bytes(4, order)
+                out += int(ar).to_bytes(4, order)
+    return bytes(out)
+
+
+def _wrap_i16(v):
+    v &= 0xFFFF
+    return v - 0x10000 if v >= 0x8000 else v
+
+
+def voxel_deserialize_spans(hf, data):  # io/voxel_tile.rs:120-176 (big-endian, lenient)
+    data = bytes(data)
+    pos = 0
+    for z in range(hf.height):
+        for x in range(hf.width):
+            if pos + 2 > len(data):
+                break
+            count = int.from_bytes(data[pos:pos + 2], "big")
+            pos += 2
+            for _ in range(count):
+                if pos + 12 > len(data):
+                    break
+                mn = _wrap_i16(int.from_bytes(data[pos:pos + 4], "big"))
+                mx = _wrap_i16(int.from_bytes(data[pos + 4:pos + 8], "big"))
+                ar = int.from_bytes(data[pos + 8:pos + 12], "big") & 0xFF
+                pos += 12
+                try:
+                    hf.add_span(x, z, mn, mx, ar)
+                except ValueError:
+                    pass  # `let _ =`
+
+
+def dynamic_reconstruct_heightfield(hf, data):  # dynamic_tile.rs:147-257 (little-endian, strict)
+    data = bytes(data)
+    if len(data) < hf.width * hf.height * 2:
+        raise WireError("recast")
+    pos = 0
+    for z in range(hf.height):
+        for x in range(hf.width):
+            if pos + 2 > len(data):
+                raise WireError("recast")
+            count = int.from_bytes(data[pos:pos + 2], "little")
+            pos += 2
+            if count == 0:
+                continue
+            if pos + count * 12 > len(data):
+                raise WireError("recast")
+            for _ in range(count):
+                mn = _wrap_i16(int.from_bytes(data[pos:pos + 4], "little"))
+                mx = _wrap_i16(int.from_bytes(data[pos + 4:pos + 8], "little"))
+                ar = int.from_bytes(data[pos + 8:pos + 12], "little") & 0xFF
+                pos += 12
+                try:
+                    hf.add_span(x, z, mn, mx, ar)
+                except ValueError:
+                    raise WireError("navmesh")
+
+
+def checkpoint_clone_heightfield(src):  # checkpoint.rs:29-60
+    dst = Heightfield(src.width, src.height, src.bmin, src.bmax, src.cs, src.ch)
+    for z in range(src.height):
+        for x in range(src.width):
+            for (mn, mx, ar) in src.column(x, z):
+                try:
+                    dst.add_span(x, z, mn, mx, ar)
+                except ValueError:
+                    pass
+    return dst

@@ -61,6 +61,9 @@ SYMBOLS = {
     "rcb_build_tiles": (_i, [_vp, _vp, _i, _u32, _i, _pp]),
     "rcb_rasterize": (_i, [_vp, _vp, _i, _vp, ctypes.c_int32, _u32, _i, _pp]),
     "rcb_build_from_spans": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _u32, _i, _pp]),
+    "rcb_build_from_span_data": (_i, [_vp, _vp, _i, _vp, _vp, _i, _u32, _i, _pp]),
+    "rcb_result_span_data_size": (_u64, [_vp]),
+    "rcb_result_serialize_spans": (_i, [_vp, _i, _vp, _u64, _vp]),
     "rcb_apply_area_ops": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _u32, _i, _pp]),
     "rcb_build_tilecache_layers": (_i, [_vp, _vp, _i, _vp, _i, ctypes.c_float, ctypes.c_float, _u32, _i, _pp]),
     "rcb_result_totals": (_i, [_vp, ctypes.POINTER(RcbTotals)]),

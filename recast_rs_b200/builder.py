@@ -20,6 +20,8 @@ from .errors import check
 STAGE_RASTER, STAGE_FILTER, STAGE_COMPACT, STAGE_ERODE, STAGE_DIST = 1, 2, 4, 8, 16
 FILTER_LOW_HANGING, FILTER_LEDGE, FILTER_LOW_HEIGHT = 0x100, 0x200, 0x400
 STAGE_ALL_BUILD = STAGE_RASTER | STAGE_FILTER | STAGE_COMPACT | STAGE_DIST
+STAGE_READD = 0x20  # re-insert given spans through Heightfield::add_span (checkpoint.rs:29-60)
+WIRE_VOXEL_TILE, WIRE_DYNAMIC_TILE = 0, 1
 NONE = 0xFFFFFFFF
 
 
@@ -95,6 +97,22 @@ class BatchResult:
             tv.dist = _np_from(v.dist, S, np.uint16)
         return tv
 
+    def span_data_size(self) -> int:
+        return int(_ffi.lib().rcb_result_span_data_size(self._h))
+
+    def serialize_spans(self, fmt: int = 0, out: Optional[np.ndarray] = None):
+        """Span data of every tile (VoxelTile::serialize_spans, io/voxel_tile.rs:70-118; fmt 1 = little-endian twin).
+        Returns (bytes as uint8 array, tile_offsets[ntiles+1]).  `out`: caller's uint8 buffer (page-locked memory
+        makes the copy run at PCIe speed)."""
+        n = self.span_data_size()
+        if out is None:
+            out = np.empty(max(n, 1), np.uint8)
+        if out.dtype != np.uint8 or out.size < n or not out.flags.c_contiguous:
+            raise ValueError(f"out must be a contiguous uint8 array of at least {n} bytes")
+        off = np.zeros(self.totals()["tiles"] + 1, np.uint64)
+        check(_ffi.lib().rcb_result_serialize_spans(self._h, fmt, _ptr(out), n, _ptr(off)), self._ctx._h)
+        return out[:n], off
+
     def tile_device_view(self, i: int) -> _ffi.RcbTileView:
         v = _ffi.RcbTileView()
         check(_ffi.lib().rcb_result_tile_device(self._h, i, ctypes.byref(v)), self._ctx._h)
@@ -128,6 +146,12 @@ class Context:
         self._h = h
         self.device = device
         self._mesh_keep = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
     def close(self):
         if self._h:
@@ -201,6 +225,19 @@ class Context:
               self._h)
         return BatchResult(self, out)
 
+
+    def build_from_span_data(self, cfgs, data, tile_offsets, fmt: int, stage_mask: int = 0, erode_radius: int = 0) -> BatchResult:
+        """Heightfields from serialized span data: fmt WIRE_VOXEL_TILE = VoxelTile::deserialize_spans
+        (io/voxel_tile.rs:120-176), WIRE_DYNAMIC_TILE = DynamicTile::reconstruct_heightfield (dynamic_tile.rs:147-257)."""
+        arr = cfgs if isinstance(cfgs, ctypes.Array) else configs_to_array(cfgs)
+        d = np.ascontiguousarray(np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray)) else data, dtype=np.uint8)
+        off = np.ascontiguousarray(tile_offsets, dtype=np.uint64)
+        if off.size != len(arr) + 1:
+            raise ValueError("tile_offsets must hold ntiles + 1 entries")
+        out = ctypes.c_void_p()
+        check(_ffi.lib().rcb_build_from_span_data(self._h, ctypes.cast(arr, ctypes.c_void_p), len(arr), _ptr(d) if d.size else None,
+                                                  _ptr(off), fmt, stage_mask, erode_radius, ctypes.byref(out)), self._h)
+        return BatchResult(self, out)
 
     def apply_area_ops(self, cfgs, cell_offset, span_min, span_max, span_area, ops, areas_override=None, stage_mask=STAGE_COMPACT,
                        erode_radius=0) -> BatchResult:

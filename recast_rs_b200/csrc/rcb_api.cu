@@ -72,7 +72,8 @@ struct rcb_ctx {
     // scratch
     DevBuf d_counters, d_cell_cnt, d_frag_off, d_frag_tmp, d_fs_tri, d_fs_mm, d_fs_area, d_scan_tmp, d_hf_off, d_conn_cnt,
         d_conn_off, d_nei16, d_t16a, d_t16b, d_t16c, d_t8a, d_t8b, d_item_cnt, d_item_off, d_items, d_tile_ub, d_tile_base, d_tile_cursor,
-        d_tile_frags, d_ts_mm, d_ts_area, d_celloff_tmp, d_lookback, d_tc_regons, d_tc_areas, d_tc_obs, d_fidx;
+        d_tile_frags, d_ts_mm, d_ts_area, d_celloff_tmp, d_lookback, d_tc_regons, d_tc_areas, d_tc_obs, d_fidx, d_wire, d_wire_off,
+        d_wire_pos, d_wire_inoff, d_wire_err;
     uint32_t clip_flags = 1;    // RCB_CLIP_FLAGS (A/B runs): bit0 min-x skip test in the clipper
     bool phase_timers = false;  // RCB_PHASE_TIMERS=1: per-phase cycle sums of the tile kernels on stderr
     bool force_global = false;  // RCB_FORCE_GLOBAL=1: never use the tile-resident back end (k_tile.cu)
@@ -349,6 +350,9 @@ struct Source {  // where the heightfield comes from
     int nops = 0;
     const float* poly_verts = nullptr;
     size_t npoly_floats = 0;
+    const uint8_t* span_data = nullptr;  // host, serialized heightfields (rcb_build_from_span_data)
+    const uint64_t* span_data_off = nullptr;
+    int wire_format = 0;
 };
 
 // Global-memory back end (v1 kernels) from a heightfield CSR that is already in the result arena:
@@ -816,6 +820,92 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             launch_gather_spans((uint32_t)Ctot, d_frag_off, ctx->d_fs_mm.as<uint32_t>(), ctx->d_fs_area.as<uint8_t>(), d_hf_off,
                                 (int16_t*)(A + res->lay.span_min), (int16_t*)(A + res->lay.span_max),
                                 (uint8_t*)(A + res->lay.span_area), st);
+    } else if (src.span_data || (stage_mask & RCB_STAGE_READD)) {
+        // ---- heightfields rebuilt through Heightfield::add_span: wire formats / checkpoint clone (k_wire.cu) ------
+        const bool bytes_in = src.span_data != nullptr;
+        const int strict = bytes_in && src.wire_format == RCB_WIRE_DYNAMIC_TILE;
+        uint64_t Sin = 0, nbytes = 0;
+        CUB(ctx->d_wire_inoff.ensure(4 * (Ctot + 1)));
+        CUB(ctx->d_wire_err.ensure(64));
+        CUB(ctx->d_cell_cnt.ensure(4 * (Ctot + 1)));
+        CUB(cudaMemsetAsync(ctx->d_wire_err.p, 0xff, 64, st));
+        uint32_t* d_in_off = ctx->d_wire_inoff.as<uint32_t>();
+        uint32_t* d_cnt = ctx->d_cell_cnt.as<uint32_t>();
+        unsigned long long* d_err = ctx->d_wire_err.as<unsigned long long>();
+        std::vector<uint32_t> goff;
+        const int16_t *d_in_min = nullptr, *d_in_max = nullptr;
+        const uint8_t* d_in_area = nullptr;
+        if (bytes_in) {
+            for (int i = 0; i < ntiles; ++i)
+                if (src.span_data_off[i + 1] < src.span_data_off[i] || src.span_data_off[i + 1] - src.span_data_off[i] >= 0xffff0000ull)
+                    return bail(fail(ctx, RCB_EARG, "tile %d: tile_offsets not ascending (or a stream of 4 GiB)", i));
+            nbytes = ntiles > 0 ? src.span_data_off[ntiles] : 0;
+            Sin = nbytes / 12 + 1;  // no span takes fewer than 12 bytes
+            if (Sin >= 0xfffffff0ull) return bail(fail(ctx, RCB_EARG, "too many spans"));
+            CUB(ctx->d_wire.ensure(nbytes + 64));
+            CUB(ctx->d_wire_off.ensure(8 * ((size_t)ntiles + 1)));
+            CUB(ctx->d_wire_pos.ensure(4 * (Ctot + 1)));
+            if (nbytes) CUB(cudaMemcpyAsync(ctx->d_wire.p, src.span_data, nbytes, cudaMemcpyHostToDevice, st));
+            CUB(cudaMemcpyAsync(ctx->d_wire_off.p, src.span_data_off, 8 * ((size_t)ntiles + 1), cudaMemcpyHostToDevice, st));
+            launch_wire_walk(d_tiles, ntiles, ctx->d_wire.as<uint8_t>(), ctx->d_wire_off.as<unsigned long long>(), strict,
+                             ctx->d_wire_pos.as<uint32_t>(), d_cnt, d_err, st);
+            launch_exclusive_scan(d_cnt, d_in_off, Ctot, ctx->d_scan_tmp.as<uint32_t>(), st);
+        } else {
+            goff.resize(Ctot + 1);
+            uint64_t sbase = 0, pos = 0;
+            for (int i = 0; i < ntiles; ++i) {
+                const uint64_t C = (uint64_t)res->tiles[i].width * res->tiles[i].height;
+                const uint32_t* co = src.cell_offset + pos;
+                if (co[0] != 0) return bail(fail(ctx, RCB_EARG, "tile %d: cell_offset[0] != 0", i));
+                for (uint64_t c = 0; c < C; ++c) {
+                    if (co[c + 1] < co[c]) return bail(fail(ctx, RCB_EARG, "tile %d: cell_offset not ascending", i));
+                    goff[res->tiles[i].cell_base + c] = (uint32_t)(sbase + co[c]);
+                }
+                sbase += co[C];
+                pos += C + 1;
+                if (sbase >= 0xfffffff0ull) return bail(fail(ctx, RCB_EARG, "too many spans"));
+            }
+            goff[Ctot] = (uint32_t)sbase;
+            Sin = sbase;
+            const size_t o_max = align_up(2 * Sin), o_area = 2 * align_up(2 * Sin);
+            CUB(ctx->d_wire.ensure(o_area + Sin + 64));
+            CUB(cudaMemcpyAsync(d_in_off, goff.data(), 4 * (Ctot + 1), cudaMemcpyHostToDevice, st));
+            if (Sin) {
+                CUB(cudaMemcpyAsync(ctx->d_wire.p, src.smin, 2 * Sin, cudaMemcpyHostToDevice, st));
+                CUB(cudaMemcpyAsync(ctx->d_wire.p + o_max, src.smax, 2 * Sin, cudaMemcpyHostToDevice, st));
+                CUB(cudaMemcpyAsync(ctx->d_wire.p + o_area, src.sarea, Sin, cudaMemcpyHostToDevice, st));
+            }
+            d_in_min = (const int16_t*)ctx->d_wire.p;
+            d_in_max = (const int16_t*)(ctx->d_wire.p + o_max);
+            d_in_area = (const uint8_t*)(ctx->d_wire.p + o_area);
+        }
+        CUB(ctx->d_fs_mm.ensure(4 * Sin + 64));
+        CUB(ctx->d_fs_area.ensure(Sin + 64));
+        launch_wire_replay(d_tiles, tm, bytes_in ? ctx->d_wire.as<uint8_t>() : nullptr, ctx->d_wire_off.as<unsigned long long>(),
+                           ctx->d_wire_pos.as<uint32_t>(), strict, d_in_min, d_in_max, d_in_area, d_in_off, ctx->d_fs_mm.as<uint32_t>(),
+                           ctx->d_fs_area.as<uint8_t>(), d_cnt, d_err, st);
+        launch_exclusive_scan(d_cnt, d_hf_off, Ctot, ctx->d_scan_tmp.as<uint32_t>(), st);
+        CUB(cudaMemcpyAsync(&ctx->h_counters[0], d_hf_off + Ctot, 4, cudaMemcpyDeviceToHost, st));
+        CUB(cudaMemcpyAsync(&ctx->h_counters[1], d_err, 8, cudaMemcpyDeviceToHost, st));
+        CUB(cudaStreamSynchronize(st));  // also covers the pageable host sources above
+        if (ctx->h_counters[1] != ~0ull) {
+            // first failure in the order the reference meets them: tiles one at a time, cells in z-major order,
+            // a cell's length checks before its spans are added
+            const unsigned long long e = ctx->h_counters[1];
+            const unsigned t = (unsigned)(e >> 33), c = (unsigned)((e >> 1) & 0xffffffffu);
+            if (e & 1ull) return bail(fail(ctx, RCB_ENAVMESH_GEN, "tile %u cell %u: Invalid span height: min > max", t, c));
+            return bail(fail(ctx, RCB_ERECAST, "tile %u cell %u: Invalid span data: insufficient data", t, c));
+        }
+        S = (uint32_t)ctx->h_counters[0];
+        res->S = S;
+        make_layout(res->lay, ntiles, Ctot, S, stage_mask);
+        CUB(pool_get(ctx->free_dev, res->lay.bytesA, false, res->devA));
+        char* A = res->devA.p;
+        CUB(cudaMemsetAsync(A + res->lay.tinfo, 0, sizeof(TileInfo) * (size_t)ntiles, st));
+        if (S > 0)
+            launch_gather_spans((uint32_t)Ctot, d_in_off, ctx->d_fs_mm.as<uint32_t>(), ctx->d_fs_area.as<uint8_t>(), d_hf_off,
+                                (int16_t*)(A + res->lay.span_min), (int16_t*)(A + res->lay.span_max),
+                                (uint8_t*)(A + res->lay.span_area), st);
     } else {
         // ---- existing heightfields (host CSR) -------------------------------------------------------------
         std::vector<uint32_t> goff(Ctot + 1);
@@ -1065,6 +1155,57 @@ int rcb_build_from_spans(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const
     s.sarea = span_area;
     s.areas_override = areas_override;
     return run_pipeline(ctx, cfgs, ntiles, stage_mask, erode_radius, s, out);
+}
+
+int rcb_build_from_span_data(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const uint8_t* data, const uint64_t* tile_offsets,
+                             int format, uint32_t stage_mask, int erode_radius, rcb_result** out) {
+    if (stage_mask & RCB_STAGE_RASTER) return fail(ctx, RCB_EARG, "rcb_build_from_span_data: RCB_STAGE_RASTER must not be set");
+    if (format != RCB_WIRE_VOXEL_TILE && format != RCB_WIRE_DYNAMIC_TILE) return fail(ctx, RCB_EARG, "unknown wire format %d", format);
+    if (!tile_offsets || (ntiles > 0 && tile_offsets[ntiles] > 0 && !data)) return fail(ctx, RCB_EARG, "null argument");
+    static const uint8_t empty = 0;
+    Source s;
+    s.span_data = data ? data : &empty;
+    s.span_data_off = tile_offsets;
+    s.wire_format = format;
+    return run_pipeline(ctx, cfgs, ntiles, stage_mask & ~(uint32_t)RCB_STAGE_READD, erode_radius, s, out);
+}
+
+uint64_t rcb_result_span_data_size(const rcb_result* res) { return res ? 2 * res->Ctot + 12 * res->S : 0; }
+
+int rcb_result_serialize_spans(rcb_result* res, int format, uint8_t* out, uint64_t capacity, uint64_t* tile_offsets) {
+    if (!res) return RCB_EARG;
+    rcb_ctx* ctx = res->ctx;
+    if (format != RCB_WIRE_VOXEL_TILE && format != RCB_WIRE_DYNAMIC_TILE) return fail(ctx, RCB_EARG, "unknown wire format %d", format);
+    const uint64_t total = rcb_result_span_data_size(res);
+    if (!out || capacity < total) return fail(ctx, RCB_EARG, "rcb_result_serialize_spans: need %llu bytes", (unsigned long long)total);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ProfInstall prof_install(ctx);
+    int r = fetch_tinfo(res);
+    if (r) return r;
+    if (tile_offsets) {
+        for (int i = 0; i < res->ntiles; ++i) tile_offsets[i] = 2ull * res->tiles[i].cell_base + 12ull * res->tinfo[i].span_base;
+        tile_offsets[res->ntiles] = total;
+    }
+    if (total == 0) return RCB_OK;
+    CU(ctx->d_wire.ensure(total + 64));
+    TileMap tm{(uint32_t)res->ntiles, 0, 0};
+    uint32_t max_cells = 0;
+    for (auto& t : res->tiles) max_cells = std::max(max_cells, (uint32_t)(t.width * t.height));
+    tm.blocks_per_tile = (max_cells + 255) / 256;
+    tm.nblocks = tm.blocks_per_tile * tm.ntiles;
+    // the tile table of this result may no longer be the one in ctx->d_tiles
+    CU(ctx->d_tiles.ensure(sizeof(TileDesc) * (size_t)res->ntiles + 64));
+    CU(cudaMemcpyAsync(ctx->d_tiles.p, res->tiles.data(), sizeof(TileDesc) * (size_t)res->ntiles, cudaMemcpyHostToDevice, st));
+    const char* A = res->devA.p;
+    launch_wire_serialize(ctx->d_tiles.as<TileDesc>(), tm, (const uint32_t*)(A + res->lay.hf_cell_offset),
+                          (const TileInfo*)(A + res->lay.tinfo), (const int16_t*)(A + res->lay.span_min),
+                          (const int16_t*)(A + res->lay.span_max), (const uint8_t*)(A + res->lay.span_area), ctx->d_wire.as<uint8_t>(),
+                          format == RCB_WIRE_VOXEL_TILE, st);
+    CU(cudaMemcpyAsync(out, ctx->d_wire.p, total, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return RCB_OK;
 }
 
 int rcb_build_tilecache_layers(rcb_ctx* ctx, const rcb_tc_layer* layers, int nlayers, const rcb_tc_obstacle* obstacles, int nobstacles,

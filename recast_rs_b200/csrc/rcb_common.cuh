@@ -206,6 +206,16 @@ struct TileMap {
 #define RCB_CELL_OF_THREAD() (blockIdx.x * blockDim.x + threadIdx.x)
 #endif
 
+// k_wire.cu — heightfield wire formats
+void launch_wire_walk(const TileDesc* tiles, int ntiles, const uint8_t* data, const unsigned long long* tile_off, int strict_le,
+                      uint32_t* cell_pos, uint32_t* cell_n, unsigned long long* err, cudaStream_t s);
+void launch_wire_serialize(const TileDesc* tiles, TileMap tm, const uint32_t* hf_cell_offset, const TileInfo* tinfo,
+                           const int16_t* smin, const int16_t* smax, const uint8_t* sarea, uint8_t* out, int big_endian,
+                           cudaStream_t s);
+void launch_wire_replay(const TileDesc* tiles, TileMap tm, const uint8_t* data, const unsigned long long* tile_off,
+                        const uint32_t* cell_pos, int strict_le, const int16_t* smin, const int16_t* smax, const uint8_t* sarea,
+                        const uint32_t* in_off, uint32_t* mm, uint8_t* ar, uint32_t* span_cnt, unsigned long long* err, cudaStream_t s);
+
 void launch_filter_spans(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smin,
                          const int16_t* smax, uint8_t* sarea, uint32_t fmask /*1 F1, 2 F2, 4 F3*/, cudaStream_t s);
 void launch_cells_and_offsets(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, uint32_t* hf_cell_offset,

@@ -7,6 +7,7 @@ RCB_ENAVMESH_GEN = -2
 RCB_ECUDA = -3
 RCB_EOVERFLOW = -4
 RCB_EARG = -5
+RCB_ERECAST = -6
 
 
 class RecastError(Exception):
@@ -19,6 +20,10 @@ class InvalidMesh(RecastError):
 
 class NavMeshGeneration(RecastError):
     """Error::NavMeshGeneration — lib.rs:199-233, heightfield.rs:103-115."""
+
+
+class Recast(RecastError):
+    """Error::Recast — detour-dynamic/src/dynamic_tile.rs:171-216 (short span data)."""
 
 
 class CudaError(RecastError):
@@ -35,6 +40,7 @@ _MAP = {
     RCB_ECUDA: CudaError,
     RCB_EOVERFLOW: PoolOverflow,
     RCB_EARG: ValueError,
+    RCB_ERECAST: Recast,
 }
 
 
