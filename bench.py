@@ -223,6 +223,18 @@ def run_tilecache(args, rank, world, local_rank):
 
     layers, obstacles = tcm.config5(256, 48, seed=args.seed + rank)
     name = "config5: 256 dirty tile-cache layers of 48x48 cells per frame, 1-3 cylinder/box/oriented-box obstacles each"
+    comp = None
+    if args.tc_compressed:
+        # the layers as TileCache stores them: TileCacheLayer::to_bytes under lz4 (liblz4 via pyarrow is the compressor)
+        import pyarrow as pa
+
+        layers, obstacles = tcm.config5_varied(256, 48, seed=args.seed + rank)
+        codec = pa.Codec("lz4_raw")
+        raws = [tcm.layer_to_bytes(l, l.cons) for l in layers]
+        comp = tcm.CompressedTiles([len(r).to_bytes(4, "little") + codec.compress(r, asbytes=True) for r in raws], obstacles,
+                                   [(l.first_obstacle, l.obstacle_count) for l in layers])
+        name = ("config5c: 256 dirty tile-cache layers of 48x48 cells per frame, stored LZ4-compressed (%d -> %d bytes), decompress + "
+                "from_bytes + build + obstacles" % (sum(map(len, raws)), int(comp.off[-1])))
     if args.impl == "reference":
         if rank != 0:
             return
@@ -231,7 +243,8 @@ def run_tilecache(args, rank, world, local_rank):
         threads = orc.hardware_concurrency()
         ms = []
         for i in range(args.warmup + args.steps):
-            secs, _ = orc.tilecache_build_timed(layers, obstacles, 0.3, 0.2, nthreads=threads)
+            secs, _ = (orc.tilecache_build_compressed_timed(comp, 0.3, 0.2, nthreads=threads) if comp is not None else
+                       orc.tilecache_build_timed(layers, obstacles, 0.3, 0.2, nthreads=threads))
             if i >= args.warmup:
                 ms.append(secs * 1e3)
         value = len(layers) / (np.mean(ms) * 1e-3)
@@ -255,9 +268,13 @@ def run_tilecache(args, rank, world, local_rank):
     ctx.set_stream(stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     packed = tcm.Packed(layers, obstacles)  # the C structs a native caller already holds
+    if comp is not None:
+        build = lambda: ctx.build_tilecache_compressed(comp, None, None, 0.3, 0.2)  # noqa: E731
+    else:
+        build = lambda: ctx.build_tilecache_layers(packed, None, 0.3, 0.2)  # noqa: E731
     tot = None
     for _ in range(max(args.warmup, 3)):
-        with ctx.build_tilecache_layers(packed, None, 0.3, 0.2) as r:
+        with build() as r:
             tot = r.totals()
     torch.cuda.synchronize()
     if dist is not None:
@@ -272,7 +289,7 @@ def run_tilecache(args, rank, world, local_rank):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         a.record(stream)
-        r = ctx.build_tilecache_layers(packed, None, 0.3, 0.2)
+        r = build()
         b.record(stream)
         r.download()
         torch.cuda.synchronize()
@@ -295,7 +312,7 @@ def run_tilecache(args, rank, world, local_rank):
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8/i16 cells + f32 obstacle tests", "data": "synthetic",
                 "config": {"workload": name, "totals_rank0": tot, "note": "value includes the H2D of the layer bytes (host data by definition)"},
-                "e2e": {"value": ntl * args.steps / (float(agg[1]) * 1e-3), "unit": "tiles/s", "h2d_bytes_per_step": int(2 * C),
+                "e2e": {"value": ntl * args.steps / (float(agg[1]) * 1e-3), "unit": "tiles/s", "h2d_bytes_per_step": int(comp.off[-1]) if comp is not None else int(2 * C),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": float(agg[1]) / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": balg / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
@@ -304,7 +321,8 @@ def run_tilecache(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu:
             from oracle import oracle as orc
 
-            secs, _ = orc.tilecache_build_timed(layers, obstacles, 0.3, 0.2, nthreads=1)
+            secs, _ = (orc.tilecache_build_compressed_timed(comp, 0.3, 0.2, nthreads=1) if comp is not None else
+                       orc.tilecache_build_timed(layers, obstacles, 0.3, 0.2, nthreads=1))
             line["cpu_baseline"] = {"value": len(layers) / secs, "unit": "tiles/s", "cores": 1, "kind": "port", "sample": "all 256 layers"}
         emit(line)
     ctx.close()
@@ -485,6 +503,7 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--tc-compressed", action="store_true", help="config 5 from LZ4-compressed tiles (SURVEY 8(f) rank 3)")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything else written to fd 1 (NCCL's version banner,

@@ -39,7 +39,9 @@ typedef enum rcb_status {
     RCB_ECUDA = -3,         /* CUDA runtime failure / no device */
     RCB_EOVERFLOW = -4,     /* an internal pool overflowed (clip polygon > RCB_MAX_POLY_VERTS) */
     RCB_EARG = -5,          /* bad argument (null pointer, bad tile index, wrong stage order) */
-    RCB_ERECAST = -6        /* Error::Recast (detour-dynamic/src/dynamic_tile.rs:171-216: short span data) */
+    RCB_ERECAST = -6,       /* Error::Recast (detour-dynamic/src/dynamic_tile.rs:171-216: short span data) */
+    RCB_EDETOUR_FAILURE = -7,      /* Error::Detour(Status::Failure): LZ4 decode failed (detour-tilecache/src/tile_cache.rs:865-870) */
+    RCB_EDETOUR_INVALID_PARAM = -8 /* Error::Detour(Status::InvalidParam): TileCacheLayer::from_bytes (tile_cache_data.rs:83-91, 129, 282-313) */
 } rcb_status;
 
 /* Stage mask for rcb_build_tiles / rcb_build_from_spans. */
@@ -289,6 +291,27 @@ typedef struct rcb_tc_obstacle {
 int rcb_build_tilecache_layers(rcb_ctx* ctx, const rcb_tc_layer* layers, int nlayers, const rcb_tc_obstacle* obstacles,
                                int nobstacles, float cs, float ch, uint32_t stage_mask, int erode_radius,
                                rcb_result** out);
+
+/* ---- tile-cache front half --------------------------------------------------------
+ * Compressed tiles as TileCache stores them (tile_cache.rs:34, 848-851): lz4_flex::compress_prepend_size =
+ * 4-byte little-endian uncompressed size + one LZ4 block; decoded they are TileCacheLayer::to_bytes
+ * (tile_cache_data.rs:261-278: 54-byte header, three u32 lengths, regons, areas, cons).
+ *
+ * rcb_decompress_tiles: TileCache::decompress_tile (tile_cache.rs:854-872) for n blobs
+ *   (blobs + blob_offsets[i] .. blob_offsets[i+1]).  out_offsets[n+1] (output) are the positions of the decoded
+ *   tiles in `out` (host; capacity out_cap bytes; pass out = NULL to only size it: out_offsets[n] is the total).
+ *   An empty blob decodes to nothing; a blob lz4_flex rejects -> RCB_EDETOUR_FAILURE (first such tile).
+ *   As lz4_flex does, a block that ends early yields FEWER bytes than its size prefix says.
+ * rcb_build_tilecache_compressed: per layer decompress_tile -> TileCacheLayer::from_bytes ->
+ *   rcb_build_tilecache_layers' pipeline, everything on the device (one small D2H of the parsed headers).
+ *   first_obstacle / obstacle_count (nullable: no obstacles): the range of `obstacles` that applies to layer i.
+ *   Errors are those of the first layer that fails, in the order the reference meets them:
+ *   RCB_EDETOUR_FAILURE, RCB_EDETOUR_INVALID_PARAM, RCB_EINVALID_MESH, RCB_ENAVMESH_GEN. */
+int rcb_decompress_tiles(rcb_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_offsets, int n, uint8_t* out, uint64_t out_cap,
+                         uint64_t* out_offsets);
+int rcb_build_tilecache_compressed(rcb_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_offsets, int nlayers,
+                                   const uint32_t* first_obstacle, const uint32_t* obstacle_count, const rcb_tc_obstacle* obstacles,
+                                   int nobstacles, float cs, float ch, uint32_t stage_mask, int erode_radius, rcb_result** out);
 
 /* ---- results ------------------------------------------------------------------------------- */
 int rcb_result_totals(const rcb_result* res, rcb_totals* out);

@@ -15,7 +15,8 @@
 // never tests (RecastBuilder, filter_ledge_spans, filter_walkable_low_height_spans,
 // build_distance_field, box_blur, erode_walkable_area, the clipper's numerics) are pinned only by
 // the source text => for those rows "parity unpinned" (see DESIGN.md).  The same holds for the
-// detour-dynamic wire formats at the end of this file (no reference test touches them).
+// detour-dynamic wire formats at the end of this file (no reference test touches them).  The LZ4 block
+// decoder (lz4_flex 0.11, not vendored) is pinned against liblz4 for valid streams only.
 //
 // Third-party arithmetic: glam 0.29.3 (Cargo.lock) Vec3 sub/cross/length/normalize used at
 // lib.rs:253-262 is restated from the published glam source (scalar Vec3):
@@ -1376,4 +1377,157 @@ orc_hf* orc_checkpoint_clone_heightfield(const orc_hf* p) {
     return (orc_hf*)dst;
 }
 
+}  // extern "C"
+
+// ======================================================================================================
+// Tile-cache front half: TileCache::decompress_tile + TileCacheLayer::from_bytes.
+// Paths relative to /root/reference/crates/detour-tilecache/src/.
+//
+// decompress_tile (tile_cache.rs:854-872) is `lz4_flex::decompress_size_prepended` — lz4_flex 0.11
+// (workspace Cargo.toml:64; the crate is a registry dependency, absent from /root/reference).  Restated here
+// from the published format and decoder: a 4-byte little-endian uncompressed size, then ONE LZ4 block:
+//   sequence = token (hi nibble literal length, lo nibble match length - 4; 15 = continue with bytes that add
+//   up until one is != 255), literals, u16 little-endian offset, match copied byte by byte (overlap = run).
+//   The block ends after the literals of the last sequence (input exhausted).
+// lz4_flex's safe decoder allocates `vec![0; size]`, fails on: missing token / length / offset byte, literal
+// run past the input, literal or match past the output size, offset beyond the bytes produced so far; and it
+// returns the bytes produced (truncate), which may be FEWER than the prefix says.  Valid streams are pinned
+// against liblz4 (pyarrow "lz4_raw") in tests/test_tilecache_lz4.py; the verdict on malformed streams is
+// restated from the crate's source as remembered and is "parity unpinned".
+// ======================================================================================================
+extern "C" {
+
+// Returns the prefixed size, or -1 when fewer than 4 bytes are present (lz4_flex: Err).
+int64_t orc_lz4_prepended_size(const uint8_t* in, uint64_t len) {
+    if (len < 4) return -1;
+    return (int64_t)((uint32_t)in[0] | ((uint32_t)in[1] << 8) | ((uint32_t)in[2] << 16) | ((uint32_t)in[3] << 24));
+}
+
+// Decodes in[4..len) into out[0..cap) (cap = the prefixed size, zero-filled by the caller).
+// Returns 0 and *produced, or RCB_EDETOUR_FAILURE (-7).
+int orc_lz4_decompress_size_prepended(const uint8_t* in, uint64_t len, uint8_t* out, uint64_t cap, uint64_t* produced) {
+    *produced = 0;
+    if (len < 4) return -7;
+    const uint8_t* ip = in + 4;
+    const uint64_t n = len - 4;
+    uint64_t i = 0, o = 0;
+    auto read_integer = [&](uint64_t& v) {  // bytes summed until one is not 255
+        for (;;) {
+            if (i >= n) return false;
+            const uint8_t b = ip[i++];
+            v += b;
+            if (b != 255) return true;
+        }
+    };
+    for (;;) {
+        if (i >= n) return -7;  // a token is expected (also: empty block)
+        const uint8_t token = ip[i++];
+        uint64_t lit = token >> 4;
+        if (lit == 15 && !read_integer(lit)) return -7;
+        if (lit > n - i) return -7;    // LiteralOutOfBounds
+        if (lit > cap - o) return -7;  // OutputTooSmall
+        memcpy(out + o, ip + i, lit);
+        i += lit;
+        o += lit;
+        if (i >= n) break;  // end of block
+        if (n - i < 2) return -7;
+        const uint64_t offset = (uint64_t)ip[i] | ((uint64_t)ip[i + 1] << 8);
+        i += 2;
+        uint64_t mlen = 4 + (token & 15u);
+        if ((token & 15u) == 15 && !read_integer(mlen)) return -7;
+        if (offset > o) return -7;      // OffsetOutOfBounds
+        if (mlen > cap - o) return -7;  // OutputTooSmall
+        for (uint64_t k = 0; k < mlen; ++k) out[o + k] = out[o + k - offset];  // offset 0 re-reads the zero fill
+        o += mlen;
+    }
+    *produced = o;
+    return 0;
+}
+
+// tile_cache_data.rs:128-232 TileCacheLayerHeader::from_bytes + :281-320 TileCacheLayer::from_bytes.
+// Fills the header fields of *out and points regons/areas INTO data.  Returns 0 or RCB_EDETOUR_INVALID_PARAM (-8).
+int orc_tilecache_layer_from_bytes(const uint8_t* data, uint64_t len, rcb_tc_layer* out, uint32_t* cons_len) {
+    if (len < 66) return -8;  // :282-285 (header 54 + 3 lengths)
+    auto u32 = [&](size_t p) { return (uint32_t)data[p] | ((uint32_t)data[p + 1] << 8) | ((uint32_t)data[p + 2] << 16) | ((uint32_t)data[p + 3] << 24); };
+    auto f32 = [&](size_t p) {
+        const uint32_t v = u32(p);
+        float f;
+        memcpy(&f, &v, 4);
+        return f;
+    };
+    if (u32(0) != 0x4C494554u || u32(4) != 1u) return -8;  // validate(): magic 'TILE', version 1 (:83-91)
+    memset(out, 0, sizeof *out);
+    for (int k = 0; k < 3; ++k) out->bmin[k] = f32(20 + 4 * k), out->bmax[k] = f32(32 + 4 * k);
+    out->hmin = (uint16_t)(data[44] | (data[45] << 8));
+    out->hmax = (uint16_t)(data[46] | (data[47] << 8));
+    out->width = data[48];
+    out->height = data[49];
+    const uint64_t rl = u32(54), al = u32(58), cl = u32(62);
+    if (66 + rl + al + cl > len) return -8;  // :311-313
+    out->regons = data + 66;
+    out->areas = data + 66 + rl;
+    out->regons_len = (uint32_t)rl;
+    out->areas_len = (uint32_t)al;
+    *cons_len = (uint32_t)cl;
+    return 0;
+}
+
+}  // extern "C"
+
+extern "C" {
+orc_chf* orc_tilecache_build(const rcb_tc_layer* layer, const rcb_tc_obstacle* obstacles, float cs, float ch, int* status);
+void orc_chf_free(orc_chf* p);
+
+// batched, timed (CPU baseline of the compressed tile-cache leg): per tile decompress_tile -> from_bytes ->
+// layer_to_compact_heightfield + rasterize_obstacles, as TileCache::build_nav_mesh_tile does (tile_cache.rs:704-712).
+// Returns seconds; totals[0] = spans, totals[1] = connections, totals[2] = tiles that failed.
+double orc_tilecache_build_compressed_batch(const uint8_t* blobs, const uint64_t* off, int n, const uint32_t* first_obstacle,
+                                            const uint32_t* obstacle_count, const rcb_tc_obstacle* obstacles, float cs, float ch,
+                                            int nthreads, uint64_t* totals) {
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<int> next{0};
+    std::vector<uint64_t> acc((size_t)nthreads * 3, 0);
+    auto t0 = std::chrono::steady_clock::now();
+    auto work = [&](int tid) {
+        std::vector<uint8_t> raw;
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= n) break;
+            const uint8_t* b = blobs + off[i];
+            const uint64_t len = off[i + 1] - off[i];
+            uint64_t produced = 0;
+            if (len) {
+                const int64_t size = orc_lz4_prepended_size(b, len);
+                if (size < 0) { ++acc[(size_t)tid * 3 + 2]; continue; }
+                raw.assign((size_t)size, 0);
+                if (orc_lz4_decompress_size_prepended(b, len, raw.data(), (uint64_t)size, &produced)) { ++acc[(size_t)tid * 3 + 2]; continue; }
+            }
+            rcb_tc_layer layer;
+            uint32_t cons = 0;
+            if (orc_tilecache_layer_from_bytes(raw.data(), produced, &layer, &cons)) { ++acc[(size_t)tid * 3 + 2]; continue; }
+            layer.first_obstacle = first_obstacle ? first_obstacle[i] : 0;
+            layer.obstacle_count = obstacle_count ? obstacle_count[i] : 0;
+            int st = 0;
+            orc_chf* c = orc_tilecache_build(&layer, obstacles, cs, ch, &st);
+            if (!c) { ++acc[(size_t)tid * 3 + 2]; continue; }
+            acc[(size_t)tid * 3] += ((Compact*)c)->smin.size();
+            acc[(size_t)tid * 3 + 1] += ((Compact*)c)->conn_ref.size();
+            orc_chf_free(c);
+        }
+    };
+    if (nthreads == 1)
+        work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < nthreads; ++i) th.emplace_back(work, i);
+        for (auto& t : th) t.join();
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (totals) {
+        totals[0] = totals[1] = totals[2] = 0;
+        for (int i = 0; i < nthreads; ++i)
+            for (int k = 0; k < 3; ++k) totals[k] += acc[(size_t)i * 3 + k];
+    }
+    return std::chrono::duration<double>(t1 - t0).count();
+}
 }  // extern "C"

@@ -77,6 +77,12 @@ def lib():
         L.orc_chf_mark_convex_poly_area.argtypes = [vp, vp, u32, f32, f32, u8]
         L.orc_chf_set_areas.argtypes = [vp, vp]
         L.orc_hardware_concurrency.restype = ctypes.c_int
+        L.orc_lz4_prepended_size.restype = ctypes.c_int64
+        L.orc_lz4_prepended_size.argtypes = [vp, ctypes.c_uint64]
+        L.orc_lz4_decompress_size_prepended.argtypes = [vp, ctypes.c_uint64, vp, ctypes.c_uint64, vp]
+        L.orc_tilecache_layer_from_bytes.argtypes = [vp, ctypes.c_uint64, vp, vp]
+        L.orc_tilecache_build_compressed_batch.restype = ctypes.c_double
+        L.orc_tilecache_build_compressed_batch.argtypes = [vp, vp, ctypes.c_int, vp, vp, vp, f32, f32, ctypes.c_int, vp]
         L.orc_voxel_serialize_spans.argtypes = [vp, ctypes.c_int, vp]
         L.orc_voxel_deserialize_spans.argtypes = [vp, vp, ctypes.c_uint64]
         L.orc_dynamic_reconstruct_heightfield.argtypes = [vp, vp, ctypes.c_uint64]
@@ -377,3 +383,59 @@ def tilecache_build_timed(layers, obstacles, cs, ch, nthreads=1):
                                         nthreads, _p(tot))
     del keep
     return s, {"spans": int(tot[0]), "connections": int(tot[1])}
+
+
+# ---- tile-cache front half (detour-tilecache) ----------------------------------------------------------
+def decompress_tile(blob) -> bytes:
+    """TileCache::decompress_tile (tile_cache.rs:854-872); OracleError(-7) where lz4_flex returns Err."""
+    d = np.frombuffer(bytes(blob), np.uint8)
+    if d.size == 0:
+        return b""
+    size = lib().orc_lz4_prepended_size(_p(d), d.size)
+    if size < 0:
+        raise OracleError(-7)
+    out = np.zeros(max(size, 1), np.uint8)
+    prod = ctypes.c_uint64(0)
+    st = lib().orc_lz4_decompress_size_prepended(_p(d), d.size, _p(out), size, ctypes.byref(prod))
+    if st:
+        raise OracleError(st)
+    return out[:prod.value].tobytes()
+
+
+def tilecache_layer_from_bytes(data, first_obstacle=0, obstacle_count=0):
+    """TileCacheLayer::from_bytes (tile_cache_data.rs:281-320) -> tilecache.TileCacheLayer; OracleError(-8) on Err."""
+    from recast_rs_b200 import tilecache as tcm
+
+    d = np.frombuffer(bytes(data), np.uint8)
+    hdr = tcm.RcbTcLayer()
+    cons = ctypes.c_uint32(0)
+    st = lib().orc_tilecache_layer_from_bytes(_p(d) if d.size else None, d.size, ctypes.byref(hdr), ctypes.byref(cons))
+    if st:
+        raise OracleError(st)
+    ro = hdr.regons - d.ctypes.data
+    ao = hdr.areas - d.ctypes.data
+    return tcm.TileCacheLayer(tuple(hdr.bmin), tuple(hdr.bmax), hdr.hmin, hdr.hmax, hdr.width, hdr.height,
+                              d[ro:ro + hdr.regons_len].copy(), d[ao:ao + hdr.areas_len].copy(), first_obstacle, obstacle_count)
+
+
+def tilecache_build_compressed(blobs, obstacles, ranges, cs, ch):
+    """Per compressed tile: ChfArrays, or the rcb_status of the first step that fails."""
+    out = []
+    for i, b in enumerate(blobs):
+        fo, oc = ranges[i] if ranges is not None else (0, 0)
+        try:
+            layer = tilecache_layer_from_bytes(decompress_tile(b), fo, oc)
+        except OracleError as e:
+            out.append(e.status)
+            continue
+        out.append(tilecache_build([layer], obstacles, cs, ch)[0])
+    return out
+
+
+def tilecache_build_compressed_timed(ct, cs, ch, nthreads=1):
+    """ct: recast_rs_b200.tilecache.CompressedTiles.  Returns (seconds, totals)."""
+    tot = np.zeros(3, dtype=np.uint64)
+    s = lib().orc_tilecache_build_compressed_batch(_p(ct.buf), _p(ct.off), ct.n, _p(ct.first) if ct.first is not None else None,
+                                                   _p(ct.count) if ct.count is not None else None,
+                                                   ctypes.cast(ct.obstacles, ctypes.c_void_p), cs, ch, nthreads, _p(tot))
+    return s, {"spans": int(tot[0]), "connections": int(tot[1]), "failed": int(tot[2])}

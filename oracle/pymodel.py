@@ -782,3 +782,78 @@ def checkpoint_clone_heightfield(src):  # checkpoint.rs:29-60
                 except ValueError:
                     pass
     return dst
+
+
+# ---- tile-cache front half (detour-tilecache/src) ----------------------------------------------------------
+class Lz4Error(Exception):
+    pass
+
+
+def lz4_decompress_size_prepended(blob):
+    """lz4_flex::decompress_size_prepended (0.11) restated from the LZ4 block format; see oracle.cpp."""
+    blob = bytes(blob)
+    if len(blob) < 4:
+        raise Lz4Error("size prefix")
+    cap = int.from_bytes(blob[:4], "little")
+    src = blob[4:]
+    n, i = len(src), 0
+    out = bytearray()
+
+    def read_integer(v):
+        nonlocal i
+        while True:
+            if i >= n:
+                raise Lz4Error("length byte")
+            b = src[i]
+            i += 1
+            v += b
+            if b != 255:
+                return v
+
+    while True:
+        if i >= n:
+            raise Lz4Error("token")
+        token = src[i]
+        i += 1
+        lit = token >> 4
+        if lit == 15:
+            lit = read_integer(lit)
+        if lit > n - i or lit > cap - len(out):
+            raise Lz4Error("literals")
+        out += src[i:i + lit]
+        i += lit
+        if i >= n:
+            break
+        if n - i < 2:
+            raise Lz4Error("offset")
+        offset = src[i] | (src[i + 1] << 8)
+        i += 2
+        mlen = 4 + (token & 15)
+        if (token & 15) == 15:
+            mlen = read_integer(mlen)
+        if offset > len(out) or mlen > cap - len(out):
+            raise Lz4Error("match")
+        for _ in range(mlen):
+            out.append(out[-offset] if offset else 0)  # offset 0 re-reads the zero fill of vec![0; size]
+    return bytes(out)
+
+
+def decompress_tile(blob):  # tile_cache.rs:854-872
+    return b"" if len(blob) == 0 else lz4_decompress_size_prepended(blob)
+
+
+def tilecache_layer_from_bytes(data):  # tile_cache_data.rs:128-232, 281-320 -> dict, or ValueError
+    data = bytes(data)
+    if len(data) < 66:
+        raise ValueError("InvalidParam")
+    u32 = lambda p: int.from_bytes(data[p:p + 4], "little")  # noqa: E731
+    if u32(0) != 0x4C494554 or u32(4) != 1:
+        raise ValueError("InvalidParam")
+    rl, al, cl = u32(54), u32(58), u32(62)
+    if 66 + rl + al + cl > len(data):
+        raise ValueError("InvalidParam")
+    import struct
+    return {"bmin": struct.unpack_from("<3f", data, 20), "bmax": struct.unpack_from("<3f", data, 32),
+            "hmin": int.from_bytes(data[44:46], "little"), "hmax": int.from_bytes(data[46:48], "little"),
+            "width": data[48], "height": data[49], "regons": data[66:66 + rl], "areas": data[66 + rl:66 + rl + al],
+            "cons": data[66 + rl + al:66 + rl + al + cl]}

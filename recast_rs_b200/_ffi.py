@@ -66,6 +66,8 @@ SYMBOLS = {
     "rcb_result_serialize_spans": (_i, [_vp, _i, _vp, _u64, _vp]),
     "rcb_apply_area_ops": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _u32, _i, _pp]),
     "rcb_build_tilecache_layers": (_i, [_vp, _vp, _i, _vp, _i, ctypes.c_float, ctypes.c_float, _u32, _i, _pp]),
+    "rcb_decompress_tiles": (_i, [_vp, _vp, _vp, _i, _vp, _u64, _vp]),
+    "rcb_build_tilecache_compressed": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, ctypes.c_float, ctypes.c_float, _u32, _i, _pp]),
     "rcb_result_totals": (_i, [_vp, ctypes.POINTER(RcbTotals)]),
     "rcb_result_download": (_i, [_vp]),
     "rcb_result_tile": (_i, [_vp, _i, ctypes.POINTER(RcbTileView)]),

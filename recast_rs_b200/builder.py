@@ -289,6 +289,42 @@ class Context:
         return BatchResult(self, out)
 
 
+    def decompress_tiles(self, blobs: Sequence[bytes]):
+        """TileCache::decompress_tile (detour-tilecache/src/tile_cache.rs:854-872) for a batch of compressed tiles;
+        returns the decoded tiles as a list of bytes.  Raises errors.DetourFailure for a blob lz4_flex rejects."""
+        buf, off = _join_blobs(blobs)
+        n = len(blobs)
+        ooff = np.zeros(n + 1, np.uint64)
+        check(_ffi.lib().rcb_decompress_tiles(self._h, _ptr(buf) if buf.size else None, _ptr(off), n, None, 0, _ptr(ooff)), self._h)
+        out = np.empty(max(int(ooff[-1]), 1), np.uint8)
+        check(_ffi.lib().rcb_decompress_tiles(self._h, _ptr(buf) if buf.size else None, _ptr(off), n, _ptr(out), int(ooff[-1]), _ptr(ooff)),
+              self._h)
+        raw = out.tobytes()
+        return [raw[int(ooff[i]):int(ooff[i + 1])] for i in range(n)]
+
+    def build_tilecache_compressed(self, blobs, obstacles, obstacle_ranges, cs: float, ch: float, stage_mask=STAGE_COMPACT,
+                                   erode_radius=0) -> BatchResult:
+        """decompress_tile -> TileCacheLayer::from_bytes -> layer_to_compact_heightfield + rasterize_obstacles, all on the
+        device (tile_cache.rs:854-872, tile_cache_data.rs:281-320, tile_cache_builder.rs:100-251).
+        blobs: list of compressed tiles, or a tilecache.CompressedTiles built once; obstacle_ranges: per layer
+        (first, count) into `obstacles` (None: no obstacles)."""
+        from . import tilecache as tcm
+
+        ct = blobs if isinstance(blobs, tcm.CompressedTiles) else tcm.CompressedTiles(blobs, obstacles, obstacle_ranges)
+        out = ctypes.c_void_p()
+        check(_ffi.lib().rcb_build_tilecache_compressed(self._h, _ptr(ct.buf) if ct.buf.size else None, _ptr(ct.off), ct.n,
+                                                        _ptr(ct.first), _ptr(ct.count), ctypes.cast(ct.obstacles, ctypes.c_void_p)
+                                                        if ct.nobstacles else None, ct.nobstacles, cs, ch, stage_mask, erode_radius,
+                                                        ctypes.byref(out)), self._h)
+        return BatchResult(self, out)
+
+
+def _join_blobs(blobs):
+    off = np.zeros(len(blobs) + 1, np.uint64)
+    off[1:] = np.cumsum([len(b) for b in blobs], dtype=np.uint64)
+    return np.frombuffer(b"".join(bytes(b) for b in blobs), np.uint8), off
+
+
 _default_ctx: Optional[Context] = None
 
 

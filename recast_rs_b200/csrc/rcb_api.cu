@@ -73,7 +73,7 @@ struct rcb_ctx {
     DevBuf d_counters, d_cell_cnt, d_frag_off, d_frag_tmp, d_fs_tri, d_fs_mm, d_fs_area, d_scan_tmp, d_hf_off, d_conn_cnt,
         d_conn_off, d_nei16, d_t16a, d_t16b, d_t16c, d_t8a, d_t8b, d_item_cnt, d_item_off, d_items, d_tile_ub, d_tile_base, d_tile_cursor,
         d_tile_frags, d_ts_mm, d_ts_area, d_celloff_tmp, d_lookback, d_tc_regons, d_tc_areas, d_tc_obs, d_fidx, d_wire, d_wire_off,
-        d_wire_pos, d_wire_inoff, d_wire_err;
+        d_wire_pos, d_wire_inoff, d_wire_err, d_tc_raw, d_tc_parsed;
     uint32_t clip_flags = 1;    // RCB_CLIP_FLAGS (A/B runs): bit0 min-x skip test in the clipper
     bool phase_timers = false;  // RCB_PHASE_TIMERS=1: per-phase cycle sums of the tile kernels on stderr
     bool force_global = false;  // RCB_FORCE_GLOBAL=1: never use the tile-resident back end (k_tile.cu)
@@ -1208,6 +1208,54 @@ int rcb_result_serialize_spans(rcb_result* res, int format, uint8_t* out, uint64
     return RCB_OK;
 }
 
+// Tile-cache layers whose regons / areas / tile table / obstacles are already on the device (d_tc_regons,
+// d_tc_areas, d_tiles, d_tc_obs): spans, connections, later stages, obstacles.  Frees res on failure.
+static int tilecache_back_end(rcb_ctx* ctx, rcb_result* res, TileMap tm, int nlayers, uint64_t Ctot, int nobstacles, uint32_t stage_mask,
+                              int erode_radius, rcb_result** out) {
+    cudaStream_t st = ctx->stream;
+    auto bail = [&](int code) {
+        rcb_result_free(res);
+        return code;
+    };
+#define CUB(expr)                                                                                            \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess)                                                                               \
+            return bail(fail(ctx, RCB_ECUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, __LINE__, #expr)); \
+    } while (0)
+    const TileDesc* d_tiles = ctx->d_tiles.as<TileDesc>();
+    CUB(ctx->d_hf_off.ensure(4 * (Ctot + 1)));
+    CUB(ctx->d_cell_cnt.ensure(4 * (Ctot + 1)));
+    CUB(ctx->d_scan_tmp.ensure(4 * scan_tmp_elems(Ctot + 1)));
+    uint32_t* d_hf_off = ctx->d_hf_off.as<uint32_t>();
+    launch_tc_count(d_tiles, tm, ctx->d_tc_regons.as<uint8_t>(), ctx->d_cell_cnt.as<uint32_t>(), st);
+    launch_exclusive_scan(ctx->d_cell_cnt.as<uint32_t>(), d_hf_off, Ctot, ctx->d_scan_tmp.as<uint32_t>(), st);
+    CUB(cudaMemcpyAsync(&ctx->h_counters[4], d_hf_off + Ctot, 4, cudaMemcpyDeviceToHost, st));
+    CUB(cudaStreamSynchronize(st));
+    const uint64_t S = (uint32_t)ctx->h_counters[4];
+    res->S = S;
+    make_layout(res->lay, nlayers, Ctot, S, stage_mask);
+    CUB(pool_get(ctx->free_dev, res->lay.bytesA, false, res->devA));
+    char* A = res->devA.p;
+    CUB(cudaMemsetAsync(A + res->lay.tinfo, 0, sizeof(TileInfo) * (size_t)nlayers, st));
+    int16_t* d_smin = (int16_t*)(A + res->lay.span_min);
+    int16_t* d_smax = (int16_t*)(A + res->lay.span_max);
+    uint8_t* d_sarea = (uint8_t*)(A + res->lay.span_area);
+    if (S > 0)
+        launch_tc_spans(d_tiles, tm, ctx->d_tc_regons.as<uint8_t>(), ctx->d_tc_areas.as<uint8_t>(), d_hf_off, d_smin, d_smax, d_sarea, st);
+    {
+        const int r = global_back_end(ctx, res, d_tiles, tm, nlayers, Ctot, S, 0, stage_mask, erode_radius, nullptr);
+        if (r) return bail(r);
+    }
+    // obstacles come AFTER the connections exist and only clear CompactSpan.area (:65-68, :309)
+    if (nobstacles > 0 && S > 0)
+        launch_tc_obstacles(d_tiles, nlayers, ctx->d_tc_obs.as<rcb_tc_obstacle>(), d_hf_off, d_smin, d_smax, d_sarea, st);
+    CUB(cudaGetLastError());
+    *out = res;
+    return RCB_OK;
+#undef CUB
+}
+
 int rcb_build_tilecache_layers(rcb_ctx* ctx, const rcb_tc_layer* layers, int nlayers, const rcb_tc_obstacle* obstacles, int nobstacles,
                                float cs, float ch, uint32_t stage_mask, int erode_radius, rcb_result** out) {
     if (!ctx || !out || nlayers < 0 || (nlayers > 0 && !layers) || nobstacles < 0 || (nobstacles > 0 && !obstacles))
@@ -1301,37 +1349,172 @@ int rcb_build_tilecache_layers(rcb_ctx* ctx, const rcb_tc_layer* layers, int nla
             CUB(cudaMemcpyAsync(ctx->d_tc_obs.p, h + o, sizeof(rcb_tc_obstacle) * (size_t)nobstacles, cudaMemcpyHostToDevice, st));
         }
     }
-    const TileDesc* d_tiles = ctx->d_tiles.as<TileDesc>();
-    CUB(ctx->d_hf_off.ensure(4 * (Ctot + 1)));
-    CUB(ctx->d_cell_cnt.ensure(4 * (Ctot + 1)));
-    CUB(ctx->d_scan_tmp.ensure(4 * scan_tmp_elems(Ctot + 1)));
-    uint32_t* d_hf_off = ctx->d_hf_off.as<uint32_t>();
-    launch_tc_count(d_tiles, tm, ctx->d_tc_regons.as<uint8_t>(), ctx->d_cell_cnt.as<uint32_t>(), st);
-    launch_exclusive_scan(ctx->d_cell_cnt.as<uint32_t>(), d_hf_off, Ctot, ctx->d_scan_tmp.as<uint32_t>(), st);
-    CUB(cudaMemcpyAsync(&ctx->h_counters[4], d_hf_off + Ctot, 4, cudaMemcpyDeviceToHost, st));
-    CUB(cudaStreamSynchronize(st));
-    const uint64_t S = (uint32_t)ctx->h_counters[4];
-    res->S = S;
-    make_layout(res->lay, nlayers, Ctot, S, stage_mask);
-    CUB(pool_get(ctx->free_dev, res->lay.bytesA, false, res->devA));
-    char* A = res->devA.p;
-    CUB(cudaMemsetAsync(A + res->lay.tinfo, 0, sizeof(TileInfo) * (size_t)nlayers, st));
-    int16_t* d_smin = (int16_t*)(A + res->lay.span_min);
-    int16_t* d_smax = (int16_t*)(A + res->lay.span_max);
-    uint8_t* d_sarea = (uint8_t*)(A + res->lay.span_area);
-    if (S > 0)
-        launch_tc_spans(d_tiles, tm, ctx->d_tc_regons.as<uint8_t>(), ctx->d_tc_areas.as<uint8_t>(), d_hf_off, d_smin, d_smax, d_sarea, st);
+    return tilecache_back_end(ctx, res, tm, nlayers, Ctot, nobstacles, stage_mask, erode_radius, out);
+#undef CUB
+}
+
+int rcb_decompress_tiles(rcb_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_offsets, int n, uint8_t* out, uint64_t out_cap,
+                         uint64_t* out_offsets) {
+    if (!ctx || n < 0 || !blob_offsets || !out_offsets || (n > 0 && blob_offsets[n] > 0 && !blobs)) return fail(ctx, RCB_EARG, "null argument");
+    std::vector<unsigned long long> cap_off((size_t)n + 1, 0);
+    for (int i = 0; i < n; ++i) {
+        if (blob_offsets[i + 1] < blob_offsets[i]) return fail(ctx, RCB_EARG, "tile %d: blob_offsets not ascending", i);
+        const uint64_t len = blob_offsets[i + 1] - blob_offsets[i];
+        if (len >= 0xffff0000ull) return fail(ctx, RCB_EARG, "tile %d: blob of 4 GiB", i);
+        const uint8_t* b = blobs + blob_offsets[i];
+        const uint64_t size = len >= 4 ? ((uint64_t)b[0] | ((uint64_t)b[1] << 8) | ((uint64_t)b[2] << 16) | ((uint64_t)b[3] << 24)) : 0;
+        cap_off[i + 1] = cap_off[i] + size;
+    }
+    const uint64_t total_cap = cap_off[n];
+    if (total_cap > (8ull << 30)) return fail(ctx, RCB_EARG, "size prefixes add up to %llu bytes", (unsigned long long)total_cap);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ProfInstall prof_install(ctx);
+    const uint64_t nbytes = n > 0 ? blob_offsets[n] : 0;
+    CU(ctx->d_wire.ensure(nbytes + 64));
+    CU(ctx->d_wire_off.ensure(16 * ((size_t)n + 1)));
+    CU(ctx->d_tc_raw.ensure(total_cap + 64));
+    CU(ctx->d_wire_err.ensure(8 * ((size_t)n + 1)));
+    unsigned long long* d_boff = ctx->d_wire_off.as<unsigned long long>();
+    unsigned long long* d_ooff = d_boff + n + 1;
+    uint32_t* d_status = ctx->d_wire_err.as<uint32_t>();
+    uint32_t* d_prod = d_status + n + 1;
+    if (nbytes) CU(cudaMemcpyAsync(ctx->d_wire.p, blobs, nbytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_boff, blob_offsets, 8 * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_ooff, cap_off.data(), 8 * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+    launch_lz4_decompress(ctx->d_wire.as<uint8_t>(), d_boff, n, ctx->d_tc_raw.as<uint8_t>(), d_ooff, d_status, d_prod, st);
+    std::vector<uint32_t> hs(2 * ((size_t)n + 1));
+    CU(cudaMemcpyAsync(hs.data(), d_status, 8 * ((size_t)n + 1), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    out_offsets[0] = 0;
+    for (int i = 0; i < n; ++i) {
+        if (hs[i]) return fail(ctx, RCB_EDETOUR_FAILURE, "tile %d: LZ4 decompression failed", i);
+        out_offsets[i + 1] = out_offsets[i] + hs[(size_t)n + 1 + i];
+    }
+    if (!out) return RCB_OK;
+    if (out_cap < out_offsets[n]) return fail(ctx, RCB_EARG, "rcb_decompress_tiles: need %llu bytes", (unsigned long long)out_offsets[n]);
+    for (int i = 0; i < n; ++i)  // produced <= size prefix: compact while copying
+        if (out_offsets[i + 1] > out_offsets[i])
+            CU(cudaMemcpyAsync(out + out_offsets[i], ctx->d_tc_raw.p + cap_off[i], out_offsets[i + 1] - out_offsets[i], cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return RCB_OK;
+}
+
+int rcb_build_tilecache_compressed(rcb_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_offsets, int nlayers,
+                                   const uint32_t* first_obstacle, const uint32_t* obstacle_count, const rcb_tc_obstacle* obstacles,
+                                   int nobstacles, float cs, float ch, uint32_t stage_mask, int erode_radius, rcb_result** out) {
+    if (!ctx || !out || nlayers < 0 || !blob_offsets || (nlayers > 0 && blob_offsets[nlayers] > 0 && !blobs) || nobstacles < 0 ||
+        (nobstacles > 0 && (!obstacles || !first_obstacle || !obstacle_count)))
+        return fail(ctx, RCB_EARG, "null argument");
+    *out = nullptr;
+    if (!(cs > 0.0f) || !(ch > 0.0f)) return fail(ctx, RCB_EINVALID_MESH, "Invalid cell size or height");
+    std::vector<unsigned long long> cap_off((size_t)nlayers + 1, 0);
+    for (int i = 0; i < nlayers; ++i) {
+        if (blob_offsets[i + 1] < blob_offsets[i]) return fail(ctx, RCB_EARG, "layer %d: blob_offsets not ascending", i);
+        const uint64_t len = blob_offsets[i + 1] - blob_offsets[i];
+        if (len >= 0xffff0000ull) return fail(ctx, RCB_EARG, "layer %d: blob of 4 GiB", i);
+        const uint8_t* b = blobs + blob_offsets[i];
+        const uint64_t size = len >= 4 ? ((uint64_t)b[0] | ((uint64_t)b[1] << 8) | ((uint64_t)b[2] << 16) | ((uint64_t)b[3] << 24)) : 0;
+        cap_off[i + 1] = cap_off[i] + size;  // exact: the decoder refuses to write past the size prefix
+        if (first_obstacle && obstacle_count && (uint64_t)first_obstacle[i] + obstacle_count[i] > (uint64_t)nobstacles)
+            return fail(ctx, RCB_EARG, "layer %d: obstacle range", i);
+    }
+    const uint64_t total_cap = cap_off[nlayers];
+    if (total_cap > (8ull << 30)) return fail(ctx, RCB_EARG, "size prefixes add up to %llu bytes", (unsigned long long)total_cap);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ProfInstall prof_install(ctx);
+    stage_mask = (stage_mask | RCB_STAGE_COMPACT) & ~(uint32_t)(RCB_STAGE_RASTER | RCB_STAGE_FILTER | 0x700u);
+    // ---- decode + parse on the device ---------------------------------------------------------------------
+    const uint64_t nbytes = nlayers > 0 ? blob_offsets[nlayers] : 0;
+    CU(ctx->d_wire.ensure(nbytes + 64));
+    CU(ctx->d_wire_off.ensure(16 * ((size_t)nlayers + 1)));
+    CU(ctx->d_tc_raw.ensure(total_cap + 64));
+    CU(ctx->d_wire_err.ensure(8 * ((size_t)nlayers + 1)));
+    CU(ctx->d_tc_parsed.ensure(sizeof(RcbTcParsed) * ((size_t)nlayers + 1)));
+    unsigned long long* d_boff = ctx->d_wire_off.as<unsigned long long>();
+    unsigned long long* d_ooff = d_boff + nlayers + 1;
+    uint32_t* d_status = ctx->d_wire_err.as<uint32_t>();
+    uint32_t* d_prod = d_status + nlayers + 1;
+    if (nbytes) CU(cudaMemcpyAsync(ctx->d_wire.p, blobs, nbytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_boff, blob_offsets, 8 * ((size_t)nlayers + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_ooff, cap_off.data(), 8 * ((size_t)nlayers + 1), cudaMemcpyHostToDevice, st));
+    launch_lz4_decompress(ctx->d_wire.as<uint8_t>(), d_boff, nlayers, ctx->d_tc_raw.as<uint8_t>(), d_ooff, d_status, d_prod, st);
+    launch_tc_parse(nlayers, ctx->d_tc_raw.as<uint8_t>(), d_ooff, d_status, d_prod, ctx->d_tc_parsed.as<RcbTcParsed>(), st);
+    std::vector<RcbTcParsed> parsed((size_t)nlayers);
+    if (nlayers) CU(cudaMemcpyAsync(parsed.data(), ctx->d_tc_parsed.p, sizeof(RcbTcParsed) * (size_t)nlayers, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    for (int i = 0; i < nlayers; ++i) {
+        switch (parsed[i].status) {
+            case 0: break;
+            case RCB_EDETOUR_FAILURE: return fail(ctx, RCB_EDETOUR_FAILURE, "layer %d: LZ4 decompression failed", i);
+            case RCB_EDETOUR_INVALID_PARAM: return fail(ctx, RCB_EDETOUR_INVALID_PARAM, "layer %d: invalid tile-cache layer data", i);
+            case RCB_EINVALID_MESH: return fail(ctx, RCB_EINVALID_MESH, "layer %d: Invalid region / area data size", i);
+            default: return fail(ctx, RCB_ENAVMESH_GEN, "layer %d: Invalid span height: min (32767) > max (-32768)", i);
+        }
+    }
+    // ---- tile table ------------------------------------------------------------------------------------------
+    auto* res = new rcb_result();
+    res->ctx = ctx;
+    res->ntiles = nlayers;
+    res->stage_mask = stage_mask;
+    res->tiles.resize(nlayers);
+    uint64_t Ctot = 0;
+    uint32_t max_cells = 0;
+    for (int i = 0; i < nlayers; ++i) {
+        const RcbTcParsed& l = parsed[i];
+        TileDesc& t = res->tiles[i];
+        memset(&t, 0, sizeof t);
+        t.width = (int32_t)l.width;
+        t.height = (int32_t)l.height;
+        for (int k = 0; k < 3; ++k) t.bmin[k] = l.bmin[k], t.bmax[k] = l.bmax[k];
+        t.cs = cs;
+        t.ch = ch;
+        t.ics = 1.0f / cs;
+        t.ich = 1.0f / ch;
+        t.aux0 = (int32_t)l.hmin;
+        t.aux1 = first_obstacle ? (int32_t)first_obstacle[i] : 0;
+        t.aux2 = obstacle_count ? (int32_t)obstacle_count[i] : 0;
+        t.cell_base = (uint32_t)Ctot;
+        t.wmagic = l.width ? ((1ull << 40) / (unsigned long long)l.width) + 1 : 0;
+        const uint32_t cells = l.width * l.height;
+        Ctot += cells;
+        if (cells > max_cells) max_cells = cells;
+    }
+    res->Ctot = Ctot;
+    TileMap tm{(uint32_t)nlayers, (max_cells + 255) / 256, 0};
+    tm.nblocks = tm.blocks_per_tile * tm.ntiles;
+    auto bail = [&](int code) {
+        rcb_result_free(res);
+        return code;
+    };
+    const size_t need = align_up(sizeof(TileDesc) * (size_t)nlayers) + align_up(sizeof(rcb_tc_obstacle) * (size_t)nobstacles) + 1024;
     {
-        const int r = global_back_end(ctx, res, d_tiles, tm, nlayers, Ctot, S, 0, stage_mask, erode_radius, nullptr);
+        int r = ensure_stage(ctx, need);
         if (r) return bail(r);
     }
-    // obstacles come AFTER the connections exist and only clear CompactSpan.area (:65-68, :309)
-    if (nobstacles > 0 && S > 0)
-        launch_tc_obstacles(d_tiles, nlayers, ctx->d_tc_obs.as<rcb_tc_obstacle>(), d_hf_off, d_smin, d_smax, d_sarea, st);
-    CUB(cudaGetLastError());
-    *out = res;
-    return RCB_OK;
-#undef CUB
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t x) { return (e = x) == cudaSuccess; };
+    if (!ok(ctx->d_tiles.ensure(sizeof(TileDesc) * (size_t)nlayers + 16)) || !ok(ctx->d_tc_regons.ensure(Ctot + 16)) ||
+        !ok(ctx->d_tc_areas.ensure(Ctot + 16)) || !ok(ctx->d_tc_obs.ensure(sizeof(rcb_tc_obstacle) * (size_t)nobstacles + 16)))
+        return bail(fail(ctx, RCB_ECUDA, "CUDA error %s (tile-cache buffers)", cudaGetErrorString(e)));
+    {
+        char* h = ctx->h_stage;
+        memcpy(h, res->tiles.data(), sizeof(TileDesc) * (size_t)nlayers);
+        if (nlayers && !ok(cudaMemcpyAsync(ctx->d_tiles.p, h, sizeof(TileDesc) * (size_t)nlayers, cudaMemcpyHostToDevice, st)))
+            return bail(fail(ctx, RCB_ECUDA, "CUDA error %s (tile table)", cudaGetErrorString(e)));
+        if (nobstacles) {
+            char* ho = h + align_up(sizeof(TileDesc) * (size_t)nlayers);
+            memcpy(ho, obstacles, sizeof(rcb_tc_obstacle) * (size_t)nobstacles);
+            if (!ok(cudaMemcpyAsync(ctx->d_tc_obs.p, ho, sizeof(rcb_tc_obstacle) * (size_t)nobstacles, cudaMemcpyHostToDevice, st)))
+                return bail(fail(ctx, RCB_ECUDA, "CUDA error %s (obstacles)", cudaGetErrorString(e)));
+        }
+    }
+    launch_tc_gather(ctx->d_tiles.as<TileDesc>(), tm, ctx->d_tc_raw.as<uint8_t>(), d_ooff, ctx->d_tc_parsed.as<RcbTcParsed>(),
+                     ctx->d_tc_regons.as<uint8_t>(), ctx->d_tc_areas.as<uint8_t>(), st);
+    return tilecache_back_end(ctx, res, tm, nlayers, Ctot, nobstacles, stage_mask, erode_radius, out);
 }
 
 int rcb_apply_area_ops(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const uint32_t* cell_offset, const int16_t* span_min,

@@ -206,6 +206,20 @@ struct TileMap {
 #define RCB_CELL_OF_THREAD() (blockIdx.x * blockDim.x + threadIdx.x)
 #endif
 
+// k_lz4.cu — tile-cache front half
+struct RcbTcParsed {  // one layer after TileCacheLayer::from_bytes; status = the rcb_status of the first failing check
+    int32_t status;
+    uint32_t width, height, hmin;
+    float bmin[3], bmax[3];
+    uint32_t regons_off, areas_off;  // inside the decoded bytes
+};
+void launch_lz4_decompress(const uint8_t* blobs, const unsigned long long* blob_off, int nlayers, uint8_t* out,
+                           const unsigned long long* out_off, uint32_t* status, uint32_t* produced, cudaStream_t s);
+void launch_tc_parse(int nlayers, const uint8_t* raw, const unsigned long long* raw_off, const uint32_t* lz_status,
+                     const uint32_t* produced, RcbTcParsed* outp, cudaStream_t s);
+void launch_tc_gather(const TileDesc* tiles, TileMap tm, const uint8_t* raw, const unsigned long long* raw_off,
+                      const RcbTcParsed* parsed, uint8_t* regons, uint8_t* areas, cudaStream_t s);
+
 // k_wire.cu — heightfield wire formats
 void launch_wire_walk(const TileDesc* tiles, int ntiles, const uint8_t* data, const unsigned long long* tile_off, int strict_le,
                       uint32_t* cell_pos, uint32_t* cell_n, unsigned long long* err, cudaStream_t s);

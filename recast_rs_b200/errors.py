@@ -8,6 +8,8 @@ RCB_ECUDA = -3
 RCB_EOVERFLOW = -4
 RCB_EARG = -5
 RCB_ERECAST = -6
+RCB_EDETOUR_FAILURE = -7
+RCB_EDETOUR_INVALID_PARAM = -8
 
 
 class RecastError(Exception):
@@ -26,6 +28,14 @@ class Recast(RecastError):
     """Error::Recast — detour-dynamic/src/dynamic_tile.rs:171-216 (short span data)."""
 
 
+class DetourFailure(RecastError):
+    """Error::Detour(Status::Failure) — LZ4 decode failed, detour-tilecache/src/tile_cache.rs:865-870."""
+
+
+class DetourInvalidParam(RecastError):
+    """Error::Detour(Status::InvalidParam) — TileCacheLayer::from_bytes, tile_cache_data.rs:83-91, 129, 282-313."""
+
+
 class CudaError(RecastError):
     """CUDA runtime failure or missing device/extension; there is no CPU fallback."""
 
@@ -41,6 +51,8 @@ _MAP = {
     RCB_EOVERFLOW: PoolOverflow,
     RCB_EARG: ValueError,
     RCB_ERECAST: Recast,
+    RCB_EDETOUR_FAILURE: DetourFailure,
+    RCB_EDETOUR_INVALID_PARAM: DetourInvalidParam,
 }
 
 

@@ -5,6 +5,7 @@ No CUDA here; used by builder.Context.build_tilecache_layers and by the oracle w
 from __future__ import annotations
 
 import ctypes
+import struct
 from dataclasses import dataclass, field
 from typing import List, Sequence, Tuple
 
@@ -38,6 +39,55 @@ class TileCacheLayer:
     areas: np.ndarray   # uint8 [width*height]
     first_obstacle: int = 0
     obstacle_count: int = 0
+    cons: "np.ndarray | None" = None  # uint8 [width*height] neighbour-connection nibbles (TileCacheLayer.cons); unused by the voxel path
+
+
+TILECACHE_MAGIC, TILECACHE_VERSION = 0x4C494554, 1  # tile_cache_data.rs:10-13
+_LAYER_HDR = struct.Struct("<IIiii6fHH6B")  # TileCacheLayerHeader::to_bytes (tile_cache_data.rs:94-125): 54 bytes
+
+
+def layer_to_bytes(layer: TileCacheLayer, cons=None, tx=0, ty=0, tlayer=0, minx=0, maxx=0, miny=0, maxy=0) -> bytes:
+    """TileCacheLayer::to_bytes (tile_cache_data.rs:261-278): header, three u32 lengths, regons, areas, cons."""
+    r = np.ascontiguousarray(layer.regons, np.uint8).tobytes()
+    a = np.ascontiguousarray(layer.areas, np.uint8).tobytes()
+    c = b"" if cons is None else np.ascontiguousarray(cons, np.uint8).tobytes()
+    h = _LAYER_HDR.pack(TILECACHE_MAGIC, TILECACHE_VERSION, tx, ty, tlayer, *[float(x) for x in layer.bmin], *[float(x) for x in layer.bmax],
+                        int(layer.hmin), int(layer.hmax), int(layer.width), int(layer.height), minx, maxx, miny, maxy)
+    return h + struct.pack("<III", len(r), len(a), len(c)) + r + a + c
+
+
+def layer_from_bytes(data: bytes) -> TileCacheLayer:
+    """TileCacheLayer::from_bytes (tile_cache_data.rs:281-320), host mirror; ValueError where the reference returns
+    Error::Detour(InvalidParam)."""
+    if len(data) < 66:
+        raise ValueError("InvalidParam")
+    f = _LAYER_HDR.unpack_from(data, 0)
+    if f[0] != TILECACHE_MAGIC or f[1] != TILECACHE_VERSION:
+        raise ValueError("InvalidParam")
+    rl, al, cl = struct.unpack_from("<III", data, 54)
+    if 66 + rl + al + cl > len(data):
+        raise ValueError("InvalidParam")
+    return TileCacheLayer(f[5:8], f[8:11], f[11], f[12], f[13], f[14], np.frombuffer(data, np.uint8, rl, 66).copy(),
+                          np.frombuffer(data, np.uint8, al, 66 + rl).copy())
+
+
+class CompressedTiles:
+    """Compressed tiles (TileCache.compressed_tiles, tile_cache.rs:34) joined into one buffer with offsets, plus the
+    obstacle table and the per-layer obstacle ranges: what a native caller hands to rcb_build_tilecache_compressed."""
+
+    def __init__(self, blobs: Sequence[bytes], obstacles: Sequence["Obstacle"] = (), obstacle_ranges=None):
+        self.n = len(blobs)
+        self.off = np.zeros(self.n + 1, np.uint64)
+        self.off[1:] = np.cumsum([len(b) for b in blobs], dtype=np.uint64)
+        self.buf = np.frombuffer(b"".join(bytes(b) for b in blobs), np.uint8)
+        _, self.obstacles, self._keep = pack([], obstacles or [])
+        self.nobstacles = len(obstacles or [])
+        if self.nobstacles:
+            rng = obstacle_ranges if obstacle_ranges is not None else [(0, 0)] * self.n
+            self.first = np.ascontiguousarray([r[0] for r in rng], dtype=np.uint32)
+            self.count = np.ascontiguousarray([r[1] for r in rng], dtype=np.uint32)
+        else:
+            self.first = self.count = None
 
 
 @dataclass
@@ -125,4 +175,30 @@ def config5(ntiles: int = 256, size: int = 48, cs: float = 0.3, ch: float = 0.2,
                 obstacles.append(Obstacle.oriented_box((cx, 2.5, cz), (0.5 + 2.0 * h(70 + k), 1.5, 0.4 + 1.5 * h(80 + k)), 3.0 * h(90 + k)))
         layers.append(TileCacheLayer(bmin, bmax, 10, 11, size, size, np.ones(size * size, np.uint8),
                                      np.full(size * size, 63, np.uint8), first, nobs))
+    return layers, obstacles
+
+
+def config5_varied(ntiles: int = 256, size: int = 48, cs: float = 0.3, ch: float = 0.2, seed: int = 1
+                   ) -> Tuple[List[TileCacheLayer], List[Obstacle]]:
+    """config5 with layer content that looks like a built tile cache instead of constants: region ids in
+    patches with ~10 % empty cells, areas mostly 63 with patches of other ids, `cons` = the 4-neighbour
+    occupancy nibble.  Same obstacles as config5.  LZ4 gets these to roughly a third of their size."""
+    layers, obstacles = config5(ntiles, size, cs, ch, seed)
+    for t, l in enumerate(layers):
+        rng = np.random.default_rng(seed * 100003 + t)
+        coarse = rng.integers(1, 9, (size // 6 + 2, size // 6 + 2), dtype=np.uint8)
+        reg = np.kron(coarse, np.ones((6, 6), np.uint8))[:size, :size].copy()
+        holes = np.kron((rng.random((size // 4 + 1, size // 4 + 1)) < 0.1).astype(np.uint8), np.ones((4, 4), np.uint8))[:size, :size]
+        reg[holes == 1] = 0
+        reg[rng.random((size, size)) < 0.01] = 0
+        area = np.full((size, size), 63, np.uint8)
+        patch = np.kron(rng.integers(0, 12, (size // 8 + 1, size // 8 + 1), dtype=np.uint8), np.ones((8, 8), np.uint8))[:size, :size]
+        area[patch == 1] = 5
+        area[patch == 2] = 0
+        occ = np.pad(reg != 0, 1)
+        cons = (occ[1:-1, :-2] * 1 + occ[2:, 1:-1] * 2 + occ[1:-1, 2:] * 4 + occ[:-2, 1:-1] * 8).astype(np.uint8)
+        cons[reg == 0] = 0
+        l.regons, l.areas, l.cons = reg.reshape(-1), area.reshape(-1), cons.reshape(-1)
+        l.hmin = int(rng.integers(0, 40))
+        l.hmax = l.hmin + 1
     return layers, obstacles
