@@ -13,14 +13,87 @@
 
 namespace {
 
+// ---- one sequence header -----------------------------------------------------------------------------------
+struct LzSeq {
+    uint32_t lit_start, lit, off, mlen, next;
+    int kind;  // 0 literals + match, 1 last sequence (literals only, input exhausted), 2 lz4_flex's Err while parsing
+};
+// max_chain bounds the 255-continuation loops (speculative parses of arbitrary bytes must stay cheap);
+// kind 3 = "longer than that, parse me for real".
+__device__ __forceinline__ LzSeq lz_parse(const uint8_t* ip, uint32_t n, uint32_t p, uint32_t max_chain) {
+    LzSeq s{0, 0, 0, 0, 0, 2};
+    if (p >= n) return s;  // a token is expected
+    const uint32_t token = ip[p];
+    uint32_t q = p + 1, lit = token >> 4;
+    if (lit == 15) {
+        for (uint32_t c = 0;; ++c) {
+            if (q >= n) return s;
+            if (c >= max_chain) { s.kind = 3; return s; }
+            const uint32_t b = ip[q++];
+            lit += b;
+            if (b != 255) break;
+        }
+    }
+    if (lit > n - q) return s;  // LiteralOutOfBounds
+    s.lit_start = q;
+    s.lit = lit;
+    uint32_t r = q + lit;
+    if (r >= n) { s.kind = 1; return s; }  // end of block
+    if (n - r < 2) return s;
+    s.off = (uint32_t)ip[r] | ((uint32_t)ip[r + 1] << 8);
+    r += 2;
+    uint32_t mlen = 4 + (token & 15u);
+    if ((token & 15u) == 15u) {
+        for (uint32_t c = 0;; ++c) {
+            if (r >= n) return s;
+            if (c >= max_chain) { s.kind = 3; return s; }
+            const uint32_t b = ip[r++];
+            mlen += b;
+            if (b != 255) break;
+        }
+    }
+    s.mlen = mlen;
+    s.next = r;
+    s.kind = 0;
+    return s;
+}
+
+// copies of one sequence by the whole warp; `op` may alias nothing but itself
+__device__ __forceinline__ void lz_copy(const uint8_t* ip, uint8_t* op, uint32_t lane, uint32_t o, uint32_t lit_start, uint32_t lit,
+                                        bool has_match, uint32_t offset, uint32_t mlen) {
+    if (lit) {
+        for (uint32_t k = lane; k < lit; k += 32) op[o + k] = ip[lit_start + k];
+        __syncwarp();  // the literals just written may be the match source
+    }
+    if (!has_match) return;
+    o += lit;
+    if (offset == 0) {  // lz4_flex decodes into vec![0; size]: offset 0 re-reads bytes not written yet
+        for (uint32_t k = lane; k < mlen; k += 32) op[o + k] = 0;
+    } else if (offset >= mlen) {
+        for (uint32_t k = lane; k < mlen; k += 32) op[o + k] = op[o - offset + k];
+    } else if (offset >= 32) {  // every lane of a 32-byte step reads bytes produced before the step
+        for (uint32_t k0 = 0; k0 < mlen; k0 += 32) {
+            if (k0 + lane < mlen) op[o + k0 + lane] = op[o + k0 + lane - offset];
+            __syncwarp();
+        }
+    } else {
+        for (uint32_t k = lane; k < mlen; k += 32) op[o + k] = op[o - offset + k % offset];
+    }
+    __syncwarp();
+}
+
 // status per layer: 0 ok, 1 = lz4_flex's Err (Error::Detour(Failure))
 //
-// Every step of a sequence depends on the one before (token -> lengths -> literals -> offset -> match), so the
-// decode time of a layer is (sequences) x (latency of that chain).  With input and output in global memory
-// the chain cost ~1000 cycles per sequence; blocks that fit are therefore staged through shared memory
-// (input <= LZ_IN_CAP, size prefix <= LZ_OUT_CAP; anything larger takes the global-memory path) and the
-// decoded bytes leave in one coalesced copy.
-constexpr uint32_t LZ_IN_CAP = 16 * 1024, LZ_OUT_CAP = 32 * 1024;
+// Every step of a sequence depends on the one before (token -> lengths -> literals -> offset -> match), and one
+// warp runs that chain at ~800 cycles per sequence when it is written as one loop.  Blocks that fit shared
+// memory (input <= LZ_IN_CAP, size prefix <= LZ_OUT_CAP) are therefore decoded in phases:
+//   A  every byte position is parsed as if a sequence started there (parallel): next[p]
+//   B  the real sequence starts are the chain 0, next[0], next[next[0]], ... (one shared-memory load per step)
+//   C  per sequence (parallel): lengths -> output positions by a warp scan; all of lz4_flex's bound checks
+//   D  copies in sequence order, headers decoded 32 sequences at a time and handed round by shuffles
+// Larger blocks take the one-loop path in global memory.
+constexpr uint32_t LZ_IN_CAP = 8 * 1024, LZ_OUT_CAP = 32 * 1024, LZ_MAX_SEQ = LZ_IN_CAP / 3 + 2;
+constexpr uint32_t LZ_SMEM = LZ_IN_CAP + LZ_OUT_CAP + 2 * (LZ_IN_CAP + 8) + 2 * 2 * ((LZ_MAX_SEQ + 7) & ~7u);
 
 __global__ void __launch_bounds__(32) k_lz4_decompress(const uint8_t* __restrict__ blobs, const unsigned long long* __restrict__ blob_off,
                                                        uint8_t* out, const unsigned long long* __restrict__ out_off,
@@ -35,72 +108,122 @@ __global__ void __launch_bounds__(32) k_lz4_decompress(const uint8_t* __restrict
     }
     const uint32_t n = (uint32_t)(blen - 4);
     const uint32_t cap = (uint32_t)(out_off[layer + 1] - out_off[layer]);  // the size prefix, exactly
-    const uint8_t* ip = blobs + b0 + 4;
+    const uint8_t* gin = blobs + b0 + 4;
     uint8_t* gout = out + out_off[layer];
-    uint8_t* op = gout;
-    if (n <= LZ_IN_CAP) {  // stage the block (bytewise: blobs are packed back to back, no alignment to rely on)
-        for (uint32_t k = lane; k < n; k += 32) lz_smem[k] = ip[k];
-        ip = lz_smem;
-    }
-    const bool out_staged = cap <= LZ_OUT_CAP;
-    if (out_staged) op = lz_smem + LZ_IN_CAP;
-    __syncwarp();
-    uint32_t i = 0, o = 0;
-    uint32_t st = 0;
-    for (;;) {
-        if (i >= n) { st = 1; break; }  // a token is expected
-        const uint32_t token = ip[i++];
-        uint32_t lit = token >> 4;
-        if (lit == 15) {
-            for (;;) {
-                if (i >= n) { st = 1; break; }
-                const uint32_t b = ip[i++];
-                lit += b;
-                if (b != 255) break;
-            }
-            if (st) break;
+    uint32_t st = 0, o = 0;
+    if (n <= LZ_IN_CAP && cap <= LZ_OUT_CAP) {
+        uint8_t* ip = lz_smem;
+        uint8_t* op = lz_smem + LZ_IN_CAP;
+        uint16_t* next = (uint16_t*)(lz_smem + LZ_IN_CAP + LZ_OUT_CAP);
+        uint16_t* seq_pos = next + LZ_IN_CAP + 8;
+        uint16_t* out_pos = seq_pos + ((LZ_MAX_SEQ + 7) & ~7u);
+        for (uint32_t k = lane; k < n; k += 32) ip[k] = gin[k];  // bytewise: blobs are packed back to back
+        __syncwarp();
+        // A
+        for (uint32_t p = lane; p < n; p += 32) {
+            const LzSeq s = lz_parse(ip, n, p, 8);
+            next[p] = s.kind == 0 ? (uint16_t)s.next : (uint16_t)(0xFFFC + s.kind);  // 0xFFFD last, 0xFFFE error, 0xFFFF long chain
         }
-        if (lit > n - i || lit > cap - o) { st = 1; break; }  // LiteralOutOfBounds / OutputTooSmall
-        for (uint32_t k = lane; k < lit; k += 32) op[o + k] = ip[i + k];
-        i += lit;
-        o += lit;
-        if (i >= n) break;  // end of block
-        if (n - i < 2) { st = 1; break; }
-        const uint32_t offset = (uint32_t)ip[i] | ((uint32_t)ip[i + 1] << 8);
-        i += 2;
-        uint32_t mlen = 4 + (token & 15u);
-        if ((token & 15u) == 15u) {
-            for (;;) {
-                if (i >= n) { st = 1; break; }
-                const uint32_t b = ip[i++];
-                mlen += b;
-                if (b != 255) break;
-            }
-            if (st) break;
-        }
-        if (offset > o || mlen > cap - o) { st = 1; break; }  // OffsetOutOfBounds / OutputTooSmall
-        __syncwarp();  // the literals just written may be the match source
-        if (offset == 0) {  // lz4_flex decodes into vec![0; size]: offset 0 re-reads bytes not written yet
-            for (uint32_t k = lane; k < mlen; k += 32) op[o + k] = 0;
-        } else {
-            const uint8_t* src = op + o - offset;
-            if (offset >= mlen) {
-                for (uint32_t k = lane; k < mlen; k += 32) op[o + k] = src[k];
-            } else if (offset >= 32) {  // every lane of a 32-byte step reads bytes produced before the step
-                for (uint32_t k0 = 0; k0 < mlen; k0 += 32) {
-                    if (k0 + lane < mlen) op[o + k0 + lane] = op[o + k0 + lane - offset];
-                    __syncwarp();
+        __syncwarp();
+        // B (uniform: every lane walks the same chain; next[n] is the "token expected" error)
+        if (lane == 0) next[n] = 0xFFFE;
+        __syncwarp();
+        uint32_t ns = 0;
+        for (uint32_t p = 0;;) {
+            uint32_t nx = next[p];
+            if (nx >= 0xFFFD) {
+                if (nx == 0xFFFF) {
+                    const LzSeq s = lz_parse(ip, n, p, 0xffffffffu);
+                    nx = s.kind == 0 ? s.next : 0xFFFCu + s.kind;
                 }
-            } else {
-                for (uint32_t k = lane; k < mlen; k += 32) op[o + k] = src[k % offset];
+                if (nx == 0xFFFE) { st = 1; break; }
+                if (nx == 0xFFFD) {
+                    if (lane == 0) seq_pos[ns] = (uint16_t)p;
+                    ++ns;
+                    break;
+                }
             }
+            if (lane == 0) seq_pos[ns] = (uint16_t)p;
+            ++ns;
+            p = nx;
         }
-        o += mlen;
         __syncwarp();
-    }
-    if (out_staged && !st) {
-        __syncwarp();
-        for (uint32_t k = lane; k < o; k += 32) gout[k] = op[k];
+        if (!st) {
+            // C
+            uint32_t carry = 0;
+            bool bad = false;
+            for (uint32_t base = 0; base < ns; base += 32) {
+                const uint32_t k = base + lane;
+                LzSeq s{0, 0, 0, 0, 0, 1};
+                if (k < ns) s = lz_parse(ip, n, seq_pos[k], 0xffffffffu);
+                const uint32_t lit = min(s.lit, cap + 1), ml = s.kind == 0 ? min(s.mlen, cap + 1) : 0;
+                uint32_t incl = k < ns ? lit + ml : 0;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= (uint32_t)d) incl += v;
+                }
+                const uint32_t ok = carry + incl - (k < ns ? lit + ml : 0);  // output position of this sequence
+                if (k < ns) {
+                    // LiteralOutOfBounds was checked by the parse; OutputTooSmall, OffsetOutOfBounds:
+                    if (ok > cap || lit > cap - ok) bad = true;
+                    else if (s.kind == 0 && (s.off > ok + lit || ml > cap - (ok + lit))) bad = true;
+                    out_pos[k] = (uint16_t)min(ok, 0xffffu);
+                }
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (__any_sync(0xffffffffu, bad)) st = 1;
+            o = carry;
+            __syncwarp();
+        }
+        if (!st) {
+            // D: the copies are the serial part (each may read what the one before wrote), so the loop body is
+            // kept short: three packed words per sequence, fetched one sequence ahead of the copy that uses them
+            for (uint32_t base = 0; base < ns; base += 32) {
+                const uint32_t k = base + lane;
+                LzSeq s{0, 0, 0, 0, 0, 1};
+                uint32_t my_o = 0;
+                if (k < ns) s = lz_parse(ip, n, seq_pos[k], 0xffffffffu), my_o = out_pos[k];
+                // two packed words per sequence: output position | offset, and match length | fast flag | magic.
+                // fast = no literals, a match of 1..32 bytes, offset != 0; magic M = 1024/off + 1 turns
+                // lane % off into lane - off * ((lane * M) >> 10) for off, lane < 32.
+                const bool fast = s.lit == 0 && s.kind == 0 && s.mlen <= 32 && s.off != 0;
+                const uint32_t magic = (s.off != 0 && s.off < 32) ? 1024u / s.off + 1u : 0u;  // 0: lane % off == lane
+                const uint32_t w0 = my_o | (s.off << 16), w1 = min(s.mlen, 0xffffu) | ((fast ? 1u : 0u) << 16) | (magic << 17);
+                const uint32_t cnt = min(32u, ns - base);
+                uint32_t n0 = __shfl_sync(0xffffffffu, w0, 0), n1 = __shfl_sync(0xffffffffu, w1, 0);
+                for (uint32_t j = 0; j < cnt; ++j) {
+                    const uint32_t c0 = n0, c1 = n1;
+                    const uint32_t jn = min(j + 1, cnt - 1);
+                    n0 = __shfl_sync(0xffffffffu, w0, jn), n1 = __shfl_sync(0xffffffffu, w1, jn);
+                    const uint32_t so = c0 & 0xffffu, off = c0 >> 16;
+                    if (c1 & 0x10000u) {  // the common case: one short match
+                        const uint32_t d = lane - off * ((lane * (c1 >> 17)) >> 10);
+                        if (lane < (c1 & 0xffffu)) op[so + lane] = op[so - off + d];
+                        __syncwarp();
+                    } else {
+                        const uint32_t lit_start = __shfl_sync(0xffffffffu, s.lit_start, j), lit = __shfl_sync(0xffffffffu, s.lit, j);
+                        const int kind = __shfl_sync(0xffffffffu, s.kind, j);
+                        lz_copy(ip, op, lane, so, lit_start, lit, kind == 0, off, c1 & 0xffffu);
+                    }
+                }
+            }
+            __syncwarp();
+            for (uint32_t k = lane; k < o; k += 32) gout[k] = op[k];
+        }
+    } else {
+        // one-loop decoder in global memory (headers read by every lane from the same address)
+        uint32_t p = 0;
+        for (;;) {
+            const LzSeq s = lz_parse(gin, n, p, 0xffffffffu);
+            if (s.kind == 2) { st = 1; break; }
+            if (s.lit > cap - o) { st = 1; break; }  // OutputTooSmall
+            if (s.kind == 0 && (s.off > o + s.lit || s.mlen > cap - (o + s.lit))) { st = 1; break; }  // OffsetOutOfBounds / OutputTooSmall
+            __syncwarp();
+            lz_copy(gin, gout, lane, o, s.lit_start, s.lit, s.kind == 0, s.off, s.mlen);
+            o += s.lit + (s.kind == 0 ? s.mlen : 0);
+            if (s.kind == 1) break;
+            p = s.next;
+        }
     }
     if (lane == 0) status[layer] = st, produced[layer] = st ? 0u : o;
 }
@@ -171,11 +294,11 @@ void launch_lz4_decompress(const uint8_t* blobs, const unsigned long long* blob_
     if (nlayers == 0) return;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_lz4_decompress, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LZ_IN_CAP + LZ_OUT_CAP));
+        cudaFuncSetAttribute(k_lz4_decompress, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZ_SMEM);
         attr_set = true;
     }
     KScope _k("k_lz4_decompress", s);
-    k_lz4_decompress<<<nlayers, 32, LZ_IN_CAP + LZ_OUT_CAP, s>>>(blobs, blob_off, out, out_off, status, produced);
+    k_lz4_decompress<<<nlayers, 32, LZ_SMEM, s>>>(blobs, blob_off, out, out_off, status, produced);
 }
 
 void launch_tc_parse(int nlayers, const uint8_t* raw, const unsigned long long* raw_off, const uint32_t* lz_status,
