@@ -27,12 +27,13 @@ __device__ __forceinline__ uint32_t rd32(const uint8_t* p, bool be) {
 // err: the first failure of the strict reader in (tile, cell, step) order, as tile << 33 | cell << 1 | kind;
 // kind 0 = short buffer (checked before the cell's spans are added), 1 = add_span refused a span
 //
-// One warp per tile.  The chase itself is serial (lane 0), so its cost is the latency of one load per cell:
-// the warp stages the stream through shared memory in 4 KB pieces (coalesced 16-byte loads) so that this
-// load is an LDS, and the (position, count) pairs go back out in coalesced runs.  A global-memory chase,
-// one thread per tile, took 1.5 ms for the 2025 tiles of config 2.
+// One warp per tile.  The warp stages the stream through shared memory in 4 KB pieces (coalesced 16-byte
+// loads).  A serial chase (lane 0) costs ~270 cycles of dependent instructions per cell (0.58 ms for the 2025
+// tiles of config 2; 1.5 ms when it chased through global memory), so the warp first tries a speculative
+// walk, 32 cells at a time, and chases serially only across stretches where that fails.
 constexpr int WALK_CHUNK = 4096;  // bytes staged per refill
 constexpr int WALK_CELLS = 512;   // cells buffered before a flush
+constexpr int WALK_SERIAL = 16;   // cells the serial chase crosses before the speculative walk gets another try
 
 __global__ void __launch_bounds__(32) k_wire_walk(const TileDesc* __restrict__ tiles, int ntiles, const uint8_t* __restrict__ data,
                                                   const unsigned long long* __restrict__ tile_off, int strict_le,
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(32) k_wire_walk(const TileDesc* __restrict__ t
     uint32_t c = 0;
     int state = (strict_le && len < 2ull * C) ? 2 : 0;  // 0 walking, 1 lenient reader ran dry, 2 strict reader failed (dynamic_tile.rs:171-175)
     uint32_t bad_cell = 0;
+    uint32_t stride = 14;  // guess: one span per cell
     while (c < C && state == 0) {
         if (end - pos >= 2 && pos + 2 > hi) {  // refill from the 16-byte line holding `pos`
             lo = pos & ~15u;
@@ -67,9 +69,57 @@ __global__ void __launch_bounds__(32) k_wire_walk(const TileDesc* __restrict__ t
                 if (lo + 16u * k < hi) ((uint4*)buf)[k] = __ldg((const uint4*)(org + lo) + k);  // the buffer carries 64 spare bytes
             __syncwarp();
         }
+        // Speculative stretch.  Lane i guesses where cell c+i starts (the previous round's scan, else a constant
+        // stride), reads the count there, and an exclusive scan of the cell lengths says where each cell really
+        // starts IF every earlier lane guessed right: the longest prefix of confirmed lanes is accepted (lane 0
+        // is always right), the rest re-guess from the scan.  Uniform columns go 32 cells a round; anything
+        // that is not a plain cell (window edge, spans past the end of the stream) stops the stretch and is
+        // left to the serial code below, which also owns the readers' end-of-data semantics.
+        {
+            uint32_t g = pos + (uint32_t)lane * stride;
+            for (;;) {
+                const bool inwin = c + lane < C && g >= lo && g + 2 <= hi && g + 2 >= g;
+                uint32_t count = 0, ln = 0;
+                bool plain = false;
+                if (inwin) {
+                    const uint32_t o = g - lo;
+                    const uint32_t w0 = *(const uint32_t*)(buf + (o & ~3u)), w1 = *(const uint32_t*)(buf + (o & ~3u) + 4);
+                    const uint32_t h = __funnelshift_r(w0, w1, (o & 3u) * 8u);
+                    count = strict_le ? (h & 0xffffu) : (__byte_perm(h, 0, 0x4401));
+                    plain = 12u * count <= end - (g + 2);
+                    ln = 2u + 12u * count;
+                }
+                uint32_t incl = ln;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, dd);
+                    if (lane >= dd) incl += v;
+                }
+                const uint32_t at = pos + incl - ln;  // where this cell starts if all earlier lanes were right
+                const unsigned wrong = __ballot_sync(0xffffffffu, !(plain && g == at));
+                const uint32_t nv = wrong ? (uint32_t)__ffs(wrong) - 1u : 32u;
+                if ((uint32_t)lane < nv) {
+                    cp[c + lane] = g + 2 - skew;
+                    cn[c + lane] = count;
+                }
+                if (nv == 0) break;
+                stride = __shfl_sync(0xffffffffu, ln, nv - 1);
+                pos += __shfl_sync(0xffffffffu, incl, nv - 1);
+                c += nv;
+                if (nv < 4) break;  // irregular stretch: cross it serially
+                if (nv == 32) {
+                    g = pos + (uint32_t)lane * stride;
+                } else {
+                    const uint32_t shifted = __shfl_down_sync(0xffffffffu, at, nv);
+                    const uint32_t last = __shfl_sync(0xffffffffu, at + ln, 31);
+                    g = (uint32_t)lane < 32u - nv ? shifted : last + ((uint32_t)lane - (32u - nv)) * stride;
+                }
+            }
+        }
+        if (!(c < C)) break;
         uint32_t nb = 0;
         if (lane == 0) {
-            while (c < C && nb < WALK_CELLS) {
+            while (c < C && nb < WALK_SERIAL) {
                 if (end - pos < 2) {  // dynamic_tile.rs:181-189; the lenient reader just stops (voxel_tile.rs:129-131)
                     state = strict_le ? 2 : 1;
                     bad_cell = c;
