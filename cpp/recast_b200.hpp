@@ -61,6 +61,17 @@ class Context {
     rcb_ctx* ctx_ = nullptr;
 };
 
+class Batch;
+// VoxelTile::deserialize_spans (io/voxel_tile.rs:120-176, RCB_WIRE_VOXEL_TILE) / DynamicTile::reconstruct_heightfield
+// (dynamic_tile.rs:147-257, RCB_WIRE_DYNAMIC_TILE) for a batch of span streams, later stages per stage_mask.
+inline Batch build_from_span_data(Context& ctx, const rcb_config* tiles, size_t ntiles, const uint8_t* data, const uint64_t* tile_offsets,
+                                  int format, uint32_t stage_mask = 0, int erode_radius = 0);
+// TileCache::decompress_tile + TileCacheLayer::from_bytes + layer_to_compact_heightfield + rasterize_obstacles
+// (detour-tilecache/src/tile_cache.rs:854-872, tile_cache_data.rs:281-320, tile_cache_builder.rs:100-251) for a batch of compressed tiles.
+inline Batch build_tilecache_compressed(Context& ctx, const uint8_t* blobs, const uint64_t* blob_offsets, size_t nlayers,
+                                        const uint32_t* first_obstacle, const uint32_t* obstacle_count, const rcb_tc_obstacle* obstacles,
+                                        size_t nobstacles, float cs, float ch, uint32_t stage_mask = RCB_STAGE_COMPACT);
+
 class Batch {
    public:
     Batch(rcb_ctx* ctx, rcb_result* res) : ctx_(ctx), res_(res) {}
@@ -82,6 +93,14 @@ class Batch {
         rcb_tile_view v{};
         check(rcb_result_tile_device(res_, i, &v), ctx_, "tile_device");
         return v;
+    }
+    // VoxelTile::serialize_spans (detour-dynamic/src/io/voxel_tile.rs:70-118) for every tile; tile_offsets gets ntiles + 1 entries.
+    std::vector<uint8_t> serialize_spans(int format = RCB_WIRE_VOXEL_TILE, std::vector<uint64_t>* tile_offsets = nullptr) const {
+        std::vector<uint8_t> out(rcb_result_span_data_size(res_));
+        if (tile_offsets) tile_offsets->assign(totals().tiles + 1, 0);
+        check(rcb_result_serialize_spans(res_, format, out.data(), out.size(), tile_offsets ? tile_offsets->data() : nullptr), ctx_,
+              "serialize_spans");
+        return out;
     }
 
    private:
@@ -117,5 +136,23 @@ class RecastBuilder {
     RecastConfig cfg_;
     Context& ctx_;
 };
+
+inline Batch build_from_span_data(Context& ctx, const rcb_config* tiles, size_t ntiles, const uint8_t* data, const uint64_t* tile_offsets,
+                                  int format, uint32_t stage_mask, int erode_radius) {
+    rcb_result* res = nullptr;
+    check(rcb_build_from_span_data(ctx.raw(), tiles, (int)ntiles, data, tile_offsets, format, stage_mask, erode_radius, &res), ctx.raw(),
+          "build_from_span_data");
+    return Batch(ctx.raw(), res);
+}
+
+inline Batch build_tilecache_compressed(Context& ctx, const uint8_t* blobs, const uint64_t* blob_offsets, size_t nlayers,
+                                        const uint32_t* first_obstacle, const uint32_t* obstacle_count, const rcb_tc_obstacle* obstacles,
+                                        size_t nobstacles, float cs, float ch, uint32_t stage_mask) {
+    rcb_result* res = nullptr;
+    check(rcb_build_tilecache_compressed(ctx.raw(), blobs, blob_offsets, (int)nlayers, first_obstacle, obstacle_count, obstacles,
+                                         (int)nobstacles, cs, ch, stage_mask, 0, &res),
+          ctx.raw(), "build_tilecache_compressed");
+    return Batch(ctx.raw(), res);
+}
 
 }  // namespace recast_b200

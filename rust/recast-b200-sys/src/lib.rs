@@ -10,11 +10,17 @@ pub const RCB_ENAVMESH_GEN: c_int = -2;
 pub const RCB_ECUDA: c_int = -3;
 pub const RCB_EOVERFLOW: c_int = -4;
 pub const RCB_EARG: c_int = -5;
+pub const RCB_ERECAST: c_int = -6;
+pub const RCB_EDETOUR_FAILURE: c_int = -7;
+pub const RCB_EDETOUR_INVALID_PARAM: c_int = -8;
 pub const RCB_STAGE_RASTER: u32 = 1;
 pub const RCB_STAGE_FILTER: u32 = 2;
 pub const RCB_STAGE_COMPACT: u32 = 4;
 pub const RCB_STAGE_ERODE: u32 = 8;
 pub const RCB_STAGE_DIST: u32 = 16;
+pub const RCB_STAGE_READD: u32 = 0x20;
+pub const RCB_WIRE_VOXEL_TILE: c_int = 0;
+pub const RCB_WIRE_DYNAMIC_TILE: c_int = 1;
 pub const RCB_FILTER_LOW_HANGING: u32 = 0x100;
 pub const RCB_FILTER_LEDGE: u32 = 0x200;
 pub const RCB_FILTER_LOW_HEIGHT: u32 = 0x400;
@@ -159,6 +165,11 @@ extern "C" {
     pub fn rcb_build_from_spans(ctx: *mut rcb_ctx, cfgs: *const rcb_config, ntiles: c_int, cell_offset: *const u32, span_min: *const i16, span_max: *const i16, span_area: *const u8, areas_override: *const u8, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
     pub fn rcb_apply_area_ops(ctx: *mut rcb_ctx, cfgs: *const rcb_config, ntiles: c_int, cell_offset: *const u32, span_min: *const i16, span_max: *const i16, span_area: *const u8, areas_override: *const u8, ops: *const rcb_area_op, nops: c_int, poly_verts: *const f32, npoly_floats: usize, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
     pub fn rcb_build_tilecache_layers(ctx: *mut rcb_ctx, layers: *const rcb_tc_layer, nlayers: c_int, obstacles: *const rcb_tc_obstacle, nobstacles: c_int, cs: f32, ch: f32, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
+    pub fn rcb_build_from_span_data(ctx: *mut rcb_ctx, cfgs: *const rcb_config, ntiles: c_int, data: *const u8, tile_offsets: *const u64, format: c_int, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
+    pub fn rcb_result_span_data_size(res: *const rcb_result) -> u64;
+    pub fn rcb_result_serialize_spans(res: *mut rcb_result, format: c_int, out: *mut u8, capacity: u64, tile_offsets: *mut u64) -> c_int;
+    pub fn rcb_decompress_tiles(ctx: *mut rcb_ctx, blobs: *const u8, blob_offsets: *const u64, n: c_int, out: *mut u8, out_cap: u64, out_offsets: *mut u64) -> c_int;
+    pub fn rcb_build_tilecache_compressed(ctx: *mut rcb_ctx, blobs: *const u8, blob_offsets: *const u64, nlayers: c_int, first_obstacle: *const u32, obstacle_count: *const u32, obstacles: *const rcb_tc_obstacle, nobstacles: c_int, cs: f32, ch: f32, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
     pub fn rcb_result_totals(res: *const rcb_result, out: *mut rcb_totals) -> c_int;
     pub fn rcb_result_download(res: *mut rcb_result) -> c_int;
     pub fn rcb_result_tile(res: *const rcb_result, tile: c_int, out: *mut rcb_tile_view) -> c_int;
