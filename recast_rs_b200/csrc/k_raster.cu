@@ -390,11 +390,12 @@ __global__ void __launch_bounds__(256) k_gather_spans(uint32_t ncells, const uin
 // One CTA per tile.  Scattering tile by tile keeps the random 4-byte writes inside the tile's own region
 // (a few hundred KB, L2-resident); scattering the whole batch at once cost 240 B of DRAM traffic per
 // fragment (13 % L2 hit rate, ncu on config 3).
-__global__ void __launch_bounds__(512) k_seg_count(const TileDesc* __restrict__ tiles, const uint32_t* __restrict__ tile_frags,
+__global__ void __launch_bounds__(512) k_seg_count(const TileDesc* __restrict__ tiles, int ntiles, const uint32_t* __restrict__ tile_frags,
                                                    const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ tile_cap,
                                                    const uint32_t* __restrict__ tile_cursor, uint32_t* __restrict__ cell_cnt,
                                                    unsigned long long* __restrict__ counters) {
-    const uint32_t tile = blockIdx.y;
+    const uint32_t tile = blockIdx.z * gridDim.y + blockIdx.y;
+    if (tile >= (uint32_t)ntiles) return;
     const uint32_t F = min(tile_cursor[tile], tile_cap[tile]);
     const uint32_t* fr = tile_frags + 3ull * tile_base[tile];
     uint32_t* cnt = cell_cnt + tiles[tile].cell_base;
@@ -403,12 +404,13 @@ __global__ void __launch_bounds__(512) k_seg_count(const TileDesc* __restrict__ 
     if (blockIdx.x == 0 && threadIdx.x == 0 && F) atomicAdd(&counters[1], (unsigned long long)F);
 }
 
-__global__ void __launch_bounds__(512) k_seg_scatter(const TileDesc* __restrict__ tiles, const uint32_t* __restrict__ tile_frags,
+__global__ void __launch_bounds__(512) k_seg_scatter(const TileDesc* __restrict__ tiles, int ntiles, const uint32_t* __restrict__ tile_frags,
                                                      const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ tile_cap,
                                                      const uint32_t* __restrict__ tile_cursor, const uint32_t* __restrict__ frag_off,
                                                      uint32_t* __restrict__ cell_cnt, uint32_t* __restrict__ fs_tri,
                                                      uint32_t* __restrict__ fs_mm, uint8_t* __restrict__ fs_area) {
-    const uint32_t tile = blockIdx.y;
+    const uint32_t tile = blockIdx.z * gridDim.y + blockIdx.y;
+    if (tile >= (uint32_t)ntiles) return;
     const uint32_t F = min(tile_cursor[tile], tile_cap[tile]);
     const uint32_t* fr = tile_frags + 3ull * tile_base[tile];
     const uint32_t cb = tiles[tile].cell_base;
@@ -432,14 +434,15 @@ static dim3 seg_grid(int ntiles, uint32_t max_tile_frags) {
     const uint32_t want = (uint32_t)((148 * 4 + ntiles - 1) / ntiles);  // enough CTAs for every SM
     slices = slices < 1 ? 1 : slices;
     if (slices > want) slices = want > 1 ? want : 1;
-    return dim3(slices, (unsigned)ntiles);
+    const unsigned gy = ntiles < 65535 ? (unsigned)ntiles : 65535u;  // tile = blockIdx.z * gridDim.y + blockIdx.y
+    return dim3(slices, gy, ((unsigned)ntiles + gy - 1) / gy);
 }
 
 void launch_seg_count(const TileDesc* tiles, int ntiles, const uint32_t* tile_frags, const uint32_t* tile_base, const uint32_t* tile_cap,
                       const uint32_t* tile_cursor, uint32_t* cell_cnt, unsigned long long* counters, uint32_t max_tile_frags, cudaStream_t s) {
     if (ntiles == 0) return;
     KScope _k("k_seg_count", s);
-    k_seg_count<<<seg_grid(ntiles, max_tile_frags), 512, 0, s>>>(tiles, tile_frags, tile_base, tile_cap, tile_cursor, cell_cnt, counters);
+    k_seg_count<<<seg_grid(ntiles, max_tile_frags), 512, 0, s>>>(tiles, ntiles, tile_frags, tile_base, tile_cap, tile_cursor, cell_cnt, counters);
 }
 
 void launch_seg_scatter(const TileDesc* tiles, int ntiles, const uint32_t* tile_frags, const uint32_t* tile_base, const uint32_t* tile_cap,
@@ -447,7 +450,7 @@ void launch_seg_scatter(const TileDesc* tiles, int ntiles, const uint32_t* tile_
                         uint8_t* fs_area, uint32_t max_tile_frags, cudaStream_t s) {
     if (ntiles == 0) return;
     KScope _k("k_seg_scatter", s);
-    k_seg_scatter<<<seg_grid(ntiles, max_tile_frags), 512, 0, s>>>(tiles, tile_frags, tile_base, tile_cap, tile_cursor, frag_off, cell_cnt, fs_tri, fs_mm, fs_area);
+    k_seg_scatter<<<seg_grid(ntiles, max_tile_frags), 512, 0, s>>>(tiles, ntiles, tile_frags, tile_base, tile_cap, tile_cursor, frag_off, cell_cnt, fs_tri, fs_mm, fs_area);
 }
 
 void launch_count_fragments(const RasterBuffers& rb, cudaStream_t s) {

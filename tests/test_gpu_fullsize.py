@@ -184,3 +184,39 @@ def test_determinism_repeated_runs():
         assert ref is None or sig == ref
         ref = sig
     ctx.close()
+
+
+def test_seventy_thousand_tiny_tiles_both_back_ends(oracle):
+    """More tiles than one grid dimension holds (65535): 2x2-cell tiles over a small terrain, both back ends."""
+    import recast_rs_b200.builder as rb
+    from recast_rs_b200 import synth
+    from recast_rs_b200.config import RecastConfig
+
+    v, t = synth.terrain(160, 1.2, 4.0, 3)
+    cfgs = synth.tile_grid(v, 2, RecastConfig(cs=0.3, ch=0.2))
+    assert len(cfgs) > 70000
+    res = []
+    for fg in (False, True):
+        ctx = _context(force_global=fg)
+        ctx.upload_mesh(v, t)
+        with ctx.build_tiles(cfgs, rb.STAGE_ALL_BUILD) as r:
+            r.download()
+            tot = r.totals()
+            pick = [0, 1, 65534, 65535, 65536, len(cfgs) - 1, len(cfgs) // 2]
+            res.append((tot, [r.tile(i) for i in pick], pick))
+            res[-1] = (tot, [(tv.span_min.copy(), tv.span_area.copy(), tv.dist.copy(), tv.conn_ref.copy(), tv) for tv in res[-1][1]], pick)
+        ctx.close()
+    a, b = res
+    a[0].pop("result_bytes"), b[0].pop("result_bytes")
+    assert a[0] == b[0] and a[0]["tiles"] == len(cfgs) and a[0]["spans"] > 0
+    for x, y in zip(a[1], b[1]):
+        for k in range(4):
+            np.testing.assert_array_equal(x[k], y[k])
+    for i, x in zip(a[2], a[1]):
+        ohf = oracle.Heightfield.from_config(cfgs[i])
+        ohf.builder_rasterize(cfgs[i], v, t)
+        oc = oracle.CompactHeightfield.build_from_heightfield(ohf)
+        oc.build_distance_field()
+        e = oc.export()
+        np.testing.assert_array_equal(x[0], e.span_min)
+        np.testing.assert_array_equal(x[2], e.dist)
