@@ -425,8 +425,11 @@ def run_native(args, rank, world, local_rank):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ctx2.upload_mesh(hv.numpy(), ht.numpy())
-        r = ctx2.build_tiles(cfg_arr, stage)
-        r.download()
+        if args.e2e_groups > 1:  # the public host-to-host call: D2H of finished tile groups overlaps the next groups
+            r = ctx2.build_tiles_streamed(cfg_arr, stage, 0, args.e2e_groups)
+        else:
+            r = ctx2.build_tiles(cfg_arr, stage)
+            r.download()
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) * 1e3
         d2h_bytes = r.totals()["result_bytes"]
@@ -464,7 +467,9 @@ def run_native(args, rank, world, local_rank):
             "tiles_per_s": tiles_all * args.steps / (max_total_ms * 1e-3),
             "wall_ms_per_step": wall * 1e3 / args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(v.nbytes + t.nbytes),
-                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": max_e2e_ms / len(e2e_ms)},
+                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": max_e2e_ms / len(e2e_ms),
+                    "call": ("rcb_upload_mesh + rcb_build_tiles_streamed(groups=%d)" % args.e2e_groups) if args.e2e_groups > 1
+                    else "rcb_upload_mesh + rcb_build_tiles + rcb_result_download"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -503,6 +508,7 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-groups", type=int, default=1, help="tile groups of the host-to-host call (1: build then download)")
     ap.add_argument("--tc-compressed", action="store_true", help="config 5 from LZ4-compressed tiles (SURVEY 8(f) rank 3)")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     args = ap.parse_args()

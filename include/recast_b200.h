@@ -180,6 +180,15 @@ int rcb_set_mesh_device(rcb_ctx* ctx, const void* d_verts, size_t nfloats, const
 int rcb_build_tiles(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stage_mask,
                     int erode_radius, rcb_result** out);
 
+/* rcb_build_tiles_streamed: rcb_build_tiles + rcb_result_download for callers that want the voxel data in HOST
+ * memory: the tiles are processed in `ngroups` consecutive groups (<= 0: 8) and the device-to-host copy of a
+ * finished group runs on a second stream while the next groups compute, so the call costs about
+ * max(compute, PCIe copy) instead of their sum.  The result is already downloaded; rcb_result_tile /
+ * _tile_device / _totals work as usual (tile indices are those of `cfgs`), rcb_result_serialize_spans does not
+ * (serialize from an rcb_build_tiles result).  Same errors as rcb_build_tiles (the first failing group's). */
+int rcb_build_tiles_streamed(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stage_mask, int erode_radius,
+                             int ngroups, rcb_result** out);
+
 /* rcb_rasterize: the free function rasterize_triangles(verts, tris, tri_area_ids, n, hf, thr)
  * (rasterization.rs:405-428) per tile, with caller-provided per-triangle areas and merge
  * threshold; no slope classification, no degenerate-triangle skip.  Later stages per stage_mask. */

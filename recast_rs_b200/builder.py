@@ -211,6 +211,15 @@ class Context:
                                        stage_mask, erode_radius, ctypes.byref(out)), self._h)
         return BatchResult(self, out)
 
+    def build_tiles_streamed(self, cfgs, stage_mask: int = STAGE_ALL_BUILD, erode_radius: int = 0, groups: int = 8) -> BatchResult:
+        """build_tiles + download with the device-to-host copy of finished tile groups overlapped with the
+        computation of the next ones; the result is already in host memory."""
+        arr = cfgs if isinstance(cfgs, ctypes.Array) else configs_to_array(cfgs)
+        out = ctypes.c_void_p()
+        check(_ffi.lib().rcb_build_tiles_streamed(self._h, ctypes.cast(arr, ctypes.c_void_p), len(arr), stage_mask, erode_radius, groups,
+                                                  ctypes.byref(out)), self._h)
+        return BatchResult(self, out)
+
     def build_from_spans(self, cfgs, cell_offset, span_min, span_max, span_area, stage_mask, erode_radius=0,
                          areas_override=None) -> BatchResult:
         arr = cfgs if isinstance(cfgs, ctypes.Array) else configs_to_array(cfgs)

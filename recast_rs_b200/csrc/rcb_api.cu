@@ -7,6 +7,7 @@
 //   rcb_build_from_spans = the same stages starting from existing Heightfields
 // No CPU fallback exists in this file: every stage is a CUDA kernel launch.
 #include <cmath>
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -60,6 +61,7 @@ struct ArenaLayout {  // byte offsets inside arena A (cells + spans) and arena B
 struct rcb_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // D2H of finished tile groups while later groups compute (rcb_build_tiles_streamed)
     std::string err;
     unsigned long long launches0 = 0;
     // mesh
@@ -108,6 +110,9 @@ struct rcb_result {
     bool tile_mode = false;  // connections arena sized by an upper bound (Kcap); exact K comes from tinfo
     uint64_t Kcap = 0;
     std::vector<TileInfo> tinfo;
+    // composite result of rcb_build_tiles_streamed: tiles [first[g], first[g+1]) live in children[g]
+    std::vector<rcb_result*> children;
+    std::vector<int> child_first;
 };
 
 namespace {
@@ -212,7 +217,7 @@ cudaError_t pool_get(std::vector<Arena>& pool, size_t bytes, bool host, Arena& o
 
 void pool_put(std::vector<Arena>& pool, Arena& a, bool host) {
     if (!a.p) return;
-    if (pool.size() >= 8) {  // bound the pool: release the smallest
+    if (pool.size() >= 64) {  // bound the pool (a streamed build holds 2 arenas per tile group): release the smallest
         size_t m = 0;
         for (size_t i = 1; i < pool.size(); ++i)
             if (pool[i].cap < pool[m].cap) m = i;
@@ -949,14 +954,15 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
 #undef CUB
 }
 
-int fetch_tinfo(rcb_result* res) {
+int fetch_tinfo(rcb_result* res, cudaStream_t on = nullptr, bool use_on = false) {
     rcb_ctx* ctx = res->ctx;
     if (res->have_tinfo) return RCB_OK;
+    const cudaStream_t st = use_on ? on : ctx->stream;
     res->tinfo.resize(res->ntiles);
     if (res->ntiles > 0) {
         CU(cudaMemcpyAsync(res->tinfo.data(), res->devA.p + res->lay.tinfo, sizeof(TileInfo) * (size_t)res->ntiles,
-                           cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
+                           cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
     }
     res->have_tinfo = true;
     if (res->tile_mode) {
@@ -1005,7 +1011,8 @@ void rcb_destroy(rcb_ctx* ctx) {
                       &ctx->d_fs_area, &ctx->d_scan_tmp, &ctx->d_hf_off, &ctx->d_conn_cnt, &ctx->d_conn_off, &ctx->d_nei16,
                       &ctx->d_t16a, &ctx->d_t16b, &ctx->d_t16c, &ctx->d_t8a, &ctx->d_t8b, &ctx->d_item_cnt, &ctx->d_item_off, &ctx->d_items, &ctx->d_tile_ub, &ctx->d_tile_base,
                       &ctx->d_tile_cursor, &ctx->d_tile_frags, &ctx->d_ts_mm, &ctx->d_ts_area, &ctx->d_celloff_tmp, &ctx->d_lookback, &ctx->d_tc_regons, &ctx->d_tc_areas,
-                      &ctx->d_tc_obs, &ctx->d_fidx};
+                      &ctx->d_tc_obs, &ctx->d_fidx, &ctx->d_wire, &ctx->d_wire_off, &ctx->d_wire_pos, &ctx->d_wire_inoff, &ctx->d_wire_err,
+                      &ctx->d_tc_raw, &ctx->d_tc_parsed};
     for (auto* b : bufs) b->release();
     for (auto& a : ctx->free_dev) cudaFree(a.p);
     for (auto& a : ctx->free_host) cudaFreeHost(a.p);
@@ -1014,6 +1021,7 @@ void rcb_destroy(rcb_ctx* ctx) {
     prof_collect(ctx);
     for (auto e : ctx->prof_free) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
 }
 
@@ -1133,6 +1141,78 @@ int rcb_build_tiles(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t s
     return run_pipeline(ctx, cfgs, ntiles, stage_mask, erode_radius, s, out);
 }
 
+static int download_on(rcb_result* res, cudaStream_t st, bool wait);
+
+int rcb_build_tiles_streamed(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stage_mask, int erode_radius, int ngroups,
+                             rcb_result** out) {
+    if (!ctx || !out || ntiles < 0 || (ntiles > 0 && !cfgs)) return fail(ctx, RCB_EARG, "null argument");
+    *out = nullptr;
+    if (!(stage_mask & RCB_STAGE_RASTER)) return fail(ctx, RCB_EARG, "rcb_build_tiles_streamed needs RCB_STAGE_RASTER");
+    if (ngroups < 1) ngroups = 8;
+    if (ngroups > ntiles) ngroups = ntiles > 0 ? ntiles : 1;
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    Source s;
+    s.raster = true;
+    s.merge_thr = 1;  // lib.rs:273
+    auto* res = new rcb_result();
+    res->ctx = ctx;
+    res->ntiles = ntiles;
+    res->stage_mask = stage_mask;
+    std::vector<cudaEvent_t> done;
+    auto cleanup = [&](int code) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        for (auto e : done) cudaEventDestroy(e);
+        if (code != RCB_OK) {
+            rcb_result_free(res);
+            res = nullptr;
+        }
+        return code;
+    };
+    // Group g computes on the context's stream while the copy stream drains group g-1 (a group is complete on the
+    // device by the time the next group's pipeline has passed its first host synchronization).
+    for (int g = 0; g < ngroups; ++g) {
+        const int first = (int)((long long)ntiles * g / ngroups), last = (int)((long long)ntiles * (g + 1) / ngroups);
+        rcb_result* child = nullptr;
+        int r = run_pipeline(ctx, cfgs + first, last - first, stage_mask, erode_radius, s, &child);
+        if (r) return cleanup(r);
+        res->children.push_back(child);
+        res->child_first.push_back(first);
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(e, ctx->stream) != cudaSuccess)
+            return cleanup(fail(ctx, RCB_ECUDA, "CUDA event failure"));
+        done.push_back(e);
+        if (g > 0) {
+            if (cudaStreamWaitEvent(ctx->copy_stream, done[g - 1], 0) != cudaSuccess) return cleanup(fail(ctx, RCB_ECUDA, "cudaStreamWaitEvent"));
+            r = download_on(res->children[g - 1], ctx->copy_stream, false);
+            if (r) return cleanup(r);
+        }
+    }
+    if (!res->children.empty()) {
+        if (cudaStreamWaitEvent(ctx->copy_stream, done.back(), 0) != cudaSuccess) return cleanup(fail(ctx, RCB_ECUDA, "cudaStreamWaitEvent"));
+        int r = download_on(res->children.back(), ctx->copy_stream, false);
+        if (r) return cleanup(r);
+    }
+    if (cudaStreamSynchronize(ctx->copy_stream) != cudaSuccess) return cleanup(fail(ctx, RCB_ECUDA, "copy stream failed"));
+    for (auto* c : res->children) {
+        c->tinfo.assign((TileInfo*)(c->hostA.p + c->lay.tinfo), (TileInfo*)(c->hostA.p + c->lay.tinfo) + c->ntiles);
+        c->have_tinfo = true;
+        if (c->tile_mode && !c->have_K) {
+            uint64_t k = 0;
+            for (auto& t : c->tinfo) k += t.conn_count;
+            c->K = k, c->have_K = true;
+        }
+        c->downloaded = true;
+        res->Ctot += c->Ctot, res->S += c->S;
+    }
+    res->Ctot = 0, res->S = 0;  // sizes live in the children (rcb_result_span_data_size sums them)
+    res->downloaded = true;
+    res->have_tinfo = true;
+    cleanup(RCB_OK);
+    *out = res;
+    return RCB_OK;
+}
+
 int rcb_rasterize(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const uint8_t* tri_areas, int32_t flag_merge_threshold,
                   uint32_t stage_mask, int erode_radius, rcb_result** out) {
     if (!tri_areas && ctx && ctx->nidx) return fail(ctx, RCB_EARG, "tri_areas is null");
@@ -1170,12 +1250,18 @@ int rcb_build_from_span_data(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, c
     return run_pipeline(ctx, cfgs, ntiles, stage_mask & ~(uint32_t)RCB_STAGE_READD, erode_radius, s, out);
 }
 
-uint64_t rcb_result_span_data_size(const rcb_result* res) { return res ? 2 * res->Ctot + 12 * res->S : 0; }
+uint64_t rcb_result_span_data_size(const rcb_result* res) {
+    if (!res) return 0;
+    uint64_t n = 2 * res->Ctot + 12 * res->S;
+    for (auto* c : res->children) n += rcb_result_span_data_size(c);
+    return n;
+}
 
 int rcb_result_serialize_spans(rcb_result* res, int format, uint8_t* out, uint64_t capacity, uint64_t* tile_offsets) {
     if (!res) return RCB_EARG;
     rcb_ctx* ctx = res->ctx;
     if (format != RCB_WIRE_VOXEL_TILE && format != RCB_WIRE_DYNAMIC_TILE) return fail(ctx, RCB_EARG, "unknown wire format %d", format);
+    if (!res->children.empty()) return fail(ctx, RCB_EARG, "rcb_result_serialize_spans: not available on a streamed result");
     const uint64_t total = rcb_result_span_data_size(res);
     if (!out || capacity < total) return fail(ctx, RCB_EARG, "rcb_result_serialize_spans: need %llu bytes", (unsigned long long)total);
     CU(cudaSetDevice(ctx->device));
@@ -1396,7 +1482,7 @@ int rcb_decompress_tiles(rcb_ctx* ctx, const uint8_t* blobs, const uint64_t* blo
     if (out_cap < out_offsets[n]) return fail(ctx, RCB_EARG, "rcb_decompress_tiles: need %llu bytes", (unsigned long long)out_offsets[n]);
     for (int i = 0; i < n; ++i)  // produced <= size prefix: compact while copying
         if (out_offsets[i + 1] > out_offsets[i])
-            CU(cudaMemcpyAsync(out + out_offsets[i], ctx->d_tc_raw.p + cap_off[i], out_offsets[i + 1] - out_offsets[i], cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(out + out_offsets[i], (const char*)ctx->d_tc_raw.p + cap_off[i], out_offsets[i + 1] - out_offsets[i], cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return RCB_OK;
 }
@@ -1545,6 +1631,18 @@ int rcb_apply_area_ops(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const u
 int rcb_result_totals(const rcb_result* cres, rcb_totals* out) {
     auto* res = const_cast<rcb_result*>(cres);
     if (!res || !out) return RCB_EARG;
+    if (!res->children.empty()) {
+        memset(out, 0, sizeof *out);
+        for (auto* c : res->children) {
+            rcb_totals t;
+            int r = rcb_result_totals(c, &t);
+            if (r) return r;
+            out->tiles += t.tiles, out->cells += t.cells, out->fragments += t.fragments, out->spans += t.spans;
+            out->connections += t.connections, out->walkable_spans += t.walkable_spans, out->result_bytes += t.result_bytes;
+            out->triangles = t.triangles, out->vertices = t.vertices;
+        }
+        return RCB_OK;
+    }
     int r = fetch_tinfo(res);
     if (r) return r;
     memset(out, 0, sizeof *out);
@@ -1560,33 +1658,51 @@ int rcb_result_totals(const rcb_result* cres, rcb_totals* out) {
     return RCB_OK;
 }
 
+// D2H of one result's arenas on `st`; with wait == false the copies are left in flight (the caller synchronizes
+// `st` before anything reads the host arenas).
+static int download_on(rcb_result* res, cudaStream_t st, bool wait) {
+    rcb_ctx* ctx = res->ctx;
+    if (res->downloaded) return RCB_OK;
+    CU(pool_get(ctx->free_host, res->lay.bytesA, true, res->hostA));
+    if (res->lay.bytesB) {
+        CU(pool_get(ctx->free_host, res->lay.bytesB, true, res->hostB));
+        if (res->tile_mode) {  // the arena is sized by a bound on K: copy the used prefix of each array
+            int r = fetch_tinfo(res, st, true);
+            if (r) return r;
+            const size_t K = res->K;
+            if (K) {
+                CU(cudaMemcpyAsync(res->hostB.p + res->lay.conn_ref, res->devB.p + res->lay.conn_ref, 4 * K, cudaMemcpyDeviceToHost, st));
+                CU(cudaMemcpyAsync(res->hostB.p + res->lay.conn_next, res->devB.p + res->lay.conn_next, 4 * K, cudaMemcpyDeviceToHost, st));
+                CU(cudaMemcpyAsync(res->hostB.p + res->lay.conn_dir, res->devB.p + res->lay.conn_dir, K, cudaMemcpyDeviceToHost, st));
+            }
+        } else {
+            CU(cudaMemcpyAsync(res->hostB.p, res->devB.p, res->lay.bytesB, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CU(cudaMemcpyAsync(res->hostA.p, res->devA.p, res->lay.bytesA, cudaMemcpyDeviceToHost, st));
+    if (wait) {
+        CU(cudaStreamSynchronize(st));
+        res->tinfo.assign((TileInfo*)(res->hostA.p + res->lay.tinfo), (TileInfo*)(res->hostA.p + res->lay.tinfo) + res->ntiles);
+        res->have_tinfo = true;
+        res->downloaded = true;
+    }
+    return RCB_OK;
+}
+
 int rcb_result_download(rcb_result* res) {
     if (!res) return RCB_EARG;
     rcb_ctx* ctx = res->ctx;
     if (res->downloaded) return RCB_OK;
     CU(cudaSetDevice(ctx->device));
-    CU(pool_get(ctx->free_host, res->lay.bytesA, true, res->hostA));
-    CU(cudaMemcpyAsync(res->hostA.p, res->devA.p, res->lay.bytesA, cudaMemcpyDeviceToHost, ctx->stream));
-    if (res->lay.bytesB) {
-        CU(pool_get(ctx->free_host, res->lay.bytesB, true, res->hostB));
-        if (res->tile_mode) {  // the arena is sized by a bound on K: copy the used prefix of each array
-            int r = fetch_tinfo(res);
+    if (!res->children.empty()) {
+        for (auto* c : res->children) {
+            int r = rcb_result_download(c);
             if (r) return r;
-            const size_t K = res->K;
-            if (K) {
-                CU(cudaMemcpyAsync(res->hostB.p + res->lay.conn_ref, res->devB.p + res->lay.conn_ref, 4 * K, cudaMemcpyDeviceToHost, ctx->stream));
-                CU(cudaMemcpyAsync(res->hostB.p + res->lay.conn_next, res->devB.p + res->lay.conn_next, 4 * K, cudaMemcpyDeviceToHost, ctx->stream));
-                CU(cudaMemcpyAsync(res->hostB.p + res->lay.conn_dir, res->devB.p + res->lay.conn_dir, K, cudaMemcpyDeviceToHost, ctx->stream));
-            }
-        } else {
-            CU(cudaMemcpyAsync(res->hostB.p, res->devB.p, res->lay.bytesB, cudaMemcpyDeviceToHost, ctx->stream));
         }
+        res->downloaded = true;
+        return RCB_OK;
     }
-    CU(cudaStreamSynchronize(ctx->stream));
-    res->tinfo.assign((TileInfo*)(res->hostA.p + res->lay.tinfo), (TileInfo*)(res->hostA.p + res->lay.tinfo) + res->ntiles);
-    res->have_tinfo = true;
-    res->downloaded = true;
-    return RCB_OK;
+    return download_on(res, ctx->stream, true);
 }
 
 static int fill_view(const rcb_result* res, int tile, rcb_tile_view* v, const char* A, const char* B) {
@@ -1621,13 +1737,28 @@ static int fill_view(const rcb_result* res, int tile, rcb_tile_view* v, const ch
     return RCB_OK;
 }
 
+static const rcb_result* child_of(const rcb_result* res, int& tile) {
+    const size_t g = (size_t)(std::upper_bound(res->child_first.begin(), res->child_first.end(), tile) - res->child_first.begin()) - 1;
+    tile -= res->child_first[g];
+    return res->children[g];
+}
+
 int rcb_result_tile(const rcb_result* res, int tile, rcb_tile_view* out) {
     if (!res || !out || tile < 0 || tile >= res->ntiles) return RCB_EARG;
+    if (!res->children.empty()) {
+        const rcb_result* c = child_of(res, tile);
+        return rcb_result_tile(c, tile, out);
+    }
     if (!res->downloaded) return fail(res->ctx, RCB_EARG, "rcb_result_tile: call rcb_result_download first");
     return fill_view(res, tile, out, res->hostA.p, res->hostB.p);
 }
 
 int rcb_result_tile_device(const rcb_result* cres, int tile, rcb_tile_view* out) {
+    if (cres && !cres->children.empty()) {
+        if (!out || tile < 0 || tile >= cres->ntiles) return RCB_EARG;
+        const rcb_result* c = child_of(cres, tile);
+        return rcb_result_tile_device(c, tile, out);
+    }
     auto* res = const_cast<rcb_result*>(cres);
     if (!res || !out || tile < 0 || tile >= res->ntiles) return RCB_EARG;
     int r = fetch_tinfo(res);
@@ -1637,6 +1768,7 @@ int rcb_result_tile_device(const rcb_result* cres, int tile, rcb_tile_view* out)
 
 void rcb_result_free(rcb_result* res) {
     if (!res) return;
+    for (auto* c : res->children) rcb_result_free(c);
     rcb_ctx* ctx = res->ctx;
     if (ctx) {
         cudaSetDevice(ctx->device);

@@ -220,3 +220,33 @@ def test_seventy_thousand_tiny_tiles_both_back_ends(oracle):
         e = oc.export()
         np.testing.assert_array_equal(x[0], e.span_min)
         np.testing.assert_array_equal(x[2], e.dist)
+
+
+@pytest.mark.parametrize("groups", [1, 3, 8, 5000])
+def test_streamed_build_equals_plain_build(groups):
+    """rcb_build_tiles_streamed (D2H of finished tile groups overlapped with the next groups) returns the same bytes."""
+    import recast_rs_b200.builder as rb
+    from recast_rs_b200 import errors, synth
+
+    v, t, cfgs = synth.config2(nq=240)  # 256 tiles
+    ctx = _context()
+    ctx.upload_mesh(v, t)
+    with ctx.build_tiles(cfgs, rb.STAGE_ALL_BUILD) as a, ctx.build_tiles_streamed(cfgs, rb.STAGE_ALL_BUILD, groups=groups) as b:
+        a.download()
+        ta, tb = a.totals(), b.totals()
+        ta.pop("result_bytes"), tb.pop("result_bytes")
+        assert ta == tb
+        for i in range(len(cfgs)):
+            x, y = a.tile(i), b.tile(i)
+            for k in ("hf_cell_offset", "span_min", "span_max", "span_area", "cell_index", "cell_count", "areas", "con", "first_conn",
+                      "conn_ref", "conn_dir", "conn_next", "dist"):
+                assert np.array_equal(getattr(x, k), getattr(y, k)), (i, k)
+            assert (x.max_distance, x.max_height, x.walkable_span_count) == (y.max_distance, y.max_height, y.walkable_span_count)
+    with ctx.build_tiles_streamed([], rb.STAGE_ALL_BUILD) as e:
+        assert e.totals()["tiles"] == 0
+    bad = t.copy()
+    bad[-1] = 10 ** 7
+    ctx.upload_mesh(v, bad)
+    with pytest.raises(errors.NavMeshGeneration):
+        ctx.build_tiles_streamed(cfgs, rb.STAGE_ALL_BUILD)
+    ctx.close()
