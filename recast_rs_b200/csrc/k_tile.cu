@@ -413,8 +413,10 @@ __device__ __forceinline__ T sat_add(T v, unsigned b) {
 }
 
 // boundary -> forward rows -> backward gather, on shared memory.  ERODE: thresholds areas; else D + max.
-template <typename T, bool ERODE>
-__device__ void tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_t* sh_max, PhaseClock* pc = nullptr) {
+// The forward sweep occupies only the warps that own a column; `idle_work(rank, count)` runs meanwhile on the
+// others (work that touches neither the sweep buffers nor areas).  Returns whether idle_work ran.
+template <typename T, bool ERODE, class Work>
+__device__ bool tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_t* sh_max, PhaseClock* pc, Work&& idle_work) {
     const int W = g.W, H = g.H;
     const uint32_t TN = g.S;  // "no neighbour" == the dummy span
     const T inf = (T)~(T)0;
@@ -512,6 +514,8 @@ __device__ void tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_
                 row_barrier();
             }
         }
+    } else {
+        idle_work(threadIdx.x - (uint32_t)sweep_threads, (uint32_t)(TILE_THREADS - sweep_threads));
     }
     __syncthreads();
     if (pc) pc->mark(9);
@@ -539,6 +543,7 @@ __device__ void tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_
             if ((unsigned)init[s] < thr) g.areas[s] = 0;  // area.rs:226-231
         __syncthreads();
     }
+    return sweep_threads < TILE_THREADS;
 }
 
 // Decoupled look-back over tiles, split in two so that nobody waits: a tile PUBLISHES its connection count
@@ -743,17 +748,62 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
     if (threadIdx.x == 0) lookback_publish(look, tile, K);
     pc.mark(2);
     const TileB g{soff, areas, nid, S, S2, W, H, wmagic};
+    // 7 (hoisted). The connection list (compact_heightfield.rs:375-389: reverse direction order, next -> previously
+    //    pushed, first_connection = last pushed) needs only the neighbour table and the tile's first connection
+    //    index, so the warps that sit out the row-sequential forward sweep write it meanwhile.
+    auto conn_work = [&](uint32_t rank, uint32_t nworkers) {
+        if (rank < 32) {
+            const uint32_t excl = lookback_resolve(look, tile, K);
+            if (rank == 0) {
+                sh_misc[1] = excl;
+                a.tinfo[tile].conn_base = excl;
+                a.tinfo[tile].conn_count = K;
+            }
+        }
+        if (nworkers == TILE_THREADS)
+            __syncthreads();
+        else
+            asm volatile("bar.sync 2, %0;" ::"r"(nworkers) : "memory");
+        const uint32_t conn_base = sh_misc[1];
+        for (uint32_t c = rank; c < C; c += nworkers) {
+            const uint32_t b = soff[c], e = soff[c + 1];
+            if (b == e) continue;
+            uint32_t k = coff[c];
+            for (uint32_t s = b; s < e; ++s) {
+                uint32_t first = RCB_NONE;
+                uint32_t nn[8];
+#pragma unroll
+                for (int d = 0; d < 8; ++d) nn[d] = nid[(uint32_t)d * S2 + s];  // eight independent loads
+#pragma unroll
+                for (int d = 7; d >= 0; --d) {
+                    if (nn[d] == TN) continue;
+                    a.conn_ref[conn_base + k] = nn[d];
+                    a.conn_dir[conn_base + k] = (uint8_t)d;
+                    a.conn_next[conn_base + k] = first;
+                    first = k;
+                    ++k;
+                }
+                a.first_conn[span_base + s] = first;
+            }
+        }
+    };
+    auto no_work = [](uint32_t, uint32_t) {};
+    bool conn_written = false;
     // 5. erosion (area.rs:73-234) — before the distance field when both are requested.  mm is dead: its
     //    bytes are the sweep buffers d16a / d16b from here on.
     if (a.do_erode) {
         const unsigned thr = (unsigned)(uint8_t)(uint32_t)(a.erode_radius * 2);
-        tile_sweep<uint8_t, true>(g, reinterpret_cast<uint8_t*>(d16a), reinterpret_cast<uint8_t*>(d16b), thr, nullptr);
+        conn_written = tile_sweep<uint8_t, true>(g, reinterpret_cast<uint8_t*>(d16a), reinterpret_cast<uint8_t*>(d16b), thr, nullptr,
+                                                 nullptr, conn_work);
     }
     for (uint32_t s = threadIdx.x; s < S; s += TILE_THREADS) a.areas[span_base + s] = areas[s];
     pc.mark(3);
     // 6. distance field (compact_heightfield.rs:514-727)
     if (a.do_dist) {
-        tile_sweep<uint16_t, false>(g, d16a, d16b, 0, &sh_misc[2], &pc);
+        if (conn_written)
+            tile_sweep<uint16_t, false>(g, d16a, d16b, 0, &sh_misc[2], &pc, no_work);
+        else
+            conn_written = tile_sweep<uint16_t, false>(g, d16a, d16b, 0, &sh_misc[2], &pc, conn_work);
         pc.mark(4);
         // box blur: d16a holds D; result to global
         for (uint32_t s = threadIdx.x; s < S; s += TILE_THREADS) {
@@ -778,45 +828,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
             }
             a.dist[span_base + s] = (uint16_t)r;
         }
+        if (threadIdx.x == 0) a.tinfo[tile].max_distance = sh_misc[2];
         pc.mark(5);
     } else {
         for (uint32_t s = threadIdx.x; s < S; s += TILE_THREADS) a.dist[span_base + s] = 0;  // compact_heightfield.rs:253
     }
-    // 7. resolve the tile's first connection index, then the connection list (compact_heightfield.rs:375-389):
-    //    reverse direction order, next -> previously pushed, first_connection = last pushed
-    if (threadIdx.x < 32) {
-        const uint32_t excl = lookback_resolve(look, tile, K);
-        if (threadIdx.x == 0) {
-            sh_misc[1] = excl;
-            a.tinfo[tile].conn_base = excl;
-            a.tinfo[tile].conn_count = K;
-            if (a.do_dist) a.tinfo[tile].max_distance = sh_misc[2];
-        }
-    }
-    __syncthreads();
     pc.mark(6);
-    const uint32_t conn_base = sh_misc[1];
-    for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
-        const uint32_t b = soff[c], e = soff[c + 1];
-        if (b == e) continue;
-        uint32_t k = coff[c];
-        for (uint32_t s = b; s < e; ++s) {
-            uint32_t first = RCB_NONE;
-            uint32_t nn[8];
-#pragma unroll
-            for (int d = 0; d < 8; ++d) nn[d] = nid[(uint32_t)d * S2 + s];  // eight independent loads
-#pragma unroll
-            for (int d = 7; d >= 0; --d) {
-                if (nn[d] == TN) continue;
-                a.conn_ref[conn_base + k] = nn[d];
-                a.conn_dir[conn_base + k] = (uint8_t)d;
-                a.conn_next[conn_base + k] = first;
-                first = k;
-                ++k;
-            }
-            a.first_conn[span_base + s] = first;
-        }
-    }
+    if (!conn_written) conn_work(threadIdx.x, TILE_THREADS);  // no sweep ran, or the tile is as wide as the block
     pc.mark(7);
 }
 
