@@ -1531,3 +1531,342 @@ double orc_tilecache_build_compressed_batch(const uint8_t* blobs, const uint64_t
     return std::chrono::duration<double>(t1 - t0).count();
 }
 }  // extern "C"
+
+// ======================================================================================================
+// Region building: watershed::build_regions_watershed (watershed.rs:364-510), the
+// function behind CompactHeightfield::build_regions (compact_heightfield.rs:770-778) that
+// RecastBuilder::build_mesh calls next (lib.rs:83-87).  Paths relative to crates/recast/src/.
+// The reference holds no test for watershed.rs: "parity unpinned"; cross-checked against oracle/pymodel.py.
+// ======================================================================================================
+namespace {
+
+constexpr uint16_t BORDER_REG = 0x8000;  // watershed.rs:8
+struct LevelEntry {
+    int32_t x, y;
+    uint32_t index;  // NONE = usize::MAX marker
+};
+
+// neighbour through span.con[dir] (watershed.rs:173-176): 63 means "not connected" even when it is a real offset
+inline uint32_t ws_con_neighbor(const Compact& c, int32_t x, int32_t y, uint32_t i, int dir, int32_t& ax, int32_t& ay) {
+    static const int OX[4] = {-1, 0, 1, 0}, OY[4] = {0, 1, 0, -1};  // compact_heightfield.rs:748-767
+    const uint16_t k = c.con[(size_t)i * 4 + dir];
+    if (k == 63) return NONE;
+    ax = x + OX[dir];
+    ay = y + OY[dir];
+    return c.cell_index[(size_t)ay * c.width + ax] + k;
+}
+
+// watershed.rs:65-119
+void ws_sort_cells_by_level(uint16_t start_level, const Compact& c, const std::vector<uint16_t>& src_reg,
+                            std::vector<LevelEntry>* stacks, int nb_stacks, int log_levels) {
+    start_level = (uint16_t)(start_level >> log_levels);
+    for (int s = 0; s < nb_stacks; ++s) stacks[s].clear();
+    for (int32_t y = 0; y < c.height; ++y)
+        for (int32_t x = 0; x < c.width; ++x) {
+            const size_t ci = (size_t)y * c.width + x;
+            if (c.cell_index[ci] == NONE) continue;
+            for (uint32_t s = 0; s < c.cell_count[ci]; ++s) {
+                const uint32_t i = c.cell_index[ci] + s;
+                if (c.areas[i] == 0 || src_reg[i] != 0) continue;
+                const uint16_t level = (uint16_t)(c.dist[i] >> log_levels);
+                const uint32_t sid = start_level > level ? (uint32_t)(start_level - level) : 0u;  // saturating_sub
+                if ((int)sid < nb_stacks) stacks[sid].push_back(LevelEntry{x, y, i});
+            }
+        }
+}
+
+// watershed.rs:136-242
+bool ws_flood_region(int32_t x, int32_t y, uint32_t i, uint16_t level, uint16_t r, const Compact& c, std::vector<uint16_t>& src_reg,
+                     std::vector<uint16_t>& src_dist, std::vector<LevelEntry>& stack) {
+    const uint8_t area = c.areas[i];
+    stack.clear();
+    stack.push_back(LevelEntry{x, y, i});
+    src_reg[i] = r;
+    src_dist[i] = 0;
+    const uint16_t lev = level >= 2 ? (uint16_t)(level - 2) : 0;
+    int count = 0;
+    while (!stack.empty()) {
+        const LevelEntry back = stack.back();
+        stack.pop_back();
+        const int32_t cx = back.x, cy = back.y;
+        const uint32_t ci = back.index;
+        uint16_t ar = 0;
+        for (int dir = 0; dir < 4; ++dir) {
+            int32_t ax, ay;
+            const uint32_t ai = ws_con_neighbor(c, cx, cy, ci, dir, ax, ay);
+            if (ai == NONE) continue;
+            if (c.areas[ai] != area) continue;
+            const uint16_t nr = src_reg[ai];
+            if (nr & BORDER_REG) continue;
+            if (nr != 0 && nr != r) {
+                ar = nr;
+                break;
+            }
+            const int dir2 = (dir + 1) & 3;
+            int32_t ax2, ay2;
+            const uint32_t ai2 = ws_con_neighbor(c, ax, ay, ai, dir2, ax2, ay2);
+            if (ai2 == NONE) continue;
+            if (c.areas[ai2] != area) continue;
+            const uint16_t nr2 = src_reg[ai2];
+            if (nr2 != 0 && nr2 != r) {
+                ar = nr2;
+                break;
+            }
+        }
+        if (ar != 0) {
+            src_reg[ci] = 0;
+            continue;
+        }
+        ++count;
+        for (int dir = 0; dir < 4; ++dir) {
+            int32_t ax, ay;
+            const uint32_t ai = ws_con_neighbor(c, cx, cy, ci, dir, ax, ay);
+            if (ai == NONE) continue;
+            if (c.areas[ai] != area) continue;
+            if (c.dist[ai] >= lev && src_reg[ai] == 0) {
+                src_reg[ai] = r;
+                src_dist[ai] = 0;
+                stack.push_back(LevelEntry{ax, ay, ai});
+            }
+        }
+    }
+    return count > 0;
+}
+
+// watershed.rs:245-361
+void ws_expand_regions(int max_iter, uint16_t level, const Compact& c, std::vector<uint16_t>& src_reg, std::vector<uint16_t>& src_dist,
+                       std::vector<LevelEntry>& stack, bool fill_stack) {
+    if (fill_stack) {
+        stack.clear();
+        for (int32_t y = 0; y < c.height; ++y)
+            for (int32_t x = 0; x < c.width; ++x) {
+                const size_t ci = (size_t)y * c.width + x;
+                if (c.cell_index[ci] == NONE) continue;
+                for (uint32_t s = 0; s < c.cell_count[ci]; ++s) {
+                    const uint32_t i = c.cell_index[ci] + s;
+                    if (c.dist[i] >= level && src_reg[i] == 0 && c.areas[i] != 0) stack.push_back(LevelEntry{x, y, i});
+                }
+            }
+    } else {
+        for (auto& e : stack)
+            if (src_reg[e.index] != 0) e.index = NONE;
+    }
+    int iter = 0;
+    struct Dirty {
+        uint32_t idx;
+        uint16_t reg, dist;
+    };
+    std::vector<Dirty> dirty;
+    std::vector<size_t> marks;
+    while (!stack.empty()) {
+        size_t failed = 0;
+        dirty.clear();
+        marks.clear();
+        for (size_t j = 0; j < stack.size(); ++j) {
+            const LevelEntry& e = stack[j];
+            const uint32_t i = e.index;
+            if (i == NONE) {
+                ++failed;
+                continue;
+            }
+            uint16_t r = src_reg[i];
+            uint16_t d2 = 0xffff;
+            const uint8_t area = c.areas[i];
+            for (int dir = 0; dir < 4; ++dir) {
+                int32_t ax, ay;
+                const uint32_t ai = ws_con_neighbor(c, e.x, e.y, i, dir, ax, ay);
+                if (ai == NONE) continue;
+                if (c.areas[ai] != area) continue;
+                if (src_reg[ai] > 0 && (src_reg[ai] & BORDER_REG) == 0 && (uint16_t)(src_dist[ai] + 2) < d2) {
+                    r = src_reg[ai];
+                    d2 = (uint16_t)(src_dist[ai] + 2);
+                }
+            }
+            if (r != 0) {
+                marks.push_back(j);
+                dirty.push_back(Dirty{i, r, d2});
+            } else {
+                ++failed;
+            }
+        }
+        for (size_t j : marks) stack[j].index = NONE;
+        for (const Dirty& d : dirty) {
+            src_reg[d.idx] = d.reg;
+            src_dist[d.idx] = d.dist;
+        }
+        stack.erase(std::remove_if(stack.begin(), stack.end(), [](const LevelEntry& e) { return e.index == NONE; }), stack.end());
+        if (failed * 3 >= stack.size() * 2) break;  // :350 — compared with the length AFTER the retain
+        if (level > 0) {
+            ++iter;
+            if (iter >= max_iter) break;
+        }
+    }
+}
+
+void ws_paint_rect(int32_t minx, int32_t maxx, int32_t miny, int32_t maxy, uint16_t reg, const Compact& c, std::vector<uint16_t>& src_reg) {
+    for (int32_t y = miny; y < maxy; ++y)
+        for (int32_t x = minx; x < maxx; ++x) {
+            const long long ci = (long long)y * c.width + x;  // watershed.rs:524-526: the bound is on the flat index
+            if (ci < 0 || ci >= (long long)c.cell_index.size()) continue;
+            if (c.cell_index[(size_t)ci] == NONE) continue;
+            for (uint32_t s = 0; s < c.cell_count[(size_t)ci]; ++s) {
+                const uint32_t i = c.cell_index[(size_t)ci] + s;
+                if (c.areas[i] != 0) src_reg[i] = reg;
+            }
+        }
+}
+
+struct WsRegion {
+    int32_t span_count = 0;
+    uint16_t id = 0;
+    bool connects_to_border = false;
+    std::vector<uint32_t> connections;
+};
+
+// watershed.rs:543-633, 636-716, 719-746
+void ws_merge_and_filter(int32_t min_region_area, int32_t merge_region_area, uint16_t max_region_id, const Compact& c,
+                         std::vector<uint16_t>& src_reg) {
+    static const uint8_t DIR8[4] = {7, 5, 3, 1};  // compact_heightfield.rs:737-743
+    std::vector<WsRegion> regions(max_region_id);
+    for (uint16_t i = 0; i < max_region_id; ++i) regions[i].id = i;
+    const size_t S = c.smin.size();
+    for (size_t s = 0; s < S; ++s) {
+        const uint16_t rid = src_reg[s];
+        if (rid == 0 || (rid & BORDER_REG)) continue;
+        WsRegion& reg = regions[rid];
+        reg.span_count++;
+        for (int dir = 0; dir < 4; ++dir) {
+            const uint32_t n = c.get_neighbor((uint32_t)s, DIR8[dir]);
+            if (n == NONE) continue;
+            const uint16_t nr = src_reg[n];
+            if (nr == rid || nr == 0) continue;
+            if (nr & BORDER_REG) {
+                reg.connects_to_border = true;
+                continue;
+            }
+            if (std::find(reg.connections.begin(), reg.connections.end(), (uint32_t)nr) == reg.connections.end())
+                reg.connections.push_back(nr);
+        }
+    }
+    // remove small regions (:598-622)
+    for (uint16_t i = 0; i < max_region_id; ++i) {
+        WsRegion& reg = regions[i];
+        if (reg.id == 0 || (reg.id & BORDER_REG) || reg.span_count == 0) continue;
+        if (reg.span_count < min_region_area && !reg.connects_to_border) {
+            const uint16_t old = reg.id;
+            reg.id = 0;
+            for (auto& v : src_reg)
+                if (v == old) v = 0;
+        }
+    }
+    // merge small regions (:636-716): decisions of one round are taken before any of them is applied
+    if (merge_region_area > 0) {
+        for (;;) {
+            struct Merge {
+                size_t idx;
+                uint16_t old_id, best;
+                int32_t count;
+            };
+            std::vector<Merge> merges;
+            for (size_t i = 0; i < regions.size(); ++i) {
+                const WsRegion& reg = regions[i];
+                if (reg.id == 0 || (reg.id & BORDER_REG) || reg.span_count == 0) continue;
+                if (reg.span_count < merge_region_area && !reg.connects_to_border) {
+                    uint16_t best = 0;
+                    int32_t best_size = 0;
+                    for (uint32_t nid : reg.connections) {
+                        if (nid >= regions.size()) continue;
+                        const WsRegion& nb = regions[nid];
+                        if (nb.id == 0 || (nb.id & BORDER_REG)) continue;
+                        if (nb.span_count > best_size) {
+                            best = nb.id;
+                            best_size = nb.span_count;
+                        }
+                    }
+                    if (best > 0) merges.push_back(Merge{i, reg.id, best, reg.span_count});
+                }
+            }
+            for (const Merge& m : merges) {
+                for (auto& v : src_reg)
+                    if (v == m.old_id) v = m.best;
+                regions[m.idx].id = 0;
+                for (auto& r : regions)
+                    if (r.id == m.best) {
+                        r.span_count += m.count;
+                        break;
+                    }
+            }
+            if (merges.empty()) break;
+        }
+    }
+    // compact ids (:719-746)
+    std::vector<uint16_t> remap(regions.size(), 0);
+    uint16_t new_id = 1;
+    for (size_t i = 0; i < regions.size(); ++i) {
+        if (regions[i].id == 0) continue;
+        if (regions[i].id & BORDER_REG)
+            remap[i] = regions[i].id;
+        else
+            remap[i] = new_id++;
+    }
+    for (auto& v : src_reg)
+        if (v < (uint16_t)remap.size()) v = remap[v];  // :739 — `remap.len() as u16`
+}
+
+}  // namespace
+
+extern "C" {
+
+// watershed.rs:364-510.  reg: [S] out.  Returns 0 or RCB_ERECAST (-6, "Region ID overflow"); *max_regions = chf.max_regions.
+// Runs build_distance_field first, as the reference does (:375).
+int orc_chf_build_regions(orc_chf* p, int32_t border_size, int32_t min_region_area, int32_t merge_region_area, uint16_t* reg,
+                          uint16_t* max_regions) {
+    Compact& c = *(Compact*)p;
+    const int32_t w = c.width, h = c.height;
+    const size_t S = c.smin.size();
+    build_distance_field(c);
+    std::vector<uint16_t> src_reg(S, 0), src_dist(S, 0);
+    constexpr int LOG_NB_STACKS = 3, NB_STACKS = 1 << LOG_NB_STACKS;
+    std::vector<LevelEntry> lvl[NB_STACKS], stack;
+    uint16_t region_id = 1;
+    uint16_t level = (uint16_t)((c.max_distance + 1) & ~1);
+    const int expand_iters = 8;
+    if (border_size > 0) {
+        const int32_t bw = std::min(w, border_size), bh = std::min(h, border_size);
+        ws_paint_rect(0, bw, 0, h, region_id | BORDER_REG, c, src_reg);
+        region_id++;
+        ws_paint_rect(w - bw, w, 0, h, region_id | BORDER_REG, c, src_reg);
+        region_id++;
+        ws_paint_rect(0, w, 0, bh, region_id | BORDER_REG, c, src_reg);
+        region_id++;
+        ws_paint_rect(0, w, h - bh, h, region_id | BORDER_REG, c, src_reg);
+        region_id++;
+    }
+    int s_id = -1;
+    while (level > 0) {
+        level = level >= 2 ? (uint16_t)(level - 2) : 0;
+        s_id = (s_id + 1) & (NB_STACKS - 1);
+        if (s_id == 0) {
+            ws_sort_cells_by_level(level, c, src_reg, lvl, NB_STACKS, 1);
+        } else {
+            for (const LevelEntry& e : lvl[s_id - 1])  // append_stacks (:122-133)
+                if (e.index != NONE && e.index < S && src_reg[e.index] == 0) lvl[s_id].push_back(e);
+        }
+        ws_expand_regions(expand_iters, level, c, src_reg, src_dist, lvl[s_id], false);
+        for (size_t j = 0; j < lvl[s_id].size(); ++j) {
+            const LevelEntry cur = lvl[s_id][j];
+            if (cur.index < S && src_reg[cur.index] == 0 &&
+                ws_flood_region(cur.x, cur.y, cur.index, level, region_id, c, src_reg, src_dist, stack)) {
+                if (region_id == 0xFFFF) return -6;
+                region_id++;
+            }
+        }
+    }
+    ws_expand_regions(expand_iters * 8, 0, c, src_reg, src_dist, stack, true);
+    if (max_regions) *max_regions = region_id;
+    ws_merge_and_filter(min_region_area, merge_region_area, region_id, c, src_reg);
+    if (reg && S) memcpy(reg, src_reg.data(), 2 * S);
+    return 0;
+}
+
+}  // extern "C"

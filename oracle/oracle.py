@@ -83,6 +83,7 @@ def lib():
         L.orc_tilecache_layer_from_bytes.argtypes = [vp, ctypes.c_uint64, vp, vp]
         L.orc_tilecache_build_compressed_batch.restype = ctypes.c_double
         L.orc_tilecache_build_compressed_batch.argtypes = [vp, vp, ctypes.c_int, vp, vp, vp, f32, f32, ctypes.c_int, vp]
+        L.orc_chf_build_regions.argtypes = [vp, i32, i32, i32, vp, vp]
         L.orc_voxel_serialize_spans.argtypes = [vp, ctypes.c_int, vp]
         L.orc_voxel_deserialize_spans.argtypes = [vp, vp, ctypes.c_uint64]
         L.orc_dynamic_reconstruct_heightfield.argtypes = [vp, vp, ctypes.c_uint64]
@@ -288,6 +289,18 @@ class CompactHeightfield:
     def set_areas(self, areas):
         a = np.ascontiguousarray(areas, dtype=np.uint8)
         lib().orc_chf_set_areas(self._h, _p(a))
+
+    def build_regions(self, border_size=0, min_region_area=8, merge_region_area=20):
+        """CompactHeightfield::build_regions -> watershed::build_regions_watershed (watershed.rs:364-510).
+        Returns (reg u16[S], max_regions); raises OracleError(-6) on region id overflow."""
+        sizes = np.zeros(8, dtype=np.uint64)
+        lib().orc_chf_sizes(self._h, _p(sizes))
+        reg = np.zeros(max(int(sizes[1]), 1), dtype=np.uint16)
+        mr = ctypes.c_uint16(0)
+        st = lib().orc_chf_build_regions(self._h, border_size, min_region_area, merge_region_area, _p(reg), ctypes.byref(mr))
+        if st:
+            raise OracleError(st)
+        return reg[:int(sizes[1])], int(mr.value)
 
     def get_neighbor(self, span, dir8):
         r = lib().orc_chf_get_neighbor(self._h, span, dir8)

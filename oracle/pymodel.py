@@ -857,3 +857,230 @@ def tilecache_layer_from_bytes(data):  # tile_cache_data.rs:128-232, 281-320 -> 
             "hmin": int.from_bytes(data[44:46], "little"), "hmax": int.from_bytes(data[46:48], "little"),
             "width": data[48], "height": data[49], "regons": data[66:66 + rl], "areas": data[66 + rl:66 + rl + al],
             "cons": data[66 + rl + al:66 + rl + al + cl]}
+
+
+# ---- region building: watershed.rs:364-746 (written from the Rust, independently of oracle.cpp) ---------------
+RC_BORDER_REG = 0x8000
+_OX, _OY = (-1, 0, 1, 0), (0, 1, 0, -1)  # compact_heightfield.rs:748-767
+
+
+def _ws_nei(c, x, y, i, d):
+    """neighbour through span.con[dir] as flood/expand use it (watershed.rs:173-176); None if con == 63."""
+    k = c.spans[i]["con"][d]
+    if k == 63:
+        return None
+    ax, ay = x + _OX[d], y + _OY[d]
+    return ax, ay, c.cells[ay * c.width + ax][0] + k
+
+
+def build_regions_watershed(c, border_size, min_region_area, merge_region_area):
+    """-> (src_reg list, max_regions).  `c` is a Compact; build_distance_field is run first (:375)."""
+    w, h, S = c.width, c.height, len(c.spans)
+    c.build_distance_field()
+    src_reg, src_dist = [0] * S, [0] * S
+    NB = 8
+    lvl = [[] for _ in range(NB)]
+    region_id = 1
+    level = (c.max_distance + 1) & ~1
+
+    def paint(minx, maxx, miny, maxy, reg):
+        for y in range(miny, maxy):
+            for x in range(minx, maxx):
+                ci = y * w + x
+                if 0 <= ci < len(c.cells) and c.cells[ci][0] is not None:
+                    for i in range(c.cells[ci][0], c.cells[ci][0] + c.cells[ci][1]):
+                        if c.areas[i] != 0:
+                            src_reg[i] = reg
+
+    if border_size > 0:
+        bw, bh = min(w, border_size), min(h, border_size)
+        for rect in ((0, bw, 0, h), (w - bw, w, 0, h), (0, w, 0, bh), (0, w, h - bh, h)):
+            paint(*rect, region_id | RC_BORDER_REG)
+            region_id += 1
+
+    def sort_cells(start_level):
+        start = start_level >> 1
+        for s in lvl:
+            s.clear()
+        for y in range(h):
+            for x in range(w):
+                idx, cnt = c.cells[y * w + x]
+                if idx is None:
+                    continue
+                for i in range(idx, idx + cnt):
+                    if c.areas[i] == 0 or src_reg[i] != 0:
+                        continue
+                    sid = max(start - (c.dist[i] >> 1), 0)
+                    if sid < NB:
+                        lvl[sid].append([x, y, i])
+
+    def expand(max_iter, level, stack, fill):
+        if fill:
+            stack.clear()
+            for y in range(h):
+                for x in range(w):
+                    idx, cnt = c.cells[y * w + x]
+                    if idx is None:
+                        continue
+                    for i in range(idx, idx + cnt):
+                        if c.dist[i] >= level and src_reg[i] == 0 and c.areas[i] != 0:
+                            stack.append([x, y, i])
+        else:
+            for e in stack:
+                if src_reg[e[2]] != 0:
+                    e[2] = None
+        it = 0
+        while stack:
+            failed, dirty = 0, []
+            for e in stack:
+                x, y, i = e
+                if i is None:
+                    failed += 1
+                    continue
+                r, d2, area = src_reg[i], 0xFFFF, c.areas[i]
+                for d in range(4):
+                    n = _ws_nei(c, x, y, i, d)
+                    if n is None or c.areas[n[2]] != area:
+                        continue
+                    ai = n[2]
+                    if src_reg[ai] > 0 and not (src_reg[ai] & RC_BORDER_REG) and src_dist[ai] + 2 < d2:
+                        r, d2 = src_reg[ai], src_dist[ai] + 2
+                if r != 0:
+                    dirty.append((e, i, r, d2))
+                else:
+                    failed += 1
+            for (e, i, r, d2) in dirty:
+                e[2] = None
+            for (e, i, r, d2) in dirty:
+                src_reg[i], src_dist[i] = r, d2
+            stack[:] = [e for e in stack if e[2] is not None]
+            if failed * 3 >= len(stack) * 2:
+                break
+            if level > 0:
+                it += 1
+                if it >= max_iter:
+                    break
+
+    def flood(x, y, i, level, r):
+        area = c.areas[i]
+        st = [(x, y, i)]
+        src_reg[i], src_dist[i] = r, 0
+        lev = max(level - 2, 0)
+        count = 0
+        while st:
+            cx, cy, ci = st.pop()
+            ar = 0
+            for d in range(4):
+                n = _ws_nei(c, cx, cy, ci, d)
+                if n is None:
+                    continue
+                ax, ay, ai = n
+                if c.areas[ai] != area:
+                    continue
+                nr = src_reg[ai]
+                if nr & RC_BORDER_REG:
+                    continue
+                if nr != 0 and nr != r:
+                    ar = nr
+                    break
+                n2 = _ws_nei(c, ax, ay, ai, (d + 1) & 3)
+                if n2 is None or c.areas[n2[2]] != area:
+                    continue
+                nr2 = src_reg[n2[2]]
+                if nr2 != 0 and nr2 != r:
+                    ar = nr2
+                    break
+            if ar != 0:
+                src_reg[ci] = 0
+                continue
+            count += 1
+            for d in range(4):
+                n = _ws_nei(c, cx, cy, ci, d)
+                if n is None:
+                    continue
+                ax, ay, ai = n
+                if c.areas[ai] != area:
+                    continue
+                if c.dist[ai] >= lev and src_reg[ai] == 0:
+                    src_reg[ai], src_dist[ai] = r, 0
+                    st.append((ax, ay, ai))
+        return count > 0
+
+    s_id = -1
+    while level > 0:
+        level = max(level - 2, 0)
+        s_id = (s_id + 1) & (NB - 1)
+        if s_id == 0:
+            sort_cells(level)
+        else:
+            lvl[s_id].extend([list(e) for e in lvl[s_id - 1] if e[2] is not None and src_reg[e[2]] == 0])
+        expand(8, level, lvl[s_id], False)
+        for e in lvl[s_id]:
+            x, y, i = e
+            if i is not None and src_reg[i] == 0 and flood(x, y, i, level, region_id):
+                if region_id == 0xFFFF:
+                    raise OverflowError("Region ID overflow")
+                region_id += 1
+    expand(64, 0, [], True)
+    max_regions = region_id
+
+    # merge_and_filter_regions (:543-633)
+    regs = [{"n": 0, "id": i, "border": False, "conn": []} for i in range(region_id)]
+    for s in range(S):
+        rid = src_reg[s]
+        if rid == 0 or rid & RC_BORDER_REG:
+            continue
+        reg = regs[rid]
+        reg["n"] += 1
+        for d8 in (7, 5, 3, 1):
+            n = c.get_neighbor(s, d8)
+            if n is None:
+                continue
+            nr = src_reg[n]
+            if nr == rid or nr == 0:
+                continue
+            if nr & RC_BORDER_REG:
+                reg["border"] = True
+                continue
+            if nr not in reg["conn"]:
+                reg["conn"].append(nr)
+    removals = [(i, reg["id"]) for i, reg in enumerate(regs)
+                if reg["id"] != 0 and reg["n"] != 0 and reg["n"] < min_region_area and not reg["border"]]
+    for (i, old) in removals:
+        regs[i]["id"] = 0
+        for s in range(S):
+            if src_reg[s] == old:
+                src_reg[s] = 0
+    if merge_region_area > 0:
+        while True:
+            merges = []
+            for i, reg in enumerate(regs):
+                if reg["id"] == 0 or reg["n"] == 0:
+                    continue
+                if reg["n"] < merge_region_area and not reg["border"]:
+                    best, best_n = 0, 0
+                    for nid in reg["conn"]:
+                        if nid < len(regs) and regs[nid]["id"] != 0 and regs[nid]["n"] > best_n:
+                            best, best_n = regs[nid]["id"], regs[nid]["n"]
+                    if best > 0:
+                        merges.append((i, reg["id"], best, reg["n"]))
+            for (i, old, best, n) in merges:
+                for s in range(S):
+                    if src_reg[s] == old:
+                        src_reg[s] = best
+                regs[i]["id"] = 0
+                for r2 in regs:
+                    if r2["id"] == best:
+                        r2["n"] += n
+                        break
+            if not merges:
+                break
+    remap, new_id = [0] * len(regs), 1
+    for i, reg in enumerate(regs):
+        if reg["id"] != 0:
+            remap[i] = new_id
+            new_id += 1
+    for s in range(S):
+        if src_reg[s] < len(remap):
+            src_reg[s] = remap[src_reg[s]]
+    return src_reg, max_regions
