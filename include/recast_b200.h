@@ -51,6 +51,8 @@ enum {
     RCB_STAGE_COMPACT = 4u, /* compact_heightfield.rs:175-430 build_from_heightfield + build_connections */
     RCB_STAGE_ERODE = 8u,   /* area.rs:73-234 erode_walkable_area (runs before DIST when both set) */
     RCB_STAGE_DIST = 16u,   /* compact_heightfield.rs:514-727 build_distance_field */
+    RCB_STAGE_REGIONS = 0x40u, /* CompactHeightfield::build_regions -> watershed::build_regions_watershed (watershed.rs:364-510)
+                                  with the tile's border_size / min_region_area / merge_region_area; implies COMPACT | DIST */
     /* individual filters (Heightfield::filter_* called one at a time); RCB_STAGE_FILTER = all three */
     RCB_FILTER_LOW_HANGING = 0x100u, /* heightfield.rs:286 */
     RCB_FILTER_LEDGE = 0x200u,       /* heightfield.rs:332 */
@@ -129,6 +131,9 @@ typedef struct rcb_tile_view {
     const uint8_t* conn_dir;        /* [K]  0..7 = NW,N,NE,E,SE,S,SW,W */
     const uint32_t* conn_next;      /* [K]  RCB_NONE = None */
     const uint16_t* dist;           /* [S]  zeros unless DIST ran (compact_heightfield.rs:253) */
+    const uint16_t* reg;            /* [S]  CompactSpan.reg (watershed.rs:505-507); NULL unless REGIONS ran */
+    uint32_t max_regions;           /* chf.max_regions (watershed.rs:491: the id counter BEFORE filtering); 0 unless REGIONS ran */
+    uint32_t _pad;
 } rcb_tile_view;
 
 /* ---- context ------------------------------------------------------------------------------ */

@@ -11,7 +11,7 @@ from .errors import RecastError, InvalidMesh, NavMeshGeneration, CudaError, Pool
 def __getattr__(name):  # lazy: importing the package must not need the native library
     if name in ("RecastBuilder", "Heightfield", "CompactHeightfield", "Context", "BatchResult", "TileVoxels",
                 "erode_walkable_area", "STAGE_RASTER", "STAGE_FILTER", "STAGE_COMPACT", "STAGE_ERODE", "STAGE_DIST",
-                "STAGE_ALL_BUILD", "FILTER_LOW_HANGING", "FILTER_LEDGE", "FILTER_LOW_HEIGHT", "STAGE_READD", "WIRE_VOXEL_TILE",
+                "STAGE_ALL_BUILD", "FILTER_LOW_HANGING", "FILTER_LEDGE", "FILTER_LOW_HEIGHT", "STAGE_READD", "STAGE_REGIONS", "WIRE_VOXEL_TILE",
                 "WIRE_DYNAMIC_TILE"):
         from . import builder
 

@@ -31,6 +31,7 @@ class RcbTileView(ctypes.Structure):
         ("hf_cell_offset", _vp), ("span_min", _vp), ("span_max", _vp), ("span_area", _vp),
         ("cell_index", _vp), ("cell_count_arr", _vp), ("areas", _vp), ("con", _vp), ("first_conn", _vp),
         ("conn_ref", _vp), ("conn_dir", _vp), ("conn_next", _vp), ("dist", _vp),
+        ("reg", _vp), ("max_regions", _u32), ("_pad", _u32),
     ]
 
 

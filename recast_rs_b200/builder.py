@@ -20,6 +20,7 @@ from .errors import check
 STAGE_RASTER, STAGE_FILTER, STAGE_COMPACT, STAGE_ERODE, STAGE_DIST = 1, 2, 4, 8, 16
 FILTER_LOW_HANGING, FILTER_LEDGE, FILTER_LOW_HEIGHT = 0x100, 0x200, 0x400
 STAGE_ALL_BUILD = STAGE_RASTER | STAGE_FILTER | STAGE_COMPACT | STAGE_DIST
+STAGE_REGIONS = 0x40  # CompactHeightfield::build_regions (watershed.rs:364-510); implies COMPACT | DIST
 STAGE_READD = 0x20  # re-insert given spans through Heightfield::add_span (checkpoint.rs:29-60)
 WIRE_VOXEL_TILE, WIRE_DYNAMIC_TILE = 0, 1
 NONE = 0xFFFFFFFF
@@ -61,6 +62,8 @@ class TileVoxels:
     conn_dir: Optional[np.ndarray] = None
     conn_next: Optional[np.ndarray] = None
     dist: Optional[np.ndarray] = None
+    reg: Optional[np.ndarray] = None  # CompactSpan.reg, when REGIONS ran
+    max_regions: int = 0
 
 
 class BatchResult:
@@ -95,6 +98,8 @@ class BatchResult:
             tv.conn_dir = _np_from(v.conn_dir, K, np.uint8)
             tv.conn_next = _np_from(v.conn_next, K, np.uint32)
             tv.dist = _np_from(v.dist, S, np.uint16)
+            if v.reg:
+                tv.reg, tv.max_regions = _np_from(v.reg, S, np.uint16), int(v.max_regions)
         return tv
 
     def span_data_size(self) -> int:
@@ -434,6 +439,16 @@ class CompactHeightfield:
     def build_distance_field(self):  # compact_heightfield.rs:514
         tv = self._rerun(STAGE_DIST)
         self.dist, self.max_distance = tv.dist, tv.max_distance
+
+    def build_regions(self, border_size: int, min_region_area: int, merge_region_area: int):
+        """CompactHeightfield::build_regions (compact_heightfield.rs:770-778 -> watershed.rs:364-510): rebuilds the distance
+        field, then fills `reg` (CompactSpan.reg) and `max_regions`."""
+        hf = self._hf
+        cfg = hf._cfg(border_size=int(border_size), min_region_area=int(min_region_area), merge_region_area=int(merge_region_area))
+        with self._ctx.build_from_spans([cfg], hf.cell_offset, hf.span_min, hf.span_max, hf.span_area, STAGE_COMPACT | STAGE_REGIONS,
+                                        areas_override=self.areas) as r:
+            tv = r.download().tile(0)
+        self.dist, self.max_distance, self.reg, self.max_regions = tv.dist, tv.max_distance, tv.reg, tv.max_regions
 
     def erode_walkable_area(self, radius: int):  # area.rs:73
         self.areas = self._rerun(STAGE_ERODE, radius).areas

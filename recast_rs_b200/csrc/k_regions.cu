@@ -1,0 +1,511 @@
+// k_regions.cu — region building: watershed::build_regions_watershed
+// (crates/recast/src/watershed.rs:364-510), the function behind CompactHeightfield::build_regions
+// (compact_heightfield.rs:770-778) that RecastBuilder::build_mesh runs right after the distance field
+// (lib.rs:83-87).  One CTA per tile, all tiles of the batch in one launch.
+//
+// The reference is a sequential program; what makes a parallel restatement possible, step by step:
+//   sort_cells_by_level / append_stacks (:65-133)  ordered filters of span lists -> block-wide ordered compaction
+//   expand_regions (:245-361)                      gathers from the labels of the PREVIOUS pass (the `dirty_entries`
+//                                                  list is applied after the loop): every entry in parallel
+//   flood_region (:136-242)                        whether a cell stays in the region depends only on labels of
+//                                                  OTHER regions, which do not change during the flood, so the DFS
+//                                                  order is immaterial: breadth-first waves, cells claimed with a
+//                                                  16-bit compare-and-swap.  Seeds are tried in stack order; a seed
+//                                                  that fails now fails for good (other regions only grow), so the
+//                                                  next flood starts from the first entry that is still unlabelled
+//                                                  and passes the test.
+//   merge_and_filter_regions (:543-746)            per-region counts by atomics; the connection LIST of a region only
+//                                                  matters through "first neighbour with the largest span count",
+//                                                  i.e. the maximum of (count, -first occurrence) — one 64-bit
+//                                                  atomicMax per region; merges of a round are decided together and
+//                                                  applied in index order, which a per-region pointer chase reproduces.
+// flood / expand reach neighbours through span.con[] (63 = not connected, even when it is a real offset);
+// merge_and_filter goes through get_neighbor_connection -> the connection list, as the reference does.
+#include "rcb_common.cuh"
+
+namespace {
+
+constexpr int BT = 256;
+constexpr uint32_t NONE32 = 0xFFFFFFFFu;
+constexpr uint32_t BORDER = 0x8000u;
+
+struct BlockSh {
+    uint32_t warp[BT / 32 + 1];
+    uint32_t misc[4];
+};
+
+// exclusive prefix of v over the block; *total = block sum.  Two barriers.
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total, BlockSh& sh) {
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (uint32_t)d) inc += n;
+    }
+    if (lane == 31) sh.warp[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t t = lane < BT / 32 ? sh.warp[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < BT / 32; d <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, t, d);
+            if (lane >= (uint32_t)d) t += n;
+        }
+        if (lane < BT / 32) sh.warp[lane] = t;  // inclusive warp totals
+    }
+    __syncthreads();
+    const uint32_t before = w ? sh.warp[w - 1] : 0;
+    *total = sh.warp[BT / 32 - 1];
+    const uint32_t r = before + inc - v;
+    __syncthreads();  // sh.warp is reused by the next call
+    return r;
+}
+
+__device__ __forceinline__ uint32_t block_sum(uint32_t v, BlockSh& sh) {
+    uint32_t t;
+    block_excl_scan(v, &t, sh);
+    return t;
+}
+
+__device__ __forceinline__ uint32_t block_min(uint32_t v, BlockSh& sh) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = min(v, __shfl_down_sync(0xffffffffu, v, d));
+    if ((threadIdx.x & 31) == 0) sh.warp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t r = sh.warp[0];
+#pragma unroll
+    for (int k = 1; k < BT / 32; ++k) r = min(r, sh.warp[k]);
+    __syncthreads();
+    return r;
+}
+
+// ordered compaction of the indices i in [0, n) with pred(i) to emit(position, i); positions start at out_base.
+template <class Pred, class Emit>
+__device__ uint32_t block_compact(uint32_t n, uint32_t out_base, BlockSh& sh, Pred pred, Emit emit) {
+    for (uint32_t c0 = 0; c0 < n; c0 += BT) {
+        const uint32_t i = c0 + threadIdx.x;
+        uint32_t payload = 0;
+        const bool p = i < n && pred(i, payload);
+        uint32_t total;
+        const uint32_t ex = block_excl_scan(p ? 1u : 0u, &total, sh);
+        if (p) emit(out_base + ex, payload);
+        out_base += total;
+    }
+    return out_base;
+}
+
+struct Tile {
+    uint32_t S, C;
+    int W, H;
+    const uint32_t* cidx;
+    const uint32_t* ccnt;
+    const uint8_t* areas;
+    const uint16_t* con;
+    const uint16_t* dist;
+    const uint32_t* first_conn;
+    const uint32_t* conn_ref;
+    const uint8_t* conn_dir;
+    const uint32_t* conn_next;
+    uint16_t* reg;    // src_reg, also the result
+    uint16_t* sdist;  // src_dist
+    uint16_t* reg0;   // labels before merge_and_filter (its connection lists are built once, from these)
+    uint32_t* nb[4];  // con-based neighbour (tile-relative span) or NONE32
+    uint32_t* stack[8];
+    uint32_t* bufA;
+    uint32_t* bufB;
+};
+
+// does cell ci stay in region r?  (watershed.rs:167-216) — false when a 4-neighbour, or the neighbour reached from it by
+// turning clockwise, of the same area carries another region.
+__device__ __forceinline__ bool ws_kept(const Tile& t, uint32_t ci, uint32_t r, uint32_t area) {
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        const uint32_t ai = t.nb[d][ci];
+        if (ai == NONE32) continue;
+        if (t.areas[ai] != area) continue;
+        const uint32_t nr = *(volatile uint16_t*)&t.reg[ai];
+        if (nr & BORDER) continue;  // skips the diagonal too
+        if (nr != 0 && nr != r) return false;
+        const uint32_t ai2 = t.nb[(d + 1) & 3][ai];
+        if (ai2 == NONE32) continue;
+        if (t.areas[ai2] != area) continue;
+        const uint32_t nr2 = *(volatile uint16_t*)&t.reg[ai2];
+        if (nr2 != 0 && nr2 != r) return false;  // no border test here (:205-210)
+    }
+    return true;
+}
+
+__device__ __forceinline__ uint32_t cas16(uint16_t* p, uint16_t cmp, uint16_t val) {
+    return (uint32_t)atomicCAS((unsigned short*)p, (unsigned short)cmp, (unsigned short)val);
+}
+
+// watershed.rs:245-361.  `len` is the stack length (uniform); returns the new length.
+__device__ uint32_t ws_expand(const Tile& t, int max_iter, uint32_t level, uint32_t* stack, uint32_t len, bool fill, BlockSh& sh) {
+    if (fill) {
+        len = block_compact(t.S, 0, sh, [&](uint32_t s, uint32_t& pl) { pl = s; return t.dist[s] >= level && t.reg[s] == 0 && t.areas[s] != 0; },
+                            [&](uint32_t pos, uint32_t s) { stack[pos] = s; });
+    } else {
+        for (uint32_t j = threadIdx.x; j < len; j += BT) {
+            const uint32_t v = stack[j];
+            if (v != NONE32 && t.reg[v] != 0) stack[j] = NONE32;
+        }
+    }
+    __syncthreads();
+    int iter = 0;
+    while (len > 0) {
+        uint32_t failed = 0;
+        for (uint32_t j = threadIdx.x; j < len; j += BT) {
+            const uint32_t i = stack[j];
+            uint32_t res = 0;
+            if (i == NONE32) {
+                failed++;
+            } else {
+                uint32_t r = t.reg[i], d2 = 0xffffu;
+                const uint32_t area = t.areas[i];
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    const uint32_t ai = t.nb[d][i];
+                    if (ai == NONE32) continue;
+                    if (t.areas[ai] != area) continue;
+                    const uint32_t ra = t.reg[ai];
+                    const uint32_t da = (uint32_t)(uint16_t)(t.sdist[ai] + 2);
+                    if (ra > 0 && (ra & BORDER) == 0 && da < d2) {
+                        r = ra;
+                        d2 = da;
+                    }
+                }
+                if (r != 0)
+                    res = r | (d2 << 16);
+                else
+                    failed++;
+            }
+            t.bufA[j] = res;
+        }
+        __syncthreads();  // every gather saw the labels of the previous pass
+        for (uint32_t j = threadIdx.x; j < len; j += BT) {
+            const uint32_t res = t.bufA[j];
+            if (res != 0) {
+                const uint32_t i = stack[j];
+                t.reg[i] = (uint16_t)(res & 0xffffu);
+                t.sdist[i] = (uint16_t)(res >> 16);
+                stack[j] = NONE32;
+            }
+        }
+        __syncthreads();
+        const uint32_t nfailed = block_sum(failed, sh);
+        len = block_compact(len, 0, sh, [&](uint32_t j, uint32_t& pl) { pl = stack[j]; return pl != NONE32; },
+                            [&](uint32_t pos, uint32_t v) { stack[pos] = v; });
+        __syncthreads();
+        if ((unsigned long long)nfailed * 3ull >= (unsigned long long)len * 2ull) break;  // :350, length AFTER the retain
+        if (level > 0) {
+            if (++iter >= max_iter) break;
+        }
+    }
+    return len;
+}
+
+__device__ __forceinline__ uint32_t list_neighbor(const Tile& t, uint32_t s, uint32_t d8) {  // compact_heightfield.rs:495-510
+    uint32_t c = t.first_conn[s];
+    while (c != NONE32) {
+        if (t.conn_dir[c] == d8) return t.conn_ref[c];
+        c = t.conn_next[c];
+    }
+    return NONE32;
+}
+
+__global__ void __launch_bounds__(BT) k_regions(RegionArgs a) {
+    __shared__ BlockSh sh;
+    __shared__ uint32_t sh_len[8];
+    __shared__ uint32_t sh_next;
+    const uint32_t tile = blockIdx.x;
+    const TileDesc& td = a.tiles[tile];
+    const TileInfo ti = a.tinfo[tile];
+    Tile t;
+    t.S = ti.span_count;
+    t.W = td.width;
+    t.H = td.height;
+    t.C = (uint32_t)(t.W * t.H);
+    const size_t sb = ti.span_base;
+    t.cidx = a.cell_index + td.cell_base;
+    t.ccnt = a.cell_count + td.cell_base;
+    t.areas = a.areas + sb;
+    t.con = a.con + 4 * sb;
+    t.dist = a.dist + sb;
+    t.first_conn = a.first_conn + sb;
+    t.conn_ref = a.conn_ref + ti.conn_base;
+    t.conn_dir = a.conn_dir + ti.conn_base;
+    t.conn_next = a.conn_next + ti.conn_base;
+    t.reg = a.reg + sb;
+    t.sdist = a.src_dist + sb;
+    t.reg0 = a.reg0 + sb;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) t.nb[d] = a.nb4 + (size_t)d * a.Stot + sb;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t.stack[k] = a.stacks + (size_t)k * a.Stot + sb;
+    t.bufA = a.bufA + sb;
+    t.bufB = a.bufB + sb;
+    const uint32_t S = t.S;
+    const int W = t.W, H = t.H;
+
+    // ---- 0. working arrays; neighbours through con[] -----------------------------------------------------
+    for (uint32_t s = threadIdx.x; s < S; s += BT) t.reg[s] = 0, t.sdist[s] = 0;
+    for (uint32_t c = threadIdx.x; c < t.C; c += BT) {
+        const uint32_t b = t.cidx[c];
+        if (b == NONE32) continue;
+        const uint32_t n = t.ccnt[c];
+        const int y = (int)(c / (uint32_t)W), x = (int)c - y * W;
+        for (uint32_t s = b; s < b + n; ++s) {
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const uint32_t k = t.con[4 * (size_t)s + d];
+                const int ox = d == 0 ? -1 : (d == 2 ? 1 : 0), oy = d == 1 ? 1 : (d == 3 ? -1 : 0);  // compact_heightfield.rs:748-767
+                t.nb[d][s] = k == 63u ? NONE32 : t.cidx[(uint32_t)((y + oy) * W + (x + ox))] + k;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- border regions (:393-426) ----------------------------------------------------------------------------
+    uint32_t region_id = 1;
+    if (td.aux0 > 0) {
+        const int bw = min(W, td.aux0), bh = min(H, td.aux0);
+        const int rx0[4] = {0, W - bw, 0, 0}, rx1[4] = {bw, W, W, W}, ry0[4] = {0, 0, 0, H - bh}, ry1[4] = {H, H, bh, H};
+        for (int k = 0; k < 4; ++k) {
+            for (uint32_t c = threadIdx.x; c < t.C; c += BT) {
+                const int y = (int)(c / (uint32_t)W), x = (int)c - y * W;
+                if (x < rx0[k] || x >= rx1[k] || y < ry0[k] || y >= ry1[k]) continue;
+                const uint32_t b = t.cidx[c];
+                if (b == NONE32) continue;
+                for (uint32_t s = b; s < b + t.ccnt[c]; ++s)
+                    if (t.areas[s] != 0) t.reg[s] = (uint16_t)(region_id | BORDER);
+            }
+            region_id++;
+            __syncthreads();
+        }
+    }
+
+    // ---- watershed levels (:431-477) ---------------------------------------------------------------------------
+    uint32_t level = ((uint32_t)ti.max_distance + 1u) & ~1u;
+    int s_id = -1;
+    bool overflow = false;
+    while (level > 0 && !overflow) {
+        level = level >= 2 ? level - 2 : 0;
+        s_id = (s_id + 1) & 7;
+        uint32_t len;
+        if (s_id == 0) {  // sort_cells_by_level (:65-119), log_levels_per_stack = 1
+            const uint32_t start = level >> 1;
+            for (uint32_t k = 0; k < 8; ++k) {
+                const uint32_t n = block_compact(S, 0, sh,
+                                                 [&](uint32_t s, uint32_t& pl) {
+                                                     pl = s;
+                                                     if (t.areas[s] == 0 || t.reg[s] != 0) return false;
+                                                     const uint32_t lv = (uint32_t)t.dist[s] >> 1;
+                                                     return (start > lv ? start - lv : 0u) == k;
+                                                 },
+                                                 [&](uint32_t pos, uint32_t s) { t.stack[k][pos] = s; });
+                if (threadIdx.x == 0) sh_len[k] = n;
+            }
+            __syncthreads();
+            len = sh_len[0];
+        } else {  // append_stacks (:122-133)
+            const uint32_t* src = t.stack[s_id - 1];
+            uint32_t* dst = t.stack[s_id];
+            len = block_compact(sh_len[s_id - 1], sh_len[s_id], sh,
+                                [&](uint32_t j, uint32_t& pl) { pl = src[j]; return pl != NONE32 && t.reg[pl] == 0; },
+                                [&](uint32_t pos, uint32_t v) { dst[pos] = v; });
+            __syncthreads();
+        }
+        uint32_t* stack = t.stack[s_id];
+        len = ws_expand(t, 8, level, stack, len, false, sh);
+        if (threadIdx.x == 0) sh_len[s_id] = len;
+        __syncthreads();
+        // new regions (:454-476): entries in order; the first one that is unlabelled and survives its own test floods
+        const uint32_t lev = level >= 2 ? level - 2 : 0;
+        uint32_t cursor = 0;
+        for (;;) {
+            uint32_t mine = NONE32;
+            for (uint32_t j = cursor + threadIdx.x; j < len; j += BT) {
+                const uint32_t v = stack[j];
+                if (t.reg[v] == 0 && ws_kept(t, v, region_id, t.areas[v])) {
+                    mine = j;
+                    break;
+                }
+            }
+            const uint32_t jmin = block_min(mine, sh);
+            if (jmin == NONE32) break;
+            const uint32_t seed = stack[jmin];
+            const uint32_t area = t.areas[seed];
+            if (threadIdx.x == 0) {
+                t.reg[seed] = (uint16_t)region_id;
+                t.sdist[seed] = 0;
+                t.bufA[0] = seed;
+            }
+            uint32_t ncur = 1;
+            uint32_t* cur = t.bufA;
+            uint32_t* nxt = t.bufB;
+            while (ncur > 0) {
+                if (threadIdx.x == 0) sh_next = 0;
+                __syncthreads();
+                for (uint32_t k = threadIdx.x; k < ncur; k += BT) {
+                    const uint32_t ci = cur[k];
+                    if (!ws_kept(t, ci, region_id, area)) {
+                        t.reg[ci] = 0;  // :218-221
+                        continue;
+                    }
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {
+                        const uint32_t ai = t.nb[d][ci];
+                        if (ai == NONE32) continue;
+                        if (t.areas[ai] != area) continue;
+                        if (t.dist[ai] >= lev && cas16(&t.reg[ai], 0, (uint16_t)region_id) == 0) {
+                            t.sdist[ai] = 0;
+                            nxt[atomicAdd(&sh_next, 1u)] = ai;
+                        }
+                    }
+                }
+                __syncthreads();
+                ncur = sh_next;
+                uint32_t* tmp = cur;
+                cur = nxt;
+                nxt = tmp;
+                __syncthreads();
+            }
+            if (region_id == 0xFFFFu) {  // :469-471
+                overflow = true;
+                break;
+            }
+            region_id++;
+            cursor = jmin + 1;
+        }
+    }
+    if (overflow) {
+        if (threadIdx.x == 0) atomicMin(a.err, tile);
+        return;
+    }
+    // ---- final expansion (:480-488) ----------------------------------------------------------------------------
+    ws_expand(t, 64, 0, t.stack[0], 0, true, sh);
+    if (threadIdx.x == 0) a.tinfo[tile].max_regions = region_id;  // :491, before filtering
+
+    // ---- merge_and_filter_regions (:543-633) ----------------------------------------------------------------
+    const uint32_t R = region_id;
+    const size_t rb = sb + 2 * (size_t)tile;  // R <= S + 1 entries per tile
+    int32_t* cnt = a.r_cnt + rb;
+    int32_t* cadd = a.r_cadd + rb;
+    uint16_t* alive = a.r_alive + rb;
+    uint8_t* border = a.r_border + rb;
+    unsigned long long* best = a.r_best + rb;
+    uint16_t* target = a.r_target + rb;
+    uint16_t* fin = a.r_fin + rb;
+    const int32_t min_area = td.aux1, merge_area = td.aux2;
+    for (uint32_t i = threadIdx.x; i < R; i += BT) cnt[i] = 0, alive[i] = (uint16_t)i, border[i] = 0;
+    for (uint32_t s = threadIdx.x; s < S; s += BT) t.reg0[s] = t.reg[s];
+    __syncthreads();
+    for (uint32_t s = threadIdx.x; s < S; s += BT) {
+        const uint32_t rid = t.reg0[s];
+        if (rid == 0 || (rid & BORDER)) continue;
+        atomicAdd(&cnt[rid], 1);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const uint32_t n = list_neighbor(t, s, 7u - 2u * (uint32_t)d);  // W, S, E, N (compact_heightfield.rs:737-743)
+            if (n == NONE32) continue;
+            const uint32_t nr = t.reg0[n];
+            if (nr & BORDER) border[rid] = 1;
+        }
+    }
+    __syncthreads();
+    // small regions (:598-622)
+    for (uint32_t i = threadIdx.x; i < R; i += BT) {
+        uint16_t f = (uint16_t)i;
+        if (alive[i] != 0 && cnt[i] != 0 && cnt[i] < min_area && !border[i]) {
+            alive[i] = 0;
+            f = 0;
+        }
+        fin[i] = f;
+    }
+    __syncthreads();
+    for (uint32_t s = threadIdx.x; s < S; s += BT) {
+        const uint32_t v = t.reg[s];
+        if (v < R) t.reg[s] = fin[v];
+    }
+    __syncthreads();
+    // merges (:636-716): a round's decisions are taken from the state before the round
+    if (merge_area > 0) {
+        for (;;) {
+            for (uint32_t i = threadIdx.x; i < R; i += BT) best[i] = 0ull, target[i] = 0, cadd[i] = 0;
+            __syncthreads();
+            for (int pass = 0; pass < 2; ++pass) {
+                for (uint32_t s = threadIdx.x; s < S; s += BT) {
+                    const uint32_t rid = t.reg0[s];
+                    if (rid == 0 || (rid & BORDER)) continue;
+                    if (!(alive[rid] != 0 && cnt[rid] != 0 && cnt[rid] < merge_area && !border[rid])) continue;
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {
+                        const uint32_t n = list_neighbor(t, s, 7u - 2u * (uint32_t)d);
+                        if (n == NONE32) continue;
+                        const uint32_t nr = t.reg0[n];
+                        if (nr == rid || nr == 0 || (nr & BORDER) || nr >= R) continue;
+                        if (alive[nr] == 0 || cnt[nr] <= 0) continue;
+                        // first neighbour in list order with the largest span count == max of (count, -first occurrence)
+                        const unsigned long long key = ((unsigned long long)(uint32_t)cnt[nr] << 32) | (uint32_t)~(s * 4u + (uint32_t)d);
+                        if (pass == 0)
+                            atomicMax(&best[rid], key);
+                        else if (key == best[rid])
+                            target[rid] = (uint16_t)nr;
+                    }
+                }
+                __syncthreads();
+            }
+            uint32_t nm = 0;
+            for (uint32_t i = threadIdx.x; i < R; i += BT) nm += target[i] != 0;
+            if (block_sum(nm, sh) == 0) break;
+            // applied in index order: a label follows the merges that come after the one that produced it
+            for (uint32_t v = threadIdx.x; v < R; v += BT) {
+                uint32_t cur = v;
+                int last = -1;
+                while (target[cur] != 0 && (int)cur > last) {
+                    last = (int)cur;
+                    cur = target[cur];
+                }
+                fin[v] = (uint16_t)cur;
+                const uint32_t b = target[v];
+                if (b != 0 && !(target[b] != 0 && b < v)) atomicAdd(&cadd[b], cnt[v]);  // the target is still a region (:700-706)
+            }
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < R; i += BT) {
+                if (target[i] != 0) alive[i] = 0;
+                cnt[i] += cadd[i];
+            }
+            for (uint32_t s = threadIdx.x; s < S; s += BT) {
+                const uint32_t v = t.reg[s];
+                if (v < R) t.reg[s] = fin[v];
+            }
+            __syncthreads();
+        }
+    }
+    // compact ids (:719-746)
+    {
+        uint32_t base = 1;
+        for (uint32_t c0 = 0; c0 < R; c0 += BT) {
+            const uint32_t i = c0 + threadIdx.x;
+            const bool live = i < R && alive[i] != 0;
+            uint32_t total;
+            const uint32_t ex = block_excl_scan(live ? 1u : 0u, &total, sh);
+            if (i < R) fin[i] = live ? (uint16_t)(base + ex) : (uint16_t)0;
+            base += total;
+        }
+        __syncthreads();
+        for (uint32_t s = threadIdx.x; s < S; s += BT) {
+            const uint32_t v = t.reg[s];
+            if (v < R) t.reg[s] = fin[v];
+        }
+    }
+}
+
+}  // namespace
+
+void launch_regions(const RegionArgs& a, int ntiles, cudaStream_t s) {
+    if (ntiles == 0) return;
+    KScope _k("k_regions", s);
+    k_regions<<<ntiles, BT, 0, s>>>(a);
+}

@@ -52,7 +52,7 @@ struct Arena {
 };
 
 struct ArenaLayout {  // byte offsets inside arena A (cells + spans) and arena B (connections)
-    size_t tinfo, hf_cell_offset, cell_index, cell_count, span_min, span_max, span_area, areas, con, first_conn, dist;
+    size_t tinfo, hf_cell_offset, cell_index, cell_count, span_min, span_max, span_area, areas, con, first_conn, dist, reg;
     size_t bytesA;
     size_t conn_ref, conn_dir, conn_next;
     size_t bytesB;
@@ -75,7 +75,7 @@ struct rcb_ctx {
     DevBuf d_counters, d_cell_cnt, d_frag_off, d_frag_tmp, d_fs_tri, d_fs_mm, d_fs_area, d_scan_tmp, d_hf_off, d_conn_cnt,
         d_conn_off, d_nei16, d_t16a, d_t16b, d_t16c, d_t8a, d_t8b, d_item_cnt, d_item_off, d_items, d_tile_ub, d_tile_base, d_tile_cursor,
         d_tile_frags, d_ts_mm, d_ts_area, d_celloff_tmp, d_lookback, d_tc_regons, d_tc_areas, d_tc_obs, d_fidx, d_wire, d_wire_off,
-        d_wire_pos, d_wire_inoff, d_wire_err, d_tc_raw, d_tc_parsed;
+        d_wire_pos, d_wire_inoff, d_wire_err, d_tc_raw, d_tc_parsed, d_rg_a, d_rg_b;
     uint32_t clip_flags = 1;    // RCB_CLIP_FLAGS (A/B runs): bit0 min-x skip test in the clipper
     bool phase_timers = false;  // RCB_PHASE_TIMERS=1: per-phase cycle sums of the tile kernels on stderr
     bool force_global = false;  // RCB_FORCE_GLOBAL=1: never use the tile-resident back end (k_tile.cu)
@@ -325,6 +325,7 @@ void make_layout(ArenaLayout& l, int ntiles, uint64_t C, uint64_t S, uint32_t st
     l.con = put(compact ? 8 * S : 0);
     l.first_conn = put(compact ? 4 * S : 0);
     l.dist = put(compact ? 2 * S : 0);
+    l.reg = put((stage_mask & RCB_STAGE_REGIONS) ? 2 * S : 0);
     l.bytesA = o;
 }
 void make_layout_conn(ArenaLayout& l, uint64_t K) {
@@ -456,6 +457,66 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
     return RCB_OK;
 }
 
+// CompactHeightfield::build_regions on a finished result (both back ends): k_regions.cu.
+int build_regions_stage(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, int ntiles, uint64_t S) {
+    if (ntiles == 0) return RCB_OK;
+    cudaStream_t st = ctx->stream;
+    char* A = res->devA.p;
+    char* B = res->devB.p;
+    const size_t Sp = (size_t)S + 2 * (size_t)ntiles + 8;  // per-region tables: span_count + 2 entries per tile
+    size_t o = 0;
+    auto put = [&o](size_t bytes) {
+        size_t r = o;
+        o = align_up(o + bytes);
+        return r;
+    };
+    const size_t o_sdist = put(2 * S + 16), o_reg0 = put(2 * S + 16), o_nb4 = put(16 * S + 16), o_stacks = put(32 * S + 16), o_a = put(4 * S + 16),
+                 o_b = put(4 * S + 16);
+    CU(ctx->d_rg_a.ensure(o + 256));
+    o = 0;
+    const size_t o_cnt = put(4 * Sp), o_cadd = put(4 * Sp), o_alive = put(2 * Sp), o_border = put(Sp), o_best = put(8 * Sp), o_target = put(2 * Sp),
+                 o_fin = put(2 * Sp), o_err = put(16);
+    CU(ctx->d_rg_b.ensure(o + 256));
+    char* a = (char*)ctx->d_rg_a.p;
+    char* b = (char*)ctx->d_rg_b.p;
+    CU(cudaMemsetAsync(b + o_err, 0xff, 16, st));
+    RegionArgs ra{};
+    ra.tiles = d_tiles;
+    ra.tinfo = (TileInfo*)(A + res->lay.tinfo);
+    ra.cell_index = (const uint32_t*)(A + res->lay.cell_index);
+    ra.cell_count = (const uint32_t*)(A + res->lay.cell_count);
+    ra.areas = (const uint8_t*)(A + res->lay.areas);
+    ra.con = (const uint16_t*)(A + res->lay.con);
+    ra.dist = (const uint16_t*)(A + res->lay.dist);
+    ra.first_conn = (const uint32_t*)(A + res->lay.first_conn);
+    ra.conn_ref = (const uint32_t*)(B + res->lay.conn_ref);
+    ra.conn_dir = (const uint8_t*)(B + res->lay.conn_dir);
+    ra.conn_next = (const uint32_t*)(B + res->lay.conn_next);
+    ra.reg = (uint16_t*)(A + res->lay.reg);
+    ra.Stot = (size_t)S;
+    ra.src_dist = (uint16_t*)(a + o_sdist);
+    ra.reg0 = (uint16_t*)(a + o_reg0);
+    ra.nb4 = (uint32_t*)(a + o_nb4);
+    ra.stacks = (uint32_t*)(a + o_stacks);
+    ra.bufA = (uint32_t*)(a + o_a);
+    ra.bufB = (uint32_t*)(a + o_b);
+    ra.r_cnt = (int32_t*)(b + o_cnt);
+    ra.r_cadd = (int32_t*)(b + o_cadd);
+    ra.r_alive = (uint16_t*)(b + o_alive);
+    ra.r_border = (uint8_t*)(b + o_border);
+    ra.r_best = (unsigned long long*)(b + o_best);
+    ra.r_target = (uint16_t*)(b + o_target);
+    ra.r_fin = (uint16_t*)(b + o_fin);
+    ra.err = (unsigned int*)(b + o_err);
+    launch_regions(ra, ntiles, st);
+    CU(cudaMemcpyAsync(&ctx->h_counters[7], b + o_err, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    const uint32_t bad = (uint32_t)ctx->h_counters[7];
+    if (bad != 0xffffffffu) return fail(ctx, RCB_ERECAST, "tile %u: Region ID overflow", bad);
+    return RCB_OK;
+}
+
 int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stage_mask, int erode_radius,
                  const Source& src, rcb_result** out) {
     if (!ctx || !out || (ntiles > 0 && !cfgs) || ntiles < 0) return fail(ctx, RCB_EARG, "null argument");
@@ -463,6 +524,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     ProfInstall prof_install(ctx);
+    if (stage_mask & RCB_STAGE_REGIONS) stage_mask |= RCB_STAGE_COMPACT | RCB_STAGE_DIST;  // watershed.rs:375 builds the distance field itself
     if ((stage_mask & (RCB_STAGE_ERODE | RCB_STAGE_DIST)) && !(stage_mask & RCB_STAGE_COMPACT))
         return fail(ctx, RCB_EARG, "ERODE/DIST need RCB_STAGE_COMPACT");
     uint32_t fmask = 0;
@@ -498,6 +560,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         t.walkable_height = as_i16(c.walkable_height);
         t.walkable_climb = as_i16(c.walkable_climb);
         t.neg_climb = (int32_t)(int16_t)(-(int16_t)t.walkable_climb);
+        t.aux0 = c.border_size, t.aux1 = c.min_region_area, t.aux2 = c.merge_region_area;  // k_regions
         const uint64_t cells = (uint64_t)c.width * (uint64_t)c.height;
         if (cells > 0x7fffffffull || Ctot + cells + ntiles >= 0xffffffffull) {
             delete res;
@@ -758,6 +821,10 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             res->tile_mode = true;
             res->Kcap = Kcap;
             CUB(cudaGetLastError());
+            if (stage_mask & RCB_STAGE_REGIONS) {
+                const int r = build_regions_stage(ctx, res, d_tiles, ntiles, S);
+                if (r) return bail(r);
+            }
             *out = res;
             return RCB_OK;
         }
@@ -949,6 +1016,10 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         if (r) return bail(r);
     }
     CUB(cudaGetLastError());
+    if (stage_mask & RCB_STAGE_REGIONS) {
+        const int r = build_regions_stage(ctx, res, d_tiles, ntiles, S);
+        if (r) return bail(r);
+    }
     *out = res;
     return RCB_OK;
 #undef CUB
@@ -1012,7 +1083,7 @@ void rcb_destroy(rcb_ctx* ctx) {
                       &ctx->d_t16a, &ctx->d_t16b, &ctx->d_t16c, &ctx->d_t8a, &ctx->d_t8b, &ctx->d_item_cnt, &ctx->d_item_off, &ctx->d_items, &ctx->d_tile_ub, &ctx->d_tile_base,
                       &ctx->d_tile_cursor, &ctx->d_tile_frags, &ctx->d_ts_mm, &ctx->d_ts_area, &ctx->d_celloff_tmp, &ctx->d_lookback, &ctx->d_tc_regons, &ctx->d_tc_areas,
                       &ctx->d_tc_obs, &ctx->d_fidx, &ctx->d_wire, &ctx->d_wire_off, &ctx->d_wire_pos, &ctx->d_wire_inoff, &ctx->d_wire_err,
-                      &ctx->d_tc_raw, &ctx->d_tc_parsed};
+                      &ctx->d_tc_raw, &ctx->d_tc_parsed, &ctx->d_rg_a, &ctx->d_rg_b};
     for (auto* b : bufs) b->release();
     for (auto& a : ctx->free_dev) cudaFree(a.p);
     for (auto& a : ctx->free_host) cudaFreeHost(a.p);
@@ -1733,6 +1804,10 @@ static int fill_view(const rcb_result* res, int tile, rcb_tile_view* v, const ch
         v->conn_ref = (const uint32_t*)(B + l.conn_ref) + ti.conn_base;
         v->conn_dir = (const uint8_t*)(B + l.conn_dir) + ti.conn_base;
         v->conn_next = (const uint32_t*)(B + l.conn_next) + ti.conn_base;
+        if (res->stage_mask & RCB_STAGE_REGIONS) {
+            v->reg = (const uint16_t*)(A + l.reg) + ti.span_base;
+            v->max_regions = ti.max_regions;
+        }
     }
     return RCB_OK;
 }

@@ -44,6 +44,7 @@ struct TileInfo {
     uint32_t max_height;    // u16 value
     uint32_t max_distance;  // u16 value
     uint32_t status;
+    uint32_t max_regions;   // chf.max_regions (watershed.rs:491), 0 unless REGIONS ran
 };
 
 // Uniform locator grid over the tile AABBs: maps a triangle AABB to candidate tiles.
@@ -205,6 +206,40 @@ struct TileMap {
 #define RCB_TILE_OF_BLOCK() (blockIdx.z * gridDim.y + blockIdx.y)
 #define RCB_CELL_OF_THREAD() (blockIdx.x * blockDim.x + threadIdx.x)
 #endif
+
+// k_regions.cu — watershed region building.  All span arrays are batch-wide (indexed by the tile's span_base);
+// tiles[].aux0/1/2 carry border_size / min_region_area / merge_region_area.
+struct RegionArgs {
+    const TileDesc* tiles;
+    TileInfo* tinfo;
+    const uint32_t* cell_index;
+    const uint32_t* cell_count;
+    const uint8_t* areas;
+    const uint16_t* con;
+    const uint16_t* dist;
+    const uint32_t* first_conn;
+    const uint32_t* conn_ref;
+    const uint8_t* conn_dir;
+    const uint32_t* conn_next;
+    uint16_t* reg;  // out
+    size_t Stot;
+    // scratch
+    uint16_t* src_dist;
+    uint16_t* reg0;
+    uint32_t* nb4;     // [4][Stot]
+    uint32_t* stacks;  // [8][Stot]
+    uint32_t* bufA;
+    uint32_t* bufB;
+    int32_t* r_cnt;    // per-region tables: tile t owns entries [span_base + 2t, +span_count + 2)
+    int32_t* r_cadd;
+    uint16_t* r_alive;
+    uint8_t* r_border;
+    unsigned long long* r_best;
+    uint16_t* r_target;
+    uint16_t* r_fin;
+    unsigned int* err;  // first tile whose region ids overflowed (init 0xffffffff)
+};
+void launch_regions(const RegionArgs& a, int ntiles, cudaStream_t s);
 
 // k_lz4.cu — tile-cache front half
 struct RcbTcParsed {  // one layer after TileCacheLayer::from_bytes; status = the rcb_status of the first failing check

@@ -19,6 +19,7 @@ pub const RCB_STAGE_COMPACT: u32 = 4;
 pub const RCB_STAGE_ERODE: u32 = 8;
 pub const RCB_STAGE_DIST: u32 = 16;
 pub const RCB_STAGE_READD: u32 = 0x20;
+pub const RCB_STAGE_REGIONS: u32 = 0x40;
 pub const RCB_WIRE_VOXEL_TILE: c_int = 0;
 pub const RCB_WIRE_DYNAMIC_TILE: c_int = 1;
 pub const RCB_FILTER_LOW_HANGING: u32 = 0x100;
@@ -87,6 +88,9 @@ pub struct rcb_tile_view {
     pub conn_dir: *const u8,
     pub conn_next: *const u32,
     pub dist: *const u16,
+    pub reg: *const u16,
+    pub max_regions: u32,
+    pub _pad: u32,
 }
 
 #[repr(C)]
