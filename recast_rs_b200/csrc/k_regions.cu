@@ -25,7 +25,7 @@
 
 namespace {
 
-constexpr int BT = 256;
+constexpr int BT = 64;
 constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 constexpr uint32_t BORDER = 0x8000u;
 
@@ -81,15 +81,28 @@ __device__ __forceinline__ uint32_t block_min(uint32_t v, BlockSh& sh) {
 }
 
 // ordered compaction of the indices i in [0, n) with pred(i) to emit(position, i); positions start at out_base.
+// Source and destination must not alias.  Every thread owns a contiguous run of up to 64 indices (one scan per BT*64 indices instead of one per BT: the
+// kernel's time is the number of barrier-separated phases times a memory round trip).
 template <class Pred, class Emit>
 __device__ uint32_t block_compact(uint32_t n, uint32_t out_base, BlockSh& sh, Pred pred, Emit emit) {
-    for (uint32_t c0 = 0; c0 < n; c0 += BT) {
-        const uint32_t i = c0 + threadIdx.x;
-        uint32_t payload = 0;
-        const bool p = i < n && pred(i, payload);
+    for (uint32_t c0 = 0; c0 < n; c0 += BT * 64u) {
+        const uint32_t m = min(n - c0, (uint32_t)BT * 64u);
+        const uint32_t per = (m + BT - 1) / BT;  // <= 64
+        const uint32_t lo = c0 + threadIdx.x * per, hi = min(lo + per, c0 + m);
+        unsigned long long mask = 0;
+        for (uint32_t i = lo; i < hi; ++i) {
+            uint32_t payload;
+            if (pred(i, payload)) mask |= 1ull << (i - lo);
+        }
         uint32_t total;
-        const uint32_t ex = block_excl_scan(p ? 1u : 0u, &total, sh);
-        if (p) emit(out_base + ex, payload);
+        uint32_t pos = out_base + block_excl_scan((uint32_t)__popcll(mask), &total, sh);
+        while (mask) {
+            const uint32_t k = (uint32_t)__ffsll((long long)mask) - 1u;
+            mask &= mask - 1;
+            uint32_t payload = 0;
+            pred(lo + k, payload);
+            emit(pos++, payload);
+        }
         out_base += total;
     }
     return out_base;
@@ -110,24 +123,34 @@ struct Tile {
     uint16_t* reg;    // src_reg, also the result
     uint16_t* sdist;  // src_dist
     uint16_t* reg0;   // labels before merge_and_filter (its connection lists are built once, from these)
-    uint32_t* nb[4];  // con-based neighbour (tile-relative span) or NONE32
+    uint32_t* nb[4];  // con-based neighbour (tile-relative span) or NONE32 — global-memory mode
+    uint16_t* nb16;   // the same as u16[4][S] in shared memory (0xFFFF = none) — shared-memory mode, else nullptr
+    bool walk_lists;  // some cell holds 64+ spans: con == 63 may hide a real neighbour (merge_and_filter follows the list)
     uint32_t* stack[8];
     uint32_t* bufA;
     uint32_t* bufB;
 };
+
+__device__ __forceinline__ uint32_t nbr(const Tile& t, int d, uint32_t s) {
+    if (t.nb16) {
+        const uint32_t v = t.nb16[(uint32_t)d * t.S + s];
+        return v == 0xFFFFu ? NONE32 : v;
+    }
+    return __ldg(&t.nb[d][s]);
+}
 
 // does cell ci stay in region r?  (watershed.rs:167-216) — false when a 4-neighbour, or the neighbour reached from it by
 // turning clockwise, of the same area carries another region.
 __device__ __forceinline__ bool ws_kept(const Tile& t, uint32_t ci, uint32_t r, uint32_t area) {
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
-        const uint32_t ai = t.nb[d][ci];
+        const uint32_t ai = nbr(t, d, ci);
         if (ai == NONE32) continue;
         if (t.areas[ai] != area) continue;
         const uint32_t nr = *(volatile uint16_t*)&t.reg[ai];
         if (nr & BORDER) continue;  // skips the diagonal too
         if (nr != 0 && nr != r) return false;
-        const uint32_t ai2 = t.nb[(d + 1) & 3][ai];
+        const uint32_t ai2 = nbr(t, (d + 1) & 3, ai);
         if (ai2 == NONE32) continue;
         if (t.areas[ai2] != area) continue;
         const uint32_t nr2 = *(volatile uint16_t*)&t.reg[ai2];
@@ -141,7 +164,9 @@ __device__ __forceinline__ uint32_t cas16(uint16_t* p, uint16_t cmp, uint16_t va
 }
 
 // watershed.rs:245-361.  `len` is the stack length (uniform); returns the new length.
-__device__ uint32_t ws_expand(const Tile& t, int max_iter, uint32_t level, uint32_t* stack, uint32_t len, bool fill, BlockSh& sh) {
+// The stack is t.stack[sidx]; the retain step compacts it into t.bufB and the two buffers trade places.
+__device__ uint32_t ws_expand(Tile& t, int max_iter, uint32_t level, int sidx, uint32_t len, bool fill, BlockSh& sh) {
+    uint32_t* stack = t.stack[sidx];
     if (fill) {
         len = block_compact(t.S, 0, sh, [&](uint32_t s, uint32_t& pl) { pl = s; return t.dist[s] >= level && t.reg[s] == 0 && t.areas[s] != 0; },
                             [&](uint32_t pos, uint32_t s) { stack[pos] = s; });
@@ -165,7 +190,7 @@ __device__ uint32_t ws_expand(const Tile& t, int max_iter, uint32_t level, uint3
                 const uint32_t area = t.areas[i];
 #pragma unroll
                 for (int d = 0; d < 4; ++d) {
-                    const uint32_t ai = t.nb[d][i];
+                    const uint32_t ai = nbr(t, d, i);
                     if (ai == NONE32) continue;
                     if (t.areas[ai] != area) continue;
                     const uint32_t ra = t.reg[ai];
@@ -194,8 +219,13 @@ __device__ uint32_t ws_expand(const Tile& t, int max_iter, uint32_t level, uint3
         }
         __syncthreads();
         const uint32_t nfailed = block_sum(failed, sh);
-        len = block_compact(len, 0, sh, [&](uint32_t j, uint32_t& pl) { pl = stack[j]; return pl != NONE32; },
-                            [&](uint32_t pos, uint32_t v) { stack[pos] = v; });
+        {
+            uint32_t* dst = t.bufB;
+            len = block_compact(len, 0, sh, [&](uint32_t j, uint32_t& pl) { pl = stack[j]; return pl != NONE32; },
+                                [&](uint32_t pos, uint32_t v) { dst[pos] = v; });
+            t.bufB = stack;
+            t.stack[sidx] = stack = dst;
+        }
         __syncthreads();
         if ((unsigned long long)nfailed * 3ull >= (unsigned long long)len * 2ull) break;  // :350, length AFTER the retain
         if (level > 0) {
@@ -205,7 +235,12 @@ __device__ uint32_t ws_expand(const Tile& t, int max_iter, uint32_t level, uint3
     return len;
 }
 
-__device__ __forceinline__ uint32_t list_neighbor(const Tile& t, uint32_t s, uint32_t d8) {  // compact_heightfield.rs:495-510
+// get_neighbor_connection (compact_heightfield.rs:732-745, 495-510): the connection list; it agrees with con[] unless
+// a neighbour sits at offset 63 of its cell, which takes a cell of 64+ spans
+__device__ __forceinline__ uint32_t list_neighbor(const Tile& t, uint32_t s, int d4) {
+    const uint32_t viacon = nbr(t, d4, s);
+    if (viacon != NONE32 || !t.walk_lists) return viacon;
+    const uint32_t d8 = 7u - 2u * (uint32_t)d4;  // W, S, E, N
     uint32_t c = t.first_conn[s];
     while (c != NONE32) {
         if (t.conn_dir[c] == d8) return t.conn_ref[c];
@@ -214,8 +249,24 @@ __device__ __forceinline__ uint32_t list_neighbor(const Tile& t, uint32_t s, uin
     return NONE32;
 }
 
+struct RegClock {
+    unsigned long long* acc;
+    long long t;
+    __device__ RegClock(unsigned long long* a) : acc(a), t(0) {
+        if (acc && threadIdx.x == 0) t = clock64();
+    }
+    __device__ void mark(int id) {
+        if (acc && threadIdx.x == 0) {
+            const long long n = clock64();
+            atomicAdd(&acc[id], (unsigned long long)(n - t));
+            t = n;
+        }
+    }
+};
+
 __global__ void __launch_bounds__(BT) k_regions(RegionArgs a) {
     __shared__ BlockSh sh;
+    RegClock pc(a.phase);
     __shared__ uint32_t sh_len[8];
     __shared__ uint32_t sh_next;
     const uint32_t tile = blockIdx.x;
@@ -249,23 +300,36 @@ __global__ void __launch_bounds__(BT) k_regions(RegionArgs a) {
     const int W = t.W, H = t.H;
 
     // ---- 0. working arrays; neighbours through con[] -----------------------------------------------------
+    // Tiles whose hot arrays fit keep them in shared memory for the whole kernel: the algorithm is a long
+    // sequence of short dependent phases, and its time is (phases) x (latency of one access).
+    extern __shared__ __align__(16) unsigned char rg_smem[];
+    uint16_t* const g_reg = t.reg;
+    const bool in_smem = a.smem_spans >= S && S < 0xFFFFu;
+    t.nb16 = nullptr;
+    if (in_smem) {
+        // labels and the neighbour table (10 B per span) are what the floods hammer; the rest is read through L1
+        t.reg = (uint16_t*)rg_smem;
+    }
     for (uint32_t s = threadIdx.x; s < S; s += BT) t.reg[s] = 0, t.sdist[s] = 0;
+    uint32_t maxcnt = 0;
     for (uint32_t c = threadIdx.x; c < t.C; c += BT) {
         const uint32_t b = t.cidx[c];
         if (b == NONE32) continue;
         const uint32_t n = t.ccnt[c];
+        maxcnt = max(maxcnt, n);
         const int y = (int)(c / (uint32_t)W), x = (int)c - y * W;
         for (uint32_t s = b; s < b + n; ++s) {
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
                 const uint32_t k = t.con[4 * (size_t)s + d];
                 const int ox = d == 0 ? -1 : (d == 2 ? 1 : 0), oy = d == 1 ? 1 : (d == 3 ? -1 : 0);  // compact_heightfield.rs:748-767
-                t.nb[d][s] = k == 63u ? NONE32 : t.cidx[(uint32_t)((y + oy) * W + (x + ox))] + k;
+                const uint32_t v = k == 63u ? NONE32 : t.cidx[(uint32_t)((y + oy) * W + (x + ox))] + k;
+                t.nb[d][s] = v;
             }
         }
     }
-    __syncthreads();
-
+    t.walk_lists = __syncthreads_or(maxcnt > 63u) != 0;
+    pc.mark(0);
     // ---- border regions (:393-426) ----------------------------------------------------------------------------
     uint32_t region_id = 1;
     if (td.aux0 > 0) {
@@ -308,6 +372,7 @@ __global__ void __launch_bounds__(BT) k_regions(RegionArgs a) {
             }
             __syncthreads();
             len = sh_len[0];
+            pc.mark(1);
         } else {  // append_stacks (:122-133)
             const uint32_t* src = t.stack[s_id - 1];
             uint32_t* dst = t.stack[s_id];
@@ -315,9 +380,11 @@ __global__ void __launch_bounds__(BT) k_regions(RegionArgs a) {
                                 [&](uint32_t j, uint32_t& pl) { pl = src[j]; return pl != NONE32 && t.reg[pl] == 0; },
                                 [&](uint32_t pos, uint32_t v) { dst[pos] = v; });
             __syncthreads();
+            pc.mark(2);
         }
+        len = ws_expand(t, 8, level, s_id, len, false, sh);
+        pc.mark(3);
         uint32_t* stack = t.stack[s_id];
-        len = ws_expand(t, 8, level, stack, len, false, sh);
         if (threadIdx.x == 0) sh_len[s_id] = len;
         __syncthreads();
         // new regions (:454-476): entries in order; the first one that is unlabelled and survives its own test floods
@@ -333,6 +400,7 @@ __global__ void __launch_bounds__(BT) k_regions(RegionArgs a) {
                 }
             }
             const uint32_t jmin = block_min(mine, sh);
+            pc.mark(4);
             if (jmin == NONE32) break;
             const uint32_t seed = stack[jmin];
             const uint32_t area = t.areas[seed];
@@ -355,7 +423,7 @@ __global__ void __launch_bounds__(BT) k_regions(RegionArgs a) {
                     }
 #pragma unroll
                     for (int d = 0; d < 4; ++d) {
-                        const uint32_t ai = t.nb[d][ci];
+                        const uint32_t ai = nbr(t, d, ci);
                         if (ai == NONE32) continue;
                         if (t.areas[ai] != area) continue;
                         if (t.dist[ai] >= lev && cas16(&t.reg[ai], 0, (uint16_t)region_id) == 0) {
@@ -371,6 +439,7 @@ __global__ void __launch_bounds__(BT) k_regions(RegionArgs a) {
                 nxt = tmp;
                 __syncthreads();
             }
+            pc.mark(5);
             if (region_id == 0xFFFFu) {  // :469-471
                 overflow = true;
                 break;
@@ -384,7 +453,8 @@ __global__ void __launch_bounds__(BT) k_regions(RegionArgs a) {
         return;
     }
     // ---- final expansion (:480-488) ----------------------------------------------------------------------------
-    ws_expand(t, 64, 0, t.stack[0], 0, true, sh);
+    ws_expand(t, 64, 0, 0, 0, true, sh);
+    pc.mark(6);
     if (threadIdx.x == 0) a.tinfo[tile].max_regions = region_id;  // :491, before filtering
 
     // ---- merge_and_filter_regions (:543-633) ----------------------------------------------------------------
@@ -407,7 +477,7 @@ __global__ void __launch_bounds__(BT) k_regions(RegionArgs a) {
         atomicAdd(&cnt[rid], 1);
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
-            const uint32_t n = list_neighbor(t, s, 7u - 2u * (uint32_t)d);  // W, S, E, N (compact_heightfield.rs:737-743)
+            const uint32_t n = list_neighbor(t, s, d);
             if (n == NONE32) continue;
             const uint32_t nr = t.reg0[n];
             if (nr & BORDER) border[rid] = 1;
@@ -441,7 +511,7 @@ __global__ void __launch_bounds__(BT) k_regions(RegionArgs a) {
                     if (!(alive[rid] != 0 && cnt[rid] != 0 && cnt[rid] < merge_area && !border[rid])) continue;
 #pragma unroll
                     for (int d = 0; d < 4; ++d) {
-                        const uint32_t n = list_neighbor(t, s, 7u - 2u * (uint32_t)d);
+                        const uint32_t n = list_neighbor(t, s, d);
                         if (n == NONE32) continue;
                         const uint32_t nr = t.reg0[n];
                         if (nr == rid || nr == 0 || (nr & BORDER) || nr >= R) continue;
@@ -497,15 +567,20 @@ __global__ void __launch_bounds__(BT) k_regions(RegionArgs a) {
         __syncthreads();
         for (uint32_t s = threadIdx.x; s < S; s += BT) {
             const uint32_t v = t.reg[s];
-            if (v < R) t.reg[s] = fin[v];
+            g_reg[s] = v < R ? fin[v] : (uint16_t)v;
         }
     }
+    pc.mark(7);
 }
 
 }  // namespace
 
+size_t regions_smem_bytes(uint32_t max_spans) { return 2 * (size_t)((max_spans + 7u) & ~7u) + 16; }
+
 void launch_regions(const RegionArgs& a, int ntiles, cudaStream_t s) {
     if (ntiles == 0) return;
+    const size_t smem = a.smem_spans ? regions_smem_bytes(a.smem_spans) : 0;
+    cudaFuncSetAttribute(k_regions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     KScope _k("k_regions", s);
-    k_regions<<<ntiles, BT, 0, s>>>(a);
+    k_regions<<<ntiles, BT, smem, s>>>(a);
 }

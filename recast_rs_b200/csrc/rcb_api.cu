@@ -457,6 +457,8 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
     return RCB_OK;
 }
 
+int fetch_tinfo(rcb_result* res, cudaStream_t on = nullptr, bool use_on = false);
+
 // CompactHeightfield::build_regions on a finished result (both back ends): k_regions.cu.
 int build_regions_stage(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, int ntiles, uint64_t S) {
     if (ntiles == 0) return RCB_OK;
@@ -475,11 +477,12 @@ int build_regions_stage(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, 
     CU(ctx->d_rg_a.ensure(o + 256));
     o = 0;
     const size_t o_cnt = put(4 * Sp), o_cadd = put(4 * Sp), o_alive = put(2 * Sp), o_border = put(Sp), o_best = put(8 * Sp), o_target = put(2 * Sp),
-                 o_fin = put(2 * Sp), o_err = put(16);
+                 o_fin = put(2 * Sp), o_err = put(16), o_phase = put(8 * 16);
     CU(ctx->d_rg_b.ensure(o + 256));
     char* a = (char*)ctx->d_rg_a.p;
     char* b = (char*)ctx->d_rg_b.p;
     CU(cudaMemsetAsync(b + o_err, 0xff, 16, st));
+    CU(cudaMemsetAsync(b + o_phase, 0, 8 * 16, st));
     RegionArgs ra{};
     ra.tiles = d_tiles;
     ra.tinfo = (TileInfo*)(A + res->lay.tinfo);
@@ -508,10 +511,25 @@ int build_regions_stage(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, 
     ra.r_target = (uint16_t*)(b + o_target);
     ra.r_fin = (uint16_t*)(b + o_fin);
     ra.err = (unsigned int*)(b + o_err);
+    ra.phase = ctx->phase_timers ? (unsigned long long*)(b + o_phase) : nullptr;
+    {
+        // shared-memory residency is decided per launch: it takes the largest tile of the batch to fit
+        int r = fetch_tinfo(res, nullptr, false);
+        if (r) return r;
+        uint32_t smax = 0;
+        for (auto& ti : res->tinfo) smax = std::max(smax, ti.span_count);
+        ra.smem_spans = (smax < 0xFFFFu && regions_smem_bytes(smax) <= 100 * 1024) ? std::max(smax, 1u) : 0u;
+    }
     launch_regions(ra, ntiles, st);
     CU(cudaMemcpyAsync(&ctx->h_counters[7], b + o_err, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
+    if (ctx->phase_timers) {
+        unsigned long long ph[8];
+        cudaMemcpy(ph, b + o_phase, sizeof ph, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[rcb phase cycles/tile] regions: init %llu sort %llu append %llu expand %llu seed-search %llu flood %llu final-expand %llu merge %llu\n",
+                ph[0] / ntiles, ph[1] / ntiles, ph[2] / ntiles, ph[3] / ntiles, ph[4] / ntiles, ph[5] / ntiles, ph[6] / ntiles, ph[7] / ntiles);
+    }
     const uint32_t bad = (uint32_t)ctx->h_counters[7];
     if (bad != 0xffffffffu) return fail(ctx, RCB_ERECAST, "tile %u: Region ID overflow", bad);
     return RCB_OK;
@@ -944,12 +962,12 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             CUB(cudaMemcpyAsync(d_in_off, goff.data(), 4 * (Ctot + 1), cudaMemcpyHostToDevice, st));
             if (Sin) {
                 CUB(cudaMemcpyAsync(ctx->d_wire.p, src.smin, 2 * Sin, cudaMemcpyHostToDevice, st));
-                CUB(cudaMemcpyAsync(ctx->d_wire.p + o_max, src.smax, 2 * Sin, cudaMemcpyHostToDevice, st));
-                CUB(cudaMemcpyAsync(ctx->d_wire.p + o_area, src.sarea, Sin, cudaMemcpyHostToDevice, st));
+                CUB(cudaMemcpyAsync((char*)ctx->d_wire.p + o_max, src.smax, 2 * Sin, cudaMemcpyHostToDevice, st));
+                CUB(cudaMemcpyAsync((char*)ctx->d_wire.p + o_area, src.sarea, Sin, cudaMemcpyHostToDevice, st));
             }
             d_in_min = (const int16_t*)ctx->d_wire.p;
-            d_in_max = (const int16_t*)(ctx->d_wire.p + o_max);
-            d_in_area = (const uint8_t*)(ctx->d_wire.p + o_area);
+            d_in_max = (const int16_t*)((const char*)ctx->d_wire.p + o_max);
+            d_in_area = (const uint8_t*)((const char*)ctx->d_wire.p + o_area);
         }
         CUB(ctx->d_fs_mm.ensure(4 * Sin + 64));
         CUB(ctx->d_fs_area.ensure(Sin + 64));
@@ -1025,7 +1043,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
 #undef CUB
 }
 
-int fetch_tinfo(rcb_result* res, cudaStream_t on = nullptr, bool use_on = false) {
+int fetch_tinfo(rcb_result* res, cudaStream_t on, bool use_on) {
     rcb_ctx* ctx = res->ctx;
     if (res->have_tinfo) return RCB_OK;
     const cudaStream_t st = use_on ? on : ctx->stream;

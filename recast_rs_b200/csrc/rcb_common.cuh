@@ -238,7 +238,10 @@ struct RegionArgs {
     uint16_t* r_target;
     uint16_t* r_fin;
     unsigned int* err;  // first tile whose region ids overflowed (init 0xffffffff)
+    unsigned long long* phase;  // RCB_PHASE_TIMERS: cycle sums per phase (thread 0 of every tile), or nullptr
+    uint32_t smem_spans;        // tiles with at most this many spans keep their arrays in shared memory (0: none do)
 };
+size_t regions_smem_bytes(uint32_t max_spans);
 void launch_regions(const RegionArgs& a, int ntiles, cudaStream_t s);
 
 // k_lz4.cu — tile-cache front half
