@@ -124,7 +124,8 @@ struct Tile {
     uint16_t* sdist;  // src_dist
     uint16_t* reg0;   // labels before merge_and_filter (its connection lists are built once, from these)
     uint32_t* nb[4];  // con-based neighbour (tile-relative span) or NONE32 — global-memory mode
-    uint16_t* nb16;   // the same as u16[4][S] in shared memory (0xFFFF = none) — shared-memory mode, else nullptr
+    uint16_t* nb16[4];  // the same table with 16-bit entries (0xFFFF = none) when the tile has fewer than 65535 spans: half the
+                        // footprint in L1/L2; nb16[0] == nullptr otherwise
     bool walk_lists;  // some cell holds 64+ spans: con == 63 may hide a real neighbour (merge_and_filter follows the list)
     uint32_t* stack[8];
     uint32_t* bufA;
@@ -132,8 +133,8 @@ struct Tile {
 };
 
 __device__ __forceinline__ uint32_t nbr(const Tile& t, int d, uint32_t s) {
-    if (t.nb16) {
-        const uint32_t v = t.nb16[(uint32_t)d * t.S + s];
+    if (t.nb16[0]) {
+        const uint32_t v = __ldg(&t.nb16[d][s]);
         return v == 0xFFFFu ? NONE32 : v;
     }
     return __ldg(&t.nb[d][s]);
@@ -305,7 +306,9 @@ __global__ void __launch_bounds__(BT) k_regions(RegionArgs a) {
     extern __shared__ __align__(16) unsigned char rg_smem[];
     uint16_t* const g_reg = t.reg;
     const bool in_smem = a.smem_spans >= S && S < 0xFFFFu;
-    t.nb16 = nullptr;
+    const bool small = S < 0xFFFFu;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) t.nb16[d] = small ? (uint16_t*)a.nb4 + (size_t)d * a.Stot + sb : nullptr;
     if (in_smem) {
         // labels and the neighbour table (10 B per span) are what the floods hammer; the rest is read through L1
         t.reg = (uint16_t*)rg_smem;
@@ -324,7 +327,10 @@ __global__ void __launch_bounds__(BT) k_regions(RegionArgs a) {
                 const uint32_t k = t.con[4 * (size_t)s + d];
                 const int ox = d == 0 ? -1 : (d == 2 ? 1 : 0), oy = d == 1 ? 1 : (d == 3 ? -1 : 0);  // compact_heightfield.rs:748-767
                 const uint32_t v = k == 63u ? NONE32 : t.cidx[(uint32_t)((y + oy) * W + (x + ox))] + k;
-                t.nb[d][s] = v;
+                if (small)
+                    t.nb16[d][s] = (uint16_t)v;  // NONE32 -> 0xFFFF
+                else
+                    t.nb[d][s] = v;
             }
         }
     }
