@@ -138,3 +138,23 @@ def test_gpu_regions_config2_invariants_and_sample(oracle):
                                                                                          cfgs[i].merge_region_area)
         assert out[0][i][1] == wmr
         np.testing.assert_array_equal(out[0][i][0], want)
+
+
+@pytest.mark.gpu
+def test_gpu_regions_tall_tile_global_memory_path(oracle):
+    """A tile with more than 65535 spans (18 floors over 64x64 cells): 32-bit neighbour table, labels in global memory."""
+    import recast_rs_b200.builder as rb
+
+    v, t = synth.interior(18, 17, 1.2, 0.2, 3, 3.0)
+    cfg = synth.single_tile_config(v, RecastConfig(cs=0.3, ch=0.2, min_region_area=8, merge_region_area=20))
+    ohf = oracle.Heightfield.from_config(cfg)
+    ohf.builder_rasterize(cfg, v, t)
+    oc = oracle.CompactHeightfield.build_from_heightfield(ohf)
+    want, wmr = oc.build_regions(0, 8, 20)
+    assert want.size > 65535
+    with rb.Context(0) as ctx:
+        ctx.upload_mesh(v, t)
+        with ctx.build_tiles([cfg], rb.STAGE_ALL_BUILD | rb.STAGE_REGIONS) as r:
+            tv = r.download().tile(0)
+    assert tv.max_regions == wmr
+    np.testing.assert_array_equal(tv.reg, want)
