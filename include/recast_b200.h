@@ -237,6 +237,27 @@ int rcb_apply_area_ops(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const u
                        int nops, const float* poly_verts, size_t npoly_floats, uint32_t stage_mask, int erode_radius,
                        rcb_result** out);
 
+/* ---- convex volumes (ConvexVolumeSet::apply_to_heightfield, convex_volume.rs:392-430) -------------
+ * rcb_build_tiles_with_volumes: RecastBuilder::build_heightfield_with_volumes / build_mesh_with_volumes
+ * (lib.rs:293-361): rcb_build_tiles with the volumes applied to the SOLID heightfield after the filters and
+ * before compaction.  Every span takes the area_type of the LAST volume that contains the point
+ * (tile bmin.x + (x + 0.5) * cs, bmin.y + span.max * ch, bmin.z + (z + 0.5) * cs) — get_area_at_point (:375-389),
+ * contains_point (:130-164: min_height <= y <= max_height and an odd number of crossings in xz).
+ * A volume is what ConvexVolume::new (:28-68) accepts: 3..32 vertices (xyz triples at poly_verts[3*first_vert ..]),
+ * min_height <= max_height, convex in xz (is_convex :166-199); otherwise RCB_EINVALID_MESH.
+ * rcb_apply_convex_volumes: the same on existing heightfields (CSR as rcb_build_from_spans). */
+typedef struct rcb_convex_volume {
+    uint32_t first_vert, num_verts;
+    float min_height, max_height;
+    uint32_t area_type; /* u8 */
+} rcb_convex_volume;
+int rcb_build_tiles_with_volumes(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stage_mask, int erode_radius,
+                                 const rcb_convex_volume* volumes, int nvolumes, const float* poly_verts, size_t npoly_floats,
+                                 rcb_result** out);
+int rcb_apply_convex_volumes(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const uint32_t* cell_offset, const int16_t* span_min,
+                             const int16_t* span_max, const uint8_t* span_area, const rcb_convex_volume* volumes, int nvolumes,
+                             const float* poly_verts, size_t npoly_floats, uint32_t stage_mask, int erode_radius, rcb_result** out);
+
 /* ---- heightfield wire formats of detour-dynamic ----------------------------------------
  * A tile's span data is, per cell in z-major order, `u16 count` then count x (`u32 min, u32 max, u32 area`).
  *   RCB_WIRE_VOXEL_TILE    big-endian.  Writer: VoxelTile::serialize_spans (io/voxel_tile.rs:70-118, `min as u32`

@@ -1870,3 +1870,73 @@ int orc_chf_build_regions(orc_chf* p, int32_t border_size, int32_t min_region_ar
 }
 
 }  // extern "C"
+
+// ======================================================================================================
+// Convex volumes (second half): ConvexVolume / ConvexVolumeSet of convex_volume.rs, as used by
+// RecastBuilder::build_mesh_with_volumes / build_heightfield_with_volumes (lib.rs:293-361): after the filters,
+// every span of the SOLID heightfield takes the area of the last volume that contains the point
+// (cell centre, span top).  Pinned by the reference's own tests (convex_volume.rs:434-558) in
+// tests/test_convex_volumes.py.
+// ======================================================================================================
+extern "C" {
+
+// convex_volume.rs:166-199 is_convex (xz-plane cross products; zero crosses ignored).  verts: n xyz triples.
+int orc_convex_is_convex(const float* v, uint32_t n) {
+    if (n < 3) return 0;
+    float sign = 0.0f;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t j = (i + 1) % n, k = (i + 2) % n;
+        const float dx1 = v[j * 3] - v[i * 3], dz1 = v[j * 3 + 2] - v[i * 3 + 2];
+        const float dx2 = v[k * 3] - v[j * 3], dz2 = v[k * 3 + 2] - v[j * 3 + 2];
+        const float cross = dx1 * dz2 - dz1 * dx2;
+        if (cross != 0.0f) {
+            if (sign == 0.0f)
+                sign = cross;
+            else if ((cross > 0.0f) != (sign > 0.0f))
+                return 0;
+        }
+    }
+    return 1;
+}
+
+// ConvexVolume::new (:28-68): 0 or RCB_EINVALID_MESH
+int orc_convex_volume_validate(const float* v, uint32_t n, float min_h, float max_h) {
+    if (n < 3 || n > 32 || min_h > max_h || !orc_convex_is_convex(v, n)) return RCB_EINVALID_MESH;
+    return 0;
+}
+
+// contains_point (:130-138) + point_in_polygon_2d (:140-164)
+int orc_convex_contains_point(const float* v, uint32_t n, float min_h, float max_h, const float* p) {
+    if (p[1] < min_h || p[1] > max_h) return 0;
+    const float x = p[0], z = p[2];
+    bool inside = false;
+    for (uint32_t i = 0, j = n - 1; i < n; j = i++) {
+        const float* vi = v + i * 3;
+        const float* vj = v + j * 3;
+        if ((vi[2] > z) == (vj[2] > z)) continue;
+        if (x >= (vj[0] - vi[0]) * (z - vi[2]) / (vj[2] - vi[2]) + vi[0]) continue;
+        inside = !inside;
+    }
+    return inside ? 1 : 0;
+}
+
+// ConvexVolumeSet::apply_to_heightfield (:392-430) with get_area_at_point (:375-389): later volumes win.
+void orc_hf_apply_convex_volumes(orc_hf* p, const rcb_convex_volume* vols, int nvols, const float* verts) {
+    Heightfield& hf = *(Heightfield*)p;
+    for (int32_t z = 0; z < hf.height; ++z)
+        for (int32_t x = 0; x < hf.width; ++x) {
+            const float wx = hf.bmin[0] + ((float)x + 0.5f) * hf.cs;
+            const float wz = hf.bmin[2] + ((float)z + 0.5f) * hf.cs;
+            for (uint32_t s = hf.first[(size_t)z * hf.width + x]; s != NONE; s = hf.pool[s].next) {
+                const float pt[3] = {wx, hf.bmin[1] + (float)hf.pool[s].smax * hf.ch, wz};
+                uint8_t area = hf.pool[s].area;
+                for (int k = 0; k < nvols; ++k)
+                    if (orc_convex_contains_point(verts + 3 * (size_t)vols[k].first_vert, vols[k].num_verts, vols[k].min_height,
+                                                  vols[k].max_height, pt))
+                        area = (uint8_t)vols[k].area_type;
+                hf.pool[s].area = area;
+            }
+        }
+}
+
+}  // extern "C"

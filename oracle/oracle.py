@@ -84,6 +84,10 @@ def lib():
         L.orc_tilecache_build_compressed_batch.restype = ctypes.c_double
         L.orc_tilecache_build_compressed_batch.argtypes = [vp, vp, ctypes.c_int, vp, vp, vp, f32, f32, ctypes.c_int, vp]
         L.orc_chf_build_regions.argtypes = [vp, i32, i32, i32, vp, vp]
+        L.orc_convex_is_convex.argtypes = [vp, u32]
+        L.orc_convex_volume_validate.argtypes = [vp, u32, f32, f32]
+        L.orc_convex_contains_point.argtypes = [vp, u32, f32, f32, vp]
+        L.orc_hf_apply_convex_volumes.argtypes = [vp, vp, ctypes.c_int, vp]
         L.orc_voxel_serialize_spans.argtypes = [vp, ctypes.c_int, vp]
         L.orc_voxel_deserialize_spans.argtypes = [vp, vp, ctypes.c_uint64]
         L.orc_dynamic_reconstruct_heightfield.argtypes = [vp, vp, ctypes.c_uint64]
@@ -188,6 +192,11 @@ class Heightfield:
 
     def filter_walkable_low_height_spans(self, height):
         lib().orc_filter_walkable_low_height_spans(self._h, height)
+
+    def apply_convex_volumes(self, volume_set):
+        """ConvexVolumeSet::apply_to_heightfield (convex_volume.rs:392-430); volume_set: recast_rs_b200.convex_volume.ConvexVolumeSet."""
+        va, vv = volume_set.pack()
+        lib().orc_hf_apply_convex_volumes(self._h, ctypes.cast(va, ctypes.c_void_p), len(volume_set.volumes), _p(vv) if vv.size else None)
 
     # ---- wire formats (detour-dynamic) ----
     def serialize_spans(self, big_endian=True) -> np.ndarray:
@@ -452,3 +461,20 @@ def tilecache_build_compressed_timed(ct, cs, ch, nthreads=1):
                                                    _p(ct.count) if ct.count is not None else None,
                                                    ctypes.cast(ct.obstacles, ctypes.c_void_p), cs, ch, nthreads, _p(tot))
     return s, {"spans": int(tot[0]), "connections": int(tot[1]), "failed": int(tot[2])}
+
+
+# ---- convex volumes (crates/recast/src/convex_volume.rs) ----------------------------------------------
+def convex_is_convex(verts) -> bool:
+    v = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3)
+    return bool(lib().orc_convex_is_convex(_p(v), len(v)))
+
+
+def convex_volume_validate(verts, min_height, max_height) -> int:
+    v = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3)
+    return int(lib().orc_convex_volume_validate(_p(v), len(v), min_height, max_height))
+
+
+def convex_contains_point(verts, min_height, max_height, point) -> bool:
+    v = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3)
+    p = _f3(point)
+    return bool(lib().orc_convex_contains_point(_p(v), len(v), min_height, max_height, _p(p)))

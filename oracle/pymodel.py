@@ -1084,3 +1084,37 @@ def build_regions_watershed(c, border_size, min_region_area, merge_region_area):
         if src_reg[s] < len(remap):
             src_reg[s] = remap[src_reg[s]]
     return src_reg, max_regions
+
+
+# ---- convex volumes: convex_volume.rs:130-164, 375-430 (independent restatement) ------------------------------------
+def convex_contains_point(verts, min_h, max_h, p):
+    if f32(p[1]) < f32(min_h) or f32(p[1]) > f32(max_h):
+        return False
+    x, z = f32(p[0]), f32(p[2])
+    inside, n = False, len(verts)
+    j = n - 1
+    for i in range(n):
+        vi, vj = verts[i], verts[j]
+        j = i
+        if (f32(vi[2]) > z) == (f32(vj[2]) > z):
+            continue
+        xi = f32(f32(f32(f32(vj[0]) - f32(vi[0])) * f32(z - f32(vi[2]))) / f32(f32(vj[2]) - f32(vi[2]))) + f32(vi[0])
+        if x >= f32(xi):
+            continue
+        inside = not inside
+    return inside
+
+
+def apply_convex_volumes(hf, volumes):
+    """volumes: list of (verts[n][3], min_height, max_height, area_type); later entries win."""
+    for z in range(hf.height):
+        for x in range(hf.width):
+            wx = f32(hf.bmin[0] + f32(f32(f32(x) + f32(0.5)) * hf.cs))
+            wz = f32(hf.bmin[2] + f32(f32(f32(z) + f32(0.5)) * hf.cs))
+            s = hf.spans[(x, z)]
+            while s is not None:
+                wy = f32(hf.bmin[1] + f32(f32(s.max) * hf.ch))
+                for (verts, mn, mx, area) in volumes:
+                    if convex_contains_point(verts, mn, mx, (wx, wy, wz)):
+                        s.area = area
+                s = s.next

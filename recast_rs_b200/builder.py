@@ -240,6 +240,32 @@ class Context:
         return BatchResult(self, out)
 
 
+    def build_tiles_with_volumes(self, cfgs, volumes, stage_mask: int = STAGE_ALL_BUILD, erode_radius: int = 0) -> BatchResult:
+        """RecastBuilder::build_mesh_with_volumes' voxel half (lib.rs:293-316): build_tiles with a ConvexVolumeSet applied to
+        the solid heightfield after the filters (convex_volume.rs:392-430)."""
+        arr = cfgs if isinstance(cfgs, ctypes.Array) else configs_to_array(cfgs)
+        va, vv = volumes.pack()
+        out = ctypes.c_void_p()
+        check(_ffi.lib().rcb_build_tiles_with_volumes(self._h, ctypes.cast(arr, ctypes.c_void_p), len(arr), stage_mask, erode_radius,
+                                                      ctypes.cast(va, ctypes.c_void_p), len(volumes.volumes), _ptr(vv) if vv.size else None,
+                                                      vv.size, ctypes.byref(out)), self._h)
+        return BatchResult(self, out)
+
+    def apply_convex_volumes(self, cfgs, cell_offset, span_min, span_max, span_area, volumes, stage_mask: int = 0,
+                             erode_radius: int = 0) -> BatchResult:
+        """ConvexVolumeSet::apply_to_heightfield (convex_volume.rs:392-430) on existing heightfields (CSR), later stages optional."""
+        arr = cfgs if isinstance(cfgs, ctypes.Array) else configs_to_array(cfgs)
+        co = np.ascontiguousarray(cell_offset, dtype=np.uint32)
+        a = np.ascontiguousarray(span_min, dtype=np.int16)
+        b = np.ascontiguousarray(span_max, dtype=np.int16)
+        c = np.ascontiguousarray(span_area, dtype=np.uint8)
+        va, vv = volumes.pack()
+        out = ctypes.c_void_p()
+        check(_ffi.lib().rcb_apply_convex_volumes(self._h, ctypes.cast(arr, ctypes.c_void_p), len(arr), _ptr(co), _ptr(a), _ptr(b), _ptr(c),
+                                                  ctypes.cast(va, ctypes.c_void_p), len(volumes.volumes), _ptr(vv) if vv.size else None, vv.size,
+                                                  stage_mask, erode_radius, ctypes.byref(out)), self._h)
+        return BatchResult(self, out)
+
     def build_from_span_data(self, cfgs, data, tile_offsets, fmt: int, stage_mask: int = 0, erode_radius: int = 0) -> BatchResult:
         """Heightfields from serialized span data: fmt WIRE_VOXEL_TILE = VoxelTile::deserialize_spans
         (io/voxel_tile.rs:120-176), WIRE_DYNAMIC_TILE = DynamicTile::reconstruct_heightfield (dynamic_tile.rs:147-257)."""
@@ -527,6 +553,14 @@ class RecastBuilder:
             tv = r.download().tile(0)
         heightfield.cell_offset, heightfield.span_min = tv.hf_cell_offset, tv.span_min
         heightfield.span_max, heightfield.span_area = tv.span_max, tv.span_area
+
+    def build_heightfield_with_volumes(self, vertices, indices, convex_volumes) -> Heightfield:  # lib.rs:346-361
+        c = self._config
+        ctx = self._context()
+        ctx.upload_mesh(vertices, indices)
+        with ctx.build_tiles_with_volumes([c], convex_volumes, STAGE_RASTER | STAGE_FILTER) as r:
+            tv = r.download().tile(0)
+        return Heightfield(c.width, c.height, c.bmin, c.bmax, c.cs, c.ch, tv.hf_cell_offset, tv.span_min, tv.span_max, tv.span_area, ctx=ctx)
 
     def build_compact_heightfield(self, heightfield: Heightfield) -> CompactHeightfield:
         return CompactHeightfield.build_from_heightfield(heightfield, self._context())

@@ -142,7 +142,52 @@ __global__ void __launch_bounds__(256) k_area_median(const TileDesc* __restrict_
     }
 }
 
+// ConvexVolumeSet::apply_to_heightfield (convex_volume.rs:392-430) on the SOLID heightfield: one thread per column;
+// every span takes the area of the last volume that contains (cell centre, span top).
+__global__ void __launch_bounds__(256) k_convex_volumes(const TileDesc* __restrict__ tiles, TileMap tm, const uint32_t* __restrict__ hf_off,
+                                                        const int16_t* __restrict__ smax, uint8_t* __restrict__ sarea,
+                                                        const rcb_convex_volume* __restrict__ vols, int nvols,
+                                                        const float* __restrict__ verts) {
+    const uint32_t tile = RCB_TILE_OF_BLOCK();
+    if (tile >= tm.ntiles) return;
+    const TileDesc& td = tiles[tile];
+    const uint32_t lc = RCB_CELL_OF_THREAD();
+    if (lc >= (uint32_t)(td.width * td.height)) return;
+    const uint32_t g = td.cell_base + lc;
+    const uint32_t b = hf_off[g], e = hf_off[g + 1];
+    if (b == e) return;
+    const int z = (int)(lc / (uint32_t)td.width), x = (int)lc - z * td.width;
+    const float wx = __fadd_rn(td.bmin[0], __fmul_rn(__fadd_rn((float)x, 0.5f), td.cs));  // :405-406
+    const float wz = __fadd_rn(td.bmin[2], __fmul_rn(__fadd_rn((float)z, 0.5f), td.cs));
+    for (uint32_t s = b; s < e; ++s) {
+        const float wy = __fadd_rn(td.bmin[1], __fmul_rn((float)smax[s], td.ch));  // :417
+        uint32_t area = sarea[s];
+        for (int k = 0; k < nvols; ++k) {
+            const rcb_convex_volume v = vols[k];
+            if (wy < v.min_height || wy > v.max_height) continue;  // :132-134
+            const float* p = verts + 3ull * v.first_vert;
+            bool inside = false;
+            for (uint32_t i = 0, j = v.num_verts - 1; i < v.num_verts; j = i++) {  // :140-164
+                const float vix = p[3 * i], viz = p[3 * i + 2], vjx = p[3 * j], vjz = p[3 * j + 2];
+                if ((viz > wz) == (vjz > wz)) continue;
+                const float xi = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(vjx, vix), __fsub_rn(wz, viz)), __fsub_rn(vjz, viz)), vix);
+                if (wx >= xi) continue;
+                inside = !inside;
+            }
+            if (inside) area = v.area_type & 0xffu;  // later volumes win (:383-387)
+        }
+        sarea[s] = (uint8_t)area;
+    }
+}
+
 }  // namespace
+
+void launch_convex_volumes(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smax, uint8_t* sarea,
+                           const rcb_convex_volume* vols, int nvols, const float* verts, cudaStream_t s) {
+    if (tm.nblocks == 0 || nvols <= 0) return;
+    KScope _k("k_convex_volumes", s);
+    k_convex_volumes<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, smax, sarea, vols, nvols, verts);
+}
 
 void launch_area_marks(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smin, uint8_t* areas,
                        const rcb_area_op* ops, int op0, int op1, const float* poly_verts, cudaStream_t s) {

@@ -356,6 +356,10 @@ struct Source {  // where the heightfield comes from
     int nops = 0;
     const float* poly_verts = nullptr;
     size_t npoly_floats = 0;
+    const rcb_convex_volume* vols = nullptr;  // host, convex volumes applied after the filters (rcb_*_with_volumes)
+    int nvols = 0;
+    const float* vol_verts = nullptr;
+    size_t nvol_floats = 0;
     const uint8_t* span_data = nullptr;  // host, serialized heightfields (rcb_build_from_span_data)
     const uint64_t* span_data_off = nullptr;
     int wire_format = 0;
@@ -365,7 +369,8 @@ struct Source {  // where the heightfield comes from
 // filters -> cells/offsets -> link + connection list -> erosion -> distance field.
 int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, TileMap tm, int ntiles, uint64_t Ctot, uint64_t S,
                     uint32_t fmask, uint32_t stage_mask, int erode_radius, const uint8_t* areas_override,
-                    const rcb_area_op* ops = nullptr, int nops = 0, const float* poly_verts = nullptr, size_t npoly_floats = 0) {
+                    const rcb_area_op* ops = nullptr, int nops = 0, const float* poly_verts = nullptr, size_t npoly_floats = 0,
+                    const rcb_convex_volume* vols = nullptr, int nvols = 0, const float* vol_verts = nullptr, size_t nvol_floats = 0) {
     cudaStream_t st = ctx->stream;
     uint32_t* d_hf_off = ctx->d_hf_off.as<uint32_t>();
     char* A = res->devA.p;
@@ -376,6 +381,17 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
 
     // ---- FILTER ------------------------------------------------------------------------------------------
     if (fmask && S > 0) launch_filter_spans(d_tiles, tm, d_hf_off, d_smin, d_smax, d_sarea, fmask, st);
+
+    // ---- convex volumes on the solid heightfield (lib.rs:306, convex_volume.rs:392) -------------------------------
+    if (nvols > 0 && S > 0) {
+        const size_t vb = align_up(sizeof(rcb_convex_volume) * (size_t)nvols);
+        CU(ctx->d_rg_b.ensure(vb + 4 * nvol_floats + 64));
+        char* d = (char*)ctx->d_rg_b.p;
+        CU(cudaMemcpyAsync(d, vols, sizeof(rcb_convex_volume) * (size_t)nvols, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + vb, vol_verts, 4 * nvol_floats, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));  // pageable host sources
+        launch_convex_volumes(d_tiles, tm, d_hf_off, d_smax, d_sarea, (const rcb_convex_volume*)d, nvols, (const float*)(d + vb), st);
+    }
 
     // ---- cells / offsets ---------------------------------------------------------------------------------
     const bool compact = stage_mask & RCB_STAGE_COMPACT;
@@ -695,7 +711,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                 r2.item_cnt = ctx->d_item_cnt.as<uint32_t>();
                 // tile-resident back end candidates: moderate tiles (the CSR arrays of a tile must fit shared memory)
                 // (fragment records carry a 24-bit triangle index)
-                want_tile = !ctx->force_global && !src.no_tile_mode && 8ull * max_cells + 4096 <= kTileSmem && ntris < (1u << 24);
+                want_tile = !ctx->force_global && !src.no_tile_mode && src.nvols == 0 && 8ull * max_cells + 4096 <= kTileSmem && ntris < (1u << 24);
                 // per-tile fragment bounds -> per-tile segments (both back ends consume fragments tile by tile)
                 CUB(ctx->d_tile_ub.ensure(4 * ((size_t)ntiles + 1)));
                 CUB(ctx->d_tile_base.ensure(4 * ((size_t)ntiles + 2)));
@@ -1030,7 +1046,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
 
     {
         const int r = global_back_end(ctx, res, d_tiles, tm, ntiles, Ctot, S, fmask, stage_mask, erode_radius, src.areas_override, src.ops,
-                                      src.nops, src.poly_verts, src.npoly_floats);
+                                      src.nops, src.poly_verts, src.npoly_floats, src.vols, src.nvols, src.vol_verts, src.nvol_floats);
         if (r) return bail(r);
     }
     CUB(cudaGetLastError());
@@ -1323,6 +1339,63 @@ int rcb_build_from_spans(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const
     s.smax = span_max;
     s.sarea = span_area;
     s.areas_override = areas_override;
+    return run_pipeline(ctx, cfgs, ntiles, stage_mask, erode_radius, s, out);
+}
+
+// ConvexVolume::new (convex_volume.rs:28-68) for every volume of a set
+static int check_volumes(rcb_ctx* ctx, const rcb_convex_volume* vols, int nvols, const float* verts, size_t nfloats) {
+    if (nvols < 0 || (nvols > 0 && (!vols || !verts))) return fail(ctx, RCB_EARG, "null argument");
+    for (int k = 0; k < nvols; ++k) {
+        const rcb_convex_volume& v = vols[k];
+        if (3ull * ((uint64_t)v.first_vert + v.num_verts) > nfloats) return fail(ctx, RCB_EARG, "volume %d: vertices out of range", k);
+        if (v.num_verts < 3) return fail(ctx, RCB_EINVALID_MESH, "Convex volume requires at least 3 vertices");
+        if (v.num_verts > 32) return fail(ctx, RCB_EINVALID_MESH, "Convex volume has too many vertices: %u (max: 32)", v.num_verts);
+        if (v.min_height > v.max_height) return fail(ctx, RCB_EINVALID_MESH, "Convex volume min_height > max_height");
+        const float* p = verts + 3ull * v.first_vert;
+        float sign = 0.0f;  // is_convex (:166-199)
+        for (uint32_t i = 0; i < v.num_verts; ++i) {
+            const uint32_t j = (i + 1) % v.num_verts, l = (i + 2) % v.num_verts;
+            const float dx1 = p[3 * j] - p[3 * i], dz1 = p[3 * j + 2] - p[3 * i + 2];
+            const float dx2 = p[3 * l] - p[3 * j], dz2 = p[3 * l + 2] - p[3 * j + 2];
+            const volatile float m1 = dx1 * dz2, m2 = dz1 * dx2;  // no contraction: two products, one subtraction
+            const float cross = m1 - m2;
+            if (cross != 0.0f) {
+                if (sign == 0.0f)
+                    sign = cross;
+                else if ((cross > 0.0f) != (sign > 0.0f))
+                    return fail(ctx, RCB_EINVALID_MESH, "Vertices do not form a convex polygon");
+            }
+        }
+    }
+    return RCB_OK;
+}
+
+int rcb_build_tiles_with_volumes(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stage_mask, int erode_radius,
+                                 const rcb_convex_volume* volumes, int nvolumes, const float* poly_verts, size_t npoly_floats,
+                                 rcb_result** out) {
+    if (!(stage_mask & RCB_STAGE_RASTER)) return fail(ctx, RCB_EARG, "rcb_build_tiles_with_volumes needs RCB_STAGE_RASTER");
+    int r = check_volumes(ctx, volumes, nvolumes, poly_verts, npoly_floats);
+    if (r) return r;
+    Source s;
+    s.raster = true;
+    s.merge_thr = 1;  // lib.rs:273
+    s.vols = volumes, s.nvols = nvolumes, s.vol_verts = poly_verts, s.nvol_floats = npoly_floats;
+    return run_pipeline(ctx, cfgs, ntiles, stage_mask, erode_radius, s, out);
+}
+
+int rcb_apply_convex_volumes(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const uint32_t* cell_offset, const int16_t* span_min,
+                             const int16_t* span_max, const uint8_t* span_area, const rcb_convex_volume* volumes, int nvolumes,
+                             const float* poly_verts, size_t npoly_floats, uint32_t stage_mask, int erode_radius, rcb_result** out) {
+    if (stage_mask & RCB_STAGE_RASTER) return fail(ctx, RCB_EARG, "rcb_apply_convex_volumes: RCB_STAGE_RASTER must not be set");
+    if (ntiles > 0 && !cell_offset) return fail(ctx, RCB_EARG, "cell_offset is null");
+    int r = check_volumes(ctx, volumes, nvolumes, poly_verts, npoly_floats);
+    if (r) return r;
+    Source s;
+    s.cell_offset = cell_offset;
+    s.smin = span_min;
+    s.smax = span_max;
+    s.sarea = span_area;
+    s.vols = volumes, s.nvols = nvolumes, s.vol_verts = poly_verts, s.nvol_floats = npoly_floats;
     return run_pipeline(ctx, cfgs, ntiles, stage_mask, erode_radius, s, out);
 }
 

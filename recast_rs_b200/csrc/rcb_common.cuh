@@ -289,6 +289,8 @@ void launch_erode(const TileDesc* tiles, int ntiles, TileMap tm, const uint32_t*
                   size_t S, uint8_t* areas, uint8_t* tmp_init, uint8_t* tmp_f, int radius, uint4* fidx, cudaStream_t s);
 
 // area operators (k_area.cu)
+void launch_convex_volumes(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smax, uint8_t* sarea,
+                           const rcb_convex_volume* vols, int nvols, const float* verts, cudaStream_t s);
 void launch_area_marks(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smin, uint8_t* areas,
                        const rcb_area_op* ops, int op0, int op1, const float* poly_verts, cudaStream_t s);
 void launch_area_median(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const uint16_t* nei16, size_t S, const uint8_t* areas,

@@ -149,6 +149,16 @@ pub struct rcb_result {
     _private: [u8; 0],
 }
 
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct rcb_convex_volume {
+    pub first_vert: u32,
+    pub num_verts: u32,
+    pub min_height: f32,
+    pub max_height: f32,
+    pub area_type: u32,
+}
+
 extern "C" {
     pub fn rcb_create(device: c_int, out: *mut *mut rcb_ctx) -> c_int;
     pub fn rcb_destroy(ctx: *mut rcb_ctx);
@@ -170,6 +180,8 @@ extern "C" {
     pub fn rcb_build_from_spans(ctx: *mut rcb_ctx, cfgs: *const rcb_config, ntiles: c_int, cell_offset: *const u32, span_min: *const i16, span_max: *const i16, span_area: *const u8, areas_override: *const u8, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
     pub fn rcb_apply_area_ops(ctx: *mut rcb_ctx, cfgs: *const rcb_config, ntiles: c_int, cell_offset: *const u32, span_min: *const i16, span_max: *const i16, span_area: *const u8, areas_override: *const u8, ops: *const rcb_area_op, nops: c_int, poly_verts: *const f32, npoly_floats: usize, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
     pub fn rcb_build_tilecache_layers(ctx: *mut rcb_ctx, layers: *const rcb_tc_layer, nlayers: c_int, obstacles: *const rcb_tc_obstacle, nobstacles: c_int, cs: f32, ch: f32, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
+    pub fn rcb_build_tiles_with_volumes(ctx: *mut rcb_ctx, cfgs: *const rcb_config, ntiles: c_int, stage_mask: u32, erode_radius: c_int, volumes: *const rcb_convex_volume, nvolumes: c_int, poly_verts: *const f32, npoly_floats: usize, out: *mut *mut rcb_result) -> c_int;
+    pub fn rcb_apply_convex_volumes(ctx: *mut rcb_ctx, cfgs: *const rcb_config, ntiles: c_int, cell_offset: *const u32, span_min: *const i16, span_max: *const i16, span_area: *const u8, volumes: *const rcb_convex_volume, nvolumes: c_int, poly_verts: *const f32, npoly_floats: usize, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
     pub fn rcb_build_from_span_data(ctx: *mut rcb_ctx, cfgs: *const rcb_config, ntiles: c_int, data: *const u8, tile_offsets: *const u64, format: c_int, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
     pub fn rcb_result_span_data_size(res: *const rcb_result) -> u64;
     pub fn rcb_result_serialize_spans(res: *mut rcb_result, format: c_int, out: *mut u8, capacity: u64, tile_offsets: *mut u64) -> c_int;
