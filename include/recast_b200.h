@@ -200,6 +200,17 @@ int rcb_build_tiles_streamed(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, u
 int rcb_rasterize(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const uint8_t* tri_areas,
                   int32_t flag_merge_threshold, uint32_t stage_mask, int erode_radius, rcb_result** out);
 
+/* rcb_rasterize_onto: rasterize the uploaded mesh onto heightfields that ALREADY hold spans (host CSR as for
+ * rcb_build_from_spans): what rasterize_triangles (rasterization.rs:405-428) and RecastBuilder::rasterize_triangles
+ * (lib.rs:186-290) do when the &mut Heightfield they are given is not empty — detour-dynamic re-applies colliders to a
+ * restored checkpoint this way (dynamic_tile.rs).  The existing spans are the initial state of every column's list;
+ * the new fragments are merged into it in triangle order with add_span_internal's rule.  tri_areas == NULL: areas by
+ * slope as RecastBuilder does (flag_merge_threshold should then be 1, lib.rs:273); else the given areas.
+ * Later stages per stage_mask (filters run over the whole heightfield, as lib.rs:276-287 does). */
+int rcb_rasterize_onto(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const uint32_t* cell_offset, const int16_t* span_min,
+                       const int16_t* span_max, const uint8_t* span_area, const uint8_t* tri_areas, int32_t flag_merge_threshold,
+                       uint32_t stage_mask, int erode_radius, rcb_result** out);
+
 /* rcb_build_from_spans: start from existing heightfields (host CSR, one per tile, concatenated):
  * Heightfield::filter_* (heightfield.rs:286,332,492), CompactHeightfield::build_from_heightfield
  * (compact_heightfield.rs:175), build_distance_field (:514), erode_walkable_area (area.rs:73).

@@ -62,6 +62,7 @@ SYMBOLS = {
     "rcb_build_tiles": (_i, [_vp, _vp, _i, _u32, _i, _pp]),
     "rcb_build_tiles_streamed": (_i, [_vp, _vp, _i, _u32, _i, _i, _pp]),
     "rcb_rasterize": (_i, [_vp, _vp, _i, _vp, ctypes.c_int32, _u32, _i, _pp]),
+    "rcb_rasterize_onto": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, ctypes.c_int32, _u32, _i, _pp]),
     "rcb_build_from_spans": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _u32, _i, _pp]),
     "rcb_build_tiles_with_volumes": (_i, [_vp, _vp, _i, _u32, _i, _vp, _i, _vp, _sz, _pp]),
     "rcb_apply_convex_volumes": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _u32, _i, _pp]),

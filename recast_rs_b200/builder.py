@@ -225,6 +225,21 @@ class Context:
                                                   ctypes.byref(out)), self._h)
         return BatchResult(self, out)
 
+    def rasterize_onto(self, cfgs, cell_offset, span_min, span_max, span_area, stage_mask: int = 0, tri_areas=None,
+                       flag_merge_threshold: int = 1, erode_radius: int = 0) -> BatchResult:
+        """Rasterize the uploaded mesh onto heightfields that already hold spans (rasterization.rs:405-428 / lib.rs:186-290 on a
+        non-empty Heightfield).  tri_areas None: areas by slope, as RecastBuilder does."""
+        arr = cfgs if isinstance(cfgs, ctypes.Array) else configs_to_array(cfgs)
+        co = np.ascontiguousarray(cell_offset, dtype=np.uint32)
+        a = np.ascontiguousarray(span_min, dtype=np.int16)
+        b = np.ascontiguousarray(span_max, dtype=np.int16)
+        c = np.ascontiguousarray(span_area, dtype=np.uint8)
+        ta = None if tri_areas is None else np.ascontiguousarray(tri_areas, dtype=np.uint8)
+        out = ctypes.c_void_p()
+        check(_ffi.lib().rcb_rasterize_onto(self._h, ctypes.cast(arr, ctypes.c_void_p), len(arr), _ptr(co), _ptr(a), _ptr(b), _ptr(c), _ptr(ta),
+                                            flag_merge_threshold, stage_mask, erode_radius, ctypes.byref(out)), self._h)
+        return BatchResult(self, out)
+
     def build_from_spans(self, cfgs, cell_offset, span_min, span_max, span_area, stage_mask, erode_radius=0,
                          areas_override=None) -> BatchResult:
         arr = cfgs if isinstance(cfgs, ctypes.Array) else configs_to_array(cfgs)
@@ -547,10 +562,13 @@ class RecastBuilder:
         c = self._config
         cfg = RecastConfig(**{**vars(c), "width": heightfield.width, "height": heightfield.height, "bmin": heightfield.bmin,
                               "bmax": heightfield.bmax, "cs": heightfield.cs, "ch": heightfield.ch})
-        if heightfield.get_span_count() != 0:
-            raise NotImplementedError("rasterizing onto a non-empty heightfield is a SURVEY §8(f) 'next' row")
-        with ctx.build_tiles([cfg], STAGE_RASTER | STAGE_FILTER) as r:
-            tv = r.download().tile(0)
+        if heightfield.get_span_count() != 0:  # e.g. a restored checkpoint that gets its colliders back
+            hf = heightfield
+            with ctx.rasterize_onto([cfg], hf.cell_offset, hf.span_min, hf.span_max, hf.span_area, STAGE_FILTER) as r:
+                tv = r.download().tile(0)
+        else:
+            with ctx.build_tiles([cfg], STAGE_RASTER | STAGE_FILTER) as r:
+                tv = r.download().tile(0)
         heightfield.cell_offset, heightfield.span_min = tv.hf_cell_offset, tv.span_min
         heightfield.span_max, heightfield.span_area = tv.span_max, tv.span_area
 

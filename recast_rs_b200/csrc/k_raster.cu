@@ -287,11 +287,13 @@ __global__ void __launch_bounds__(256) k_scatter_fragments(const uint4* __restri
 __global__ void __launch_bounds__(256) k_replay_columns(uint32_t ncells, const uint32_t* __restrict__ frag_off,
                                                         uint32_t* __restrict__ fs_tri, uint32_t* __restrict__ fs_mm,
                                                         uint8_t* __restrict__ fs_area, uint32_t* __restrict__ span_cnt,
-                                                        int32_t thr) {
+                                                        int32_t thr, const uint32_t* __restrict__ ex_off) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncells) return;
     const uint32_t b = frag_off[c], e = frag_off[c + 1];
     const uint32_t n = e - b;
+    // rasterizing onto a non-empty heightfield: the column's first nex entries are its existing spans, already a list
+    const uint32_t nex = ex_off ? ex_off[c + 1] - ex_off[c] : 0u;
     if (n == 0) {
         span_cnt[c] = 0;
         return;
@@ -300,11 +302,11 @@ __global__ void __launch_bounds__(256) k_replay_columns(uint32_t ncells, const u
     uint32_t* mm = fs_mm + b;
     uint8_t* ar = fs_area + b;
     // insertion sort by triangle index (typical n: 2-4 on terrain, ~40 in the 16-floor interior)
-    for (uint32_t i = 1; i < n; ++i) {
+    for (uint32_t i = nex + 1; i < n; ++i) {
         const uint32_t kt = tri[i], km = mm[i];
         const uint8_t ka = ar[i];
         uint32_t j = i;
-        while (j > 0 && tri[j - 1] > kt) {
+        while (j > nex && tri[j - 1] > kt) {
             tri[j] = tri[j - 1];
             mm[j] = mm[j - 1];
             ar[j] = ar[j - 1];
@@ -315,8 +317,8 @@ __global__ void __launch_bounds__(256) k_replay_columns(uint32_t ncells, const u
         ar[j] = ka;
     }
     // replay (rasterization.rs:51-168) on the array form of the list
-    uint32_t ns = 0;
-    for (uint32_t i = 0; i < n; ++i) {
+    uint32_t ns = nex;
+    for (uint32_t i = nex; i < n; ++i) {
         const uint32_t w = mm[i];
         const int smin = (int16_t)(w & 0xffffu), smax = (int16_t)(w >> 16);
         const uint32_t area = ar[i];
@@ -482,12 +484,42 @@ void launch_scatter_fragments(const uint4* frag_tmp, const unsigned long long* n
 }
 
 void launch_replay_columns(uint32_t ncells, const uint32_t* frag_off, uint32_t* fs_tri, uint32_t* fs_mm,
-                           uint8_t* fs_area, uint32_t* span_cnt, int32_t merge_thr, cudaStream_t s) {
+                           uint8_t* fs_area, uint32_t* span_cnt, int32_t merge_thr, cudaStream_t s, const uint32_t* ex_off) {
     if (ncells == 0) return;
     {
         KScope _k("k_replay_columns", s);
-        k_replay_columns<<<(ncells + 255) / 256, 256, 0, s>>>(ncells, frag_off, fs_tri, fs_mm, fs_area, span_cnt, merge_thr);
+        k_replay_columns<<<(ncells + 255) / 256, 256, 0, s>>>(ncells, frag_off, fs_tri, fs_mm, fs_area, span_cnt, merge_thr, ex_off);
     }
+}
+
+// Rasterizing onto a non-empty heightfield (rasterize_triangles on a Heightfield that already holds spans,
+// rasterization.rs:405-428 / lib.rs:186-290): sign = +1 adds the existing span counts to the per-column fragment
+// counts before the offsets are scanned; the second call (sign = -1) takes them out again, so that the scatter fills
+// the END of each column's range, and copies the existing spans to its beginning.
+__global__ void __launch_bounds__(256) k_onto(uint32_t ncells, const uint32_t* __restrict__ ex_off, uint32_t* __restrict__ cell_cnt,
+                                              int place, const uint32_t* __restrict__ frag_off, const int16_t* __restrict__ smin,
+                                              const int16_t* __restrict__ smax, const uint8_t* __restrict__ sarea,
+                                              uint32_t* __restrict__ fs_mm, uint8_t* __restrict__ fs_area) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const uint32_t b = ex_off[c], n = ex_off[c + 1] - b;
+    if (!place) {
+        cell_cnt[c] += n;
+        return;
+    }
+    cell_cnt[c] -= n;
+    const uint32_t o = frag_off[c];
+    for (uint32_t k = 0; k < n; ++k) {
+        fs_mm[o + k] = ((uint32_t)(uint16_t)smin[b + k]) | ((uint32_t)(uint16_t)smax[b + k] << 16);
+        fs_area[o + k] = sarea[b + k];
+    }
+}
+
+void launch_onto(uint32_t ncells, const uint32_t* ex_off, uint32_t* cell_cnt, int place, const uint32_t* frag_off, const int16_t* smin,
+                 const int16_t* smax, const uint8_t* sarea, uint32_t* fs_mm, uint8_t* fs_area, cudaStream_t s) {
+    if (ncells == 0) return;
+    KScope _k("k_onto", s);
+    k_onto<<<(ncells + 255) / 256, 256, 0, s>>>(ncells, ex_off, cell_cnt, place, frag_off, smin, smax, sarea, fs_mm, fs_area);
 }
 
 void launch_gather_spans(uint32_t ncells, const uint32_t* frag_off, const uint32_t* fs_mm, const uint8_t* fs_area,

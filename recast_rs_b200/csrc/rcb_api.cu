@@ -620,6 +620,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
     if (src.raster) {
         if (ctx->nfloats == 0 || ctx->nidx == 0) {
             do_raster = false;  // Ok(()) with untouched heightfields
+            if (src.cell_offset) fmask = 0;  // lib.rs:195 returns before the filters: an existing heightfield stays as it is
         } else {
             if (ctx->nfloats % 3 != 0) return bail(fail(ctx, RCB_ENAVMESH_GEN, "Vertex array length must be a multiple of 3"));
             if (ctx->nidx % 3 != 0) return bail(fail(ctx, RCB_ENAVMESH_GEN, "Index array length must be a multiple of 3"));
@@ -711,7 +712,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                 r2.item_cnt = ctx->d_item_cnt.as<uint32_t>();
                 // tile-resident back end candidates: moderate tiles (the CSR arrays of a tile must fit shared memory)
                 // (fragment records carry a 24-bit triangle index)
-                want_tile = !ctx->force_global && !src.no_tile_mode && src.nvols == 0 && 8ull * max_cells + 4096 <= kTileSmem && ntris < (1u << 24);
+                want_tile = !ctx->force_global && !src.no_tile_mode && src.nvols == 0 && !src.cell_offset && 8ull * max_cells + 4096 <= kTileSmem && ntris < (1u << 24);
                 // per-tile fragment bounds -> per-tile segments (both back ends consume fragments tile by tile)
                 CUB(ctx->d_tile_ub.ensure(4 * ((size_t)ntiles + 1)));
                 CUB(ctx->d_tile_base.ensure(4 * ((size_t)ntiles + 2)));
@@ -863,10 +864,52 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             return RCB_OK;
         }
         uint32_t* d_frag_off = ctx->d_frag_off.as<uint32_t>();
+        // ---- rasterizing onto heightfields that already hold spans (rasterization.rs:405 / lib.rs:186 on a non-empty hf) ----
+        const bool onto = src.cell_offset != nullptr;
+        uint64_t Sex = 0;
+        const uint32_t* d_ex_off = nullptr;
+        const int16_t *d_ex_min = nullptr, *d_ex_max = nullptr;
+        const uint8_t* d_ex_area = nullptr;
+        std::vector<uint32_t> gex;
+        if (onto) {
+            if (!v2 && do_raster) return bail(fail(ctx, RCB_EARG, "rasterizing onto a non-empty heightfield needs the v2 clipper (tile too wide, or a clip polygon overflowed)"));
+            gex.resize(Ctot + 1);
+            uint64_t pos = 0;
+            for (int i = 0; i < ntiles; ++i) {
+                const uint64_t C = (uint64_t)res->tiles[i].width * res->tiles[i].height;
+                const uint32_t* co = src.cell_offset + pos;
+                if (co[0] != 0) return bail(fail(ctx, RCB_EARG, "tile %d: cell_offset[0] != 0", i));
+                for (uint64_t c = 0; c < C; ++c) {
+                    if (co[c + 1] < co[c]) return bail(fail(ctx, RCB_EARG, "tile %d: cell_offset not ascending", i));
+                    gex[res->tiles[i].cell_base + c] = (uint32_t)(Sex + co[c]);
+                }
+                Sex += co[C];
+                pos += C + 1;
+                if (Sex + ub >= 0xfffffff0ull) return bail(fail(ctx, RCB_EARG, "too many spans"));
+            }
+            gex[Ctot] = (uint32_t)Sex;
+            const size_t o_max = align_up(2 * Sex + 16), o_area = 2 * o_max;
+            CUB(ctx->d_wire.ensure(o_area + Sex + 64));
+            CUB(ctx->d_wire_inoff.ensure(4 * (Ctot + 1)));
+            CUB(cudaMemcpyAsync(ctx->d_wire_inoff.p, gex.data(), 4 * (Ctot + 1), cudaMemcpyHostToDevice, st));
+            if (Sex) {
+                CUB(cudaMemcpyAsync(ctx->d_wire.p, src.smin, 2 * Sex, cudaMemcpyHostToDevice, st));
+                CUB(cudaMemcpyAsync((char*)ctx->d_wire.p + o_max, src.smax, 2 * Sex, cudaMemcpyHostToDevice, st));
+                CUB(cudaMemcpyAsync((char*)ctx->d_wire.p + o_area, src.sarea, Sex, cudaMemcpyHostToDevice, st));
+            }
+            CUB(cudaStreamSynchronize(st));  // pageable host sources
+            d_ex_off = ctx->d_wire_inoff.as<uint32_t>();
+            d_ex_min = (const int16_t*)ctx->d_wire.p;
+            d_ex_max = (const int16_t*)((const char*)ctx->d_wire.p + o_max);
+            d_ex_area = (const uint8_t*)((const char*)ctx->d_wire.p + o_area);
+        }
+        const uint64_t cap = ub + Sex;
+        if (cap > 0) {
+            CUB(ctx->d_fs_tri.ensure(4 * cap));
+            CUB(ctx->d_fs_mm.ensure(4 * cap));
+            CUB(ctx->d_fs_area.ensure(cap));
+        }
         if (ub > 0) {
-            CUB(ctx->d_fs_tri.ensure(4 * ub));
-            CUB(ctx->d_fs_mm.ensure(4 * ub));
-            CUB(ctx->d_fs_area.ensure(ub));
             if (v2) {
                 // fragments go to per-tile segments; each tile then counts and scatters its own columns
                 CUB(ctx->d_tile_frags.ensure(12 * ub + 64));
@@ -887,7 +930,11 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                 launch_clip_emit(rb, d_tinfo_tmp, st);
             }
         }
+        if (onto) launch_onto((uint32_t)Ctot, d_ex_off, rb.cell_cnt, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st);
         launch_exclusive_scan(rb.cell_cnt, d_frag_off, Ctot, ctx->d_scan_tmp.as<uint32_t>(), st);
+        if (onto)
+            launch_onto((uint32_t)Ctot, d_ex_off, rb.cell_cnt, 1, d_frag_off, d_ex_min, d_ex_max, d_ex_area, ctx->d_fs_mm.as<uint32_t>(),
+                        ctx->d_fs_area.as<uint8_t>(), st);
         if (ub > 0) {
             if (v2)
                 launch_seg_scatter(d_tiles, ntiles, r2.tile_frags, r2.tile_base, r2.tile_cap, r2.tile_cursor, d_frag_off, rb.cell_cnt,
@@ -896,9 +943,10 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             else
                 launch_scatter_fragments(rb.frag_tmp, rb.counters + 1, (uint32_t)ub, d_frag_off, ctx->d_fs_tri.as<uint32_t>(),
                                          ctx->d_fs_mm.as<uint32_t>(), ctx->d_fs_area.as<uint8_t>(), st);
-            launch_replay_columns((uint32_t)Ctot, d_frag_off, ctx->d_fs_tri.as<uint32_t>(), ctx->d_fs_mm.as<uint32_t>(),
-                                  ctx->d_fs_area.as<uint8_t>(), rb.cell_cnt, src.merge_thr, st);
         }
+        if (cap > 0)
+            launch_replay_columns((uint32_t)Ctot, d_frag_off, ctx->d_fs_tri.as<uint32_t>(), ctx->d_fs_mm.as<uint32_t>(),
+                                  ctx->d_fs_area.as<uint8_t>(), rb.cell_cnt, src.merge_thr, st, d_ex_off);
         launch_exclusive_scan(rb.cell_cnt, d_hf_off, Ctot, ctx->d_scan_tmp.as<uint32_t>(), st);
         CUB(cudaMemcpyAsync(&ctx->h_counters[4], d_hf_off + Ctot, 4, cudaMemcpyDeviceToHost, st));
         CUB(cudaMemcpyAsync(&ctx->h_counters[5], ctx->d_counters.as<unsigned long long>() + 1, 8, cudaMemcpyDeviceToHost, st));
@@ -1247,6 +1295,21 @@ int rcb_build_tiles(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t s
 }
 
 static int download_on(rcb_result* res, cudaStream_t st, bool wait);
+
+int rcb_rasterize_onto(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const uint32_t* cell_offset, const int16_t* span_min,
+                       const int16_t* span_max, const uint8_t* span_area, const uint8_t* tri_areas, int32_t flag_merge_threshold,
+                       uint32_t stage_mask, int erode_radius, rcb_result** out) {
+    if (ntiles > 0 && !cell_offset) return fail(ctx, RCB_EARG, "cell_offset is null");
+    Source s;
+    s.raster = true;
+    s.tri_areas = tri_areas;
+    s.merge_thr = flag_merge_threshold;
+    s.cell_offset = cell_offset;
+    s.smin = span_min;
+    s.smax = span_max;
+    s.sarea = span_area;
+    return run_pipeline(ctx, cfgs, ntiles, stage_mask | RCB_STAGE_RASTER, erode_radius, s, out);
+}
 
 int rcb_build_tiles_streamed(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stage_mask, int erode_radius, int ngroups,
                              rcb_result** out) {

@@ -97,7 +97,9 @@ void launch_scatter_fragments(const uint4* frag_tmp, const unsigned long long* n
                               const uint32_t* frag_off, uint32_t* fs_tri, uint32_t* fs_mm, uint8_t* fs_area,
                               cudaStream_t s);
 void launch_replay_columns(uint32_t ncells, const uint32_t* frag_off, uint32_t* fs_tri, uint32_t* fs_mm,
-                           uint8_t* fs_area, uint32_t* span_cnt, int32_t merge_thr, cudaStream_t s);
+                           uint8_t* fs_area, uint32_t* span_cnt, int32_t merge_thr, cudaStream_t s, const uint32_t* ex_off = nullptr);
+void launch_onto(uint32_t ncells, const uint32_t* ex_off, uint32_t* cell_cnt, int place, const uint32_t* frag_off, const int16_t* smin,
+                 const int16_t* smax, const uint8_t* sarea, uint32_t* fs_mm, uint8_t* fs_area, cudaStream_t s);
 void launch_gather_spans(uint32_t ncells, const uint32_t* frag_off, const uint32_t* fs_mm, const uint8_t* fs_area,
                          const uint32_t* hf_off, int16_t* smin, int16_t* smax, uint8_t* sarea, cudaStream_t s);
 

@@ -177,6 +177,7 @@ extern "C" {
     pub fn rcb_build_tiles(ctx: *mut rcb_ctx, cfgs: *const rcb_config, ntiles: c_int, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
     pub fn rcb_build_tiles_streamed(ctx: *mut rcb_ctx, cfgs: *const rcb_config, ntiles: c_int, stage_mask: u32, erode_radius: c_int, ngroups: c_int, out: *mut *mut rcb_result) -> c_int;
     pub fn rcb_rasterize(ctx: *mut rcb_ctx, cfgs: *const rcb_config, ntiles: c_int, tri_areas: *const u8, flag_merge_threshold: i32, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
+    pub fn rcb_rasterize_onto(ctx: *mut rcb_ctx, cfgs: *const rcb_config, ntiles: c_int, cell_offset: *const u32, span_min: *const i16, span_max: *const i16, span_area: *const u8, tri_areas: *const u8, flag_merge_threshold: i32, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
     pub fn rcb_build_from_spans(ctx: *mut rcb_ctx, cfgs: *const rcb_config, ntiles: c_int, cell_offset: *const u32, span_min: *const i16, span_max: *const i16, span_area: *const u8, areas_override: *const u8, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
     pub fn rcb_apply_area_ops(ctx: *mut rcb_ctx, cfgs: *const rcb_config, ntiles: c_int, cell_offset: *const u32, span_min: *const i16, span_max: *const i16, span_area: *const u8, areas_override: *const u8, ops: *const rcb_area_op, nops: c_int, poly_verts: *const f32, npoly_floats: usize, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
     pub fn rcb_build_tilecache_layers(ctx: *mut rcb_ctx, layers: *const rcb_tc_layer, nlayers: c_int, obstacles: *const rcb_tc_obstacle, nobstacles: c_int, cs: f32, ch: f32, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;

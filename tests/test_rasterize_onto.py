@@ -1,0 +1,104 @@
+"""Rasterizing onto a heightfield that already holds spans ("colliders re-applied incrementally"):
+rasterize_triangles (rasterization.rs:405-428) and RecastBuilder::rasterize_triangles (lib.rs:186-290) given a non-empty
+&mut Heightfield.  The oracle does it natively (its columns are lists); the device path seeds every column with its
+existing spans and replays the new fragments behind them."""
+import numpy as np
+import pytest
+
+from oracle import pymodel as pm
+from recast_rs_b200.config import RecastConfig
+from tests.parity import random_soup
+
+
+def _case(seed):
+    rng = np.random.default_rng(seed)
+    w, h, cs, ch = int(rng.integers(6, 26)), int(rng.integers(6, 26)), 0.5, 0.25
+    cfg = RecastConfig(width=w, height=h, cs=cs, ch=ch, bmin=(0.0, -1.0, 0.0), bmax=(w * cs, 8.0, h * cs), walkable_height=3, walkable_climb=2)
+    v1, i1 = random_soup(rng, 60, 0.0, max(w, h) * cs, -0.5, 4.0, small=cs * 3)
+    v2, i2 = random_soup(rng, 60, 0.0, max(w, h) * cs, -0.5, 5.0, small=cs * 3)
+    return cfg, v1, i1, v2, i2
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_oracle_vs_pymodel_two_meshes_in_sequence(oracle, seed):
+    cfg, v1, i1, v2, i2 = _case(seed)
+    ohf = oracle.Heightfield.from_config(cfg)
+    ohf.builder_rasterize(cfg, v1, i1)
+    ohf.builder_rasterize(cfg, v2, i2)
+    phf = pm.Heightfield(cfg.width, cfg.height, cfg.bmin, cfg.bmax, cfg.cs, cfg.ch)
+    pm.builder_rasterize(phf, cfg, v1, i1)
+    pm.builder_rasterize(phf, cfg, v2, i2)
+    a, b = ohf.export(), phf.export()
+    assert np.array_equal(a.cell_offset, b[0]) and np.array_equal(a.span_min, b[1]) and np.array_equal(a.span_max, b[2])
+    assert np.array_equal(a.span_area, b[3])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(6))
+def test_gpu_rasterize_onto(oracle, seed):
+    import recast_rs_b200.builder as rb
+    from tests.parity import assert_tile_equal
+
+    cfg, v1, i1, v2, i2 = _case(20 + seed)
+    first = oracle.Heightfield.from_config(cfg)
+    first.builder_rasterize(cfg, v1, i1)
+    e = first.export()
+    want_hf = oracle.Heightfield.from_csr(cfg.width, cfg.height, cfg.bmin, cfg.bmax, cfg.cs, cfg.ch, e.cell_offset, e.span_min, e.span_max, e.span_area)
+    want_hf.builder_rasterize(cfg, v2, i2)  # second mesh onto the first one's heightfield, filters again (lib.rs:276-287)
+    oc = oracle.CompactHeightfield.build_from_heightfield(want_hf)
+    oc.build_distance_field()
+    with rb.Context(0) as ctx:
+        builder = rb.RecastBuilder(cfg, ctx)
+        hf = builder.build_heightfield(v1, i1)
+        builder.rasterize_triangles(hf, v2, i2)  # the reference-shaped call on a non-empty heightfield
+        w = want_hf.export()
+        for a, b in ((hf.cell_offset, w.cell_offset), (hf.span_min, w.span_min), (hf.span_max, w.span_max), (hf.span_area, w.span_area)):
+            np.testing.assert_array_equal(a, b)
+        # batched, with later stages in the same call
+        ctx.upload_mesh(v2, i2)
+        with ctx.rasterize_onto([cfg], e.cell_offset, e.span_min, e.span_max, e.span_area, rb.STAGE_FILTER | rb.STAGE_COMPACT | rb.STAGE_DIST) as r:
+            assert_tile_equal(r.download().tile(0), w, oc.export(), what="onto")
+        # explicit areas + merge threshold: the free function rasterize_triangles (rasterization.rs:405)
+        rng = np.random.default_rng(seed)
+        areas = rng.integers(0, 4, i2.size // 3).astype(np.uint8)
+        o2 = oracle.Heightfield.from_csr(cfg.width, cfg.height, cfg.bmin, cfg.bmax, cfg.cs, cfg.ch, e.cell_offset, e.span_min, e.span_max, e.span_area)
+        o2.rasterize_triangles(v2, i2, areas, 2)
+        with ctx.rasterize_onto([cfg], e.cell_offset, e.span_min, e.span_max, e.span_area, 0, tri_areas=areas, flag_merge_threshold=2) as r:
+            assert_tile_equal(r.download().tile(0), o2.export(), what="onto, explicit areas")
+        # an empty mesh leaves the heightfield untouched, filters included (lib.rs:195)
+        ctx.upload_mesh(np.zeros(0, np.float32), np.zeros(0, np.int32))
+        with ctx.rasterize_onto([cfg], e.cell_offset, e.span_min, e.span_max, e.span_area, rb.STAGE_FILTER) as r:
+            assert_tile_equal(r.download().tile(0), e, what="onto, empty mesh")
+
+
+@pytest.mark.gpu
+def test_gpu_rasterize_onto_many_tiles(oracle):
+    """Two halves of a terrain rasterized one after the other onto the same tiles == both at once is NOT expected
+    (span areas depend on the order); the reference order (first half, then second half) is."""
+    import recast_rs_b200.builder as rb
+    from recast_rs_b200 import synth
+
+    v, t = synth.terrain(40, 1.2, 4.0, 9)
+    cfgs = synth.tile_grid(v, 32, RecastConfig(cs=0.3, ch=0.2))
+    tris = t.reshape(-1, 3)
+    ta, tb = np.ascontiguousarray(tris[::2].reshape(-1)), np.ascontiguousarray(tris[1::2].reshape(-1))
+    with rb.Context(0) as ctx:
+        ctx.upload_mesh(v, ta)
+        with ctx.build_tiles(cfgs, rb.STAGE_RASTER | rb.STAGE_FILTER) as r:
+            r.download()
+            tiles = [r.tile(i) for i in range(len(cfgs))]
+            off = np.concatenate([tv.hf_cell_offset for tv in tiles])
+            mn, mx, ar = (np.concatenate([getattr(tv, k) for tv in tiles]) for k in ("span_min", "span_max", "span_area"))
+        ctx.upload_mesh(v, tb)
+        with ctx.rasterize_onto(cfgs, off, mn, mx, ar, rb.STAGE_FILTER | rb.STAGE_COMPACT | rb.STAGE_DIST) as r:
+            r.download()
+            for i, c in enumerate(cfgs):
+                ohf = oracle.Heightfield.from_config(c)
+                ohf.builder_rasterize(c, v, ta)
+                ohf.builder_rasterize(c, v, tb)
+                oc = oracle.CompactHeightfield.build_from_heightfield(ohf)
+                oc.build_distance_field()
+                tv = r.tile(i)
+                np.testing.assert_array_equal(tv.span_min, oc.export().span_min, err_msg=str(i))
+                np.testing.assert_array_equal(tv.span_area, oc.export().span_area, err_msg=str(i))
+                np.testing.assert_array_equal(tv.dist, oc.export().dist, err_msg=str(i))
