@@ -252,9 +252,12 @@ __device__ __forceinline__ uint32_t list_neighbor(const Tile& t, uint32_t s, int
 
 struct RegClock {
     unsigned long long* acc;
-    long long t;
-    __device__ RegClock(unsigned long long* a) : acc(a), t(0) {
-        if (acc && threadIdx.x == 0) t = clock64();
+    long long t, t0;
+    __device__ RegClock(unsigned long long* a) : acc(a), t(0), t0(0) {
+        if (acc && threadIdx.x == 0) t = t0 = clock64();
+    }
+    __device__ void finish() {  // slowest tile
+        if (acc && threadIdx.x == 0) atomicMax(&acc[8], (unsigned long long)(clock64() - t0));
     }
     __device__ void mark(int id) {
         if (acc && threadIdx.x == 0) {
@@ -421,21 +424,42 @@ __global__ void __launch_bounds__(BT) k_regions(RegionArgs a) {
             while (ncur > 0) {
                 if (threadIdx.x == 0) sh_next = 0;
                 __syncthreads();
-                for (uint32_t k = threadIdx.x; k < ncur; k += BT) {
-                    const uint32_t ci = cur[k];
-                    if (!ws_kept(t, ci, region_id, area)) {
-                        t.reg[ci] = 0;  // :218-221
+                // four lanes per frontier cell, one per direction: a wave's latency is the instruction chain of one
+                // lane, and a lane that handles one neighbour (and its clockwise diagonal) has a quarter of it
+                for (uint32_t k0 = 0; k0 < ncur; k0 += BT / 4) {
+                    const uint32_t k = k0 + (threadIdx.x >> 2);
+                    const int d = (int)(threadIdx.x & 3u);
+                    const bool valid = k < ncur;
+                    uint32_t ci = 0, ai = NONE32;
+                    bool bad = false, same = false;
+                    if (valid) {
+                        ci = cur[k];
+                        ai = nbr(t, d, ci);
+                        if (ai != NONE32 && t.areas[ai] == area) {
+                            same = true;
+                            const uint32_t nr = *(volatile uint16_t*)&t.reg[ai];
+                            if (!(nr & BORDER)) {  // a border neighbour skips its diagonal too (:183-186)
+                                if (nr != 0 && nr != region_id) {
+                                    bad = true;
+                                } else {
+                                    const uint32_t ai2 = nbr(t, (d + 1) & 3, ai);
+                                    if (ai2 != NONE32 && t.areas[ai2] == area) {
+                                        const uint32_t nr2 = *(volatile uint16_t*)&t.reg[ai2];
+                                        if (nr2 != 0 && nr2 != region_id) bad = true;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    const unsigned grp = (__ballot_sync(0xffffffffu, bad) >> ((threadIdx.x & 31u) & ~3u)) & 0xfu;
+                    if (!valid) continue;
+                    if (grp) {
+                        if (d == 0) t.reg[ci] = 0;  // :218-221
                         continue;
                     }
-#pragma unroll
-                    for (int d = 0; d < 4; ++d) {
-                        const uint32_t ai = nbr(t, d, ci);
-                        if (ai == NONE32) continue;
-                        if (t.areas[ai] != area) continue;
-                        if (t.dist[ai] >= lev && cas16(&t.reg[ai], 0, (uint16_t)region_id) == 0) {
-                            t.sdist[ai] = 0;
-                            nxt[atomicAdd(&sh_next, 1u)] = ai;
-                        }
+                    if (same && t.dist[ai] >= lev && cas16(&t.reg[ai], 0, (uint16_t)region_id) == 0) {
+                        t.sdist[ai] = 0;
+                        nxt[atomicAdd(&sh_next, 1u)] = ai;
                     }
                 }
                 __syncthreads();
@@ -577,6 +601,7 @@ __global__ void __launch_bounds__(BT) k_regions(RegionArgs a) {
         }
     }
     pc.mark(7);
+    pc.finish();
 }
 
 }  // namespace

@@ -541,10 +541,10 @@ int build_regions_stage(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, 
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
     if (ctx->phase_timers) {
-        unsigned long long ph[8];
+        unsigned long long ph[9];
         cudaMemcpy(ph, b + o_phase, sizeof ph, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[rcb phase cycles/tile] regions: init %llu sort %llu append %llu expand %llu seed-search %llu flood %llu final-expand %llu merge %llu\n",
-                ph[0] / ntiles, ph[1] / ntiles, ph[2] / ntiles, ph[3] / ntiles, ph[4] / ntiles, ph[5] / ntiles, ph[6] / ntiles, ph[7] / ntiles);
+        fprintf(stderr, "[rcb phase cycles/tile] regions: init %llu sort %llu append %llu expand %llu seed-search %llu flood %llu final-expand %llu merge %llu | slowest tile %llu\n",
+                ph[0] / ntiles, ph[1] / ntiles, ph[2] / ntiles, ph[3] / ntiles, ph[4] / ntiles, ph[5] / ntiles, ph[6] / ntiles, ph[7] / ntiles, ph[8]);
     }
     const uint32_t bad = (uint32_t)ctx->h_counters[7];
     if (bad != 0xffffffffu) return fail(ctx, RCB_ERECAST, "tile %u: Region ID overflow", bad);
