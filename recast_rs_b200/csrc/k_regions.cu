@@ -400,15 +400,21 @@ __global__ void __launch_bounds__(BT) k_regions(RegionArgs a) {
         const uint32_t lev = level >= 2 ? level - 2 : 0;
         uint32_t cursor = 0;
         for (;;) {
-            uint32_t mine = NONE32;
-            for (uint32_t j = cursor + threadIdx.x; j < len; j += BT) {
-                const uint32_t v = stack[j];
-                if (t.reg[v] == 0 && ws_kept(t, v, region_id, t.areas[v])) {
-                    mine = j;
-                    break;
+            // the next seed: the first entry at or after the cursor that is still unlabelled and passes its own test.
+            // One window of BT entries per step (one entry per thread): entries before the hit are done for good,
+            // and nobody walks the whole stack on its own.
+            uint32_t jmin = NONE32;
+            while (cursor < len) {
+                const uint32_t j = cursor + threadIdx.x;
+                uint32_t mine = NONE32;
+                if (j < len) {
+                    const uint32_t v = stack[j];
+                    if (t.reg[v] == 0 && ws_kept(t, v, region_id, t.areas[v])) mine = j;
                 }
+                jmin = block_min(mine, sh);
+                if (jmin != NONE32) break;
+                cursor += BT;
             }
-            const uint32_t jmin = block_min(mine, sh);
             pc.mark(4);
             if (jmin == NONE32) break;
             const uint32_t seed = stack[jmin];
