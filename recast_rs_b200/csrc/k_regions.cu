@@ -268,7 +268,8 @@ struct RegClock {
     }
 };
 
-__global__ void __launch_bounds__(BT) k_regions(RegionArgs a) {
+// 14 CTAs per SM (<= 73 registers): the 2025 tiles of config 2 are all resident at once
+__global__ void __launch_bounds__(BT, 14) k_regions(RegionArgs a) {
     __shared__ BlockSh sh;
     RegClock pc(a.phase);
     __shared__ uint32_t sh_len[8];
@@ -367,17 +368,54 @@ __global__ void __launch_bounds__(BT) k_regions(RegionArgs a) {
         s_id = (s_id + 1) & 7;
         uint32_t len;
         if (s_id == 0) {  // sort_cells_by_level (:65-119), log_levels_per_stack = 1
+            // all eight stacks in one sweep: every thread classifies a contiguous run of spans (4 bits each, kept in
+            // registers), the eight per-thread counts are scanned two to a word, then the run is written out in order
             const uint32_t start = level >> 1;
-            for (uint32_t k = 0; k < 8; ++k) {
-                const uint32_t n = block_compact(S, 0, sh,
-                                                 [&](uint32_t s, uint32_t& pl) {
-                                                     pl = s;
-                                                     if (t.areas[s] == 0 || t.reg[s] != 0) return false;
-                                                     const uint32_t lv = (uint32_t)t.dist[s] >> 1;
-                                                     return (start > lv ? start - lv : 0u) == k;
-                                                 },
-                                                 [&](uint32_t pos, uint32_t s) { t.stack[k][pos] = s; });
-                if (threadIdx.x == 0) sh_len[k] = n;
+            uint32_t base8[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) base8[k] = 0;
+            for (uint32_t c0 = 0; c0 < S; c0 += BT * 64u) {
+                const uint32_t m = min(S - c0, (uint32_t)BT * 64u);
+                const uint32_t per = (m + BT - 1) / BT;  // <= 64
+                const uint32_t lo = c0 + threadIdx.x * per, hi = min(lo + per, c0 + m);
+                unsigned long long nib[4] = {0, 0, 0, 0};
+                uint32_t cnt[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) cnt[k] = 0;
+                for (uint32_t i = lo; i < hi; ++i) {
+                    uint32_t sid = 15;
+                    if (t.areas[i] != 0 && t.reg[i] == 0) {
+                        const uint32_t lv = (uint32_t)t.dist[i] >> 1;
+                        const uint32_t d = start > lv ? start - lv : 0u;  // saturating_sub (:97)
+                        if (d < 8) sid = d;
+                    }
+                    const uint32_t q = i - lo;
+                    nib[q >> 4] |= (unsigned long long)sid << ((q & 15u) * 4u);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) cnt[k] += sid == (uint32_t)k;
+                }
+                uint32_t ex[8];
+#pragma unroll
+                for (int k = 0; k < 8; k += 2) {  // at most BT * 64 = 4096 entries per sweep: 16 bits hold a prefix
+                    uint32_t total;
+                    const uint32_t e = block_excl_scan(cnt[k] | (cnt[k + 1] << 16), &total, sh);
+                    ex[k] = base8[k] + (e & 0xffffu);
+                    ex[k + 1] = base8[k + 1] + (e >> 16);
+                    base8[k] += total & 0xffffu;
+                    base8[k + 1] += total >> 16;
+                }
+                for (uint32_t i = lo; i < hi; ++i) {
+                    const uint32_t q = i - lo;
+                    const uint32_t sid = (uint32_t)(nib[q >> 4] >> ((q & 15u) * 4u)) & 15u;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (sid == (uint32_t)k) t.stack[k][ex[k]++] = i;
+                }
+            }
+            if (threadIdx.x < 8) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (threadIdx.x == (uint32_t)k) sh_len[k] = base8[k];
             }
             __syncthreads();
             len = sh_len[0];
