@@ -576,8 +576,12 @@ __global__ void __launch_bounds__(BT, 14) k_regions(RegionArgs a) {
     // merges (:636-716): a round's decisions are taken from the state before the round
     if (merge_area > 0) {
         for (;;) {
-            for (uint32_t i = threadIdx.x; i < R; i += BT) best[i] = 0ull, target[i] = 0, cadd[i] = 0;
-            __syncthreads();
+            uint32_t ncand = 0;  // regions that would merge if they find a neighbour: none -> no span pass needed
+            for (uint32_t i = threadIdx.x; i < R; i += BT) {
+                best[i] = 0ull, target[i] = 0, cadd[i] = 0;
+                ncand += alive[i] != 0 && cnt[i] != 0 && cnt[i] < merge_area && !border[i];
+            }
+            if (block_sum(ncand, sh) == 0) break;
             for (int pass = 0; pass < 2; ++pass) {
                 for (uint32_t s = threadIdx.x; s < S; s += BT) {
                     const uint32_t rid = t.reg0[s];
