@@ -83,7 +83,7 @@ __device__ uint32_t block_scan_array(const uint32_t* cnt, OutT* out, uint32_t n,
 __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_spans(TileSpansArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t sh_warp[TILE_THREADS / 32 + 1];
-    __shared__ uint32_t sh_red[2];
+    __shared__ uint32_t sh_red[4];  // [0] walkable spans, [1] max height, [3] replay work-list length
     const uint32_t tile = blockIdx.x;
     const TileDesc& td = a.tiles[tile];
     const int W = td.width, H = td.height;
@@ -138,9 +138,25 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_spans(TileSpansArgs a)
     pc.mark(2);
     // 4. per-column replay (rasterization.rs:51-168), spans built in place over the consumed prefix
     const int thr = a.merge_thr;
-    for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
+    // Only columns with two or more fragments need a replay (an empty column, or a single fragment which is its own
+    // span, is done).  They are listed first (soff is free until the spans are counted), so that every lane of every
+    // warp has a column to work on instead of two lanes in three idling next to the busy ones.
+    if (threadIdx.x == 0) sh_red[3] = 0;
+    __syncthreads();
+    for (uint32_t c0 = 0; c0 < C; c0 += TILE_THREADS) {
+        const uint32_t c = c0 + threadIdx.x;
+        const bool w = c < C && cnt[c] >= 2;
+        const unsigned m = __ballot_sync(0xffffffffu, w);
+        uint32_t base = 0;
+        if ((threadIdx.x & 31) == 0 && m) base = atomicAdd(&sh_red[3], (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (w) soff[base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = (uint16_t)c;
+    }
+    __syncthreads();
+    const uint32_t nwork = sh_red[3];
+    for (uint32_t k = threadIdx.x; k < nwork; k += TILE_THREADS) {
+        const uint32_t c = soff[k];
         const uint32_t n = cnt[c];
-        if (n <= 1) continue;  // empty column, or a single fragment which is its own span
         uint2* r = rec + off[c];
         for (uint32_t i = 1; i < n; ++i) {  // insertion sort by triangle index
             const uint2 key = r[i];
