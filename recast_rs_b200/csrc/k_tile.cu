@@ -596,7 +596,7 @@ __device__ uint32_t lookback_resolve(volatile unsigned long long* look, uint32_t
 __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t sh_warp[TILE_THREADS / 32 + 1];
-    __shared__ uint32_t sh_misc[4];  // [0] tile id, [1] conn base, [2] max distance, [3] overflow
+    __shared__ uint32_t sh_misc[4];  // [0] tile id, [1] conn base, [2] max distance, [3] link work-list length
     // dynamic tile id: tiles start in order, which the look-back relies on
     if (threadIdx.x == 0) {
         sh_misc[0] = atomicAdd(a.tile_ticket, 1u);
@@ -697,64 +697,86 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
     }
     __syncthreads();
     pc.mark(0);
-    // 2. cells (compact_heightfield.rs:203-223) + 3. link (:297-372) + con[4] (:392-427)
-    for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
-        const uint32_t b = soff[c], e = soff[c + 1];
-        a.cell_index[td.cell_base + c] = e > b ? b : RCB_NONE;
-        a.cell_count[td.cell_base + c] = e - b;
-        uint32_t nconn = 0;
-        if (e > b) {
-            const int z = (int)rcb_div_w(c, wmagic), x = (int)c - z * W;
-            uint32_t nb[8], ne[8];
-#pragma unroll
-            for (int d = 0; d < 8; ++d) {
-                const int nx = x + t_dirx[d], nz = z + t_dirz[d];
-                if (nx < 0 || nz < 0 || nx >= W || nz >= H) {
-                    nb[d] = ne[d] = 0;
-                } else {
-                    nb[d] = soff[nz * W + nx];
-                    ne[d] = soff[nz * W + nx + 1];
-                }
-            }
-            for (uint32_t s = b; s < e; ++s) {
-                const uint32_t w = mm[s];
-                const int mn = (int16_t)(w & 0xffffu), mx = (int16_t)(w >> 16);
-                uint32_t c4[4] = {63, 63, 63, 63};
-                if (areas[s] != 0) {
-#pragma unroll
-                    for (int d = 0; d < 8; ++d) {
-                        uint32_t best = TN;
-                        int best_diff = 0x7fffffff;
-                        for (uint32_t ns = nb[d]; ns < ne[d]; ++ns) {
-                            if (areas[ns] == 0) continue;
-                            const uint32_t nw = mm[ns];
-                            const int nmn = (int16_t)(nw & 0xffffu), nmx = (int16_t)(nw >> 16);
-                            if (max(nmn, mn) > min(nmx, mx)) continue;
-                            const int diff = (int)(uint16_t)(abs(nmn - mn) + abs(nmx - mx));
-                            if (diff < best_diff) {
-                                best_diff = diff;
-                                best = ns;
-                            }
-                        }
-                        nid[(uint32_t)d * S2 + s] = (uint16_t)best;
-                        if (best != TN) {
-                            nconn++;
-                            const uint32_t o = best - nb[d];  // offset inside the neighbour cell (:418-421)
-                            if (d == 7) c4[0] = o;
-                            if (d == 5) c4[1] = o;
-                            if (d == 3) c4[2] = o;
-                            if (d == 1) c4[3] = o;
-                        }
-                    }
+    // 2. cells (compact_heightfield.rs:203-223); spans that cannot link get their defaults; the walkable ones are listed.
+    //    Only ~45 % of the spans are walkable: linking straight out of the cell loop left most lanes idle next to the
+    //    busy ones.  The list lives in the tile's ts_mm segment, which is dead once mm is loaded.
+    uint32_t* const work = const_cast<uint32_t*>(a.ts_mm) + tb;
+    if (threadIdx.x == 0) sh_misc[3] = 0;
+    __syncthreads();
+    for (uint32_t c0 = 0; c0 < C; c0 += TILE_THREADS) {
+        const uint32_t c = c0 + threadIdx.x;
+        uint32_t b = 0, e = 0, nw = 0;
+        if (c < C) {
+            b = soff[c], e = soff[c + 1];
+            a.cell_index[td.cell_base + c] = e > b ? b : RCB_NONE;
+            a.cell_count[td.cell_base + c] = e - b;
+            coff[c] = 0;
+            for (uint32_t sp = b; sp < e; ++sp) {
+                if (areas[sp] != 0) {
+                    ++nw;
                 } else {
 #pragma unroll
-                    for (int d = 0; d < 8; ++d) nid[(uint32_t)d * S2 + s] = (uint16_t)TN;
+                    for (int d = 0; d < 8; ++d) nid[(uint32_t)d * S2 + sp] = (uint16_t)TN;
+                    *reinterpret_cast<uint2*>(a.con + 4ull * (span_base + sp)) = make_uint2(63u | (63u << 16), 63u | (63u << 16));
                 }
-                *reinterpret_cast<uint2*>(a.con + 4ull * (span_base + s)) =
-                    make_uint2((c4[0] & 0xffffu) | (c4[1] << 16), (c4[2] & 0xffffu) | (c4[3] << 16));
             }
         }
-        coff[c] = nconn;
+        uint32_t incl = nw;  // warp-aggregated append: one atomic per warp
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((threadIdx.x & 31) >= (uint32_t)d) incl += v;
+        }
+        uint32_t base = 0;
+        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+        if ((threadIdx.x & 31) == 31 && tot) base = atomicAdd(&sh_misc[3], tot);
+        base = __shfl_sync(0xffffffffu, base, 31) + incl - nw;
+        for (uint32_t sp = b; sp < e; ++sp)
+            if (areas[sp] != 0) work[base++] = (c << 16) | sp;
+    }
+    __syncthreads();
+    // 3. link (:297-372) + con[4] (:392-427), one listed span per thread
+    const uint32_t nwork = sh_misc[3];
+    for (uint32_t k = threadIdx.x; k < nwork; k += TILE_THREADS) {
+        const uint32_t item = work[k];
+        const uint32_t c = item >> 16, sp = item & 0xffffu;
+        const int z = (int)rcb_div_w(c, wmagic), x = (int)c - z * W;
+        const uint32_t w = mm[sp];
+        const int mn = (int16_t)(w & 0xffffu), mx = (int16_t)(w >> 16);
+        uint32_t c4[4] = {63, 63, 63, 63};
+        uint32_t nconn = 0;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+            const int nx = x + t_dirx[d], nz = z + t_dirz[d];
+            uint32_t best = TN;
+            if (!(nx < 0 || nz < 0 || nx >= W || nz >= H)) {
+                const uint32_t nb = soff[nz * W + nx], ne = soff[nz * W + nx + 1];
+                int best_diff = 0x7fffffff;
+                for (uint32_t ns = nb; ns < ne; ++ns) {
+                    if (areas[ns] == 0) continue;
+                    const uint32_t nw = mm[ns];
+                    const int nmn = (int16_t)(nw & 0xffffu), nmx = (int16_t)(nw >> 16);
+                    if (max(nmn, mn) > min(nmx, mx)) continue;
+                    const int diff = (int)(uint16_t)(abs(nmn - mn) + abs(nmx - mx));
+                    if (diff < best_diff) {
+                        best_diff = diff;
+                        best = ns;
+                    }
+                }
+                if (best != TN) {
+                    nconn++;
+                    const uint32_t o = best - nb;  // offset inside the neighbour cell (:418-421)
+                    if (d == 7) c4[0] = o;
+                    if (d == 5) c4[1] = o;
+                    if (d == 3) c4[2] = o;
+                    if (d == 1) c4[3] = o;
+                }
+            }
+            nid[(uint32_t)d * S2 + sp] = (uint16_t)best;
+        }
+        *reinterpret_cast<uint2*>(a.con + 4ull * (span_base + sp)) =
+            make_uint2((c4[0] & 0xffffu) | (c4[1] << 16), (c4[2] & 0xffffu) | (c4[3] << 16));
+        if (nconn) atomicAdd(&coff[c], nconn);
     }
     if (threadIdx.x < 8) nid[threadIdx.x * S2 + S] = (uint16_t)S;  // the dummy span's neighbours are itself
     __syncthreads();
