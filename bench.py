@@ -77,6 +77,12 @@ def make_sharded_workload(config: int, seed: int, rank: int, world: int):
     if world == 1:
         v, t, cfgs, name = make_workload(config, seed)
         return v, t, cfgs, name, t.size // 3, len(cfgs)
+    if config == 3:  # BASELINE configs[2]: ONE 10M-triangle world, its tiles sharded over the ranks (strong scaling)
+        v, t, all_cfgs, name = make_workload(3, seed)
+        ids = shard.shard_tiles(len(all_cfgs), rank, world, "slab")
+        cfgs = [all_cfgs[i] for i in ids]
+        sv, st = shard.prebin_mesh(v, t, cfgs)
+        return sv, st, cfgs, name + f", one world slab-sharded over {world} ranks", t.size // 3, len(all_cfgs)
     if config != 2:
         v, t, cfgs, name = make_workload(config, seed + rank)  # independent replicas of the named config
         return v, t, cfgs, name + f" x {world} independent slabs", (t.size // 3) * world, len(cfgs) * world
@@ -469,7 +475,8 @@ def run_native(args, rank, world, local_rank):
         ksum = sum(kern_ms.values())
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if (args.config == 3 and world > 1) else "weak",
+            "vs_baseline": None,
             "dtype": "f32 clip + i16/u16 spans", "data": "synthetic",
             "config": {"workload": name,
                        "seed": args.seed, "stages": "raster+filters+compact+connections+distance_field",
