@@ -67,7 +67,7 @@ def make_workload(config: int, seed: int):
     return v, t, cfgs, name
 
 
-def make_sharded_workload(config: int, seed: int, rank: int, world: int):
+def make_sharded_workload(config: int, seed: int, rank: int, world: int, mode: str = "slab"):
     """N > 1: ONE world with ~world x the triangles of the single-GPU workload (weak scaling); tiles are
     split into contiguous slabs of tile rows, one per rank, and each rank receives the triangles over its
     slab (order preserved).  No data moves between ranks on the build path.
@@ -79,10 +79,10 @@ def make_sharded_workload(config: int, seed: int, rank: int, world: int):
         return v, t, cfgs, name, t.size // 3, len(cfgs)
     if config == 3:  # BASELINE configs[2]: ONE 10M-triangle world, its tiles sharded over the ranks (strong scaling)
         v, t, all_cfgs, name = make_workload(3, seed)
-        ids = shard.shard_tiles(len(all_cfgs), rank, world, "slab")
+        ids = shard.shard_tiles(len(all_cfgs), rank, world, mode)
         cfgs = [all_cfgs[i] for i in ids]
         sv, st = shard.prebin_mesh(v, t, cfgs)
-        return sv, st, cfgs, name + f", one world slab-sharded over {world} ranks", t.size // 3, len(all_cfgs)
+        return sv, st, cfgs, name + f", one world {mode}-sharded over {world} ranks", t.size // 3, len(all_cfgs)
     if config != 2:
         v, t, cfgs, name = make_workload(config, seed + rank)  # independent replicas of the named config
         return v, t, cfgs, name + f" x {world} independent slabs", (t.size // 3) * world, len(cfgs) * world
@@ -362,7 +362,7 @@ def run_native(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # every rank owns one slab of the world: its own tiles and the triangles over them
-    v, t, cfgs, name, T_world, tiles_world = make_sharded_workload(args.config, args.seed, rank, world)
+    v, t, cfgs, name, T_world, tiles_world = make_sharded_workload(args.config, args.seed, rank, world, args.shard)
     from recast_rs_b200.config import configs_to_array
 
     cfg_arr = configs_to_array(cfgs)
@@ -526,6 +526,7 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--shard", default="slab", choices=["slab", "block_cyclic"], help="how config 3's tiles are dealt to the ranks")
     ap.add_argument("--e2e-groups", type=int, default=1, help="tile groups of the host-to-host call (1: build then download)")
     ap.add_argument("--tc-compressed", action="store_true", help="config 5 from LZ4-compressed tiles (SURVEY 8(f) rank 3)")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
