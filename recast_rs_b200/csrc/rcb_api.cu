@@ -534,7 +534,16 @@ int build_regions_stage(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, 
         if (r) return r;
         uint32_t smax = 0;
         for (auto& ti : res->tinfo) smax = std::max(smax, ti.span_count);
-        ra.smem_spans = (smax < 0xFFFFu && regions_smem_bytes(smax) <= 100 * 1024) ? std::max(smax, 1u) : 0u;
+        // Labels in shared memory make a tile ~1.6x faster, but the kernel ends with its slowest tile and a tile is a long
+        // dependent chain: what counts is how many waves of CTAs the batch needs (14 CTAs per SM by registers).
+        const size_t bytes = regions_smem_bytes(smax);
+        const bool fits = smax < 0xFFFFu && bytes <= 100 * 1024;
+        const size_t per_sm_smem = fits ? std::min<size_t>(14, (227 * 1024) / (bytes + 1024)) : 0;
+        const double waves_smem = per_sm_smem ? std::ceil((double)ntiles / (148.0 * (double)per_sm_smem)) : 1e30;
+        const double waves_glob = std::ceil((double)ntiles / (148.0 * 14.0));
+        bool use_smem = fits && waves_smem <= 1.6 * waves_glob;
+        if (const char* e = getenv("RCB_REGIONS_SMEM")) use_smem = fits && atoi(e) != 0;
+        ra.smem_spans = use_smem ? std::max(smax, 1u) : 0u;
     }
     launch_regions(ra, ntiles, st);
     CU(cudaMemcpyAsync(&ctx->h_counters[7], b + o_err, 4, cudaMemcpyDeviceToHost, st));
