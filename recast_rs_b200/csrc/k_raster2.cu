@@ -224,6 +224,8 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
                                                              TileInfo* __restrict__ tinfo) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ClipSmem& sm = *reinterpret_cast<ClipSmem*>(smem_raw);
+    const bool timed = (rb.flags & 0x100u) != 0 && threadIdx.x == 0;  // RCB_PHASE_TIMERS: counters[40..43]
+    long long tclk = timed ? clock64() : 0;
     if (threadIdx.x < NBUCK) sm.nb[threadIdx.x] = sm.cur[threadIdx.x] = 0;
     if (threadIdx.x == 0) sm.nlist = 0;
 #pragma unroll
@@ -334,6 +336,11 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
         }
     }
     __syncthreads();
+    if (timed) {
+        const long long n = clock64();
+        atomicAdd(&rb.counters[40], (unsigned long long)(n - tclk));
+        tclk = n;
+    }
 
     // ---------------- phase 2: x-chain, one row polygon per thread at a time ------------------------------
     const bool use_minx = (rb.flags & 1u) != 0;
@@ -357,6 +364,11 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
         }
     }
     __syncthreads();
+    if (timed) {
+        const long long n = clock64();
+        atomicAdd(&rb.counters[41], (unsigned long long)(n - tclk));
+        tclk = n;
+    }
     for (uint32_t li = threadIdx.x; li < nlist; li += CLIP_THREADS) {
         const uint32_t* slot = sm.slots + (uint32_t)sm.list[li] * SLOT_WORDS;
         const uint32_t tri = slot[0], tile = slot[1];
@@ -446,6 +458,10 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
             atomicOr(&tinfo[tile].status, 1u);
             atomicOr(&rb.counters[2], 1ull);
         }
+    }
+    if (timed) {  // thread 0's own share of phase 2 (no barrier behind it: the CTA ends when its slowest thread does)
+        atomicAdd(&rb.counters[42], (unsigned long long)(clock64() - tclk));
+        atomicAdd(&rb.counters[43], 1ull);
     }
 }
 

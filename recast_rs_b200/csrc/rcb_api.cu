@@ -710,7 +710,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         r2.mesh = rb.mesh;
         r2.counters = rb.counters;
         r2.cell_cnt = rb.cell_cnt;
-        r2.flags = ctx->clip_flags;
+        r2.flags = ctx->clip_flags | (ctx->phase_timers ? 0x100u : 0u);
         uint64_t ub = 0, nitems = 0;
         bool want_tile = false;
         if (do_raster && ntiles > 0) {
@@ -856,6 +856,8 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                 unsigned long long ph[32];
                 cudaMemcpyAsync(ph, r2.counters + 16, sizeof ph, cudaMemcpyDeviceToHost, st);
                 cudaStreamSynchronize(st);
+                fprintf(stderr, "[rcb phase cycles/CTA] clip: z-chain %llu list %llu x-chain(thread 0) %llu | ", ph[24] / (ph[27] ? ph[27] : 1),
+                        ph[25] / (ph[27] ? ph[27] : 1), ph[26] / (ph[27] ? ph[27] : 1));
                 fprintf(stderr, "[rcb phase cycles/tile] spans:");
                 for (int i = 0; i < 7; ++i) fprintf(stderr, " %llu", ph[i] / (unsigned long long)ntiles);
                 fprintf(stderr, " | compact:");
