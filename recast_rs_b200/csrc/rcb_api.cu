@@ -539,11 +539,14 @@ int build_regions_stage(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, 
         const size_t bytes = regions_smem_bytes(smax);
         const bool fits = smax < 0xFFFFu && bytes <= 100 * 1024;
         const size_t per_sm_smem = fits ? std::min<size_t>(14, (227 * 1024) / (bytes + 1024)) : 0;
-        const double waves_smem = per_sm_smem ? std::ceil((double)ntiles / (148.0 * (double)per_sm_smem)) : 1e30;
-        const double waves_glob = std::ceil((double)ntiles / (148.0 * 14.0));
-        bool use_smem = fits && waves_smem <= 1.6 * waves_glob;
-        if (const char* e = getenv("RCB_REGIONS_SMEM")) use_smem = fits && atoi(e) != 0;
-        ra.smem_spans = use_smem ? std::max(smax, 1u) : 0u;
+        // relative cost of one tile: 1.0 with labels in shared memory, ~1.6 with labels in global memory (either CTA size)
+        const double t_smem = per_sm_smem ? std::ceil((double)ntiles / (148.0 * (double)per_sm_smem)) : 1e30;
+        const double t_wide = 1.6 * std::ceil((double)ntiles / (148.0 * 14.0));
+        const double t_narrow = 1.6 * std::ceil((double)ntiles / (148.0 * 32.0));
+        int mode = t_smem <= t_wide && t_smem <= t_narrow ? 0 : (t_wide <= t_narrow ? 1 : 2);
+        if (const char* e = getenv("RCB_REGIONS_MODE")) mode = atoi(e) == 0 && !fits ? 1 : atoi(e);  // 0 smem, 1 wide, 2 narrow
+        ra.smem_spans = mode == 0 ? std::max(smax, 1u) : 0u;
+        ra.narrow = mode == 2;
     }
     launch_regions(ra, ntiles, st);
     CU(cudaMemcpyAsync(&ctx->h_counters[7], b + o_err, 4, cudaMemcpyDeviceToHost, st));
