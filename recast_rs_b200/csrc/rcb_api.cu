@@ -546,7 +546,9 @@ int build_regions_stage(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, 
         int mode = t_smem <= t_wide && t_smem <= t_narrow ? 0 : (t_wide <= t_narrow ? 1 : 2);
         if (const char* e = getenv("RCB_REGIONS_MODE")) mode = atoi(e) == 0 && !fits ? 1 : atoi(e);  // 0 smem, 1 wide, 2 narrow
         ra.smem_spans = mode == 0 ? std::max(smax, 1u) : 0u;
-        ra.narrow = mode == 2;
+        ra.narrow = mode == 2 ? 1 : 0;
+        if (mode != 2 && ntiles <= 148 * 2 && smax >= 16384) ra.narrow = 2;  // few, very large tiles: 256 threads each
+        if (const char* e = getenv("RCB_REGIONS_WIDE256")) ra.narrow = atoi(e) ? 2 : ra.narrow == 2 ? 0 : ra.narrow;
     }
     launch_regions(ra, ntiles, st);
     CU(cudaMemcpyAsync(&ctx->h_counters[7], b + o_err, 4, cudaMemcpyDeviceToHost, st));

@@ -242,7 +242,8 @@ struct RegionArgs {
     unsigned int* err;  // first tile whose region ids overflowed (init 0xffffffff)
     unsigned long long* phase;  // RCB_PHASE_TIMERS: cycle sums per phase (thread 0 of every tile), or nullptr
     uint32_t smem_spans;        // tiles with at most this many spans keep their arrays in shared memory (0: none do)
-    int narrow;                 // 1: the 32-thread build (32 CTAs per SM), for batches that would not be resident otherwise
+    int narrow;                 // 0: 64 threads; 1: the 32-thread build (32 CTAs per SM), for batches that would not be resident
+                                // otherwise; 2: the 256-thread build, for a few very large tiles
 };
 size_t regions_smem_bytes(uint32_t max_spans);
 void launch_regions(const RegionArgs& a, int ntiles, cudaStream_t s);
