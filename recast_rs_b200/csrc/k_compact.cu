@@ -52,129 +52,153 @@ __global__ void __launch_bounds__(256) k_cells(const TileDesc* __restrict__ tile
     }
 }
 
-// One thread per column: for every walkable span pick, per direction, the first neighbour span with
-// minimal |dmin|+|dmax| among the walkable overlapping ones (compact_heightfield.rs:316-368).
-__global__ void __launch_bounds__(256) k_link_spans(const TileDesc* __restrict__ tiles, TileMap tm,
-                                                    const uint32_t* __restrict__ hf_off,
-                                                    const int16_t* __restrict__ smin, const int16_t* __restrict__ smax,
-                                                    const uint8_t* __restrict__ sarea, uint8_t* __restrict__ areas,
-                                                    uint16_t* __restrict__ nei16, size_t S, uint16_t* __restrict__ con,
-                                                    uint32_t* __restrict__ cell_conn_cnt, TileInfo* __restrict__ tinfo) {
+// ---- span-parallel linking ---------------------------------------------------------------------------------
+// One thread per SPAN instead of one per column: a column of a multi-level interior holds 16+ spans, each probing up to
+// 8 x 16 neighbour spans, and a thread that walks its column alone leaves the machine mostly empty (config 4: 590 k
+// columns, 8 M spans).  k_span_cells records (tile, cell) per span; the connection offsets are then a scan over spans.
+__global__ void __launch_bounds__(256) k_span_cells(const TileDesc* __restrict__ tiles, TileMap tm, const uint32_t* __restrict__ hf_off,
+                                                    uint2* __restrict__ span_cell) {
     const uint32_t tile = RCB_TILE_OF_BLOCK();
     if (tile >= tm.ntiles) return;
     const TileDesc& td = tiles[tile];
-    const int W = td.width, H = td.height;
     const uint32_t lc = RCB_CELL_OF_THREAD();
-    uint32_t walkable = 0, maxh = 0;
-    if (lc < (uint32_t)(W * H)) {
-        const int x = lc % W, z = lc / W;
-        const uint32_t g = td.cell_base + lc;
-        const uint32_t b = hf_off[g], e = hf_off[g + 1];
-        uint32_t nconn = 0;
-        if (e > b) {
-            uint32_t nb[8], ne[8];
-#pragma unroll
-            for (int d = 0; d < 8; ++d) {
-                const int nx = x + c_dirx[d], nz = z + c_dirz[d];
-                if (nx < 0 || nz < 0 || nx >= W || nz >= H) {
-                    nb[d] = ne[d] = 0;
-                } else {
-                    const uint32_t ng = td.cell_base + (uint32_t)nz * W + nx;
-                    nb[d] = hf_off[ng];
-                    ne[d] = hf_off[ng + 1];
-                }
-            }
-            for (uint32_t s = b; s < e; ++s) {
-                const int mn = smin[s], mx = smax[s];
-                const uint32_t a = sarea[s];
-                areas[s] = (uint8_t)a;                       // :237
-                maxh = max(maxh, (uint32_t)(uint16_t)mx);    // :240
-                uint16_t c4[4] = {63, 63, 63, 63};
-                if (a != 0) {
-                    walkable++;  // :243-245
-#pragma unroll
-                    for (int d = 0; d < 8; ++d) {
-                        uint32_t best = RCB_NEI_NONE;
-                        int best_diff = 0x7fffffff;
-                        for (uint32_t ns = nb[d]; ns < ne[d]; ++ns) {
-                            if (sarea[ns] == 0) continue;
-                            const int nmn = smin[ns], nmx = smax[ns];
-                            if (max(nmn, mn) > min(nmx, mx)) continue;
-                            const int diff = (int)(uint16_t)(abs(nmn - mn) + abs(nmx - mx));
-                            if (diff < best_diff) {
-                                best_diff = diff;
-                                best = ns - nb[d];
-                            }
-                        }
-                        nei16[(size_t)d * S + s] = (uint16_t)best;
-                        if (best != RCB_NEI_NONE) {
-                            nconn++;
-                            if (d == 7) c4[0] = (uint16_t)best;  // :404-410
-                            if (d == 5) c4[1] = (uint16_t)best;
-                            if (d == 3) c4[2] = (uint16_t)best;
-                            if (d == 1) c4[3] = (uint16_t)best;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int d = 0; d < 8; ++d) nei16[(size_t)d * S + s] = RCB_NEI_NONE;
-                }
-                *reinterpret_cast<uint2*>(con + 4 * (size_t)s) =
-                    make_uint2((uint32_t)c4[0] | ((uint32_t)c4[1] << 16), (uint32_t)c4[2] | ((uint32_t)c4[3] << 16));
-            }
-        }
-        cell_conn_cnt[g] = nconn;
-    }
-    // per-tile reductions (every block belongs to exactly one tile)
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        walkable += __shfl_down_sync(0xffffffffu, walkable, d);
-        maxh = max(maxh, __shfl_down_sync(0xffffffffu, maxh, d));
-    }
-    if (lane_id() == 0) {
-        if (walkable) atomicAdd(&tinfo[tile].walkable_span_count, walkable);
-        if (maxh) atomicMax(&tinfo[tile].max_height, maxh);
-    }
+    if (lc >= (uint32_t)(td.width * td.height)) return;
+    const uint32_t g = td.cell_base + lc;
+    for (uint32_t s = hf_off[g]; s < hf_off[g + 1]; ++s) span_cell[s] = make_uint2(tile, lc);
 }
 
-// Connection list layout (compact_heightfield.rs:375-389): spans in index order; each span pushes its
-// connections in REVERSE direction order, next -> previously pushed, first_connection = last pushed.
-__global__ void __launch_bounds__(256) k_write_connections(const TileDesc* __restrict__ tiles, TileMap tm,
-                                                           const uint32_t* __restrict__ hf_off,
-                                                           const uint16_t* __restrict__ nei16, size_t S,
-                                                           const uint32_t* __restrict__ conn_off,
-                                                           const TileInfo* __restrict__ tinfo,
-                                                           uint32_t* __restrict__ first_conn, uint32_t* __restrict__ conn_ref,
-                                                           uint8_t* __restrict__ conn_dir, uint32_t* __restrict__ conn_next) {
-    const uint32_t tile = RCB_TILE_OF_BLOCK();
-    if (tile >= tm.ntiles) return;
+__global__ void __launch_bounds__(256) k_link_spans2(const TileDesc* __restrict__ tiles, uint32_t S, const uint2* __restrict__ span_cell,
+                                                     const uint32_t* __restrict__ hf_off, const int16_t* __restrict__ smin,
+                                                     const int16_t* __restrict__ smax, const uint8_t* __restrict__ sarea,
+                                                     uint8_t* __restrict__ areas, uint16_t* __restrict__ nei16, uint16_t* __restrict__ con,
+                                                     uint32_t* __restrict__ span_conn_cnt, TileInfo* __restrict__ tinfo) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const uint2 sc = span_cell[s];
+    const uint32_t tile = sc.x, lc = sc.y;
     const TileDesc& td = tiles[tile];
     const int W = td.width, H = td.height;
-    const uint32_t lc = RCB_CELL_OF_THREAD();
-    if (lc >= (uint32_t)(W * H)) return;
-    const int x = lc % W, z = lc / W;
-    const uint32_t g = td.cell_base + lc;
-    const uint32_t b = hf_off[g], e = hf_off[g + 1];
-    if (b == e) return;
-    const uint32_t span_base = tinfo[tile].span_base, conn_base = tinfo[tile].conn_base;
-    uint32_t k = conn_off[g];  // global connection cursor of this column
-    for (uint32_t s = b; s < e; ++s) {
-        uint32_t first = RCB_NONE;
-        for (int d = 7; d >= 0; --d) {
-            const uint32_t o = nei16[(size_t)d * S + s];
-            if (o == RCB_NEI_NONE) continue;
-            const uint32_t ng = td.cell_base + (uint32_t)(z + c_dirz[d]) * W + (x + c_dirx[d]);
-            conn_ref[k] = hf_off[ng] + o - span_base;
-            conn_dir[k] = (uint8_t)d;
-            conn_next[k] = first;
-            first = k - conn_base;
-            ++k;
+    const int z = (int)(lc / (uint32_t)W), x = (int)lc - z * W;
+    const int mn = smin[s], mx = smax[s];
+    const uint32_t a = sarea[s];
+    areas[s] = (uint8_t)a;  // :237
+    {  // per-tile reductions, one atomic per (warp, tile): :240, :243-245
+        const unsigned peers = __match_any_sync(__activemask(), tile);
+        const uint32_t wsum = __reduce_add_sync(peers, a != 0 ? 1u : 0u);
+        const uint32_t hmax = __reduce_max_sync(peers, (uint32_t)(uint16_t)mx);
+        if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+            if (wsum) atomicAdd(&tinfo[tile].walkable_span_count, wsum);
+            if (hmax) atomicMax(&tinfo[tile].max_height, hmax);
         }
-        first_conn[s] = first;
     }
+    uint16_t c4[4] = {63, 63, 63, 63};
+    uint32_t nconn = 0;
+    if (a != 0) {
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+            const int nx = x + c_dirx[d], nz = z + c_dirz[d];
+            uint32_t best = RCB_NEI_NONE;
+            if (!(nx < 0 || nz < 0 || nx >= W || nz >= H)) {
+                const uint32_t ng = td.cell_base + (uint32_t)nz * W + nx;
+                const uint32_t nb = hf_off[ng], ne = hf_off[ng + 1];
+                int best_diff = 0x7fffffff;
+                for (uint32_t ns = nb; ns < ne; ++ns) {
+                    if (sarea[ns] == 0) continue;
+                    const int nmn = smin[ns], nmx = smax[ns];
+                    if (max(nmn, mn) > min(nmx, mx)) continue;
+                    const int diff = (int)(uint16_t)(abs(nmn - mn) + abs(nmx - mx));
+                    if (diff < best_diff) {
+                        best_diff = diff;
+                        best = ns - nb;
+                    }
+                }
+            }
+            nei16[(size_t)d * S + s] = (uint16_t)best;
+            if (best != RCB_NEI_NONE) {
+                nconn++;
+                if (d == 7) c4[0] = (uint16_t)best;  // :404-410
+                if (d == 5) c4[1] = (uint16_t)best;
+                if (d == 3) c4[2] = (uint16_t)best;
+                if (d == 1) c4[3] = (uint16_t)best;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int d = 0; d < 8; ++d) nei16[(size_t)d * S + s] = RCB_NEI_NONE;
+    }
+    *reinterpret_cast<uint2*>(con + 4 * (size_t)s) =
+        make_uint2((uint32_t)c4[0] | ((uint32_t)c4[1] << 16), (uint32_t)c4[2] | ((uint32_t)c4[3] << 16));
+    span_conn_cnt[s] = nconn;
+}
+
+__global__ void k_tile_conn_bases(int ntiles, const uint32_t* __restrict__ conn_off_span, TileInfo* __restrict__ tinfo) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const uint32_t b = tinfo[t].span_base, e = b + tinfo[t].span_count;
+    tinfo[t].conn_base = conn_off_span[b];
+    tinfo[t].conn_count = conn_off_span[e] - conn_off_span[b];
+}
+
+__global__ void __launch_bounds__(256) k_write_connections2(const TileDesc* __restrict__ tiles, uint32_t S, const uint2* __restrict__ span_cell,
+                                                            const uint32_t* __restrict__ hf_off, const uint16_t* __restrict__ nei16,
+                                                            const uint32_t* __restrict__ conn_off_span, const TileInfo* __restrict__ tinfo,
+                                                            uint32_t* __restrict__ first_conn, uint32_t* __restrict__ conn_ref,
+                                                            uint8_t* __restrict__ conn_dir, uint32_t* __restrict__ conn_next) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const uint2 sc = span_cell[s];
+    const uint32_t tile = sc.x, lc = sc.y;
+    const TileDesc& td = tiles[tile];
+    const int W = td.width;
+    const int z = (int)(lc / (uint32_t)W), x = (int)lc - z * W;
+    const uint32_t span_base = tinfo[tile].span_base, conn_base = tinfo[tile].conn_base;
+    uint32_t k = conn_off_span[s];
+    uint32_t first = RCB_NONE;
+#pragma unroll
+    for (int d = 7; d >= 0; --d) {
+        const uint32_t o = nei16[(size_t)d * S + s];
+        if (o == RCB_NEI_NONE) continue;
+        const uint32_t ng = td.cell_base + (uint32_t)(z + c_dirz[d]) * W + (x + c_dirx[d]);
+        conn_ref[k] = hf_off[ng] + o - span_base;
+        conn_dir[k] = (uint8_t)d;
+        conn_next[k] = first;
+        first = k - conn_base;
+        ++k;
+    }
+    first_conn[s] = first;
 }
 
 }  // namespace
+
+void launch_span_cells(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, uint2* span_cell, cudaStream_t s) {
+    if (tm.nblocks == 0) return;
+    KScope _k("k_span_cells", s);
+    k_span_cells<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, span_cell);
+}
+
+void launch_link_spans2(const TileDesc* tiles, size_t S, const uint2* span_cell, const uint32_t* hf_off, const int16_t* smin,
+                        const int16_t* smax, const uint8_t* sarea, uint8_t* areas, uint16_t* nei16, uint16_t* con, uint32_t* span_conn_cnt,
+                        TileInfo* tinfo, cudaStream_t s) {
+    if (S == 0) return;
+    KScope _k("k_link_spans2", s);
+    k_link_spans2<<<(unsigned)((S + 255) / 256), 256, 0, s>>>(tiles, (uint32_t)S, span_cell, hf_off, smin, smax, sarea, areas, nei16, con,
+                                                              span_conn_cnt, tinfo);
+}
+
+void launch_tile_conn_bases(int ntiles, const uint32_t* conn_off_span, TileInfo* tinfo, cudaStream_t s) {
+    if (ntiles == 0) return;
+    KScope _k("k_tile_conn_bases", s);
+    k_tile_conn_bases<<<(ntiles + 127) / 128, 128, 0, s>>>(ntiles, conn_off_span, tinfo);
+}
+
+void launch_write_connections2(const TileDesc* tiles, size_t S, const uint2* span_cell, const uint32_t* hf_off, const uint16_t* nei16,
+                               const uint32_t* conn_off_span, const TileInfo* tinfo, uint32_t* first_conn, uint32_t* conn_ref,
+                               uint8_t* conn_dir, uint32_t* conn_next, cudaStream_t s) {
+    if (S == 0) return;
+    KScope _k("k_write_connections2", s);
+    k_write_connections2<<<(unsigned)((S + 255) / 256), 256, 0, s>>>(tiles, (uint32_t)S, span_cell, hf_off, nei16, conn_off_span, tinfo,
+                                                                     first_conn, conn_ref, conn_dir, conn_next);
+}
 
 void launch_tile_bases(const TileDesc* tiles, int ntiles, const uint32_t* hf_off, const uint32_t* conn_off,
                        TileInfo* tinfo, cudaStream_t s) {
@@ -191,27 +215,5 @@ void launch_cells_and_offsets(const TileDesc* tiles, TileMap tm, const uint32_t*
     {
         KScope _k("k_cells", s);
         k_cells<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, hf_cell_offset, cell_index, cell_count, tinfo);
-    }
-}
-
-void launch_link_spans(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smin,
-                       const int16_t* smax, const uint8_t* sarea, uint8_t* areas, uint16_t* nei16, size_t S,
-                       uint16_t* con, uint32_t* cell_conn_cnt, TileInfo* tinfo, cudaStream_t s) {
-    if (tm.nblocks == 0) return;
-    {
-        KScope _k("k_link_spans", s);
-        k_link_spans<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, smin, smax, sarea, areas, nei16, S, con, cell_conn_cnt,
-                                            tinfo);
-    }
-}
-
-void launch_write_connections(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const uint16_t* nei16,
-                              size_t S, const uint32_t* conn_off, const TileInfo* tinfo, uint32_t* first_conn,
-                              uint32_t* conn_ref, uint8_t* conn_dir, uint32_t* conn_next, cudaStream_t s) {
-    if (tm.nblocks == 0) return;
-    {
-        KScope _k("k_write_connections", s);
-        k_write_connections<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, conn_off, tinfo, first_conn, conn_ref,
-                                                   conn_dir, conn_next);
     }
 }

@@ -402,17 +402,27 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
 
     // ---- COMPACT: link, connection list ----------------------------------------------------------------------
     if (compact) {
-        CU(ctx->d_conn_cnt.ensure(4 * (Ctot + 1)));
-        CU(ctx->d_conn_off.ensure(4 * (Ctot + 1)));
+        // span-parallel linking (k_link_spans2): counts and offsets are per SPAN
+        CU(ctx->d_conn_cnt.ensure(4 * (S + 1)));
+        CU(ctx->d_conn_off.ensure(4 * (S + 1)));
+        CU(ctx->d_scan_tmp.ensure(4 * scan_tmp_elems(std::max<uint64_t>(S, Ctot) + 1)));
         CU(ctx->d_nei16.ensure(16 * S + 256));
+        CU(ctx->d_fidx.ensure(16 * (S + 1)));  // first (tile, cell) per span, later the forward-sweep gather ids
         uint32_t* d_conn_cnt = ctx->d_conn_cnt.as<uint32_t>();
         uint32_t* d_conn_off = ctx->d_conn_off.as<uint32_t>();
         uint16_t* d_nei16 = ctx->d_nei16.as<uint16_t>();
+        uint2* d_span_cell = ctx->d_fidx.as<uint2>();
         uint8_t* d_areas = (uint8_t*)(A + res->lay.areas);
-        launch_link_spans(d_tiles, tm, d_hf_off, d_smin, d_smax, d_sarea, d_areas, d_nei16, S, (uint16_t*)(A + res->lay.con),
-                          d_conn_cnt, d_tinfo, st);
-        launch_exclusive_scan(d_conn_cnt, d_conn_off, Ctot, ctx->d_scan_tmp.as<uint32_t>(), st);
-        CU(cudaMemcpyAsync(&ctx->h_counters[4], d_conn_off + Ctot, 4, cudaMemcpyDeviceToHost, st));
+        launch_span_cells(d_tiles, tm, d_hf_off, d_span_cell, st);
+        launch_link_spans2(d_tiles, S, d_span_cell, d_hf_off, d_smin, d_smax, d_sarea, d_areas, d_nei16, (uint16_t*)(A + res->lay.con),
+                           d_conn_cnt, d_tinfo, st);
+        ctx->h_counters[4] = 0;
+        if (S > 0) {
+            launch_exclusive_scan(d_conn_cnt, d_conn_off, S, ctx->d_scan_tmp.as<uint32_t>(), st);
+            CU(cudaMemcpyAsync(&ctx->h_counters[4], d_conn_off + S, 4, cudaMemcpyDeviceToHost, st));
+        } else {
+            CU(cudaMemsetAsync(d_conn_off, 0, 4, st));
+        }
         CU(cudaStreamSynchronize(st));
         const uint64_t K = (uint32_t)ctx->h_counters[4];
         res->K = K;
@@ -420,11 +430,11 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
         make_layout_conn(res->lay, K);
         CU(pool_get(ctx->free_dev, res->lay.bytesB, false, res->devB));
         char* B = res->devB.p;
-        launch_tile_bases(d_tiles, ntiles, nullptr, d_conn_off, d_tinfo, st);
+        launch_tile_conn_bases(ntiles, d_conn_off, d_tinfo, st);
         if (S > 0)
-            launch_write_connections(d_tiles, tm, d_hf_off, d_nei16, S, d_conn_off, d_tinfo, (uint32_t*)(A + res->lay.first_conn),
-                                     (uint32_t*)(B + res->lay.conn_ref), (uint8_t*)(B + res->lay.conn_dir),
-                                     (uint32_t*)(B + res->lay.conn_next), st);
+            launch_write_connections2(d_tiles, S, d_span_cell, d_hf_off, d_nei16, d_conn_off, d_tinfo, (uint32_t*)(A + res->lay.first_conn),
+                                      (uint32_t*)(B + res->lay.conn_ref), (uint8_t*)(B + res->lay.conn_dir),
+                                      (uint32_t*)(B + res->lay.conn_next), st);
         CU(cudaMemsetAsync(A + res->lay.dist, 0, 2 * S, st));  // compact_heightfield.rs:253
         if (areas_override && S > 0) {
             CU(cudaMemcpyAsync(d_areas, areas_override, S, cudaMemcpyHostToDevice, st));

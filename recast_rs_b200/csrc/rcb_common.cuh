@@ -277,12 +277,14 @@ void launch_filter_spans(const TileDesc* tiles, TileMap tm, const uint32_t* hf_o
 void launch_cells_and_offsets(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, uint32_t* hf_cell_offset,
                               uint32_t* cell_index, uint32_t* cell_count, TileInfo* tinfo, int ntiles,
                               cudaStream_t s);
-void launch_link_spans(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smin,
-                       const int16_t* smax, const uint8_t* sarea, uint8_t* areas, uint16_t* nei16, size_t S,
-                       uint16_t* con, uint32_t* cell_conn_cnt, TileInfo* tinfo, cudaStream_t s);
-void launch_write_connections(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const uint16_t* nei16,
-                              size_t S, const uint32_t* conn_off, const TileInfo* tinfo, uint32_t* first_conn,
-                              uint32_t* conn_ref, uint8_t* conn_dir, uint32_t* conn_next, cudaStream_t s);
+void launch_span_cells(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, uint2* span_cell, cudaStream_t s);
+void launch_link_spans2(const TileDesc* tiles, size_t S, const uint2* span_cell, const uint32_t* hf_off, const int16_t* smin,
+                        const int16_t* smax, const uint8_t* sarea, uint8_t* areas, uint16_t* nei16, uint16_t* con, uint32_t* span_conn_cnt,
+                        TileInfo* tinfo, cudaStream_t s);
+void launch_tile_conn_bases(int ntiles, const uint32_t* conn_off_span, TileInfo* tinfo, cudaStream_t s);
+void launch_write_connections2(const TileDesc* tiles, size_t S, const uint2* span_cell, const uint32_t* hf_off, const uint16_t* nei16,
+                               const uint32_t* conn_off_span, const TileInfo* tinfo, uint32_t* first_conn, uint32_t* conn_ref,
+                               uint8_t* conn_dir, uint32_t* conn_next, cudaStream_t s);
 void launch_tile_bases(const TileDesc* tiles, int ntiles, const uint32_t* hf_off, const uint32_t* conn_off,
                        TileInfo* tinfo, cudaStream_t s);
 
