@@ -380,7 +380,16 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
     uint8_t* d_sarea = (uint8_t*)(A + res->lay.span_area);
 
     // ---- FILTER ------------------------------------------------------------------------------------------
-    if (fmask && S > 0) launch_filter_spans(d_tiles, tm, d_hf_off, d_smin, d_smax, d_sarea, fmask, st);
+    const bool need_span_cells = S > 0 && (fmask || (stage_mask & RCB_STAGE_COMPACT));
+    if (need_span_cells) {
+        CU(ctx->d_fidx.ensure(16 * (S + 1)));  // first (tile, cell) per span, later the forward-sweep gather ids
+        launch_span_cells(d_tiles, tm, d_hf_off, ctx->d_fidx.as<uint2>(), st);
+    }
+    if (fmask && S > 0) {  // span-parallel, out of place (F1 reads the previous span's original area)
+        CU(ctx->d_t8a.ensure(S + 16));
+        launch_filter_spans2(d_tiles, S, ctx->d_fidx.as<uint2>(), d_hf_off, d_smin, d_smax, d_sarea, ctx->d_t8a.as<uint8_t>(), fmask, st);
+        CU(cudaMemcpyAsync(d_sarea, ctx->d_t8a.p, S, cudaMemcpyDeviceToDevice, st));
+    }
 
     // ---- convex volumes on the solid heightfield (lib.rs:306, convex_volume.rs:392) -------------------------------
     if (nvols > 0 && S > 0) {
@@ -407,13 +416,11 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
         CU(ctx->d_conn_off.ensure(4 * (S + 1)));
         CU(ctx->d_scan_tmp.ensure(4 * scan_tmp_elems(std::max<uint64_t>(S, Ctot) + 1)));
         CU(ctx->d_nei16.ensure(16 * S + 256));
-        CU(ctx->d_fidx.ensure(16 * (S + 1)));  // first (tile, cell) per span, later the forward-sweep gather ids
         uint32_t* d_conn_cnt = ctx->d_conn_cnt.as<uint32_t>();
         uint32_t* d_conn_off = ctx->d_conn_off.as<uint32_t>();
         uint16_t* d_nei16 = ctx->d_nei16.as<uint16_t>();
         uint2* d_span_cell = ctx->d_fidx.as<uint2>();
         uint8_t* d_areas = (uint8_t*)(A + res->lay.areas);
-        launch_span_cells(d_tiles, tm, d_hf_off, d_span_cell, st);
         launch_link_spans2(d_tiles, S, d_span_cell, d_hf_off, d_smin, d_smax, d_sarea, d_areas, d_nei16, (uint16_t*)(A + res->lay.con),
                            d_conn_cnt, d_tinfo, st);
         ctx->h_counters[4] = 0;

@@ -272,11 +272,11 @@ void launch_wire_replay(const TileDesc* tiles, TileMap tm, const uint8_t* data, 
                         const uint32_t* cell_pos, int strict_le, const int16_t* smin, const int16_t* smax, const uint8_t* sarea,
                         const uint32_t* in_off, uint32_t* mm, uint8_t* ar, uint32_t* span_cnt, unsigned long long* err, cudaStream_t s);
 
-void launch_filter_spans(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smin,
-                         const int16_t* smax, uint8_t* sarea, uint32_t fmask /*1 F1, 2 F2, 4 F3*/, cudaStream_t s);
 void launch_cells_and_offsets(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, uint32_t* hf_cell_offset,
                               uint32_t* cell_index, uint32_t* cell_count, TileInfo* tinfo, int ntiles,
                               cudaStream_t s);
+void launch_filter_spans2(const TileDesc* tiles, size_t S, const uint2* span_cell, const uint32_t* hf_off, const int16_t* smin,
+                          const int16_t* smax, const uint8_t* sarea, uint8_t* area_out, uint32_t fmask, cudaStream_t s);
 void launch_span_cells(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, uint2* span_cell, cudaStream_t s);
 void launch_link_spans2(const TileDesc* tiles, size_t S, const uint2* span_cell, const uint32_t* hf_off, const int16_t* smin,
                         const int16_t* smax, const uint8_t* sarea, uint8_t* areas, uint16_t* nei16, uint16_t* con, uint32_t* span_conn_cnt,
