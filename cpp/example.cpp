@@ -19,6 +19,12 @@ int main() {
         Batch b = builder.build_tiles(verts, 12, tris, 6, &cfg, 1);
         rcb_tile_view v = b.tile(0);
         std::printf("cells %u spans %u connections %u max_distance %u\n", v.cell_count, v.span_count, v.conn_count, v.max_distance);
+        // the same tile with regions (CompactHeightfield::build_regions) and its VoxelTile span data
+        Batch r = builder.build_tiles(verts, 12, tris, 6, &cfg, 1, RCB_STAGE_ALL_BUILD | RCB_STAGE_REGIONS);
+        rcb_tile_view w = r.tile(0);
+        unsigned nreg = 0;
+        for (uint32_t i = 0; i < w.span_count; ++i) nreg = w.reg[i] > nreg ? w.reg[i] : nreg;
+        std::printf("regions %u max_regions %u span_data %zu\n", nreg, w.max_regions, r.serialize_spans().size());
     } catch (const Error& e) {
         std::printf("error %d: %s\n", e.status, e.what());  // RCB_ECUDA on a box without a GPU
         return e.status == RCB_ECUDA ? 0 : 1;

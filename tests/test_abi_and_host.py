@@ -150,3 +150,33 @@ def test_cpp_wrapper_compiles_and_fails_loudly_without_gpu(tmp_path):
         assert "error -3" in out.stdout
     else:
         assert "cells 441 spans" in out.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_example_matches_oracle_on_gpu(oracle, tmp_path):
+    """The C++ caller of the C ABI (cpp/example.cpp) on a GPU: its numbers are the oracle's."""
+    import subprocess
+
+    import numpy as np
+
+    from recast_rs_b200 import build
+    from recast_rs_b200.config import RecastConfig
+
+    build.build_native()
+    exe = tmp_path / "example"
+    libdir = os.path.join(ROOT, "recast_rs_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", os.path.join(ROOT, "cpp", "example.cpp"), "-L" + libdir, "-lrecast_b200",
+                           "-Wl,-rpath," + libdir, "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    v = np.array([0, 1, 0, 10, 1, 0, 10, 1, 10, 0, 1, 10], np.float32)
+    t = np.array([0, 2, 1, 0, 3, 2], np.int32)
+    cfg = oracle.calculate_grid_size(RecastConfig(cs=0.5), (0, 0, 0), (10, 5, 10))
+    hf = oracle.Heightfield.from_config(cfg)
+    hf.builder_rasterize(cfg, v, t)
+    c = oracle.CompactHeightfield.build_from_heightfield(hf)
+    reg, mr = c.build_regions(cfg.border_size, cfg.min_region_area, cfg.merge_region_area)
+    e = c.export()
+    want1 = f"cells {cfg.width * cfg.height} spans {e.span_min.size} connections {e.conn_ref.size} max_distance {e.max_distance}"
+    want2 = f"regions {int(reg.max(initial=0))} max_regions {mr} span_data {2 * cfg.width * cfg.height + 12 * e.span_min.size}"
+    assert want1 in out.stdout and want2 in out.stdout, out.stdout
