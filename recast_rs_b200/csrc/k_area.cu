@@ -9,9 +9,6 @@
 
 namespace {
 
-__constant__ int a_dirx[8] = {-1, 0, 1, 1, 1, 0, -1, -1};
-__constant__ int a_dirz[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
-
 __device__ __forceinline__ int trunc_div(float v, float origin, float cell) {  // ((v - origin) / cell) as i32
     return __float2int_rz(__fdiv_rn(__fsub_rn(v, origin), cell));
 }
@@ -90,29 +87,15 @@ __global__ void __launch_bounds__(256) k_area_marks(const TileDesc* __restrict__
     }
 }
 
-__device__ __forceinline__ uint32_t anei(const uint32_t* hf_off, const uint16_t* nei16, size_t S, uint32_t cell_base, int W, uint32_t s,
-                                         int x, int z, int dir) {
-    const uint32_t o = nei16[(size_t)dir * S + s];
-    if (o == RCB_NEI_NONE) return RCB_NONE;
-    return hf_off[cell_base + (uint32_t)(z + a_dirz[dir]) * W + (x + a_dirx[dir])] + o;
-}
-
-__global__ void __launch_bounds__(256) k_area_median(const TileDesc* __restrict__ tiles, TileMap tm, const uint32_t* __restrict__ hf_off,
-                                                     const uint16_t* __restrict__ nei16, size_t S, const uint8_t* __restrict__ areas,
+__global__ void __launch_bounds__(256) k_area_median(const uint32_t* __restrict__ nid, size_t S, const uint8_t* __restrict__ areas,
                                                      uint8_t* __restrict__ out) {
-    const uint32_t tile = RCB_TILE_OF_BLOCK();
-    if (tile >= tm.ntiles) return;
-    const TileDesc& td = tiles[tile];
-    const int W = td.width, H = td.height;
-    const uint32_t lc = RCB_CELL_OF_THREAD();
-    if (lc >= (uint32_t)(W * H)) return;
-    const int x = lc % W, z = lc / W;
-    const uint32_t g = td.cell_base + lc;
-    for (uint32_t s = hf_off[g]; s < hf_off[g + 1]; ++s) {
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    {
         const uint8_t own = areas[s];
         if (own == 0) {  // :256-259
             out[s] = 0;
-            continue;
+            return;
         }
         uint8_t n[9];
 #pragma unroll
@@ -120,10 +103,10 @@ __global__ void __launch_bounds__(256) k_area_median(const TileDesc* __restrict_
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int dir = 1 + 2 * i;
-            const uint32_t a = anei(hf_off, nei16, S, td.cell_base, W, s, x, z, dir);
+            const uint32_t a = nid[(size_t)dir * S + s];
             if (a == RCB_NONE) continue;
             if (areas[a] != 0) n[i * 2] = areas[a];
-            const uint32_t bb = anei(hf_off, nei16, S, td.cell_base, W, a, x + a_dirx[dir], z + a_dirz[dir], (dir + 1) & 7);
+            const uint32_t bb = nid[(size_t)((dir + 1) & 7) * S + a];
             if (bb != RCB_NONE && areas[bb] != 0) n[i * 2 + 1] = areas[bb];
         }
         // median of nine: rank by counting (same value as the reference's insertion sort, :283-284)
@@ -196,9 +179,8 @@ void launch_area_marks(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off
     k_area_marks<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, smin, areas, ops, op0, op1, poly_verts);
 }
 
-void launch_area_median(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const uint16_t* nei16, size_t S, const uint8_t* areas,
-                        uint8_t* out, cudaStream_t s) {
-    if (tm.nblocks == 0) return;
+void launch_area_median(const uint32_t* nid, size_t S, const uint8_t* areas, uint8_t* out, cudaStream_t s) {
+    if (S == 0) return;
     KScope _k("k_area_median", s);
-    k_area_median<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, areas, out);
+    k_area_median<<<(unsigned)((S + 255) / 256), 256, 0, s>>>(nid, S, areas, out);
 }

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) k_span_cells(const TileDesc* __restrict__
 __global__ void __launch_bounds__(256) k_link_spans2(const TileDesc* __restrict__ tiles, uint32_t S, const uint2* __restrict__ span_cell,
                                                      const uint32_t* __restrict__ hf_off, const int16_t* __restrict__ smin,
                                                      const int16_t* __restrict__ smax, const uint8_t* __restrict__ sarea,
-                                                     uint8_t* __restrict__ areas, uint16_t* __restrict__ nei16, uint16_t* __restrict__ con,
+                                                     uint8_t* __restrict__ areas, uint32_t* __restrict__ nid, uint16_t* __restrict__ con,
                                                      uint32_t* __restrict__ span_conn_cnt, TileInfo* __restrict__ tinfo) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
@@ -97,10 +97,11 @@ __global__ void __launch_bounds__(256) k_link_spans2(const TileDesc* __restrict_
 #pragma unroll
         for (int d = 0; d < 8; ++d) {
             const int nx = x + c_dirx[d], nz = z + c_dirz[d];
-            uint32_t best = RCB_NEI_NONE;
+            uint32_t best = RCB_NEI_NONE, nb = 0;
             if (!(nx < 0 || nz < 0 || nx >= W || nz >= H)) {
                 const uint32_t ng = td.cell_base + (uint32_t)nz * W + nx;
-                const uint32_t nb = hf_off[ng], ne = hf_off[ng + 1];
+                nb = hf_off[ng];
+                const uint32_t ne = hf_off[ng + 1];
                 int best_diff = 0x7fffffff;
                 for (uint32_t ns = nb; ns < ne; ++ns) {
                     if (sarea[ns] == 0) continue;
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(256) k_link_spans2(const TileDesc* __restrict_
                     }
                 }
             }
-            nei16[(size_t)d * S + s] = (uint16_t)best;
+            nid[(size_t)d * S + s] = best != RCB_NEI_NONE ? nb + best : RCB_NONE;  // absolute span id for every later stage
             if (best != RCB_NEI_NONE) {
                 nconn++;
                 if (d == 7) c4[0] = (uint16_t)best;  // :404-410
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(256) k_link_spans2(const TileDesc* __restrict_
         }
     } else {
 #pragma unroll
-        for (int d = 0; d < 8; ++d) nei16[(size_t)d * S + s] = RCB_NEI_NONE;
+        for (int d = 0; d < 8; ++d) nid[(size_t)d * S + s] = RCB_NONE;
     }
     *reinterpret_cast<uint2*>(con + 4 * (size_t)s) =
         make_uint2((uint32_t)c4[0] | ((uint32_t)c4[1] << 16), (uint32_t)c4[2] | ((uint32_t)c4[3] << 16));
@@ -139,33 +140,38 @@ __global__ void k_tile_conn_bases(int ntiles, const uint32_t* __restrict__ conn_
     tinfo[t].conn_count = conn_off_span[e] - conn_off_span[b];
 }
 
-__global__ void __launch_bounds__(256) k_write_connections2(const TileDesc* __restrict__ tiles, uint32_t S, const uint2* __restrict__ span_cell,
-                                                            const uint32_t* __restrict__ hf_off, const uint16_t* __restrict__ nei16,
+// The connections of 256 consecutive spans are one contiguous range of the list: build it in shared memory, store it coalesced.
+__global__ void __launch_bounds__(256) k_write_connections2(uint32_t S, const uint2* __restrict__ span_cell, const uint32_t* __restrict__ nid,
                                                             const uint32_t* __restrict__ conn_off_span, const TileInfo* __restrict__ tinfo,
                                                             uint32_t* __restrict__ first_conn, uint32_t* __restrict__ conn_ref,
                                                             uint8_t* __restrict__ conn_dir, uint32_t* __restrict__ conn_next) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= S) return;
-    const uint2 sc = span_cell[s];
-    const uint32_t tile = sc.x, lc = sc.y;
-    const TileDesc& td = tiles[tile];
-    const int W = td.width;
-    const int z = (int)(lc / (uint32_t)W), x = (int)lc - z * W;
-    const uint32_t span_base = tinfo[tile].span_base, conn_base = tinfo[tile].conn_base;
-    uint32_t k = conn_off_span[s];
-    uint32_t first = RCB_NONE;
+    __shared__ uint32_t sh_ref[2048], sh_next[2048];
+    __shared__ uint8_t sh_dir[2048];
+    const uint32_t s0 = blockIdx.x * 256u, s = s0 + threadIdx.x;
+    const uint32_t k0 = conn_off_span[s0], k1 = conn_off_span[min(S, s0 + 256u)];
+    if (s < S) {
+        const uint32_t tile = span_cell[s].x;
+        const uint32_t span_base = tinfo[tile].span_base, conn_base = tinfo[tile].conn_base;
+        uint32_t k = conn_off_span[s];
+        uint32_t first = RCB_NONE;
 #pragma unroll
-    for (int d = 7; d >= 0; --d) {
-        const uint32_t o = nei16[(size_t)d * S + s];
-        if (o == RCB_NEI_NONE) continue;
-        const uint32_t ng = td.cell_base + (uint32_t)(z + c_dirz[d]) * W + (x + c_dirx[d]);
-        conn_ref[k] = hf_off[ng] + o - span_base;
-        conn_dir[k] = (uint8_t)d;
-        conn_next[k] = first;
-        first = k - conn_base;
-        ++k;
+        for (int d = 7; d >= 0; --d) {
+            const uint32_t n = nid[(size_t)d * S + s];
+            if (n == RCB_NONE) continue;
+            sh_ref[k - k0] = n - span_base;
+            sh_dir[k - k0] = (uint8_t)d;
+            sh_next[k - k0] = first;
+            first = k - conn_base;
+            ++k;
+        }
+        first_conn[s] = first;
     }
-    first_conn[s] = first;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < k1 - k0; i += 256u) {
+        conn_ref[k0 + i] = sh_ref[i];
+        conn_next[k0 + i] = sh_next[i];
+        conn_dir[k0 + i] = sh_dir[i];
+    }
 }
 
 }  // namespace
@@ -177,11 +183,11 @@ void launch_span_cells(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off
 }
 
 void launch_link_spans2(const TileDesc* tiles, size_t S, const uint2* span_cell, const uint32_t* hf_off, const int16_t* smin,
-                        const int16_t* smax, const uint8_t* sarea, uint8_t* areas, uint16_t* nei16, uint16_t* con, uint32_t* span_conn_cnt,
+                        const int16_t* smax, const uint8_t* sarea, uint8_t* areas, uint32_t* nid, uint16_t* con, uint32_t* span_conn_cnt,
                         TileInfo* tinfo, cudaStream_t s) {
     if (S == 0) return;
     KScope _k("k_link_spans2", s);
-    k_link_spans2<<<(unsigned)((S + 255) / 256), 256, 0, s>>>(tiles, (uint32_t)S, span_cell, hf_off, smin, smax, sarea, areas, nei16, con,
+    k_link_spans2<<<(unsigned)((S + 255) / 256), 256, 0, s>>>(tiles, (uint32_t)S, span_cell, hf_off, smin, smax, sarea, areas, nid, con,
                                                               span_conn_cnt, tinfo);
 }
 
@@ -191,12 +197,11 @@ void launch_tile_conn_bases(int ntiles, const uint32_t* conn_off_span, TileInfo*
     k_tile_conn_bases<<<(ntiles + 127) / 128, 128, 0, s>>>(ntiles, conn_off_span, tinfo);
 }
 
-void launch_write_connections2(const TileDesc* tiles, size_t S, const uint2* span_cell, const uint32_t* hf_off, const uint16_t* nei16,
-                               const uint32_t* conn_off_span, const TileInfo* tinfo, uint32_t* first_conn, uint32_t* conn_ref,
+void launch_write_connections2(size_t S, const uint2* span_cell, const uint32_t* nid, const uint32_t* conn_off_span, const TileInfo* tinfo, uint32_t* first_conn, uint32_t* conn_ref,
                                uint8_t* conn_dir, uint32_t* conn_next, cudaStream_t s) {
     if (S == 0) return;
     KScope _k("k_write_connections2", s);
-    k_write_connections2<<<(unsigned)((S + 255) / 256), 256, 0, s>>>(tiles, (uint32_t)S, span_cell, hf_off, nei16, conn_off_span, tinfo,
+    k_write_connections2<<<(unsigned)((S + 255) / 256), 256, 0, s>>>((uint32_t)S, span_cell, nid, conn_off_span, tinfo,
                                                                      first_conn, conn_ref, conn_dir, conn_next);
 }
 

@@ -24,21 +24,13 @@ namespace {
 __constant__ int d_dirx[8] = {-1, 0, 1, 1, 1, 0, -1, -1};
 __constant__ int d_dirz[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
 
+// neighbour `dir` of span `s`: global span index or RCB_NONE.  k_link_spans2 leaves the 8-direction table as absolute
+// span ids (u32[8][S]), so nothing below needs to know which cell or tile a span belongs to: one thread per span.
 struct Grid {
-    const uint32_t* hf_off;
-    const uint16_t* nei16;
+    const uint32_t* nid;
     size_t S;
-    uint32_t cell_base;
-    int W, H;
 };
-
-// neighbour `dir` of span `s` that lives in cell (x,z); returns global span index or RCB_NONE
-__device__ __forceinline__ uint32_t nei(const Grid& g, uint32_t s, int x, int z, int dir) {
-    const uint32_t o = g.nei16[(size_t)dir * g.S + s];
-    if (o == RCB_NEI_NONE) return RCB_NONE;
-    const int nx = x + d_dirx[dir], nz = z + d_dirz[dir];
-    return g.hf_off[g.cell_base + (uint32_t)nz * g.W + nx] + o;
-}
+__device__ __forceinline__ uint32_t nei(const Grid& g, uint32_t s, int dir) { return g.nid[(size_t)dir * g.S + s]; }
 
 template <typename T>
 __device__ __forceinline__ T sat_add(T a, unsigned b) {
@@ -51,35 +43,23 @@ __device__ __forceinline__ T sat_add(T a, unsigned b) {
 // DIST : every span with fewer than 4 cardinal neighbours of EQUAL areas[] -> 0 (compact_heightfield.rs:556-585)
 // ERODE: areas==0 -> 0; else 0 unless all of W,S,E,N exist with areas != 0        (area.rs:91-125)
 template <typename T, bool ERODE>
-__global__ void __launch_bounds__(256) k_boundary(const TileDesc* __restrict__ tiles, TileMap tm,
-                                                  const uint32_t* __restrict__ hf_off,
-                                                  const uint16_t* __restrict__ nei16, size_t S,
-                                                  const uint8_t* __restrict__ areas, T* __restrict__ init) {
-    const uint32_t tile = RCB_TILE_OF_BLOCK();
-    if (tile >= tm.ntiles) return;
-    const TileDesc& td = tiles[tile];
-    const int W = td.width, H = td.height;
-    const uint32_t lc = RCB_CELL_OF_THREAD();
-    if (lc >= (uint32_t)(W * H)) return;
-    const int x = lc % W, z = lc / W;
-    const Grid g{hf_off, nei16, S, td.cell_base, W, H};
-    const uint32_t gc = td.cell_base + lc;
-    const uint32_t b = hf_off[gc], e = hf_off[gc + 1];
+__global__ void __launch_bounds__(256) k_boundary(const uint32_t* __restrict__ nid, size_t S, const uint8_t* __restrict__ areas,
+                                                  T* __restrict__ init) {
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const Grid g{nid, S};
     const T inf = (T)~(T)0;
-    for (uint32_t s = b; s < e; ++s) {
-        const uint8_t a = areas[s];
-        int cnt = 0;
-        if (!ERODE || a != 0) {
+    const uint8_t a = areas[s];
+    int cnt = 0;
+    if (!ERODE || a != 0) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int dir = 7 - 2 * k;  // 7,5,3,1
-                const uint32_t n = nei(g, s, x, z, dir);
-                if (n == RCB_NONE) continue;
-                if (ERODE ? (areas[n] != 0) : (areas[n] == a)) cnt++;
-            }
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t n = nei(g, (uint32_t)s, 7 - 2 * k);  // 7,5,3,1
+            if (n == RCB_NONE) continue;
+            if (ERODE ? (areas[n] != 0) : (areas[n] == a)) cnt++;
         }
-        init[s] = (cnt == 4) ? inf : (T)0;
     }
+    init[s] = (cnt == 4) ? inf : (T)0;
 }
 
 // ---- forward sweep ----------------------------------------------------------------------------------------
@@ -88,32 +68,23 @@ __global__ void __launch_bounds__(256) k_boundary(const TileDesc* __restrict__ t
 // (value inf), which makes the sweep body branch-free, and "+2 / +3" needs no clamp because the running
 // minimum never exceeds inf.  k_forward2 then walks the rows of a tile with one CTA: per row one 16-byte
 // index load (prefetched one row ahead) and the distance loads.
-__global__ void __launch_bounds__(256) k_fwd_index(const TileDesc* __restrict__ tiles, TileMap tm, const uint32_t* __restrict__ hf_off,
-                                                   const uint16_t* __restrict__ nei16, size_t S, uint4* __restrict__ fidx) {
-    const uint32_t tile = RCB_TILE_OF_BLOCK();
-    if (tile >= tm.ntiles) return;
-    const TileDesc& td = tiles[tile];
-    const int W = td.width, H = td.height;
-    const uint32_t lc = RCB_CELL_OF_THREAD();
-    if (lc >= (uint32_t)(W * H)) return;
-    const int x = lc % W, z = lc / W;
-    const Grid g{hf_off, nei16, S, td.cell_base, W, H};
-    const uint32_t gc = td.cell_base + lc;
+__global__ void __launch_bounds__(256) k_fwd_index(const uint32_t* __restrict__ nid, size_t S, uint4* __restrict__ fidx) {
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const Grid g{nid, S};
     const uint32_t dummy = (uint32_t)S;
-    for (uint32_t s = hf_off[gc]; s < hf_off[gc + 1]; ++s) {
-        uint32_t a0 = nei(g, s, x, z, 0), a1 = dummy, b0 = nei(g, s, x, z, 3), b1 = dummy;
-        if (a0 != RCB_NONE) {
-            const uint32_t t = nei(g, a0, x - 1, z - 1, 3);
-            if (t != RCB_NONE) a1 = t;
-        } else
-            a0 = dummy;
-        if (b0 != RCB_NONE) {
-            const uint32_t t = nei(g, b0, x + 1, z, 2);
-            if (t != RCB_NONE) b1 = t;
-        } else
-            b0 = dummy;
-        fidx[s] = make_uint4(a0, a1, b0, b1);
-    }
+    uint32_t a0 = nei(g, (uint32_t)s, 0), a1 = dummy, b0 = nei(g, (uint32_t)s, 3), b1 = dummy;
+    if (a0 != RCB_NONE) {
+        const uint32_t t = nei(g, a0, 3);
+        if (t != RCB_NONE) a1 = t;
+    } else
+        a0 = dummy;
+    if (b0 != RCB_NONE) {
+        const uint32_t t = nei(g, b0, 2);
+        if (t != RCB_NONE) b1 = t;
+    } else
+        b0 = dummy;
+    fidx[s] = make_uint4(a0, a1, b0, b1);
 }
 
 template <typename T>
@@ -177,102 +148,79 @@ __global__ void __launch_bounds__(1024) k_forward2(const TileDesc* __restrict__ 
 // DIST : D = gather, per-tile max (before blur) -> tinfo.max_distance
 // ERODE: D < thr  =>  areas = 0 (area.rs:226-231)
 template <typename T, bool ERODE>
-__global__ void __launch_bounds__(256) k_backward(const TileDesc* __restrict__ tiles, TileMap tm,
-                                                  const uint32_t* __restrict__ hf_off,
-                                                  const uint16_t* __restrict__ nei16, size_t S,
-                                                  const T* __restrict__ F, T* __restrict__ D, uint8_t* areas,
-                                                  unsigned thr, TileInfo* __restrict__ tinfo) {
-    const uint32_t tile = RCB_TILE_OF_BLOCK();
-    if (tile >= tm.ntiles) return;
-    const TileDesc& td = tiles[tile];
-    const int W = td.width, H = td.height;
-    const uint32_t lc = RCB_CELL_OF_THREAD();
-    uint32_t vmax = 0;
-    if (lc < (uint32_t)(W * H)) {
-        const int x = lc % W, z = lc / W;
-        const Grid g{hf_off, nei16, S, td.cell_base, W, H};
-        const uint32_t gc = td.cell_base + lc;
-        const uint32_t b = hf_off[gc], e = hf_off[gc + 1];
-        for (uint32_t s = b; s < e; ++s) {
-            T v = F[s];
-            const uint32_t a = nei(g, s, x, z, 2);  // NE
-            if (a != RCB_NONE) {
-                v = min(v, sat_add<T>(F[a], 2));
-                const uint32_t aa = nei(g, a, x + 1, z - 1, 1);  // NE.N
-                if (aa != RCB_NONE) v = min(v, sat_add<T>(F[aa], 3));
-            }
-            const uint32_t bn = nei(g, s, x, z, 1);  // N
-            if (bn != RCB_NONE) {
-                v = min(v, sat_add<T>(F[bn], 2));
-                const uint32_t bb = nei(g, bn, x, z - 1, 0);  // N.NW
-                if (bb != RCB_NONE) v = min(v, sat_add<T>(F[bb], 3));
-            }
-            if (ERODE) {
-                if ((unsigned)v < thr) areas[s] = 0;
-            } else {
-                D[s] = v;
-                vmax = max(vmax, (uint32_t)v);
-            }
-        }
+__global__ void __launch_bounds__(256) k_backward(const uint32_t* __restrict__ nid, size_t S, const uint2* __restrict__ span_cell,
+                                                  const T* __restrict__ F, T* __restrict__ D, uint8_t* areas, unsigned thr,
+                                                  TileInfo* __restrict__ tinfo) {
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const Grid g{nid, S};
+    T v = F[s];
+    const uint32_t a = nei(g, (uint32_t)s, 2);  // NE
+    if (a != RCB_NONE) {
+        v = min(v, sat_add<T>(F[a], 2));
+        const uint32_t aa = nei(g, a, 1);  // NE.N
+        if (aa != RCB_NONE) v = min(v, sat_add<T>(F[aa], 3));
     }
-    if (!ERODE) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) vmax = max(vmax, __shfl_down_sync(0xffffffffu, vmax, d));
-        if (lane_id() == 0 && vmax) atomicMax(&tinfo[tile].max_distance, vmax);
+    const uint32_t bn = nei(g, (uint32_t)s, 1);  // N
+    if (bn != RCB_NONE) {
+        v = min(v, sat_add<T>(F[bn], 2));
+        const uint32_t bb = nei(g, bn, 0);  // N.NW
+        if (bb != RCB_NONE) v = min(v, sat_add<T>(F[bb], 3));
+    }
+    if (ERODE) {
+        if ((unsigned)v < thr) areas[s] = 0;
+    } else {
+        D[s] = v;
+        // per-tile maximum (before the blur): one atomic per (warp, tile)
+        const uint32_t tile = span_cell[s].x;
+        const unsigned peers = __match_any_sync(__activemask(), tile);
+        const uint32_t vmax = __reduce_max_sync(peers, (uint32_t)v);
+        if ((int)lane_id() == __ffs(peers) - 1 && vmax) atomicMax(&tinfo[tile].max_distance, vmax);
     }
 }
 
 // ---- box blur (compact_heightfield.rs:679-727, threshold 1 -> thr 2) ----------------------------------
-__global__ void __launch_bounds__(256) k_blur(const TileDesc* __restrict__ tiles, TileMap tm,
-                                              const uint32_t* __restrict__ hf_off, const uint16_t* __restrict__ nei16,
-                                              size_t S, const uint16_t* __restrict__ D, uint16_t* __restrict__ dist) {
-    const uint32_t tile = RCB_TILE_OF_BLOCK();
-    if (tile >= tm.ntiles) return;
-    const TileDesc& td = tiles[tile];
-    const int W = td.width, H = td.height;
-    const uint32_t lc = RCB_CELL_OF_THREAD();
-    if (lc >= (uint32_t)(W * H)) return;
-    const int x = lc % W, z = lc / W;
-    const Grid g{hf_off, nei16, S, td.cell_base, W, H};
-    const uint32_t gc = td.cell_base + lc;
-    const uint32_t b = hf_off[gc], e = hf_off[gc + 1];
-    for (uint32_t s = b; s < e; ++s) {
-        const uint32_t cd = D[s];
-        if (cd <= 2) {
-            dist[s] = (uint16_t)cd;
-            continue;
-        }
-        int d = (int)cd, n = 1;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int dir = 1 + 2 * k;  // 1,3,5,7
-            const uint32_t nb = nei(g, s, x, z, dir);
-            if (nb == RCB_NONE) continue;
-            d += D[nb];
-            n++;
-            const uint32_t dg = nei(g, nb, x + d_dirx[dir], z + d_dirz[dir], (dir + 1) & 7);
-            if (dg != RCB_NONE) {
-                d += D[dg];
-                n++;
-            }
-        }
-        dist[s] = (uint16_t)(d / n);
+__global__ void __launch_bounds__(256) k_blur(const uint32_t* __restrict__ nid, size_t S, const uint16_t* __restrict__ D,
+                                              uint16_t* __restrict__ dist) {
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const Grid g{nid, S};
+    const uint32_t cd = D[s];
+    if (cd <= 2) {
+        dist[s] = (uint16_t)cd;
+        return;
     }
+    int d = (int)cd, n = 1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int dir = 1 + 2 * k;  // 1,3,5,7
+        const uint32_t nb = nei(g, (uint32_t)s, dir);
+        if (nb == RCB_NONE) continue;
+        d += D[nb];
+        n++;
+        const uint32_t dg = nei(g, nb, (dir + 1) & 7);
+        if (dg != RCB_NONE) {
+            d += D[dg];
+            n++;
+        }
+    }
+    dist[s] = (uint16_t)(d / n);
 }
 
 }  // namespace
 
-void launch_distance_field(const TileDesc* tiles, int ntiles, TileMap tm, const uint32_t* hf_off,
-                           const uint16_t* nei16, size_t S, const uint8_t* areas, uint16_t* tmp_init, uint16_t* tmp_f,
-                           uint16_t* tmp_d, uint16_t* dist, TileInfo* tinfo, uint4* fidx, cudaStream_t s) {
-    if (tm.nblocks == 0 || ntiles == 0) return;
+void launch_distance_field(const TileDesc* tiles, int ntiles, const uint32_t* hf_off, const uint32_t* nid, const uint2* span_cell, size_t S,
+                           const uint8_t* areas, uint16_t* tmp_init, uint16_t* tmp_f, uint16_t* tmp_d, uint16_t* dist, TileInfo* tinfo,
+                           uint4* fidx, cudaStream_t s) {
+    if (S == 0 || ntiles == 0) return;
+    const unsigned nb = (unsigned)((S + 255) / 256);
     {
         KScope _k("k_boundary", s);
-        k_boundary<uint16_t, false><<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, areas, tmp_init);
+        k_boundary<uint16_t, false><<<nb, 256, 0, s>>>(nid, S, areas, tmp_init);
     }
     {
         KScope _k("k_fwd_index", s);
-        k_fwd_index<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, fidx);
+        k_fwd_index<<<nb, 256, 0, s>>>(nid, S, fidx);
     }
     {
         KScope _k("k_forward2", s);
@@ -280,25 +228,26 @@ void launch_distance_field(const TileDesc* tiles, int ntiles, TileMap tm, const 
     }
     {
         KScope _k("k_backward", s);
-        k_backward<uint16_t, false><<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, tmp_f, tmp_d, nullptr, 0, tinfo);
+        k_backward<uint16_t, false><<<nb, 256, 0, s>>>(nid, S, span_cell, tmp_f, tmp_d, nullptr, 0, tinfo);
     }
     {
         KScope _k("k_blur", s);
-        k_blur<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, tmp_d, dist);
+        k_blur<<<nb, 256, 0, s>>>(nid, S, tmp_d, dist);
     }
 }
 
-void launch_erode(const TileDesc* tiles, int ntiles, TileMap tm, const uint32_t* hf_off, const uint16_t* nei16,
-                  size_t S, uint8_t* areas, uint8_t* tmp_init, uint8_t* tmp_f, int radius, uint4* fidx, cudaStream_t s) {
-    if (tm.nblocks == 0 || ntiles == 0) return;
+void launch_erode(const TileDesc* tiles, int ntiles, const uint32_t* hf_off, const uint32_t* nid, size_t S, uint8_t* areas,
+                  uint8_t* tmp_init, uint8_t* tmp_f, int radius, uint4* fidx, cudaStream_t s) {
+    if (S == 0 || ntiles == 0) return;
+    const unsigned nb = (unsigned)((S + 255) / 256);
     const unsigned thr = (unsigned)(uint8_t)(uint32_t)(radius * 2);  // area.rs:226 `(radius*2) as u8`
     {
         KScope _k("k_boundary", s);
-        k_boundary<uint8_t, true><<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, areas, tmp_init);
+        k_boundary<uint8_t, true><<<nb, 256, 0, s>>>(nid, S, areas, tmp_init);
     }
     {
         KScope _k("k_fwd_index", s);
-        k_fwd_index<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, fidx);
+        k_fwd_index<<<nb, 256, 0, s>>>(nid, S, fidx);
     }
     {
         KScope _k("k_forward2", s);
@@ -306,6 +255,6 @@ void launch_erode(const TileDesc* tiles, int ntiles, TileMap tm, const uint32_t*
     }
     {
         KScope _k("k_backward", s);
-        k_backward<uint8_t, true><<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, nei16, S, tmp_f, nullptr, areas, thr, nullptr);
+        k_backward<uint8_t, true><<<nb, 256, 0, s>>>(nid, S, nullptr, tmp_f, nullptr, areas, thr, nullptr);
     }
 }

@@ -74,7 +74,7 @@ struct rcb_ctx {
     // scratch
     DevBuf d_counters, d_cell_cnt, d_frag_off, d_frag_tmp, d_fs_tri, d_fs_mm, d_fs_area, d_scan_tmp, d_hf_off, d_conn_cnt,
         d_conn_off, d_nei16, d_t16a, d_t16b, d_t16c, d_t8a, d_t8b, d_item_cnt, d_item_off, d_items, d_tile_ub, d_tile_base, d_tile_cursor,
-        d_tile_frags, d_ts_mm, d_ts_area, d_celloff_tmp, d_lookback, d_tc_regons, d_tc_areas, d_tc_obs, d_fidx, d_wire, d_wire_off,
+        d_tile_frags, d_ts_mm, d_ts_area, d_celloff_tmp, d_lookback, d_tc_regons, d_tc_areas, d_tc_obs, d_fidx, d_span_cell, d_wire, d_wire_off,
         d_wire_pos, d_wire_inoff, d_wire_err, d_tc_raw, d_tc_parsed, d_rg_a, d_rg_b;
     uint32_t clip_flags = 1;    // RCB_CLIP_FLAGS (A/B runs): bit0 min-x skip test in the clipper
     bool phase_timers = false;  // RCB_PHASE_TIMERS=1: per-phase cycle sums of the tile kernels on stderr
@@ -382,12 +382,12 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
     // ---- FILTER ------------------------------------------------------------------------------------------
     const bool need_span_cells = S > 0 && (fmask || (stage_mask & RCB_STAGE_COMPACT));
     if (need_span_cells) {
-        CU(ctx->d_fidx.ensure(16 * (S + 1)));  // first (tile, cell) per span, later the forward-sweep gather ids
-        launch_span_cells(d_tiles, tm, d_hf_off, ctx->d_fidx.as<uint2>(), st);
+        CU(ctx->d_span_cell.ensure(8 * (S + 1)));  // (tile, cell) per span: every later stage is one thread per span
+        launch_span_cells(d_tiles, tm, d_hf_off, ctx->d_span_cell.as<uint2>(), st);
     }
     if (fmask && S > 0) {  // span-parallel, out of place (F1 reads the previous span's original area)
         CU(ctx->d_t8a.ensure(S + 16));
-        launch_filter_spans2(d_tiles, S, ctx->d_fidx.as<uint2>(), d_hf_off, d_smin, d_smax, d_sarea, ctx->d_t8a.as<uint8_t>(), fmask, st);
+        launch_filter_spans2(d_tiles, S, ctx->d_span_cell.as<uint2>(), d_hf_off, d_smin, d_smax, d_sarea, ctx->d_t8a.as<uint8_t>(), fmask, st);
         CU(cudaMemcpyAsync(d_sarea, ctx->d_t8a.p, S, cudaMemcpyDeviceToDevice, st));
     }
 
@@ -415,13 +415,13 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
         CU(ctx->d_conn_cnt.ensure(4 * (S + 1)));
         CU(ctx->d_conn_off.ensure(4 * (S + 1)));
         CU(ctx->d_scan_tmp.ensure(4 * scan_tmp_elems(std::max<uint64_t>(S, Ctot) + 1)));
-        CU(ctx->d_nei16.ensure(16 * S + 256));
+        CU(ctx->d_nei16.ensure(32 * S + 256));  // u32[8][S] absolute neighbour ids
         uint32_t* d_conn_cnt = ctx->d_conn_cnt.as<uint32_t>();
         uint32_t* d_conn_off = ctx->d_conn_off.as<uint32_t>();
-        uint16_t* d_nei16 = ctx->d_nei16.as<uint16_t>();
-        uint2* d_span_cell = ctx->d_fidx.as<uint2>();
+        uint32_t* d_nid = ctx->d_nei16.as<uint32_t>();
+        uint2* d_span_cell = ctx->d_span_cell.as<uint2>();
         uint8_t* d_areas = (uint8_t*)(A + res->lay.areas);
-        launch_link_spans2(d_tiles, S, d_span_cell, d_hf_off, d_smin, d_smax, d_sarea, d_areas, d_nei16, (uint16_t*)(A + res->lay.con),
+        launch_link_spans2(d_tiles, S, d_span_cell, d_hf_off, d_smin, d_smax, d_sarea, d_areas, d_nid, (uint16_t*)(A + res->lay.con),
                            d_conn_cnt, d_tinfo, st);
         ctx->h_counters[4] = 0;
         if (S > 0) {
@@ -439,7 +439,7 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
         char* B = res->devB.p;
         launch_tile_conn_bases(ntiles, d_conn_off, d_tinfo, st);
         if (S > 0)
-            launch_write_connections2(d_tiles, S, d_span_cell, d_hf_off, d_nei16, d_conn_off, d_tinfo, (uint32_t*)(A + res->lay.first_conn),
+            launch_write_connections2(S, d_span_cell, d_nid, d_conn_off, d_tinfo, (uint32_t*)(A + res->lay.first_conn),
                                       (uint32_t*)(B + res->lay.conn_ref), (uint8_t*)(B + res->lay.conn_dir),
                                       (uint32_t*)(B + res->lay.conn_next), st);
         CU(cudaMemsetAsync(A + res->lay.dist, 0, 2 * S, st));  // compact_heightfield.rs:253
@@ -459,7 +459,7 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
             int i = 0;
             while (i < nops) {
                 if (ops[i].type == RCB_AREA_OP_MEDIAN) {
-                    launch_area_median(d_tiles, tm, d_hf_off, d_nei16, S, d_areas, ctx->d_t8a.as<uint8_t>(), st);
+                    launch_area_median(d_nid, S, d_areas, ctx->d_t8a.as<uint8_t>(), st);
                     CU(cudaMemcpyAsync(d_areas, ctx->d_t8a.p, S, cudaMemcpyDeviceToDevice, st));  // area.rs:291
                     ++i;
                 } else {
@@ -474,7 +474,7 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
             CU(ctx->d_t8a.ensure(S + 16));
             CU(ctx->d_t8b.ensure(S + 16));
             CU(ctx->d_fidx.ensure(16 * (S + 1)));
-            launch_erode(d_tiles, ntiles, tm, d_hf_off, d_nei16, S, d_areas, ctx->d_t8a.as<uint8_t>(), ctx->d_t8b.as<uint8_t>(),
+            launch_erode(d_tiles, ntiles, d_hf_off, d_nid, S, d_areas, ctx->d_t8a.as<uint8_t>(), ctx->d_t8b.as<uint8_t>(),
                          erode_radius, ctx->d_fidx.as<uint4>(), st);
         }
         if ((stage_mask & RCB_STAGE_DIST) && S > 0) {
@@ -482,7 +482,7 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
             CU(ctx->d_t16b.ensure(2 * S + 16));
             CU(ctx->d_t16c.ensure(2 * S + 16));
             CU(ctx->d_fidx.ensure(16 * (S + 1)));
-            launch_distance_field(d_tiles, ntiles, tm, d_hf_off, d_nei16, S, d_areas, ctx->d_t16a.as<uint16_t>(),
+            launch_distance_field(d_tiles, ntiles, d_hf_off, d_nid, d_span_cell, S, d_areas, ctx->d_t16a.as<uint16_t>(),
                                   ctx->d_t16b.as<uint16_t>(), ctx->d_t16c.as<uint16_t>(), (uint16_t*)(A + res->lay.dist), d_tinfo,
                                   ctx->d_fidx.as<uint4>(), st);
         }
@@ -1197,7 +1197,7 @@ void rcb_destroy(rcb_ctx* ctx) {
                       &ctx->d_fs_area, &ctx->d_scan_tmp, &ctx->d_hf_off, &ctx->d_conn_cnt, &ctx->d_conn_off, &ctx->d_nei16,
                       &ctx->d_t16a, &ctx->d_t16b, &ctx->d_t16c, &ctx->d_t8a, &ctx->d_t8b, &ctx->d_item_cnt, &ctx->d_item_off, &ctx->d_items, &ctx->d_tile_ub, &ctx->d_tile_base,
                       &ctx->d_tile_cursor, &ctx->d_tile_frags, &ctx->d_ts_mm, &ctx->d_ts_area, &ctx->d_celloff_tmp, &ctx->d_lookback, &ctx->d_tc_regons, &ctx->d_tc_areas,
-                      &ctx->d_tc_obs, &ctx->d_fidx, &ctx->d_wire, &ctx->d_wire_off, &ctx->d_wire_pos, &ctx->d_wire_inoff, &ctx->d_wire_err,
+                      &ctx->d_tc_obs, &ctx->d_fidx, &ctx->d_span_cell, &ctx->d_wire, &ctx->d_wire_off, &ctx->d_wire_pos, &ctx->d_wire_inoff, &ctx->d_wire_err,
                       &ctx->d_tc_raw, &ctx->d_tc_parsed, &ctx->d_rg_a, &ctx->d_rg_b};
     for (auto* b : bufs) b->release();
     for (auto& a : ctx->free_dev) cudaFree(a.p);

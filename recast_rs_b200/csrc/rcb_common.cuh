@@ -279,28 +279,27 @@ void launch_filter_spans2(const TileDesc* tiles, size_t S, const uint2* span_cel
                           const int16_t* smax, const uint8_t* sarea, uint8_t* area_out, uint32_t fmask, cudaStream_t s);
 void launch_span_cells(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, uint2* span_cell, cudaStream_t s);
 void launch_link_spans2(const TileDesc* tiles, size_t S, const uint2* span_cell, const uint32_t* hf_off, const int16_t* smin,
-                        const int16_t* smax, const uint8_t* sarea, uint8_t* areas, uint16_t* nei16, uint16_t* con, uint32_t* span_conn_cnt,
+                        const int16_t* smax, const uint8_t* sarea, uint8_t* areas, uint32_t* nid, uint16_t* con, uint32_t* span_conn_cnt,
                         TileInfo* tinfo, cudaStream_t s);
 void launch_tile_conn_bases(int ntiles, const uint32_t* conn_off_span, TileInfo* tinfo, cudaStream_t s);
-void launch_write_connections2(const TileDesc* tiles, size_t S, const uint2* span_cell, const uint32_t* hf_off, const uint16_t* nei16,
-                               const uint32_t* conn_off_span, const TileInfo* tinfo, uint32_t* first_conn, uint32_t* conn_ref,
-                               uint8_t* conn_dir, uint32_t* conn_next, cudaStream_t s);
+void launch_write_connections2(size_t S, const uint2* span_cell, const uint32_t* nid, const uint32_t* conn_off_span, const TileInfo* tinfo,
+                               uint32_t* first_conn, uint32_t* conn_ref, uint8_t* conn_dir, uint32_t* conn_next, cudaStream_t s);
 void launch_tile_bases(const TileDesc* tiles, int ntiles, const uint32_t* hf_off, const uint32_t* conn_off,
                        TileInfo* tinfo, cudaStream_t s);
 
-void launch_distance_field(const TileDesc* tiles, int ntiles, TileMap tm, const uint32_t* hf_off,
-                           const uint16_t* nei16, size_t S, const uint8_t* areas, uint16_t* tmp_init, uint16_t* tmp_f,
-                           uint16_t* tmp_d, uint16_t* dist, TileInfo* tinfo, uint4* fidx, cudaStream_t s);
-void launch_erode(const TileDesc* tiles, int ntiles, TileMap tm, const uint32_t* hf_off, const uint16_t* nei16,
-                  size_t S, uint8_t* areas, uint8_t* tmp_init, uint8_t* tmp_f, int radius, uint4* fidx, cudaStream_t s);
+// `nid` = u32[8][S] absolute neighbour span ids (k_link_spans2), `span_cell` = (tile, local cell) per span
+void launch_distance_field(const TileDesc* tiles, int ntiles, const uint32_t* hf_off, const uint32_t* nid, const uint2* span_cell, size_t S,
+                           const uint8_t* areas, uint16_t* tmp_init, uint16_t* tmp_f, uint16_t* tmp_d, uint16_t* dist, TileInfo* tinfo,
+                           uint4* fidx, cudaStream_t s);
+void launch_erode(const TileDesc* tiles, int ntiles, const uint32_t* hf_off, const uint32_t* nid, size_t S, uint8_t* areas,
+                  uint8_t* tmp_init, uint8_t* tmp_f, int radius, uint4* fidx, cudaStream_t s);
 
 // area operators (k_area.cu)
 void launch_convex_volumes(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smax, uint8_t* sarea,
                            const rcb_convex_volume* vols, int nvols, const float* verts, cudaStream_t s);
 void launch_area_marks(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smin, uint8_t* areas,
                        const rcb_area_op* ops, int op0, int op1, const float* poly_verts, cudaStream_t s);
-void launch_area_median(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const uint16_t* nei16, size_t S, const uint8_t* areas,
-                        uint8_t* out, cudaStream_t s);
+void launch_area_median(const uint32_t* nid, size_t S, const uint8_t* areas, uint8_t* out, cudaStream_t s);
 
 // tile-cache layers (k_tilecache.cu)
 void launch_tc_count(const TileDesc* tiles, TileMap tm, const uint8_t* regons, uint32_t* cell_cnt, cudaStream_t s);

@@ -22,4 +22,4 @@ for _ in range(7):
 ctx.profile_enable(True); ctx.profile_reset()
 for _ in range(3): flush.zero_(); ctx.build_tiles(arr).free()
 k = ctx.profile_read()
-print(f"cfg{cfgno} flags={os.environ.get('RCB_CLIP_FLAGS','-')} median {np.median(ms):.3f} ms  min {min(ms):.3f}  |", {n: round(m / 3, 3) for n, (m, c) in sorted(k.items(), key=lambda kv: -kv[1][0])[:6]})
+print(f"cfg{cfgno} flags={os.environ.get('RCB_CLIP_FLAGS','-')} median {np.median(ms):.3f} ms  min {min(ms):.3f}  |", {n: round(m / 3, 3) for n, (m, c) in sorted(k.items(), key=lambda kv: -kv[1][0])[:int(os.environ.get("QB_TOP", "6"))]})
