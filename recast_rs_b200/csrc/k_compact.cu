@@ -56,7 +56,12 @@ __global__ void __launch_bounds__(256) k_cells(const TileDesc* __restrict__ tile
 // One thread per SPAN instead of one per column: a column of a multi-level interior holds 16+ spans, each probing up to
 // 8 x 16 neighbour spans, and a thread that walks its column alone leaves the machine mostly empty (config 4: 590 k
 // columns, 8 M spans).  k_span_cells records (tile, cell) per span; the connection offsets are then a scan over spans.
+// It also finds out whether every column is ordered (min and max both non-decreasing), which is what the rasterizer
+// produces but Heightfield::add_span and a caller's CSR need not: span_cell[S].x != 0 = some column is not.  In an ordered
+// column the spans that can overlap / face a given span are one contiguous run, found by bisection (k_link_spans2,
+// k_filter_spans2) instead of a walk over the whole column.
 __global__ void __launch_bounds__(256) k_span_cells(const TileDesc* __restrict__ tiles, TileMap tm, const uint32_t* __restrict__ hf_off,
+                                                    const int16_t* __restrict__ smin, const int16_t* __restrict__ smax, size_t S,
                                                     uint2* __restrict__ span_cell) {
     const uint32_t tile = RCB_TILE_OF_BLOCK();
     if (tile >= tm.ntiles) return;
@@ -64,7 +69,19 @@ __global__ void __launch_bounds__(256) k_span_cells(const TileDesc* __restrict__
     const uint32_t lc = RCB_CELL_OF_THREAD();
     if (lc >= (uint32_t)(td.width * td.height)) return;
     const uint32_t g = td.cell_base + lc;
-    for (uint32_t s = hf_off[g]; s < hf_off[g + 1]; ++s) span_cell[s] = make_uint2(tile, lc);
+    const uint32_t b = hf_off[g], e = hf_off[g + 1];
+    bool unordered = false;
+    int pmn = -0x8000, pmx = -0x8000;
+    for (uint32_t s = b; s < e; ++s) {
+        span_cell[s] = make_uint2(tile, lc);
+        if (e - b > 1) {
+            const int mn = smin[s], mx = smax[s];
+            unordered |= mn < pmn || mx < pmx;
+            pmn = mn;
+            pmx = mx;
+        }
+    }
+    if (unordered) span_cell[S].x = 1u;
 }
 
 __global__ void __launch_bounds__(256) k_link_spans2(const TileDesc* __restrict__ tiles, uint32_t S, const uint2* __restrict__ span_cell,
@@ -75,6 +92,7 @@ __global__ void __launch_bounds__(256) k_link_spans2(const TileDesc* __restrict_
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const uint2 sc = span_cell[s];
+    const bool ordered = span_cell[S].x == 0;
     const uint32_t tile = sc.x, lc = sc.y;
     const TileDesc& td = tiles[tile];
     const int W = td.width, H = td.height;
@@ -103,9 +121,21 @@ __global__ void __launch_bounds__(256) k_link_spans2(const TileDesc* __restrict_
                 nb = hf_off[ng];
                 const uint32_t ne = hf_off[ng + 1];
                 int best_diff = 0x7fffffff;
-                for (uint32_t ns = nb; ns < ne; ++ns) {
-                    if (sarea[ns] == 0) continue;
+                uint32_t ns = nb;
+                if (ordered && ne - nb > 2) {  // first span whose top reaches this one's bottom
+                    uint32_t hi = ne;
+                    while (ns < hi) {
+                        const uint32_t mid = (ns + hi) >> 1;
+                        if ((int)smax[mid] < mn)
+                            ns = mid + 1;
+                        else
+                            hi = mid;
+                    }
+                }
+                for (; ns < ne; ++ns) {
                     const int nmn = smin[ns], nmx = smax[ns];
+                    if (ordered && nmn > mx) break;  // nor can any later one overlap
+                    if (sarea[ns] == 0) continue;
                     if (max(nmn, mn) > min(nmx, mx)) continue;
                     const int diff = (int)(uint16_t)(abs(nmn - mn) + abs(nmx - mx));
                     if (diff < best_diff) {
@@ -176,10 +206,12 @@ __global__ void __launch_bounds__(256) k_write_connections2(uint32_t S, const ui
 
 }  // namespace
 
-void launch_span_cells(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, uint2* span_cell, cudaStream_t s) {
+void launch_span_cells(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smin, const int16_t* smax, size_t S,
+                       uint2* span_cell, cudaStream_t s) {
     if (tm.nblocks == 0) return;
+    cudaMemsetAsync(span_cell + S, 0, sizeof(uint2), s);  // the "some column is not ordered" flag
     KScope _k("k_span_cells", s);
-    k_span_cells<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, span_cell);
+    k_span_cells<<<tm.grid(), 256, 0, s>>>(tiles, tm, hf_off, smin, smax, S, span_cell);
 }
 
 void launch_link_spans2(const TileDesc* tiles, size_t S, const uint2* span_cell, const uint32_t* hf_off, const int16_t* smin,

@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256) k_filter_spans2(const TileDesc* __restric
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const uint2 sc = span_cell[s];
+    const bool ordered = span_cell[S].x == 0;  // every column ordered (k_span_cells): bisect instead of walking the column
     const TileDesc& td = tiles[sc.x];
     const uint32_t lc = sc.y;
     const int W = td.width, H = td.height;
@@ -63,8 +64,23 @@ __global__ void __launch_bounds__(256) k_filter_spans2(const TileDesc* __restric
                 ledge = true;
                 break;
             }
-            for (uint32_t ns = nb; ns < ne; ++ns) {  // :409-447
+            // :409-447.  The `break` below only skips work: once it is taken, lowest < neg_climb decides the span.  In an
+            // ordered column the gaps that can pass the height test are one run: from the first whose ceiling clears
+            // floor + height to the last whose floor stays under ceiling - height.
+            uint32_t ns = nb;
+            if (ordered && ne - nb > 2) {
+                uint32_t top = ne - 1;  // the top gap's ceiling is MAXH
+                while (ns < top) {
+                    const uint32_t mid = (ns + top) >> 1;
+                    if ((int)smin[mid + 1] - floor < height)
+                        ns = mid + 1;
+                    else
+                        top = mid;
+                }
+            }
+            for (; ns < ne; ++ns) {
                 const int nfloor = smax[ns];
+                if (ordered && ceiling - nfloor < height) break;
                 nceil = (ns + 1 < ne) ? (int)smin[ns + 1] : MAXH;
                 if (min(ceiling, nceil) - max(floor, nfloor) < height) continue;
                 const int diff = nfloor - floor;

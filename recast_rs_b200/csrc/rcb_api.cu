@@ -383,7 +383,7 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
     const bool need_span_cells = S > 0 && (fmask || (stage_mask & RCB_STAGE_COMPACT));
     if (need_span_cells) {
         CU(ctx->d_span_cell.ensure(8 * (S + 1)));  // (tile, cell) per span: every later stage is one thread per span
-        launch_span_cells(d_tiles, tm, d_hf_off, ctx->d_span_cell.as<uint2>(), st);
+        launch_span_cells(d_tiles, tm, d_hf_off, d_smin, d_smax, S, ctx->d_span_cell.as<uint2>(), st);
     }
     if (fmask && S > 0) {  // span-parallel, out of place (F1 reads the previous span's original area)
         CU(ctx->d_t8a.ensure(S + 16));

@@ -277,7 +277,8 @@ void launch_cells_and_offsets(const TileDesc* tiles, TileMap tm, const uint32_t*
                               cudaStream_t s);
 void launch_filter_spans2(const TileDesc* tiles, size_t S, const uint2* span_cell, const uint32_t* hf_off, const int16_t* smin,
                           const int16_t* smax, const uint8_t* sarea, uint8_t* area_out, uint32_t fmask, cudaStream_t s);
-void launch_span_cells(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, uint2* span_cell, cudaStream_t s);
+void launch_span_cells(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smin, const int16_t* smax, size_t S,
+                       uint2* span_cell, cudaStream_t s);  // span_cell[S].x = "some column is not ordered"
 void launch_link_spans2(const TileDesc* tiles, size_t S, const uint2* span_cell, const uint32_t* hf_off, const int16_t* smin,
                         const int16_t* smax, const uint8_t* sarea, uint8_t* areas, uint32_t* nid, uint16_t* con, uint32_t* span_conn_cnt,
                         TileInfo* tinfo, cudaStream_t s);

@@ -320,3 +320,49 @@ def test_heterogeneous_tile_sizes_in_one_batch(oracle, rb, ctx):
                                    bmax=(bx + w * cs, float(rng.uniform(4, 7)), bz + h * cs), walkable_height=int(rng.integers(1, 6)),
                                    walkable_climb=int(rng.integers(0, 4)), walkable_slope_angle=float(rng.uniform(20, 70))))
     _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_ALL_BUILD)
+
+
+# ---- ordered / unordered columns: the bisection fast path of the span-parallel link and ledge filter --------------
+def _columns_case(rng, w, h, depth, ordered):
+    """CSR heightfield with up to `depth` spans per column.  ordered: disjoint ascending spans (what the rasterizer
+    leaves); else: some columns shuffled and overlapping, as Heightfield::add_span or a caller's CSR can hold."""
+    off, mn, mx, ar = [0], [], [], []
+    for _ in range(w * h):
+        n = int(rng.integers(0, depth + 1))
+        y, col = int(rng.integers(0, 6)), []
+        for _ in range(n):
+            t = int(rng.integers(1, 5))
+            col.append((y, y + t, int(rng.choice([0, 1, 1, 1, 63]))))
+            y += t + int(rng.integers(0, 9))
+        if not ordered and n > 1 and rng.random() < 0.4:
+            rng.shuffle(col)
+            col = [(a - int(rng.integers(0, 3)), b + int(rng.integers(0, 3)), c) for a, b, c in col]
+        for a, b, c in col:
+            mn.append(a); mx.append(b); ar.append(c)
+        off.append(len(mn))
+    return np.array(off, np.uint32), np.array(mn, np.int16), np.array(mx, np.int16), np.array(ar, np.uint8)
+
+
+@pytest.mark.parametrize("ordered", [True, False])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_deep_columns_filters_link_distance(oracle, rb, ctx, seed, ordered):
+    rng = np.random.default_rng(100 + seed)
+    w, h = 23, 17
+    off, mn, mx, ar = _columns_case(rng, w, h, 24 if seed else 5, ordered)
+    bmax = (w * 0.5, 200.0, h * 0.5)
+    height, climb = (4, 2) if seed != 2 else (9, 5)
+    o = oracle.Heightfield.from_csr(w, h, (0, 0, 0), bmax, 0.5, 0.5, off, mn, mx, ar)
+    o.filter_low_hanging_walkable_obstacles(climb)
+    o.filter_ledge_spans(height, climb)
+    o.filter_walkable_low_height_spans(height)
+    hfa = o.export()
+    oc = oracle.CompactHeightfield.build_from_heightfield(o)
+    oc.erode_walkable_area(1)
+    oc.build_distance_field()
+    chfa = oc.export()
+    from recast_rs_b200.config import RecastConfig
+    cfg = RecastConfig(width=w, height=h, cs=0.5, ch=0.5, bmin=(0, 0, 0), bmax=bmax, walkable_height=height, walkable_climb=climb)
+    bits = rb.STAGE_FILTER | rb.STAGE_COMPACT | rb.STAGE_ERODE | rb.STAGE_DIST
+    with ctx.build_from_spans([cfg], off, mn, mx, ar, bits, 1) as r:
+        r.download()
+        assert_tile_equal(r.tile(0), hfa, chfa, what=f"deep columns ordered={ordered}")
