@@ -84,78 +84,92 @@ __global__ void __launch_bounds__(256) k_span_cells(const TileDesc* __restrict__
     if (unordered) span_cell[S].x = 1u;
 }
 
+// Only walkable spans link (:262); on real geometry they are about half of all spans, scattered through every warp.  Each
+// thread first settles its own span's trivial outputs, then the block's walkable spans are compacted so that the eight
+// neighbour searches run in full warps.
 __global__ void __launch_bounds__(256) k_link_spans2(const TileDesc* __restrict__ tiles, uint32_t S, const uint2* __restrict__ span_cell,
                                                      const uint32_t* __restrict__ hf_off, const int16_t* __restrict__ smin,
                                                      const int16_t* __restrict__ smax, const uint8_t* __restrict__ sarea,
                                                      uint8_t* __restrict__ areas, uint32_t* __restrict__ nid, uint16_t* __restrict__ con,
                                                      uint32_t* __restrict__ span_conn_cnt, TileInfo* __restrict__ tinfo) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= S) return;
+    __shared__ uint32_t sh_list[256], sh_wcnt[8];
+    const uint32_t s0 = blockIdx.x * blockDim.x;
+    bool walk = false;
+    {
+        const uint32_t s = s0 + threadIdx.x;
+        if (s < S) {
+            const uint32_t tile = span_cell[s].x;
+            const uint32_t a = sarea[s];
+            areas[s] = (uint8_t)a;  // :237
+            // per-tile reductions, one atomic per (warp, tile): :240, :243-245
+            const unsigned peers = __match_any_sync(__activemask(), tile);
+            const uint32_t wsum = __reduce_add_sync(peers, a != 0 ? 1u : 0u);
+            const uint32_t hmax = __reduce_max_sync(peers, (uint32_t)(uint16_t)smax[s]);
+            if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+                if (wsum) atomicAdd(&tinfo[tile].walkable_span_count, wsum);
+                if (hmax) atomicMax(&tinfo[tile].max_height, hmax);
+            }
+            walk = a != 0;
+            if (!walk) {
+#pragma unroll
+                for (int d = 0; d < 8; ++d) nid[(size_t)d * S + s] = RCB_NONE;
+                *reinterpret_cast<uint2*>(con + 4 * (size_t)s) = make_uint2(63u | (63u << 16), 63u | (63u << 16));
+                span_conn_cnt[s] = 0;
+            }
+        }
+    }
+    const uint32_t nwalk = compact_block256(walk, sh_list, sh_wcnt);
+    if (threadIdx.x >= nwalk) return;
+    const uint32_t s = s0 + sh_list[threadIdx.x];
     const uint2 sc = span_cell[s];
     const bool ordered = span_cell[S].x == 0;
-    const uint32_t tile = sc.x, lc = sc.y;
-    const TileDesc& td = tiles[tile];
+    const uint32_t lc = sc.y;
+    const TileDesc& td = tiles[sc.x];
     const int W = td.width, H = td.height;
     const int z = (int)(lc / (uint32_t)W), x = (int)lc - z * W;
     const int mn = smin[s], mx = smax[s];
-    const uint32_t a = sarea[s];
-    areas[s] = (uint8_t)a;  // :237
-    {  // per-tile reductions, one atomic per (warp, tile): :240, :243-245
-        const unsigned peers = __match_any_sync(__activemask(), tile);
-        const uint32_t wsum = __reduce_add_sync(peers, a != 0 ? 1u : 0u);
-        const uint32_t hmax = __reduce_max_sync(peers, (uint32_t)(uint16_t)mx);
-        if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
-            if (wsum) atomicAdd(&tinfo[tile].walkable_span_count, wsum);
-            if (hmax) atomicMax(&tinfo[tile].max_height, hmax);
-        }
-    }
     uint16_t c4[4] = {63, 63, 63, 63};
     uint32_t nconn = 0;
-    if (a != 0) {
 #pragma unroll
-        for (int d = 0; d < 8; ++d) {
-            const int nx = x + c_dirx[d], nz = z + c_dirz[d];
-            uint32_t best = RCB_NEI_NONE, nb = 0;
-            if (!(nx < 0 || nz < 0 || nx >= W || nz >= H)) {
-                const uint32_t ng = td.cell_base + (uint32_t)nz * W + nx;
-                nb = hf_off[ng];
-                const uint32_t ne = hf_off[ng + 1];
-                int best_diff = 0x7fffffff;
-                uint32_t ns = nb;
-                if (ordered && ne - nb > 2) {  // first span whose top reaches this one's bottom
-                    uint32_t hi = ne;
-                    while (ns < hi) {
-                        const uint32_t mid = (ns + hi) >> 1;
-                        if ((int)smax[mid] < mn)
-                            ns = mid + 1;
-                        else
-                            hi = mid;
-                    }
-                }
-                for (; ns < ne; ++ns) {
-                    const int nmn = smin[ns], nmx = smax[ns];
-                    if (ordered && nmn > mx) break;  // nor can any later one overlap
-                    if (sarea[ns] == 0) continue;
-                    if (max(nmn, mn) > min(nmx, mx)) continue;
-                    const int diff = (int)(uint16_t)(abs(nmn - mn) + abs(nmx - mx));
-                    if (diff < best_diff) {
-                        best_diff = diff;
-                        best = ns - nb;
-                    }
+    for (int d = 0; d < 8; ++d) {
+        const int nx = x + c_dirx[d], nz = z + c_dirz[d];
+        uint32_t best = RCB_NEI_NONE, nb = 0;
+        if (!(nx < 0 || nz < 0 || nx >= W || nz >= H)) {
+            const uint32_t ng = td.cell_base + (uint32_t)nz * W + nx;
+            nb = hf_off[ng];
+            const uint32_t ne = hf_off[ng + 1];
+            int best_diff = 0x7fffffff;
+            uint32_t ns = nb;
+            if (ordered && ne - nb > 2) {  // first span whose top reaches this one's bottom
+                uint32_t hi = ne;
+                while (ns < hi) {
+                    const uint32_t mid = (ns + hi) >> 1;
+                    if ((int)smax[mid] < mn)
+                        ns = mid + 1;
+                    else
+                        hi = mid;
                 }
             }
-            nid[(size_t)d * S + s] = best != RCB_NEI_NONE ? nb + best : RCB_NONE;  // absolute span id for every later stage
-            if (best != RCB_NEI_NONE) {
-                nconn++;
-                if (d == 7) c4[0] = (uint16_t)best;  // :404-410
-                if (d == 5) c4[1] = (uint16_t)best;
-                if (d == 3) c4[2] = (uint16_t)best;
-                if (d == 1) c4[3] = (uint16_t)best;
+            for (; ns < ne; ++ns) {
+                const int nmn = smin[ns], nmx = smax[ns];
+                if (ordered && nmn > mx) break;  // nor can any later one overlap
+                if (sarea[ns] == 0) continue;
+                if (max(nmn, mn) > min(nmx, mx)) continue;
+                const int diff = (int)(uint16_t)(abs(nmn - mn) + abs(nmx - mx));
+                if (diff < best_diff) {
+                    best_diff = diff;
+                    best = ns - nb;
+                }
             }
         }
-    } else {
-#pragma unroll
-        for (int d = 0; d < 8; ++d) nid[(size_t)d * S + s] = RCB_NONE;
+        nid[(size_t)d * S + s] = best != RCB_NEI_NONE ? nb + best : RCB_NONE;  // absolute span id for every later stage
+        if (best != RCB_NEI_NONE) {
+            nconn++;
+            if (d == 7) c4[0] = (uint16_t)best;  // :404-410
+            if (d == 5) c4[1] = (uint16_t)best;
+            if (d == 3) c4[2] = (uint16_t)best;
+            if (d == 1) c4[3] = (uint16_t)best;
+        }
     }
     *reinterpret_cast<uint2*>(con + 4 * (size_t)s) =
         make_uint2((uint32_t)c4[0] | ((uint32_t)c4[1] << 16), (uint32_t)c4[2] | ((uint32_t)c4[3] << 16));

@@ -272,6 +272,26 @@ void launch_wire_replay(const TileDesc* tiles, TileMap tm, const uint8_t* data, 
                         const uint32_t* cell_pos, int strict_le, const int16_t* smin, const int16_t* smax, const uint8_t* sarea,
                         const uint32_t* in_off, uint32_t* mm, uint8_t* ar, uint32_t* span_cnt, unsigned long long* err, cudaStream_t s);
 
+#ifdef __CUDACC__
+// Block-ordered compaction of the threads that have work: returns how many, sh_list[i] = local index of the i-th.
+__device__ __forceinline__ uint32_t compact_block256(bool pred, uint32_t* sh_list, uint32_t* sh_wcnt) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (lane == 0) sh_wcnt[warp] = __popc(m);
+    __syncthreads();
+    uint32_t base = 0, total = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < 8; ++w) {
+        const uint32_t c = sh_wcnt[w];
+        if (w < warp) base += c;
+        total += c;
+    }
+    if (pred) sh_list[base + __popc(m & ((1u << lane) - 1u))] = threadIdx.x;
+    __syncthreads();
+    return total;
+}
+#endif
+
 void launch_cells_and_offsets(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, uint32_t* hf_cell_offset,
                               uint32_t* cell_index, uint32_t* cell_count, TileInfo* tinfo, int ntiles,
                               cudaStream_t s);
