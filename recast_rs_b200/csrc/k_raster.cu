@@ -263,31 +263,43 @@ __global__ void __launch_bounds__(128) k_clip_emit(RasterBuffers rb, TileInfo* _
     });
 }
 
+// Column segments hold one record per fragment {triangle, min | max << 16, area}: one scattered store per fragment, and
+// the replay's sort moves a record at a time.  8 bytes while triangle indices fit 24 bits, 16 bytes beyond.
+struct Rec8 {
+    uint2 v;
+    __device__ __forceinline__ static Rec8 make(uint32_t tri, uint32_t mm, uint32_t area) { return Rec8{make_uint2((tri << 8) | area, mm)}; }
+    __device__ __forceinline__ uint32_t key() const { return v.x; }  // triangle index in the high bits
+    __device__ __forceinline__ uint32_t mm() const { return v.y; }
+    __device__ __forceinline__ uint32_t area() const { return v.x & 0xffu; }
+};
+struct Rec16 {
+    uint4 v;
+    __device__ __forceinline__ static Rec16 make(uint32_t tri, uint32_t mm, uint32_t area) { return Rec16{make_uint4(tri, mm, area, 0u)}; }
+    __device__ __forceinline__ uint32_t key() const { return v.x; }
+    __device__ __forceinline__ uint32_t mm() const { return v.y; }
+    __device__ __forceinline__ uint32_t area() const { return v.z; }
+};
+
 // ---- pass 3: scatter fragments to their column segment --------------------------------------------
+template <typename R>
 __global__ void __launch_bounds__(256) k_scatter_fragments(const uint4* __restrict__ frag_tmp,
                                                            const unsigned long long* __restrict__ nfrag_dev,
-                                                           const uint32_t* __restrict__ frag_off,
-                                                           uint32_t* __restrict__ fs_tri, uint32_t* __restrict__ fs_mm,
-                                                           uint8_t* __restrict__ fs_area) {
+                                                           const uint32_t* __restrict__ frag_off, R* __restrict__ rec) {
     const unsigned long long n = *nfrag_dev;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const uint4 r = frag_tmp[i];
-        const uint32_t pos = frag_off[r.x] + (r.w & 0xffffffu);
-        fs_tri[pos] = r.y;
-        fs_mm[pos] = r.z;
-        fs_area[pos] = (uint8_t)(r.w >> 24);
+        rec[frag_off[r.x] + (r.w & 0xffffffu)] = R::make(r.y, r.z, r.w >> 24);
     }
 }
 
 // ---- pass 4: per-column ordered replay of add_span_internal ----------------------------------------
-// One thread per column.  The column's fragments occupy [frag_off[c], frag_off[c+1]) in arbitrary
-// order; they are sorted by triangle index in place, then replayed.  The span list is built in place
-// over the consumed prefix of the same segment (#spans <= #fragments consumed).
-__global__ void __launch_bounds__(256) k_replay_columns(uint32_t ncells, const uint32_t* __restrict__ frag_off,
-                                                        uint32_t* __restrict__ fs_tri, uint32_t* __restrict__ fs_mm,
-                                                        uint8_t* __restrict__ fs_area, uint32_t* __restrict__ span_cnt,
-                                                        int32_t thr, const uint32_t* __restrict__ ex_off) {
+// One thread per column.  The column's fragment records occupy [frag_off[c], frag_off[c+1]) in arbitrary order.  They
+// are sorted by triangle index in place, then replayed; the span list is built in place over the consumed prefix of
+// the same segment (#spans <= #fragments consumed).
+template <typename R>
+__global__ void __launch_bounds__(256) k_replay_columns(uint32_t ncells, const uint32_t* __restrict__ frag_off, R* __restrict__ rec,
+                                                        uint32_t* __restrict__ span_cnt, int32_t thr, const uint32_t* __restrict__ ex_off) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncells) return;
     const uint32_t b = frag_off[c], e = frag_off[c + 1];
@@ -298,34 +310,29 @@ __global__ void __launch_bounds__(256) k_replay_columns(uint32_t ncells, const u
         span_cnt[c] = 0;
         return;
     }
-    uint32_t* tri = fs_tri + b;
-    uint32_t* mm = fs_mm + b;
-    uint8_t* ar = fs_area + b;
+    R* r = rec + b;
     // insertion sort by triangle index (typical n: 2-4 on terrain, ~40 in the 16-floor interior)
     for (uint32_t i = nex + 1; i < n; ++i) {
-        const uint32_t kt = tri[i], km = mm[i];
-        const uint8_t ka = ar[i];
+        const R key = r[i];
         uint32_t j = i;
-        while (j > nex && tri[j - 1] > kt) {
-            tri[j] = tri[j - 1];
-            mm[j] = mm[j - 1];
-            ar[j] = ar[j - 1];
+        while (j > nex && r[j - 1].key() > key.key()) {
+            r[j] = r[j - 1];
             --j;
         }
-        tri[j] = kt;
-        mm[j] = km;
-        ar[j] = ka;
+        if (j != i) r[j] = key;
     }
     // replay (rasterization.rs:51-168) on the array form of the list
     uint32_t ns = nex;
     for (uint32_t i = nex; i < n; ++i) {
-        const uint32_t w = mm[i];
+        const R f = r[i];
+        const uint32_t w = f.mm();
         const int smin = (int16_t)(w & 0xffffu), smax = (int16_t)(w >> 16);
-        const uint32_t area = ar[i];
+        const uint32_t area = f.area();
         uint32_t p = 0;
         bool done = false;
         while (p < ns) {
-            const uint32_t cw = mm[p];
+            const R cur = r[p];
+            const uint32_t cw = cur.mm();
             const int cmin = (int16_t)(cw & 0xffffu), cmax = (int16_t)(cw >> 16);
             if (smax < cmin) break;  // insert before p
             if (smin > cmax) {
@@ -336,34 +343,26 @@ __global__ void __launch_bounds__(256) k_replay_columns(uint32_t ncells, const u
             const int mmin = min(smin, cmin);
             int mmax = max(smax, cmax);
             uint32_t marea = area;
-            if (abs(mmax - cmax) <= thr) marea = max(marea, (uint32_t)ar[p]);
+            if (abs(mmax - cmax) <= thr) marea = max(marea, cur.area());
             uint32_t q = p + 1;
             while (q < ns) {
-                const uint32_t nw = mm[q];
+                const uint32_t nw = r[q].mm();
                 if ((int)(int16_t)(nw & 0xffffu) > mmax) break;
                 mmax = max(mmax, (int)(int16_t)(nw >> 16));
                 ++q;
             }
-            mm[p] = ((uint32_t)mmin & 0xffffu) | ((uint32_t)mmax << 16);
-            ar[p] = (uint8_t)marea;
+            r[p] = R::make(0u, ((uint32_t)mmin & 0xffffu) | ((uint32_t)mmax << 16), marea);
             if (q > p + 1) {  // drop absorbed spans (p, q)
                 const uint32_t drop = q - (p + 1);
-                for (uint32_t k = q; k < ns; ++k) {
-                    mm[k - drop] = mm[k];
-                    ar[k - drop] = ar[k];
-                }
+                for (uint32_t k = q; k < ns; ++k) r[k - drop] = r[k];
                 ns -= drop;
             }
             done = true;
             break;
         }
         if (!done) {  // insert at p (p == ns: append)
-            for (uint32_t k = ns; k > p; --k) {
-                mm[k] = mm[k - 1];
-                ar[k] = ar[k - 1];
-            }
-            mm[p] = w;
-            ar[p] = (uint8_t)area;
+            for (uint32_t k = ns; k > p; --k) r[k] = r[k - 1];
+            if (p != i) r[p] = f;
             ++ns;
         }
     }
@@ -388,6 +387,22 @@ __global__ void __launch_bounds__(256) k_gather_spans(uint32_t ncells, const uin
     }
 }
 
+template <typename R>
+__global__ void __launch_bounds__(256) k_gather_records(uint32_t ncells, const uint32_t* __restrict__ frag_off, const R* __restrict__ rec,
+                                                        const uint32_t* __restrict__ hf_off, int16_t* __restrict__ smin,
+                                                        int16_t* __restrict__ smax, uint8_t* __restrict__ sarea) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const uint32_t src = frag_off[c];
+    const uint32_t dst = hf_off[c], n = hf_off[c + 1] - dst;
+    for (uint32_t k = 0; k < n; ++k) {
+        const R f = rec[src + k];
+        smin[dst + k] = (int16_t)(f.mm() & 0xffffu);
+        smax[dst + k] = (int16_t)(f.mm() >> 16);
+        sarea[dst + k] = (uint8_t)f.area();
+    }
+}
+
 // ---- per-tile fragment segments -> column order (global back end behind the v2 clipper) ------------------
 // One CTA per tile.  Scattering tile by tile keeps the random 4-byte writes inside the tile's own region
 // (a few hundred KB, L2-resident); scattering the whole batch at once cost 240 B of DRAM traffic per
@@ -406,11 +421,11 @@ __global__ void __launch_bounds__(512) k_seg_count(const TileDesc* __restrict__ 
     if (blockIdx.x == 0 && threadIdx.x == 0 && F) atomicAdd(&counters[1], (unsigned long long)F);
 }
 
+template <typename R>
 __global__ void __launch_bounds__(512) k_seg_scatter(const TileDesc* __restrict__ tiles, int ntiles, const uint32_t* __restrict__ tile_frags,
                                                      const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ tile_cap,
                                                      const uint32_t* __restrict__ tile_cursor, const uint32_t* __restrict__ frag_off,
-                                                     uint32_t* __restrict__ cell_cnt, uint32_t* __restrict__ fs_tri,
-                                                     uint32_t* __restrict__ fs_mm, uint8_t* __restrict__ fs_area) {
+                                                     uint32_t* __restrict__ cell_cnt, R* __restrict__ rec) {
     const uint32_t tile = blockIdx.z * gridDim.y + blockIdx.y;
     if (tile >= (uint32_t)ntiles) return;
     const uint32_t F = min(tile_cursor[tile], tile_cap[tile]);
@@ -422,9 +437,7 @@ __global__ void __launch_bounds__(512) k_seg_scatter(const TileDesc* __restrict_
         // the column's counter runs back to zero; slots fill in arrival order, which is close to triangle
         // order, so the replay's insertion sort stays near its best case
         const uint32_t pos = frag_off[g + 1] - atomicSub(&cell_cnt[g], 1u);
-        fs_tri[pos] = r2;
-        fs_mm[pos] = r1;
-        fs_area[pos] = (uint8_t)(r0 >> 24);
+        rec[pos] = R::make(r2, r1, r0 >> 24);
     }
 }
 
@@ -448,11 +461,14 @@ void launch_seg_count(const TileDesc* tiles, int ntiles, const uint32_t* tile_fr
 }
 
 void launch_seg_scatter(const TileDesc* tiles, int ntiles, const uint32_t* tile_frags, const uint32_t* tile_base, const uint32_t* tile_cap,
-                        const uint32_t* tile_cursor, const uint32_t* frag_off, uint32_t* cell_cnt, uint32_t* fs_tri, uint32_t* fs_mm,
-                        uint8_t* fs_area, uint32_t max_tile_frags, cudaStream_t s) {
+                        const uint32_t* tile_cursor, const uint32_t* frag_off, uint32_t* cell_cnt, void* rec, bool wide,
+                        uint32_t max_tile_frags, cudaStream_t s) {
     if (ntiles == 0) return;
     KScope _k("k_seg_scatter", s);
-    k_seg_scatter<<<seg_grid(ntiles, max_tile_frags), 512, 0, s>>>(tiles, ntiles, tile_frags, tile_base, tile_cap, tile_cursor, frag_off, cell_cnt, fs_tri, fs_mm, fs_area);
+    if (wide)
+        k_seg_scatter<Rec16><<<seg_grid(ntiles, max_tile_frags), 512, 0, s>>>(tiles, ntiles, tile_frags, tile_base, tile_cap, tile_cursor, frag_off, cell_cnt, (Rec16*)rec);
+    else
+        k_seg_scatter<Rec8><<<seg_grid(ntiles, max_tile_frags), 512, 0, s>>>(tiles, ntiles, tile_frags, tile_base, tile_cap, tile_cursor, frag_off, cell_cnt, (Rec8*)rec);
 }
 
 void launch_count_fragments(const RasterBuffers& rb, cudaStream_t s) {
@@ -472,23 +488,28 @@ void launch_clip_emit(const RasterBuffers& rb, TileInfo* tinfo, cudaStream_t s) 
 }
 
 void launch_scatter_fragments(const uint4* frag_tmp, const unsigned long long* nfrag_dev, uint32_t nfrag_hint,
-                              const uint32_t* frag_off, uint32_t* fs_tri, uint32_t* fs_mm, uint8_t* fs_area,
-                              cudaStream_t s) {
+                              const uint32_t* frag_off, void* rec, bool wide, cudaStream_t s) {
     if (nfrag_hint == 0) return;
     unsigned blocks = (unsigned)((nfrag_hint + 255ull) / 256ull);
     if (blocks > 148u * 64u) blocks = 148u * 64u;
     {
         KScope _k("k_scatter_fragments", s);
-        k_scatter_fragments<<<blocks, 256, 0, s>>>(frag_tmp, nfrag_dev, frag_off, fs_tri, fs_mm, fs_area);
+        if (wide)
+            k_scatter_fragments<Rec16><<<blocks, 256, 0, s>>>(frag_tmp, nfrag_dev, frag_off, (Rec16*)rec);
+        else
+            k_scatter_fragments<Rec8><<<blocks, 256, 0, s>>>(frag_tmp, nfrag_dev, frag_off, (Rec8*)rec);
     }
 }
 
-void launch_replay_columns(uint32_t ncells, const uint32_t* frag_off, uint32_t* fs_tri, uint32_t* fs_mm,
-                           uint8_t* fs_area, uint32_t* span_cnt, int32_t merge_thr, cudaStream_t s, const uint32_t* ex_off) {
+void launch_replay_columns(uint32_t ncells, const uint32_t* frag_off, void* rec, bool wide, uint32_t* span_cnt, int32_t merge_thr,
+                           cudaStream_t s, const uint32_t* ex_off) {
     if (ncells == 0) return;
     {
         KScope _k("k_replay_columns", s);
-        k_replay_columns<<<(ncells + 255) / 256, 256, 0, s>>>(ncells, frag_off, fs_tri, fs_mm, fs_area, span_cnt, merge_thr, ex_off);
+        if (wide)
+            k_replay_columns<Rec16><<<(ncells + 255) / 256, 256, 0, s>>>(ncells, frag_off, (Rec16*)rec, span_cnt, merge_thr, ex_off);
+        else
+            k_replay_columns<Rec8><<<(ncells + 255) / 256, 256, 0, s>>>(ncells, frag_off, (Rec8*)rec, span_cnt, merge_thr, ex_off);
     }
 }
 
@@ -496,10 +517,10 @@ void launch_replay_columns(uint32_t ncells, const uint32_t* frag_off, uint32_t* 
 // rasterization.rs:405-428 / lib.rs:186-290): sign = +1 adds the existing span counts to the per-column fragment
 // counts before the offsets are scanned; the second call (sign = -1) takes them out again, so that the scatter fills
 // the END of each column's range, and copies the existing spans to its beginning.
+template <typename R>
 __global__ void __launch_bounds__(256) k_onto(uint32_t ncells, const uint32_t* __restrict__ ex_off, uint32_t* __restrict__ cell_cnt,
                                               int place, const uint32_t* __restrict__ frag_off, const int16_t* __restrict__ smin,
-                                              const int16_t* __restrict__ smax, const uint8_t* __restrict__ sarea,
-                                              uint32_t* __restrict__ fs_mm, uint8_t* __restrict__ fs_area) {
+                                              const int16_t* __restrict__ smax, const uint8_t* __restrict__ sarea, R* __restrict__ rec) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncells) return;
     const uint32_t b = ex_off[c], n = ex_off[c + 1] - b;
@@ -509,17 +530,28 @@ __global__ void __launch_bounds__(256) k_onto(uint32_t ncells, const uint32_t* _
     }
     cell_cnt[c] -= n;
     const uint32_t o = frag_off[c];
-    for (uint32_t k = 0; k < n; ++k) {
-        fs_mm[o + k] = ((uint32_t)(uint16_t)smin[b + k]) | ((uint32_t)(uint16_t)smax[b + k] << 16);
-        fs_area[o + k] = sarea[b + k];
-    }
+    for (uint32_t k = 0; k < n; ++k)
+        rec[o + k] = R::make(0u, ((uint32_t)(uint16_t)smin[b + k]) | ((uint32_t)(uint16_t)smax[b + k] << 16), sarea[b + k]);
 }
 
 void launch_onto(uint32_t ncells, const uint32_t* ex_off, uint32_t* cell_cnt, int place, const uint32_t* frag_off, const int16_t* smin,
-                 const int16_t* smax, const uint8_t* sarea, uint32_t* fs_mm, uint8_t* fs_area, cudaStream_t s) {
+                 const int16_t* smax, const uint8_t* sarea, void* rec, bool wide, cudaStream_t s) {
     if (ncells == 0) return;
     KScope _k("k_onto", s);
-    k_onto<<<(ncells + 255) / 256, 256, 0, s>>>(ncells, ex_off, cell_cnt, place, frag_off, smin, smax, sarea, fs_mm, fs_area);
+    if (wide)
+        k_onto<Rec16><<<(ncells + 255) / 256, 256, 0, s>>>(ncells, ex_off, cell_cnt, place, frag_off, smin, smax, sarea, (Rec16*)rec);
+    else
+        k_onto<Rec8><<<(ncells + 255) / 256, 256, 0, s>>>(ncells, ex_off, cell_cnt, place, frag_off, smin, smax, sarea, (Rec8*)rec);
+}
+
+void launch_gather_records(uint32_t ncells, const uint32_t* frag_off, const void* rec, bool wide, const uint32_t* hf_off, int16_t* smin,
+                           int16_t* smax, uint8_t* sarea, cudaStream_t s) {
+    if (ncells == 0) return;
+    KScope _k("k_gather_spans", s);
+    if (wide)
+        k_gather_records<Rec16><<<(ncells + 255) / 256, 256, 0, s>>>(ncells, frag_off, (const Rec16*)rec, hf_off, smin, smax, sarea);
+    else
+        k_gather_records<Rec8><<<(ncells + 255) / 256, 256, 0, s>>>(ncells, frag_off, (const Rec8*)rec, hf_off, smin, smax, sarea);
 }
 
 void launch_gather_spans(uint32_t ncells, const uint32_t* frag_off, const uint32_t* fs_mm, const uint8_t* fs_area,

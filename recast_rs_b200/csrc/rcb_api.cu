@@ -938,10 +938,10 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         }
         const uint64_t cap = ub + Sex;
         if (cap > 0) {
-            CUB(ctx->d_fs_tri.ensure(4 * cap));
-            CUB(ctx->d_fs_mm.ensure(4 * cap));
-            CUB(ctx->d_fs_area.ensure(cap));
+            CUB(ctx->d_fs_tri.ensure(16 * cap));  // fragment records
         }
+        void* d_rec = ctx->d_fs_tri.p;
+        const bool wide_rec = ntris > (1u << 24) || getenv("RCB_WIDE_RECORDS") != nullptr;  // 8-byte records hold 24-bit triangle indices
         if (ub > 0) {
             if (v2) {
                 // fragments go to per-tile segments; each tile then counts and scatters its own columns
@@ -963,23 +963,19 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                 launch_clip_emit(rb, d_tinfo_tmp, st);
             }
         }
-        if (onto) launch_onto((uint32_t)Ctot, d_ex_off, rb.cell_cnt, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st);
+        if (onto) launch_onto((uint32_t)Ctot, d_ex_off, rb.cell_cnt, 0, nullptr, nullptr, nullptr, nullptr, nullptr, false, st);
         launch_exclusive_scan(rb.cell_cnt, d_frag_off, Ctot, ctx->d_scan_tmp.as<uint32_t>(), st);
         if (onto)
-            launch_onto((uint32_t)Ctot, d_ex_off, rb.cell_cnt, 1, d_frag_off, d_ex_min, d_ex_max, d_ex_area, ctx->d_fs_mm.as<uint32_t>(),
-                        ctx->d_fs_area.as<uint8_t>(), st);
+            launch_onto((uint32_t)Ctot, d_ex_off, rb.cell_cnt, 1, d_frag_off, d_ex_min, d_ex_max, d_ex_area, d_rec, wide_rec, st);
         if (ub > 0) {
             if (v2)
-                launch_seg_scatter(d_tiles, ntiles, r2.tile_frags, r2.tile_base, r2.tile_cap, r2.tile_cursor, d_frag_off, rb.cell_cnt,
-                                   ctx->d_fs_tri.as<uint32_t>(), ctx->d_fs_mm.as<uint32_t>(), ctx->d_fs_area.as<uint8_t>(),
-                                   (uint32_t)ctx->h_counters[5], st);
+                launch_seg_scatter(d_tiles, ntiles, r2.tile_frags, r2.tile_base, r2.tile_cap, r2.tile_cursor, d_frag_off, rb.cell_cnt, d_rec,
+                                   wide_rec, (uint32_t)ctx->h_counters[5], st);
             else
-                launch_scatter_fragments(rb.frag_tmp, rb.counters + 1, (uint32_t)ub, d_frag_off, ctx->d_fs_tri.as<uint32_t>(),
-                                         ctx->d_fs_mm.as<uint32_t>(), ctx->d_fs_area.as<uint8_t>(), st);
+                launch_scatter_fragments(rb.frag_tmp, rb.counters + 1, (uint32_t)ub, d_frag_off, d_rec, wide_rec, st);
         }
         if (cap > 0)
-            launch_replay_columns((uint32_t)Ctot, d_frag_off, ctx->d_fs_tri.as<uint32_t>(), ctx->d_fs_mm.as<uint32_t>(),
-                                  ctx->d_fs_area.as<uint8_t>(), rb.cell_cnt, src.merge_thr, st, d_ex_off);
+            launch_replay_columns((uint32_t)Ctot, d_frag_off, d_rec, wide_rec, rb.cell_cnt, src.merge_thr, st, d_ex_off);
         launch_exclusive_scan(rb.cell_cnt, d_hf_off, Ctot, ctx->d_scan_tmp.as<uint32_t>(), st);
         CUB(cudaMemcpyAsync(&ctx->h_counters[4], d_hf_off + Ctot, 4, cudaMemcpyDeviceToHost, st));
         CUB(cudaMemcpyAsync(&ctx->h_counters[5], ctx->d_counters.as<unsigned long long>() + 1, 8, cudaMemcpyDeviceToHost, st));
@@ -1004,9 +1000,8 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         char* A = res->devA.p;
         CUB(cudaMemcpyAsync(A + res->lay.tinfo, d_tinfo_tmp, sizeof(TileInfo) * (size_t)ntiles, cudaMemcpyDeviceToDevice, st));
         if (S > 0)
-            launch_gather_spans((uint32_t)Ctot, d_frag_off, ctx->d_fs_mm.as<uint32_t>(), ctx->d_fs_area.as<uint8_t>(), d_hf_off,
-                                (int16_t*)(A + res->lay.span_min), (int16_t*)(A + res->lay.span_max),
-                                (uint8_t*)(A + res->lay.span_area), st);
+            launch_gather_records((uint32_t)Ctot, d_frag_off, d_rec, wide_rec, d_hf_off, (int16_t*)(A + res->lay.span_min),
+                                  (int16_t*)(A + res->lay.span_max), (uint8_t*)(A + res->lay.span_area), st);
     } else if (src.span_data || (stage_mask & RCB_STAGE_READD)) {
         // ---- heightfields rebuilt through Heightfield::add_span: wire formats / checkpoint clone (k_wire.cu) ------
         const bool bytes_in = src.span_data != nullptr;

@@ -93,13 +93,16 @@ struct RasterBuffers {
 
 void launch_count_fragments(const RasterBuffers& rb, cudaStream_t s);
 void launch_clip_emit(const RasterBuffers& rb, TileInfo* tinfo, cudaStream_t s);
+// column segments hold fragment records `rec` = {triangle, min | max << 16, area}: 8 bytes each, 16 (`wide`) when triangle
+// indices need more than 24 bits
 void launch_scatter_fragments(const uint4* frag_tmp, const unsigned long long* nfrag_dev, uint32_t nfrag_hint,
-                              const uint32_t* frag_off, uint32_t* fs_tri, uint32_t* fs_mm, uint8_t* fs_area,
-                              cudaStream_t s);
-void launch_replay_columns(uint32_t ncells, const uint32_t* frag_off, uint32_t* fs_tri, uint32_t* fs_mm,
-                           uint8_t* fs_area, uint32_t* span_cnt, int32_t merge_thr, cudaStream_t s, const uint32_t* ex_off = nullptr);
+                              const uint32_t* frag_off, void* rec, bool wide, cudaStream_t s);
+void launch_replay_columns(uint32_t ncells, const uint32_t* frag_off, void* rec, bool wide, uint32_t* span_cnt, int32_t merge_thr,
+                           cudaStream_t s, const uint32_t* ex_off = nullptr);
 void launch_onto(uint32_t ncells, const uint32_t* ex_off, uint32_t* cell_cnt, int place, const uint32_t* frag_off, const int16_t* smin,
-                 const int16_t* smax, const uint8_t* sarea, uint32_t* fs_mm, uint8_t* fs_area, cudaStream_t s);
+                 const int16_t* smax, const uint8_t* sarea, void* rec, bool wide, cudaStream_t s);
+void launch_gather_records(uint32_t ncells, const uint32_t* frag_off, const void* rec, bool wide, const uint32_t* hf_off, int16_t* smin,
+                           int16_t* smax, uint8_t* sarea, cudaStream_t s);
 void launch_gather_spans(uint32_t ncells, const uint32_t* frag_off, const uint32_t* fs_mm, const uint8_t* fs_area,
                          const uint32_t* hf_off, int16_t* smin, int16_t* smax, uint8_t* sarea, cudaStream_t s);
 
@@ -184,8 +187,8 @@ void launch_tile_compact(const TileCompactArgs& a, int ntiles, cudaStream_t s);
 void launch_seg_count(const TileDesc* tiles, int ntiles, const uint32_t* tile_frags, const uint32_t* tile_base, const uint32_t* tile_cap,
                       const uint32_t* tile_cursor, uint32_t* cell_cnt, unsigned long long* counters, uint32_t max_tile_frags, cudaStream_t s);
 void launch_seg_scatter(const TileDesc* tiles, int ntiles, const uint32_t* tile_frags, const uint32_t* tile_base, const uint32_t* tile_cap,
-                        const uint32_t* tile_cursor, const uint32_t* frag_off, uint32_t* cell_cnt, uint32_t* fs_tri, uint32_t* fs_mm,
-                        uint8_t* fs_area, uint32_t max_tile_frags, cudaStream_t s);
+                        const uint32_t* tile_cursor, const uint32_t* frag_off, uint32_t* cell_cnt, void* rec, bool wide,
+                        uint32_t max_tile_frags, cudaStream_t s);
 
 // exclusive scan of n u32 values, out has n+1 entries (out[n] = total).  tmp: >= scan_tmp_elems(n) u32.
 size_t scan_tmp_elems(size_t n);
