@@ -209,9 +209,16 @@ __global__ void __launch_bounds__(256) k_blur(const uint32_t* __restrict__ nid, 
 
 }  // namespace
 
+// one thread per column of the widest tile (<= 1024; wider tiles stride): a 1024-thread CTA on a 140-cell-wide tile is
+// 86 % idle threads that still hold their SM's warp slots
+static int forward_threads(int max_width) {
+    const int t = (max_width + 31) & ~31;
+    return t < 64 ? 64 : (t > 1024 ? 1024 : t);
+}
+
 void launch_distance_field(const TileDesc* tiles, int ntiles, const uint32_t* hf_off, const uint32_t* nid, const uint2* span_cell, size_t S,
                            const uint8_t* areas, uint16_t* tmp_init, uint16_t* tmp_f, uint16_t* tmp_d, uint16_t* dist, TileInfo* tinfo,
-                           uint4* fidx, cudaStream_t s) {
+                           uint4* fidx, int max_width, cudaStream_t s) {
     if (S == 0 || ntiles == 0) return;
     const unsigned nb = (unsigned)((S + 255) / 256);
     {
@@ -224,7 +231,7 @@ void launch_distance_field(const TileDesc* tiles, int ntiles, const uint32_t* hf
     }
     {
         KScope _k("k_forward2", s);
-        k_forward2<uint16_t><<<ntiles, 1024, 0, s>>>(tiles, hf_off, fidx, S, tmp_init, tmp_f);
+        k_forward2<uint16_t><<<ntiles, forward_threads(max_width), 0, s>>>(tiles, hf_off, fidx, S, tmp_init, tmp_f);
     }
     {
         KScope _k("k_backward", s);
@@ -237,7 +244,7 @@ void launch_distance_field(const TileDesc* tiles, int ntiles, const uint32_t* hf
 }
 
 void launch_erode(const TileDesc* tiles, int ntiles, const uint32_t* hf_off, const uint32_t* nid, size_t S, uint8_t* areas,
-                  uint8_t* tmp_init, uint8_t* tmp_f, int radius, uint4* fidx, cudaStream_t s) {
+                  uint8_t* tmp_init, uint8_t* tmp_f, int radius, uint4* fidx, int max_width, cudaStream_t s) {
     if (S == 0 || ntiles == 0) return;
     const unsigned nb = (unsigned)((S + 255) / 256);
     const unsigned thr = (unsigned)(uint8_t)(uint32_t)(radius * 2);  // area.rs:226 `(radius*2) as u8`
@@ -251,7 +258,7 @@ void launch_erode(const TileDesc* tiles, int ntiles, const uint32_t* hf_off, con
     }
     {
         KScope _k("k_forward2", s);
-        k_forward2<uint8_t><<<ntiles, 1024, 0, s>>>(tiles, hf_off, fidx, S, tmp_init, tmp_f);
+        k_forward2<uint8_t><<<ntiles, forward_threads(max_width), 0, s>>>(tiles, hf_off, fidx, S, tmp_init, tmp_f);
     }
     {
         KScope _k("k_backward", s);

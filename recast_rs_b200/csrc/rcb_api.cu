@@ -470,12 +470,14 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
                 }
             }
         }
+        int max_width = 0;  // the forward sweep runs one thread per column of a tile
+        for (const TileDesc& t : res->tiles) max_width = std::max(max_width, (int)t.width);
         if ((stage_mask & RCB_STAGE_ERODE) && S > 0) {
             CU(ctx->d_t8a.ensure(S + 16));
             CU(ctx->d_t8b.ensure(S + 16));
             CU(ctx->d_fidx.ensure(16 * (S + 1)));
             launch_erode(d_tiles, ntiles, d_hf_off, d_nid, S, d_areas, ctx->d_t8a.as<uint8_t>(), ctx->d_t8b.as<uint8_t>(),
-                         erode_radius, ctx->d_fidx.as<uint4>(), st);
+                         erode_radius, ctx->d_fidx.as<uint4>(), max_width, st);
         }
         if ((stage_mask & RCB_STAGE_DIST) && S > 0) {
             CU(ctx->d_t16a.ensure(2 * S + 16));
@@ -484,7 +486,7 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
             CU(ctx->d_fidx.ensure(16 * (S + 1)));
             launch_distance_field(d_tiles, ntiles, d_hf_off, d_nid, d_span_cell, S, d_areas, ctx->d_t16a.as<uint16_t>(),
                                   ctx->d_t16b.as<uint16_t>(), ctx->d_t16c.as<uint16_t>(), (uint16_t*)(A + res->lay.dist), d_tinfo,
-                                  ctx->d_fidx.as<uint4>(), st);
+                                  ctx->d_fidx.as<uint4>(), max_width, st);
         }
     }
     return RCB_OK;

@@ -314,9 +314,9 @@ void launch_tile_bases(const TileDesc* tiles, int ntiles, const uint32_t* hf_off
 // `nid` = u32[8][S] absolute neighbour span ids (k_link_spans2), `span_cell` = (tile, local cell) per span
 void launch_distance_field(const TileDesc* tiles, int ntiles, const uint32_t* hf_off, const uint32_t* nid, const uint2* span_cell, size_t S,
                            const uint8_t* areas, uint16_t* tmp_init, uint16_t* tmp_f, uint16_t* tmp_d, uint16_t* dist, TileInfo* tinfo,
-                           uint4* fidx, cudaStream_t s);
+                           uint4* fidx, int max_width, cudaStream_t s);
 void launch_erode(const TileDesc* tiles, int ntiles, const uint32_t* hf_off, const uint32_t* nid, size_t S, uint8_t* areas,
-                  uint8_t* tmp_init, uint8_t* tmp_f, int radius, uint4* fidx, cudaStream_t s);
+                  uint8_t* tmp_init, uint8_t* tmp_f, int radius, uint4* fidx, int max_width, cudaStream_t s);
 
 // area operators (k_area.cu)
 void launch_convex_volumes(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smax, uint8_t* sarea,
