@@ -27,7 +27,7 @@
 // matters is that every tile of the batch is resident at once:
 //   64 threads, 14 CTAs per SM (<= 73 registers) — labels in shared memory; the 2025 tiles of config 2 in one wave
 //   32 threads, 32 CTAs per SM (64 registers)    — labels in global memory; the 4761 128x128 tiles of config 3 in two
-//   256 threads                                   — a few very large tiles (config 4: 144 tiles of 56 k spans): wider phases
+//   256 / 1024 threads                            — a few very large tiles (config 4: 144 tiles of 56 k spans): wider phases
 #define RG_BT 64
 #define RG_MIN_CTAS 14
 #define RG_NS rg64
@@ -49,6 +49,13 @@
 #undef RG_BT
 #undef RG_MIN_CTAS
 #undef RG_NS
+#define RG_BT 1024
+#define RG_MIN_CTAS 1
+#define RG_NS rg1024
+#include "k_regions_impl.cuh"
+#undef RG_BT
+#undef RG_MIN_CTAS
+#undef RG_NS
 
 size_t regions_smem_bytes(uint32_t max_spans) { return 2 * (size_t)((max_spans + 7u) & ~7u) + 16; }
 
@@ -58,6 +65,9 @@ void launch_regions(const RegionArgs& a, int ntiles, cudaStream_t s) {
     KScope _k("k_regions", s);
     if (a.narrow == 1) {
         rg32::k_regions<<<ntiles, 32, smem, s>>>(a);
+    } else if (a.narrow == 3) {
+        cudaFuncSetAttribute(rg1024::k_regions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        rg1024::k_regions<<<ntiles, 1024, smem, s>>>(a);
     } else if (a.narrow == 2) {
         cudaFuncSetAttribute(rg256::k_regions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         rg256::k_regions<<<ntiles, 256, smem, s>>>(a);

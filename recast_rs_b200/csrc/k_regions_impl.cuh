@@ -352,9 +352,10 @@ __global__ void __launch_bounds__(BT, RG_MIN_CTAS) k_regions(RegionArgs a) {
             uint32_t base8[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) base8[k] = 0;
-            for (uint32_t c0 = 0; c0 < S; c0 += BT * 64u) {
-                const uint32_t m = min(S - c0, (uint32_t)BT * 64u);
-                const uint32_t per = (m + BT - 1) / BT;  // <= 64
+            constexpr uint32_t RUN = BT >= 1024 ? 32u : 64u;  // BT * RUN < 65536: 16 bits hold a prefix
+            for (uint32_t c0 = 0; c0 < S; c0 += BT * RUN) {
+                const uint32_t m = min(S - c0, (uint32_t)BT * RUN);
+                const uint32_t per = (m + BT - 1) / BT;  // <= RUN
                 const uint32_t lo = c0 + threadIdx.x * per, hi = min(lo + per, c0 + m);
                 unsigned long long nib[4] = {0, 0, 0, 0};
                 uint32_t cnt[8];
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(BT, RG_MIN_CTAS) k_regions(RegionArgs a) {
                 }
                 uint32_t ex[8];
 #pragma unroll
-                for (int k = 0; k < 8; k += 2) {  // at most BT * 64 = 4096 entries per sweep: 16 bits hold a prefix
+                for (int k = 0; k < 8; k += 2) {  // two 16-bit counts to a word
                     uint32_t total;
                     const uint32_t e = block_excl_scan(cnt[k] | (cnt[k + 1] << 16), &total, sh);
                     ex[k] = base8[k] + (e & 0xffffu);

@@ -568,6 +568,7 @@ int build_regions_stage(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, 
         ra.narrow = mode == 2 ? 1 : 0;
         if (mode != 2 && ntiles <= 148 * 2 && smax >= 16384) ra.narrow = 2;  // few, very large tiles: 256 threads each
         if (const char* e = getenv("RCB_REGIONS_WIDE256")) ra.narrow = atoi(e) ? 2 : ra.narrow == 2 ? 0 : ra.narrow;
+        if (const char* e = getenv("RCB_REGIONS_BT")) ra.narrow = atoi(e) == 1024 ? 3 : atoi(e) == 256 ? 2 : atoi(e) == 32 ? 1 : 0;
     }
     launch_regions(ra, ntiles, st);
     CU(cudaMemcpyAsync(&ctx->h_counters[7], b + o_err, 4, cudaMemcpyDeviceToHost, st));
