@@ -68,7 +68,9 @@ __global__ void __launch_bounds__(256) k_boundary(const uint32_t* __restrict__ n
 // (value inf), which makes the sweep body branch-free, and "+2 / +3" needs no clamp because the running
 // minimum never exceeds inf.  k_forward2 then walks the rows of a tile with one CTA: per row one 16-byte
 // index load (prefetched one row ahead) and the distance loads.
-__global__ void __launch_bounds__(256) k_fwd_index(const uint32_t* __restrict__ nid, size_t S, uint4* __restrict__ fidx) {
+template <typename T>
+__global__ void __launch_bounds__(256) k_fwd_index(const uint32_t* __restrict__ nid, size_t S, const T* __restrict__ init,
+                                                   uint4* __restrict__ fidx) {
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const Grid g{nid, S};
@@ -79,28 +81,28 @@ __global__ void __launch_bounds__(256) k_fwd_index(const uint32_t* __restrict__ 
         if (t != RCB_NONE) a1 = t;
     } else
         a0 = dummy;
+    // the part of the relaxation that does not depend on the sweep: the span's own initial value and its E neighbour's
+    uint32_t base = init[s];
     if (b0 != RCB_NONE) {
+        base = min(base, (uint32_t)init[b0] + 2u);
         const uint32_t t = nei(g, b0, 2);
         if (t != RCB_NONE) b1 = t;
-    } else
-        b0 = dummy;
-    fidx[s] = make_uint4(a0, a1, b0, b1);
+    }
+    fidx[s] = make_uint4(a0, a1, base, b1);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(1024) k_forward2(const TileDesc* __restrict__ tiles, const uint32_t* __restrict__ hf_off,
-                                                   const uint4* __restrict__ fidx, size_t S, T* init, T* F) {
+                                                   const uint4* __restrict__ fidx, size_t S, T* F) {
     const TileDesc& td = tiles[blockIdx.x];
     const int W = td.width, H = td.height;
     const T inf = (T)~(T)0;
-    if (blockIdx.x == 0 && threadIdx.x == 0) init[S] = inf;  // dummy span (every CTA only ever reads it)
-    if (threadIdx.x == 0) F[S] = inf;                       // same value from every CTA: benign
+    if (threadIdx.x == 0) F[S] = inf;  // dummy span; the same value from every CTA: benign
     __syncthreads();
-    auto relax = [&](uint32_t s, const uint4 ix) {
-        uint32_t v = init[s];
+    auto relax = [&](uint32_t, const uint4 ix) {
+        uint32_t v = ix.z;  // min(init[s], init[E] + 2), folded in by k_fwd_index
         v = min(v, (uint32_t)F[ix.x] + 2u);
         v = min(v, (uint32_t)F[ix.y] + 3u);
-        v = min(v, (uint32_t)init[ix.z] + 2u);
         v = min(v, (uint32_t)F[ix.w] + 3u);
         return (T)v;
     };
@@ -227,11 +229,11 @@ void launch_distance_field(const TileDesc* tiles, int ntiles, const uint32_t* hf
     }
     {
         KScope _k("k_fwd_index", s);
-        k_fwd_index<<<nb, 256, 0, s>>>(nid, S, fidx);
+        k_fwd_index<uint16_t><<<nb, 256, 0, s>>>(nid, S, tmp_init, fidx);
     }
     {
         KScope _k("k_forward2", s);
-        k_forward2<uint16_t><<<ntiles, forward_threads(max_width), 0, s>>>(tiles, hf_off, fidx, S, tmp_init, tmp_f);
+        k_forward2<uint16_t><<<ntiles, forward_threads(max_width), 0, s>>>(tiles, hf_off, fidx, S, tmp_f);
     }
     {
         KScope _k("k_backward", s);
@@ -254,11 +256,11 @@ void launch_erode(const TileDesc* tiles, int ntiles, const uint32_t* hf_off, con
     }
     {
         KScope _k("k_fwd_index", s);
-        k_fwd_index<<<nb, 256, 0, s>>>(nid, S, fidx);
+        k_fwd_index<uint8_t><<<nb, 256, 0, s>>>(nid, S, tmp_init, fidx);
     }
     {
         KScope _k("k_forward2", s);
-        k_forward2<uint8_t><<<ntiles, forward_threads(max_width), 0, s>>>(tiles, hf_off, fidx, S, tmp_init, tmp_f);
+        k_forward2<uint8_t><<<ntiles, forward_threads(max_width), 0, s>>>(tiles, hf_off, fidx, S, tmp_f);
     }
     {
         KScope _k("k_backward", s);
