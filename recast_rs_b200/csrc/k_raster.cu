@@ -329,6 +329,18 @@ __global__ void __launch_bounds__(256) k_replay_columns(uint32_t ncells, const u
         const int smin = (int16_t)(w & 0xffffu), smax = (int16_t)(w >> 16);
         const uint32_t area = f.area();
         uint32_t p = 0;
+        if (nex == 0 && ns > 4) {
+            // a list this rule built from nothing is ordered and disjoint: every span that ends below smin is skipped
+            // by the walk below, so start at the first that does not
+            uint32_t hi = ns;
+            while (p < hi) {
+                const uint32_t mid = (p + hi) >> 1;
+                if ((int)(int16_t)(r[mid].mm() >> 16) < smin)
+                    p = mid + 1;
+                else
+                    hi = mid;
+            }
+        }
         bool done = false;
         while (p < ns) {
             const R cur = r[p];
