@@ -38,8 +38,8 @@ def _stale(target: str, deps) -> bool:
 
 def build_native(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
-    hdrs = [os.path.join(CSRC, "rcb_common.cuh"), os.path.join(os.path.dirname(HERE), "include", "recast_b200.h"),
-            os.path.abspath(__file__)]
+    hdrs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))  # every header: k_regions_impl.cuh too
+    hdrs += [os.path.join(os.path.dirname(HERE), "include", "recast_b200.h"), os.path.abspath(__file__)]
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
     jobs = []

@@ -121,21 +121,30 @@ __device__ __forceinline__ uint32_t nbr(const Tile& t, int d, uint32_t s) {
 // does cell ci stay in region r?  (watershed.rs:167-216) — false when a 4-neighbour, or the neighbour reached from it by
 // turning clockwise, of the same area carries another region.
 __device__ __forceinline__ bool ws_kept(const Tile& t, uint32_t ci, uint32_t r, uint32_t area) {
+    // The verdict is an AND over the four directions, so their order is immaterial: all first-level neighbours are
+    // fetched together, then all second-level ones - two table round trips deep instead of up to eight (the reference's
+    // early exits only skip work).
+    uint32_t a1[4], a2[4], ar1[4], nr1[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) a1[d] = nbr(t, d, ci);
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
-        const uint32_t ai = nbr(t, d, ci);
-        if (ai == NONE32) continue;
-        if (t.areas[ai] != area) continue;
-        const uint32_t nr = *(volatile uint16_t*)&t.reg[ai];
-        if (nr & BORDER) continue;  // skips the diagonal too
-        if (nr != 0 && nr != r) return false;
-        const uint32_t ai2 = nbr(t, (d + 1) & 3, ai);
-        if (ai2 == NONE32) continue;
-        if (t.areas[ai2] != area) continue;
-        const uint32_t nr2 = *(volatile uint16_t*)&t.reg[ai2];
-        if (nr2 != 0 && nr2 != r) return false;  // no border test here (:205-210)
+        const uint32_t i = a1[d] != NONE32 ? a1[d] : ci;
+        ar1[d] = t.areas[i];
+        nr1[d] = *(volatile uint16_t*)&t.reg[i];
+        a2[d] = nbr(t, (d + 1) & 3, i);
     }
-    return true;
+    bool bad = false;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        const bool v1 = a1[d] != NONE32 && ar1[d] == area && !(nr1[d] & BORDER);  // a border neighbour skips its diagonal too
+        bad |= v1 && nr1[d] != 0 && nr1[d] != r;
+        const uint32_t i2 = a2[d] != NONE32 ? a2[d] : ci;
+        const uint32_t ar2 = t.areas[i2];
+        const uint32_t nr2 = *(volatile uint16_t*)&t.reg[i2];
+        bad |= v1 && a2[d] != NONE32 && ar2 == area && nr2 != 0 && nr2 != r;  // no border test here (:205-210)
+    }
+    return !bad;
 }
 
 __device__ __forceinline__ uint32_t cas16(uint16_t* p, uint16_t cmp, uint16_t val) {
