@@ -462,20 +462,24 @@ __global__ void __launch_bounds__(BT, RG_MIN_CTAS) k_regions(RegionArgs a) {
                     const uint32_t k = k0 + (threadIdx.x >> 2);
                     const int d = (int)(threadIdx.x & 3u);
                     const bool valid = k < ncur;
-                    uint32_t ci = 0, ai = NONE32;
+                    uint32_t ci = 0, ai = NONE32, dai = 0;
                     bool bad = false, same = false;
                     if (valid) {
                         ci = cur[k];
                         ai = nbr(t, d, ci);
-                        if (ai != NONE32 && t.areas[ai] == area) {
-                            same = true;
+                        if (ai != NONE32) {
+                            // everything that hangs off ai is fetched together: its area, label, distance (needed after
+                            // the group vote) and its clockwise neighbour
+                            dai = t.dist[ai];
+                            const uint32_t ar = t.areas[ai];
                             const uint32_t nr = *(volatile uint16_t*)&t.reg[ai];
-                            if (!(nr & BORDER)) {  // a border neighbour skips its diagonal too (:183-186)
-                                if (nr != 0 && nr != region_id) {
-                                    bad = true;
-                                } else {
-                                    const uint32_t ai2 = nbr(t, (d + 1) & 3, ai);
-                                    if (ai2 != NONE32 && t.areas[ai2] == area) {
+                            const uint32_t ai2 = nbr(t, (d + 1) & 3, ai);
+                            if (ar == area) {
+                                same = true;
+                                if (!(nr & BORDER)) {  // a border neighbour skips its diagonal too (:183-186)
+                                    if (nr != 0 && nr != region_id) {
+                                        bad = true;
+                                    } else if (ai2 != NONE32 && t.areas[ai2] == area) {
                                         const uint32_t nr2 = *(volatile uint16_t*)&t.reg[ai2];
                                         if (nr2 != 0 && nr2 != region_id) bad = true;
                                     }
@@ -489,7 +493,7 @@ __global__ void __launch_bounds__(BT, RG_MIN_CTAS) k_regions(RegionArgs a) {
                         if (d == 0) t.reg[ci] = 0;  // :218-221
                         continue;
                     }
-                    if (same && t.dist[ai] >= lev && cas16(&t.reg[ai], 0, (uint16_t)region_id) == 0) {
+                    if (same && dai >= lev && cas16(&t.reg[ai], 0, (uint16_t)region_id) == 0) {
                         t.sdist[ai] = 0;
                         nxt[atomicAdd(&sh_next, 1u)] = ai;
                     }
@@ -533,17 +537,21 @@ __global__ void __launch_bounds__(BT, RG_MIN_CTAS) k_regions(RegionArgs a) {
     for (uint32_t i = threadIdx.x; i < R; i += BT) cnt[i] = 0, alive[i] = (uint16_t)i, border[i] = 0;
     for (uint32_t s = threadIdx.x; s < S; s += BT) t.reg0[s] = t.reg[s];
     __syncthreads();
+    // the span passes below fetch a span's four neighbours, then their four labels, together (a chain two loads deep
+    // however many directions matter)
     for (uint32_t s = threadIdx.x; s < S; s += BT) {
         const uint32_t rid = t.reg0[s];
+        uint32_t nn[4], nr[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) nn[d] = list_neighbor(t, s, d);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) nr[d] = t.reg0[nn[d] != NONE32 ? nn[d] : s];
         if (rid == 0 || (rid & BORDER)) continue;
         atomicAdd(&cnt[rid], 1);
+        bool at_border = false;
 #pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            const uint32_t n = list_neighbor(t, s, d);
-            if (n == NONE32) continue;
-            const uint32_t nr = t.reg0[n];
-            if (nr & BORDER) border[rid] = 1;
-        }
+        for (int d = 0; d < 4; ++d) at_border |= nn[d] != NONE32 && (nr[d] & BORDER);
+        if (at_border) border[rid] = 1;
     }
     __syncthreads();
     // small regions (:598-622)
@@ -575,11 +583,15 @@ __global__ void __launch_bounds__(BT, RG_MIN_CTAS) k_regions(RegionArgs a) {
                     const uint32_t rid = t.reg0[s];
                     if (rid == 0 || (rid & BORDER)) continue;
                     if (!(alive[rid] != 0 && cnt[rid] != 0 && cnt[rid] < merge_area && !border[rid])) continue;
+                    uint32_t nn[4], nrs[4];
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) nn[d] = list_neighbor(t, s, d);
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) nrs[d] = t.reg0[nn[d] != NONE32 ? nn[d] : s];
 #pragma unroll
                     for (int d = 0; d < 4; ++d) {
-                        const uint32_t n = list_neighbor(t, s, d);
-                        if (n == NONE32) continue;
-                        const uint32_t nr = t.reg0[n];
+                        if (nn[d] == NONE32) continue;
+                        const uint32_t nr = nrs[d];
                         if (nr == rid || nr == 0 || (nr & BORDER) || nr >= R) continue;
                         if (alive[nr] == 0 || cnt[nr] <= 0) continue;
                         // first neighbour in list order with the largest span count == max of (count, -first occurrence)
