@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(BT, RG_MIN_CTAS) k_regions(RegionArgs a) {
     extern __shared__ __align__(16) unsigned char rg_smem[];
     uint16_t* const g_reg = t.reg;
     const bool in_smem = a.smem_spans >= S && S < 0xFFFFu;
-    const bool small = S < 0xFFFFu;
+    const bool small = a.all_small != 0;  // S < 0xFFFF for every tile of the batch
 #pragma unroll
     for (int d = 0; d < 4; ++d) t.nb16[d] = small ? (uint16_t*)a.nb4 + (size_t)d * a.Stot + sb : nullptr;
     if (in_smem) {

@@ -564,6 +564,7 @@ int build_regions_stage(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, 
         const double t_narrow = 1.6 * std::ceil((double)ntiles / (148.0 * 32.0));
         int mode = t_smem <= t_wide && t_smem <= t_narrow ? 0 : (t_wide <= t_narrow ? 1 : 2);
         if (const char* e = getenv("RCB_REGIONS_MODE")) mode = atoi(e) == 0 && !fits ? 1 : atoi(e);  // 0 smem, 1 wide, 2 narrow
+        ra.all_small = smax < 0xFFFFu ? 1u : 0u;
         ra.smem_spans = mode == 0 ? std::max(smax, 1u) : 0u;
         ra.narrow = mode == 2 ? 1 : 0;
         if (mode != 2 && ntiles <= 148 * 2 && smax >= 16384) ra.narrow = 2;  // few, very large tiles: 256 threads each

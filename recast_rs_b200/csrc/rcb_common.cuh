@@ -245,6 +245,8 @@ struct RegionArgs {
     unsigned int* err;  // first tile whose region ids overflowed (init 0xffffffff)
     unsigned long long* phase;  // RCB_PHASE_TIMERS: cycle sums per phase (thread 0 of every tile), or nullptr
     uint32_t smem_spans;        // tiles with at most this many spans keep their arrays in shared memory (0: none do)
+    uint32_t all_small;         // every tile of the batch has fewer than 65535 spans: 16-bit neighbour table (one layout per batch:
+                                // 16- and 32-bit planes of different tiles would overlap)
     int narrow;                 // 0: 64 threads; 1: the 32-thread build (32 CTAs per SM), for batches that would not be resident
                                 // otherwise; 2: the 256-thread build, for a few very large tiles
 };

@@ -158,3 +158,29 @@ def test_gpu_regions_tall_tile_global_memory_path(oracle):
             tv = r.download().tile(0)
     assert tv.max_regions == wmr
     np.testing.assert_array_equal(tv.reg, want)
+
+
+@pytest.mark.gpu
+def test_gpu_regions_mixed_batch_one_huge_tile_among_small_ones(oracle):
+    """One tile past 65535 spans in a batch of small ones: the width of the neighbour table is a property of the batch
+    (16- and 32-bit planes of different tiles would overlap in the shared scratch)."""
+    import recast_rs_b200.builder as rb
+
+    v, t = synth.interior(18, 17, 1.2, 0.2, 3, 3.0)
+    base = RecastConfig(cs=0.3, ch=0.2, min_region_area=8, merge_region_area=20)
+    big = synth.single_tile_config(v, base)
+    small = synth.tile_grid(v, 24, base)[:5]
+    cfgs = small[:2] + [big] + small[2:]
+    with rb.Context(0) as ctx:
+        ctx.upload_mesh(v, t)
+        with ctx.build_tiles(cfgs, rb.STAGE_ALL_BUILD | rb.STAGE_REGIONS) as r:
+            r.download()
+            sizes = [r.tile(i).reg.size for i in range(len(cfgs))]
+            assert max(sizes) > 65535 and min(sizes) < 65535
+            for i, c in enumerate(cfgs):
+                ohf = oracle.Heightfield.from_config(c)
+                ohf.builder_rasterize(c, v, t)
+                want, wmr = oracle.CompactHeightfield.build_from_heightfield(ohf).build_regions(c.border_size, c.min_region_area,
+                                                                                                 c.merge_region_area)
+                assert r.tile(i).max_regions == wmr, i
+                np.testing.assert_array_equal(r.tile(i).reg, want, err_msg=f"tile {i}")
