@@ -803,26 +803,54 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
         else
             asm volatile("bar.sync 2, %0;" ::"r"(nworkers) : "memory");
         const uint32_t conn_base = sh_misc[1];
-        for (uint32_t c = rank; c < C; c += nworkers) {
-            const uint32_t b = soff[c], e = soff[c + 1];
-            if (b == e) continue;
-            uint32_t k = coff[c];
-            for (uint32_t s = b; s < e; ++s) {
-                uint32_t first = RCB_NONE;
-                uint32_t nn[8];
+        // Each worker warp takes a contiguous run of cells, i.e. of spans and of the list, 32 spans at a time: a lane
+        // counts its span's connections, then the lanes turn to the run's list SLOTS - slot t belongs to the span whose
+        // range holds t (bisection over the lanes' offsets) and is its j-th present direction from 7 downwards - so the
+        // three stores of a round are coalesced.  (One span per thread wrote its own 5-8 slots: ~20 sectors per store.)
+        const uint32_t lane = rank & 31u, wid = rank >> 5, nwarps = nworkers >> 5;
+        const uint32_t cpw = (C + nwarps - 1) / nwarps;
+        const uint32_t cw0 = min(wid * cpw, C), cw1 = min(cw0 + cpw, C);
+        uint32_t kbase = coff[cw0];
+        for (uint32_t s0 = soff[cw0], s1 = soff[cw1]; s0 < s1; s0 += 32) {
+            const uint32_t s = s0 + lane;
+            uint32_t mask = 0;
+            if (s < s1) {
 #pragma unroll
-                for (int d = 0; d < 8; ++d) nn[d] = nid[(uint32_t)d * S2 + s];  // eight independent loads
-#pragma unroll
-                for (int d = 7; d >= 0; --d) {
-                    if (nn[d] == TN) continue;
-                    a.conn_ref[conn_base + k] = nn[d];
-                    a.conn_dir[conn_base + k] = (uint8_t)d;
-                    a.conn_next[conn_base + k] = first;
-                    first = k;
-                    ++k;
-                }
-                a.first_conn[span_base + s] = first;
+                for (int d = 0; d < 8; ++d) mask |= (nid[(uint32_t)d * S2 + s] != (uint16_t)TN ? 1u : 0u) << d;
             }
+            const uint32_t cnt = __popc(mask);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl += v;
+            }
+            const uint32_t excl = incl - cnt, T = __shfl_sync(0xffffffffu, incl, 31);
+            if (s < s1) a.first_conn[span_base + s] = cnt ? kbase + incl - 1 : RCB_NONE;  // the last one pushed
+            const uint32_t rmask = __brev(mask) >> 24;  // bit i = direction 7 - i: the order the list is pushed in
+            for (uint32_t t = lane; t < ((T + 31u) & ~31u); t += 32) {
+                // owner = the last lane whose range starts at or before t (empty ranges share their successor's start)
+                uint32_t lo = 0, hi = 31;
+#pragma unroll
+                for (int it = 0; it < 5; ++it) {
+                    const uint32_t mid = (lo + hi + 1) >> 1;
+                    const uint32_t em = __shfl_sync(0xffffffffu, excl, mid);
+                    if (em <= t)
+                        lo = mid;
+                    else
+                        hi = mid - 1;
+                }
+                const uint32_t oex = __shfl_sync(0xffffffffu, excl, lo), orm = __shfl_sync(0xffffffffu, rmask, lo);
+                if (t < T) {
+                    const uint32_t j = t - oex;
+                    const uint32_t d = 7u - (uint32_t)__fns(orm, 0, (int)j + 1);
+                    const uint32_t k = kbase + t;
+                    a.conn_ref[conn_base + k] = nid[d * S2 + s0 + lo];
+                    a.conn_dir[conn_base + k] = (uint8_t)d;
+                    a.conn_next[conn_base + k] = j ? k - 1 : RCB_NONE;
+                }
+            }
+            kbase += T;
         }
     };
     auto no_work = [](uint32_t, uint32_t) {};
