@@ -73,21 +73,42 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_blocksums(uint32_t* __res
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
                                                              size_t n, const uint32_t* __restrict__ block_sums) {
-    // thread owns SCAN_ITEMS consecutive items so the scan order equals the memory order
+    // thread owns SCAN_ITEMS consecutive items so the scan order equals the memory order; full tiles move them as two
+    // 16-byte vectors (eight scalar accesses at a 32-byte lane stride were eight times the LSU transactions)
     const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+    static_assert(SCAN_ITEMS == 8, "two uint4 per thread");
+    const bool full = (size_t)(blockIdx.x + 1) * SCAN_TILE <= n && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
     uint32_t v[SCAN_ITEMS];
     uint32_t s = 0;
+    if (full) {
+        const uint4 a = *reinterpret_cast<const uint4*>(in + base), b = *reinterpret_cast<const uint4*>(in + base + 4);
+        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-        v[i] = (base + i < n) ? in[base + i] : 0;
-        s += v[i];
+        for (int i = 0; i < SCAN_ITEMS; ++i) s += v[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            v[i] = (base + i < n) ? in[base + i] : 0;
+            s += v[i];
+        }
     }
     uint32_t total;
     uint32_t ex = block_exclusive_scan(s, &total) + block_sums[blockIdx.x];
+    if (full) {
+        uint32_t o[SCAN_ITEMS];
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-        if (base + i < n) out[base + i] = ex;
-        ex += v[i];
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            o[i] = ex;
+            ex += v[i];
+        }
+        *reinterpret_cast<uint4*>(out + base) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(out + base + 4) = make_uint4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            if (base + i < n) out[base + i] = ex;
+            ex += v[i];
+        }
     }
 }
 
