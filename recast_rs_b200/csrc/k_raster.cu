@@ -416,33 +416,20 @@ __global__ void __launch_bounds__(256) k_gather_records(uint32_t ncells, const u
 }
 
 // ---- per-tile fragment segments -> column order (global back end behind the v2 clipper) ------------------
-// One CTA per tile.  Scattering tile by tile keeps the random 4-byte writes inside the tile's own region
+// One CTA per tile.  Scattering tile by tile keeps the random writes inside the tile's own region
 // (a few hundred KB, L2-resident); scattering the whole batch at once cost 240 B of DRAM traffic per
-// fragment (13 % L2 hit rate, ncu on config 3).
-__global__ void __launch_bounds__(512) k_seg_count(const TileDesc* __restrict__ tiles, int ntiles, const uint32_t* __restrict__ tile_frags,
-                                                   const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ tile_cap,
-                                                   const uint32_t* __restrict__ tile_cursor, uint32_t* __restrict__ cell_cnt,
-                                                   unsigned long long* __restrict__ counters) {
-    const uint32_t tile = blockIdx.z * gridDim.y + blockIdx.y;
-    if (tile >= (uint32_t)ntiles) return;
-    const uint32_t F = min(tile_cursor[tile], tile_cap[tile]);
-    const uint32_t* fr = tile_frags + 3ull * tile_base[tile];
-    uint32_t* cnt = cell_cnt + tiles[tile].cell_base;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < F; i += gridDim.x * blockDim.x)
-        atomicAdd(&cnt[fr[3ull * i] & 0xffffffu], 1u);
-    if (blockIdx.x == 0 && threadIdx.x == 0 && F) atomicAdd(&counters[1], (unsigned long long)F);
-}
-
+// fragment (13 % L2 hit rate, ncu on config 3).  The per-column counts come from the clipper itself (flag 0x200).
 template <typename R>
 __global__ void __launch_bounds__(512) k_seg_scatter(const TileDesc* __restrict__ tiles, int ntiles, const uint32_t* __restrict__ tile_frags,
                                                      const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ tile_cap,
                                                      const uint32_t* __restrict__ tile_cursor, const uint32_t* __restrict__ frag_off,
-                                                     uint32_t* __restrict__ cell_cnt, R* __restrict__ rec) {
+                                                     uint32_t* __restrict__ cell_cnt, R* __restrict__ rec, unsigned long long* __restrict__ counters) {
     const uint32_t tile = blockIdx.z * gridDim.y + blockIdx.y;
     if (tile >= (uint32_t)ntiles) return;
     const uint32_t F = min(tile_cursor[tile], tile_cap[tile]);
     const uint32_t* fr = tile_frags + 3ull * tile_base[tile];
     const uint32_t cb = tiles[tile].cell_base;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && F) atomicAdd(&counters[1], (unsigned long long)F);  // fragments of the batch
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < F; i += gridDim.x * blockDim.x) {
         const uint32_t r0 = fr[3ull * i], r1 = fr[3ull * i + 1], r2 = fr[3ull * i + 2];
         const uint32_t g = cb + (r0 & 0xffffffu);
@@ -465,22 +452,15 @@ static dim3 seg_grid(int ntiles, uint32_t max_tile_frags) {
     return dim3(slices, gy, ((unsigned)ntiles + gy - 1) / gy);
 }
 
-void launch_seg_count(const TileDesc* tiles, int ntiles, const uint32_t* tile_frags, const uint32_t* tile_base, const uint32_t* tile_cap,
-                      const uint32_t* tile_cursor, uint32_t* cell_cnt, unsigned long long* counters, uint32_t max_tile_frags, cudaStream_t s) {
-    if (ntiles == 0) return;
-    KScope _k("k_seg_count", s);
-    k_seg_count<<<seg_grid(ntiles, max_tile_frags), 512, 0, s>>>(tiles, ntiles, tile_frags, tile_base, tile_cap, tile_cursor, cell_cnt, counters);
-}
-
 void launch_seg_scatter(const TileDesc* tiles, int ntiles, const uint32_t* tile_frags, const uint32_t* tile_base, const uint32_t* tile_cap,
                         const uint32_t* tile_cursor, const uint32_t* frag_off, uint32_t* cell_cnt, void* rec, bool wide,
-                        uint32_t max_tile_frags, cudaStream_t s) {
+                        unsigned long long* counters, uint32_t max_tile_frags, cudaStream_t s) {
     if (ntiles == 0) return;
     KScope _k("k_seg_scatter", s);
     if (wide)
-        k_seg_scatter<Rec16><<<seg_grid(ntiles, max_tile_frags), 512, 0, s>>>(tiles, ntiles, tile_frags, tile_base, tile_cap, tile_cursor, frag_off, cell_cnt, (Rec16*)rec);
+        k_seg_scatter<Rec16><<<seg_grid(ntiles, max_tile_frags), 512, 0, s>>>(tiles, ntiles, tile_frags, tile_base, tile_cap, tile_cursor, frag_off, cell_cnt, (Rec16*)rec, counters);
     else
-        k_seg_scatter<Rec8><<<seg_grid(ntiles, max_tile_frags), 512, 0, s>>>(tiles, ntiles, tile_frags, tile_base, tile_cap, tile_cursor, frag_off, cell_cnt, (Rec8*)rec);
+        k_seg_scatter<Rec8><<<seg_grid(ntiles, max_tile_frags), 512, 0, s>>>(tiles, ntiles, tile_frags, tile_base, tile_cap, tile_cursor, frag_off, cell_cnt, (Rec8*)rec, counters);
 }
 
 void launch_count_fragments(const RasterBuffers& rb, cudaStream_t s) {

@@ -201,6 +201,8 @@ __device__ __forceinline__ void emit_fragment(const Raster2& rb, const TileDesc&
             rec[0] = lcell | (area << 24);
             rec[1] = mm;
             rec[2] = tri;
+            // global back end: the per-column counts its scatter needs (a pass over the fragment list otherwise)
+            if (rb.flags & 0x200u) atomicAdd(&rb.cell_cnt[td.cell_base + lcell], 1u);
         } else {
             atomicOr(&rb.counters[2], 2ull);
         }

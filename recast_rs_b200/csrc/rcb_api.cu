@@ -957,9 +957,8 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                 r2.tile_frags = ctx->d_tile_frags.as<uint32_t>();
                 launch_exclusive_scan(r2.item_cnt, ctx->d_item_off.as<uint32_t>(), ntris, ctx->d_scan_tmp.as<uint32_t>(), st);
                 launch_fill_items(r2, ctx->d_item_off.as<uint32_t>(), ctx->d_items.as<uint2>(), st);
+                r2.flags |= 0x200u;  // the clipper counts fragments per column as it emits them
                 launch_clip_items(r2, ctx->d_items.as<uint2>(), (uint32_t)nitems, d_tinfo_tmp, st);
-                launch_seg_count(d_tiles, ntiles, r2.tile_frags, r2.tile_base, r2.tile_cap, r2.tile_cursor, rb.cell_cnt, rb.counters,
-                                 (uint32_t)ctx->h_counters[5], st);
             } else {
                 CUB(ctx->d_frag_tmp.ensure(16 * ub));
                 rb.frag_tmp = ctx->d_frag_tmp.as<uint4>();
@@ -974,7 +973,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         if (ub > 0) {
             if (v2)
                 launch_seg_scatter(d_tiles, ntiles, r2.tile_frags, r2.tile_base, r2.tile_cap, r2.tile_cursor, d_frag_off, rb.cell_cnt, d_rec,
-                                   wide_rec, (uint32_t)ctx->h_counters[5], st);
+                                   wide_rec, rb.counters, (uint32_t)ctx->h_counters[5], st);
             else
                 launch_scatter_fragments(rb.frag_tmp, rb.counters + 1, (uint32_t)ub, d_frag_off, d_rec, wide_rec, st);
         }

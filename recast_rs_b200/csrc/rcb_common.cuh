@@ -184,11 +184,9 @@ void launch_tile_segments(const uint32_t* tile_ub, uint32_t* tile_base, int ntil
 void launch_tile_scan(TileInfo* tinfo, int ntiles, unsigned long long* counters, cudaStream_t s);
 void launch_tile_compact(const TileCompactArgs& a, int ntiles, cudaStream_t s);
 
-void launch_seg_count(const TileDesc* tiles, int ntiles, const uint32_t* tile_frags, const uint32_t* tile_base, const uint32_t* tile_cap,
-                      const uint32_t* tile_cursor, uint32_t* cell_cnt, unsigned long long* counters, uint32_t max_tile_frags, cudaStream_t s);
 void launch_seg_scatter(const TileDesc* tiles, int ntiles, const uint32_t* tile_frags, const uint32_t* tile_base, const uint32_t* tile_cap,
                         const uint32_t* tile_cursor, const uint32_t* frag_off, uint32_t* cell_cnt, void* rec, bool wide,
-                        uint32_t max_tile_frags, cudaStream_t s);
+                        unsigned long long* counters, uint32_t max_tile_frags, cudaStream_t s);
 
 // exclusive scan of n u32 values, out has n+1 entries (out[n] = total).  tmp: >= scan_tmp_elems(n) u32.
 size_t scan_tmp_elems(size_t n);
