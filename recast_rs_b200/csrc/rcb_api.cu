@@ -72,7 +72,7 @@ struct rcb_ctx {
     // per batch
     DevBuf d_tiles, d_bin_off, d_bin_tiles;
     // scratch
-    DevBuf d_counters, d_cell_cnt, d_frag_off, d_frag_tmp, d_fs_tri, d_fs_mm, d_fs_area, d_scan_tmp, d_hf_off, d_conn_cnt,
+    DevBuf d_counters, d_cell_cnt, d_frag_off, d_frag_tmp, d_frag_rec, d_fs_mm, d_fs_area, d_scan_tmp, d_hf_off, d_conn_cnt,
         d_conn_off, d_nei16, d_t16a, d_t16b, d_t16c, d_t8a, d_t8b, d_item_cnt, d_item_off, d_items, d_tile_ub, d_tile_base, d_tile_cursor,
         d_tile_frags, d_ts_mm, d_ts_area, d_celloff_tmp, d_lookback, d_tc_regons, d_tc_areas, d_tc_obs, d_fidx, d_span_cell, d_wire, d_wire_off,
         d_wire_pos, d_wire_inoff, d_wire_err, d_tc_raw, d_tc_parsed, d_rg_a, d_rg_b;
@@ -942,9 +942,9 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         }
         const uint64_t cap = ub + Sex;
         if (cap > 0) {
-            CUB(ctx->d_fs_tri.ensure(16 * cap));  // fragment records
+            CUB(ctx->d_frag_rec.ensure(16 * cap));  // fragment records
         }
-        void* d_rec = ctx->d_fs_tri.p;
+        void* d_rec = ctx->d_frag_rec.p;
         const bool wide_rec = ntris > (1u << 24) || getenv("RCB_WIDE_RECORDS") != nullptr;  // 8-byte records hold 24-bit triangle indices
         if (ub > 0) {
             if (v2) {
@@ -1191,7 +1191,7 @@ void rcb_destroy(rcb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&ctx->d_verts, &ctx->d_tris, &ctx->d_tri_areas, &ctx->d_tiles, &ctx->d_bin_off, &ctx->d_bin_tiles,
-                      &ctx->d_counters, &ctx->d_cell_cnt, &ctx->d_frag_off, &ctx->d_frag_tmp, &ctx->d_fs_tri, &ctx->d_fs_mm,
+                      &ctx->d_counters, &ctx->d_cell_cnt, &ctx->d_frag_off, &ctx->d_frag_tmp, &ctx->d_frag_rec, &ctx->d_fs_mm,
                       &ctx->d_fs_area, &ctx->d_scan_tmp, &ctx->d_hf_off, &ctx->d_conn_cnt, &ctx->d_conn_off, &ctx->d_nei16,
                       &ctx->d_t16a, &ctx->d_t16b, &ctx->d_t16c, &ctx->d_t8a, &ctx->d_t8b, &ctx->d_item_cnt, &ctx->d_item_off, &ctx->d_items, &ctx->d_tile_ub, &ctx->d_tile_base,
                       &ctx->d_tile_cursor, &ctx->d_tile_frags, &ctx->d_ts_mm, &ctx->d_ts_area, &ctx->d_celloff_tmp, &ctx->d_lookback, &ctx->d_tc_regons, &ctx->d_tc_areas,
