@@ -4,6 +4,7 @@ namespace RG_NS {
 
 
 constexpr int BT = RG_BT;
+constexpr int MERGE_Q = BT == 32 ? 1 : 4;  // spans per thread and step in the merge passes (the 32-thread build has no registers to spare)
 constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 constexpr uint32_t BORDER = 0x8000u;
 
@@ -579,27 +580,46 @@ __global__ void __launch_bounds__(BT, RG_MIN_CTAS) k_regions(RegionArgs a) {
             }
             if (block_sum(ncand, sh) == 0) break;
             for (int pass = 0; pass < 2; ++pass) {
-                for (uint32_t s = threadIdx.x; s < S; s += BT) {
-                    const uint32_t rid = t.reg0[s];
-                    if (rid == 0 || (rid & BORDER)) continue;
-                    if (!(alive[rid] != 0 && cnt[rid] != 0 && cnt[rid] < merge_area && !border[rid])) continue;
-                    uint32_t nn[4], nrs[4];
+                // MERGE_Q spans per thread and step: nearly all of them only find out that their region is no candidate, and
+                // one span at a time that was two dependent loads per span, S / BT times in a row
+                for (uint32_t s0 = threadIdx.x; s0 < S; s0 += MERGE_Q * BT) {
+                    uint32_t rid4[MERGE_Q];
+                    bool cand[MERGE_Q];
 #pragma unroll
-                    for (int d = 0; d < 4; ++d) nn[d] = list_neighbor(t, s, d);
+                    for (int q = 0; q < MERGE_Q; ++q) {
+                        const uint32_t sq = s0 + (uint32_t)q * BT;
+                        rid4[q] = sq < S ? (uint32_t)t.reg0[sq] : 0u;
+                    }
 #pragma unroll
-                    for (int d = 0; d < 4; ++d) nrs[d] = t.reg0[nn[d] != NONE32 ? nn[d] : s];
+                    for (int q = 0; q < MERGE_Q; ++q) {
+                        const bool lab = rid4[q] != 0 && !(rid4[q] & BORDER);
+                        const uint32_t ri = lab ? rid4[q] : 0u;  // entry 0 is always there
+                        const uint32_t al = alive[ri], bo = border[ri];
+                        const int32_t cn = cnt[ri];
+                        cand[q] = lab && al != 0 && cn != 0 && cn < merge_area && !bo;
+                    }
 #pragma unroll
-                    for (int d = 0; d < 4; ++d) {
-                        if (nn[d] == NONE32) continue;
-                        const uint32_t nr = nrs[d];
-                        if (nr == rid || nr == 0 || (nr & BORDER) || nr >= R) continue;
-                        if (alive[nr] == 0 || cnt[nr] <= 0) continue;
-                        // first neighbour in list order with the largest span count == max of (count, -first occurrence)
-                        const unsigned long long key = ((unsigned long long)(uint32_t)cnt[nr] << 32) | (uint32_t)~(s * 4u + (uint32_t)d);
-                        if (pass == 0)
-                            atomicMax(&best[rid], key);
-                        else if (key == best[rid])
-                            target[rid] = (uint16_t)nr;
+                    for (int q = 0; q < MERGE_Q; ++q) {
+                        if (!cand[q]) continue;
+                        const uint32_t s = s0 + (uint32_t)q * BT, rid = rid4[q];
+                        uint32_t nn[4], nrs[4];
+#pragma unroll
+                        for (int d = 0; d < 4; ++d) nn[d] = list_neighbor(t, s, d);
+#pragma unroll
+                        for (int d = 0; d < 4; ++d) nrs[d] = t.reg0[nn[d] != NONE32 ? nn[d] : s];
+#pragma unroll
+                        for (int d = 0; d < 4; ++d) {
+                            if (nn[d] == NONE32) continue;
+                            const uint32_t nr = nrs[d];
+                            if (nr == rid || nr == 0 || (nr & BORDER) || nr >= R) continue;
+                            if (alive[nr] == 0 || cnt[nr] <= 0) continue;
+                            // first neighbour in list order with the largest span count == max of (count, -first occurrence)
+                            const unsigned long long key = ((unsigned long long)(uint32_t)cnt[nr] << 32) | (uint32_t)~(s * 4u + (uint32_t)d);
+                            if (pass == 0)
+                                atomicMax(&best[rid], key);
+                            else if (key == best[rid])
+                                target[rid] = (uint16_t)nr;
+                        }
                     }
                 }
                 __syncthreads();
