@@ -177,13 +177,22 @@ __device__ uint32_t ws_expand(Tile& t, int max_iter, uint32_t level, int sidx, u
             } else {
                 uint32_t r = t.reg[i], d2 = 0xffffu;
                 const uint32_t area = t.areas[i];
+                // the four neighbours, then what hangs off them, fetched together; combined in direction order
+                uint32_t an[4], aar[4], ara[4], asd[4];
+#pragma unroll
+                for (int d = 0; d < 4; ++d) an[d] = nbr(t, d, i);
 #pragma unroll
                 for (int d = 0; d < 4; ++d) {
-                    const uint32_t ai = nbr(t, d, i);
-                    if (ai == NONE32) continue;
-                    if (t.areas[ai] != area) continue;
-                    const uint32_t ra = t.reg[ai];
-                    const uint32_t da = (uint32_t)(uint16_t)(t.sdist[ai] + 2);
+                    const uint32_t q = an[d] != NONE32 ? an[d] : i;
+                    aar[d] = t.areas[q];
+                    ara[d] = t.reg[q];
+                    asd[d] = t.sdist[q];
+                }
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    if (an[d] == NONE32 || aar[d] != area) continue;
+                    const uint32_t ra = ara[d];
+                    const uint32_t da = (uint32_t)(uint16_t)(asd[d] + 2);
                     if (ra > 0 && (ra & BORDER) == 0 && da < d2) {
                         r = ra;
                         d2 = da;
