@@ -366,3 +366,20 @@ def test_deep_columns_filters_link_distance(oracle, rb, ctx, seed, ordered):
     with ctx.build_from_spans([cfg], off, mn, mx, ar, bits, 1) as r:
         r.download()
         assert_tile_equal(r.tile(0), hfa, chfa, what=f"deep columns ordered={ordered}")
+
+
+def test_global_raster_with_16_byte_fragment_records(oracle, rb, monkeypatch):
+    """The global rasterizer packs fragments into 8-byte records while triangle indices fit 24 bits and into 16-byte
+    ones beyond; RCB_WIDE_RECORDS forces the wide form so that it is exercised without a 16 M-triangle mesh."""
+    from recast_rs_b200 import synth
+    from recast_rs_b200.config import RecastConfig
+    from tests.test_gpu_fullsize import _context
+
+    v, t = synth.interior(5, 14, 1.2, 0.3, 7, 1.5)
+    cfgs = synth.tile_grid(v, 32, RecastConfig(cs=0.3, ch=0.2))
+    monkeypatch.setenv("RCB_WIDE_RECORDS", "1")
+    c = _context(True)
+    try:
+        _check_batch(oracle, rb, c, v, t, cfgs, rb.STAGE_ALL_BUILD)
+    finally:
+        c.close()
