@@ -73,7 +73,7 @@ struct rcb_ctx {
     DevBuf d_tiles, d_bin_off, d_bin_tiles;
     // scratch
     DevBuf d_counters, d_cell_cnt, d_frag_off, d_frag_tmp, d_frag_rec, d_fs_mm, d_fs_area, d_scan_tmp, d_hf_off, d_conn_cnt,
-        d_conn_off, d_nei16, d_t16a, d_t16b, d_t16c, d_t8a, d_t8b, d_item_cnt, d_item_off, d_items, d_tile_ub, d_tile_base, d_tile_cursor,
+        d_conn_off, d_nid, d_t16a, d_t16b, d_t16c, d_t8a, d_t8b, d_item_cnt, d_item_off, d_items, d_tile_ub, d_tile_base, d_tile_cursor,
         d_tile_frags, d_ts_mm, d_ts_area, d_celloff_tmp, d_lookback, d_tc_regons, d_tc_areas, d_tc_obs, d_fidx, d_span_cell, d_wire, d_wire_off,
         d_wire_pos, d_wire_inoff, d_wire_err, d_tc_raw, d_tc_parsed, d_rg_a, d_rg_b;
     uint32_t clip_flags = 1;    // RCB_CLIP_FLAGS (A/B runs): bit0 min-x skip test in the clipper
@@ -415,10 +415,10 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
         CU(ctx->d_conn_cnt.ensure(4 * (S + 1)));
         CU(ctx->d_conn_off.ensure(4 * (S + 1)));
         CU(ctx->d_scan_tmp.ensure(4 * scan_tmp_elems(std::max<uint64_t>(S, Ctot) + 1)));
-        CU(ctx->d_nei16.ensure(32 * S + 256));  // u32[8][S] absolute neighbour ids
+        CU(ctx->d_nid.ensure(32 * S + 256));  // u32[8][S] absolute neighbour ids
         uint32_t* d_conn_cnt = ctx->d_conn_cnt.as<uint32_t>();
         uint32_t* d_conn_off = ctx->d_conn_off.as<uint32_t>();
-        uint32_t* d_nid = ctx->d_nei16.as<uint32_t>();
+        uint32_t* d_nid = ctx->d_nid.as<uint32_t>();
         uint2* d_span_cell = ctx->d_span_cell.as<uint2>();
         uint8_t* d_areas = (uint8_t*)(A + res->lay.areas);
         launch_link_spans2(d_tiles, S, d_span_cell, d_hf_off, d_smin, d_smax, d_sarea, d_areas, d_nid, (uint16_t*)(A + res->lay.con),
@@ -1192,7 +1192,7 @@ void rcb_destroy(rcb_ctx* ctx) {
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&ctx->d_verts, &ctx->d_tris, &ctx->d_tri_areas, &ctx->d_tiles, &ctx->d_bin_off, &ctx->d_bin_tiles,
                       &ctx->d_counters, &ctx->d_cell_cnt, &ctx->d_frag_off, &ctx->d_frag_tmp, &ctx->d_frag_rec, &ctx->d_fs_mm,
-                      &ctx->d_fs_area, &ctx->d_scan_tmp, &ctx->d_hf_off, &ctx->d_conn_cnt, &ctx->d_conn_off, &ctx->d_nei16,
+                      &ctx->d_fs_area, &ctx->d_scan_tmp, &ctx->d_hf_off, &ctx->d_conn_cnt, &ctx->d_conn_off, &ctx->d_nid,
                       &ctx->d_t16a, &ctx->d_t16b, &ctx->d_t16c, &ctx->d_t8a, &ctx->d_t8b, &ctx->d_item_cnt, &ctx->d_item_off, &ctx->d_items, &ctx->d_tile_ub, &ctx->d_tile_base,
                       &ctx->d_tile_cursor, &ctx->d_tile_frags, &ctx->d_ts_mm, &ctx->d_ts_area, &ctx->d_celloff_tmp, &ctx->d_lookback, &ctx->d_tc_regons, &ctx->d_tc_areas,
                       &ctx->d_tc_obs, &ctx->d_fidx, &ctx->d_span_cell, &ctx->d_wire, &ctx->d_wire_off, &ctx->d_wire_pos, &ctx->d_wire_inoff, &ctx->d_wire_err,
