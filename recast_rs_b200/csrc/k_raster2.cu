@@ -23,9 +23,14 @@ namespace {
 
 constexpr int CLIP_THREADS = 128;
 constexpr int CLIP_ROWS = RCB_CLIP_ROWS;                  // rows per work item
-constexpr int ZCAP = 6;                                   // z-chain polygon capacity (geometric bound 4-5)
-constexpr int XCAP = 6;                                   // row / rest polygon capacity (geometric bound 5-6)
-constexpr int SLOT_WORDS = 4 + 2 * XCAP + 1;              // header + verts + pad (odd stride: no bank conflicts)
+// Capacities = the combinatorial bounds (a cut crosses a convex polygon's boundary twice): what is left of a triangle
+// behind a row line has <= 4 vertices, a row strip of it <= 5, what is left of that behind a column line <= 6.  A
+// polygon that outgrows its slot raises the overflow flag and the batch is redone by the 12-vertex clipper.  Shared
+// memory per thread decides how many CTAs an SM holds, and this kernel's time follows its occupancy (5 -> 3 CTAs: +49 %).
+constexpr int ZCAP = 4;                                   // z-chain polygon capacity
+constexpr int RCAP = 5;                                   // row polygon capacity (slots)
+constexpr int XCAP = 6;                                   // x-chain rest polygon capacity
+constexpr int SLOT_WORDS = 4 + 2 * RCAP + 1;              // header + verts + pad (odd stride: no bank conflicts)
 static_assert(2 * XCAP * 2 <= 2 * ZCAP * 3, "phase-2 buffers alias the z-chain scratch");
 constexpr int NSLOTS = CLIP_THREADS * CLIP_ROWS;
 constexpr int NBUCK = 16;  // phase-2 rows are grouped by (vertex count 3..6+, columns spanned 1..4+): a scheduling hint only
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
                     const int sj = vjz < cz ? -1 : (vjz > cz ? 1 : 0);
                     if (si <= 0) {
                         if (keep) {
-                            if (nrow < XCAP) {
+                            if (nrow < RCAP) {
                                 slot[4 + 2 * nrow] = __float_as_uint(vix);
                                 slot[5 + 2 * nrow] = __float_as_uint(viy);
                             } else
@@ -299,7 +304,7 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
                         const float py = __fadd_rn(viy, __fmul_rn(tt, __fsub_rn(vjy, viy)));
                         const float pz = __fadd_rn(viz, __fmul_rn(tt, __fsub_rn(vjz, viz)));
                         if (keep) {
-                            if (nrow < XCAP) {
+                            if (nrow < RCAP) {
                                 slot[4 + 2 * nrow] = __float_as_uint(px);
                                 slot[5 + 2 * nrow] = __float_as_uint(py);
                             } else
@@ -322,10 +327,10 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
                 if (keep && nrow >= 3 && z >= 0) {  // rasterization.rs:308-311
                     slot[0] = tri;
                     slot[1] = tile;
-                    slot[2] = (uint32_t)z | ((uint32_t)min(nrow, XCAP) << 16) | (area << 24);
+                    slot[2] = (uint32_t)z | ((uint32_t)min(nrow, RCAP) << 16) | (area << 24);
                     slot[3] = (uint32_t)x0 | ((uint32_t)x1 << 16);
                     const int ncols = min(max(__float2int_rz((rmaxx - rminx) * td.ics), 0), 3);
-                    const int bk = min(min(nrow, XCAP) - 3, 3) * 4 + ncols;
+                    const int bk = min(min(nrow, RCAP) - 3, 3) * 4 + ncols;
                     slot[SLOT_WORDS - 1] = (uint32_t)bk;  // the pad word carries the bucket
                     // bucket by vertex count so the lanes of a warp run vertex loops of equal length
                     atomicAdd(&sm.nb[bk], 1u);
