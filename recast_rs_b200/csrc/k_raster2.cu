@@ -30,7 +30,8 @@ constexpr int CLIP_ROWS = RCB_CLIP_ROWS;                  // rows per work item
 constexpr int ZCAP = 4;                                   // z-chain polygon capacity
 constexpr int RCAP = 5;                                   // row polygon capacity (slots)
 constexpr int XCAP = 6;                                   // x-chain rest polygon capacity
-constexpr int SLOT_WORDS = 4 + 2 * RCAP + 1;              // header + verts + pad (odd stride: no bank conflicts)
+constexpr int SLOT_WORDS = 1 + 2 * RCAP;                  // row word + verts (odd stride: no bank conflicts)
+constexpr int HDR_WORDS = 3;                              // per work item: triangle, tile, x0 | x1 << 16 (shared by its rows)
 static_assert(2 * XCAP * 2 <= 2 * ZCAP * 3, "phase-2 buffers alias the z-chain scratch");
 constexpr int NSLOTS = CLIP_THREADS * CLIP_ROWS;
 constexpr int NBUCK = 16;  // phase-2 rows are grouped by (vertex count 3..6+, columns spanned 1..4+): a scheduling hint only
@@ -180,7 +181,9 @@ __global__ void __launch_bounds__(256) k_fill_items(Raster2 rb, const uint32_t* 
 // ---- clip --------------------------------------------------------------------------------------------
 struct ClipSmem {
     float zbuf[2 * ZCAP * 3 * CLIP_THREADS];  // phase 1: [(buf*ZCAP + v)*3 + k][tid]; phase 2: two x/y buffers per thread
-    uint32_t slots[NSLOTS * SLOT_WORDS];      // slot tid*CLIP_ROWS + r belongs to thread tid, row r of its chunk
+    uint32_t slots[NSLOTS * SLOT_WORDS];      // slot tid*CLIP_ROWS + r belongs to thread tid, row r of its chunk:
+                                              // [0] = z | vertices << 16 | bucket << 20 | area << 24 (0: empty), then x,y pairs
+    uint32_t hdr[CLIP_THREADS * HDR_WORDS];   // what the rows of one work item have in common
     uint16_t list[NSLOTS];                    // compacted ids of the slots that hold a row polygon
     uint32_t nb[NBUCK], cur[NBUCK];           // rows per (vertex count, columns spanned) bucket and fill cursors
     uint32_t nlist;
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
     if (threadIdx.x < NBUCK) sm.nb[threadIdx.x] = sm.cur[threadIdx.x] = 0;
     if (threadIdx.x == 0) sm.nlist = 0;
 #pragma unroll
-    for (int r = 0; r < CLIP_ROWS; ++r) sm.slots[(threadIdx.x * CLIP_ROWS + r) * SLOT_WORDS + 2] = 0;  // slot empty
+    for (int r = 0; r < CLIP_ROWS; ++r) sm.slots[(threadIdx.x * CLIP_ROWS + r) * SLOT_WORDS] = 0;  // slot empty
     __syncthreads();
 
     // ---------------- phase 1: z-chain of one work item ------------------------------------------------
@@ -251,6 +254,9 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
         bool ok = load_triangle(rb.mesh, tri, t) && tile_footprint(t, td, x0, x1, z0, z1);
         if (ok && !rb.mesh.tri_areas) ok = classify(t, td.slope_thr, area);  // lib.rs:258-260: degenerate => skipped
         if (ok) {
+            sm.hdr[threadIdx.x * HDR_WORDS] = tri;
+            sm.hdr[threadIdx.x * HDR_WORDS + 1] = tile;
+            sm.hdr[threadIdx.x * HDR_WORDS + 2] = (uint32_t)x0 | ((uint32_t)x1 << 16);
             const int zs = max(z0, 0) + (int)chunk * CLIP_ROWS;
             const int ze = min(zs + CLIP_ROWS - 1, z1);
             bool ovf = false;
@@ -279,8 +285,8 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
                     if (si <= 0) {
                         if (keep) {
                             if (nrow < RCAP) {
-                                slot[4 + 2 * nrow] = __float_as_uint(vix);
-                                slot[5 + 2 * nrow] = __float_as_uint(viy);
+                                slot[1 + 2 * nrow] = __float_as_uint(vix);
+                                slot[2 + 2 * nrow] = __float_as_uint(viy);
                             } else
                                 ovf = true;
                             rminx = fminf(rminx, vix);
@@ -305,8 +311,8 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
                         const float pz = __fadd_rn(viz, __fmul_rn(tt, __fsub_rn(vjz, viz)));
                         if (keep) {
                             if (nrow < RCAP) {
-                                slot[4 + 2 * nrow] = __float_as_uint(px);
-                                slot[5 + 2 * nrow] = __float_as_uint(py);
+                                slot[1 + 2 * nrow] = __float_as_uint(px);
+                                slot[2 + 2 * nrow] = __float_as_uint(py);
                             } else
                                 ovf = true;
                             rminx = fminf(rminx, px);
@@ -325,13 +331,9 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
                 cur = nxt;
                 n = min(nrest, ZCAP);
                 if (keep && nrow >= 3 && z >= 0) {  // rasterization.rs:308-311
-                    slot[0] = tri;
-                    slot[1] = tile;
-                    slot[2] = (uint32_t)z | ((uint32_t)min(nrow, RCAP) << 16) | (area << 24);
-                    slot[3] = (uint32_t)x0 | ((uint32_t)x1 << 16);
                     const int ncols = min(max(__float2int_rz((rmaxx - rminx) * td.ics), 0), 3);
                     const int bk = min(min(nrow, RCAP) - 3, 3) * 4 + ncols;
-                    slot[SLOT_WORDS - 1] = (uint32_t)bk;  // the pad word carries the bucket
+                    slot[0] = (uint32_t)z | ((uint32_t)min(nrow, RCAP) << 16) | ((uint32_t)bk << 20) | (area << 24);
                     // bucket by vertex count so the lanes of a warp run vertex loops of equal length
                     atomicAdd(&sm.nb[bk], 1u);
                 }
@@ -361,9 +363,9 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
 #pragma unroll
     for (int r = 0; r < CLIP_ROWS; ++r) {
         const uint32_t slot_id = threadIdx.x * CLIP_ROWS + r;
-        const uint32_t* sl = sm.slots + slot_id * SLOT_WORDS;
-        if (((sl[2] >> 16) & 0xffu) >= 3) {
-            const uint32_t bk = sl[SLOT_WORDS - 1];
+        const uint32_t w0 = sm.slots[slot_id * SLOT_WORDS];
+        if (((w0 >> 16) & 0xfu) >= 3) {
+            const uint32_t bk = (w0 >> 20) & 0xfu;
             uint32_t o = 0;
 #pragma unroll
             for (int k = 0; k < NBUCK; ++k) o = (k == (int)bk) ? boff[k] : o;
@@ -377,20 +379,22 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const u
         tclk = n;
     }
     for (uint32_t li = threadIdx.x; li < nlist; li += CLIP_THREADS) {
-        const uint32_t* slot = sm.slots + (uint32_t)sm.list[li] * SLOT_WORDS;
-        const uint32_t tri = slot[0], tile = slot[1];
-        const uint32_t h2 = slot[2], h3 = slot[3];
+        const uint32_t sid = sm.list[li];
+        const uint32_t* slot = sm.slots + sid * SLOT_WORDS;
+        const uint32_t* hdr = sm.hdr + (sid / CLIP_ROWS) * HDR_WORDS;
+        const uint32_t tri = hdr[0], tile = hdr[1];
+        const uint32_t h2 = slot[0], h3 = hdr[2];
         const int z = (int)(h2 & 0xffffu);
-        int n = (int)((h2 >> 16) & 0xffu);
+        int n = (int)((h2 >> 16) & 0xfu);
         const uint32_t area = h2 >> 24;
         const int x0 = (int)(h3 & 0xffffu), x1 = (int)(h3 >> 16);
         const TileDesc& td = rb.tiles[tile];
         float minx = 0.f;
         bool has_nan = false;
         for (int v = 0; v < n; ++v) {
-            const float vx = __uint_as_float(slot[4 + 2 * v]);
+            const float vx = __uint_as_float(slot[1 + 2 * v]);
             XB(0, v, 0) = vx;
-            XB(0, v, 1) = __uint_as_float(slot[5 + 2 * v]);
+            XB(0, v, 1) = __uint_as_float(slot[2 + 2 * v]);
             has_nan = has_nan || (vx != vx);
             minx = v ? fminf(minx, vx) : vx;
         }
