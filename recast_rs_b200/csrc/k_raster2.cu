@@ -230,7 +230,7 @@ __device__ __forceinline__ void emit_fragment(const Raster2& rb, const TileDesc&
     }
 }
 
-__global__ void __launch_bounds__(CLIP_THREADS) k_clip_items(Raster2 rb, const uint2* __restrict__ items, uint32_t nitems,
+__global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, const uint2* __restrict__ items, uint32_t nitems,
                                                              TileInfo* __restrict__ tinfo) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ClipSmem& sm = *reinterpret_cast<ClipSmem*>(smem_raw);
