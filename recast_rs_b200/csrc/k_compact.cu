@@ -7,7 +7,8 @@
 //                                     array in reverse direction order per span, con[4])
 //   :433-442 get_cell_index_for_span (O(cells) scan in the reference; the neighbour cell is known here)
 // The heightfield CSR (hf_off) is already the compaction prefix sum, so "compaction" is a gather of
-// offsets; linking is a per-column stencil over the 8 neighbour columns.
+// offsets; linking is a per-span stencil over the 8 neighbour columns (one thread per span, walkable spans compacted
+// per block, ordered columns bisected).
 #include "rcb_common.cuh"
 
 namespace {

@@ -15,14 +15,12 @@
 // (x.y means "neighbour y of neighbour x"; all additions saturate in u16 / u8.)
 // tests/test_oracle_* pin this equivalence against the literal sequential sweeps of the oracle.
 //
-// Kernels: init (boundary marking) -> forward (one CTA per tile, H sequential row steps with
-// __syncthreads) -> backward gather [+ max | + erosion threshold] -> blur.
+// Kernels: init (boundary marking) -> gather ids + static part of the relaxation -> forward (one CTA per tile, H
+// sequential row steps with __syncthreads) -> backward gather [+ max | + erosion threshold] -> blur.  All but the forward
+// sweep are one thread per span over the absolute neighbour ids k_link_spans2 leaves behind.
 #include "rcb_common.cuh"
 
 namespace {
-
-__constant__ int d_dirx[8] = {-1, 0, 1, 1, 1, 0, -1, -1};
-__constant__ int d_dirz[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
 
 // neighbour `dir` of span `s`: global span index or RCB_NONE.  k_link_spans2 leaves the 8-direction table as absolute
 // span ids (u32[8][S]), so nothing below needs to know which cell or tile a span belongs to: one thread per span.
