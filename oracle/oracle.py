@@ -269,7 +269,7 @@ class CompactHeightfield:
         return cls(lib().orc_chf_build(hf._h), hf.width, hf.height)
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:  # module globals may be gone at interpreter exit
             lib().orc_chf_free(self._h)
             self._h = None
 
