@@ -41,3 +41,20 @@ def test_native_arm_line():
     assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < d["value"]
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["kind"] == "port"
+
+
+def test_committed_headline_profile_is_a_contract_line():
+    """profiles/ holds the bench line the round's numbers are quoted from: it must be a full native-arm line of config 2."""
+    import glob
+    import re
+
+    files = [(int(m.group(1)), f) for f in glob.glob(os.path.join(ROOT, "profiles", "r01_bench_v*.json"))
+             if (m := re.fullmatch(r"r01_bench_v(\d+)\.json", os.path.basename(f)))]
+    assert files
+    d = json.load(open(max(files)[1]))
+    assert BASE_KEYS | {"gpu_launches", "clocks", "roofline"} <= set(d) and "impl" not in d
+    assert d["n_gpus"] == 1 and d["config"]["workload"].startswith("config2") and d["gpu_launches"] > 0
+    r = d["roofline"]
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"]
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert d["steps"] * d["config"]["totals_rank0"]["triangles"] / (d["ms_per_step"] * d["steps"] * 1e-3) == pytest.approx(d["value"], rel=1e-6)
