@@ -180,3 +180,16 @@ def test_cpp_example_matches_oracle_on_gpu(oracle, tmp_path):
     want1 = f"cells {cfg.width * cfg.height} spans {e.span_min.size} connections {e.conn_ref.size} max_distance {e.max_distance}"
     want2 = f"regions {int(reg.max(initial=0))} max_regions {mr} span_data {2 * cfg.width * cfg.height + 12 * e.span_min.size}"
     assert want1 in out.stdout and want2 in out.stdout, out.stdout
+
+
+def test_build_tracks_every_kernel_header():
+    """k_regions.cu includes k_regions_impl.cuh several times; a header the build does not track silently leaves stale objects
+    (it happened: three experiments were 'measured' on an unchanged binary).  Every header under csrc/ must be a dependency."""
+    import inspect
+
+    from recast_rs_b200 import build as b
+
+    src = inspect.getsource(b.build_native)
+    assert '.endswith((".cuh", ".h"))' in src or "glob" in src
+    csrc = os.path.join(os.path.dirname(os.path.abspath(b.__file__)), "csrc")
+    assert "k_regions_impl.cuh" in os.listdir(csrc)
