@@ -57,7 +57,19 @@ enum {
     RCB_FILTER_LOW_HANGING = 0x100u, /* heightfield.rs:286 */
     RCB_FILTER_LEDGE = 0x200u,       /* heightfield.rs:332 */
     RCB_FILTER_LOW_HEIGHT = 0x400u,  /* heightfield.rs:492 */
-    RCB_STAGE_ALL_BUILD = 1u | 2u | 4u | 16u /* what RecastBuilder::build_mesh reaches (lib.rs:77-87 → watershed.rs:375) */
+    RCB_STAGE_ALL_BUILD = 1u | 2u | 4u | 16u, /* what RecastBuilder::build_mesh reaches (lib.rs:77-87 → watershed.rs:375) */
+    /* Result layout flag (not a stage): rcb_result_download copies only what the host cannot rebuild.  The host views then
+     * carry hf_cell_offset = first_conn = conn_next = conn_dir = conn_ref = NULL and instead
+     *   conn_mask[S]   bit d set <=> the span has a connection in direction d.  Connections are laid out in span order and,
+     *                  inside a span, in DESCENDING direction (compact_heightfield.rs:375-389 pushes dir 7..0 with
+     *                  next -> the one pushed before, first_connection = the last pushed), so
+     *                  first_conn[s] = (connections of spans <= s) - 1 (or NONE), conn_dir = the mask's bits from 7 down,
+     *                  conn_next[k] = k - 1 inside a span's block, NONE at its start;
+     *   conn_ref16[K]  conn_ref as u16 (tile-relative span indices) - when a tile holds 65536+ spans the views carry the
+     *                  32-bit conn_ref instead and conn_ref16 = NULL;
+     * hf_cell_offset is the exclusive prefix sum of cell_count_arr.  INTEGRATION.md has the rebuild loop.  Device views
+     * (rcb_result_tile_device) always carry the full arrays. */
+    RCB_RESULT_SLIM = 0x1000u
 };
 
 /* Field-for-field RecastConfig (config.rs:7-51). */
@@ -134,6 +146,8 @@ typedef struct rcb_tile_view {
     const uint16_t* reg;            /* [S]  CompactSpan.reg (watershed.rs:505-507); NULL unless REGIONS ran */
     uint32_t max_regions;           /* chf.max_regions (watershed.rs:491: the id counter BEFORE filtering); 0 unless REGIONS ran */
     uint32_t _pad;
+    const uint8_t* conn_mask;       /* [S]  RCB_RESULT_SLIM only: directions in which the span is connected (bit d) */
+    const uint16_t* conn_ref16;     /* [K]  RCB_RESULT_SLIM only: conn_ref in 16 bits (NULL when a tile has 65536+ spans) */
 } rcb_tile_view;
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -147,6 +161,10 @@ int rcb_set_stream(rcb_ctx* ctx, void* cuda_stream);
 int rcb_use_own_stream(rcb_ctx* ctx);
 /* Number of kernel launches issued by this context since creation (bench `gpu_launches`). */
 uint64_t rcb_launch_count(const rcb_ctx* ctx);
+/* Diagnostics: out[0] = batches issued without a host round trip (sizes taken from the previous build of the same
+ * configurations and verified on the device), out[1] = how many of those had to be rebuilt because a size was short,
+ * out[2] = configuration batches cached by the context.  The reference has no counterpart (it has no device). */
+int rcb_ctx_stats(const rcb_ctx* ctx, uint64_t out[4]);
 
 /* Per-stage device timers (CUDA events around every kernel launch), the device-side counterpart of
  * RecastContext::start_timer/stop_timer with TimerCategory::{Rasterization, Filtering,

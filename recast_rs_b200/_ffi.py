@@ -32,6 +32,7 @@ class RcbTileView(ctypes.Structure):
         ("cell_index", _vp), ("cell_count_arr", _vp), ("areas", _vp), ("con", _vp), ("first_conn", _vp),
         ("conn_ref", _vp), ("conn_dir", _vp), ("conn_next", _vp), ("dist", _vp),
         ("reg", _vp), ("max_regions", _u32), ("_pad", _u32),
+        ("conn_mask", _vp), ("conn_ref16", _vp),
     ]
 
 
@@ -54,6 +55,7 @@ SYMBOLS = {
     "rcb_set_stream": (_i, [_vp, _vp]),
     "rcb_use_own_stream": (_i, [_vp]),
     "rcb_launch_count": (_u64, [_vp]),
+    "rcb_ctx_stats": (_i, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
     "rcb_config_default": (None, [ctypes.POINTER(RcbConfig)]),
     "rcb_config_calculate_grid_size": (None, [ctypes.POINTER(RcbConfig), _vp, _vp]),
     "rcb_config_validate": (_i, [ctypes.POINTER(RcbConfig)]),

@@ -22,6 +22,7 @@ FILTER_LOW_HANGING, FILTER_LEDGE, FILTER_LOW_HEIGHT = 0x100, 0x200, 0x400
 STAGE_ALL_BUILD = STAGE_RASTER | STAGE_FILTER | STAGE_COMPACT | STAGE_DIST
 STAGE_REGIONS = 0x40  # CompactHeightfield::build_regions (watershed.rs:364-510); implies COMPACT | DIST
 STAGE_READD = 0x20  # re-insert given spans through Heightfield::add_span (checkpoint.rs:29-60)
+RESULT_SLIM = 0x1000  # rcb_result_download copies only what the host cannot rebuild (see TileVoxels.expand_slim)
 WIRE_VOXEL_TILE, WIRE_DYNAMIC_TILE = 0, 1
 NONE = 0xFFFFFFFF
 
@@ -64,6 +65,31 @@ class TileVoxels:
     dist: Optional[np.ndarray] = None
     reg: Optional[np.ndarray] = None  # CompactSpan.reg, when REGIONS ran
     max_regions: int = 0
+    conn_mask: Optional[np.ndarray] = None   # RESULT_SLIM: u8[S], bit d = the span is connected in direction d
+    conn_ref16: Optional[np.ndarray] = None  # RESULT_SLIM: u16[K] conn_ref (None when a tile holds 65536+ spans)
+
+    def expand_slim(self) -> "TileVoxels":
+        """Rebuilds, on the host, the arrays a RESULT_SLIM download leaves out, from the layout rule of
+        compact_heightfield.rs:375-389: connections lie in span order and, inside a span, in descending direction
+        (dir 7..0 are pushed with `next` -> the one pushed before, `first_connection` = the last pushed).  Pure index
+        bookkeeping of the binding layer (the Rust shim does the same loop while it fills Vec<CompactSpan>)."""
+        if self.conn_mask is None:
+            return self
+        S = self.span_count
+        self.hf_cell_offset = np.concatenate([[0], np.cumsum(self.cell_count, dtype=np.uint64)]).astype(np.uint32)
+        bits = np.unpackbits(self.conn_mask.reshape(-1, 1), axis=1)  # column j = direction 7 - j: already descending
+        cnt = bits.sum(axis=1, dtype=np.int64)
+        ends = np.cumsum(cnt)
+        self.first_conn = np.where(cnt > 0, ends - 1, NONE).astype(np.uint32)
+        self.conn_dir = (7 - np.nonzero(bits)[1]).astype(np.uint8)
+        K = int(ends[-1]) if S else 0
+        nxt = np.arange(-1, K - 1, dtype=np.int64)
+        nxt[(ends - cnt)[cnt > 0]] = NONE  # the first connection pushed of every block
+        self.conn_next = nxt.astype(np.uint32)
+        if self.conn_ref is None:
+            self.conn_ref = self.conn_ref16.astype(np.uint32)
+        assert K == self.conn_count
+        return self
 
 
 class BatchResult:
@@ -81,23 +107,34 @@ class BatchResult:
         check(_ffi.lib().rcb_result_download(self._h), self._ctx._h)
         return self
 
-    def tile(self, i: int) -> TileVoxels:
+    def tile(self, i: int, expand: bool = True) -> TileVoxels:
+        """One tile of a downloaded result.  For a RESULT_SLIM result `expand` rebuilds the arrays the download left out."""
         v = _ffi.RcbTileView()
         check(_ffi.lib().rcb_result_tile(self._h, i, ctypes.byref(v)), self._ctx._h)
         C, S, K = v.cell_count, v.span_count, v.conn_count
         tv = TileVoxels(v.width, v.height, S, K, v.walkable_span_count, v.max_height, v.max_distance, v.status,
-                        _np_from(v.hf_cell_offset, C + 1, np.uint32), _np_from(v.span_min, S, np.int16),
+                        _np_from(v.hf_cell_offset, C + 1, np.uint32) if v.hf_cell_offset else None, _np_from(v.span_min, S, np.int16),
                         _np_from(v.span_max, S, np.int16), _np_from(v.span_area, S, np.uint8))
         if v.cell_index:
             tv.cell_index = _np_from(v.cell_index, C, np.uint32)
             tv.cell_count = _np_from(v.cell_count_arr, C, np.uint32)
             tv.areas = _np_from(v.areas, S, np.uint8)
             tv.con = _np_from(v.con, 4 * S, np.uint16)
-            tv.first_conn = _np_from(v.first_conn, S, np.uint32)
-            tv.conn_ref = _np_from(v.conn_ref, K, np.uint32)
-            tv.conn_dir = _np_from(v.conn_dir, K, np.uint8)
-            tv.conn_next = _np_from(v.conn_next, K, np.uint32)
             tv.dist = _np_from(v.dist, S, np.uint16)
+            if v.conn_mask:  # RESULT_SLIM: the binding layer rebuilds the rest (expand_slim)
+                tv.hf_cell_offset = None
+                tv.conn_mask = _np_from(v.conn_mask, S, np.uint8)
+                if v.conn_ref16:
+                    tv.conn_ref16 = _np_from(v.conn_ref16, K, np.uint16)
+                else:
+                    tv.conn_ref = _np_from(v.conn_ref, K, np.uint32)
+                if expand:
+                    tv.expand_slim()
+            else:
+                tv.first_conn = _np_from(v.first_conn, S, np.uint32)
+                tv.conn_ref = _np_from(v.conn_ref, K, np.uint32)
+                tv.conn_dir = _np_from(v.conn_dir, K, np.uint8)
+                tv.conn_next = _np_from(v.conn_next, K, np.uint32)
             if v.reg:
                 tv.reg, tv.max_regions = _np_from(v.reg, S, np.uint16), int(v.max_regions)
         return tv
@@ -124,6 +161,8 @@ class BatchResult:
         return v
 
     def free(self):
+        # safe after Context.close(): rcb_destroy releases the arenas of results that are still alive and leaves the
+        # handle valid for exactly this call
         if self._h:
             _ffi.lib().rcb_result_free(self._h)
             self._h = None
@@ -190,6 +229,13 @@ class Context:
 
     def launch_count(self) -> int:
         return int(_ffi.lib().rcb_launch_count(self._h))
+
+    def stats(self) -> dict:
+        """{'speculative': batches issued without a host round trip, 'rebuilt': of those, redone because a size was short,
+        'cached_batches': configuration batches the context remembers}."""
+        a = (ctypes.c_uint64 * 4)()
+        check(_ffi.lib().rcb_ctx_stats(self._h, a), self._h)
+        return {"speculative": int(a[0]), "rebuilt": int(a[1]), "cached_batches": int(a[2])}
 
     def upload_mesh(self, vertices, indices):
         v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1)

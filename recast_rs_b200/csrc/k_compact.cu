@@ -9,6 +9,8 @@
 // The heightfield CSR (hf_off) is already the compaction prefix sum, so "compaction" is a gather of
 // offsets; linking is a per-span stencil over the 8 neighbour columns (one thread per span, walkable spans compacted
 // per block, ordered columns bisected).
+#include <algorithm>
+
 #include "rcb_common.cuh"
 
 namespace {
@@ -219,7 +221,42 @@ __global__ void __launch_bounds__(256) k_write_connections2(uint32_t S, const ui
     }
 }
 
+// Slim result layout (RCB_RESULT_SLIM): what the host cannot rebuild from the layout rule of compact_heightfield.rs:375-389
+// is WHICH directions a span is connected in - one byte per span - and the neighbour per connection.  first_connection,
+// next and dir follow from the mask (blocks in span order, directions descending inside a block).
+__global__ void __launch_bounds__(256) k_slim_pack(const TileInfo* __restrict__ tinfo, const uint32_t* __restrict__ first_conn,
+                                                   const uint32_t* __restrict__ conn_ref, const uint8_t* __restrict__ conn_dir,
+                                                   const uint32_t* __restrict__ conn_next, uint8_t* __restrict__ conn_mask,
+                                                   uint16_t* __restrict__ conn_ref16, unsigned long long* __restrict__ flag) {
+    const TileInfo ti = tinfo[blockIdx.x];
+    bool wide = false;
+    for (uint32_t s = blockIdx.y * 256u + threadIdx.x; s < ti.span_count; s += gridDim.y * 256u) {
+        uint32_t mask = 0;
+        for (uint32_t k = first_conn[ti.span_base + s]; k != RCB_NONE; k = conn_next[ti.conn_base + k]) mask |= 1u << conn_dir[ti.conn_base + k];
+        conn_mask[ti.span_base + s] = (uint8_t)mask;
+    }
+    for (uint32_t k = blockIdx.y * 256u + threadIdx.x; k < ti.conn_count; k += gridDim.y * 256u) {
+        const uint32_t r = conn_ref[ti.conn_base + k];
+        wide = wide || r > 0xffffu;
+        conn_ref16[ti.conn_base + k] = (uint16_t)r;
+    }
+    if (__syncthreads_or(wide) && threadIdx.x == 0) atomicOr(flag, 1ull);
+}
+
 }  // namespace
+
+void launch_slim_pack(const TileInfo* tinfo, int ntiles, uint32_t max_cells, const uint32_t* first_conn, const uint32_t* conn_ref,
+                      const uint8_t* conn_dir, const uint32_t* conn_next, uint8_t* conn_mask, uint16_t* conn_ref16,
+                      unsigned long long* flag, cudaStream_t s) {
+    if (ntiles == 0) return;
+    KScope _k("k_slim_pack", s);
+    // connections outnumber cells several times: a block walks ~8 k of them
+    const unsigned gy = std::max(1u, std::min(64u, (max_cells + 2047u) / 2048u));
+    for (int t0 = 0; t0 < ntiles; t0 += 65535) {
+        const int n = std::min(65535, ntiles - t0);
+        k_slim_pack<<<dim3((unsigned)n, gy), 256, 0, s>>>(tinfo + t0, first_conn, conn_ref, conn_dir, conn_next, conn_mask, conn_ref16, flag);
+    }
+}
 
 void launch_span_cells(const TileDesc* tiles, TileMap tm, const uint32_t* hf_off, const int16_t* smin, const int16_t* smax, size_t S,
                        uint2* span_cell, cudaStream_t s) {

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(32) k_lz4_decompress(const uint8_t* __restrict
         return;
     }
     const uint32_t n = (uint32_t)(blen - 4);
-    const uint32_t cap = (uint32_t)(out_off[layer + 1] - out_off[layer]);  // the size prefix, exactly
+    const uint32_t cap = (uint32_t)(out_off[layer + 1] - out_off[layer]);  // the size prefix (or LZ4's 255x ceiling on this input, if that is smaller)
     const uint8_t* gin = blobs + b0 + 4;
     uint8_t* gout = out + out_off[layer];
     uint32_t st = 0, o = 0;
@@ -292,11 +292,8 @@ __global__ void __launch_bounds__(256) k_tc_gather(const TileDesc* __restrict__ 
 void launch_lz4_decompress(const uint8_t* blobs, const unsigned long long* blob_off, int nlayers, uint8_t* out,
                            const unsigned long long* out_off, uint32_t* status, uint32_t* produced, cudaStream_t s) {
     if (nlayers == 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_lz4_decompress, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZ_SMEM);
-        attr_set = true;
-    }
+    // the attribute is per device, and a process may drive several: set it with every launch
+    cudaFuncSetAttribute(k_lz4_decompress, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZ_SMEM);
     KScope _k("k_lz4_decompress", s);
     k_lz4_decompress<<<nlayers, 32, LZ_SMEM, s>>>(blobs, blob_off, out, out_off, status, produced);
 }

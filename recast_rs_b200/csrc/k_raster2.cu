@@ -17,6 +17,8 @@
 //            polygon unchanged and an empty cell piece, so skipping is exact).
 // Fragments go either to one global list with a per-column rank (v1 back end) or to per-tile segments
 // (tile-resident back end, k_tile.cu).
+#include <algorithm>
+
 #include "rcb_common.cuh"
 
 namespace {
@@ -162,10 +164,20 @@ __global__ void __launch_bounds__(256) k_bin_count(Raster2 rb) {
     }
 }
 
+// lib.rs:224-233: any index outside [0, nverts) fails the build (a negative i32 becomes a huge usize)
+__global__ void __launch_bounds__(256) k_check_indices(const int32_t* __restrict__ tris, size_t nidx, uint32_t nverts,
+                                                       unsigned long long* __restrict__ flag) {
+    bool bad = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nidx; i += (size_t)gridDim.x * blockDim.x)
+        bad = bad || (uint32_t)tris[i] >= nverts;
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1ull);
+}
+
 // ---- pass 2: write the work items (tri, tile, chunk) in triangle order -------------------------------
 __global__ void __launch_bounds__(256) k_fill_items(Raster2 rb, const uint32_t* __restrict__ item_off, uint2* __restrict__ items) {
     const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
     if (tri >= rb.mesh.ntris) return;
+    if (rb.counters[2] & RCB_FLAG_ABORT) return;  // speculative issue: the item buffer is too small
     uint32_t o = item_off[tri];
     if (item_off[tri + 1] == o) return;
     Tri t;
@@ -234,6 +246,11 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
                                                              TileInfo* __restrict__ tinfo) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ClipSmem& sm = *reinterpret_cast<ClipSmem*>(smem_raw);
+    if (rb.spec) {  // issued before the host knew the item count: the grid covers the capacity, the count is on the device
+        if (rb.counters[2] & RCB_FLAG_ABORT) return;
+        nitems = (uint32_t)min((unsigned long long)nitems, rb.counters[4]);
+        if (blockIdx.x * CLIP_THREADS >= nitems) return;
+    }
     const bool timed = (rb.flags & 0x100u) != 0 && threadIdx.x == 0;  // RCB_PHASE_TIMERS: counters[40..43]
     long long tclk = timed ? clock64() : 0;
     if (threadIdx.x < NBUCK) sm.nb[threadIdx.x] = sm.cur[threadIdx.x] = 0;
@@ -484,6 +501,13 @@ void launch_bin_count(const Raster2& rb, cudaStream_t s) {
     k_bin_count<<<(rb.mesh.ntris + 255) / 256, 256, 0, s>>>(rb);
 }
 
+void launch_check_indices(const int32_t* tris, size_t nidx, uint32_t nverts, unsigned long long* flag, cudaStream_t s) {
+    if (nidx == 0) return;
+    KScope _k("k_check_indices", s);
+    const unsigned blocks = (unsigned)std::min<size_t>((nidx + 255) / 256, 148 * 16);
+    k_check_indices<<<blocks, 256, 0, s>>>(tris, nidx, nverts, flag);
+}
+
 void launch_fill_items(const Raster2& rb, const uint32_t* item_off, uint2* items, cudaStream_t s) {
     if (rb.mesh.ntris == 0) return;
     KScope _k("k_fill_items", s);
@@ -492,11 +516,8 @@ void launch_fill_items(const Raster2& rb, const uint32_t* item_off, uint2* items
 
 void launch_clip_items(const Raster2& rb, const uint2* items, uint32_t nitems, TileInfo* tinfo, cudaStream_t s) {
     if (nitems == 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_clip_items, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClipSmem));
-        attr_set = true;
-    }
+    // per device, so per call: a process may drive several devices
+    cudaFuncSetAttribute(k_clip_items, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClipSmem));
     KScope _k("k_clip_items", s);
     k_clip_items<<<(nitems + CLIP_THREADS - 1) / CLIP_THREADS, CLIP_THREADS, sizeof(ClipSmem), s>>>(rb, items, nitems, tinfo);
 }

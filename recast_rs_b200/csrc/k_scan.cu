@@ -4,8 +4,7 @@
 // configured sizes (8 M cells = 32 MB).
 #include "rcb_common.cuh"
 
-unsigned long long g_rcb_launches = 0;
-RcbProfHook g_rcb_prof = {nullptr, nullptr};
+thread_local RcbProfHook g_rcb_prof = {nullptr, nullptr, nullptr};
 
 namespace {
 

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_spans(TileSpansArgs a)
     __shared__ uint32_t sh_warp[TILE_THREADS / 32 + 1];
     __shared__ uint32_t sh_red[4];  // [0] walkable spans, [1] max height, [3] replay work-list length
     const uint32_t tile = blockIdx.x;
+    if (a.counters[2] & RCB_FLAG_ABORT) return;  // a speculative size was too small: the host redoes the batch
     const TileDesc& td = a.tiles[tile];
     const int W = td.width, H = td.height;
     const uint32_t C = (uint32_t)(W * H);
@@ -325,7 +326,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_spans(TileSpansArgs a)
 }
 
 // span_base per tile + batch totals (counters[6] = S, counters[7] = walkable spans); one block
-__global__ void __launch_bounds__(1024) k_tile_scan(TileInfo* __restrict__ tinfo, int ntiles, unsigned long long* counters) {
+__global__ void __launch_bounds__(1024) k_tile_scan(TileInfo* __restrict__ tinfo, int ntiles, unsigned long long* counters,
+                                                    unsigned long long span_cap) {
     __shared__ uint32_t sh[33];
     __shared__ unsigned long long sh_walk;
     if (threadIdx.x == 0) sh_walk = 0;
@@ -367,12 +369,15 @@ __global__ void __launch_bounds__(1024) k_tile_scan(TileInfo* __restrict__ tinfo
         counters[6] = carry;
         counters[7] = sh_walk;
         counters[8] = sh_maxs;
+        // speculative issue: more spans than the arena was laid out for, or a tile that did not fit shared memory
+        if (carry > span_cap || (span_cap != ~0ull && (counters[2] & 4ull))) atomicOr(&counters[2], RCB_FLAG_ABORT);
     }
 }
 
 // tile_base = exclusive scan of the per-tile fragment bounds; counters[5] = largest bound; one block
 __global__ void __launch_bounds__(1024) k_tile_segments(const uint32_t* __restrict__ tile_ub, uint32_t* __restrict__ tile_base,
-                                                        int ntiles, unsigned long long* counters) {
+                                                        int ntiles, unsigned long long* counters, unsigned long long cap_frags,
+                                                        unsigned long long cap_items) {
     __shared__ uint32_t sh[33];
     __shared__ uint32_t sh_max;
     if (threadIdx.x == 0) sh_max = 0;
@@ -403,6 +408,7 @@ __global__ void __launch_bounds__(1024) k_tile_segments(const uint32_t* __restri
     if (threadIdx.x == 0) {
         tile_base[ntiles] = carry;
         counters[5] = sh_max;
+        if (carry > cap_frags || counters[4] > cap_items) atomicOr(&counters[2], RCB_FLAG_ABORT);
     }
 }
 
@@ -597,6 +603,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t sh_warp[TILE_THREADS / 32 + 1];
     __shared__ uint32_t sh_misc[4];  // [0] tile id, [1] conn base, [2] max distance, [3] link work-list length
+    if (a.counters[2] & RCB_FLAG_ABORT) return;  // uniform over the grid: nobody is left waiting in the look-back
     // dynamic tile id: tiles start in order, which the look-back relies on
     if (threadIdx.x == 0) {
         sh_misc[0] = atomicAdd(a.tile_ticket, 1u);
@@ -796,6 +803,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
                 sh_misc[1] = excl;
                 a.tinfo[tile].conn_base = excl;
                 a.tinfo[tile].conn_count = K;
+                if (K) atomicAdd(&a.counters[9], (unsigned long long)K);
+                if ((unsigned long long)excl + K > a.Kcap) {
+                    atomicOr(&a.counters[2], RCB_FLAG_CONN);
+                    sh_misc[1] = 0xffffffffu;
+                }
             }
         }
         if (nworkers == TILE_THREADS)
@@ -803,6 +815,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
         else
             asm volatile("bar.sync 2, %0;" ::"r"(nworkers) : "memory");
         const uint32_t conn_base = sh_misc[1];
+        if (conn_base == 0xffffffffu) return;  // the connection arena is too small for this tile: the host redoes the batch
         // Each worker warp takes a contiguous run of cells, i.e. of spans and of the list, 32 spans at a time: a lane
         // counts its span's connections, then the lanes turn to the run's list SLOTS - slot t belongs to the span whose
         // range holds t (bisection over the lanes' offsets) and is its j-th present direction from 7 downwards - so the
@@ -917,14 +930,15 @@ void launch_tile_spans(const TileSpansArgs& a, int ntiles, cudaStream_t s) {
     k_tile_spans<<<ntiles, TILE_THREADS, a.smem_bytes, s>>>(a);
 }
 
-void launch_tile_segments(const uint32_t* tile_ub, uint32_t* tile_base, int ntiles, unsigned long long* counters, cudaStream_t s) {
+void launch_tile_segments(const uint32_t* tile_ub, uint32_t* tile_base, int ntiles, unsigned long long* counters,
+                          unsigned long long cap_frags, unsigned long long cap_items, cudaStream_t s) {
     KScope _k("k_tile_segments", s);
-    k_tile_segments<<<1, 1024, 0, s>>>(tile_ub, tile_base, ntiles, counters);
+    k_tile_segments<<<1, 1024, 0, s>>>(tile_ub, tile_base, ntiles, counters, cap_frags, cap_items);
 }
 
-void launch_tile_scan(TileInfo* tinfo, int ntiles, unsigned long long* counters, cudaStream_t s) {
+void launch_tile_scan(TileInfo* tinfo, int ntiles, unsigned long long* counters, unsigned long long span_cap, cudaStream_t s) {
     KScope _k("k_tile_scan", s);
-    k_tile_scan<<<1, 1024, 0, s>>>(tinfo, ntiles, counters);
+    k_tile_scan<<<1, 1024, 0, s>>>(tinfo, ntiles, counters, span_cap);
 }
 
 void launch_tile_compact(const TileCompactArgs& a, int ntiles, cudaStream_t s) {

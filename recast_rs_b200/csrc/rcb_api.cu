@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -52,10 +53,50 @@ struct Arena {
 };
 
 struct ArenaLayout {  // byte offsets inside arena A (cells + spans) and arena B (connections)
-    size_t tinfo, hf_cell_offset, cell_index, cell_count, span_min, span_max, span_area, areas, con, first_conn, dist, reg;
+    size_t tinfo, hf_cell_offset, cell_index, cell_count, span_min, span_max, span_area, areas, con, first_conn, dist, reg, conn_mask;
     size_t bytesA;
-    size_t conn_ref, conn_dir, conn_next;
+    size_t slimA;  // the arrays a slim download copies are the first slimA bytes of arena A
+    size_t conn_ref, conn_dir, conn_next, conn_ref16;
     size_t bytesB;
+    size_t slimB;
+    uint64_t Scap, Kcap;  // the span / connection counts the offsets were computed for (>= the real ones)
+};
+
+struct HostLocator {
+    Locator loc{};
+    std::vector<uint32_t> bin_off, bin_tiles;
+};
+
+// What the previous build of the same batch found out, so that the next one can be issued without waiting for the
+// device: buffer sizes, shared-memory sizes and arena layouts are chosen from these numbers (plus a margin), the
+// kernels check them on the device, and a failed check makes the host redo the batch the slow way (BatchHint::valid
+// then holds the new numbers).
+struct BatchHint {
+    bool valid = false;
+    uint64_t ntris = 0, nverts = 0;
+    uint32_t stage_mask = 0;
+    int32_t merge_thr = 0;
+    uint64_t ub = 0, nitems = 0, ub_max = 0, S = 0, walk = 0, s_max = 0, K = 0;
+};
+
+// Everything about a batch that depends only on its configurations: validated tile descriptors, the locator grid over
+// the tile bounds and their device copies.  Cached per context (keyed on the configuration bytes), so a caller that
+// rebuilds the same tiles - every frame of a dynamic nav mesh, every step of a benchmark - does not pay for them again.
+struct BatchEntry {
+    std::vector<rcb_config> cfgs;  // the key
+    std::vector<TileDesc> tiles;
+    HostLocator L;
+    uint64_t Ctot = 0;
+    uint32_t max_cells = 0;
+    DevBuf d_tiles, d_bin_off, d_bin_tiles;
+    bool have_locator = false, uploaded_tiles = false, uploaded_locator = false;
+    BatchHint hint;
+    unsigned long long last_use = 0;
+    ~BatchEntry() {
+        d_tiles.release();
+        d_bin_off.release();
+        d_bin_tiles.release();
+    }
 };
 
 struct rcb_ctx {
@@ -63,14 +104,20 @@ struct rcb_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // D2H of finished tile groups while later groups compute (rcb_build_tiles_streamed)
     std::string err;
-    unsigned long long launches0 = 0;
+    unsigned long long launches = 0;  // kernel launches issued by this context
     // mesh
     DevBuf d_verts, d_tris, d_tri_areas;
     const float* verts = nullptr;
     const int32_t* tris = nullptr;
     size_t nfloats = 0, nidx = 0;
+    bool mesh_bad = false;  // an index >= nverts (checked on the device when the mesh is set: lib.rs:224-233)
     // per batch
     DevBuf d_tiles, d_bin_off, d_bin_tiles;
+    std::vector<std::shared_ptr<BatchEntry>> batch_cache;  // most recent configurations (tile tables, locator, hints)
+    unsigned long long use_clock = 0;
+    bool no_spec = false;     // RCB_NO_SPEC=1: never issue a batch speculatively (always the synchronous path)
+    uint64_t spec_runs = 0, spec_fallbacks = 0;
+    std::vector<rcb_result*> live;  // results not yet freed (rcb_destroy releases their arenas)
     // scratch
     DevBuf d_counters, d_cell_cnt, d_frag_off, d_frag_tmp, d_frag_rec, d_fs_mm, d_fs_area, d_scan_tmp, d_hf_off, d_conn_cnt,
         d_conn_off, d_nid, d_t16a, d_t16b, d_t16c, d_t8a, d_t8b, d_item_cnt, d_item_off, d_items, d_tile_ub, d_tile_base, d_tile_cursor,
@@ -83,7 +130,9 @@ struct rcb_ctx {
     // pinned staging
     char* h_stage = nullptr;
     size_t h_stage_cap = 0;
-    unsigned long long* h_counters = nullptr;  // pinned, 8 entries
+    unsigned long long* h_counters = nullptr;  // pinned, 32 entries
+    unsigned long long* h_slots = nullptr;     // pinned, kSlots x 16: counters of results issued speculatively
+    std::vector<int> free_slots;
     // pools
     std::vector<Arena> free_dev, free_host;
     // per-stage timers
@@ -101,7 +150,23 @@ struct rcb_result {
     rcb_ctx* ctx = nullptr;
     int ntiles = 0;
     uint32_t stage_mask = 0;
-    std::vector<TileDesc> tiles;
+    std::shared_ptr<BatchEntry> entry;  // run_pipeline results: the tile table lives in the cached batch entry
+    std::vector<TileDesc> own_tiles;    // tile-cache results: their own table
+    const std::vector<TileDesc>& tiles() const { return entry ? entry->tiles : own_tiles; }
+    // a batch issued speculatively (sizes from BatchHint): nothing is known on the host until `done` has passed
+    bool pending = false;
+    int slot = -1;
+    cudaEvent_t done = nullptr;
+    int redo_erode = 0;  // what a failed speculation needs to run again (the configurations are entry->cfgs)
+    bool slim = false;         // RCB_RESULT_SLIM: conn_mask / conn_ref16 exist, the download copies the slim prefix only
+    bool slim_ref16 = false;   // conn_ref16 is valid (every tile-relative span index fits 16 bits)
+    bool slim_host = false;    // the host copy holds only the slim arrays
+    bool slim_packed = false;  // k_slim_pack has run on this result
+    bool spec = false;         // issued speculatively (pending: the device may still raise a flag)
+    int failed = 0;            // a rebuild after a failed speculation failed with this status
+    unsigned long long* slim_flag = nullptr;  // pinned: k_slim_pack met a span reference that needs more than 16 bits
+    uint64_t copied_bytes = 0;                // bytes the download moved
+    bool copy_in_flight = false;
     uint64_t Ctot = 0, S = 0, K = 0, F = 0, ntris = 0, nverts = 0;
     bool have_K = false;
     ArenaLayout lay{};
@@ -147,11 +212,12 @@ void prof_mark(void* user, const char* name, int begin, cudaStream_t s) {
     else if (!ctx->prof_pending.empty())
         ctx->prof_pending.back().b = e;
 }
-struct ProfInstall {  // installs the hook for the duration of one pipeline run
-    explicit ProfInstall(rcb_ctx* ctx) {
-        if (ctx->prof_on) g_rcb_prof = RcbProfHook{prof_mark, ctx};
+struct ProfInstall {  // installs this context's hooks on the calling thread for the duration of one pipeline run
+    RcbProfHook prev;
+    explicit ProfInstall(rcb_ctx* ctx) : prev(g_rcb_prof) {
+        g_rcb_prof = RcbProfHook{ctx->prof_on ? prof_mark : nullptr, ctx, &ctx->launches};
     }
-    ~ProfInstall() { g_rcb_prof = RcbProfHook{nullptr, nullptr}; }
+    ~ProfInstall() { g_rcb_prof = prev; }
 };
 
 void prof_collect(rcb_ctx* ctx) {
@@ -250,11 +316,6 @@ int ensure_stage(rcb_ctx* ctx, size_t bytes) {
 // `as i16` of an i32 config value (lib.rs:278-287): wraps
 inline int32_t as_i16(int32_t v) { return (int32_t)(int16_t)(uint16_t)(uint32_t)v; }
 
-struct HostLocator {
-    Locator loc{};
-    std::vector<uint32_t> bin_off, bin_tiles;
-};
-
 void build_locator(std::vector<TileDesc>& tiles, HostLocator& L) {
     const int n = (int)tiles.size();
     float gx0 = INFINITY, gz0 = INFINITY, gx1 = -INFINITY, gz1 = -INFINITY, bsx = 0, bsz = 0;
@@ -306,6 +367,91 @@ void build_locator(std::vector<TileDesc>& tiles, HostLocator& L) {
             for (int x = r[4 * i]; x <= r[4 * i + 1]; ++x) L.bin_tiles[cur[(size_t)z * nbx + x]++] = (uint32_t)i;
 }
 
+// Finds (or creates) the cached entry of a batch of configurations: validation (lib.rs:74 / config.rs:110-136), tile
+// descriptors, cell bases.  The key is the configuration bytes themselves (compared in full, most recent first).
+int get_batch_entry(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, std::shared_ptr<BatchEntry>& out) {
+    ctx->use_clock++;
+    for (auto& e : ctx->batch_cache)
+        if ((int)e->cfgs.size() == ntiles && (ntiles == 0 || memcmp(e->cfgs.data(), cfgs, sizeof(rcb_config) * (size_t)ntiles) == 0)) {
+            e->last_use = ctx->use_clock;
+            out = e;
+            return RCB_OK;
+        }
+    auto e = std::make_shared<BatchEntry>();
+    e->tiles.resize(ntiles);
+    uint64_t Ctot = 0;
+    uint32_t max_cells = 0;
+    for (int i = 0; i < ntiles; ++i) {
+        const rcb_config& c = cfgs[i];
+        const int v = rcb_config_validate(&c);
+        if (v != RCB_OK)
+            return fail(ctx, v, "tile %d: invalid configuration (width/height <= 0, cs/ch <= 0, slope outside [0,90] or max_verts < 3)", i);
+        TileDesc& t = e->tiles[i];
+        memset(&t, 0, sizeof t);
+        t.width = c.width;
+        t.height = c.height;
+        for (int k = 0; k < 3; ++k) t.bmin[k] = c.bmin[k], t.bmax[k] = c.bmax[k];
+        t.cs = c.cs;
+        t.ch = c.ch;
+        t.ics = 1.0f / c.cs;
+        t.ich = 1.0f / c.ch;
+        t.slope_thr = cosf(c.walkable_slope_angle * 3.14159265358979323846f / 180.0f);  // lib.rs:212-213
+        t.walkable_height = as_i16(c.walkable_height);
+        t.walkable_climb = as_i16(c.walkable_climb);
+        t.neg_climb = (int32_t)(int16_t)(-(int16_t)t.walkable_climb);
+        t.aux0 = c.border_size, t.aux1 = c.min_region_area, t.aux2 = c.merge_region_area;  // k_regions
+        const uint64_t cells = (uint64_t)c.width * (uint64_t)c.height;
+        if (cells > 0x7fffffffull || Ctot + cells + ntiles >= 0xffffffffull) return fail(ctx, RCB_EARG, "batch too large: more than 2^32 cells");
+        t.cell_base = (uint32_t)Ctot;
+        t.wmagic = ((1ull << 40) / (unsigned long long)c.width) + 1;
+        Ctot += cells;
+        if (cells > max_cells) max_cells = (uint32_t)cells;
+    }
+    e->cfgs.assign(cfgs, cfgs + ntiles);
+    e->Ctot = Ctot;
+    e->max_cells = max_cells;
+    e->last_use = ctx->use_clock;
+    if (ctx->batch_cache.size() >= 24) {  // bounded: drop the least recently used (results that still use it keep it alive)
+        size_t m = 0;
+        for (size_t i = 1; i < ctx->batch_cache.size(); ++i)
+            if (ctx->batch_cache[i]->last_use < ctx->batch_cache[m]->last_use) m = i;
+        ctx->batch_cache.erase(ctx->batch_cache.begin() + m);
+    }
+    ctx->batch_cache.insert(ctx->batch_cache.begin(), e);
+    out = e;
+    return RCB_OK;
+}
+
+// Device copies of an entry's tables (once per entry; the locator only when a rasterizing call needs it).
+int upload_batch_entry(rcb_ctx* ctx, BatchEntry& e, bool need_locator) {
+    const size_t ntiles = e.tiles.size();
+    if (need_locator && !e.have_locator) {
+        build_locator(e.tiles, e.L);  // also sets bin_x0 / bin_z0 of the tile descriptors
+        e.have_locator = true;
+        e.uploaded_tiles = false;
+    }
+    const bool up_tiles = !e.uploaded_tiles, up_loc = need_locator && !e.uploaded_locator;
+    if (!up_tiles && !up_loc) return RCB_OK;
+    // these copies read the entry's own host vectors, which outlive the copy (the entry is kept by the result)
+    if (up_tiles) {
+        CU(e.d_tiles.ensure(sizeof(TileDesc) * ntiles + 64));
+        if (ntiles) CU(cudaMemcpyAsync(e.d_tiles.p, e.tiles.data(), sizeof(TileDesc) * ntiles, cudaMemcpyHostToDevice, ctx->stream));
+        e.uploaded_tiles = true;
+    }
+    if (up_loc) {
+        CU(e.d_bin_off.ensure(4 * e.L.bin_off.size() + 64));
+        CU(e.d_bin_tiles.ensure(4 * e.L.bin_tiles.size() + 64));
+        CU(cudaMemcpyAsync(e.d_bin_off.p, e.L.bin_off.data(), 4 * e.L.bin_off.size(), cudaMemcpyHostToDevice, ctx->stream));
+        if (!e.L.bin_tiles.empty())
+            CU(cudaMemcpyAsync(e.d_bin_tiles.p, e.L.bin_tiles.data(), 4 * e.L.bin_tiles.size(), cudaMemcpyHostToDevice, ctx->stream));
+        e.uploaded_locator = true;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));  // pageable sources; once per entry
+    return RCB_OK;
+}
+
+// Arena A: per-tile info, cells, spans.  The arrays a slim download copies come first (one copy of a prefix);
+// hf_cell_offset and first_conn, which the slim layout leaves on the device, come last.
 void make_layout(ArenaLayout& l, int ntiles, uint64_t C, uint64_t S, uint32_t stage_mask) {
     size_t o = 0;
     auto put = [&o](size_t bytes) {
@@ -314,8 +460,8 @@ void make_layout(ArenaLayout& l, int ntiles, uint64_t C, uint64_t S, uint32_t st
         return r;
     };
     const bool compact = stage_mask & RCB_STAGE_COMPACT;
+    const bool slim = (stage_mask & RCB_RESULT_SLIM) && compact;
     l.tinfo = put(sizeof(TileInfo) * (size_t)ntiles);
-    l.hf_cell_offset = put(4 * (C + ntiles));
     l.span_min = put(2 * S);
     l.span_max = put(2 * S);
     l.span_area = put(S);
@@ -323,22 +469,29 @@ void make_layout(ArenaLayout& l, int ntiles, uint64_t C, uint64_t S, uint32_t st
     l.cell_count = put(compact ? 4 * C : 0);
     l.areas = put(compact ? S : 0);
     l.con = put(compact ? 8 * S : 0);
-    l.first_conn = put(compact ? 4 * S : 0);
     l.dist = put(compact ? 2 * S : 0);
     l.reg = put((stage_mask & RCB_STAGE_REGIONS) ? 2 * S : 0);
+    l.conn_mask = put(slim ? S : 0);
+    l.slimA = o;
+    l.hf_cell_offset = put(4 * (C + ntiles));
+    l.first_conn = put(compact ? 4 * S : 0);
     l.bytesA = o;
+    l.Scap = S;
 }
-void make_layout_conn(ArenaLayout& l, uint64_t K) {
+void make_layout_conn(ArenaLayout& l, uint64_t K, bool slim) {
     size_t o = 0;
     auto put = [&o](size_t bytes) {
         size_t r = o;
         o = align_up(o + bytes);
         return r;
     };
+    l.conn_ref16 = put(slim ? 2 * K : 0);
+    l.slimB = o;
     l.conn_ref = put(4 * K);
     l.conn_next = put(4 * K);
     l.conn_dir = put(K);
     l.bytesB = o;
+    l.Kcap = K;
 }
 
 struct Source {  // where the heightfield comes from
@@ -350,6 +503,7 @@ struct Source {  // where the heightfield comes from
     const int16_t* smax = nullptr;
     const uint8_t* sarea = nullptr;
     const uint8_t* areas_override = nullptr;  // host, optional
+    bool no_spec = false;                     // the synchronous path, whatever the entry's hint says
     bool no_tile_mode = false;                // set when the tile-resident back end reported an overflow
     bool wide_clip = false;                   // set when the 6-vertex clipper overflowed: use the 12-vertex one
     const rcb_area_op* ops = nullptr;         // host, area operators applied after linking (rcb_apply_area_ops)
@@ -434,7 +588,7 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
         const uint64_t K = (uint32_t)ctx->h_counters[4];
         res->K = K;
         res->have_K = true;
-        make_layout_conn(res->lay, K);
+        make_layout_conn(res->lay, K, res->slim);
         CU(pool_get(ctx->free_dev, res->lay.bytesB, false, res->devB));
         char* B = res->devB.p;
         launch_tile_conn_bases(ntiles, d_conn_off, d_tinfo, st);
@@ -471,7 +625,7 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
             }
         }
         int max_width = 0;  // the forward sweep runs one thread per column of a tile
-        for (const TileDesc& t : res->tiles) max_width = std::max(max_width, (int)t.width);
+        for (const TileDesc& t : res->tiles()) max_width = std::max(max_width, (int)t.width);
         if ((stage_mask & RCB_STAGE_ERODE) && S > 0) {
             CU(ctx->d_t8a.ensure(S + 16));
             CU(ctx->d_t8b.ensure(S + 16));
@@ -493,6 +647,8 @@ int global_back_end(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, Tile
 }
 
 int fetch_tinfo(rcb_result* res, cudaStream_t on = nullptr, bool use_on = false);
+int post_counters(rcb_ctx* ctx, rcb_result* res, bool spec);
+int resolve_result(rcb_result* res);
 
 // CompactHeightfield::build_regions on a finished result (both back ends): k_regions.cu.
 int build_regions_stage(rcb_ctx* ctx, rcb_result* res, const TileDesc* d_tiles, int ntiles, uint64_t S) {
@@ -602,44 +758,21 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
     if (stage_mask & RCB_FILTER_LEDGE) fmask |= 2;
     if (stage_mask & RCB_FILTER_LOW_HEIGHT) fmask |= 4;
 
-    // ---- configs -> tile descriptors ---------------------------------------------------------------
+    // ---- configs -> tile descriptors (cached per context: SURVEY R2 callers rebuild the same tiles again and again) ----
+    std::shared_ptr<BatchEntry> entry;
+    {
+        const int r = get_batch_entry(ctx, cfgs, ntiles, entry);
+        if (r) return r;
+    }
     auto* res = new rcb_result();
     res->ctx = ctx;
     res->ntiles = ntiles;
     res->stage_mask = stage_mask;
-    res->tiles.resize(ntiles);
-    uint64_t Ctot = 0;
-    uint32_t max_cells = 0;
-    for (int i = 0; i < ntiles; ++i) {
-        const rcb_config& c = cfgs[i];
-        const int v = rcb_config_validate(&c);  // lib.rs:74 / config.rs:110-136
-        if (v != RCB_OK) {
-            delete res;
-            return fail(ctx, v, "tile %d: invalid configuration (width/height <= 0, cs/ch <= 0, slope outside [0,90] or max_verts < 3)", i);
-        }
-        TileDesc& t = res->tiles[i];
-        t.width = c.width;
-        t.height = c.height;
-        for (int k = 0; k < 3; ++k) t.bmin[k] = c.bmin[k], t.bmax[k] = c.bmax[k];
-        t.cs = c.cs;
-        t.ch = c.ch;
-        t.ics = 1.0f / c.cs;
-        t.ich = 1.0f / c.ch;
-        t.slope_thr = cosf(c.walkable_slope_angle * 3.14159265358979323846f / 180.0f);  // lib.rs:212-213
-        t.walkable_height = as_i16(c.walkable_height);
-        t.walkable_climb = as_i16(c.walkable_climb);
-        t.neg_climb = (int32_t)(int16_t)(-(int16_t)t.walkable_climb);
-        t.aux0 = c.border_size, t.aux1 = c.min_region_area, t.aux2 = c.merge_region_area;  // k_regions
-        const uint64_t cells = (uint64_t)c.width * (uint64_t)c.height;
-        if (cells > 0x7fffffffull || Ctot + cells + ntiles >= 0xffffffffull) {
-            delete res;
-            return fail(ctx, RCB_EARG, "batch too large: more than 2^32 cells");
-        }
-        t.cell_base = (uint32_t)Ctot;
-        t.wmagic = ((1ull << 40) / (unsigned long long)c.width) + 1;
-        Ctot += cells;
-        if (cells > max_cells) max_cells = (uint32_t)cells;
-    }
+    res->entry = entry;
+    res->slim = (stage_mask & RCB_RESULT_SLIM) && (stage_mask & RCB_STAGE_COMPACT);
+    ctx->live.push_back(res);
+    const uint64_t Ctot = entry->Ctot;
+    const uint32_t max_cells = entry->max_cells;
     res->Ctot = Ctot;
     TileMap tm{(uint32_t)ntiles, (max_cells + 255) / 256, 0};
     tm.nblocks = tm.blocks_per_tile * tm.ntiles;
@@ -667,23 +800,22 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
     res->ntris = ntris;
     res->nverts = nverts;
 
-    // ---- upload per-batch tables --------------------------------------------------------------------
-    HostLocator L;
-    if (do_raster) build_locator(res->tiles, L);
+    if (do_raster && ntiles > 0 && ctx->mesh_bad)  // lib.rs:224-233 (the indices were checked on the device when the mesh was set)
+        return bail(fail(ctx, RCB_ENAVMESH_GEN, "Triangle index out of bounds (max: %zu)", nverts - 1));
+
+    // ---- per-batch tables on the device (cached with the entry) -----------------------------------------
     {
-        const size_t need = align_up(sizeof(TileDesc) * (size_t)ntiles) + align_up(4 * L.bin_off.size()) +
-                            align_up(4 * L.bin_tiles.size()) + align_up(ntris) + 1024;
-        int r = ensure_stage(ctx, need);
+        int r = upload_batch_entry(ctx, *entry, do_raster);
         if (r) return bail(r);
-        size_t so = 0;
-        if ((r = stage_upload(ctx, ctx->d_tiles, res->tiles.data(), sizeof(TileDesc) * (size_t)ntiles, so))) return bail(r);
-        if (do_raster) {
-            if ((r = stage_upload(ctx, ctx->d_bin_off, L.bin_off.data(), 4 * L.bin_off.size(), so))) return bail(r);
-            if ((r = stage_upload(ctx, ctx->d_bin_tiles, L.bin_tiles.data(), 4 * L.bin_tiles.size(), so))) return bail(r);
-            if (src.tri_areas && (r = stage_upload(ctx, ctx->d_tri_areas, src.tri_areas, ntris, so))) return bail(r);
+        if (do_raster && src.tri_areas) {
+            if ((r = ensure_stage(ctx, align_up(ntris) + 1024))) return bail(r);
+            size_t so = 0;
+            if ((r = stage_upload(ctx, ctx->d_tri_areas, src.tri_areas, ntris, so))) return bail(r);
         }
     }
-    const TileDesc* d_tiles = ctx->d_tiles.as<TileDesc>();
+    const HostLocator& L = entry->L;
+    const TileDesc* d_tiles = entry->d_tiles.as<TileDesc>();
+    const std::vector<TileDesc>& tiles = entry->tiles;
 
 #define CUB(expr)                                                                                            \
     do {                                                                                                     \
@@ -713,14 +845,16 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         // v2 front end (k_raster2.cu) needs 16-bit cell coordinates and the (tile, chunk) item encoding
         bool v2 = ntiles <= (1 << 20) && !ctx->force_v1 && !src.wide_clip;
         for (int i = 0; i < ntiles && v2; ++i)
-            if (res->tiles[i].width > 65535 || res->tiles[i].height > 4096 * RCB_CLIP_ROWS) v2 = false;
+            if (tiles[i].width > 65535 || tiles[i].height > 4096 * RCB_CLIP_ROWS ||
+                (uint64_t)tiles[i].width * (uint64_t)tiles[i].height > (1ull << 24))  // fragment records carry a 24-bit cell
+                v2 = false;
 
         RasterBuffers rb{};
         rb.tiles = d_tiles;
         rb.ntiles = ntiles;
         rb.loc = L.loc;
-        rb.loc.bin_off = ctx->d_bin_off.as<uint32_t>();
-        rb.loc.bin_tiles = ctx->d_bin_tiles.as<uint32_t>();
+        rb.loc.bin_off = entry->d_bin_off.as<uint32_t>();
+        rb.loc.bin_tiles = entry->d_bin_tiles.as<uint32_t>();
         rb.mesh.verts = ctx->verts;
         rb.mesh.tris = ctx->tris;
         rb.mesh.ntris = (uint32_t)ntris;
@@ -737,17 +871,27 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         r2.counters = rb.counters;
         r2.cell_cnt = rb.cell_cnt;
         r2.flags = ctx->clip_flags | (ctx->phase_timers ? 0x100u : 0u);
-        uint64_t ub = 0, nitems = 0;
+        uint64_t ub = 0, nitems = 0, ub_max = 0;
         bool want_tile = false;
+        // tile-resident back end candidates: moderate tiles (the CSR arrays of a tile must fit shared memory; fragment
+        // records carry a 24-bit triangle index)
+        const bool tile_ok = v2 && !ctx->force_global && !src.no_tile_mode && src.nvols == 0 && !src.cell_offset &&
+                             8ull * max_cells + 4096 <= kTileSmem && ntris < (1u << 24);
+        // Speculative issue: the previous build of this batch left its sizes in the entry's hint.  With them every
+        // buffer, shared-memory size and arena layout can be chosen now, so the whole step is enqueued without a single
+        // host round trip; the kernels verify the sizes on the device and rcb_result_* redo the batch if one was short.
+        const BatchHint h = entry->hint;
+        const bool spec = do_raster && ntiles > 0 && tile_ok && !ctx->no_spec && !src.no_spec && !src.tri_areas && h.valid && h.ub > 0 &&
+                          h.ntris == ntris && h.nverts == nverts && h.stage_mask == stage_mask && h.merge_thr == src.merge_thr &&
+                          !(stage_mask & RCB_STAGE_REGIONS) && !ctx->phase_timers;
+        auto margin = [](uint64_t v) { return v + v / 64 + 256; };
+        const bool compact = (stage_mask & RCB_STAGE_COMPACT) != 0;
         if (do_raster && ntiles > 0) {
             if (v2) {
                 CUB(ctx->d_item_cnt.ensure(4 * (ntris + 2)));
                 CUB(ctx->d_item_off.ensure(4 * (ntris + 2)));
                 CUB(ctx->d_scan_tmp.ensure(4 * scan_tmp_elems(ntris + 1)));
                 r2.item_cnt = ctx->d_item_cnt.as<uint32_t>();
-                // tile-resident back end candidates: moderate tiles (the CSR arrays of a tile must fit shared memory)
-                // (fragment records carry a 24-bit triangle index)
-                want_tile = !ctx->force_global && !src.no_tile_mode && src.nvols == 0 && !src.cell_offset && 8ull * max_cells + 4096 <= kTileSmem && ntris < (1u << 24);
                 // per-tile fragment bounds -> per-tile segments (both back ends consume fragments tile by tile)
                 CUB(ctx->d_tile_ub.ensure(4 * ((size_t)ntiles + 1)));
                 CUB(ctx->d_tile_base.ensure(4 * ((size_t)ntiles + 2)));
@@ -756,23 +900,30 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                 CUB(cudaMemsetAsync(ctx->d_tile_cursor.p, 0, 4 * ((size_t)ntiles + 1), st));
                 r2.tile_ub = ctx->d_tile_ub.as<uint32_t>();
                 launch_bin_count(r2, st);
-                launch_tile_segments(r2.tile_ub, ctx->d_tile_base.as<uint32_t>(), ntiles, r2.counters, st);
+                // speculative: the fragment / work-item totals must stay within what the buffers were sized for
+                launch_tile_segments(r2.tile_ub, ctx->d_tile_base.as<uint32_t>(), ntiles, r2.counters, spec ? margin(h.ub) : ~0ull,
+                                     spec ? margin(h.nitems) : ~0ull, st);
             } else {
                 launch_count_fragments(rb, st);
             }
-            CUB(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-            CUB(cudaStreamSynchronize(st));
-            if (ctx->h_counters[3]) return bail(fail(ctx, RCB_ENAVMESH_GEN, "Triangle index out of bounds (max: %zu)", nverts - 1));
-            ub = ctx->h_counters[0];
-            nitems = ctx->h_counters[4];
-            if (ub >= 0xfffffff0ull || nitems >= 0xfffffff0ull)
-                return bail(fail(ctx, RCB_EARG, "batch too large: fragment bound %llu", (unsigned long long)ub));
-            // the bound counts whole footprints; real fragment counts are about half of it on triangle meshes
-            if (want_tile && 8ull * max_cells + 8ull * (ctx->h_counters[5] / 3) + 4096 > kTileSmem) want_tile = false;
+            if (spec) {
+                ub = margin(h.ub), nitems = margin(h.nitems), ub_max = margin(h.ub_max);
+                want_tile = true;
+            } else {
+                CUB(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                CUB(cudaStreamSynchronize(st));
+                if (ctx->h_counters[3]) return bail(fail(ctx, RCB_ENAVMESH_GEN, "Triangle index out of bounds (max: %zu)", nverts - 1));
+                ub = ctx->h_counters[0];
+                nitems = ctx->h_counters[4];
+                ub_max = ctx->h_counters[5];
+                if (ub >= 0xfffffff0ull || nitems >= 0xfffffff0ull)
+                    return bail(fail(ctx, RCB_EARG, "batch too large: fragment bound %llu", (unsigned long long)ub));
+                // the bound counts whole footprints; real fragment counts are about half of it on triangle meshes
+                want_tile = tile_ok && 8ull * max_cells + 8ull * (ub_max / 3) + 4096 <= kTileSmem;
+            }
         }
         if (want_tile && ub > 0) {
             // ================= tile-resident back end (k_tile.cu) ==============================================
-            const uint64_t ub_max = ctx->h_counters[5];
             CUB(ctx->d_tile_frags.ensure(12 * ub + 64));
             CUB(ctx->d_ts_mm.ensure(4 * ub + 64));
             CUB(ctx->d_ts_area.ensure(ub + 64));
@@ -784,6 +935,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             r2.tile_base = ctx->d_tile_base.as<uint32_t>();
             r2.tile_cap = ctx->d_tile_ub.as<uint32_t>();
             r2.tile_frags = ctx->d_tile_frags.as<uint32_t>();
+            r2.spec = spec ? 1u : 0u;
             launch_exclusive_scan(r2.item_cnt, ctx->d_item_off.as<uint32_t>(), ntris, ctx->d_scan_tmp.as<uint32_t>(), st);
             launch_fill_items(r2, ctx->d_item_off.as<uint32_t>(), ctx->d_items.as<uint2>(), st);
             launch_clip_items(r2, ctx->d_items.as<uint2>(), (uint32_t)nitems, d_tinfo_tmp, st);
@@ -817,33 +969,48 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                     launch_tile_spans(ta, ntiles, st);
                 }
             }
-            launch_tile_scan(d_tinfo_tmp, ntiles, r2.counters, st);
-            CUB(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-            CUB(cudaStreamSynchronize(st));
-            bool overflow = (ctx->h_counters[2] & 6ull) != 0;
-            const bool poly_overflow = (ctx->h_counters[2] & 1ull) != 0;  // a clip polygon outgrew the 6-vertex slots
-            S = ctx->h_counters[6];
-            const uint64_t walk = ctx->h_counters[7], s_max = ctx->h_counters[8];
-            const bool compact = (stage_mask & RCB_STAGE_COMPACT) != 0;
-            const uint64_t needB = compact ? 6ull * (max_cells + 2) + 21ull * s_max + 192 : 64;
-            if (compact && s_max >= 0xffffu) overflow = true;  // tile-local span ids are 16 bit
-            if (needB > kTileSmem) overflow = true;
-            if (overflow || poly_overflow) {  // redo the batch on the global-memory back end (and the wide clipper)
-                Source s2 = src;
-                s2.no_tile_mode = true;
-                s2.wide_clip = src.wide_clip || poly_overflow;
-                rcb_result_free(res);
-                return run_pipeline(ctx, cfgs, ntiles, stage_mask, erode_radius, s2, out);
+            uint64_t walk = 0, s_max = 0, Kcap = 0;
+            if (spec) {
+                S = margin(h.S), walk = margin(h.walk), s_max = margin(h.s_max);
+                Kcap = compact ? (h.K ? margin(h.K) : 8ull * walk) : 0;
+                if (s_max > 0xfffeu) s_max = 0xfffeu;
+                launch_tile_scan(d_tinfo_tmp, ntiles, r2.counters, S, st);
+            } else {
+                launch_tile_scan(d_tinfo_tmp, ntiles, r2.counters, ~0ull, st);
+                CUB(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                CUB(cudaStreamSynchronize(st));
+                bool overflow = (ctx->h_counters[2] & 6ull) != 0;
+                const bool poly_overflow = (ctx->h_counters[2] & 1ull) != 0;  // a clip polygon outgrew the 6-vertex slots
+                S = ctx->h_counters[6];
+                walk = ctx->h_counters[7], s_max = ctx->h_counters[8];
+                const uint64_t needB0 = compact ? 6ull * (max_cells + 2) + 21ull * s_max + 192 : 64;
+                if (compact && s_max >= 0xffffu) overflow = true;  // tile-local span ids are 16 bit
+                if (needB0 > kTileSmem) overflow = true;
+                if (overflow || poly_overflow) {  // redo the batch on the global-memory back end (and the wide clipper)
+                    Source s2 = src;
+                    s2.no_tile_mode = true;
+                    s2.wide_clip = src.wide_clip || poly_overflow;
+                    rcb_result_free(res);
+                    return run_pipeline(ctx, cfgs, ntiles, stage_mask, erode_radius, s2, out);
+                }
+                Kcap = compact ? 8ull * walk : 0;
+                res->S = S;
+                res->F = ctx->h_counters[1];
+                // what the next build of this batch may assume (BatchHint); K follows when the result is resolved
+                BatchHint nh;
+                nh.valid = true;
+                nh.ntris = ntris, nh.nverts = nverts, nh.stage_mask = stage_mask, nh.merge_thr = src.merge_thr;
+                nh.ub = ub, nh.nitems = nitems, nh.ub_max = ub_max, nh.S = S, nh.walk = walk, nh.s_max = s_max;
+                nh.K = (h.valid && h.S == S && h.walk == walk) ? h.K : 0;
+                entry->hint = nh;
             }
-            res->S = S;
-            res->F = ctx->h_counters[1];
+            const uint64_t needB = compact ? 6ull * (max_cells + 2) + 21ull * s_max + 192 : 64;
             make_layout(res->lay, ntiles, Ctot, S, stage_mask);
             CUB(pool_get(ctx->free_dev, res->lay.bytesA, false, res->devA));
             char* A = res->devA.p;
             TileInfo* d_tinfo = (TileInfo*)(A + res->lay.tinfo);
             CUB(cudaMemcpyAsync(d_tinfo, d_tinfo_tmp, sizeof(TileInfo) * (size_t)ntiles, cudaMemcpyDeviceToDevice, st));
-            const uint64_t Kcap = compact ? 8ull * walk : 0;
-            make_layout_conn(res->lay, Kcap);
+            make_layout_conn(res->lay, Kcap, res->slim);
             if (compact) CUB(pool_get(ctx->free_dev, res->lay.bytesB, false, res->devB));
             char* B = res->devB.p;
             TileCompactArgs tc{};
@@ -871,12 +1038,13 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                 tc.conn_dir = (uint8_t*)(B + res->lay.conn_dir);
                 tc.conn_next = (uint32_t*)(B + res->lay.conn_next);
             }
+            tc.Kcap = Kcap;
             tc.do_compact = compact;
             tc.do_erode = (stage_mask & RCB_STAGE_ERODE) != 0;
             tc.do_dist = (stage_mask & RCB_STAGE_DIST) != 0;
             tc.erode_radius = erode_radius;
             tc.phase = ctx->phase_timers ? r2.counters + 16 : nullptr;
-            tc.smem_bytes = (uint32_t)needB;
+            tc.smem_bytes = (uint32_t)std::min<uint64_t>(needB, kTileSmem);
             launch_tile_compact(tc, ntiles, st);
             if (ctx->phase_timers) {
                 unsigned long long ph[32];
@@ -892,7 +1060,13 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             }
             res->tile_mode = true;
             res->Kcap = Kcap;
+            res->redo_erode = erode_radius;
             CUB(cudaGetLastError());
+            // the batch's counters follow the work into a pinned slot; nobody waits here (resolve_result does, later)
+            {
+                const int r = post_counters(ctx, res, spec);
+                if (r) return bail(r);
+            }
             if (stage_mask & RCB_STAGE_REGIONS) {
                 const int r = build_regions_stage(ctx, res, d_tiles, ntiles, S);
                 if (r) return bail(r);
@@ -913,12 +1087,12 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             gex.resize(Ctot + 1);
             uint64_t pos = 0;
             for (int i = 0; i < ntiles; ++i) {
-                const uint64_t C = (uint64_t)res->tiles[i].width * res->tiles[i].height;
+                const uint64_t C = (uint64_t)tiles[i].width * tiles[i].height;
                 const uint32_t* co = src.cell_offset + pos;
                 if (co[0] != 0) return bail(fail(ctx, RCB_EARG, "tile %d: cell_offset[0] != 0", i));
                 for (uint64_t c = 0; c < C; ++c) {
                     if (co[c + 1] < co[c]) return bail(fail(ctx, RCB_EARG, "tile %d: cell_offset not ascending", i));
-                    gex[res->tiles[i].cell_base + c] = (uint32_t)(Sex + co[c]);
+                    gex[tiles[i].cell_base + c] = (uint32_t)(Sex + co[c]);
                 }
                 Sex += co[C];
                 pos += C + 1;
@@ -1039,12 +1213,12 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             goff.resize(Ctot + 1);
             uint64_t sbase = 0, pos = 0;
             for (int i = 0; i < ntiles; ++i) {
-                const uint64_t C = (uint64_t)res->tiles[i].width * res->tiles[i].height;
+                const uint64_t C = (uint64_t)tiles[i].width * tiles[i].height;
                 const uint32_t* co = src.cell_offset + pos;
                 if (co[0] != 0) return bail(fail(ctx, RCB_EARG, "tile %d: cell_offset[0] != 0", i));
                 for (uint64_t c = 0; c < C; ++c) {
                     if (co[c + 1] < co[c]) return bail(fail(ctx, RCB_EARG, "tile %d: cell_offset not ascending", i));
-                    goff[res->tiles[i].cell_base + c] = (uint32_t)(sbase + co[c]);
+                    goff[tiles[i].cell_base + c] = (uint32_t)(sbase + co[c]);
                 }
                 sbase += co[C];
                 pos += C + 1;
@@ -1096,11 +1270,11 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         std::vector<uint32_t> goff(Ctot + 1);
         uint64_t sbase = 0, pos = 0;
         for (int i = 0; i < ntiles; ++i) {
-            const uint64_t C = (uint64_t)res->tiles[i].width * res->tiles[i].height;
+            const uint64_t C = (uint64_t)tiles[i].width * tiles[i].height;
             const uint32_t* co = src.cell_offset + pos;
             for (uint64_t c = 0; c < C; ++c) {
                 if (co[c + 1] < co[c]) return bail(fail(ctx, RCB_EARG, "tile %d: cell_offset not ascending", i));
-                goff[res->tiles[i].cell_base + c] = (uint32_t)(sbase + co[c]);
+                goff[tiles[i].cell_base + c] = (uint32_t)(sbase + co[c]);
             }
             if (co[0] != 0) return bail(fail(ctx, RCB_EARG, "tile %d: cell_offset[0] != 0", i));
             sbase += co[C];
@@ -1138,8 +1312,121 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
 #undef CUB
 }
 
+constexpr int kSlots = 256;     // results whose counters may be in flight at once
+constexpr int kSlotWords = 16;  // unsigned long long per slot
+
+// The batch's device counters follow the kernels into a pinned slot of their own, with an event behind them.  Nobody
+// waits here: resolve_result does when the host first needs a number.
+int post_counters(rcb_ctx* ctx, rcb_result* res, bool spec) {
+    if (ctx->free_slots.empty()) {  // more results in flight than slots: wait for this one now
+        CU(cudaMemcpyAsync(ctx->h_counters + 16, ctx->d_counters.p, kSlotWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        res->slot = -2;  // values are in h_counters + 16 right now
+        res->pending = true;
+        res->spec = spec;
+        return resolve_result(res);
+    }
+    res->slot = ctx->free_slots.back();
+    ctx->free_slots.pop_back();
+    CU(cudaMemcpyAsync(ctx->h_slots + (size_t)res->slot * kSlotWords, ctx->d_counters.p, kSlotWords * sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    if (!res->done) CU(cudaEventCreateWithFlags(&res->done, cudaEventDisableTiming));
+    CU(cudaEventRecord(res->done, ctx->stream));
+    res->pending = true;
+    res->spec = spec;
+    if (spec) ctx->spec_runs++;
+    return RCB_OK;
+}
+
+void release_slot(rcb_result* res) {
+    if (res->slot >= 0 && res->ctx) res->ctx->free_slots.push_back(res->slot);
+    res->slot = -1;
+}
+
+// Takes over everything `from` holds (a rebuilt batch) and leaves it empty.
+void adopt_result(rcb_result* res, rcb_result* from) {
+    rcb_ctx* ctx = res->ctx;
+    pool_put(ctx->free_dev, res->devA, false);
+    pool_put(ctx->free_dev, res->devB, false);
+    pool_put(ctx->free_host, res->hostA, true);
+    pool_put(ctx->free_host, res->hostB, true);
+    res->Ctot = from->Ctot, res->S = from->S, res->K = from->K, res->F = from->F, res->ntris = from->ntris, res->nverts = from->nverts;
+    res->have_K = from->have_K;
+    res->lay = from->lay;
+    res->devA = from->devA, res->devB = from->devB, res->hostA = from->hostA, res->hostB = from->hostB;
+    from->devA = from->devB = from->hostA = from->hostB = Arena{};
+    res->downloaded = from->downloaded, res->have_tinfo = from->have_tinfo, res->tile_mode = from->tile_mode;
+    res->Kcap = from->Kcap;
+    res->tinfo.swap(from->tinfo);
+    res->entry = from->entry;
+    res->slim_ref16 = from->slim_ref16, res->slim_host = from->slim_host, res->slim_packed = from->slim_packed;
+    res->pending = false;
+    res->spec = false;
+}
+
+// First host use of a result whose counters are still in flight: wait for them; a speculative batch whose sizes
+// turned out too small (any flag raised on the device) is rebuilt here the synchronous way, in place.
+int resolve_result(rcb_result* res) {
+    if (!res->pending) return res->failed;
+    rcb_ctx* ctx = res->ctx;
+    const unsigned long long* c = ctx->h_counters + 16;
+    if (res->slot >= 0) {
+        CU(cudaEventSynchronize(res->done));
+        c = ctx->h_slots + (size_t)res->slot * kSlotWords;
+    }
+    const unsigned long long flags = c[2];
+    res->pending = false;
+    if (!res->spec || flags == 0) {
+        res->S = c[6], res->F = c[1], res->K = c[9];
+        res->have_K = true;
+        if (res->entry && res->entry->hint.valid && res->entry->hint.stage_mask == res->stage_mask) {
+            BatchHint& h = res->entry->hint;  // what the next build of this batch may assume
+            if (res->spec) {
+                h.ub = c[0], h.nitems = c[4], h.S = c[6], h.walk = c[7];
+                h.ub_max = std::max<uint64_t>(h.ub_max, c[5]);
+                h.s_max = std::max<uint64_t>(h.s_max, c[8]);
+                h.K = c[9];
+            } else if (h.S == c[6] && h.walk == c[7]) {
+                h.K = c[9];
+            }
+        }
+        release_slot(res);
+        return RCB_OK;
+    }
+    release_slot(res);
+    ctx->spec_fallbacks++;
+    if (res->entry) res->entry->hint.valid = false;
+    Source s;
+    s.raster = true;
+    s.merge_thr = 1;  // lib.rs:273
+    s.no_spec = true;
+    s.wide_clip = (flags & 1ull) != 0;
+    s.no_tile_mode = s.wide_clip;
+    rcb_result* again = nullptr;
+    const std::shared_ptr<BatchEntry> entry = res->entry;
+    const int r = run_pipeline(ctx, entry->cfgs.data(), res->ntiles, res->stage_mask, res->redo_erode, s, &again);
+    if (r) {
+        res->failed = r;
+        return r;
+    }
+    int r2 = resolve_result(again);
+    if (r2) {
+        rcb_result_free(again);
+        res->failed = r2;
+        return r2;
+    }
+    release_slot(again);
+    adopt_result(res, again);
+    rcb_result_free(again);
+    return RCB_OK;
+}
+
 int fetch_tinfo(rcb_result* res, cudaStream_t on, bool use_on) {
     rcb_ctx* ctx = res->ctx;
+    {
+        const int r = resolve_result(res);
+        if (r) return r;
+    }
     if (res->have_tinfo) return RCB_OK;
     const cudaStream_t st = use_on ? on : ctx->stream;
     res->tinfo.resize(res->ntiles);
@@ -1149,7 +1436,7 @@ int fetch_tinfo(rcb_result* res, cudaStream_t on, bool use_on) {
         CU(cudaStreamSynchronize(st));
     }
     res->have_tinfo = true;
-    if (res->tile_mode) {
+    if (res->tile_mode && !res->have_K) {
         uint64_t k = 0;
         for (auto& t : res->tinfo) k += t.conn_count;
         res->K = k;
@@ -1172,16 +1459,18 @@ int rcb_create(int device, rcb_ctx** out) {
     auto* ctx = new rcb_ctx();
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMallocHost((void**)&ctx->h_counters, 32 * sizeof(unsigned long long)) != cudaSuccess) {
+        cudaMallocHost((void**)&ctx->h_counters, 32 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMallocHost((void**)&ctx->h_slots, (size_t)kSlots * kSlotWords * sizeof(unsigned long long)) != cudaSuccess) {
         delete ctx;
         return RCB_ECUDA;
     }
+    for (int i = kSlots - 1; i >= 0; --i) ctx->free_slots.push_back(i);
     ctx->stream = ctx->own_stream;
-    ctx->launches0 = g_rcb_launches;
     if (const char* e = getenv("RCB_FORCE_V1")) ctx->force_v1 = e[0] == '1';
     if (const char* e = getenv("RCB_FORCE_GLOBAL")) ctx->force_global = e[0] == '1';
     if (const char* e = getenv("RCB_PHASE_TIMERS")) ctx->phase_timers = e[0] == '1';
     if (const char* e = getenv("RCB_CLIP_FLAGS")) ctx->clip_flags = (uint32_t)atoi(e);
+    if (const char* e = getenv("RCB_NO_SPEC")) ctx->no_spec = e[0] == '1';
     *out = ctx;
     return RCB_OK;
 }
@@ -1190,6 +1479,18 @@ void rcb_destroy(rcb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    // results the caller still holds: their arenas go with the context, the handles stay valid for rcb_result_free only
+    for (rcb_result* r : ctx->live) {
+        for (Arena* a : {&r->devA, &r->devB})
+            if (a->p) cudaFree(a->p), *a = Arena{};
+        for (Arena* a : {&r->hostA, &r->hostB})
+            if (a->p) cudaFreeHost(a->p), *a = Arena{};
+        if (r->done) cudaEventDestroy(r->done), r->done = nullptr;
+        r->entry.reset();
+        r->ctx = nullptr;
+    }
+    ctx->live.clear();
+    ctx->batch_cache.clear();
     DevBuf* bufs[] = {&ctx->d_verts, &ctx->d_tris, &ctx->d_tri_areas, &ctx->d_tiles, &ctx->d_bin_off, &ctx->d_bin_tiles,
                       &ctx->d_counters, &ctx->d_cell_cnt, &ctx->d_frag_off, &ctx->d_frag_tmp, &ctx->d_frag_rec, &ctx->d_fs_mm,
                       &ctx->d_fs_area, &ctx->d_scan_tmp, &ctx->d_hf_off, &ctx->d_conn_cnt, &ctx->d_conn_off, &ctx->d_nid,
@@ -1202,6 +1503,7 @@ void rcb_destroy(rcb_ctx* ctx) {
     for (auto& a : ctx->free_host) cudaFreeHost(a.p);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
     prof_collect(ctx);
     for (auto e : ctx->prof_free) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1245,7 +1547,14 @@ int rcb_profile_reset(rcb_ctx* ctx) {
     return RCB_OK;
 }
 
-uint64_t rcb_launch_count(const rcb_ctx* ctx) { return ctx ? g_rcb_launches - ctx->launches0 : 0; }
+uint64_t rcb_launch_count(const rcb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+/* out[0] batches issued speculatively, out[1] of those rebuilt because a size was short, out[2] cached batch entries */
+int rcb_ctx_stats(const rcb_ctx* ctx, uint64_t out[4]) {
+    if (!ctx || !out) return RCB_EARG;
+    out[0] = ctx->spec_runs, out[1] = ctx->spec_fallbacks, out[2] = ctx->batch_cache.size(), out[3] = 0;
+    return RCB_OK;
+}
 
 // config.rs:53-76
 void rcb_config_default(rcb_config* c) {
@@ -1292,6 +1601,25 @@ int rcb_config_validate(const rcb_config* c) {
     return RCB_OK;
 }
 
+// lib.rs:224-233: the reference fails the build at the first triangle with an index >= vertices.len()/3.  The indices are
+// looked at once, here, when the mesh is set (the builds then start without a host round trip for this check); a build over
+// a mesh with a bad index fails with RCB_ENAVMESH_GEN before anything is rasterized, which is what the reference's caller sees.
+static int check_mesh_indices(rcb_ctx* ctx) {
+    ctx->mesh_bad = false;
+    ctx->h_counters[31] = 0;
+    if (ctx->nidx && ctx->nfloats) {
+        CU(ctx->d_counters.ensure(48 * sizeof(unsigned long long)));
+        unsigned long long* flag = ctx->d_counters.as<unsigned long long>() + 47;
+        CU(cudaMemsetAsync(flag, 0, sizeof(unsigned long long), ctx->stream));
+        launch_check_indices(ctx->tris, ctx->nidx - ctx->nidx % 3, (uint32_t)std::min<size_t>(ctx->nfloats / 3, 0x7fffffffu), flag, ctx->stream);
+        CU(cudaMemcpyAsync(&ctx->h_counters[31], flag, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    ctx->mesh_bad = ctx->h_counters[31] != 0;
+    return RCB_OK;
+}
+
 int rcb_upload_mesh(rcb_ctx* ctx, const float* verts, size_t nfloats, const int32_t* tris, size_t nidx) {
     if (!ctx || (nfloats && !verts) || (nidx && !tris)) return fail(ctx, RCB_EARG, "null mesh pointer");
     CU(cudaSetDevice(ctx->device));
@@ -1299,12 +1627,11 @@ int rcb_upload_mesh(rcb_ctx* ctx, const float* verts, size_t nfloats, const int3
     CU(ctx->d_tris.ensure(4 * nidx + 16));
     if (nfloats) CU(cudaMemcpyAsync(ctx->d_verts.p, verts, 4 * nfloats, cudaMemcpyHostToDevice, ctx->stream));
     if (nidx) CU(cudaMemcpyAsync(ctx->d_tris.p, tris, 4 * nidx, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));  // the caller's buffers are only borrowed for this call
     ctx->verts = ctx->d_verts.as<float>();
     ctx->tris = ctx->d_tris.as<int32_t>();
     ctx->nfloats = nfloats;
     ctx->nidx = nidx;
-    return RCB_OK;
+    return check_mesh_indices(ctx);  // synchronizes: the caller's buffers are only borrowed for this call
 }
 
 int rcb_set_mesh_device(rcb_ctx* ctx, const void* d_verts, size_t nfloats, const void* d_tris, size_t nidx) {
@@ -1313,7 +1640,8 @@ int rcb_set_mesh_device(rcb_ctx* ctx, const void* d_verts, size_t nfloats, const
     ctx->tris = (const int32_t*)d_tris;
     ctx->nfloats = nfloats;
     ctx->nidx = nidx;
-    return RCB_OK;
+    CU(cudaSetDevice(ctx->device));
+    return check_mesh_indices(ctx);
 }
 
 int rcb_build_tiles(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stage_mask, int erode_radius,
@@ -1326,6 +1654,8 @@ int rcb_build_tiles(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t s
 }
 
 static int download_on(rcb_result* res, cudaStream_t st, bool wait);
+static int finish_download(rcb_result* res, cudaStream_t st);
+static uint64_t download_bytes(const rcb_result* res);
 
 int rcb_rasterize_onto(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const uint32_t* cell_offset, const int16_t* span_min,
                        const int16_t* span_max, const uint8_t* span_area, const uint8_t* tri_areas, int32_t flag_merge_threshold,
@@ -1358,6 +1688,7 @@ int rcb_build_tiles_streamed(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, u
     res->ctx = ctx;
     res->ntiles = ntiles;
     res->stage_mask = stage_mask;
+    ctx->live.push_back(res);
     std::vector<cudaEvent_t> done;
     auto cleanup = [&](int code) {
         cudaStreamSynchronize(ctx->copy_stream);
@@ -1368,8 +1699,8 @@ int rcb_build_tiles_streamed(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, u
         }
         return code;
     };
-    // Group g computes on the context's stream while the copy stream drains group g-1 (a group is complete on the
-    // device by the time the next group's pipeline has passed its first host synchronization).
+    // Group g computes on the context's stream while the copy stream drains group g-1.  When the groups are issued
+    // speculatively (BatchHint) the host never waits inside the loop: every group's kernels and copies are simply queued.
     for (int g = 0; g < ngroups; ++g) {
         const int first = (int)((long long)ntiles * g / ngroups), last = (int)((long long)ntiles * (g + 1) / ngroups);
         rcb_result* child = nullptr;
@@ -1381,28 +1712,14 @@ int rcb_build_tiles_streamed(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, u
         if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(e, ctx->stream) != cudaSuccess)
             return cleanup(fail(ctx, RCB_ECUDA, "CUDA event failure"));
         done.push_back(e);
-        if (g > 0) {
-            if (cudaStreamWaitEvent(ctx->copy_stream, done[g - 1], 0) != cudaSuccess) return cleanup(fail(ctx, RCB_ECUDA, "cudaStreamWaitEvent"));
-            r = download_on(res->children[g - 1], ctx->copy_stream, false);
-            if (r) return cleanup(r);
-        }
-    }
-    if (!res->children.empty()) {
-        if (cudaStreamWaitEvent(ctx->copy_stream, done.back(), 0) != cudaSuccess) return cleanup(fail(ctx, RCB_ECUDA, "cudaStreamWaitEvent"));
-        int r = download_on(res->children.back(), ctx->copy_stream, false);
+        if (cudaStreamWaitEvent(ctx->copy_stream, e, 0) != cudaSuccess) return cleanup(fail(ctx, RCB_ECUDA, "cudaStreamWaitEvent"));
+        r = download_on(child, ctx->copy_stream, false);
         if (r) return cleanup(r);
     }
     if (cudaStreamSynchronize(ctx->copy_stream) != cudaSuccess) return cleanup(fail(ctx, RCB_ECUDA, "copy stream failed"));
     for (auto* c : res->children) {
-        c->tinfo.assign((TileInfo*)(c->hostA.p + c->lay.tinfo), (TileInfo*)(c->hostA.p + c->lay.tinfo) + c->ntiles);
-        c->have_tinfo = true;
-        if (c->tile_mode && !c->have_K) {
-            uint64_t k = 0;
-            for (auto& t : c->tinfo) k += t.conn_count;
-            c->K = k, c->have_K = true;
-        }
-        c->downloaded = true;
-        res->Ctot += c->Ctot, res->S += c->S;
+        const int r = finish_download(c, ctx->copy_stream);
+        if (r) return cleanup(r);
     }
     res->Ctot = 0, res->S = 0;  // sizes live in the children (rcb_result_span_data_size sums them)
     res->downloaded = true;
@@ -1526,19 +1843,19 @@ int rcb_result_serialize_spans(rcb_result* res, int format, uint8_t* out, uint64
     int r = fetch_tinfo(res);
     if (r) return r;
     if (tile_offsets) {
-        for (int i = 0; i < res->ntiles; ++i) tile_offsets[i] = 2ull * res->tiles[i].cell_base + 12ull * res->tinfo[i].span_base;
+        for (int i = 0; i < res->ntiles; ++i) tile_offsets[i] = 2ull * res->tiles()[i].cell_base + 12ull * res->tinfo[i].span_base;
         tile_offsets[res->ntiles] = total;
     }
     if (total == 0) return RCB_OK;
     CU(ctx->d_wire.ensure(total + 64));
     TileMap tm{(uint32_t)res->ntiles, 0, 0};
     uint32_t max_cells = 0;
-    for (auto& t : res->tiles) max_cells = std::max(max_cells, (uint32_t)(t.width * t.height));
+    for (auto& t : res->tiles()) max_cells = std::max(max_cells, (uint32_t)(t.width * t.height));
     tm.blocks_per_tile = (max_cells + 255) / 256;
     tm.nblocks = tm.blocks_per_tile * tm.ntiles;
     // the tile table of this result may no longer be the one in ctx->d_tiles
     CU(ctx->d_tiles.ensure(sizeof(TileDesc) * (size_t)res->ntiles + 64));
-    CU(cudaMemcpyAsync(ctx->d_tiles.p, res->tiles.data(), sizeof(TileDesc) * (size_t)res->ntiles, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_tiles.p, res->tiles().data(), sizeof(TileDesc) * (size_t)res->ntiles, cudaMemcpyHostToDevice, st));
     const char* A = res->devA.p;
     launch_wire_serialize(ctx->d_tiles.as<TileDesc>(), tm, (const uint32_t*)(A + res->lay.hf_cell_offset),
                           (const TileInfo*)(A + res->lay.tinfo), (const int16_t*)(A + res->lay.span_min),
@@ -1612,7 +1929,7 @@ int rcb_build_tilecache_layers(rcb_ctx* ctx, const rcb_tc_layer* layers, int nla
     res->ctx = ctx;
     res->ntiles = nlayers;
     res->stage_mask = stage_mask;
-    res->tiles.resize(nlayers);
+    res->own_tiles.resize(nlayers);
     uint64_t Ctot = 0;
     uint32_t max_cells = 0;
     auto bail = [&](int code) {
@@ -1630,7 +1947,7 @@ int rcb_build_tilecache_layers(rcb_ctx* ctx, const rcb_tc_layer* layers, int nla
             for (uint32_t c = 0; c < cells; ++c)
                 if (l.regons[c] != 0) return bail(fail(ctx, RCB_ENAVMESH_GEN, "Invalid span height: min (32767) > max (-32768)"));
         }
-        TileDesc& t = res->tiles[i];
+        TileDesc& t = res->own_tiles[i];
         memset(&t, 0, sizeof t);
         t.width = l.width;
         t.height = l.height;
@@ -1669,7 +1986,7 @@ int rcb_build_tilecache_layers(rcb_ctx* ctx, const rcb_tc_layer* layers, int nla
     {
         char* h = ctx->h_stage;
         size_t o = 0;
-        memcpy(h + o, res->tiles.data(), sizeof(TileDesc) * (size_t)nlayers);
+        memcpy(h + o, res->own_tiles.data(), sizeof(TileDesc) * (size_t)nlayers);
         if (nlayers) CUB(cudaMemcpyAsync(ctx->d_tiles.p, h + o, sizeof(TileDesc) * (size_t)nlayers, cudaMemcpyHostToDevice, st));
         o += align_up(sizeof(TileDesc) * (size_t)nlayers);
         char* hr = h + o;
@@ -1679,8 +1996,8 @@ int rcb_build_tilecache_layers(rcb_ctx* ctx, const rcb_tc_layer* layers, int nla
         for (int i = 0; i < nlayers; ++i) {
             const uint32_t cells = (uint32_t)layers[i].width * layers[i].height;
             if (!cells) continue;
-            memcpy(hr + res->tiles[i].cell_base, layers[i].regons, cells);
-            memcpy(ha + res->tiles[i].cell_base, layers[i].areas, cells);
+            memcpy(hr + res->own_tiles[i].cell_base, layers[i].regons, cells);
+            memcpy(ha + res->own_tiles[i].cell_base, layers[i].areas, cells);
         }
         if (Ctot) {
             CUB(cudaMemcpyAsync(ctx->d_tc_regons.p, hr, Ctot, cudaMemcpyHostToDevice, st));
@@ -1705,7 +2022,9 @@ int rcb_decompress_tiles(rcb_ctx* ctx, const uint8_t* blobs, const uint64_t* blo
         if (len >= 0xffff0000ull) return fail(ctx, RCB_EARG, "tile %d: blob of 4 GiB", i);
         const uint8_t* b = blobs + blob_offsets[i];
         const uint64_t size = len >= 4 ? ((uint64_t)b[0] | ((uint64_t)b[1] << 8) | ((uint64_t)b[2] << 16) | ((uint64_t)b[3] << 24)) : 0;
-        cap_off[i + 1] = cap_off[i] + size;
+        // an LZ4 block cannot produce more than 255 bytes per input byte: a larger size prefix only means a short output
+        // (lz4_flex allocates the prefix; here the allocation is device memory that stays with the context)
+        cap_off[i + 1] = cap_off[i] + std::min<uint64_t>(size, 255ull * len + 1024);
     }
     const uint64_t total_cap = cap_off[n];
     if (total_cap > (8ull << 30)) return fail(ctx, RCB_EARG, "size prefixes add up to %llu bytes", (unsigned long long)total_cap);
@@ -1758,7 +2077,8 @@ int rcb_build_tilecache_compressed(rcb_ctx* ctx, const uint8_t* blobs, const uin
         if (len >= 0xffff0000ull) return fail(ctx, RCB_EARG, "layer %d: blob of 4 GiB", i);
         const uint8_t* b = blobs + blob_offsets[i];
         const uint64_t size = len >= 4 ? ((uint64_t)b[0] | ((uint64_t)b[1] << 8) | ((uint64_t)b[2] << 16) | ((uint64_t)b[3] << 24)) : 0;
-        cap_off[i + 1] = cap_off[i] + size;  // exact: the decoder refuses to write past the size prefix
+        cap_off[i + 1] = cap_off[i] + std::min<uint64_t>(size, 255ull * len + 1024);  // the decoder refuses to write past it (255 B of
+                                                                                       // output per input byte is LZ4's ceiling)
         if (first_obstacle && obstacle_count && (uint64_t)first_obstacle[i] + obstacle_count[i] > (uint64_t)nobstacles)
             return fail(ctx, RCB_EARG, "layer %d: obstacle range", i);
     }
@@ -1802,12 +2122,12 @@ int rcb_build_tilecache_compressed(rcb_ctx* ctx, const uint8_t* blobs, const uin
     res->ctx = ctx;
     res->ntiles = nlayers;
     res->stage_mask = stage_mask;
-    res->tiles.resize(nlayers);
+    res->own_tiles.resize(nlayers);
     uint64_t Ctot = 0;
     uint32_t max_cells = 0;
     for (int i = 0; i < nlayers; ++i) {
         const RcbTcParsed& l = parsed[i];
-        TileDesc& t = res->tiles[i];
+        TileDesc& t = res->own_tiles[i];
         memset(&t, 0, sizeof t);
         t.width = (int32_t)l.width;
         t.height = (int32_t)l.height;
@@ -1844,7 +2164,7 @@ int rcb_build_tilecache_compressed(rcb_ctx* ctx, const uint8_t* blobs, const uin
         return bail(fail(ctx, RCB_ECUDA, "CUDA error %s (tile-cache buffers)", cudaGetErrorString(e)));
     {
         char* h = ctx->h_stage;
-        memcpy(h, res->tiles.data(), sizeof(TileDesc) * (size_t)nlayers);
+        memcpy(h, res->own_tiles.data(), sizeof(TileDesc) * (size_t)nlayers);
         if (nlayers && !ok(cudaMemcpyAsync(ctx->d_tiles.p, h, sizeof(TileDesc) * (size_t)nlayers, cudaMemcpyHostToDevice, st)))
             return bail(fail(ctx, RCB_ECUDA, "CUDA error %s (tile table)", cudaGetErrorString(e)));
         if (nobstacles) {
@@ -1887,6 +2207,7 @@ int rcb_apply_area_ops(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const u
 int rcb_result_totals(const rcb_result* cres, rcb_totals* out) {
     auto* res = const_cast<rcb_result*>(cres);
     if (!res || !out) return RCB_EARG;
+    if (!res->ctx) return RCB_EARG;  // the context is gone (rcb_destroy): only rcb_result_free is left
     if (!res->children.empty()) {
         memset(out, 0, sizeof *out);
         for (auto* c : res->children) {
@@ -1910,44 +2231,129 @@ int rcb_result_totals(const rcb_result* cres, rcb_totals* out) {
     out->spans = res->S;
     out->connections = res->K;
     for (auto& t : res->tinfo) out->walkable_spans += t.walkable_span_count;
-    out->result_bytes = res->lay.bytesA + (res->tile_mode ? 9 * res->K : res->lay.bytesB);
+    out->result_bytes = res->copied_bytes ? res->copied_bytes : download_bytes(res);
     return RCB_OK;
 }
 
-// D2H of one result's arenas on `st`; with wait == false the copies are left in flight (the caller synchronizes
-// `st` before anything reads the host arenas).
+// Bytes a download of this result moves (what rcb_totals.result_bytes reports before the download has happened).
+static uint64_t download_bytes(const rcb_result* res) {
+    const ArenaLayout& l = res->lay;
+    if (res->slim) return l.slimA + l.slimB;
+    if (res->tile_mode && res->have_K && res->lay.bytesB) return l.bytesA + 9 * res->K;
+    return l.bytesA + l.bytesB;
+}
+
+// Slim layout: conn_mask / conn_ref16 are derived on the device from the full arrays right before the first download.
+static int slim_pack(rcb_result* res, cudaStream_t st) {
+    rcb_ctx* ctx = res->ctx;
+    if (!res->slim || res->slim_packed) return RCB_OK;
+    res->slim_packed = true;
+    if (res->ntiles == 0 || !res->lay.bytesB) return RCB_OK;
+    char* A = res->devA.p;
+    char* B = res->devB.p;
+    CU(ctx->d_wire_err.ensure(64));
+    if (!res->slim_flag) CU(cudaMallocHost((void**)&res->slim_flag, sizeof(unsigned long long)));
+    *res->slim_flag = 0;
+    CU(cudaMemsetAsync(ctx->d_wire_err.p, 0, 8, st));
+    launch_slim_pack((const TileInfo*)(A + res->lay.tinfo), res->ntiles, res->entry ? res->entry->max_cells : 4096u,
+                     (const uint32_t*)(A + res->lay.first_conn), (const uint32_t*)(B + res->lay.conn_ref),
+                     (const uint8_t*)(B + res->lay.conn_dir), (const uint32_t*)(B + res->lay.conn_next), (uint8_t*)(A + res->lay.conn_mask),
+                     (uint16_t*)(B + res->lay.conn_ref16), ctx->d_wire_err.as<unsigned long long>(), st);
+    CU(cudaMemcpyAsync(res->slim_flag, ctx->d_wire_err.p, 8, cudaMemcpyDeviceToHost, st));
+    return RCB_OK;
+}
+
+// D2H of one result's arenas on `st`.  A result that is still pending is copied by its CAPACITIES (the layout was made for
+// Scap spans / Kcap connections, tight bounds of a speculative batch), so nothing waits for the device here; with
+// wait == false the copies are left in flight and finish_download completes the bookkeeping once `st` has been synchronized.
 static int download_on(rcb_result* res, cudaStream_t st, bool wait) {
     rcb_ctx* ctx = res->ctx;
     if (res->downloaded) return RCB_OK;
-    CU(pool_get(ctx->free_host, res->lay.bytesA, true, res->hostA));
-    if (res->lay.bytesB) {
-        CU(pool_get(ctx->free_host, res->lay.bytesB, true, res->hostB));
-        if (res->tile_mode) {  // the arena is sized by a bound on K: copy the used prefix of each array
-            int r = fetch_tinfo(res, st, true);
-            if (r) return r;
-            const size_t K = res->K;
-            if (K) {
-                CU(cudaMemcpyAsync(res->hostB.p + res->lay.conn_ref, res->devB.p + res->lay.conn_ref, 4 * K, cudaMemcpyDeviceToHost, st));
-                CU(cudaMemcpyAsync(res->hostB.p + res->lay.conn_next, res->devB.p + res->lay.conn_next, 4 * K, cudaMemcpyDeviceToHost, st));
-                CU(cudaMemcpyAsync(res->hostB.p + res->lay.conn_dir, res->devB.p + res->lay.conn_dir, K, cudaMemcpyDeviceToHost, st));
+    ProfInstall prof_install(ctx);
+    const bool on_own = st == ctx->stream;
+    if (!(res->pending && res->spec)) {  // sizes are known (or cheap to know): copy exactly what exists
+        int r = on_own ? fetch_tinfo(res) : fetch_tinfo(res, st, true);
+        if (r) return r;
+    }
+    if (res->slim) {
+        int r = slim_pack(res, st);
+        if (r) return r;
+    }
+    const ArenaLayout& l = res->lay;
+    CU(pool_get(ctx->free_host, res->slim ? l.slimA : l.bytesA, true, res->hostA));
+    uint64_t copied = 0;
+    if (l.bytesB) {
+        if (res->slim) {
+            if (l.slimB) {
+                CU(pool_get(ctx->free_host, l.bytesB, true, res->hostB));  // room for conn_ref should 16 bits not do
+                CU(cudaMemcpyAsync(res->hostB.p, res->devB.p, l.slimB, cudaMemcpyDeviceToHost, st));
+                copied += l.slimB;
             }
         } else {
-            CU(cudaMemcpyAsync(res->hostB.p, res->devB.p, res->lay.bytesB, cudaMemcpyDeviceToHost, st));
+            CU(pool_get(ctx->free_host, l.bytesB, true, res->hostB));
+            if (res->tile_mode && !res->pending) {  // the arena is sized by a bound on K: copy the used prefix of each array
+                const size_t K = res->K;
+                if (K) {
+                    CU(cudaMemcpyAsync(res->hostB.p + l.conn_ref, res->devB.p + l.conn_ref, 4 * K, cudaMemcpyDeviceToHost, st));
+                    CU(cudaMemcpyAsync(res->hostB.p + l.conn_next, res->devB.p + l.conn_next, 4 * K, cudaMemcpyDeviceToHost, st));
+                    CU(cudaMemcpyAsync(res->hostB.p + l.conn_dir, res->devB.p + l.conn_dir, K, cudaMemcpyDeviceToHost, st));
+                    copied += 9 * K;
+                }
+            } else {
+                CU(cudaMemcpyAsync(res->hostB.p, res->devB.p, l.bytesB, cudaMemcpyDeviceToHost, st));
+                copied += l.bytesB;
+            }
         }
     }
-    CU(cudaMemcpyAsync(res->hostA.p, res->devA.p, res->lay.bytesA, cudaMemcpyDeviceToHost, st));
+    const size_t nA = res->slim ? l.slimA : l.bytesA;
+    CU(cudaMemcpyAsync(res->hostA.p, res->devA.p, nA, cudaMemcpyDeviceToHost, st));
+    copied += nA;
+    res->copied_bytes = copied;
+    res->copy_in_flight = true;
     if (wait) {
         CU(cudaStreamSynchronize(st));
-        res->tinfo.assign((TileInfo*)(res->hostA.p + res->lay.tinfo), (TileInfo*)(res->hostA.p + res->lay.tinfo) + res->ntiles);
-        res->have_tinfo = true;
-        res->downloaded = true;
+        return finish_download(res, st);
     }
+    return RCB_OK;
+}
+
+// After the copies of download_on have completed: host-side bookkeeping; a speculative batch that failed on the device
+// is rebuilt (resolve_result) and downloaded again, synchronously.
+static int finish_download(rcb_result* res, cudaStream_t st) {
+    rcb_ctx* ctx = res->ctx;
+    if (res->downloaded || !res->copy_in_flight) return RCB_OK;
+    res->copy_in_flight = false;
+    const bool was_spec = res->pending && res->spec;
+    int r = resolve_result(res);
+    if (r) return r;
+    if (was_spec && !res->hostA.p) {  // rebuilt: the arenas copied above are gone
+        res->copied_bytes = 0;
+        return download_on(res, ctx->stream, true);
+    }
+    if (res->slim && res->lay.slimB) {
+        res->slim_ref16 = res->slim_flag && *res->slim_flag == 0;
+        if (!res->slim_ref16 && res->K) {  // a tile with 65536+ spans: its span references need the 32-bit array after all
+            CU(cudaMemcpyAsync(res->hostB.p + res->lay.conn_ref, res->devB.p + res->lay.conn_ref, 4 * res->K, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            res->copied_bytes += 4 * res->K;
+        }
+    }
+    res->slim_host = res->slim;
+    res->tinfo.assign((TileInfo*)(res->hostA.p + res->lay.tinfo), (TileInfo*)(res->hostA.p + res->lay.tinfo) + res->ntiles);
+    res->have_tinfo = true;
+    if (res->tile_mode && !res->have_K) {
+        uint64_t k = 0;
+        for (auto& t : res->tinfo) k += t.conn_count;
+        res->K = k, res->have_K = true;
+    }
+    res->downloaded = true;
     return RCB_OK;
 }
 
 int rcb_result_download(rcb_result* res) {
     if (!res) return RCB_EARG;
     rcb_ctx* ctx = res->ctx;
+    if (!ctx) return RCB_EARG;
     if (res->downloaded) return RCB_OK;
     CU(cudaSetDevice(ctx->device));
     if (!res->children.empty()) {
@@ -1961,10 +2367,11 @@ int rcb_result_download(rcb_result* res) {
     return download_on(res, ctx->stream, true);
 }
 
-static int fill_view(const rcb_result* res, int tile, rcb_tile_view* v, const char* A, const char* B) {
-    const TileDesc& td = res->tiles[tile];
+static int fill_view(const rcb_result* res, int tile, rcb_tile_view* v, const char* A, const char* B, bool host) {
+    const TileDesc& td = res->tiles()[tile];
     const TileInfo& ti = res->tinfo[tile];
     const ArenaLayout& l = res->lay;
+    const bool slim = host && res->slim_host;  // the host copy of a slim result lacks what the host can rebuild
     memset(v, 0, sizeof *v);
     v->width = td.width;
     v->height = td.height;
@@ -1975,7 +2382,7 @@ static int fill_view(const rcb_result* res, int tile, rcb_tile_view* v, const ch
     v->max_height = (uint16_t)ti.max_height;
     v->max_distance = (uint16_t)ti.max_distance;
     v->status = ti.status;
-    v->hf_cell_offset = (const uint32_t*)(A + l.hf_cell_offset) + td.cell_base + tile;
+    if (!slim) v->hf_cell_offset = (const uint32_t*)(A + l.hf_cell_offset) + td.cell_base + tile;
     v->span_min = (const int16_t*)(A + l.span_min) + ti.span_base;
     v->span_max = (const int16_t*)(A + l.span_max) + ti.span_base;
     v->span_area = (const uint8_t*)(A + l.span_area) + ti.span_base;
@@ -1984,11 +2391,20 @@ static int fill_view(const rcb_result* res, int tile, rcb_tile_view* v, const ch
         v->cell_count_arr = (const uint32_t*)(A + l.cell_count) + td.cell_base;
         v->areas = (const uint8_t*)(A + l.areas) + ti.span_base;
         v->con = (const uint16_t*)(A + l.con) + 4 * (size_t)ti.span_base;
-        v->first_conn = (const uint32_t*)(A + l.first_conn) + ti.span_base;
         v->dist = (const uint16_t*)(A + l.dist) + ti.span_base;
-        v->conn_ref = (const uint32_t*)(B + l.conn_ref) + ti.conn_base;
-        v->conn_dir = (const uint8_t*)(B + l.conn_dir) + ti.conn_base;
-        v->conn_next = (const uint32_t*)(B + l.conn_next) + ti.conn_base;
+        if (!slim) {
+            v->first_conn = (const uint32_t*)(A + l.first_conn) + ti.span_base;
+            v->conn_ref = (const uint32_t*)(B + l.conn_ref) + ti.conn_base;
+            v->conn_dir = (const uint8_t*)(B + l.conn_dir) + ti.conn_base;
+            v->conn_next = (const uint32_t*)(B + l.conn_next) + ti.conn_base;
+        }
+        if (res->slim && res->slim_packed) {
+            v->conn_mask = (const uint8_t*)(A + l.conn_mask) + ti.span_base;
+            if (!host || res->slim_ref16)
+                v->conn_ref16 = (const uint16_t*)(B + l.conn_ref16) + ti.conn_base;
+            else
+                v->conn_ref = (const uint32_t*)(B + l.conn_ref) + ti.conn_base;
+        }
         if (res->stage_mask & RCB_STAGE_REGIONS) {
             v->reg = (const uint16_t*)(A + l.reg) + ti.span_base;
             v->max_regions = ti.max_regions;
@@ -2009,8 +2425,9 @@ int rcb_result_tile(const rcb_result* res, int tile, rcb_tile_view* out) {
         const rcb_result* c = child_of(res, tile);
         return rcb_result_tile(c, tile, out);
     }
+    if (!res->ctx) return RCB_EARG;
     if (!res->downloaded) return fail(res->ctx, RCB_EARG, "rcb_result_tile: call rcb_result_download first");
-    return fill_view(res, tile, out, res->hostA.p, res->hostB.p);
+    return fill_view(res, tile, out, res->hostA.p, res->hostB.p, true);
 }
 
 int rcb_result_tile_device(const rcb_result* cres, int tile, rcb_tile_view* out) {
@@ -2020,10 +2437,10 @@ int rcb_result_tile_device(const rcb_result* cres, int tile, rcb_tile_view* out)
         return rcb_result_tile_device(c, tile, out);
     }
     auto* res = const_cast<rcb_result*>(cres);
-    if (!res || !out || tile < 0 || tile >= res->ntiles) return RCB_EARG;
+    if (!res || !out || tile < 0 || tile >= res->ntiles || !res->ctx) return RCB_EARG;
     int r = fetch_tinfo(res);
     if (r) return r;
-    return fill_view(res, tile, out, res->devA.p, res->devB.p);
+    return fill_view(res, tile, out, res->devA.p, res->devB.p, false);
 }
 
 void rcb_result_free(rcb_result* res) {
@@ -2032,12 +2449,22 @@ void rcb_result_free(rcb_result* res) {
     rcb_ctx* ctx = res->ctx;
     if (ctx) {
         cudaSetDevice(ctx->device);
+        for (size_t i = 0; i < ctx->live.size(); ++i)
+            if (ctx->live[i] == res) {
+                ctx->live[i] = ctx->live.back();
+                ctx->live.pop_back();
+                break;
+            }
+        if (res->copy_in_flight) cudaDeviceSynchronize();  // a host arena must not return to the pool under a running copy
+        release_slot(res);
+        if (res->done) cudaEventDestroy(res->done);
         // arenas go back to the pool; work that still reads them is ordered on the same stream
         pool_put(ctx->free_dev, res->devA, false);
         pool_put(ctx->free_dev, res->devB, false);
         pool_put(ctx->free_host, res->hostA, true);
         pool_put(ctx->free_host, res->hostB, true);
     }
+    if (res->slim_flag) cudaFreeHost(res->slim_flag);
     delete res;
 }
 

@@ -126,7 +126,13 @@ struct Raster2 {
     const uint32_t* tile_cap;  // [ntiles]
     uint32_t* tile_frags;      // 3 words per record: cell | area<<24, smin | smax<<16, triangle
     uint32_t flags;            // bit0: min-x skip test (0: explicit per-vertex test; kept for A/B runs)
+    uint32_t spec;             // 1: issued speculatively - the work-item count is read from counters[4] on the device
 };
+// counters[2] flag bits: 1 clip polygon overflow, 2 fragment pool overflow, 4 a tile does not fit shared memory,
+// 8 a speculative size was too small (every later kernel of the batch returns at once), 16 connection arena too small
+#define RCB_FLAG_ABORT 8ull
+#define RCB_FLAG_CONN 16ull
+void launch_check_indices(const int32_t* tris, size_t nidx, uint32_t nverts, unsigned long long* flag, cudaStream_t s);
 void launch_bin_count(const Raster2& rb, cudaStream_t s);
 void launch_fill_items(const Raster2& rb, const uint32_t* item_off, uint2* items, cudaStream_t s);
 void launch_clip_items(const Raster2& rb, const uint2* items, uint32_t nitems, TileInfo* tinfo, cudaStream_t s);
@@ -176,12 +182,19 @@ struct TileCompactArgs {
     uint32_t* conn_next;
     int do_compact, do_erode, do_dist, erode_radius;
     uint32_t smem_bytes;
+    unsigned long long Kcap;    // capacity of the connection arrays (a tile that would pass it sets RCB_FLAG_CONN)
     unsigned long long* phase;  // optional [16]: slots 8.. are this kernel's phases
 };
 void launch_tile_spans(const TileSpansArgs& a, int ntiles, cudaStream_t s);
-void launch_tile_segments(const uint32_t* tile_ub, uint32_t* tile_base, int ntiles, unsigned long long* counters, cudaStream_t s);
-void launch_tile_segments(const uint32_t* tile_ub, uint32_t* tile_base, int ntiles, unsigned long long* counters, cudaStream_t s);
-void launch_tile_scan(TileInfo* tinfo, int ntiles, unsigned long long* counters, cudaStream_t s);
+// cap_frags / cap_items: what the fragment and work-item buffers hold (~0: no check); beyond -> RCB_FLAG_ABORT
+void launch_tile_segments(const uint32_t* tile_ub, uint32_t* tile_base, int ntiles, unsigned long long* counters,
+                          unsigned long long cap_frags, unsigned long long cap_items, cudaStream_t s);
+// span_cap: what the result arena was laid out for (~0: no check); beyond -> RCB_FLAG_ABORT
+void launch_tile_scan(TileInfo* tinfo, int ntiles, unsigned long long* counters, unsigned long long span_cap, cudaStream_t s);
+// slim result layout: conn_mask[s] = the span's directions, conn_ref16[k] = (u16)conn_ref[k]; *flag |= 1 if a reference needs 17 bits
+void launch_slim_pack(const TileInfo* tinfo, int ntiles, uint32_t max_cells, const uint32_t* first_conn, const uint32_t* conn_ref,
+                      const uint8_t* conn_dir, const uint32_t* conn_next, uint8_t* conn_mask, uint16_t* conn_ref16,
+                      unsigned long long* flag, cudaStream_t s);
 void launch_tile_compact(const TileCompactArgs& a, int ntiles, cudaStream_t s);
 
 void launch_seg_scatter(const TileDesc* tiles, int ntiles, const uint32_t* tile_frags, const uint32_t* tile_base, const uint32_t* tile_cap,
@@ -332,16 +345,15 @@ void launch_tc_spans(const TileDesc* tiles, TileMap tm, const uint8_t* regons, c
 void launch_tc_obstacles(const TileDesc* tiles, int ntiles, const rcb_tc_obstacle* obs, const uint32_t* hf_off, const int16_t* smin,
                          const int16_t* smax, uint8_t* sarea, cudaStream_t s);
 
-// number of kernel launches issued through the launchers above since process start
-extern unsigned long long g_rcb_launches;
-
-// Per-kernel timing hook (rcb_profile_*): the pipeline installs a callback; every launcher brackets
-// each kernel with a KScope so device time is attributed per kernel name.
+// Per-kernel hooks of the context that is running a pipeline on THIS host thread (one rcb_ctx per host thread): the launch
+// counter behind rcb_launch_count and, when rcb_profile_enable is on, an event pair around every kernel so device time is
+// attributed per kernel name.  Thread-local: contexts on other threads neither see nor clear them.
 struct RcbProfHook {
     void (*mark)(void* user, const char* name, int begin, cudaStream_t s);
     void* user;
+    unsigned long long* launches;
 };
-extern RcbProfHook g_rcb_prof;
+extern thread_local RcbProfHook g_rcb_prof;
 struct KScope {
     const char* name;
     cudaStream_t s;
@@ -349,7 +361,7 @@ struct KScope {
         if (g_rcb_prof.mark) g_rcb_prof.mark(g_rcb_prof.user, name, 1, s);
     }
     ~KScope() {
-        g_rcb_launches++;
+        if (g_rcb_prof.launches) ++*g_rcb_prof.launches;
         if (g_rcb_prof.mark) g_rcb_prof.mark(g_rcb_prof.user, name, 0, s);
     }
 };
