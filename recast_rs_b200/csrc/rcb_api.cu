@@ -907,7 +907,9 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                 launch_count_fragments(rb, st);
             }
             if (spec) {
-                ub = margin(h.ub), nitems = margin(h.nitems), ub_max = margin(h.ub_max);
+                // shared-memory sizes decide how many CTAs an SM holds: no margin on the per-tile maxima (a tile that
+                // outgrows them raises its flag and the batch is rebuilt with the new maxima)
+                ub = margin(h.ub), nitems = margin(h.nitems), ub_max = h.ub_max;
                 want_tile = true;
             } else {
                 CUB(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -971,7 +973,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             }
             uint64_t walk = 0, s_max = 0, Kcap = 0;
             if (spec) {
-                S = margin(h.S), walk = margin(h.walk), s_max = margin(h.s_max);
+                S = margin(h.S), walk = margin(h.walk), s_max = h.s_max;
                 Kcap = compact ? (h.K ? margin(h.K) : 8ull * walk) : 0;
                 if (s_max > 0xfffeu) s_max = 0xfffeu;
                 launch_tile_scan(d_tinfo_tmp, ntiles, r2.counters, S, st);

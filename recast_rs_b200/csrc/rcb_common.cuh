@@ -47,6 +47,26 @@ struct TileInfo {
     uint32_t max_regions;   // chf.max_regions (watershed.rs:491), 0 unless REGIONS ran
 };
 
+// A band = rows [z0, z1) of one tile, the unit of work of the tile-resident kernels (k_tile.cu).  A tile whose working set
+// fits shared memory is one band; a larger one (128x128 cells, deep columns) is cut into bands of equal height that run as
+// independent CTAs.  What a band needs from its neighbours is one halo row on either side, [hz0, hz1) = [z0-1, z1+1) clamped
+// to the tile: the ledge filter and the 8-direction linking look one cell away, and the distance field's row-sequential
+// sweep hands its last row to the next band through global memory.
+struct BandDesc {
+    uint32_t tile;
+    int32_t z0, z1;    // own rows
+    int32_t hz0, hz1;  // rows held in shared memory (own + halo)
+};
+struct BandInfo {  // device-written per band
+    uint32_t span_base;   // first own span, batch-wide (k_tile_scan)
+    uint32_t span_count;  // own spans
+    uint32_t top_spans;   // spans of the first own row (what the previous band keeps as its bottom halo)
+    uint32_t bot_spans;   // spans of the last own row
+    uint32_t walkable, max_height;
+    uint32_t pub_base;    // byte offset of this band's hand-over records (k_tile_scan)
+    uint32_t status;
+};
+
 // Uniform locator grid over the tile AABBs: maps a triangle AABB to candidate tiles.
 struct Locator {
     float gx0, gz0;      // origin
@@ -115,15 +135,17 @@ struct Raster2 {
     unsigned long long* counters;  // [0] frag upper bound [1] frag cursor [2] flags (1 poly overflow, 2 pool overflow)
                                    // [3] bad index [4] work items
     uint32_t* item_cnt;            // [ntris + 1]
-    uint32_t* tile_ub;             // [ntiles] per-tile fragment upper bound (nullable)
+    uint32_t* tile_ub;             // [nbands] per-band fragment upper bound (nullable)
+    const uint32_t* band_first;    // [ntiles + 1] first band of every tile (bands of a tile are consecutive)
+    uint32_t band_cells;           // cells per band the tiles were cut by: a tile's bands have rcb_band_rows() rows
     // global-list mode (v1 back end)
     uint32_t* cell_cnt;
     uint4* frag_tmp;
     uint32_t frag_cap;
-    // per-tile segment mode (tile-resident back end); enabled when tile_cursor != nullptr
-    uint32_t* tile_cursor;     // [ntiles]
-    const uint32_t* tile_base; // [ntiles] first record of the tile's segment
-    const uint32_t* tile_cap;  // [ntiles]
+    // per-band segment mode (tile-resident back end); enabled when tile_cursor != nullptr
+    uint32_t* tile_cursor;     // [nbands]
+    const uint32_t* tile_base; // [nbands] first record of the band's segment
+    const uint32_t* tile_cap;  // [nbands]
     uint32_t* tile_frags;      // 3 words per record: cell | area<<24, smin | smax<<16, triangle
     uint32_t flags;            // bit0: min-x skip test (0: explicit per-vertex test; kept for A/B runs)
     uint32_t spec;             // 1: issued speculatively - the work-item count is read from counters[4] on the device
@@ -137,9 +159,24 @@ void launch_bin_count(const Raster2& rb, cudaStream_t s);
 void launch_fill_items(const Raster2& rb, const uint32_t* item_off, uint2* items, cudaStream_t s);
 void launch_clip_items(const Raster2& rb, const uint2* items, uint32_t nitems, TileInfo* tinfo, cudaStream_t s);
 
+// Rows per band of a tile of `width` x `height` cells when tiles are cut into bands of about `band_cells` cells: the
+// smallest number of bands that keeps a band within band_cells, all bands equal (the last may be shorter), never fewer
+// than two rows (a band hands its last TWO rows' values to the next one).  Same function on host and device.
+__host__ __device__ inline int32_t rcb_band_rows(int32_t width, int32_t height, uint32_t band_cells) {
+    if ((unsigned long long)width * (unsigned long long)height <= band_cells) return height;
+    long long r = (long long)(band_cells / (uint32_t)width);
+    if (r < 2) r = 2;
+    const long long nb = (height + r - 1) / r;
+    r = (height + nb - 1) / nb;
+    if (r < 2) r = 2;
+    return (int32_t)r;
+}
+
 // tile-resident back end (k_tile.cu)
 struct TileSpansArgs {
     const TileDesc* tiles;
+    const BandDesc* bands;
+    BandInfo* binfo;
     const uint32_t* tile_frags;   // 3 words per record, per-tile segments
     const uint32_t* tile_base;    // [ntiles] first record of the segment (also the base of ts_* below)
     const uint32_t* tile_cap;     // [ntiles]
@@ -147,7 +184,6 @@ struct TileSpansArgs {
     uint32_t* hf_cell_offset;     // [Ctot + ntiles] tile-relative CSR offsets (C+1 per tile)
     uint32_t* ts_mm;              // tile-local compact spans: smin | smax << 16
     uint8_t* ts_area;
-    TileInfo* tinfo;
     unsigned long long* counters;
     uint32_t fmask;
     int32_t merge_thr;
@@ -158,6 +194,13 @@ struct TileSpansArgs {
 };
 struct TileCompactArgs {
     const TileDesc* tiles;
+    const BandDesc* bands;
+    const BandInfo* binfo;
+    const uint32_t* band_first;  // [ntiles + 1]
+    uint32_t* work;              // per-band scratch lists (the bands' fragment segments, dead by now): 3 words per segment record
+    unsigned char* pub;          // hand-over records between the bands of a tile (BandInfo::pub_base)
+    uint32_t* flag_f;            // [nbands] zeroed: band's forward sweep published
+    uint32_t* flag_d;            // [nbands] zeroed: band's distance values published
     const uint32_t* tile_base;
     const uint32_t* hf_cell_offset_in;  // from k_tile_spans
     const uint32_t* ts_mm;
@@ -185,17 +228,21 @@ struct TileCompactArgs {
     unsigned long long Kcap;    // capacity of the connection arrays (a tile that would pass it sets RCB_FLAG_CONN)
     unsigned long long* phase;  // optional [16]: slots 8.. are this kernel's phases
 };
-void launch_tile_spans(const TileSpansArgs& a, int ntiles, cudaStream_t s);
+void launch_tile_spans(const TileSpansArgs& a, int nbands, cudaStream_t s);
 // cap_frags / cap_items: what the fragment and work-item buffers hold (~0: no check); beyond -> RCB_FLAG_ABORT
 void launch_tile_segments(const uint32_t* tile_ub, uint32_t* tile_base, int ntiles, unsigned long long* counters,
                           unsigned long long cap_frags, unsigned long long cap_items, cudaStream_t s);
 // span_cap: what the result arena was laid out for (~0: no check); beyond -> RCB_FLAG_ABORT
-void launch_tile_scan(TileInfo* tinfo, int ntiles, unsigned long long* counters, unsigned long long span_cap, cudaStream_t s);
+// counters[6] spans, [7] walkable spans, [8] shared-memory bytes the largest band needs in k_tile_compact, [10] hand-over bytes
+void launch_tile_scan(const BandDesc* bands, BandInfo* binfo, int nbands, const TileDesc* tiles, const uint32_t* band_first, TileInfo* tinfo,
+                      int ntiles, unsigned long long* counters, unsigned long long span_cap, unsigned long long pub_cap, int compact,
+                      cudaStream_t s);
 // slim result layout: conn_mask[s] = the span's directions, conn_ref16[k] = (u16)conn_ref[k]; *flag |= 1 if a reference needs 17 bits
 void launch_slim_pack(const TileInfo* tinfo, int ntiles, uint32_t max_cells, const uint32_t* first_conn, const uint32_t* conn_ref,
                       const uint8_t* conn_dir, const uint32_t* conn_next, uint8_t* conn_mask, uint16_t* conn_ref16,
                       unsigned long long* flag, cudaStream_t s);
-void launch_tile_compact(const TileCompactArgs& a, int ntiles, cudaStream_t s);
+void launch_tile_compact(const TileCompactArgs& a, int nbands, cudaStream_t s);
+size_t tile_compact_smem_bytes(uint32_t own_cells, uint32_t held_cells, uint32_t held_spans, uint32_t top_spans, uint32_t bot_spans);
 
 void launch_seg_scatter(const TileDesc* tiles, int ntiles, const uint32_t* tile_frags, const uint32_t* tile_base, const uint32_t* tile_cap,
                         const uint32_t* tile_cursor, const uint32_t* frag_off, uint32_t* cell_cnt, void* rec, bool wide,

@@ -65,19 +65,22 @@ def test_second_build_is_speculative_and_identical(oracle):
 
 
 def test_speculation_that_falls_short_is_rebuilt(oracle):
-    """Same configurations and mesh size, but a mesh with more relief: more fragments, spans and connections than the
-    hint allows.  The device raises the flag, the result is rebuilt behind rcb_result_download and equals a fresh build."""
+    """Same configurations and mesh size, but the mesh is folded: more fragments and spans per tile than the first build
+    measured.  The device raises the flag, the result is rebuilt behind rcb_result_download and equals a fresh build."""
     import recast_rs_b200.builder as rb
     from recast_rs_b200 import synth
 
     v, t, cfgs = synth.config2(seed=2, nq=150, tile=64)
+    # the same triangles folded onto half the area, the folded half lifted by 8 units: twice the spans per column there,
+    # so the largest tile outgrows the shared memory the first build measured
     v2 = v.copy().reshape(-1, 3)
-    v2[:, 1] = v2[:, 1] * 4.0 + 3.0 * np.sin(v2[:, 0] * 2.1) * np.cos(v2[:, 2] * 1.7)  # steeper: more cells per triangle column
-    mn = v.reshape(-1, 3)[:, 1].min()
-    v2[:, 1] += mn - v2[:, 1].min()
+    mid = 0.5 * float(v2[:, 0].max())
+    right = v2[:, 0] > mid
+    v2[right, 0] = 2.0 * mid - v2[right, 0]
+    v2[right, 1] += 8.0
     v2 = np.ascontiguousarray(v2.reshape(-1), np.float32)
     for c in cfgs:  # the y range of the tiles must hold both meshes
-        c.bmax = (c.bmax[0], float(max(v2.reshape(-1, 3)[:, 1].max(), c.bmax[1])) + 1.0, c.bmax[2])
+        c.bmax = (c.bmax[0], float(v2.reshape(-1, 3)[:, 1].max()) + 1.0, c.bmax[2])
     ctx = _ctx(RCB_NO_SPEC=0)
     ctx.upload_mesh(v, t)
     ctx.build_tiles(cfgs, rb.STAGE_ALL_BUILD).free()
