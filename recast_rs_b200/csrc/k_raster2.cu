@@ -121,17 +121,28 @@ __global__ void __launch_bounds__(256) k_bin_count(Raster2 rb) {
     if (tri < rb.mesh.ntris) {
         Tri t;
         if (load_triangle(rb.mesh, tri, t)) {
-            for_each_tile(t, rb.loc, rb.tiles, [&](uint32_t tile, const TileDesc&, int x0, int x1, int z0, int z1) {
+            for_each_tile(t, rb.loc, rb.tiles, [&](uint32_t tile, const TileDesc& td, int x0, int x1, int z0, int z1) {
                 const int zz0 = max(z0, 0);
                 if (x1 < x0 || z1 < zz0) return;
-                const uint32_t nrows = (uint32_t)(z1 - zz0 + 1);
-                const uint32_t f = (uint32_t)(x1 - x0 + 1) * nrows;
+                const uint32_t nrows = (uint32_t)(z1 - zz0 + 1), ncols = (uint32_t)(x1 - x0 + 1);
                 items += (nrows + CLIP_ROWS - 1) / CLIP_ROWS;
-                ub += f;
-                if (rb.tile_ub) {  // neighbouring triangles mostly share the tile: one atomic per (warp, tile)
-                    const unsigned peers = __match_any_sync(__activemask(), tile);
-                    const uint32_t sum = __reduce_add_sync(peers, f);
-                    if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&rb.tile_ub[tile], sum);
+                ub += ncols * nrows;
+                if (rb.tile_ub) {
+                    // per band: the rows of the footprint the band holds, its halo rows included (a border row counts
+                    // for both bands, as emit_fragment writes it to both)
+                    const int R = rcb_band_rows(td.width, td.height, rb.band_cells);
+                    const uint32_t b0 = rb.band_first[tile];
+                    const int bl = max(zz0 - 1, 0) / R, bh = min(z1 + 1, td.height - 1) / R;
+                    for (int b = bl; b <= bh; ++b) {
+                        const int hz0 = max(b * R - 1, 0), hz1 = min((b + 1) * R + 1, td.height);  // rows held: [hz0, hz1)
+                        const int r0 = max(zz0, hz0), r1 = min(z1, hz1 - 1);
+                        if (r1 < r0) continue;
+                        const uint32_t f = ncols * (uint32_t)(r1 - r0 + 1);
+                        // neighbouring triangles mostly share the band: one atomic per (warp, band)
+                        const unsigned peers = __match_any_sync(__activemask(), b0 + (uint32_t)b);
+                        const uint32_t sum = __reduce_add_sync(peers, f);
+                        if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&rb.tile_ub[b0 + (uint32_t)b], sum);
+                    }
                 }
             });
         } else {
@@ -204,30 +215,48 @@ struct ClipSmem {
 #define ZB(buf, v, k) sm.zbuf[(((buf) * ZCAP + (v)) * 3 + (k)) * CLIP_THREADS + threadIdx.x]
 #define XB(buf, v, k) sm.zbuf[(((buf) * XCAP + (v)) * 2 + (k)) * CLIP_THREADS + threadIdx.x]
 
-__device__ __forceinline__ void emit_fragment(const Raster2& rb, const TileDesc& td, uint32_t tile, uint32_t lcell,
+// One record into the segment of band `seg`; `lcell` is the cell inside the band's held rows.
+__device__ __forceinline__ void emit_to_segment(const Raster2& rb, const TileDesc& td, uint32_t seg, uint32_t lcell, uint32_t tcell, uint32_t tri,
+                                                uint32_t mm, uint32_t area) {
+    // lanes of a warp mostly hit the same band
+    const unsigned act = __activemask();
+    const unsigned peers = __match_any_sync(act, seg);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if ((int)lane_id() == leader) base = atomicAdd(&rb.tile_cursor[seg], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const uint32_t pos = base + __popc(peers & ((1u << lane_id()) - 1u));
+    if (pos < rb.tile_cap[seg]) {
+        uint32_t* rec = rb.tile_frags + 3ull * (rb.tile_base[seg] + pos);
+        rec[0] = lcell | (area << 24);
+        rec[1] = mm;
+        rec[2] = tri;
+        // global back end: the per-column counts its scatter needs (a pass over the fragment list otherwise)
+        if (rb.flags & 0x200u) atomicAdd(&rb.cell_cnt[td.cell_base + tcell], 1u);
+    } else {
+        atomicOr(&rb.counters[2], 2ull);
+    }
+}
+
+__device__ __forceinline__ void emit_fragment(const Raster2& rb, const TileDesc& td, uint32_t tile, int x, int z,
                                               uint32_t tri, int smin, int smax, uint32_t area) {
     const uint32_t mm = ((uint32_t)smin & 0xffffu) | ((uint32_t)smax << 16);
+    const uint32_t tcell = (uint32_t)z * td.width + x;
     if (rb.tile_cursor) {
-        // per-tile segment (tile-resident back end); lanes of a warp mostly hit the same tile
-        const unsigned act = __activemask();
-        const unsigned peers = __match_any_sync(act, tile);
-        const int leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if ((int)lane_id() == leader) base = atomicAdd(&rb.tile_cursor[tile], (uint32_t)__popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        const uint32_t pos = base + __popc(peers & ((1u << lane_id()) - 1u));
-        if (pos < rb.tile_cap[tile]) {
-            uint32_t* rec = rb.tile_frags + 3ull * (rb.tile_base[tile] + pos);
-            rec[0] = lcell | (area << 24);
-            rec[1] = mm;
-            rec[2] = tri;
-            // global back end: the per-column counts its scatter needs (a pass over the fragment list otherwise)
-            if (rb.flags & 0x200u) atomicAdd(&rb.cell_cnt[td.cell_base + lcell], 1u);
-        } else {
-            atomicOr(&rb.counters[2], 2ull);
+        // per-band segments (tile-resident back end, and the global back end's per-tile scatter with whole-tile bands).
+        // The band that owns row z, and - a band keeps one halo row on either side - the band above when z is its
+        // neighbour's first row, the band below when z is its neighbour's last row.
+        const int R = rcb_band_rows(td.width, td.height, rb.band_cells);
+        const uint32_t b0 = rb.band_first[tile];
+        const int b = z / R;
+        const int hz0 = max(b * R - 1, 0);
+        emit_to_segment(rb, td, b0 + (uint32_t)b, (uint32_t)(z - hz0) * td.width + x, tcell, tri, mm, area);
+        if (R < td.height) {
+            if (z == b * R && b > 0) emit_to_segment(rb, td, b0 + (uint32_t)b - 1u, (uint32_t)(z - max((b - 1) * R - 1, 0)) * td.width + x, tcell, tri, mm, area);
+            if (z == (b + 1) * R - 1 && z + 1 < td.height) emit_to_segment(rb, td, b0 + (uint32_t)b + 1u, (uint32_t)x, tcell, tri, mm, area);
         }
     } else {
-        const uint32_t gcell = td.cell_base + lcell;
+        const uint32_t gcell = td.cell_base + tcell;
         const uint32_t rank = atomicAdd(&rb.cell_cnt[gcell], 1u);
         const unsigned m = __activemask();
         const int leader = __ffs(m) - 1;
@@ -479,7 +508,7 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
                 smin = min(max(smin, -32768), 32767);
                 smax = min(max(smax, -32768), 32767);
                 smin = max(smin, 0);
-                emit_fragment(rb, td, tile, (uint32_t)z * td.width + x, tri, smin, smax, area);
+                emit_fragment(rb, td, tile, x, z, tri, smin, smax, area);
             }
         }
         if (ovf) {

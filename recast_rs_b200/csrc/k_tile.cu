@@ -1,4 +1,5 @@
-// k_tile.cu — tile-resident back end: one CTA owns one tile and keeps its working set in shared memory.
+// k_tile.cu — tile-resident back end: one CTA owns one BAND of a tile (all of it when the tile is small enough, else a run
+// of rows, see BandDesc) and keeps its working set in shared memory.
 //
 //   k_tile_spans   (A)  fragments of the tile (per-tile segment written by k_clip_items)
 //                       -> bucket by column (shared-memory histogram + scan)
@@ -83,28 +84,31 @@ __device__ uint32_t block_scan_array(const uint32_t* cnt, OutT* out, uint32_t n,
 __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_spans(TileSpansArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t sh_warp[TILE_THREADS / 32 + 1];
-    __shared__ uint32_t sh_red[4];  // [0] walkable spans, [1] max height, [3] replay work-list length
-    const uint32_t tile = blockIdx.x;
+    __shared__ uint32_t sh_red[4];  // [0] walkable spans, [1] max height, [2] own fragments, [3] replay work-list length
+    const uint32_t band = blockIdx.x;
     if (a.counters[2] & RCB_FLAG_ABORT) return;  // a speculative size was too small: the host redoes the batch
-    const TileDesc& td = a.tiles[tile];
+    const BandDesc bd = a.bands[band];
+    const TileDesc& td = a.tiles[bd.tile];
     const int W = td.width, H = td.height;
-    const uint32_t C = (uint32_t)(W * H);
+    const uint32_t C = (uint32_t)(W * (bd.hz1 - bd.hz0));                                    // cells held: own rows + halo rows
+    const uint32_t oc0 = (uint32_t)(W * (bd.z0 - bd.hz0)), oc1 = (uint32_t)(W * (bd.z1 - bd.hz0));  // own cells [oc0, oc1)
     const unsigned long long wmagic = td.wmagic;
-    const uint32_t F = min(a.tile_cursor[tile], a.tile_cap[tile]);
+    const uint32_t F = min(a.tile_cursor[band], a.tile_cap[band]);
     // Two launches share this kernel: pass 0 runs with a shared-memory size that lets two CTAs share an SM
-    // and defers the tiles that need more; pass 1 (large allocation) handles only the deferred tiles.
+    // and defers the bands that need more; pass 1 (large allocation) handles only the deferred bands.
     constexpr uint32_t DEFERRED = 0x80000000u;
-    if (a.pass == 1 && !(a.tinfo[tile].status & DEFERRED)) return;
+    if (a.pass == 1 && !(a.binfo[band].status & DEFERRED)) return;
     // layout: cnt u32[C] | off u16[C+1] | soff u16[C+1] | rec[F] (uint2: area << 24 | triangle, smin | smax << 16)
     const size_t need = 8ull * (C + 4) + 8ull * F + 16;
     if (need > a.smem_bytes || F >= 0xffffu) {
         if (threadIdx.x == 0) {
             if (a.pass == 0 && a.defer) {
-                a.tinfo[tile].status |= DEFERRED;
+                a.binfo[band].status |= DEFERRED;
             } else {
-                atomicOr(&a.counters[2], 4ull);  // does not fit: the host reruns the batch on the v1 back end
-                a.tinfo[tile].span_count = 0;
-                a.tinfo[tile].walkable_span_count = 0;
+                atomicOr(&a.counters[2], 4ull);  // does not fit: the host reruns the batch with smaller bands / the v1 back end
+                a.binfo[band].span_count = 0;
+                a.binfo[band].walkable = 0;
+                a.binfo[band].top_spans = a.binfo[band].bot_spans = 0;
             }
         }
         return;
@@ -113,11 +117,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_spans(TileSpansArgs a)
     uint16_t* off = reinterpret_cast<uint16_t*>(cnt + C);
     uint16_t* soff = off + ((C + 2) & ~1u);
     uint2* rec = reinterpret_cast<uint2*>((reinterpret_cast<uintptr_t>(soff + ((C + 2) & ~1u)) + 7) & ~(uintptr_t)7);
-    const uint32_t* frags = a.tile_frags + 3ull * a.tile_base[tile];
+    const uint32_t* frags = a.tile_frags + 3ull * a.tile_base[band];
 
     PhaseClock pc(a.phase);
     for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) cnt[c] = 0;
-    if (threadIdx.x < 2) sh_red[threadIdx.x] = 0;
+    if (threadIdx.x < 3) sh_red[threadIdx.x] = 0;
     __syncthreads();
     // 1. histogram by column
     for (uint32_t i = threadIdx.x; i < F; i += TILE_THREADS) atomicAdd(&cnt[frags[3ull * i] & 0xffffffu], 1u);
@@ -129,11 +133,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_spans(TileSpansArgs a)
     __syncthreads();
     pc.mark(1);
     // 3. scatter into column order (order inside a column is arbitrary; the replay sorts by triangle)
+    uint32_t fown = 0;  // fragments of the band's own rows (halo rows are also some other band's own)
     for (uint32_t i = threadIdx.x; i < F; i += TILE_THREADS) {
         const uint32_t r0 = frags[3ull * i], r1 = frags[3ull * i + 1], r2 = frags[3ull * i + 2];
         const uint32_t cell = r0 & 0xffffffu;
         const uint32_t pos = off[cell] + atomicAdd(&cnt[cell], 1u);
         rec[pos] = make_uint2((r0 & 0xff000000u) | (r2 & 0xffffffu), r1);
+        fown += cell >= oc0 && cell < oc1;
     }
     __syncthreads();
     pc.mark(2);
@@ -215,18 +221,20 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_spans(TileSpansArgs a)
     }
     __syncthreads();
     pc.mark(3);
-    // 5. span offsets (tile-local compact order)
-    const uint32_t S = block_scan_array(cnt, soff, C, sh_warp);
+    // 5. span offsets (band-local compact order)
+    block_scan_array(cnt, soff, C, sh_warp);
     pc.mark(4);
 
-    // 6. filters, fused (see k_filter.cu for why one bottom-up walk per column is exact)
+    // 6. filters, fused (see k_filter.cu for why one bottom-up walk per column is exact); own rows only - the halo rows are
+    //    here for their geometry (the ledge filter reads the four neighbour columns' spans, never their areas)
     uint32_t walkable = 0, maxh = 0;
     const uint32_t fmask = a.fmask;
     const int height = td.walkable_height, climb = td.walkable_climb, neg_climb = td.neg_climb;
-    for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
+    for (uint32_t c = oc0 + threadIdx.x; c < oc1; c += TILE_THREADS) {
         const uint32_t b = off[c], e = b + cnt[c];
         if (b == e) continue;
-        const int z = (int)rcb_div_w(c, wmagic), x = (int)c - z * W;
+        const int zl = (int)rcb_div_w(c, wmagic), x = (int)c - zl * W;
+        const int z = zl + bd.hz0;  // row in the tile
         const int dx[4] = {0, 1, 0, -1}, dz[4] = {-1, 0, 1, 0};
         uint32_t nb[4], ne[4];
         bool oob[4];
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_spans(TileSpansArgs a)
         for (int d = 0; d < 4; ++d) {
             const int nx = x + dx[d], nz = z + dz[d];
             oob[d] = nx < 0 || nz < 0 || nx >= W || nz >= H;
-            const uint32_t nc = oob[d] ? c : (uint32_t)(nz * W + nx);
+            const uint32_t nc = oob[d] ? c : (uint32_t)((nz - bd.hz0) * W + nx);
             nb[d] = off[nc];
             ne[d] = oob[d] ? nb[d] : nb[d] + cnt[nc];
         }
@@ -292,12 +300,14 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_spans(TileSpansArgs a)
     }
     __syncthreads();
     pc.mark(5);
-    // 7. outputs: final heightfield CSR offsets, spans in tile-local compact order
-    uint32_t* out_off = a.hf_cell_offset + td.cell_base + tile;
-    const uint32_t tb = a.tile_base[tile];
-    for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) {
-        const uint32_t so = soff[c], n = cnt[c], b = off[c];
-        out_off[c] = so;
+    // 7. outputs for the own rows: heightfield CSR offsets (band-local; k_tile_compact makes them tile-relative), spans in
+    //    band-local compact order
+    uint32_t* out_off = a.hf_cell_offset + td.cell_base + bd.tile + (uint32_t)(W * bd.z0);
+    const uint32_t tb = a.tile_base[band];
+    const uint32_t so0 = soff[oc0];
+    for (uint32_t c = oc0 + threadIdx.x; c < oc1; c += TILE_THREADS) {
+        const uint32_t so = soff[c] - so0, n = cnt[c], b = off[c];
+        out_off[c - oc0] = so;
         for (uint32_t k = 0; k < n; ++k) {
             const uint2 sp = rec[b + k];
             a.ts_mm[tb + so + k] = sp.y;
@@ -308,69 +318,117 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_spans(TileSpansArgs a)
     for (int d = 16; d > 0; d >>= 1) {
         walkable += __shfl_down_sync(0xffffffffu, walkable, d);
         maxh = max(maxh, __shfl_down_sync(0xffffffffu, maxh, d));
+        fown += __shfl_down_sync(0xffffffffu, fown, d);
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(&sh_red[0], walkable);
         atomicMax(&sh_red[1], maxh);
+        atomicAdd(&sh_red[2], fown);
     }
     __syncthreads();
     pc.mark(6);
     if (threadIdx.x == 0) {
-        out_off[C] = S;
-        if (F) atomicAdd(&a.counters[1], (unsigned long long)F);
-        a.tinfo[tile].span_count = S;
-        a.tinfo[tile].walkable_span_count = sh_red[0];
-        a.tinfo[tile].max_height = sh_red[1];
-        if (a.pass == 1) a.tinfo[tile].status &= ~DEFERRED;
+        if (sh_red[2]) atomicAdd(&a.counters[1], (unsigned long long)sh_red[2]);
+        BandInfo& bi = a.binfo[band];
+        bi.span_count = soff[oc1] - so0;
+        bi.top_spans = soff[oc0 + (uint32_t)W] - so0;
+        bi.bot_spans = soff[oc1] - soff[oc1 - (uint32_t)W];
+        bi.walkable = sh_red[0];
+        bi.max_height = sh_red[1];
+        if (a.pass == 1) bi.status &= ~DEFERRED;
     }
 }
 
-// span_base per tile + batch totals (counters[6] = S, counters[7] = walkable spans); one block
-__global__ void __launch_bounds__(1024) k_tile_scan(TileInfo* __restrict__ tinfo, int ntiles, unsigned long long* counters,
-                                                    unsigned long long span_cap) {
-    __shared__ uint32_t sh[33];
+// Shared memory k_tile_compact needs for a band that holds `held_cells` cells (own + halo rows) with `held_spans` spans, of
+// which `top` / `bot` belong to the halo rows: coff u32[own_cells + 1] | mm u32 (aliased by the two u16 sweep buffers, which
+// also hold a dummy span and the ghost values handed over by the neighbour bands) | nid u16[8][held + dummy] | soff u16 | areas u8.
+__host__ __device__ inline size_t compact_smem_need(uint32_t own_cells, uint32_t held_cells, uint32_t held_spans, uint32_t top, uint32_t bot) {
+    const size_t G2 = ((size_t)held_spans + 1 + 4ull * top + bot + 1) & ~(size_t)1;
+    const size_t S2 = ((size_t)held_spans + 2) & ~(size_t)1;
+    return 4ull * (own_cells + 1) + 4ull * G2 + 16ull * S2 + 2ull * (((size_t)held_cells + 2) & ~(size_t)1) + held_spans + 64;
+}
+
+// span_base / hand-over base per band (exclusive scans over bands), per-tile totals, batch totals; one block.
+// counters[6] = S, [7] = walkable spans, [8] = largest compact_smem_need, [10] = hand-over bytes
+__global__ void __launch_bounds__(1024) k_tile_scan(const BandDesc* __restrict__ bands, BandInfo* __restrict__ binfo, int nbands,
+                                                    const TileDesc* __restrict__ tiles, const uint32_t* __restrict__ band_first,
+                                                    TileInfo* __restrict__ tinfo, int ntiles, unsigned long long* counters,
+                                                    unsigned long long span_cap, unsigned long long pub_cap, int compact) {
+    __shared__ uint32_t sh[33], sh2[33];
     __shared__ unsigned long long sh_walk;
-    if (threadIdx.x == 0) sh_walk = 0;
+    __shared__ uint32_t sh_need;
+    if (threadIdx.x == 0) sh_walk = 0, sh_need = 0;
     __syncthreads();
-    __shared__ uint32_t sh_maxs;
-    if (threadIdx.x == 0) sh_maxs = 0;
-    uint32_t carry = 0, maxs = 0;
+    uint32_t carry = 0, carry2 = 0, need = 0;
     unsigned long long walk = 0;
-    for (int base = 0; base < ntiles; base += 1024) {
-        const int t = base + threadIdx.x;
-        const uint32_t v = t < ntiles ? tinfo[t].span_count : 0;
-        if (t < ntiles) walk += tinfo[t].walkable_span_count;
-        maxs = max(maxs, v);
-        const uint32_t inc = warp_incl_scan(v);
-        if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = inc;
+    for (int base = 0; base < nbands; base += 1024) {
+        const int b = base + threadIdx.x;
+        uint32_t v = 0, p = 0;
+        if (b < nbands) {
+            const BandInfo bi = binfo[b];
+            const BandDesc bd = bands[b];
+            v = bi.span_count;
+            walk += bi.walkable;
+            const bool has_top = bd.hz0 < bd.z0, has_bot = bd.hz1 > bd.z1;
+            // what this band hands over: 16 B per span of its last row (to the next band) and of its first row (to the previous)
+            p = (has_bot ? 16u * bi.bot_spans : 0u) + (has_top ? 16u * bi.top_spans : 0u);
+            if (compact) {
+                const uint32_t W = (uint32_t)tiles[bd.tile].width;
+                const uint32_t top = has_top ? binfo[b - 1].bot_spans : 0u, bot = has_bot ? binfo[b + 1].top_spans : 0u;
+                const size_t n = compact_smem_need(W * (uint32_t)(bd.z1 - bd.z0), W * (uint32_t)(bd.hz1 - bd.hz0), v + top + bot, top, bot);
+                need = max(need, (uint32_t)min(n, (size_t)0xffffffffu));
+                if ((size_t)v + 1 + 5ull * top + 2ull * bot >= 0xfff0u) need = 0xffffffffu;  // band-local span ids are 16 bit
+            }
+        }
+        const uint32_t inc = warp_incl_scan(v), inc2 = warp_incl_scan(p);
+        if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = inc, sh2[threadIdx.x >> 5] = inc2;
         __syncthreads();
         if (threadIdx.x < 32) {
-            const uint32_t w = sh[threadIdx.x];
-            const uint32_t winc = warp_incl_scan(w);
-            sh[threadIdx.x] = winc - w;
-            if (threadIdx.x == 31) sh[32] = winc;
+            const uint32_t w = sh[threadIdx.x], w2 = sh2[threadIdx.x];
+            const uint32_t winc = warp_incl_scan(w), winc2 = warp_incl_scan(w2);
+            sh[threadIdx.x] = winc - w, sh2[threadIdx.x] = winc2 - w2;
+            if (threadIdx.x == 31) sh[32] = winc, sh2[32] = winc2;
         }
         __syncthreads();
-        if (t < ntiles) tinfo[t].span_base = carry + inc - v + sh[threadIdx.x >> 5];
+        if (b < nbands) {
+            binfo[b].span_base = carry + inc - v + sh[threadIdx.x >> 5];
+            binfo[b].pub_base = carry2 + inc2 - p + sh2[threadIdx.x >> 5];
+        }
         carry += sh[32];
+        carry2 += sh2[32];
         __syncthreads();
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {  // one shared-memory atomic per warp, not per thread
         walk += __shfl_down_sync(0xffffffffu, walk, d);
-        maxs = max(maxs, __shfl_down_sync(0xffffffffu, maxs, d));
+        need = max(need, __shfl_down_sync(0xffffffffu, need, d));
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(&sh_walk, walk);
-        atomicMax(&sh_maxs, maxs);
+        atomicMax(&sh_need, need);
     }
-    __syncthreads();
+    __syncthreads();  // also: every band's span_base is visible to the block
+    // per-tile totals (TileInfo is what the C ABI reports; bands are an internal unit)
+    for (int t = threadIdx.x; t < ntiles; t += 1024) {
+        const uint32_t b0 = band_first[t], b1 = band_first[t + 1];
+        uint32_t sc = 0, wk = 0, mh = 0;
+        for (uint32_t b = b0; b < b1; ++b) {
+            sc += binfo[b].span_count;
+            wk += binfo[b].walkable;
+            mh = max(mh, binfo[b].max_height);
+        }
+        tinfo[t].span_base = b1 > b0 ? binfo[b0].span_base : carry;
+        tinfo[t].span_count = sc;
+        tinfo[t].walkable_span_count = wk;
+        tinfo[t].max_height = mh;
+    }
     if (threadIdx.x == 0) {
         counters[6] = carry;
         counters[7] = sh_walk;
-        counters[8] = sh_maxs;
-        // speculative issue: more spans than the arena was laid out for, or a tile that did not fit shared memory
-        if (carry > span_cap || (span_cap != ~0ull && (counters[2] & 4ull))) atomicOr(&counters[2], RCB_FLAG_ABORT);
+        counters[8] = sh_need;
+        counters[10] = carry2;
+        // speculative issue: more spans than the arena was laid out for, or a band that did not fit shared memory
+        if (carry > span_cap || carry2 > pub_cap || (span_cap != ~0ull && (counters[2] & 4ull))) atomicOr(&counters[2], RCB_FLAG_ABORT);
     }
 }
 
@@ -415,14 +473,28 @@ __global__ void __launch_bounds__(1024) k_tile_segments(const uint32_t* __restri
 // ======================================================================================================
 // B: spans -> compact heightfield, connections, erosion, distance field
 // ======================================================================================================
+// Band-local span numbering: [0, nt) the previous band's last row (top halo), [own0, own1) the band's own spans,
+// [own1, S) the next band's first row (bottom halo), S the dummy span, [G0, G0 + 4 nt) four ghost values per top-halo span,
+// [G0 + 4 nt, +nbot) one per bottom-halo span.  The numbering is contiguous in the tile's span order, so
+// tile-relative index = band_off + local - nt for own and halo spans alike.
 struct TileB {
-    const uint16_t* soff;  // [C+1] first span of every cell (tile-local)
+    const uint16_t* soff;  // [held cells + 1] first span of every held cell (band-local ids)
     uint8_t* areas;        // [S] chf.areas (erosion writes it)
-    const uint16_t* nid;   // [8][S2] tile-local id of the neighbour span per direction; S = none.  Entry S of
+    uint16_t* nid;         // [8][S2] band-local id of the neighbour span per direction; S = none.  Entry S of
                            // every row is a dummy span whose neighbours are itself (branch-free sweeps)
-    uint32_t S, S2;        // S2 >= S + 1: row pitch of nid and of the sweep buffers
-    int W, H;
-    unsigned long long wmagic;
+    uint32_t S, S2;        // S2 >= S + 1: row pitch of nid
+    uint32_t own0, own1;   // the band's own spans
+    uint32_t nt, nbot, G0; // halo spans above / below, first ghost slot
+    int W, rows, row0;     // own rows are the held rows [row0, row0 + rows)
+    // hand-over between the bands of a tile (nullptr / 0 for a band without that neighbour)
+    uint32_t band;
+    bool has_top, has_bot;
+    const uint4* in_top;         // previous band's records for its last row = my top halo
+    const uint4* in_bot;         // next band's records for its first row = my bottom halo
+    uint4* out_down;             // my last row, for the next band
+    uint4* out_up;               // my first row, for the previous band (16 B records keep every region 16-byte aligned)
+    uint32_t* flag_f;
+    uint32_t* flag_d;
 };
 
 __device__ __forceinline__ uint32_t tnei(const TileB& g, uint32_t s, int dir) { return g.nid[(uint32_t)dir * g.S2 + s]; }
@@ -434,16 +506,23 @@ __device__ __forceinline__ T sat_add(T v, unsigned b) {
     return (T)(r > mx ? mx : r);
 }
 
+__device__ __forceinline__ void wait_flag(const uint32_t* flag) {
+    while (*reinterpret_cast<const volatile uint32_t*>(flag) == 0) __nanosleep(64);
+    __threadfence();
+}
+
 // boundary -> forward rows -> backward gather, on shared memory.  ERODE: thresholds areas; else D + max.
 // The forward sweep occupies only the warps that own a column; `idle_work(rank, count)` runs meanwhile on the
 // others (work that touches neither the sweep buffers nor areas).  Returns whether idle_work ran.
+// Bands (never with ERODE): the sweep starts from the previous band's last row and hands its own last row on; the
+// gather and the blur read one / two rows beyond the band, which arrive as halo + ghost values (see TileB).
 template <typename T, bool ERODE, class Work>
 __device__ bool tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_t* sh_max, PhaseClock* pc, Work&& idle_work) {
-    const int W = g.W, H = g.H;
+    const int W = g.W, H = g.rows;
     const uint32_t TN = g.S;  // "no neighbour" == the dummy span
     const T inf = (T)~(T)0;
     // boundary marking (compact_heightfield.rs:556-585 / area.rs:91-125)
-    for (uint32_t s = threadIdx.x; s < g.S; s += TILE_THREADS) {
+    for (uint32_t s = g.own0 + threadIdx.x; s < g.own1; s += TILE_THREADS) {
         const uint8_t ar = g.areas[s];
         int cnt = 0;
         if (!ERODE || ar != 0) {
@@ -465,7 +544,7 @@ __device__ bool tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_
     // Only the warps that own a column take part in the H row barriers (named barrier 1).
     const int sweep_threads = min(TILE_THREADS, ((W + 31) / 32) * 32);
     if ((int)threadIdx.x < sweep_threads) {
-        const uint16_t* __restrict__ soff = g.soff;
+        const uint16_t* __restrict__ soff = g.soff + g.row0 * W;  // own rows
         const uint16_t* __restrict__ nid0 = g.nid;             // NW
         const uint16_t* __restrict__ nid2 = g.nid + 2 * g.S2;  // NE
         const uint16_t* __restrict__ nid3 = g.nid + 3 * g.S2;  // E
@@ -484,6 +563,20 @@ __device__ bool tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_
             else
                 asm volatile("bar.sync 1, %0;" ::"r"(sweep_threads) : "memory");
         };
+        if (!ERODE && g.has_top) {
+            // the previous band's last row: its forward values, and through three ghost slots per span the values of that
+            // span's E, N and NW neighbours (the only things the relaxation and the gather reach THROUGH a halo span)
+            if (threadIdx.x == 0) wait_flag(&g.flag_f[g.band - 1]);
+            row_barrier();
+            for (uint32_t j = threadIdx.x; j < g.nt; j += (uint32_t)sweep_threads) {
+                const uint4 r = __ldcg(&g.in_top[j]);
+                Fw[j] = (T)(r.x & 0xffffu);
+                Fw[g.G0 + 4 * j] = (T)(r.x >> 16);
+                Fw[g.G0 + 4 * j + 1] = (T)(r.y & 0xffffu);
+                Fw[g.G0 + 4 * j + 2] = (T)(r.y >> 16);
+            }
+            row_barrier();
+        }
         if (W <= sweep_threads) {
             // One column per thread, software-pipelined three rows deep: the neighbour ids of a span do not
             // depend on distances, so while row z is relaxed the ids of row z+1 (second hop), row z+2 (first
@@ -541,9 +634,23 @@ __device__ bool tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_
     }
     __syncthreads();
     if (pc) pc->mark(9);
+    const uint32_t lr0 = g.soff[(g.row0 + g.rows - 1) * W], fr1 = g.soff[(g.row0 + 1) * W];  // last own row = [lr0, own1), first = [own0, fr1)
+    if (!ERODE && g.has_bot) {
+        // hand the last own row's forward values to the next band (+ those of each span's E, N, NW neighbours)
+        for (uint32_t s = lr0 + threadIdx.x; s < g.own1; s += TILE_THREADS) {
+            uint4 r;
+            r.x = (uint32_t)Fw[s] | ((uint32_t)Fw[tnei(g, s, 3)] << 16);
+            r.y = (uint32_t)Fw[tnei(g, s, 1)] | ((uint32_t)Fw[tnei(g, s, 0)] << 16);
+            r.z = r.w = 0;
+            g.out_down[s - lr0] = r;
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(&g.flag_f[g.band]) = 1u;
+    }
     // backward = gather from forward values; D overwrites init (init is dead)
     uint32_t vmax = 0;
-    for (uint32_t s = threadIdx.x; s < g.S; s += TILE_THREADS) {
+    for (uint32_t s = g.own0 + threadIdx.x; s < g.own1; s += TILE_THREADS) {
         const uint32_t a0 = tnei(g, s, 2), b0 = tnei(g, s, 1);    // NE, N
         const uint32_t a1 = tnei(g, a0, 1), b1 = tnei(g, b0, 0);  // NE.N, N.NW
         uint32_t v = Fw[s];
@@ -561,17 +668,57 @@ __device__ bool tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_
     }
     __syncthreads();
     if (ERODE) {
-        for (uint32_t s = threadIdx.x; s < g.S; s += TILE_THREADS)
+        for (uint32_t s = g.own0 + threadIdx.x; s < g.own1; s += TILE_THREADS)
             if ((unsigned)init[s] < thr) g.areas[s] = 0;  // area.rs:226-231
+        __syncthreads();
+    }
+    if (!ERODE && (g.has_top || g.has_bot)) {
+        // The box blur reads D one row beyond the band, and through that row's spans one row further (N then NE, S then SW):
+        // each band publishes D of its border rows together with D of the NE / SW neighbour (and whether there is one).
+        if (g.has_bot)
+            for (uint32_t s = lr0 + threadIdx.x; s < g.own1; s += TILE_THREADS) {
+                const uint32_t ne = tnei(g, s, 2);
+                uint4 r = g.out_down[s - lr0];
+                r.z = (uint32_t)init[s] | ((uint32_t)(ne != TN ? init[ne] : (T)0) << 16);
+                r.w = ne != TN ? 1u : 0u;
+                g.out_down[s - lr0] = r;
+            }
+        if (g.has_top)
+            for (uint32_t s = g.own0 + threadIdx.x; s < fr1; s += TILE_THREADS) {
+                const uint32_t sw = tnei(g, s, 6);
+                g.out_up[s - g.own0] = make_uint4((uint32_t)init[s] | ((uint32_t)(sw != TN ? init[sw] : (T)0) << 16), sw != TN ? 1u : 0u, 0u, 0u);
+            }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            *reinterpret_cast<volatile uint32_t*>(&g.flag_d[g.band]) = 1u;
+            if (g.has_top) wait_flag(&g.flag_d[g.band - 1]);
+            if (g.has_bot) wait_flag(&g.flag_d[g.band + 1]);
+        }
+        __syncthreads();
+        uint16_t* nid2 = g.nid + 2 * g.S2;
+        uint16_t* nid6 = g.nid + 6 * g.S2;
+        for (uint32_t j = threadIdx.x; j < g.nt; j += TILE_THREADS) {
+            const uint4 r = __ldcg(&g.in_top[j]);
+            init[j] = (T)(r.z & 0xffffu);
+            init[g.G0 + 4 * j + 3] = (T)(r.z >> 16);
+            nid2[j] = (uint16_t)(r.w ? g.G0 + 4 * j + 3 : TN);
+        }
+        for (uint32_t j = threadIdx.x; j < g.nbot; j += TILE_THREADS) {
+            const uint4 r = __ldcg(&g.in_bot[j]);
+            init[g.own1 + j] = (T)(r.x & 0xffffu);
+            init[g.G0 + 4 * g.nt + j] = (T)(r.x >> 16);
+            nid6[g.own1 + j] = (uint16_t)(r.y ? g.G0 + 4 * g.nt + j : TN);
+        }
         __syncthreads();
     }
     return sweep_threads < TILE_THREADS;
 }
 
-// Decoupled look-back over tiles, split in two so that nobody waits: a tile PUBLISHES its connection count
+// Decoupled look-back over bands, split in two so that nobody waits: a band PUBLISHES its connection count
 // as soon as it is known and RESOLVES its exclusive prefix only when it needs it (after the distance field),
-// by which time every predecessor has published.  look[t] = flag << 62 | value; flag 1 = tile aggregate,
-// 2 = inclusive prefix.  Tile ids come from a ticket counter, so predecessors are running or done.
+// by which time every predecessor has published.  look[t] = flag << 62 | value; flag 1 = band aggregate,
+// 2 = inclusive prefix.  Band ids come from a ticket counter, so predecessors are running or done.
 __device__ __forceinline__ void lookback_publish(volatile unsigned long long* look, uint32_t tile, uint32_t mine) {
     look[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | mine;
 }
@@ -598,48 +745,73 @@ __device__ uint32_t lookback_resolve(volatile unsigned long long* look, uint32_t
     if (lane == 0 && tile != 0) look[tile] = (2ull << 62) | (unsigned long long)(excl + mine);
     return excl;
 }
+// inclusive prefix of band `t` (t < my band): it resolves without waiting for anything after it
+__device__ __forceinline__ uint32_t lookback_inclusive(volatile unsigned long long* look, int t) {
+    if (t < 0) return 0;
+    unsigned long long v;
+    do {
+        v = look[t];
+    } while ((v >> 62) != 2);
+    return (uint32_t)(v & 0xffffffffull);
+}
 
 __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t sh_warp[TILE_THREADS / 32 + 1];
-    __shared__ uint32_t sh_misc[4];  // [0] tile id, [1] conn base, [2] max distance, [3] link work-list length
+    __shared__ uint32_t sh_misc[6];  // [0] band id, [1] conn base, [2] max distance, [3] link work-list length, [4] tile conn base
     if (a.counters[2] & RCB_FLAG_ABORT) return;  // uniform over the grid: nobody is left waiting in the look-back
-    // dynamic tile id: tiles start in order, which the look-back relies on
+    // dynamic band id: bands start in order, which the look-back and the hand-over between bands rely on
     if (threadIdx.x == 0) {
         sh_misc[0] = atomicAdd(a.tile_ticket, 1u);
         sh_misc[2] = 0;
         sh_misc[3] = 0;
     }
     __syncthreads();
-    const uint32_t tile = sh_misc[0];
+    const uint32_t band = sh_misc[0];
+    const BandDesc bd = a.bands[band];
+    const uint32_t tile = bd.tile;
     const TileDesc& td = a.tiles[tile];
     const int W = td.width, H = td.height;
-    const uint32_t C = (uint32_t)(W * H);
+    const int rows = bd.z1 - bd.z0, row0 = bd.z0 - bd.hz0;
+    const uint32_t C = (uint32_t)(W * rows);                 // own cells
+    const uint32_t Ch = (uint32_t)(W * (bd.hz1 - bd.hz0));  // held cells
+    const uint32_t oc0 = (uint32_t)(W * row0);
     const unsigned long long wmagic = td.wmagic;
-    const uint32_t S = a.tinfo[tile].span_count;
-    const uint32_t span_base = a.tinfo[tile].span_base;
-    // layout: coff u32[C+1] | mm u32[S] (aliased later by d16a,d16b u16[S2]) | nid u16[8][S2] | soff u16[C+1] | areas u8[S]
+    const bool has_top = bd.hz0 < bd.z0, has_bot = bd.hz1 > bd.z1;
+    const BandInfo bi = a.binfo[band];
+    const uint32_t So = bi.span_count;        // own spans
+    const uint32_t span_base = bi.span_base;  // batch-wide index of the first own span
+    const uint32_t nt = has_top ? a.binfo[band - 1].bot_spans : 0u, nbot = has_bot ? a.binfo[band + 1].top_spans : 0u;
+    const uint32_t S = nt + So + nbot;  // held spans
+    const uint32_t own0 = nt, own1 = nt + So;
+    const uint32_t tile_span_base = a.tinfo[tile].span_base;
+    const uint32_t band_off = span_base - tile_span_base;  // tile-relative index of the first own span
+    // layout: coff u32[C+1] | mm u32[G2] (aliased later by d16a,d16b u16[G2]) | nid u16[8][S2] | soff u16[Ch+1] | areas u8[S]
     const uint32_t S2 = (S + 2) & ~1u;  // >= S + 1: one dummy span behind the real ones
     const uint32_t TN = S;              // "no neighbour" is the dummy span's id
-    const size_t need = 6ull * (C + 2) + 21ull * S + 160;
-    const bool fits = a.do_compact ? (need <= a.smem_bytes && S < 0xffffu) : true;
+    const uint32_t G0 = S + 1;
+    const uint32_t G2 = (G0 + 4 * nt + nbot + 1) & ~1u;
+    const size_t need = compact_smem_need(C, Ch, S, nt, nbot);
+    const bool fits = a.do_compact ? (need <= a.smem_bytes && G2 < 0xfff0u) : true;
     uint32_t* coff = smem;
     uint32_t* mm = coff + (C + 1);
     uint16_t* d16a = reinterpret_cast<uint16_t*>(mm);
-    uint16_t* d16b = d16a + S2;
-    uint16_t* nid = reinterpret_cast<uint16_t*>(mm + S2);
+    uint16_t* d16b = d16a + G2;
+    uint16_t* nid = reinterpret_cast<uint16_t*>(mm + G2);
     uint16_t* soff = nid + 8ull * S2;
-    uint8_t* areas = reinterpret_cast<uint8_t*>(soff + ((C + 2) & ~1u));
+    uint8_t* areas = reinterpret_cast<uint8_t*>(soff + ((Ch + 2) & ~1u));
 
     volatile unsigned long long* look = a.lookback;
-    const uint32_t* g_off = a.hf_cell_offset_in + td.cell_base + tile;
+    const uint32_t* g_off = a.hf_cell_offset_in + td.cell_base + tile;  // band-local offsets written by k_tile_spans, tile cell order
     uint32_t* g_off_out = a.hf_cell_offset + td.cell_base + tile;
-    const uint32_t tb = a.tile_base[tile];
+    const uint32_t tb = a.tile_base[band];
+    const uint32_t c_tile0 = (uint32_t)(W * bd.z0);  // first own cell in the tile
     if (!a.do_compact || !fits) {
-        // heightfield-only result, or a tile too large for shared memory (the host then reruns the batch on
-        // the global back end): copy the spans through, keep the look-back chain alive
-        for (uint32_t c = threadIdx.x; c <= C; c += TILE_THREADS) g_off_out[c] = g_off[c];
-        for (uint32_t s = threadIdx.x; s < S; s += TILE_THREADS) {
+        // heightfield-only result, or a band too large for shared memory (the host then reruns the batch with smaller
+        // bands or on the global back end): copy the spans through, keep the look-back chain and the hand-over alive
+        for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) g_off_out[c_tile0 + c] = band_off + g_off[c_tile0 + c];
+        if (bd.z1 == H && threadIdx.x == 0) g_off_out[(uint32_t)(W * H)] = a.tinfo[tile].span_count;
+        for (uint32_t s = threadIdx.x; s < So; s += TILE_THREADS) {
             const uint32_t w = a.ts_mm[tb + s];
             a.smin[span_base + s] = (int16_t)(w & 0xffffu);
             a.smax[span_base + s] = (int16_t)(w >> 16);
@@ -648,11 +820,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
         if (a.do_compact && threadIdx.x < 32) {
             if (threadIdx.x == 0) {
                 atomicOr(&a.counters[2], 4ull);
-                lookback_publish(look, tile, 0);
+                lookback_publish(look, band, 0);
+                *reinterpret_cast<volatile uint32_t*>(&a.flag_f[band]) = 1u;
+                *reinterpret_cast<volatile uint32_t*>(&a.flag_d[band]) = 1u;
             }
             __syncwarp();
-            const uint32_t excl = lookback_resolve(look, tile, 0);
-            if (threadIdx.x == 0) {
+            const uint32_t excl = lookback_resolve(look, band, 0);
+            if (threadIdx.x == 0 && bd.z0 == 0) {
                 a.tinfo[tile].conn_base = excl;
                 a.tinfo[tile].conn_count = 0;
             }
@@ -660,45 +834,70 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
         return;
     }
     PhaseClock pc(a.phase ? a.phase + 8 : nullptr);
-    // 1. load the tile's spans; final span attributes (compact_heightfield.rs:231-237).  Loads are issued in
+    // 1. load the band's spans and its halo rows; final span attributes (compact_heightfield.rs:231-237).  Loads are issued in
     //    batches of four per thread so their latencies overlap.
     {
-        const uint32_t* __restrict__ in_off = g_off;
+        const uint32_t* __restrict__ in_off = g_off + c_tile0;
         const uint32_t* __restrict__ in_mm = a.ts_mm + tb;
         const uint8_t* __restrict__ in_ar = a.ts_area + tb;
         int16_t* __restrict__ o_min = a.smin + span_base;
         int16_t* __restrict__ o_max = a.smax + span_base;
         uint8_t* __restrict__ o_ar = a.sarea + span_base;
-        for (uint32_t c0 = threadIdx.x; c0 <= C; c0 += 4 * TILE_THREADS) {
+        uint16_t* __restrict__ so_own = soff + oc0;
+        for (uint32_t c0 = threadIdx.x; c0 < C; c0 += 4 * TILE_THREADS) {
             uint32_t o[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) o[u] = (c0 + u * TILE_THREADS <= C) ? in_off[c0 + u * TILE_THREADS] : 0u;
+            for (int u = 0; u < 4; ++u) o[u] = (c0 + u * TILE_THREADS < C) ? in_off[c0 + u * TILE_THREADS] : 0u;
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (c0 + u * TILE_THREADS <= C) {
-                    soff[c0 + u * TILE_THREADS] = (uint16_t)o[u];
-                    g_off_out[c0 + u * TILE_THREADS] = o[u];
+                if (c0 + u * TILE_THREADS < C) {
+                    so_own[c0 + u * TILE_THREADS] = (uint16_t)(nt + o[u]);
+                    g_off_out[c_tile0 + c0 + u * TILE_THREADS] = band_off + o[u];
                 }
         }
-        for (uint32_t s0 = threadIdx.x; s0 < S; s0 += 4 * TILE_THREADS) {
+        if (threadIdx.x == 0) {
+            so_own[C] = (uint16_t)own1;  // == soff of the first bottom-halo cell, or of the end
+            soff[Ch] = (uint16_t)S;
+            if (bd.z1 == H) g_off_out[(uint32_t)(W * H)] = a.tinfo[tile].span_count;
+        }
+        for (uint32_t s0 = threadIdx.x; s0 < So; s0 += 4 * TILE_THREADS) {
             uint32_t w[4];
             uint8_t ar[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const uint32_t i = s0 + u * TILE_THREADS;
-                w[u] = i < S ? in_mm[i] : 0u;
-                ar[u] = i < S ? in_ar[i] : (uint8_t)0;
+                w[u] = i < So ? in_mm[i] : 0u;
+                ar[u] = i < So ? in_ar[i] : (uint8_t)0;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const uint32_t i = s0 + u * TILE_THREADS;
-                if (i < S) {
-                    mm[i] = w[u];
-                    areas[i] = ar[u];  // chf.areas == span area until erosion runs
+                if (i < So) {
+                    mm[own0 + i] = w[u];
+                    areas[own0 + i] = ar[u];  // chf.areas == span area until erosion runs
                     o_min[i] = (int16_t)(w[u] & 0xffffu);
                     o_max[i] = (int16_t)(w[u] >> 16);
                     o_ar[i] = ar[u];
                 }
+            }
+        }
+        if (has_top) {  // the previous band's last row: offsets relative to that row's first span, spans at the end of its segment
+            const uint32_t* __restrict__ p_off = g_off + c_tile0 - (uint32_t)W;
+            const uint32_t pb = a.tile_base[band - 1] + (a.binfo[band - 1].span_count - nt);
+            const uint32_t row_first = p_off[0];
+            for (uint32_t x = threadIdx.x; x < (uint32_t)W; x += TILE_THREADS) soff[x] = (uint16_t)(p_off[x] - row_first);
+            for (uint32_t i = threadIdx.x; i < nt; i += TILE_THREADS) {
+                mm[i] = a.ts_mm[pb + i];
+                areas[i] = a.ts_area[pb + i];
+            }
+        }
+        if (has_bot) {  // the next band's first row: the head of its segment
+            const uint32_t* __restrict__ n_off = g_off + c_tile0 + C;
+            const uint32_t nb0 = a.tile_base[band + 1];
+            for (uint32_t x = threadIdx.x; x < (uint32_t)W; x += TILE_THREADS) soff[oc0 + C + x] = (uint16_t)(own1 + n_off[x]);
+            for (uint32_t i = threadIdx.x; i < nbot; i += TILE_THREADS) {
+                mm[own1 + i] = a.ts_mm[nb0 + i];
+                areas[own1 + i] = a.ts_area[nb0 + i];
             }
         }
     }
@@ -706,17 +905,30 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
     pc.mark(0);
     // 2. cells (compact_heightfield.rs:203-223); spans that cannot link get their defaults; the walkable ones are listed.
     //    Only ~45 % of the spans are walkable: linking straight out of the cell loop left most lanes idle next to the
-    //    busy ones.  The list lives in the tile's ts_mm segment, which is dead once mm is loaded.
-    uint32_t* const work = const_cast<uint32_t*>(a.ts_mm) + tb;
+    //    busy ones.  The list lives in the band's fragment segment, which is dead since k_tile_spans.
+    uint32_t* const work = a.work + 3ull * tb;
     if (threadIdx.x == 0) sh_misc[3] = 0;
+    // halo spans take part as link targets only: no neighbours of their own (the ghost links are set by the sweeps)
+    for (uint32_t s = threadIdx.x; s < nt + nbot; s += TILE_THREADS) {
+        const uint32_t sp = s < nt ? s : own1 + (s - nt);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) nid[(uint32_t)d * S2 + sp] = (uint16_t)TN;
+    }
+    if (has_top) {  // what the sweeps reach THROUGH a top-halo span: its E, N and NW neighbours' values, as ghost spans
+        for (uint32_t j = threadIdx.x; j < nt; j += TILE_THREADS) {
+            nid[3u * S2 + j] = (uint16_t)(G0 + 4 * j);
+            nid[1u * S2 + j] = (uint16_t)(G0 + 4 * j + 1);
+            nid[0u * S2 + j] = (uint16_t)(G0 + 4 * j + 2);
+        }
+    }
     __syncthreads();
     for (uint32_t c0 = 0; c0 < C; c0 += TILE_THREADS) {
         const uint32_t c = c0 + threadIdx.x;
         uint32_t b = 0, e = 0, nw = 0;
         if (c < C) {
-            b = soff[c], e = soff[c + 1];
-            a.cell_index[td.cell_base + c] = e > b ? b : RCB_NONE;
-            a.cell_count[td.cell_base + c] = e - b;
+            b = soff[oc0 + c], e = soff[oc0 + c + 1];
+            a.cell_index[td.cell_base + c_tile0 + c] = e > b ? band_off + (b - nt) : RCB_NONE;
+            a.cell_count[td.cell_base + c_tile0 + c] = e - b;
             coff[c] = 0;
             for (uint32_t sp = b; sp < e; ++sp) {
                 if (areas[sp] != 0) {
@@ -724,7 +936,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
                 } else {
 #pragma unroll
                     for (int d = 0; d < 8; ++d) nid[(uint32_t)d * S2 + sp] = (uint16_t)TN;
-                    *reinterpret_cast<uint2*>(a.con + 4ull * (span_base + sp)) = make_uint2(63u | (63u << 16), 63u | (63u << 16));
+                    *reinterpret_cast<uint2*>(a.con + 4ull * (span_base + sp - nt)) = make_uint2(63u | (63u << 16), 63u | (63u << 16));
                 }
             }
         }
@@ -739,15 +951,16 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
         if ((threadIdx.x & 31) == 31 && tot) base = atomicAdd(&sh_misc[3], tot);
         base = __shfl_sync(0xffffffffu, base, 31) + incl - nw;
         for (uint32_t sp = b; sp < e; ++sp)
-            if (areas[sp] != 0) work[base++] = (c << 16) | sp;
+            if (areas[sp] != 0) work[base++] = ((oc0 + c) << 16) | sp;
     }
     __syncthreads();
     // 3. link (:297-372) + con[4] (:392-427), one listed span per thread
     const uint32_t nwork = sh_misc[3];
     for (uint32_t k = threadIdx.x; k < nwork; k += TILE_THREADS) {
         const uint32_t item = work[k];
-        const uint32_t c = item >> 16, sp = item & 0xffffu;
-        const int z = (int)rcb_div_w(c, wmagic), x = (int)c - z * W;
+        const uint32_t c = item >> 16, sp = item & 0xffffu;  // c: held-cell index
+        const int zl = (int)rcb_div_w(c, wmagic), x = (int)c - zl * W;
+        const int z = zl + bd.hz0;  // row in the tile
         const uint32_t w = mm[sp];
         const int mn = (int16_t)(w & 0xffffu), mx = (int16_t)(w >> 16);
         uint32_t c4[4] = {63, 63, 63, 63};
@@ -757,7 +970,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
             const int nx = x + t_dirx[d], nz = z + t_dirz[d];
             uint32_t best = TN;
             if (!(nx < 0 || nz < 0 || nx >= W || nz >= H)) {
-                const uint32_t nb = soff[nz * W + nx], ne = soff[nz * W + nx + 1];
+                const uint32_t ncell = (uint32_t)((nz - bd.hz0) * W + nx);
+                const uint32_t nb = soff[ncell], ne = soff[ncell + 1];
                 int best_diff = 0x7fffffff;
                 for (uint32_t ns = nb; ns < ne; ++ns) {
                     if (areas[ns] == 0) continue;
@@ -781,29 +995,46 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
             }
             nid[(uint32_t)d * S2 + sp] = (uint16_t)best;
         }
-        *reinterpret_cast<uint2*>(a.con + 4ull * (span_base + sp)) =
+        *reinterpret_cast<uint2*>(a.con + 4ull * (span_base + sp - nt)) =
             make_uint2((c4[0] & 0xffffu) | (c4[1] << 16), (c4[2] & 0xffffu) | (c4[3] << 16));
-        if (nconn) atomicAdd(&coff[c], nconn);
+        if (nconn) atomicAdd(&coff[c - oc0], nconn);
     }
     if (threadIdx.x < 8) nid[threadIdx.x * S2 + S] = (uint16_t)S;  // the dummy span's neighbours are itself
     __syncthreads();
     pc.mark(1);
-    // 4. connection offsets inside the tile; publish the tile's count (nobody waits here)
+    // 4. connection offsets inside the band; publish the band's count (nobody waits here)
     const uint32_t K = block_scan_array(coff, coff, C, sh_warp);
-    if (threadIdx.x == 0) lookback_publish(look, tile, K);
+    if (threadIdx.x == 0) lookback_publish(look, band, K);
     pc.mark(2);
-    const TileB g{soff, areas, nid, S, S2, W, H, wmagic};
+    TileB g;
+    g.soff = soff, g.areas = areas, g.nid = nid, g.S = S, g.S2 = S2, g.own0 = own0, g.own1 = own1, g.nt = nt, g.nbot = nbot, g.G0 = G0;
+    g.W = W, g.rows = rows, g.row0 = row0, g.band = band, g.has_top = has_top, g.has_bot = has_bot;
+    g.flag_f = a.flag_f, g.flag_d = a.flag_d;
+    g.in_top = has_top ? reinterpret_cast<const uint4*>(a.pub + a.binfo[band - 1].pub_base) : nullptr;
+    g.out_down = reinterpret_cast<uint4*>(a.pub + bi.pub_base);
+    g.out_up = reinterpret_cast<uint4*>(a.pub + bi.pub_base + (has_bot ? 16ull * bi.bot_spans : 0ull));
+    g.in_bot = nullptr;
+    if (has_bot) {
+        const BandInfo nb_i = a.binfo[band + 1];  // its bottom hand-over (if any) comes first, then the records for me
+        const bool n_has_bot = a.bands[band + 1].hz1 > a.bands[band + 1].z1;
+        g.in_bot = reinterpret_cast<const uint4*>(a.pub + nb_i.pub_base + (n_has_bot ? 16ull * nb_i.bot_spans : 0ull));
+    }
     // 7 (hoisted). The connection list (compact_heightfield.rs:375-389: reverse direction order, next -> previously
     //    pushed, first_connection = last pushed) needs only the neighbour table and the tile's first connection
     //    index, so the warps that sit out the row-sequential forward sweep write it meanwhile.
     auto conn_work = [&](uint32_t rank, uint32_t nworkers) {
         if (rank < 32) {
-            const uint32_t excl = lookback_resolve(look, tile, K);
+            const uint32_t excl = lookback_resolve(look, band, K);
+            // first_connection / next are tile-relative: the tile's base is the prefix in front of its first band
+            const uint32_t tile_base_k = bd.z0 == 0 ? excl : lookback_inclusive(look, (int)a.band_first[tile] - 1);
             if (rank == 0) {
                 sh_misc[1] = excl;
-                a.tinfo[tile].conn_base = excl;
-                a.tinfo[tile].conn_count = K;
-                if (K) atomicAdd(&a.counters[9], (unsigned long long)K);
+                sh_misc[4] = tile_base_k;
+                if (bd.z0 == 0) a.tinfo[tile].conn_base = excl;
+                if (K) {
+                    atomicAdd(&a.tinfo[tile].conn_count, K);
+                    atomicAdd(&a.counters[9], (unsigned long long)K);
+                }
                 if ((unsigned long long)excl + K > a.Kcap) {
                     atomicOr(&a.counters[2], RCB_FLAG_CONN);
                     sh_misc[1] = 0xffffffffu;
@@ -815,7 +1046,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
         else
             asm volatile("bar.sync 2, %0;" ::"r"(nworkers) : "memory");
         const uint32_t conn_base = sh_misc[1];
-        if (conn_base == 0xffffffffu) return;  // the connection arena is too small for this tile: the host redoes the batch
+        if (conn_base == 0xffffffffu) return;  // the connection arena is too small for this band: the host redoes the batch
+        const uint32_t krel = conn_base - sh_misc[4];  // the band's first connection, tile-relative
+        const uint32_t ref_off = band_off - nt;        // band-local span id -> tile-relative
         // Each worker warp takes a contiguous run of cells, i.e. of spans and of the list, 32 spans at a time: a lane
         // counts its span's connections, then the lanes turn to the run's list SLOTS - slot t belongs to the span whose
         // range holds t (bisection over the lanes' offsets) and is its j-th present direction from 7 downwards - so the
@@ -824,7 +1057,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
         const uint32_t cpw = (C + nwarps - 1) / nwarps;
         const uint32_t cw0 = min(wid * cpw, C), cw1 = min(cw0 + cpw, C);
         uint32_t kbase = coff[cw0];
-        for (uint32_t s0 = soff[cw0], s1 = soff[cw1]; s0 < s1; s0 += 32) {
+        for (uint32_t s0 = soff[oc0 + cw0], s1 = soff[oc0 + cw1]; s0 < s1; s0 += 32) {
             const uint32_t s = s0 + lane;
             uint32_t mask = 0;
             if (s < s1) {
@@ -839,7 +1072,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
                 if (lane >= (uint32_t)d) incl += v;
             }
             const uint32_t excl = incl - cnt, T = __shfl_sync(0xffffffffu, incl, 31);
-            if (s < s1) a.first_conn[span_base + s] = cnt ? kbase + incl - 1 : RCB_NONE;  // the last one pushed
+            if (s < s1) a.first_conn[span_base + s - nt] = cnt ? krel + kbase + incl - 1 : RCB_NONE;  // the last one pushed
             const uint32_t rmask = __brev(mask) >> 24;  // bit i = direction 7 - i: the order the list is pushed in
             for (uint32_t t = lane; t < ((T + 31u) & ~31u); t += 32) {
                 // owner = the last lane whose range starts at or before t (empty ranges share their successor's start)
@@ -858,9 +1091,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
                     const uint32_t j = t - oex;
                     const uint32_t d = 7u - (uint32_t)__fns(orm, 0, (int)j + 1);
                     const uint32_t k = kbase + t;
-                    a.conn_ref[conn_base + k] = nid[d * S2 + s0 + lo];
+                    a.conn_ref[conn_base + k] = ref_off + nid[d * S2 + s0 + lo];
                     a.conn_dir[conn_base + k] = (uint8_t)d;
-                    a.conn_next[conn_base + k] = j ? k - 1 : RCB_NONE;
+                    a.conn_next[conn_base + k] = j ? krel + k - 1 : RCB_NONE;
                 }
             }
             kbase += T;
@@ -869,13 +1102,14 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
     auto no_work = [](uint32_t, uint32_t) {};
     bool conn_written = false;
     // 5. erosion (area.rs:73-234) — before the distance field when both are requested.  mm is dead: its
-    //    bytes are the sweep buffers d16a / d16b from here on.
+    //    bytes are the sweep buffers d16a / d16b from here on.  (Whole-tile bands only: the host never cuts a tile when
+    //    erosion is asked for.)
     if (a.do_erode) {
         const unsigned thr = (unsigned)(uint8_t)(uint32_t)(a.erode_radius * 2);
         conn_written = tile_sweep<uint8_t, true>(g, reinterpret_cast<uint8_t*>(d16a), reinterpret_cast<uint8_t*>(d16b), thr, nullptr,
                                                  nullptr, conn_work);
     }
-    for (uint32_t s = threadIdx.x; s < S; s += TILE_THREADS) a.areas[span_base + s] = areas[s];
+    for (uint32_t s = threadIdx.x; s < So; s += TILE_THREADS) a.areas[span_base + s] = areas[own0 + s];
     pc.mark(3);
     // 6. distance field (compact_heightfield.rs:514-727)
     if (a.do_dist) {
@@ -885,7 +1119,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
             conn_written = tile_sweep<uint16_t, false>(g, d16a, d16b, 0, &sh_misc[2], &pc, conn_work);
         pc.mark(4);
         // box blur: d16a holds D; result to global
-        for (uint32_t s = threadIdx.x; s < S; s += TILE_THREADS) {
+        for (uint32_t s = own0 + threadIdx.x; s < own1; s += TILE_THREADS) {
             const uint32_t cd = d16a[s];
             uint32_t r = cd;
             if (cd > 2) {
@@ -905,12 +1139,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
                 }
                 r = (uint32_t)(d / n);
             }
-            a.dist[span_base + s] = (uint16_t)r;
+            a.dist[span_base + s - nt] = (uint16_t)r;
         }
-        if (threadIdx.x == 0) a.tinfo[tile].max_distance = sh_misc[2];
+        if (threadIdx.x == 0 && sh_misc[2]) atomicMax(&a.tinfo[tile].max_distance, sh_misc[2]);
         pc.mark(5);
     } else {
-        for (uint32_t s = threadIdx.x; s < S; s += TILE_THREADS) a.dist[span_base + s] = 0;  // compact_heightfield.rs:253
+        for (uint32_t s = threadIdx.x; s < So; s += TILE_THREADS) a.dist[span_base + s] = 0;  // compact_heightfield.rs:253
     }
     pc.mark(6);
     if (!conn_written) conn_work(threadIdx.x, TILE_THREADS);  // no sweep ran, or the tile is as wide as the block
@@ -923,11 +1157,11 @@ static void set_smem_attr(const void* fn, size_t bytes) {
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-void launch_tile_spans(const TileSpansArgs& a, int ntiles, cudaStream_t s) {
-    if (ntiles == 0) return;
+void launch_tile_spans(const TileSpansArgs& a, int nbands, cudaStream_t s) {
+    if (nbands == 0) return;
     set_smem_attr((const void*)k_tile_spans, a.smem_bytes);
     KScope _k("k_tile_spans", s);
-    k_tile_spans<<<ntiles, TILE_THREADS, a.smem_bytes, s>>>(a);
+    k_tile_spans<<<nbands, TILE_THREADS, a.smem_bytes, s>>>(a);
 }
 
 void launch_tile_segments(const uint32_t* tile_ub, uint32_t* tile_base, int ntiles, unsigned long long* counters,
@@ -936,14 +1170,20 @@ void launch_tile_segments(const uint32_t* tile_ub, uint32_t* tile_base, int ntil
     k_tile_segments<<<1, 1024, 0, s>>>(tile_ub, tile_base, ntiles, counters, cap_frags, cap_items);
 }
 
-void launch_tile_scan(TileInfo* tinfo, int ntiles, unsigned long long* counters, unsigned long long span_cap, cudaStream_t s) {
+void launch_tile_scan(const BandDesc* bands, BandInfo* binfo, int nbands, const TileDesc* tiles, const uint32_t* band_first, TileInfo* tinfo,
+                      int ntiles, unsigned long long* counters, unsigned long long span_cap, unsigned long long pub_cap, int compact,
+                      cudaStream_t s) {
     KScope _k("k_tile_scan", s);
-    k_tile_scan<<<1, 1024, 0, s>>>(tinfo, ntiles, counters, span_cap);
+    k_tile_scan<<<1, 1024, 0, s>>>(bands, binfo, nbands, tiles, band_first, tinfo, ntiles, counters, span_cap, pub_cap, compact);
 }
 
-void launch_tile_compact(const TileCompactArgs& a, int ntiles, cudaStream_t s) {
-    if (ntiles == 0) return;
+size_t tile_compact_smem_bytes(uint32_t own_cells, uint32_t held_cells, uint32_t held_spans, uint32_t top_spans, uint32_t bot_spans) {
+    return compact_smem_need(own_cells, held_cells, held_spans, top_spans, bot_spans);
+}
+
+void launch_tile_compact(const TileCompactArgs& a, int nbands, cudaStream_t s) {
+    if (nbands == 0) return;
     set_smem_attr((const void*)k_tile_compact, a.smem_bytes);
     KScope _k("k_tile_compact", s);
-    k_tile_compact<<<ntiles, TILE_THREADS, a.smem_bytes, s>>>(a);
+    k_tile_compact<<<nbands, TILE_THREADS, a.smem_bytes, s>>>(a);
 }

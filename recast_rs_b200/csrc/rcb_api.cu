@@ -76,7 +76,10 @@ struct BatchHint {
     uint64_t ntris = 0, nverts = 0;
     uint32_t stage_mask = 0;
     int32_t merge_thr = 0;
-    uint64_t ub = 0, nitems = 0, ub_max = 0, S = 0, walk = 0, s_max = 0, K = 0;
+    uint64_t ub = 0, nitems = 0, ub_max = 0, S = 0, walk = 0, K = 0;
+    uint64_t need_b = 0;     // shared memory of k_tile_compact's largest band
+    uint64_t pub = 0;        // bytes handed over between the bands of a tile
+    uint32_t band_cells = 0;  // how the tiles were cut (the sizes above belong to this cut)
 };
 
 // Everything about a batch that depends only on its configurations: validated tile descriptors, the locator grid over
@@ -90,12 +93,20 @@ struct BatchEntry {
     uint32_t max_cells = 0;
     DevBuf d_tiles, d_bin_off, d_bin_tiles;
     bool have_locator = false, uploaded_tiles = false, uploaded_locator = false;
+    // how the tiles are cut into bands for the tile-resident kernels (BandDesc), for the current band_cells
+    uint32_t band_cells = 0;
+    std::vector<BandDesc> bands;
+    std::vector<uint32_t> band_first;  // [ntiles + 1]
+    uint32_t max_held_cells = 0, max_bands_per_tile = 0;
+    DevBuf d_bands, d_band_first;
     BatchHint hint;
     unsigned long long last_use = 0;
     ~BatchEntry() {
         d_tiles.release();
         d_bin_off.release();
         d_bin_tiles.release();
+        d_bands.release();
+        d_band_first.release();
     }
 };
 
@@ -122,7 +133,8 @@ struct rcb_ctx {
     DevBuf d_counters, d_cell_cnt, d_frag_off, d_frag_tmp, d_frag_rec, d_fs_mm, d_fs_area, d_scan_tmp, d_hf_off, d_conn_cnt,
         d_conn_off, d_nid, d_t16a, d_t16b, d_t16c, d_t8a, d_t8b, d_item_cnt, d_item_off, d_items, d_tile_ub, d_tile_base, d_tile_cursor,
         d_tile_frags, d_ts_mm, d_ts_area, d_celloff_tmp, d_lookback, d_tc_regons, d_tc_areas, d_tc_obs, d_fidx, d_span_cell, d_wire, d_wire_off,
-        d_wire_pos, d_wire_inoff, d_wire_err, d_tc_raw, d_tc_parsed, d_rg_a, d_rg_b;
+        d_wire_pos, d_wire_inoff, d_wire_err, d_tc_raw, d_tc_parsed, d_rg_a, d_rg_b, d_binfo, d_pub;
+    uint32_t band_cells = 4608;  // RCB_BAND_CELLS: cells per band of the tile-resident kernels (a 64x64 tile and a bit stays whole)
     uint32_t clip_flags = 1;    // RCB_CLIP_FLAGS (A/B runs): bit0 min-x skip test in the clipper
     bool phase_timers = false;  // RCB_PHASE_TIMERS=1: per-phase cycle sums of the tile kernels on stderr
     bool force_global = false;  // RCB_FORCE_GLOBAL=1: never use the tile-resident back end (k_tile.cu)
@@ -450,6 +462,42 @@ int upload_batch_entry(rcb_ctx* ctx, BatchEntry& e, bool need_locator) {
     return RCB_OK;
 }
 
+// Cuts every tile of the entry into bands of about `band_cells` cells (rcb_band_rows: whole tiles when they are small enough)
+// and puts the tables on the device; kept with the entry until another cut is asked for.
+int make_bands(rcb_ctx* ctx, BatchEntry& e, uint32_t band_cells) {
+    if (e.band_cells == band_cells && !e.band_first.empty()) return RCB_OK;
+    const size_t ntiles = e.tiles.size();
+    e.bands.clear();
+    e.band_first.assign(ntiles + 1, 0);
+    e.max_held_cells = 0;
+    e.max_bands_per_tile = 0;
+    for (size_t t = 0; t < ntiles; ++t) {
+        const TileDesc& td = e.tiles[t];
+        const int R = rcb_band_rows(td.width, td.height, band_cells);
+        e.band_first[t] = (uint32_t)e.bands.size();
+        uint32_t nb = 0;
+        for (int z0 = 0; z0 < td.height; z0 += R, ++nb) {
+            BandDesc b;
+            b.tile = (uint32_t)t;
+            b.z0 = z0;
+            b.z1 = std::min(z0 + R, td.height);
+            b.hz0 = std::max(z0 - 1, 0);
+            b.hz1 = std::min(b.z1 + 1, td.height);
+            e.bands.push_back(b);
+            e.max_held_cells = std::max(e.max_held_cells, (uint32_t)(td.width * (b.hz1 - b.hz0)));
+        }
+        e.max_bands_per_tile = std::max(e.max_bands_per_tile, nb);
+    }
+    e.band_first[ntiles] = (uint32_t)e.bands.size();
+    e.band_cells = band_cells;
+    CU(e.d_bands.ensure(sizeof(BandDesc) * e.bands.size() + 64));
+    CU(e.d_band_first.ensure(4 * (ntiles + 1) + 64));
+    if (!e.bands.empty()) CU(cudaMemcpyAsync(e.d_bands.p, e.bands.data(), sizeof(BandDesc) * e.bands.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(e.d_band_first.p, e.band_first.data(), 4 * (ntiles + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // pageable sources; once per cut
+    return RCB_OK;
+}
+
 // Arena A: per-tile info, cells, spans.  The arrays a slim download copies come first (one copy of a prefix);
 // hf_cell_offset and first_conn, which the slim layout leaves on the device, come last.
 void make_layout(ArenaLayout& l, int ntiles, uint64_t C, uint64_t S, uint32_t stage_mask) {
@@ -504,6 +552,7 @@ struct Source {  // where the heightfield comes from
     const uint8_t* sarea = nullptr;
     const uint8_t* areas_override = nullptr;  // host, optional
     bool no_spec = false;                     // the synchronous path, whatever the entry's hint says
+    uint32_t band_cells = 0;                  // cut the tiles into bands of about this many cells (0: the default / the hint's)
     bool no_tile_mode = false;                // set when the tile-resident back end reported an overflow
     bool wide_clip = false;                   // set when the 6-vertex clipper overflowed: use the 12-vertex one
     const rcb_area_op* ops = nullptr;         // host, area operators applied after linking (rcb_apply_area_ops)
@@ -873,41 +922,69 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         r2.flags = ctx->clip_flags | (ctx->phase_timers ? 0x100u : 0u);
         uint64_t ub = 0, nitems = 0, ub_max = 0;
         bool want_tile = false;
-        // tile-resident back end candidates: moderate tiles (the CSR arrays of a tile must fit shared memory; fragment
-        // records carry a 24-bit triangle index)
+        // tile-resident back end candidates: a band of two rows (plus its halo rows) must fit shared memory; fragment
+        // records carry a 24-bit triangle index
+        int max_width = 0;
+        for (const TileDesc& t : tiles) max_width = std::max(max_width, (int)t.width);
         const bool tile_ok = v2 && !ctx->force_global && !src.no_tile_mode && src.nvols == 0 && !src.cell_offset &&
-                             8ull * max_cells + 4096 <= kTileSmem && ntris < (1u << 24);
+                             8ull * 4ull * (uint64_t)max_width + 4096 <= kTileSmem / 2 && ntris < (1u << 24);
         // Speculative issue: the previous build of this batch left its sizes in the entry's hint.  With them every
         // buffer, shared-memory size and arena layout can be chosen now, so the whole step is enqueued without a single
         // host round trip; the kernels verify the sizes on the device and rcb_result_* redo the batch if one was short.
         const BatchHint h = entry->hint;
         const bool spec = do_raster && ntiles > 0 && tile_ok && !ctx->no_spec && !src.no_spec && !src.tri_areas && h.valid && h.ub > 0 &&
                           h.ntris == ntris && h.nverts == nverts && h.stage_mask == stage_mask && h.merge_thr == src.merge_thr &&
-                          !(stage_mask & RCB_STAGE_REGIONS) && !ctx->phase_timers;
+                          !(stage_mask & RCB_STAGE_REGIONS) && !ctx->phase_timers && (src.band_cells == 0 || src.band_cells == h.band_cells);
         auto margin = [](uint64_t v) { return v + v / 64 + 256; };
         const bool compact = (stage_mask & RCB_STAGE_COMPACT) != 0;
+        // How the tiles are cut into bands: whole tiles when they fit (4608 cells: a 64x64 tile and a bit), else equal runs of
+        // rows; erosion is a second row-sequential sweep that the bands do not hand over, so it keeps tiles whole.
+        uint32_t band_cells = src.band_cells ? src.band_cells : (h.valid && h.band_cells ? h.band_cells : ctx->band_cells);
+        if ((stage_mask & RCB_STAGE_ERODE) || !tile_ok) band_cells = 0x7fffffffu;
+        int nbands = ntiles;
+        auto retry_with = [&](uint64_t need, uint64_t budget) -> int {  // a band needs `need` bytes of `budget`: cut finer, or give up
+            Source s2 = src;
+            s2.no_spec = true;
+            const uint64_t cur = std::min<uint64_t>(band_cells, entry->max_held_cells);
+            uint64_t next = need ? cur * budget / need * 7 / 8 : 0;
+            if (next >= cur) next = cur * 3 / 4;
+            if ((stage_mask & RCB_STAGE_ERODE) || next < 4ull * (uint64_t)max_width || (uint64_t)max_width * 2 > next)
+                s2.no_tile_mode = true;  // bands of two rows would still not fit: the global-memory back end
+            else
+                s2.band_cells = (uint32_t)next;
+            rcb_result_free(res);
+            return run_pipeline(ctx, cfgs, ntiles, stage_mask, erode_radius, s2, out);
+        };
         if (do_raster && ntiles > 0) {
             if (v2) {
+                {
+                    const int r = make_bands(ctx, *entry, band_cells);
+                    if (r) return bail(r);
+                }
+                nbands = (int)entry->bands.size();
                 CUB(ctx->d_item_cnt.ensure(4 * (ntris + 2)));
                 CUB(ctx->d_item_off.ensure(4 * (ntris + 2)));
                 CUB(ctx->d_scan_tmp.ensure(4 * scan_tmp_elems(ntris + 1)));
                 r2.item_cnt = ctx->d_item_cnt.as<uint32_t>();
-                // per-tile fragment bounds -> per-tile segments (both back ends consume fragments tile by tile)
-                CUB(ctx->d_tile_ub.ensure(4 * ((size_t)ntiles + 1)));
-                CUB(ctx->d_tile_base.ensure(4 * ((size_t)ntiles + 2)));
-                CUB(ctx->d_tile_cursor.ensure(4 * ((size_t)ntiles + 1)));
-                CUB(cudaMemsetAsync(ctx->d_tile_ub.p, 0, 4 * ((size_t)ntiles + 1), st));
-                CUB(cudaMemsetAsync(ctx->d_tile_cursor.p, 0, 4 * ((size_t)ntiles + 1), st));
+                // per-band fragment bounds -> per-band segments (both back ends consume fragments segment by segment;
+                // the global one always with whole-tile bands)
+                CUB(ctx->d_tile_ub.ensure(4 * ((size_t)nbands + 1)));
+                CUB(ctx->d_tile_base.ensure(4 * ((size_t)nbands + 2)));
+                CUB(ctx->d_tile_cursor.ensure(4 * ((size_t)nbands + 1)));
+                CUB(cudaMemsetAsync(ctx->d_tile_ub.p, 0, 4 * ((size_t)nbands + 1), st));
+                CUB(cudaMemsetAsync(ctx->d_tile_cursor.p, 0, 4 * ((size_t)nbands + 1), st));
                 r2.tile_ub = ctx->d_tile_ub.as<uint32_t>();
+                r2.band_first = entry->d_band_first.as<uint32_t>();
+                r2.band_cells = band_cells;
                 launch_bin_count(r2, st);
                 // speculative: the fragment / work-item totals must stay within what the buffers were sized for
-                launch_tile_segments(r2.tile_ub, ctx->d_tile_base.as<uint32_t>(), ntiles, r2.counters, spec ? margin(h.ub) : ~0ull,
+                launch_tile_segments(r2.tile_ub, ctx->d_tile_base.as<uint32_t>(), nbands, r2.counters, spec ? margin(h.ub) : ~0ull,
                                      spec ? margin(h.nitems) : ~0ull, st);
             } else {
                 launch_count_fragments(rb, st);
             }
             if (spec) {
-                // shared-memory sizes decide how many CTAs an SM holds: no margin on the per-tile maxima (a tile that
+                // shared-memory sizes decide how many CTAs an SM holds: no margin on the per-band maxima (a band that
                 // outgrows them raises its flag and the batch is rebuilt with the new maxima)
                 ub = margin(h.ub), nitems = margin(h.nitems), ub_max = h.ub_max;
                 want_tile = true;
@@ -920,19 +997,36 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                 ub_max = ctx->h_counters[5];
                 if (ub >= 0xfffffff0ull || nitems >= 0xfffffff0ull)
                     return bail(fail(ctx, RCB_EARG, "batch too large: fragment bound %llu", (unsigned long long)ub));
-                // the bound counts whole footprints; real fragment counts are about half of it on triangle meshes
-                want_tile = tile_ok && 8ull * max_cells + 8ull * (ub_max / 3) + 4096 <= kTileSmem;
+                if (tile_ok) {
+                    // the bound counts whole footprints; real fragment counts are about half of it on triangle meshes
+                    const uint64_t needA = 8ull * entry->max_held_cells + 8ull * (ub_max / 3) + 4096;
+                    want_tile = needA <= kTileSmem && entry->max_bands_per_tile <= 16;
+                    if (!want_tile && band_cells != 0x7fffffffu && entry->max_bands_per_tile <= 16) return retry_with(needA, kTileSmem);
+                    if (!want_tile && entry->bands.size() != (size_t)ntiles) {  // the global back end wants whole-tile segments
+                        Source s2 = src;
+                        s2.no_tile_mode = true;
+                        rcb_result_free(res);
+                        return run_pipeline(ctx, cfgs, ntiles, stage_mask, erode_radius, s2, out);
+                    }
+                }
             }
         }
         if (want_tile && ub > 0) {
             // ================= tile-resident back end (k_tile.cu) ==============================================
+            const uint32_t max_held = entry->max_held_cells;
+            const BandDesc* d_bands = entry->d_bands.as<BandDesc>();
             CUB(ctx->d_tile_frags.ensure(12 * ub + 64));
             CUB(ctx->d_ts_mm.ensure(4 * ub + 64));
             CUB(ctx->d_ts_area.ensure(ub + 64));
             CUB(ctx->d_celloff_tmp.ensure(4 * (Ctot + ntiles) + 64));
-            CUB(ctx->d_lookback.ensure(8 * ((size_t)ntiles + 2)));
+            // look-back words, the ticket, and the two hand-over flags per band
+            const size_t look_bytes = 8 * ((size_t)nbands + 2), flags_bytes = 4 * (size_t)nbands;
+            CUB(ctx->d_lookback.ensure(look_bytes + 2 * flags_bytes + 64));
+            CUB(ctx->d_binfo.ensure(sizeof(BandInfo) * (size_t)nbands + 64));
             CUB(ctx->d_items.ensure(8 * nitems + 64));
-            CUB(cudaMemsetAsync(ctx->d_lookback.p, 0, 8 * ((size_t)ntiles + 2), st));
+            CUB(cudaMemsetAsync(ctx->d_lookback.p, 0, look_bytes + 2 * flags_bytes, st));
+            CUB(cudaMemsetAsync(ctx->d_binfo.p, 0, sizeof(BandInfo) * (size_t)nbands, st));
+            BandInfo* d_binfo = ctx->d_binfo.as<BandInfo>();
             r2.tile_cursor = ctx->d_tile_cursor.as<uint32_t>();
             r2.tile_base = ctx->d_tile_base.as<uint32_t>();
             r2.tile_cap = ctx->d_tile_ub.as<uint32_t>();
@@ -943,6 +1037,8 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             launch_clip_items(r2, ctx->d_items.as<uint2>(), (uint32_t)nitems, d_tinfo_tmp, st);
             TileSpansArgs ta{};
             ta.tiles = d_tiles;
+            ta.bands = d_bands;
+            ta.binfo = d_binfo;
             ta.tile_frags = r2.tile_frags;
             ta.tile_base = r2.tile_base;
             ta.tile_cap = r2.tile_cap;
@@ -950,44 +1046,41 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             ta.hf_cell_offset = ctx->d_celloff_tmp.as<uint32_t>();
             ta.ts_mm = ctx->d_ts_mm.as<uint32_t>();
             ta.ts_area = ctx->d_ts_area.as<uint8_t>();
-            ta.tinfo = d_tinfo_tmp;
             ta.counters = r2.counters;
             ta.fmask = fmask;
             ta.merge_thr = src.merge_thr;
             ta.phase = ctx->phase_timers ? r2.counters + 16 : nullptr;
             {
                 // exact bound: never overflows when it fits.  Above the two-CTAs-per-SM budget the first
-                // launch runs small and defers the few tiles that need more to a second, large launch.
-                const uint64_t exact = 8ull * (max_cells + 4) + 8ull * ub_max + 64;
+                // launch runs small and defers the few bands that need more to a second, large launch.
+                const uint64_t exact = 8ull * (max_held + 4) + 8ull * ub_max + 64;
                 const uint64_t small = kTileSmem / 2 - 2048;
                 ta.pass = 0;
                 ta.defer = exact > small;
                 ta.smem_bytes = (uint32_t)(exact <= small ? exact : small);
-                launch_tile_spans(ta, ntiles, st);
+                launch_tile_spans(ta, nbands, st);
                 if (ta.defer) {
                     ta.pass = 1;
                     ta.defer = 0;
                     ta.smem_bytes = (uint32_t)(exact <= kTileSmem ? exact : kTileSmem);
-                    launch_tile_spans(ta, ntiles, st);
+                    launch_tile_spans(ta, nbands, st);
                 }
             }
-            uint64_t walk = 0, s_max = 0, Kcap = 0;
+            uint64_t walk = 0, needB = 64, Kcap = 0, pub = 0;
             if (spec) {
-                S = margin(h.S), walk = margin(h.walk), s_max = h.s_max;
+                S = margin(h.S), walk = margin(h.walk), needB = h.need_b, pub = margin(h.pub);
                 Kcap = compact ? (h.K ? margin(h.K) : 8ull * walk) : 0;
-                if (s_max > 0xfffeu) s_max = 0xfffeu;
-                launch_tile_scan(d_tinfo_tmp, ntiles, r2.counters, S, st);
+                launch_tile_scan(d_bands, d_binfo, nbands, d_tiles, r2.band_first, d_tinfo_tmp, ntiles, r2.counters, S, pub, compact ? 1 : 0, st);
             } else {
-                launch_tile_scan(d_tinfo_tmp, ntiles, r2.counters, ~0ull, st);
-                CUB(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                launch_tile_scan(d_bands, d_binfo, nbands, d_tiles, r2.band_first, d_tinfo_tmp, ntiles, r2.counters, ~0ull, ~0ull, compact ? 1 : 0, st);
+                CUB(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 11 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
                 CUB(cudaStreamSynchronize(st));
-                bool overflow = (ctx->h_counters[2] & 6ull) != 0;
+                const bool overflow = (ctx->h_counters[2] & 6ull) != 0;
                 const bool poly_overflow = (ctx->h_counters[2] & 1ull) != 0;  // a clip polygon outgrew the 6-vertex slots
                 S = ctx->h_counters[6];
-                walk = ctx->h_counters[7], s_max = ctx->h_counters[8];
-                const uint64_t needB0 = compact ? 6ull * (max_cells + 2) + 21ull * s_max + 192 : 64;
-                if (compact && s_max >= 0xffffu) overflow = true;  // tile-local span ids are 16 bit
-                if (needB0 > kTileSmem) overflow = true;
+                walk = ctx->h_counters[7];
+                needB = compact ? ctx->h_counters[8] : 64;
+                pub = ctx->h_counters[10];
                 if (overflow || poly_overflow) {  // redo the batch on the global-memory back end (and the wide clipper)
                     Source s2 = src;
                     s2.no_tile_mode = true;
@@ -995,6 +1088,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                     rcb_result_free(res);
                     return run_pipeline(ctx, cfgs, ntiles, stage_mask, erode_radius, s2, out);
                 }
+                if (needB > kTileSmem) return retry_with(needB, kTileSmem);  // the largest band does not fit: cut finer
                 Kcap = compact ? 8ull * walk : 0;
                 res->S = S;
                 res->F = ctx->h_counters[1];
@@ -1002,11 +1096,12 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                 BatchHint nh;
                 nh.valid = true;
                 nh.ntris = ntris, nh.nverts = nverts, nh.stage_mask = stage_mask, nh.merge_thr = src.merge_thr;
-                nh.ub = ub, nh.nitems = nitems, nh.ub_max = ub_max, nh.S = S, nh.walk = walk, nh.s_max = s_max;
-                nh.K = (h.valid && h.S == S && h.walk == walk) ? h.K : 0;
+                nh.ub = ub, nh.nitems = nitems, nh.ub_max = ub_max, nh.S = S, nh.walk = walk, nh.need_b = needB, nh.pub = pub;
+                nh.band_cells = band_cells;
+                nh.K = (h.valid && h.S == S && h.walk == walk && h.band_cells == band_cells) ? h.K : 0;
                 entry->hint = nh;
             }
-            const uint64_t needB = compact ? 6ull * (max_cells + 2) + 21ull * s_max + 192 : 64;
+            CUB(ctx->d_pub.ensure(pub + 64));
             make_layout(res->lay, ntiles, Ctot, S, stage_mask);
             CUB(pool_get(ctx->free_dev, res->lay.bytesA, false, res->devA));
             char* A = res->devA.p;
@@ -1017,6 +1112,13 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             char* B = res->devB.p;
             TileCompactArgs tc{};
             tc.tiles = d_tiles;
+            tc.bands = d_bands;
+            tc.binfo = d_binfo;
+            tc.band_first = r2.band_first;
+            tc.work = r2.tile_frags;
+            tc.pub = (unsigned char*)ctx->d_pub.p;
+            tc.flag_f = (uint32_t*)((char*)ctx->d_lookback.p + look_bytes);
+            tc.flag_d = tc.flag_f + nbands;
             tc.tile_base = r2.tile_base;
             tc.hf_cell_offset_in = ctx->d_celloff_tmp.as<uint32_t>();
             tc.ts_mm = ctx->d_ts_mm.as<uint32_t>();
@@ -1024,7 +1126,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             tc.tinfo = d_tinfo;
             tc.counters = r2.counters;
             tc.lookback = ctx->d_lookback.as<unsigned long long>();
-            tc.tile_ticket = (uint32_t*)(ctx->d_lookback.as<unsigned long long>() + ntiles);
+            tc.tile_ticket = (uint32_t*)(ctx->d_lookback.as<unsigned long long>() + nbands);
             tc.hf_cell_offset = (uint32_t*)(A + res->lay.hf_cell_offset);
             tc.smin = (int16_t*)(A + res->lay.span_min);
             tc.smax = (int16_t*)(A + res->lay.span_max);
@@ -1046,18 +1148,18 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             tc.do_dist = (stage_mask & RCB_STAGE_DIST) != 0;
             tc.erode_radius = erode_radius;
             tc.phase = ctx->phase_timers ? r2.counters + 16 : nullptr;
-            tc.smem_bytes = (uint32_t)std::min<uint64_t>(needB, kTileSmem);
-            launch_tile_compact(tc, ntiles, st);
+            tc.smem_bytes = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(needB, 64), kTileSmem);
+            launch_tile_compact(tc, nbands, st);
             if (ctx->phase_timers) {
                 unsigned long long ph[32];
                 cudaMemcpyAsync(ph, r2.counters + 16, sizeof ph, cudaMemcpyDeviceToHost, st);
                 cudaStreamSynchronize(st);
                 fprintf(stderr, "[rcb phase cycles/CTA] clip: z-chain %llu list %llu x-chain(thread 0) %llu | ", ph[24] / (ph[27] ? ph[27] : 1),
                         ph[25] / (ph[27] ? ph[27] : 1), ph[26] / (ph[27] ? ph[27] : 1));
-                fprintf(stderr, "[rcb phase cycles/tile] spans:");
-                for (int i = 0; i < 7; ++i) fprintf(stderr, " %llu", ph[i] / (unsigned long long)ntiles);
+                fprintf(stderr, "[rcb phase cycles/band] (%d bands) spans:", nbands);
+                for (int i = 0; i < 7; ++i) fprintf(stderr, " %llu", ph[i] / (unsigned long long)nbands);
                 fprintf(stderr, " | compact:");
-                for (int i = 8; i < 20; ++i) fprintf(stderr, " %llu", ph[i] / (unsigned long long)ntiles);
+                for (int i = 8; i < 20; ++i) fprintf(stderr, " %llu", ph[i] / (unsigned long long)nbands);
                 fprintf(stderr, "\n");
             }
             res->tile_mode = true;
@@ -1386,7 +1488,8 @@ int resolve_result(rcb_result* res) {
             if (res->spec) {
                 h.ub = c[0], h.nitems = c[4], h.S = c[6], h.walk = c[7];
                 h.ub_max = std::max<uint64_t>(h.ub_max, c[5]);
-                h.s_max = std::max<uint64_t>(h.s_max, c[8]);
+                h.need_b = std::max<uint64_t>(h.need_b, c[8]);
+                h.pub = c[10];
                 h.K = c[9];
             } else if (h.S == c[6] && h.walk == c[7]) {
                 h.K = c[9];
@@ -1473,6 +1576,7 @@ int rcb_create(int device, rcb_ctx** out) {
     if (const char* e = getenv("RCB_PHASE_TIMERS")) ctx->phase_timers = e[0] == '1';
     if (const char* e = getenv("RCB_CLIP_FLAGS")) ctx->clip_flags = (uint32_t)atoi(e);
     if (const char* e = getenv("RCB_NO_SPEC")) ctx->no_spec = e[0] == '1';
+    if (const char* e = getenv("RCB_BAND_CELLS")) ctx->band_cells = (uint32_t)std::max(1, atoi(e));
     *out = ctx;
     return RCB_OK;
 }
@@ -1499,7 +1603,7 @@ void rcb_destroy(rcb_ctx* ctx) {
                       &ctx->d_t16a, &ctx->d_t16b, &ctx->d_t16c, &ctx->d_t8a, &ctx->d_t8b, &ctx->d_item_cnt, &ctx->d_item_off, &ctx->d_items, &ctx->d_tile_ub, &ctx->d_tile_base,
                       &ctx->d_tile_cursor, &ctx->d_tile_frags, &ctx->d_ts_mm, &ctx->d_ts_area, &ctx->d_celloff_tmp, &ctx->d_lookback, &ctx->d_tc_regons, &ctx->d_tc_areas,
                       &ctx->d_tc_obs, &ctx->d_fidx, &ctx->d_span_cell, &ctx->d_wire, &ctx->d_wire_off, &ctx->d_wire_pos, &ctx->d_wire_inoff, &ctx->d_wire_err,
-                      &ctx->d_tc_raw, &ctx->d_tc_parsed, &ctx->d_rg_a, &ctx->d_rg_b};
+                      &ctx->d_tc_raw, &ctx->d_tc_parsed, &ctx->d_rg_a, &ctx->d_rg_b, &ctx->d_binfo, &ctx->d_pub};
     for (auto* b : bufs) b->release();
     for (auto& a : ctx->free_dev) cudaFree(a.p);
     for (auto& a : ctx->free_host) cudaFreeHost(a.p);
