@@ -397,17 +397,27 @@ def run_native(args, rank, world, local_rank):
     l0 = ctx.launch_count()
     barrier()
     wall0 = time.perf_counter()
+    held = []
     for _ in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations (outside the event pair)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         r = step()
         b.record(stream)
-        r.free()
+        held.append(r)  # the host does not wait inside the step: what it produced is checked after the timed region
         evs.append((a, b))
     barrier()
     wall = time.perf_counter() - wall0
     launches = ctx.launch_count() - l0
+    st0 = ctx.stats()
+    for r in held:  # every timed step must have produced the full result without being rebuilt
+        tt = r.totals()
+        if {k: x for k, x in tt.items() if k != "result_bytes"} != {k: x for k, x in tot.items() if k != "result_bytes"}:
+            raise SystemExit(f"bench.py: a timed step produced {tt}, expected {tot}")
+        r.free()
+    st1 = ctx.stats()
+    if st1["rebuilt"] != st0["rebuilt"]:
+        raise SystemExit(f"bench.py: {st1['rebuilt'] - st0['rebuilt']} timed steps had to be rebuilt (sizes assumed from the previous build were short)")
     # the timed region lasts tens of milliseconds, less than one nvidia-smi period: keep the same load running
     # (untimed) until the sampler has seen it, so the clocks line describes this workload and not an idle GPU
     while time.perf_counter() - wall0 < 0.7:
@@ -532,6 +542,7 @@ def run_native(args, rank, world, local_rank):
                     else "rcb_upload_mesh + rcb_build_tiles + rcb_result_download",
                     **({"pipelined": pipe} if pipe else {})},
             "gpu_launches": int(launches),
+            "issue": {"steps_issued_without_host_round_trip": st1["speculative"], "steps_rebuilt": st1["rebuilt"]},
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (read_traffic() or {}).get("main_kernels_sum") if args.config == 2 and world == 1 else None,

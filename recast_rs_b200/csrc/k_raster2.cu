@@ -126,18 +126,19 @@ __global__ void __launch_bounds__(256) k_bin_count(Raster2 rb) {
                 if (x1 < x0 || z1 < zz0) return;
                 const uint32_t nrows = (uint32_t)(z1 - zz0 + 1), ncols = (uint32_t)(x1 - x0 + 1);
                 items += (nrows + CLIP_ROWS - 1) / CLIP_ROWS;
-                ub += ncols * nrows;
+                if (!rb.tile_ub) ub += ncols * nrows;
                 if (rb.tile_ub) {
                     // per band: the rows of the footprint the band holds, its halo rows included (a border row counts
                     // for both bands, as emit_fragment writes it to both)
-                    const int R = rcb_band_rows(td.width, td.height, rb.band_cells);
-                    const uint32_t b0 = rb.band_first[tile];
+                    const int R = td.band_rows;
+                    const uint32_t b0 = td.band_first;
                     const int bl = max(zz0 - 1, 0) / R, bh = min(z1 + 1, td.height - 1) / R;
                     for (int b = bl; b <= bh; ++b) {
                         const int hz0 = max(b * R - 1, 0), hz1 = min((b + 1) * R + 1, td.height);  // rows held: [hz0, hz1)
                         const int r0 = max(zz0, hz0), r1 = min(z1, hz1 - 1);
                         if (r1 < r0) continue;
                         const uint32_t f = ncols * (uint32_t)(r1 - r0 + 1);
+                        ub += f;  // the segments' total: a border row is held by two bands
                         // neighbouring triangles mostly share the band: one atomic per (warp, band)
                         const unsigned peers = __match_any_sync(__activemask(), b0 + (uint32_t)b);
                         const uint32_t sum = __reduce_add_sync(peers, f);
@@ -246,14 +247,15 @@ __device__ __forceinline__ void emit_fragment(const Raster2& rb, const TileDesc&
         // per-band segments (tile-resident back end, and the global back end's per-tile scatter with whole-tile bands).
         // The band that owns row z, and - a band keeps one halo row on either side - the band above when z is its
         // neighbour's first row, the band below when z is its neighbour's last row.
-        const int R = rcb_band_rows(td.width, td.height, rb.band_cells);
-        const uint32_t b0 = rb.band_first[tile];
-        const int b = z / R;
-        const int hz0 = max(b * R - 1, 0);
-        emit_to_segment(rb, td, b0 + (uint32_t)b, (uint32_t)(z - hz0) * td.width + x, tcell, tri, mm, area);
-        if (R < td.height) {
-            if (z == b * R && b > 0) emit_to_segment(rb, td, b0 + (uint32_t)b - 1u, (uint32_t)(z - max((b - 1) * R - 1, 0)) * td.width + x, tcell, tri, mm, area);
-            if (z == (b + 1) * R - 1 && z + 1 < td.height) emit_to_segment(rb, td, b0 + (uint32_t)b + 1u, (uint32_t)x, tcell, tri, mm, area);
+        const int R = td.band_rows;
+        if (R >= td.height) {  // the tile is one band
+            emit_to_segment(rb, td, td.band_first, tcell, tcell, tri, mm, area);
+        } else {
+            const int b = (int)rcb_div_w((uint32_t)z, td.bmagic);
+            const uint32_t seg = td.band_first + (uint32_t)b;
+            emit_to_segment(rb, td, seg, (uint32_t)(z - max(b * R - 1, 0)) * td.width + x, tcell, tri, mm, area);
+            if (z == b * R && b > 0) emit_to_segment(rb, td, seg - 1u, (uint32_t)(z - max((b - 1) * R - 1, 0)) * td.width + x, tcell, tri, mm, area);
+            if (z == (b + 1) * R - 1 && z + 1 < td.height) emit_to_segment(rb, td, seg + 1u, (uint32_t)x, tcell, tri, mm, area);
         }
     } else {
         const uint32_t gcell = td.cell_base + tcell;

@@ -472,9 +472,12 @@ int make_bands(rcb_ctx* ctx, BatchEntry& e, uint32_t band_cells) {
     e.max_held_cells = 0;
     e.max_bands_per_tile = 0;
     for (size_t t = 0; t < ntiles; ++t) {
-        const TileDesc& td = e.tiles[t];
+        TileDesc& td = e.tiles[t];
         const int R = rcb_band_rows(td.width, td.height, band_cells);
         e.band_first[t] = (uint32_t)e.bands.size();
+        td.band_rows = R;
+        td.band_first = (uint32_t)e.bands.size();
+        td.bmagic = ((1ull << 40) / (unsigned long long)R) + 1;
         uint32_t nb = 0;
         for (int z0 = 0; z0 < td.height; z0 += R, ++nb) {
             BandDesc b;
@@ -490,6 +493,8 @@ int make_bands(rcb_ctx* ctx, BatchEntry& e, uint32_t band_cells) {
     }
     e.band_first[ntiles] = (uint32_t)e.bands.size();
     e.band_cells = band_cells;
+    CU(e.d_tiles.ensure(sizeof(TileDesc) * ntiles + 64));  // the tile descriptors carry their cut
+    if (ntiles) CU(cudaMemcpyAsync(e.d_tiles.p, e.tiles.data(), sizeof(TileDesc) * ntiles, cudaMemcpyHostToDevice, ctx->stream));
     CU(e.d_bands.ensure(sizeof(BandDesc) * e.bands.size() + 64));
     CU(e.d_band_first.ensure(4 * (ntiles + 1) + 64));
     if (!e.bands.empty()) CU(cudaMemcpyAsync(e.d_bands.p, e.bands.data(), sizeof(BandDesc) * e.bands.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -974,8 +979,6 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                 CUB(cudaMemsetAsync(ctx->d_tile_ub.p, 0, 4 * ((size_t)nbands + 1), st));
                 CUB(cudaMemsetAsync(ctx->d_tile_cursor.p, 0, 4 * ((size_t)nbands + 1), st));
                 r2.tile_ub = ctx->d_tile_ub.as<uint32_t>();
-                r2.band_first = entry->d_band_first.as<uint32_t>();
-                r2.band_cells = band_cells;
                 launch_bin_count(r2, st);
                 // speculative: the fragment / work-item totals must stay within what the buffers were sized for
                 launch_tile_segments(r2.tile_ub, ctx->d_tile_base.as<uint32_t>(), nbands, r2.counters, spec ? margin(h.ub) : ~0ull,
@@ -1000,8 +1003,8 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                 if (tile_ok) {
                     // the bound counts whole footprints; real fragment counts are about half of it on triangle meshes
                     const uint64_t needA = 8ull * entry->max_held_cells + 8ull * (ub_max / 3) + 4096;
-                    want_tile = needA <= kTileSmem && entry->max_bands_per_tile <= 16;
-                    if (!want_tile && band_cells != 0x7fffffffu && entry->max_bands_per_tile <= 16) return retry_with(needA, kTileSmem);
+                    want_tile = needA <= kTileSmem && entry->max_bands_per_tile <= 32;
+                    if (!want_tile && band_cells != 0x7fffffffu && entry->max_bands_per_tile <= 32) return retry_with(needA, kTileSmem);
                     if (!want_tile && entry->bands.size() != (size_t)ntiles) {  // the global back end wants whole-tile segments
                         Source s2 = src;
                         s2.no_tile_mode = true;
@@ -1070,9 +1073,9 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             if (spec) {
                 S = margin(h.S), walk = margin(h.walk), needB = h.need_b, pub = margin(h.pub);
                 Kcap = compact ? (h.K ? margin(h.K) : 8ull * walk) : 0;
-                launch_tile_scan(d_bands, d_binfo, nbands, d_tiles, r2.band_first, d_tinfo_tmp, ntiles, r2.counters, S, pub, compact ? 1 : 0, st);
+                launch_tile_scan(d_bands, d_binfo, nbands, d_tiles, entry->d_band_first.as<uint32_t>(), d_tinfo_tmp, ntiles, r2.counters, S, pub, compact ? 1 : 0, st);
             } else {
-                launch_tile_scan(d_bands, d_binfo, nbands, d_tiles, r2.band_first, d_tinfo_tmp, ntiles, r2.counters, ~0ull, ~0ull, compact ? 1 : 0, st);
+                launch_tile_scan(d_bands, d_binfo, nbands, d_tiles, entry->d_band_first.as<uint32_t>(), d_tinfo_tmp, ntiles, r2.counters, ~0ull, ~0ull, compact ? 1 : 0, st);
                 CUB(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 11 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
                 CUB(cudaStreamSynchronize(st));
                 const bool overflow = (ctx->h_counters[2] & 6ull) != 0;
@@ -1114,7 +1117,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             tc.tiles = d_tiles;
             tc.bands = d_bands;
             tc.binfo = d_binfo;
-            tc.band_first = r2.band_first;
+            tc.band_first = entry->d_band_first.as<uint32_t>();
             tc.work = r2.tile_frags;
             tc.pub = (unsigned char*)ctx->d_pub.p;
             tc.flag_f = (uint32_t*)((char*)ctx->d_lookback.p + look_bytes);

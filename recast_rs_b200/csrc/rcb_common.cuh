@@ -30,6 +30,10 @@ struct TileDesc {
     int32_t bin_x0, bin_z0;  // lower corner of the tile's range in the locator grid (dedup rule)
     int32_t aux0, aux1, aux2;   // tile-cache layers: hmin, first obstacle, obstacle count
     unsigned long long wmagic;  // ceil(2^40 / width): c / width == (c * wmagic) >> 40 for c < 2^24, width < 2^16
+    // how the tile is cut into bands for the tile-resident kernels (BandDesc below); whole tile: band_rows == height
+    int32_t band_rows;
+    uint32_t band_first;        // index of the tile's first band (the bands of a tile are consecutive)
+    unsigned long long bmagic;  // ceil(2^40 / band_rows): z / band_rows == (z * bmagic) >> 40
 };
 
 __host__ __device__ inline uint32_t rcb_div_w(uint32_t c, unsigned long long wmagic) {
@@ -136,8 +140,6 @@ struct Raster2 {
                                    // [3] bad index [4] work items
     uint32_t* item_cnt;            // [ntris + 1]
     uint32_t* tile_ub;             // [nbands] per-band fragment upper bound (nullable)
-    const uint32_t* band_first;    // [ntiles + 1] first band of every tile (bands of a tile are consecutive)
-    uint32_t band_cells;           // cells per band the tiles were cut by: a tile's bands have rcb_band_rows() rows
     // global-list mode (v1 back end)
     uint32_t* cell_cnt;
     uint4* frag_tmp;
