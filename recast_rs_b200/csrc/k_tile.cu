@@ -19,7 +19,6 @@
 
 namespace {
 
-constexpr int TILE_THREADS = 512;
 constexpr int MAXH = 0xffff;
 __constant__ int t_dirx[8] = {-1, 0, 1, 1, 1, 0, -1, -1};  // compact_heightfield.rs:109-111
 __constant__ int t_dirz[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
@@ -53,7 +52,7 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
 // Exclusive scan of cnt[0..n) into out[0..n], out[n] = total (cnt and out may alias).  Rounds of
 // TILE_THREADS consecutive elements (thread t takes element r*TILE_THREADS + t: conflict-free), each
 // round one block-wide scan with a running carry.  Uses sh_warp[TILE_THREADS/32 + 1].
-template <typename OutT>
+template <int TILE_THREADS, typename OutT>
 __device__ uint32_t block_scan_array(const uint32_t* cnt, OutT* out, uint32_t n, uint32_t* sh_warp) {
     uint32_t carry = 0;
     for (uint32_t base = 0; base < n; base += TILE_THREADS) {
@@ -81,7 +80,10 @@ __device__ uint32_t block_scan_array(const uint32_t* cnt, OutT* out, uint32_t n,
 // ======================================================================================================
 // A: fragments -> spans
 // ======================================================================================================
-__global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_spans(TileSpansArgs a) {
+// TILE_THREADS = 512 (two CTAs per SM) for whole tiles; 256 (four per SM) for tiles cut into bands: a band waits for its
+// predecessor's forward sweep, and more resident CTAs keep the SM busy meanwhile.
+template <int TILE_THREADS>
+__global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_spans(TileSpansArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t sh_warp[TILE_THREADS / 32 + 1];
     __shared__ uint32_t sh_red[4];  // [0] walkable spans, [1] max height, [2] own fragments, [3] replay work-list length
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_spans(TileSpansArgs a)
     __syncthreads();
     pc.mark(0);
     // 2. column offsets
-    block_scan_array(cnt, off, C, sh_warp);
+    block_scan_array<TILE_THREADS>(cnt, off, C, sh_warp);
     for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) cnt[c] = 0;
     __syncthreads();
     pc.mark(1);
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_spans(TileSpansArgs a)
     __syncthreads();
     pc.mark(3);
     // 5. span offsets (band-local compact order)
-    block_scan_array(cnt, soff, C, sh_warp);
+    block_scan_array<TILE_THREADS>(cnt, soff, C, sh_warp);
     pc.mark(4);
 
     // 6. filters, fused (see k_filter.cu for why one bottom-up walk per column is exact); own rows only - the halo rows are
@@ -349,17 +351,18 @@ __host__ __device__ inline size_t compact_smem_need(uint32_t own_cells, uint32_t
 }
 
 // span_base / hand-over base per band (exclusive scans over bands), per-tile totals, batch totals; one block.
-// counters[6] = S, [7] = walkable spans, [8] = largest compact_smem_need, [10] = hand-over bytes
+// counters[6] = S, [7] = walkable spans, [8] = largest compact_smem_need, [10] = hand-over bytes, [11] = most fragments in a band
 __global__ void __launch_bounds__(1024) k_tile_scan(const BandDesc* __restrict__ bands, BandInfo* __restrict__ binfo, int nbands,
                                                     const TileDesc* __restrict__ tiles, const uint32_t* __restrict__ band_first,
                                                     TileInfo* __restrict__ tinfo, int ntiles, unsigned long long* counters,
-                                                    unsigned long long span_cap, unsigned long long pub_cap, int compact) {
+                                                    unsigned long long span_cap, unsigned long long pub_cap, int compact,
+                                                    const uint32_t* __restrict__ seg_cursor, const uint32_t* __restrict__ seg_cap) {
     __shared__ uint32_t sh[33], sh2[33];
     __shared__ unsigned long long sh_walk;
-    __shared__ uint32_t sh_need;
-    if (threadIdx.x == 0) sh_walk = 0, sh_need = 0;
+    __shared__ uint32_t sh_need, sh_fmax;
+    if (threadIdx.x == 0) sh_walk = 0, sh_need = 0, sh_fmax = 0;
     __syncthreads();
-    uint32_t carry = 0, carry2 = 0, need = 0;
+    uint32_t carry = 0, carry2 = 0, need = 0, fmax = 0;
     unsigned long long walk = 0;
     for (int base = 0; base < nbands; base += 1024) {
         const int b = base + threadIdx.x;
@@ -369,6 +372,7 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const BandDesc* __restrict__
             const BandDesc bd = bands[b];
             v = bi.span_count;
             walk += bi.walkable;
+            fmax = max(fmax, min(seg_cursor[b], seg_cap[b]));
             const bool has_top = bd.hz0 < bd.z0, has_bot = bd.hz1 > bd.z1;
             // what this band hands over: 16 B per span of its last row (to the next band) and of its first row (to the previous)
             p = (has_bot ? 16u * bi.bot_spans : 0u) + (has_top ? 16u * bi.top_spans : 0u);
@@ -402,10 +406,12 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const BandDesc* __restrict__
     for (int d = 16; d > 0; d >>= 1) {  // one shared-memory atomic per warp, not per thread
         walk += __shfl_down_sync(0xffffffffu, walk, d);
         need = max(need, __shfl_down_sync(0xffffffffu, need, d));
+        fmax = max(fmax, __shfl_down_sync(0xffffffffu, fmax, d));
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(&sh_walk, walk);
         atomicMax(&sh_need, need);
+        atomicMax(&sh_fmax, fmax);
     }
     __syncthreads();  // also: every band's span_base is visible to the block
     // per-tile totals (TileInfo is what the C ABI reports; bands are an internal unit)
@@ -427,6 +433,7 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const BandDesc* __restrict__
         counters[7] = sh_walk;
         counters[8] = sh_need;
         counters[10] = carry2;
+        counters[11] = sh_fmax;  // the most fragments any band received (its bound, counters[5], is about twice that)
         // speculative issue: more spans than the arena was laid out for, or a band that did not fit shared memory
         if (carry > span_cap || carry2 > pub_cap || (span_cap != ~0ull && (counters[2] & 4ull))) atomicOr(&counters[2], RCB_FLAG_ABORT);
     }
@@ -516,7 +523,7 @@ __device__ __forceinline__ void wait_flag(const uint32_t* flag) {
 // others (work that touches neither the sweep buffers nor areas).  Returns whether idle_work ran.
 // Bands (never with ERODE): the sweep starts from the previous band's last row and hands its own last row on; the
 // gather and the blur read one / two rows beyond the band, which arrive as halo + ghost values (see TileB).
-template <typename T, bool ERODE, class Work>
+template <int TILE_THREADS, typename T, bool ERODE, class Work>
 __device__ bool tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_t* sh_max, PhaseClock* pc, Work&& idle_work) {
     const int W = g.W, H = g.rows;
     const uint32_t TN = g.S;  // "no neighbour" == the dummy span
@@ -755,7 +762,8 @@ __device__ __forceinline__ uint32_t lookback_inclusive(volatile unsigned long lo
     return (uint32_t)(v & 0xffffffffull);
 }
 
-__global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArgs a) {
+template <int TILE_THREADS>
+__global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_compact(TileCompactArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t sh_warp[TILE_THREADS / 32 + 1];
     __shared__ uint32_t sh_misc[6];  // [0] band id, [1] conn base, [2] max distance, [3] link work-list length, [4] tile conn base
@@ -1003,7 +1011,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
     __syncthreads();
     pc.mark(1);
     // 4. connection offsets inside the band; publish the band's count (nobody waits here)
-    const uint32_t K = block_scan_array(coff, coff, C, sh_warp);
+    const uint32_t K = block_scan_array<TILE_THREADS>(coff, coff, C, sh_warp);
     if (threadIdx.x == 0) lookback_publish(look, band, K);
     pc.mark(2);
     TileB g;
@@ -1106,7 +1114,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
     //    erosion is asked for.)
     if (a.do_erode) {
         const unsigned thr = (unsigned)(uint8_t)(uint32_t)(a.erode_radius * 2);
-        conn_written = tile_sweep<uint8_t, true>(g, reinterpret_cast<uint8_t*>(d16a), reinterpret_cast<uint8_t*>(d16b), thr, nullptr,
+        conn_written = tile_sweep<TILE_THREADS, uint8_t, true>(g, reinterpret_cast<uint8_t*>(d16a), reinterpret_cast<uint8_t*>(d16b), thr, nullptr,
                                                  nullptr, conn_work);
     }
     for (uint32_t s = threadIdx.x; s < So; s += TILE_THREADS) a.areas[span_base + s] = areas[own0 + s];
@@ -1114,9 +1122,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_compact(TileCompactArg
     // 6. distance field (compact_heightfield.rs:514-727)
     if (a.do_dist) {
         if (conn_written)
-            tile_sweep<uint16_t, false>(g, d16a, d16b, 0, &sh_misc[2], &pc, no_work);
+            tile_sweep<TILE_THREADS, uint16_t, false>(g, d16a, d16b, 0, &sh_misc[2], &pc, no_work);
         else
-            conn_written = tile_sweep<uint16_t, false>(g, d16a, d16b, 0, &sh_misc[2], &pc, conn_work);
+            conn_written = tile_sweep<TILE_THREADS, uint16_t, false>(g, d16a, d16b, 0, &sh_misc[2], &pc, conn_work);
         pc.mark(4);
         // box blur: d16a holds D; result to global
         for (uint32_t s = own0 + threadIdx.x; s < own1; s += TILE_THREADS) {
@@ -1159,9 +1167,14 @@ static void set_smem_attr(const void* fn, size_t bytes) {
 
 void launch_tile_spans(const TileSpansArgs& a, int nbands, cudaStream_t s) {
     if (nbands == 0) return;
-    set_smem_attr((const void*)k_tile_spans, a.smem_bytes);
     KScope _k("k_tile_spans", s);
-    k_tile_spans<<<nbands, TILE_THREADS, a.smem_bytes, s>>>(a);
+    if (a.threads == 256) {
+        set_smem_attr((const void*)k_tile_spans<256>, a.smem_bytes);
+        k_tile_spans<256><<<nbands, 256, a.smem_bytes, s>>>(a);
+    } else {
+        set_smem_attr((const void*)k_tile_spans<512>, a.smem_bytes);
+        k_tile_spans<512><<<nbands, 512, a.smem_bytes, s>>>(a);
+    }
 }
 
 void launch_tile_segments(const uint32_t* tile_ub, uint32_t* tile_base, int ntiles, unsigned long long* counters,
@@ -1172,9 +1185,10 @@ void launch_tile_segments(const uint32_t* tile_ub, uint32_t* tile_base, int ntil
 
 void launch_tile_scan(const BandDesc* bands, BandInfo* binfo, int nbands, const TileDesc* tiles, const uint32_t* band_first, TileInfo* tinfo,
                       int ntiles, unsigned long long* counters, unsigned long long span_cap, unsigned long long pub_cap, int compact,
-                      cudaStream_t s) {
+                      const uint32_t* seg_cursor, const uint32_t* seg_cap, cudaStream_t s) {
     KScope _k("k_tile_scan", s);
-    k_tile_scan<<<1, 1024, 0, s>>>(bands, binfo, nbands, tiles, band_first, tinfo, ntiles, counters, span_cap, pub_cap, compact);
+    k_tile_scan<<<1, 1024, 0, s>>>(bands, binfo, nbands, tiles, band_first, tinfo, ntiles, counters, span_cap, pub_cap, compact, seg_cursor,
+                                   seg_cap);
 }
 
 size_t tile_compact_smem_bytes(uint32_t own_cells, uint32_t held_cells, uint32_t held_spans, uint32_t top_spans, uint32_t bot_spans) {
@@ -1183,7 +1197,12 @@ size_t tile_compact_smem_bytes(uint32_t own_cells, uint32_t held_cells, uint32_t
 
 void launch_tile_compact(const TileCompactArgs& a, int nbands, cudaStream_t s) {
     if (nbands == 0) return;
-    set_smem_attr((const void*)k_tile_compact, a.smem_bytes);
     KScope _k("k_tile_compact", s);
-    k_tile_compact<<<nbands, TILE_THREADS, a.smem_bytes, s>>>(a);
+    if (a.threads == 256) {
+        set_smem_attr((const void*)k_tile_compact<256>, a.smem_bytes);
+        k_tile_compact<256><<<nbands, 256, a.smem_bytes, s>>>(a);
+    } else {
+        set_smem_attr((const void*)k_tile_compact<512>, a.smem_bytes);
+        k_tile_compact<512><<<nbands, 512, a.smem_bytes, s>>>(a);
+    }
 }

@@ -77,6 +77,7 @@ struct BatchHint {
     uint32_t stage_mask = 0;
     int32_t merge_thr = 0;
     uint64_t ub = 0, nitems = 0, ub_max = 0, S = 0, walk = 0, K = 0;
+    uint64_t f_max = 0;      // most fragments one band received (ub_max is the bound it was given room for)
     uint64_t need_b = 0;     // shared memory of k_tile_compact's largest band
     uint64_t pub = 0;        // bytes handed over between the bands of a tile
     uint32_t band_cells = 0;  // how the tiles were cut (the sizes above belong to this cut)
@@ -134,6 +135,7 @@ struct rcb_ctx {
         d_conn_off, d_nid, d_t16a, d_t16b, d_t16c, d_t8a, d_t8b, d_item_cnt, d_item_off, d_items, d_tile_ub, d_tile_base, d_tile_cursor,
         d_tile_frags, d_ts_mm, d_ts_area, d_celloff_tmp, d_lookback, d_tc_regons, d_tc_areas, d_tc_obs, d_fidx, d_span_cell, d_wire, d_wire_off,
         d_wire_pos, d_wire_inoff, d_wire_err, d_tc_raw, d_tc_parsed, d_rg_a, d_rg_b, d_binfo, d_pub;
+    int tile_threads = 0;        // RCB_TILE_THREADS: 256 / 512 (0: by whether the tiles are cut)
     uint32_t band_cells = 4608;  // RCB_BAND_CELLS: cells per band of the tile-resident kernels (a 64x64 tile and a bit stays whole)
     uint32_t clip_flags = 1;    // RCB_CLIP_FLAGS (A/B runs): bit0 min-x skip test in the clipper
     bool phase_timers = false;  // RCB_PHASE_TIMERS=1: per-phase cycle sums of the tile kernels on stderr
@@ -1053,11 +1055,22 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             ta.fmask = fmask;
             ta.merge_thr = src.merge_thr;
             ta.phase = ctx->phase_timers ? r2.counters + 16 : nullptr;
-            {
-                // exact bound: never overflows when it fits.  Above the two-CTAs-per-SM budget the first
-                // launch runs small and defers the few bands that need more to a second, large launch.
+            // whole tiles: 512 threads, two CTAs per SM; tiles cut into bands: 256 threads, four per SM (a band waits for its
+            // predecessor's sweep: more resident CTAs keep the SM busy meanwhile)
+            const int threads = ctx->tile_threads ? ctx->tile_threads : ((size_t)nbands != (size_t)ntiles ? 256 : 512);
+            const uint64_t ctas_per_sm = 1024 / threads;
+            ta.threads = threads;
+            if (spec && h.f_max) {
+                // the previous build measured the fullest band: its size exactly, one launch
+                ta.pass = 0;
+                ta.defer = 0;
+                ta.smem_bytes = (uint32_t)std::min<uint64_t>(8ull * (max_held + 4) + 8ull * h.f_max + 64, kTileSmem);
+                launch_tile_spans(ta, nbands, st);
+            } else {
+                // exact bound: never overflows when it fits.  Above the budget that lets the SM hold its full complement of
+                // CTAs the first launch runs small and defers the few bands that need more to a second, large launch.
                 const uint64_t exact = 8ull * (max_held + 4) + 8ull * ub_max + 64;
-                const uint64_t small = kTileSmem / 2 - 2048;
+                const uint64_t small = kTileSmem / ctas_per_sm - 2048;
                 ta.pass = 0;
                 ta.defer = exact > small;
                 ta.smem_bytes = (uint32_t)(exact <= small ? exact : small);
@@ -1073,10 +1086,10 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             if (spec) {
                 S = margin(h.S), walk = margin(h.walk), needB = h.need_b, pub = margin(h.pub);
                 Kcap = compact ? (h.K ? margin(h.K) : 8ull * walk) : 0;
-                launch_tile_scan(d_bands, d_binfo, nbands, d_tiles, entry->d_band_first.as<uint32_t>(), d_tinfo_tmp, ntiles, r2.counters, S, pub, compact ? 1 : 0, st);
+                launch_tile_scan(d_bands, d_binfo, nbands, d_tiles, entry->d_band_first.as<uint32_t>(), d_tinfo_tmp, ntiles, r2.counters, S, pub, compact ? 1 : 0, r2.tile_cursor, r2.tile_cap, st);
             } else {
-                launch_tile_scan(d_bands, d_binfo, nbands, d_tiles, entry->d_band_first.as<uint32_t>(), d_tinfo_tmp, ntiles, r2.counters, ~0ull, ~0ull, compact ? 1 : 0, st);
-                CUB(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 11 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                launch_tile_scan(d_bands, d_binfo, nbands, d_tiles, entry->d_band_first.as<uint32_t>(), d_tinfo_tmp, ntiles, r2.counters, ~0ull, ~0ull, compact ? 1 : 0, r2.tile_cursor, r2.tile_cap, st);
+                CUB(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
                 CUB(cudaStreamSynchronize(st));
                 const bool overflow = (ctx->h_counters[2] & 6ull) != 0;
                 const bool poly_overflow = (ctx->h_counters[2] & 1ull) != 0;  // a clip polygon outgrew the 6-vertex slots
@@ -1100,6 +1113,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                 nh.valid = true;
                 nh.ntris = ntris, nh.nverts = nverts, nh.stage_mask = stage_mask, nh.merge_thr = src.merge_thr;
                 nh.ub = ub, nh.nitems = nitems, nh.ub_max = ub_max, nh.S = S, nh.walk = walk, nh.need_b = needB, nh.pub = pub;
+                nh.f_max = ctx->h_counters[11];
                 nh.band_cells = band_cells;
                 nh.K = (h.valid && h.S == S && h.walk == walk && h.band_cells == band_cells) ? h.K : 0;
                 entry->hint = nh;
@@ -1151,6 +1165,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             tc.do_dist = (stage_mask & RCB_STAGE_DIST) != 0;
             tc.erode_radius = erode_radius;
             tc.phase = ctx->phase_timers ? r2.counters + 16 : nullptr;
+            tc.threads = threads;
             tc.smem_bytes = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(needB, 64), kTileSmem);
             launch_tile_compact(tc, nbands, st);
             if (ctx->phase_timers) {
@@ -1492,6 +1507,7 @@ int resolve_result(rcb_result* res) {
                 h.ub = c[0], h.nitems = c[4], h.S = c[6], h.walk = c[7];
                 h.ub_max = std::max<uint64_t>(h.ub_max, c[5]);
                 h.need_b = std::max<uint64_t>(h.need_b, c[8]);
+                h.f_max = std::max<uint64_t>(h.f_max, c[11]);
                 h.pub = c[10];
                 h.K = c[9];
             } else if (h.S == c[6] && h.walk == c[7]) {
@@ -1580,6 +1596,7 @@ int rcb_create(int device, rcb_ctx** out) {
     if (const char* e = getenv("RCB_CLIP_FLAGS")) ctx->clip_flags = (uint32_t)atoi(e);
     if (const char* e = getenv("RCB_NO_SPEC")) ctx->no_spec = e[0] == '1';
     if (const char* e = getenv("RCB_BAND_CELLS")) ctx->band_cells = (uint32_t)std::max(1, atoi(e));
+    if (const char* e = getenv("RCB_TILE_THREADS")) ctx->tile_threads = atoi(e) == 256 ? 256 : atoi(e) == 512 ? 512 : 0;
     *out = ctx;
     return RCB_OK;
 }

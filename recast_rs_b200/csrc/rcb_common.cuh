@@ -191,6 +191,7 @@ struct TileSpansArgs {
     int32_t merge_thr;
     uint32_t smem_bytes;
     unsigned long long* phase;  // optional [16] per-phase cycle accumulators (nullptr = off)
+    int threads;                // CTA size: 512 (whole tiles) or 256 (tiles cut into bands)
     int pass;                   // 0: first launch, 1: second launch for tiles deferred by pass 0
     int defer;                  // pass 0 may defer tiles that need more shared memory (a pass 1 follows)
 };
@@ -226,6 +227,7 @@ struct TileCompactArgs {
     uint8_t* conn_dir;
     uint32_t* conn_next;
     int do_compact, do_erode, do_dist, erode_radius;
+    int threads;                // CTA size: 512 (whole tiles) or 256 (tiles cut into bands)
     uint32_t smem_bytes;
     unsigned long long Kcap;    // capacity of the connection arrays (a tile that would pass it sets RCB_FLAG_CONN)
     unsigned long long* phase;  // optional [16]: slots 8.. are this kernel's phases
@@ -238,7 +240,7 @@ void launch_tile_segments(const uint32_t* tile_ub, uint32_t* tile_base, int ntil
 // counters[6] spans, [7] walkable spans, [8] shared-memory bytes the largest band needs in k_tile_compact, [10] hand-over bytes
 void launch_tile_scan(const BandDesc* bands, BandInfo* binfo, int nbands, const TileDesc* tiles, const uint32_t* band_first, TileInfo* tinfo,
                       int ntiles, unsigned long long* counters, unsigned long long span_cap, unsigned long long pub_cap, int compact,
-                      cudaStream_t s);
+                      const uint32_t* seg_cursor, const uint32_t* seg_cap, cudaStream_t s);
 // slim result layout: conn_mask[s] = the span's directions, conn_ref16[k] = (u16)conn_ref[k]; *flag |= 1 if a reference needs 17 bits
 void launch_slim_pack(const TileInfo* tinfo, int ntiles, uint32_t max_cells, const uint32_t* first_conn, const uint32_t* conn_ref,
                       const uint8_t* conn_dir, const uint32_t* conn_next, uint8_t* conn_mask, uint16_t* conn_ref16,

@@ -96,7 +96,7 @@ def test_open_world_128_tiles_are_cut_by_default(oracle):
     from recast_rs_b200 import synth
 
     v, t, cfgs = synth.config3(seed=2, nq=275, lattice=20)
-    ct, cg = _ctx(RCB_FORCE_GLOBAL=0), _ctx(RCB_FORCE_GLOBAL=1)
+    ct, cg = _ctx(RCB_FORCE_GLOBAL=0, RCB_BAND_CELLS=4608), _ctx(RCB_FORCE_GLOBAL=1)
     for c in (ct, cg):
         c.upload_mesh(v, t)
     ct.profile_enable(True)

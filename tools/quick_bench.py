@@ -14,7 +14,8 @@ st = torch.cuda.Stream(); torch.cuda.set_stream(st); assert st.cuda_stream != 0;
 dv, dt = torch.from_numpy(v).cuda(), torch.from_numpy(t).cuda()
 ctx.set_mesh_device(dv.data_ptr(), dv.numel(), dt.data_ptr(), dt.numel(), keep=(dv, dt))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for _ in range(3): ctx.build_tiles(arr).free()
+for _ in range(3):
+    with ctx.build_tiles(arr) as r0: tot = r0.totals()
 ms = []
 for _ in range(7):
     flush.zero_(); a, b = torch.cuda.Event(True), torch.cuda.Event(True)
@@ -22,4 +23,5 @@ for _ in range(7):
 ctx.profile_enable(True); ctx.profile_reset()
 for _ in range(3): flush.zero_(); ctx.build_tiles(arr).free()
 k = ctx.profile_read()
-print(f"cfg{cfgno} flags={os.environ.get('RCB_CLIP_FLAGS','-')} median {np.median(ms):.3f} ms  min {min(ms):.3f}  |", {n: round(m / 3, 3) for n, (m, c) in sorted(k.items(), key=lambda kv: -kv[1][0])[:int(os.environ.get("QB_TOP", "6"))]})
+with ctx.build_tiles(arr) as r0: assert r0.totals()["spans"] == tot["spans"]
+print(f"cfg{cfgno} band_cells={os.environ.get('RCB_BAND_CELLS','-')} {ctx.stats()} spans={tot['spans']} median {np.median(ms):.3f} ms  min {min(ms):.3f}  |", {n: round(m / 3, 3) for n, (m, c) in sorted(k.items(), key=lambda kv: -kv[1][0])[:int(os.environ.get("QB_TOP", "6"))]})
