@@ -573,7 +573,11 @@ __device__ bool tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_
         if (!ERODE && g.has_top) {
             // the previous band's last row: its forward values, and through three ghost slots per span the values of that
             // span's E, N and NW neighbours (the only things the relaxation and the gather reach THROUGH a halo span)
-            if (threadIdx.x == 0) wait_flag(&g.flag_f[g.band - 1]);
+            if (threadIdx.x == 0) {
+                const long long t0 = pc && pc->acc ? clock64() : 0;
+                wait_flag(&g.flag_f[g.band - 1]);
+                if (pc && pc->acc) atomicAdd(&pc->acc[10], (unsigned long long)(clock64() - t0));
+            }
             row_barrier();
             for (uint32_t j = threadIdx.x; j < g.nt; j += (uint32_t)sweep_threads) {
                 const uint4 r = __ldcg(&g.in_top[j]);
@@ -636,25 +640,30 @@ __device__ bool tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_
                 row_barrier();
             }
         }
+        if (!ERODE && g.has_bot) {
+            // hand the last own row's forward values to the next band (+ those of each span's E, N, NW neighbours) as soon
+            // as the sweep is through: the next band's sweep waits for exactly this, not for this band's connection list
+            const uint32_t lr0s = g.soff[(g.row0 + g.rows - 1) * W];
+            for (uint32_t s = lr0s + threadIdx.x; s < g.own1; s += (uint32_t)sweep_threads) {
+                uint4 r;
+                r.x = (uint32_t)Fw[s] | ((uint32_t)Fw[tnei(g, s, 3)] << 16);
+                r.y = (uint32_t)Fw[tnei(g, s, 1)] | ((uint32_t)Fw[tnei(g, s, 0)] << 16);
+                r.z = r.w = 0;
+                g.out_down[s - lr0s] = r;
+            }
+            __threadfence();
+            row_barrier();
+            if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(&g.flag_f[g.band]) = 1u;
+        }
+        if (pc && pc->acc && threadIdx.x == 0) atomicAdd(&pc->acc[12], (unsigned long long)(clock64() - pc->t));  // sweep incl. its wait
     } else {
+        const long long t0 = pc && pc->acc ? clock64() : 0;
         idle_work(threadIdx.x - (uint32_t)sweep_threads, (uint32_t)(TILE_THREADS - sweep_threads));
+        if (pc && pc->acc && (int)threadIdx.x == sweep_threads) atomicAdd(&pc->acc[13], (unsigned long long)(clock64() - t0));  // connection list
     }
     __syncthreads();
     if (pc) pc->mark(9);
     const uint32_t lr0 = g.soff[(g.row0 + g.rows - 1) * W], fr1 = g.soff[(g.row0 + 1) * W];  // last own row = [lr0, own1), first = [own0, fr1)
-    if (!ERODE && g.has_bot) {
-        // hand the last own row's forward values to the next band (+ those of each span's E, N, NW neighbours)
-        for (uint32_t s = lr0 + threadIdx.x; s < g.own1; s += TILE_THREADS) {
-            uint4 r;
-            r.x = (uint32_t)Fw[s] | ((uint32_t)Fw[tnei(g, s, 3)] << 16);
-            r.y = (uint32_t)Fw[tnei(g, s, 1)] | ((uint32_t)Fw[tnei(g, s, 0)] << 16);
-            r.z = r.w = 0;
-            g.out_down[s - lr0] = r;
-        }
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(&g.flag_f[g.band]) = 1u;
-    }
     // backward = gather from forward values; D overwrites init (init is dead)
     uint32_t vmax = 0;
     for (uint32_t s = g.own0 + threadIdx.x; s < g.own1; s += TILE_THREADS) {
@@ -699,8 +708,10 @@ __device__ bool tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_
         __syncthreads();
         if (threadIdx.x == 0) {
             *reinterpret_cast<volatile uint32_t*>(&g.flag_d[g.band]) = 1u;
+            const long long t0 = pc && pc->acc ? clock64() : 0;
             if (g.has_top) wait_flag(&g.flag_d[g.band - 1]);
             if (g.has_bot) wait_flag(&g.flag_d[g.band + 1]);
+            if (pc && pc->acc) atomicAdd(&pc->acc[11], (unsigned long long)(clock64() - t0));
         }
         __syncthreads();
         uint16_t* nid2 = g.nid + 2 * g.S2;

@@ -136,7 +136,9 @@ struct rcb_ctx {
         d_tile_frags, d_ts_mm, d_ts_area, d_celloff_tmp, d_lookback, d_tc_regons, d_tc_areas, d_tc_obs, d_fidx, d_span_cell, d_wire, d_wire_off,
         d_wire_pos, d_wire_inoff, d_wire_err, d_tc_raw, d_tc_parsed, d_rg_a, d_rg_b, d_binfo, d_pub;
     int tile_threads = 0;        // RCB_TILE_THREADS: 256 / 512 (0: by whether the tiles are cut)
-    uint32_t band_cells = 4608;  // RCB_BAND_CELLS: cells per band of the tile-resident kernels (a 64x64 tile and a bit stays whole)
+    uint32_t band_cells = 0x7fffffffu;  // RCB_BAND_CELLS: cut tiles into bands of about this many cells for the tile-resident kernels.
+                                        // Default: never cut - a tile that does not fit shared memory whole takes the global back
+                                        // end, which measured faster than bands on BASELINE configs 3 and 4
     uint32_t clip_flags = 1;    // RCB_CLIP_FLAGS (A/B runs): bit0 min-x skip test in the clipper
     bool phase_timers = false;  // RCB_PHASE_TIMERS=1: per-phase cycle sums of the tile kernels on stderr
     bool force_global = false;  // RCB_FORCE_GLOBAL=1: never use the tile-resident back end (k_tile.cu)
@@ -955,7 +957,8 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             const uint64_t cur = std::min<uint64_t>(band_cells, entry->max_held_cells);
             uint64_t next = need ? cur * budget / need * 7 / 8 : 0;
             if (next >= cur) next = cur * 3 / 4;
-            if ((stage_mask & RCB_STAGE_ERODE) || next < 4ull * (uint64_t)max_width || (uint64_t)max_width * 2 > next)
+            const bool cutting = ctx->band_cells != 0x7fffffffu;  // RCB_BAND_CELLS opted in
+            if (!cutting || (stage_mask & RCB_STAGE_ERODE) || next < 4ull * (uint64_t)max_width || (uint64_t)max_width * 2 > next)
                 s2.no_tile_mode = true;  // bands of two rows would still not fit: the global-memory back end
             else
                 s2.band_cells = (uint32_t)next;
@@ -1055,9 +1058,8 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             ta.fmask = fmask;
             ta.merge_thr = src.merge_thr;
             ta.phase = ctx->phase_timers ? r2.counters + 16 : nullptr;
-            // whole tiles: 512 threads, two CTAs per SM; tiles cut into bands: 256 threads, four per SM (a band waits for its
-            // predecessor's sweep: more resident CTAs keep the SM busy meanwhile)
-            const int threads = ctx->tile_threads ? ctx->tile_threads : ((size_t)nbands != (size_t)ntiles ? 256 : 512);
+            // 512 threads, two CTAs per SM (RCB_TILE_THREADS=256: four per SM, for A/B runs)
+            const int threads = ctx->tile_threads ? ctx->tile_threads : 512;  // measured: 256 threads / 4 CTAs per SM is slower on both
             const uint64_t ctas_per_sm = 1024 / threads;
             ta.threads = threads;
             if (spec && h.f_max) {
@@ -1177,7 +1179,8 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                 fprintf(stderr, "[rcb phase cycles/band] (%d bands) spans:", nbands);
                 for (int i = 0; i < 7; ++i) fprintf(stderr, " %llu", ph[i] / (unsigned long long)nbands);
                 fprintf(stderr, " | compact:");
-                for (int i = 8; i < 20; ++i) fprintf(stderr, " %llu", ph[i] / (unsigned long long)nbands);
+                for (int i = 8; i < 22; ++i) fprintf(stderr, " %llu", ph[i] / (unsigned long long)nbands);
+                fprintf(stderr, " (load link scan areas dist blur - conn-at-end boundary forward | wait-F wait-D sweep conn-list)");
                 fprintf(stderr, "\n");
             }
             res->tile_mode = true;
