@@ -71,21 +71,22 @@ def make_sharded_workload(config: int, seed: int, rank: int, world: int, mode: s
     """N > 1: ONE world with ~world x the triangles of the single-GPU workload (weak scaling); tiles are
     split into contiguous slabs of tile rows, one per rank, and each rank receives the triangles over its
     slab (order preserved).  No data moves between ranks on the build path.
-    Returns (verts, tris, cfgs, name, world_triangles, world_tiles)."""
+    Returns (verts, tris, cfgs, name, world_triangles, world_tiles, (world_verts, world_tris)): the last pair is the
+    UNSHARDED mesh, which the parity check feeds to the oracle."""
     from recast_rs_b200 import shard, synth
 
     if world == 1:
         v, t, cfgs, name = make_workload(config, seed)
-        return v, t, cfgs, name, t.size // 3, len(cfgs)
+        return v, t, cfgs, name, t.size // 3, len(cfgs), (v, t)
     if config == 3:  # BASELINE configs[2]: ONE 10M-triangle world, its tiles sharded over the ranks (strong scaling)
         v, t, all_cfgs, name = make_workload(3, seed)
-        ids = shard.shard_tiles(len(all_cfgs), rank, world, mode)
+        ids = shard.shard_tiles_weighted(v, t, all_cfgs, rank, world) if mode == "weighted" else shard.shard_tiles(len(all_cfgs), rank, world, mode)
         cfgs = [all_cfgs[i] for i in ids]
         sv, st = shard.prebin_mesh(v, t, cfgs)
-        return sv, st, cfgs, name + f", one world {mode}-sharded over {world} ranks", t.size // 3, len(all_cfgs)
+        return sv, st, cfgs, name + f", one world {mode}-sharded over {world} ranks", t.size // 3, len(all_cfgs), (v, t)
     if config != 2:
         v, t, cfgs, name = make_workload(config, seed + rank)  # independent replicas of the named config
-        return v, t, cfgs, name + f" x {world} independent slabs", (t.size // 3) * world, len(cfgs) * world
+        return v, t, cfgs, name + f" x {world} independent slabs", (t.size // 3) * world, len(cfgs) * world, (v, t)
     nq = shard.weak_scaling_world(708, world)
     v, t = synth.terrain(nq, 1.2, 4.0, seed)
     all_cfgs = synth.tile_grid(v, 64)
@@ -94,7 +95,7 @@ def make_sharded_workload(config: int, seed: int, rank: int, world: int, mode: s
     sv, st = shard.prebin_mesh(v, t, cfgs)
     name = (f"config2 scaled x{world}: {t.size // 3}-triangle terrain(nq={nq}), 64x64-cell tiles ({len(all_cfgs)} tiles), "
             f"slab-sharded over {world} ranks, cs=0.3 ch=0.2")
-    return sv, st, cfgs, name, t.size // 3, len(all_cfgs)
+    return sv, st, cfgs, name, t.size // 3, len(all_cfgs), (v, t)
 
 
 def alg_bytes(tot):
@@ -187,17 +188,10 @@ def run_reference(args, rank, world):
         return
     from oracle import oracle as orc
 
-    world_n = max(world, args.gpus)
-    if world_n > 1 and args.config == 2:  # the same scaled world the native arm shards over its ranks
-        from recast_rs_b200 import shard, synth
-
-        nq = shard.weak_scaling_world(708, world_n)
-        v, t = synth.terrain(nq, 1.2, 4.0, args.seed)
-        cfgs = synth.tile_grid(v, 64)
-        name = (f"config2 scaled x{world_n}: {t.size // 3}-triangle terrain(nq={nq}), 64x64-cell tiles ({len(cfgs)} tiles), "
-                f"cs=0.3 ch=0.2 (whole world on the host cores)")
-    else:
-        v, t, cfgs, name = make_workload(args.config, args.seed)
+    # Always the single-GPU world of the named config: the reference scans the whole mesh for every tile (lib.rs:217), so its
+    # triangles/s fall with the size of the world; timing it on the N-times larger world of the native arm's weak scaling
+    # would measure that quadratic loop, not the host.  (The driver divides the native arm's value by this line's.)
+    v, t, cfgs, name = make_workload(args.config, args.seed)
     threads = orc.hardware_concurrency()
     vals, ms = [], []
     sample = ""
@@ -207,13 +201,18 @@ def run_reference(args, rank, world):
             vals.append(val)
             ms.append(secs * 1e3)
     value = float(np.mean(vals))
+    # the same port when every tile is handed only the triangles over it (what a caller with a spatial index would do;
+    # the reference has none): reported so the native/reference ratio can be read both ways
+    pre_val, pre_sample, _ = cpu_leg(v, t, cfgs, threads, budget_s=6.0, prebinned=True)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 clip + i16/u16 spans", "data": "synthetic",
         "config": {"workload": name, "seed": args.seed},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                         "note": "C++ restatement of recast-rs (oracle/), not the Rust build: no cargo/rustc in the image"},
+                         "prebinned_value": pre_val, "prebinned_sample": pre_sample,
+                         "note": "C++ restatement of recast-rs (oracle/), not the Rust build: no cargo/rustc in the image; at N > 1 "
+                                 "still the single-GPU world of the config"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -340,6 +339,68 @@ def run_tilecache(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def config3_leg(args, rank, world, local_rank, ctx, stream, flush, dist, dev, barrier):
+    """BASELINE configs[2] (the north_star's target): ONE 10M-triangle open world, 128x128-cell tiles, its tiles dealt to
+    the ranks in cost-balanced slabs (strong scaling).  Returns the sub-record rank 0 prints (None elsewhere)."""
+    import torch
+
+    import recast_rs_b200.builder as rb
+    from oracle import oracle as orc
+    from recast_rs_b200.config import configs_to_array
+    from tests.parity import assert_tile_equal
+
+    v, t, cfgs, name, T_world, tiles_world, whole = make_sharded_workload(3, args.seed, rank, world, "weighted")
+    arr = configs_to_array(cfgs)
+    d_v, d_t = torch.from_numpy(v).to(dev), torch.from_numpy(t).to(dev)
+    ctx.set_mesh_device(d_v.data_ptr(), d_v.numel(), d_t.data_ptr(), d_t.numel(), keep=(d_v, d_t))
+    tot = None
+    for _ in range(3):
+        with ctx.build_tiles(arr, rb.STAGE_ALL_BUILD) as r:
+            tot = r.totals()
+    steps = max(3, min(args.steps, 5))
+    warm = [ctx.build_tiles(arr, rb.STAGE_ALL_BUILD) for _ in range(steps)]  # arena pool: one pair per timed step
+    for r in warm:
+        r.totals()
+        r.free()
+    barrier()
+    evs, held = [], []
+    for _ in range(steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        held.append(ctx.build_tiles(arr, rb.STAGE_ALL_BUILD))
+        b.record(stream)
+        evs.append((a, b))
+    barrier()
+    for r in held:
+        tt = r.totals()
+        assert {k: x for k, x in tt.items() if k != "result_bytes"} == {k: x for k, x in tot.items() if k != "result_bytes"}, tt
+        r.free()
+    ms = float(sum(a.elapsed_time(b) for a, b in evs))
+    with ctx.build_tiles(arr, rb.STAGE_ALL_BUILD) as r:  # parity: the slab's border tiles against the oracle on the whole world
+        r.download()
+        for i in sorted({0, len(cfgs) - 1}):
+            hfa, chfa = orc.build_tile(cfgs[i], whole[0], whole[1])
+            assert_tile_equal(r.tile(i), hfa, chfa, what=f"config3 rank {rank} tile {i}")
+    agg = torch.tensor([ms], dtype=torch.float64, device=dev)
+    mn = torch.tensor([ms], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float(alg_bytes(tot)), float(len(cfgs)), float(v.nbytes + t.nbytes)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    if rank != 0:
+        return None
+    peak, _ = read_peaks()
+    ms_step = float(agg[0]) / steps
+    achieved = float(cnt[0]) / world / (ms_step * 1e-3) / 1e9
+    return {"workload": name, "scaling": "strong", "n_gpus": world, "steps": steps, "ms_per_step": ms_step,
+            "ms_per_step_fastest_rank": float(mn[0]) / steps, "value": T_world / (ms_step * 1e-3), "unit": UNIT,
+            "tiles_per_s": tiles_world / (ms_step * 1e-3), "roofline_frac": achieved / peak, "achieved_gbs_per_gpu": achieved,
+            "h2d_bytes_all_ranks": int(cnt[2]), "h2d_bytes_whole_world": int(whole[0].nbytes + whole[1].nbytes),
+            "parity_check": {"tiles": 2 * world, "ok": True}, "sharding": "contiguous tile slabs cut by estimated cost (shard.shard_tiles_weighted)"}
+
+
 def run_native(args, rank, world, local_rank):
     import torch
 
@@ -362,7 +423,7 @@ def run_native(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # every rank owns one slab of the world: its own tiles and the triangles over them
-    v, t, cfgs, name, T_world, tiles_world = make_sharded_workload(args.config, args.seed, rank, world, args.shard)
+    v, t, cfgs, name, T_world, tiles_world, whole = make_sharded_workload(args.config, args.seed, rank, world, args.shard)
     from recast_rs_b200.config import configs_to_array
 
     cfg_arr = configs_to_array(cfgs)
@@ -387,6 +448,12 @@ def run_native(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         r = step()
         tot = r.totals()
+        r.free()
+    # the timed steps keep their results until the region is over (they are checked then): let the context's arena pool
+    # hold that many arenas now, so that no step allocates device memory inside the timed region
+    warm = [step() for _ in range(args.steps)]
+    for r in warm:
+        r.totals()
         r.free()
     barrier()
 
@@ -441,32 +508,47 @@ def run_native(args, rank, world, local_rank):
     kern_ms = {k: ms / nprof for k, (ms, _) in kern.items()}
 
     # ---- e2e: host buffers in, host buffers out ------------------------------------------------------------
+    # The public host-to-host call: rcb_upload_mesh + rcb_build_tiles_streamed with the slim result layout
+    # (RCB_RESULT_SLIM: the arrays the binding layer rebuilds from the layout rule stay on the device).  The D2H
+    # of a finished tile group overlaps the kernels of the next ones.  The full-layout, one-group call is timed
+    # beside it (`e2e.full_layout`): same metric, 1.7x the bytes.
     hv = torch.from_numpy(v).pin_memory()
     ht = torch.from_numpy(t).pin_memory()
-    e2e_ms = []
-    d2h_bytes = 0
     ctx2 = rb.Context(local_rank)  # a context that owns its mesh copy
     ctx2.set_stream(stream.cuda_stream)
-    for i in range(2 + args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        ctx2.upload_mesh(hv.numpy(), ht.numpy())
-        if args.e2e_groups > 1:  # the public host-to-host call: D2H of finished tile groups overlaps the next groups
-            r = ctx2.build_tiles_streamed(cfg_arr, stage, 0, args.e2e_groups)
-        else:
-            r = ctx2.build_tiles(cfg_arr, stage)
-            r.download()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) * 1e3
-        d2h_bytes = r.totals()["result_bytes"]
-        r.free()
-        if i >= 2:
-            e2e_ms.append(dt)
+
+    def e2e_leg(slim, groups, reps):
+        ms, nbytes, check = [], 0, None
+        mask = stage | (rb.RESULT_SLIM if slim else 0)
+        for i in range(2 + reps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ctx2.upload_mesh(hv.numpy(), ht.numpy())
+            if groups > 1:
+                r = ctx2.build_tiles_streamed(cfg_arr, mask, 0, groups)
+            else:
+                r = ctx2.build_tiles(cfg_arr, mask)
+                r.download()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) * 1e3
+            tt = r.totals()
+            nbytes = tt["result_bytes"]
+            if {k: x for k, x in tt.items() if k != "result_bytes"} != {k: x for k, x in tot.items() if k != "result_bytes"}:
+                raise SystemExit(f"bench.py: an end-to-end step produced {tt}, expected {tot}")
+            if i == 2 + reps - 1:
+                check = r.tile(0)  # host arrays of the last step (the parity check below reads them)
+            r.free()
+            if i >= 2:
+                ms.append(dt)
+        return ms, nbytes, check
+
+    e2e_ms, d2h_bytes, e2e_tile0 = e2e_leg(True, max(args.e2e_groups, 1), args.steps)
+    full_ms, full_bytes, _ = e2e_leg(False, 1, max(3, args.steps // 2))
     # the same call from two host threads, one context (and stream) each, taking alternate steps: the D2H of one step's
     # results overlaps the upload and the kernels of the next.  Reported beside the one-context number, never instead of it.
     pipe = None
-    if world == 1 and args.e2e_groups == 1:
+    if world == 1:
         try:
             import threading
             nctx = 2
@@ -479,7 +561,7 @@ def run_native(args, rank, world, local_rank):
                 try:
                     for _ in range(j, n, nctx):
                         pctx[j].upload_mesh(hv.numpy(), ht.numpy())
-                        rr = pctx[j].build_tiles(cfg_arr, stage)
+                        rr = pctx[j].build_tiles(cfg_arr, stage | rb.RESULT_SLIM)
                         rr.download()
                         rr.free()
                 except Exception as e:  # noqa: BLE001
@@ -501,19 +583,46 @@ def run_native(args, rank, world, local_rank):
             pms = run(npipe)
             if not err:
                 pipe = {"value": T_world * npipe / (pms * 1e-3), "unit": UNIT, "ms_per_step": pms / npipe, "steps": npipe,
-                        "call": "%d host threads, one rcb_ctx each, alternate steps of rcb_upload_mesh + rcb_build_tiles + rcb_result_download; no L2 flush between steps" % nctx}
+                        "call": "%d host threads, one rcb_ctx each, alternate steps of rcb_upload_mesh + rcb_build_tiles(RCB_RESULT_SLIM) + rcb_result_download; no L2 flush between steps" % nctx}
             pctx[1].close()
         except Exception:  # noqa: BLE001 - an extra figure, never a reason to lose the line
             pipe = None
     barrier()
 
+    # ---- parity check (outside every timed region): this rank's first and last tile - the borders of its slab -
+    # against the oracle run on the UNSHARDED world; fails the run on a mismatch --------------------------------
+    parity = None
+    if not args.no_parity:
+        from oracle import oracle as orc
+        from tests.parity import assert_tile_equal
+
+        wv, wt = whole
+        with ctx.build_tiles(cfg_arr, stage) as r:
+            r.download()
+            picks = sorted({0, len(cfgs) - 1}) if len(cfgs) else []
+            for i in picks:
+                hfa, chfa = orc.build_tile(cfgs[i], wv, wt)
+                assert_tile_equal(r.tile(i), hfa, chfa, what=f"rank {rank} tile {i}")
+        if e2e_tile0 is not None and len(cfgs):  # the slim, streamed host-to-host path returns the same tile
+            hfa, chfa = orc.build_tile(cfgs[0], wv, wt)
+            assert_tile_equal(e2e_tile0, hfa, chfa, what=f"rank {rank} e2e tile 0")
+        parity = len(picks) + (1 if e2e_tile0 is not None and len(cfgs) else 0)
+    pc = torch.tensor([float(parity or 0)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(pc, op=dist.ReduceOp.SUM)
+
+    # ---- BASELINE configs[2] beside the headline at N > 1: ONE 10M-triangle world, tiles cost-balanced over the ranks -------
+    c3 = None
+    if world > 1 and args.config == 2 and not args.no_config3:
+        c3 = config3_leg(args, rank, world, local_rank, ctx, stream, flush, dist, dev, barrier)
+
     # ---- aggregate over ranks ------------------------------------------------------------------------------
-    agg = torch.tensor([total_ms, float(sum(e2e_ms))], dtype=torch.float64, device=dev)
+    agg = torch.tensor([total_ms, float(sum(e2e_ms)), float(sum(full_ms))], dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(alg_bytes(tot))], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(agg, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    max_total_ms, max_e2e_ms = float(agg[0]), float(agg[1])
+    max_total_ms, max_e2e_ms, max_full_ms = float(agg[0]), float(agg[1]), float(agg[2])
     # triangles of the WORLD (a triangle on a slab border is rasterized by two ranks but counted once)
     T_all, tiles_all, balg_all = float(T_world), float(tiles_world), float(cnt[0])
 
@@ -538,10 +647,17 @@ def run_native(args, rank, world, local_rank):
             "wall_ms_per_step": wall * 1e3 / args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(v.nbytes + t.nbytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": max_e2e_ms / len(e2e_ms),
-                    "call": ("rcb_upload_mesh + rcb_build_tiles_streamed(groups=%d)" % args.e2e_groups) if args.e2e_groups > 1
-                    else "rcb_upload_mesh + rcb_build_tiles + rcb_result_download",
+                    "call": ("rcb_upload_mesh + rcb_build_tiles_streamed(groups=%d, RCB_RESULT_SLIM)" % args.e2e_groups) if args.e2e_groups > 1
+                    else "rcb_upload_mesh + rcb_build_tiles(RCB_RESULT_SLIM) + rcb_result_download",
+                    "layout": "slim: conn_mask u8[S] + conn_ref16 u16[K] instead of first_conn, conn_next, conn_dir, conn_ref; "
+                              "hf_cell_offset left out (prefix sum of cell_count); rebuilt by the binding layer (INTEGRATION.md)",
+                    "full_layout": {"value": T_world * len(full_ms) / (max_full_ms * 1e-3), "unit": UNIT, "ms_per_step": max_full_ms / len(full_ms),
+                                    "d2h_bytes_per_step": int(full_bytes), "call": "rcb_upload_mesh + rcb_build_tiles + rcb_result_download"},
                     **({"pipelined": pipe} if pipe else {})},
             "gpu_launches": int(launches),
+            "parity_check": {"tiles": int(pc[0]), "ok": True, "against": "oracle on the unsharded world: first and last tile of every rank's slab, "
+                             "plus tile 0 of the slim streamed end-to-end call"} if not args.no_parity else None,
+            **({"config3": c3} if c3 else {}),
             "issue": {"steps_issued_without_host_round_trip": st1["speculative"], "steps_rebuilt": st1["rebuilt"]},
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -580,10 +696,12 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--shard", default="slab", choices=["slab", "block_cyclic"], help="how config 3's tiles are dealt to the ranks")
-    ap.add_argument("--e2e-groups", type=int, default=1, help="tile groups of the host-to-host call (1: build then download)")
+    ap.add_argument("--shard", default="weighted", choices=["weighted", "slab", "block_cyclic"], help="how config 3's tiles are dealt to the ranks")
+    ap.add_argument("--e2e-groups", type=int, default=4, help="tile groups of the host-to-host call (1: build then download)")
     ap.add_argument("--tc-compressed", action="store_true", help="config 5 from LZ4-compressed tiles (SURVEY 8(f) rank 3)")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of this rank's border tiles")
+    ap.add_argument("--no-config3", action="store_true", help="N > 1: skip the strong-scaling sub-record of BASELINE configs[2]")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything else written to fd 1 (NCCL's version banner,
     # library chatter) is rerouted to stderr

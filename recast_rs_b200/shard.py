@@ -30,13 +30,16 @@ def shard_tiles(ntiles: int, rank: int, world: int, mode: str = "block_cyclic") 
     raise ValueError(mode)
 
 
-def prebin_mesh(verts: np.ndarray, tris: np.ndarray, cfgs: Sequence[RecastConfig]) -> Tuple[np.ndarray, np.ndarray]:
+def prebin_mesh(verts: np.ndarray, tris: np.ndarray, cfgs: Sequence[RecastConfig], compact_vertices: bool = True
+                ) -> Tuple[np.ndarray, np.ndarray]:
     """Sub-mesh containing, IN THE ORIGINAL ORDER, every triangle whose AABB touches the union AABB of the
     given tiles (inclusive test in f32, the same comparison as rasterization.rs:370-377, so no triangle the
     reference would rasterize into these tiles is dropped).  Order matters: span areas depend on it.
-    Vertices are kept whole (indices stay valid); returns (verts, tris_subset)."""
+    compact_vertices: keep only the vertices those triangles use (in their original order) and renumber the
+    indices, so a rank uploads its slab's share of the vertex array instead of the whole world's; the
+    coordinates are untouched, so every tile's result is the same bytes.  Returns (verts, tris_subset)."""
     if len(cfgs) == 0:
-        return verts, tris[:0]
+        return (verts[:0] if compact_vertices else verts), tris[:0]
     v = verts.reshape(-1, 3)
     t = tris.reshape(-1, 3)
     bmin = np.array([c.bmin for c in cfgs], dtype=np.float32).min(axis=0)
@@ -44,7 +47,51 @@ def prebin_mesh(verts: np.ndarray, tris: np.ndarray, cfgs: Sequence[RecastConfig
     tv = v[t]  # [T,3,3]
     tmin, tmax = tv.min(axis=1), tv.max(axis=1)
     keep = np.all((tmin <= bmax) & (tmax >= bmin), axis=1)
-    return verts, np.ascontiguousarray(t[keep]).reshape(-1)
+    sub = np.ascontiguousarray(t[keep])
+    if not compact_vertices:
+        return verts, sub.reshape(-1)
+    used = np.zeros(v.shape[0], dtype=bool)
+    used[sub.reshape(-1)] = True
+    remap = np.cumsum(used, dtype=np.int64) - 1  # old vertex id -> new id (order preserved)
+    return np.ascontiguousarray(v[used]).reshape(-1), remap[sub].astype(np.int32).reshape(-1)
+
+
+def tile_costs(verts: np.ndarray, tris: np.ndarray, cfgs: Sequence[RecastConfig]) -> np.ndarray:
+    """Estimated build cost per tile: the cell footprints of the triangles over it (what the clipper's work and
+    the fragment count follow) plus its cells (what everything behind the clipper follows).  Cheap: every
+    triangle's footprint goes to the tile holding the centre of its AABB."""
+    n = len(cfgs)
+    if n == 0:
+        return np.zeros(0)
+    v = verts.reshape(-1, 3)
+    tv = v[tris.reshape(-1, 3)]
+    tmin, tmax = tv.min(axis=1), tv.max(axis=1)
+    cs = float(cfgs[0].cs)
+    foot = (np.floor((tmax[:, 0] - tmin[:, 0]) / cs) + 1.0) * (np.floor((tmax[:, 2] - tmin[:, 2]) / cs) + 1.0)
+    bmin = np.array([c.bmin for c in cfgs], dtype=np.float64)
+    bmax = np.array([c.bmax for c in cfgs], dtype=np.float64)
+    xs, zs = np.unique(bmin[:, 0]), np.unique(bmin[:, 2])  # the tiles form a grid (synth.tile_grid)
+    cx, cz = 0.5 * (tmin[:, 0] + tmax[:, 0]), 0.5 * (tmin[:, 2] + tmax[:, 2])
+    ix = np.clip(np.searchsorted(xs, cx, side="right") - 1, 0, len(xs) - 1)
+    iz = np.clip(np.searchsorted(zs, cz, side="right") - 1, 0, len(zs) - 1)
+    grid = np.zeros((len(zs), len(xs)))
+    np.add.at(grid, (iz, ix), foot)
+    tx = np.searchsorted(xs, bmin[:, 0])
+    tz = np.searchsorted(zs, bmin[:, 2])
+    cells = np.array([c.width * c.height for c in cfgs], dtype=np.float64)
+    return grid[tz, tx] + 2.0 * cells
+
+
+def shard_tiles_weighted(verts: np.ndarray, tris: np.ndarray, cfgs: Sequence[RecastConfig], rank: int, world: int) -> np.ndarray:
+    """Contiguous slabs like shard_tiles(mode='slab'), but cut where the cumulative estimated COST (tile_costs)
+    crosses k/world of the total: uneven worlds (config 3's buildings) then take about the same time on every
+    rank.  The static alternative to a work-stealing queue (BASELINE.json north_star allows either)."""
+    cost = np.cumsum(tile_costs(verts, tris, cfgs))
+    total = cost[-1] if len(cost) else 0.0
+    cuts = [0] + [int(np.searchsorted(cost, total * k / world)) for k in range(1, world)] + [len(cfgs)]
+    for k in range(1, len(cuts)):
+        cuts[k] = max(cuts[k], cuts[k - 1])
+    return np.arange(cuts[rank], cuts[rank + 1], dtype=np.int64)
 
 
 def gather_tile_counts(local_ids: np.ndarray, local_counts: np.ndarray, ntiles: int, world: int) -> np.ndarray:

@@ -91,17 +91,33 @@ def test_prebin_keeps_order_and_results(oracle):
     v, t, cfgs = synth.config2(seed=2, nq=30, tile=32)
     sub = cfgs[:3]
     sv, st = shard.prebin_mesh(v, t, sub)
-    tt = t.reshape(-1, 3)
-    ss = st.reshape(-1, 3)
-    # subsequence of the original triangle list, same order
+    assert sv.size < v.size  # only the vertices the slab's triangles use travel to the rank
+    # subsequence of the original triangle list, same order, same coordinates (vertices are renumbered, not moved)
+    tv = v.reshape(-1, 3)[t.reshape(-1, 3)]
+    sc = sv.reshape(-1, 3)[st.reshape(-1, 3)]
     pos = 0
-    for row in ss:
-        while not np.array_equal(tt[pos], row):
+    for row in sc:
+        while not np.array_equal(tv[pos], row):
             pos += 1
         pos += 1
+    kv, kt = shard.prebin_mesh(v, t, sub, compact_vertices=False)
+    assert kv is v and np.array_equal(v.reshape(-1, 3)[kt.reshape(-1, 3)], sc)
     for c in sub:
         a, ca = oracle.build_tile(c, v, t)
         b, cb = oracle.build_tile(c, sv, st)
         np.testing.assert_array_equal(a.span_area, b.span_area)
         np.testing.assert_array_equal(ca.dist, cb.dist)
         np.testing.assert_array_equal(ca.conn_ref, cb.conn_ref)
+
+
+def test_weighted_slabs_cover_the_tiles_and_balance_cost():
+    from recast_rs_b200 import shard, synth
+
+    v, t, cfgs = synth.config3(seed=1, nq=300, lattice=22)
+    cost = shard.tile_costs(v, t, cfgs)
+    assert cost.shape == (len(cfgs),) and (cost > 0).all()
+    for world in (1, 2, 4, 8):
+        parts = [shard.shard_tiles_weighted(v, t, cfgs, r, world) for r in range(world)]
+        np.testing.assert_array_equal(np.concatenate(parts), np.arange(len(cfgs)))  # contiguous, in order, complete
+        loads = np.array([cost[p].sum() for p in parts])
+        assert loads.max() <= loads.mean() + cost.max() * 1.01  # within one tile of the mean
