@@ -384,6 +384,36 @@ int rcb_result_tile(const rcb_result* res, int tile, rcb_tile_view* out);       
 int rcb_result_tile_device(const rcb_result* res, int tile, rcb_tile_view* out); /* device pointers; scalars need download */
 void rcb_result_free(rcb_result* res);
 
+/* ---- several devices of one box --------------------------------------------------------------------
+ * The multi-tile loop of detour-dynamic (DynamicNavMesh::build / build_async, crates/detour-dynamic/src/dynamic_navmesh.rs:
+ * 558-684: `for key in tile_keys` -> DynamicTile::build) over the GPUs of one box, from ONE host thread of the caller:
+ *   rcb_multi_create        one rcb_ctx per listed device.
+ *   rcb_multi_upload_mesh   the mesh goes host -> devices[0] once and from there to the other devices (peer copy over NVLink);
+ *                           indices are validated as in rcb_upload_mesh.
+ *   rcb_multi_build_tiles   tiles are independent (no halo, border_size 0 on every multi-tile path of the reference), so the
+ *                           configurations are cut into groups of `tiles_per_group` consecutive tiles (<= 0: about eight
+ *                           groups per device) and one internal host thread per device pulls groups from a shared counter
+ *                           until none is left: a device that finishes early takes more (work stealing).  No data moves
+ *                           between devices.  download != 0: every group's result is also copied to pinned host memory by
+ *                           its device's thread (rcb_multi_result_tile then works at once).
+ *   rcb_multi_result_*      as rcb_result_*: tile indices are those of `cfgs`; rcb_multi_result_tile_device also reports the
+ *                           device that holds the tile.  tiles_per_device (nullable, ndevices entries): how the queue dealt.
+ * Errors: the first failing group's status (same kinds as rcb_build_tiles). */
+typedef struct rcb_multi rcb_multi;
+typedef struct rcb_multi_result rcb_multi_result;
+int rcb_multi_create(const int* devices, int ndevices, rcb_multi** out);
+void rcb_multi_destroy(rcb_multi* m);
+const char* rcb_multi_last_error(const rcb_multi* m);
+int rcb_multi_device_count(const rcb_multi* m);
+int rcb_multi_upload_mesh(rcb_multi* m, const float* verts, size_t nfloats, const int32_t* tris, size_t nidx);
+int rcb_multi_build_tiles(rcb_multi* m, const rcb_config* cfgs, int ntiles, uint32_t stage_mask, int erode_radius,
+                          int tiles_per_group, int download, rcb_multi_result** out);
+int rcb_multi_result_download(rcb_multi_result* res);
+int rcb_multi_result_totals(const rcb_multi_result* res, rcb_totals* out, int* tiles_per_device, int ndevices);
+int rcb_multi_result_tile(const rcb_multi_result* res, int tile, rcb_tile_view* out);
+int rcb_multi_result_tile_device(const rcb_multi_result* res, int tile, rcb_tile_view* out, int* device);
+void rcb_multi_result_free(rcb_multi_result* res);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,17 @@ SYMBOLS = {
     "rcb_result_tile": (_i, [_vp, _i, ctypes.POINTER(RcbTileView)]),
     "rcb_result_tile_device": (_i, [_vp, _i, ctypes.POINTER(RcbTileView)]),
     "rcb_result_free": (None, [_vp]),
+    "rcb_multi_create": (_i, [ctypes.POINTER(ctypes.c_int), _i, _pp]),
+    "rcb_multi_destroy": (None, [_vp]),
+    "rcb_multi_last_error": (ctypes.c_char_p, [_vp]),
+    "rcb_multi_device_count": (_i, [_vp]),
+    "rcb_multi_upload_mesh": (_i, [_vp, _vp, _sz, _vp, _sz]),
+    "rcb_multi_build_tiles": (_i, [_vp, _vp, _i, _u32, _i, _i, _i, _pp]),
+    "rcb_multi_result_download": (_i, [_vp]),
+    "rcb_multi_result_totals": (_i, [_vp, ctypes.POINTER(RcbTotals), ctypes.POINTER(ctypes.c_int), _i]),
+    "rcb_multi_result_tile": (_i, [_vp, _i, ctypes.POINTER(RcbTileView)]),
+    "rcb_multi_result_tile_device": (_i, [_vp, _i, ctypes.POINTER(RcbTileView), ctypes.POINTER(ctypes.c_int)]),
+    "rcb_multi_result_free": (None, [_vp]),
 }
 
 _lib = None

@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librecast_b200.so")
-SOURCES = ["rcb_api.cu", "k_scan.cu", "k_raster.cu", "k_raster2.cu", "k_tile.cu", "k_tilecache.cu", "k_area.cu", "k_wire.cu", "k_lz4.cu", "k_regions.cu", "k_filter.cu", "k_compact.cu", "k_dist.cu"]
+SOURCES = ["rcb_api.cu", "rcb_multi.cu", "k_scan.cu", "k_raster.cu", "k_raster2.cu", "k_tile.cu", "k_tilecache.cu", "k_area.cu", "k_wire.cu", "k_lz4.cu", "k_regions.cu", "k_filter.cu", "k_compact.cu", "k_dist.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false",
@@ -63,7 +63,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
         for l in logs:
             sys.stderr.write(l)
     if jobs or force or _stale(OUT, objs):
-        run([nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+        run([nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-pthread"])
     return OUT
 
 

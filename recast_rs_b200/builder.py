@@ -92,6 +92,36 @@ class TileVoxels:
         return self
 
 
+def _tile_from_view(v, expand: bool = True) -> "TileVoxels":
+    """TileVoxels (host copies) of a filled rcb_tile_view with host pointers."""
+    C, S, K = v.cell_count, v.span_count, v.conn_count
+    tv = TileVoxels(v.width, v.height, S, K, v.walkable_span_count, v.max_height, v.max_distance, v.status,
+                    _np_from(v.hf_cell_offset, C + 1, np.uint32) if v.hf_cell_offset else None, _np_from(v.span_min, S, np.int16),
+                    _np_from(v.span_max, S, np.int16), _np_from(v.span_area, S, np.uint8))
+    if v.cell_index:
+        tv.cell_index = _np_from(v.cell_index, C, np.uint32)
+        tv.cell_count = _np_from(v.cell_count_arr, C, np.uint32)
+        tv.areas = _np_from(v.areas, S, np.uint8)
+        tv.con = _np_from(v.con, 4 * S, np.uint16)
+        tv.dist = _np_from(v.dist, S, np.uint16)
+        if v.conn_mask:  # RESULT_SLIM: the binding layer rebuilds the rest (expand_slim)
+            tv.hf_cell_offset = None
+            tv.conn_mask = _np_from(v.conn_mask, S, np.uint8)
+            if v.conn_ref16:
+                tv.conn_ref16 = _np_from(v.conn_ref16, K, np.uint16)
+            else:
+                tv.conn_ref = _np_from(v.conn_ref, K, np.uint32)
+            if expand:
+                tv.expand_slim()
+        else:
+            tv.first_conn = _np_from(v.first_conn, S, np.uint32)
+            tv.conn_ref = _np_from(v.conn_ref, K, np.uint32)
+            tv.conn_dir = _np_from(v.conn_dir, K, np.uint8)
+            tv.conn_next = _np_from(v.conn_next, K, np.uint32)
+        if v.reg:
+            tv.reg, tv.max_regions = _np_from(v.reg, S, np.uint16), int(v.max_regions)
+    return tv
+
 class BatchResult:
     """Owner of an rcb_result (device arena + optional pinned host copy)."""
 
@@ -111,33 +141,7 @@ class BatchResult:
         """One tile of a downloaded result.  For a RESULT_SLIM result `expand` rebuilds the arrays the download left out."""
         v = _ffi.RcbTileView()
         check(_ffi.lib().rcb_result_tile(self._h, i, ctypes.byref(v)), self._ctx._h)
-        C, S, K = v.cell_count, v.span_count, v.conn_count
-        tv = TileVoxels(v.width, v.height, S, K, v.walkable_span_count, v.max_height, v.max_distance, v.status,
-                        _np_from(v.hf_cell_offset, C + 1, np.uint32) if v.hf_cell_offset else None, _np_from(v.span_min, S, np.int16),
-                        _np_from(v.span_max, S, np.int16), _np_from(v.span_area, S, np.uint8))
-        if v.cell_index:
-            tv.cell_index = _np_from(v.cell_index, C, np.uint32)
-            tv.cell_count = _np_from(v.cell_count_arr, C, np.uint32)
-            tv.areas = _np_from(v.areas, S, np.uint8)
-            tv.con = _np_from(v.con, 4 * S, np.uint16)
-            tv.dist = _np_from(v.dist, S, np.uint16)
-            if v.conn_mask:  # RESULT_SLIM: the binding layer rebuilds the rest (expand_slim)
-                tv.hf_cell_offset = None
-                tv.conn_mask = _np_from(v.conn_mask, S, np.uint8)
-                if v.conn_ref16:
-                    tv.conn_ref16 = _np_from(v.conn_ref16, K, np.uint16)
-                else:
-                    tv.conn_ref = _np_from(v.conn_ref, K, np.uint32)
-                if expand:
-                    tv.expand_slim()
-            else:
-                tv.first_conn = _np_from(v.first_conn, S, np.uint32)
-                tv.conn_ref = _np_from(v.conn_ref, K, np.uint32)
-                tv.conn_dir = _np_from(v.conn_dir, K, np.uint8)
-                tv.conn_next = _np_from(v.conn_next, K, np.uint32)
-            if v.reg:
-                tv.reg, tv.max_regions = _np_from(v.reg, S, np.uint16), int(v.max_regions)
-        return tv
+        return _tile_from_view(v, expand)
 
     def span_data_size(self) -> int:
         return int(_ffi.lib().rcb_result_span_data_size(self._h))
@@ -418,6 +422,110 @@ class Context:
                                                         if ct.nobstacles else None, ct.nobstacles, cs, ch, stage_mask, erode_radius,
                                                         ctypes.byref(out)), self._h)
         return BatchResult(self, out)
+
+
+class MultiResult:
+    """Owner of an rcb_multi_result: the groups of a multi-device build, addressed by the caller's tile index."""
+
+    def __init__(self, mctx: "MultiContext", handle):
+        self._m, self._h = mctx, handle
+
+    def _check(self, status):
+        if status != 0:
+            raw = _ffi.lib().rcb_multi_last_error(self._m._h) if self._m._h else b""
+            check(status, None, raw.decode("utf-8", "replace") if raw else "")
+
+    def totals(self) -> dict:
+        t = _ffi.RcbTotals()
+        per = (ctypes.c_int * self._m.ndevices)()
+        self._check(_ffi.lib().rcb_multi_result_totals(self._h, ctypes.byref(t), per, self._m.ndevices))
+        d = {n: int(getattr(t, n)) for n, _ in _ffi.RcbTotals._fields_}
+        d["tiles_per_device"] = [int(x) for x in per]
+        return d
+
+    def download(self) -> "MultiResult":
+        self._check(_ffi.lib().rcb_multi_result_download(self._h))
+        return self
+
+    def tile(self, i: int, expand: bool = True) -> TileVoxels:
+        v = _ffi.RcbTileView()
+        self._check(_ffi.lib().rcb_multi_result_tile(self._h, i, ctypes.byref(v)))
+        return _tile_from_view(v, expand)
+
+    def tile_device(self, i: int):
+        """(device ordinal, rcb_tile_view with device pointers) of tile i."""
+        v, dev = _ffi.RcbTileView(), ctypes.c_int(-1)
+        self._check(_ffi.lib().rcb_multi_result_tile_device(self._h, i, ctypes.byref(v), ctypes.byref(dev)))
+        return int(dev.value), v
+
+    def free(self):
+        if self._h and self._m._h:
+            _ffi.lib().rcb_multi_result_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.free()
+
+
+class MultiContext:
+    """rcb_multi: the devices of one box behind one handle.  The multi-tile loop of detour-dynamic
+    (DynamicNavMesh::build, dynamic_navmesh.rs:558-578) with the tiles dealt to the GPUs group by group from a shared
+    queue; results stay on the device that built them (or are downloaded by that device's thread)."""
+
+    def __init__(self, devices: Sequence[int]):
+        arr = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+        h = ctypes.c_void_p()
+        check(_ffi.lib().rcb_multi_create(arr, len(devices), ctypes.byref(h)), None,
+              f"rcb_multi_create({list(devices)}) failed: no such CUDA device (recast_rs_b200 has no CPU fallback)")
+        self._h, self.ndevices, self._live = h, len(devices), []
+
+    def _check(self, status):
+        if status != 0:
+            raw = _ffi.lib().rcb_multi_last_error(self._h)
+            check(status, None, raw.decode("utf-8", "replace") if raw else "")
+
+    def upload_mesh(self, vertices, indices):
+        v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1)
+        t = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1)
+        self._check(_ffi.lib().rcb_multi_upload_mesh(self._h, _ptr(v), v.size, _ptr(t), t.size))
+
+    def build_tiles(self, cfgs, stage_mask=STAGE_ALL_BUILD, erode_radius=0, tiles_per_group: int = 0, download: bool = False) -> MultiResult:
+        arr = cfgs if isinstance(cfgs, ctypes.Array) else configs_to_array(cfgs)
+        out = ctypes.c_void_p()
+        self._check(_ffi.lib().rcb_multi_build_tiles(self._h, ctypes.cast(arr, ctypes.c_void_p), len(arr), stage_mask, erode_radius,
+                                                     tiles_per_group, int(download), ctypes.byref(out)))
+        r = MultiResult(self, out)
+        self._live.append(r)
+        return r
+
+    def close(self):
+        if self._h:
+            for r in self._live:  # results hold arenas of the per-device contexts: release them first
+                r.free()
+            self._live = []
+            _ffi.lib().rcb_multi_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _join_blobs(blobs):

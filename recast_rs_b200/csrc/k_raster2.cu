@@ -115,6 +115,17 @@ __device__ __forceinline__ void for_each_tile(const Tri& t, const Locator& loc, 
 // ---- pass 1: validate indices; per triangle: number of work items; per tile: fragment upper bound ----
 __global__ void __launch_bounds__(256) k_bin_count(Raster2 rb) {
     const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rb.mesh.blocks) {
+        // A batch that covers part of the world (a tile group of a streamed or multi-GPU build) meets mostly triangles
+        // that lie elsewhere: the 256 consecutive triangles of this CTA are skipped together when their common AABB misses
+        // the batch's extent (inclusive comparison, as overlap_bounds, rasterization.rs:370-377; fminf / fmaxf ignore NaN
+        // as f32::min / max do, so the block box holds every triangle box).
+        const float4 b = rb.mesh.blocks[blockIdx.x];
+        if (!(b.x <= rb.loc.ex1 && b.z >= rb.loc.ex0 && b.y <= rb.loc.ez1 && b.w >= rb.loc.ez0)) {
+            if (tri < rb.mesh.ntris) rb.item_cnt[tri] = 0;
+            return;
+        }
+    }
     unsigned long long ub = 0;
     uint32_t items = 0;
     bool bad = false;
@@ -183,6 +194,41 @@ __global__ void __launch_bounds__(256) k_check_indices(const int32_t* __restrict
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nidx; i += (size_t)gridDim.x * blockDim.x)
         bad = bad || (uint32_t)tris[i] >= nverts;
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1ull);
+}
+
+// xz AABB per run of RCB_MESH_BLOCK consecutive triangles (k_bin_count's early reject); a run with an index out of range
+// gets an infinite box (the build fails on it anyway, lib.rs:224-233)
+__global__ void __launch_bounds__(RCB_MESH_BLOCK) k_mesh_blocks(const float* __restrict__ verts, const int32_t* __restrict__ tris, uint32_t ntris,
+                                                                uint32_t nverts, float4* __restrict__ blocks) {
+    const uint32_t tri = blockIdx.x * RCB_MESH_BLOCK + threadIdx.x;
+    float x0 = INFINITY, z0 = INFINITY, x1 = -INFINITY, z1 = -INFINITY;
+    if (tri < ntris) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t i = (uint32_t)tris[tri * 3ull + k];
+            if (i >= nverts) {
+                x0 = z0 = -INFINITY, x1 = z1 = INFINITY;
+                break;
+            }
+            const float x = verts[i * 3ull], z = verts[i * 3ull + 2];
+            x0 = fminf(x0, x), x1 = fmaxf(x1, x), z0 = fminf(z0, z), z1 = fmaxf(z1, z);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        x0 = fminf(x0, __shfl_down_sync(0xffffffffu, x0, d));
+        z0 = fminf(z0, __shfl_down_sync(0xffffffffu, z0, d));
+        x1 = fmaxf(x1, __shfl_down_sync(0xffffffffu, x1, d));
+        z1 = fmaxf(z1, __shfl_down_sync(0xffffffffu, z1, d));
+    }
+    __shared__ float sh[4][RCB_MESH_BLOCK / 32];
+    if ((threadIdx.x & 31) == 0) sh[0][threadIdx.x >> 5] = x0, sh[1][threadIdx.x >> 5] = z0, sh[2][threadIdx.x >> 5] = x1, sh[3][threadIdx.x >> 5] = z1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < RCB_MESH_BLOCK / 32; ++w)
+            x0 = fminf(x0, sh[0][w]), z0 = fminf(z0, sh[1][w]), x1 = fmaxf(x1, sh[2][w]), z1 = fmaxf(z1, sh[3][w]);
+        blocks[blockIdx.x] = make_float4(x0, z0, x1, z1);
+    }
 }
 
 // ---- pass 2: write the work items (tri, tile, chunk) in triangle order -------------------------------
@@ -537,6 +583,12 @@ void launch_check_indices(const int32_t* tris, size_t nidx, uint32_t nverts, uns
     KScope _k("k_check_indices", s);
     const unsigned blocks = (unsigned)std::min<size_t>((nidx + 255) / 256, 148 * 16);
     k_check_indices<<<blocks, 256, 0, s>>>(tris, nidx, nverts, flag);
+}
+
+void launch_mesh_blocks(const float* verts, const int32_t* tris, uint32_t ntris, uint32_t nverts, float4* blocks, cudaStream_t s) {
+    if (ntris == 0) return;
+    KScope _k("k_mesh_blocks", s);
+    k_mesh_blocks<<<(ntris + RCB_MESH_BLOCK - 1) / RCB_MESH_BLOCK, RCB_MESH_BLOCK, 0, s>>>(verts, tris, ntris, nverts, blocks);
 }
 
 void launch_fill_items(const Raster2& rb, const uint32_t* item_off, uint2* items, cudaStream_t s) {

@@ -118,7 +118,8 @@ struct rcb_ctx {
     std::string err;
     unsigned long long launches = 0;  // kernel launches issued by this context
     // mesh
-    DevBuf d_verts, d_tris, d_tri_areas;
+    DevBuf d_verts, d_tris, d_tri_areas, d_mesh_blocks;
+    const float4* mesh_blocks = nullptr;  // xz AABB per 256 consecutive triangles of the current mesh
     const float* verts = nullptr;
     const int32_t* tris = nullptr;
     size_t nfloats = 0, nidx = 0;
@@ -343,6 +344,10 @@ void build_locator(std::vector<TileDesc>& tiles, HostLocator& L) {
         bsx = fmaxf(bsx, t.bmax[0] - t.bmin[0]);
         bsz = fmaxf(bsz, t.bmax[2] - t.bmin[2]);
     }
+    // extent for the early reject of whole triangle blocks (k_bin_count): exact tile bounds, or everything
+    L.loc.ex0 = gx0, L.loc.ez0 = gz0, L.loc.ex1 = gx1, L.loc.ez1 = gz1;
+    if (!std::isfinite(gx0) || !std::isfinite(gz0) || !std::isfinite(gx1) || !std::isfinite(gz1) || n == 0)
+        L.loc.ex0 = L.loc.ez0 = -INFINITY, L.loc.ex1 = L.loc.ez1 = INFINITY;
     if (!(bsx > 0) || !std::isfinite(bsx)) bsx = 1.0f;
     if (!(bsz > 0) || !std::isfinite(bsz)) bsz = 1.0f;
     if (!std::isfinite(gx0)) gx0 = 0;
@@ -427,7 +432,7 @@ int get_batch_entry(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, std::share
     e->Ctot = Ctot;
     e->max_cells = max_cells;
     e->last_use = ctx->use_clock;
-    if (ctx->batch_cache.size() >= 24) {  // bounded: drop the least recently used (results that still use it keep it alive)
+    if (ctx->batch_cache.size() >= 96) {  // bounded: drop the least recently used (results that still use it keep it alive)
         size_t m = 0;
         for (size_t i = 1; i < ctx->batch_cache.size(); ++i)
             if (ctx->batch_cache[i]->last_use < ctx->batch_cache[m]->last_use) m = i;
@@ -919,6 +924,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         rb.mesh.nverts = (uint32_t)nverts;
         rb.mesh.tri_areas = src.tri_areas ? ctx->d_tri_areas.as<uint8_t>() : nullptr;
         rb.mesh.merge_thr = src.merge_thr;
+        rb.mesh.blocks = ctx->mesh_blocks;
         rb.counters = ctx->d_counters.as<unsigned long long>();
         rb.cell_cnt = ctx->d_cell_cnt.as<uint32_t>();
         Raster2 r2{};
@@ -1620,7 +1626,7 @@ void rcb_destroy(rcb_ctx* ctx) {
     }
     ctx->live.clear();
     ctx->batch_cache.clear();
-    DevBuf* bufs[] = {&ctx->d_verts, &ctx->d_tris, &ctx->d_tri_areas, &ctx->d_tiles, &ctx->d_bin_off, &ctx->d_bin_tiles,
+    DevBuf* bufs[] = {&ctx->d_verts, &ctx->d_tris, &ctx->d_tri_areas, &ctx->d_mesh_blocks, &ctx->d_tiles, &ctx->d_bin_off, &ctx->d_bin_tiles,
                       &ctx->d_counters, &ctx->d_cell_cnt, &ctx->d_frag_off, &ctx->d_frag_tmp, &ctx->d_frag_rec, &ctx->d_fs_mm,
                       &ctx->d_fs_area, &ctx->d_scan_tmp, &ctx->d_hf_off, &ctx->d_conn_cnt, &ctx->d_conn_off, &ctx->d_nid,
                       &ctx->d_t16a, &ctx->d_t16b, &ctx->d_t16c, &ctx->d_t8a, &ctx->d_t8b, &ctx->d_item_cnt, &ctx->d_item_off, &ctx->d_items, &ctx->d_tile_ub, &ctx->d_tile_base,
@@ -1735,7 +1741,16 @@ int rcb_config_validate(const rcb_config* c) {
 // a mesh with a bad index fails with RCB_ENAVMESH_GEN before anything is rasterized, which is what the reference's caller sees.
 static int check_mesh_indices(rcb_ctx* ctx) {
     ctx->mesh_bad = false;
+    ctx->mesh_blocks = nullptr;
     ctx->h_counters[31] = 0;
+    if (ctx->nidx && ctx->nfloats && ctx->nidx % 3 == 0 && ctx->nfloats % 3 == 0 && ctx->nidx / 3 <= 0xffffffffull / 3) {
+        const uint32_t ntris = (uint32_t)(ctx->nidx / 3);
+        const size_t nblocks = ((size_t)ntris + RCB_MESH_BLOCK - 1) / RCB_MESH_BLOCK;
+        CU(ctx->d_mesh_blocks.ensure(sizeof(float4) * nblocks + 64));
+        launch_mesh_blocks(ctx->verts, ctx->tris, ntris, (uint32_t)std::min<size_t>(ctx->nfloats / 3, 0x7fffffffu), ctx->d_mesh_blocks.as<float4>(),
+                           ctx->stream);
+        ctx->mesh_blocks = ctx->d_mesh_blocks.as<float4>();
+    }
     if (ctx->nidx && ctx->nfloats) {
         CU(ctx->d_counters.ensure(48 * sizeof(unsigned long long)));
         unsigned long long* flag = ctx->d_counters.as<unsigned long long>() + 47;

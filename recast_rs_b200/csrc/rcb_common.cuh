@@ -78,6 +78,7 @@ struct Locator {
     int32_t nbx, nbz;
     const uint32_t* bin_off;    // [nbx*nbz + 1]
     const uint32_t* bin_tiles;  // tile ids
+    float ex0, ez0, ex1, ez1;  // xz extent of the batch's tiles (infinite when a tile bound is not finite)
 };
 
 // Device-side bin coordinate; monotone in v, identical on host and device (sub, mul, floor, clamp).
@@ -95,6 +96,12 @@ struct MeshView {
     uint32_t nverts;
     const uint8_t* tri_areas;  // explicit areas (rcb_rasterize) or nullptr (classify by slope)
     int32_t merge_thr;         // flag_merge_threshold
+    const float4* blocks;      // nullable: xz AABB (min x, min z, max x, max z) of every run of 256 consecutive triangles
+};
+#define RCB_MESH_BLOCK 256
+void launch_mesh_blocks(const float* verts, const int32_t* tris, uint32_t ntris, uint32_t nverts, float4* blocks, cudaStream_t s);
+struct RcbUnused_ {
+    int unused;
 };
 
 #ifdef __CUDACC__

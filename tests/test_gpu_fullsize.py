@@ -11,18 +11,23 @@ from tests.parity import assert_tile_equal
 pytestmark = pytest.mark.gpu
 
 
-def _context(force_global=False):
+def _context(force_global=False, band_cells=None):
+    """band_cells: cut tiles that do not fit shared memory whole into bands of about that many cells (RCB_BAND_CELLS)."""
     import recast_rs_b200.builder as rb
 
-    old = os.environ.get("RCB_FORCE_GLOBAL")
-    os.environ["RCB_FORCE_GLOBAL"] = "1" if force_global else "0"
+    env = {"RCB_FORCE_GLOBAL": "1" if force_global else "0"}
+    if band_cells is not None:
+        env["RCB_BAND_CELLS"] = str(band_cells)
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
     try:
         return rb.Context(0)
     finally:
-        if old is None:
-            os.environ.pop("RCB_FORCE_GLOBAL", None)
-        else:
-            os.environ["RCB_FORCE_GLOBAL"] = old
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
 def _invariants(tv, what, eroded=False):
@@ -101,7 +106,10 @@ def test_config2_full(oracle):
         _compare_results(r1, r2, len(cfgs), NAMES)
         for i in range(0, len(cfgs), 7):
             _invariants(r1.tile(i), f"config2 tile {i}")
-        for i in (0, 44, 1012, 1980, 2024):  # corners + centre against the oracle
+        # corners, centre, the partial tiles of the last row / column and a spread of interior tiles against the oracle
+        picks = sorted({0, 44, 1012, 1980, 2024, 22, 45 * 22, 45 * 22 + 44, 2002} | set(range(3, 2025, 127)))
+        assert len(picks) >= 25
+        for i in picks:
             hfa, chfa = oracle.build_tile(cfgs[i], v, t)
             assert_tile_equal(r1.tile(i), hfa, chfa, what=f"config2 tile {i}")
     ct.close(), cg.close()
@@ -130,18 +138,24 @@ def test_config4_full_interior(oracle):
 
     v, t, cfgs = synth.config4(seed=1)
     assert t.size // 3 == 1002528
-    ctx = _context(False)
-    ctx.upload_mesh(v, t)
-    with ctx.build_tiles(cfgs, rb.STAGE_ALL_BUILD) as r:
-        r.download()
-        tot = r.totals()
+    ctx, cb = _context(False), _context(False, band_cells=512)  # global-memory back end / shared-memory bands of 8 rows
+    for c in (ctx, cb):
+        c.upload_mesh(v, t)
+    cb.profile_enable(True)
+    with ctx.build_tiles(cfgs, rb.STAGE_ALL_BUILD) as r, cb.build_tiles(cfgs, rb.STAGE_ALL_BUILD) as r2:
+        r.download(), r2.download()
+        tot, tot2 = r.totals(), r2.totals()
         assert tot["spans"] >= 15 * tot["cells"] * 0.9
+        tot.pop("result_bytes"), tot2.pop("result_bytes")
+        assert tot == tot2
+        _compare_results(r, r2, len(cfgs), NAMES)  # the two back ends agree on every tile
         for i in range(0, len(cfgs), 5):
             _invariants(r.tile(i), f"config4 tile {i}")
         for i in (0, len(cfgs) // 2, len(cfgs) - 1):
             hfa, chfa = oracle.build_tile(cfgs[i], v, t)
             assert_tile_equal(r.tile(i), hfa, chfa, what=f"config4 tile {i}")
-    ctx.close()
+    assert "k_tile_compact" in cb.profile_read()  # the banded context really took the tile-resident kernels
+    ctx.close(), cb.close()
 
 
 def test_config3_scaled_open_world(oracle):
@@ -166,6 +180,35 @@ def test_config3_scaled_open_world(oracle):
             hfa, chfa = oracle.build_tile(cfgs[i], v, t)
             assert_tile_equal(r1.tile(i), hfa, chfa, what=f"config3 tile {i}")
     ct.close(), cg.close()
+
+
+def test_config3_full(oracle):
+    """BASELINE config 3 at FULL size: the 10M-triangle open world, 4761 tiles of 128x128 cells.  Both back ends (global
+    memory; shared-memory bands of 32 rows) must agree on every tile; invariants on a stride; corners, centre and the
+    building-densest tiles against the oracle (which scans all 10M triangles per tile, as lib.rs:217 does)."""
+    import recast_rs_b200.builder as rb
+    from recast_rs_b200 import shard, synth
+
+    v, t, cfgs = synth.config3(seed=1)
+    assert t.size // 3 == 10002752 and len(cfgs) == 69 * 69
+    cg, cb = _context(True), _context(False, band_cells=4608)
+    for c in (cg, cb):
+        c.upload_mesh(v, t)
+    cb.profile_enable(True)
+    with cg.build_tiles(cfgs, rb.STAGE_ALL_BUILD) as r1, cb.build_tiles(cfgs, rb.STAGE_ALL_BUILD) as r2:
+        r1.download(), r2.download()
+        ta, tb = r1.totals(), r2.totals()
+        ta.pop("result_bytes"), tb.pop("result_bytes")
+        assert ta == tb and ta["tiles"] == 4761 and ta["triangles"] == 10002752
+        _compare_results(r1, r2, len(cfgs), NAMES)
+        for i in range(0, len(cfgs), 37):
+            _invariants(r1.tile(i), f"config3 tile {i}")
+        dense = np.argsort(shard.tile_costs(v, t, cfgs))[-2:].tolist()  # the two tiles with the most building area
+        for i in sorted({0, 68, 69 * 34 + 34, 69 * 68, 4760} | set(dense)):
+            hfa, chfa = oracle.build_tile(cfgs[i], v, t)
+            assert_tile_equal(r1.tile(i), hfa, chfa, what=f"config3 tile {i}")
+    assert "k_tile_compact" in cb.profile_read()
+    cg.close(), cb.close()
 
 
 def test_determinism_repeated_runs():
