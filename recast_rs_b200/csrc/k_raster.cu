@@ -427,11 +427,12 @@ __global__ void __launch_bounds__(512) k_seg_scatter(const TileDesc* __restrict_
     const uint32_t tile = blockIdx.z * gridDim.y + blockIdx.y;
     if (tile >= (uint32_t)ntiles) return;
     const uint32_t F = min(tile_cursor[tile], tile_cap[tile]);
-    const uint32_t* fr = tile_frags + 3ull * tile_base[tile];
+    const uint32_t* fr = tile_frags + 3ull * tile_base[tile];  // three arrays of `cap` words
+    const uint32_t cap = tile_cap[tile];
     const uint32_t cb = tiles[tile].cell_base;
     if (blockIdx.x == 0 && threadIdx.x == 0 && F) atomicAdd(&counters[1], (unsigned long long)F);  // fragments of the batch
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < F; i += gridDim.x * blockDim.x) {
-        const uint32_t r0 = fr[3ull * i], r1 = fr[3ull * i + 1], r2 = fr[3ull * i + 2];
+        const uint32_t r0 = fr[i], r1 = fr[cap + i], r2 = fr[2ull * cap + i];
         const uint32_t g = cb + (r0 & 0xffffffu);
         // the column's counter runs back to zero; slots fill in arrival order, which is close to triangle
         // order, so the replay's insertion sort stays near its best case

@@ -37,6 +37,8 @@ constexpr int HDR_WORDS = 3;                              // per work item: tria
 static_assert(2 * XCAP * 2 <= 2 * ZCAP * 3, "phase-2 buffers alias the z-chain scratch");
 constexpr int NSLOTS = CLIP_THREADS * CLIP_ROWS;
 constexpr int NBUCK = 16;  // phase-2 rows are grouped by (vertex count 3..6+, columns spanned 1..4+): a scheduling hint only
+                           // (six column classes - 1, 2, 3, 4, 5-8, 9+ - were tried for config 3's roofs and walls: no change there,
+                           // +1 % on config 2 for the extra barrier)
 
 struct Tri {
     float v0[3], v1[3], v2[3];
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(256) k_fill_items(Raster2 rb, const uint32_t* 
 struct ClipSmem {
     float zbuf[2 * ZCAP * 3 * CLIP_THREADS];  // phase 1: [(buf*ZCAP + v)*3 + k][tid]; phase 2: two x/y buffers per thread
     uint32_t slots[NSLOTS * SLOT_WORDS];      // slot tid*CLIP_ROWS + r belongs to thread tid, row r of its chunk:
-                                              // [0] = z | vertices << 16 | bucket << 20 | area << 24 (0: empty), then x,y pairs
+                                              // [0] = z | vertices << 16 (3 bits) | bucket << 19 (5 bits) | area << 24 (0: empty), then x,y pairs
     uint32_t hdr[CLIP_THREADS * HDR_WORDS];   // what the rows of one work item have in common
     uint16_t list[NSLOTS];                    // compacted ids of the slots that hold a row polygon
     uint32_t nb[NBUCK], cur[NBUCK];           // rows per (vertex count, columns spanned) bucket and fill cursors
@@ -263,6 +265,9 @@ struct ClipSmem {
 #define XB(buf, v, k) sm.zbuf[(((buf) * XCAP + (v)) * 2 + (k)) * CLIP_THREADS + threadIdx.x]
 
 // One record into the segment of band `seg`; `lcell` is the cell inside the band's held rows.
+// (Tried: one atomic per lane with the record written an iteration later, so that the x-chain runs during the round trip:
+// k_clip_items 0.57 -> 2.69 ms on config 2 - six thousand same-address atomics per tile serialize in L2.  The warp-aggregated
+// form below stays: one atomic per (warp, band).)
 __device__ __forceinline__ void emit_to_segment(const Raster2& rb, const TileDesc& td, uint32_t seg, uint32_t lcell, uint32_t tcell, uint32_t tri,
                                                 uint32_t mm, uint32_t area) {
     // lanes of a warp mostly hit the same band
@@ -274,10 +279,13 @@ __device__ __forceinline__ void emit_to_segment(const Raster2& rb, const TileDes
     base = __shfl_sync(peers, base, leader);
     const uint32_t pos = base + __popc(peers & ((1u << lane_id()) - 1u));
     if (pos < rb.tile_cap[seg]) {
-        uint32_t* rec = rb.tile_frags + 3ull * (rb.tile_base[seg] + pos);
+        // the segment holds three arrays of `cap` words (cell | area << 24, smin | smax << 16, triangle): consecutive slots
+        // of a warp are consecutive words of each
+        const uint32_t cap = rb.tile_cap[seg];
+        uint32_t* rec = rb.tile_frags + 3ull * rb.tile_base[seg] + pos;
         rec[0] = lcell | (area << 24);
-        rec[1] = mm;
-        rec[2] = tri;
+        rec[cap] = mm;
+        rec[2ull * cap] = tri;
         // global back end: the per-column counts its scatter needs (a pass over the fragment list otherwise)
         if (rb.flags & 0x200u) atomicAdd(&rb.cell_cnt[td.cell_base + tcell], 1u);
     } else {
@@ -427,7 +435,7 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
                 if (keep && nrow >= 3 && z >= 0) {  // rasterization.rs:308-311
                     const int ncols = min(max(__float2int_rz((rmaxx - rminx) * td.ics), 0), 3);
                     const int bk = min(min(nrow, RCAP) - 3, 3) * 4 + ncols;
-                    slot[0] = (uint32_t)z | ((uint32_t)min(nrow, RCAP) << 16) | ((uint32_t)bk << 20) | (area << 24);
+                    slot[0] = (uint32_t)z | ((uint32_t)min(nrow, RCAP) << 16) | ((uint32_t)bk << 19) | (area << 24);
                     // bucket by vertex count so the lanes of a warp run vertex loops of equal length
                     atomicAdd(&sm.nb[bk], 1u);
                 }
@@ -458,8 +466,8 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
     for (int r = 0; r < CLIP_ROWS; ++r) {
         const uint32_t slot_id = threadIdx.x * CLIP_ROWS + r;
         const uint32_t w0 = sm.slots[slot_id * SLOT_WORDS];
-        if (((w0 >> 16) & 0xfu) >= 3) {
-            const uint32_t bk = (w0 >> 20) & 0xfu;
+        if (((w0 >> 16) & 0x7u) >= 3) {
+            const uint32_t bk = (w0 >> 19) & 0x1fu;
             uint32_t o = 0;
 #pragma unroll
             for (int k = 0; k < NBUCK; ++k) o = (k == (int)bk) ? boff[k] : o;
@@ -479,7 +487,7 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
         const uint32_t tri = hdr[0], tile = hdr[1];
         const uint32_t h2 = slot[0], h3 = hdr[2];
         const int z = (int)(h2 & 0xffffu);
-        int n = (int)((h2 >> 16) & 0xfu);
+        int n = (int)((h2 >> 16) & 0x7u);
         const uint32_t area = h2 >> 24;
         const int x0 = (int)(h3 & 0xffffu), x1 = (int)(h3 >> 16);
         const TileDesc& td = rb.tiles[tile];

@@ -49,32 +49,41 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
     return v;
 }
 
-// Exclusive scan of cnt[0..n) into out[0..n], out[n] = total (cnt and out may alias).  Rounds of
-// TILE_THREADS consecutive elements (thread t takes element r*TILE_THREADS + t: conflict-free), each
-// round one block-wide scan with a running carry.  Uses sh_warp[TILE_THREADS/32 + 1].
+// Exclusive scan of cnt[0..n) into out[0..n], out[n] = total (cnt and out may alias when they have the same type).
+// Every warp owns one contiguous chunk: it first adds its chunk up, the chunk totals are scanned by warp 0, and a second
+// pass over the chunk writes the offsets - two block barriers in all.  (Rounds of one element per thread with a block-wide
+// scan each cost 2 barriers per TILE_THREADS elements: 8 k cycles for a 64x64 tile, three times per tile.)
+// Uses sh_warp[TILE_THREADS/32 + 1].
 template <int TILE_THREADS, typename OutT>
 __device__ uint32_t block_scan_array(const uint32_t* cnt, OutT* out, uint32_t n, uint32_t* sh_warp) {
-    uint32_t carry = 0;
-    for (uint32_t base = 0; base < n; base += TILE_THREADS) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < n ? cnt[i] : 0;
-        const uint32_t inc = warp_incl_scan(v);
-        if ((threadIdx.x & 31) == 31) sh_warp[threadIdx.x >> 5] = inc;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            const uint32_t w = threadIdx.x < TILE_THREADS / 32 ? sh_warp[threadIdx.x] : 0;
-            const uint32_t winc = warp_incl_scan(w);
-            if (threadIdx.x < TILE_THREADS / 32) sh_warp[threadIdx.x] = winc - w;
-            if (threadIdx.x == 31) sh_warp[TILE_THREADS / 32] = winc;
-        }
-        __syncthreads();
-        if (i < n) out[i] = (OutT)(carry + inc - v + sh_warp[threadIdx.x >> 5]);
-        carry += sh_warp[TILE_THREADS / 32];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) out[n] = (OutT)carry;
+    constexpr uint32_t NW = TILE_THREADS / 32;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t chunk = ((n + NW - 1) / NW + 31u) & ~31u;  // elements per warp, a multiple of 32
+    const uint32_t c0 = min(warp * chunk, n), c1 = min(c0 + chunk, n);
+    uint32_t sum = 0;
+    for (uint32_t i = c0 + lane; i < c1; i += 32) sum += cnt[i];
+    sum = __reduce_add_sync(0xffffffffu, sum);
+    if (lane == 0) sh_warp[warp] = sum;
     __syncthreads();
-    return carry;
+    if (warp == 0) {
+        const uint32_t w = lane < NW ? sh_warp[lane] : 0;
+        const uint32_t winc = warp_incl_scan(w);
+        if (lane < NW) sh_warp[lane] = winc - w;
+        if (lane == NW - 1) sh_warp[NW] = winc;
+    }
+    __syncthreads();
+    uint32_t carry = sh_warp[warp];
+    const uint32_t total = sh_warp[NW];
+    for (uint32_t i0 = c0; i0 < c1; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const uint32_t v = i < c1 ? cnt[i] : 0;
+        const uint32_t inc = warp_incl_scan(v);
+        if (i < c1) out[i] = (OutT)(carry + inc - v);
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (threadIdx.x == 0) out[n] = (OutT)total;
+    __syncthreads();
+    return total;
 }
 
 // ======================================================================================================
@@ -125,8 +134,16 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_span
     for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) cnt[c] = 0;
     if (threadIdx.x < 3) sh_red[threadIdx.x] = 0;
     __syncthreads();
-    // 1. histogram by column
-    for (uint32_t i = threadIdx.x; i < F; i += TILE_THREADS) atomicAdd(&cnt[frags[3ull * i] & 0xffffffu], 1u);
+    // 1. histogram by column (the segment is three arrays of `cap` words: this pass reads the first; four loads in flight)
+    const uint32_t cap = a.tile_cap[band];
+    for (uint32_t i0 = threadIdx.x; i0 < F; i0 += 4 * TILE_THREADS) {
+        uint32_t c4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c4[u] = (i0 + u * TILE_THREADS < F) ? frags[i0 + u * TILE_THREADS] : 0xffffffffu;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (c4[u] != 0xffffffffu) atomicAdd(&cnt[c4[u] & 0xffffffu], 1u);
+    }
     __syncthreads();
     pc.mark(0);
     // 2. column offsets
@@ -136,12 +153,24 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_span
     pc.mark(1);
     // 3. scatter into column order (order inside a column is arbitrary; the replay sorts by triangle)
     uint32_t fown = 0;  // fragments of the band's own rows (halo rows are also some other band's own)
-    for (uint32_t i = threadIdx.x; i < F; i += TILE_THREADS) {
-        const uint32_t r0 = frags[3ull * i], r1 = frags[3ull * i + 1], r2 = frags[3ull * i + 2];
-        const uint32_t cell = r0 & 0xffffffu;
-        const uint32_t pos = off[cell] + atomicAdd(&cnt[cell], 1u);
-        rec[pos] = make_uint2((r0 & 0xff000000u) | (r2 & 0xffffffu), r1);
-        fown += cell >= oc0 && cell < oc1;
+    for (uint32_t i0 = threadIdx.x; i0 < F; i0 += 2 * TILE_THREADS) {
+        uint32_t r0[2], r1[2], r2[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const uint32_t i = i0 + u * TILE_THREADS;
+            const bool in = i < F;
+            r0[u] = in ? frags[i] : 0xffffffffu;
+            r1[u] = in ? frags[cap + i] : 0u;
+            r2[u] = in ? frags[2ull * cap + i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (i0 + u * TILE_THREADS >= F) continue;
+            const uint32_t cell = r0[u] & 0xffffffu;
+            const uint32_t pos = off[cell] + atomicAdd(&cnt[cell], 1u);
+            rec[pos] = make_uint2((r0[u] & 0xff000000u) | (r2[u] & 0xffffffu), r1[u]);
+            fown += cell >= oc0 && cell < oc1;
+        }
     }
     __syncthreads();
     pc.mark(2);
@@ -1076,6 +1105,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_comp
         const uint32_t cpw = (C + nwarps - 1) / nwarps;
         const uint32_t cw0 = min(wid * cpw, C), cw1 = min(cw0 + cpw, C);
         uint32_t kbase = coff[cw0];
+        // coff is dead once every worker holds its kbase: its bytes become one 256-entry slot table per warp
+        if (nworkers == TILE_THREADS)
+            __syncthreads();
+        else
+            asm volatile("bar.sync 2, %0;" ::"r"(nworkers) : "memory");
+        uint16_t* const slot_tab = reinterpret_cast<uint16_t*>(coff) + 256u * wid;  // <= 16 warps x 512 B <= 4 (C + 1) B for C >= 2047
+        const bool tab_ok = 512u * nwarps <= 4u * (C + 1u);
         for (uint32_t s0 = soff[oc0 + cw0], s1 = soff[oc0 + cw1]; s0 < s1; s0 += 32) {
             const uint32_t s = s0 + lane;
             uint32_t mask = 0;
@@ -1092,27 +1128,50 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_comp
             }
             const uint32_t excl = incl - cnt, T = __shfl_sync(0xffffffffu, incl, 31);
             if (s < s1) a.first_conn[span_base + s - nt] = cnt ? krel + kbase + incl - 1 : RCB_NONE;  // the last one pushed
-            const uint32_t rmask = __brev(mask) >> 24;  // bit i = direction 7 - i: the order the list is pushed in
-            for (uint32_t t = lane; t < ((T + 31u) & ~31u); t += 32) {
-                // owner = the last lane whose range starts at or before t (empty ranges share their successor's start)
-                uint32_t lo = 0, hi = 31;
+            if (tab_ok) {
+                // every lane files its span's slots: owner lane | direction << 5 | first-of-its-block << 8, directions from 7 down
+                // (the order the list is pushed in); then the lanes turn to the SLOTS, so the three stores of a round are coalesced
+                uint32_t o = excl;
 #pragma unroll
-                for (int it = 0; it < 5; ++it) {
-                    const uint32_t mid = (lo + hi + 1) >> 1;
-                    const uint32_t em = __shfl_sync(0xffffffffu, excl, mid);
-                    if (em <= t)
-                        lo = mid;
-                    else
-                        hi = mid - 1;
-                }
-                const uint32_t oex = __shfl_sync(0xffffffffu, excl, lo), orm = __shfl_sync(0xffffffffu, rmask, lo);
-                if (t < T) {
-                    const uint32_t j = t - oex;
-                    const uint32_t d = 7u - (uint32_t)__fns(orm, 0, (int)j + 1);
+                for (int d = 7; d >= 0; --d)
+                    if (mask & (1u << d)) {
+                        slot_tab[o] = (uint16_t)(lane | ((uint32_t)d << 5) | (o == excl ? 0x100u : 0u));
+                        ++o;
+                    }
+                __syncwarp();
+                for (uint32_t t = lane; t < T; t += 32) {
+                    const uint32_t e = slot_tab[t];
+                    const uint32_t d = (e >> 5) & 7u;
                     const uint32_t k = kbase + t;
-                    a.conn_ref[conn_base + k] = ref_off + nid[d * S2 + s0 + lo];
+                    a.conn_ref[conn_base + k] = ref_off + nid[d * S2 + s0 + (e & 31u)];
                     a.conn_dir[conn_base + k] = (uint8_t)d;
-                    a.conn_next[conn_base + k] = j ? krel + k - 1 : RCB_NONE;
+                    a.conn_next[conn_base + k] = (e & 0x100u) ? RCB_NONE : krel + k - 1;
+                }
+                __syncwarp();
+            } else {
+                // (tiny tiles: no room for the tables) slot t belongs to the span whose range holds t - bisection over the lanes'
+                // offsets - and is its j-th present direction from 7 downwards
+                const uint32_t rmask = __brev(mask) >> 24;  // bit i = direction 7 - i: the order the list is pushed in
+                for (uint32_t t = lane; t < ((T + 31u) & ~31u); t += 32) {
+                    uint32_t lo = 0, hi = 31;
+#pragma unroll
+                    for (int it = 0; it < 5; ++it) {
+                        const uint32_t mid = (lo + hi + 1) >> 1;
+                        const uint32_t em = __shfl_sync(0xffffffffu, excl, mid);
+                        if (em <= t)
+                            lo = mid;
+                        else
+                            hi = mid - 1;
+                    }
+                    const uint32_t oex = __shfl_sync(0xffffffffu, excl, lo), orm = __shfl_sync(0xffffffffu, rmask, lo);
+                    if (t < T) {
+                        const uint32_t j = t - oex;
+                        const uint32_t d = 7u - (uint32_t)__fns(orm, 0, (int)j + 1);
+                        const uint32_t k = kbase + t;
+                        a.conn_ref[conn_base + k] = ref_off + nid[d * S2 + s0 + lo];
+                        a.conn_dir[conn_base + k] = (uint8_t)d;
+                        a.conn_next[conn_base + k] = j ? krel + k - 1 : RCB_NONE;
+                    }
                 }
             }
             kbase += T;

@@ -155,7 +155,7 @@ struct Raster2 {
     uint32_t* tile_cursor;     // [nbands]
     const uint32_t* tile_base; // [nbands] first record of the band's segment
     const uint32_t* tile_cap;  // [nbands]
-    uint32_t* tile_frags;      // 3 words per record: cell | area<<24, smin | smax<<16, triangle
+    uint32_t* tile_frags;      // per segment three arrays of tile_cap words: cell | area<<24, smin | smax<<16, triangle
     uint32_t flags;            // bit0: min-x skip test (0: explicit per-vertex test; kept for A/B runs)
     uint32_t spec;             // 1: issued speculatively - the work-item count is read from counters[4] on the device
 };
@@ -186,7 +186,7 @@ struct TileSpansArgs {
     const TileDesc* tiles;
     const BandDesc* bands;
     BandInfo* binfo;
-    const uint32_t* tile_frags;   // 3 words per record, per-tile segments
+    const uint32_t* tile_frags;   // per-band segments: three arrays of tile_cap words each (3 words per record in all)
     const uint32_t* tile_base;    // [ntiles] first record of the segment (also the base of ts_* below)
     const uint32_t* tile_cap;     // [ntiles]
     const uint32_t* tile_cursor;  // [ntiles] records written
