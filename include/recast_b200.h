@@ -190,6 +190,12 @@ int rcb_config_validate(const rcb_config* cfg);                                 
  * rcb_upload_mesh copies host -> device; rcb_set_mesh_device borrows device memory (zero-copy). */
 int rcb_upload_mesh(rcb_ctx* ctx, const float* verts, size_t nfloats, const int32_t* tris, size_t nidx);
 int rcb_set_mesh_device(rcb_ctx* ctx, const void* d_verts, size_t nfloats, const void* d_tris, size_t nidx);
+/* The other two index forms of the reference's free functions; rcb_rasterize then is
+ *   rasterize_triangles_u16 (rasterization.rs:432-455)   rcb_upload_mesh_u16: `tris[i] as usize`, widened on the device;
+ *   rasterize_triangle_soup (rasterization.rs:459-476)   rcb_upload_triangle_soup: 9 floats per triangle, no index list.
+ * (rcb_build_tiles works on them too.) */
+int rcb_upload_mesh_u16(rcb_ctx* ctx, const float* verts, size_t nfloats, const uint16_t* tris, size_t nidx);
+int rcb_upload_triangle_soup(rcb_ctx* ctx, const float* verts, size_t ntris);
 
 /* ---- batched tile build ---------------------------------------------------------------------
  * rcb_build_tiles: for every tile config runs RecastBuilder::build_heightfield (lib.rs:116-135 ->

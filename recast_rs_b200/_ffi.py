@@ -61,6 +61,8 @@ SYMBOLS = {
     "rcb_config_validate": (_i, [ctypes.POINTER(RcbConfig)]),
     "rcb_upload_mesh": (_i, [_vp, _vp, _sz, _vp, _sz]),
     "rcb_set_mesh_device": (_i, [_vp, _vp, _sz, _vp, _sz]),
+    "rcb_upload_mesh_u16": (_i, [_vp, _vp, _sz, _vp, _sz]),
+    "rcb_upload_triangle_soup": (_i, [_vp, _vp, _sz]),
     "rcb_build_tiles": (_i, [_vp, _vp, _i, _u32, _i, _pp]),
     "rcb_build_tiles_streamed": (_i, [_vp, _vp, _i, _u32, _i, _i, _pp]),
     "rcb_rasterize": (_i, [_vp, _vp, _i, _vp, ctypes.c_int32, _u32, _i, _pp]),

@@ -246,6 +246,19 @@ class Context:
         t = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1)
         check(_ffi.lib().rcb_upload_mesh(self._h, _ptr(v), v.size, _ptr(t), t.size), self._h)
 
+    def upload_mesh_u16(self, vertices, indices_u16):
+        """The mesh of rasterize_triangles_u16 (rasterization.rs:432): u16 indices, widened on the device."""
+        v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1)
+        t = np.ascontiguousarray(indices_u16, dtype=np.uint16).reshape(-1)
+        check(_ffi.lib().rcb_upload_mesh_u16(self._h, _ptr(v), v.size, _ptr(t), t.size), self._h)
+
+    def upload_triangle_soup(self, vertices):
+        """The mesh of rasterize_triangle_soup (rasterization.rs:459): 9 floats per triangle, no index list."""
+        v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1)
+        if v.size % 9:
+            raise ValueError("a triangle soup holds 9 floats per triangle")
+        check(_ffi.lib().rcb_upload_triangle_soup(self._h, _ptr(v), v.size // 9), self._h)
+
     def set_mesh_device(self, d_verts_ptr: int, nfloats: int, d_tris_ptr: int, nidx: int, keep=None):
         self._mesh_keep = keep  # keeps the owning tensors alive
         check(_ffi.lib().rcb_set_mesh_device(self._h, ctypes.c_void_p(d_verts_ptr), nfloats,

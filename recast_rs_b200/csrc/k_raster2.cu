@@ -198,6 +198,13 @@ __global__ void __launch_bounds__(256) k_check_indices(const int32_t* __restrict
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1ull);
 }
 
+// rasterize_triangles_u16 (rasterization.rs:432-455) indexes with `tris[i] as usize`: the indices widened, nothing else;
+// rasterize_triangle_soup (:459-476) reads vertex 3 i + k of triangle i: the identity index list.  src == nullptr: identity.
+__global__ void __launch_bounds__(256) k_widen_indices(const uint16_t* __restrict__ src, int32_t* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src ? (int32_t)src[i] : (int32_t)i;
+}
+
 // xz AABB per run of RCB_MESH_BLOCK consecutive triangles (k_bin_count's early reject); a run with an index out of range
 // gets an infinite box (the build fails on it anyway, lib.rs:224-233)
 __global__ void __launch_bounds__(RCB_MESH_BLOCK) k_mesh_blocks(const float* __restrict__ verts, const int32_t* __restrict__ tris, uint32_t ntris,
@@ -591,6 +598,12 @@ void launch_check_indices(const int32_t* tris, size_t nidx, uint32_t nverts, uns
     KScope _k("k_check_indices", s);
     const unsigned blocks = (unsigned)std::min<size_t>((nidx + 255) / 256, 148 * 16);
     k_check_indices<<<blocks, 256, 0, s>>>(tris, nidx, nverts, flag);
+}
+
+void launch_widen_indices(const uint16_t* src, int32_t* dst, size_t n, cudaStream_t s) {
+    if (n == 0) return;
+    KScope _k("k_widen_indices", s);
+    k_widen_indices<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, s>>>(src, dst, n);
 }
 
 void launch_mesh_blocks(const float* verts, const int32_t* tris, uint32_t ntris, uint32_t nverts, float4* blocks, cudaStream_t s) {

@@ -1778,6 +1778,40 @@ int rcb_upload_mesh(rcb_ctx* ctx, const float* verts, size_t nfloats, const int3
     return check_mesh_indices(ctx);  // synchronizes: the caller's buffers are only borrowed for this call
 }
 
+// rasterize_triangles_u16 (rasterization.rs:432): the same mesh with `u16` indices, widened on the device
+int rcb_upload_mesh_u16(rcb_ctx* ctx, const float* verts, size_t nfloats, const uint16_t* tris, size_t nidx) {
+    if (!ctx || (nfloats && !verts) || (nidx && !tris)) return fail(ctx, RCB_EARG, "null mesh pointer");
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->d_verts.ensure(4 * nfloats + 16));
+    CU(ctx->d_tris.ensure(4 * nidx + 16));
+    CU(ctx->d_tri_areas.ensure(2 * nidx + 16));  // staging of the 16-bit indices
+    if (nfloats) CU(cudaMemcpyAsync(ctx->d_verts.p, verts, 4 * nfloats, cudaMemcpyHostToDevice, ctx->stream));
+    if (nidx) CU(cudaMemcpyAsync(ctx->d_tri_areas.p, tris, 2 * nidx, cudaMemcpyHostToDevice, ctx->stream));
+    launch_widen_indices(ctx->d_tri_areas.as<uint16_t>(), ctx->d_tris.as<int32_t>(), nidx, ctx->stream);
+    ctx->verts = ctx->d_verts.as<float>();
+    ctx->tris = ctx->d_tris.as<int32_t>();
+    ctx->nfloats = nfloats;
+    ctx->nidx = nidx;
+    return check_mesh_indices(ctx);
+}
+
+// rasterize_triangle_soup (rasterization.rs:459): sequential vertices, triangle i = vertices 3 i, 3 i + 1, 3 i + 2
+int rcb_upload_triangle_soup(rcb_ctx* ctx, const float* verts, size_t ntris) {
+    if (!ctx || (ntris && !verts)) return fail(ctx, RCB_EARG, "null mesh pointer");
+    if (ntris > 0x7fffffffull / 3) return fail(ctx, RCB_EARG, "mesh too large");
+    CU(cudaSetDevice(ctx->device));
+    const size_t nfloats = 9 * ntris, nidx = 3 * ntris;
+    CU(ctx->d_verts.ensure(4 * nfloats + 16));
+    CU(ctx->d_tris.ensure(4 * nidx + 16));
+    if (nfloats) CU(cudaMemcpyAsync(ctx->d_verts.p, verts, 4 * nfloats, cudaMemcpyHostToDevice, ctx->stream));
+    launch_widen_indices(nullptr, ctx->d_tris.as<int32_t>(), nidx, ctx->stream);
+    ctx->verts = ctx->d_verts.as<float>();
+    ctx->tris = ctx->d_tris.as<int32_t>();
+    ctx->nfloats = nfloats;
+    ctx->nidx = nidx;
+    return check_mesh_indices(ctx);
+}
+
 int rcb_set_mesh_device(rcb_ctx* ctx, const void* d_verts, size_t nfloats, const void* d_tris, size_t nidx) {
     if (!ctx || (nfloats && !d_verts) || (nidx && !d_tris)) return fail(ctx, RCB_EARG, "null mesh pointer");
     ctx->verts = (const float*)d_verts;

@@ -99,6 +99,7 @@ struct MeshView {
     const float4* blocks;      // nullable: xz AABB (min x, min z, max x, max z) of every run of 256 consecutive triangles
 };
 #define RCB_MESH_BLOCK 256
+void launch_widen_indices(const uint16_t* src_or_null, int32_t* dst, size_t n, cudaStream_t s);
 void launch_mesh_blocks(const float* verts, const int32_t* tris, uint32_t ntris, uint32_t nverts, float4* blocks, cudaStream_t s);
 struct RcbUnused_ {
     int unused;

@@ -25,6 +25,7 @@ pub const RCB_WIRE_DYNAMIC_TILE: c_int = 1;
 pub const RCB_FILTER_LOW_HANGING: u32 = 0x100;
 pub const RCB_FILTER_LEDGE: u32 = 0x200;
 pub const RCB_FILTER_LOW_HEIGHT: u32 = 0x400;
+pub const RCB_RESULT_SLIM: u32 = 0x1000;
 
 #[repr(C)]
 #[derive(Clone, Copy, Debug)]
@@ -91,6 +92,8 @@ pub struct rcb_tile_view {
     pub reg: *const u16,
     pub max_regions: u32,
     pub _pad: u32,
+    pub conn_mask: *const u8,
+    pub conn_ref16: *const u16,
 }
 
 #[repr(C)]
@@ -148,6 +151,14 @@ pub struct rcb_ctx {
 pub struct rcb_result {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct rcb_multi {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct rcb_multi_result {
+    _private: [u8; 0],
+}
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -166,6 +177,7 @@ extern "C" {
     pub fn rcb_set_stream(ctx: *mut rcb_ctx, cuda_stream: *mut c_void) -> c_int;
     pub fn rcb_use_own_stream(ctx: *mut rcb_ctx) -> c_int;
     pub fn rcb_launch_count(ctx: *const rcb_ctx) -> u64;
+    pub fn rcb_ctx_stats(ctx: *const rcb_ctx, out: *mut u64) -> c_int;
     pub fn rcb_profile_enable(ctx: *mut rcb_ctx, on: c_int) -> c_int;
     pub fn rcb_profile_read(ctx: *mut rcb_ctx, out: *mut rcb_stage_time, cap: c_int) -> c_int;
     pub fn rcb_profile_reset(ctx: *mut rcb_ctx) -> c_int;
@@ -173,6 +185,8 @@ extern "C" {
     pub fn rcb_config_calculate_grid_size(cfg: *mut rcb_config, bmin: *const f32, bmax: *const f32);
     pub fn rcb_config_validate(cfg: *const rcb_config) -> c_int;
     pub fn rcb_upload_mesh(ctx: *mut rcb_ctx, verts: *const f32, nfloats: usize, tris: *const i32, nidx: usize) -> c_int;
+    pub fn rcb_upload_mesh_u16(ctx: *mut rcb_ctx, verts: *const f32, nfloats: usize, tris: *const u16, nidx: usize) -> c_int;
+    pub fn rcb_upload_triangle_soup(ctx: *mut rcb_ctx, verts: *const f32, ntris: usize) -> c_int;
     pub fn rcb_set_mesh_device(ctx: *mut rcb_ctx, d_verts: *const c_void, nfloats: usize, d_tris: *const c_void, nidx: usize) -> c_int;
     pub fn rcb_build_tiles(ctx: *mut rcb_ctx, cfgs: *const rcb_config, ntiles: c_int, stage_mask: u32, erode_radius: c_int, out: *mut *mut rcb_result) -> c_int;
     pub fn rcb_build_tiles_streamed(ctx: *mut rcb_ctx, cfgs: *const rcb_config, ntiles: c_int, stage_mask: u32, erode_radius: c_int, ngroups: c_int, out: *mut *mut rcb_result) -> c_int;
@@ -193,4 +207,15 @@ extern "C" {
     pub fn rcb_result_tile(res: *const rcb_result, tile: c_int, out: *mut rcb_tile_view) -> c_int;
     pub fn rcb_result_tile_device(res: *const rcb_result, tile: c_int, out: *mut rcb_tile_view) -> c_int;
     pub fn rcb_result_free(res: *mut rcb_result);
+    pub fn rcb_multi_create(devices: *const c_int, ndevices: c_int, out: *mut *mut rcb_multi) -> c_int;
+    pub fn rcb_multi_destroy(m: *mut rcb_multi);
+    pub fn rcb_multi_last_error(m: *const rcb_multi) -> *const c_char;
+    pub fn rcb_multi_device_count(m: *const rcb_multi) -> c_int;
+    pub fn rcb_multi_upload_mesh(m: *mut rcb_multi, verts: *const f32, nfloats: usize, tris: *const i32, nidx: usize) -> c_int;
+    pub fn rcb_multi_build_tiles(m: *mut rcb_multi, cfgs: *const rcb_config, ntiles: c_int, stage_mask: u32, erode_radius: c_int, tiles_per_group: c_int, download: c_int, out: *mut *mut rcb_multi_result) -> c_int;
+    pub fn rcb_multi_result_download(res: *mut rcb_multi_result) -> c_int;
+    pub fn rcb_multi_result_totals(res: *const rcb_multi_result, out: *mut rcb_totals, tiles_per_device: *mut c_int, ndevices: c_int) -> c_int;
+    pub fn rcb_multi_result_tile(res: *const rcb_multi_result, tile: c_int, out: *mut rcb_tile_view) -> c_int;
+    pub fn rcb_multi_result_tile_device(res: *const rcb_multi_result, tile: c_int, out: *mut rcb_tile_view, device: *mut c_int) -> c_int;
+    pub fn rcb_multi_result_free(res: *mut rcb_multi_result);
 }

@@ -29,6 +29,17 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_ffi.SYMBOLS) == names, "ctypes binding out of sync with the header"
 
 
+def test_rust_sys_crate_declares_every_symbol():
+    """rust/recast-b200-sys cannot be compiled here (no cargo / rustc in the image): at least its extern block must name
+    exactly the functions of the header, so that the crate a maintainer builds links against everything and nothing else."""
+    src = open(os.path.join(ROOT, "rust", "recast-b200-sys", "src", "lib.rs")).read()
+    assert sorted(set(re.findall(r"\bpub fn (rcb_[a-z_0-9]+)\s*\(", src))) == _declared_functions()
+    view = re.search(r"pub struct rcb_tile_view \{(.*?)\}", src, flags=re.S).group(1)
+    from recast_rs_b200 import _ffi
+
+    assert re.findall(r"pub (\w+):", view) == [n for n, _ in _ffi.RcbTileView._fields_]
+
+
 def test_struct_layouts_match_header(tmp_path):
     """sizeof/offsetof as gcc sees include/recast_b200.h == the ctypes mirrors."""
     import subprocess

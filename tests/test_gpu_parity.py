@@ -383,3 +383,37 @@ def test_global_raster_with_16_byte_fragment_records(oracle, rb, monkeypatch):
         _check_batch(oracle, rb, c, v, t, cfgs, rb.STAGE_ALL_BUILD)
     finally:
         c.close()
+
+
+def test_u16_indices_and_triangle_soup_entries(oracle):
+    """rasterize_triangles_u16 (rasterization.rs:432) and rasterize_triangle_soup (:459): the same rasterizer behind two
+    other index forms.  Both must give the heightfield of the i32-indexed call on the same triangles."""
+    import recast_rs_b200.builder as rb
+    from recast_rs_b200.config import RecastConfig
+
+    rng = np.random.default_rng(11)
+    v, t = random_soup(rng, 500, 0.0, 12.0, 0.0, 5.0)
+    areas = rng.integers(0, 4, size=t.size // 3).astype(np.uint8)
+    cfg = RecastConfig(width=40, height=40, cs=0.3, ch=0.2, bmin=(0.0, 0.0, 0.0), bmax=(12.0, 6.0, 12.0))
+    ohf = oracle.Heightfield.from_config(cfg)
+    ohf.rasterize_triangles(v, t, areas, 2)
+    want = ohf.export()
+    ctx = rb.Context(0)
+    got = []
+    ctx.upload_mesh(v, t)
+    with ctx.rasterize([cfg], areas, 2) as r:
+        got.append(r.download().tile(0))
+    ctx.upload_mesh_u16(v, t.astype(np.uint16))
+    with ctx.rasterize([cfg], areas, 2) as r:
+        got.append(r.download().tile(0))
+    ctx.upload_triangle_soup(v.reshape(-1, 3)[t].reshape(-1))
+    with ctx.rasterize([cfg], areas, 2) as r:
+        got.append(r.download().tile(0))
+    for g in got:
+        np.testing.assert_array_equal(g.hf_cell_offset, want.cell_offset)
+        np.testing.assert_array_equal(g.span_min, want.span_min)
+        np.testing.assert_array_equal(g.span_max, want.span_max)
+        np.testing.assert_array_equal(g.span_area, want.span_area)
+    with pytest.raises(ValueError):
+        ctx.upload_triangle_soup(np.zeros(10, np.float32))
+    ctx.close()
