@@ -1187,6 +1187,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_comp
         conn_written = tile_sweep<TILE_THREADS, uint8_t, true>(g, reinterpret_cast<uint8_t*>(d16a), reinterpret_cast<uint8_t*>(d16b), thr, nullptr,
                                                  nullptr, conn_work);
     }
+    // (Tried: areas - the one result array that is complete in shared memory - as ONE cp.async.bulk per tile, shared -> global,
+    // issued by one thread: SASS UBLKCP.G.S, no measurable change, profiles/r02_bulk_store_ab.txt.  It is 2 % of a tile's output;
+    // everything else is produced in registers and there is no shared memory left to stage it in.)
     for (uint32_t s = threadIdx.x; s < So; s += TILE_THREADS) a.areas[span_base + s] = areas[own0 + s];
     pc.mark(3);
     // 6. distance field (compact_heightfield.rs:514-727)
