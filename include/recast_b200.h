@@ -165,6 +165,13 @@ uint64_t rcb_launch_count(const rcb_ctx* ctx);
  * configurations and verified on the device), out[1] = how many of those had to be rebuilt because a size was short,
  * out[2] = configuration batches cached by the context.  The reference has no counterpart (it has no device). */
 int rcb_ctx_stats(const rcb_ctx* ctx, uint64_t out[4]);
+/* Memory-safety stand-in for compute-sanitizer (closed on this GPU pool): librecast_b200_dbg.so is the same library built
+ * with -DRCB_BOUNDS, in which every index into the hand-laid-out shared-memory regions and per-tile arena slices of the
+ * clipper, the tile-resident kernels and the region builder goes through a checked accessor.  Returns 1 in that build (0 in
+ * the normal one, where the accessors are raw pointers) and fills out[0] = violations since the last reset on this
+ * context's device, out[1] = file id << 32 | line of the first, out[2] = its index, out[3] = the array's size.
+ * reset: 0 keep the counters, 1 clear them, 2 first commit one deliberate violation (self-test of the checked build), then as 1. */
+int rcb_debug_bounds_report(rcb_ctx* ctx, uint64_t out[4], int reset);
 
 /* Per-stage device timers (CUDA events around every kernel launch), the device-side counterpart of
  * RecastContext::start_timer/stop_timer with TimerCategory::{Rasterization, Filtering,

@@ -11,7 +11,8 @@ import os
 from .config import RcbConfig
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librecast_b200.so")
+# RCB_DEBUG_SO=1: the -DRCB_BOUNDS build (checked accessors in the hand-laid-out kernels; see rcb_debug_bounds_report)
+LIB_PATH = os.path.join(_HERE, "librecast_b200_dbg.so" if os.environ.get("RCB_DEBUG_SO") == "1" else "librecast_b200.so")
 
 # name -> (restype, argtypes); must list EVERY function declared in include/recast_b200.h
 _vp, _i, _u32, _u64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_size_t
@@ -56,6 +57,7 @@ SYMBOLS = {
     "rcb_use_own_stream": (_i, [_vp]),
     "rcb_launch_count": (_u64, [_vp]),
     "rcb_ctx_stats": (_i, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
+    "rcb_debug_bounds_report": (_i, [_vp, ctypes.POINTER(ctypes.c_uint64), _i]),
     "rcb_config_default": (None, [ctypes.POINTER(RcbConfig)]),
     "rcb_config_calculate_grid_size": (None, [ctypes.POINTER(RcbConfig), _vp, _vp]),
     "rcb_config_validate": (_i, [ctypes.POINTER(RcbConfig)]),

@@ -36,11 +36,14 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_native(force: bool = False, verbose: bool = False) -> str:
+def build_native(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
+    """debug: librecast_b200_dbg.so, the same sources with -DRCB_BOUNDS (checked accessors, csrc/rcb_bounds.cuh)."""
     nvcc = _nvcc()
     hdrs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))  # every header: k_regions_impl.cuh too
     hdrs += [os.path.join(os.path.dirname(HERE), "include", "recast_b200.h"), os.path.abspath(__file__)]
-    objdir = os.path.join(CSRC, "build")
+    objdir = os.path.join(CSRC, "build_dbg" if debug else "build")
+    out = OUT.replace(".so", "_dbg.so") if debug else OUT
+    flags = NVCC_FLAGS + (["-DRCB_BOUNDS"] if debug else [])
     os.makedirs(objdir, exist_ok=True)
     jobs = []
     objs = []
@@ -49,7 +52,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(objdir, s.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
-            jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
+            jobs.append([nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -62,10 +65,11 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         for l in logs:
             sys.stderr.write(l)
-    if jobs or force or _stale(OUT, objs):
-        run([nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-pthread"])
-    return OUT
+    if jobs or force or _stale(out, objs):
+        run([nvcc, "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-pthread"])
+    return out
 
 
 if __name__ == "__main__":
     print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv, debug=True))

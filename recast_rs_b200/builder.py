@@ -241,6 +241,13 @@ class Context:
         check(_ffi.lib().rcb_ctx_stats(self._h, a), self._h)
         return {"speculative": int(a[0]), "rebuilt": int(a[1]), "cached_batches": int(a[2])}
 
+    def bounds_report(self, reset: bool = False) -> dict:
+        """The -DRCB_BOUNDS build's verdict (RCB_DEBUG_SO=1): {'instrumented', 'violations', 'first': (file id, line, index, size)}."""
+        a = (ctypes.c_uint64 * 4)()
+        r = _ffi.lib().rcb_debug_bounds_report(self._h, a, int(reset))
+        check(min(r, 0), self._h)
+        return {"instrumented": r == 1, "violations": int(a[0]), "first": (int(a[1]) >> 32, int(a[1]) & 0xFFFFFFFF, int(a[2]), int(a[3]))}
+
     def upload_mesh(self, vertices, indices):
         v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1)
         t = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1)
@@ -505,6 +512,13 @@ class MultiContext:
         if status != 0:
             raw = _ffi.lib().rcb_multi_last_error(self._h)
             check(status, None, raw.decode("utf-8", "replace") if raw else "")
+
+    def bounds_report(self, reset: bool = False) -> dict:
+        """The -DRCB_BOUNDS build's verdict (RCB_DEBUG_SO=1): {'instrumented', 'violations', 'first': (file id, line, index, size)}."""
+        a = (ctypes.c_uint64 * 4)()
+        r = _ffi.lib().rcb_debug_bounds_report(self._h, a, int(reset))
+        check(min(r, 0), self._h)
+        return {"instrumented": r == 1, "violations": int(a[0]), "first": (int(a[1]) >> 32, int(a[1]) & 0xFFFFFFFF, int(a[2]), int(a[3]))}
 
     def upload_mesh(self, vertices, indices):
         v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1)

@@ -20,6 +20,8 @@
 #include <algorithm>
 
 #include "rcb_common.cuh"
+#define RCB_FILE_ID 2
+#include "rcb_bounds.cuh"
 
 namespace {
 
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(256) k_fill_items(Raster2 rb, const uint32_t* 
         const int zz0 = max(z0, 0);
         if (x1 < x0 || z1 < zz0) return;
         const uint32_t nchunks = ((uint32_t)(z1 - zz0 + 1) + CLIP_ROWS - 1) / CLIP_ROWS;
-        for (uint32_t c = 0; c < nchunks; ++c) items[o++] = make_uint2(tri, (tile << 12) | c);
+        for (uint32_t c = 0; c < nchunks; ++c, ++o) items[RCB_IX(o, item_off[tri + 1])] = make_uint2(tri, (tile << 12) | c);
     });
 }
 
@@ -268,8 +270,8 @@ struct ClipSmem {
     uint32_t nlist;
 };
 
-#define ZB(buf, v, k) sm.zbuf[(((buf) * ZCAP + (v)) * 3 + (k)) * CLIP_THREADS + threadIdx.x]
-#define XB(buf, v, k) sm.zbuf[(((buf) * XCAP + (v)) * 2 + (k)) * CLIP_THREADS + threadIdx.x]
+#define ZB(buf, v, k) sm.zbuf[(((buf) * ZCAP + RCB_IX(v, ZCAP)) * 3 + (k)) * CLIP_THREADS + threadIdx.x]
+#define XB(buf, v, k) sm.zbuf[(((buf) * XCAP + RCB_IX(v, XCAP)) * 2 + (k)) * CLIP_THREADS + threadIdx.x]
 
 // One record into the segment of band `seg`; `lcell` is the cell inside the band's held rows.
 // (Tried: one atomic per lane with the record written an iteration later, so that the x-chain runs during the round trip:
@@ -289,6 +291,7 @@ __device__ __forceinline__ void emit_to_segment(const Raster2& rb, const TileDes
         // the segment holds three arrays of `cap` words (cell | area << 24, smin | smax << 16, triangle): consecutive slots
         // of a warp are consecutive words of each
         const uint32_t cap = rb.tile_cap[seg];
+        RCB_CHECK(tcell < (uint32_t)(td.width * td.height) && (lcell & 0xff000000u) == 0 && (uint32_t)(td.band_first) <= seg);
         uint32_t* rec = rb.tile_frags + 3ull * rb.tile_base[seg] + pos;
         rec[0] = lcell | (area << 24);
         rec[cap] = mm;
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
     const uint32_t it = blockIdx.x * CLIP_THREADS + threadIdx.x;
     if (it < nitems) {
         const uint2 item = items[it];
-        const uint32_t tri = item.x, tile = item.y >> 12, chunk = item.y & 0xfffu;
+        const uint32_t tri = RCB_IX(item.x, rb.mesh.ntris), tile = RCB_IX(item.y >> 12, rb.ntiles), chunk = item.y & 0xfffu;
         const TileDesc& td = rb.tiles[tile];
         Tri t;
         int x0 = 0, x1 = 0, z0 = 0, z1 = 0;
@@ -394,8 +397,8 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
                     if (si <= 0) {
                         if (keep) {
                             if (nrow < RCAP) {
-                                slot[1 + 2 * nrow] = __float_as_uint(vix);
-                                slot[2 + 2 * nrow] = __float_as_uint(viy);
+                                slot[1 + 2 * RCB_IX(nrow, RCAP)] = __float_as_uint(vix);
+                                slot[2 + 2 * RCB_IX(nrow, RCAP)] = __float_as_uint(viy);
                             } else
                                 ovf = true;
                             rminx = fminf(rminx, vix);
@@ -420,8 +423,8 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
                         const float pz = __fadd_rn(viz, __fmul_rn(tt, __fsub_rn(vjz, viz)));
                         if (keep) {
                             if (nrow < RCAP) {
-                                slot[1 + 2 * nrow] = __float_as_uint(px);
-                                slot[2 + 2 * nrow] = __float_as_uint(py);
+                                slot[1 + 2 * RCB_IX(nrow, RCAP)] = __float_as_uint(px);
+                                slot[2 + 2 * RCB_IX(nrow, RCAP)] = __float_as_uint(py);
                             } else
                                 ovf = true;
                             rminx = fminf(rminx, px);
@@ -478,7 +481,7 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
             uint32_t o = 0;
 #pragma unroll
             for (int k = 0; k < NBUCK; ++k) o = (k == (int)bk) ? boff[k] : o;
-            sm.list[o + atomicAdd(&sm.cur[bk], 1u)] = (uint16_t)slot_id;
+            sm.list[RCB_IX(o + atomicAdd(&sm.cur[RCB_IX(bk, NBUCK)], 1u), NSLOTS)] = (uint16_t)slot_id;
         }
     }
     __syncthreads();
@@ -488,7 +491,7 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
         tclk = n;
     }
     for (uint32_t li = threadIdx.x; li < nlist; li += CLIP_THREADS) {
-        const uint32_t sid = sm.list[li];
+        const uint32_t sid = RCB_IX(sm.list[li], NSLOTS);
         const uint32_t* slot = sm.slots + sid * SLOT_WORDS;
         const uint32_t* hdr = sm.hdr + (sid / CLIP_ROWS) * HDR_WORDS;
         const uint32_t tri = hdr[0], tile = hdr[1];
@@ -586,6 +589,8 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
 }
 
 }  // namespace
+
+RCB_BOUNDS_EXPORT(rcb_bounds_read_raster2)
 
 void launch_bin_count(const Raster2& rb, cudaStream_t s) {
     if (rb.mesh.ntris == 0) return;

@@ -22,6 +22,8 @@
 // flood / expand reach neighbours through span.con[] (63 = not connected, even when it is a real offset);
 // merge_and_filter goes through get_neighbor_connection -> the connection list, as the reference does.
 #include "rcb_common.cuh"
+#define RCB_FILE_ID 3
+#include "rcb_bounds.cuh"
 
 // Two builds of the same kernel.  A tile is one long dependent chain and the kernel ends with its slowest tile, so what
 // matters is that every tile of the batch is resident at once:
@@ -76,3 +78,5 @@ void launch_regions(const RegionArgs& a, int ntiles, cudaStream_t s) {
         rg64::k_regions<<<ntiles, 64, smem, s>>>(a);
     }
 }
+
+RCB_BOUNDS_EXPORT(rcb_bounds_read_regions)

@@ -90,29 +90,30 @@ __device__ uint32_t block_compact(uint32_t n, uint32_t out_base, BlockSh& sh, Pr
 struct Tile {
     uint32_t S, C;
     int W, H;
-    const uint32_t* cidx;
-    const uint32_t* ccnt;
-    const uint8_t* areas;
-    const uint16_t* con;
-    const uint16_t* dist;
-    const uint32_t* first_conn;
-    const uint32_t* conn_ref;
-    const uint8_t* conn_dir;
-    const uint32_t* conn_next;
-    uint16_t* reg;    // src_reg, also the result
-    uint16_t* sdist;  // src_dist
-    uint16_t* reg0;   // labels before merge_and_filter (its connection lists are built once, from these)
-    uint32_t* nb[4];  // con-based neighbour (tile-relative span) or NONE32 — global-memory mode
-    uint16_t* nb16[4];  // the same table with 16-bit entries (0xFFFF = none) when the tile has fewer than 65535 spans: half the
+    // every array is the tile's slice of a batch-wide one, behind a checked accessor in the -DRCB_BOUNDS build (rcb_bounds.cuh)
+    RCB_A(const uint32_t) cidx;
+    RCB_A(const uint32_t) ccnt;
+    RCB_A(const uint8_t) areas;
+    RCB_A(const uint16_t) con;
+    RCB_A(const uint16_t) dist;
+    RCB_A(const uint32_t) first_conn;
+    RCB_A(const uint32_t) conn_ref;
+    RCB_A(const uint8_t) conn_dir;
+    RCB_A(const uint32_t) conn_next;
+    RCB_A(uint16_t) reg;    // src_reg, also the result
+    RCB_A(uint16_t) sdist;  // src_dist
+    RCB_A(uint16_t) reg0;   // labels before merge_and_filter (its connection lists are built once, from these)
+    RCB_A(uint32_t) nb[4];  // con-based neighbour (tile-relative span) or NONE32 — global-memory mode
+    RCB_A(uint16_t) nb16[4];  // the same table with 16-bit entries (0xFFFF = none) when the tile has fewer than 65535 spans: half the
                         // footprint in L1/L2; nb16[0] == nullptr otherwise
     bool walk_lists;  // some cell holds 64+ spans: con == 63 may hide a real neighbour (merge_and_filter follows the list)
-    uint32_t* stack[8];
-    uint32_t* bufA;
-    uint32_t* bufB;
+    RCB_A(uint32_t) stack[8];
+    RCB_A(uint32_t) bufA;
+    RCB_A(uint32_t) bufB;
 };
 
 __device__ __forceinline__ uint32_t nbr(const Tile& t, int d, uint32_t s) {
-    if (t.nb16[0]) {
+    if (RCB_RAW(t.nb16[0])) {
         const uint32_t v = __ldg(&t.nb16[d][s]);
         return v == 0xFFFFu ? NONE32 : v;
     }
@@ -155,7 +156,7 @@ __device__ __forceinline__ uint32_t cas16(uint16_t* p, uint16_t cmp, uint16_t va
 // watershed.rs:245-361.  `len` is the stack length (uniform); returns the new length.
 // The stack is t.stack[sidx]; the retain step compacts it into t.bufB and the two buffers trade places.
 __device__ uint32_t ws_expand(Tile& t, int max_iter, uint32_t level, int sidx, uint32_t len, bool fill, BlockSh& sh) {
-    uint32_t* stack = t.stack[sidx];
+    RCB_A(uint32_t) stack = t.stack[sidx];
     if (fill) {
         len = block_compact(t.S, 0, sh, [&](uint32_t s, uint32_t& pl) { pl = s; return t.dist[s] >= level && t.reg[s] == 0 && t.areas[s] != 0; },
                             [&](uint32_t pos, uint32_t s) { stack[pos] = s; });
@@ -218,7 +219,7 @@ __device__ uint32_t ws_expand(Tile& t, int max_iter, uint32_t level, int sidx, u
         __syncthreads();
         const uint32_t nfailed = block_sum(failed, sh);
         {
-            uint32_t* dst = t.bufB;
+            RCB_A(uint32_t) dst = t.bufB;
             len = block_compact(len, 0, sh, [&](uint32_t j, uint32_t& pl) { pl = stack[j]; return pl != NONE32; },
                                 [&](uint32_t pos, uint32_t v) { dst[pos] = v; });
             t.bufB = stack;
@@ -280,24 +281,24 @@ __global__ void __launch_bounds__(BT, RG_MIN_CTAS) k_regions(RegionArgs a) {
     t.H = td.height;
     t.C = (uint32_t)(t.W * t.H);
     const size_t sb = ti.span_base;
-    t.cidx = a.cell_index + td.cell_base;
-    t.ccnt = a.cell_count + td.cell_base;
-    t.areas = a.areas + sb;
-    t.con = a.con + 4 * sb;
-    t.dist = a.dist + sb;
-    t.first_conn = a.first_conn + sb;
-    t.conn_ref = a.conn_ref + ti.conn_base;
-    t.conn_dir = a.conn_dir + ti.conn_base;
-    t.conn_next = a.conn_next + ti.conn_base;
-    t.reg = a.reg + sb;
-    t.sdist = a.src_dist + sb;
-    t.reg0 = a.reg0 + sb;
+    t.cidx = RCB_MK(const uint32_t, a.cell_index + td.cell_base, t.C);
+    t.ccnt = RCB_MK(const uint32_t, a.cell_count + td.cell_base, t.C);
+    t.areas = RCB_MK(const uint8_t, a.areas + sb, t.S);
+    t.con = RCB_MK(const uint16_t, a.con + 4 * sb, 4ull * t.S);
+    t.dist = RCB_MK(const uint16_t, a.dist + sb, t.S);
+    t.first_conn = RCB_MK(const uint32_t, a.first_conn + sb, t.S);
+    t.conn_ref = RCB_MK(const uint32_t, a.conn_ref + ti.conn_base, ti.conn_count);
+    t.conn_dir = RCB_MK(const uint8_t, a.conn_dir + ti.conn_base, ti.conn_count);
+    t.conn_next = RCB_MK(const uint32_t, a.conn_next + ti.conn_base, ti.conn_count);
+    t.reg = RCB_MK(uint16_t, a.reg + sb, t.S);
+    t.sdist = RCB_MK(uint16_t, a.src_dist + sb, t.S);
+    t.reg0 = RCB_MK(uint16_t, a.reg0 + sb, t.S);
 #pragma unroll
-    for (int d = 0; d < 4; ++d) t.nb[d] = a.nb4 + (size_t)d * a.Stot + sb;
+    for (int d = 0; d < 4; ++d) t.nb[d] = RCB_MK(uint32_t, a.nb4 + (size_t)d * a.Stot + sb, t.S);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t.stack[k] = a.stacks + (size_t)k * a.Stot + sb;
-    t.bufA = a.bufA + sb;
-    t.bufB = a.bufB + sb;
+    for (int k = 0; k < 8; ++k) t.stack[k] = RCB_MK(uint32_t, a.stacks + (size_t)k * a.Stot + sb, t.S);
+    t.bufA = RCB_MK(uint32_t, a.bufA + sb, t.S);
+    t.bufB = RCB_MK(uint32_t, a.bufB + sb, t.S);
     const uint32_t S = t.S;
     const int W = t.W, H = t.H;
 
@@ -305,14 +306,14 @@ __global__ void __launch_bounds__(BT, RG_MIN_CTAS) k_regions(RegionArgs a) {
     // Tiles whose hot arrays fit keep them in shared memory for the whole kernel: the algorithm is a long
     // sequence of short dependent phases, and its time is (phases) x (latency of one access).
     extern __shared__ __align__(16) unsigned char rg_smem[];
-    uint16_t* const g_reg = t.reg;
+    RCB_A(uint16_t) const g_reg = t.reg;
     const bool in_smem = a.smem_spans >= S && S < 0xFFFFu;
     const bool small = a.all_small != 0;  // S < 0xFFFF for every tile of the batch
 #pragma unroll
-    for (int d = 0; d < 4; ++d) t.nb16[d] = small ? (uint16_t*)a.nb4 + (size_t)d * a.Stot + sb : nullptr;
+    for (int d = 0; d < 4; ++d) t.nb16[d] = RCB_MK(uint16_t, small ? (uint16_t*)a.nb4 + (size_t)d * a.Stot + sb : nullptr, small ? t.S : 0u);
     if (in_smem) {
         // labels and the neighbour table (10 B per span) are what the floods hammer; the rest is read through L1
-        t.reg = (uint16_t*)rg_smem;
+        t.reg = RCB_MK(uint16_t, rg_smem, S);
     }
     for (uint32_t s = threadIdx.x; s < S; s += BT) t.reg[s] = 0, t.sdist[s] = 0;
     uint32_t maxcnt = 0;
@@ -419,8 +420,8 @@ __global__ void __launch_bounds__(BT, RG_MIN_CTAS) k_regions(RegionArgs a) {
             len = sh_len[0];
             pc.mark(1);
         } else {  // append_stacks (:122-133)
-            const uint32_t* src = t.stack[s_id - 1];
-            uint32_t* dst = t.stack[s_id];
+            RCB_A(uint32_t) src = t.stack[s_id - 1];
+            RCB_A(uint32_t) dst = t.stack[s_id];
             len = block_compact(sh_len[s_id - 1], sh_len[s_id], sh,
                                 [&](uint32_t j, uint32_t& pl) { pl = src[j]; return pl != NONE32 && t.reg[pl] == 0; },
                                 [&](uint32_t pos, uint32_t v) { dst[pos] = v; });
@@ -429,7 +430,7 @@ __global__ void __launch_bounds__(BT, RG_MIN_CTAS) k_regions(RegionArgs a) {
         }
         len = ws_expand(t, 8, level, s_id, len, false, sh);
         pc.mark(3);
-        uint32_t* stack = t.stack[s_id];
+        RCB_A(uint32_t) stack = t.stack[s_id];
         if (threadIdx.x == 0) sh_len[s_id] = len;
         __syncthreads();
         // new regions (:454-476): entries in order; the first one that is unlabelled and survives its own test floods
@@ -461,8 +462,8 @@ __global__ void __launch_bounds__(BT, RG_MIN_CTAS) k_regions(RegionArgs a) {
                 t.bufA[0] = seed;
             }
             uint32_t ncur = 1;
-            uint32_t* cur = t.bufA;
-            uint32_t* nxt = t.bufB;
+            RCB_A(uint32_t) cur = t.bufA;
+            RCB_A(uint32_t) nxt = t.bufB;
             while (ncur > 0) {
                 if (threadIdx.x == 0) sh_next = 0;
                 __syncthreads();
@@ -510,7 +511,7 @@ __global__ void __launch_bounds__(BT, RG_MIN_CTAS) k_regions(RegionArgs a) {
                 }
                 __syncthreads();
                 ncur = sh_next;
-                uint32_t* tmp = cur;
+                RCB_A(uint32_t) tmp = cur;
                 cur = nxt;
                 nxt = tmp;
                 __syncthreads();
@@ -536,13 +537,14 @@ __global__ void __launch_bounds__(BT, RG_MIN_CTAS) k_regions(RegionArgs a) {
     // ---- merge_and_filter_regions (:543-633) ----------------------------------------------------------------
     const uint32_t R = region_id;
     const size_t rb = sb + 2 * (size_t)tile;  // R <= S + 1 entries per tile
-    int32_t* cnt = a.r_cnt + rb;
-    int32_t* cadd = a.r_cadd + rb;
-    uint16_t* alive = a.r_alive + rb;
-    uint8_t* border = a.r_border + rb;
-    unsigned long long* best = a.r_best + rb;
-    uint16_t* target = a.r_target + rb;
-    uint16_t* fin = a.r_fin + rb;
+    // per-region tables: the tile owns span_count + 2 entries of each
+    RCB_A(int32_t) cnt = RCB_MK(int32_t, a.r_cnt + rb, S + 2);
+    RCB_A(int32_t) cadd = RCB_MK(int32_t, a.r_cadd + rb, S + 2);
+    RCB_A(uint16_t) alive = RCB_MK(uint16_t, a.r_alive + rb, S + 2);
+    RCB_A(uint8_t) border = RCB_MK(uint8_t, a.r_border + rb, S + 2);
+    RCB_A(unsigned long long) best = RCB_MK(unsigned long long, a.r_best + rb, S + 2);
+    RCB_A(uint16_t) target = RCB_MK(uint16_t, a.r_target + rb, S + 2);
+    RCB_A(uint16_t) fin = RCB_MK(uint16_t, a.r_fin + rb, S + 2);
     const int32_t min_area = td.aux1, merge_area = td.aux2;
     for (uint32_t i = threadIdx.x; i < R; i += BT) cnt[i] = 0, alive[i] = (uint16_t)i, border[i] = 0;
     for (uint32_t s = threadIdx.x; s < S; s += BT) t.reg0[s] = t.reg[s];

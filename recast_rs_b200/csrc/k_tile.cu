@@ -16,6 +16,8 @@
 // every result array written once.  Semantics are identical to the v1 kernels (k_raster.cu, k_filter.cu,
 // k_compact.cu, k_dist.cu), which stay as the fallback for tiles whose working set exceeds shared memory.
 #include "rcb_common.cuh"
+#define RCB_FILE_ID 1
+#include "rcb_bounds.cuh"
 
 namespace {
 
@@ -55,7 +57,7 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
 // scan each cost 2 barriers per TILE_THREADS elements: 8 k cycles for a 64x64 tile, three times per tile.)
 // Uses sh_warp[TILE_THREADS/32 + 1].
 template <int TILE_THREADS, typename OutT>
-__device__ uint32_t block_scan_array(const uint32_t* cnt, OutT* out, uint32_t n, uint32_t* sh_warp) {
+__device__ uint32_t block_scan_array(RCB_A(uint32_t) cnt, RCB_A(OutT) out, uint32_t n, uint32_t* sh_warp) {
     constexpr uint32_t NW = TILE_THREADS / 32;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t chunk = ((n + NW - 1) / NW + 31u) & ~31u;  // elements per warp, a multiple of 32
@@ -124,11 +126,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_span
         }
         return;
     }
-    uint32_t* cnt = smem;
-    uint16_t* off = reinterpret_cast<uint16_t*>(cnt + C);
-    uint16_t* soff = off + ((C + 2) & ~1u);
-    uint2* rec = reinterpret_cast<uint2*>((reinterpret_cast<uintptr_t>(soff + ((C + 2) & ~1u)) + 7) & ~(uintptr_t)7);
-    const uint32_t* frags = a.tile_frags + 3ull * a.tile_base[band];
+    RCB_A(uint32_t) cnt = RCB_MK(uint32_t, smem, C);
+    RCB_A(uint16_t) off = RCB_MK(uint16_t, smem + C, C + 1);
+    RCB_A(uint16_t) soff = RCB_MK(uint16_t, reinterpret_cast<uint16_t*>(smem + C) + ((C + 2) & ~1u), C + 1);
+    RCB_A(uint2) rec = RCB_MK(uint2, (reinterpret_cast<uintptr_t>(reinterpret_cast<uint16_t*>(smem + C) + 2 * ((C + 2) & ~1u)) + 7) & ~(uintptr_t)7, F);
+    RCB_A(const uint32_t) frags = RCB_MK(const uint32_t, a.tile_frags + 3ull * a.tile_base[band], 3ull * a.tile_cap[band]);
 
     PhaseClock pc(a.phase);
     for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) cnt[c] = 0;
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_span
     for (uint32_t k = threadIdx.x; k < nwork; k += TILE_THREADS) {
         const uint32_t c = soff[k];
         const uint32_t n = cnt[c];
-        uint2* r = rec + off[c];
+        RCB_A(uint2) r = rec + off[c];
         for (uint32_t i = 1; i < n; ++i) {  // insertion sort by triangle index
             const uint2 key = r[i];
             const uint32_t kt = key.x & 0xffffffu;
@@ -333,16 +335,17 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_span
     pc.mark(5);
     // 7. outputs for the own rows: heightfield CSR offsets (band-local; k_tile_compact makes them tile-relative), spans in
     //    band-local compact order
-    uint32_t* out_off = a.hf_cell_offset + td.cell_base + bd.tile + (uint32_t)(W * bd.z0);
-    const uint32_t tb = a.tile_base[band];
+    RCB_A(uint32_t) out_off = RCB_MK(uint32_t, a.hf_cell_offset + td.cell_base + bd.tile + (uint32_t)(W * bd.z0), oc1 - oc0);
+    RCB_A(uint32_t) ts_mm = RCB_MK(uint32_t, a.ts_mm + a.tile_base[band], a.tile_cap[band]);
+    RCB_A(uint8_t) ts_area = RCB_MK(uint8_t, a.ts_area + a.tile_base[band], a.tile_cap[band]);
     const uint32_t so0 = soff[oc0];
     for (uint32_t c = oc0 + threadIdx.x; c < oc1; c += TILE_THREADS) {
         const uint32_t so = soff[c] - so0, n = cnt[c], b = off[c];
         out_off[c - oc0] = so;
         for (uint32_t k = 0; k < n; ++k) {
             const uint2 sp = rec[b + k];
-            a.ts_mm[tb + so + k] = sp.y;
-            a.ts_area[tb + so + k] = (uint8_t)(sp.x >> 24);
+            ts_mm[so + k] = sp.y;
+            ts_area[so + k] = (uint8_t)(sp.x >> 24);
         }
     }
 #pragma unroll
@@ -514,9 +517,9 @@ __global__ void __launch_bounds__(1024) k_tile_segments(const uint32_t* __restri
 // [G0 + 4 nt, +nbot) one per bottom-halo span.  The numbering is contiguous in the tile's span order, so
 // tile-relative index = band_off + local - nt for own and halo spans alike.
 struct TileB {
-    const uint16_t* soff;  // [held cells + 1] first span of every held cell (band-local ids)
-    uint8_t* areas;        // [S] chf.areas (erosion writes it)
-    uint16_t* nid;         // [8][S2] band-local id of the neighbour span per direction; S = none.  Entry S of
+    RCB_A(uint16_t) soff;  // [held cells + 1] first span of every held cell (band-local ids)
+    RCB_A(uint8_t) areas;  // [S] chf.areas (erosion writes it)
+    RCB_A(uint16_t) nid;   // [8][S2] band-local id of the neighbour span per direction; S = none.  Entry S of
                            // every row is a dummy span whose neighbours are itself (branch-free sweeps)
     uint32_t S, S2;        // S2 >= S + 1: row pitch of nid
     uint32_t own0, own1;   // the band's own spans
@@ -525,10 +528,10 @@ struct TileB {
     // hand-over between the bands of a tile (nullptr / 0 for a band without that neighbour)
     uint32_t band;
     bool has_top, has_bot;
-    const uint4* in_top;         // previous band's records for its last row = my top halo
-    const uint4* in_bot;         // next band's records for its first row = my bottom halo
-    uint4* out_down;             // my last row, for the next band
-    uint4* out_up;               // my first row, for the previous band (16 B records keep every region 16-byte aligned)
+    RCB_A(const uint4) in_top;   // previous band's records for its last row = my top halo
+    RCB_A(const uint4) in_bot;   // next band's records for its first row = my bottom halo
+    RCB_A(uint4) out_down;       // my last row, for the next band
+    RCB_A(uint4) out_up;         // my first row, for the previous band (16 B records keep every region 16-byte aligned)
     uint32_t* flag_f;
     uint32_t* flag_d;
 };
@@ -553,7 +556,7 @@ __device__ __forceinline__ void wait_flag(const uint32_t* flag) {
 // Bands (never with ERODE): the sweep starts from the previous band's last row and hands its own last row on; the
 // gather and the blur read one / two rows beyond the band, which arrive as halo + ghost values (see TileB).
 template <int TILE_THREADS, typename T, bool ERODE, class Work>
-__device__ bool tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_t* sh_max, PhaseClock* pc, Work&& idle_work) {
+__device__ bool tile_sweep(const TileB& g, RCB_A(T) init, RCB_A(T) Fw, unsigned thr, uint32_t* sh_max, PhaseClock* pc, Work&& idle_work) {
     const int W = g.W, H = g.rows;
     const uint32_t TN = g.S;  // "no neighbour" == the dummy span
     const T inf = (T)~(T)0;
@@ -580,10 +583,10 @@ __device__ bool tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_
     // Only the warps that own a column take part in the H row barriers (named barrier 1).
     const int sweep_threads = min(TILE_THREADS, ((W + 31) / 32) * 32);
     if ((int)threadIdx.x < sweep_threads) {
-        const uint16_t* __restrict__ soff = g.soff + g.row0 * W;  // own rows
-        const uint16_t* __restrict__ nid0 = g.nid;             // NW
-        const uint16_t* __restrict__ nid2 = g.nid + 2 * g.S2;  // NE
-        const uint16_t* __restrict__ nid3 = g.nid + 3 * g.S2;  // E
+        RCB_AR(uint16_t) soff = g.soff + g.row0 * W;  // own rows
+        RCB_AR(uint16_t) nid0 = g.nid;               // NW
+        RCB_AR(uint16_t) nid2 = g.nid + 2 * g.S2;    // NE
+        RCB_AR(uint16_t) nid3 = g.nid + 3 * g.S2;    // E
         const uint32_t DUMMY = g.S;
         auto relax = [&](uint32_t s, uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
             uint32_t v = init[s];
@@ -743,8 +746,8 @@ __device__ bool tile_sweep(const TileB& g, T* init, T* Fw, unsigned thr, uint32_
             if (pc && pc->acc) atomicAdd(&pc->acc[11], (unsigned long long)(clock64() - t0));
         }
         __syncthreads();
-        uint16_t* nid2 = g.nid + 2 * g.S2;
-        uint16_t* nid6 = g.nid + 6 * g.S2;
+        RCB_A(uint16_t) nid2 = g.nid + 2 * g.S2;
+        RCB_A(uint16_t) nid6 = g.nid + 6 * g.S2;
         for (uint32_t j = threadIdx.x; j < g.nt; j += TILE_THREADS) {
             const uint4 r = __ldcg(&g.in_top[j]);
             init[j] = (T)(r.z & 0xffffu);
@@ -841,18 +844,25 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_comp
     const uint32_t G2 = (G0 + 4 * nt + nbot + 1) & ~1u;
     const size_t need = compact_smem_need(C, Ch, S, nt, nbot);
     const bool fits = a.do_compact ? (need <= a.smem_bytes && G2 < 0xfff0u) : true;
-    uint32_t* coff = smem;
-    uint32_t* mm = coff + (C + 1);
-    uint16_t* d16a = reinterpret_cast<uint16_t*>(mm);
-    uint16_t* d16b = d16a + G2;
-    uint16_t* nid = reinterpret_cast<uint16_t*>(mm + G2);
-    uint16_t* soff = nid + 8ull * S2;
-    uint8_t* areas = reinterpret_cast<uint8_t*>(soff + ((Ch + 2) & ~1u));
+    RCB_A(uint32_t) coff = RCB_MK(uint32_t, smem, C + 1);
+    RCB_A(uint32_t) mm = RCB_MK(uint32_t, smem + (C + 1), G2);
+    RCB_A(uint16_t) d16a = RCB_MK(uint16_t, smem + (C + 1), G2);
+    RCB_A(uint16_t) d16b = RCB_MK(uint16_t, reinterpret_cast<uint16_t*>(smem + (C + 1)) + G2, G2);
+    RCB_A(uint16_t) nid = RCB_MK(uint16_t, smem + (C + 1) + G2, 8ull * S2);
+    RCB_A(uint16_t) soff = RCB_MK(uint16_t, reinterpret_cast<uint16_t*>(smem + (C + 1) + G2) + 8ull * S2, Ch + 1);
+    RCB_A(uint8_t) areas = RCB_MK(uint8_t, reinterpret_cast<uint16_t*>(smem + (C + 1) + G2) + 8ull * S2 + ((Ch + 2) & ~1u), S);
 
     volatile unsigned long long* look = a.lookback;
-    const uint32_t* g_off = a.hf_cell_offset_in + td.cell_base + tile;  // band-local offsets written by k_tile_spans, tile cell order
-    uint32_t* g_off_out = a.hf_cell_offset + td.cell_base + tile;
+    // band-local offsets written by k_tile_spans, tile cell order (W * H + 1 words per tile in both arrays)
+    RCB_A(const uint32_t) g_off = RCB_MK(const uint32_t, a.hf_cell_offset_in + td.cell_base + tile, (uint32_t)(W * H) + 1u);
+    RCB_A(uint32_t) g_off_out = RCB_MK(uint32_t, a.hf_cell_offset + td.cell_base + tile, (uint32_t)(W * H) + 1u);
     const uint32_t tb = a.tile_base[band];
+    // this band's slices of the batch-wide arrays
+    RCB_A(const uint32_t) my_mm = RCB_MK(const uint32_t, a.ts_mm + tb, So);
+    RCB_A(const uint8_t) my_ar = RCB_MK(const uint8_t, a.ts_area + tb, So);
+    RCB_A(int16_t) o_smin = RCB_MK(int16_t, a.smin + span_base, So);
+    RCB_A(int16_t) o_smax = RCB_MK(int16_t, a.smax + span_base, So);
+    RCB_A(uint8_t) o_sarea = RCB_MK(uint8_t, a.sarea + span_base, So);
     const uint32_t c_tile0 = (uint32_t)(W * bd.z0);  // first own cell in the tile
     if (!a.do_compact || !fits) {
         // heightfield-only result, or a band too large for shared memory (the host then reruns the batch with smaller
@@ -860,10 +870,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_comp
         for (uint32_t c = threadIdx.x; c < C; c += TILE_THREADS) g_off_out[c_tile0 + c] = band_off + g_off[c_tile0 + c];
         if (bd.z1 == H && threadIdx.x == 0) g_off_out[(uint32_t)(W * H)] = a.tinfo[tile].span_count;
         for (uint32_t s = threadIdx.x; s < So; s += TILE_THREADS) {
-            const uint32_t w = a.ts_mm[tb + s];
-            a.smin[span_base + s] = (int16_t)(w & 0xffffu);
-            a.smax[span_base + s] = (int16_t)(w >> 16);
-            a.sarea[span_base + s] = a.ts_area[tb + s];
+            const uint32_t w = my_mm[s];
+            o_smin[s] = (int16_t)(w & 0xffffu);
+            o_smax[s] = (int16_t)(w >> 16);
+            o_sarea[s] = my_ar[s];
         }
         if (a.do_compact && threadIdx.x < 32) {
             if (threadIdx.x == 0) {
@@ -885,13 +895,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_comp
     // 1. load the band's spans and its halo rows; final span attributes (compact_heightfield.rs:231-237).  Loads are issued in
     //    batches of four per thread so their latencies overlap.
     {
-        const uint32_t* __restrict__ in_off = g_off + c_tile0;
-        const uint32_t* __restrict__ in_mm = a.ts_mm + tb;
-        const uint8_t* __restrict__ in_ar = a.ts_area + tb;
-        int16_t* __restrict__ o_min = a.smin + span_base;
-        int16_t* __restrict__ o_max = a.smax + span_base;
-        uint8_t* __restrict__ o_ar = a.sarea + span_base;
-        uint16_t* __restrict__ so_own = soff + oc0;
+        RCB_AR(const uint32_t) in_off = g_off + c_tile0;
+        RCB_AR(const uint32_t) in_mm = my_mm;
+        RCB_AR(const uint8_t) in_ar = my_ar;
+        RCB_AR(int16_t) o_min = o_smin;
+        RCB_AR(int16_t) o_max = o_smax;
+        RCB_AR(uint8_t) o_ar = o_sarea;
+        RCB_AR(uint16_t) so_own = soff + oc0;
         for (uint32_t c0 = threadIdx.x; c0 < C; c0 += 4 * TILE_THREADS) {
             uint32_t o[4];
 #pragma unroll
@@ -930,22 +940,26 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_comp
             }
         }
         if (has_top) {  // the previous band's last row: offsets relative to that row's first span, spans at the end of its segment
-            const uint32_t* __restrict__ p_off = g_off + c_tile0 - (uint32_t)W;
+            RCB_AR(const uint32_t) p_off = g_off + (c_tile0 - (uint32_t)W);
             const uint32_t pb = a.tile_base[band - 1] + (a.binfo[band - 1].span_count - nt);
+            RCB_A(const uint32_t) p_mm = RCB_MK(const uint32_t, a.ts_mm + pb, nt);
+            RCB_A(const uint8_t) p_ar = RCB_MK(const uint8_t, a.ts_area + pb, nt);
             const uint32_t row_first = p_off[0];
             for (uint32_t x = threadIdx.x; x < (uint32_t)W; x += TILE_THREADS) soff[x] = (uint16_t)(p_off[x] - row_first);
             for (uint32_t i = threadIdx.x; i < nt; i += TILE_THREADS) {
-                mm[i] = a.ts_mm[pb + i];
-                areas[i] = a.ts_area[pb + i];
+                mm[i] = p_mm[i];
+                areas[i] = p_ar[i];
             }
         }
         if (has_bot) {  // the next band's first row: the head of its segment
-            const uint32_t* __restrict__ n_off = g_off + c_tile0 + C;
+            RCB_AR(const uint32_t) n_off = g_off + (c_tile0 + C);
             const uint32_t nb0 = a.tile_base[band + 1];
+            RCB_A(const uint32_t) n_mm = RCB_MK(const uint32_t, a.ts_mm + nb0, nbot);
+            RCB_A(const uint8_t) n_ar = RCB_MK(const uint8_t, a.ts_area + nb0, nbot);
             for (uint32_t x = threadIdx.x; x < (uint32_t)W; x += TILE_THREADS) soff[oc0 + C + x] = (uint16_t)(own1 + n_off[x]);
             for (uint32_t i = threadIdx.x; i < nbot; i += TILE_THREADS) {
-                mm[own1 + i] = a.ts_mm[nb0 + i];
-                areas[own1 + i] = a.ts_area[nb0 + i];
+                mm[own1 + i] = n_mm[i];
+                areas[own1 + i] = n_ar[i];
             }
         }
     }
@@ -954,7 +968,17 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_comp
     // 2. cells (compact_heightfield.rs:203-223); spans that cannot link get their defaults; the walkable ones are listed.
     //    Only ~45 % of the spans are walkable: linking straight out of the cell loop left most lanes idle next to the
     //    busy ones.  The list lives in the band's fragment segment, which is dead since k_tile_spans.
-    uint32_t* const work = a.work + 3ull * tb;
+    RCB_A(uint32_t) work = RCB_MK(uint32_t, a.work + 3ull * tb, 3ull * a.tile_cap[band]);
+    // per-band slices of the compact arrays (cells of the own rows; spans; the connection arrays up to their capacity)
+    RCB_A(uint32_t) o_cell_index = RCB_MK(uint32_t, a.cell_index + td.cell_base + c_tile0, C);
+    RCB_A(uint32_t) o_cell_count = RCB_MK(uint32_t, a.cell_count + td.cell_base + c_tile0, C);
+    RCB_A(uint16_t) o_con = RCB_MK(uint16_t, a.con + 4ull * span_base, 4ull * So);
+    RCB_A(uint32_t) o_first_conn = RCB_MK(uint32_t, a.first_conn + span_base, So);
+    RCB_A(uint8_t) o_areas = RCB_MK(uint8_t, a.areas + span_base, So);
+    RCB_A(uint16_t) o_dist = RCB_MK(uint16_t, a.dist + span_base, So);
+    RCB_A(uint32_t) o_conn_ref = RCB_MK(uint32_t, a.conn_ref, a.Kcap);
+    RCB_A(uint8_t) o_conn_dir = RCB_MK(uint8_t, a.conn_dir, a.Kcap);
+    RCB_A(uint32_t) o_conn_next = RCB_MK(uint32_t, a.conn_next, a.Kcap);
     if (threadIdx.x == 0) sh_misc[3] = 0;
     // halo spans take part as link targets only: no neighbours of their own (the ghost links are set by the sweeps)
     for (uint32_t s = threadIdx.x; s < nt + nbot; s += TILE_THREADS) {
@@ -975,8 +999,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_comp
         uint32_t b = 0, e = 0, nw = 0;
         if (c < C) {
             b = soff[oc0 + c], e = soff[oc0 + c + 1];
-            a.cell_index[td.cell_base + c_tile0 + c] = e > b ? band_off + (b - nt) : RCB_NONE;
-            a.cell_count[td.cell_base + c_tile0 + c] = e - b;
+            o_cell_index[c] = e > b ? band_off + (b - nt) : RCB_NONE;
+            o_cell_count[c] = e - b;
             coff[c] = 0;
             for (uint32_t sp = b; sp < e; ++sp) {
                 if (areas[sp] != 0) {
@@ -984,7 +1008,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_comp
                 } else {
 #pragma unroll
                     for (int d = 0; d < 8; ++d) nid[(uint32_t)d * S2 + sp] = (uint16_t)TN;
-                    *reinterpret_cast<uint2*>(a.con + 4ull * (span_base + sp - nt)) = make_uint2(63u | (63u << 16), 63u | (63u << 16));
+                    *reinterpret_cast<uint2*>(&o_con[4ull * (sp - nt)]) = make_uint2(63u | (63u << 16), 63u | (63u << 16));
                 }
             }
         }
@@ -1043,7 +1067,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_comp
             }
             nid[(uint32_t)d * S2 + sp] = (uint16_t)best;
         }
-        *reinterpret_cast<uint2*>(a.con + 4ull * (span_base + sp - nt)) =
+        *reinterpret_cast<uint2*>(&o_con[4ull * (sp - nt)]) =
             make_uint2((c4[0] & 0xffffu) | (c4[1] << 16), (c4[2] & 0xffffu) | (c4[3] << 16));
         if (nconn) atomicAdd(&coff[c - oc0], nconn);
     }
@@ -1058,14 +1082,14 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_comp
     g.soff = soff, g.areas = areas, g.nid = nid, g.S = S, g.S2 = S2, g.own0 = own0, g.own1 = own1, g.nt = nt, g.nbot = nbot, g.G0 = G0;
     g.W = W, g.rows = rows, g.row0 = row0, g.band = band, g.has_top = has_top, g.has_bot = has_bot;
     g.flag_f = a.flag_f, g.flag_d = a.flag_d;
-    g.in_top = has_top ? reinterpret_cast<const uint4*>(a.pub + a.binfo[band - 1].pub_base) : nullptr;
-    g.out_down = reinterpret_cast<uint4*>(a.pub + bi.pub_base);
-    g.out_up = reinterpret_cast<uint4*>(a.pub + bi.pub_base + (has_bot ? 16ull * bi.bot_spans : 0ull));
-    g.in_bot = nullptr;
+    g.in_top = RCB_MK(const uint4, has_top ? a.pub + a.binfo[band - 1].pub_base : nullptr, nt);
+    g.out_down = RCB_MK(uint4, a.pub + bi.pub_base, has_bot ? bi.bot_spans : 0u);
+    g.out_up = RCB_MK(uint4, a.pub + bi.pub_base + (has_bot ? 16ull * bi.bot_spans : 0ull), has_top ? bi.top_spans : 0u);
+    g.in_bot = RCB_MK(const uint4, nullptr, 0);
     if (has_bot) {
         const BandInfo nb_i = a.binfo[band + 1];  // its bottom hand-over (if any) comes first, then the records for me
         const bool n_has_bot = a.bands[band + 1].hz1 > a.bands[band + 1].z1;
-        g.in_bot = reinterpret_cast<const uint4*>(a.pub + nb_i.pub_base + (n_has_bot ? 16ull * nb_i.bot_spans : 0ull));
+        g.in_bot = RCB_MK(const uint4, a.pub + nb_i.pub_base + (n_has_bot ? 16ull * nb_i.bot_spans : 0ull), nbot);
     }
     // 7 (hoisted). The connection list (compact_heightfield.rs:375-389: reverse direction order, next -> previously
     //    pushed, first_connection = last pushed) needs only the neighbour table and the tile's first connection
@@ -1110,7 +1134,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_comp
             __syncthreads();
         else
             asm volatile("bar.sync 2, %0;" ::"r"(nworkers) : "memory");
-        uint16_t* const slot_tab = reinterpret_cast<uint16_t*>(coff) + 256u * wid;  // <= 16 warps x 512 B <= 4 (C + 1) B for C >= 2047
+        RCB_A(uint16_t) slot_tab = RCB_MK(uint16_t, reinterpret_cast<uint16_t*>(RCB_RAW(coff)) + 256u * wid, 256);  // <= 16 warps x 512 B <= 4 (C + 1) B for C >= 2047
         const bool tab_ok = 512u * nwarps <= 4u * (C + 1u);
         for (uint32_t s0 = soff[oc0 + cw0], s1 = soff[oc0 + cw1]; s0 < s1; s0 += 32) {
             const uint32_t s = s0 + lane;
@@ -1127,7 +1151,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_comp
                 if (lane >= (uint32_t)d) incl += v;
             }
             const uint32_t excl = incl - cnt, T = __shfl_sync(0xffffffffu, incl, 31);
-            if (s < s1) a.first_conn[span_base + s - nt] = cnt ? krel + kbase + incl - 1 : RCB_NONE;  // the last one pushed
+            if (s < s1) o_first_conn[s - nt] = cnt ? krel + kbase + incl - 1 : RCB_NONE;  // the last one pushed
             if (tab_ok) {
                 // every lane files its span's slots: owner lane | direction << 5 | first-of-its-block << 8, directions from 7 down
                 // (the order the list is pushed in); then the lanes turn to the SLOTS, so the three stores of a round are coalesced
@@ -1143,9 +1167,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_comp
                     const uint32_t e = slot_tab[t];
                     const uint32_t d = (e >> 5) & 7u;
                     const uint32_t k = kbase + t;
-                    a.conn_ref[conn_base + k] = ref_off + nid[d * S2 + s0 + (e & 31u)];
-                    a.conn_dir[conn_base + k] = (uint8_t)d;
-                    a.conn_next[conn_base + k] = (e & 0x100u) ? RCB_NONE : krel + k - 1;
+                    o_conn_ref[conn_base + k] = ref_off + nid[d * S2 + s0 + (e & 31u)];
+                    o_conn_dir[conn_base + k] = (uint8_t)d;
+                    o_conn_next[conn_base + k] = (e & 0x100u) ? RCB_NONE : krel + k - 1;
                 }
                 __syncwarp();
             } else {
@@ -1168,9 +1192,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_comp
                         const uint32_t j = t - oex;
                         const uint32_t d = 7u - (uint32_t)__fns(orm, 0, (int)j + 1);
                         const uint32_t k = kbase + t;
-                        a.conn_ref[conn_base + k] = ref_off + nid[d * S2 + s0 + lo];
-                        a.conn_dir[conn_base + k] = (uint8_t)d;
-                        a.conn_next[conn_base + k] = j ? krel + k - 1 : RCB_NONE;
+                        o_conn_ref[conn_base + k] = ref_off + nid[d * S2 + s0 + lo];
+                        o_conn_dir[conn_base + k] = (uint8_t)d;
+                        o_conn_next[conn_base + k] = j ? krel + k - 1 : RCB_NONE;
                     }
                 }
             }
@@ -1184,13 +1208,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_comp
     //    erosion is asked for.)
     if (a.do_erode) {
         const unsigned thr = (unsigned)(uint8_t)(uint32_t)(a.erode_radius * 2);
-        conn_written = tile_sweep<TILE_THREADS, uint8_t, true>(g, reinterpret_cast<uint8_t*>(d16a), reinterpret_cast<uint8_t*>(d16b), thr, nullptr,
-                                                 nullptr, conn_work);
+        conn_written = tile_sweep<TILE_THREADS, uint8_t, true>(g, RCB_MK(uint8_t, RCB_RAW(d16a), 2ull * G2), RCB_MK(uint8_t, RCB_RAW(d16b), 2ull * G2),
+                                                               thr, nullptr, nullptr, conn_work);
     }
     // (Tried: areas - the one result array that is complete in shared memory - as ONE cp.async.bulk per tile, shared -> global,
     // issued by one thread: SASS UBLKCP.G.S, no measurable change, profiles/r02_bulk_store_ab.txt.  It is 2 % of a tile's output;
     // everything else is produced in registers and there is no shared memory left to stage it in.)
-    for (uint32_t s = threadIdx.x; s < So; s += TILE_THREADS) a.areas[span_base + s] = areas[own0 + s];
+    for (uint32_t s = threadIdx.x; s < So; s += TILE_THREADS) o_areas[s] = areas[own0 + s];
     pc.mark(3);
     // 6. distance field (compact_heightfield.rs:514-727)
     if (a.do_dist) {
@@ -1220,12 +1244,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_comp
                 }
                 r = (uint32_t)(d / n);
             }
-            a.dist[span_base + s - nt] = (uint16_t)r;
+            o_dist[s - nt] = (uint16_t)r;
         }
         if (threadIdx.x == 0 && sh_misc[2]) atomicMax(&a.tinfo[tile].max_distance, sh_misc[2]);
         pc.mark(5);
     } else {
-        for (uint32_t s = threadIdx.x; s < So; s += TILE_THREADS) a.dist[span_base + s] = 0;  // compact_heightfield.rs:253
+        for (uint32_t s = threadIdx.x; s < So; s += TILE_THREADS) o_dist[s] = 0;  // compact_heightfield.rs:253
     }
     pc.mark(6);
     if (!conn_written) conn_work(threadIdx.x, TILE_THREADS);  // no sweep ran, or the tile is as wide as the block
@@ -1233,6 +1257,21 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile_comp
 }
 
 }  // namespace
+
+RCB_BOUNDS_EXPORT(rcb_bounds_read_tile)
+
+// proof that the checked accessors bite: one deliberate access one element past an array of eight (debug build only)
+__global__ void k_bounds_selftest(uint32_t* p) {
+    RCB_A(uint32_t) a = RCB_MK(uint32_t, p, 8);
+    a[8 - (threadIdx.x == 1 ? 0 : 1)] = 1u;  // thread 1 writes a[8]
+}
+void rcb_bounds_selftest(uint32_t* scratch16, cudaStream_t s) {
+#ifdef RCB_BOUNDS
+    k_bounds_selftest<<<1, 2, 0, s>>>(scratch16);
+#else
+    (void)scratch16, (void)s;
+#endif
+}
 
 static void set_smem_attr(const void* fn, size_t bytes) {
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);

@@ -1145,6 +1145,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             tc.flag_f = (uint32_t*)((char*)ctx->d_lookback.p + look_bytes);
             tc.flag_d = tc.flag_f + nbands;
             tc.tile_base = r2.tile_base;
+            tc.tile_cap = r2.tile_cap;
             tc.hf_cell_offset_in = ctx->d_celloff_tmp.as<uint32_t>();
             tc.ts_mm = ctx->d_ts_mm.as<uint32_t>();
             tc.ts_area = ctx->d_ts_area.as<uint8_t>();
@@ -1683,6 +1684,30 @@ int rcb_profile_reset(rcb_ctx* ctx) {
 }
 
 uint64_t rcb_launch_count(const rcb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int rcb_debug_bounds_report(rcb_ctx* ctx, uint64_t out[4], int reset) {
+    if (!ctx || !out) return RCB_EARG;
+    cudaSetDevice(ctx->device);
+    if (reset == 2) {  // self-test: trip one violation on purpose, then report as with reset == 1
+        if (ctx->d_counters.ensure(48 * sizeof(unsigned long long)) != cudaSuccess) return RCB_ECUDA;
+        rcb_bounds_selftest(ctx->d_counters.as<uint32_t>() + 64, ctx->stream);
+        reset = 1;
+    }
+    cudaDeviceSynchronize();
+    out[0] = out[1] = out[2] = out[3] = 0;
+    void (*readers[])(unsigned long long*, int) = {rcb_bounds_read_tile, rcb_bounds_read_raster2, rcb_bounds_read_regions};
+    for (auto rd : readers) {
+        unsigned long long v[4] = {0, 0, 0, 0};
+        rd(v, reset);
+        if (v[0] && !out[0]) out[1] = v[1], out[2] = v[2], out[3] = v[3];
+        out[0] += v[0];
+    }
+#ifdef RCB_BOUNDS
+    return 1;
+#else
+    return 0;
+#endif
+}
 
 /* out[0] batches issued speculatively, out[1] of those rebuilt because a size was short, out[2] cached batch entries */
 int rcb_ctx_stats(const rcb_ctx* ctx, uint64_t out[4]) {

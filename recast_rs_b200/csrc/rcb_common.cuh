@@ -212,6 +212,7 @@ struct TileCompactArgs {
     unsigned char* pub;          // hand-over records between the bands of a tile (BandInfo::pub_base)
     uint32_t* flag_f;            // [nbands] zeroed: band's forward sweep published
     uint32_t* flag_d;            // [nbands] zeroed: band's distance values published
+    const uint32_t* tile_cap;    // [nbands] records a band's fragment segment holds (bounds of `work`)
     const uint32_t* tile_base;
     const uint32_t* hf_cell_offset_in;  // from k_tile_spans
     const uint32_t* ts_mm;
@@ -403,6 +404,12 @@ void launch_tc_spans(const TileDesc* tiles, TileMap tm, const uint8_t* regons, c
                      int16_t* smin, int16_t* smax, uint8_t* sarea, cudaStream_t s);
 void launch_tc_obstacles(const TileDesc* tiles, int ntiles, const rcb_tc_obstacle* obs, const uint32_t* hf_off, const int16_t* smin,
                          const int16_t* smax, uint8_t* sarea, cudaStream_t s);
+
+// -DRCB_BOUNDS build: per translation unit, the violations its checked accessors saw (rcb_bounds.cuh); zeros otherwise
+void rcb_bounds_read_tile(unsigned long long out[4], int reset);
+void rcb_bounds_read_raster2(unsigned long long out[4], int reset);
+void rcb_bounds_read_regions(unsigned long long out[4], int reset);
+void rcb_bounds_selftest(uint32_t* scratch16, cudaStream_t s);  // one deliberate violation (debug build; no-op otherwise)
 
 // Per-kernel hooks of the context that is running a pipeline on THIS host thread (one rcb_ctx per host thread): the launch
 // counter behind rcb_launch_count and, when rcb_profile_enable is on, an event pair around every kernel so device time is

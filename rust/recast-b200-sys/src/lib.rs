@@ -178,6 +178,7 @@ extern "C" {
     pub fn rcb_use_own_stream(ctx: *mut rcb_ctx) -> c_int;
     pub fn rcb_launch_count(ctx: *const rcb_ctx) -> u64;
     pub fn rcb_ctx_stats(ctx: *const rcb_ctx, out: *mut u64) -> c_int;
+    pub fn rcb_debug_bounds_report(ctx: *mut rcb_ctx, out: *mut u64, reset: c_int) -> c_int;
     pub fn rcb_profile_enable(ctx: *mut rcb_ctx, on: c_int) -> c_int;
     pub fn rcb_profile_read(ctx: *mut rcb_ctx, out: *mut rcb_stage_time, cap: c_int) -> c_int;
     pub fn rcb_profile_reset(ctx: *mut rcb_ctx) -> c_int;

@@ -240,3 +240,28 @@ def test_tile_of_more_than_2_pow_24_cells(oracle):
     np.testing.assert_array_equal(tv.span_area, e.span_area)
     assert int(np.flatnonzero(np.diff(e.cell_offset.astype(np.int64)))[-1]) > (1 << 24)
     ctx.close()
+
+
+def test_bounds_build_reports(request):
+    """RCB_DEBUG_SO=1 (librecast_b200_dbg.so, -DRCB_BOUNDS): the checked accessors must bite on a deliberate violation and
+    must have seen none from the real kernels so far; the normal build says it is not instrumented."""
+    import recast_rs_b200.builder as rb
+    from recast_rs_b200 import synth
+
+    ctx = _ctx()
+    v, t, cfgs = synth.config2(seed=1, nq=64, tile=64)
+    ctx.upload_mesh(v, t)
+    with ctx.build_tiles(cfgs, rb.STAGE_ALL_BUILD | rb.STAGE_REGIONS) as r:
+        r.download()
+    rep = ctx.bounds_report()
+    if os.environ.get("RCB_DEBUG_SO") == "1":
+        assert rep["instrumented"] and rep["violations"] == 0, rep
+        a = (__import__("ctypes").c_uint64 * 4)()
+        from recast_rs_b200 import _ffi
+
+        assert _ffi.lib().rcb_debug_bounds_report(ctx._h, a, 2) == 1
+        assert a[0] == 1 and (a[1] >> 32) == 1 and a[2] == 8 and a[3] == 8, list(a)  # file 1 (k_tile.cu), index 8 of 8
+        assert ctx.bounds_report()["violations"] == 0  # cleared: the session-end verdict counts real kernels only
+    else:
+        assert not rep["instrumented"] and rep["violations"] == 0
+    ctx.close()
