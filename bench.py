@@ -179,7 +179,8 @@ def cpu_leg(v, t, cfgs, threads, budget_s, prebinned=False):
     per_tile = max(s0 / probe, 1e-6)
     m = int(min(ntiles, max(probe, budget_s / per_tile)))
     secs, _ = orc.build_tiles_timed(v, t, cfgs[:m], nthreads=threads, prebinned=prebinned)
-    return T * (m / ntiles) / secs, f"first {m} of {ntiles} tiles (each scans the whole mesh as lib.rs:217 does)", secs
+    how = "each handed only the triangles over it" if prebinned else "each scans the whole mesh as lib.rs:217 does"
+    return T * (m / ntiles) / secs, f"first {m} of {ntiles} tiles ({how})", secs
 
 
 def run_reference(args, rank, world):
@@ -663,6 +664,8 @@ def run_native(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (read_traffic() or {}).get("main_kernels_sum") if args.config == 2 and world == 1 else None,
                          "traffic_per_kernel": (read_traffic() or {}).get("per_launch_dram_bytes") if args.config == 2 and world == 1 else None,
+                         # the kernels are instruction-issue / latency bound, not HBM bound: the roofline that applies to them
+                         "issue_roofline": (read_traffic() or {}).get("issue_roofline") if args.config == 2 and world == 1 else None,
                          "peak_source": peak_src, "kernel": "whole step (all launches)",
                          "alg_bytes_per_step_per_gpu": balg_all / world,
                          "alg_bytes_per_triangle": balg_all / T_all,
