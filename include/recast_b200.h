@@ -58,17 +58,23 @@ enum {
     RCB_FILTER_LEDGE = 0x200u,       /* heightfield.rs:332 */
     RCB_FILTER_LOW_HEIGHT = 0x400u,  /* heightfield.rs:492 */
     RCB_STAGE_ALL_BUILD = 1u | 2u | 4u | 16u, /* what RecastBuilder::build_mesh reaches (lib.rs:77-87 → watershed.rs:375) */
-    /* Result layout flag (not a stage): rcb_result_download copies only what the host cannot rebuild.  The host views then
-     * carry hf_cell_offset = first_conn = conn_next = conn_dir = conn_ref = NULL and instead
-     *   conn_mask[S]   bit d set <=> the span has a connection in direction d.  Connections are laid out in span order and,
-     *                  inside a span, in DESCENDING direction (compact_heightfield.rs:375-389 pushes dir 7..0 with
-     *                  next -> the one pushed before, first_connection = the last pushed), so
-     *                  first_conn[s] = (connections of spans <= s) - 1 (or NONE), conn_dir = the mask's bits from 7 down,
-     *                  conn_next[k] = k - 1 inside a span's block, NONE at its start;
-     *   conn_ref16[K]  conn_ref as u16 (tile-relative span indices) - when a tile holds 65536+ spans the views carry the
-     *                  32-bit conn_ref instead and conn_ref16 = NULL;
-     * hf_cell_offset is the exclusive prefix sum of cell_count_arr.  INTEGRATION.md has the rebuild loop.  Device views
-     * (rcb_result_tile_device) always carry the full arrays. */
+    /* Result layout flag (not a stage): rcb_result_download copies only what the host cannot rebuild, in the narrowest form
+     * that holds it - the copy, not the kernels, is what an end-to-end build waits for (PCIe).  The HOST views then carry
+     * hf_cell_offset = cell_index = first_conn = conn_next = conn_dir = NULL and
+     *   conn_mask[S]      bit d set <=> the span has a connection in direction d.  Connections are laid out in span order and,
+     *                     inside a span, in DESCENDING direction (compact_heightfield.rs:375-389 pushes dir 7..0 with
+     *                     next -> the one pushed before, first_connection = the last pushed), so
+     *                     first_conn[s] = (connections of spans <= s) - 1 (or NONE), conn_dir = the mask's bits from 7 down,
+     *                     conn_next[k] = k - 1 inside a span's block, NONE at its start;
+     *   conn_ref16[K]     conn_ref (tile-relative span indices) as u16 - with conn_ref = NULL - unless a tile holds 65536+
+     *                     spans: then conn_ref (u32) is there and conn_ref16 = NULL;
+     *   cell_count16[C]   cell_count_arr as u16 (cell_count_arr = NULL; the wide one instead should a cell hold 65536+ spans);
+     *                     hf_cell_offset is its exclusive prefix sum, cell_index the same with NONE for empty cells;
+     *   con8[4*S]         con as u8 (con = NULL; the wide one instead should a cell hold more than 256 spans - the values are
+     *                     offsets inside the neighbour cell, 63 = none);
+     *   areas             NULL while CompactHeightfield.areas still equals CompactSpan.area (span_area): nothing that writes
+     *                     it ran (no ERODE, no area operator, no areas_override).
+     * INTEGRATION.md has the rebuild loop.  Device views (rcb_result_tile_device) always carry the full arrays. */
     RCB_RESULT_SLIM = 0x1000u
 };
 
@@ -148,6 +154,8 @@ typedef struct rcb_tile_view {
     uint32_t _pad;
     const uint8_t* conn_mask;       /* [S]  RCB_RESULT_SLIM only: directions in which the span is connected (bit d) */
     const uint16_t* conn_ref16;     /* [K]  RCB_RESULT_SLIM only: conn_ref in 16 bits (NULL when a tile has 65536+ spans) */
+    const uint16_t* cell_count16;   /* [C]  RCB_RESULT_SLIM only: cell_count_arr in 16 bits */
+    const uint8_t* con8;            /* [4*S] RCB_RESULT_SLIM only: con in 8 bits */
 } rcb_tile_view;
 
 /* ---- context ------------------------------------------------------------------------------ */

@@ -67,6 +67,8 @@ class TileVoxels:
     max_regions: int = 0
     conn_mask: Optional[np.ndarray] = None   # RESULT_SLIM: u8[S], bit d = the span is connected in direction d
     conn_ref16: Optional[np.ndarray] = None  # RESULT_SLIM: u16[K] conn_ref (None when a tile holds 65536+ spans)
+    cell_count16: Optional[np.ndarray] = None  # RESULT_SLIM: u16[C] cell_count
+    con8: Optional[np.ndarray] = None  # RESULT_SLIM: u8[4S] con
 
     def expand_slim(self) -> "TileVoxels":
         """Rebuilds, on the host, the arrays a RESULT_SLIM download leaves out, from the layout rule of
@@ -76,7 +78,14 @@ class TileVoxels:
         if self.conn_mask is None:
             return self
         S = self.span_count
+        if self.cell_count is None:
+            self.cell_count = self.cell_count16.astype(np.uint32)
+        if self.con is None:
+            self.con = self.con8.astype(np.uint16)
+        if self.areas is None:  # nothing wrote CompactHeightfield.areas: still the copy of CompactSpan.area it starts as
+            self.areas = self.span_area.copy()
         self.hf_cell_offset = np.concatenate([[0], np.cumsum(self.cell_count, dtype=np.uint64)]).astype(np.uint32)
+        self.cell_index = np.where(self.cell_count > 0, self.hf_cell_offset[:-1], NONE).astype(np.uint32)
         bits = np.unpackbits(self.conn_mask.reshape(-1, 1), axis=1)  # column j = direction 7 - j: already descending
         cnt = bits.sum(axis=1, dtype=np.int64)
         ends = np.cumsum(cnt)
@@ -98,22 +107,31 @@ def _tile_from_view(v, expand: bool = True) -> "TileVoxels":
     tv = TileVoxels(v.width, v.height, S, K, v.walkable_span_count, v.max_height, v.max_distance, v.status,
                     _np_from(v.hf_cell_offset, C + 1, np.uint32) if v.hf_cell_offset else None, _np_from(v.span_min, S, np.int16),
                     _np_from(v.span_max, S, np.int16), _np_from(v.span_area, S, np.uint8))
-    if v.cell_index:
-        tv.cell_index = _np_from(v.cell_index, C, np.uint32)
-        tv.cell_count = _np_from(v.cell_count_arr, C, np.uint32)
-        tv.areas = _np_from(v.areas, S, np.uint8)
-        tv.con = _np_from(v.con, 4 * S, np.uint16)
+    if v.dist:
         tv.dist = _np_from(v.dist, S, np.uint16)
-        if v.conn_mask:  # RESULT_SLIM: the binding layer rebuilds the rest (expand_slim)
+        if v.conn_mask and not v.first_conn:  # RESULT_SLIM host view: the binding layer rebuilds the rest (expand_slim)
             tv.hf_cell_offset = None
             tv.conn_mask = _np_from(v.conn_mask, S, np.uint8)
+            tv.areas = _np_from(v.areas, S, np.uint8) if v.areas else None
             if v.conn_ref16:
                 tv.conn_ref16 = _np_from(v.conn_ref16, K, np.uint16)
             else:
                 tv.conn_ref = _np_from(v.conn_ref, K, np.uint32)
+            if v.cell_count16:
+                tv.cell_count16 = _np_from(v.cell_count16, C, np.uint16)
+            else:
+                tv.cell_count = _np_from(v.cell_count_arr, C, np.uint32)
+            if v.con8:
+                tv.con8 = _np_from(v.con8, 4 * S, np.uint8)
+            else:
+                tv.con = _np_from(v.con, 4 * S, np.uint16)
             if expand:
                 tv.expand_slim()
         else:
+            tv.cell_index = _np_from(v.cell_index, C, np.uint32)
+            tv.cell_count = _np_from(v.cell_count_arr, C, np.uint32)
+            tv.areas = _np_from(v.areas, S, np.uint8)
+            tv.con = _np_from(v.con, 4 * S, np.uint16)
             tv.first_conn = _np_from(v.first_conn, S, np.uint32)
             tv.conn_ref = _np_from(v.conn_ref, K, np.uint32)
             tv.conn_dir = _np_from(v.conn_dir, K, np.uint8)

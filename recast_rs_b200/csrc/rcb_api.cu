@@ -54,6 +54,8 @@ struct Arena {
 
 struct ArenaLayout {  // byte offsets inside arena A (cells + spans) and arena B (connections)
     size_t tinfo, hf_cell_offset, cell_index, cell_count, span_min, span_max, span_area, areas, con, first_conn, dist, reg, conn_mask;
+    size_t cell_count16, con8;  // slim layout: the narrow twins of cell_count (u16) and con (4 x u8)
+    bool areas_in_slim;         // chf.areas differs from CompactSpan.area (erosion, area operators): part of the slim download
     size_t bytesA;
     size_t slimA;  // the arrays a slim download copies are the first slimA bytes of arena A
     size_t conn_ref, conn_dir, conn_next, conn_ref16;
@@ -177,6 +179,8 @@ struct rcb_result {
     int redo_erode = 0;  // what a failed speculation needs to run again (the configurations are entry->cfgs)
     bool slim = false;         // RCB_RESULT_SLIM: conn_mask / conn_ref16 exist, the download copies the slim prefix only
     bool slim_ref16 = false;   // conn_ref16 is valid (every tile-relative span index fits 16 bits)
+    bool slim_con8 = false;    // con8 is valid (every offset inside a neighbour cell fits 8 bits)
+    bool slim_cnt16 = false;   // cell_count16 is valid (no cell holds 65536+ spans)
     bool slim_host = false;    // the host copy holds only the slim arrays
     bool slim_packed = false;  // k_slim_pack has run on this result
     bool spec = false;         // issued speculatively (pending: the device may still raise a flag)
@@ -512,9 +516,11 @@ int make_bands(rcb_ctx* ctx, BatchEntry& e, uint32_t band_cells) {
     return RCB_OK;
 }
 
-// Arena A: per-tile info, cells, spans.  The arrays a slim download copies come first (one copy of a prefix);
-// hf_cell_offset and first_conn, which the slim layout leaves on the device, come last.
-void make_layout(ArenaLayout& l, int ntiles, uint64_t C, uint64_t S, uint32_t stage_mask) {
+// Arena A: per-tile info, cells, spans.  The arrays a slim download copies come first (one copy of a prefix): span geometry
+// and areas, dist, reg, and the narrow forms k_slim_pack derives - conn_mask u8[S], cell_count16 u16[C], con8 u8[4S].  What the
+// binding layer rebuilds (hf_cell_offset, cell_index, first_conn) or gets in the narrow form (cell_count, con) comes last,
+// as does chf.areas while it still equals CompactSpan.area (nothing ran that writes it).
+void make_layout(ArenaLayout& l, int ntiles, uint64_t C, uint64_t S, uint32_t stage_mask, bool areas_written = true) {
     size_t o = 0;
     auto put = [&o](size_t bytes) {
         size_t r = o;
@@ -523,18 +529,22 @@ void make_layout(ArenaLayout& l, int ntiles, uint64_t C, uint64_t S, uint32_t st
     };
     const bool compact = stage_mask & RCB_STAGE_COMPACT;
     const bool slim = (stage_mask & RCB_RESULT_SLIM) && compact;
+    l.areas_in_slim = !slim || areas_written || (stage_mask & RCB_STAGE_ERODE);
     l.tinfo = put(sizeof(TileInfo) * (size_t)ntiles);
     l.span_min = put(2 * S);
     l.span_max = put(2 * S);
     l.span_area = put(S);
-    l.cell_index = put(compact ? 4 * C : 0);
-    l.cell_count = put(compact ? 4 * C : 0);
-    l.areas = put(compact ? S : 0);
-    l.con = put(compact ? 8 * S : 0);
+    if (l.areas_in_slim) l.areas = put(compact ? S : 0);
     l.dist = put(compact ? 2 * S : 0);
     l.reg = put((stage_mask & RCB_STAGE_REGIONS) ? 2 * S : 0);
     l.conn_mask = put(slim ? S : 0);
+    l.cell_count16 = put(slim ? 2 * C : 0);
+    l.con8 = put(slim ? 4 * S : 0);
     l.slimA = o;
+    if (!l.areas_in_slim) l.areas = put(compact ? S : 0);
+    l.cell_index = put(compact ? 4 * C : 0);
+    l.cell_count = put(compact ? 4 * C : 0);
+    l.con = put(compact ? 8 * S : 0);
     l.hf_cell_offset = put(4 * (C + ntiles));
     l.first_conn = put(compact ? 4 * S : 0);
     l.bytesA = o;
@@ -1127,7 +1137,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
                 entry->hint = nh;
             }
             CUB(ctx->d_pub.ensure(pub + 64));
-            make_layout(res->lay, ntiles, Ctot, S, stage_mask);
+            make_layout(res->lay, ntiles, Ctot, S, stage_mask, src.areas_override != nullptr || src.nops > 0);
             CUB(pool_get(ctx->free_dev, res->lay.bytesA, false, res->devA));
             char* A = res->devA.p;
             TileInfo* d_tinfo = (TileInfo*)(A + res->lay.tinfo);
@@ -1304,7 +1314,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
             return bail(fail(ctx, RCB_EOVERFLOW, "clip polygon exceeded %d vertices", RCB_MAX_POLY_VERTS));
         res->F = F;
         res->S = S;
-        make_layout(res->lay, ntiles, Ctot, S, stage_mask);
+        make_layout(res->lay, ntiles, Ctot, S, stage_mask, src.areas_override != nullptr || src.nops > 0);
         CUB(pool_get(ctx->free_dev, res->lay.bytesA, false, res->devA));
         char* A = res->devA.p;
         CUB(cudaMemcpyAsync(A + res->lay.tinfo, d_tinfo_tmp, sizeof(TileInfo) * (size_t)ntiles, cudaMemcpyDeviceToDevice, st));
@@ -1389,7 +1399,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         }
         S = (uint32_t)ctx->h_counters[0];
         res->S = S;
-        make_layout(res->lay, ntiles, Ctot, S, stage_mask);
+        make_layout(res->lay, ntiles, Ctot, S, stage_mask, src.areas_override != nullptr || src.nops > 0);
         CUB(pool_get(ctx->free_dev, res->lay.bytesA, false, res->devA));
         char* A = res->devA.p;
         CUB(cudaMemsetAsync(A + res->lay.tinfo, 0, sizeof(TileInfo) * (size_t)ntiles, st));
@@ -1416,7 +1426,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         goff[Ctot] = (uint32_t)sbase;
         S = sbase;
         res->S = S;
-        make_layout(res->lay, ntiles, Ctot, S, stage_mask);
+        make_layout(res->lay, ntiles, Ctot, S, stage_mask, src.areas_override != nullptr || src.nops > 0);
         CUB(pool_get(ctx->free_dev, res->lay.bytesA, false, res->devA));
         char* A = res->devA.p;
         CUB(cudaMemsetAsync(A + res->lay.tinfo, 0, sizeof(TileInfo) * (size_t)ntiles, st));
@@ -1492,6 +1502,7 @@ void adopt_result(rcb_result* res, rcb_result* from) {
     res->tinfo.swap(from->tinfo);
     res->entry = from->entry;
     res->slim_ref16 = from->slim_ref16, res->slim_host = from->slim_host, res->slim_packed = from->slim_packed;
+    res->slim_con8 = from->slim_con8, res->slim_cnt16 = from->slim_cnt16;
     res->pending = false;
     res->spec = false;
 }
@@ -2451,17 +2462,18 @@ static int slim_pack(rcb_result* res, cudaStream_t st) {
     rcb_ctx* ctx = res->ctx;
     if (!res->slim || res->slim_packed) return RCB_OK;
     res->slim_packed = true;
-    if (res->ntiles == 0 || !res->lay.bytesB) return RCB_OK;
+    if (res->ntiles == 0 || !res->entry) return RCB_OK;
     char* A = res->devA.p;
     char* B = res->devB.p;
     CU(ctx->d_wire_err.ensure(64));
     if (!res->slim_flag) CU(cudaMallocHost((void**)&res->slim_flag, sizeof(unsigned long long)));
     *res->slim_flag = 0;
     CU(cudaMemsetAsync(ctx->d_wire_err.p, 0, 8, st));
-    launch_slim_pack((const TileInfo*)(A + res->lay.tinfo), res->ntiles, res->entry ? res->entry->max_cells : 4096u,
+    launch_slim_pack(res->entry->d_tiles.as<TileDesc>(), (const TileInfo*)(A + res->lay.tinfo), res->ntiles, res->entry->max_cells,
                      (const uint32_t*)(A + res->lay.first_conn), (const uint32_t*)(B + res->lay.conn_ref),
-                     (const uint8_t*)(B + res->lay.conn_dir), (const uint32_t*)(B + res->lay.conn_next), (uint8_t*)(A + res->lay.conn_mask),
-                     (uint16_t*)(B + res->lay.conn_ref16), ctx->d_wire_err.as<unsigned long long>(), st);
+                     (const uint8_t*)(B + res->lay.conn_dir), (const uint32_t*)(B + res->lay.conn_next), (const uint32_t*)(A + res->lay.cell_count),
+                     (const uint16_t*)(A + res->lay.con), (uint8_t*)(A + res->lay.conn_mask), (uint16_t*)(B + res->lay.conn_ref16),
+                     (uint16_t*)(A + res->lay.cell_count16), (uint8_t*)(A + res->lay.con8), ctx->d_wire_err.as<unsigned long long>(), st);
     CU(cudaMemcpyAsync(res->slim_flag, ctx->d_wire_err.p, 8, cudaMemcpyDeviceToHost, st));
     return RCB_OK;
 }
@@ -2483,7 +2495,7 @@ static int download_on(rcb_result* res, cudaStream_t st, bool wait) {
         if (r) return r;
     }
     const ArenaLayout& l = res->lay;
-    CU(pool_get(ctx->free_host, res->slim ? l.slimA : l.bytesA, true, res->hostA));
+    CU(pool_get(ctx->free_host, l.bytesA, true, res->hostA));  // slim: only the prefix is copied; the rest is room for a wide fallback
     uint64_t copied = 0;
     if (l.bytesB) {
         if (res->slim) {
@@ -2533,13 +2545,23 @@ static int finish_download(rcb_result* res, cudaStream_t st) {
         res->copied_bytes = 0;
         return download_on(res, ctx->stream, true);
     }
-    if (res->slim && res->lay.slimB) {
-        res->slim_ref16 = res->slim_flag && *res->slim_flag == 0;
+    if (res->slim) {
+        const unsigned long long f = res->slim_flag ? *res->slim_flag : (res->ntiles == 0 ? 0ull : 7ull);
+        res->slim_ref16 = !(f & 1ull), res->slim_con8 = !(f & 2ull), res->slim_cnt16 = !(f & 4ull);
+        bool more = false;
         if (!res->slim_ref16 && res->K) {  // a tile with 65536+ spans: its span references need the 32-bit array after all
             CU(cudaMemcpyAsync(res->hostB.p + res->lay.conn_ref, res->devB.p + res->lay.conn_ref, 4 * res->K, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            res->copied_bytes += 4 * res->K;
+            res->copied_bytes += 4 * res->K, more = true;
         }
+        if (!res->slim_con8 && res->S) {  // a cell with 257+ spans: offsets inside it need the 16-bit con
+            CU(cudaMemcpyAsync(res->hostA.p + res->lay.con, res->devA.p + res->lay.con, 8 * res->S, cudaMemcpyDeviceToHost, st));
+            res->copied_bytes += 8 * res->S, more = true;
+        }
+        if (!res->slim_cnt16 && res->Ctot) {
+            CU(cudaMemcpyAsync(res->hostA.p + res->lay.cell_count, res->devA.p + res->lay.cell_count, 4 * res->Ctot, cudaMemcpyDeviceToHost, st));
+            res->copied_bytes += 4 * res->Ctot, more = true;
+        }
+        if (more) CU(cudaStreamSynchronize(st));
     }
     res->slim_host = res->slim;
     res->tinfo.assign((TileInfo*)(res->hostA.p + res->lay.tinfo), (TileInfo*)(res->hostA.p + res->lay.tinfo) + res->ntiles);
@@ -2590,16 +2612,26 @@ static int fill_view(const rcb_result* res, int tile, rcb_tile_view* v, const ch
     v->span_max = (const int16_t*)(A + l.span_max) + ti.span_base;
     v->span_area = (const uint8_t*)(A + l.span_area) + ti.span_base;
     if (res->stage_mask & RCB_STAGE_COMPACT) {
-        v->cell_index = (const uint32_t*)(A + l.cell_index) + td.cell_base;
-        v->cell_count_arr = (const uint32_t*)(A + l.cell_count) + td.cell_base;
-        v->areas = (const uint8_t*)(A + l.areas) + ti.span_base;
-        v->con = (const uint16_t*)(A + l.con) + 4 * (size_t)ti.span_base;
         v->dist = (const uint16_t*)(A + l.dist) + ti.span_base;
         if (!slim) {
+            v->cell_index = (const uint32_t*)(A + l.cell_index) + td.cell_base;
+            v->cell_count_arr = (const uint32_t*)(A + l.cell_count) + td.cell_base;
+            v->areas = (const uint8_t*)(A + l.areas) + ti.span_base;
+            v->con = (const uint16_t*)(A + l.con) + 4 * (size_t)ti.span_base;
             v->first_conn = (const uint32_t*)(A + l.first_conn) + ti.span_base;
             v->conn_ref = (const uint32_t*)(B + l.conn_ref) + ti.conn_base;
             v->conn_dir = (const uint8_t*)(B + l.conn_dir) + ti.conn_base;
             v->conn_next = (const uint32_t*)(B + l.conn_next) + ti.conn_base;
+        } else {  // the host copy of a slim result: narrow forms, or the wide array where a narrow one did not do
+            if (l.areas_in_slim) v->areas = (const uint8_t*)(A + l.areas) + ti.span_base;  // else NULL: areas == span_area
+            if (res->slim_cnt16)
+                v->cell_count16 = (const uint16_t*)(A + l.cell_count16) + td.cell_base;
+            else
+                v->cell_count_arr = (const uint32_t*)(A + l.cell_count) + td.cell_base;
+            if (res->slim_con8)
+                v->con8 = (const uint8_t*)(A + l.con8) + 4 * (size_t)ti.span_base;
+            else
+                v->con = (const uint16_t*)(A + l.con) + 4 * (size_t)ti.span_base;
         }
         if (res->slim && res->slim_packed) {
             v->conn_mask = (const uint8_t*)(A + l.conn_mask) + ti.span_base;
@@ -2607,6 +2639,10 @@ static int fill_view(const rcb_result* res, int tile, rcb_tile_view* v, const ch
                 v->conn_ref16 = (const uint16_t*)(B + l.conn_ref16) + ti.conn_base;
             else
                 v->conn_ref = (const uint32_t*)(B + l.conn_ref) + ti.conn_base;
+            if (!host) {
+                v->cell_count16 = (const uint16_t*)(A + l.cell_count16) + td.cell_base;
+                v->con8 = (const uint8_t*)(A + l.con8) + 4 * (size_t)ti.span_base;
+            }
         }
         if (res->stage_mask & RCB_STAGE_REGIONS) {
             v->reg = (const uint16_t*)(A + l.reg) + ti.span_base;

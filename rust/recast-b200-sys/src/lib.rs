@@ -94,6 +94,8 @@ pub struct rcb_tile_view {
     pub _pad: u32,
     pub conn_mask: *const u8,
     pub conn_ref16: *const u16,
+    pub cell_count16: *const u16,
+    pub con8: *const u8,
 }
 
 #[repr(C)]
