@@ -350,14 +350,55 @@ def config3_leg(args, rank, world, local_rank, ctx, stream, flush, dist, dev, ba
     from recast_rs_b200.config import configs_to_array
     from tests.parity import assert_tile_equal
 
-    v, t, cfgs, name, T_world, tiles_world, whole = make_sharded_workload(3, args.seed, rank, world, "weighted")
-    arr = configs_to_array(cfgs)
-    d_v, d_t = torch.from_numpy(v).to(dev), torch.from_numpy(t).to(dev)
-    ctx.set_mesh_device(d_v.data_ptr(), d_v.numel(), d_t.data_ptr(), d_t.numel(), keep=(d_v, d_t))
-    tot = None
-    for _ in range(3):
-        with ctx.build_tiles(arr, rb.STAGE_ALL_BUILD) as r:
-            tot = r.totals()
+    from recast_rs_b200 import shard
+
+    wv, wt, all_cfgs, name = make_workload(3, args.seed)
+    T_world, tiles_world, whole = wt.size // 3, len(all_cfgs), (wv, wt)
+    cost = shard.tile_costs(wv, wt, all_cfgs)
+    rounds = []
+
+    def load(cost):
+        cuts = shard.cut_by_cost(cost, world)
+        cfgs = all_cfgs[cuts[rank]:cuts[rank + 1]]
+        v, t = shard.prebin_mesh(wv, wt, cfgs)
+        arr = configs_to_array(cfgs)
+        d_v, d_t = torch.from_numpy(v).to(dev), torch.from_numpy(t).to(dev)
+        ctx.set_mesh_device(d_v.data_ptr(), d_v.numel(), d_t.data_ptr(), d_t.numel(), keep=(d_v, d_t))
+        tot = None
+        for _ in range(3):
+            with ctx.build_tiles(arr, rb.STAGE_ALL_BUILD) as r:
+                tot = r.totals()
+        return cuts, cfgs, v, t, arr, tot
+
+    def measure(arr, n):
+        evs = []
+        for _ in range(n):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            ctx.build_tiles(arr, rb.STAGE_ALL_BUILD).free()
+            b.record(stream)
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return float(np.median([a.elapsed_time(b) for a, b in evs]))
+
+    # static slabs cut by ESTIMATED cost, then one round of feedback: every rank times its slab, the slabs are re-priced by
+    # what they measured and cut again (shard.refine_costs) - untimed set-up, like the pre-binning itself
+    cuts, cfgs, v, t, arr, tot = load(cost)
+    for it in range(2):
+        mine = torch.tensor([measure(arr, 3)], dtype=torch.float64, device=dev)
+        allms = [torch.zeros_like(mine) for _ in range(world)]
+        if dist is not None:
+            dist.all_gather(allms, mine)
+        else:
+            allms = [mine]
+        ms_all = [float(x[0]) for x in allms]
+        rounds.append({"cuts": [int(c) for c in cuts], "ms_per_rank": [round(x, 3) for x in ms_all]})
+        if it == 1 or world == 1:
+            break
+        cost = shard.refine_costs(cost, cuts, ms_all)
+        cuts, cfgs, v, t, arr, tot = load(cost)
+    name += f", one world sharded over {world} ranks (contiguous slabs cut by estimated cost, re-cut once by measured time)"
     steps = max(3, min(args.steps, 5))
     warm = [ctx.build_tiles(arr, rb.STAGE_ALL_BUILD) for _ in range(steps)]  # arena pool: one pair per timed step
     for r in warm:
@@ -399,7 +440,9 @@ def config3_leg(args, rank, world, local_rank, ctx, stream, flush, dist, dev, ba
             "ms_per_step_fastest_rank": float(mn[0]) / steps, "value": T_world / (ms_step * 1e-3), "unit": UNIT,
             "tiles_per_s": tiles_world / (ms_step * 1e-3), "roofline_frac": achieved / peak, "achieved_gbs_per_gpu": achieved,
             "h2d_bytes_all_ranks": int(cnt[2]), "h2d_bytes_whole_world": int(whole[0].nbytes + whole[1].nbytes),
-            "parity_check": {"tiles": 2 * world, "ok": True}, "sharding": "contiguous tile slabs cut by estimated cost (shard.shard_tiles_weighted)"}
+            "parity_check": {"tiles": 2 * world, "ok": True},
+            "sharding": "contiguous tile slabs cut by estimated cost (shard.tile_costs), re-cut once by the time every rank measured (shard.refine_costs)",
+            "sharding_rounds": rounds}
 
 
 def run_native(args, rank, world, local_rank):

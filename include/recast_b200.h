@@ -412,9 +412,9 @@ void rcb_result_free(rcb_result* res);
  *   rcb_multi_upload_mesh   the mesh goes host -> devices[0] once and from there to the other devices (peer copy over NVLink);
  *                           indices are validated as in rcb_upload_mesh.
  *   rcb_multi_build_tiles   tiles are independent (no halo, border_size 0 on every multi-tile path of the reference), so the
- *                           configurations are cut into groups of `tiles_per_group` consecutive tiles (<= 0: about eight
- *                           groups per device) and one internal host thread per device pulls groups from a shared counter
- *                           until none is left: a device that finishes early takes more (work stealing).  No data moves
+ *                           configurations are cut into groups of `tiles_per_group` consecutive tiles (<= 0: about four
+ *                           groups per device) and one internal host thread per device works through its own share of
+ *                           the groups, then steals from the device with the most left (work stealing).  No data moves
  *                           between devices.  download != 0: every group's result is also copied to pinned host memory by
  *                           its device's thread (rcb_multi_result_tile then works at once).
  *   rcb_multi_result_*      as rcb_result_*: tile indices are those of `cfgs`; rcb_multi_result_tile_device also reports the

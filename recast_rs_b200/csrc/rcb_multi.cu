@@ -4,13 +4,14 @@
 //
 // Tiles are independent units (no halo, border_size 0), so nothing but the mesh and the results ever moves:
 //   * the mesh is uploaded ONCE (host -> first device) and handed to the other devices over NVLink (cudaMemcpyPeer);
-//   * the tiles are cut into groups of consecutive tiles; one host thread per device pulls groups from a shared atomic
-//     counter (work stealing: a device that finishes early simply takes more groups - the static slabs of round 1 lost
-//     24 % on BASELINE config 3, whose buildings are unevenly spread) and runs the ordinary single-device pipeline
-//     (rcb_build_tiles) on each, two groups in flight per device;
+//   * the tiles are cut into groups of consecutive tiles; one host thread per device works through its own share of the
+//     groups and then steals from the device with the most left (the static slabs of round 1 lost 24 % on BASELINE
+//     config 3, whose buildings are unevenly spread), running the ordinary single-device pipeline (rcb_build_tiles) on
+//     each group, two groups in flight per device;
 //   * a group meets mostly triangles that lie elsewhere; k_bin_count skips them 256 at a time (MeshView::blocks).
 // Built on the public single-device entry points of rcb_api.cu; no collective is involved.
 #include <atomic>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -142,9 +143,9 @@ int rcb_multi_build_tiles(rcb_multi* m, const rcb_config* cfgs, int ntiles, uint
     *out = nullptr;
     const int ndev = (int)m->devices.size();
     if (tiles_per_group <= 0) {
-        // about eight groups per device: a straggler costs at most 1/8 of a device's share, and a group is still thousands
-        // of cells' worth of kernels
-        tiles_per_group = (ntiles + 8 * ndev - 1) / (8 * ndev);
+        // about four groups per device: a straggler costs at most a quarter of a device's share before the others step in,
+        // and the fixed cost of a build (a dozen small launches) stays a few per cent of a group
+        tiles_per_group = (ntiles + 4 * ndev - 1) / (4 * ndev);
         if (tiles_per_group < 1) tiles_per_group = 1;
     }
     auto* res = new rcb_multi_result();
@@ -156,7 +157,20 @@ int rcb_multi_build_tiles(rcb_multi* m, const rcb_config* cfgs, int ntiles, uint
     res->group_res.assign(ngroups, nullptr);
     res->group_dev.assign(ngroups, -1);
     res->dev_ms.assign(ndev, 0.0);
-    std::atomic<int> next{0};
+    // Every device starts on its own contiguous share of the groups (the same (group, device) pairs build after build, so
+    // each context already knows the group's sizes and issues it without a host round trip) and, when that is used up,
+    // steals from the back of the share with the most groups left.
+    std::mutex qm;
+    std::vector<int> lo(ndev), hi(ndev);
+    for (int d = 0; d < ndev; ++d) lo[d] = (int)((long long)ngroups * d / ndev), hi[d] = (int)((long long)ngroups * (d + 1) / ndev);
+    auto take = [&](int d) -> int {
+        std::lock_guard<std::mutex> lk(qm);
+        if (lo[d] < hi[d]) return lo[d]++;
+        int victim = -1;
+        for (int k = 0; k < ndev; ++k)
+            if (hi[k] - lo[k] > (victim < 0 ? 0 : hi[victim] - lo[victim])) victim = k;
+        return victim < 0 ? -1 : --hi[victim];
+    };
     std::vector<int> status(ndev, RCB_OK);
     std::vector<std::string> msg(ndev);
     auto worker = [&](int d) {
@@ -170,8 +184,8 @@ int rcb_multi_build_tiles(rcb_multi* m, const rcb_config* cfgs, int ntiles, uint
             if (r != RCB_OK && status[d] == RCB_OK) status[d] = r, msg[d] = rcb_last_error(ctx);
         };
         for (;;) {
-            const int g = next.fetch_add(1);
-            if (g >= ngroups || status[d] != RCB_OK) break;
+            const int g = status[d] == RCB_OK ? take(d) : -1;
+            if (g < 0) break;
             const int first = res->group_first[g], n = res->group_first[g + 1] - first;
             rcb_result* r = nullptr;
             const int rc = rcb_build_tiles(ctx, cfgs + first, n, stage_mask, erode_radius, &r);

@@ -82,16 +82,36 @@ def tile_costs(verts: np.ndarray, tris: np.ndarray, cfgs: Sequence[RecastConfig]
     return grid[tz, tx] + 2.0 * cells
 
 
-def shard_tiles_weighted(verts: np.ndarray, tris: np.ndarray, cfgs: Sequence[RecastConfig], rank: int, world: int) -> np.ndarray:
-    """Contiguous slabs like shard_tiles(mode='slab'), but cut where the cumulative estimated COST (tile_costs)
-    crosses k/world of the total: uneven worlds (config 3's buildings) then take about the same time on every
-    rank.  The static alternative to a work-stealing queue (BASELINE.json north_star allows either)."""
-    cost = np.cumsum(tile_costs(verts, tris, cfgs))
-    total = cost[-1] if len(cost) else 0.0
-    cuts = [0] + [int(np.searchsorted(cost, total * k / world)) for k in range(1, world)] + [len(cfgs)]
+def cut_by_cost(cost: np.ndarray, world: int) -> List[int]:
+    """world + 1 tile indices: slab k = tiles [cuts[k], cuts[k+1]), cut where the cumulative cost crosses k/world of the total."""
+    cum = np.cumsum(cost)
+    total = cum[-1] if len(cum) else 0.0
+    cuts = [0] + [int(np.searchsorted(cum, total * k / world)) for k in range(1, world)] + [len(cost)]
     for k in range(1, len(cuts)):
         cuts[k] = max(cuts[k], cuts[k - 1])
+    return cuts
+
+
+def shard_tiles_weighted(verts: np.ndarray, tris: np.ndarray, cfgs: Sequence[RecastConfig], rank: int, world: int,
+                         cost: np.ndarray | None = None) -> np.ndarray:
+    """Contiguous slabs like shard_tiles(mode='slab'), but cut where the cumulative estimated COST (tile_costs, or the
+    given per-tile costs) crosses k/world of the total: uneven worlds (config 3's buildings) then take about the same
+    time on every rank.  The static alternative to a work-stealing queue (BASELINE.json north_star allows either)."""
+    cuts = cut_by_cost(tile_costs(verts, tris, cfgs) if cost is None else cost, world)
     return np.arange(cuts[rank], cuts[rank + 1], dtype=np.int64)
+
+
+def refine_costs(cost: np.ndarray, cuts: Sequence[int], measured_ms: Sequence[float]) -> np.ndarray:
+    """One round of feedback for a static partition: every slab's tiles are re-priced so that the slab's estimated cost
+    matches the time its rank measured (the estimate's error is mostly a per-region factor: how many buildings, how
+    steep).  Cutting the re-priced costs again (cut_by_cost) moves tiles from slow ranks to fast ones."""
+    out = np.asarray(cost, dtype=np.float64).copy()
+    for k, ms in enumerate(measured_ms):
+        lo, hi = cuts[k], cuts[k + 1]
+        est = out[lo:hi].sum()
+        if hi > lo and est > 0 and ms > 0:
+            out[lo:hi] *= ms / est
+    return out
 
 
 def gather_tile_counts(local_ids: np.ndarray, local_counts: np.ndarray, ntiles: int, world: int) -> np.ndarray:

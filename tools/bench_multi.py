@@ -41,6 +41,6 @@ with rb.MultiContext(list(range(ndev))) as m:
         r.free()
     T = t.size // 3
     print(json.dumps({"entry": "rcb_multi_build_tiles", "config": cfgno, "n_devices": ndev, "tiles": len(cfgs), "triangles": T,
-                      "tiles_per_group": tpg or "default (8 groups per device)", "upload_mesh_ms": up_ms, "ms_per_build_median": float(np.median(ms)),
+                      "tiles_per_group": tpg or "default (4 groups per device)", "upload_mesh_ms": up_ms, "ms_per_build_median": float(np.median(ms)),
                       "ms_per_build_min": float(min(ms)), "triangles_per_s": T / (float(np.median(ms)) * 1e-3), "tiles_per_device_last_build": last,
                       "timing": "host wall clock around rcb_multi_build_tiles + rcb_multi_result_totals (which waits for every group)"}))
