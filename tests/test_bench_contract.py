@@ -48,13 +48,14 @@ def test_committed_headline_profile_is_a_contract_line():
     import glob
     import re
 
-    files = [(int(m.group(1)), f) for f in glob.glob(os.path.join(ROOT, "profiles", "r01_bench_v*.json"))
-             if (m := re.fullmatch(r"r01_bench_v(\d+)\.json", os.path.basename(f)))]
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9]_bench.json")))  # one headline line per round from round 2 on
     assert files
-    d = json.load(open(max(files)[1]))
+    d = json.load(open(files[-1]))
     assert BASE_KEYS | {"gpu_launches", "clocks", "roofline"} <= set(d) and "impl" not in d
     assert d["n_gpus"] == 1 and d["config"]["workload"].startswith("config2") and d["gpu_launches"] > 0
     r = d["roofline"]
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"]
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert d["parity_check"]["ok"] and d["issue"]["steps_rebuilt"] == 0 and r["issue_roofline"]["kernels"]
+    assert 0 < d["e2e"]["value"] < d["value"] and d["e2e"]["d2h_bytes_per_step"] < d["e2e"]["full_layout"]["d2h_bytes_per_step"]
     assert d["steps"] * d["config"]["totals_rank0"]["triangles"] / (d["ms_per_step"] * d["steps"] * 1e-3) == pytest.approx(d["value"], rel=1e-6)
