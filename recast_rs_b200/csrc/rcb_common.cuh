@@ -101,9 +101,6 @@ struct MeshView {
 #define RCB_MESH_BLOCK 256
 void launch_widen_indices(const uint16_t* src_or_null, int32_t* dst, size_t n, cudaStream_t s);
 void launch_mesh_blocks(const float* verts, const int32_t* tris, uint32_t ntris, uint32_t nverts, float4* blocks, cudaStream_t s);
-struct RcbUnused_ {
-    int unused;
-};
 
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }

@@ -242,3 +242,21 @@ def test_gpu_tilecache_compressed_config5_matches_packed_route():
                 x, y = a.tile(i), b.tile(i)
                 for k in ("span_min", "span_area", "areas", "con", "conn_ref", "conn_dir"):
                     assert np.array_equal(getattr(x, k), getattr(y, k)), (i, k)
+
+
+@pytest.mark.gpu
+def test_gpu_decompress_huge_size_prefix_allocates_by_the_input(oracle):
+    """a 4-byte size prefix is untrusted.  A valid small block behind a prefix of 256 MiB decodes to the block's bytes
+    (lz4_flex allocates the prefix and returns the bytes produced); the device scratch must follow LZ4's 255x ceiling on the
+    INPUT, not the prefix - 64 such blobs would otherwise ask for 16 GiB of device memory (and be refused)."""
+    import recast_rs_b200.builder as rb
+
+    rng = np.random.default_rng(7)
+    payload = bytes(rng.integers(0, 4, 3000, dtype=np.uint8))
+    z = _compress(payload)
+    huge = (1 << 28).to_bytes(4, "little") + z[4:]
+    want = _oracle_dec(oracle, huge)
+    assert want == payload  # the oracle (lz4_flex's rule): fewer bytes than the prefix says, no error
+    with rb.Context(0) as ctx:
+        got = ctx.decompress_tiles([huge] * 64 + [z])
+        assert all(g == payload for g in got)
