@@ -66,12 +66,16 @@ enum {
      *                     next -> the one pushed before, first_connection = the last pushed), so
      *                     first_conn[s] = (connections of spans <= s) - 1 (or NONE), conn_dir = the mask's bits from 7 down,
      *                     conn_next[k] = k - 1 inside a span's block, NONE at its start;
-     *   conn_ref16[K]     conn_ref (tile-relative span indices) as u16 - with conn_ref = NULL - unless a tile holds 65536+
-     *                     spans: then conn_ref (u32) is there and conn_ref16 = NULL;
+     *   conn_off8[K]      per connection, the OFFSET of the span it reaches inside that span's cell (u8).  The cell is the
+     *                     neighbour cell of the connection's direction (DIR_OFFSET_X/Z, compact_heightfield.rs:109-111), its
+     *                     first span is cell_index, so conn_ref[k] = cell_index[neighbour cell] + conn_off8[k]; and con[d4] of
+     *                     the span is the same offset for the four cardinal directions (7 -> 0, 5 -> 1, 3 -> 2, 1 -> 3,
+     *                     :397-427), 63 where the mask has none.  conn_ref = conn_ref16 = con = con8 = NULL then.
+     *                     Should an offset pass 255 (a cell with 257+ spans) conn_off8 = NULL and the references and con are
+     *                     there instead: conn_ref16 (u16; conn_ref u32 if a tile holds 65536+ spans), con8 (u8; con if an
+     *                     offset passes 255 there too);
      *   cell_count16[C]   cell_count_arr as u16 (cell_count_arr = NULL; the wide one instead should a cell hold 65536+ spans);
      *                     hf_cell_offset is its exclusive prefix sum, cell_index the same with NONE for empty cells;
-     *   con8[4*S]         con as u8 (con = NULL; the wide one instead should a cell hold more than 256 spans - the values are
-     *                     offsets inside the neighbour cell, 63 = none);
      *   areas             NULL while CompactHeightfield.areas still equals CompactSpan.area (span_area): nothing that writes
      *                     it ran (no ERODE, no area operator, no areas_override).
      * INTEGRATION.md has the rebuild loop.  Device views (rcb_result_tile_device) always carry the full arrays. */
@@ -156,6 +160,7 @@ typedef struct rcb_tile_view {
     const uint16_t* conn_ref16;     /* [K]  RCB_RESULT_SLIM only: conn_ref in 16 bits (NULL when a tile has 65536+ spans) */
     const uint16_t* cell_count16;   /* [C]  RCB_RESULT_SLIM only: cell_count_arr in 16 bits */
     const uint8_t* con8;            /* [4*S] RCB_RESULT_SLIM only: con in 8 bits */
+    const uint8_t* conn_off8;       /* [K]  RCB_RESULT_SLIM only: offset of the connected span inside its (neighbour) cell */
 } rcb_tile_view;
 
 /* ---- context ------------------------------------------------------------------------------ */

@@ -33,7 +33,7 @@ class RcbTileView(ctypes.Structure):
         ("cell_index", _vp), ("cell_count_arr", _vp), ("areas", _vp), ("con", _vp), ("first_conn", _vp),
         ("conn_ref", _vp), ("conn_dir", _vp), ("conn_next", _vp), ("dist", _vp),
         ("reg", _vp), ("max_regions", _u32), ("_pad", _u32),
-        ("conn_mask", _vp), ("conn_ref16", _vp), ("cell_count16", _vp), ("con8", _vp),
+        ("conn_mask", _vp), ("conn_ref16", _vp), ("cell_count16", _vp), ("con8", _vp), ("conn_off8", _vp),
     ]
 
 

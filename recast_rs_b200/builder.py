@@ -69,6 +69,7 @@ class TileVoxels:
     conn_ref16: Optional[np.ndarray] = None  # RESULT_SLIM: u16[K] conn_ref (None when a tile holds 65536+ spans)
     cell_count16: Optional[np.ndarray] = None  # RESULT_SLIM: u16[C] cell_count
     con8: Optional[np.ndarray] = None  # RESULT_SLIM: u8[4S] con
+    conn_off8: Optional[np.ndarray] = None  # RESULT_SLIM: u8[K] offset of the connected span inside its (neighbour) cell
 
     def expand_slim(self) -> "TileVoxels":
         """Rebuilds, on the host, the arrays a RESULT_SLIM download leaves out, from the layout rule of
@@ -80,8 +81,6 @@ class TileVoxels:
         S = self.span_count
         if self.cell_count is None:
             self.cell_count = self.cell_count16.astype(np.uint32)
-        if self.con is None:
-            self.con = self.con8.astype(np.uint16)
         if self.areas is None:  # nothing wrote CompactHeightfield.areas: still the copy of CompactSpan.area it starts as
             self.areas = self.span_area.copy()
         self.hf_cell_offset = np.concatenate([[0], np.cumsum(self.cell_count, dtype=np.uint64)]).astype(np.uint32)
@@ -95,8 +94,26 @@ class TileVoxels:
         nxt = np.arange(-1, K - 1, dtype=np.int64)
         nxt[(ends - cnt)[cnt > 0]] = NONE  # the first connection pushed of every block
         self.conn_next = nxt.astype(np.uint32)
-        if self.conn_ref is None:
-            self.conn_ref = self.conn_ref16.astype(np.uint32)
+        if self.conn_off8 is not None:
+            # conn_ref = first span of the neighbour cell (by direction) + offset; con = the offsets of the cardinal directions
+            span_cell = np.repeat(np.arange(self.cell_count.size, dtype=np.int64), self.cell_count)
+            owner = np.repeat(np.arange(S, dtype=np.int64), cnt)  # the span every connection belongs to
+            d = self.conn_dir.astype(np.int64)
+            dx = np.array([-1, 0, 1, 1, 1, 0, -1, -1], np.int64)  # compact_heightfield.rs:109-111
+            dz = np.array([-1, -1, -1, 0, 1, 1, 1, 0], np.int64)
+            ncell = span_cell[owner] + dz[d] * self.width + dx[d]
+            off = self.conn_off8.astype(np.int64)
+            self.conn_ref = (self.cell_index[ncell].astype(np.int64) + off).astype(np.uint32)
+            con = np.full((S, 4), 63, np.uint16)
+            d4 = np.array([-1, 3, -1, 2, -1, 1, -1, 0], np.int64)[d]  # 8-direction -> con slot (:397-427), -1: diagonal
+            card = d4 >= 0
+            con[owner[card], d4[card]] = off[card].astype(np.uint16)
+            self.con = con.reshape(-1)
+        else:
+            if self.conn_ref is None:
+                self.conn_ref = self.conn_ref16.astype(np.uint32)
+            if self.con is None:
+                self.con = self.con8.astype(np.uint16)
         assert K == self.conn_count
         return self
 
@@ -113,18 +130,21 @@ def _tile_from_view(v, expand: bool = True) -> "TileVoxels":
             tv.hf_cell_offset = None
             tv.conn_mask = _np_from(v.conn_mask, S, np.uint8)
             tv.areas = _np_from(v.areas, S, np.uint8) if v.areas else None
-            if v.conn_ref16:
-                tv.conn_ref16 = _np_from(v.conn_ref16, K, np.uint16)
-            else:
-                tv.conn_ref = _np_from(v.conn_ref, K, np.uint32)
             if v.cell_count16:
                 tv.cell_count16 = _np_from(v.cell_count16, C, np.uint16)
             else:
                 tv.cell_count = _np_from(v.cell_count_arr, C, np.uint32)
-            if v.con8:
-                tv.con8 = _np_from(v.con8, 4 * S, np.uint8)
-            else:
-                tv.con = _np_from(v.con, 4 * S, np.uint16)
+            if v.conn_off8:
+                tv.conn_off8 = _np_from(v.conn_off8, K, np.uint8)
+            else:  # an offset passed 255: references and con in the narrowest form that holds them
+                if v.conn_ref16:
+                    tv.conn_ref16 = _np_from(v.conn_ref16, K, np.uint16)
+                else:
+                    tv.conn_ref = _np_from(v.conn_ref, K, np.uint32)
+                if v.con8:
+                    tv.con8 = _np_from(v.con8, 4 * S, np.uint8)
+                else:
+                    tv.con = _np_from(v.con, 4 * S, np.uint16)
             if expand:
                 tv.expand_slim()
         else:

@@ -222,39 +222,50 @@ __global__ void __launch_bounds__(256) k_write_connections2(uint32_t S, const ui
 }
 
 // Slim result layout (RCB_RESULT_SLIM): what the host cannot rebuild from the layout rule of compact_heightfield.rs:375-389
-// is WHICH directions a span is connected in - one byte per span - and the neighbour per connection.  first_connection,
-// next and dir follow from the mask (blocks in span order, directions descending inside a block).  The other arrays go out
-// in the narrowest form that holds them: span references and cell counts in 16 bits, the four con offsets in 8 (flag bits 1,
-// 4, 2 say where a value did not fit; the host then takes the wide array).
+// is WHICH directions a span is connected in - one byte per span (conn_mask) - and, per connection, which span of the
+// neighbour cell it reaches: its offset inside that cell, one byte (conn_off8; the cell is known from the direction, its
+// first span from the cell counts).  first_connection, next, dir, ref and con all follow.  The wider forms (conn_ref16, con8)
+// are derived as well and travel only when an offset passes 255; flag bits 8 / 1 / 2 / 4 say what did not fit
+// (offset in 8 bits, reference in 16, con in 8, cell count in 16).
 __global__ void __launch_bounds__(256) k_slim_pack(const TileDesc* __restrict__ tiles, const TileInfo* __restrict__ tinfo,
                                                    const uint32_t* __restrict__ first_conn, const uint32_t* __restrict__ conn_ref,
                                                    const uint8_t* __restrict__ conn_dir, const uint32_t* __restrict__ conn_next,
-                                                   const uint32_t* __restrict__ cell_count, const uint16_t* __restrict__ con,
-                                                   uint8_t* __restrict__ conn_mask, uint16_t* __restrict__ conn_ref16,
+                                                   const uint32_t* __restrict__ cell_index, const uint32_t* __restrict__ cell_count,
+                                                   const uint16_t* __restrict__ con, uint8_t* __restrict__ conn_mask,
+                                                   uint16_t* __restrict__ conn_ref16, uint8_t* __restrict__ conn_off8,
                                                    uint16_t* __restrict__ cell_count16, uint8_t* __restrict__ con8,
                                                    unsigned long long* __restrict__ flag) {
     const TileInfo ti = tinfo[blockIdx.x];
     const TileDesc& td = tiles[blockIdx.x];
-    const uint32_t C = (uint32_t)(td.width * td.height);
+    const int W = td.width;
+    const uint32_t C = (uint32_t)(W * td.height);
     unsigned wide = 0;
-    for (uint32_t s = blockIdx.y * 256u + threadIdx.x; s < ti.span_count; s += gridDim.y * 256u) {
-        uint32_t mask = 0;
-        for (uint32_t k = first_conn[ti.span_base + s]; k != RCB_NONE; k = conn_next[ti.conn_base + k]) mask |= 1u << conn_dir[ti.conn_base + k];
-        conn_mask[ti.span_base + s] = (uint8_t)mask;
-        const uint2 c4 = *reinterpret_cast<const uint2*>(con + 4ull * (ti.span_base + s));  // 4 x u16, 8-byte aligned
-        const uint32_t c0 = c4.x & 0xffffu, c1 = c4.x >> 16, c2 = c4.y & 0xffffu, c3 = c4.y >> 16;
-        if ((c0 | c1 | c2 | c3) > 0xffu) wide |= 2u;
-        *reinterpret_cast<uint32_t*>(con8 + 4ull * (ti.span_base + s)) = (c0 & 0xffu) | ((c1 & 0xffu) << 8) | ((c2 & 0xffu) << 16) | (c3 << 24);
-    }
-    for (uint32_t k = blockIdx.y * 256u + threadIdx.x; k < ti.conn_count; k += gridDim.y * 256u) {
-        const uint32_t r = conn_ref[ti.conn_base + k];
-        if (r > 0xffffu) wide |= 1u;
-        conn_ref16[ti.conn_base + k] = (uint16_t)r;
-    }
     for (uint32_t c = blockIdx.y * 256u + threadIdx.x; c < C; c += gridDim.y * 256u) {
         const uint32_t n = cell_count[td.cell_base + c];
         if (n > 0xffffu) wide |= 4u;
         cell_count16[td.cell_base + c] = (uint16_t)n;
+        if (n == 0) continue;
+        const uint32_t first = cell_index[td.cell_base + c];
+        for (uint32_t s = first; s < first + n; ++s) {
+            uint32_t mask = 0;
+            for (uint32_t k = first_conn[ti.span_base + s]; k != RCB_NONE; k = conn_next[ti.conn_base + k]) {
+                const uint32_t d = conn_dir[ti.conn_base + k];
+                mask |= 1u << d;
+                // the neighbour cell of direction d exists (there is a connection into it) and is not empty
+                const uint32_t nc = (uint32_t)((int)c + c_dirz[d] * W + c_dirx[d]);
+                const uint32_t r = conn_ref[ti.conn_base + k];
+                const uint32_t off = r - cell_index[td.cell_base + nc];
+                if (off > 0xffu) wide |= 8u;
+                if (r > 0xffffu) wide |= 1u;
+                conn_off8[ti.conn_base + k] = (uint8_t)off;
+                conn_ref16[ti.conn_base + k] = (uint16_t)r;
+            }
+            conn_mask[ti.span_base + s] = (uint8_t)mask;
+            const uint2 c4 = *reinterpret_cast<const uint2*>(con + 4ull * (ti.span_base + s));  // 4 x u16, 8-byte aligned
+            const uint32_t c0 = c4.x & 0xffffu, c1 = c4.x >> 16, c2 = c4.y & 0xffffu, c3 = c4.y >> 16;
+            if ((c0 | c1 | c2 | c3) > 0xffu) wide |= 2u;
+            *reinterpret_cast<uint32_t*>(con8 + 4ull * (ti.span_base + s)) = (c0 & 0xffu) | ((c1 & 0xffu) << 8) | ((c2 & 0xffu) << 16) | (c3 << 24);
+        }
     }
     wide = __reduce_or_sync(0xffffffffu, wide);
     if (wide && (threadIdx.x & 31) == 0) atomicOr(flag, (unsigned long long)wide);
@@ -263,17 +274,16 @@ __global__ void __launch_bounds__(256) k_slim_pack(const TileDesc* __restrict__ 
 }  // namespace
 
 void launch_slim_pack(const TileDesc* tiles, const TileInfo* tinfo, int ntiles, uint32_t max_cells, const uint32_t* first_conn,
-                      const uint32_t* conn_ref, const uint8_t* conn_dir, const uint32_t* conn_next, const uint32_t* cell_count,
-                      const uint16_t* con, uint8_t* conn_mask, uint16_t* conn_ref16, uint16_t* cell_count16, uint8_t* con8,
-                      unsigned long long* flag, cudaStream_t s) {
+                      const uint32_t* conn_ref, const uint8_t* conn_dir, const uint32_t* conn_next, const uint32_t* cell_index,
+                      const uint32_t* cell_count, const uint16_t* con, uint8_t* conn_mask, uint16_t* conn_ref16, uint8_t* conn_off8,
+                      uint16_t* cell_count16, uint8_t* con8, unsigned long long* flag, cudaStream_t s) {
     if (ntiles == 0) return;
     KScope _k("k_slim_pack", s);
-    // connections outnumber cells several times: a block walks ~8 k of them
-    const unsigned gy = std::max(1u, std::min(64u, (max_cells + 2047u) / 2048u));
+    const unsigned gy = std::max(1u, std::min(64u, (max_cells + 1023u) / 1024u));  // a block takes ~1 k cells
     for (int t0 = 0; t0 < ntiles; t0 += 65535) {
         const int n = std::min(65535, ntiles - t0);
-        k_slim_pack<<<dim3((unsigned)n, gy), 256, 0, s>>>(tiles + t0, tinfo + t0, first_conn, conn_ref, conn_dir, conn_next, cell_count, con,
-                                                          conn_mask, conn_ref16, cell_count16, con8, flag);
+        k_slim_pack<<<dim3((unsigned)n, gy), 256, 0, s>>>(tiles + t0, tinfo + t0, first_conn, conn_ref, conn_dir, conn_next, cell_index, cell_count,
+                                                          con, conn_mask, conn_ref16, conn_off8, cell_count16, con8, flag);
     }
 }
 

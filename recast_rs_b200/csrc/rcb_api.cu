@@ -58,7 +58,7 @@ struct ArenaLayout {  // byte offsets inside arena A (cells + spans) and arena B
     bool areas_in_slim;         // chf.areas differs from CompactSpan.area (erosion, area operators): part of the slim download
     size_t bytesA;
     size_t slimA;  // the arrays a slim download copies are the first slimA bytes of arena A
-    size_t conn_ref, conn_dir, conn_next, conn_ref16;
+    size_t conn_ref, conn_dir, conn_next, conn_ref16, conn_off8;
     size_t bytesB;
     size_t slimB;
     uint64_t Scap, Kcap;  // the span / connection counts the offsets were computed for (>= the real ones)
@@ -178,6 +178,8 @@ struct rcb_result {
     cudaEvent_t done = nullptr;
     int redo_erode = 0;  // what a failed speculation needs to run again (the configurations are entry->cfgs)
     bool slim = false;         // RCB_RESULT_SLIM: conn_mask / conn_ref16 exist, the download copies the slim prefix only
+    bool slim_off8 = false;    // conn_off8 is valid (every connection's offset inside the neighbour cell fits 8 bits): the
+                               // host copy then holds neither conn_ref16 nor con8
     bool slim_ref16 = false;   // conn_ref16 is valid (every tile-relative span index fits 16 bits)
     bool slim_con8 = false;    // con8 is valid (every offset inside a neighbour cell fits 8 bits)
     bool slim_cnt16 = false;   // cell_count16 is valid (no cell holds 65536+ spans)
@@ -539,8 +541,8 @@ void make_layout(ArenaLayout& l, int ntiles, uint64_t C, uint64_t S, uint32_t st
     l.reg = put((stage_mask & RCB_STAGE_REGIONS) ? 2 * S : 0);
     l.conn_mask = put(slim ? S : 0);
     l.cell_count16 = put(slim ? 2 * C : 0);
-    l.con8 = put(slim ? 4 * S : 0);
     l.slimA = o;
+    l.con8 = put(slim ? 4 * S : 0);  // travels only when a connection's offset does not fit conn_off8
     if (!l.areas_in_slim) l.areas = put(compact ? S : 0);
     l.cell_index = put(compact ? 4 * C : 0);
     l.cell_count = put(compact ? 4 * C : 0);
@@ -557,8 +559,9 @@ void make_layout_conn(ArenaLayout& l, uint64_t K, bool slim) {
         o = align_up(o + bytes);
         return r;
     };
-    l.conn_ref16 = put(slim ? 2 * K : 0);
+    l.conn_off8 = put(slim ? K : 0);
     l.slimB = o;
+    l.conn_ref16 = put(slim ? 2 * K : 0);  // travels only when an offset does not fit conn_off8
     l.conn_ref = put(4 * K);
     l.conn_next = put(4 * K);
     l.conn_dir = put(K);
@@ -1502,7 +1505,7 @@ void adopt_result(rcb_result* res, rcb_result* from) {
     res->tinfo.swap(from->tinfo);
     res->entry = from->entry;
     res->slim_ref16 = from->slim_ref16, res->slim_host = from->slim_host, res->slim_packed = from->slim_packed;
-    res->slim_con8 = from->slim_con8, res->slim_cnt16 = from->slim_cnt16;
+    res->slim_con8 = from->slim_con8, res->slim_cnt16 = from->slim_cnt16, res->slim_off8 = from->slim_off8;
     res->pending = false;
     res->spec = false;
 }
@@ -2471,9 +2474,10 @@ static int slim_pack(rcb_result* res, cudaStream_t st) {
     CU(cudaMemsetAsync(ctx->d_wire_err.p, 0, 8, st));
     launch_slim_pack(res->entry->d_tiles.as<TileDesc>(), (const TileInfo*)(A + res->lay.tinfo), res->ntiles, res->entry->max_cells,
                      (const uint32_t*)(A + res->lay.first_conn), (const uint32_t*)(B + res->lay.conn_ref),
-                     (const uint8_t*)(B + res->lay.conn_dir), (const uint32_t*)(B + res->lay.conn_next), (const uint32_t*)(A + res->lay.cell_count),
-                     (const uint16_t*)(A + res->lay.con), (uint8_t*)(A + res->lay.conn_mask), (uint16_t*)(B + res->lay.conn_ref16),
-                     (uint16_t*)(A + res->lay.cell_count16), (uint8_t*)(A + res->lay.con8), ctx->d_wire_err.as<unsigned long long>(), st);
+                     (const uint8_t*)(B + res->lay.conn_dir), (const uint32_t*)(B + res->lay.conn_next), (const uint32_t*)(A + res->lay.cell_index),
+                     (const uint32_t*)(A + res->lay.cell_count), (const uint16_t*)(A + res->lay.con), (uint8_t*)(A + res->lay.conn_mask),
+                     (uint16_t*)(B + res->lay.conn_ref16), (uint8_t*)(B + res->lay.conn_off8), (uint16_t*)(A + res->lay.cell_count16),
+                     (uint8_t*)(A + res->lay.con8), ctx->d_wire_err.as<unsigned long long>(), st);
     CU(cudaMemcpyAsync(res->slim_flag, ctx->d_wire_err.p, 8, cudaMemcpyDeviceToHost, st));
     return RCB_OK;
 }
@@ -2546,16 +2550,24 @@ static int finish_download(rcb_result* res, cudaStream_t st) {
         return download_on(res, ctx->stream, true);
     }
     if (res->slim) {
-        const unsigned long long f = res->slim_flag ? *res->slim_flag : (res->ntiles == 0 ? 0ull : 7ull);
-        res->slim_ref16 = !(f & 1ull), res->slim_con8 = !(f & 2ull), res->slim_cnt16 = !(f & 4ull);
+        const unsigned long long f = res->slim_flag ? *res->slim_flag : (res->ntiles == 0 ? 0ull : 15ull);
+        res->slim_ref16 = !(f & 1ull), res->slim_con8 = !(f & 2ull), res->slim_cnt16 = !(f & 4ull), res->slim_off8 = !(f & 8ull);
         bool more = false;
-        if (!res->slim_ref16 && res->K) {  // a tile with 65536+ spans: its span references need the 32-bit array after all
-            CU(cudaMemcpyAsync(res->hostB.p + res->lay.conn_ref, res->devB.p + res->lay.conn_ref, 4 * res->K, cudaMemcpyDeviceToHost, st));
-            res->copied_bytes += 4 * res->K, more = true;
-        }
-        if (!res->slim_con8 && res->S) {  // a cell with 257+ spans: offsets inside it need the 16-bit con
-            CU(cudaMemcpyAsync(res->hostA.p + res->lay.con, res->devA.p + res->lay.con, 8 * res->S, cudaMemcpyDeviceToHost, st));
-            res->copied_bytes += 8 * res->S, more = true;
+        if (!res->slim_off8) {
+            // a connection whose offset inside the neighbour cell passes 255 (a cell with 257+ spans): the references and
+            // con travel after all, each in the narrowest form that holds it
+            if (res->slim_ref16 && res->K) {
+                CU(cudaMemcpyAsync(res->hostB.p + res->lay.conn_ref16, res->devB.p + res->lay.conn_ref16, 2 * res->K, cudaMemcpyDeviceToHost, st));
+                res->copied_bytes += 2 * res->K, more = true;
+            } else if (res->K) {
+                CU(cudaMemcpyAsync(res->hostB.p + res->lay.conn_ref, res->devB.p + res->lay.conn_ref, 4 * res->K, cudaMemcpyDeviceToHost, st));
+                res->copied_bytes += 4 * res->K, more = true;
+            }
+            if (res->S) {
+                const size_t off = res->slim_con8 ? res->lay.con8 : res->lay.con, n = (res->slim_con8 ? 4 : 8) * res->S;
+                CU(cudaMemcpyAsync(res->hostA.p + off, res->devA.p + off, n, cudaMemcpyDeviceToHost, st));
+                res->copied_bytes += n, more = true;
+            }
         }
         if (!res->slim_cnt16 && res->Ctot) {
             CU(cudaMemcpyAsync(res->hostA.p + res->lay.cell_count, res->devA.p + res->lay.cell_count, 4 * res->Ctot, cudaMemcpyDeviceToHost, st));
@@ -2628,20 +2640,26 @@ static int fill_view(const rcb_result* res, int tile, rcb_tile_view* v, const ch
                 v->cell_count16 = (const uint16_t*)(A + l.cell_count16) + td.cell_base;
             else
                 v->cell_count_arr = (const uint32_t*)(A + l.cell_count) + td.cell_base;
-            if (res->slim_con8)
-                v->con8 = (const uint8_t*)(A + l.con8) + 4 * (size_t)ti.span_base;
-            else
-                v->con = (const uint16_t*)(A + l.con) + 4 * (size_t)ti.span_base;
+            if (!res->slim_off8) {
+                if (res->slim_con8)
+                    v->con8 = (const uint8_t*)(A + l.con8) + 4 * (size_t)ti.span_base;
+                else
+                    v->con = (const uint16_t*)(A + l.con) + 4 * (size_t)ti.span_base;
+            }
         }
         if (res->slim && res->slim_packed) {
             v->conn_mask = (const uint8_t*)(A + l.conn_mask) + ti.span_base;
-            if (!host || res->slim_ref16)
-                v->conn_ref16 = (const uint16_t*)(B + l.conn_ref16) + ti.conn_base;
-            else
-                v->conn_ref = (const uint32_t*)(B + l.conn_ref) + ti.conn_base;
             if (!host) {
+                v->conn_off8 = (const uint8_t*)(B + l.conn_off8) + ti.conn_base;
+                v->conn_ref16 = (const uint16_t*)(B + l.conn_ref16) + ti.conn_base;
                 v->cell_count16 = (const uint16_t*)(A + l.cell_count16) + td.cell_base;
                 v->con8 = (const uint8_t*)(A + l.con8) + 4 * (size_t)ti.span_base;
+            } else if (res->slim_off8) {
+                v->conn_off8 = (const uint8_t*)(B + l.conn_off8) + ti.conn_base;
+            } else if (res->slim_ref16) {
+                v->conn_ref16 = (const uint16_t*)(B + l.conn_ref16) + ti.conn_base;
+            } else {
+                v->conn_ref = (const uint32_t*)(B + l.conn_ref) + ti.conn_base;
             }
         }
         if (res->stage_mask & RCB_STAGE_REGIONS) {

@@ -247,12 +247,12 @@ void launch_tile_segments(const uint32_t* tile_ub, uint32_t* tile_base, int ntil
 void launch_tile_scan(const BandDesc* bands, BandInfo* binfo, int nbands, const TileDesc* tiles, const uint32_t* band_first, TileInfo* tinfo,
                       int ntiles, unsigned long long* counters, unsigned long long span_cap, unsigned long long pub_cap, int compact,
                       const uint32_t* seg_cursor, const uint32_t* seg_cap, cudaStream_t s);
-// slim result layout: conn_mask[s] = the span's directions, conn_ref16 / cell_count16 / con8 = the narrow forms of conn_ref,
-// cell_count, con; *flag |= 1 / 4 / 2 where a value does not fit its narrow form
+// slim result layout: conn_mask[s] = the span's directions, conn_off8[k] = the connection's offset inside the neighbour cell;
+// conn_ref16 / cell_count16 / con8 = narrow forms of conn_ref, cell_count, con; *flag |= 8 / 1 / 4 / 2 where a value does not fit
 void launch_slim_pack(const TileDesc* tiles, const TileInfo* tinfo, int ntiles, uint32_t max_cells, const uint32_t* first_conn,
-                      const uint32_t* conn_ref, const uint8_t* conn_dir, const uint32_t* conn_next, const uint32_t* cell_count,
-                      const uint16_t* con, uint8_t* conn_mask, uint16_t* conn_ref16, uint16_t* cell_count16, uint8_t* con8,
-                      unsigned long long* flag, cudaStream_t s);
+                      const uint32_t* conn_ref, const uint8_t* conn_dir, const uint32_t* conn_next, const uint32_t* cell_index,
+                      const uint32_t* cell_count, const uint16_t* con, uint8_t* conn_mask, uint16_t* conn_ref16, uint8_t* conn_off8,
+                      uint16_t* cell_count16, uint8_t* con8, unsigned long long* flag, cudaStream_t s);
 void launch_tile_compact(const TileCompactArgs& a, int nbands, cudaStream_t s);
 size_t tile_compact_smem_bytes(uint32_t own_cells, uint32_t held_cells, uint32_t held_spans, uint32_t top_spans, uint32_t bot_spans);
 

@@ -96,6 +96,7 @@ pub struct rcb_tile_view {
     pub conn_ref16: *const u16,
     pub cell_count16: *const u16,
     pub con8: *const u8,
+    pub conn_off8: *const u8,
 }
 
 #[repr(C)]

@@ -122,13 +122,13 @@ def test_slim_layout_expands_to_the_full_layout(force_global):
         with ctx.build_tiles(cfgs, rb.STAGE_ALL_BUILD) as full, ctx.build_tiles(cfgs, rb.STAGE_ALL_BUILD | rb.RESULT_SLIM) as slim:
             full.download(), slim.download()
             bf, bs = full.totals()["result_bytes"], slim.totals()["result_bytes"]
-            assert bs < 0.40 * bf, (bs, bf)
+            assert bs < 0.27 * bf, (bs, bf)
             for i in range(len(cfgs)):
                 raw = slim.tile(i, expand=False)
                 assert raw.hf_cell_offset is None and raw.first_conn is None and raw.conn_next is None and raw.conn_dir is None
-                assert raw.conn_mask is not None and raw.conn_ref16 is not None and raw.conn_ref is None
+                assert raw.conn_mask is not None and raw.conn_off8 is not None and raw.conn_ref16 is None and raw.conn_ref is None
                 assert raw.cell_index is None and raw.cell_count is None and raw.cell_count16 is not None
-                assert raw.con is None and raw.con8 is not None and raw.areas is None  # areas == span_area: nothing wrote it
+                assert raw.con is None and raw.con8 is None and raw.areas is None  # areas == span_area: nothing wrote it
                 _same(slim.tile(i), full.tile(i), f"rep {rep} tile {i}")
             dv = slim.tile_device_view(0)  # device views keep the full arrays
             assert dv.first_conn and dv.conn_next and dv.conn_ref and dv.hf_cell_offset
@@ -136,7 +136,8 @@ def test_slim_layout_expands_to_the_full_layout(force_global):
 
 
 def test_slim_layout_with_a_tile_of_more_than_65535_spans():
-    """16-bit span references do not fit: the slim download carries the 32-bit conn_ref instead."""
+    """A tile of 100 k spans: span references would not fit 16 bits, but the slim layout ships offsets inside the neighbour
+    cell, which do."""
     import recast_rs_b200.builder as rb
     from recast_rs_b200 import synth
 
@@ -147,7 +148,7 @@ def test_slim_layout_with_a_tile_of_more_than_65535_spans():
         full.download(), slim.download()
         assert full.tile(0).span_count > 65535
         raw = slim.tile(0, expand=False)
-        assert raw.conn_ref16 is None and raw.conn_ref is not None and raw.conn_mask is not None
+        assert raw.conn_off8 is not None and raw.conn_ref16 is None and raw.conn_ref is None and raw.conn_mask is not None
         _same(slim.tile(0), full.tile(0), "single big tile")
     ctx.close()
 
@@ -270,8 +271,9 @@ def test_bounds_build_reports(request):
 
 
 def test_slim_layout_wide_fallbacks_and_written_areas(oracle):
-    """Columns of 300 spans: the offsets in con pass 255, so the slim download carries the 16-bit con; and with erosion
-    CompactHeightfield.areas differs from CompactSpan.area, so it travels too."""
+    """Columns of 300 spans: offsets inside a cell pass 255, so the slim download falls back to span references (16 bits:
+    7500 spans; 32 bits for the 17x17 grid's 86700) and the 16-bit con; and with erosion CompactHeightfield.areas differs
+    from CompactSpan.area, so it travels too."""
     import recast_rs_b200.builder as rb
     from recast_rs_b200.config import RecastConfig
 
@@ -288,8 +290,8 @@ def test_slim_layout_wide_fallbacks_and_written_areas(oracle):
             ctx.build_from_spans([cfg], off, smin, smax, area, mask | rb.RESULT_SLIM, 1) as slim:
         full.download(), slim.download()
         raw = slim.tile(0, expand=False)
-        assert raw.con8 is None and raw.con is not None and int(raw.con.max()) > 255  # the wide array instead
-        assert raw.cell_count16 is not None and raw.conn_ref16 is not None
+        assert raw.conn_off8 is None and raw.con8 is None and raw.con is not None and int(raw.con.max()) > 255  # the wide arrays instead
+        assert raw.cell_count16 is not None and raw.conn_ref16 is not None and raw.conn_ref is None
         assert raw.areas is not None and (raw.areas != raw.span_area).any()  # eroded
         _same(slim.tile(0), full.tile(0), "deep columns")
     ohf = oracle.Heightfield.from_csr(W, H, cfg.bmin, cfg.bmax, cfg.cs, cfg.ch, off, smin, smax, area)
@@ -299,4 +301,18 @@ def test_slim_layout_wide_fallbacks_and_written_areas(oracle):
     e = oc.export()
     np.testing.assert_array_equal(raw.areas, e.areas)
     np.testing.assert_array_equal(raw.con, e.con)
+    # 17 x 17 columns of 300 spans: 86700 spans in the tile, references need 32 bits as well
+    W2 = 17
+    off2 = np.arange(W2 * W2 + 1, dtype=np.uint32) * n
+    smin2 = np.tile(np.arange(n, dtype=np.int16) * 4, W2 * W2)
+    cfg2 = RecastConfig(width=W2, height=W2, cs=1.0, ch=1.0, bmin=(0.0, 0.0, 0.0), bmax=(17.0, 2000.0, 17.0))
+    a2 = np.ones(W2 * W2 * n, np.uint8)
+    m2 = rb.STAGE_COMPACT | rb.STAGE_DIST
+    with ctx.build_from_spans([cfg2], off2, smin2, (smin2 + 1).astype(np.int16), a2, m2) as full, \
+            ctx.build_from_spans([cfg2], off2, smin2, (smin2 + 1).astype(np.int16), a2, m2 | rb.RESULT_SLIM) as slim:
+        full.download(), slim.download()
+        raw = slim.tile(0, expand=False)
+        assert raw.conn_off8 is None and raw.conn_ref16 is None and raw.conn_ref is not None and int(raw.conn_ref.max()) > 65535
+        assert raw.areas is None
+        _same(slim.tile(0), full.tile(0), "deep columns, wide references")
     ctx.close()
