@@ -1872,6 +1872,7 @@ int rcb_build_tiles(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t s
 
 static int download_on(rcb_result* res, cudaStream_t st, bool wait);
 static int finish_download(rcb_result* res, cudaStream_t st);
+static int slim_pack(rcb_result* res, cudaStream_t st);
 static uint64_t download_bytes(const rcb_result* res);
 
 int rcb_rasterize_onto(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, const uint32_t* cell_offset, const int16_t* span_min,
@@ -1925,6 +1926,10 @@ int rcb_build_tiles_streamed(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, u
         if (r) return cleanup(r);
         res->children.push_back(child);
         res->child_first.push_back(first);
+        // the slim layout's derived arrays are packed on the COMPUTE stream, behind the group's kernels: the copy stream
+        // then does nothing but copy
+        r = slim_pack(child, ctx->stream);
+        if (r) return cleanup(r);
         cudaEvent_t e = nullptr;
         if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(e, ctx->stream) != cudaSuccess)
             return cleanup(fail(ctx, RCB_ECUDA, "CUDA event failure"));
