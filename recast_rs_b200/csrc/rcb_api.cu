@@ -1926,10 +1926,8 @@ int rcb_build_tiles_streamed(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, u
         if (r) return cleanup(r);
         res->children.push_back(child);
         res->child_first.push_back(first);
-        // the slim layout's derived arrays are packed on the COMPUTE stream, behind the group's kernels: the copy stream
-        // then does nothing but copy
-        r = slim_pack(child, ctx->stream);
-        if (r) return cleanup(r);
+        // (the slim layout's derived arrays are packed on the COPY stream, by download_on: packed on the compute stream,
+        // which already carries H2D + every group's kernels, the build measured 3.2 ms instead of 3.0 on config 2)
         cudaEvent_t e = nullptr;
         if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(e, ctx->stream) != cudaSuccess)
             return cleanup(fail(ctx, RCB_ECUDA, "CUDA event failure"));
