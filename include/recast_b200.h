@@ -418,8 +418,9 @@ void rcb_result_free(rcb_result* res);
  *                           indices are validated as in rcb_upload_mesh.
  *   rcb_multi_build_tiles   tiles are independent (no halo, border_size 0 on every multi-tile path of the reference), so the
  *                           configurations are cut into groups of `tiles_per_group` consecutive tiles (<= 0: about four
- *                           groups per device) and one internal host thread per device works through its own share of
- *                           the groups, then steals from the device with the most left (work stealing).  No data moves
+ *                           groups per device); two internal workers per device (a context and a host thread each, so that
+ *                           two groups run side by side on a GPU) work through their own shares of the groups, then steal
+ *                           from the worker with the most left.  No data moves
  *                           between devices.  download != 0: every group's result is also copied to pinned host memory by
  *                           its device's thread (rcb_multi_result_tile then works at once).
  *   rcb_multi_result_*      as rcb_result_*: tile indices are those of `cfgs`; rcb_multi_result_tile_device also reports the

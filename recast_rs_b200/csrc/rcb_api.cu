@@ -2045,6 +2045,7 @@ int rcb_build_from_span_data(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, c
 
 uint64_t rcb_result_span_data_size(const rcb_result* res) {
     if (!res) return 0;
+    if (res->pending && res->ctx) resolve_result(const_cast<rcb_result*>(res));  // the span count of an issued build is on the device
     uint64_t n = 2 * res->Ctot + 12 * res->S;
     for (auto* c : res->children) n += rcb_result_span_data_size(c);
     return n;

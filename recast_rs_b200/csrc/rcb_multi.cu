@@ -4,10 +4,10 @@
 //
 // Tiles are independent units (no halo, border_size 0), so nothing but the mesh and the results ever moves:
 //   * the mesh is uploaded ONCE (host -> first device) and handed to the other devices over NVLink (cudaMemcpyPeer);
-//   * the tiles are cut into groups of consecutive tiles; one host thread per device works through its own share of the
-//     groups and then steals from the device with the most left (the static slabs of round 1 lost 24 % on BASELINE
-//     config 3, whose buildings are unevenly spread), running the ordinary single-device pipeline (rcb_build_tiles) on
-//     each group, two groups in flight per device;
+//   * the tiles are cut into groups of consecutive tiles; two workers per device (a context and a host thread each) work
+//     through their own shares of the groups and then steal from the worker with the most left (the static slabs of round 1
+//     lost 24 % on BASELINE config 3, whose buildings are unevenly spread), running the ordinary single-device pipeline
+//     (rcb_build_tiles) on each group, two groups in flight per worker;
 //   * a group meets mostly triangles that lie elsewhere; k_bin_count skips them 256 at a time (MeshView::blocks).
 // Built on the public single-device entry points of rcb_api.cu; no collective is involved.
 #include <atomic>
@@ -22,9 +22,14 @@
 
 #include "../../include/recast_b200.h"
 
+// Two contexts (streams, scratch buffers, host threads) per device: the groups a device builds are small enough that the
+// latency-bound stretches of one (the row-sequential sweeps, the read-backs of the global back end) leave the GPU idle;
+// a second group running beside it fills them.  Context w belongs to device w / kLanes.
+constexpr int kLanes = 2;
+
 struct rcb_multi {
     std::vector<int> devices;
-    std::vector<rcb_ctx*> ctx;
+    std::vector<rcb_ctx*> ctx;  // [devices * kLanes]
     std::vector<void*> d_verts, d_tris;  // per device copies of the mesh
     std::vector<size_t> cap_verts, cap_tris;
     size_t nfloats = 0, nidx = 0;
@@ -36,7 +41,7 @@ struct rcb_multi_result {
     int ntiles = 0;
     std::vector<int> group_first;       // [ngroups + 1]
     std::vector<rcb_result*> group_res;  // [ngroups]
-    std::vector<int> group_dev;          // index into m->devices
+    std::vector<int> group_dev;          // the context (worker) that built the group: device = m->devices[w / kLanes]
     std::vector<double> dev_ms;          // per device: host time spent building its groups
 };
 
@@ -56,15 +61,17 @@ int rcb_multi_create(const int* devices, int ndevices, rcb_multi** out) {
     *out = nullptr;
     auto* m = new rcb_multi();
     for (int i = 0; i < ndevices; ++i) {
-        rcb_ctx* c = nullptr;
-        const int r = rcb_create(devices[i], &c);
-        if (r) {
-            for (auto* x : m->ctx) rcb_destroy(x);
-            delete m;
-            return r;
+        for (int l = 0; l < kLanes; ++l) {
+            rcb_ctx* c = nullptr;
+            const int r = rcb_create(devices[i], &c);
+            if (r) {
+                for (auto* x : m->ctx) rcb_destroy(x);
+                delete m;
+                return r;
+            }
+            m->ctx.push_back(c);
         }
         m->devices.push_back(devices[i]);
-        m->ctx.push_back(c);
     }
     m->d_verts.assign(ndevices, nullptr);
     m->d_tris.assign(ndevices, nullptr);
@@ -85,8 +92,8 @@ int rcb_multi_create(const int* devices, int ndevices, rcb_multi** out) {
 
 void rcb_multi_destroy(rcb_multi* m) {
     if (!m) return;
-    for (size_t i = 0; i < m->ctx.size(); ++i) {
-        rcb_destroy(m->ctx[i]);
+    for (auto* c : m->ctx) rcb_destroy(c);
+    for (size_t i = 0; i < m->devices.size(); ++i) {
         cudaSetDevice(m->devices[i]);
         if (m->d_verts[i]) cudaFree(m->d_verts[i]);
         if (m->d_tris[i]) cudaFree(m->d_tris[i]);
@@ -129,8 +136,10 @@ int rcb_multi_upload_mesh(rcb_multi* m, const float* verts, size_t nfloats, cons
     for (int i = 0; i < n; ++i) {
         cudaSetDevice(m->devices[i]);
         cudaDeviceSynchronize();
-        const int r = rcb_set_mesh_device(m->ctx[i], m->d_verts[i], nfloats, m->d_tris[i], nidx);  // also checks the indices there
-        if (r) return mfail(m, r, rcb_last_error(m->ctx[i]));
+        for (int l = 0; l < kLanes; ++l) {  // both contexts of the device borrow the same copy (and check its indices)
+            const int r = rcb_set_mesh_device(m->ctx[i * kLanes + l], m->d_verts[i], nfloats, m->d_tris[i], nidx);
+            if (r) return mfail(m, r, rcb_last_error(m->ctx[i * kLanes + l]));
+        }
     }
     m->nfloats = nfloats;
     m->nidx = nidx;
@@ -157,25 +166,26 @@ int rcb_multi_build_tiles(rcb_multi* m, const rcb_config* cfgs, int ntiles, uint
     res->group_res.assign(ngroups, nullptr);
     res->group_dev.assign(ngroups, -1);
     res->dev_ms.assign(ndev, 0.0);
-    // Every device starts on its own contiguous share of the groups (the same (group, device) pairs build after build, so
-    // each context already knows the group's sizes and issues it without a host round trip) and, when that is used up,
-    // steals from the back of the share with the most groups left.
+    // Every worker (a context and its host thread; kLanes per device) starts on its own contiguous share of the groups - the
+    // same (group, context) pairs build after build, so each context already knows the group's sizes and issues it without a
+    // host round trip - and, when that is used up, steals from the back of the share with the most groups left.
+    const int nw = ndev * kLanes;
     std::mutex qm;
-    std::vector<int> lo(ndev), hi(ndev);
-    for (int d = 0; d < ndev; ++d) lo[d] = (int)((long long)ngroups * d / ndev), hi[d] = (int)((long long)ngroups * (d + 1) / ndev);
-    auto take = [&](int d) -> int {
+    std::vector<int> lo(nw), hi(nw);
+    for (int w = 0; w < nw; ++w) lo[w] = (int)((long long)ngroups * w / nw), hi[w] = (int)((long long)ngroups * (w + 1) / nw);
+    auto take = [&](int w) -> int {
         std::lock_guard<std::mutex> lk(qm);
-        if (lo[d] < hi[d]) return lo[d]++;
+        if (lo[w] < hi[w]) return lo[w]++;
         int victim = -1;
-        for (int k = 0; k < ndev; ++k)
+        for (int k = 0; k < nw; ++k)
             if (hi[k] - lo[k] > (victim < 0 ? 0 : hi[victim] - lo[victim])) victim = k;
         return victim < 0 ? -1 : --hi[victim];
     };
-    std::vector<int> status(ndev, RCB_OK);
-    std::vector<std::string> msg(ndev);
-    auto worker = [&](int d) {
+    std::vector<int> status(nw, RCB_OK);
+    std::vector<std::string> msg(nw);
+    auto worker = [&](int d) {  // d: worker index
         rcb_ctx* ctx = m->ctx[d];
-        cudaSetDevice(m->devices[d]);
+        cudaSetDevice(m->devices[d / kLanes]);
         int prev = -1;
         auto settle = [&](int g) {  // the first host use waits for the group (and rebuilds it, should a size have been short)
             rcb_totals t;
@@ -203,9 +213,9 @@ int rcb_multi_build_tiles(rcb_multi* m, const rcb_config* cfgs, int ntiles, uint
         if (prev >= 0) settle(prev);
     };
     std::vector<std::thread> th;
-    for (int d = 0; d < ndev; ++d) th.emplace_back(worker, d);
+    for (int w = 0; w < nw; ++w) th.emplace_back(worker, w);
     for (auto& t : th) t.join();
-    for (int d = 0; d < ndev; ++d)
+    for (int d = 0; d < nw; ++d)
         if (status[d] != RCB_OK) {
             const int code = status[d];
             m->err = msg[d];
@@ -237,18 +247,18 @@ int rcb_multi_result_tile(const rcb_multi_result* res, int tile, rcb_tile_view* 
 int rcb_multi_result_tile_device(const rcb_multi_result* res, int tile, rcb_tile_view* out, int* device) {
     if (!res || !out || tile < 0 || tile >= res->ntiles) return RCB_EARG;
     const int g = group_of(res, tile);
-    if (device) *device = res->m->devices[res->group_dev[g]];
+    if (device) *device = res->m->devices[res->group_dev[g] / kLanes];
     return rcb_result_tile_device(res->group_res[g], tile - res->group_first[g], out);
 }
 
 int rcb_multi_result_download(rcb_multi_result* res) {
     if (!res) return RCB_EARG;
-    const int ndev = (int)res->m->devices.size();
+    const int ndev = (int)res->m->ctx.size();  // one thread per context: a context is driven by one thread at a time
     std::vector<int> status(ndev, RCB_OK);
     std::vector<std::thread> th;
     for (int d = 0; d < ndev; ++d)
         th.emplace_back([&, d]() {
-            cudaSetDevice(res->m->devices[d]);
+            cudaSetDevice(res->m->devices[d / kLanes]);
             for (size_t g = 0; g < res->group_res.size(); ++g)
                 if (res->group_dev[g] == d) {
                     const int r = rcb_result_download(res->group_res[g]);
@@ -272,7 +282,7 @@ int rcb_multi_result_totals(const rcb_multi_result* res, rcb_totals* out, int* t
         out->tiles += t.tiles, out->cells += t.cells, out->fragments += t.fragments, out->spans += t.spans;
         out->connections += t.connections, out->walkable_spans += t.walkable_spans, out->result_bytes += t.result_bytes;
         out->triangles = t.triangles, out->vertices = t.vertices;
-        if (tiles_per_device && res->group_dev[g] < ndevices) tiles_per_device[res->group_dev[g]] += (int)t.tiles;
+        if (tiles_per_device && res->group_dev[g] / kLanes < ndevices) tiles_per_device[res->group_dev[g] / kLanes] += (int)t.tiles;
     }
     return RCB_OK;
 }
@@ -281,7 +291,7 @@ void rcb_multi_result_free(rcb_multi_result* res) {
     if (!res) return;
     for (size_t g = 0; g < res->group_res.size(); ++g)
         if (res->group_res[g]) {
-            if (res->group_dev[g] >= 0) cudaSetDevice(res->m->devices[res->group_dev[g]]);
+            if (res->group_dev[g] >= 0) cudaSetDevice(res->m->devices[res->group_dev[g] / kLanes]);
             rcb_result_free(res->group_res[g]);
         }
     delete res;
