@@ -271,7 +271,6 @@ struct ClipSmem {
 };
 
 #define ZB(buf, v, k) sm.zbuf[(((buf) * ZCAP + RCB_IX(v, ZCAP)) * 3 + (k)) * CLIP_THREADS + threadIdx.x]
-#define XB(buf, v, k) sm.zbuf[(((buf) * XCAP + RCB_IX(v, XCAP)) * 2 + (k)) * CLIP_THREADS + threadIdx.x]
 
 // One record into the segment of band `seg`; `lcell` is the cell inside the band's held rows.
 // (Tried: one atomic per lane with the record written an iteration later, so that the x-chain runs during the round trip:
@@ -379,26 +378,39 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
                 ZB(0, 1, k) = t.v1[k];
                 ZB(0, 2, k) = t.v2[k];
             }
+            // The polygons of one thread are a column of `zbuf` (element stride CLIP_THREADS): the loops below walk them
+            // with pointers and carry vertex j into the next iteration's vertex i, instead of indexing (buffer, vertex,
+            // component) afresh for every access (three multiply-adds per address, three to four loads per vertex).
+            constexpr int ZV = 3 * CLIP_THREADS, ZBUF = ZCAP * ZV;  // floats per vertex / per buffer
+            float* const zb = sm.zbuf + threadIdx.x;
+            const float tz0 = td.bmin[2], tcs = td.cs, tics = td.ics;
             for (int z = z0; z <= ze && n > 0; ++z) {  // rasterization.rs:300-311
-                const float cz = __fadd_rn(td.bmin[2], __fmul_rn((float)(z + 1), td.cs));
+                const float cz = __fadd_rn(tz0, __fmul_rn((float)(z + 1), tcs));
                 const bool keep = z >= zs;  // rows before the chunk only advance the chain
                 const uint32_t slot_id = threadIdx.x * CLIP_ROWS + (uint32_t)(keep ? z - zs : 0);
-                uint32_t* slot = sm.slots + slot_id * SLOT_WORDS;
+                uint32_t* const slot = sm.slots + slot_id * SLOT_WORDS;
+                uint32_t* ps = slot + 1;
                 int nrow = 0, nrest = 0;
                 float rminx = 3.0e38f, rmaxx = -3.0e38f;  // x-extent of the row polygon (bucketing hint)
-                const int nxt = cur ^ 1;
-                // divide_poly(p1 -> in_row (slot, x/y only), rest (zbuf[nxt]))  rasterization.rs:172-242
+                const float* pi = zb + cur * ZBUF;
+                float* po = zb + (cur ^ 1) * ZBUF;
+                const float v0x = pi[0], v0y = pi[CLIP_THREADS], v0z = pi[2 * CLIP_THREADS];
+                float vix = v0x, viy = v0y, viz = v0z;
+                // divide_poly(p1 -> in_row (slot, x/y only), rest (the other buffer))  rasterization.rs:172-242
                 for (int i = 0; i < n; ++i) {
-                    const int j = (i + 1 == n) ? 0 : i + 1;
-                    const float vix = ZB(cur, i, 0), viy = ZB(cur, i, 1), viz = ZB(cur, i, 2);
-                    const float vjz = ZB(cur, j, 2);
-                    const int si = viz < cz ? -1 : (viz > cz ? 1 : 0);
-                    const int sj = vjz < cz ? -1 : (vjz > cz ? 1 : 0);
-                    if (si <= 0) {
+                    float vjx = v0x, vjy = v0y, vjz = v0z;
+                    if (i + 1 < n) {
+                        pi += ZV;
+                        vjx = pi[0], vjy = pi[CLIP_THREADS], vjz = pi[2 * CLIP_THREADS];
+                    }
+                    const bool il = viz < cz, ig = viz > cz;  // si = il ? -1 : ig ? 1 : 0 (NaN: 0)
+                    if (!ig) {
                         if (keep) {
                             if (nrow < RCAP) {
-                                slot[1 + 2 * RCB_IX(nrow, RCAP)] = __float_as_uint(vix);
-                                slot[2 + 2 * RCB_IX(nrow, RCAP)] = __float_as_uint(viy);
+                                RCB_CHECK(ps + 1 < slot + SLOT_WORDS);
+                                ps[0] = __float_as_uint(vix);
+                                ps[1] = __float_as_uint(viy);
+                                ps += 2;
                             } else
                                 ovf = true;
                             rminx = fminf(rminx, vix);
@@ -406,25 +418,25 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
                         }
                         nrow++;
                     }
-                    if (si >= 0) {
+                    if (!il) {
                         if (nrest < ZCAP) {
-                            ZB(nxt, nrest, 0) = vix;
-                            ZB(nxt, nrest, 1) = viy;
-                            ZB(nxt, nrest, 2) = viz;
+                            po[0] = vix, po[CLIP_THREADS] = viy, po[2 * CLIP_THREADS] = viz;
+                            po += ZV;
                         } else
                             ovf = true;
                         nrest++;
                     }
-                    if ((si < 0 && sj > 0) || (si > 0 && sj < 0)) {
-                        const float vjx = ZB(cur, j, 0), vjy = ZB(cur, j, 1);
+                    if ((il && vjz > cz) || (ig && vjz < cz)) {
                         const float tt = __fdiv_rn(__fsub_rn(cz, viz), __fsub_rn(vjz, viz));
                         const float px = __fadd_rn(vix, __fmul_rn(tt, __fsub_rn(vjx, vix)));
                         const float py = __fadd_rn(viy, __fmul_rn(tt, __fsub_rn(vjy, viy)));
                         const float pz = __fadd_rn(viz, __fmul_rn(tt, __fsub_rn(vjz, viz)));
                         if (keep) {
                             if (nrow < RCAP) {
-                                slot[1 + 2 * RCB_IX(nrow, RCAP)] = __float_as_uint(px);
-                                slot[2 + 2 * RCB_IX(nrow, RCAP)] = __float_as_uint(py);
+                                RCB_CHECK(ps + 1 < slot + SLOT_WORDS);
+                                ps[0] = __float_as_uint(px);
+                                ps[1] = __float_as_uint(py);
+                                ps += 2;
                             } else
                                 ovf = true;
                             rminx = fminf(rminx, px);
@@ -432,18 +444,18 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
                         }
                         nrow++;
                         if (nrest < ZCAP) {
-                            ZB(nxt, nrest, 0) = px;
-                            ZB(nxt, nrest, 1) = py;
-                            ZB(nxt, nrest, 2) = pz;
+                            po[0] = px, po[CLIP_THREADS] = py, po[2 * CLIP_THREADS] = pz;
+                            po += ZV;
                         } else
                             ovf = true;
                         nrest++;
                     }
+                    vix = vjx, viy = vjy, viz = vjz;
                 }
-                cur = nxt;
+                cur ^= 1;
                 n = min(nrest, ZCAP);
                 if (keep && nrow >= 3 && z >= 0) {  // rasterization.rs:308-311
-                    const int ncols = min(max(__float2int_rz((rmaxx - rminx) * td.ics), 0), 3);
+                    const int ncols = min(max(__float2int_rz((rmaxx - rminx) * tics), 0), 3);
                     const int bk = min(min(nrow, RCAP) - 3, 3) * 4 + ncols;
                     slot[0] = (uint32_t)z | ((uint32_t)min(nrow, RCAP) << 16) | ((uint32_t)bk << 19) | (area << 24);
                     // bucket by vertex count so the lanes of a warp run vertex loops of equal length
@@ -464,7 +476,6 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
     }
 
     // ---------------- phase 2: x-chain, one row polygon per thread at a time ------------------------------
-    const bool use_minx = (rb.flags & 1u) != 0;
     // every thread files its own row slots into `list`, grouped by bucket
     uint32_t boff[NBUCK], nlist = 0;
 #pragma unroll
@@ -501,53 +512,56 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
         const uint32_t area = h2 >> 24;
         const int x0 = (int)(h3 & 0xffffu), x1 = (int)(h3 >> 16);
         const TileDesc& td = rb.tiles[tile];
+        constexpr int XV = 2 * CLIP_THREADS, XBUF = XCAP * XV;  // floats per vertex / per buffer
+        float* const xb = sm.zbuf + threadIdx.x;
+        const float tx0 = td.bmin[0], tcs = td.cs, ty0 = td.bmin[1], tich = td.ich;
         float minx = 0.f;
         bool has_nan = false;
         for (int v = 0; v < n; ++v) {
             const float vx = __uint_as_float(slot[1 + 2 * v]);
-            XB(0, v, 0) = vx;
-            XB(0, v, 1) = __uint_as_float(slot[2 + 2 * v]);
+            xb[v * XV] = vx;
+            xb[v * XV + CLIP_THREADS] = __uint_as_float(slot[2 + 2 * v]);
             has_nan = has_nan || (vx != vx);
             minx = v ? fminf(minx, vx) : vx;
         }
+        // Exact skip: while every vertex lies strictly right of the cut, divide_poly returns the polygon unchanged and an
+        // empty cell piece.  Only the leading columns of the footprint can be skipped (what is left behind a cut starts at
+        // that cut), so the skipping is done here, ahead of the loop: the lanes of a warp then spend every iteration of
+        // the loop on a column their row really crosses, instead of idling through each other's leading columns.
+        int x = x0;
+        if (!has_nan)
+            while (x <= x1 && minx > __fadd_rn(tx0, __fmul_rn((float)(x + 1), tcs))) ++x;
         bool ovf = false;
         int cur = 0;
-        for (int x = x0; x <= x1 && n > 0; ++x) {  // rasterization.rs:317-362
-            const float cx = __fadd_rn(td.bmin[0], __fmul_rn((float)(x + 1), td.cs));
-            // exact skip: every vertex strictly right of the cut => cell piece empty, rest == polygon
-            if (use_minx) {
-                if (!has_nan && minx > cx) continue;
-            } else {
-                bool all_right = true;
-                for (int i = 0; i < n; ++i) all_right = all_right && (XB(cur, i, 0) > cx);
-                if (all_right) continue;
-            }
-            const int nxt = cur ^ 1;
+        for (; x <= x1 && n > 0; ++x) {  // rasterization.rs:317-362
+            const float cx = __fadd_rn(tx0, __fmul_rn((float)(x + 1), tcs));
             int ncell = 0, nrest = 0;
-            float miny = 0.f, maxy = 0.f, nminx = 0.f;
-            bool nnan = false;
+            float miny = 0.f, maxy = 0.f;
+            const float* pi = xb + cur * XBUF;
+            float* po = xb + (cur ^ 1) * XBUF;
+            const float v0x = pi[0], v0y = pi[CLIP_THREADS];
+            float vix = v0x, viy = v0y;
             for (int i = 0; i < n; ++i) {
-                const int j = (i + 1 == n) ? 0 : i + 1;
-                const float vix = XB(cur, i, 0), viy = XB(cur, i, 1), vjx = XB(cur, j, 0);
-                const int si = vix < cx ? -1 : (vix > cx ? 1 : 0);
-                const int sj = vjx < cx ? -1 : (vjx > cx ? 1 : 0);
-                if (si <= 0) {
+                float vjx = v0x, vjy = v0y;
+                if (i + 1 < n) {
+                    pi += XV;
+                    vjx = pi[0], vjy = pi[CLIP_THREADS];
+                }
+                const bool il = vix < cx, ig = vix > cx;  // si = il ? -1 : ig ? 1 : 0 (NaN: 0)
+                if (!ig) {
                     miny = ncell ? fminf(miny, viy) : viy;
                     maxy = ncell ? fmaxf(maxy, viy) : viy;
                     ncell++;
                 }
-                if (si >= 0) {
+                if (!il) {
                     if (nrest < XCAP) {
-                        XB(nxt, nrest, 0) = vix;
-                        XB(nxt, nrest, 1) = viy;
+                        po[0] = vix, po[CLIP_THREADS] = viy;
+                        po += XV;
                     } else
                         ovf = true;
-                    nminx = nrest ? fminf(nminx, vix) : vix;
-                    nnan = nnan || (vix != vix);
                     nrest++;
                 }
-                if ((si < 0 && sj > 0) || (si > 0 && sj < 0)) {
-                    const float vjy = XB(cur, j, 1);
+                if ((il && vjx > cx) || (ig && vjx < cx)) {
                     const float tt = __fdiv_rn(__fsub_rn(cx, vix), __fsub_rn(vjx, vix));
                     const float px = __fadd_rn(vix, __fmul_rn(tt, __fsub_rn(vjx, vix)));
                     const float py = __fadd_rn(viy, __fmul_rn(tt, __fsub_rn(vjy, viy)));
@@ -555,22 +569,19 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
                     maxy = ncell ? fmaxf(maxy, py) : py;
                     ncell++;
                     if (nrest < XCAP) {
-                        XB(nxt, nrest, 0) = px;
-                        XB(nxt, nrest, 1) = py;
+                        po[0] = px, po[CLIP_THREADS] = py;
+                        po += XV;
                     } else
                         ovf = true;
-                    nminx = nrest ? fminf(nminx, px) : px;
-                    nnan = nnan || (px != px);
                     nrest++;
                 }
+                vix = vjx, viy = vjy;
             }
-            cur = nxt;
+            cur ^= 1;
             n = min(nrest, XCAP);
-            minx = nminx;
-            has_nan = nnan;
             if (ncell >= 3) {  // rasterization.rs:325-361
-                int smin = __float2int_rz(floorf(__fmul_rn(__fsub_rn(miny, td.bmin[1]), td.ich)));
-                int smax = __float2int_rz(ceilf(__fmul_rn(__fsub_rn(maxy, td.bmin[1]), td.ich)));
+                int smin = __float2int_rz(floorf(__fmul_rn(__fsub_rn(miny, ty0), tich)));
+                int smax = __float2int_rz(ceilf(__fmul_rn(__fsub_rn(maxy, ty0), tich)));
                 smin = min(max(smin, -32768), 32767);
                 smax = min(max(smax, -32768), 32767);
                 smin = max(smin, 0);
