@@ -411,8 +411,7 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
                                 ps[0] = __float_as_uint(vix);
                                 ps[1] = __float_as_uint(viy);
                                 ps += 2;
-                            } else
-                                ovf = true;
+                            }
                             rminx = fminf(rminx, vix);
                             rmaxx = fmaxf(rmaxx, vix);
                         }
@@ -422,8 +421,7 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
                         if (nrest < ZCAP) {
                             po[0] = vix, po[CLIP_THREADS] = viy, po[2 * CLIP_THREADS] = viz;
                             po += ZV;
-                        } else
-                            ovf = true;
+                        }
                         nrest++;
                     }
                     if ((il && vjz > cz) || (ig && vjz < cz)) {
@@ -437,8 +435,7 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
                                 ps[0] = __float_as_uint(px);
                                 ps[1] = __float_as_uint(py);
                                 ps += 2;
-                            } else
-                                ovf = true;
+                            }
                             rminx = fminf(rminx, px);
                             rmaxx = fmaxf(rmaxx, px);
                         }
@@ -446,13 +443,13 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
                         if (nrest < ZCAP) {
                             po[0] = px, po[CLIP_THREADS] = py, po[2 * CLIP_THREADS] = pz;
                             po += ZV;
-                        } else
-                            ovf = true;
+                        }
                         nrest++;
                     }
                     vix = vjx, viy = vjy, viz = vjz;
                 }
                 cur ^= 1;
+                ovf = ovf || nrest > ZCAP || (keep && nrow > RCAP);  // a polygon outgrew its slot: counted, not stored
                 n = min(nrest, ZCAP);
                 if (keep && nrow >= 3 && z >= 0) {  // rasterization.rs:308-311
                     const int ncols = min(max(__float2int_rz((rmaxx - rminx) * tics), 0), 3);
@@ -536,7 +533,9 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
         for (; x <= x1 && n > 0; ++x) {  // rasterization.rs:317-362
             const float cx = __fadd_rn(tx0, __fmul_rn((float)(x + 1), tcs));
             int ncell = 0, nrest = 0;
-            float miny = 0.f, maxy = 0.f;
+            // The reference takes the first y as is and folds the others in with f32::min / max, which return the other
+            // operand when one is NaN - exactly what fminf / fmaxf do from a NaN start.
+            float miny = __int_as_float(0x7fc00000), maxy = miny;
             const float* pi = xb + cur * XBUF;
             float* po = xb + (cur ^ 1) * XBUF;
             const float v0x = pi[0], v0y = pi[CLIP_THREADS];
@@ -549,35 +548,34 @@ __global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, cons
                 }
                 const bool il = vix < cx, ig = vix > cx;  // si = il ? -1 : ig ? 1 : 0 (NaN: 0)
                 if (!ig) {
-                    miny = ncell ? fminf(miny, viy) : viy;
-                    maxy = ncell ? fmaxf(maxy, viy) : viy;
+                    miny = fminf(miny, viy);
+                    maxy = fmaxf(maxy, viy);
                     ncell++;
                 }
                 if (!il) {
                     if (nrest < XCAP) {
                         po[0] = vix, po[CLIP_THREADS] = viy;
                         po += XV;
-                    } else
-                        ovf = true;
+                    }
                     nrest++;
                 }
                 if ((il && vjx > cx) || (ig && vjx < cx)) {
                     const float tt = __fdiv_rn(__fsub_rn(cx, vix), __fsub_rn(vjx, vix));
                     const float px = __fadd_rn(vix, __fmul_rn(tt, __fsub_rn(vjx, vix)));
                     const float py = __fadd_rn(viy, __fmul_rn(tt, __fsub_rn(vjy, viy)));
-                    miny = ncell ? fminf(miny, py) : py;
-                    maxy = ncell ? fmaxf(maxy, py) : py;
+                    miny = fminf(miny, py);
+                    maxy = fmaxf(maxy, py);
                     ncell++;
                     if (nrest < XCAP) {
                         po[0] = px, po[CLIP_THREADS] = py;
                         po += XV;
-                    } else
-                        ovf = true;
+                    }
                     nrest++;
                 }
                 vix = vjx, viy = vjy;
             }
             cur ^= 1;
+            ovf = ovf || nrest > XCAP;
             n = min(nrest, XCAP);
             if (ncell >= 3) {  // rasterization.rs:325-361
                 int smin = __float2int_rz(floorf(__fmul_rn(__fsub_rn(miny, ty0), tich)));
