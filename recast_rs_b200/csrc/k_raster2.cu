@@ -38,6 +38,7 @@ constexpr int SLOT_WORDS = 1 + 2 * RCAP;                  // row word + verts (o
 constexpr int HDR_WORDS = 3;                              // per work item: triangle, tile, x0 | x1 << 16 (shared by its rows)
 static_assert(2 * XCAP * 2 <= 2 * ZCAP * 3, "phase-2 buffers alias the z-chain scratch");
 constexpr int NSLOTS = CLIP_THREADS * CLIP_ROWS;
+constexpr int CLIP_CTAS = CLIP_ROWS <= 2 ? 8 : CLIP_ROWS == 3 ? 7 : CLIP_ROWS == 4 ? 6 : 4;  // resident CTAs per SM the shared memory allows
 constexpr int NBUCK = 16;  // phase-2 rows are grouped by (vertex count 3..6+, columns spanned 1..4+): a scheduling hint only
                            // (six column classes - 1, 2, 3, 4, 5-8, 9+ - were tried for config 3's roofs and walls: no change there,
                            // +1 % on config 2 for the extra barrier)
@@ -336,7 +337,7 @@ __device__ __forceinline__ void emit_fragment(const Raster2& rb, const TileDesc&
     }
 }
 
-__global__ void __launch_bounds__(CLIP_THREADS, 7) k_clip_items(Raster2 rb, const uint2* __restrict__ items, uint32_t nitems,
+__global__ void __launch_bounds__(CLIP_THREADS, CLIP_CTAS) k_clip_items(Raster2 rb, const uint2* __restrict__ items, uint32_t nitems,
                                                              TileInfo* __restrict__ tinfo) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ClipSmem& sm = *reinterpret_cast<ClipSmem*>(smem_raw);
