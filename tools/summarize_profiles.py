@@ -10,7 +10,7 @@ for r in rows[1:]:
     n = r[i_name].split("(")[0].replace("<unnamed>::", "").replace("void ", "")
     agg.setdefault(n, [0, 0.0]); agg[n][0] += 1; agg[n][1] += float(r[i_val].replace(",", ""))
 tot = sum(v[1] for v in agg.values())
-out = [f"# {tag} — ncu launch list summary, config 2, `python bench.py --steps 2 --warmup 3 --no-cpu --no-parity` (device leg, kernel "
+out = [f"# {tag} — ncu launch list summary, config 2, `python bench.py --steps 2 --warmup 3 --no-parity --no-config3` (device leg, kernel "
        "profile pass and the two end-to-end legs: k_slim_pack belongs to the slim end-to-end leg only)",
        "# per-launch times are cold-cache/serialised: compare SHARES", "kernel,launches,total_us,share"]
 for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
