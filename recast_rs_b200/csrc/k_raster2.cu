@@ -402,6 +402,7 @@ __global__ void __launch_bounds__(CLIP_THREADS, CLIP_CTAS) k_clip_items(Raster2 
                     float vjx = v0x, vjy = v0y, vjz = v0z;
                     if (i + 1 < n) {
                         pi += ZV;
+                        RCB_CHECK(pi + 2 * CLIP_THREADS < zb + (cur + 1) * ZBUF);
                         vjx = pi[0], vjy = pi[CLIP_THREADS], vjz = pi[2 * CLIP_THREADS];
                     }
                     const bool il = viz < cz, ig = viz > cz;  // si = il ? -1 : ig ? 1 : 0 (NaN: 0)
@@ -420,6 +421,7 @@ __global__ void __launch_bounds__(CLIP_THREADS, CLIP_CTAS) k_clip_items(Raster2 
                     }
                     if (!il) {
                         if (nrest < ZCAP) {
+                            RCB_CHECK(po >= zb + (cur ^ 1) * ZBUF && po + 2 * CLIP_THREADS < zb + ((cur ^ 1) + 1) * ZBUF);
                             po[0] = vix, po[CLIP_THREADS] = viy, po[2 * CLIP_THREADS] = viz;
                             po += ZV;
                         }
@@ -442,6 +444,7 @@ __global__ void __launch_bounds__(CLIP_THREADS, CLIP_CTAS) k_clip_items(Raster2 
                         }
                         nrow++;
                         if (nrest < ZCAP) {
+                            RCB_CHECK(po >= zb + (cur ^ 1) * ZBUF && po + 2 * CLIP_THREADS < zb + ((cur ^ 1) + 1) * ZBUF);
                             po[0] = px, po[CLIP_THREADS] = py, po[2 * CLIP_THREADS] = pz;
                             po += ZV;
                         }
@@ -517,6 +520,7 @@ __global__ void __launch_bounds__(CLIP_THREADS, CLIP_CTAS) k_clip_items(Raster2 
         bool has_nan = false;
         for (int v = 0; v < n; ++v) {
             const float vx = __uint_as_float(slot[1 + 2 * v]);
+            RCB_CHECK(v < XCAP);
             xb[v * XV] = vx;
             xb[v * XV + CLIP_THREADS] = __uint_as_float(slot[2 + 2 * v]);
             has_nan = has_nan || (vx != vx);
@@ -545,6 +549,7 @@ __global__ void __launch_bounds__(CLIP_THREADS, CLIP_CTAS) k_clip_items(Raster2 
                 float vjx = v0x, vjy = v0y;
                 if (i + 1 < n) {
                     pi += XV;
+                    RCB_CHECK(pi + CLIP_THREADS < xb + (cur + 1) * XBUF);
                     vjx = pi[0], vjy = pi[CLIP_THREADS];
                 }
                 const bool il = vix < cx, ig = vix > cx;  // si = il ? -1 : ig ? 1 : 0 (NaN: 0)
@@ -555,6 +560,7 @@ __global__ void __launch_bounds__(CLIP_THREADS, CLIP_CTAS) k_clip_items(Raster2 
                 }
                 if (!il) {
                     if (nrest < XCAP) {
+                        RCB_CHECK(po >= xb + (cur ^ 1) * XBUF && po + CLIP_THREADS < xb + ((cur ^ 1) + 1) * XBUF);
                         po[0] = vix, po[CLIP_THREADS] = viy;
                         po += XV;
                     }
@@ -568,6 +574,7 @@ __global__ void __launch_bounds__(CLIP_THREADS, CLIP_CTAS) k_clip_items(Raster2 
                     maxy = fmaxf(maxy, py);
                     ncell++;
                     if (nrest < XCAP) {
+                        RCB_CHECK(po >= xb + (cur ^ 1) * XBUF && po + CLIP_THREADS < xb + ((cur ^ 1) + 1) * XBUF);
                         po[0] = px, po[CLIP_THREADS] = py;
                         po += XV;
                     }
