@@ -6,7 +6,7 @@
 // (profiles/r01_v1_*) showed 10.8 of 32 lanes active (threads walked whole triangles of very different
 // row/column counts), 610 M local-memory sectors and 716 MB of DRAM writes from polygon spills.
 //
-// Structure (one CTA = CLIP_THREADS work items):
+// Structure (one CTA = CLIP_ITEMS work items, CLIP_THREADS threads):
 //   phase 1  thread = item (tri, tile, chunk of CLIP_ROWS rows): z-chain.  The chain of a triangle is
 //            sequential (each cut interpolates from the previous cut's rounded points), so a chunk that
 //            starts at row r first replays the r cuts before it (cheap: one divide per row), then stores
@@ -37,8 +37,15 @@ constexpr int XCAP = 6;                                   // x-chain rest polygo
 constexpr int SLOT_WORDS = 1 + 2 * RCAP;                  // row word + verts (odd stride: no bank conflicts)
 constexpr int HDR_WORDS = 3;                              // per work item: triangle, tile, x0 | x1 << 16 (shared by its rows)
 static_assert(2 * XCAP * 2 <= 2 * ZCAP * 3, "phase-2 buffers alias the z-chain scratch");
-constexpr int NSLOTS = CLIP_THREADS * CLIP_ROWS;
-constexpr int CLIP_CTAS = CLIP_ROWS <= 2 ? 8 : CLIP_ROWS == 3 ? 7 : CLIP_ROWS == 4 ? 6 : 4;  // resident CTAs per SM the shared memory allows
+// A CTA holds NSLOTS row polygons whatever the rows per work item: CLIP_ITEMS = NSLOTS / CLIP_ROWS items per CTA, whose
+// z-chains (phase 1) run on the first CLIP_ITEMS threads while phase 2 spreads the rows over all CLIP_THREADS.  Rows per item
+// trade the replay of the rows before a chunk (short chunks: a 5-row triangle costs 3 + (3 + 2) chain steps in chunks of 3)
+// against idle threads in phase 1; shared memory, and with it the CTAs per SM this kernel's time follows, stays the same.
+constexpr int SLOTS_PER_THREAD = 3;
+constexpr int NSLOTS = CLIP_THREADS * SLOTS_PER_THREAD;
+constexpr int CLIP_ITEMS = NSLOTS / CLIP_ROWS;            // work items per CTA
+static_assert(CLIP_ITEMS * CLIP_ROWS == NSLOTS && CLIP_ITEMS <= CLIP_THREADS && CLIP_ITEMS >= 1, "rows per item must divide the CTA's slots");
+constexpr int CLIP_CTAS = 7;                              // resident CTAs per SM the shared memory allows
 constexpr int NBUCK = 16;  // phase-2 rows are grouped by (vertex count 3..6+, columns spanned 1..4+): a scheduling hint only
                            // (six column classes - 1, 2, 3, 4, 5-8, 9+ - were tried for config 3's roofs and walls: no change there,
                            // +1 % on config 2 for the extra barrier)
@@ -263,9 +270,9 @@ __global__ void __launch_bounds__(256) k_fill_items(Raster2 rb, const uint32_t* 
 // ---- clip --------------------------------------------------------------------------------------------
 struct ClipSmem {
     float zbuf[2 * ZCAP * 3 * CLIP_THREADS];  // phase 1: [(buf*ZCAP + v)*3 + k][tid]; phase 2: two x/y buffers per thread
-    uint32_t slots[NSLOTS * SLOT_WORDS];      // slot tid*CLIP_ROWS + r belongs to thread tid, row r of its chunk:
+    uint32_t slots[NSLOTS * SLOT_WORDS];      // slot item*CLIP_ROWS + r belongs to item `item` of the CTA, row r of its chunk:
                                               // [0] = z | vertices << 16 (3 bits) | bucket << 19 (5 bits) | area << 24 (0: empty), then x,y pairs
-    uint32_t hdr[CLIP_THREADS * HDR_WORDS];   // what the rows of one work item have in common
+    uint32_t hdr[CLIP_ITEMS * HDR_WORDS];     // what the rows of one work item have in common
     uint16_t list[NSLOTS];                    // compacted ids of the slots that hold a row polygon
     uint32_t nb[NBUCK], cur[NBUCK];           // rows per (vertex count, columns spanned) bucket and fill cursors
     uint32_t nlist;
@@ -344,19 +351,19 @@ __global__ void __launch_bounds__(CLIP_THREADS, CLIP_CTAS) k_clip_items(Raster2 
     if (rb.spec) {  // issued before the host knew the item count: the grid covers the capacity, the count is on the device
         if (rb.counters[2] & RCB_FLAG_ABORT) return;
         nitems = (uint32_t)min((unsigned long long)nitems, rb.counters[4]);
-        if (blockIdx.x * CLIP_THREADS >= nitems) return;
+        if (blockIdx.x * CLIP_ITEMS >= nitems) return;
     }
     const bool timed = (rb.flags & 0x100u) != 0 && threadIdx.x == 0;  // RCB_PHASE_TIMERS: counters[40..43]
     long long tclk = timed ? clock64() : 0;
     if (threadIdx.x < NBUCK) sm.nb[threadIdx.x] = sm.cur[threadIdx.x] = 0;
     if (threadIdx.x == 0) sm.nlist = 0;
 #pragma unroll
-    for (int r = 0; r < CLIP_ROWS; ++r) sm.slots[(threadIdx.x * CLIP_ROWS + r) * SLOT_WORDS] = 0;  // slot empty
+    for (int r = 0; r < SLOTS_PER_THREAD; ++r) sm.slots[(threadIdx.x * SLOTS_PER_THREAD + r) * SLOT_WORDS] = 0;  // slot empty
     __syncthreads();
 
     // ---------------- phase 1: z-chain of one work item ------------------------------------------------
-    const uint32_t it = blockIdx.x * CLIP_THREADS + threadIdx.x;
-    if (it < nitems) {
+    const uint32_t it = blockIdx.x * CLIP_ITEMS + threadIdx.x;
+    if (threadIdx.x < CLIP_ITEMS && it < nitems) {
         const uint2 item = items[it];
         const uint32_t tri = RCB_IX(item.x, rb.mesh.ntris), tile = RCB_IX(item.y >> 12, rb.ntiles), chunk = item.y & 0xfffu;
         const TileDesc& td = rb.tiles[tile];
@@ -485,8 +492,8 @@ __global__ void __launch_bounds__(CLIP_THREADS, CLIP_CTAS) k_clip_items(Raster2 
         nlist += sm.nb[k];
     }
 #pragma unroll
-    for (int r = 0; r < CLIP_ROWS; ++r) {
-        const uint32_t slot_id = threadIdx.x * CLIP_ROWS + r;
+    for (int r = 0; r < SLOTS_PER_THREAD; ++r) {
+        const uint32_t slot_id = threadIdx.x * SLOTS_PER_THREAD + r;
         const uint32_t w0 = sm.slots[slot_id * SLOT_WORDS];
         if (((w0 >> 16) & 0x7u) >= 3) {
             const uint32_t bk = (w0 >> 19) & 0x1fu;
@@ -645,5 +652,5 @@ void launch_clip_items(const Raster2& rb, const uint2* items, uint32_t nitems, T
     // per device, so per call: a process may drive several devices
     cudaFuncSetAttribute(k_clip_items, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClipSmem));
     KScope _k("k_clip_items", s);
-    k_clip_items<<<(nitems + CLIP_THREADS - 1) / CLIP_THREADS, CLIP_THREADS, sizeof(ClipSmem), s>>>(rb, items, nitems, tinfo);
+    k_clip_items<<<(nitems + CLIP_ITEMS - 1) / CLIP_ITEMS, CLIP_THREADS, sizeof(ClipSmem), s>>>(rb, items, nitems, tinfo);
 }

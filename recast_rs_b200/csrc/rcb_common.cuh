@@ -15,7 +15,7 @@
 #define RCB_MAX_POLY_VERTS 12  // clip polygon capacity (geometric bound is 7); overflow sets status bit0
 #define RCB_NEI_NONE 0xFFFFu
 #ifndef RCB_CLIP_ROWS
-#define RCB_CLIP_ROWS 3  // rows of one (triangle, tile) pair handled by one clip work item
+#define RCB_CLIP_ROWS 6  // rows of one (triangle, tile) pair handled by one clip work item (384 / rows items per CTA, k_raster2.cu)
 #endif
 
 // Per-tile constants, uploaded once per batch.
