@@ -292,8 +292,7 @@ __global__ void __launch_bounds__(256) k_tc_gather(const TileDesc* __restrict__ 
 void launch_lz4_decompress(const uint8_t* blobs, const unsigned long long* blob_off, int nlayers, uint8_t* out,
                            const unsigned long long* out_off, uint32_t* status, uint32_t* produced, cudaStream_t s) {
     if (nlayers == 0) return;
-    // the attribute is per device, and a process may drive several: set it with every launch
-    cudaFuncSetAttribute(k_lz4_decompress, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZ_SMEM);
+    rcb_raise_dynamic_smem((const void*)k_lz4_decompress, LZ_SMEM);  // per (kernel, device); a process may drive several
     KScope _k("k_lz4_decompress", s);
     k_lz4_decompress<<<nlayers, 32, LZ_SMEM, s>>>(blobs, blob_off, out, out_off, status, produced);
 }

@@ -649,8 +649,7 @@ void launch_fill_items(const Raster2& rb, const uint32_t* item_off, uint2* items
 
 void launch_clip_items(const Raster2& rb, const uint2* items, uint32_t nitems, TileInfo* tinfo, cudaStream_t s) {
     if (nitems == 0) return;
-    // per device, so per call: a process may drive several devices
-    cudaFuncSetAttribute(k_clip_items, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClipSmem));
+    rcb_raise_dynamic_smem((const void*)k_clip_items, sizeof(ClipSmem));  // per (kernel, device); a process may drive several
     KScope _k("k_clip_items", s);
     k_clip_items<<<(nitems + CLIP_ITEMS - 1) / CLIP_ITEMS, CLIP_THREADS, sizeof(ClipSmem), s>>>(rb, items, nitems, tinfo);
 }

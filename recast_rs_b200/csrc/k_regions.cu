@@ -68,13 +68,13 @@ void launch_regions(const RegionArgs& a, int ntiles, cudaStream_t s) {
     if (a.narrow == 1) {
         rg32::k_regions<<<ntiles, 32, smem, s>>>(a);
     } else if (a.narrow == 3) {
-        cudaFuncSetAttribute(rg1024::k_regions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        rcb_raise_dynamic_smem((const void*)rg1024::k_regions, smem);
         rg1024::k_regions<<<ntiles, 1024, smem, s>>>(a);
     } else if (a.narrow == 2) {
-        cudaFuncSetAttribute(rg256::k_regions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        rcb_raise_dynamic_smem((const void*)rg256::k_regions, smem);
         rg256::k_regions<<<ntiles, 256, smem, s>>>(a);
     } else {
-        cudaFuncSetAttribute(rg64::k_regions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        rcb_raise_dynamic_smem((const void*)rg64::k_regions, smem);
         rg64::k_regions<<<ntiles, 64, smem, s>>>(a);
     }
 }

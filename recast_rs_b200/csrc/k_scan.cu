@@ -2,9 +2,41 @@
 // Three launches: per-block reduce, single-block scan of the block sums, per-block scan + offset.
 // HBM traffic: 2 reads + 1 write of the array (12 B per cell); the arrays are L2-resident at the
 // configured sizes (8 M cells = 32 MB).
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "rcb_common.cuh"
 
 thread_local RcbProfHook g_rcb_prof = {nullptr, nullptr, nullptr};
+
+bool rcb_sync_check() {
+    static const bool on = getenv("RCB_SYNC_CHECK") != nullptr;
+    return on;
+}
+
+void rcb_sync_check_kernel(const char* name, cudaStream_t s) {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        int dev = -1;
+        cudaGetDevice(&dev);
+        fprintf(stderr, "[rcb sync check] device %d stream %p: %s: %s\n", dev, (void*)s, name, cudaGetErrorString(e));
+    }
+}
+
+void rcb_raise_dynamic_smem(const void* kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> limit;  // (kernel, device) -> what it was last raised to
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& cur = limit[std::make_pair(kernel, dev)];
+    if (bytes <= cur) return;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess) cur = bytes;
+}
 
 namespace {
 

@@ -1273,9 +1273,7 @@ void rcb_bounds_selftest(uint32_t* scratch16, cudaStream_t s) {
 #endif
 }
 
-static void set_smem_attr(const void* fn, size_t bytes) {
-    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-}
+static void set_smem_attr(const void* fn, size_t bytes) { rcb_raise_dynamic_smem(fn, bytes); }
 
 void launch_tile_spans(const TileSpansArgs& a, int nbands, cudaStream_t s) {
     if (nbands == 0) return;

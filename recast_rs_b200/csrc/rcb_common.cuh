@@ -421,6 +421,14 @@ struct RcbProfHook {
     unsigned long long* launches;
 };
 extern thread_local RcbProfHook g_rcb_prof;
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is one value per (kernel, device), shared by every host thread that drives
+// the device: two contexts on one device (rcb_multi's two workers, a pipelined caller) that set it to their own batch's
+// size and then launch can undo each other - the launch with the larger size then fails, and the kernels behind it read
+// a stale intermediate.  The limit is therefore only ever RAISED, under a lock; a launch may use less than the limit.
+void rcb_raise_dynamic_smem(const void* kernel, size_t bytes);
+bool rcb_sync_check();                                         // RCB_SYNC_CHECK set in the environment (read once)
+void rcb_sync_check_kernel(const char* name, cudaStream_t s);  // launch error / stream synchronize -> stderr
 struct KScope {
     const char* name;
     cudaStream_t s;
@@ -430,5 +438,6 @@ struct KScope {
     ~KScope() {
         if (g_rcb_prof.launches) ++*g_rcb_prof.launches;
         if (g_rcb_prof.mark) g_rcb_prof.mark(g_rcb_prof.user, name, 0, s);
+        if (rcb_sync_check()) rcb_sync_check_kernel(name, s);  // RCB_SYNC_CHECK=1: wait for the kernel, name it if it failed
     }
 };
