@@ -81,3 +81,57 @@ def test_multi_errors():
         cfgs[1].cs = -1.0
         with pytest.raises(errors.InvalidMesh):
             m.build_tiles(cfgs, rb.STAGE_ALL_BUILD, tiles_per_group=1)
+
+
+def test_two_contexts_on_one_device_with_batches_of_different_size():
+    """Two host threads, a context each, ONE device, batches whose tile kernels want different amounts of dynamic shared
+    memory, issued back to back without host round trips (rcb_multi's two workers per device do exactly this).  The limit
+    a kernel may ask for is one value per (kernel, device): set per launch by both threads it was a race - the thread with
+    the larger batch could find the limit lowered under it (an intermittent illegal access).  Forty builds per thread,
+    every one checked against the serial build of the same batch."""
+    import threading
+
+    import recast_rs_b200.builder as rb
+    from recast_rs_b200 import synth
+
+    v, t, cfgs = synth.config3(seed=5, nq=300, tile=64, lattice=14)  # 64x64 tiles (tile-resident back end) with buildings:
+    # span counts, hence shared-memory sizes, differ by tile
+    cfgs = list(cfgs)
+    order = sorted(range(len(cfgs)), key=lambda i: (cfgs[i].bmin[0], cfgs[i].bmin[2]))
+    halves = [[cfgs[i] for i in order[: len(order) // 3]], [cfgs[i] for i in order[len(order) // 3:]]]
+    serial = rb.Context(0)
+    serial.upload_mesh(v, t)
+    want = []
+    for h in halves:
+        with serial.build_tiles(h, rb.STAGE_ALL_BUILD) as r:
+            r.download()
+            tot = r.totals()
+            tot.pop("result_bytes")
+            want.append((tot, r.tile(0), r.tile(len(h) - 1)))
+    serial.close()
+    errors = []
+
+    def work(k):
+        try:
+            ctx = rb.Context(0)
+            ctx.upload_mesh(v, t)
+            for rep in range(40):
+                with ctx.build_tiles(halves[k], rb.STAGE_ALL_BUILD) as r:
+                    tot = r.totals()
+                    tot.pop("result_bytes")
+                    assert tot == want[k][0], (k, rep, tot, want[k][0])
+                    if rep % 13 == 0:
+                        r.download()
+                        _same(r.tile(0), want[k][1], f"thread {k} rep {rep} first tile")
+                        _same(r.tile(len(halves[k]) - 1), want[k][2], f"thread {k} rep {rep} last tile")
+            assert ctx.stats()["speculative"] >= 30
+            ctx.close()
+        except BaseException as e:  # noqa: BLE001 - reported by the main thread
+            errors.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errors, errors
