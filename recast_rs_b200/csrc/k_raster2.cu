@@ -7,14 +7,15 @@
 // row/column counts), 610 M local-memory sectors and 716 MB of DRAM writes from polygon spills.
 //
 // Structure (one CTA = CLIP_ITEMS work items, CLIP_THREADS threads):
-//   phase 1  thread = item (tri, tile, chunk of CLIP_ROWS rows): z-chain.  The chain of a triangle is
-//            sequential (each cut interpolates from the previous cut's rounded points), so a chunk that
-//            starts at row r first replays the r cuts before it (cheap: one divide per row), then stores
-//            the row polygons of its rows — x,y only, z is never read again — into shared-memory slots.
-//   phase 2  thread = row slot: x-chain over the columns of that row.  Only the count and the y-range of
+//   phase 1  one of the first CLIP_ITEMS threads = item (tri, tile, chunk of up to CLIP_ROWS rows): z-chain.  The chain
+//            of a triangle is sequential (each cut interpolates from the previous cut's rounded points), so a chunk that
+//            starts at row r first replays the r cuts before it (one divide per row; triangles of up to CLIP_ROWS rows
+//            are one chunk and replay nothing), then stores the row polygons of its rows — x,y only, z is never read
+//            again — into shared-memory slots.
+//   phase 2  every thread = row slot: x-chain over the columns of that row.  Only the count and the y-range of
 //            the cell piece are needed, so the cell polygon is never stored.  Columns whose cut lies
-//            strictly left of every vertex are skipped without a divide (the divide would return the
-//            polygon unchanged and an empty cell piece, so skipping is exact).
+//            strictly left of every vertex are skipped without a divide, ahead of the column loop (the divide would
+//            return the polygon unchanged and an empty cell piece, so skipping is exact).
 // Fragments go either to one global list with a per-column rank (v1 back end) or to per-tile segments
 // (tile-resident back end, k_tile.cu).
 #include <algorithm>

@@ -142,7 +142,6 @@ struct rcb_ctx {
     uint32_t band_cells = 0x7fffffffu;  // RCB_BAND_CELLS: cut tiles into bands of about this many cells for the tile-resident kernels.
                                         // Default: never cut - a tile that does not fit shared memory whole takes the global back
                                         // end, which measured faster than bands on BASELINE configs 3 and 4
-    uint32_t clip_flags = 1;    // RCB_CLIP_FLAGS (A/B runs): bit0 min-x skip test in the clipper
     bool phase_timers = false;  // RCB_PHASE_TIMERS=1: per-phase cycle sums of the tile kernels on stderr
     bool force_global = false;  // RCB_FORCE_GLOBAL=1: never use the tile-resident back end (k_tile.cu)
     bool force_v1 = false;  // RCB_FORCE_V1=1: first-generation clipper (k_raster.cu), kept as the wide-tile fallback
@@ -947,7 +946,7 @@ int run_pipeline(rcb_ctx* ctx, const rcb_config* cfgs, int ntiles, uint32_t stag
         r2.mesh = rb.mesh;
         r2.counters = rb.counters;
         r2.cell_cnt = rb.cell_cnt;
-        r2.flags = ctx->clip_flags | (ctx->phase_timers ? 0x100u : 0u);
+        r2.flags = ctx->phase_timers ? 0x100u : 0u;
         uint64_t ub = 0, nitems = 0, ub_max = 0;
         bool want_tile = false;
         // tile-resident back end candidates: a band of two rows (plus its halo rows) must fit shared memory; fragment
@@ -1617,7 +1616,6 @@ int rcb_create(int device, rcb_ctx** out) {
     if (const char* e = getenv("RCB_FORCE_V1")) ctx->force_v1 = e[0] == '1';
     if (const char* e = getenv("RCB_FORCE_GLOBAL")) ctx->force_global = e[0] == '1';
     if (const char* e = getenv("RCB_PHASE_TIMERS")) ctx->phase_timers = e[0] == '1';
-    if (const char* e = getenv("RCB_CLIP_FLAGS")) ctx->clip_flags = (uint32_t)atoi(e);
     if (const char* e = getenv("RCB_NO_SPEC")) ctx->no_spec = e[0] == '1';
     if (const char* e = getenv("RCB_BAND_CELLS")) ctx->band_cells = (uint32_t)std::max(1, atoi(e));
     if (const char* e = getenv("RCB_TILE_THREADS")) ctx->tile_threads = atoi(e) == 256 ? 256 : atoi(e) == 512 ? 512 : 0;

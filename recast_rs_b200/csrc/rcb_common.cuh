@@ -156,7 +156,7 @@ struct Raster2 {
     const uint32_t* tile_base; // [nbands] first record of the band's segment
     const uint32_t* tile_cap;  // [nbands]
     uint32_t* tile_frags;      // per segment three arrays of tile_cap words: cell | area<<24, smin | smax<<16, triangle
-    uint32_t flags;            // bit0: min-x skip test (0: explicit per-vertex test; kept for A/B runs)
+    uint32_t flags;            // 0x100: phase timers (RCB_PHASE_TIMERS); 0x200: count fragments per column while emitting (global back end)
     uint32_t spec;             // 1: issued speculatively - the work-item count is read from counters[4] on the device
 };
 // counters[2] flag bits: 1 clip polygon overflow, 2 fragment pool overflow, 4 a tile does not fit shared memory,
