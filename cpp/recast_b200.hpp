@@ -11,8 +11,13 @@
 //     auto batch = builder.build_tiles(verts, nfloats, tris, nidx, tiles.data(), tiles.size());
 //     rcb_tile_view v = batch.tile(0);                     // flat SoA of Heightfield + CompactHeightfield
 //
+// Round-2 additions: build_tiles_streamed (host-to-host, copy overlapped with compute, optionally the slim layout with
+// expand_slim() as the binding layer's rebuild), rasterize_triangles_u16 / _soup entry forms, Context::stats(), and
+// MultiContext (several GPUs of one box behind one handle, the loop of DynamicNavMesh::build).
+//
 // Errors: recast_common::Error::{InvalidMesh, NavMeshGeneration} map to the exceptions below.
 #pragma once
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -56,6 +61,16 @@ class Context {
     Context& operator=(const Context&) = delete;
     rcb_ctx* raw() const { return ctx_; }
     void set_stream(void* cuda_stream) { check(rcb_set_stream(ctx_, cuda_stream), ctx_, "set_stream"); }  // verbatim; nullptr = legacy default stream
+    struct Stats {
+        uint64_t issued_without_round_trip, rebuilt, cached_batches;
+    };
+    // builds issued with sizes assumed from the previous build of the same configurations (verified on the device), how
+    // many of those had to be redone, configuration batches cached by the context
+    Stats stats() const {
+        uint64_t o[4] = {0, 0, 0, 0};
+        check(rcb_ctx_stats(ctx_, o), ctx_, "stats");
+        return Stats{o[0], o[1], o[2]};
+    }
 
    private:
     rcb_ctx* ctx_ = nullptr;
@@ -108,6 +123,70 @@ class Batch {
     rcb_result* res_;
 };
 
+// What an RCB_RESULT_SLIM download leaves to the binding layer, rebuilt from the layout rule of
+// compact_heightfield.rs:375-389: connections lie in span order and, inside a span, in descending direction (directions 7..0
+// are pushed with `next` -> the one pushed before; `first_connection` = the last pushed).  The same loop a Rust shim runs
+// while it fills Vec<CompactSpan>; held to byte equality with the full layout by cpp/example.cpp on a GPU.
+struct SlimTile {
+    std::vector<uint32_t> hf_cell_offset, cell_index, cell_count, first_conn, conn_ref, conn_next;
+    std::vector<uint16_t> con;
+    std::vector<uint8_t> conn_dir, areas;
+};
+
+inline SlimTile expand_slim(const rcb_tile_view& v) {
+    if (!v.conn_mask) throw Error(RCB_EARG, "expand_slim: not a slim host view (download an RCB_RESULT_SLIM result first)");
+    static const int dx[8] = {-1, 0, 1, 1, 1, 0, -1, -1}, dz[8] = {-1, -1, -1, 0, 1, 1, 1, 0};  // compact_heightfield.rs:109-111
+    static const int d4[8] = {-1, 3, -1, 2, -1, 1, -1, 0};  // 8-direction -> con slot (:397-427); -1: diagonal
+    const uint32_t C = v.cell_count, S = v.span_count, K = v.conn_count;
+    SlimTile t;
+    t.cell_count.resize(C);
+    t.hf_cell_offset.resize((size_t)C + 1);
+    t.cell_index.resize(C);
+    uint32_t run = 0;
+    for (uint32_t c = 0; c < C; ++c) {
+        const uint32_t n = v.cell_count16 ? v.cell_count16[c] : v.cell_count_arr[c];
+        t.cell_count[c] = n;
+        t.hf_cell_offset[c] = run;
+        t.cell_index[c] = n ? run : RCB_NONE;
+        run += n;
+    }
+    t.hf_cell_offset[C] = run;
+    if (run != S) throw Error(RCB_EARG, "expand_slim: cell counts do not add up to the span count");
+    const uint8_t* areas = v.areas ? v.areas : v.span_area;  // nothing wrote chf.areas: still the copy of CompactSpan.area it starts as
+    t.areas.assign(areas, areas + S);
+    t.first_conn.assign(S, RCB_NONE);
+    t.conn_ref.resize(K);
+    t.conn_next.resize(K);
+    t.conn_dir.resize(K);
+    t.con.assign((size_t)4 * S, 63);
+    if (!v.conn_off8) {  // a connection's offset passed 255 somewhere: con travelled after all, in 8 or 16 bits
+        for (size_t i = 0; i < (size_t)4 * S; ++i) t.con[i] = v.con8 ? (uint16_t)v.con8[i] : v.con[i];
+    }
+    uint32_t k = 0;
+    for (uint32_t c = 0; c < C; ++c)
+        for (uint32_t sp = t.hf_cell_offset[c]; sp < t.hf_cell_offset[c + 1]; ++sp) {
+            const uint32_t mask = v.conn_mask[sp];
+            bool first = true;
+            for (int d = 7; d >= 0; --d) {
+                if (!(mask & (1u << d))) continue;
+                if (k >= K) throw Error(RCB_EARG, "expand_slim: more mask bits than connections");
+                t.conn_dir[k] = (uint8_t)d;
+                t.conn_next[k] = first ? RCB_NONE : k - 1;
+                first = false;
+                if (v.conn_off8) {
+                    const uint32_t ncell = (uint32_t)((int)c + dz[d] * v.width + dx[d]);  // in the tile: the mask says a neighbour exists
+                    t.conn_ref[k] = t.cell_index[ncell] + v.conn_off8[k];
+                    if (d4[d] >= 0) t.con[(size_t)4 * sp + d4[d]] = v.conn_off8[k];
+                } else {
+                    t.conn_ref[k] = v.conn_ref16 ? (uint32_t)v.conn_ref16[k] : v.conn_ref[k];
+                }
+                t.first_conn[sp] = k++;
+            }
+        }
+    if (k != K) throw Error(RCB_EARG, "expand_slim: mask bits do not add up to the connection count");
+    return t;
+}
+
 class RecastBuilder {
    public:
     RecastBuilder(const RecastConfig& cfg, Context& ctx) : cfg_(cfg), ctx_(ctx) {}
@@ -122,11 +201,37 @@ class RecastBuilder {
                       uint32_t stage_mask = RCB_STAGE_ALL_BUILD, int erode_radius = 0) {
         return run(verts, nfloats, tris, nidx, tiles, ntiles, stage_mask, erode_radius);
     }
+    // The host-to-host form: tiles in `ngroups` consecutive groups, a finished group's copy to pinned host memory overlapping
+    // the next groups' kernels; slim = RCB_RESULT_SLIM (a quarter of the bytes; expand_slim() rebuilds the rest per tile).
+    Batch build_tiles_streamed(const float* verts, size_t nfloats, const int32_t* tris, size_t nidx, const rcb_config* tiles, size_t ntiles,
+                               int ngroups = 4, bool slim = true, uint32_t stage_mask = RCB_STAGE_ALL_BUILD, int erode_radius = 0) {
+        check(rcb_upload_mesh(ctx_.raw(), verts, nfloats, tris, nidx), ctx_.raw(), "upload_mesh");
+        rcb_result* res = nullptr;
+        check(rcb_build_tiles_streamed(ctx_.raw(), tiles, (int)ntiles, stage_mask | (slim ? (uint32_t)RCB_RESULT_SLIM : 0u), erode_radius, ngroups,
+                                       &res),
+              ctx_.raw(), "build_tiles_streamed");
+        return Batch(ctx_.raw(), res);  // already downloaded
+    }
+    // rasterize_triangles_u16 (rasterization.rs:432-455): 16-bit indices, widened on the device.
+    Batch build_tiles_u16(const float* verts, size_t nfloats, const uint16_t* tris, size_t nidx, const rcb_config* tiles, size_t ntiles,
+                          uint32_t stage_mask = RCB_STAGE_ALL_BUILD, int erode_radius = 0) {
+        check(rcb_upload_mesh_u16(ctx_.raw(), verts, nfloats, tris, nidx), ctx_.raw(), "upload_mesh_u16");
+        return built(tiles, ntiles, stage_mask, erode_radius);
+    }
+    // rasterize_triangle_soup (rasterization.rs:459-476): nine floats per triangle, no index list.
+    Batch build_tiles_soup(const float* verts, size_t ntris, const rcb_config* tiles, size_t ntiles, uint32_t stage_mask = RCB_STAGE_ALL_BUILD,
+                           int erode_radius = 0) {
+        check(rcb_upload_triangle_soup(ctx_.raw(), verts, ntris), ctx_.raw(), "upload_triangle_soup");
+        return built(tiles, ntiles, stage_mask, erode_radius);
+    }
 
    private:
     Batch run(const float* verts, size_t nfloats, const int32_t* tris, size_t nidx, const rcb_config* tiles, size_t ntiles,
               uint32_t stage_mask, int erode_radius) {
         check(rcb_upload_mesh(ctx_.raw(), verts, nfloats, tris, nidx), ctx_.raw(), "upload_mesh");
+        return built(tiles, ntiles, stage_mask, erode_radius);
+    }
+    Batch built(const rcb_config* tiles, size_t ntiles, uint32_t stage_mask, int erode_radius) {
         rcb_result* res = nullptr;
         check(rcb_build_tiles(ctx_.raw(), tiles, (int)ntiles, stage_mask, erode_radius, &res), ctx_.raw(), "build_tiles");
         Batch b(ctx_.raw(), res);
@@ -135,6 +240,79 @@ class RecastBuilder {
     }
     RecastConfig cfg_;
     Context& ctx_;
+};
+
+// Several GPUs of one box behind one handle: the multi-tile loop of DynamicNavMesh::build / build_async
+// (detour-dynamic/src/dynamic_navmesh.rs:558-684) from ONE caller thread.  The tiles are dealt in groups to two internal
+// workers per device (own share first, then stealing); results stay on the device that built them unless download is asked for.
+class MultiBatch {
+   public:
+    MultiBatch(rcb_multi* m, rcb_multi_result* res) : m_(m), res_(res) {}
+    MultiBatch(MultiBatch&& o) noexcept : m_(o.m_), res_(std::exchange(o.res_, nullptr)) {}
+    MultiBatch(const MultiBatch&) = delete;
+    ~MultiBatch() { rcb_multi_result_free(res_); }
+    rcb_totals totals(std::vector<int>* tiles_per_device = nullptr) const {
+        rcb_totals t{};
+        const int n = rcb_multi_device_count(m_);
+        if (tiles_per_device) tiles_per_device->assign(n, 0);
+        mcheck(rcb_multi_result_totals(res_, &t, tiles_per_device ? tiles_per_device->data() : nullptr, tiles_per_device ? n : 0), "totals");
+        return t;
+    }
+    void download() { mcheck(rcb_multi_result_download(res_), "download"); }
+    rcb_tile_view tile(int i) const {  // host pointers; call download() first (or build with download = true)
+        rcb_tile_view v{};
+        mcheck(rcb_multi_result_tile(res_, i, &v), "tile");
+        return v;
+    }
+    rcb_tile_view tile_device(int i, int* device = nullptr) const {
+        rcb_tile_view v{};
+        mcheck(rcb_multi_result_tile_device(res_, i, &v, device), "tile_device");
+        return v;
+    }
+
+   private:
+    void mcheck(int st, const char* what) const {
+        if (st == RCB_OK) return;
+        std::string msg = rcb_multi_last_error(m_);
+        if (msg.empty()) msg = what;
+        if (st == RCB_EINVALID_MESH) throw InvalidMesh(st, msg);
+        if (st == RCB_ENAVMESH_GEN) throw NavMeshGeneration(st, msg);
+        throw Error(st, msg);
+    }
+    rcb_multi* m_;
+    rcb_multi_result* res_;
+};
+
+class MultiContext {
+   public:
+    explicit MultiContext(const std::vector<int>& devices) {
+        check(rcb_multi_create(devices.data(), (int)devices.size(), &m_), nullptr, "rcb_multi_create failed: no CUDA device (no CPU fallback)");
+    }
+    ~MultiContext() { rcb_multi_destroy(m_); }
+    MultiContext(const MultiContext&) = delete;
+    MultiContext& operator=(const MultiContext&) = delete;
+    int device_count() const { return rcb_multi_device_count(m_); }
+    void upload_mesh(const float* verts, size_t nfloats, const int32_t* tris, size_t nidx) {
+        const int st = rcb_multi_upload_mesh(m_, verts, nfloats, tris, nidx);
+        if (st != RCB_OK) raise(st, "upload_mesh");
+    }
+    MultiBatch build_tiles(const rcb_config* tiles, size_t ntiles, uint32_t stage_mask = RCB_STAGE_ALL_BUILD, int erode_radius = 0,
+                           int tiles_per_group = 0, bool download = false) {
+        rcb_multi_result* res = nullptr;
+        const int st = rcb_multi_build_tiles(m_, tiles, (int)ntiles, stage_mask, erode_radius, tiles_per_group, download ? 1 : 0, &res);
+        if (st != RCB_OK) raise(st, "build_tiles");
+        return MultiBatch(m_, res);
+    }
+
+   private:
+    [[noreturn]] void raise(int st, const char* what) const {
+        std::string msg = rcb_multi_last_error(m_);
+        if (msg.empty()) msg = what;
+        if (st == RCB_EINVALID_MESH) throw InvalidMesh(st, msg);
+        if (st == RCB_ENAVMESH_GEN) throw NavMeshGeneration(st, msg);
+        throw Error(st, msg);
+    }
+    rcb_multi* m_ = nullptr;
 };
 
 inline Batch build_from_span_data(Context& ctx, const rcb_config* tiles, size_t ntiles, const uint8_t* data, const uint64_t* tile_offsets,

@@ -413,7 +413,7 @@ void rcb_result_free(rcb_result* res);
 /* ---- several devices of one box --------------------------------------------------------------------
  * The multi-tile loop of detour-dynamic (DynamicNavMesh::build / build_async, crates/detour-dynamic/src/dynamic_navmesh.rs:
  * 558-684: `for key in tile_keys` -> DynamicTile::build) over the GPUs of one box, from ONE host thread of the caller:
- *   rcb_multi_create        one rcb_ctx per listed device.
+ *   rcb_multi_create        two rcb_ctx (and, during a build, two host threads) per listed device.
  *   rcb_multi_upload_mesh   the mesh goes host -> devices[0] once and from there to the other devices (peer copy over NVLink);
  *                           indices are validated as in rcb_upload_mesh.
  *   rcb_multi_build_tiles   tiles are independent (no halo, border_size 0 on every multi-tile path of the reference), so the

@@ -191,6 +191,10 @@ def test_cpp_example_matches_oracle_on_gpu(oracle, tmp_path):
     want1 = f"cells {cfg.width * cfg.height} spans {e.span_min.size} connections {e.conn_ref.size} max_distance {e.max_distance}"
     want2 = f"regions {int(reg.max(initial=0))} max_regions {mr} span_data {2 * cfg.width * cfg.height + 12 * e.span_min.size}"
     assert want1 in out.stdout and want2 in out.stdout, out.stdout
+    # the slim host-to-host call rebuilt by cpp's expand_slim() is the full layout byte for byte (two-level columns included),
+    # and the several-GPU entry agrees on the totals
+    assert "slim expand ok: tiles 9" in out.stdout and "second-level offsets yes" in out.stdout, out.stdout
+    assert "multi ok: devices 1 tiles 9" in out.stdout, out.stdout
 
 
 def test_build_tracks_every_kernel_header():
