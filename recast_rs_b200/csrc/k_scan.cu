@@ -4,9 +4,7 @@
 // configured sizes (8 M cells = 32 MB).
 #include <cstdio>
 #include <cstdlib>
-#include <map>
 #include <mutex>
-#include <utility>
 
 #include "rcb_common.cuh"
 
@@ -29,13 +27,12 @@ void rcb_sync_check_kernel(const char* name, cudaStream_t s) {
 
 void rcb_raise_dynamic_smem(const void* kernel, size_t bytes) {
     static std::mutex mu;
-    static std::map<std::pair<const void*, int>, size_t> limit;  // (kernel, device) -> what it was last raised to
-    int dev = 0;
-    cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lk(mu);
-    size_t& cur = limit[std::make_pair(kernel, dev)];
-    if (bytes <= cur) return;
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess) cur = bytes;
+    // the current limit is read back from the driver (per kernel and current device) rather than remembered here: a process
+    // that resets a device between two lives of the library starts from the default again
+    cudaFuncAttributes a{};
+    if (cudaFuncGetAttributes(&a, kernel) == cudaSuccess && (size_t)a.maxDynamicSharedSizeBytes >= bytes) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
 namespace {
