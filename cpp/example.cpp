@@ -60,6 +60,21 @@ int main() {
         }
         std::printf("slim expand %s: tiles %zu spans %llu connections %llu second-level offsets %s\n", same ? "ok" : "MISMATCH", tiles.size(), S, K,
                     any_offset ? "yes" : "no");
+        // the centre tile again, this time from its filtered spans (Heightfield -> CompactHeightfield -> distance field): same bytes
+        {
+            const rcb_tile_view a = full.tile(4);
+            const SpanInput in{a.hf_cell_offset, a.span_min, a.span_max, a.span_area};
+            ctx.profile_enable(true);
+            Batch again = build_from_spans(ctx, &tiles[4], 1, in, nullptr, RCB_STAGE_COMPACT | RCB_STAGE_DIST);
+            again.download();
+            const rcb_tile_view b = again.tile(0);
+            const bool ok = a.span_count == b.span_count && a.conn_count == b.conn_count && !std::memcmp(a.conn_ref, b.conn_ref, 4 * (size_t)a.conn_count) &&
+                            !std::memcmp(a.dist, b.dist, 2 * (size_t)a.span_count) && !std::memcmp(a.con, b.con, 8 * (size_t)a.span_count);
+            std::printf("from spans %s: spans %u connections %u kernels timed %zu\n", ok ? "ok" : "MISMATCH", b.span_count, b.conn_count,
+                        ctx.profile_read().size());
+            ctx.profile_enable(false);
+            same = same && ok;
+        }
         // the same tiles through the several-GPU entry, on however many devices the box has listed as {0}
         MultiContext multi({0});
         multi.upload_mesh(verts2, 24, tris2, 12);

@@ -61,6 +61,27 @@ class Context {
     Context& operator=(const Context&) = delete;
     rcb_ctx* raw() const { return ctx_; }
     void set_stream(void* cuda_stream) { check(rcb_set_stream(ctx_, cuda_stream), ctx_, "set_stream"); }  // verbatim; nullptr = legacy default stream
+    // The (&[f32] vertices, &[i32] indices) pair every RecastBuilder entry point takes (lib.rs:68,116,186), kept on the device
+    // for the builds that follow; indices are validated here (lib.rs:224-233 -> NavMeshGeneration).
+    void upload_mesh(const float* verts, size_t nfloats, const int32_t* tris, size_t nidx) {
+        check(rcb_upload_mesh(ctx_, verts, nfloats, tris, nidx), ctx_, "upload_mesh");
+    }
+    // A mesh that already lives on this context's device (borrowed until the next mesh call; must not change meanwhile).
+    void set_mesh_device(const void* d_verts, size_t nfloats, const void* d_tris, size_t nidx) {
+        check(rcb_set_mesh_device(ctx_, d_verts, nfloats, d_tris, nidx), ctx_, "set_mesh_device");
+    }
+    void use_own_stream() { check(rcb_use_own_stream(ctx_), ctx_, "use_own_stream"); }
+    uint64_t launch_count() const { return rcb_launch_count(ctx_); }
+    // RecastContext::start_timer / stop_timer per TimerCategory (context.rs:25-54,223-251), device side: summed kernel time per name.
+    void profile_enable(bool on) { check(rcb_profile_enable(ctx_, on ? 1 : 0), ctx_, "profile_enable"); }
+    void profile_reset() { check(rcb_profile_reset(ctx_), ctx_, "profile_reset"); }
+    std::vector<rcb_stage_time> profile_read() {
+        std::vector<rcb_stage_time> out(128);
+        const int n = rcb_profile_read(ctx_, out.data(), (int)out.size());
+        if (n < 0) check(n, ctx_, "profile_read");
+        out.resize(n < (int)out.size() ? n : (int)out.size());
+        return out;
+    }
     struct Stats {
         uint64_t issued_without_round_trip, rebuilt, cached_batches;
     };
@@ -331,6 +352,106 @@ inline Batch build_tilecache_compressed(Context& ctx, const uint8_t* blobs, cons
                                          (int)nobstacles, cs, ch, stage_mask, 0, &res),
           ctx.raw(), "build_tilecache_compressed");
     return Batch(ctx.raw(), res);
+}
+
+// An existing heightfield per tile as host CSR (cell_offset: width*height+1 tile-relative offsets per tile, concatenated;
+// spans concatenated in tile order) - the argument of every entry below that starts from spans instead of triangles.
+struct SpanInput {
+    const uint32_t* cell_offset;
+    const int16_t* span_min;
+    const int16_t* span_max;
+    const uint8_t* span_area;
+};
+
+// Heightfield::filter_* (heightfield.rs:286,332,492), CompactHeightfield::build_from_heightfield (compact_heightfield.rs:175),
+// erode_walkable_area (area.rs:73), build_distance_field (:514) on existing heightfields; RCB_STAGE_READD re-inserts the spans
+// through Heightfield::add_span first (DynamicTileCheckpoint::clone_heightfield, checkpoint.rs:29-60).  areas_override:
+// CompactHeightfield.areas as the caller last left them (nullable).
+inline Batch build_from_spans(Context& ctx, const rcb_config* tiles, size_t ntiles, const SpanInput& in, const uint8_t* areas_override,
+                              uint32_t stage_mask, int erode_radius = 0) {
+    rcb_result* res = nullptr;
+    check(rcb_build_from_spans(ctx.raw(), tiles, (int)ntiles, in.cell_offset, in.span_min, in.span_max, in.span_area, areas_override, stage_mask,
+                               erode_radius, &res),
+          ctx.raw(), "build_from_spans");
+    return Batch(ctx.raw(), res);
+}
+
+// The free function rasterize_triangles(verts, tris, tri_area_ids, n, hf, flag_merge_threshold) (rasterization.rs:405-428) on the
+// context's mesh: caller-given triangle areas, no slope classification, no degenerate-triangle skip.
+inline Batch rasterize(Context& ctx, const rcb_config* tiles, size_t ntiles, const uint8_t* tri_areas, int32_t flag_merge_threshold,
+                       uint32_t stage_mask = RCB_STAGE_RASTER, int erode_radius = 0) {
+    rcb_result* res = nullptr;
+    check(rcb_rasterize(ctx.raw(), tiles, (int)ntiles, tri_areas, flag_merge_threshold, stage_mask, erode_radius, &res), ctx.raw(), "rasterize");
+    return Batch(ctx.raw(), res);
+}
+
+// The same onto heightfields that already hold spans (a restored checkpoint that gets its colliders re-applied, dynamic_tile.rs);
+// tri_areas == nullptr: areas by slope as RecastBuilder::rasterize_triangles does (lib.rs:186-290; merge threshold 1, :273).
+inline Batch rasterize_onto(Context& ctx, const rcb_config* tiles, size_t ntiles, const SpanInput& existing, const uint8_t* tri_areas,
+                            int32_t flag_merge_threshold = 1, uint32_t stage_mask = RCB_STAGE_RASTER, int erode_radius = 0) {
+    rcb_result* res = nullptr;
+    check(rcb_rasterize_onto(ctx.raw(), tiles, (int)ntiles, existing.cell_offset, existing.span_min, existing.span_max, existing.span_area,
+                             tri_areas, flag_merge_threshold, stage_mask, erode_radius, &res),
+          ctx.raw(), "rasterize_onto");
+    return Batch(ctx.raw(), res);
+}
+
+// median_filter_walkable_area / mark_box_area / mark_cylinder_area / mark_convex_poly_area (area.rs:238-437, 544-618), applied in
+// order to every tile (rcb_area_op; polygon vertices as xyz triples in poly_verts).
+inline Batch apply_area_ops(Context& ctx, const rcb_config* tiles, size_t ntiles, const SpanInput& in, const uint8_t* areas_override,
+                            const std::vector<rcb_area_op>& ops, const std::vector<float>& poly_verts = {},
+                            uint32_t stage_mask = RCB_STAGE_COMPACT, int erode_radius = 0) {
+    rcb_result* res = nullptr;
+    check(rcb_apply_area_ops(ctx.raw(), tiles, (int)ntiles, in.cell_offset, in.span_min, in.span_max, in.span_area, areas_override, ops.data(),
+                             (int)ops.size(), poly_verts.data(), poly_verts.size(), stage_mask, erode_radius, &res),
+          ctx.raw(), "apply_area_ops");
+    return Batch(ctx.raw(), res);
+}
+
+// RecastBuilder::build_heightfield_with_volumes / build_mesh_with_volumes (lib.rs:293-361) on the context's mesh:
+// ConvexVolumeSet::apply_to_heightfield (convex_volume.rs:392-430) after the filters, before compaction.
+inline Batch build_tiles_with_volumes(Context& ctx, const rcb_config* tiles, size_t ntiles, const std::vector<rcb_convex_volume>& volumes,
+                                      const std::vector<float>& poly_verts, uint32_t stage_mask = RCB_STAGE_ALL_BUILD, int erode_radius = 0) {
+    rcb_result* res = nullptr;
+    check(rcb_build_tiles_with_volumes(ctx.raw(), tiles, (int)ntiles, stage_mask, erode_radius, volumes.data(), (int)volumes.size(),
+                                       poly_verts.data(), poly_verts.size(), &res),
+          ctx.raw(), "build_tiles_with_volumes");
+    return Batch(ctx.raw(), res);
+}
+
+// ConvexVolumeSet::apply_to_heightfield on existing heightfields.
+inline Batch apply_convex_volumes(Context& ctx, const rcb_config* tiles, size_t ntiles, const SpanInput& in,
+                                  const std::vector<rcb_convex_volume>& volumes, const std::vector<float>& poly_verts, uint32_t stage_mask = 0,
+                                  int erode_radius = 0) {
+    rcb_result* res = nullptr;
+    check(rcb_apply_convex_volumes(ctx.raw(), tiles, (int)ntiles, in.cell_offset, in.span_min, in.span_max, in.span_area, volumes.data(),
+                                   (int)volumes.size(), poly_verts.data(), poly_verts.size(), stage_mask, erode_radius, &res),
+          ctx.raw(), "apply_convex_volumes");
+    return Batch(ctx.raw(), res);
+}
+
+// TileCacheBuilder::layer_to_compact_heightfield + rasterize_obstacles (detour-tilecache/src/tile_cache_builder.rs:100-251) for a
+// batch of decoded layers.
+inline Batch build_tilecache_layers(Context& ctx, const std::vector<rcb_tc_layer>& layers, const std::vector<rcb_tc_obstacle>& obstacles, float cs,
+                                    float ch, uint32_t stage_mask = RCB_STAGE_COMPACT, int erode_radius = 0) {
+    rcb_result* res = nullptr;
+    check(rcb_build_tilecache_layers(ctx.raw(), layers.data(), (int)layers.size(), obstacles.data(), (int)obstacles.size(), cs, ch, stage_mask,
+                                     erode_radius, &res),
+          ctx.raw(), "build_tilecache_layers");
+    return Batch(ctx.raw(), res);
+}
+
+// TileCache::decompress_tile (tile_cache.rs:854-872) for n compressed tiles; returns the decoded bytes, tile i at
+// [offsets[i], offsets[i + 1]).
+inline std::vector<uint8_t> decompress_tiles(Context& ctx, const uint8_t* blobs, const uint64_t* blob_offsets, size_t n,
+                                             std::vector<uint64_t>* offsets = nullptr) {
+    std::vector<uint64_t> off(n + 1, 0);
+    check(rcb_decompress_tiles(ctx.raw(), blobs, blob_offsets, (int)n, nullptr, 0, off.data()), ctx.raw(), "decompress_tiles (sizing)");
+    std::vector<uint8_t> out(off[n]);
+    check(rcb_decompress_tiles(ctx.raw(), blobs, blob_offsets, (int)n, out.data(), out.size(), off.data()), ctx.raw(), "decompress_tiles");
+    out.resize(off[n]);  // a block that ends early yields fewer bytes than its size prefix says, as lz4_flex does
+    if (offsets) *offsets = off;
+    return out;
 }
 
 }  // namespace recast_b200

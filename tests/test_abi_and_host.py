@@ -195,6 +195,7 @@ def test_cpp_example_matches_oracle_on_gpu(oracle, tmp_path):
     # and the several-GPU entry agrees on the totals
     assert "slim expand ok: tiles 9" in out.stdout and "second-level offsets yes" in out.stdout, out.stdout
     assert "multi ok: devices 1 tiles 9" in out.stdout, out.stdout
+    assert "from spans ok" in out.stdout, out.stdout
 
 
 def test_build_tracks_every_kernel_header():
