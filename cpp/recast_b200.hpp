@@ -82,6 +82,8 @@ class Context {
         out.resize(n < (int)out.size() ? n : (int)out.size());
         return out;
     }
+    // -DRCB_BOUNDS build only (librecast_b200_dbg.so): violations the checked accessors saw; false in the normal build.
+    bool bounds_report(uint64_t out[4], int reset = 0) { return rcb_debug_bounds_report(ctx_, out, reset) == 1; }
     struct Stats {
         uint64_t issued_without_round_trip, rebuilt, cached_batches;
     };

@@ -209,3 +209,16 @@ def test_build_tracks_every_kernel_header():
     assert '.endswith((".cuh", ".h"))' in src or "glob" in src
     csrc = os.path.join(os.path.dirname(os.path.abspath(b.__file__)), "csrc")
     assert "k_regions_impl.cuh" in os.listdir(csrc)
+
+
+def test_cpp_mirror_wraps_every_entry_point():
+    """cpp/recast_b200.hpp is the host side a C++ caller sees: every function include/recast_b200.h declares must be reachable
+    through it (the Python mirror is held to the same list by SYMBOLS in _ffi.py, the Rust sys crate by the drift test)."""
+    import re
+
+    hdr = open(os.path.join(ROOT, "include", "recast_b200.h")).read()
+    cpp = open(os.path.join(ROOT, "cpp", "recast_b200.hpp")).read()
+    declared = sorted(set(re.findall(r"^\s*(?:const\s+)?[A-Za-z_0-9]+\s*\*?\s*(rcb_[a-z_0-9]+)\(", hdr, flags=re.M)))
+    assert len(declared) >= 45, declared
+    missing = [f for f in declared if not re.search(r"\b" + f + r"\(", cpp)]
+    assert not missing, missing
