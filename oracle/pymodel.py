@@ -120,18 +120,36 @@ def add_span(hf, x, z, smin, smax, area, thr):  # rasterization.rs:23-47
     add_span_internal(hf, x, z, smin, smax, area, thr)
 
 
+def _fmin(a, b):
+    """f32::min: the other operand when one is NaN (Python's min() keeps its first argument then)."""
+    if a != a:
+        return b
+    if b != b:
+        return a
+    return a if a < b else b
+
+
+def _fmax(a, b):
+    """f32::max, as _fmin."""
+    if a != a:
+        return b
+    if b != b:
+        return a
+    return a if a > b else b
+
+
 def _as_i32(v):
     v = float(v)
     if math.isnan(v):
         return 0
-    return int(max(-2147483648.0, min(2147483647.0, math.trunc(v))))
+    return int(math.trunc(max(-2147483648.0, min(2147483647.0, v))))  # saturating, infinities included (Rust `as i32`)
 
 
 def _as_i16(v):
     v = float(v)
     if math.isnan(v):
         return 0
-    return int(max(-32768.0, min(32767.0, math.trunc(v))))
+    return int(math.trunc(max(-32768.0, min(32767.0, v))))  # saturating (Rust `as i16`)
 
 
 # rasterization.rs:172-242
@@ -166,8 +184,8 @@ def rasterize_tri(v0, v1, v2, area, hf, thr):
     with np.errstate(all="ignore"):
         v0, v1, v2 = (tuple(f32(c) for c in v) for v in (v0, v1, v2))
         ics, ich = f32(f32(1.0) / hf.cs), f32(f32(1.0) / hf.ch)
-        tmin = [min(min(v0[i], v1[i]), v2[i]) for i in range(3)]
-        tmax = [max(max(v0[i], v1[i]), v2[i]) for i in range(3)]
+        tmin = [_fmin(_fmin(v0[i], v1[i]), v2[i]) for i in range(3)]  # rasterization.rs:258-264: f32::min / max
+        tmax = [_fmax(_fmax(v0[i], v1[i]), v2[i]) for i in range(3)]
         for i in range(3):
             if not (tmin[i] <= hf.bmax[i] and tmax[i] >= hf.bmin[i]):
                 return
@@ -192,7 +210,7 @@ def rasterize_tri(v0, v1, v2, area, hf, thr):
                 ys = [v[1] for v in cell]
                 mn, mx = ys[0], ys[0]
                 for y in ys[1:]:
-                    mn, mx = min(mn, y), max(mx, y)
+                    mn, mx = _fmin(mn, y), _fmax(mx, y)  # :333-339
                 smin = _as_i16(np.floor(f32(f32(mn - hf.bmin[1]) * ich)))
                 smax = _as_i16(np.ceil(f32(f32(mx - hf.bmin[1]) * ich)))
                 smin = max(smin, 0)

@@ -53,3 +53,15 @@ def random_soup(rng, ntri, lo, hi, ylo, yhi, small=0.5):
         verts += tri
     v = np.array(verts, dtype=np.float32).reshape(-1)
     return v, np.arange(ntri * 3, dtype=np.int32)
+
+
+def poison_vertices(rng, verts, frac=0.06):
+    """Some vertices get one non-finite (or barely finite) coordinate: NaN, +-inf, +-3e38.  The reference has no check for
+    them: f32::min / max skip a NaN, `as i32` / `as i16` saturate and turn NaN into 0, comparisons with NaN are false -
+    whatever comes out of that is what the GPU path has to produce too."""
+    v = np.array(verts, dtype=np.float32).reshape(-1, 3).copy()
+    rows = rng.choice(v.shape[0], size=max(1, int(frac * v.shape[0])), replace=False)
+    vals = np.array([np.nan, np.inf, -np.inf, 3.0e38, -3.0e38], np.float32)
+    for r in rows:
+        v[r, int(rng.integers(0, 3))] = vals[int(rng.integers(0, vals.size))]
+    return v.reshape(-1)

@@ -157,6 +157,32 @@ def test_random_soup_tiles(oracle, rb, ctx, seed):
     _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_ALL_BUILD | rb.STAGE_ERODE, erode_radius=1 + seed % 2)
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_non_finite_vertices(oracle, rb, ctx, seed, monkeypatch):
+    """NaN, +-inf and +-3e38 coordinates (tests/parity.py::poison_vertices): the reference checks nothing, its float rules
+    decide, and the clipper has to follow them - NaN-ignoring min / max, saturating casts, false comparisons - on both back
+    ends.  (The leading-column skip and the NaN-start min / max of k_clip_items were argued from these rules.)"""
+    import recast_rs_b200 as r
+    from recast_rs_b200 import synth
+    from tests.parity import poison_vertices
+
+    rng = np.random.default_rng(900 + seed)
+    cs, ch = [(0.3, 0.2), (0.5, 0.25)][seed % 2]
+    v, idx = random_soup(rng, 400, 0.0, 40 * cs, -1.0, 8.0, small=cs)
+    base = r.RecastConfig(cs=cs, ch=ch, walkable_height=int(rng.integers(1, 5)), walkable_climb=int(rng.integers(0, 3)))
+    cfgs = synth.tile_grid(v, [16, 13][seed % 2], base)  # the grid of the clean mesh
+    v = poison_vertices(rng, v)
+    assert not np.isfinite(v).all()
+    _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_RASTER)
+    _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_ALL_BUILD)
+    if seed == 0:
+        monkeypatch.setenv("RCB_FORCE_GLOBAL", "1")
+        cg = rb.Context(0)
+        monkeypatch.delenv("RCB_FORCE_GLOBAL")
+        _check_batch(oracle, rb, cg, v, idx, cfgs, rb.STAGE_ALL_BUILD)
+        cg.close()
+
+
 def test_permuted_triangle_order(oracle, rb, ctx):
     """Span area is order dependent: the GPU must replay fragments in triangle order."""
     import recast_rs_b200 as r

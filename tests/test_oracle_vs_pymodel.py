@@ -93,6 +93,33 @@ def test_builder_pipeline_random_soup(oracle, seed):
     _compare_chf(ochf.export(), pchf)
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_non_finite_vertices(oracle, seed):
+    """NaN, infinities and 3e38 in the vertex array: nothing in the reference rejects them, so its float rules decide -
+    f32::min / max return the other operand for a NaN (Python's min() does not: the model has its own), `as i32` / `as i16`
+    saturate with NaN -> 0, comparisons with NaN are false.  The two restatements were written independently and must
+    agree here as well (they did not until the model stopped using Python's min / max)."""
+    from tests.parity import poison_vertices
+
+    rng = np.random.default_rng(5000 + seed)
+    w, h = int(rng.integers(5, 12)), int(rng.integers(5, 12))
+    cs, ch = [(0.3, 0.2), (0.5, 0.25), (1.0, 1.0)][seed % 3]
+    bmin = (float(rng.uniform(-3, 3)), float(rng.uniform(-1, 0.5)), float(rng.uniform(-3, 3)))
+    cfg = _cfg(w, h, bmin, cs, ch, bmin[1] + 6.0, walkable_height=int(rng.integers(1, 5)), walkable_climb=int(rng.integers(0, 3)))
+    v, idx = _random_soup(rng, 60, min(bmin[0], bmin[2]), max(bmin[0] + w * cs, bmin[2] + h * cs), bmin[1] - 1.0, bmin[1] + 7.0, small=cs)
+    v = poison_vertices(rng, v, 0.1)
+    assert not np.isfinite(v).all()
+    for run_filters in (False, True):
+        ohf = oracle.Heightfield.from_config(cfg)
+        ohf.builder_rasterize(cfg, v, idx, run_filters=run_filters)
+        phf = pm.Heightfield(w, h, cfg.bmin, cfg.bmax, cs, ch)
+        pm.builder_rasterize(phf, cfg, v, idx, run_filters=run_filters)
+        _compare_hf(ohf, phf)
+    ochf, pchf = oracle.CompactHeightfield.build_from_heightfield(ohf), pm.Compact(phf)
+    ochf.build_distance_field(), pchf.build_distance_field()
+    _compare_chf(ochf.export(), pchf)
+
+
 @pytest.mark.parametrize("seed", range(4))
 def test_add_span_rules_random_columns(oracle, seed):
     """Both merge rules (rasterization.rs:51 and heightfield.rs:144) on random columns, incl.
