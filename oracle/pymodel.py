@@ -699,7 +699,7 @@ def mark_convex_poly_area(c, verts, min_y, max_y, area_id):  # area.rs:359-437
     lo = [verts[0][0], f32(min_y), verts[0][2]]
     hi = [verts[0][0], f32(max_y), verts[0][2]]
     for v in verts[1:]:
-        lo[0], lo[2], hi[0], hi[2] = min(lo[0], v[0]), min(lo[2], v[2]), max(hi[0], v[0]), max(hi[2], v[2])
+        lo[0], lo[2], hi[0], hi[2] = _fmin(lo[0], v[0]), _fmin(lo[2], v[2]), _fmax(hi[0], v[0]), _fmax(hi[2], v[2])  # f32::min / max
     minx, miny, minz = _trunc_div(lo[0], c.bmin[0], c.cs), _trunc_div(lo[1], c.bmin[1], c.ch), _trunc_div(lo[2], c.bmin[2], c.cs)
     maxx, maxy, maxz = _trunc_div(hi[0], c.bmin[0], c.cs), _trunc_div(hi[1], c.bmin[1], c.ch), _trunc_div(hi[2], c.bmin[2], c.cs)
     for x, z, s in _footprint(c, minx, maxx, minz, maxz):
