@@ -183,6 +183,41 @@ def test_non_finite_vertices(oracle, rb, ctx, seed, monkeypatch):
         cg.close()
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_vertices_on_cell_lines_and_tile_borders(oracle, rb, ctx, seed, monkeypatch):
+    """Every vertex on a multiple of the cell size (and many on tile borders): the `== offset` side of divide_poly
+    (rasterization.rs:189-216: the vertex goes to BOTH halves, no intersection is computed), the inclusive bounds test and the
+    z = -1 row of a tile's footprint all get exercised on every triangle, on both back ends."""
+    import recast_rs_b200 as r
+
+    rng = np.random.default_rng(40 + seed)
+    cs = [0.5, 1.0, 0.25][seed]
+    step = [1.0, 1.0, 0.5][seed]
+    ntri, n = 300, int(24 / step)
+    pts = rng.integers(0, n + 1, size=(ntri, 3, 2)).astype(np.float32) * np.float32(step)
+    near = rng.integers(-3, 4, size=(ntri, 2, 2)).astype(np.float32) * np.float32(step)  # keep the triangles small
+    pts[:, 1:, :] = np.clip(pts[:, :1, :] + near, 0, 24)
+    ys = rng.integers(0, 9, size=(ntri, 3)).astype(np.float32) * np.float32(0.75)
+    v = np.stack([pts[..., 0], ys, pts[..., 1]], axis=-1).reshape(-1).astype(np.float32)
+    idx = np.arange(3 * ntri, dtype=np.int32)
+    tile = 8.0  # world units per tile: borders on the lattice
+    cfgs = []
+    for tz in range(3):
+        for tx in range(3):
+            c = r.RecastConfig(cs=cs, ch=0.25, walkable_height=3, walkable_climb=2)
+            c.bmin, c.bmax = (tx * tile, -0.5, tz * tile), ((tx + 1) * tile, 7.0, (tz + 1) * tile)
+            c.width = c.height = int(tile / cs)
+            cfgs.append(c)
+    _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_RASTER)
+    _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_ALL_BUILD)
+    if seed == 0:
+        monkeypatch.setenv("RCB_FORCE_GLOBAL", "1")
+        cg = rb.Context(0)
+        monkeypatch.delenv("RCB_FORCE_GLOBAL")
+        _check_batch(oracle, rb, cg, v, idx, cfgs, rb.STAGE_ALL_BUILD)
+        cg.close()
+
+
 def test_permuted_triangle_order(oracle, rb, ctx):
     """Span area is order dependent: the GPU must replay fragments in triangle order."""
     import recast_rs_b200 as r
