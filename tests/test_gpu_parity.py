@@ -218,6 +218,22 @@ def test_vertices_on_cell_lines_and_tile_borders(oracle, rb, ctx, seed, monkeypa
         cg.close()
 
 
+def test_walkable_parameters_wrap_like_the_reference(oracle, rb, ctx):
+    """RecastConfig::walkable_height / walkable_climb are i32 and reach the filters through `as i16` (lib.rs:278-287), which
+    WRAPS (40000 -> -25536, 65540 -> 4); nothing validates them (config.rs:110-136).  One tile per odd pair, same mesh."""
+    import recast_rs_b200 as r
+
+    rng = np.random.default_rng(77)
+    v, idx = random_soup(rng, 250, 0.0, 8.0, -1.0, 7.0, small=0.5)
+    cfgs = []
+    for wh, wc in [(0, 0), (1, 0), (255, 3), (32767, 32767), (40000, 40000), (70000, 2), (-3, -1), (3, 40000), (65540, 65537), (2, -2)]:
+        c = r.RecastConfig(cs=0.5, ch=0.25, walkable_height=wh, walkable_climb=wc)
+        c.bmin, c.bmax, c.width, c.height = (0.0, -0.5, 0.0), (8.0, 7.5, 8.0), 16, 16
+        cfgs.append(c)
+    _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_RASTER | rb.STAGE_FILTER)
+    _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_ALL_BUILD)
+
+
 def test_permuted_triangle_order(oracle, rb, ctx):
     """Span area is order dependent: the GPU must replay fragments in triangle order."""
     import recast_rs_b200 as r
