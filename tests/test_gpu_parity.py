@@ -234,6 +234,31 @@ def test_walkable_parameters_wrap_like_the_reference(oracle, rb, ctx):
     _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_ALL_BUILD)
 
 
+@pytest.mark.parametrize("seed", range(2))
+def test_tiny_triangles_around_the_degenerate_threshold(oracle, rb, ctx, seed):
+    """Triangles of 1e-5 .. 3e-3 units: their cross products straddle f32::EPSILON, below which lib.rs:258-260 skips the
+    triangle; above it the slope test runs on a normal whose length is barely representable.  glam's length (x*x + y*y + z*z
+    in that order, sqrt) and normalize (times the reciprocal) have to be followed to the bit for the same triangles to drop."""
+    import recast_rs_b200 as r
+
+    rng = np.random.default_rng(60 + seed)
+    ntri = 3000
+    c = rng.uniform(0.2, 7.8, size=(ntri, 1, 3)).astype(np.float32)
+    ext = (10.0 ** rng.uniform(-5.0, -2.5, size=(ntri, 1, 1))).astype(np.float32)
+    v = c + rng.uniform(-1, 1, size=(ntri, 3, 3)).astype(np.float32) * ext
+    v[..., 1] = np.abs(v[..., 1]) % 4.0
+    v, idx = v.reshape(-1).astype(np.float32), np.arange(3 * ntri, dtype=np.int32)
+    cfgs = []
+    for tz in range(2):
+        for tx in range(2):
+            cfg = r.RecastConfig(cs=0.25, ch=0.25)
+            cfg.bmin, cfg.bmax, cfg.width, cfg.height = (4.0 * tx, -0.5, 4.0 * tz), (4.0 * tx + 4.0, 6.0, 4.0 * tz + 4.0), 16, 16
+            cfgs.append(cfg)
+    tot = _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_RASTER)
+    assert 0 < tot["fragments"] < ntri * 4  # some triangles were dropped as degenerate, some were not
+    _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_ALL_BUILD)
+
+
 def test_permuted_triangle_order(oracle, rb, ctx):
     """Span area is order dependent: the GPU must replay fragments in triangle order."""
     import recast_rs_b200 as r
