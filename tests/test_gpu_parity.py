@@ -259,6 +259,23 @@ def test_tiny_triangles_around_the_degenerate_threshold(oracle, rb, ctx, seed):
     _check_batch(oracle, rb, ctx, v, idx, cfgs, rb.STAGE_ALL_BUILD)
 
 
+def test_erosion_radius_wraps_like_the_reference(oracle, rb, ctx, monkeypatch):
+    """erode_walkable_area compares against `(erosion_radius * 2) as u8` (area.rs:226): 128 -> 0 (nothing eroded), 130 -> 4,
+    -1 -> 254 (everything within reach of a border goes).  Both back ends."""
+    import recast_rs_b200 as r
+    from recast_rs_b200 import synth
+
+    v, idx = synth.terrain(40, 1.0, 2.0, 9)
+    cfgs = synth.tile_grid(v, 32, r.RecastConfig(cs=0.5, ch=0.25))
+    monkeypatch.setenv("RCB_FORCE_GLOBAL", "1")
+    cg = rb.Context(0)
+    monkeypatch.delenv("RCB_FORCE_GLOBAL")
+    for radius in (0, 1, 127, 128, 130, -1):
+        for c in (ctx, cg):
+            _check_batch(oracle, rb, c, v, idx, cfgs, rb.STAGE_ALL_BUILD | rb.STAGE_ERODE, erode_radius=radius)
+    cg.close()
+
+
 def test_permuted_triangle_order(oracle, rb, ctx):
     """Span area is order dependent: the GPU must replay fragments in triangle order."""
     import recast_rs_b200 as r
