@@ -276,6 +276,21 @@ def test_erosion_radius_wraps_like_the_reference(oracle, rb, ctx, monkeypatch):
     cg.close()
 
 
+def test_boundary_distances_saturate_in_eight_bits(oracle, rb, ctx):
+    """One open 300x300-cell floor: erode_walkable_area keeps its distances in u8 with saturating adds (area.rs:142-219), so
+    everything further than 127 cells from the border sits at 255; a radius of 100 (threshold 200) then eats a 100-cell rim.
+    The distance field proper (u16) is far from saturating here and must come out as the oracle's as well."""
+    import recast_rs_b200 as r
+
+    v = np.array([0, 1, 0, 150, 1, 0, 150, 1, 150, 0, 1, 150], np.float32)
+    idx = np.array([0, 2, 1, 0, 3, 2], np.int32)
+    cfg = r.RecastConfig(cs=0.5, ch=0.25)
+    cfg.bmin, cfg.bmax, cfg.width, cfg.height = (0.0, 0.0, 0.0), (150.0, 5.0, 150.0), 300, 300
+    for radius in (1, 100):
+        tot = _check_batch(oracle, rb, ctx, v, idx, [cfg], rb.STAGE_ALL_BUILD | rb.STAGE_ERODE, erode_radius=radius)
+        assert tot["spans"] == 300 * 300
+
+
 def test_permuted_triangle_order(oracle, rb, ctx):
     """Span area is order dependent: the GPU must replay fragments in triangle order."""
     import recast_rs_b200 as r
