@@ -78,6 +78,54 @@ def test_oracle_vs_pymodel_area_ops(oracle, seed):
     assert changed > 0
 
 
+def _poison_ops(rng, ops):
+    """One parameter of every volume becomes NaN, +-inf, +-3e38 or 0: the reference validates none of them (area.rs:298-437,
+    544-618), its casts and comparisons decide."""
+    vals = [np.nan, np.inf, -np.inf, 3e38, -3e38, 0.0]
+    pick = lambda: float(vals[int(rng.integers(0, len(vals)))])
+    out = []
+    for op in ops:
+        op = list(op)
+        if op[0] == "box":
+            a, b = list(op[1]), list(op[2])
+            (a if rng.random() < 0.5 else b)[int(rng.integers(0, 3))] = pick()
+            op[1], op[2] = tuple(a), tuple(b)
+        elif op[0] == "cylinder":
+            k = int(rng.integers(0, 3))
+            if k == 0:
+                p = list(op[1])
+                p[int(rng.integers(0, 3))] = pick()
+                op[1] = tuple(p)
+            else:
+                op[1 + k] = pick()
+        elif op[0] == "poly":
+            k = int(rng.integers(0, 3))
+            if k == 0:
+                vv = op[1].copy()
+                vv[int(rng.integers(0, len(vv))), int(rng.choice([0, 2]))] = pick()
+                op[1] = vv
+            else:
+                op[1 + k] = pick()
+        out.append(tuple(op))
+    return out
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_oracle_vs_pymodel_area_ops_with_non_finite_parameters(oracle, seed):
+    cfg, v, idx, ops = _scene(seed)
+    ops = _poison_ops(np.random.default_rng(9000 + seed), ops)
+    ohf = oracle.Heightfield.from_config(cfg)
+    ohf.builder_rasterize(cfg, v, idx)
+    phf = pm.Heightfield(cfg.width, cfg.height, cfg.bmin, cfg.bmax, cfg.cs, cfg.ch)
+    with np.errstate(all="ignore"):
+        pm.builder_rasterize(phf, cfg, v, idx)
+        oc, pc = oracle.CompactHeightfield.build_from_heightfield(ohf), pm.Compact(phf)
+        for op in ops:
+            _apply_oracle(oc, op)
+            _apply_pm(pc, op)
+            assert oc.export().areas.tolist() == pc.areas, op[0]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed", range(4))
 def test_gpu_area_ops(oracle, seed):
@@ -111,4 +159,25 @@ def test_gpu_area_ops(oracle, seed):
     np.testing.assert_array_equal(tv.areas, want.areas)
     np.testing.assert_array_equal(tv.dist, want.dist)
     assert tv.max_distance == want.max_distance
+    ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(3))
+def test_gpu_area_ops_with_non_finite_parameters(oracle, seed):
+    import recast_rs_b200.builder as rb
+
+    cfg, v, idx, ops = _scene(30 + seed)
+    ops = _poison_ops(np.random.default_rng(9100 + seed), ops)
+    ohf = oracle.Heightfield.from_config(cfg)
+    ohf.builder_rasterize(cfg, v, idx)
+    e = ohf.export()
+    ctx = rb.Context(0)
+    hf = rb.Heightfield(cfg.width, cfg.height, cfg.bmin, cfg.bmax, cfg.cs, cfg.ch, e.cell_offset, e.span_min, e.span_max, e.span_area, ctx=ctx)
+    oc = oracle.CompactHeightfield.build_from_heightfield(ohf)
+    for op in ops:
+        _apply_oracle(oc, op)
+    with ctx.apply_area_ops([hf._cfg()], hf.cell_offset, hf.span_min, hf.span_max, hf.span_area, ops, stage_mask=rb.STAGE_COMPACT) as r:
+        tv = r.download().tile(0)
+    np.testing.assert_array_equal(tv.areas, oc.export().areas)
     ctx.close()

@@ -55,6 +55,36 @@ def test_oracle_vs_pymodel_tilecache(oracle, seed):
         _eq_pm(a, pm.tilecache_build(l, obstacles, cs, ch))
 
 
+def _poison_obstacles(rng, obstacles):
+    """One parameter of every obstacle becomes NaN, +-inf, +-3e38 or 0 (nothing in tile_cache_builder.rs:175-549 checks)."""
+    import dataclasses
+
+    vals = [np.nan, np.inf, -np.inf, 3e38, -3e38, 0.0]
+    out = []
+    for o in obstacles:
+        a, b, rot = list(o.a), list(o.b), list(o.rot_aux)
+        val = float(vals[int(rng.integers(0, len(vals)))])
+        k = int(rng.integers(0, 3))
+        if k == 0:
+            a[int(rng.integers(0, 3))] = val
+        elif k == 1:
+            b[int(rng.integers(0, 3))] = val
+        else:
+            rot[int(rng.integers(0, 2))] = val
+        out.append(dataclasses.replace(o, a=tuple(a), b=tuple(b), rot_aux=tuple(rot)))
+    return out
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_oracle_vs_pymodel_tilecache_with_non_finite_obstacles(oracle, seed):
+    layers, obstacles, cs, ch = _random_case(seed)
+    obstacles = _poison_obstacles(np.random.default_rng(4000 + seed), obstacles)
+    got = oracle.tilecache_build(layers, obstacles, cs, ch)
+    with np.errstate(all="ignore"):
+        for l, a in zip(layers, got):
+            _eq_pm(a, pm.tilecache_build(l, obstacles, cs, ch))
+
+
 def test_obstacles_clear_span_area_only(oracle):
     layers, obstacles = tc.config5(9, 16)
     got = oracle.tilecache_build(layers, obstacles, 0.3, 0.2)
@@ -93,6 +123,21 @@ def test_gpu_tilecache_random(oracle, seed):
         r.download()
         want = oracle.tilecache_build(layers, obstacles, cs, ch)
         for i, a in enumerate(want):
+            _assert_tile(r.tile(i), a, f"layer {i}")
+    ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(3))
+def test_gpu_tilecache_non_finite_obstacles(oracle, seed):
+    import recast_rs_b200.builder as rb
+
+    layers, obstacles, cs, ch = _random_case(200 + seed, nlayers=12)
+    obstacles = _poison_obstacles(np.random.default_rng(4200 + seed), obstacles)
+    ctx = rb.Context(0)
+    with ctx.build_tilecache_layers(layers, obstacles, cs, ch) as r:
+        r.download()
+        for i, a in enumerate(oracle.tilecache_build(layers, obstacles, cs, ch)):
             _assert_tile(r.tile(i), a, f"layer {i}")
     ctx.close()
 
