@@ -46,6 +46,26 @@ def test_oracle_vs_pymodel_regions(oracle, seed):
         assert (reg[oc.export().areas == 0] == 0).all()
 
 
+ODD_PARAMS = [(0, 0, 0), (1, 1, 1), (-1, 8, 20), (3, -5, 20), (3, 8, -1), (100, 8, 20), (2, 100000, 20), (2, 0, 100000), (5, 1, 0),
+              (0, 2147483647, 2147483647), (-100, -100, -100)]
+
+
+@pytest.mark.parametrize("seed", [0, 4, 8])
+def test_oracle_vs_pymodel_regions_with_odd_parameters(oracle, seed):
+    """border_size, min_region_area and merge_region_area are plain i32 that nothing validates (watershed.rs:364-375): borders
+    wider than the tile, negative sizes, areas nothing can reach.  The two restatements must take them the same way."""
+    cfg, v, idx = _scene(seed)
+    ohf = oracle.Heightfield.from_config(cfg)
+    ohf.builder_rasterize(cfg, v, idx)
+    phf = pm.Heightfield(cfg.width, cfg.height, cfg.bmin, cfg.bmax, cfg.cs, cfg.ch)
+    pm.builder_rasterize(phf, cfg, v, idx)
+    for (b, mn, mg) in ODD_PARAMS:
+        oc, pc = oracle.CompactHeightfield.build_from_heightfield(ohf), pm.Compact(phf)
+        reg, mr = oc.build_regions(b, mn, mg)
+        preg, pmr = pm.build_regions_watershed(pc, b, mn, mg)
+        assert mr == pmr and reg.tolist() == preg, (b, mn, mg)
+
+
 def test_regions_basic_properties(oracle):
     """Regions never span two plateaus that no connection joins; min_region_area only ever removes regions; every
     walkable span that keeps a region has it from a connected neighbourhood (no label without a span count)."""
@@ -79,6 +99,24 @@ def test_gpu_regions_single_tiles(oracle, seed):
     with rb.Context(0) as ctx:
         hf = rb.Heightfield(cfg.width, cfg.height, cfg.bmin, cfg.bmax, cfg.cs, cfg.ch, e.cell_offset, e.span_min, e.span_max, e.span_area, ctx=ctx)
         for (b, mn, mg) in PARAMS:
+            want, wmr = oracle.CompactHeightfield.build_from_heightfield(ohf).build_regions(b, mn, mg)
+            chf = rb.CompactHeightfield.build_from_heightfield(hf)
+            chf.build_regions(b, mn, mg)
+            assert chf.max_regions == wmr, (b, mn, mg)
+            np.testing.assert_array_equal(chf.reg, want, err_msg=str((b, mn, mg)))
+
+
+@pytest.mark.gpu
+def test_gpu_regions_with_odd_parameters(oracle):
+    import recast_rs_b200.builder as rb
+
+    cfg, v, idx = _scene(104)
+    ohf = oracle.Heightfield.from_config(cfg)
+    ohf.builder_rasterize(cfg, v, idx)
+    e = ohf.export()
+    with rb.Context(0) as ctx:
+        hf = rb.Heightfield(cfg.width, cfg.height, cfg.bmin, cfg.bmax, cfg.cs, cfg.ch, e.cell_offset, e.span_min, e.span_max, e.span_area, ctx=ctx)
+        for (b, mn, mg) in ODD_PARAMS:
             want, wmr = oracle.CompactHeightfield.build_from_heightfield(ohf).build_regions(b, mn, mg)
             chf = rb.CompactHeightfield.build_from_heightfield(hf)
             chf.build_regions(b, mn, mg)
