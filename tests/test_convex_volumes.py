@@ -108,6 +108,36 @@ def test_oracle_vs_pymodel_apply_volumes(oracle, seed):
         assert (a.span_area != before).any()
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_oracle_vs_pymodel_volumes_with_non_finite_values(oracle, seed):
+    """Volumes that carry a NaN, an infinity or 3e38 in a vertex or a height (built past ConvexVolume::new, whose `min > max`
+    test lets NaN through anyway): contains_point's comparisons (convex_volume.rs:130-164) decide, the same way in both
+    restatements."""
+    cfg, v, idx, vs = _scene(seed)
+    rng = np.random.default_rng(7000 + seed)
+    vals = [np.nan, np.inf, -np.inf, 3e38, -3e38, 0.0]
+    ps = ConvexVolumeSet()
+    for vol in vs.volumes:
+        verts = np.array(vol.vertices, dtype=np.float32).reshape(-1, 3).copy()
+        mn, mx = vol.min_height, vol.max_height
+        k, val = int(rng.integers(0, 3)), float(vals[int(rng.integers(0, len(vals)))])
+        if k == 0:
+            verts[int(rng.integers(0, len(verts))), int(rng.integers(0, 3))] = val
+        elif k == 1:
+            mn = val
+        else:
+            mx = val
+        ps.add_volume(ConvexVolume(verts, mn, mx, vol.area_type))
+    ohf = oracle.Heightfield.from_config(cfg)
+    ohf.builder_rasterize(cfg, v, idx)
+    phf = pm.Heightfield(cfg.width, cfg.height, cfg.bmin, cfg.bmax, cfg.cs, cfg.ch)
+    with np.errstate(all="ignore"):
+        pm.builder_rasterize(phf, cfg, v, idx)
+        ohf.apply_convex_volumes(ps)
+        pm.apply_convex_volumes(phf, [(np.asarray(x.vertices).tolist(), x.min_height, x.max_height, x.area_type) for x in ps.volumes])
+    assert np.array_equal(ohf.export().span_area, phf.export()[3])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed", range(6))
 def test_gpu_volumes(oracle, seed):
