@@ -120,6 +120,35 @@ def test_non_finite_vertices(oracle, seed):
     _compare_chf(ochf.export(), pchf)
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_odd_configurations(oracle, seed):
+    """Cell sizes from a centimetre to a hundred metres, cell heights from a millimetre to fifty metres, origins ten million
+    units away (where f32 has no fraction left), height ranges that saturate i16, slope limits of 0, 0.001, 89.99 and 90
+    degrees, tiles of a single cell: both restatements through rasterization, filters, compaction, distance field, erosion."""
+    rng = np.random.default_rng(20000 + seed)
+    w, h = int(rng.integers(1, 10)), int(rng.integers(1, 10))
+    cs = float(rng.choice([0.01, 0.3, 0.5, 1.0, 7.5, 100.0]))
+    ch = float(rng.choice([0.001, 0.2, 0.25, 1.0, 50.0]))
+    org = float(rng.choice([0.0, -3.0, 1e4, -1e6, 1e7]))
+    bmin = (org + float(rng.uniform(-1, 1)) * cs, float(rng.choice([0.0, -5.0, 1e4, -1e5])) * ch / 0.25, org + float(rng.uniform(-1, 1)) * cs)
+    slope = float(rng.choice([0.0, 0.001, 30.0, 45.0, 89.99, 90.0]))
+    cfg = _cfg(w, h, bmin, cs, ch, bmin[1] + float(rng.choice([6.0, 1e5])) * ch, walkable_height=int(rng.integers(0, 6)),
+               walkable_climb=int(rng.integers(0, 4)), walkable_slope_angle=slope)
+    lo = min(bmin[0], bmin[2])
+    v, idx = _random_soup(rng, 40, lo, lo + max(w, h) * cs, bmin[1] - 2 * ch, bmin[1] + float(rng.choice([30.0, 4e4, 2e5])) * ch, small=cs)
+    ohf = oracle.Heightfield.from_config(cfg)
+    ohf.builder_rasterize(cfg, v, idx, run_filters=True)
+    phf = pm.Heightfield(w, h, cfg.bmin, cfg.bmax, cs, ch)
+    with np.errstate(all="ignore"):
+        pm.builder_rasterize(phf, cfg, v, idx, run_filters=True)
+    _compare_hf(ohf, phf)
+    o, p = oracle.CompactHeightfield.build_from_heightfield(ohf), pm.Compact(phf)
+    o.build_distance_field(), p.build_distance_field()
+    _compare_chf(o.export(), p)
+    o.erode_walkable_area(1), p.erode_walkable_area(1)
+    _compare_chf(o.export(), p)
+
+
 @pytest.mark.parametrize("seed", range(4))
 def test_add_span_rules_random_columns(oracle, seed):
     """Both merge rules (rasterization.rs:51 and heightfield.rs:144) on random columns, incl.
